@@ -1,0 +1,13 @@
+"""Import alias: the product package lives in the directory `d3human-code_b200/` (the name the build
+contract fixes); Python cannot import a hyphenated name, so `import d3human_code_b200` loads that
+directory under this module name."""
+import importlib.util as _ilu
+import os as _os
+import sys as _sys
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "d3human-code_b200")
+_spec = _ilu.spec_from_file_location(__name__, _os.path.join(_real, "__init__.py"),
+                                     submodule_search_locations=[_real])
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,83 @@
+"""Shared comparison helpers for the parity tests (oracle vs golden, CUDA vs oracle, CUDA vs golden)."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+#: tolerances stated by BASELINE.json north_star
+POS_RTOL = 1e-6      # interpolated positions (we are bit-exact in practice; the assert uses exact first)
+GRAD_RTOL = 1e-5     # gradients, normwise (max |diff| / max |ref|)
+TNG_ATOL = 2e-5      # unit tangents: scatter order (and ATen's approximate CPU sqrt) differ by a few ulp
+
+
+def golden_cases():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    rec = {k: z[k] for k in z.files}
+    cls, typ, wt = [str(x) for x in rec.pop("meta")]
+    rec["cls"], rec["type"], rec["wt"] = cls, (None if typ == "None" else typ), wt == "True"
+    rec["sign"] = -1 if rec["type"] == "body" else 1
+    return rec
+
+
+def assert_exact(name, got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
+    assert got.dtype == want.dtype, f"{name}: dtype {got.dtype} != {want.dtype}"
+    if not np.array_equal(got, want):
+        bad = np.nonzero(got != want)
+        raise AssertionError(f"{name}: {len(bad[0])} mismatching elements, first at {[b[0] for b in bad]}: "
+                             f"{got[tuple(b[0] for b in bad)]} != {want[tuple(b[0] for b in bad)]}")
+
+
+def assert_close_normwise(name, got, want, rtol):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
+    if want.size == 0:
+        return
+    scale = np.abs(want).max()
+    err = np.abs(got - want).max()
+    assert err <= rtol * max(scale, 1e-30), f"{name}: max|diff|={err:.3e} > {rtol:g} * max|ref|={scale:.3e}"
+
+
+def assert_tangents_close(name, got, want, atol=TNG_ATOL):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
+    assert got.dtype == want.dtype
+    both_nan = np.isnan(got) & np.isnan(want)
+    diff = np.where(both_nan, 0.0, np.abs(got.astype(np.float64) - want.astype(np.float64)))
+    assert not np.isnan(diff).any(), f"{name}: NaN pattern differs"
+    assert diff.max(initial=0.0) <= atol, f"{name}: max|diff|={diff.max():.3e} > {atol:g}"
+
+
+def check_forward_against_golden(out, rec, tangents=True, tng_atol=TNG_ATOL):
+    """out: dict with the reference's return values (numpy). rec: golden record."""
+    assert_exact("faces_aug", out["faces_aug"], rec["faces_aug"])
+    assert_exact("verts_aug", out["verts_aug"], rec["verts_aug"])
+    assert_exact("msdf", out["msdf"], rec["extra_msdf"])
+    assert_exact("msdf_watertight", out["msdf_watertight"], rec["extra_msdf_watertight"])
+    assert_exact("msdf_boundary", out["msdf_boundary"], rec["extra_msdf_boundary"])
+    if rec["wt"]:
+        assert int(out["n_verts_watertight"]) == int(rec["extra_n_verts_watertight"])
+        assert_exact("faces_watertight", out["faces_watertight"], rec["extra_faces_watertight"])
+        assert_exact("vertices_watertight", out["vertices_watertight"], rec["extra_vertices_watertight"])
+        if tangents:
+            assert_tangents_close("v_tng_watertight", out["v_tng_watertight"], rec["extra_v_tng_watertight"], tng_atol)
+    else:
+        assert "extra_vertices_watertight" not in rec
+    if tangents:
+        assert_tangents_close("v_tng_aug", out["v_tng_aug"], rec["v_tng_aug"], tng_atol)
+
+
+def check_grads_against_golden(g_pos, g_sdf, g_msdf, rec):
+    assert_close_normwise("grad_pos", g_pos, rec["grad_pos"], GRAD_RTOL)
+    assert_close_normwise("grad_sdf", np.asarray(g_sdf).reshape(rec["grad_sdf"].shape), rec["grad_sdf"], GRAD_RTOL)
+    if "grad_msdf" in rec:
+        assert g_msdf is not None
+        assert_close_normwise("grad_msdf", g_msdf, rec["grad_msdf"], GRAD_RTOL)
+    else:
+        assert g_msdf is None, "type='body' must not produce an msdf gradient (hmsdf_tets_split.py:261-264)"

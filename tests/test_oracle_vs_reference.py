@@ -1,0 +1,97 @@
+"""The numpy oracle against the LIVE reference (only where /root/reference exists, i.e. the build container)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gshell_oracle as O
+from oracle.ref_loader import load_reference_class, reference_available
+from d3human_code_b200 import grids
+from tests import _util as U
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not reference_available(), reason="reference tree not present on this machine")]
+
+
+def test_case_tables_equal_reference():
+    ref = load_reference_class("GShell_Tets", "cpu")
+    for mine, theirs in ((O.TRIANGLE_TABLE, ref.triangle_table), (O.MESH_EDGE_TABLE, ref.mesh_edge_table),
+                         (O.TRIANGLE_TABLE_TRI, ref.triangle_table_tri), (O.TRIANGLE_TABLE_QUAD, ref.triangle_table_quad),
+                         (O.NUM_TRIANGLES_TABLE, ref.num_triangles_table), (O.BASE_TET_EDGES, ref.base_tet_edges),
+                         (O.NUM_TRIANGLES_TRI_TABLE, ref.num_triangles_tri_table),
+                         (O.NUM_TRIANGLES_QUAD_TABLE, ref.num_triangles_quad_table)):
+        assert np.array_equal(mine, theirs.numpy())
+    ref2 = load_reference_class("hmSDF_Tets", "cpu")
+    assert np.array_equal(O.TRIANGLE_TABLE_QUAD, ref2.triangle_table_quad.numpy())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 17, 100, 1254, 3548, 10033])
+def test_linspace_restatement(n):
+    want = torch.linspace(0, 1 - (1 / n), n, dtype=torch.float32).numpy()
+    assert np.array_equal(O.linspace_f32(n), want)
+
+
+def test_uv_atlas_indexed_by_vertex_id():
+    ref = load_reference_class("GShell_Tets", "cpu")
+    for num_tets in (1, 7, 750, 6000):
+        uvs, _ = ref.map_uv(torch.zeros(1, dtype=torch.long), num_tets * 2)
+        k = np.arange(uvs.shape[0])
+        assert np.array_equal(O.vertex_uv(k, num_tets), uvs.numpy())
+
+
+def test_cross_restatement():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((20000, 3)).astype(np.float32)
+    b = (a * np.float32(1.7) + rng.standard_normal((20000, 3)).astype(np.float32) * np.float32(1e-3)).astype(np.float32)
+    want = torch.cross(torch.tensor(a), torch.tensor(b), dim=-1).numpy()
+    assert np.array_equal(O._cross_f32(a, b, -1), want)
+
+
+def _run_reference(cls, typ, wt, pos, sdf, msdf, tets):
+    obj = load_reference_class(cls, "cpu")
+    tp = torch.tensor(pos, requires_grad=True)
+    ts = torch.tensor(sdf[:, None], requires_grad=True)
+    tm = torch.tensor(msdf, requires_grad=True)
+    args = (tp, ts, tm, torch.from_numpy(tets)) + ((typ,) if cls == "hmSDF_Tets" else ()) + (wt,)
+    return obj(*args), (tp, ts, tm)
+
+
+@pytest.mark.parametrize("res,field,cls,typ,wt", [
+    (16, "sphere", "GShell_Tets", None, True),
+    (20, "capsule", "hmSDF_Tets", "cloth", True),
+    (20, "capsule", "hmSDF_Tets", "body", True),
+    (10, "adv", "GShell_Tets", None, True),
+    (10, "adv", "hmSDF_Tets", "body", False),
+    (9, "adv", "GShell_Tets", None, False),
+])
+def test_oracle_matches_live_reference(res, field, cls, typ, wt):
+    pos, tets = grids.kuhn_grid(res)
+    if field == "sphere":
+        sdf, msdf = grids.sphere_plane_field(pos)
+    elif field == "capsule":
+        sdf, msdf = grids.capsule_garment_field(pos)
+    else:
+        pos, sdf, msdf = grids.adversarial_field(pos, res, seed=res)
+    (verts, faces, _, _, v_tng, extra), (tp, ts, tm) = _run_reference(cls, typ, wt, pos, sdf, msdf, tets)
+    sign = -1 if typ == "body" else 1
+    fwd = O.extract_forward(pos, sdf, msdf, tets, sign, wt)
+    U.assert_exact("faces_aug", fwd["faces_aug"], faces.numpy())
+    U.assert_exact("verts_aug", fwd["verts_aug"], verts.detach().numpy())
+    U.assert_exact("msdf", fwd["msdf"], extra["msdf"].detach().numpy())
+    U.assert_tangents_close("v_tng_aug", fwd["v_tng_aug"], v_tng.detach().numpy())
+    assert tuple(extra.keys()) == fwd["extra_keys"]
+    if wt:
+        U.assert_exact("faces_watertight", fwd["faces_watertight"], extra["faces_watertight"].numpy())
+        U.assert_exact("vertices_watertight", fwd["vertices_watertight"], extra["vertices_watertight"].detach().numpy())
+        assert extra["n_verts_watertight"] == fwd["n_verts_watertight"]
+    rng = np.random.default_rng(3)
+    gv = rng.standard_normal(fwd["verts_aug"].shape).astype(np.float32)
+    gm = rng.standard_normal(fwd["msdf"].shape).astype(np.float32)
+    loss = (verts * torch.tensor(gv)).sum() + (extra["msdf"] * torch.tensor(gm)).sum()
+    loss.backward()
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, gm)
+    U.assert_close_normwise("grad_pos", g_pos, tp.grad.numpy(), U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", g_sdf, ts.grad.numpy()[:, 0], U.GRAD_RTOL)
+    if typ == "body":
+        assert tm.grad is None and g_msdf is None
+    else:
+        U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), U.GRAD_RTOL)
