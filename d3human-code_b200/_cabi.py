@@ -1,0 +1,103 @@
+"""ctypes binding of libd3h_tets.so (C ABI declared in include/d3h_tets.h).
+
+The library is the product: there is no Python / PyTorch fallback.  If it is missing or fails to load, every
+entry point raises.  PyTorch is only used by the callers for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
+
+D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS = 0, -1, -2, -3
+
+#: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
+    "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_extract_backward",
+    "d3h_classify_range", "d3h_extract_from_records",
+)
+
+
+class Counts(C.Structure):  # d3h_counts
+    _fields_ = [("n_valid_tets", C.c_int64), ("n_tri_tets", C.c_int64), ("n_quad_tets", C.c_int64),
+                ("n_corners", C.c_int64), ("n_verts", C.c_int64), ("n_faces_aug", C.c_int64),
+                ("bucket_polys", C.c_int64 * 6), ("bad_index", C.c_int64), ("reserved", C.c_int64 * 3)]
+
+
+COUNTS_WORDS = C.sizeof(Counts) // 8  # int64 words
+
+
+class ForwardArgs(C.Structure):  # d3h_forward_args
+    _fields_ = [("pos", C.c_void_p), ("sdf", C.c_void_p), ("msdf", C.c_void_p), ("tets", C.c_void_p),
+                ("n_grid", C.c_int64), ("n_tets", C.c_int64), ("tet_begin", C.c_int64), ("tet_end", C.c_int64),
+                ("msdf_negate", C.c_int32), ("watertight_template", C.c_int32),
+                ("cap_valid_tets", C.c_int64), ("cap_verts", C.c_int64), ("cap_verts_aug", C.c_int64),
+                ("cap_faces_wt", C.c_int64), ("cap_faces_aug", C.c_int64),
+                ("verts_aug", C.c_void_p), ("v_tng_aug", C.c_void_p), ("msdf_aug", C.c_void_p),
+                ("faces_aug", C.c_void_p), ("verts_wt", C.c_void_p), ("v_tng_wt", C.c_void_p),
+                ("msdf_wt", C.c_void_p), ("faces_wt", C.c_void_p),
+                ("tape_edges", C.c_void_p), ("tape_corners", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("counts_host", C.c_void_p)]
+
+
+class BackwardArgs(C.Structure):  # d3h_backward_args
+    _fields_ = [("pos", C.c_void_p), ("sdf", C.c_void_p), ("msdf", C.c_void_p), ("n_grid", C.c_int64),
+                ("msdf_negate", C.c_int32), ("reserved0", C.c_int32),
+                ("tape_edges", C.c_void_p), ("tape_corners", C.c_void_p), ("verts_wt", C.c_void_p),
+                ("msdf_wt", C.c_void_p), ("n_verts", C.c_int64), ("n_tri_tets", C.c_int64),
+                ("n_quad_tets", C.c_int64),
+                ("g_verts_aug", C.c_void_p), ("g_msdf_aug", C.c_void_p), ("g_verts_wt", C.c_void_p),
+                ("g_msdf_wt", C.c_void_p),
+                ("g_pos", C.c_void_p), ("g_sdf", C.c_void_p), ("g_msdf", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+TET_RECORD_BYTES = 32  # sizeof(d3h_tet_record)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once.  Raises if it has not been built (`python d3human-code_b200/build.py`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA library is the only implementation of this package "
+            "(no CPU fallback). Build it with `python d3human-code_b200/build.py` (needs nvcc).")
+    L = C.CDLL(LIB_PATH)
+    L.d3h_version.restype = C.c_int
+    L.d3h_last_error_string.restype = C.c_char_p
+    L.d3h_workspace_bytes.restype = C.c_int64
+    L.d3h_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+    L.d3h_backward_workspace_bytes.restype = C.c_int64
+    L.d3h_backward_workspace_bytes.argtypes = [C.c_int64]
+    L.d3h_pack_tets_i64.restype = C.c_int
+    L.d3h_pack_tets_i64.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.d3h_check_tets_i32.restype = C.c_int
+    L.d3h_check_tets_i32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    L.d3h_extract_forward.restype = C.c_int
+    L.d3h_extract_forward.argtypes = [C.POINTER(ForwardArgs), C.c_void_p]
+    L.d3h_extract_backward.restype = C.c_int
+    L.d3h_extract_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
+    L.d3h_classify_range.restype = C.c_int
+    L.d3h_classify_range.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.d3h_extract_from_records.restype = C.c_int
+    L.d3h_extract_from_records.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    L.d3h_debug_table.restype = C.c_int
+    L.d3h_debug_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    if L.d3h_version() != 100:
+        raise RuntimeError(f"libd3h_tets.so version {L.d3h_version()} does not match this package (100); rebuild")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    """Mirror of the reference plugins' TORCH_CHECK behaviour (torch_bindings.cpp:25-31): errors become RuntimeError."""
+    if rc != 0:
+        msg = lib().d3h_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

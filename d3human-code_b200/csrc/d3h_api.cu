@@ -1,0 +1,227 @@
+// C-ABI entry points of libd3h_tets.so (declared in include/d3h_tets.h) and the workspace carving.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "d3h_internal.cuh"
+
+namespace d3h {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
+
+Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets) {
+  Workspace ws;
+  memset(&ws, 0, sizeof(ws));
+  char* p = reinterpret_cast<char*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) -> void* {
+    void* r = p ? (p + off) : nullptr;
+    off += align256(bytes > 0 ? bytes : 1);
+    return r;
+  };
+  const int64_t cap = cap_valid_tets > 0 ? cap_valid_tets : 0;
+  const int64_t capc = 4 * cap;
+  ws.cap_tets = cap;
+  ws.cap_corners = capc;
+  ws.ntiles_classify = (n_tets + kClassifyTile - 1) / kClassifyTile;
+  ws.ntiles_sort = (capc + kSortTile - 1) / kSortTile;
+  ws.ntiles_rle = (capc + kRleTile - 1) / kRleTile;
+  ws.ntiles_poly = (cap + kPolyThreads - 1) / kPolyThreads;
+  const int64_t nwords = (n_grid + 31) / 32 + 1;
+  ws.ctr = reinterpret_cast<DevCounters*>(take(sizeof(DevCounters)));
+  ws.counts = reinterpret_cast<d3h_counts*>(take(sizeof(d3h_counts)));
+  ws.occ_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
+  ws.mocc_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
+  ws.st_classify = reinterpret_cast<unsigned long long*>(take(ws.ntiles_classify * 8));
+  ws.records = reinterpret_cast<d3h_tet_record*>(take(cap * (int64_t)sizeof(d3h_tet_record)));
+  ws.keys[0] = reinterpret_cast<unsigned long long*>(take(capc * 8));
+  ws.keys[1] = reinterpret_cast<unsigned long long*>(take(capc * 8));
+  ws.vals[0] = reinterpret_cast<unsigned*>(take(capc * 4));
+  ws.vals[1] = reinterpret_cast<unsigned*>(take(capc * 4));
+  ws.radix_hist = reinterpret_cast<unsigned*>(take(kMaxPasses * kRadix * 4));
+  ws.st_sort = reinterpret_cast<unsigned*>(take(ws.ntiles_sort * kRadix * 4 * (int64_t)kMaxPasses));
+  ws.st_rle = reinterpret_cast<unsigned long long*>(take(ws.ntiles_rle * 8));
+  ws.st_poly = reinterpret_cast<unsigned*>(take(ws.ntiles_poly * 8 * 4));
+  ws.vert = reinterpret_cast<float4*>(take(capc * 16));
+  ws.tng = reinterpret_cast<float4*>(take(capc * 16));
+  ws.acc = reinterpret_cast<float*>(take(capc * 32));
+  ws.polyinfo = reinterpret_cast<unsigned*>(take(cap * 4));
+  ws.total_bytes = off;
+  return ws;
+}
+
+static int check_forward_args(const d3h_forward_args* a, const char* who) {
+  if (!a) { set_error("%s: null argument struct", who); return D3H_E_BADARG; }
+  if (a->n_grid <= 0 || a->n_grid >= (1ll << 31) || a->n_tets < 0 || a->n_tets >= (1ll << 31)) {
+    set_error("%s: n_grid=%lld / n_tets=%lld outside [1,2^31) / [0,2^31)", who, (long long)a->n_grid, (long long)a->n_tets);
+    return D3H_E_BADARG;
+  }
+  if (!a->pos || !a->sdf || !a->msdf || (!a->tets && a->n_tets > 0) || !a->workspace) {
+    set_error("%s: null input / workspace pointer", who);
+    return D3H_E_BADARG;
+  }
+  if (reinterpret_cast<uintptr_t>(a->tets) & 15) { set_error("%s: tets must be 16-byte aligned", who); return D3H_E_BADARG; }
+  if (reinterpret_cast<uintptr_t>(a->workspace) & 255) { set_error("%s: workspace must be 256-byte aligned", who); return D3H_E_BADARG; }
+  if (a->tet_begin < 0 || a->tet_end < a->tet_begin || a->tet_end > a->n_tets) {
+    set_error("%s: tet range [%lld,%lld) outside [0,%lld)", who, (long long)a->tet_begin, (long long)a->tet_end, (long long)a->n_tets);
+    return D3H_E_BADARG;
+  }
+  if (a->cap_valid_tets < 0 || a->cap_valid_tets > (1ll << 27) || a->cap_verts < 0 || a->cap_verts_aug < 0 ||
+      a->cap_faces_wt < 0 || a->cap_faces_aug < 0) {
+    set_error("%s: capacities must be >= 0 and cap_valid_tets <= 2^27", who);
+    return D3H_E_BADARG;
+  }
+  if (a->cap_valid_tets > 0 && !a->tape_corners) { set_error("%s: tape_corners (4*cap_valid_tets int32) is required", who); return D3H_E_BADARG; }
+  if ((a->cap_verts > 0 && (!a->verts_wt || !a->v_tng_wt || !a->msdf_wt || !a->tape_edges)) ||
+      (a->cap_verts_aug > 0 && (!a->verts_aug || !a->v_tng_aug || !a->msdf_aug)) ||
+      (a->cap_faces_wt > 0 && !a->faces_wt) || (a->cap_faces_aug > 0 && !a->faces_aug)) {
+    set_error("%s: an output pointer is null while its capacity is > 0", who);
+    return D3H_E_BADARG;
+  }
+  const int64_t need = carve_workspace(nullptr, a->n_tets, a->n_grid, a->cap_valid_tets).total_bytes;
+  if (a->workspace_bytes < need) {
+    set_error("%s: workspace has %lld bytes, %lld needed", who, (long long)a->workspace_bytes, (long long)need);
+    return D3H_E_SMALLWS;
+  }
+  return D3H_OK;
+}
+
+static int finish(const char* who, const Workspace& ws, d3h_counts* counts_host, cudaStream_t stream) {
+  if (counts_host) cudaMemcpyAsync(counts_host, ws.counts, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}
+
+}  // namespace d3h
+
+using namespace d3h;
+
+extern "C" int d3h_version(void) { return D3H_VERSION; }
+extern "C" const char* d3h_last_error_string(void) { return g_error; }
+
+extern "C" int64_t d3h_workspace_bytes(int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets) {
+  if (n_tets < 0 || n_grid <= 0 || cap_valid_tets < 0) return D3H_E_BADARG;
+  return carve_workspace(nullptr, n_tets, n_grid, cap_valid_tets).total_bytes;
+}
+extern "C" int64_t d3h_backward_workspace_bytes(int64_t n_verts) { return align256(32 * (n_verts > 0 ? n_verts : 0) + 256); }
+
+extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
+  int rc = check_forward_args(a, "d3h_extract_forward");
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)s;
+  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+  launch_prepare(*a, ws, stream);
+  launch_classify(*a, ws, ws.records, ws.cap_tets, stream);
+  launch_edge_sort(*a, ws, ws.records, stream);
+  launch_surface(*a, ws, ws.records, stream);
+  return finish("d3h_extract_forward", ws, a->counts_host, stream);
+}
+
+// stage 1 only: prepare + classify of [tet_begin, tet_end); the compact records land in `records_out`
+// (class ranks are local to the range) and the counts so far (n_valid/n_tri/n_quad) in `counts_dev_out`.
+__global__ void export_range_counts_kernel(const DevCounters* ctr, d3h_counts* out) {
+  memset(out, 0, sizeof(d3h_counts));
+  out->n_valid_tets = ctr->n_valid;
+  out->n_tri_tets = ctr->n_tri;
+  out->n_quad_tets = ctr->n_quad;
+  out->n_corners = 3ll * ctr->n_tri + 4ll * ctr->n_quad;
+}
+
+extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* records_out, int64_t cap_records,
+                                  d3h_counts* counts_dev_out, d3h_stream_t s) {
+  int rc = check_forward_args(a, "d3h_classify_range");
+  if (rc) return rc;
+  if ((!records_out && cap_records > 0) || cap_records < 0 || !counts_dev_out) {
+    set_error("d3h_classify_range: null records / counts pointer");
+    return D3H_E_BADARG;
+  }
+  cudaStream_t stream = (cudaStream_t)s;
+  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+  launch_prepare(*a, ws, stream);
+  launch_classify(*a, ws, records_out, cap_records, stream);
+  export_range_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, counts_dev_out);
+  if (a->counts_host) cudaMemcpyAsync(a->counts_host, counts_dev_out, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d3h_classify_range: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}
+
+// stage 2 only: `records` is the rank-order concatenation of the shards' records (= global tet order);
+// n_tri_tets + n_quad_tets records.  Class ranks are recomputed over the concatenation.
+extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet_record* records, int64_t n_tri_tets,
+                                        int64_t n_quad_tets, d3h_stream_t s) {
+  int rc = check_forward_args(a, "d3h_extract_from_records");
+  if (rc) return rc;
+  const int64_t n = n_tri_tets + n_quad_tets;
+  if (n < 0 || n_tri_tets < 0 || n_quad_tets < 0 || n > a->cap_valid_tets || (!records && n > 0)) {
+    set_error("d3h_extract_from_records: %lld records do not fit cap_valid_tets=%lld", (long long)n, (long long)a->cap_valid_tets);
+    return D3H_E_BADARG;
+  }
+  cudaStream_t stream = (cudaStream_t)s;
+  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+  d3h_forward_args b = *a;
+  b.tet_begin = b.tet_end = 0;  // prepare still resets the scan state; no tets are classified here
+  launch_prepare(b, ws, stream);
+  if (n > 0) cudaMemcpyAsync(ws.records, records, n * sizeof(d3h_tet_record), cudaMemcpyDeviceToDevice, stream);
+  launch_rank_records(ws, ws.records, n, stream);
+  launch_edge_sort(*a, ws, ws.records, stream);
+  launch_surface(*a, ws, ws.records, stream);
+  return finish("d3h_extract_from_records", ws, a->counts_host, stream);
+}
+
+extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) {
+  if (!a) { set_error("d3h_extract_backward: null argument struct"); return D3H_E_BADARG; }
+  if (a->n_grid <= 0 || a->n_verts < 0 || a->n_tri_tets < 0 || a->n_quad_tets < 0 || !a->g_pos || !a->g_sdf ||
+      !a->pos || !a->sdf || !a->msdf || !a->workspace) {
+    set_error("d3h_extract_backward: null pointer or negative size");
+    return D3H_E_BADARG;
+  }
+  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->verts_wt || !a->msdf_wt)) {
+    set_error("d3h_extract_backward: tape / saved outputs missing");
+    return D3H_E_BADARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(a->g_pos) | reinterpret_cast<uintptr_t>(a->g_sdf) |
+       reinterpret_cast<uintptr_t>(a->g_msdf) | reinterpret_cast<uintptr_t>(a->workspace)) & 15) {
+    set_error("d3h_extract_backward: gradient buffers and workspace must be 16-byte aligned");
+    return D3H_E_BADARG;
+  }
+  if (a->workspace_bytes < d3h_backward_workspace_bytes(a->n_verts)) {
+    set_error("d3h_extract_backward: workspace too small");
+    return D3H_E_SMALLWS;
+  }
+  launch_backward(*a, (cudaStream_t)s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d3h_extract_backward: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}
+
+// ---- test hook: the case tables, from the same initializer macros the __constant__ copies are built from --------
+// which: 0 num_tri[16], 1 loop_edge[16][4], 2 tri_edge[16][6], 3 cut_tri[8][6], 4 num_cut_tri[8],
+//        5 cut_quad[16][12], 6 num_cut_quad[16], 7 edge_p[6], 8 edge_q[6].  Returns the element count.  Host only.
+extern "C" int d3h_debug_table(int which, int8_t* out, int cap) {
+  static const int8_t t0[16] = D3H_T_NUM_TRI;
+  static const int8_t t1[16][4] = D3H_T_LOOP_EDGE;
+  static const int8_t t2[16][6] = D3H_T_TRI_EDGE;
+  static const int8_t t3[8][6] = D3H_T_CUT_TRI;
+  static const int8_t t4[8] = D3H_T_NUM_CUT_TRI;
+  static const int8_t t5[16][12] = D3H_T_CUT_QUAD;
+  static const int8_t t6[16] = D3H_T_NUM_CUT_QUAD;
+  static const int8_t t7[6] = D3H_T_EDGE_P;
+  static const int8_t t8[6] = D3H_T_EDGE_Q;
+  const void* src[9] = {t0, t1, t2, t3, t4, t5, t6, t7, t8};
+  const int len[9] = {16, 64, 96, 48, 8, 192, 16, 6, 6};
+  if (which < 0 || which > 8) { set_error("d3h_debug_table: unknown table %d", which); return D3H_E_BADARG; }
+  if (cap < len[which] || !out) { set_error("d3h_debug_table: buffer too small"); return D3H_E_BADARG; }
+  memcpy(out, src[which], len[which]);
+  return len[which];
+}

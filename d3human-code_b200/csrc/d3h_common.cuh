@@ -1,0 +1,149 @@
+// Shared device helpers, case tables and the workspace layout of the sm_100a extraction kernels.
+//
+// Case tables are the reference's data (geometry/gshell_tets.py:91-190).  They are stored here in the
+// forms the kernels index directly; tests/test_cabi.py checks them element-for-element against the
+// oracle's copies through d3h_debug_table().
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/d3h_tets.h"
+
+namespace d3h {
+
+constexpr int kWarp = 32;
+constexpr float kEps12 = 1e-12f;
+
+// ------------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------------
+// Each table is written once as an initializer macro so that the __constant__ copy the kernels index and the host
+// copy returned by d3h_debug_table() (compared with the oracle in tests/test_cabi.py, no GPU needed) cannot diverge.
+// number of watertight triangles per occupancy code (gshell_tets.py:186)
+#define D3H_T_NUM_TRI {0, 1, 1, 2, 1, 2, 2, 1, 1, 2, 2, 1, 2, 1, 1, 0}
+// tet edge id -> local endpoints (gshell_tets.py:187)
+#define D3H_T_EDGE_P {0, 0, 0, 1, 1, 2}
+#define D3H_T_EDGE_Q {1, 2, 3, 2, 3, 3}
+// polygon loop per code: tet edge ids of the loop corners, first 3 (tri) or 4 (quad) entries of
+// mesh_edge_table (gshell_tets.py:110-127)
+#define D3H_T_LOOP_EDGE                                                                              \
+  {{-1, -1, -1, -1}, {1, 0, 2, -1}, {4, 0, 3, -1}, {1, 3, 4, 2}, {3, 1, 5, -1}, {2, 5, 3, 0},       \
+   {1, 5, 4, 0},     {4, 2, 5, -1}, {4, 5, 2, -1}, {4, 5, 1, 0}, {3, 5, 2, 0},  {1, 3, 5, -1},      \
+   {4, 3, 1, 2},     {3, 0, 4, -1}, {2, 0, 1, -1}, {-1, -1, -1, -1}}
+// watertight triangles per code as tet edge ids (gshell_tets.py:91-108)
+#define D3H_T_TRI_EDGE                                                                               \
+  {{-1, -1, -1, -1, -1, -1}, {1, 0, 2, -1, -1, -1}, {4, 0, 3, -1, -1, -1}, {1, 4, 2, 1, 3, 4},      \
+   {3, 1, 5, -1, -1, -1},    {2, 3, 0, 2, 5, 3},    {1, 4, 0, 1, 5, 4},    {4, 2, 5, -1, -1, -1},   \
+   {4, 5, 2, -1, -1, -1},    {4, 1, 0, 4, 5, 1},    {3, 2, 0, 3, 5, 2},    {1, 3, 5, -1, -1, -1},   \
+   {4, 1, 2, 4, 3, 1},       {3, 0, 4, -1, -1, -1}, {2, 0, 1, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}}
+// mSDF cut of a triangle polygon: locals 0-2 = corners, 3-5 = boundary vertices (gshell_tets.py:130-147)
+#define D3H_T_CUT_TRI                                                                                \
+  {{-1, -1, -1, -1, -1, -1}, {4, 2, 5, -1, -1, -1}, {3, 1, 4, -1, -1, -1}, {3, 1, 2, 3, 2, 5},      \
+   {0, 3, 5, -1, -1, -1},    {0, 3, 4, 0, 4, 2},    {0, 1, 4, 0, 4, 5},    {0, 1, 2, -1, -1, -1}}
+#define D3H_T_NUM_CUT_TRI {0, 1, 1, 2, 1, 2, 2, 1}  // gshell_tets.py:189
+// mSDF cut of a quad polygon: locals 0-3 = corners, 4-7 = boundary vertices (gshell_tets.py:149-184)
+#define D3H_T_CUT_QUAD                                                                                     \
+  {{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1}, {6, 3, 7, -1, -1, -1, -1, -1, -1, -1, -1, -1},       \
+   {5, 2, 6, -1, -1, -1, -1, -1, -1, -1, -1, -1},    {5, 2, 7, 3, 7, 2, -1, -1, -1, -1, -1, -1},          \
+   {4, 1, 5, -1, -1, -1, -1, -1, -1, -1, -1, -1},    {4, 1, 5, 4, 5, 7, 5, 6, 7, 7, 6, 3},                \
+   {4, 1, 2, 6, 4, 2, -1, -1, -1, -1, -1, -1},       {4, 1, 2, 7, 4, 2, 7, 2, 3, -1, -1, -1},             \
+   {0, 4, 7, -1, -1, -1, -1, -1, -1, -1, -1, -1},    {0, 4, 6, 3, 0, 6, -1, -1, -1, -1, -1, -1},          \
+   {0, 4, 5, 0, 5, 2, 0, 2, 6, 0, 6, 7},             {0, 4, 5, 0, 5, 2, 0, 2, 3, -1, -1, -1},             \
+   {0, 1, 5, 7, 0, 5, -1, -1, -1, -1, -1, -1},       {0, 1, 5, 0, 5, 6, 0, 6, 3, -1, -1, -1},             \
+   {0, 1, 2, 0, 2, 6, 0, 6, 7, -1, -1, -1},          {0, 1, 2, 0, 2, 3, -1, -1, -1, -1, -1, -1}}
+#define D3H_T_NUM_CUT_QUAD {0, 1, 1, 2, 1, 4, 2, 3, 1, 2, 4, 3, 2, 3, 3, 2}  // gshell_tets.py:190
+
+static __device__ __constant__ int8_t c_num_tri[16] = D3H_T_NUM_TRI;
+static __device__ __constant__ int8_t c_edge_p[6] = D3H_T_EDGE_P;
+static __device__ __constant__ int8_t c_edge_q[6] = D3H_T_EDGE_Q;
+static __device__ __constant__ int8_t c_loop_edge[16][4] = D3H_T_LOOP_EDGE;
+static __device__ __constant__ int8_t c_tri_edge[16][6] = D3H_T_TRI_EDGE;
+static __device__ __constant__ int8_t c_cut_tri[8][6] = D3H_T_CUT_TRI;
+static __device__ __constant__ int8_t c_num_cut_tri[8] = D3H_T_NUM_CUT_TRI;
+static __device__ __constant__ int8_t c_cut_quad[16][12] = D3H_T_CUT_QUAD;
+static __device__ __constant__ int8_t c_num_cut_quad[16] = D3H_T_NUM_CUT_QUAD;
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+// status words of the decoupled look-back scans are self-contained (flag + value in one word), so relaxed
+// gpu-scope accesses are enough -- no fence, hence no L1 invalidation in the streaming kernels.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// streaming 16-byte load that does not allocate in L1 (the tet index stream is read exactly once)
+__device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float fsign(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// fl(xa*wa) + fl(xb*wb): the reference multiplies and adds in separate kernels (no FMA), SURVEY A.4
+__device__ __forceinline__ float lerp2(float xa, float wa, float xb, float wb) {
+  return __fadd_rn(__fmul_rn(xa, wa), __fmul_rn(xb, wb));
+}
+
+// Zero-crossing weights of edge (a,b): gshell_tets.py:292-299.  w0 multiplies the a end, w1 the b end.
+__device__ __forceinline__ void crossing_weights(float sa, float sb, float& w0, float& w1, float& dd) {
+  float e0 = sa, e1 = -sb;
+  float d = __fadd_rn(e0, e1);
+  dd = __fmul_rn(fsign(d), __fadd_rn(fabsf(d), kEps12));
+  if (dd == 0.f) dd = kEps12;
+  w0 = __fdiv_rn(e1, dd);
+  w1 = __fdiv_rn(e0, dd);
+}
+
+// Boundary-vertex weights on polygon edge i->j from the interpolated mSDF values: gshell_tets.py:353-367.
+__device__ __forceinline__ bool boundary_weights(float mi, float mj, float& u0, float& u1, float& D) {
+  bool nz = fabsf(fsign(mi) + fsign(mj)) != 2.f;
+  float nmj = -mj;
+  D = __fadd_rn(mi, nmj);
+  nz = nz && (fabsf(D) > kEps12);
+  u0 = nz ? __fdiv_rn(nmj, D) : 0.f;
+  u1 = nz ? __fdiv_rn(mi, D) : 0.f;
+  return nz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side counters (one cache line of int32 words at the head of the workspace; reset per call)
+// ------------------------------------------------------------------------------------------------
+struct DevCounters {
+  unsigned ticket_classify;  // dynamic tile ids of the classify kernel
+  unsigned ticket_sort[8];   // one per radix pass
+  unsigned ticket_rle;
+  unsigned ticket_poly;
+  unsigned n_valid;          // Fv (true count, even when the record buffer overflowed)
+  unsigned n_tri;            // T1
+  unsigned n_quad;           // T2
+  unsigned work_tri;         // T1 / T2 the surface stages operate on: equal to n_tri / n_quad, or 0 / 0 when
+  unsigned work_quad;        //   Fv exceeded the record capacity (the caller re-runs with a larger workspace)
+  unsigned n_verts;          // V
+  unsigned bucket[6];        // polygons per faces_aug bucket
+  unsigned pad[9];
+};
+static_assert(sizeof(DevCounters) == 128, "DevCounters is one 128-byte line");
+
+}  // namespace d3h

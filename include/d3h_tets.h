@@ -1,0 +1,173 @@
+/*
+ * d3h_tets.h -- C ABI of the B200-native G-Shell / mSDF marching-tetrahedra extraction.
+ *
+ * This is the drop-in boundary for ONE path of D3-Human:
+ *     GShell_Tets.__call__   geometry/gshell_tets.py:253-447
+ *     hmSDF_Tets.__call__    geometry/hmsdf_tets_split.py:254-454
+ * The reference has no native implementation of this path (it is ~200 PyTorch ops); its other
+ * plugins bind `at::Tensor` through pybind11 (render/renderutils/c_src/torch_bindings.cpp:14-31,
+ * loaded by render/renderutils/ops.py:23-87).  Here the binding is a plain C ABI instead: raw device
+ * pointers, sizes and a cudaStream_t, loaded with ctypes.CDLL by the Python host
+ * (d3human-code_b200/_cabi.py).  INTEGRATION.md shows the stub a maintainer adds to the reference.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative D3H_E_* code otherwise; the message is available
+ *     from d3h_last_error_string() (thread-local).  CUDA errors are reported as D3H_E_CUDA.
+ *   - the library never allocates device memory: inputs, outputs, tape and scratch are caller-owned
+ *     (torch tensors in the Python host).  Outputs are over-allocated to caller-chosen capacities;
+ *     the true sizes come back in d3h_counts.  A capacity that is too small is NOT an error: the
+ *     kernels drop the out-of-range writes and the caller re-runs with the sizes just reported.
+ *   - no host synchronisation inside any call; everything is enqueued on `stream` and is CUDA-graph
+ *     capturable.  d3h_counts is copied to `counts_host` (pinned) with cudaMemcpyAsync at the end of
+ *     the forward call; the caller synchronises the stream (or an event) before reading it.
+ *   - all float data is fp32; index outputs are int64 (the reference returns torch.long faces,
+ *     gshell_tets.py:413-420); tet indices are consumed as packed int32x4 (16-byte loads).
+ */
+#ifndef D3H_TETS_H_
+#define D3H_TETS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3H_VERSION 100 /* 0.1.0 */
+
+enum {
+  D3H_OK = 0,
+  D3H_E_BADARG = -1,  /* null pointer, negative size, N or F >= 2^31, misaligned tet pointer */
+  D3H_E_CUDA = -2,    /* a CUDA runtime call failed; see d3h_last_error_string() */
+  D3H_E_SMALLWS = -3  /* workspace_bytes smaller than d3h_workspace_bytes(...) */
+};
+
+/* Opaque to C callers that only pass it around; the layout is fixed so ctypes can mirror it. */
+typedef void* d3h_stream_t; /* cudaStream_t */
+
+/* Sizes produced by one forward call (device copy lives in the workspace, host copy in pinned memory).
+ * Names follow SURVEY.md section 8(a): Fv valid tets, T1/T2 tets producing 1/2 watertight triangles,
+ * P = 3*T1 + 4*T2 polygon corners (= boundary vertices), V crossing edges (= watertight vertices),
+ * Va = V + P augmented vertices, Fw = T1 + 2*T2 watertight faces, Fa open-mesh faces in 6 buckets
+ * (tri polygons cut into 1,2 triangles; quad polygons cut into 1,2,3,4 triangles; gshell_tets.py:413-420). */
+typedef struct d3h_counts {
+  int64_t n_valid_tets;   /* Fv */
+  int64_t n_tri_tets;     /* T1 */
+  int64_t n_quad_tets;    /* T2 */
+  int64_t n_corners;      /* P  */
+  int64_t n_verts;        /* V  */
+  int64_t n_faces_aug;    /* Fa */
+  int64_t bucket_polys[6];/* polygons per faces_aug bucket, in bucket order */
+  int64_t bad_index;      /* number of tet indices outside [0,N) seen by d3h_pack_tets_* (0 = clean) */
+  int64_t reserved[3];
+} d3h_counts;
+
+/* ---- forward ------------------------------------------------------------------------------------- */
+typedef struct d3h_forward_args {
+  /* inputs (device) */
+  const float* pos;        /* (N,3)  tet-grid vertex positions, `pos_nx3`, gshell_tets.py:253 */
+  const float* sdf;        /* (N)    `sdf_n` after .float(), gshell_tets.py:254 */
+  const float* msdf;       /* (N)    `msdf_n` */
+  const int32_t* tets;     /* (F,4)  packed int32x4 tet indices, 16-byte aligned (d3h_pack_tets_i64) */
+  int64_t n_grid;          /* N */
+  int64_t n_tets;          /* F  (defines the UV atlas size, gshell_tets.py:319) */
+  int64_t tet_begin;       /* classify tets [tet_begin, tet_end) only; whole grid = [0,F) */
+  int64_t tet_end;
+  int32_t msdf_negate;     /* 1 for hmSDF_Tets(type="body"): msdf is used as -msdf (hmsdf_tets_split.py:261-264) */
+  int32_t watertight_template; /* `output_watertight_template` (default 1), gshell_tets.py:272-275 */
+  /* capacities, in rows, of the caller's output / tape buffers */
+  int64_t cap_valid_tets;  /* also sizes the workspace (see d3h_workspace_bytes) */
+  int64_t cap_verts;       /* V  rows available in the *_watertight outputs and tape_edges */
+  int64_t cap_verts_aug;   /* Va rows available in verts_aug, v_tng_aug, msdf_aug */
+  int64_t cap_faces_wt;    /* Fw rows available in faces_watertight */
+  int64_t cap_faces_aug;   /* Fa rows available in faces_aug */
+  /* outputs (device); any may be NULL with capacity 0 for a counting-only run */
+  float* verts_aug;        /* (Va,3) rows not referenced by faces_aug are zero (gshell_tets.py:423-427) */
+  float* v_tng_aug;        /* (Va,3) */
+  float* msdf_aug;         /* (Va)   extra['msdf']; [V:] is extra['msdf_boundary'] */
+  int64_t* faces_aug;      /* (Fa,3) */
+  float* verts_wt;         /* (V,3)  extra['vertices_watertight'] */
+  float* v_tng_wt;         /* (V,3)  extra['v_tng_watertight'] */
+  float* msdf_wt;          /* (V)    extra['msdf_watertight'] */
+  int64_t* faces_wt;       /* (Fw,3) extra['faces_watertight'] */
+  /* tape for the backward pass (device) */
+  int32_t* tape_edges;     /* (cap_verts,2)   (a,b), a<b: grid vertices of each crossing edge, sorted (interp_v, gshell_tets.py:287) */
+  int32_t* tape_corners;   /* (4*cap_valid_tets) polygon corner -> watertight vertex id, layout [3*T1 | 4*T2] */
+  /* scratch + counts */
+  void* workspace;         /* >= d3h_workspace_bytes(F, N, cap_valid_tets) bytes, 256-byte aligned */
+  int64_t workspace_bytes;
+  d3h_counts* counts_host; /* pinned host memory, or NULL to skip the copy */
+} d3h_forward_args;
+
+/* ---- backward ------------------------------------------------------------------------------------ */
+typedef struct d3h_backward_args {
+  /* forward inputs again */
+  const float* pos;
+  const float* sdf;
+  const float* msdf;
+  int64_t n_grid;
+  int32_t msdf_negate;
+  int32_t reserved0;
+  /* saved by forward */
+  const int32_t* tape_edges;
+  const int32_t* tape_corners;
+  const float* verts_wt;   /* (V,3) */
+  const float* msdf_wt;    /* (V)   */
+  int64_t n_verts;         /* V  */
+  int64_t n_tri_tets;      /* T1 */
+  int64_t n_quad_tets;     /* T2 */
+  /* upstream gradients (device); NULL = zero */
+  const float* g_verts_aug;   /* (Va,3) */
+  const float* g_msdf_aug;    /* (Va)   */
+  const float* g_verts_wt;    /* (V,3)  */
+  const float* g_msdf_wt;     /* (V)    */
+  /* outputs (device); fully written (zero where nothing flows) */
+  float* g_pos;            /* (N,3) */
+  float* g_sdf;            /* (N)   */
+  float* g_msdf;           /* (N) or NULL (type="body" has no msdf gradient) */
+  /* scratch */
+  void* workspace;         /* >= d3h_backward_workspace_bytes(V) bytes */
+  int64_t workspace_bytes;
+} d3h_backward_args;
+
+int d3h_version(void);
+const char* d3h_last_error_string(void);
+
+/* Scratch sizes.  Replaces nothing in the reference (torch allocates every temporary there). */
+int64_t d3h_workspace_bytes(int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets);
+int64_t d3h_backward_workspace_bytes(int64_t n_verts);
+
+/* One-time conversion of the static `tet_fx4` (int64 in the reference, hmsdf.py:207-212) to packed int32x4,
+ * with a range check against N; the number of out-of-range indices is added to *bad_count_dev (device int64,
+ * caller-zeroed).  d3h_check_tets_i32 validates an int32 grid in place. */
+int d3h_pack_tets_i64(const int64_t* tets, int64_t n_tets, int64_t n_grid, int32_t* out_tets,
+                      int64_t* bad_count_dev, d3h_stream_t stream);
+int d3h_check_tets_i32(const int32_t* tets, int64_t n_tets, int64_t n_grid, int64_t* bad_count_dev,
+                       d3h_stream_t stream);
+
+/* The whole forward extraction (replaces GShell_Tets.__call__ / hmSDF_Tets.__call__ up to the return
+ * statement, gshell_tets.py:254-445). */
+int d3h_extract_forward(const d3h_forward_args* args, d3h_stream_t stream);
+
+/* Adjoint of the float pipeline (replaces autograd through gshell_tets.py:291-303, 342-397, 427). */
+int d3h_extract_backward(const d3h_backward_args* args, d3h_stream_t stream);
+
+/* Tet-range sharding (multi-GPU): stage 1 classifies tets [tet_begin, tet_end) and leaves
+ * compact valid-tet records in the caller's buffers; the ranks all-gather those (NCCL) and stage 2 runs the
+ * surface stages on the concatenated records.  d3h_extract_forward == stage 1 on [0,F) + stage 2. */
+typedef struct d3h_tet_record { /* 32 bytes */
+  int32_t v[4];            /* tet vertex ids */
+  int32_t code;            /* 4-bit occupancy code, gshell_tets.py:307-308 */
+  int32_t class_rank;      /* rank among the shard's valid tets with the same triangle count (T1 or T2 class) */
+  int32_t tet_id;          /* global tet index */
+  int32_t pad;
+} d3h_tet_record;
+
+int d3h_classify_range(const d3h_forward_args* args, d3h_tet_record* records_out, int64_t cap_records,
+                       d3h_counts* counts_dev_out, d3h_stream_t stream);
+int d3h_extract_from_records(const d3h_forward_args* args, const d3h_tet_record* records, int64_t n_tri_tets,
+                             int64_t n_quad_tets, d3h_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3H_TETS_H_ */

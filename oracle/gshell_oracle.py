@@ -292,7 +292,7 @@ def _auto_normals(verts, faces):
     a, b = (v1 - v0).astype(F32), (v2 - v0).astype(F32)
     if faces.shape[0] == 3:
         # quirk gshell_tets.py:19: torch.cross without dim takes the FIRST axis of size 3
-        fn = _cross_f32(a.T, b.T, 0)
+        fn = _cross_f32(a, b, 0)  # fn[r, c]: crossed along the face axis r
     else:
         fn = _cross_f32(a, b, -1)
     for c in range(3):

