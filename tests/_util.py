@@ -8,7 +8,12 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 #: tolerances stated by BASELINE.json north_star
 POS_RTOL = 1e-6      # interpolated positions (we are bit-exact in practice; the assert uses exact first)
 GRAD_RTOL = 1e-5     # gradients, normwise (max |diff| / max |ref|)
-TNG_ATOL = 2e-5      # unit tangents: scatter order (and ATen's approximate CPU sqrt) differ by a few ulp
+TNG_ATOL = 2e-5      # unit tangents, oracle vs reference on CPU: same scatter order, ATen's approximate sqrt -> few ulp
+#: CUDA vs oracle: the per-face tangents are ~1/denominator large (UV cells are 1/ceil(sqrt(F)) apart) and are summed
+#: with float atomics in arbitrary order (the reference's own CUDA scatter_add_ is order-nondeterministic too), so the
+#: normalised result differs by eps * sum|t_f| / |sum t_f|: bound the worst row loosely and the bulk tightly.
+TNG_CUDA_ATOL = 5e-3
+TNG_CUDA_P99 = 1e-4
 
 
 def golden_cases():
@@ -44,7 +49,7 @@ def assert_close_normwise(name, got, want, rtol):
     assert err <= rtol * max(scale, 1e-30), f"{name}: max|diff|={err:.3e} > {rtol:g} * max|ref|={scale:.3e}"
 
 
-def assert_tangents_close(name, got, want, atol=TNG_ATOL):
+def assert_tangents_close(name, got, want, atol=TNG_ATOL, p99=None):
     got, want = np.asarray(got), np.asarray(want)
     assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
     assert got.dtype == want.dtype
@@ -52,9 +57,12 @@ def assert_tangents_close(name, got, want, atol=TNG_ATOL):
     diff = np.where(both_nan, 0.0, np.abs(got.astype(np.float64) - want.astype(np.float64)))
     assert not np.isnan(diff).any(), f"{name}: NaN pattern differs"
     assert diff.max(initial=0.0) <= atol, f"{name}: max|diff|={diff.max():.3e} > {atol:g}"
+    if p99 is not None and diff.size:
+        q = np.quantile(diff.max(-1), 0.99)
+        assert q <= p99, f"{name}: 99th percentile row error {q:.3e} > {p99:g}"
 
 
-def check_forward_against_golden(out, rec, tangents=True, tng_atol=TNG_ATOL):
+def check_forward_against_golden(out, rec, tangents=True, tng_atol=TNG_ATOL, tng_p99=None):
     """out: dict with the reference's return values (numpy). rec: golden record."""
     assert_exact("faces_aug", out["faces_aug"], rec["faces_aug"])
     assert_exact("verts_aug", out["verts_aug"], rec["verts_aug"])
@@ -66,11 +74,11 @@ def check_forward_against_golden(out, rec, tangents=True, tng_atol=TNG_ATOL):
         assert_exact("faces_watertight", out["faces_watertight"], rec["extra_faces_watertight"])
         assert_exact("vertices_watertight", out["vertices_watertight"], rec["extra_vertices_watertight"])
         if tangents:
-            assert_tangents_close("v_tng_watertight", out["v_tng_watertight"], rec["extra_v_tng_watertight"], tng_atol)
+            assert_tangents_close("v_tng_watertight", out["v_tng_watertight"], rec["extra_v_tng_watertight"], tng_atol, tng_p99)
     else:
         assert "extra_vertices_watertight" not in rec
     if tangents:
-        assert_tangents_close("v_tng_aug", out["v_tng_aug"], rec["v_tng_aug"], tng_atol)
+        assert_tangents_close("v_tng_aug", out["v_tng_aug"], rec["v_tng_aug"], tng_atol, tng_p99)
 
 
 def check_grads_against_golden(g_pos, g_sdf, g_msdf, rec):
