@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: tets/s of fwd+bwd G-Shell / mSDF extraction (BASELINE.json metric) + HBM roofline fraction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 128^3 Kuhn tet grid (F=12,582,912, N=2,146,689), analytic capsule-union SDF +
+garment mSDF, hmSDF_Tets(type="cloth") forward + backward with upstream gradients on verts_aug and extra['msdf'].
+Each rank runs `--frames-per-rank` frames per step (default 2: 16 frames/step at 8 GPUs = configs[3]); a frame is one
+full extraction with its own per-frame tet-vertex offsets (seed = global frame index); sdf/msdf are shared, so their
+gradients accumulate over the rank's frames and are all-reduced (NCCL) with the summed offset gradient when N > 1.
+Weak scaling: per-GPU work is fixed.  value = N * frames_per_rank * F / (max-over-ranks device time per step).
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "tets/s fwd+bwd G-Shell extraction"
+UNIT = "tets/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=128, help="Kuhn grid resolution (128 = BASELINE configs[1])")
+    ap.add_argument("--frames-per-rank", type=int, default=2)
+    ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=20)
+    return ap.parse_args()
+
+
+def make_inputs(res, field):
+    from d3human_code_b200 import grids
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = (grids.capsule_garment_field if field == "capsule" else grids.sphere_plane_field)(pos)
+    return pos, sdf, msdf, tets
+
+
+def workload_name(args):
+    return (f"configs[1]: {args.res}^3 Kuhn grid, {'capsule-union SDF + garment mSDF' if args.field == 'capsule' else 'sphere SDF + plane mSDF'}"
+            f", hmSDF_Tets(cloth) fwd+bwd, {args.frames_per_rank} frame(s)/rank/step with per-frame offsets")
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while a region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # pragma: no cover
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # pragma: no cover
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path, timed on this box's host cores: the numpy port in oracle/
+    (the reference itself is PyTorch code that does not travel to the GPU box)."""
+    if rank != 0:
+        return
+    from oracle import gshell_oracle as O
+    cores = os.cpu_count() or 1
+    pos, sdf, msdf, tets = make_inputs(args.res, args.field)
+    F = tets.shape[0]
+    from d3human_code_b200 import grids
+    pos = pos + grids.frame_offsets(pos.shape[0], args.res, 0)
+
+    def step():
+        fwd = O.extract_forward(pos, sdf, msdf, tets, 1, True, n_threads=cores)
+        gv = np.ones_like(fwd["verts_aug"])
+        gm = np.ones_like(fwd["msdf"])
+        O.extract_backward(fwd, gv, gm)
+
+    # bounded sample: every step is ONE frame of the workload (fwd+bwd); cap the whole run at ~2 minutes
+    step()
+    t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
+    steps = max(1, min(args.steps, int(100.0 / max(one, 1e-3))))
+    warm = max(0, min(args.warmup, 3))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = F / dt
+    sample = f"{steps} step(s), each one full fwd+bwd extraction of one frame of the workload on the host CPU"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(args), "F": int(F), "N": int(pos.shape[0])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+    from d3human_code_b200 import _cabi, grids
+    from d3human_code_b200 import extract as E
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+
+    pos_np, sdf_np, msdf_np, tets_np = make_inputs(args.res, args.field)
+    F, N = int(tets_np.shape[0]), int(pos_np.shape[0])
+    fpr = args.frames_per_rank
+    frames = [rank * fpr + i for i in range(fpr)]
+    hm = hmSDF_Tets()
+    tets = torch.from_numpy(tets_np).to(dev)                      # int64 like hmsdf.py:207-212; packed once (static)
+    sdf = torch.from_numpy(sdf_np[:, None].copy()).to(dev).requires_grad_(True)   # (N,1) like the SDF MLP output
+    msdf = torch.from_numpy(msdf_np).to(dev).requires_grad_(True)
+    host_pos = [torch.from_numpy(pos_np + grids.frame_offsets(N, args.res, f)).pin_memory() for f in frames]
+    host_sdf = torch.from_numpy(sdf_np[:, None].copy()).pin_memory()
+    host_msdf = torch.from_numpy(msdf_np).pin_memory()
+    pos = [hp.to(dev).requires_grad_(True) for hp in host_pos]
+
+    # dry run: shapes of the upstream gradients (constant across steps: inputs are fixed)
+    ups, counts = [], []
+    for p in pos:
+        verts, faces, _, _, v_tng, extra = hm(p, sdf, msdf, tets, "cloth")
+        g = torch.Generator(device=dev).manual_seed(1234)
+        ups.append((torch.randn(verts.shape, device=dev, generator=g), torch.randn(extra["msdf"].shape, device=dev, generator=g)))
+        counts.append(dict(E.last_counts()))
+    c0 = counts[0]
+    balg = grids.surface_counts_bytes(F, N, c0["n_verts"], c0["n_verts_aug"], c0["n_faces_watertight"], c0["n_faces_aug"])
+    launches_per_frame = E._ExtractFn.last_launches + 3
+
+    def step():
+        sdf.grad = None
+        msdf.grad = None
+        for p, (gv, gm) in zip(pos, ups):
+            p.grad = None
+            verts, faces, _, _, v_tng, extra = hm(p, sdf, msdf, tets, "cloth")
+            torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
+        if world > 1:
+            gp = pos[0].grad if fpr == 1 else torch.stack([p.grad for p in pos]).sum(0)
+            dist.all_reduce(gp)
+            dist.all_reduce(sdf.grad)
+            dist.all_reduce(msdf.grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    tmax = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = world * fpr * F / (ms_step * 1e-3)
+
+    # ---- per-kernel device time (CUDA events on the launching stream, recorded by the library) ----
+    prof = {}
+    if rank == 0:
+        _cabi.profile_enable(True)
+        for _ in range(args.profile_steps):
+            step() if world == 1 else [hm(p, sdf, msdf, tets, "cloth") for p in pos]
+        torch.cuda.synchronize()
+        prof = _cabi.profile_read()
+        _cabi.profile_enable(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- end to end through the public API with HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        d_sdf = torch.empty_like(sdf)
+        d_msdf = torch.empty_like(msdf)
+        d_pos = [torch.empty_like(p) for p in pos]
+        outs_host = None
+        k_e2e = max(3, min(args.steps, 30))
+
+        def e2e_step():
+            nonlocal outs_host
+            h2d = d2h = 0
+            for dst, src in ((d_sdf, host_sdf), (d_msdf, host_msdf)):
+                dst.requires_grad_(False)
+                dst.copy_(src, non_blocking=True)
+                dst.requires_grad_(True)
+                dst.grad = None
+            h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
+            res = []
+            for dp, hp, (gv, gm) in zip(d_pos, host_pos, ups):
+                dp.requires_grad_(False)
+                dp.copy_(hp, non_blocking=True)
+                dp.requires_grad_(True)
+                dp.grad = None
+                h2d += hp.numel() * 4
+                verts, faces, _, _, v_tng, extra = hm(dp, d_sdf, d_msdf, tets, "cloth")
+                torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
+                res.append((verts.detach(), faces, extra["msdf"].detach(), dp.grad))
+            res_flat = [t for r in res for t in r] + [d_sdf.grad, d_msdf.grad]
+            if outs_host is None:
+                outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_flat]
+            for h, t in zip(outs_host, res_flat):
+                h.copy_(t, non_blocking=True)
+                d2h += t.numel() * t.element_size()
+            torch.cuda.synchronize()
+            return h2d, d2h
+
+        for _ in range(3):
+            h2d_b, d2h_b = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * fpr * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
+               "d2h_bytes_per_step": int(d2h_b), "steps": k_e2e, "ms_per_step": float(dt.item()) * 1e3,
+               "note": "hmSDF_Tets() called with inputs copied from pinned host memory each step (pos per frame, sdf, "
+                       "msdf); verts_aug, faces_aug, msdf and the three dense gradients copied back; static tet "
+                       "indices stay resident"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (classify: the only O(F) kernel) ----
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    roofline = None
+    kern = {}
+    if prof:
+        kern = {k: {"ms_total": round(v[0], 4), "launches": v[1], "us_avg": round(1e3 * v[0] / v[1], 3)} for k, v in prof.items()}
+        ms, n = prof.get("classify", (0.0, 0))
+        if n:
+            t = ms / n * 1e-3
+            achieved = 16.0 * F / t / 1e9
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "classify_traffic.json")) as fh:
+                    tj = json.load(fh)
+                    if int(tj.get("F", 0)) == F:
+                        traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            roofline = {"kernel": "classify_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": 16 * F, "us_per_launch": t * 1e6}
+    dev_ms_frame = sum(v[0] for v in prof.values()) / max(args.profile_steps * fpr, 1) if prof else None
+    path_roofline = {"algorithmic_bytes_per_frame": int(balg),
+                     "achieved_GBps_step": balg * fpr / (ms_step * 1e-3) / 1e9,
+                     "frac_step": balg * fpr / (ms_step * 1e-3) / 1e9 / peak,
+                     "kernel_ms_per_frame": dev_ms_frame,
+                     "frac_kernels_only": (balg / (dev_ms_frame * 1e-3) / 1e9 / peak) if dev_ms_frame else None}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import gshell_oracle as O
+        cores = os.cpu_count() or 1
+        p0 = host_pos[0].numpy()
+
+        def cpu_step():
+            fwd = O.extract_forward(p0, sdf_np, msdf_np, tets_np, 1, True, n_threads=cores)
+            O.extract_backward(fwd, np.ones_like(fwd["verts_aug"]), np.ones_like(fwd["msdf"]))
+
+        cpu_step()
+        reps, best, t_all = 0, 1e9, time.perf_counter()
+        while reps < 20 and time.perf_counter() - t_all < 15.0:
+            t0 = time.perf_counter(); cpu_step(); best = min(best, time.perf_counter() - t0); reps += 1
+        cpu_baseline = {"value": F / best, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"best of {reps} full fwd+bwd extractions of one frame of the same workload, numpy oracle "
+                                  f"with the O(F) stage on {cores} threads",
+                        "ms_per_frame": best * 1e3}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "F": F, "N": N, "frames_per_step": world * fpr,
+                       "counts_frame0": c0, "l2": "tet index stream is 16*F = %d MB > 126 MB L2; no explicit flush" % (16 * F // 1000000),
+                       "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
+            "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches_per_frame * fpr * args.steps), "kernels": kern,
+            "clocks": sampler.result()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

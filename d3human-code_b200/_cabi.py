@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_extract_backward",
     "d3h_classify_range", "d3h_extract_from_records",
+    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_debug_table",
 )
 
 
@@ -88,12 +89,33 @@ def lib() -> C.CDLL:
     L.d3h_classify_range.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_from_records.restype = C.c_int
     L.d3h_extract_from_records.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    L.d3h_profile_enable.restype = C.c_int
+    L.d3h_profile_enable.argtypes = [C.c_int]
+    L.d3h_profile_kinds.restype = C.c_int
+    L.d3h_profile_kernel_name.restype = C.c_char_p
+    L.d3h_profile_kernel_name.argtypes = [C.c_int]
+    L.d3h_profile_read.restype = C.c_int
+    L.d3h_profile_read.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_debug_table.restype = C.c_int
     L.d3h_debug_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
     if L.d3h_version() != 100:
         raise RuntimeError(f"libd3h_tets.so version {L.d3h_version()} does not match this package (100); rebuild")
     _lib = L
     return L
+
+
+def profile_enable(on: bool) -> None:
+    lib().d3h_profile_enable(int(bool(on)))
+
+
+def profile_read():
+    """-> {kernel name: (total ms, launches)} since the last read; synchronises the recorded events."""
+    L = lib()
+    n = L.d3h_profile_kinds()
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    check(L.d3h_profile_read(ms, cnt), "d3h_profile_read")
+    return {L.d3h_profile_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}
 
 
 def check(rc: int, what: str) -> None:

@@ -16,6 +16,25 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- profiler -------------------------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static ProfRec g_prof[4096];
+static int g_prof_n = 0;
+
+ProfScope::ProfScope(int kind, cudaStream_t st) : slot(-1), stream(st) {
+  if (!g_prof_on || g_prof_n >= 4096) return;
+  slot = g_prof_n++;
+  ProfRec& r = g_prof[slot];
+  r.kind = kind;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, stream);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+
 static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets) {
@@ -203,6 +222,36 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_extract_backward: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
   return D3H_OK;
+}
+
+// ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
+static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "emit_keys", "radix_pass", "rle_interp", "poly_faces",
+                                            "vertex_frame", "poly_cut", "zero", "boundary_adjoint", "crossing_adjoint",
+                                            "rank_records"};
+extern "C" int d3h_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return D3H_OK;
+}
+extern "C" int d3h_profile_kinds(void) { return K_COUNT; }
+extern "C" const char* d3h_profile_kernel_name(int k) { return (k >= 0 && k < K_COUNT) ? kKernelNames[k] : ""; }
+// Synchronises the recorded events, adds their durations (ms) and launch counts per kernel kind, then clears the log.
+extern "C" int d3h_profile_read(float* ms_by_kind, int* launches_by_kind) {
+  if (!ms_by_kind || !launches_by_kind) { set_error("d3h_profile_read: null output"); return D3H_E_BADARG; }
+  for (int k = 0; k < K_COUNT; ++k) { ms_by_kind[k] = 0.f; launches_by_kind[k] = 0; }
+  int rc = D3H_OK;
+  for (int i = 0; i < g_prof_n; ++i) {
+    ProfRec& r = g_prof[i];
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess) { set_error("d3h_profile_read: %s", cudaGetErrorString(e)); rc = D3H_E_CUDA; }
+    ms_by_kind[r.kind] += ms;
+    launches_by_kind[r.kind] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_n = 0;
+  return rc;
 }
 
 // ---- test hook: the case tables, from the same initializer macros the __constant__ copies are built from --------

@@ -177,13 +177,19 @@ void launch_backward(const d3h_backward_args& a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   // unaligned buffers (never produced by torch) fall back to the scalar tail path in a loop-free kernel: reject instead
-  zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b0, n0, b1, n1, b2, n2, reinterpret_cast<float4*>(acc), 2 * nv, t0,
-                                                    tn0, t1, tn1, t2, tn2);
+  {
+    ProfScope ps(K_ZERO, stream);
+    zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b0, n0, b1, n1, b2, n2, reinterpret_cast<float4*>(acc), 2 * nv,
+                                                      t0, tn0, t1, tn1, t2, tn2);
+  }
   if (nv <= 0) return;
   const int64_t ncorn = 3 * a.n_tri_tets + 4 * a.n_quad_tets;
-  if (ncorn > 0 && (a.g_verts_aug != nullptr || a.g_msdf_aug != nullptr))
+  if (ncorn > 0 && (a.g_verts_aug != nullptr || a.g_msdf_aug != nullptr)) {
+    ProfScope ps(K_BOUNDARY_ADJ, stream);
     boundary_adjoint_kernel<<<(unsigned)((ncorn + 255) / 256), 256, 0, stream>>>(
         a.tape_corners, a.verts_wt, a.msdf_wt, nv, a.n_tri_tets, a.n_quad_tets, a.g_verts_aug, a.g_msdf_aug, acc);
+  }
+  ProfScope ps(K_CROSSING_ADJ, stream);
   crossing_adjoint_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(
       a.tape_edges, a.pos, a.sdf, a.msdf, a.msdf_negate, nv, a.msdf_wt, a.g_verts_aug, a.g_msdf_aug, a.g_verts_wt,
       a.g_msdf_wt, acc, a.g_pos, a.g_sdf, a.g_msdf);

@@ -50,6 +50,7 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
   int64_t blocks = (nwords * 32 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps(K_PREPARE, stream);
   prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.sdf, a.msdf, a.n_grid, a.msdf_negate,
                                                          a.watertight_template ? 0 : 1, ws.occ_bits, ws.mocc_bits, ws);
 }
@@ -193,6 +194,7 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   const int64_t n = a.tet_end - a.tet_begin;
   const int64_t ntiles = (n + kClassifyTile - 1) / kClassifyTile;
   if (ntiles <= 0) return;
+  ProfScope ps(K_CLASSIFY, stream);
   classify_kernel<<<(unsigned)ntiles, kClassifyThreads, 0, stream>>>(
       reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits,
       a.watertight_template ? nullptr : ws.mocc_bits, ws.st_classify, ws.ctr, records, cap_records, ntiles);
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(1024) rank_records_kernel(d3h_tet_record* __re
 }
 
 void launch_rank_records(const Workspace& ws, d3h_tet_record* records, int64_t n_records, cudaStream_t stream) {
+  ProfScope ps(K_RANK_RECORDS, stream);
   rank_records_kernel<<<1, 1024, 0, stream>>>(records, n_records, ws.ctr);
 }
 

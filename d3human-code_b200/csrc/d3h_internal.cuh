@@ -65,4 +65,16 @@ void launch_backward(const d3h_backward_args& a, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 
+// ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
+enum KernelKind {
+  K_PREPARE = 0, K_CLASSIFY, K_EMIT_KEYS, K_RADIX_PASS, K_RLE_INTERP, K_POLY_FACES, K_VERTEX_FRAME, K_POLY_CUT,
+  K_ZERO, K_BOUNDARY_ADJ, K_CROSSING_ADJ, K_RANK_RECORDS, K_COUNT
+};
+struct ProfScope {
+  ProfScope(int kind, cudaStream_t stream);
+  ~ProfScope();
+  int slot;
+  cudaStream_t stream;
+};
+
 }  // namespace d3h

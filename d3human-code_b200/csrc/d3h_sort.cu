@@ -322,17 +322,20 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, const d3h_
   {
     int64_t blocks = (cap + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
+    ProfScope ps(K_EMIT_KEYS, stream);
     emit_keys_kernel<<<(unsigned)blocks, 256, 0, stream>>>(records, ws.ctr, cap, key_bits, npass, ws.keys[0], ws.vals[0],
                                                            ws.radix_hist, ws.st_sort,
                                                            ws.ntiles_sort * (int64_t)kRadix);
   }
   int cur = 0;
   for (int p = 0; p < npass; ++p) {
+    ProfScope ps(K_RADIX_PASS, stream);
     radix_pass_kernel<<<(unsigned)ws.ntiles_sort, kSortThreads, 0, stream>>>(
         ws.keys[cur], ws.vals[cur], ws.keys[cur ^ 1], ws.vals[cur ^ 1], ws.ctr, ws.radix_hist + p * kRadix,
         ws.st_sort + (int64_t)p * ws.ntiles_sort * kRadix, p, p * kRadixBits);
     cur ^= 1;
   }
+  ProfScope ps(K_RLE_INTERP, stream);
   rle_interp_kernel<<<(unsigned)ws.ntiles_rle, kRleThreads, 0, stream>>>(
       ws.keys[cur], ws.vals[cur], ws.ctr, ws.st_rle, key_bits, a.pos, a.sdf, a.msdf, a.msdf_negate, a.tape_corners,
       a.tape_edges, a.cap_verts, a.cap_verts_aug, ws.vert, ws.acc, a.verts_wt, a.msdf_wt, a.verts_aug, a.msdf_aug);

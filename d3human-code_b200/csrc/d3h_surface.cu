@@ -366,13 +366,18 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
   }
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   if (ws.cap_tets > 0) {
-    poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, ws.st_poly, a.tape_corners, ws.vert, ws.acc,
-                                                         ws.polyinfo, a.faces_wt, a.cap_faces_wt, uvp);
+    {
+      ProfScope ps(K_POLY_FACES, stream);
+      poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, ws.st_poly, a.tape_corners, ws.vert, ws.acc,
+                                                           ws.polyinfo, a.faces_wt, a.cap_faces_wt, uvp);
+    }
     int64_t vb = (ws.cap_corners + 255) / 256;
     if (vb > 148 * 8) vb = 148 * 8;
+    ProfScope ps(K_VERTEX_FRAME, stream);
     vertex_frame_kernel<<<(unsigned)vb, 256, 0, stream>>>(ws.ctr, ws.acc, ws.tng, a.v_tng_wt, a.cap_verts,
                                                           a.v_tng_aug, a.cap_verts_aug);
   }
+  ProfScope ps(K_POLY_CUT, stream);
   poly_cut_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, a.tape_corners, ws.vert, ws.tng, ws.polyinfo,
                                                      a.verts_aug, a.v_tng_aug, a.msdf_aug, a.cap_verts_aug, a.faces_aug,
                                                      a.cap_faces_aug, ws.counts);

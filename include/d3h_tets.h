@@ -167,6 +167,20 @@ int d3h_classify_range(const d3h_forward_args* args, d3h_tet_record* records_out
 int d3h_extract_from_records(const d3h_forward_args* args, const d3h_tet_record* records, int64_t n_tri_tets,
                              int64_t n_quad_tets, d3h_stream_t stream);
 
+/* ---- diagnostics (no counterpart in the reference) ------------------------------------------------------------- */
+/* Per-kernel device time: when enabled, every kernel launch of this library is bracketed by cudaEventRecord on the
+ * launching stream.  d3h_profile_read synchronises those events, returns the summed milliseconds and launch counts
+ * per kernel kind (arrays of d3h_profile_kinds() entries, names from d3h_profile_kernel_name) and clears the log. */
+int d3h_profile_enable(int on);
+int d3h_profile_kinds(void);
+const char* d3h_profile_kernel_name(int kind);
+int d3h_profile_read(float* ms_by_kind, int* launches_by_kind);
+/* Host copies of the case tables the kernels index (same initialisers as the __constant__ copies; no GPU needed).
+ * which: 0 num_triangles[16], 1 polygon loop edges[16][4], 2 triangle_table[16][6], 3 triangle_table_tri[8][6],
+ * 4 num_triangles_tri[8], 5 triangle_table_quad[16][12], 6 num_triangles_quad[16], 7/8 tet-edge endpoints[6].
+ * Returns the element count written to `out`. */
+int d3h_debug_table(int which, int8_t* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,7 +143,29 @@ def _safe_normalize(x):
 # --------------------------------------------------------------------------------------
 # forward
 # --------------------------------------------------------------------------------------
-def extract_forward(pos, sdf, msdf, tets, msdf_sign: int = 1, output_watertight_template: bool = True):
+def _classify(occ, mpos, tets, n_threads):
+    """4-bit occupancy code and validity of every tet (gshell_tets.py:260-275, 307-308); the only O(F) stage.
+    Chunked over a thread pool when n_threads > 1 (numpy releases the GIL in take / compare)."""
+    def one(chunk):
+        code = (occ[chunk] * np.array([1, 2, 4, 8])).sum(-1)
+        valid = (code != 0) & (code != 15)
+        if mpos is not None:
+            valid &= mpos[chunk].any(-1)
+        ids = np.nonzero(valid)[0]
+        return ids, code[ids]
+    n = tets.shape[0]
+    if n_threads <= 1 or n < (1 << 16):
+        return one(tets)
+    from concurrent.futures import ThreadPoolExecutor
+    bounds = np.linspace(0, n, 4 * n_threads + 1).astype(np.int64)
+    with ThreadPoolExecutor(n_threads) as pool:
+        parts = list(pool.map(lambda i: one(tets[bounds[i]:bounds[i + 1]]), range(4 * n_threads)))
+    ids = np.concatenate([p[0] + bounds[i] for i, p in enumerate(parts)])
+    return ids, np.concatenate([p[1] for p in parts])
+
+
+def extract_forward(pos, sdf, msdf, tets, msdf_sign: int = 1, output_watertight_template: bool = True,
+                    n_threads: int = 1):
     """Forward pass.  Returns a dict holding every returned tensor of the reference plus the
     integer intermediates the parity tests compare (valid ids, codes, sorted edge keys, corner array).
 
@@ -155,19 +177,15 @@ def extract_forward(pos, sdf, msdf, tets, msdf_sign: int = 1, output_watertight_
     m = np.ascontiguousarray(msdf, dtype=F32).reshape(-1)
     if msdf_sign < 0:
         m = -m
-    tets = np.ascontiguousarray(tets).astype(np.int64)
+    tets = np.ascontiguousarray(tets)
+    if tets.dtype != np.int64:
+        tets = tets.astype(np.int64)
     n_grid = pos.shape[0]
     num_tets = tets.shape[0]
 
     # --- classification (gshell_tets.py:260-275, 307-309) ---
     occ = s > 0
-    occ4 = occ[tets]
-    code_all = (occ4 * np.array([1, 2, 4, 8])).sum(-1)
-    valid = (code_all != 0) & (code_all != 15)
-    if not output_watertight_template:
-        valid &= (m[tets] > 0).any(-1)
-    valid_ids = np.nonzero(valid)[0]
-    code = code_all[valid_ids]
+    valid_ids, code = _classify(occ, None if output_watertight_template else (m > 0), tets, n_threads)
     tv = tets[valid_ids]
     ntri = NUM_TRIANGLES_TABLE[code]
     fv = valid_ids.shape[0]
