@@ -51,8 +51,8 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   const int64_t capc = 4 * cap;
   ws.cap_tets = cap;
   ws.cap_corners = capc;
-  ws.ntiles_classify = (n_tets + kClassifyTile - 1) / kClassifyTile;
-  ws.ntiles_sort = (capc + kSortTile - 1) / kSortTile;
+  const int64_t nwords_f = ((n_tets + 32 * kClassifyItems - 1) / (32 * kClassifyItems)) * kClassifyItems;
+  ws.ntiles_compact = (nwords_f + kCompactThreads * kCompactWords - 1) / (kCompactThreads * kCompactWords);
   ws.ntiles_rle = (capc + kRleTile - 1) / kRleTile;
   ws.ntiles_poly = (cap + kPolyThreads - 1) / kPolyThreads;
   const int64_t nwords = (n_grid + 31) / 32 + 1;
@@ -60,16 +60,21 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.counts = reinterpret_cast<d3h_counts*>(take(sizeof(d3h_counts)));
   ws.occ_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
   ws.mocc_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
-  ws.st_classify = reinterpret_cast<unsigned long long*>(take(ws.ntiles_classify * 8));
+  ws.m1_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactWords) * 4));
+  ws.m2_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactWords) * 4));
+  ws.st_compact = reinterpret_cast<unsigned long long*>(take(ws.ntiles_compact * 8));
   ws.records = reinterpret_cast<d3h_tet_record*>(take(cap * (int64_t)sizeof(d3h_tet_record)));
-  ws.keys[0] = reinterpret_cast<unsigned long long*>(take(capc * 8));
-  ws.keys[1] = reinterpret_cast<unsigned long long*>(take(capc * 8));
-  ws.vals[0] = reinterpret_cast<unsigned*>(take(capc * 4));
-  ws.vals[1] = reinterpret_cast<unsigned*>(take(capc * 4));
-  ws.radix_hist = reinterpret_cast<unsigned*>(take(kMaxPasses * kRadix * 4));
-  ws.st_sort = reinterpret_cast<unsigned*>(take(ws.ntiles_sort * kRadix * 4 * (int64_t)kMaxPasses));
+  ws.keys = reinterpret_cast<unsigned long long*>(take(capc * 8));
+  ws.vals = reinterpret_cast<unsigned*>(take(capc * 4));
+  ws.keys2 = reinterpret_cast<unsigned long long*>(take(capc * 8));
+  ws.vals2 = reinterpret_cast<unsigned*>(take(capc * 4));
+  ws.keys_scratch = reinterpret_cast<unsigned long long*>(take(2 * capc * 8));
+  ws.vals_scratch = reinterpret_cast<unsigned*>(take(2 * capc * 4));
+  ws.msd_hist = reinterpret_cast<unsigned*>(take(kMsdBins * 4));
+  ws.msd_base = reinterpret_cast<unsigned*>(take((kMsdBins + 1) * 4));
+  ws.msd_cursor = reinterpret_cast<unsigned*>(take(kMsdBins * 4));
   ws.st_rle = reinterpret_cast<unsigned long long*>(take(ws.ntiles_rle * 8));
-  ws.st_poly = reinterpret_cast<unsigned*>(take(ws.ntiles_poly * 8 * 4));
+  ws.st_poly = reinterpret_cast<unsigned long long*>(take(ws.ntiles_poly * 3 * 8));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));
   ws.tng = reinterpret_cast<float4*>(take(capc * 16));
   ws.acc = reinterpret_cast<float*>(take(capc * 32));
@@ -140,8 +145,8 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   cudaStream_t stream = (cudaStream_t)s;
   Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
   launch_prepare(*a, ws, stream);
-  launch_classify(*a, ws, ws.records, ws.cap_tets, stream);
-  launch_edge_sort(*a, ws, ws.records, stream);
+  launch_classify(*a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream);
+  launch_edge_sort(*a, ws, stream);
   launch_surface(*a, ws, ws.records, stream);
   return finish("d3h_extract_forward", ws, a->counts_host, stream);
 }
@@ -167,7 +172,7 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* rec
   cudaStream_t stream = (cudaStream_t)s;
   Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
   launch_prepare(*a, ws, stream);
-  launch_classify(*a, ws, records_out, cap_records, stream);
+  launch_classify(*a, ws, records_out, cap_records, /*emit_keys=*/false, stream);
   export_range_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, counts_dev_out);
   if (a->counts_host) cudaMemcpyAsync(a->counts_host, counts_dev_out, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
   cudaError_t e = cudaGetLastError();
@@ -192,8 +197,8 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet
   b.tet_begin = b.tet_end = 0;  // prepare still resets the scan state; no tets are classified here
   launch_prepare(b, ws, stream);
   if (n > 0) cudaMemcpyAsync(ws.records, records, n * sizeof(d3h_tet_record), cudaMemcpyDeviceToDevice, stream);
-  launch_rank_records(ws, ws.records, n, stream);
-  launch_edge_sort(*a, ws, ws.records, stream);
+  launch_rank_records(*a, ws, ws.records, n, stream);
+  launch_edge_sort(*a, ws, stream);
   launch_surface(*a, ws, ws.records, stream);
   return finish("d3h_extract_from_records", ws, a->counts_host, stream);
 }
@@ -225,9 +230,9 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 }
 
 // ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
-static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "emit_keys", "radix_pass", "rle_interp", "poly_faces",
-                                            "vertex_frame", "poly_cut", "zero", "boundary_adjoint", "crossing_adjoint",
-                                            "rank_records"};
+static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "partition", "local_sort", "rle_interp",
+                                            "poly_faces", "vertex_frame", "poly_cut", "zero", "boundary_adjoint",
+                                            "crossing_adjoint", "rank_records"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

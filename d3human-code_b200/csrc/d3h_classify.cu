@@ -1,12 +1,20 @@
-// Stage 1 of the extraction: occupancy bitmap + the only O(F) kernel (classify + ordered compaction).
+// Stage 1 of the extraction: occupancy bitmap, the only O(F) kernel (streaming classification) and the ordered
+// compaction of the valid tets.
 //
 // Replaces gshell_tets.py:260-275 (occ_n, occ_fx4, occ_sum, valid_tets), :307-309 (tetindex, num_triangles)
 // and the boolean-mask compactions `tet_fx4[valid_tets]`, `idx_map[num_triangles == k]` (:277, :323-324).
 //
-// HBM traffic: 16 B per tet (one int32x4 load, streamed once, no L1 allocation) + 4 B per grid vertex for the
-// bitmap build.  The four per-tet sign lookups hit a N/8-byte bitmap (268 KB at 128^3) that stays in L1/L2.
-// Ordered compaction uses warp ballots, one block scan of per-warp counts and a decoupled look-back over
-// tile aggregates (single pass over the tet stream; status words are self-contained so no fences are needed).
+//   prepare_kernel   N-sized: sign bitmap of sdf (N/8 bytes: 268 KB at 128^3, L1/L2 resident) + reset of scan state.
+//   classify_kernel  F-sized, pure stream: every warp loads 8 x 32 tets with 16-byte no-allocate loads, looks the four
+//                    signs up in the bitmap and writes two ballot words per 32 tets (tet yields 1 / 2 triangles).
+//                    No shared memory, no barrier, no atomics: the kernel is bound by the 16 B/tet HBM stream.
+//   compact_kernel   scans the two class bitmaps (F/4 bytes, L2 resident) with a decoupled look-back, then visits only
+//                    the valid tets (~1 %) in tet order: re-reads their indices, writes the compact records and, in the
+//                    fused single-GPU path, the sort keys of their crossing edges + the MSD histogram.
+//
+// v1 of this file classified and compacted in one kernel (ticket + block scan + look-back per 2048-tet tile): ncu showed
+// 45 % of the warp samples parked on the barrier behind the ticket atomic and 16 % DRAM utilisation
+// (profiles/r01a_launches_v1.csv); splitting the ordered part off removes every dependency from the stream.
 #include "d3h_internal.cuh"
 
 namespace d3h {
@@ -14,40 +22,56 @@ namespace d3h {
 // ------------------------------------------------------------------------------------------------
 // K0: occupancy bitmaps + reset of all per-call scan state
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load4_guarded(const float* __restrict__ p, int64_t q, int64_t n) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (4 * q + 3 < n) {
+    s = __ldg(reinterpret_cast<const float4*>(p) + q);
+  } else if (4 * q < n) {
+    s.x = p[4 * q];
+    if (4 * q + 1 < n) s.y = p[4 * q + 1];
+    if (4 * q + 2 < n) s.z = p[4 * q + 2];
+  }
+  return s;
+}
+
 __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ sdf, const float* __restrict__ msdf,
                                                       int64_t n_grid, int msdf_negate, int want_mocc,
                                                       unsigned* __restrict__ occ_bits,
                                                       unsigned* __restrict__ mocc_bits, Workspace ws) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  // reset (tiny): counters, classify / rle / poly status words, radix histograms
   if (tid < (int64_t)(sizeof(DevCounters) / 4)) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
-  for (int64_t i = tid; i < ws.ntiles_classify; i += nthreads) ws.st_classify[i] = 0ull;
+  for (int64_t i = tid; i < ws.ntiles_compact; i += nthreads) ws.st_compact[i] = 0ull;
   for (int64_t i = tid; i < ws.ntiles_rle; i += nthreads) ws.st_rle[i] = 0ull;
-  for (int64_t i = tid; i < ws.ntiles_poly * 8; i += nthreads) ws.st_poly[i] = 0u;
-  for (int64_t i = tid; i < kMaxPasses * kRadix; i += nthreads) ws.radix_hist[i] = 0u;
+  for (int64_t i = tid; i < ws.ntiles_poly * 3; i += nthreads) ws.st_poly[i] = 0ull;
+  for (int64_t i = tid; i < kMsdBins; i += nthreads) ws.msd_hist[i] = 0u;
 
-  // bitmaps: one 32-bit word per warp iteration, coalesced 128 B reads
-  const int64_t nwords = (n_grid + 31) / 32;
-  const int64_t warp = tid >> 5, nwarps = nthreads >> 5;
+  // bitmaps: each lane takes 4 consecutive vertices (one 16-byte load), 8 lanes make one 32-bit word
+  const int64_t nquads = (n_grid + 3) / 4;
   const unsigned lane = lane_id();
-  for (int64_t w = warp; w < nwords; w += nwarps) {
-    const int64_t v = w * 32 + lane;
-    float s = (v < n_grid) ? __ldg(sdf + v) : 0.f;
-    unsigned word = __ballot_sync(0xffffffffu, s > 0.f);
-    if (lane == 0) occ_bits[w] = word;
+  for (int64_t q0 = tid - lane; q0 < nquads; q0 += nthreads) {  // warp-uniform trip count
+    const int64_t q = q0 + lane;
+    const float4 s = load4_guarded(sdf, q, n_grid);
+    unsigned word = ((s.x > 0.f) | ((s.y > 0.f) << 1) | ((s.z > 0.f) << 2) | ((s.w > 0.f) << 3)) << (4 * (lane & 7));
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+    if ((lane & 7) == 0 && 4 * q < n_grid) occ_bits[q >> 3] = word;
     if (want_mocc) {
-      float m = (v < n_grid) ? __ldg(msdf + v) : 0.f;
-      if (msdf_negate) m = -m;
-      unsigned mw = __ballot_sync(0xffffffffu, m > 0.f);
-      if (lane == 0) mocc_bits[w] = mw;
+      float4 m = load4_guarded(msdf, q, n_grid);
+      if (msdf_negate) { m.x = -m.x; m.y = -m.y; m.z = -m.z; m.w = -m.w; }
+      unsigned mw = ((m.x > 0.f) | ((m.y > 0.f) << 1) | ((m.z > 0.f) << 2) | ((m.w > 0.f) << 3)) << (4 * (lane & 7));
+      mw |= __shfl_xor_sync(0xffffffffu, mw, 1);
+      mw |= __shfl_xor_sync(0xffffffffu, mw, 2);
+      mw |= __shfl_xor_sync(0xffffffffu, mw, 4);
+      if ((lane & 7) == 0 && 4 * q < n_grid) mocc_bits[q >> 3] = mw;
     }
   }
 }
 
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
-  const int64_t nwords = (a.n_grid + 31) / 32;
-  int64_t blocks = (nwords * 32 + 255) / 256;
+  const int64_t nquads = (a.n_grid + 3) / 4;
+  int64_t blocks = (nquads + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope ps(K_PREPARE, stream);
@@ -56,13 +80,8 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: classify + ordered compaction
+// K1: streaming classification
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned long long kFlagAgg = 1ull << 62;  // tile aggregate published
-constexpr unsigned long long kFlagInc = 2ull << 62;  // inclusive prefix published
-constexpr unsigned long long kValMask = (1ull << 62) - 1;
-// value = count(T1 class) in bits [0,31) | count(T2 class) in bits [31,62)
-
 __device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, int v) {
   return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u;
 }
@@ -70,66 +89,153 @@ __device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, in
 __global__ void __launch_bounds__(kClassifyThreads)
 classify_kernel(const int4* __restrict__ tets, int64_t tet_begin, int64_t tet_end,
                 const unsigned* __restrict__ occ_bits, const unsigned* __restrict__ mocc_bits,
-                unsigned long long* __restrict__ status, DevCounters* __restrict__ ctr,
-                d3h_tet_record* __restrict__ records, int64_t cap_records, int64_t ntiles) {
-  constexpr int WARPS = kClassifyThreads / 32;
-  __shared__ unsigned s_tile;
-  __shared__ unsigned s_seg[kClassifyItems * WARPS];  // packed per-(item,warp) counts: T1 | T2 << 16
-  __shared__ unsigned long long s_excl;
+                unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words) {
+  const unsigned lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * kClassifyThreads + threadIdx.x) >> 5;
+  const int64_t base = tet_begin + warp * (32 * kClassifyItems);
+  if (base >= tet_end) return;
 
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_classify, 1u);
-  __syncthreads();
-  const unsigned tile = s_tile;
-  if ((int64_t)tile >= ntiles) return;
-  const int64_t base = tet_begin + (int64_t)tile * kClassifyTile;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-
-  // 8 independent 16-byte streaming loads per thread
   int4 t[kClassifyItems];
 #pragma unroll
   for (int j = 0; j < kClassifyItems; ++j) {
-    const int64_t idx = base + j * kClassifyThreads + threadIdx.x;
+    const int64_t idx = base + j * 32 + lane;
     t[j] = (idx < tet_end) ? ld_stream_int4(tets + idx) : make_int4(0, 0, 0, 0);
   }
-  unsigned code[kClassifyItems], m1[kClassifyItems], m2[kClassifyItems];
+  unsigned w1 = 0, w2 = 0;  // lane j keeps the ballot words of item j
 #pragma unroll
   for (int j = 0; j < kClassifyItems; ++j) {
-    const int64_t idx = base + j * kClassifyThreads + threadIdx.x;
-    unsigned c = occ_of(occ_bits, t[j].x) | (occ_of(occ_bits, t[j].y) << 1) | (occ_of(occ_bits, t[j].z) << 2) |
-                 (occ_of(occ_bits, t[j].w) << 3);
-    if (idx >= tet_end) c = 0u;
-    int nocc = __popc(c);
-    bool valid = (nocc != 0) && (nocc != 4);
+    const int64_t idx = base + j * 32 + lane;
+    const unsigned c = occ_of(occ_bits, t[j].x) + occ_of(occ_bits, t[j].y) + occ_of(occ_bits, t[j].z) +
+                       occ_of(occ_bits, t[j].w);
+    bool valid = (c != 0u) && (c != 4u) && (idx < tet_end);
     if (mocc_bits != nullptr && valid) {  // open-mesh prefilter, gshell_tets.py:275
-      unsigned any_m = occ_of(mocc_bits, t[j].x) | occ_of(mocc_bits, t[j].y) | occ_of(mocc_bits, t[j].z) |
-                       occ_of(mocc_bits, t[j].w);
-      valid = any_m != 0u;
+      valid = (occ_of(mocc_bits, t[j].x) | occ_of(mocc_bits, t[j].y) | occ_of(mocc_bits, t[j].z) |
+               occ_of(mocc_bits, t[j].w)) != 0u;
     }
-    code[j] = valid ? c : 0u;
-    m1[j] = __ballot_sync(0xffffffffu, valid && (nocc != 2));  // 1 or 3 occupied -> one triangle
-    m2[j] = __ballot_sync(0xffffffffu, valid && (nocc == 2));  // 2 occupied      -> two triangles (quad)
-    if (lane == 0) s_seg[j * WARPS + warp] = (unsigned)__popc(m1[j]) | ((unsigned)__popc(m2[j]) << 16);
+    const unsigned b1 = __ballot_sync(0xffffffffu, valid && (c != 2u));  // 1 or 3 inside -> one triangle
+    const unsigned b2 = __ballot_sync(0xffffffffu, valid && (c == 2u));  // 2 inside      -> two triangles
+    if (lane == (unsigned)j) { w1 = b1; w2 = b2; }
   }
+  if (lane < (unsigned)kClassifyItems) {
+    const int64_t w = ((base - tet_begin) >> 5) + lane;
+    m1_words[w] = w1;
+    m2_words[w] = w2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: ordered compaction of the valid tets (+ fused key emission)
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long kFlagAgg = 1ull << 62;  // tile aggregate published
+constexpr unsigned long long kFlagInc = 2ull << 62;  // inclusive prefix published
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+// value = count(T1 class) in bits [0,31) | count(T2 class) in bits [31,62)
+
+// Writes the sort keys of one valid tet: one key per polygon corner (= crossing edge, in mesh_edge_table order).
+// Slots are dense in valid-tet order (3 per tri tet, 4 per quad tet); the value encodes the final corner slot
+// [3*T1 | 4*T2] as (class, 4*class_rank + k) because T1 is not known yet.
+__device__ __forceinline__ void emit_polygon_keys(const int4 v4, int code, bool quad, unsigned class_rank,
+                                                  unsigned other_before, int key_bits, int msd_shift,
+                                                  unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
+                                                  unsigned* __restrict__ s_hist) {
+  const int vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  const int n = quad ? 4 : 3;
+  const int64_t slot0 = quad ? (4ll * class_rank + 3ll * other_before) : (3ll * class_rank + 4ll * other_before);
+  for (int k = 0; k < n; ++k) {
+    const int e = c_loop_edge[code][k];
+    const int p = vv[c_edge_p[e]], q = vv[c_edge_q[e]];
+    const unsigned long long a = (unsigned)min(p, q), b = (unsigned)max(p, q);
+    keys[slot0 + k] = (a << key_bits) | b;
+    vals[slot0 + k] = (quad ? 0x80000000u : 0u) | (4u * class_rank + (unsigned)k);
+    atomicAdd(&s_hist[(unsigned)(a >> msd_shift)], 1u);
+  }
+}
+
+// Last-arriving CTA: exclusive scan of the MSD histogram -> bucket bases and scatter cursors.
+__device__ void msd_scan_epilogue(const unsigned* __restrict__ hist, unsigned* __restrict__ base,
+                                  unsigned* __restrict__ cursor, unsigned* s_tmp /* >= 32 words */) {
+  const int per = (kMsdBins + blockDim.x - 1) / blockDim.x;  // each thread a contiguous run of bins
+  const int b0 = threadIdx.x * per;
+  unsigned sum = 0;
+  for (int i = 0; i < per; ++i)
+    if (b0 + i < kMsdBins) sum += __ldcg(hist + b0 + i);
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += n;
+  }
+  __syncthreads();  // s_tmp may alias a buffer the caller used before
+  if (lane == 31) s_tmp[warp] = incl;
   __syncthreads();
+  unsigned wpre = 0;
+  for (unsigned w = 0; w < warp; ++w) wpre += s_tmp[w];
+  unsigned run = wpre + incl - sum;
+  for (int i = 0; i < per; ++i) {
+    if (b0 + i < kMsdBins) {
+      base[b0 + i] = run;
+      cursor[b0 + i] = run;
+      run += __ldcg(hist + b0 + i);
+    }
+  }
+  if (threadIdx.x == blockDim.x - 1) base[kMsdBins] = run;
+}
+
+template <bool EMIT_KEYS>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict__ m2_words, int64_t nwords,
+               const int4* __restrict__ tets, int64_t tet_begin, const unsigned* __restrict__ occ_bits,
+               unsigned long long* __restrict__ status, DevCounters* __restrict__ ctr,
+               d3h_tet_record* __restrict__ records, int64_t cap_records, int64_t ntiles, int key_bits, int msd_shift,
+               unsigned long long* __restrict__ keys, unsigned* __restrict__ vals, unsigned* __restrict__ msd_hist,
+               unsigned* __restrict__ msd_base, unsigned* __restrict__ msd_cursor) {
+  constexpr int WARPS = kCompactThreads / 32;
+  __shared__ unsigned s_pre1[kCompactThreads], s_pre2[kCompactThreads];  // exclusive per-thread prefixes in the tile
+  __shared__ unsigned s_w1[32], s_w2[32];
+  __shared__ unsigned long long s_excl;
+  __shared__ unsigned s_total[2];
+  __shared__ unsigned s_hist[EMIT_KEYS ? kMsdBins : 1];
+  __shared__ unsigned s_tile, s_last;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_compact, 1u);
+  if (EMIT_KEYS)
+    for (int i = threadIdx.x; i < kMsdBins; i += kCompactThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+
+  // each thread owns kCompactWords consecutive words of both bitmaps (= 32*kCompactWords consecutive tets)
+  const int64_t w0 = ((int64_t)tile * kCompactThreads + threadIdx.x) * kCompactWords;
+  unsigned c1 = 0, c2 = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactWords; ++j) {
+    if (w0 + j < nwords) {
+      c1 += __popc(__ldcg(m1_words + w0 + j));
+      c2 += __popc(__ldcg(m2_words + w0 + j));
+    }
+  }
+  // block exclusive scan of (c1, c2)
+  unsigned i1 = c1, i2 = c2;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned n1 = __shfl_up_sync(0xffffffffu, i1, o), n2 = __shfl_up_sync(0xffffffffu, i2, o);
+    if (lane >= (unsigned)o) { i1 += n1; i2 += n2; }
+  }
+  if (lane == 31) { s_w1[warp] = i1; s_w2[warp] = i2; }
+  __syncthreads();
+  unsigned p1 = 0, p2 = 0, tot1 = 0, tot2 = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    if (w < (int)warp) { p1 += s_w1[w]; p2 += s_w2[w]; }
+    tot1 += s_w1[w];
+    tot2 += s_w2[w];
+  }
+  s_pre1[threadIdx.x] = p1 + i1 - c1;
+  s_pre2[threadIdx.x] = p2 + i2 - c2;
 
   if (warp == 0) {
-    // exclusive scan of the 64 segment counts (2 per lane), order = (item, warp) = tet order
-    constexpr int NSEG = kClassifyItems * WARPS;
-    static_assert(NSEG == 64, "two segments per lane");
-    unsigned a0 = s_seg[2 * lane], a1 = s_seg[2 * lane + 1];
-    unsigned sum = a0 + a1, incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += n;
-    }
-    unsigned excl = incl - sum;
-    s_seg[2 * lane] = excl;
-    s_seg[2 * lane + 1] = excl + a0;
-    unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned long long agg = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 31);
-
-    // decoupled look-back, 32 predecessors per step
+    const unsigned long long agg = (unsigned long long)tot1 | ((unsigned long long)tot2 << 31);
     unsigned long long excl_tiles = 0ull;
     if (tile == 0) {
       if (lane == 0) st_relaxed_u64(status, kFlagInc | agg);
@@ -155,6 +261,8 @@ classify_kernel(const int4* __restrict__ tets, int64_t tet_begin, int64_t tet_en
     }
     if (lane == 0) {
       s_excl = excl_tiles;
+      s_total[0] = tot1;
+      s_total[1] = tot2;
       if ((int64_t)tile == ntiles - 1) {  // grid totals
         const unsigned long long incl_all = excl_tiles + agg;
         const unsigned t1 = (unsigned)(incl_all & 0x7fffffffull), t2 = (unsigned)(incl_all >> 31);
@@ -169,40 +277,97 @@ classify_kernel(const int4* __restrict__ tets, int64_t tet_begin, int64_t tet_en
   }
   __syncthreads();
 
-  const unsigned long long ex = s_excl;
-  const unsigned e1 = (unsigned)(ex & 0x7fffffffull), e2 = (unsigned)(ex >> 31);
-  const unsigned lt = lanemask_lt();
-#pragma unroll
-  for (int j = 0; j < kClassifyItems; ++j) {
-    if (code[j] == 0u) continue;
-    const unsigned seg = s_seg[j * WARPS + warp];
-    const unsigned r1 = e1 + (seg & 0xffffu) + __popc(m1[j] & lt);
-    const unsigned r2 = e2 + (seg >> 16) + __popc(m2[j] & lt);
-    const bool quad = (m2[j] >> lane) & 1u;
-    const int64_t slot = (int64_t)r1 + r2;  // rank among all valid tets = tet order
-    if (slot < cap_records) {
-      const int64_t idx = base + j * kClassifyThreads + threadIdx.x;
-      int4* out = reinterpret_cast<int4*>(records + slot);
-      out[0] = t[j];
-      out[1] = make_int4((int)code[j], (int)(quad ? r2 : r1), (int)idx, 0);
+  // ---- visit the tile's valid tets, one per thread per round, in tet order ----
+  const unsigned e1 = (unsigned)(s_excl & 0x7fffffffull), e2 = (unsigned)(s_excl >> 31);
+  const unsigned nvalid_tile = s_total[0] + s_total[1];
+  for (unsigned i = threadIdx.x; i < nvalid_tile; i += kCompactThreads) {
+    int lo = 0, hi = kCompactThreads - 1;  // owner thread: last th with pre1[th] + pre2[th] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_pre1[mid] + s_pre2[mid] <= i) lo = mid; else hi = mid - 1;
     }
+    const int th = lo;
+    unsigned r1 = s_pre1[th], r2 = s_pre2[th];
+    unsigned rem = i - (r1 + r2);
+    const int64_t wb = ((int64_t)tile * kCompactThreads + th) * kCompactWords;
+    unsigned b1 = 0, b2 = 0;
+    int64_t word = wb;
+#pragma unroll 1
+    for (int j = 0; j < kCompactWords; ++j) {
+      word = wb + j;
+      b1 = __ldcg(m1_words + word);
+      b2 = __ldcg(m2_words + word);
+      const unsigned cnt = __popc(b1 | b2);
+      if (rem < cnt) break;
+      rem -= cnt;
+      r1 += __popc(b1);
+      r2 += __popc(b2);
+    }
+    const unsigned both = b1 | b2;
+    const int bit = (int)__fns(both, 0, (int)rem + 1);  // position of the (rem+1)-th set bit
+    const unsigned below = (1u << bit) - 1u;
+    r1 += __popc(b1 & below);
+    r2 += __popc(b2 & below);
+    const bool quad = (b2 >> bit) & 1u;
+    const unsigned g1 = e1 + r1, g2 = e2 + r2;  // tri / quad valid tets before this one, grid-wide
+    const int64_t slot = (int64_t)g1 + g2;
+    const int64_t tet = tet_begin + word * 32 + bit;
+    if (slot < cap_records) {
+      const int4 v4 = __ldg(tets + tet);
+      const int code = (int)(occ_of(occ_bits, v4.x) | (occ_of(occ_bits, v4.y) << 1) | (occ_of(occ_bits, v4.z) << 2) |
+                             (occ_of(occ_bits, v4.w) << 3));
+      int4* out = reinterpret_cast<int4*>(records + slot);
+      out[0] = v4;
+      out[1] = make_int4(code, (int)(quad ? g2 : g1), (int)tet, (int)(quad ? g1 : g2));
+      if (EMIT_KEYS)
+        emit_polygon_keys(v4, code, quad, quad ? g2 : g1, quad ? g1 : g2, key_bits, msd_shift, keys, vals, s_hist);
+    }
+  }
+  if (EMIT_KEYS) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMsdBins; i += kCompactThreads) {
+      const unsigned c = s_hist[i];
+      if (c) atomicAdd(&msd_hist[i], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->compact_done, 1u) == (unsigned)(ntiles - 1));
+    __syncthreads();
+    if (s_last) msd_scan_epilogue(msd_hist, msd_base, msd_cursor, s_w1);
   }
 }
 
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
-                     cudaStream_t stream) {
+                     bool emit_keys, cudaStream_t stream) {
   const int64_t n = a.tet_end - a.tet_begin;
-  const int64_t ntiles = (n + kClassifyTile - 1) / kClassifyTile;
-  if (ntiles <= 0) return;
-  ProfScope ps(K_CLASSIFY, stream);
-  classify_kernel<<<(unsigned)ntiles, kClassifyThreads, 0, stream>>>(
-      reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits,
-      a.watertight_template ? nullptr : ws.mocc_bits, ws.st_classify, ws.ctr, records, cap_records, ntiles);
+  if (n <= 0) return;
+  const int64_t nwarps = (n + 32 * kClassifyItems - 1) / (32 * kClassifyItems);
+  const int64_t nblocks = (nwarps * 32 + kClassifyThreads - 1) / kClassifyThreads;
+  {
+    ProfScope ps(K_CLASSIFY, stream);
+    classify_kernel<<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
+        reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits,
+        a.watertight_template ? nullptr : ws.mocc_bits, ws.m1_words, ws.m2_words);
+  }
+  const int64_t nwords = nwarps * kClassifyItems;  // every word of a launched warp is written
+  const int64_t ntiles = (nwords + kCompactThreads * kCompactWords - 1) / (kCompactThreads * kCompactWords);
+  const int key_bits = key_bits_for(a.n_grid);
+  const int msd_shift = msd_shift_for(a.n_grid);
+  ProfScope ps(K_COMPACT, stream);
+  if (emit_keys)
+    compact_kernel<true><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
+        ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.st_compact,
+        ws.ctr, records, cap_records, ntiles, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist, ws.msd_base,
+        ws.msd_cursor);
+  else
+    compact_kernel<false><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
+        ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.st_compact,
+        ws.ctr, records, cap_records, ntiles, key_bits, msd_shift, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
-// records gathered from several shards: recompute the class ranks over the concatenation
-// (single block; the merged list is O(surface))
+// records gathered from several shards: recompute the ranks over the concatenation, then emit keys
+// (single block for the ranks; the merged list is O(surface))
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) rank_records_kernel(d3h_tet_record* __restrict__ records, int64_t n,
                                                             DevCounters* __restrict__ ctr) {
@@ -224,8 +389,9 @@ __global__ void __launch_bounds__(1024) rank_records_kernel(d3h_tet_record* __re
       tot1 += s_w1[w]; tot2 += s_w2[w];
     }
     const unsigned lt = lanemask_lt();
-    if (cls == 1) records[i].class_rank = (int)(s_run1 + p1 + __popc(b1 & lt));
-    if (cls == 2) records[i].class_rank = (int)(s_run2 + p2 + __popc(b2 & lt));
+    const unsigned g1 = s_run1 + p1 + __popc(b1 & lt), g2 = s_run2 + p2 + __popc(b2 & lt);
+    if (cls == 1) { records[i].class_rank = (int)g1; records[i].other_before = (int)g2; }
+    if (cls == 2) { records[i].class_rank = (int)g2; records[i].other_before = (int)g1; }
     __syncthreads();
     if (threadIdx.x == 0) { s_run1 += tot1; s_run2 += tot2; }
     __syncthreads();
@@ -239,9 +405,49 @@ __global__ void __launch_bounds__(1024) rank_records_kernel(d3h_tet_record* __re
   }
 }
 
-void launch_rank_records(const Workspace& ws, d3h_tet_record* records, int64_t n_records, cudaStream_t stream) {
-  ProfScope ps(K_RANK_RECORDS, stream);
-  rank_records_kernel<<<1, 1024, 0, stream>>>(records, n_records, ws.ctr);
+__global__ void __launch_bounds__(256)
+keys_from_records_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __restrict__ ctr, int key_bits,
+                         int msd_shift, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
+                         unsigned* __restrict__ msd_hist, unsigned* __restrict__ msd_base,
+                         unsigned* __restrict__ msd_cursor) {
+  __shared__ unsigned s_hist[kMsdBins];
+  __shared__ unsigned s_tmp[32];
+  __shared__ unsigned s_last;
+  for (int i = threadIdx.x; i < kMsdBins; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  const int64_t n = (int64_t)ctr->work_tri + ctr->work_quad;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int4 v4 = reinterpret_cast<const int4*>(records + i)[0];
+    const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
+    emit_polygon_keys(v4, meta.x, __popc((unsigned)meta.x) == 2, (unsigned)meta.y, (unsigned)meta.w, key_bits, msd_shift,
+                      keys, vals, s_hist);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMsdBins; i += blockDim.x) {
+    const unsigned c = s_hist[i];
+    if (c) atomicAdd(&msd_hist[i], c);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->compact_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) msd_scan_epilogue(msd_hist, msd_base, msd_cursor, s_tmp);
+}
+
+void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
+                         cudaStream_t stream) {
+  {
+    ProfScope ps(K_RANK_RECORDS, stream);
+    rank_records_kernel<<<1, 1024, 0, stream>>>(records, n_records, ws.ctr);
+  }
+  int64_t blocks = (n_records + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  ProfScope ps(K_COMPACT, stream);
+  keys_from_records_kernel<<<(unsigned)blocks, 256, 0, stream>>>(records, ws.ctr, key_bits_for(a.n_grid),
+                                                                 msd_shift_for(a.n_grid), ws.keys, ws.vals, ws.msd_hist,
+                                                                 ws.msd_base, ws.msd_cursor);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -131,10 +131,10 @@ __device__ __forceinline__ bool boundary_weights(float mi, float mj, float& u0, 
 // device-side counters (one cache line of int32 words at the head of the workspace; reset per call)
 // ------------------------------------------------------------------------------------------------
 struct DevCounters {
-  unsigned ticket_classify;  // dynamic tile ids of the classify kernel
-  unsigned ticket_sort[8];   // one per radix pass
+  unsigned ticket_compact;   // dynamic tile ids of the ordered kernels
   unsigned ticket_rle;
   unsigned ticket_poly;
+  unsigned compact_done;     // CTAs of the key-emitting kernel that have flushed their histogram
   unsigned n_valid;          // Fv (true count, even when the record buffer overflowed)
   unsigned n_tri;            // T1
   unsigned n_quad;           // T2
@@ -142,7 +142,7 @@ struct DevCounters {
   unsigned work_quad;        //   Fv exceeded the record capacity (the caller re-runs with a larger workspace)
   unsigned n_verts;          // V
   unsigned bucket[6];        // polygons per faces_aug bucket
-  unsigned pad[9];
+  unsigned pad[16];
 };
 static_assert(sizeof(DevCounters) == 128, "DevCounters is one 128-byte line");
 

@@ -7,21 +7,22 @@ namespace d3h {
 
 // ---- tile shapes ----------------------------------------------------------------------------------
 constexpr int kClassifyThreads = 256;
-constexpr int kClassifyItems = 8;  // tets per thread: 8 x 16 B loads in flight
-constexpr int kClassifyTile = kClassifyThreads * kClassifyItems;
+constexpr int kClassifyItems = 8;   // tets per lane: 8 x 16 B loads in flight, one ballot word per item
 
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 4;
-constexpr int kSortTile = kSortThreads * kSortItems;
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
-constexpr int kMaxPasses = 8;
+constexpr int kCompactThreads = 256;
+constexpr int kCompactWords = 4;    // bitmap words per thread: a tile covers 256*4*32 = 32768 tets
+
+constexpr int kMsdBits = 11;        // MSD radix digit: top bits of the smaller endpoint
+constexpr int kMsdBins = 1 << kMsdBits;
+constexpr int kSortGroup = 2048;    // group quantum of the block-local finish
+constexpr int kLocalSortCap = 4096; // keys a CTA sorts in shared memory (48 KB); larger groups use global scratch
+constexpr int kLocalSortThreads = 512;
 
 constexpr int kRleThreads = 256;
-constexpr int kRleItems = 4;
+constexpr int kRleItems = 8;
 constexpr int kRleTile = kRleThreads * kRleItems;
 
-constexpr int kPolyThreads = 256;  // one valid tet (= one polygon) per thread
+constexpr int kPolyThreads = 256;   // one valid tet (= one polygon) per thread
 
 // ---- workspace ------------------------------------------------------------------------------------
 // Every region is 256-byte aligned.  Sizes depend on (F, N, cap_valid_tets) only.
@@ -30,45 +31,53 @@ struct Workspace {
   d3h_counts* counts;             // device copy of the public counts
   unsigned* occ_bits;             // ceil(N/32) words: sdf > 0
   unsigned* mocc_bits;            // ceil(N/32) words: (+-)msdf > 0 (open-mesh prefilter only)
-  unsigned long long* st_classify;// one status word per classify tile
+  unsigned* m1_words;             // ceil(F/32) words: tet yields one triangle
+  unsigned* m2_words;             // ceil(F/32) words: tet yields two triangles
+  unsigned long long* st_compact; // one status word per compaction tile
   d3h_tet_record* records;        // cap_valid_tets
-  unsigned long long* keys[2];    // 4*cap_valid_tets each
-  unsigned* vals[2];              // 4*cap_valid_tets each
-  unsigned* radix_hist;           // kMaxPasses * 256
-  unsigned* st_sort;              // kMaxPasses * ntiles_sort * 256
+  unsigned long long* keys;       // 4*cap_valid_tets: edge keys in valid-tet order
+  unsigned* vals;
+  unsigned long long* keys2;      // 4*cap_valid_tets: partitioned, then sorted in place
+  unsigned* vals2;
+  unsigned long long* keys_scratch;  // 8*cap_valid_tets: padded copies of oversized buckets
+  unsigned* vals_scratch;
+  unsigned* msd_hist;             // kMsdBins
+  unsigned* msd_base;             // kMsdBins + 1
+  unsigned* msd_cursor;           // kMsdBins
   unsigned long long* st_rle;     // ntiles_rle
-  unsigned* st_poly;              // ntiles_poly * 8 (6 used)
+  unsigned long long* st_poly;    // ntiles_poly * 3 (two 31-bit bucket counters per word)
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets
   float4* tng;                    // (tx,ty,tz,-) per watertight vertex
-  float* acc;                     // 8 floats per watertight vertex: normal xyz, tangent xyz, count, pad
+  float* acc;                     // 8 floats per watertight vertex: normal xyz + count, tangent xyz + pad
   unsigned* polyinfo;             // per valid tet: (bucket rank << 4) | mSDF case
   int64_t cap_tets, cap_corners;
-  int64_t ntiles_classify, ntiles_sort, ntiles_rle, ntiles_poly;
+  int64_t ntiles_compact, ntiles_rle, ntiles_poly;
   int64_t total_bytes;
 };
 
 // Carves `base` (may be nullptr when only the size is wanted).
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets);
 
-int key_bits_for(int64_t n_grid);  // bits per endpoint in the packed edge key
+int key_bits_for(int64_t n_grid);   // bits per endpoint in the packed edge key
+int msd_shift_for(int64_t n_grid);  // endpoint >> shift = MSD bucket
 
 // ---- stage launchers (all asynchronous on `stream`) -------------------------------------------------
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
-                     cudaStream_t stream);
-void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
-                      cudaStream_t stream);
+                     bool emit_keys, cudaStream_t stream);
+void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream);
-void launch_rank_records(const Workspace& ws, d3h_tet_record* records, int64_t n_records, cudaStream_t stream);
+void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
+                         cudaStream_t stream);
 void launch_backward(const d3h_backward_args& a, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 
 // ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
 enum KernelKind {
-  K_PREPARE = 0, K_CLASSIFY, K_EMIT_KEYS, K_RADIX_PASS, K_RLE_INTERP, K_POLY_FACES, K_VERTEX_FRAME, K_POLY_CUT,
-  K_ZERO, K_BOUNDARY_ADJ, K_CROSSING_ADJ, K_RANK_RECORDS, K_COUNT
+  K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_PARTITION, K_LOCAL_SORT, K_RLE_INTERP, K_POLY_FACES, K_VERTEX_FRAME,
+  K_POLY_CUT, K_ZERO, K_BOUNDARY_ADJ, K_CROSSING_ADJ, K_RANK_RECORDS, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

@@ -9,11 +9,18 @@
 // Each valid tet contributes its polygon corners (3 or 4 crossing edges, in mesh_edge_table order), so the inverse map
 // of the sort *is* the polygon corner array, laid out [3*T1 | 4*T2] like the boundary vertices (:406-407).
 //
-//   emit_keys     : key = (min << bits) | max, value = corner slot; all radix histograms in the same pass
-//   radix_pass    : LSD, 8-bit digits, one kernel per digit ("onesweep": per-tile digit counts chained by decoupled
-//                   look-back; stable ranks from warp match_any + per-warp counters)
-//   rle_interp    : head flags + scan (look-back) = vertex ids in sorted order; scatters ids to the corner array,
-//                   writes the (a,b) tape and interpolates position / mSDF of every new vertex.
+// The sort is an MSD radix sort with a block-local finish (keys are (min << bits) | max, 2*bits <= 62):
+//   partition_kernel  one radix pass on the top 11 bits of `min` (<= 2048 buckets; histogram and bucket bases come from
+//                     the compaction kernel).  The pass need not be stable (equal keys are merged afterwards), so slots
+//                     are claimed with warp-aggregated atomics -- no inter-tile dependency.
+//   local_sort_kernel one CTA per group of whole buckets (<= 4096 keys): bitonic sort of (key, value) in shared memory.
+//                     A bucket too large for shared memory (surface concentrated in a few thousand consecutive vertex
+//                     ids, e.g. an axis-aligned plane) is sorted by its CTA in global memory instead: slower, still exact.
+//   rle_interp_kernel head flags + scan (decoupled look-back) = vertex ids in sorted order; scatters the ids to the
+//                     corner array, writes the (a,b) tape and interpolates position / mSDF of every new vertex.
+//
+// v1 used six chained 8-bit LSD passes (look-back per digit and tile): 11 us per pass under ncu for 192k keys
+// (profiles/r01a_launches_v1.csv) -- the chains, not the data volume, set the time.
 #include "d3h_internal.cuh"
 
 namespace d3h {
@@ -23,163 +30,123 @@ int key_bits_for(int64_t n_grid) {
   while ((1ll << b) < n_grid) ++b;
   return b;
 }
-
-// ------------------------------------------------------------------------------------------------
-// K2: keys + histograms
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-emit_keys_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* __restrict__ ctr,
-                 int64_t cap_records, int key_bits, int npass, unsigned long long* __restrict__ keys,
-                 unsigned* __restrict__ vals, unsigned* __restrict__ radix_hist, unsigned* __restrict__ st_sort,
-                 int64_t st_sort_pass_stride) {
-  __shared__ unsigned s_hist[kMaxPasses * kRadix];
-  for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) s_hist[i] = 0u;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  // zero the look-back state of the radix passes that will actually run
-  const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
-  {
-    const int64_t ncorn = 3ll * t1 + 4ll * t2;
-    const int64_t per_pass = ((ncorn + kSortTile - 1) / kSortTile) * kRadix;
-    for (int64_t i = tid; i < per_pass * npass; i += nthreads)
-      st_sort[(i / per_pass) * st_sort_pass_stride + (i % per_pass)] = 0u;
-  }
-  __syncthreads();
-  const int64_t nvalid = (int64_t)t1 + t2;
-  for (int64_t i = tid; i < nvalid; i += nthreads) {
-    const int4 v4 = reinterpret_cast<const int4*>(records + i)[0];
-    const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
-    const int code = meta.x, rank = meta.y;
-    const int vv[4] = {v4.x, v4.y, v4.z, v4.w};
-    const bool quad = __popc((unsigned)code) == 2;
-    const int n = quad ? 4 : 3;
-    const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
-    for (int k = 0; k < n; ++k) {
-      const int e = c_loop_edge[code][k];
-      const int p = vv[c_edge_p[e]], q = vv[c_edge_q[e]];
-      const unsigned long long a = (unsigned)min(p, q), b = (unsigned)max(p, q);
-      const unsigned long long key = (a << key_bits) | b;
-      keys[p0 + k] = key;
-      vals[p0 + k] = (unsigned)(p0 + k);
-      for (int ps = 0; ps < npass; ++ps) atomicAdd(&s_hist[ps * kRadix + (unsigned)((key >> (8 * ps)) & 0xffu)], 1u);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) {
-    const unsigned c = s_hist[i];
-    if (c) atomicAdd(&radix_hist[i], c);
-  }
+int msd_shift_for(int64_t n_grid) {
+  const int b = key_bits_for(n_grid);
+  return b > kMsdBits ? b - kMsdBits : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// radix pass (stable LSD, 8-bit digit)
+// MSD partition
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned kSFlagAgg = 1u << 30, kSFlagInc = 2u << 30, kSValMask = (1u << 30) - 1;
+__global__ void __launch_bounds__(256)
+partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
+                 unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out,
+                 const DevCounters* __restrict__ ctr, unsigned* __restrict__ cursor, int digit_shift) {
+  const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = i < ncorn;
+  unsigned long long key = 0;
+  unsigned val = 0;
+  int bin = -1 - (int)lane_id();  // idle lanes match nobody
+  if (ok) {
+    key = keys_in[i];
+    val = vals_in[i];
+    bin = (int)(key >> digit_shift);
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (!ok) return;
+  const int leader = __ffs(peers) - 1;
+  unsigned pos = 0;
+  if ((int)lane_id() == leader) pos = atomicAdd(&cursor[bin], (unsigned)__popc(peers));
+  pos = __shfl_sync(peers, pos, leader) + __popc(peers & lanemask_lt());
+  keys_out[pos] = key;
+  vals_out[pos] = val;
+}
 
-__global__ void __launch_bounds__(kSortThreads)
-radix_pass_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
-                  unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out,
-                  DevCounters* __restrict__ ctr, const unsigned* __restrict__ hist /* this pass, 256 */,
-                  unsigned* __restrict__ status /* this pass: ntiles x 256 */, int pass, int shift) {
-  constexpr int WARPS = kSortThreads / 32;
-  __shared__ unsigned s_tile;
-  __shared__ unsigned s_whist[WARPS][kRadix];  // per-warp digit counters, then exclusive offsets over warps
-  __shared__ unsigned s_base[kRadix];          // global base of each digit for this tile
-  __shared__ unsigned s_scan[WARPS];
+// ------------------------------------------------------------------------------------------------
+// block-local finish
+// ------------------------------------------------------------------------------------------------
+// Group g owns key positions [snap(g*G), snap((g+1)*G)) where snap(x) = start of the bucket that contains position x:
+// groups are unions of whole buckets, tile [0,P) exactly, and hold < G + (largest bucket) keys.
+template <typename KeyPtr, typename ValPtr>
+__device__ __forceinline__ void bitonic_sort_block(KeyPtr k, ValPtr v, unsigned npow2) {
+  for (unsigned size = 2; size <= npow2; size <<= 1) {
+    for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+      for (unsigned t = threadIdx.x; t < (npow2 >> 1); t += blockDim.x) {
+        const unsigned lo = 2 * t - (t & (stride - 1));
+        const unsigned hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long ka = k[lo], kb = k[hi];
+        if ((ka > kb) == up) {
+          const unsigned va = v[lo], vb = v[hi];
+          k[lo] = kb; k[hi] = ka;
+          v[lo] = vb; v[hi] = va;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLocalSortThreads)
+local_sort_kernel(unsigned long long* keys, unsigned* vals, unsigned long long* scratch_keys, unsigned* scratch_vals,
+                  const DevCounters* __restrict__ ctr, const unsigned* __restrict__ msd_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned* s_val = reinterpret_cast<unsigned*>(s_key + kLocalSortCap);
+  __shared__ unsigned s_lo, s_hi;
 
   const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
-  const int64_t ntiles = (ncorn + kSortTile - 1) / kSortTile;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_sort[pass], 1u);
-  for (int i = threadIdx.x; i < WARPS * kRadix; i += kSortThreads) (&s_whist[0][0])[i] = 0u;
+  const int64_t g = blockIdx.x;
+  if (g * kSortGroup >= ncorn) return;
+  // snap(x): largest bucket base <= x (bases are non-decreasing; empty buckets share their successor's base)
+  if (threadIdx.x == 0) { s_lo = 0u; s_hi = 0u; }
   __syncthreads();
-  const unsigned tile = s_tile;
-  if ((int64_t)tile >= ntiles) return;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const unsigned lt = lanemask_lt();
-
-  // warp-striped tile: warp w owns keys [w*32*ITEMS, (w+1)*32*ITEMS), item j of lane l is at j*32 + l
-  const int64_t wbase = (int64_t)tile * kSortTile + (int64_t)warp * (32 * kSortItems);
-  unsigned long long key[kSortItems];
-  unsigned val[kSortItems], rank[kSortItems];
-  int digit[kSortItems];
-#pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    const int64_t idx = wbase + j * 32 + lane;
-    const bool ok = idx < ncorn;
-    key[j] = ok ? keys_in[idx] : ~0ull;
-    val[j] = ok ? vals_in[idx] : 0u;
-    digit[j] = ok ? (int)((key[j] >> shift) & 0xffu) : -1;
-  }
-  // stable rank inside the warp's chunk
-#pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    const int dmatch = digit[j] >= 0 ? digit[j] : (kRadix + (int)lane);  // padding lanes match nobody
-    const unsigned peers = __match_any_sync(0xffffffffu, dmatch);
-    const int leader = __ffs(peers) - 1;
-    unsigned prev = 0;
-    if (digit[j] >= 0 && (int)lane == leader) {
-      prev = s_whist[warp][digit[j]];
-      s_whist[warp][digit[j]] = prev + __popc(peers);
-    }
-    prev = __shfl_sync(0xffffffffu, prev, leader);
-    rank[j] = prev + __popc(peers & lt);
-    __syncwarp();
-  }
-  __syncthreads();
-
-  // thread d owns digit d: offsets over warps, tile count, global exclusive scan of the pass histogram, look-back
   {
-    const int d = threadIdx.x;
-    unsigned run = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      const unsigned c = s_whist[w][d];
-      s_whist[w][d] = run;
-      run += c;
+    const unsigned x0 = (unsigned)(g * kSortGroup);
+    const unsigned x1 = (unsigned)min((int64_t)(g + 1) * kSortGroup, ncorn);
+    unsigned best0 = 0, best1 = 0;
+    for (int b = threadIdx.x; b <= kMsdBins; b += kLocalSortThreads) {
+      const unsigned base = __ldg(msd_base + b);
+      if (base <= x0) best0 = max(best0, base);
+      if (base <= x1) best1 = max(best1, base);
     }
-    const unsigned tile_count = run;
-    // exclusive scan over digits of the global histogram (block scan of 256 values)
-    const unsigned h = hist[d];
-    unsigned incl = h;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += n;
-    }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    unsigned wpre = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w)
-      if (w < (int)warp) wpre += s_scan[w];
-    const unsigned digit_base = wpre + incl - h;
-
-    unsigned excl = 0;
-    unsigned* my = status + (int64_t)tile * kRadix + d;
-    if (tile == 0) {
-      st_relaxed_u32(my, kSFlagInc | tile_count);
-    } else {
-      st_relaxed_u32(my, kSFlagAgg | tile_count);
-      int64_t look = (int64_t)tile - 1;
-      while (true) {
-        unsigned w;
-        do { w = ld_relaxed_u32(status + look * kRadix + d); } while ((w >> 30) == 0u);
-        excl += w & kSValMask;
-        if ((w >> 30) == 2u || look == 0) break;
-        --look;
-      }
-      st_relaxed_u32(my, kSFlagInc | (excl + tile_count));
-    }
-    s_base[d] = digit_base + excl;
+    if (best0) atomicMax(&s_lo, best0);
+    if (best1) atomicMax(&s_hi, best1);
   }
   __syncthreads();
+  const unsigned lo = s_lo;
+  const unsigned hi = ((int64_t)(g + 1) * kSortGroup >= ncorn) ? (unsigned)ncorn : s_hi;
+  if (hi <= lo) return;  // this group's positions belong to a bucket that started in an earlier group
+  const unsigned n = hi - lo;
+  unsigned npow2 = 2;
+  while (npow2 < n) npow2 <<= 1;
 
-#pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    if (digit[j] < 0) continue;
-    const unsigned pos = s_base[digit[j]] + s_whist[warp][digit[j]] + rank[j];
-    keys_out[pos] = key[j];
-    vals_out[pos] = val[j];
+  if (n <= (unsigned)kLocalSortCap) {
+    for (unsigned i = threadIdx.x; i < npow2; i += kLocalSortThreads) {
+      s_key[i] = (i < n) ? keys[lo + i] : ~0ull;
+      s_val[i] = (i < n) ? vals[lo + i] : 0u;
+    }
+    __syncthreads();
+    bitonic_sort_block(s_key, s_val, npow2);
+    for (unsigned i = threadIdx.x; i < n; i += kLocalSortThreads) {
+      keys[lo + i] = s_key[i];
+      vals[lo + i] = s_val[i];
+    }
+  } else {
+    // oversized bucket: same network on a padded copy in global scratch (exact, slower; only degenerate inputs)
+    unsigned long long* gk = scratch_keys + 2ull * lo;  // padded copies of disjoint ranges cannot overlap at 2*lo
+    unsigned* gv = scratch_vals + 2ull * lo;
+    for (unsigned i = threadIdx.x; i < npow2; i += kLocalSortThreads) {
+      gk[i] = (i < n) ? keys[lo + i] : ~0ull;
+      gv[i] = (i < n) ? vals[lo + i] : 0u;
+    }
+    __syncthreads();
+    bitonic_sort_block(gk, gv, npow2);
+    for (unsigned i = threadIdx.x; i < n; i += kLocalSortThreads) {
+      keys[lo + i] = gk[i];
+      vals[lo + i] = gv[i];
+    }
   }
 }
 
@@ -193,7 +160,7 @@ rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
                   DevCounters* __restrict__ ctr, unsigned long long* __restrict__ status, int key_bits,
                   const float* __restrict__ pos, const float* __restrict__ sdf, const float* __restrict__ msdf,
                   int msdf_negate, int32_t* __restrict__ tape_corners, int32_t* __restrict__ tape_edges,
-                  int64_t cap_verts, int64_t cap_verts_aug, float4* __restrict__ w_vert, float* __restrict__ w_acc,
+                  int64_t cap_verts, int64_t cap_verts_aug, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
                   float* __restrict__ verts_wt, float* __restrict__ msdf_wt, float* __restrict__ verts_aug,
                   float* __restrict__ msdf_aug) {
   constexpr int WARPS = kRleThreads / 32;
@@ -201,7 +168,8 @@ rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
   __shared__ unsigned s_wsum[WARPS];
   __shared__ unsigned long long s_excl;
 
-  const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
+  const unsigned t1 = ctr->work_tri;
+  const int64_t ncorn = 3ll * t1 + 4ll * ctr->work_quad;
   const int64_t ntiles = (ncorn + kRleTile - 1) / kRleTile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_rle, 1u);
   __syncthreads();
@@ -209,7 +177,7 @@ rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
   if ((int64_t)tile >= ntiles) return;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 
-  // blocked: thread owns 4 consecutive sorted keys
+  // blocked: thread owns kRleItems consecutive sorted keys
   const int64_t i0 = (int64_t)tile * kRleTile + (int64_t)threadIdx.x * kRleItems;
   unsigned long long k[kRleItems];
   unsigned long long prev = (i0 > 0 && i0 - 1 < ncorn) ? keys[i0 - 1] : ~0ull;
@@ -224,7 +192,6 @@ rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
     prev = k[j];
     nhead += head[j];
   }
-  // block exclusive scan of nhead
   unsigned incl = nhead;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -289,9 +256,8 @@ rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
       const float z = lerp2(__ldg(pos + 3ll * a + 2), w0, __ldg(pos + 3ll * b + 2), w1);
       const float m = lerp2(ma, w0, mb, w1);
       w_vert[vid] = make_float4(x, y, z, m);
-      float4* acc4 = reinterpret_cast<float4*>(w_acc + 8 * vid);
-      acc4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      acc4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (vid < cap_verts) {
         tape_edges[2 * vid] = a;
         tape_edges[2 * vid + 1] = b;
@@ -308,37 +274,41 @@ rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
         msdf_aug[vid] = m;
       }
     }
-    tape_corners[vals[idx]] = (int32_t)vid;
+    // value = (class, 4*class_rank + k) -> corner slot in the [3*T1 | 4*T2] layout
+    const unsigned val = vals[idx];
+    const unsigned r4 = val & 0x7fffffffu;
+    const int64_t slot = (val >> 31) ? (3ll * t1 + r4) : (3ll * (r4 >> 2) + (r4 & 3u));
+    tape_corners[slot] = (int32_t)vid;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
-                      cudaStream_t stream) {
+void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const int key_bits = key_bits_for(a.n_grid);
-  const int npass = (2 * key_bits + kRadixBits - 1) / kRadixBits;
-  const int64_t cap = ws.cap_tets;
-  if (cap <= 0) return;
+  const int64_t capc = ws.cap_corners;
+  if (capc <= 0) return;
   {
-    int64_t blocks = (cap + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    ProfScope ps(K_EMIT_KEYS, stream);
-    emit_keys_kernel<<<(unsigned)blocks, 256, 0, stream>>>(records, ws.ctr, cap, key_bits, npass, ws.keys[0], ws.vals[0],
-                                                           ws.radix_hist, ws.st_sort,
-                                                           ws.ntiles_sort * (int64_t)kRadix);
+    ProfScope ps(K_PARTITION, stream);
+    partition_kernel<<<(unsigned)((capc + 255) / 256), 256, 0, stream>>>(ws.keys, ws.vals, ws.keys2, ws.vals2, ws.ctr,
+                                                                          ws.msd_cursor,
+                                                                          key_bits + msd_shift_for(a.n_grid));
   }
-  int cur = 0;
-  for (int p = 0; p < npass; ++p) {
-    ProfScope ps(K_RADIX_PASS, stream);
-    radix_pass_kernel<<<(unsigned)ws.ntiles_sort, kSortThreads, 0, stream>>>(
-        ws.keys[cur], ws.vals[cur], ws.keys[cur ^ 1], ws.vals[cur ^ 1], ws.ctr, ws.radix_hist + p * kRadix,
-        ws.st_sort + (int64_t)p * ws.ntiles_sort * kRadix, p, p * kRadixBits);
-    cur ^= 1;
+  {
+    static bool attr_set = false;
+    const int smem = kLocalSortCap * 12;
+    if (!attr_set) {
+      cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    ProfScope ps(K_LOCAL_SORT, stream);
+    local_sort_kernel<<<(unsigned)(capc / kSortGroup + 1), kLocalSortThreads, smem, stream>>>(
+        ws.keys2, ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.msd_base);
   }
   ProfScope ps(K_RLE_INTERP, stream);
   rle_interp_kernel<<<(unsigned)ws.ntiles_rle, kRleThreads, 0, stream>>>(
-      ws.keys[cur], ws.vals[cur], ws.ctr, ws.st_rle, key_bits, a.pos, a.sdf, a.msdf, a.msdf_negate, a.tape_corners,
-      a.tape_edges, a.cap_verts, a.cap_verts_aug, ws.vert, ws.acc, a.verts_wt, a.msdf_wt, a.verts_aug, a.msdf_aug);
+      ws.keys2, ws.vals2, ws.ctr, ws.st_rle, key_bits, a.pos, a.sdf, a.msdf, a.msdf_negate, a.tape_corners, a.tape_edges,
+      a.cap_verts, a.cap_verts_aug, ws.vert, reinterpret_cast<float4*>(ws.acc), a.verts_wt, a.msdf_wt, a.verts_aug,
+      a.msdf_aug);
 }
 
 }  // namespace d3h

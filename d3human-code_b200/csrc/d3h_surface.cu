@@ -46,11 +46,11 @@ __device__ __forceinline__ float cross_comp(float ai, float bj, float aj, float 
   return __fmaf_rn(ai, bj, -__fmul_rn(aj, bi));
 }
 
-constexpr unsigned kPFlagAgg = 1u << 30, kPFlagInc = 2u << 30, kPValMask = (1u << 30) - 1;
+constexpr unsigned long long kPFlagAgg = 1ull << 62, kPFlagInc = 2ull << 62, kPValMask = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(kPolyThreads)
 poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __restrict__ ctr,
-                  unsigned* __restrict__ status, const int32_t* __restrict__ corners,
+                  unsigned long long* __restrict__ status, const int32_t* __restrict__ corners,
                   const float4* __restrict__ w_vert, float* __restrict__ w_acc, unsigned* __restrict__ polyinfo,
                   int64_t* __restrict__ faces_wt, int64_t cap_faces_wt, UvParams uvp) {
   constexpr int WARPS = kPolyThreads / 32;
@@ -107,16 +107,16 @@ poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __res
       }
       const float ax = __fsub_rn(pv[1].x, pv[0].x), ay = __fsub_rn(pv[1].y, pv[0].y), az = __fsub_rn(pv[1].z, pv[0].z);
       const float bx = __fsub_rn(pv[2].x, pv[0].x), by = __fsub_rn(pv[2].y, pv[0].y), bz = __fsub_rn(pv[2].z, pv[0].z);
+      // accumulator row of a vertex: [nx ny nz count | tx ty tz -]; one 16-byte vector atomic per half (sm_90+)
+      float nx = 0.f, ny = 0.f, nz = 0.f;
       if (!cross_quirk) {
-        const float nx = cross_comp(ay, bz, az, by), ny = cross_comp(az, bx, ax, bz), nz = cross_comp(ax, by, ay, bx);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float* acc = w_acc + 8ll * vi[c];
-          atomicAdd(acc + 0, nx);
-          atomicAdd(acc + 1, ny);
-          atomicAdd(acc + 2, nz);
-        }
+        nx = cross_comp(ay, bz, az, by);
+        ny = cross_comp(az, bx, ax, bz);
+        nz = cross_comp(ax, by, ay, bx);
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        atomicAdd(reinterpret_cast<float4*>(w_acc + 8ll * vi[c]), make_float4(nx, ny, nz, 1.f));
       // tangent of this face
       const float2 uv0 = vertex_uv(uvp, vi[0]), uv1 = vertex_uv(uvp, vi[1]), uv2 = vertex_uv(uvp, vi[2]);
       const float u1x = __fsub_rn(uv1.x, uv0.x), u1y = __fsub_rn(uv1.y, uv0.y);
@@ -127,13 +127,8 @@ poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __res
       const float ty = __fdiv_rn(__fsub_rn(__fmul_rn(ay, u2y), __fmul_rn(by, u1y)), den);
       const float tz = __fdiv_rn(__fsub_rn(__fmul_rn(az, u2y), __fmul_rn(bz, u1y)), den);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float* acc = w_acc + 8ll * vi[c];
-        atomicAdd(acc + 3, tx);
-        atomicAdd(acc + 4, ty);
-        atomicAdd(acc + 5, tz);
-        atomicAdd(acc + 6, 1.f);
-      }
+      for (int c = 0; c < 3; ++c)
+        atomicAdd(reinterpret_cast<float4*>(w_acc + 8ll * vi[c]) + 1, make_float4(tx, ty, tz, 0.f));
     }
     // ---- mSDF cut case (sign of the interpolated mSDF at the polygon corners) ----
     const unsigned mo0 = P[0].w > 0.f, mo1 = P[1].w > 0.f, mo2 = P[2].w > 0.f, mo3 = P[3].w > 0.f;
@@ -158,33 +153,56 @@ poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __res
     if (lane == 0) s_cnt[b][warp] = __popc(m);
   }
   __syncthreads();
-  if (warp == 0 && lane < 6) {
-    const int b = lane;
+  if (warp == 0) {
+    // exclusive offsets over the warps + tile totals, lanes 0..5 = buckets
     unsigned run = 0;
+    if (lane < 6) {
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      const unsigned c = s_cnt[b][w];
-      s_cnt[b][w] = run;
-      run += c;
-    }
-    unsigned excl = 0;
-    unsigned* my = status + (int64_t)tile * 8 + b;
-    if (tile == 0) {
-      st_relaxed_u32(my, kPFlagInc | run);
-    } else {
-      st_relaxed_u32(my, kPFlagAgg | run);
-      int64_t look = (int64_t)tile - 1;
-      while (true) {
-        unsigned w;
-        do { w = ld_relaxed_u32(status + look * 8 + b); } while ((w >> 30) == 0u);
-        excl += w & kPValMask;
-        if ((w >> 30) == 2u || look == 0) break;
-        --look;
+      for (int w = 0; w < WARPS; ++w) {
+        const unsigned c = s_cnt[lane][w];
+        s_cnt[lane][w] = run;
+        run += c;
       }
-      st_relaxed_u32(my, kPFlagInc | (excl + run));
     }
-    s_tile_excl[b] = excl;
-    if ((int64_t)tile == ntiles - 1) ctr->bucket[b] = excl + run;
+    // three status words per tile, each packing two 31-bit bucket counters; 32 predecessors per look-back step
+#pragma unroll 1
+    for (int wd = 0; wd < 3; ++wd) {
+      const unsigned lo_cnt = __shfl_sync(0xffffffffu, run, 2 * wd), hi_cnt = __shfl_sync(0xffffffffu, run, 2 * wd + 1);
+      const unsigned long long agg = (unsigned long long)lo_cnt | ((unsigned long long)hi_cnt << 31);
+      unsigned long long excl = 0ull;
+      unsigned long long* my = status + (int64_t)tile * 3 + wd;
+      if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(my, kPFlagInc | agg);
+      } else {
+        if (lane == 0) st_relaxed_u64(my, kPFlagAgg | agg);
+        int64_t look = (int64_t)tile - 1;
+        while (true) {
+          const int64_t idx = look - lane;
+          unsigned long long w = kPFlagInc;
+          if (idx >= 0) {
+            do { w = ld_relaxed_u64(status + idx * 3 + wd); } while ((w >> 62) == 0ull);
+          }
+          const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+          const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+          unsigned long long contrib = ((int)lane <= first) ? (w & kPValMask) : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+          excl += contrib;
+          if (inc_mask) break;
+          look -= 32;
+        }
+        if (lane == 0) st_relaxed_u64(my, kPFlagInc | (excl + agg));
+      }
+      if (lane == 0) {
+        const unsigned e_lo = (unsigned)(excl & 0x7fffffffull), e_hi = (unsigned)(excl >> 31);
+        s_tile_excl[2 * wd] = e_lo;
+        s_tile_excl[2 * wd + 1] = e_hi;
+        if ((int64_t)tile == ntiles - 1) {
+          ctr->bucket[2 * wd] = e_lo + lo_cnt;
+          ctr->bucket[2 * wd + 1] = e_hi + hi_cnt;
+        }
+      }
+    }
   }
   __syncthreads();
   if (i < npoly) {
@@ -218,7 +236,7 @@ poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __res
       fn[1] = cross_comp(a[2][c], b[0][c], a[0][c], b[2][c]);
       fn[2] = cross_comp(a[0][c], b[1][c], a[1][c], b[0][c]);
       for (int r = 0; r < 3; ++r)
-        for (int k = 0; k < 3; ++k) atomicAdd(w_acc + 8ll * fv[r][k] + c, fn[r]);
+        for (int k = 0; k < 3; ++k) atomicAdd(w_acc + 8ll * fv[r][k] + c, fn[r]);  // counts were added above
     }
   }
 }
@@ -245,8 +263,8 @@ vertex_frame_kernel(const DevCounters* __restrict__ ctr, const float* __restrict
     if (!(d > 1e-20f)) { nx = 0.f; ny = 0.f; nz = 1.f; }
     const float3 n = safe_normalize3(nx, ny, nz);
     // compute_tangents tail, gshell_tets.py:69-73
-    const float cnt = a1.z;
-    float3 t = safe_normalize3(__fdiv_rn(a0.w, cnt), __fdiv_rn(a1.x, cnt), __fdiv_rn(a1.y, cnt));
+    const float cnt = a0.w;
+    float3 t = safe_normalize3(__fdiv_rn(a1.x, cnt), __fdiv_rn(a1.y, cnt), __fdiv_rn(a1.z, cnt));
     const float dp = __fadd_rn(__fadd_rn(__fmul_rn(t.x, n.x), __fmul_rn(t.y, n.y)), __fmul_rn(t.z, n.z));
     t = safe_normalize3(__fsub_rn(t.x, __fmul_rn(dp, n.x)), __fsub_rn(t.y, __fmul_rn(dp, n.y)),
                         __fsub_rn(t.z, __fmul_rn(dp, n.z)));

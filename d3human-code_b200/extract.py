@@ -209,11 +209,9 @@ def _shrink(cap: int, need: int) -> int:
 
 
 def _launches_forward(n_grid: int, cap_tets: int) -> int:
-    """Kernels one d3h_extract_forward enqueues (prepare, classify, emit_keys, radix passes, rle, 3 surface kernels)."""
-    if cap_tets <= 0:
-        return 3  # prepare + classify + poly_cut (counts)
-    bits = max(1, (n_grid - 1).bit_length())
-    return 2 + 1 + (2 * bits + 7) // 8 + 1 + 3
+    """Kernels one d3h_extract_forward enqueues: prepare, classify, compact, [partition, local_sort, rle_interp,
+    poly_faces, vertex_frame,] poly_cut."""
+    return 4 if cap_tets <= 0 else 9
 
 
 # --------------------------------------------------------------------------------------------------
@@ -302,6 +300,12 @@ def last_counts() -> Optional[Dict[str, int]]:
     return _ExtractFn.last_counts
 
 
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (the kernels use 16-byte vector loads); a view at an odd offset is cloned."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_watertight_template: bool = True):
     """Shared body of GShell_Tets.__call__ / hmSDF_Tets.__call__: returns the reference's 6-tuple."""
     if not pos_nx3.is_cuda:
@@ -314,8 +318,7 @@ def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_w
     msdf = msdf_n.float().reshape(-1)
     if sdf.shape[0] != n_grid or msdf.shape[0] != n_grid:
         raise ValueError("sdf_n / msdf_n must have one value per grid vertex")
-    pos = pos_nx3.float().contiguous()
-    sdf, msdf = sdf.contiguous(), msdf.contiguous()
+    pos, sdf, msdf = _aligned(pos_nx3.float()), _aligned(sdf), _aligned(msdf)
     tets = packed_tets(tet_fx4, n_grid)
     verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, faces_aug, faces_wt = _ExtractFn.apply(
         pos, sdf, msdf, tets, bool(msdf_negate), bool(output_watertight_template))

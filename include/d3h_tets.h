@@ -159,7 +159,7 @@ typedef struct d3h_tet_record { /* 32 bytes */
   int32_t code;            /* 4-bit occupancy code, gshell_tets.py:307-308 */
   int32_t class_rank;      /* rank among the shard's valid tets with the same triangle count (T1 or T2 class) */
   int32_t tet_id;          /* global tet index */
-  int32_t pad;
+  int32_t other_before;    /* number of the shard's valid tets of the OTHER class that precede this one */
 } d3h_tet_record;
 
 int d3h_classify_range(const d3h_forward_args* args, d3h_tet_record* records_out, int64_t cap_records,
