@@ -70,9 +70,11 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.vals2 = reinterpret_cast<unsigned*>(take(capc * 4));
   ws.keys_scratch = reinterpret_cast<unsigned long long*>(take(2 * capc * 8));
   ws.vals_scratch = reinterpret_cast<unsigned*>(take(2 * capc * 4));
-  ws.msd_hist = reinterpret_cast<unsigned*>(take(kMsdBins * 4));
-  ws.msd_base = reinterpret_cast<unsigned*>(take((kMsdBins + 1) * 4));
-  ws.msd_cursor = reinterpret_cast<unsigned*>(take(kMsdBins * 4));
+  ws.msd_bins = ((n_grid - 1) >> msd_shift_for(n_grid)) + 1;
+  ws.msd_hist = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
+  ws.msd_fill = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
+  ws.msd_base = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
+  ws.group_start = reinterpret_cast<unsigned*>(take((capc / kSortGroup + 2) * 4));
   ws.st_rle = reinterpret_cast<unsigned long long*>(take(ws.ntiles_rle * 8));
   ws.st_poly = reinterpret_cast<unsigned long long*>(take(ws.ntiles_poly * 3 * 8));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));

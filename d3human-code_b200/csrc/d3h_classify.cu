@@ -44,7 +44,10 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
   for (int64_t i = tid; i < ws.ntiles_compact; i += nthreads) ws.st_compact[i] = 0ull;
   for (int64_t i = tid; i < ws.ntiles_rle; i += nthreads) ws.st_rle[i] = 0ull;
   for (int64_t i = tid; i < ws.ntiles_poly * 3; i += nthreads) ws.st_poly[i] = 0ull;
-  for (int64_t i = tid; i < kMsdBins; i += nthreads) ws.msd_hist[i] = 0u;
+  for (int64_t i = tid; i < ws.msd_bins + 8; i += nthreads) {
+    ws.msd_hist[i] = 0u;
+    ws.msd_fill[i] = 0u;
+  }
 
   // bitmaps: each lane takes 4 consecutive vertices (one 16-byte load), 8 lanes make one 32-bit word
   const int64_t nquads = (n_grid + 3) / 4;
@@ -137,7 +140,7 @@ constexpr unsigned long long kValMask = (1ull << 62) - 1;
 __device__ __forceinline__ void emit_polygon_keys(const int4 v4, int code, bool quad, unsigned class_rank,
                                                   unsigned other_before, int key_bits, int msd_shift,
                                                   unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
-                                                  unsigned* __restrict__ s_hist) {
+                                                  unsigned* __restrict__ msd_hist) {
   const int vv[4] = {v4.x, v4.y, v4.z, v4.w};
   const int n = quad ? 4 : 3;
   const int64_t slot0 = quad ? (4ll * class_rank + 3ll * other_before) : (3ll * class_rank + 4ll * other_before);
@@ -147,18 +150,24 @@ __device__ __forceinline__ void emit_polygon_keys(const int4 v4, int code, bool 
     const unsigned long long a = (unsigned)min(p, q), b = (unsigned)max(p, q);
     keys[slot0 + k] = (a << key_bits) | b;
     vals[slot0 + k] = (quad ? 0x80000000u : 0u) | (4u * class_rank + (unsigned)k);
-    atomicAdd(&s_hist[(unsigned)(a >> msd_shift)], 1u);
+    atomicAdd(&msd_hist[(unsigned)(a >> msd_shift)], 1u);  // global RED; buckets are fine-grained, contention is low
   }
 }
 
-// Last-arriving CTA: exclusive scan of the MSD histogram -> bucket bases and scatter cursors.
+// Last-arriving CTA: exclusive scan of the MSD histogram -> bucket bases, and the first key of every sort group.
+// Group g owns key positions [snap(g*G), snap((g+1)*G)), snap(x) = base of the bucket that contains position x: groups
+// are unions of whole buckets, tile [0,P) exactly and hold fewer than G + (largest bucket) keys.
 __device__ void msd_scan_epilogue(const unsigned* __restrict__ hist, unsigned* __restrict__ base,
-                                  unsigned* __restrict__ cursor, unsigned* s_tmp /* >= 32 words */) {
-  const int per = (kMsdBins + blockDim.x - 1) / blockDim.x;  // each thread a contiguous run of bins
+                                  unsigned* __restrict__ group_start, int nbins, unsigned* s_tmp /* >= 32 words */) {
+  const int per = ((nbins + (int)blockDim.x - 1) / (int)blockDim.x + 3) & ~3;  // bins per thread, multiple of 4
   const int b0 = threadIdx.x * per;
   unsigned sum = 0;
-  for (int i = 0; i < per; ++i)
-    if (b0 + i < kMsdBins) sum += __ldcg(hist + b0 + i);
+  for (int i = 0; i < per; i += 4) {
+    if (b0 + i < nbins) {  // hist is padded by 8 zeroed words: the vector load may run past nbins
+      const uint4 h = __ldcg(reinterpret_cast<const uint4*>(hist + b0 + i));
+      sum += h.x + h.y + h.z + h.w;
+    }
+  }
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned incl = sum;
 #pragma unroll
@@ -173,13 +182,21 @@ __device__ void msd_scan_epilogue(const unsigned* __restrict__ hist, unsigned* _
   for (unsigned w = 0; w < warp; ++w) wpre += s_tmp[w];
   unsigned run = wpre + incl - sum;
   for (int i = 0; i < per; ++i) {
-    if (b0 + i < kMsdBins) {
-      base[b0 + i] = run;
-      cursor[b0 + i] = run;
-      run += __ldcg(hist + b0 + i);
+    const int b = b0 + i;
+    if (b < nbins) {
+      const unsigned c = __ldcg(hist + b);
+      base[b] = run;
+      if (c) {
+        for (unsigned g = (run + kSortGroup - 1) / kSortGroup; (uint64_t)g * kSortGroup < (uint64_t)run + c; ++g)
+          group_start[g] = run;
+      }
+      run += c;
     }
   }
-  if (threadIdx.x == blockDim.x - 1) base[kMsdBins] = run;
+  if (threadIdx.x == blockDim.x - 1) {
+    base[nbins] = run;  // = P
+    group_start[(run + kSortGroup - 1) / kSortGroup] = run;
+  }
 }
 
 template <bool EMIT_KEYS>
@@ -189,18 +206,16 @@ compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict
                unsigned long long* __restrict__ status, DevCounters* __restrict__ ctr,
                d3h_tet_record* __restrict__ records, int64_t cap_records, int64_t ntiles, int key_bits, int msd_shift,
                unsigned long long* __restrict__ keys, unsigned* __restrict__ vals, unsigned* __restrict__ msd_hist,
-               unsigned* __restrict__ msd_base, unsigned* __restrict__ msd_cursor) {
+               unsigned* __restrict__ msd_base, unsigned* __restrict__ group_start, int msd_bins) {
   constexpr int WARPS = kCompactThreads / 32;
   __shared__ unsigned s_pre1[kCompactThreads], s_pre2[kCompactThreads];  // exclusive per-thread prefixes in the tile
+  __shared__ unsigned s_m1[kCompactThreads * kCompactWords], s_m2[kCompactThreads * kCompactWords];
   __shared__ unsigned s_w1[32], s_w2[32];
   __shared__ unsigned long long s_excl;
   __shared__ unsigned s_total[2];
-  __shared__ unsigned s_hist[EMIT_KEYS ? kMsdBins : 1];
   __shared__ unsigned s_tile, s_last;
 
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_compact, 1u);
-  if (EMIT_KEYS)
-    for (int i = threadIdx.x; i < kMsdBins; i += kCompactThreads) s_hist[i] = 0u;
   __syncthreads();
   const unsigned tile = s_tile;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -210,10 +225,12 @@ compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict
   unsigned c1 = 0, c2 = 0;
 #pragma unroll
   for (int j = 0; j < kCompactWords; ++j) {
-    if (w0 + j < nwords) {
-      c1 += __popc(__ldcg(m1_words + w0 + j));
-      c2 += __popc(__ldcg(m2_words + w0 + j));
-    }
+    const unsigned a1 = (w0 + j < nwords) ? __ldcg(m1_words + w0 + j) : 0u;
+    const unsigned a2 = (w0 + j < nwords) ? __ldcg(m2_words + w0 + j) : 0u;
+    s_m1[threadIdx.x * kCompactWords + j] = a1;
+    s_m2[threadIdx.x * kCompactWords + j] = a2;
+    c1 += __popc(a1);
+    c2 += __popc(a2);
   }
   // block exclusive scan of (c1, c2)
   unsigned i1 = c1, i2 = c2;
@@ -292,11 +309,11 @@ compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict
     const int64_t wb = ((int64_t)tile * kCompactThreads + th) * kCompactWords;
     unsigned b1 = 0, b2 = 0;
     int64_t word = wb;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < kCompactWords; ++j) {
+      b1 = s_m1[th * kCompactWords + j];
+      b2 = s_m2[th * kCompactWords + j];
       word = wb + j;
-      b1 = __ldcg(m1_words + word);
-      b2 = __ldcg(m2_words + word);
       const unsigned cnt = __popc(b1 | b2);
       if (rem < cnt) break;
       rem -= cnt;
@@ -320,20 +337,18 @@ compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict
       out[0] = v4;
       out[1] = make_int4(code, (int)(quad ? g2 : g1), (int)tet, (int)(quad ? g1 : g2));
       if (EMIT_KEYS)
-        emit_polygon_keys(v4, code, quad, quad ? g2 : g1, quad ? g1 : g2, key_bits, msd_shift, keys, vals, s_hist);
+        emit_polygon_keys(v4, code, quad, quad ? g2 : g1, quad ? g1 : g2, key_bits, msd_shift, keys, vals, msd_hist);
     }
   }
   if (EMIT_KEYS) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kMsdBins; i += kCompactThreads) {
-      const unsigned c = s_hist[i];
-      if (c) atomicAdd(&msd_hist[i], c);
-    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->compact_done, 1u) == (unsigned)(ntiles - 1));
     __syncthreads();
-    if (s_last) msd_scan_epilogue(msd_hist, msd_base, msd_cursor, s_w1);
+    if (s_last) {
+      __threadfence();
+      msd_scan_epilogue(msd_hist, msd_base, group_start, msd_bins, s_w1);
+    }
   }
 }
 
@@ -358,11 +373,11 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
     compact_kernel<true><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
         ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.st_compact,
         ws.ctr, records, cap_records, ntiles, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist, ws.msd_base,
-        ws.msd_cursor);
+        ws.group_start, (int)ws.msd_bins);
   else
     compact_kernel<false><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
         ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.st_compact,
-        ws.ctr, records, cap_records, ntiles, key_bits, msd_shift, nullptr, nullptr, nullptr, nullptr, nullptr);
+        ws.ctr, records, cap_records, ntiles, key_bits, msd_shift, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,30 +424,25 @@ __global__ void __launch_bounds__(256)
 keys_from_records_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __restrict__ ctr, int key_bits,
                          int msd_shift, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
                          unsigned* __restrict__ msd_hist, unsigned* __restrict__ msd_base,
-                         unsigned* __restrict__ msd_cursor) {
-  __shared__ unsigned s_hist[kMsdBins];
+                         unsigned* __restrict__ group_start, int msd_bins) {
   __shared__ unsigned s_tmp[32];
   __shared__ unsigned s_last;
-  for (int i = threadIdx.x; i < kMsdBins; i += blockDim.x) s_hist[i] = 0u;
-  __syncthreads();
   const int64_t n = (int64_t)ctr->work_tri + ctr->work_quad;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int4 v4 = reinterpret_cast<const int4*>(records + i)[0];
     const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
     emit_polygon_keys(v4, meta.x, __popc((unsigned)meta.x) == 2, (unsigned)meta.y, (unsigned)meta.w, key_bits, msd_shift,
-                      keys, vals, s_hist);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kMsdBins; i += blockDim.x) {
-    const unsigned c = s_hist[i];
-    if (c) atomicAdd(&msd_hist[i], c);
+                      keys, vals, msd_hist);
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->compact_done, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (s_last) msd_scan_epilogue(msd_hist, msd_base, msd_cursor, s_tmp);
+  if (s_last) {
+    __threadfence();
+    msd_scan_epilogue(msd_hist, msd_base, group_start, msd_bins, s_tmp);
+  }
 }
 
 void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
@@ -447,7 +457,7 @@ void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet
   ProfScope ps(K_COMPACT, stream);
   keys_from_records_kernel<<<(unsigned)blocks, 256, 0, stream>>>(records, ws.ctr, key_bits_for(a.n_grid),
                                                                  msd_shift_for(a.n_grid), ws.keys, ws.vals, ws.msd_hist,
-                                                                 ws.msd_base, ws.msd_cursor);
+                                                                 ws.msd_base, ws.group_start, (int)ws.msd_bins);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -10,11 +10,11 @@ constexpr int kClassifyThreads = 256;
 constexpr int kClassifyItems = 8;   // tets per lane: 8 x 16 B loads in flight, one ballot word per item
 
 constexpr int kCompactThreads = 256;
-constexpr int kCompactWords = 4;    // bitmap words per thread: a tile covers 256*4*32 = 32768 tets
+constexpr int kCompactWords = 1;    // bitmap words per thread: a tile covers 256*32 = 8192 tets
 
-constexpr int kMsdBits = 11;        // MSD radix digit: top bits of the smaller endpoint
+constexpr int kMsdBits = 17;        // MSD radix digit: top bits of the smaller endpoint (<= 131072 buckets, global hist)
 constexpr int kMsdBins = 1 << kMsdBits;
-constexpr int kSortGroup = 2048;    // group quantum of the block-local finish
+constexpr int kSortGroup = 1024;    // group quantum of the block-local finish
 constexpr int kLocalSortCap = 4096; // keys a CTA sorts in shared memory (48 KB); larger groups use global scratch
 constexpr int kLocalSortThreads = 512;
 
@@ -41,9 +41,11 @@ struct Workspace {
   unsigned* vals2;
   unsigned long long* keys_scratch;  // 8*cap_valid_tets: padded copies of oversized buckets
   unsigned* vals_scratch;
-  unsigned* msd_hist;             // kMsdBins
-  unsigned* msd_base;             // kMsdBins + 1
-  unsigned* msd_cursor;           // kMsdBins
+  unsigned* msd_hist;             // msd_bins (+pad): keys per bucket
+  unsigned* msd_fill;             // msd_bins: scatter cursors of the partition pass
+  unsigned* msd_base;             // msd_bins + 1: exclusive scan of msd_hist
+  unsigned* group_start;          // cap_corners / kSortGroup + 2: first key of every block-local sort group
+  int64_t msd_bins;               // buckets actually used for this grid: ((N-1) >> msd_shift) + 1
   unsigned long long* st_rle;     // ntiles_rle
   unsigned long long* st_poly;    // ntiles_poly * 3 (two 31-bit bucket counters per word)
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets

@@ -10,7 +10,7 @@
 // of the sort *is* the polygon corner array, laid out [3*T1 | 4*T2] like the boundary vertices (:406-407).
 //
 // The sort is an MSD radix sort with a block-local finish (keys are (min << bits) | max, 2*bits <= 62):
-//   partition_kernel  one radix pass on the top 11 bits of `min` (<= 2048 buckets; histogram and bucket bases come from
+//   partition_kernel  one radix pass on the top <= 17 bits of `min` (32-64 vertex ids per bucket; histogram, bases and groups come from
 //                     the compaction kernel).  The pass need not be stable (equal keys are merged afterwards), so slots
 //                     are claimed with warp-aggregated atomics -- no inter-tile dependency.
 //   local_sort_kernel one CTA per group of whole buckets (<= 4096 keys): bitonic sort of (key, value) in shared memory.
@@ -41,7 +41,8 @@ int msd_shift_for(int64_t n_grid) {
 __global__ void __launch_bounds__(256)
 partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
                  unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out,
-                 const DevCounters* __restrict__ ctr, unsigned* __restrict__ cursor, int digit_shift) {
+                 const DevCounters* __restrict__ ctr, const unsigned* __restrict__ base, unsigned* __restrict__ fill,
+                 int digit_shift) {
   const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool ok = i < ncorn;
@@ -57,7 +58,7 @@ partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned*
   if (!ok) return;
   const int leader = __ffs(peers) - 1;
   unsigned pos = 0;
-  if ((int)lane_id() == leader) pos = atomicAdd(&cursor[bin], (unsigned)__popc(peers));
+  if ((int)lane_id() == leader) pos = __ldg(base + bin) + atomicAdd(&fill[bin], (unsigned)__popc(peers));
   pos = __shfl_sync(peers, pos, leader) + __popc(peers & lanemask_lt());
   keys_out[pos] = key;
   vals_out[pos] = val;
@@ -90,33 +91,16 @@ __device__ __forceinline__ void bitonic_sort_block(KeyPtr k, ValPtr v, unsigned 
 
 __global__ void __launch_bounds__(kLocalSortThreads)
 local_sort_kernel(unsigned long long* keys, unsigned* vals, unsigned long long* scratch_keys, unsigned* scratch_vals,
-                  const DevCounters* __restrict__ ctr, const unsigned* __restrict__ msd_base) {
+                  const DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
   unsigned* s_val = reinterpret_cast<unsigned*>(s_key + kLocalSortCap);
-  __shared__ unsigned s_lo, s_hi;
 
   const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
   const int64_t g = blockIdx.x;
   if (g * kSortGroup >= ncorn) return;
-  // snap(x): largest bucket base <= x (bases are non-decreasing; empty buckets share their successor's base)
-  if (threadIdx.x == 0) { s_lo = 0u; s_hi = 0u; }
-  __syncthreads();
-  {
-    const unsigned x0 = (unsigned)(g * kSortGroup);
-    const unsigned x1 = (unsigned)min((int64_t)(g + 1) * kSortGroup, ncorn);
-    unsigned best0 = 0, best1 = 0;
-    for (int b = threadIdx.x; b <= kMsdBins; b += kLocalSortThreads) {
-      const unsigned base = __ldg(msd_base + b);
-      if (base <= x0) best0 = max(best0, base);
-      if (base <= x1) best1 = max(best1, base);
-    }
-    if (best0) atomicMax(&s_lo, best0);
-    if (best1) atomicMax(&s_hi, best1);
-  }
-  __syncthreads();
-  const unsigned lo = s_lo;
-  const unsigned hi = ((int64_t)(g + 1) * kSortGroup >= ncorn) ? (unsigned)ncorn : s_hi;
+  const unsigned lo = __ldg(group_start + g);
+  const unsigned hi = ((g + 1) * kSortGroup >= ncorn) ? (unsigned)ncorn : __ldg(group_start + g + 1);
   if (hi <= lo) return;  // this group's positions belong to a bucket that started in an earlier group
   const unsigned n = hi - lo;
   unsigned npow2 = 2;
@@ -290,7 +274,7 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
   {
     ProfScope ps(K_PARTITION, stream);
     partition_kernel<<<(unsigned)((capc + 255) / 256), 256, 0, stream>>>(ws.keys, ws.vals, ws.keys2, ws.vals2, ws.ctr,
-                                                                          ws.msd_cursor,
+                                                                          ws.msd_base, ws.msd_fill,
                                                                           key_bits + msd_shift_for(a.n_grid));
   }
   {
@@ -302,7 +286,7 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
     }
     ProfScope ps(K_LOCAL_SORT, stream);
     local_sort_kernel<<<(unsigned)(capc / kSortGroup + 1), kLocalSortThreads, smem, stream>>>(
-        ws.keys2, ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.msd_base);
+        ws.keys2, ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.group_start);
   }
   ProfScope ps(K_RLE_INTERP, stream);
   rle_interp_kernel<<<(unsigned)ws.ntiles_rle, kRleThreads, 0, stream>>>(
