@@ -197,7 +197,7 @@ def main():
         counts.append(dict(E.last_counts()))
     c0 = counts[0]
     balg = grids.surface_counts_bytes(F, N, c0["n_verts"], c0["n_verts_aug"], c0["n_faces_watertight"], c0["n_faces_aug"])
-    launches_per_frame = E._ExtractFn.last_launches + 3
+    launches_per_frame = E._ExtractFn.last_launches + E.LAUNCHES_BACKWARD
 
     def step():
         sdf.grad = None

@@ -11,12 +11,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
-D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS = 0, -1, -2, -3
+D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
+VERSION = 200
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
-    "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_extract_backward",
+    "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
     "d3h_classify_range", "d3h_extract_from_records",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_debug_table",
 )
@@ -25,7 +26,8 @@ EXPORTED_SYMBOLS = (
 class Counts(C.Structure):  # d3h_counts
     _fields_ = [("n_valid_tets", C.c_int64), ("n_tri_tets", C.c_int64), ("n_quad_tets", C.c_int64),
                 ("n_corners", C.c_int64), ("n_verts", C.c_int64), ("n_faces_aug", C.c_int64),
-                ("bucket_polys", C.c_int64 * 6), ("bad_index", C.c_int64), ("reserved", C.c_int64 * 3)]
+                ("bucket_polys", C.c_int64 * 6), ("bad_index", C.c_int64), ("overflow", C.c_int64), ("seq", C.c_int64),
+                ("reserved", C.c_int64)]
 
 
 COUNTS_WORDS = C.sizeof(Counts) // 8  # int64 words
@@ -40,14 +42,18 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("verts_aug", C.c_void_p), ("v_tng_aug", C.c_void_p), ("msdf_aug", C.c_void_p),
                 ("faces_aug", C.c_void_p), ("verts_wt", C.c_void_p), ("v_tng_wt", C.c_void_p),
                 ("msdf_wt", C.c_void_p), ("faces_wt", C.c_void_p),
-                ("tape_edges", C.c_void_p), ("tape_corners", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("counts_host", C.c_void_p)]
+                ("tape_edges", C.c_void_p), ("tape_corners", C.c_void_p), ("tape_slots", C.c_void_p),
+                ("tape_runs", C.c_void_p),
+                ("zero_g_pos", C.c_void_p), ("zero_g_sdf", C.c_void_p), ("zero_g_msdf", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("counts_host", C.c_void_p),
+                ("seq", C.c_int64)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args
     _fields_ = [("pos", C.c_void_p), ("sdf", C.c_void_p), ("msdf", C.c_void_p), ("n_grid", C.c_int64),
-                ("msdf_negate", C.c_int32), ("reserved0", C.c_int32),
-                ("tape_edges", C.c_void_p), ("tape_corners", C.c_void_p), ("verts_wt", C.c_void_p),
+                ("msdf_negate", C.c_int32), ("grads_prezeroed", C.c_int32),
+                ("tape_edges", C.c_void_p), ("tape_corners", C.c_void_p), ("tape_slots", C.c_void_p),
+                ("tape_runs", C.c_void_p), ("verts_wt", C.c_void_p),
                 ("msdf_wt", C.c_void_p), ("n_verts", C.c_int64), ("n_tri_tets", C.c_int64),
                 ("n_quad_tets", C.c_int64),
                 ("g_verts_aug", C.c_void_p), ("g_msdf_aug", C.c_void_p), ("g_verts_wt", C.c_void_p),
@@ -83,6 +89,8 @@ def lib() -> C.CDLL:
     L.d3h_check_tets_i32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_forward.restype = C.c_int
     L.d3h_extract_forward.argtypes = [C.POINTER(ForwardArgs), C.c_void_p]
+    L.d3h_wait_counts.restype = C.c_int
+    L.d3h_wait_counts.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.d3h_extract_backward.restype = C.c_int
     L.d3h_extract_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
     L.d3h_classify_range.restype = C.c_int
@@ -98,8 +106,8 @@ def lib() -> C.CDLL:
     L.d3h_profile_read.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_debug_table.restype = C.c_int
     L.d3h_debug_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
-    if L.d3h_version() != 100:
-        raise RuntimeError(f"libd3h_tets.so version {L.d3h_version()} does not match this package (100); rebuild")
+    if L.d3h_version() != VERSION:
+        raise RuntimeError(f"libd3h_tets.so version {L.d3h_version()} does not match this package ({VERSION}); rebuild")
     _lib = L
     return L
 

@@ -1,5 +1,7 @@
 // C-ABI entry points of libd3h_tets.so (declared in include/d3h_tets.h) and the workspace carving.
+#include <chrono>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -51,18 +53,22 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   const int64_t capc = 4 * cap;
   ws.cap_tets = cap;
   ws.cap_corners = capc;
-  const int64_t nwords_f = ((n_tets + 32 * kClassifyItems - 1) / (32 * kClassifyItems)) * kClassifyItems;
-  ws.ntiles_compact = (nwords_f + kCompactThreads * kCompactWords - 1) / (kCompactThreads * kCompactWords);
-  ws.ntiles_rle = (capc + kRleTile - 1) / kRleTile;
+  const int64_t nchunks = (n_tets + kChunkTets - 1) / kChunkTets;
+  const int64_t nwords_f = nchunks * kClassifyItems;
+  ws.ntiles_compact = (n_tets + kTileTets - 1) / kTileTets;
+  ws.ngroups = capc / kSortGroup + 1;
   ws.ntiles_poly = (cap + kPolyThreads - 1) / kPolyThreads;
+  ws.msd_bins = ((n_grid - 1) >> msd_shift_for(n_grid)) + 1;
+  ws.nscan_ctas = (ws.msd_bins + kScanThreads - 1) / kScanThreads;
   const int64_t nwords = (n_grid + 31) / 32 + 1;
   ws.ctr = reinterpret_cast<DevCounters*>(take(sizeof(DevCounters)));
   ws.counts = reinterpret_cast<d3h_counts*>(take(sizeof(d3h_counts)));
   ws.occ_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
   ws.mocc_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
-  ws.m1_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactWords) * 4));
-  ws.m2_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactWords) * 4));
-  ws.st_compact = reinterpret_cast<unsigned long long*>(take(ws.ntiles_compact * 8));
+  ws.m1_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactThreads) * 4));
+  ws.m2_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactThreads) * 4));
+  ws.tile_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_compact + 1) * 4));
+  ws.tile_excl = reinterpret_cast<uint2*>(take((ws.ntiles_compact + 1) * 8));
   ws.records = reinterpret_cast<d3h_tet_record*>(take(cap * (int64_t)sizeof(d3h_tet_record)));
   ws.keys = reinterpret_cast<unsigned long long*>(take(capc * 8));
   ws.vals = reinterpret_cast<unsigned*>(take(capc * 4));
@@ -70,19 +76,37 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.vals2 = reinterpret_cast<unsigned*>(take(capc * 4));
   ws.keys_scratch = reinterpret_cast<unsigned long long*>(take(2 * capc * 8));
   ws.vals_scratch = reinterpret_cast<unsigned*>(take(2 * capc * 4));
-  ws.msd_bins = ((n_grid - 1) >> msd_shift_for(n_grid)) + 1;
-  ws.msd_hist = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
+  ws.msd_hist = reinterpret_cast<unsigned*>(take((ws.msd_bins + 12) * 4));
   ws.msd_fill = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
   ws.msd_base = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
-  ws.group_start = reinterpret_cast<unsigned*>(take((capc / kSortGroup + 2) * 4));
-  ws.st_rle = reinterpret_cast<unsigned long long*>(take(ws.ntiles_rle * 8));
-  ws.st_poly = reinterpret_cast<unsigned long long*>(take(ws.ntiles_poly * 3 * 8));
+  ws.st_scan = reinterpret_cast<unsigned long long*>(take(ws.nscan_ctas * 8));
+  ws.group_start = reinterpret_cast<unsigned*>(take((ws.ngroups + 2) * 4));
+  ws.st_unique = reinterpret_cast<unsigned long long*>(take(ws.ngroups * 8));
+  ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
+  ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));
-  ws.tng = reinterpret_cast<float4*>(take(capc * 16));
   ws.acc = reinterpret_cast<float*>(take(capc * 32));
-  ws.polyinfo = reinterpret_cast<unsigned*>(take(cap * 4));
+  ws.owner = reinterpret_cast<int32_t*>(take(capc * 4));
   ws.total_bytes = off;
   return ws;
+}
+
+// Device-visible alias of the caller's pinned counts buffer, or nullptr when the pointer is not mapped host memory
+// (then the counts are copied with cudaMemcpyAsync at the end of the call instead).  One driver query per new pointer.
+d3h_counts* mapped_counts_pointer(d3h_counts* host) {
+  static thread_local d3h_counts* last_host = nullptr;
+  static thread_local d3h_counts* last_dev = nullptr;
+  if (host == nullptr) return nullptr;
+  if (host == last_host) return last_dev;
+  cudaPointerAttributes at;
+  d3h_counts* dev = nullptr;
+  if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
+    dev = reinterpret_cast<d3h_counts*>(at.devicePointer);
+  else
+    cudaGetLastError();  // plain pageable memory: clear the sticky error of the query
+  last_host = host;
+  last_dev = dev;
+  return dev;
 }
 
 static int check_forward_args(const d3h_forward_args* a, const char* who) {
@@ -106,7 +130,15 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: capacities must be >= 0 and cap_valid_tets <= 2^27", who);
     return D3H_E_BADARG;
   }
-  if (a->cap_valid_tets > 0 && !a->tape_corners) { set_error("%s: tape_corners (4*cap_valid_tets int32) is required", who); return D3H_E_BADARG; }
+  if (a->cap_valid_tets > 0 && (!a->tape_corners || !a->tape_slots || !a->tape_runs)) {
+    set_error("%s: tape_corners / tape_slots (4*cap_valid_tets int32) and tape_runs (cap_verts+1 int32) are required", who);
+    return D3H_E_BADARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(a->zero_g_pos) | reinterpret_cast<uintptr_t>(a->zero_g_sdf) |
+       reinterpret_cast<uintptr_t>(a->zero_g_msdf)) & 15) {
+    set_error("%s: zero_g_* buffers must be 16-byte aligned", who);
+    return D3H_E_BADARG;
+  }
   if ((a->cap_verts > 0 && (!a->verts_wt || !a->v_tng_wt || !a->msdf_wt || !a->tape_edges)) ||
       (a->cap_verts_aug > 0 && (!a->verts_aug || !a->v_tng_aug || !a->msdf_aug)) ||
       (a->cap_faces_wt > 0 && !a->faces_wt) || (a->cap_faces_aug > 0 && !a->faces_aug)) {
@@ -121,8 +153,11 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
   return D3H_OK;
 }
 
-static int finish(const char* who, const Workspace& ws, d3h_counts* counts_host, cudaStream_t stream) {
-  if (counts_host) cudaMemcpyAsync(counts_host, ws.counts, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
+static int finish(const char* who, const d3h_forward_args* a, const Workspace& ws, cudaStream_t stream) {
+  if (a->zero_g_pos || a->zero_g_sdf || a->zero_g_msdf)
+    launch_zero_grads(a->zero_g_pos, a->zero_g_sdf, a->zero_g_msdf, a->n_grid, stream);
+  if (a->counts_host && mapped_counts_pointer(a->counts_host) == nullptr)  // not device-mapped: copy at the end
+    cudaMemcpyAsync(a->counts_host, ws.counts, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return D3H_E_CUDA; }
   return D3H_OK;
@@ -139,7 +174,26 @@ extern "C" int64_t d3h_workspace_bytes(int64_t n_tets, int64_t n_grid, int64_t c
   if (n_tets < 0 || n_grid <= 0 || cap_valid_tets < 0) return D3H_E_BADARG;
   return carve_workspace(nullptr, n_tets, n_grid, cap_valid_tets).total_bytes;
 }
-extern "C" int64_t d3h_backward_workspace_bytes(int64_t n_verts) { return align256(32 * (n_verts > 0 ? n_verts : 0) + 256); }
+extern "C" int64_t d3h_backward_workspace_bytes(int64_t n_verts) { (void)n_verts; return 0; }
+
+extern "C" int d3h_wait_counts(const d3h_counts* counts_host, int64_t seq, int64_t timeout_us) {
+  if (!counts_host) { set_error("d3h_wait_counts: null pointer"); return D3H_E_BADARG; }
+  const volatile int64_t* flag = &counts_host->seq;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0;; ++spins) {
+    if (*flag == seq) {
+      __atomic_thread_fence(__ATOMIC_ACQUIRE);
+      return D3H_OK;
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if (timeout_us > 0 && (spins & 1023u) == 1023u) {
+      const auto dt = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > timeout_us) { set_error("d3h_wait_counts: seq %lld not published after %lld us", (long long)seq, (long long)dt); return D3H_E_TIMEOUT; }
+    }
+  }
+}
 
 extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   int rc = check_forward_args(a, "d3h_extract_forward");
@@ -150,17 +204,19 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   launch_classify(*a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream);
   launch_edge_sort(*a, ws, stream);
   launch_surface(*a, ws, ws.records, stream);
-  return finish("d3h_extract_forward", ws, a->counts_host, stream);
+  return finish("d3h_extract_forward", a, ws, stream);
 }
 
 // stage 1 only: prepare + classify of [tet_begin, tet_end); the compact records land in `records_out`
 // (class ranks are local to the range) and the counts so far (n_valid/n_tri/n_quad) in `counts_dev_out`.
-__global__ void export_range_counts_kernel(const DevCounters* ctr, d3h_counts* out) {
+__global__ void export_range_counts_kernel(const DevCounters* ctr, d3h_counts* out, int64_t seq) {
   memset(out, 0, sizeof(d3h_counts));
   out->n_valid_tets = ctr->n_valid;
   out->n_tri_tets = ctr->n_tri;
   out->n_quad_tets = ctr->n_quad;
   out->n_corners = 3ll * ctr->n_tri + 4ll * ctr->n_quad;
+  out->overflow = (ctr->n_valid != ctr->work_tri + ctr->work_quad) ? 1 : 0;
+  out->seq = seq;
 }
 
 extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* records_out, int64_t cap_records,
@@ -175,7 +231,7 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* rec
   Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
   launch_prepare(*a, ws, stream);
   launch_classify(*a, ws, records_out, cap_records, /*emit_keys=*/false, stream);
-  export_range_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, counts_dev_out);
+  export_range_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, counts_dev_out, a->seq);
   if (a->counts_host) cudaMemcpyAsync(a->counts_host, counts_dev_out, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_classify_range: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
@@ -202,28 +258,24 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet
   launch_rank_records(*a, ws, ws.records, n, stream);
   launch_edge_sort(*a, ws, stream);
   launch_surface(*a, ws, ws.records, stream);
-  return finish("d3h_extract_from_records", ws, a->counts_host, stream);
+  return finish("d3h_extract_from_records", a, ws, stream);
 }
 
 extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) {
   if (!a) { set_error("d3h_extract_backward: null argument struct"); return D3H_E_BADARG; }
   if (a->n_grid <= 0 || a->n_verts < 0 || a->n_tri_tets < 0 || a->n_quad_tets < 0 || !a->g_pos || !a->g_sdf ||
-      !a->pos || !a->sdf || !a->msdf || !a->workspace) {
+      !a->pos || !a->sdf || !a->msdf) {
     set_error("d3h_extract_backward: null pointer or negative size");
     return D3H_E_BADARG;
   }
-  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->verts_wt || !a->msdf_wt)) {
+  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->tape_slots || !a->tape_runs || !a->verts_wt || !a->msdf_wt)) {
     set_error("d3h_extract_backward: tape / saved outputs missing");
     return D3H_E_BADARG;
   }
   if ((reinterpret_cast<uintptr_t>(a->g_pos) | reinterpret_cast<uintptr_t>(a->g_sdf) |
-       reinterpret_cast<uintptr_t>(a->g_msdf) | reinterpret_cast<uintptr_t>(a->workspace)) & 15) {
-    set_error("d3h_extract_backward: gradient buffers and workspace must be 16-byte aligned");
+       reinterpret_cast<uintptr_t>(a->g_msdf)) & 15) {
+    set_error("d3h_extract_backward: gradient buffers must be 16-byte aligned");
     return D3H_E_BADARG;
-  }
-  if (a->workspace_bytes < d3h_backward_workspace_bytes(a->n_verts)) {
-    set_error("d3h_extract_backward: workspace too small");
-    return D3H_E_SMALLWS;
   }
   launch_backward(*a, (cudaStream_t)s);
   cudaError_t e = cudaGetLastError();
@@ -232,9 +284,8 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 }
 
 // ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
-static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "partition", "local_sort", "rle_interp",
-                                            "poly_faces", "vertex_frame", "poly_cut", "zero", "boundary_adjoint",
-                                            "crossing_adjoint", "rank_records"};
+static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "unique",
+                                            "poly_faces", "poly_cut", "zero", "adjoint", "rank_records"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

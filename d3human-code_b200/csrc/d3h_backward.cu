@@ -1,12 +1,18 @@
 // Backward of the float pipeline (the reference relies on autograd through gshell_tets.py:291-303, 342-397, 427).
 //
-//   zero_kernel      : dense (N,3)+(N)+(N) gradients and the per-vertex accumulators, one launch, 16-byte stores
-//   boundary_adjoint : one thread per polygon corner p (= boundary vertex V+p): pulls g_verts_aug / g_msdf_aug of that
-//                      row back onto the two watertight vertices of its polygon edge and onto their mSDF values
-//   crossing_adjoint : one thread per watertight vertex (= crossing edge (a,b), sorted by a): adds its own upstream
-//                      rows, then scatters into pos / sdf / msdf of the two grid vertices.  Edges are sorted by `a`,
-//                      so lanes that share `a` are adjacent: their a-side contributions are combined with a segmented
-//                      warp reduction before one atomic per run; b-side contributions use plain float atomics.
+//   zero_kernel    : dense (N,3)+(N)+(N) gradients, one launch, 16-byte stores.  Normally enqueued by the FORWARD call
+//                    (d3h_forward_args.zero_g_*) behind the size publication, where it overlaps the host's wake-up.
+//   adjoint_kernel : one thread per watertight vertex v (= crossing edge (a,b), sorted by a).  The forward sort left, for
+//                    every vertex, the list of polygon corners that reference it (tape_runs / tape_slots), so the
+//                    boundary-vertex adjoints are GATHERED: for each corner the thread evaluates the two polygon edges
+//                    that meet there and pulls g_verts_aug / g_msdf_aug of their boundary rows onto v -- no atomics, no
+//                    accumulator buffer, a fixed summation order.  It then adds its own upstream rows and scatters into
+//                    pos / sdf / msdf of the two grid vertices.  Edges are sorted by `a`, so lanes that share `a` are
+//                    adjacent: their a-side contributions are combined with a segmented warp reduction before one
+//                    atomic per run; b-side contributions use plain float atomics (fan-in ~4, max 11).
+//
+// v2 scattered the boundary adjoints with float atomics into an (V,8) accumulator that a third kernel consumed
+// (zero 8.7 + boundary 5.2 + crossing 5.4 us at 128^3).
 //
 // Gradient formulas: SURVEY.md appendix A.5 (verified against the reference's autograd in tests/).
 #include "d3h_internal.cuh"
@@ -14,75 +20,40 @@
 namespace d3h {
 
 __global__ void __launch_bounds__(256) zero_kernel(float4* __restrict__ p0, int64_t n0, float4* __restrict__ p1,
-                                                   int64_t n1, float4* __restrict__ p2, int64_t n2,
-                                                   float4* __restrict__ p3, int64_t n3, float* t0, int64_t tn0,
-                                                   float* t1, int64_t tn1, float* t2, int64_t tn2) {
+                                                   int64_t n1, float4* __restrict__ p2, int64_t n2, float* t0,
+                                                   int64_t tn0, float* t1, int64_t tn1, float* t2, int64_t tn2) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = tid; i < n0; i += stride) p0[i] = z;
   for (int64_t i = tid; i < n1; i += stride) p1[i] = z;
   for (int64_t i = tid; i < n2; i += stride) p2[i] = z;
-  for (int64_t i = tid; i < n3; i += stride) p3[i] = z;
   // scalar tails (buffers are only guaranteed 4-byte granular in length)
   if (tid < tn0) t0[tid] = 0.f;
   if (tid < tn1) t1[tid] = 0.f;
   if (tid < tn2) t2[tid] = 0.f;
 }
 
-// accumulators per watertight vertex: [0..2] g_vert, [3] g_sg (stop-grad mSDF attribute), [4] g_mv (mSDF through
-// the boundary coefficients); stride 8 floats
-__global__ void __launch_bounds__(256)
-boundary_adjoint_kernel(const int32_t* __restrict__ corners, const float* __restrict__ verts_wt,
-                        const float* __restrict__ msdf_wt, int64_t nv, int64_t t1, int64_t t2,
-                        const float* __restrict__ g_verts_aug, const float* __restrict__ g_msdf_aug,
-                        float* __restrict__ acc) {
-  const int64_t ncorn = 3 * t1 + 4 * t2;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= ncorn) return;
-  int64_t pn;  // next corner of the same polygon
-  if (p < 3 * t1) {
-    const int64_t b = p - p % 3;
-    pn = b + (p % 3 + 1) % 3;
-  } else {
-    const int64_t q = p - 3 * t1;
-    const int64_t b = 3 * t1 + (q - q % 4);
-    pn = b + (q % 4 + 1) % 4;
-  }
-  const int i = corners[p], j = corners[pn];
-  const float mi = __ldg(msdf_wt + i), mj = __ldg(msdf_wt + j);
-  float u0, u1, D;
-  const bool nz = boundary_weights(mi, mj, u0, u1, D);
-  const int64_t row = nv + p;
-  // the row is zeroed in forward unless its polygon's cut references it (gshell_tets.py:423-427):
-  // that is exactly when the mSDF sign changes across the edge
-  const bool used = (mi > 0.f) != (mj > 0.f);
-  float gx = 0.f, gy = 0.f, gz = 0.f, gm = 0.f;
-  if (g_verts_aug != nullptr && used) {
-    gx = __ldg(g_verts_aug + 3 * row);
-    gy = __ldg(g_verts_aug + 3 * row + 1);
-    gz = __ldg(g_verts_aug + 3 * row + 2);
-  }
-  if (g_msdf_aug != nullptr) gm = __ldg(g_msdf_aug + row);
-  if (gx == 0.f && gy == 0.f && gz == 0.f && gm == 0.f) return;
-  float* ai = acc + 8ll * i;
-  float* aj = acc + 8ll * j;
-  if (u0 != 0.f) {
-    atomicAdd(ai + 0, gx * u0); atomicAdd(ai + 1, gy * u0); atomicAdd(ai + 2, gz * u0);
-    atomicAdd(ai + 3, gm * u0);
-  }
-  if (u1 != 0.f) {
-    atomicAdd(aj + 0, gx * u1); atomicAdd(aj + 1, gy * u1); atomicAdd(aj + 2, gz * u1);
-    atomicAdd(aj + 3, gm * u1);
-  }
-  if (nz) {
-    const float gu0 = gx * __ldg(verts_wt + 3ll * i) + gy * __ldg(verts_wt + 3ll * i + 1) + gz * __ldg(verts_wt + 3ll * i + 2);
-    const float gu1 = gx * __ldg(verts_wt + 3ll * j) + gy * __ldg(verts_wt + 3ll * j + 1) + gz * __ldg(verts_wt + 3ll * j + 2);
-    const float inv = 1.f / D;
-    const float gD = -(gu0 * u0 + gu1 * u1) * inv;
-    atomicAdd(ai + 4, gu1 * inv + gD);
-    atomicAdd(aj + 4, -(gu0 * inv + gD));
-  }
+void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n, cudaStream_t stream) {
+  // split every buffer in a 16-byte-aligned body and a scalar tail
+  auto body = [](float* p, int64_t len, float4*& b4, int64_t& n4, float*& tail, int64_t& ntail) {
+    n4 = len / 4;
+    b4 = reinterpret_cast<float4*>(p);
+    tail = p + 4 * n4;
+    ntail = len - 4 * n4;
+  };
+  float4 *b0, *b1, *b2;
+  int64_t n0, n1, n2, tn0, tn1, tn2;
+  float *t0, *t1, *t2;
+  body(g_pos, g_pos ? 3 * n : 0, b0, n0, t0, tn0);
+  body(g_sdf, g_sdf ? n : 0, b1, n1, t1, tn1);
+  body(g_msdf, g_msdf ? n : 0, b2, n2, t2, tn2);
+  const int64_t work = n0 + n1 + n2;
+  int64_t blocks = (work / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps(K_ZERO, stream);
+  zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b0, n0, b1, n1, b2, n2, t0, tn0, t1, tn1, t2, tn2);
 }
 
 // segmented (by key) inclusive suffix-sum inside a warp; lanes with equal key must be contiguous.
@@ -98,22 +69,84 @@ __device__ __forceinline__ float seg_reduce_to_head(float v, int key, unsigned a
   return v;
 }
 
+struct EdgePull {  // what one polygon edge i -> j contributes to its two end vertices
+  float gx_i, gy_i, gz_i, gsg_i, gmv_i;
+  float gx_j, gy_j, gz_j, gsg_j, gmv_j;
+};
+
+// Adjoint of the boundary vertex on polygon edge i -> j whose row in the augmented arrays is `row`
+// (gshell_tets.py:353-385 forward).
+__device__ __forceinline__ EdgePull pull_edge(int64_t row, float mi, float mj, const float* __restrict__ vi,
+                                              const float* __restrict__ vj, const float* __restrict__ g_verts_aug,
+                                              const float* __restrict__ g_msdf_aug) {
+  EdgePull r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float u0, u1, D;
+  const bool nz = boundary_weights(mi, mj, u0, u1, D);
+  // the row is zeroed in forward unless its polygon's cut references it (gshell_tets.py:423-427):
+  // that is exactly when the mSDF sign changes across the edge
+  const bool used = (mi > 0.f) != (mj > 0.f);
+  float gx = 0.f, gy = 0.f, gz = 0.f, gm = 0.f;
+  if (g_verts_aug != nullptr && used) {
+    gx = __ldg(g_verts_aug + 3 * row);
+    gy = __ldg(g_verts_aug + 3 * row + 1);
+    gz = __ldg(g_verts_aug + 3 * row + 2);
+  }
+  if (g_msdf_aug != nullptr) gm = __ldg(g_msdf_aug + row);
+  r.gx_i = gx * u0; r.gy_i = gy * u0; r.gz_i = gz * u0; r.gsg_i = gm * u0;
+  r.gx_j = gx * u1; r.gy_j = gy * u1; r.gz_j = gz * u1; r.gsg_j = gm * u1;
+  if (nz) {
+    const float gu0 = gx * vi[0] + gy * vi[1] + gz * vi[2];
+    const float gu1 = gx * vj[0] + gy * vj[1] + gz * vj[2];
+    const float inv = 1.f / D;
+    const float gD = -(gu0 * u0 + gu1 * u1) * inv;
+    r.gmv_i = gu1 * inv + gD;
+    r.gmv_j = -(gu0 * inv + gD);
+  }
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
-crossing_adjoint_kernel(const int32_t* __restrict__ edges, const float* __restrict__ pos,
-                        const float* __restrict__ sdf, const float* __restrict__ msdf, int msdf_negate, int64_t nv,
-                        const float* __restrict__ msdf_wt, const float* __restrict__ g_verts_aug,
-                        const float* __restrict__ g_msdf_aug, const float* __restrict__ g_verts_wt,
-                        const float* __restrict__ g_msdf_wt, const float* __restrict__ acc, float* __restrict__ g_pos,
-                        float* __restrict__ g_sdf, float* __restrict__ g_msdf) {
+adjoint_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ corners,
+               const int32_t* __restrict__ slots, const int32_t* __restrict__ runs, const float* __restrict__ pos,
+               const float* __restrict__ sdf, const float* __restrict__ msdf, int msdf_negate, int64_t nv, int64_t t1,
+               const float* __restrict__ verts_wt, const float* __restrict__ msdf_wt,
+               const float* __restrict__ g_verts_aug, const float* __restrict__ g_msdf_aug,
+               const float* __restrict__ g_verts_wt, const float* __restrict__ g_msdf_wt, float* __restrict__ g_pos,
+               float* __restrict__ g_sdf, float* __restrict__ g_msdf) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = v < nv;
   const unsigned active = __ballot_sync(0xffffffffu, live);
   if (!live) return;
+  const float mv = __ldg(msdf_wt + v);
+  const float pv[3] = {__ldg(verts_wt + 3 * v), __ldg(verts_wt + 3 * v + 1), __ldg(verts_wt + 3 * v + 2)};
+  // g_vert, g_sg (stop-grad mSDF attribute), g_mv (mSDF through the boundary coefficients)
+  float gx = 0.f, gy = 0.f, gz = 0.f, gsg = 0.f, gmv = 0.f;
+
+  if (g_verts_aug != nullptr || g_msdf_aug != nullptr) {
+    const int s0 = __ldg(runs + v), s1 = __ldg(runs + v + 1);
+    for (int s = s0; s < s1; ++s) {
+      const int64_t p = __ldg(slots + s);  // a corner of some polygon that sits on vertex v
+      int64_t pbase;
+      int n, k;
+      if (p < 3 * t1) { k = (int)(p % 3); pbase = p - k; n = 3; }
+      else { const int64_t q = p - 3 * t1; k = (int)(q & 3); pbase = p - k; n = 4; }
+      const int64_t pn = pbase + (k + 1 == n ? 0 : k + 1), pp = pbase + (k == 0 ? n - 1 : k - 1);
+      const int64_t jn = __ldg(corners + pn), jp = __ldg(corners + pp);
+      const float vn[3] = {__ldg(verts_wt + 3 * jn), __ldg(verts_wt + 3 * jn + 1), __ldg(verts_wt + 3 * jn + 2)};
+      const float vp[3] = {__ldg(verts_wt + 3 * jp), __ldg(verts_wt + 3 * jp + 1), __ldg(verts_wt + 3 * jp + 2)};
+      // edge p -> pn: v is the i end (row nv + p); edge pp -> p: v is the j end (row nv + pp)
+      const EdgePull e0 = pull_edge(nv + p, mv, __ldg(msdf_wt + jn), pv, vn, g_verts_aug, g_msdf_aug);
+      const EdgePull e1 = pull_edge(nv + pp, __ldg(msdf_wt + jp), mv, vp, pv, g_verts_aug, g_msdf_aug);
+      gx += e0.gx_i + e1.gx_j;
+      gy += e0.gy_i + e1.gy_j;
+      gz += e0.gz_i + e1.gz_j;
+      gsg += e0.gsg_i + e1.gsg_j;
+      gmv += e0.gmv_i + e1.gmv_j;
+    }
+  }
+
   const int a = edges[2 * v], b = edges[2 * v + 1];
-  const float4 c0 = reinterpret_cast<const float4*>(acc + 8 * v)[0];
-  const float c1 = acc[8 * v + 4];
-  float gx = c0.x, gy = c0.y, gz = c0.z, gsg = c0.w, gmv = c1;
-  const bool used = __ldg(msdf_wt + v) > 0.f;  // verts_aug[v] was zeroed in forward otherwise
+  const bool used = mv > 0.f;  // verts_aug[v] was zeroed in forward otherwise
   if (g_verts_aug != nullptr && used) {
     gx += __ldg(g_verts_aug + 3 * v); gy += __ldg(g_verts_aug + 3 * v + 1); gz += __ldg(g_verts_aug + 3 * v + 2);
   }
@@ -156,43 +189,13 @@ crossing_adjoint_kernel(const int32_t* __restrict__ edges, const float* __restri
 }
 
 void launch_backward(const d3h_backward_args& a, cudaStream_t stream) {
-  const int64_t n = a.n_grid, nv = a.n_verts;
-  float* acc = reinterpret_cast<float*>(a.workspace);
-  // split every buffer in a 16-byte-aligned body and a scalar tail
-  auto body = [](float* p, int64_t len, float4*& b4, int64_t& n4, float*& tail, int64_t& ntail) {
-    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    n4 = aligned ? len / 4 : 0;
-    b4 = reinterpret_cast<float4*>(p);
-    tail = p + 4 * n4;
-    ntail = len - 4 * n4;
-  };
-  float4 *b0, *b1, *b2;
-  int64_t n0, n1, n2, tn0, tn1, tn2;
-  float *t0, *t1, *t2;
-  body(a.g_pos, 3 * n, b0, n0, t0, tn0);
-  body(a.g_sdf, n, b1, n1, t1, tn1);
-  body(a.g_msdf, a.g_msdf ? n : 0, b2, n2, t2, tn2);
-  int64_t work = n0 + n1 + n2 + 2 * nv;
-  int64_t blocks = (work / 4 + 255) / 256;
-  if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  // unaligned buffers (never produced by torch) fall back to the scalar tail path in a loop-free kernel: reject instead
-  {
-    ProfScope ps(K_ZERO, stream);
-    zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b0, n0, b1, n1, b2, n2, reinterpret_cast<float4*>(acc), 2 * nv,
-                                                      t0, tn0, t1, tn1, t2, tn2);
-  }
+  const int64_t nv = a.n_verts;
+  if (!a.grads_prezeroed) launch_zero_grads(a.g_pos, a.g_sdf, a.g_msdf, a.n_grid, stream);
   if (nv <= 0) return;
-  const int64_t ncorn = 3 * a.n_tri_tets + 4 * a.n_quad_tets;
-  if (ncorn > 0 && (a.g_verts_aug != nullptr || a.g_msdf_aug != nullptr)) {
-    ProfScope ps(K_BOUNDARY_ADJ, stream);
-    boundary_adjoint_kernel<<<(unsigned)((ncorn + 255) / 256), 256, 0, stream>>>(
-        a.tape_corners, a.verts_wt, a.msdf_wt, nv, a.n_tri_tets, a.n_quad_tets, a.g_verts_aug, a.g_msdf_aug, acc);
-  }
-  ProfScope ps(K_CROSSING_ADJ, stream);
-  crossing_adjoint_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(
-      a.tape_edges, a.pos, a.sdf, a.msdf, a.msdf_negate, nv, a.msdf_wt, a.g_verts_aug, a.g_msdf_aug, a.g_verts_wt,
-      a.g_msdf_wt, acc, a.g_pos, a.g_sdf, a.g_msdf);
+  ProfScope ps(K_ADJOINT, stream);
+  adjoint_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(
+      a.tape_edges, a.tape_corners, a.tape_slots, a.tape_runs, a.pos, a.sdf, a.msdf, a.msdf_negate, nv, a.n_tri_tets,
+      a.verts_wt, a.msdf_wt, a.g_verts_aug, a.g_msdf_aug, a.g_verts_wt, a.g_msdf_wt, a.g_pos, a.g_sdf, a.g_msdf);
 }
 
 }  // namespace d3h

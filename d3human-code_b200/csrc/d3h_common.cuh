@@ -131,10 +131,10 @@ __device__ __forceinline__ bool boundary_weights(float mi, float mj, float& u0, 
 // device-side counters (one cache line of int32 words at the head of the workspace; reset per call)
 // ------------------------------------------------------------------------------------------------
 struct DevCounters {
-  unsigned ticket_compact;   // dynamic tile ids of the ordered kernels
-  unsigned ticket_rle;
-  unsigned ticket_poly;
-  unsigned compact_done;     // CTAs of the key-emitting kernel that have flushed their histogram
+  unsigned ticket_scan;      // dynamic CTA ids of the ordered kernels (bucket scan, vertex numbering)
+  unsigned ticket_unique;
+  unsigned classify_done;    // CTAs of the classification kernel that have flushed their tile counts
+  unsigned poly_done;        // CTAs of the polygon kernel that have stored their bucket counts
   unsigned n_valid;          // Fv (true count, even when the record buffer overflowed)
   unsigned n_tri;            // T1
   unsigned n_quad;           // T2

@@ -8,19 +8,16 @@ namespace d3h {
 // ---- tile shapes ----------------------------------------------------------------------------------
 constexpr int kClassifyThreads = 256;
 constexpr int kClassifyItems = 8;   // tets per lane: 8 x 16 B loads in flight, one ballot word per item
+constexpr int kChunkTets = 32 * kClassifyItems;  // tets one warp classifies per loop trip (256)
 
-constexpr int kCompactThreads = 256;
-constexpr int kCompactWords = 1;    // bitmap words per thread: a tile covers 256*32 = 8192 tets
+constexpr int kCompactThreads = 256;             // one bitmap word (32 tets) per thread
+constexpr int kTileTets = 32 * kCompactThreads;  // tets per compaction tile (8192 = 32 warp chunks)
 
-constexpr int kMsdBits = 17;        // MSD radix digit: top bits of the smaller endpoint (<= 131072 buckets, global hist)
-constexpr int kMsdBins = 1 << kMsdBits;
-constexpr int kSortGroup = 1024;    // group quantum of the block-local finish
-constexpr int kLocalSortCap = 4096; // keys a CTA sorts in shared memory (48 KB); larger groups use global scratch
-constexpr int kLocalSortThreads = 512;
-
-constexpr int kRleThreads = 256;
-constexpr int kRleItems = 8;
-constexpr int kRleTile = kRleThreads * kRleItems;
+constexpr int kMsdBits = 17;        // MSD radix digit: top bits of the smaller endpoint (<= 131072 buckets)
+constexpr int kScanThreads = 1024;  // bucket_scan: one bucket per thread
+constexpr int kSortGroup = 512;     // group quantum of the block-local finish
+constexpr int kLocalSortCap = 2048; // keys a CTA sorts in shared memory (24 KB); larger groups use global scratch
+constexpr int kUniqueThreads = 256;
 
 constexpr int kPolyThreads = 256;   // one valid tet (= one polygon) per thread
 
@@ -33,27 +30,29 @@ struct Workspace {
   unsigned* mocc_bits;            // ceil(N/32) words: (+-)msdf > 0 (open-mesh prefilter only)
   unsigned* m1_words;             // ceil(F/32) words: tet yields one triangle
   unsigned* m2_words;             // ceil(F/32) words: tet yields two triangles
-  unsigned long long* st_compact; // one status word per compaction tile
+  unsigned* tile_cnt;             // per compaction tile: T1-class count | T2-class count << 16
+  uint2* tile_excl;               // per compaction tile: exclusive (T1, T2) prefix
   d3h_tet_record* records;        // cap_valid_tets
   unsigned long long* keys;       // 4*cap_valid_tets: edge keys in valid-tet order
   unsigned* vals;
-  unsigned long long* keys2;      // 4*cap_valid_tets: partitioned, then sorted in place
+  unsigned long long* keys2;      // 4*cap_valid_tets: partitioned by bucket (unsorted inside a bucket)
   unsigned* vals2;
-  unsigned long long* keys_scratch;  // 8*cap_valid_tets: padded copies of oversized buckets
+  unsigned long long* keys_scratch;  // 8*cap_valid_tets: padded copies of oversized groups
   unsigned* vals_scratch;
   unsigned* msd_hist;             // msd_bins (+pad): keys per bucket
-  unsigned* msd_fill;             // msd_bins: scatter cursors of the partition pass
+  unsigned* msd_fill;             // msd_bins: absolute scatter cursors of the partition pass
   unsigned* msd_base;             // msd_bins + 1: exclusive scan of msd_hist
+  unsigned long long* st_scan;    // one status word per bucket_scan CTA
   unsigned* group_start;          // cap_corners / kSortGroup + 2: first key of every block-local sort group
   int64_t msd_bins;               // buckets actually used for this grid: ((N-1) >> msd_shift) + 1
-  unsigned long long* st_rle;     // ntiles_rle
-  unsigned long long* st_poly;    // ntiles_poly * 3 (two 31-bit bucket counters per word)
+  unsigned long long* st_unique;  // one status word per sort group (vertex numbering look-back)
+  unsigned* poly_cnt;             // ntiles_poly * 8: polygons per faces_aug bucket in each polygon tile
+  unsigned* poly_excl;            // ntiles_poly * 8: exclusive prefix of poly_cnt over the tiles
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets
-  float4* tng;                    // (tx,ty,tz,-) per watertight vertex
   float* acc;                     // 8 floats per watertight vertex: normal xyz + count, tangent xyz + pad
-  unsigned* polyinfo;             // per valid tet: (bucket rank << 4) | mSDF case
+  int32_t* owner;                 // per watertight vertex: the polygon corner slot that writes its tangent rows
   int64_t cap_tets, cap_corners;
-  int64_t ntiles_compact, ntiles_rle, ntiles_poly;
+  int64_t ntiles_compact, nscan_ctas, ngroups, ntiles_poly;
   int64_t total_bytes;
 };
 
@@ -62,6 +61,9 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
 
 int key_bits_for(int64_t n_grid);   // bits per endpoint in the packed edge key
 int msd_shift_for(int64_t n_grid);  // endpoint >> shift = MSD bucket
+
+// grid size of a persistent kernel: SM count x resident CTAs per SM (queried once per kernel)
+int persistent_grid(const void* kernel, int threads, size_t dyn_smem);
 
 // ---- stage launchers (all asynchronous on `stream`) -------------------------------------------------
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
@@ -72,14 +74,16 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
                     cudaStream_t stream);
 void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
                          cudaStream_t stream);
+void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n_grid, cudaStream_t stream);
 void launch_backward(const d3h_backward_args& a, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
+d3h_counts* mapped_counts_pointer(d3h_counts* host);
 
 // ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
 enum KernelKind {
-  K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_PARTITION, K_LOCAL_SORT, K_RLE_INTERP, K_POLY_FACES, K_VERTEX_FRAME,
-  K_POLY_CUT, K_ZERO, K_BOUNDARY_ADJ, K_CROSSING_ADJ, K_RANK_RECORDS, K_COUNT
+  K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_UNIQUE, K_POLY_FACES, K_POLY_CUT, K_ZERO,
+  K_ADJOINT, K_RANK_RECORDS, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

@@ -1,8 +1,8 @@
 // Stage 2: edge de-duplication and vertex numbering.
 //
 // Replaces gshell_tets.py:277-287: `sort_edges` (:209-217), `torch.unique(all_edges, dim=0, return_inverse=True)`
-// (:279), the crossing mask (:282) and `mapping`/`idx_map`/`interp_v` (:283-287) -- and, fused into the run-length
-// kernel, the zero-crossing interpolation of :291-303.
+// (:279), the crossing mask (:282) and `mapping`/`idx_map`/`interp_v` (:283-287) -- and, fused into the same kernel,
+// the zero-crossing interpolation of :291-303.
 //
 // Only *crossing* edges are sorted: a non-crossing edge maps to -1 in the reference and is never read again, and the
 // rank of a crossing edge among crossing unique edges in (min,max) lexicographic order does not depend on the others.
@@ -10,17 +10,20 @@
 // of the sort *is* the polygon corner array, laid out [3*T1 | 4*T2] like the boundary vertices (:406-407).
 //
 // The sort is an MSD radix sort with a block-local finish (keys are (min << bits) | max, 2*bits <= 62):
-//   partition_kernel  one radix pass on the top <= 17 bits of `min` (32-64 vertex ids per bucket; histogram, bases and groups come from
-//                     the compaction kernel).  The pass need not be stable (equal keys are merged afterwards), so slots
-//                     are claimed with warp-aggregated atomics -- no inter-tile dependency.
-//   local_sort_kernel one CTA per group of whole buckets (<= 4096 keys): bitonic sort of (key, value) in shared memory.
-//                     A bucket too large for shared memory (surface concentrated in a few thousand consecutive vertex
-//                     ids, e.g. an axis-aligned plane) is sorted by its CTA in global memory instead: slower, still exact.
-//   rle_interp_kernel head flags + scan (decoupled look-back) = vertex ids in sorted order; scatters the ids to the
-//                     corner array, writes the (a,b) tape and interpolates position / mSDF of every new vertex.
+//   bucket_scan_kernel  exclusive scan of the MSD histogram (<= 2^17 buckets of 16-64 vertex ids, filled by the
+//                       compaction kernel): one bucket per thread, CTA aggregates chained through status words; also
+//                       snaps the sort groups to bucket boundaries.
+//   partition_kernel    one radix pass: scatters (key, value) to its bucket.  The pass need not be stable (equal keys
+//                       are merged afterwards), so slots are claimed with warp-aggregated atomics.
+//   unique_kernel       one CTA per group of whole buckets (~512 keys): bitonic sort of (key, value) in shared memory,
+//                       head flags + block scan + decoupled look-back over the groups = vertex ids in sorted order;
+//                       scatters the ids to the corner array, writes the (a,b) tape and the per-vertex corner runs the
+//                       backward pass gathers over, and interpolates position / mSDF of every new vertex.
+//                       A group too large for shared memory (surface concentrated in a few consecutive vertex ids) is
+//                       sorted in global memory instead: slower, still exact.
 //
-// v1 used six chained 8-bit LSD passes (look-back per digit and tile): 11 us per pass under ncu for 192k keys
-// (profiles/r01a_launches_v1.csv) -- the chains, not the data volume, set the time.
+// v1 used six chained 8-bit LSD passes (11 us per pass for 192k keys: the chains set the time); v2 sorted 1024-4096 key
+// groups with 512 threads (40 us) and ran the run-length pass as a separate look-back kernel (13 us).
 #include "d3h_internal.cuh"
 
 namespace d3h {
@@ -35,14 +38,79 @@ int msd_shift_for(int64_t n_grid) {
   return b > kMsdBits ? b - kMsdBits : 0;
 }
 
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagInc = 2ull << 62, kValMask = (1ull << 62) - 1;
+
+// ------------------------------------------------------------------------------------------------
+// bucket scan
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads)
+bucket_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ base, unsigned* __restrict__ fill,
+                   unsigned* __restrict__ group_start, int nbins, DevCounters* __restrict__ ctr,
+                   unsigned long long* __restrict__ status) {
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_cta;
+  __shared__ unsigned s_excl;
+  if (threadIdx.x == 0) s_cta = atomicAdd(&ctr->ticket_scan, 1u);  // CTAs are numbered in start order: no deadlock
+  __syncthreads();
+  const unsigned cta = s_cta;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const int bin = (int)(cta * kScanThreads + threadIdx.x);
+  const unsigned c = (bin < nbins) ? __ldcg(hist + bin) : 0u;
+  unsigned incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += n;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  unsigned wpre = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    if (w < (int)warp) wpre += s_w[w];
+    total += s_w[w];
+  }
+  if (threadIdx.x == 0) st_relaxed_u64(status + cta, kFlagAgg | total);
+  // sum of the aggregates of all earlier CTAs (<= 128 of them: one per thread, no chain)
+  unsigned prev = 0;
+  for (unsigned j = threadIdx.x; j < cta; j += kScanThreads) {
+    unsigned long long w;
+    do { w = ld_relaxed_u64(status + j); } while ((w >> 62) == 0ull);
+    prev += (unsigned)(w & kValMask);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) prev += __shfl_xor_sync(0xffffffffu, prev, o);
+  __syncthreads();  // s_w is reused
+  if (lane == 0) s_w[warp] = prev;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned e = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) e += s_w[w];
+    s_excl = e;
+  }
+  __syncthreads();
+  const unsigned run = s_excl + wpre + incl - c;
+  if (bin < nbins) {
+    base[bin] = run;
+    fill[bin] = run;
+    if (c) {
+      for (unsigned g = (run + kSortGroup - 1) / kSortGroup; (uint64_t)g * kSortGroup < (uint64_t)run + c; ++g)
+        group_start[g] = run;
+    }
+    if (bin == nbins - 1) {
+      base[nbins] = run + c;  // = P
+      group_start[(run + c + kSortGroup - 1) / kSortGroup] = run + c;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MSD partition
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
                  unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out,
-                 const DevCounters* __restrict__ ctr, const unsigned* __restrict__ base, unsigned* __restrict__ fill,
-                 int digit_shift) {
+                 const DevCounters* __restrict__ ctr, unsigned* __restrict__ fill, int digit_shift) {
   const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool ok = i < ncorn;
@@ -58,17 +126,15 @@ partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned*
   if (!ok) return;
   const int leader = __ffs(peers) - 1;
   unsigned pos = 0;
-  if ((int)lane_id() == leader) pos = __ldg(base + bin) + atomicAdd(&fill[bin], (unsigned)__popc(peers));
+  if ((int)lane_id() == leader) pos = atomicAdd(&fill[bin], (unsigned)__popc(peers));  // cursor starts at the bucket base
   pos = __shfl_sync(peers, pos, leader) + __popc(peers & lanemask_lt());
   keys_out[pos] = key;
   vals_out[pos] = val;
 }
 
 // ------------------------------------------------------------------------------------------------
-// block-local finish
+// block-local finish: sort + run-length + numbering + zero-crossing interpolation
 // ------------------------------------------------------------------------------------------------
-// Group g owns key positions [snap(g*G), snap((g+1)*G)) where snap(x) = start of the bucket that contains position x:
-// groups are unions of whole buckets, tile [0,P) exactly, and hold < G + (largest bucket) keys.
 template <typename KeyPtr, typename ValPtr>
 __device__ __forceinline__ void bitonic_sort_block(KeyPtr k, ValPtr v, unsigned npow2) {
   for (unsigned size = 2; size <= npow2; size <<= 1) {
@@ -89,180 +155,181 @@ __device__ __forceinline__ void bitonic_sort_block(KeyPtr k, ValPtr v, unsigned 
   }
 }
 
-__global__ void __launch_bounds__(kLocalSortThreads)
-local_sort_kernel(unsigned long long* keys, unsigned* vals, unsigned long long* scratch_keys, unsigned* scratch_vals,
-                  const DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
-  unsigned* s_val = reinterpret_cast<unsigned*>(s_key + kLocalSortCap);
+struct UniqueOut {
+  int key_bits;
+  const float* pos;
+  const float* sdf;
+  const float* msdf;
+  int msdf_negate;
+  int32_t* tape_corners;
+  int32_t* tape_edges;
+  int32_t* tape_slots;
+  int32_t* tape_runs;
+  int64_t cap_verts, cap_verts_aug;
+  float4* w_vert;
+  float4* w_acc;
+  int32_t* owner;
+  float* verts_wt;
+  float* msdf_wt;
+  float* verts_aug;
+  float* msdf_aug;
+};
 
-  const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
-  const int64_t g = blockIdx.x;
-  if (g * kSortGroup >= ncorn) return;
-  const unsigned lo = __ldg(group_start + g);
-  const unsigned hi = ((g + 1) * kSortGroup >= ncorn) ? (unsigned)ncorn : __ldg(group_start + g + 1);
-  if (hi <= lo) return;  // this group's positions belong to a bucket that started in an earlier group
-  const unsigned n = hi - lo;
-  unsigned npow2 = 2;
-  while (npow2 < n) npow2 <<= 1;
-
-  if (n <= (unsigned)kLocalSortCap) {
-    for (unsigned i = threadIdx.x; i < npow2; i += kLocalSortThreads) {
-      s_key[i] = (i < n) ? keys[lo + i] : ~0ull;
-      s_val[i] = (i < n) ? vals[lo + i] : 0u;
-    }
-    __syncthreads();
-    bitonic_sort_block(s_key, s_val, npow2);
-    for (unsigned i = threadIdx.x; i < n; i += kLocalSortThreads) {
-      keys[lo + i] = s_key[i];
-      vals[lo + i] = s_val[i];
-    }
-  } else {
-    // oversized bucket: same network on a padded copy in global scratch (exact, slower; only degenerate inputs)
-    unsigned long long* gk = scratch_keys + 2ull * lo;  // padded copies of disjoint ranges cannot overlap at 2*lo
-    unsigned* gv = scratch_vals + 2ull * lo;
-    for (unsigned i = threadIdx.x; i < npow2; i += kLocalSortThreads) {
-      gk[i] = (i < n) ? keys[lo + i] : ~0ull;
-      gv[i] = (i < n) ? vals[lo + i] : 0u;
-    }
-    __syncthreads();
-    bitonic_sort_block(gk, gv, npow2);
-    for (unsigned i = threadIdx.x; i < n; i += kLocalSortThreads) {
-      keys[lo + i] = gk[i];
-      vals[lo + i] = gv[i];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// run-length + numbering + zero-crossing interpolation
-// ------------------------------------------------------------------------------------------------
-constexpr unsigned long long kRFlagAgg = 1ull << 62, kRFlagInc = 2ull << 62, kRValMask = (1ull << 62) - 1;
-
-__global__ void __launch_bounds__(kRleThreads)
-rle_interp_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
-                  DevCounters* __restrict__ ctr, unsigned long long* __restrict__ status, int key_bits,
-                  const float* __restrict__ pos, const float* __restrict__ sdf, const float* __restrict__ msdf,
-                  int msdf_negate, int32_t* __restrict__ tape_corners, int32_t* __restrict__ tape_edges,
-                  int64_t cap_verts, int64_t cap_verts_aug, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
-                  float* __restrict__ verts_wt, float* __restrict__ msdf_wt, float* __restrict__ verts_aug,
-                  float* __restrict__ msdf_aug) {
-  constexpr int WARPS = kRleThreads / 32;
-  __shared__ unsigned s_tile;
-  __shared__ unsigned s_wsum[WARPS];
-  __shared__ unsigned long long s_excl;
-
-  const unsigned t1 = ctr->work_tri;
-  const int64_t ncorn = 3ll * t1 + 4ll * ctr->work_quad;
-  const int64_t ntiles = (ncorn + kRleTile - 1) / kRleTile;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_rle, 1u);
-  __syncthreads();
-  const unsigned tile = s_tile;
-  if ((int64_t)tile >= ntiles) return;
+// Sorted keys k[0..n) of group [lo, lo+n): numbers the runs (vertex ids), emits everything that hangs off a vertex.
+template <typename KeyPtr, typename ValPtr>
+__device__ __forceinline__ void number_and_emit(KeyPtr k, ValPtr v, unsigned n, unsigned lo, unsigned group,
+                                                unsigned ngroups_used, unsigned t1, int64_t ncorn,
+                                                DevCounters* __restrict__ ctr, unsigned long long* __restrict__ status,
+                                                const UniqueOut& o, unsigned* s_w, unsigned long long* s_excl) {
+  constexpr int WARPS = kUniqueThreads / 32;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-
-  // blocked: thread owns kRleItems consecutive sorted keys
-  const int64_t i0 = (int64_t)tile * kRleTile + (int64_t)threadIdx.x * kRleItems;
-  unsigned long long k[kRleItems];
-  unsigned long long prev = (i0 > 0 && i0 - 1 < ncorn) ? keys[i0 - 1] : ~0ull;
-  bool head[kRleItems];
+  const unsigned ipt = (n + kUniqueThreads - 1) / kUniqueThreads;  // items per thread, blocked
+  const unsigned i0 = threadIdx.x * ipt;
   unsigned nhead = 0;
-#pragma unroll
-  for (int j = 0; j < kRleItems; ++j) {
-    const int64_t idx = i0 + j;
-    const bool ok = idx < ncorn;
-    k[j] = ok ? keys[idx] : ~0ull;
-    head[j] = ok && (idx == 0 || k[j] != prev);
-    prev = k[j];
-    nhead += head[j];
+  for (unsigned j = 0; j < ipt; ++j) {
+    const unsigned i = i0 + j;
+    if (i < n) nhead += (i == 0 || k[i] != k[i - 1]);  // a group starts on a bucket boundary: i == 0 is always a head
   }
   unsigned incl = nhead;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (unsigned)o) incl += n;
+  for (int of = 1; of < 32; of <<= 1) {
+    const unsigned nb = __shfl_up_sync(0xffffffffu, incl, of);
+    if (lane >= (unsigned)of) incl += nb;
   }
-  if (lane == 31) s_wsum[warp] = incl;
+  if (lane == 31) s_w[warp] = incl;
   __syncthreads();
   unsigned wpre = 0, total = 0;
 #pragma unroll
   for (int w = 0; w < WARPS; ++w) {
-    if (w < (int)warp) wpre += s_wsum[w];
-    total += s_wsum[w];
+    if (w < (int)warp) wpre += s_w[w];
+    total += s_w[w];
   }
-  if (warp == 0) {
-    unsigned long long excl_tiles = 0ull;
-    if (tile == 0) {
-      if (lane == 0) st_relaxed_u64(status, kRFlagInc | total);
+  if (warp == 0) {  // decoupled look-back over the groups
+    unsigned long long excl = 0ull;
+    if (group == 0) {
+      if (lane == 0) st_relaxed_u64(status, kFlagInc | total);
     } else {
-      if (lane == 0) st_relaxed_u64(status + tile, kRFlagAgg | total);
-      int64_t look = (int64_t)tile - 1;
+      if (lane == 0) st_relaxed_u64(status + group, kFlagAgg | total);
+      int64_t look = (int64_t)group - 1;
       while (true) {
         const int64_t idx = look - lane;
-        unsigned long long w = kRFlagInc;
+        unsigned long long w = kFlagInc;  // virtual group -1: inclusive prefix 0
         if (idx >= 0) {
           do { w = ld_relaxed_u64(status + idx); } while ((w >> 62) == 0ull);
         }
         const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
         const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-        unsigned long long contrib = ((int)lane <= first) ? (w & kRValMask) : 0ull;
+        unsigned long long contrib = ((int)lane <= first) ? (w & kValMask) : 0ull;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl_tiles += contrib;
+        for (int of = 16; of > 0; of >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, of);
+        excl += contrib;
         if (inc_mask) break;
         look -= 32;
       }
-      if (lane == 0) st_relaxed_u64(status + tile, kRFlagInc | (excl_tiles + total));
+      if (lane == 0) st_relaxed_u64(status + group, kFlagInc | (excl + total));
     }
     if (lane == 0) {
-      s_excl = excl_tiles;
-      if ((int64_t)tile == ntiles - 1) ctr->n_verts = (unsigned)(excl_tiles + total);
+      *s_excl = excl;
+      if (group + 1 == ngroups_used) {
+        const unsigned nv = (unsigned)(excl + total);
+        ctr->n_verts = nv;
+        if ((int64_t)nv <= o.cap_verts) o.tape_runs[nv] = (int32_t)ncorn;
+      }
     }
   }
   __syncthreads();
 
-  int64_t vid = (int64_t)s_excl + wpre + (incl - nhead) - 1;  // id of the run that precedes this thread's keys
-  const unsigned long long bmask = (1ull << key_bits) - 1;
-#pragma unroll
-  for (int j = 0; j < kRleItems; ++j) {
-    const int64_t idx = i0 + j;
-    if (idx >= ncorn) break;
-    if (head[j]) {
+  int64_t vid = (int64_t)(*s_excl) + wpre + (incl - nhead) - 1;  // id of the run that precedes this thread's keys
+  const unsigned long long bmask = (1ull << o.key_bits) - 1;
+  for (unsigned j = 0; j < ipt; ++j) {
+    const unsigned i = i0 + j;
+    if (i >= n) break;
+    const unsigned long long key = k[i];
+    // value = (class, 4*class_rank + corner) -> corner slot in the [3*T1 | 4*T2] layout
+    const unsigned val = v[i];
+    const unsigned r4 = val & 0x7fffffffu;
+    const int64_t slot = (val >> 31) ? (3ll * t1 + r4) : (3ll * (r4 >> 2) + (r4 & 3u));
+    if (i == 0 || key != k[i - 1]) {
       ++vid;
-      const int a = (int)(k[j] >> key_bits), b = (int)(k[j] & bmask);
+      const int a = (int)(key >> o.key_bits), b = (int)(key & bmask);
       // zero-crossing interpolation, gshell_tets.py:291-303 (op order: SURVEY A.4)
       float w0, w1, dd;
-      crossing_weights(__ldg(sdf + a), __ldg(sdf + b), w0, w1, dd);
-      float ma = __ldg(msdf + a), mb = __ldg(msdf + b);
-      if (msdf_negate) { ma = -ma; mb = -mb; }
-      const float x = lerp2(__ldg(pos + 3ll * a + 0), w0, __ldg(pos + 3ll * b + 0), w1);
-      const float y = lerp2(__ldg(pos + 3ll * a + 1), w0, __ldg(pos + 3ll * b + 1), w1);
-      const float z = lerp2(__ldg(pos + 3ll * a + 2), w0, __ldg(pos + 3ll * b + 2), w1);
+      crossing_weights(__ldg(o.sdf + a), __ldg(o.sdf + b), w0, w1, dd);
+      float ma = __ldg(o.msdf + a), mb = __ldg(o.msdf + b);
+      if (o.msdf_negate) { ma = -ma; mb = -mb; }
+      const float x = lerp2(__ldg(o.pos + 3ll * a + 0), w0, __ldg(o.pos + 3ll * b + 0), w1);
+      const float y = lerp2(__ldg(o.pos + 3ll * a + 1), w0, __ldg(o.pos + 3ll * b + 1), w1);
+      const float z = lerp2(__ldg(o.pos + 3ll * a + 2), w0, __ldg(o.pos + 3ll * b + 2), w1);
       const float m = lerp2(ma, w0, mb, w1);
-      w_vert[vid] = make_float4(x, y, z, m);
-      w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
-      w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (vid < cap_verts) {
-        tape_edges[2 * vid] = a;
-        tape_edges[2 * vid + 1] = b;
-        verts_wt[3 * vid] = x; verts_wt[3 * vid + 1] = y; verts_wt[3 * vid + 2] = z;
-        msdf_wt[vid] = m;
+      o.w_vert[vid] = make_float4(x, y, z, m);
+      o.w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      o.w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      o.owner[vid] = (int32_t)slot;
+      if (vid < o.cap_verts) {
+        o.tape_edges[2 * vid] = a;
+        o.tape_edges[2 * vid + 1] = b;
+        o.tape_runs[vid] = (int32_t)(lo + i);
+        o.verts_wt[3 * vid] = x; o.verts_wt[3 * vid + 1] = y; o.verts_wt[3 * vid + 2] = z;
+        o.msdf_wt[vid] = m;
       }
-      if (vid < cap_verts_aug) {
+      if (vid < o.cap_verts_aug) {
         // rows of verts_aug not referenced by faces_aug are zero (gshell_tets.py:423-427); a watertight vertex is
         // referenced iff its mSDF is positive (every cut case keeps exactly the positive corners)
         const bool used = m > 0.f;
-        verts_aug[3 * vid] = used ? x : 0.f;
-        verts_aug[3 * vid + 1] = used ? y : 0.f;
-        verts_aug[3 * vid + 2] = used ? z : 0.f;
-        msdf_aug[vid] = m;
+        o.verts_aug[3 * vid] = used ? x : 0.f;
+        o.verts_aug[3 * vid + 1] = used ? y : 0.f;
+        o.verts_aug[3 * vid + 2] = used ? z : 0.f;
+        o.msdf_aug[vid] = m;
       }
     }
-    // value = (class, 4*class_rank + k) -> corner slot in the [3*T1 | 4*T2] layout
-    const unsigned val = vals[idx];
-    const unsigned r4 = val & 0x7fffffffu;
-    const int64_t slot = (val >> 31) ? (3ll * t1 + r4) : (3ll * (r4 >> 2) + (r4 & 3u));
-    tape_corners[slot] = (int32_t)vid;
+    o.tape_corners[slot] = (int32_t)vid;
+    o.tape_slots[lo + i] = (int32_t)slot;
+  }
+}
+
+__global__ void __launch_bounds__(kUniqueThreads)
+unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
+              unsigned long long* __restrict__ scratch_keys, unsigned* __restrict__ scratch_vals,
+              DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start,
+              unsigned long long* __restrict__ status, UniqueOut o) {
+  __shared__ __align__(16) unsigned long long s_key[kLocalSortCap];
+  __shared__ unsigned s_val[kLocalSortCap];
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned long long s_excl;
+  __shared__ unsigned s_group;
+
+  const unsigned t1 = ctr->work_tri;
+  const int64_t ncorn = 3ll * t1 + 4ll * ctr->work_quad;
+  const unsigned ngroups_used = (unsigned)((ncorn + kSortGroup - 1) / kSortGroup);
+  if (threadIdx.x == 0) s_group = atomicAdd(&ctr->ticket_unique, 1u);  // groups are numbered in CTA start order
+  __syncthreads();
+  const unsigned g = s_group;
+  if (g >= ngroups_used) return;
+  const unsigned lo = __ldcg(group_start + g);
+  const unsigned hi = (g + 1 == ngroups_used) ? (unsigned)ncorn : __ldcg(group_start + g + 1);
+  const unsigned n = hi > lo ? hi - lo : 0u;  // 0: this group's positions belong to a bucket that started earlier
+  unsigned npow2 = 2;
+  while (npow2 < n) npow2 <<= 1;
+
+  if (n <= (unsigned)kLocalSortCap) {
+    for (unsigned i = threadIdx.x; i < npow2 && n > 0; i += kUniqueThreads) {
+      s_key[i] = (i < n) ? keys[lo + i] : ~0ull;
+      s_val[i] = (i < n) ? vals[lo + i] : 0u;
+    }
+    __syncthreads();
+    if (n > 1) bitonic_sort_block(s_key, s_val, npow2);
+    number_and_emit(s_key, s_val, n, lo, g, ngroups_used, t1, ncorn, ctr, status, o, s_w, &s_excl);
+  } else {
+    // oversized group: same network on a padded copy in global scratch (exact, slower; only degenerate inputs)
+    unsigned long long* gk = scratch_keys + 2ull * lo;  // padded copies of disjoint ranges cannot overlap at 2*lo
+    unsigned* gv = scratch_vals + 2ull * lo;
+    for (unsigned i = threadIdx.x; i < npow2; i += kUniqueThreads) {
+      gk[i] = (i < n) ? keys[lo + i] : ~0ull;
+      gv[i] = (i < n) ? vals[lo + i] : 0u;
+    }
+    __syncthreads();
+    bitonic_sort_block(gk, gv, npow2);
+    number_and_emit(gk, gv, n, lo, g, ngroups_used, t1, ncorn, ctr, status, o, s_w, &s_excl);
   }
 }
 
@@ -272,27 +339,27 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
   const int64_t capc = ws.cap_corners;
   if (capc <= 0) return;
   {
-    ProfScope ps(K_PARTITION, stream);
-    partition_kernel<<<(unsigned)((capc + 255) / 256), 256, 0, stream>>>(ws.keys, ws.vals, ws.keys2, ws.vals2, ws.ctr,
-                                                                          ws.msd_base, ws.msd_fill,
-                                                                          key_bits + msd_shift_for(a.n_grid));
+    ProfScope ps(K_BUCKET_SCAN, stream);
+    bucket_scan_kernel<<<(unsigned)ws.nscan_ctas, kScanThreads, 0, stream>>>(
+        ws.msd_hist, ws.msd_base, ws.msd_fill, ws.group_start, (int)ws.msd_bins, ws.ctr, ws.st_scan);
   }
   {
-    static bool attr_set = false;
-    const int smem = kLocalSortCap * 12;
-    if (!attr_set) {
-      cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr_set = true;
-    }
-    ProfScope ps(K_LOCAL_SORT, stream);
-    local_sort_kernel<<<(unsigned)(capc / kSortGroup + 1), kLocalSortThreads, smem, stream>>>(
-        ws.keys2, ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.group_start);
+    ProfScope ps(K_PARTITION, stream);
+    partition_kernel<<<(unsigned)((capc + 255) / 256), 256, 0, stream>>>(ws.keys, ws.vals, ws.keys2, ws.vals2, ws.ctr,
+                                                                          ws.msd_fill,
+                                                                          key_bits + msd_shift_for(a.n_grid));
   }
-  ProfScope ps(K_RLE_INTERP, stream);
-  rle_interp_kernel<<<(unsigned)ws.ntiles_rle, kRleThreads, 0, stream>>>(
-      ws.keys2, ws.vals2, ws.ctr, ws.st_rle, key_bits, a.pos, a.sdf, a.msdf, a.msdf_negate, a.tape_corners, a.tape_edges,
-      a.cap_verts, a.cap_verts_aug, ws.vert, reinterpret_cast<float4*>(ws.acc), a.verts_wt, a.msdf_wt, a.verts_aug,
-      a.msdf_aug);
+  UniqueOut o;
+  o.key_bits = key_bits;
+  o.pos = a.pos; o.sdf = a.sdf; o.msdf = a.msdf; o.msdf_negate = a.msdf_negate;
+  o.tape_corners = a.tape_corners; o.tape_edges = a.tape_edges; o.tape_slots = a.tape_slots; o.tape_runs = a.tape_runs;
+  o.cap_verts = a.cap_verts; o.cap_verts_aug = a.cap_verts_aug;
+  o.w_vert = ws.vert; o.w_acc = reinterpret_cast<float4*>(ws.acc); o.owner = ws.owner;
+  o.verts_wt = a.verts_wt; o.msdf_wt = a.msdf_wt; o.verts_aug = a.verts_aug; o.msdf_aug = a.msdf_aug;
+  ProfScope ps(K_UNIQUE, stream);
+  unique_kernel<<<(unsigned)ws.ngroups, kUniqueThreads, 0, stream>>>(ws.keys2, ws.vals2, ws.keys_scratch,
+                                                                      ws.vals_scratch, ws.ctr, ws.group_start,
+                                                                      ws.st_unique, o);
 }
 
 }  // namespace d3h

@@ -1,12 +1,14 @@
 // Stage 3: per-polygon work on the O(surface) records.
 //
-//   poly_faces_kernel   : watertight faces from triangle_table (gshell_tets.py:322-325), face normals / tangents
-//                         splatted to the watertight vertices (auto_normals :9-34, compute_tangents :40-78 with the
-//                         "UV indexed by vertex id" quirk of :327), mSDF cut case per polygon (:338-339, :401-404) and
-//                         the ordered rank of every polygon inside its faces_aug bucket (6-way scan with look-back).
-//   vertex_frame_kernel : normalise the splatted normals, average + Gram-Schmidt the tangents (:28-29, :69-73).
-//   poly_cut_kernel     : boundary vertices on every polygon edge (:342-397), zeroing of unreferenced rows (:423-427),
-//                         faces_aug emission in the reference's 6-bucket order (:406-420), final counts.
+//   poly_faces_kernel : watertight faces from triangle_table (gshell_tets.py:322-325), face normals / tangents
+//                       splatted to the watertight vertices (auto_normals :9-34, compute_tangents :40-78 with the
+//                       "UV indexed by vertex id" quirk of :327), mSDF cut case per polygon (:338-339, :401-404) and
+//                       the number of polygons per faces_aug bucket in every 256-polygon tile.  The last CTA to finish
+//                       scans those tile counts and PUBLISHES the final sizes of the call to the host (d3h_counts in
+//                       mapped pinned memory): the host wakes up while the kernel below is still running.
+//   poly_cut_kernel   : per-corner vertex frame (normalised normal, averaged + Gram-Schmidt tangent, :28-29, :69-73),
+//                       boundary vertices on every polygon edge (:342-397), zeroing of unreferenced rows (:423-427),
+//                       faces_aug emission in the reference's 6-bucket order (:406-420) from in-tile ballot ranks.
 #include "d3h_internal.cuh"
 
 namespace d3h {
@@ -46,197 +48,239 @@ __device__ __forceinline__ float cross_comp(float ai, float bj, float aj, float 
   return __fmaf_rn(ai, bj, -__fmul_rn(aj, bi));
 }
 
-constexpr unsigned long long kPFlagAgg = 1ull << 62, kPFlagInc = 2ull << 62, kPValMask = (1ull << 62) - 1;
+// mSDF cut case of a polygon from the interpolated mSDF at its corners (gshell_tets.py:338-339, 401-404) and the
+// faces_aug bucket it lands in: tri polygons cut into 1,2 triangles -> buckets 0,1; quad into 1..4 -> buckets 2..5.
+__device__ __forceinline__ int cut_case(bool quad, float m0, float m1, float m2, float m3, unsigned& mcase, int& ncut) {
+  const unsigned mo0 = m0 > 0.f, mo1 = m1 > 0.f, mo2 = m2 > 0.f, mo3 = m3 > 0.f;
+  if (quad) {
+    mcase = (mo0 << 3) | (mo1 << 2) | (mo2 << 1) | mo3;
+    ncut = c_num_cut_quad[mcase];
+    return ncut ? (1 + ncut) : -1;
+  }
+  mcase = (mo0 << 2) | (mo1 << 1) | mo2;
+  ncut = c_num_cut_tri[mcase];
+  return ncut ? (ncut - 1) : -1;
+}
 
 __global__ void __launch_bounds__(kPolyThreads)
 poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __restrict__ ctr,
-                  unsigned long long* __restrict__ status, const int32_t* __restrict__ corners,
-                  const float4* __restrict__ w_vert, float* __restrict__ w_acc, unsigned* __restrict__ polyinfo,
-                  int64_t* __restrict__ faces_wt, int64_t cap_faces_wt, UvParams uvp) {
+                  const int32_t* __restrict__ corners, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
+                  unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_excl, int64_t* __restrict__ faces_wt,
+                  int64_t cap_faces_wt, UvParams uvp, d3h_counts* __restrict__ counts_dev,
+                  d3h_counts* __restrict__ counts_mapped, int64_t seq) {
   constexpr int WARPS = kPolyThreads / 32;
-  __shared__ unsigned s_tile;
   __shared__ unsigned s_cnt[6][WARPS];
-  __shared__ unsigned s_tile_excl[6];
+  __shared__ unsigned s_last;
+  __shared__ unsigned long long s_scan[3][32];
 
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
   const int64_t npoly = (int64_t)t1 + t2;
   const int64_t ntiles = (npoly + kPolyThreads - 1) / kPolyThreads;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->ticket_poly, 1u);
-  __syncthreads();
-  const unsigned tile = s_tile;
-  if ((int64_t)tile >= ntiles) return;
+  const unsigned tile = blockIdx.x;
+  // CTAs past the data still take part in the "last CTA out" count (the grid is sized from the capacity)
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)tile * kPolyThreads + threadIdx.x;
   const int64_t n_faces_total = (int64_t)t1 + 2ll * t2;
   const bool cross_quirk = (n_faces_total == 3);  // torch.cross without dim on a (3,3) tensor, gshell_tets.py:19
 
-  int bucket = -1;
-  unsigned mcase = 0;
-  if (i < npoly) {
-    const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
-    const int code = meta.x, rank = meta.y;
-    const bool quad = __popc((unsigned)code) == 2;
-    const int n = quad ? 4 : 3;
-    const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
-    int L[4];
-    float4 P[4];
+  if ((int64_t)tile < ntiles) {
+    int bucket = -1;
+    if (i < npoly) {
+      const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
+      const int code = meta.x, rank = meta.y;
+      const bool quad = __popc((unsigned)code) == 2;
+      const int n = quad ? 4 : 3;
+      const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
+      int L[4];
+      float4 P[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      L[k] = (k < n) ? corners[p0 + k] : 0;
-      P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 4; ++k) {
+        L[k] = (k < n) ? corners[p0 + k] : 0;
+        P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // ---- watertight faces + splats ----
+      const int ntri = quad ? 2 : 1;
+      for (int t = 0; t < ntri; ++t) {
+        const int64_t row = quad ? ((int64_t)t1 + 2ll * rank + t) : (int64_t)rank;
+        int lp[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lp[c] = pos_in_loop(code, c_tri_edge[code][3 * t + c]);
+        // select without dynamic register indexing
+        int vi[3];
+        float4 pv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          vi[c] = lp[c] == 0 ? L[0] : lp[c] == 1 ? L[1] : lp[c] == 2 ? L[2] : L[3];
+          pv[c] = lp[c] == 0 ? P[0] : lp[c] == 1 ? P[1] : lp[c] == 2 ? P[2] : P[3];
+        }
+        if (row < cap_faces_wt) {
+          faces_wt[3 * row + 0] = vi[0];
+          faces_wt[3 * row + 1] = vi[1];
+          faces_wt[3 * row + 2] = vi[2];
+        }
+        const float ax = __fsub_rn(pv[1].x, pv[0].x), ay = __fsub_rn(pv[1].y, pv[0].y), az = __fsub_rn(pv[1].z, pv[0].z);
+        const float bx = __fsub_rn(pv[2].x, pv[0].x), by = __fsub_rn(pv[2].y, pv[0].y), bz = __fsub_rn(pv[2].z, pv[0].z);
+        // accumulator row of a vertex: [nx ny nz count | tx ty tz -]; one 16-byte vector atomic per half (sm_90+)
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (!cross_quirk) {
+          nx = cross_comp(ay, bz, az, by);
+          ny = cross_comp(az, bx, ax, bz);
+          nz = cross_comp(ax, by, ay, bx);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          atomicAdd(reinterpret_cast<float4*>(w_acc + 8ll * vi[c]), make_float4(nx, ny, nz, 1.f));
+        // tangent of this face
+        const float2 uv0 = vertex_uv(uvp, vi[0]), uv1 = vertex_uv(uvp, vi[1]), uv2 = vertex_uv(uvp, vi[2]);
+        const float u1x = __fsub_rn(uv1.x, uv0.x), u1y = __fsub_rn(uv1.y, uv0.y);
+        const float u2x = __fsub_rn(uv2.x, uv0.x), u2y = __fsub_rn(uv2.y, uv0.y);
+        float den = __fsub_rn(__fmul_rn(u1x, u2y), __fmul_rn(u1y, u2x));
+        den = (den > 0.f) ? fmaxf(den, 1e-6f) : fminf(den, -1e-6f);
+        const float tx = __fdiv_rn(__fsub_rn(__fmul_rn(ax, u2y), __fmul_rn(bx, u1y)), den);
+        const float ty = __fdiv_rn(__fsub_rn(__fmul_rn(ay, u2y), __fmul_rn(by, u1y)), den);
+        const float tz = __fdiv_rn(__fsub_rn(__fmul_rn(az, u2y), __fmul_rn(bz, u1y)), den);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          atomicAdd(reinterpret_cast<float4*>(w_acc + 8ll * vi[c]) + 1, make_float4(tx, ty, tz, 0.f));
+      }
+      unsigned mcase;
+      int ncut;
+      bucket = cut_case(quad, P[0].w, P[1].w, P[2].w, P[3].w, mcase, ncut);
     }
-    // ---- watertight faces + splats ----
-    const int ntri = quad ? 2 : 1;
-    for (int t = 0; t < ntri; ++t) {
-      const int64_t row = quad ? ((int64_t)t1 + 2ll * rank + t) : (int64_t)rank;
-      int lp[3];
+    // ---- polygons per bucket in this tile ----
 #pragma unroll
-      for (int c = 0; c < 3; ++c) lp[c] = pos_in_loop(code, c_tri_edge[code][3 * t + c]);
-      // select without dynamic register indexing
-      int vi[3];
-      float4 pv[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        vi[c] = lp[c] == 0 ? L[0] : lp[c] == 1 ? L[1] : lp[c] == 2 ? L[2] : L[3];
-        pv[c] = lp[c] == 0 ? P[0] : lp[c] == 1 ? P[1] : lp[c] == 2 ? P[2] : P[3];
-      }
-      if (row < cap_faces_wt) {
-        faces_wt[3 * row + 0] = vi[0];
-        faces_wt[3 * row + 1] = vi[1];
-        faces_wt[3 * row + 2] = vi[2];
-      }
-      const float ax = __fsub_rn(pv[1].x, pv[0].x), ay = __fsub_rn(pv[1].y, pv[0].y), az = __fsub_rn(pv[1].z, pv[0].z);
-      const float bx = __fsub_rn(pv[2].x, pv[0].x), by = __fsub_rn(pv[2].y, pv[0].y), bz = __fsub_rn(pv[2].z, pv[0].z);
-      // accumulator row of a vertex: [nx ny nz count | tx ty tz -]; one 16-byte vector atomic per half (sm_90+)
-      float nx = 0.f, ny = 0.f, nz = 0.f;
-      if (!cross_quirk) {
-        nx = cross_comp(ay, bz, az, by);
-        ny = cross_comp(az, bx, ax, bz);
-        nz = cross_comp(ax, by, ay, bx);
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        atomicAdd(reinterpret_cast<float4*>(w_acc + 8ll * vi[c]), make_float4(nx, ny, nz, 1.f));
-      // tangent of this face
-      const float2 uv0 = vertex_uv(uvp, vi[0]), uv1 = vertex_uv(uvp, vi[1]), uv2 = vertex_uv(uvp, vi[2]);
-      const float u1x = __fsub_rn(uv1.x, uv0.x), u1y = __fsub_rn(uv1.y, uv0.y);
-      const float u2x = __fsub_rn(uv2.x, uv0.x), u2y = __fsub_rn(uv2.y, uv0.y);
-      float den = __fsub_rn(__fmul_rn(u1x, u2y), __fmul_rn(u1y, u2x));
-      den = (den > 0.f) ? fmaxf(den, 1e-6f) : fminf(den, -1e-6f);
-      const float tx = __fdiv_rn(__fsub_rn(__fmul_rn(ax, u2y), __fmul_rn(bx, u1y)), den);
-      const float ty = __fdiv_rn(__fsub_rn(__fmul_rn(ay, u2y), __fmul_rn(by, u1y)), den);
-      const float tz = __fdiv_rn(__fsub_rn(__fmul_rn(az, u2y), __fmul_rn(bz, u1y)), den);
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        atomicAdd(reinterpret_cast<float4*>(w_acc + 8ll * vi[c]) + 1, make_float4(tx, ty, tz, 0.f));
+    for (int b = 0; b < 6; ++b) {
+      const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
+      if (lane == 0) s_cnt[b][warp] = __popc(m);
     }
-    // ---- mSDF cut case (sign of the interpolated mSDF at the polygon corners) ----
-    const unsigned mo0 = P[0].w > 0.f, mo1 = P[1].w > 0.f, mo2 = P[2].w > 0.f, mo3 = P[3].w > 0.f;
-    int ncut;
-    if (quad) {
-      mcase = (mo0 << 3) | (mo1 << 2) | (mo2 << 1) | mo3;
-      ncut = c_num_cut_quad[mcase];
-      bucket = ncut ? (1 + ncut) : -1;  // buckets 2..5
-    } else {
-      mcase = (mo0 << 2) | (mo1 << 1) | mo2;
-      ncut = c_num_cut_tri[mcase];
-      bucket = ncut ? (ncut - 1) : -1;  // buckets 0..1
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      unsigned run = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) run += s_cnt[threadIdx.x][w];
+      poly_cnt[(int64_t)tile * 8 + threadIdx.x] = run;
+    }
+    // the (3,3) torch.cross quirk: the three face normals are crossed along the *face* axis
+    if (cross_quirk && i == 0) {
+      float a[3][3], b[3][3];
+      int fv[3][3];
+      for (int64_t q = 0; q < npoly; ++q) {
+        const int4 meta = reinterpret_cast<const int4*>(records + q)[1];
+        const int code = meta.x, rank = meta.y;
+        const bool quad = __popc((unsigned)code) == 2;
+        const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
+        for (int t = 0; t < (quad ? 2 : 1); ++t) {
+          const int64_t row = quad ? ((int64_t)t1 + 2ll * rank + t) : (int64_t)rank;
+          float4 pv[3];
+          for (int c = 0; c < 3; ++c) {
+            fv[row][c] = corners[p0 + pos_in_loop(code, c_tri_edge[code][3 * t + c])];
+            pv[c] = w_vert[fv[row][c]];
+          }
+          a[row][0] = __fsub_rn(pv[1].x, pv[0].x); a[row][1] = __fsub_rn(pv[1].y, pv[0].y); a[row][2] = __fsub_rn(pv[1].z, pv[0].z);
+          b[row][0] = __fsub_rn(pv[2].x, pv[0].x); b[row][1] = __fsub_rn(pv[2].y, pv[0].y); b[row][2] = __fsub_rn(pv[2].z, pv[0].z);
+        }
+      }
+      for (int c = 0; c < 3; ++c) {  // column c: vectors (a[0][c], a[1][c], a[2][c]) x (b[0][c], b[1][c], b[2][c])
+        float fn[3];
+        fn[0] = cross_comp(a[1][c], b[2][c], a[2][c], b[1][c]);
+        fn[1] = cross_comp(a[2][c], b[0][c], a[0][c], b[2][c]);
+        fn[2] = cross_comp(a[0][c], b[1][c], a[1][c], b[0][c]);
+        for (int r = 0; r < 3; ++r)
+          for (int k = 0; k < 3; ++k) atomicAdd(w_acc + 8ll * fv[r][k] + c, fn[r]);  // counts were added above
+      }
     }
   }
 
-  // ---- ordered rank of the polygon inside its bucket ----
-  unsigned my_ballot = 0;
+  // ---- last CTA out: scan the tile counts, finalise and publish the sizes of this call ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->poly_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // thread t owns tiles [t*per, (t+1)*per); buckets are scanned as three pairs packed in 64-bit words
+  const int64_t per = (ntiles + kPolyThreads - 1) / kPolyThreads;
+  const int64_t tl0 = (int64_t)threadIdx.x * per;
+  unsigned long long sum[3] = {0ull, 0ull, 0ull};
+  for (int64_t q = 0; q < per; ++q) {
+    if (tl0 + q < ntiles) {
+      const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(poly_cnt + (tl0 + q) * 8));
+      const uint2 c45 = __ldcg(reinterpret_cast<const uint2*>(poly_cnt + (tl0 + q) * 8 + 4));
+      sum[0] += (unsigned long long)c03.x | ((unsigned long long)c03.y << 32);
+      sum[1] += (unsigned long long)c03.z | ((unsigned long long)c03.w << 32);
+      sum[2] += (unsigned long long)c45.x | ((unsigned long long)c45.y << 32);
+    }
+  }
+  unsigned long long incl[3], run[3], total[3];
 #pragma unroll
-  for (int b = 0; b < 6; ++b) {
-    const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
-    if (bucket == b) my_ballot = m;
-    if (lane == 0) s_cnt[b][warp] = __popc(m);
+  for (int wd = 0; wd < 3; ++wd) {
+    incl[wd] = sum[wd];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long nb = __shfl_up_sync(0xffffffffu, incl[wd], o);
+      if (lane >= (unsigned)o) incl[wd] += nb;
+    }
+    if (lane == 31) s_scan[wd][warp] = incl[wd];
   }
   __syncthreads();
-  if (warp == 0) {
-    // exclusive offsets over the warps + tile totals, lanes 0..5 = buckets
-    unsigned run = 0;
-    if (lane < 6) {
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        const unsigned c = s_cnt[lane][w];
-        s_cnt[lane][w] = run;
-        run += c;
-      }
+  for (int wd = 0; wd < 3; ++wd) {
+    unsigned long long wpre = 0ull, tot = 0ull;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      if (w < (int)warp) wpre += s_scan[wd][w];
+      tot += s_scan[wd][w];
     }
-    // three status words per tile, each packing two 31-bit bucket counters; 32 predecessors per look-back step
-#pragma unroll 1
+    run[wd] = wpre + incl[wd] - sum[wd];
+    total[wd] = tot;
+  }
+  for (int64_t q = 0; q < per; ++q) {
+    if (tl0 + q < ntiles) {
+      const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(poly_cnt + (tl0 + q) * 8));
+      const uint2 c45 = __ldcg(reinterpret_cast<const uint2*>(poly_cnt + (tl0 + q) * 8 + 4));
+      unsigned* e = poly_excl + (tl0 + q) * 8;
+      e[0] = (unsigned)run[0]; e[1] = (unsigned)(run[0] >> 32);
+      e[2] = (unsigned)run[1]; e[3] = (unsigned)(run[1] >> 32);
+      e[4] = (unsigned)run[2]; e[5] = (unsigned)(run[2] >> 32);
+      run[0] += (unsigned long long)c03.x | ((unsigned long long)c03.y << 32);
+      run[1] += (unsigned long long)c03.z | ((unsigned long long)c03.w << 32);
+      run[2] += (unsigned long long)c45.x | ((unsigned long long)c45.y << 32);
+    }
+  }
+  if (threadIdx.x == 0) {
+    unsigned bk[6];
+#pragma unroll
     for (int wd = 0; wd < 3; ++wd) {
-      const unsigned lo_cnt = __shfl_sync(0xffffffffu, run, 2 * wd), hi_cnt = __shfl_sync(0xffffffffu, run, 2 * wd + 1);
-      const unsigned long long agg = (unsigned long long)lo_cnt | ((unsigned long long)hi_cnt << 31);
-      unsigned long long excl = 0ull;
-      unsigned long long* my = status + (int64_t)tile * 3 + wd;
-      if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(my, kPFlagInc | agg);
-      } else {
-        if (lane == 0) st_relaxed_u64(my, kPFlagAgg | agg);
-        int64_t look = (int64_t)tile - 1;
-        while (true) {
-          const int64_t idx = look - lane;
-          unsigned long long w = kPFlagInc;
-          if (idx >= 0) {
-            do { w = ld_relaxed_u64(status + idx * 3 + wd); } while ((w >> 62) == 0ull);
-          }
-          const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
-          const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-          unsigned long long contrib = ((int)lane <= first) ? (w & kPValMask) : 0ull;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-          excl += contrib;
-          if (inc_mask) break;
-          look -= 32;
-        }
-        if (lane == 0) st_relaxed_u64(my, kPFlagInc | (excl + agg));
-      }
-      if (lane == 0) {
-        const unsigned e_lo = (unsigned)(excl & 0x7fffffffull), e_hi = (unsigned)(excl >> 31);
-        s_tile_excl[2 * wd] = e_lo;
-        s_tile_excl[2 * wd + 1] = e_hi;
-        if ((int64_t)tile == ntiles - 1) {
-          ctr->bucket[2 * wd] = e_lo + lo_cnt;
-          ctr->bucket[2 * wd + 1] = e_hi + hi_cnt;
-        }
-      }
+      bk[2 * wd] = (unsigned)total[wd];
+      bk[2 * wd + 1] = (unsigned)(total[wd] >> 32);
     }
-  }
-  __syncthreads();
-  if (i < npoly) {
-    unsigned rank_in_bucket = 0;
-    if (bucket >= 0) rank_in_bucket = s_tile_excl[bucket] + s_cnt[bucket][warp] + __popc(my_ballot & lanemask_lt());
-    polyinfo[i] = (rank_in_bucket << 4) | mcase;
-  }
-  // the (3,3) torch.cross quirk: the three face normals are crossed along the *face* axis
-  if (cross_quirk && i == 0) {
-    float a[3][3], b[3][3];
-    int fv[3][3];
-    for (int64_t q = 0; q < npoly; ++q) {
-      const int4 meta = reinterpret_cast<const int4*>(records + q)[1];
-      const int code = meta.x, rank = meta.y;
-      const bool quad = __popc((unsigned)code) == 2;
-      const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
-      for (int t = 0; t < (quad ? 2 : 1); ++t) {
-        const int64_t row = quad ? ((int64_t)t1 + 2ll * rank + t) : (int64_t)rank;
-        float4 pv[3];
-        for (int c = 0; c < 3; ++c) {
-          fv[row][c] = corners[p0 + pos_in_loop(code, c_tri_edge[code][3 * t + c])];
-          pv[c] = w_vert[fv[row][c]];
-        }
-        a[row][0] = __fsub_rn(pv[1].x, pv[0].x); a[row][1] = __fsub_rn(pv[1].y, pv[0].y); a[row][2] = __fsub_rn(pv[1].z, pv[0].z);
-        b[row][0] = __fsub_rn(pv[2].x, pv[0].x); b[row][1] = __fsub_rn(pv[2].y, pv[0].y); b[row][2] = __fsub_rn(pv[2].z, pv[0].z);
-      }
+    const int ncut_of[6] = {1, 2, 1, 2, 3, 4};
+    int64_t fa = 0;
+    d3h_counts c;
+    for (int b = 0; b < 6; ++b) {
+      ctr->bucket[b] = bk[b];
+      c.bucket_polys[b] = bk[b];
+      fa += (int64_t)bk[b] * ncut_of[b];
     }
-    for (int c = 0; c < 3; ++c) {  // column c: vectors (a[0][c], a[1][c], a[2][c]) x (b[0][c], b[1][c], b[2][c])
-      float fn[3];
-      fn[0] = cross_comp(a[1][c], b[2][c], a[2][c], b[1][c]);
-      fn[1] = cross_comp(a[2][c], b[0][c], a[0][c], b[2][c]);
-      fn[2] = cross_comp(a[0][c], b[1][c], a[1][c], b[0][c]);
-      for (int r = 0; r < 3; ++r)
-        for (int k = 0; k < 3; ++k) atomicAdd(w_acc + 8ll * fv[r][k] + c, fn[r]);  // counts were added above
+    c.n_valid_tets = ctr->n_valid;
+    c.n_tri_tets = ctr->n_tri;
+    c.n_quad_tets = ctr->n_quad;
+    c.n_corners = 3ll * ctr->n_tri + 4ll * ctr->n_quad;
+    c.n_verts = ctr->n_verts;
+    c.n_faces_aug = fa;
+    c.bad_index = 0;
+    c.overflow = (ctr->n_valid != t1 + t2) ? 1 : 0;  // record buffer overflowed: surface stages skipped
+    c.seq = seq;
+    c.reserved = 0;
+    *counts_dev = c;
+    if (counts_mapped != nullptr) {  // straight into pinned host memory; `seq` last, after a system-scope fence
+      volatile int64_t* dst = reinterpret_cast<volatile int64_t*>(counts_mapped);
+      const int64_t* src = reinterpret_cast<const int64_t*>(&c);
+      constexpr int kSeqWord = (int)(offsetof(d3h_counts, seq) / 8);
+      for (int w = 0; w < (int)(sizeof(d3h_counts) / 8); ++w)
+        if (w != kSeqWord) dst[w] = src[w];
+      __threadfence_system();
+      dst[kSeqWord] = seq;
     }
   }
 }
@@ -248,87 +292,87 @@ __device__ __forceinline__ float3 safe_normalize3(float x, float y, float z) {  
   return make_float3(__fdiv_rn(x, len), __fdiv_rn(y, len), __fdiv_rn(z, len));
 }
 
-__global__ void __launch_bounds__(256)
-vertex_frame_kernel(const DevCounters* __restrict__ ctr, const float* __restrict__ w_acc, float4* __restrict__ w_tng,
-                    float* __restrict__ v_tng_wt, int64_t cap_verts, float* __restrict__ v_tng_aug,
-                    int64_t cap_verts_aug) {
-  const int64_t nv = ctr->n_verts;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
-    const float4 a0 = reinterpret_cast<const float4*>(w_acc + 8 * v)[0];
-    const float4 a1 = reinterpret_cast<const float4*>(w_acc + 8 * v)[1];
-    // auto_normals tail, gshell_tets.py:28-29
-    float nx = a0.x, ny = a0.y, nz = a0.z;
-    const float d = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz));
-    if (!(d > 1e-20f)) { nx = 0.f; ny = 0.f; nz = 1.f; }
-    const float3 n = safe_normalize3(nx, ny, nz);
-    // compute_tangents tail, gshell_tets.py:69-73
-    const float cnt = a0.w;
-    float3 t = safe_normalize3(__fdiv_rn(a1.x, cnt), __fdiv_rn(a1.y, cnt), __fdiv_rn(a1.z, cnt));
-    const float dp = __fadd_rn(__fadd_rn(__fmul_rn(t.x, n.x), __fmul_rn(t.y, n.y)), __fmul_rn(t.z, n.z));
-    t = safe_normalize3(__fsub_rn(t.x, __fmul_rn(dp, n.x)), __fsub_rn(t.y, __fmul_rn(dp, n.y)),
-                        __fsub_rn(t.z, __fmul_rn(dp, n.z)));
-    w_tng[v] = make_float4(t.x, t.y, t.z, 0.f);
-    if (v < cap_verts) { v_tng_wt[3 * v] = t.x; v_tng_wt[3 * v + 1] = t.y; v_tng_wt[3 * v + 2] = t.z; }
-    if (v < cap_verts_aug) { v_tng_aug[3 * v] = t.x; v_tng_aug[3 * v + 1] = t.y; v_tng_aug[3 * v + 2] = t.z; }
-  }
+// Tangent of one watertight vertex from its splat accumulators: auto_normals tail (gshell_tets.py:28-29) and
+// compute_tangents tail (:69-73).  Every corner of the vertex evaluates the same expression on the same inputs.
+__device__ __forceinline__ float3 vertex_tangent(const float* __restrict__ w_acc, int v) {
+  const float4 a0 = __ldcg(reinterpret_cast<const float4*>(w_acc + 8ll * v));
+  const float4 a1 = __ldcg(reinterpret_cast<const float4*>(w_acc + 8ll * v) + 1);
+  float nx = a0.x, ny = a0.y, nz = a0.z;
+  const float d = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz));
+  if (!(d > 1e-20f)) { nx = 0.f; ny = 0.f; nz = 1.f; }
+  const float3 n = safe_normalize3(nx, ny, nz);
+  const float cnt = a0.w;
+  float3 t = safe_normalize3(__fdiv_rn(a1.x, cnt), __fdiv_rn(a1.y, cnt), __fdiv_rn(a1.z, cnt));
+  const float dp = __fadd_rn(__fadd_rn(__fmul_rn(t.x, n.x), __fmul_rn(t.y, n.y)), __fmul_rn(t.z, n.z));
+  return safe_normalize3(__fsub_rn(t.x, __fmul_rn(dp, n.x)), __fsub_rn(t.y, __fmul_rn(dp, n.y)),
+                         __fsub_rn(t.z, __fmul_rn(dp, n.z)));
 }
 
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* __restrict__ ctr,
                 const int32_t* __restrict__ corners, const float4* __restrict__ w_vert,
-                const float4* __restrict__ w_tng, const unsigned* __restrict__ polyinfo,
-                float* __restrict__ verts_aug, float* __restrict__ v_tng_aug, float* __restrict__ msdf_aug,
-                int64_t cap_verts_aug, int64_t* __restrict__ faces_aug, int64_t cap_faces_aug,
-                d3h_counts* __restrict__ counts) {
+                const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
+                const unsigned* __restrict__ poly_excl, float* __restrict__ verts_aug, float* __restrict__ v_tng_aug,
+                float* __restrict__ msdf_aug, int64_t cap_verts_aug, float* __restrict__ v_tng_wt, int64_t cap_verts,
+                int64_t* __restrict__ faces_aug, int64_t cap_faces_aug) {
+  constexpr int WARPS = kPolyThreads / 32;
+  __shared__ unsigned s_cnt[6][WARPS];
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
   const int64_t npoly = (int64_t)t1 + t2;
+  const unsigned tile = blockIdx.x;
+  if ((int64_t)tile * kPolyThreads >= npoly) return;
   const int64_t nv = ctr->n_verts;
-  // face-row base of each bucket: buckets hold polygons cut into (1,2 | 1,2,3,4) triangles
-  int64_t fbase[7];
-  {
-    const int ncut_of[6] = {1, 2, 1, 2, 3, 4};
-    int64_t run = 0;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)tile * kPolyThreads + threadIdx.x;
+
+  int bucket = -1, ncut = 0, n = 3;
+  unsigned mcase = 0;
+  bool quad = false;
+  int64_t p0 = 0;
+  int L[4] = {0, 0, 0, 0};
+  float4 P[4];
+  float3 T[4];
+  if (i < npoly) {
+    const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
+    const int code = meta.x, rank = meta.y;
+    quad = __popc((unsigned)code) == 2;
+    n = quad ? 4 : 3;
+    p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
 #pragma unroll
-    for (int b = 0; b < 6; ++b) {
-      fbase[b] = run;
-      run += (int64_t)ctr->bucket[b] * ncut_of[b];
+    for (int k = 0; k < 4; ++k) {
+      L[k] = (k < n) ? corners[p0 + k] : 0;
+      P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      T[k] = (k < n) ? vertex_tangent(w_acc, L[k]) : make_float3(0.f, 0.f, 0.f);
+      // the corner that opened the vertex's run in the sorted key array writes the vertex's own tangent rows
+      if (k < n && owner[L[k]] == (int32_t)(p0 + k)) {
+        const int64_t v = L[k];
+        if (v < cap_verts) { v_tng_wt[3 * v] = T[k].x; v_tng_wt[3 * v + 1] = T[k].y; v_tng_wt[3 * v + 2] = T[k].z; }
+        if (v < cap_verts_aug) { v_tng_aug[3 * v] = T[k].x; v_tng_aug[3 * v + 1] = T[k].y; v_tng_aug[3 * v + 2] = T[k].z; }
+      }
     }
-    fbase[6] = run;
+    bucket = cut_case(quad, P[0].w, P[1].w, P[2].w, P[3].w, mcase, ncut);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    counts->n_valid_tets = ctr->n_valid;
-    counts->n_tri_tets = ctr->n_tri;
-    counts->n_quad_tets = ctr->n_quad;
-    counts->n_corners = 3ll * ctr->n_tri + 4ll * ctr->n_quad;
-    counts->n_verts = nv;
-    counts->n_faces_aug = fbase[6];
-    for (int b = 0; b < 6; ++b) counts->bucket_polys[b] = ctr->bucket[b];
-    counts->bad_index = 0;
-    counts->reserved[0] = (ctr->n_valid != t1 + t2) ? 1 : 0;  // record buffer overflowed: surface stages skipped
-    counts->reserved[1] = 0;
-    counts->reserved[2] = 0;
-  }
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npoly) return;
-  const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
-  const int code = meta.x, rank = meta.y;
-  const bool quad = __popc((unsigned)code) == 2;
-  const int n = quad ? 4 : 3;
-  const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
-  int L[4];
-  float4 P[4], T[4];
+  // ---- ordered rank of the polygon inside its bucket: tile prefix + warps before + lanes before ----
+  unsigned my_ballot = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    L[k] = (k < n) ? corners[p0 + k] : 0;
-    P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
-    T[k] = (k < n) ? w_tng[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < 6; ++b) {
+    const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
+    if (bucket == b) my_ballot = m;
+    if (lane == 0) s_cnt[b][warp] = __popc(m);
   }
-  const unsigned info = polyinfo[i];
-  const unsigned mcase = info & 15u;
-  const int64_t brank = info >> 4;
-  const int ncut = quad ? c_num_cut_quad[mcase] : c_num_cut_tri[mcase];
+  __syncthreads();
+  if (i >= npoly) return;
+  // face-row base of each bucket: buckets hold polygons cut into (1,2 | 1,2,3,4) triangles
+  int64_t fbase = 0, brank = 0;
+  if (bucket >= 0) {
+    const int ncut_of[6] = {1, 2, 1, 2, 3, 4};
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+      if (b < bucket) fbase += (int64_t)ctr->bucket[b] * ncut_of[b];
+    unsigned before = poly_excl[(int64_t)tile * 8 + bucket];
+    for (int w = 0; w < (int)warp; ++w) before += s_cnt[bucket][w];
+    brank = (int64_t)before + __popc(my_ballot & lanemask_lt());
+  }
   // locals referenced by this polygon's cut triangles
   unsigned used_mask = 0;
   for (int e = 0; e < 3 * ncut; ++e) used_mask |= 1u << (quad ? c_cut_quad[mcase][e] : c_cut_tri[mcase][e]);
@@ -339,7 +383,7 @@ poly_cut_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* _
     if (k >= n) break;
     const int kn = (k + 1 == n) ? 0 : k + 1;
     const float4 pi = P[k], pj = (kn == 0) ? P[0] : (kn == 1) ? P[1] : (kn == 2) ? P[2] : P[3];
-    const float4 ti = T[k], tj = (kn == 0) ? T[0] : (kn == 1) ? T[1] : (kn == 2) ? T[2] : T[3];
+    const float3 ti = T[k], tj = (kn == 0) ? T[0] : (kn == 1) ? T[1] : (kn == 2) ? T[2] : T[3];
     float u0, u1, D;
     boundary_weights(pi.w, pj.w, u0, u1, D);
     const int64_t row = nv + p0 + k;
@@ -356,8 +400,7 @@ poly_cut_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* _
   }
   // ---- cut triangles ----
   if (ncut > 0) {
-    const int bucket = quad ? (1 + ncut) : (ncut - 1);
-    const int64_t row0 = fbase[bucket] + brank * ncut;
+    const int64_t row0 = fbase + brank * ncut;
     for (int e = 0; e < 3 * ncut; ++e) {
       const int loc = quad ? c_cut_quad[mcase][e] : c_cut_tri[mcase][e];
       int64_t g;
@@ -366,6 +409,29 @@ poly_cut_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* _
       const int64_t frow = row0 + e / 3;
       if (frow < cap_faces_aug) faces_aug[3 * frow + (e % 3)] = g;
     }
+  }
+}
+
+// Sizes of a call whose surface stages do not run at all (cap_valid_tets == 0: counting run).
+__global__ void publish_counts_kernel(const DevCounters* __restrict__ ctr, d3h_counts* __restrict__ counts_dev,
+                                      d3h_counts* __restrict__ counts_mapped, int64_t seq) {
+  d3h_counts c;
+  memset(&c, 0, sizeof(c));
+  c.n_valid_tets = ctr->n_valid;
+  c.n_tri_tets = ctr->n_tri;
+  c.n_quad_tets = ctr->n_quad;
+  c.n_corners = 3ll * ctr->n_tri + 4ll * ctr->n_quad;
+  c.overflow = (ctr->n_valid != ctr->work_tri + ctr->work_quad) ? 1 : 0;
+  c.seq = seq;
+  *counts_dev = c;
+  if (counts_mapped != nullptr) {
+    volatile int64_t* dst = reinterpret_cast<volatile int64_t*>(counts_mapped);
+    const int64_t* src = reinterpret_cast<const int64_t*>(&c);
+    constexpr int kSeqWord = (int)(offsetof(d3h_counts, seq) / 8);
+    for (int w = 0; w < (int)(sizeof(d3h_counts) / 8); ++w)
+      if (w != kSeqWord) dst[w] = src[w];
+    __threadfence_system();
+    dst[kSeqWord] = seq;
   }
 }
 
@@ -382,23 +448,23 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
     uvp.step = (uvp.nuv > 1) ? uvp.end / (float)(uvp.nuv - 1) : 0.f;
     uvp.pad = (float)(0.9 / (double)uvp.nuv);
   }
+  d3h_counts* mapped = mapped_counts_pointer(a.counts_host);
+  if (ws.cap_tets <= 0) {
+    ProfScope ps(K_POLY_FACES, stream);
+    publish_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, ws.counts, mapped, a.seq);
+    return;
+  }
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
-  if (ws.cap_tets > 0) {
-    {
-      ProfScope ps(K_POLY_FACES, stream);
-      poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, ws.st_poly, a.tape_corners, ws.vert, ws.acc,
-                                                           ws.polyinfo, a.faces_wt, a.cap_faces_wt, uvp);
-    }
-    int64_t vb = (ws.cap_corners + 255) / 256;
-    if (vb > 148 * 8) vb = 148 * 8;
-    ProfScope ps(K_VERTEX_FRAME, stream);
-    vertex_frame_kernel<<<(unsigned)vb, 256, 0, stream>>>(ws.ctr, ws.acc, ws.tng, a.v_tng_wt, a.cap_verts,
-                                                          a.v_tng_aug, a.cap_verts_aug);
+  {
+    ProfScope ps(K_POLY_FACES, stream);
+    poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, a.tape_corners, ws.vert, ws.acc, ws.poly_cnt,
+                                                         ws.poly_excl, a.faces_wt, a.cap_faces_wt, uvp, ws.counts, mapped,
+                                                         a.seq);
   }
   ProfScope ps(K_POLY_CUT, stream);
-  poly_cut_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, a.tape_corners, ws.vert, ws.tng, ws.polyinfo,
-                                                     a.verts_aug, a.v_tng_aug, a.msdf_aug, a.cap_verts_aug, a.faces_aug,
-                                                     a.cap_faces_aug, ws.counts);
+  poly_cut_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, a.tape_corners, ws.vert, ws.acc, ws.owner,
+                                                     ws.poly_excl, a.verts_aug, a.v_tng_aug, a.msdf_aug, a.cap_verts_aug,
+                                                     a.v_tng_wt, a.cap_verts, a.faces_aug, a.cap_faces_aug);
 }
 
 }  // namespace d3h

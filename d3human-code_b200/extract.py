@@ -81,30 +81,35 @@ class _Plan:
     cap_va: int = 0
     cap_fw: int = 0
     cap_fa: int = 0
+    seq: int = 0
     workspace: Optional[torch.Tensor] = None
+    workspace_ptr: int = 0
+    workspace_cap_tets: int = -1
     counts_host: Optional[torch.Tensor] = None
-    bwd_workspace: Optional[torch.Tensor] = None
+    counts_ptr: int = 0
+    counts: Optional[_cabi.Counts] = None
     args: _cabi.ForwardArgs = field(default_factory=_cabi.ForwardArgs)
+    bargs: _cabi.BackwardArgs = field(default_factory=_cabi.BackwardArgs)
 
     def ensure_workspace(self):
-        need = _cabi.lib().d3h_workspace_bytes(self.n_tets, self.n_grid, self.cap_tets)
-        if self.workspace is None or self.workspace.numel() < need:
-            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if self.workspace_cap_tets != self.cap_tets:
+            need = _cabi.lib().d3h_workspace_bytes(self.n_tets, self.n_grid, self.cap_tets)
+            if self.workspace is None or self.workspace.numel() < need:
+                self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self.workspace_ptr = self.workspace.data_ptr()
+            self.workspace_cap_tets = self.cap_tets
         if self.counts_host is None:
+            # pinned host memory is device-mapped (UVA): the kernel that finalises the sizes writes them here directly
             self.counts_host = torch.zeros(_cabi.COUNTS_WORDS, dtype=torch.int64).pin_memory()
-
-    def ensure_bwd_workspace(self, n_verts: int) -> torch.Tensor:
-        need = _cabi.lib().d3h_backward_workspace_bytes(n_verts)
-        if self.bwd_workspace is None or self.bwd_workspace.numel() < need:
-            self.bwd_workspace = torch.empty(_grow(need), dtype=torch.uint8, device=self.device)
-        return self.bwd_workspace
+            self.counts_ptr = self.counts_host.data_ptr()
+            self.counts = _cabi.Counts.from_address(self.counts_ptr)
 
 
 _plans: Dict[Tuple, _Plan] = {}
 
 
 def _plan_for(device: torch.device, n_tets: int, n_grid: int) -> _Plan:
-    key = (device.type, device.index, n_tets, n_grid)
+    key = (device.index, n_tets, n_grid)
     p = _plans.get(key)
     if p is None:
         p = _plans[key] = _Plan(device=device, n_tets=n_tets, n_grid=n_grid)
@@ -127,57 +132,92 @@ class ForwardResult:
     v_tng_wt: torch.Tensor
     msdf_wt: torch.Tensor
     faces_wt: torch.Tensor
-    tape_edges: torch.Tensor
-    tape_corners: torch.Tensor
+    tape: torch.Tensor          # int32 slab: edges (V,2) | corners (P) | slots (P) | runs (V+1)
+    tape_ptrs: Tuple[int, int, int, int]
     n_verts: int
     n_tri: int
     n_quad: int
     counts: Dict[str, int]
     launches: int
+    zero_grads: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]]
+
+    # views used by the tests
+    @property
+    def tape_edges(self):
+        return self.tape[:2 * self.n_verts].view(-1, 2)
+
+    @property
+    def tape_corners(self):
+        p = 3 * self.n_tri + 4 * self.n_quad
+        o = (self.tape_ptrs[1] - self.tape_ptrs[0]) // 4
+        return self.tape[o:o + p]
+
+
+def _r4(n: int) -> int:
+    """round a row count up so that the next region of a slab stays 16-byte aligned"""
+    return (n + 3) & ~3
+
+
+_WAIT_TIMEOUT_US = 60_000_000
 
 
 def forward_raw(pos: torch.Tensor, sdf: torch.Tensor, msdf: torch.Tensor, tets_i32: torch.Tensor, msdf_negate: bool,
-                watertight_template: bool, tet_range: Optional[Tuple[int, int]] = None) -> ForwardResult:
+                watertight_template: bool, tet_range: Optional[Tuple[int, int]] = None,
+                want_grads: Tuple[bool, bool, bool] = (False, False, False)) -> ForwardResult:
     """One forward extraction on the current stream.  Inputs: contiguous fp32 CUDA tensors, packed int32 tets.
-    Synchronises the stream once to learn the output sizes (the reference syncs ~40 times per call)."""
+
+    The host blocks exactly once, on the sizes of the outputs (the reference blocks ~40 times per call): the kernel that
+    finalises them writes d3h_counts into pinned host memory ahead of the output-writing kernels and this function
+    spins on its sequence word, so the views below are built while the GPU is still finishing the call.
+    If `want_grads` names any input, the dense gradient buffers of the coming backward call are allocated here and
+    zero-filled by the forward call's tail (they are returned in `zero_grads`)."""
     L = _cabi.lib()
     dev = pos.device
     n_grid, n_tets = pos.shape[0], tets_i32.shape[0]
     plan = _plan_for(dev, n_tets, n_grid)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
     launches = 0
+    a = plan.args
     with torch.cuda.device(dev):
+        zero_grads = None
+        if any(want_grads):
+            zero_grads = (torch.empty_like(pos), torch.empty_like(sdf), torch.empty_like(msdf) if want_grads[2] else None)
+            a.zero_g_pos, a.zero_g_sdf = zero_grads[0].data_ptr(), zero_grads[1].data_ptr()
+            a.zero_g_msdf = zero_grads[2].data_ptr() if zero_grads[2] is not None else None
+        else:
+            a.zero_g_pos = a.zero_g_sdf = a.zero_g_msdf = None
+        a.pos, a.sdf, a.msdf, a.tets = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), tets_i32.data_ptr()
+        a.n_grid, a.n_tets = n_grid, n_tets
+        a.tet_begin, a.tet_end = (0, n_tets) if tet_range is None else tet_range
+        a.msdf_negate, a.watertight_template = int(bool(msdf_negate)), int(bool(watertight_template))
         for attempt in range(6):
             plan.ensure_workspace()
             cv, cva, cfw, cfa, ct = plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets
-            f32 = dict(dtype=torch.float32, device=dev)
-            verts_aug = torch.empty((cva, 3), **f32)
-            v_tng_aug = torch.empty((cva, 3), **f32)
-            msdf_aug = torch.empty((cva,), **f32)
-            faces_aug = torch.empty((cfa, 3), dtype=torch.int64, device=dev)
-            verts_wt = torch.empty((cv, 3), **f32)
-            v_tng_wt = torch.empty((cv, 3), **f32)
-            msdf_wt = torch.empty((cv,), **f32)
-            faces_wt = torch.empty((cfw, 3), dtype=torch.int64, device=dev)
-            tape_edges = torch.empty((cv, 2), dtype=torch.int32, device=dev)
-            tape_corners = torch.empty((max(4 * ct, 1),), dtype=torch.int32, device=dev)
-            a = plan.args
-            a.pos, a.sdf, a.msdf, a.tets = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), tets_i32.data_ptr()
-            a.n_grid, a.n_tets = n_grid, n_tets
-            a.tet_begin, a.tet_end = (0, n_tets) if tet_range is None else tet_range
-            a.msdf_negate, a.watertight_template = int(bool(msdf_negate)), int(bool(watertight_template))
+            # three slabs: float outputs, int64 faces, int32 tape
+            o_vaug, o_tng, o_maug = 0, 3 * _r4(cva), 6 * _r4(cva)
+            o_vwt = o_maug + _r4(cva)
+            o_twt, o_mwt = o_vwt + 3 * _r4(cv), o_vwt + 6 * _r4(cv)
+            fslab = torch.empty(o_mwt + _r4(cv), dtype=torch.float32, device=dev)
+            islab = torch.empty(3 * (cfa + cfw), dtype=torch.int64, device=dev)
+            t_corn, t_slot = 2 * _r4(cv), 2 * _r4(cv) + 4 * ct
+            t_runs = t_slot + 4 * ct
+            tape = torch.empty(t_runs + cv + 1, dtype=torch.int32, device=dev)
+            fp, ip, tp = fslab.data_ptr(), islab.data_ptr(), tape.data_ptr()
             a.cap_valid_tets, a.cap_verts, a.cap_verts_aug, a.cap_faces_wt, a.cap_faces_aug = ct, cv, cva, cfw, cfa
-            a.verts_aug, a.v_tng_aug, a.msdf_aug = verts_aug.data_ptr(), v_tng_aug.data_ptr(), msdf_aug.data_ptr()
-            a.faces_aug, a.verts_wt, a.v_tng_wt = faces_aug.data_ptr(), verts_wt.data_ptr(), v_tng_wt.data_ptr()
-            a.msdf_wt, a.faces_wt = msdf_wt.data_ptr(), faces_wt.data_ptr()
-            a.tape_edges, a.tape_corners = tape_edges.data_ptr(), tape_corners.data_ptr()
-            a.workspace, a.workspace_bytes = plan.workspace.data_ptr(), plan.workspace.numel()
-            a.counts_host = plan.counts_host.data_ptr()
-            _cabi.check(L.d3h_extract_forward(C.byref(a), stream.cuda_stream), "d3h_extract_forward")
-            launches += _launches_forward(n_grid, ct)
-            stream.synchronize()
-            c = plan.counts_host.tolist()
-            fv, t1, t2, p, v, fa = c[0], c[1], c[2], c[3], c[4], c[5]
+            a.verts_aug, a.v_tng_aug, a.msdf_aug = fp + 4 * o_vaug, fp + 4 * o_tng, fp + 4 * o_maug
+            a.verts_wt, a.v_tng_wt, a.msdf_wt = fp + 4 * o_vwt, fp + 4 * o_twt, fp + 4 * o_mwt
+            a.faces_aug, a.faces_wt = ip, ip + 24 * cfa
+            tape_ptrs = (tp, tp + 4 * t_corn, tp + 4 * t_slot, tp + 4 * t_runs)
+            a.tape_edges, a.tape_corners, a.tape_slots, a.tape_runs = tape_ptrs
+            a.workspace, a.workspace_bytes = plan.workspace_ptr, plan.workspace.numel()
+            a.counts_host = plan.counts_ptr
+            plan.seq += 1
+            a.seq = plan.seq
+            _cabi.check(L.d3h_extract_forward(C.byref(a), stream), "d3h_extract_forward")
+            launches += _launches_forward(ct, zero_grads is not None)
+            _cabi.check(L.d3h_wait_counts(plan.counts_ptr, plan.seq, _WAIT_TIMEOUT_US), "d3h_wait_counts")
+            c = plan.counts
+            fv, t1, t2, p, v, fa = c.n_valid_tets, c.n_tri_tets, c.n_quad_tets, c.n_corners, c.n_verts, c.n_faces_aug
             if fv > ct:  # record buffer too small: surface stages were skipped, sizes below are not known yet
                 plan.cap_tets = _grow(fv)
                 # upper bounds that cannot overflow, so the next attempt is final
@@ -192,15 +232,20 @@ def forward_raw(pos: torch.Tensor, sdf: torch.Tensor, msdf: torch.Tensor, tets_i
             break
         else:  # pragma: no cover
             raise RuntimeError("d3h_extract_forward: capacities did not converge")
+        bucket_polys = tuple(c.bucket_polys)
         # next call: predict from this call's sizes (the surface moves slowly between training iterations)
         plan.cap_tets = max(_grow(fv), min(plan.cap_tets, 2 * _grow(fv)))
         plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va)
         plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw), _shrink(plan.cap_fa, fa)
-    counts = dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
-                  n_faces_watertight=fw, n_faces_aug=fa, bucket_polys=tuple(c[6:12]))
-    return ForwardResult(verts_aug[:va], v_tng_aug[:va], msdf_aug[:va], faces_aug[:fa], verts_wt[:v], v_tng_wt[:v],
-                         msdf_wt[:v], faces_wt[:fw], tape_edges[:v], tape_corners[:max(p, 0)], v, t1, t2, counts,
-                         launches)
+        ast = torch.as_strided
+        res = ForwardResult(
+            ast(fslab, (va, 3), (3, 1), o_vaug), ast(fslab, (va, 3), (3, 1), o_tng), ast(fslab, (va,), (1,), o_maug),
+            ast(islab, (fa, 3), (3, 1), 0), ast(fslab, (v, 3), (3, 1), o_vwt), ast(fslab, (v, 3), (3, 1), o_twt),
+            ast(fslab, (v,), (1,), o_mwt), ast(islab, (fw, 3), (3, 1), 3 * cfa), tape, tape_ptrs, v, t1, t2,
+            dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
+                 n_faces_watertight=fw, n_faces_aug=fa, bucket_polys=bucket_polys),
+            launches, zero_grads)
+    return res
 
 
 def _shrink(cap: int, need: int) -> int:
@@ -208,10 +253,13 @@ def _shrink(cap: int, need: int) -> int:
     return g if (cap < g or cap > 2 * g) else cap
 
 
-def _launches_forward(n_grid: int, cap_tets: int) -> int:
-    """Kernels one d3h_extract_forward enqueues: prepare, classify, compact, [partition, local_sort, rle_interp,
-    poly_faces, vertex_frame,] poly_cut."""
-    return 4 if cap_tets <= 0 else 9
+LAUNCHES_BACKWARD = 1  # adjoint_kernel (the zero-fill of the dense gradients rides on the forward call)
+
+
+def _launches_forward(cap_tets: int, zero: bool) -> int:
+    """Kernels one d3h_extract_forward enqueues: prepare, classify, compact, [bucket_scan, partition, unique,
+    poly_faces, poly_cut | publish_counts] (+ zero_kernel when the gradient buffers are pre-zeroed)."""
+    return (4 if cap_tets <= 0 else 8) + (1 if zero else 0)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -227,12 +275,14 @@ class _ExtractFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pos, sdf, msdf, tets_i32, msdf_negate, watertight_template):
-        r = forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template)
-        ctx.save_for_backward(pos, sdf, msdf, r.tape_edges, r.tape_corners, r.verts_wt, r.msdf_wt)
-        ctx.meta = (r.n_verts, r.n_tri, r.n_quad, bool(msdf_negate), tets_i32.shape[0])
+        need = ctx.needs_input_grad
+        want = (need[0] or need[1] or need[2], need[0] or need[1] or need[2], bool(need[2]) and not msdf_negate)
+        r = forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template, want_grads=want)
+        ctx.save_for_backward(pos, sdf, msdf, r.tape, r.verts_wt, r.msdf_wt)
+        ctx.meta = (r.n_verts, r.n_tri, r.n_quad, bool(msdf_negate), tets_i32.shape[0], r.tape_ptrs)
+        ctx.zero_grads = r.zero_grads
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r.faces_aug, r.faces_wt)
-        ctx.counts = r.counts
         _ExtractFn.last_counts = r.counts
         _ExtractFn.last_launches = r.launches
         return r.verts_aug, r.v_tng_aug, r.msdf_aug, r.verts_wt, r.v_tng_wt, r.msdf_wt, r.faces_aug, r.faces_wt
@@ -243,16 +293,17 @@ class _ExtractFn(torch.autograd.Function):
             raise NotImplementedError(
                 "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
                 "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
-        pos, sdf, msdf, tape_edges, tape_corners, verts_wt, msdf_wt = ctx.saved_tensors
-        n_verts, n_tri, n_quad, negate, n_tets = ctx.meta
-        g_pos, g_sdf, g_msdf = backward_raw(pos, sdf, msdf, tape_edges, tape_corners, verts_wt, msdf_wt, n_verts, n_tri,
-                                            n_quad, negate, n_tets, g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt,
-                                            want_msdf=ctx.needs_input_grad[2] and not negate)
+        pos, sdf, msdf, tape, verts_wt, msdf_wt = ctx.saved_tensors
+        n_verts, n_tri, n_quad, negate, n_tets, tape_ptrs = ctx.meta
+        zg, ctx.zero_grads = ctx.zero_grads, None  # the pre-zeroed buffers serve ONE backward pass
+        g_pos, g_sdf, g_msdf = backward_raw(pos, sdf, msdf, tape_ptrs, verts_wt, msdf_wt, n_verts, n_tri, n_quad,
+                                            negate, n_tets, g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt,
+                                            want_msdf=ctx.needs_input_grad[2] and not negate, prezeroed=zg)
         return g_pos, g_sdf, g_msdf, None, None, None
 
 
-def backward_raw(pos, sdf, msdf, tape_edges, tape_corners, verts_wt, msdf_wt, n_verts, n_tri, n_quad, negate, n_tets,
-                 g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt, want_msdf=True):
+def backward_raw(pos, sdf, msdf, tape_ptrs, verts_wt, msdf_wt, n_verts, n_tri, n_quad, negate, n_tets,
+                 g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt, want_msdf=True, prezeroed=None):
     L = _cabi.lib()
     dev = pos.device
     n_grid = pos.shape[0]
@@ -272,20 +323,27 @@ def backward_raw(pos, sdf, msdf, tape_edges, tape_corners, verts_wt, msdf_wt, n_
         g_msdf_aug, p_gma = ptr(g_msdf_aug, (va,))
         g_verts_wt, p_gvw = ptr(g_verts_wt, (n_verts, 3))
         g_msdf_wt, p_gmw = ptr(g_msdf_wt, (n_verts,))
-        g_pos = torch.empty_like(pos)
-        g_sdf = torch.empty_like(sdf)
-        g_msdf = torch.empty_like(msdf) if want_msdf else None
-        ws = plan.ensure_bwd_workspace(n_verts)
-        b = _cabi.BackwardArgs()
+        if prezeroed is not None:
+            g_pos, g_sdf, g_msdf = prezeroed
+            if not want_msdf:
+                g_msdf = None
+            elif g_msdf is None:
+                g_msdf = torch.zeros_like(msdf)
+        else:
+            g_pos = torch.empty_like(pos)
+            g_sdf = torch.empty_like(sdf)
+            g_msdf = torch.empty_like(msdf) if want_msdf else None
+        b = plan.bargs
         b.pos, b.sdf, b.msdf, b.n_grid = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), n_grid
         b.msdf_negate = int(negate)
-        b.tape_edges, b.tape_corners = tape_edges.data_ptr(), tape_corners.data_ptr()
+        b.grads_prezeroed = int(prezeroed is not None)
+        b.tape_edges, b.tape_corners, b.tape_slots, b.tape_runs = tape_ptrs
         b.verts_wt, b.msdf_wt = verts_wt.data_ptr(), msdf_wt.data_ptr()
         b.n_verts, b.n_tri_tets, b.n_quad_tets = n_verts, n_tri, n_quad
         b.g_verts_aug, b.g_msdf_aug, b.g_verts_wt, b.g_msdf_wt = p_gva, p_gma, p_gvw, p_gmw
         b.g_pos, b.g_sdf = g_pos.data_ptr(), g_sdf.data_ptr()
         b.g_msdf = g_msdf.data_ptr() if g_msdf is not None else None
-        b.workspace, b.workspace_bytes = ws.data_ptr(), ws.numel()
+        b.workspace, b.workspace_bytes = None, 0
         _cabi.check(L.d3h_extract_backward(C.byref(b), torch.cuda.current_stream(dev).cuda_stream),
                     "d3h_extract_backward")
     return g_pos, g_sdf, g_msdf

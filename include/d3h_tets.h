@@ -18,8 +18,10 @@
  *     the true sizes come back in d3h_counts.  A capacity that is too small is NOT an error: the
  *     kernels drop the out-of-range writes and the caller re-runs with the sizes just reported.
  *   - no host synchronisation inside any call; everything is enqueued on `stream` and is CUDA-graph
- *     capturable.  d3h_counts is copied to `counts_host` (pinned) with cudaMemcpyAsync at the end of
- *     the forward call; the caller synchronises the stream (or an event) before reading it.
+ *     capturable.  d3h_counts is written to `counts_host` (pinned, device-mapped host memory) by the
+ *     kernel that finalises it, ahead of the output-writing kernels; the caller polls counts_host->seq
+ *     (d3h_wait_counts) or synchronises the stream before reading it.  If the pointer is not device
+ *     accessible the library falls back to a cudaMemcpyAsync at the end of the call.
  *   - all float data is fp32; index outputs are int64 (the reference returns torch.long faces,
  *     gshell_tets.py:413-420); tet indices are consumed as packed int32x4 (16-byte loads).
  */
@@ -32,13 +34,14 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 100 /* 0.1.0 */
+#define D3H_VERSION 200 /* 0.2.0 */
 
 enum {
   D3H_OK = 0,
   D3H_E_BADARG = -1,  /* null pointer, negative size, N or F >= 2^31, misaligned tet pointer */
   D3H_E_CUDA = -2,    /* a CUDA runtime call failed; see d3h_last_error_string() */
-  D3H_E_SMALLWS = -3  /* workspace_bytes smaller than d3h_workspace_bytes(...) */
+  D3H_E_SMALLWS = -3, /* workspace_bytes smaller than d3h_workspace_bytes(...) */
+  D3H_E_TIMEOUT = -4  /* d3h_wait_counts gave up */
 };
 
 /* Opaque to C callers that only pass it around; the layout is fixed so ctypes can mirror it. */
@@ -58,7 +61,9 @@ typedef struct d3h_counts {
   int64_t n_faces_aug;    /* Fa */
   int64_t bucket_polys[6];/* polygons per faces_aug bucket, in bucket order */
   int64_t bad_index;      /* number of tet indices outside [0,N) seen by d3h_pack_tets_* (0 = clean) */
-  int64_t reserved[3];
+  int64_t overflow;       /* 1: Fv exceeded cap_valid_tets, the surface stages were skipped (re-run with more room) */
+  int64_t seq;            /* d3h_forward_args.seq of the call that produced these counts; written LAST */
+  int64_t reserved;
 } d3h_counts;
 
 /* ---- forward ------------------------------------------------------------------------------------- */
@@ -92,10 +97,20 @@ typedef struct d3h_forward_args {
   /* tape for the backward pass (device) */
   int32_t* tape_edges;     /* (cap_verts,2)   (a,b), a<b: grid vertices of each crossing edge, sorted (interp_v, gshell_tets.py:287) */
   int32_t* tape_corners;   /* (4*cap_valid_tets) polygon corner -> watertight vertex id, layout [3*T1 | 4*T2] */
+  int32_t* tape_slots;     /* (4*cap_valid_tets) corner slots grouped by watertight vertex (the sorted inverse map) */
+  int32_t* tape_runs;      /* (cap_verts + 1) start of every vertex's run in tape_slots; [V] = P */
+  /* optional: dense gradient buffers of the coming backward call, zero-filled here while the latency-bound surface
+   * stages leave HBM idle (pass them to d3h_extract_backward with grads_prezeroed = 1); NULL = not wanted */
+  float* zero_g_pos;       /* (N,3) */
+  float* zero_g_sdf;       /* (N)   */
+  float* zero_g_msdf;      /* (N)   */
   /* scratch + counts */
   void* workspace;         /* >= d3h_workspace_bytes(F, N, cap_valid_tets) bytes, 256-byte aligned */
   int64_t workspace_bytes;
-  d3h_counts* counts_host; /* pinned host memory, or NULL to skip the copy */
+  d3h_counts* counts_host; /* pinned host memory, or NULL to skip the copy.  The counts are published as soon as they
+                              are final -- before the kernels that only write outputs have run -- and `seq` is the
+                              last word written: poll it with d3h_wait_counts() instead of synchronising the stream */
+  int64_t seq;             /* caller-chosen non-zero tag of this call, echoed in counts_host->seq */
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */
@@ -106,10 +121,12 @@ typedef struct d3h_backward_args {
   const float* msdf;
   int64_t n_grid;
   int32_t msdf_negate;
-  int32_t reserved0;
+  int32_t grads_prezeroed; /* 1: g_pos / g_sdf / g_msdf were zero-filled by the forward call (zero_g_*) */
   /* saved by forward */
   const int32_t* tape_edges;
   const int32_t* tape_corners;
+  const int32_t* tape_slots;
+  const int32_t* tape_runs;
   const float* verts_wt;   /* (V,3) */
   const float* msdf_wt;    /* (V)   */
   int64_t n_verts;         /* V  */
@@ -124,8 +141,8 @@ typedef struct d3h_backward_args {
   float* g_pos;            /* (N,3) */
   float* g_sdf;            /* (N)   */
   float* g_msdf;           /* (N) or NULL (type="body" has no msdf gradient) */
-  /* scratch */
-  void* workspace;         /* >= d3h_backward_workspace_bytes(V) bytes */
+  /* scratch (unused since the adjoint became a gather over tape_slots; kept for ABI stability, may be NULL) */
+  void* workspace;
   int64_t workspace_bytes;
 } d3h_backward_args;
 
@@ -147,6 +164,11 @@ int d3h_check_tets_i32(const int32_t* tets, int64_t n_tets, int64_t n_grid, int6
 /* The whole forward extraction (replaces GShell_Tets.__call__ / hmSDF_Tets.__call__ up to the return
  * statement, gshell_tets.py:254-445). */
 int d3h_extract_forward(const d3h_forward_args* args, d3h_stream_t stream);
+
+/* Host-side wait for the counts of call `seq`: spins on counts_host->seq (the reference blocks the host ~40 times per
+ * call on boolean-mask sizes; this is the single size read of this implementation).  Returns 0, or D3H_E_TIMEOUT after
+ * timeout_us microseconds (<= 0: wait forever). */
+int d3h_wait_counts(const d3h_counts* counts_host, int64_t seq, int64_t timeout_us);
 
 /* Adjoint of the float pipeline (replaces autograd through gshell_tets.py:291-303, 342-397, 427). */
 int d3h_extract_backward(const d3h_backward_args* args, d3h_stream_t stream);

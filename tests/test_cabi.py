@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(_cabi.EXPORTED_SYMBOLS), (declared, _cabi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"libd3h_tets.so does not export {name}"
-    assert lib.d3h_version() == 100
+    assert lib.d3h_version() == _cabi.VERSION
 
 
 def test_struct_layouts_match_header():
     # sizes computed by hand from include/d3h_tets.h (all members are 8-byte aligned except two int32 pairs)
     assert C.sizeof(_cabi.Counts) == 16 * 8
-    assert C.sizeof(_cabi.ForwardArgs) == 27 * 8
-    assert C.sizeof(_cabi.BackwardArgs) == 21 * 8
+    assert C.sizeof(_cabi.ForwardArgs) == 33 * 8
+    assert C.sizeof(_cabi.BackwardArgs) == 23 * 8
 
 
 def test_workspace_bytes_contract():
@@ -43,7 +43,7 @@ def test_workspace_bytes_contract():
     assert 0 < a < b < c
     assert (c - b) < 2 * (b - a)
     assert lib.d3h_workspace_bytes(-1, 10, 0) == _cabi.D3H_E_BADARG
-    assert lib.d3h_backward_workspace_bytes(1000) >= 32 * 1000
+    assert lib.d3h_backward_workspace_bytes(1000) == 0
 
 
 def test_bad_arguments_are_rejected_before_any_launch():
