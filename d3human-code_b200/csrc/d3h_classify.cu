@@ -270,40 +270,59 @@ compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict
   s_pre[threadIdx.x] = wpre + incl - c;
   __syncthreads();
 
-  // ---- visit the tile's valid tets, one per thread per round, in tet order ----
+  // ---- visit the tile's valid tets in tet order: up to kRounds per thread at a time, so that the dependent
+  // chain (index load -> bitmap look-ups -> stores) of several tets is in flight together ----
   const uint2 ex = tile_excl[tile];
   const unsigned e1 = ex.x, e2 = ex.y;
   const unsigned nvalid_tile = (tc & 0xffffu) + (tc >> 16);
-  for (unsigned i = threadIdx.x; i < nvalid_tile; i += kCompactThreads) {
-    int lo = 0, hi = kCompactThreads - 1;  // owner thread: last th with pre1[th] + pre2[th] <= i
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      const unsigned pm = s_pre[mid];
-      if ((pm & 0xffffu) + (pm >> 16) <= i) lo = mid; else hi = mid - 1;
+  constexpr int kRounds = 4;
+  for (unsigned i0 = threadIdx.x; i0 < nvalid_tile; i0 += kRounds * kCompactThreads) {
+    int4 v4[kRounds];
+    unsigned g1[kRounds], g2[kRounds];
+    int64_t tet[kRounds];
+    bool quad[kRounds], live[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const unsigned i = i0 + r * kCompactThreads;
+      live[r] = i < nvalid_tile;
+      v4[r] = make_int4(0, 0, 0, 0);
+      g1[r] = g2[r] = 0;
+      tet[r] = 0;
+      quad[r] = false;
+      if (live[r]) {
+        int lo = 0, hi = kCompactThreads - 1;  // owner thread: last th with pre1[th] + pre2[th] <= i
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          const unsigned pm = s_pre[mid];
+          if ((pm & 0xffffu) + (pm >> 16) <= i) lo = mid; else hi = mid - 1;
+        }
+        const int th = lo;
+        const unsigned pt = s_pre[th];
+        unsigned r1 = pt & 0xffffu, r2 = pt >> 16;
+        const unsigned rem = i - (r1 + r2);
+        const unsigned b1 = s_m1[th], b2 = s_m2[th];
+        const int bit = (int)__fns(b1 | b2, 0, (int)rem + 1);  // position of the (rem+1)-th set bit
+        const unsigned below = (1u << bit) - 1u;
+        r1 += __popc(b1 & below);
+        r2 += __popc(b2 & below);
+        quad[r] = (b2 >> bit) & 1u;
+        g1[r] = e1 + r1;  // tri / quad valid tets before this one, grid-wide
+        g2[r] = e2 + r2;
+        tet[r] = tet_begin + ((int64_t)tile * kCompactThreads + th) * 32 + bit;
+        live[r] = (int64_t)g1[r] + g2[r] < cap_records;
+        if (live[r]) v4[r] = __ldg(tets + tet[r]);
+      }
     }
-    const int th = lo;
-    const unsigned pt = s_pre[th];
-    unsigned r1 = pt & 0xffffu, r2 = pt >> 16;
-    const unsigned rem = i - (r1 + r2);
-    const unsigned b1 = s_m1[th], b2 = s_m2[th];
-    const unsigned both = b1 | b2;
-    const int bit = (int)__fns(both, 0, (int)rem + 1);  // position of the (rem+1)-th set bit
-    const unsigned below = (1u << bit) - 1u;
-    r1 += __popc(b1 & below);
-    r2 += __popc(b2 & below);
-    const bool quad = (b2 >> bit) & 1u;
-    const unsigned g1 = e1 + r1, g2 = e2 + r2;  // tri / quad valid tets before this one, grid-wide
-    const int64_t slot = (int64_t)g1 + g2;
-    const int64_t tet = tet_begin + ((int64_t)tile * kCompactThreads + th) * 32 + bit;
-    if (slot < cap_records) {
-      const int4 v4 = __ldg(tets + tet);
-      const int code = (int)(occ_of(occ_bits, v4.x) | (occ_of(occ_bits, v4.y) << 1) | (occ_of(occ_bits, v4.z) << 2) |
-                             (occ_of(occ_bits, v4.w) << 3));
-      int4* out = reinterpret_cast<int4*>(records + slot);
-      out[0] = v4;
-      out[1] = make_int4(code, (int)(quad ? g2 : g1), (int)tet, (int)(quad ? g1 : g2));
-      if (EMIT_KEYS)
-        emit_polygon_keys(v4, code, quad, quad ? g2 : g1, quad ? g1 : g2, key_bits, msd_shift, keys, vals, msd_hist);
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      if (!live[r]) continue;
+      const int code = (int)(occ_of(occ_bits, v4[r].x) | (occ_of(occ_bits, v4[r].y) << 1) |
+                             (occ_of(occ_bits, v4[r].z) << 2) | (occ_of(occ_bits, v4[r].w) << 3));
+      const unsigned cr = quad[r] ? g2[r] : g1[r], ob = quad[r] ? g1[r] : g2[r];
+      int4* out = reinterpret_cast<int4*>(records + ((int64_t)g1[r] + g2[r]));
+      out[0] = v4[r];
+      out[1] = make_int4(code, (int)cr, (int)tet[r], (int)ob);
+      if (EMIT_KEYS) emit_polygon_keys(v4[r], code, quad[r], cr, ob, key_bits, msd_shift, keys, vals, msd_hist);
     }
   }
 }

@@ -135,6 +135,7 @@ partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned*
 // ------------------------------------------------------------------------------------------------
 // block-local finish: sort + run-length + numbering + zero-crossing interpolation
 // ------------------------------------------------------------------------------------------------
+// Classic shared/global-memory bitonic network (one barrier per step): only used for oversized groups in global scratch.
 template <typename KeyPtr, typename ValPtr>
 __device__ __forceinline__ void bitonic_sort_block(KeyPtr k, ValPtr v, unsigned npow2) {
   for (unsigned size = 2; size <= npow2; size <<= 1) {
@@ -153,6 +154,81 @@ __device__ __forceinline__ void bitonic_sort_block(KeyPtr k, ValPtr v, unsigned 
       __syncthreads();
     }
   }
+}
+
+// Bitonic sort of 256*E (key, value) pairs held E per thread in registers, blocked layout (element e = thread*E + r).
+// Strides below E are compare-exchanges between a thread's own registers, strides E..16E are warp shuffles, and only
+// the three top strides of the three last stages cross warps through shared memory: 9 barriers instead of one per
+// step (55 for 1024 keys), which is where v2/v3a of this kernel spent 42 % of their warp samples.
+template <int E>
+__device__ __forceinline__ void sort_group_regs(const unsigned long long* __restrict__ gkeys,
+                                                const unsigned* __restrict__ gvals, unsigned n,
+                                                unsigned long long* s_key, unsigned* s_val) {
+  constexpr unsigned NP = kUniqueThreads * E;
+  const unsigned t = threadIdx.x;
+  unsigned long long k[E];
+  unsigned v[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const unsigned e = t * E + r;
+    k[r] = (e < n) ? gkeys[e] : ~0ull;
+    v[r] = (e < n) ? gvals[e] : 0u;
+  }
+#pragma unroll 1
+  for (unsigned size = 2; size <= NP; size <<= 1) {
+    unsigned stride = size >> 1;
+    if (stride >= 32u * E) {  // cross-warp strides: through shared memory
+#pragma unroll
+      for (int r = 0; r < E; ++r) { s_key[t * E + r] = k[r]; s_val[t * E + r] = v[r]; }
+      __syncthreads();
+      for (; stride >= 32u * E; stride >>= 1) {
+        for (unsigned q = t; q < NP / 2; q += kUniqueThreads) {
+          const unsigned lo = 2 * q - (q & (stride - 1));
+          const unsigned hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const unsigned long long ka = s_key[lo], kb = s_key[hi];
+          if ((ka > kb) == up) {
+            const unsigned va = s_val[lo], vb = s_val[hi];
+            s_key[lo] = kb; s_key[hi] = ka;
+            s_val[lo] = vb; s_val[hi] = va;
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < E; ++r) { k[r] = s_key[t * E + r]; v[r] = s_val[t * E + r]; }
+    }
+    for (; stride >= (unsigned)E; stride >>= 1) {  // partner = same register of lane ^ (stride / E)
+      const unsigned m = stride / E;
+      const bool lower = (t & m) == 0;
+#pragma unroll
+      for (int r = 0; r < E; ++r) {
+        const unsigned long long pk = __shfl_xor_sync(0xffffffffu, k[r], m);
+        const unsigned pv = __shfl_xor_sync(0xffffffffu, v[r], m);
+        const bool up = ((t * E + r) & size) == 0;
+        const bool take = (lower == up) ? (pk < k[r]) : (pk > k[r]);  // ties keep their own pair on both sides
+        if (take) { k[r] = pk; v[r] = pv; }
+      }
+    }
+#pragma unroll
+    for (int sr = E / 2; sr >= 1; sr >>= 1) {  // in-register strides
+      if ((unsigned)sr < size) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          if ((r & sr) == 0) {
+            const bool up = ((t * E + r) & size) == 0;
+            if ((k[r] > k[r + sr]) == up) {
+              const unsigned long long tk = k[r]; k[r] = k[r + sr]; k[r + sr] = tk;
+              const unsigned tv = v[r]; v[r] = v[r + sr]; v[r + sr] = tv;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < E; ++r) { s_key[t * E + r] = k[r]; s_val[t * E + r] = v[r]; }
+  __syncthreads();
 }
 
 struct UniqueOut {
@@ -287,7 +363,7 @@ __device__ __forceinline__ void number_and_emit(KeyPtr k, ValPtr v, unsigned n, 
   }
 }
 
-__global__ void __launch_bounds__(kUniqueThreads)
+__global__ void __launch_bounds__(kUniqueThreads, 2)
 unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
               unsigned long long* __restrict__ scratch_keys, unsigned* __restrict__ scratch_vals,
               DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start,
@@ -308,19 +384,16 @@ unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __res
   const unsigned lo = __ldcg(group_start + g);
   const unsigned hi = (g + 1 == ngroups_used) ? (unsigned)ncorn : __ldcg(group_start + g + 1);
   const unsigned n = hi > lo ? hi - lo : 0u;  // 0: this group's positions belong to a bucket that started earlier
-  unsigned npow2 = 2;
-  while (npow2 < n) npow2 <<= 1;
 
   if (n <= (unsigned)kLocalSortCap) {
-    for (unsigned i = threadIdx.x; i < npow2 && n > 0; i += kUniqueThreads) {
-      s_key[i] = (i < n) ? keys[lo + i] : ~0ull;
-      s_val[i] = (i < n) ? vals[lo + i] : 0u;
-    }
-    __syncthreads();
-    if (n > 1) bitonic_sort_block(s_key, s_val, npow2);
+    if (n > 4u * kUniqueThreads) sort_group_regs<8>(keys + lo, vals + lo, n, s_key, s_val);
+    else if (n > 2u * kUniqueThreads) sort_group_regs<4>(keys + lo, vals + lo, n, s_key, s_val);
+    else if (n > 0u) sort_group_regs<2>(keys + lo, vals + lo, n, s_key, s_val);
     number_and_emit(s_key, s_val, n, lo, g, ngroups_used, t1, ncorn, ctr, status, o, s_w, &s_excl);
   } else {
     // oversized group: same network on a padded copy in global scratch (exact, slower; only degenerate inputs)
+    unsigned npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
     unsigned long long* gk = scratch_keys + 2ull * lo;  // padded copies of disjoint ranges cannot overlap at 2*lo
     unsigned* gv = scratch_vals + 2ull * lo;
     for (unsigned i = threadIdx.x; i < npow2; i += kUniqueThreads) {
