@@ -68,7 +68,6 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.m1_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactThreads) * 4));
   ws.m2_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactThreads) * 4));
   ws.tile_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_compact + 1) * 4));
-  ws.tile_excl = reinterpret_cast<uint2*>(take((ws.ntiles_compact + 1) * 8));
   ws.records = reinterpret_cast<d3h_tet_record*>(take(cap * (int64_t)sizeof(d3h_tet_record)));
   ws.keys = reinterpret_cast<unsigned long long*>(take(capc * 8));
   ws.vals = reinterpret_cast<unsigned*>(take(capc * 4));
@@ -82,6 +81,7 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.st_scan = reinterpret_cast<unsigned long long*>(take(ws.nscan_ctas * 8));
   ws.group_start = reinterpret_cast<unsigned*>(take((ws.ngroups + 2) * 4));
   ws.st_unique = reinterpret_cast<unsigned long long*>(take(ws.ngroups * 8));
+  ws.st_ublock = reinterpret_cast<unsigned long long*>(take((ws.ngroups / 256 + 1) * 8));
   ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
   ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));

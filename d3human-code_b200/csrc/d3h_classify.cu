@@ -8,11 +8,11 @@
 //   classify_kernel  F-sized, pure stream, persistent grid: every warp loads 8 x 32 tets with 16-byte no-allocate
 //                    loads, looks the four signs up in the bitmap, writes two ballot words per 32 tets (tet yields
 //                    1 / 2 triangles) and adds its (T1,T2) count to the counter of its 8192-tet tile (one RED per
-//                    non-empty warp chunk).  The last CTA to finish scans the tile counters (1536 at 128^3).
+//                    non-empty warp chunk).  No barrier, no fence, no tail.
 //   compact_kernel   one CTA per tile, no inter-CTA dependency: empty tiles (most of the grid) exit on the tile
-//                    counter; the others rank their valid tets inside the tile, add the tile's exclusive prefix and
-//                    write the compact records and, in the fused single-GPU path, the sort keys of their crossing
-//                    edges + the MSD histogram.
+//                    counter; the others sum the counters of the earlier tiles (1536 words at 128^3, from L2), rank
+//                    their valid tets inside the tile and write the compact records and, in the fused single-GPU
+//                    path, the sort keys of their crossing edges + the MSD histogram.
 //
 // History (profiles/): v1 classified and compacted in one kernel (ticket + block scan + look-back per 2048-tet tile):
 // 45 % of the warp samples parked on the barrier behind the ticket atomic, 16 % DRAM utilisation.  v2 split the stream
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
   for (int64_t i = tid; i < ws.ntiles_compact; i += nthreads) ws.tile_cnt[i] = 0u;
   for (int64_t i = tid; i < ws.nscan_ctas; i += nthreads) ws.st_scan[i] = 0ull;
   for (int64_t i = tid; i < ws.ngroups; i += nthreads) ws.st_unique[i] = 0ull;
+  for (int64_t i = tid; i < ws.ngroups / 256 + 1; i += nthreads) ws.st_ublock[i] = 0ull;
   for (int64_t i = tid; i < (ws.msd_bins + 8 + 3) / 4; i += nthreads)  // msd_hist: 256-byte aligned region, padded by 8
     reinterpret_cast<uint4*>(ws.msd_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -103,87 +104,44 @@ __device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, in
   return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u;
 }
 
-// Exclusive scan of the per-tile (T1,T2) counters by ONE CTA (the last classification CTA, or the single CTA of
-// rank_records): tile_excl[t] = counts of all tiles before t; grid totals go to the device counters.
-__device__ void scan_tile_counts(const unsigned* __restrict__ tile_cnt, uint2* __restrict__ tile_excl, int64_t ntiles,
-                                 DevCounters* __restrict__ ctr, int64_t cap_records,
-                                 unsigned long long* s_tmp /* >= 32 words */) {
-  const int nthr = blockDim.x;
-  const int64_t per = (ntiles + nthr - 1) / nthr;
-  const int64_t t0 = (int64_t)threadIdx.x * per;
-  unsigned long long sum = 0ull;  // T1 in the low half, T2 in the high half
-  for (int64_t i = 0; i < per; ++i) {
-    if (t0 + i < ntiles) {
-      const unsigned c = __ldcg(tile_cnt + t0 + i);
-      sum += (unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32);
-    }
-  }
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  unsigned long long incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (unsigned)o) incl += n;
-  }
-  __syncthreads();  // s_tmp may alias a buffer the caller used before
-  if (lane == 31) s_tmp[warp] = incl;
-  __syncthreads();
-  unsigned long long wpre = 0ull, total = 0ull;
-  for (unsigned w = 0; w < (unsigned)(nthr >> 5); ++w) {
-    if (w < warp) wpre += s_tmp[w];
-    total += s_tmp[w];
-  }
-  unsigned long long run = wpre + incl - sum;
-  for (int64_t i = 0; i < per; ++i) {
-    if (t0 + i < ntiles) {
-      const unsigned c = __ldcg(tile_cnt + t0 + i);
-      tile_excl[t0 + i] = make_uint2((unsigned)(run & 0xffffffffull), (unsigned)(run >> 32));
-      run += (unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32);
-    }
-  }
-  if (threadIdx.x == 0) {
-    const unsigned t1 = (unsigned)(total & 0xffffffffull), t2 = (unsigned)(total >> 32);
-    ctr->n_tri = t1;
-    ctr->n_quad = t2;
-    ctr->n_valid = t1 + t2;
-    const bool fits = (int64_t)t1 + t2 <= cap_records;
-    ctr->work_tri = fits ? t1 : 0u;
-    ctr->work_quad = fits ? t2 : 0u;
-  }
-}
-
+// One warp classifies kChunkTets consecutive tets per loop trip.  MOCC adds the open-mesh prefilter (gshell_tets.py:275).
+// A tet past the end of the range is loaded as (0,0,0,0): four equal vertices are never a sign change, so the tail needs
+// no per-tet bounds test.  c = number of occupied vertices: c odd -> one triangle, c == 2 -> two, c in {0,4} -> none.
+template <bool MOCC>
 __global__ void __launch_bounds__(kClassifyThreads)
 classify_kernel(const int4* __restrict__ tets, int64_t tet_begin, int64_t tet_end,
                 const unsigned* __restrict__ occ_bits, const unsigned* __restrict__ mocc_bits,
                 unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words, unsigned* __restrict__ tile_cnt,
-                uint2* __restrict__ tile_excl, int64_t nchunks, int64_t ntiles, DevCounters* __restrict__ ctr,
-                int64_t cap_records) {
-  __shared__ unsigned long long s_tmp[32];
-  __shared__ unsigned s_last;
+                int64_t nchunks) {
   const unsigned lane = lane_id();
   const int64_t warps_total = (int64_t)gridDim.x * (kClassifyThreads / 32);
   for (int64_t chunk = ((int64_t)blockIdx.x * kClassifyThreads + threadIdx.x) >> 5; chunk < nchunks;
        chunk += warps_total) {
     const int64_t base = tet_begin + chunk * kChunkTets;
+    const int4* p = tets + base + lane;
     int4 t[kClassifyItems];
+    if (base + kChunkTets <= tet_end) {
 #pragma unroll
-    for (int j = 0; j < kClassifyItems; ++j) {
-      const int64_t idx = base + j * 32 + lane;
-      t[j] = (idx < tet_end) ? ld_stream_int4(tets + idx) : make_int4(0, 0, 0, 0);
+      for (int j = 0; j < kClassifyItems; ++j) t[j] = ld_stream_int4(p + j * 32);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kClassifyItems; ++j)
+        t[j] = (base + j * 32 + lane < tet_end) ? ld_stream_int4(p + j * 32) : make_int4(0, 0, 0, 0);
     }
     unsigned w1 = 0, w2 = 0;  // lane j keeps the ballot words of item j
 #pragma unroll
     for (int j = 0; j < kClassifyItems; ++j) {
-      const int64_t idx = base + j * 32 + lane;
       const unsigned c = occ_of(occ_bits, t[j].x) + occ_of(occ_bits, t[j].y) + occ_of(occ_bits, t[j].z) +
                          occ_of(occ_bits, t[j].w);
-      bool valid = (c != 0u) && (c != 4u) && (idx < tet_end);
-      if (mocc_bits != nullptr && valid) {  // open-mesh prefilter, gshell_tets.py:275
-        valid = (occ_of(mocc_bits, t[j].x) | occ_of(mocc_bits, t[j].y) | occ_of(mocc_bits, t[j].z) |
-                 occ_of(mocc_bits, t[j].w)) != 0u;
+      bool tri = (c & 1u) != 0u, quad = (c == 2u);
+      if (MOCC) {
+        const bool keep = (occ_of(mocc_bits, t[j].x) | occ_of(mocc_bits, t[j].y) | occ_of(mocc_bits, t[j].z) |
+                           occ_of(mocc_bits, t[j].w)) != 0u;
+        tri = tri && keep;
+        quad = quad && keep;
       }
-      const unsigned b1 = __ballot_sync(0xffffffffu, valid && (c != 2u));  // 1 or 3 inside -> one triangle
-      const unsigned b2 = __ballot_sync(0xffffffffu, valid && (c == 2u));  // 2 inside      -> two triangles
+      const unsigned b1 = __ballot_sync(0xffffffffu, tri);
+      const unsigned b2 = __ballot_sync(0xffffffffu, quad);
       if (lane == (unsigned)j) { w1 = b1; w2 = b2; }
     }
     if (lane < (unsigned)kClassifyItems) {
@@ -196,15 +154,6 @@ classify_kernel(const int4* __restrict__ tets, int64_t tet_begin, int64_t tet_en
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
     if (lane == 0 && cnt != 0u) atomicAdd(tile_cnt + (chunk * kChunkTets) / kTileTets, cnt);
-  }
-  // last CTA out scans the tile counters
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->classify_done, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    scan_tile_counts(tile_cnt, tile_excl, ntiles, ctr, cap_records, s_tmp);
   }
 }
 
@@ -235,18 +184,31 @@ template <bool EMIT_KEYS>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict__ m2_words, int64_t nwords,
                const int4* __restrict__ tets, int64_t tet_begin, const unsigned* __restrict__ occ_bits,
-               const unsigned* __restrict__ tile_cnt, const uint2* __restrict__ tile_excl,
+               const unsigned* __restrict__ tile_cnt, int64_t ntiles, DevCounters* __restrict__ ctr,
                d3h_tet_record* __restrict__ records, int64_t cap_records, int key_bits, int msd_shift,
                unsigned long long* __restrict__ keys, unsigned* __restrict__ vals, unsigned* __restrict__ msd_hist) {
   constexpr int WARPS = kCompactThreads / 32;
   __shared__ unsigned s_pre[kCompactThreads];  // exclusive per-thread prefix in the tile: T1 | T2 << 16
   __shared__ unsigned s_m1[kCompactThreads], s_m2[kCompactThreads];
   __shared__ unsigned s_w[WARPS];
+  __shared__ unsigned long long s_sum[WARPS];
 
   const unsigned tile = blockIdx.x;
   const unsigned tc = __ldcg(tile_cnt + tile);
-  if (tc == 0u) return;  // most tiles hold no surface
+  const bool is_last = (int64_t)tile == ntiles - 1;
+  if (tc == 0u && !is_last) return;  // most tiles hold no surface
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+
+  // (T1,T2) valid tets in all earlier tiles: every non-empty tile sums the tile counters itself (a few KB from L2,
+  // all loads independent) -- no scan kernel, no look-back chain.  The last tile also publishes the grid totals.
+  unsigned long long sum = 0ull;  // T1 in the low half, T2 in the high half
+  for (unsigned i = threadIdx.x; i < tile; i += kCompactThreads) {
+    const unsigned c = __ldcg(tile_cnt + i);
+    sum += (unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_sum[warp] = sum;
 
   // each thread owns one word of both bitmaps (= 32 consecutive tets)
   const int64_t w0 = (int64_t)tile * kCompactThreads + threadIdx.x;
@@ -264,16 +226,28 @@ compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict
   if (lane == 31) s_w[warp] = incl;
   __syncthreads();
   unsigned wpre = 0;
+  unsigned long long excl = 0ull;
 #pragma unroll
-  for (int w = 0; w < WARPS; ++w)
+  for (int w = 0; w < WARPS; ++w) {
     if (w < (int)warp) wpre += s_w[w];
+    excl += s_sum[w];
+  }
   s_pre[threadIdx.x] = wpre + incl - c;
+  const unsigned e1 = (unsigned)(excl & 0xffffffffull), e2 = (unsigned)(excl >> 32);
+  if (is_last && threadIdx.x == 0) {
+    const unsigned t1 = e1 + (tc & 0xffffu), t2 = e2 + (tc >> 16);
+    ctr->n_tri = t1;
+    ctr->n_quad = t2;
+    ctr->n_valid = t1 + t2;
+    const bool fits = (int64_t)t1 + t2 <= cap_records;
+    ctr->work_tri = fits ? t1 : 0u;
+    ctr->work_quad = fits ? t2 : 0u;
+  }
+  if (tc == 0u) return;
   __syncthreads();
 
   // ---- visit the tile's valid tets in tet order: up to kRounds per thread at a time, so that the dependent
   // chain (index load -> bitmap look-ups -> stores) of several tets is in flight together ----
-  const uint2 ex = tile_excl[tile];
-  const unsigned e1 = ex.x, e2 = ex.y;
   const unsigned nvalid_tile = (tc & 0xffffu) + (tc >> 16);
   constexpr int kRounds = 4;
   for (unsigned i0 = threadIdx.x; i0 < nvalid_tile; i0 += kRounds * kCompactThreads) {
@@ -334,15 +308,22 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   const int64_t nchunks = (n + kChunkTets - 1) / kChunkTets;
   const int64_t ntiles = (n + kTileTets - 1) / kTileTets;
   {
-    static int max_grid = 0;
-    if (max_grid == 0) max_grid = persistent_grid(reinterpret_cast<const void*>(classify_kernel), kClassifyThreads, 0);
+    static int max_grid[2] = {0, 0};
+    const int mocc = a.watertight_template ? 0 : 1;
+    if (max_grid[mocc] == 0)
+      max_grid[mocc] = persistent_grid(mocc ? reinterpret_cast<const void*>(classify_kernel<true>)
+                                            : reinterpret_cast<const void*>(classify_kernel<false>), kClassifyThreads, 0);
     int64_t nblocks = (nchunks * 32 + kClassifyThreads - 1) / kClassifyThreads;
-    if (nblocks > max_grid) nblocks = max_grid;
+    if (nblocks > max_grid[mocc]) nblocks = max_grid[mocc];
     ProfScope ps(K_CLASSIFY, stream);
-    classify_kernel<<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
-        reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits,
-        a.watertight_template ? nullptr : ws.mocc_bits, ws.m1_words, ws.m2_words, ws.tile_cnt, ws.tile_excl, nchunks,
-        ntiles, ws.ctr, cap_records);
+    if (mocc)
+      classify_kernel<true><<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
+          reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits, ws.mocc_bits, ws.m1_words,
+          ws.m2_words, ws.tile_cnt, nchunks);
+    else
+      classify_kernel<false><<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
+          reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits, nullptr, ws.m1_words,
+          ws.m2_words, ws.tile_cnt, nchunks);
   }
   const int64_t nwords = nchunks * kClassifyItems;  // every word of a visited chunk is written
   const int key_bits = key_bits_for(a.n_grid);
@@ -351,11 +332,11 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   if (emit_keys)
     compact_kernel<true><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
         ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.tile_cnt,
-        ws.tile_excl, records, cap_records, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist);
+        ntiles, ws.ctr, records, cap_records, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist);
   else
     compact_kernel<false><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
         ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.tile_cnt,
-        ws.tile_excl, records, cap_records, key_bits, msd_shift, nullptr, nullptr, nullptr);
+        ntiles, ws.ctr, records, cap_records, key_bits, msd_shift, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ constexpr int kTileTets = 32 * kCompactThreads;  // tets per compaction tile (81
 
 constexpr int kMsdBits = 17;        // MSD radix digit: top bits of the smaller endpoint (<= 131072 buckets)
 constexpr int kScanThreads = 1024;  // bucket_scan: one bucket per thread
-constexpr int kSortGroup = 512;     // group quantum of the block-local finish
+constexpr int kSortGroup = 256;     // group quantum of the block-local finish
 constexpr int kLocalSortCap = 2048; // keys a CTA sorts in shared memory (24 KB); larger groups use global scratch
 constexpr int kUniqueThreads = 256;
 
@@ -31,7 +31,6 @@ struct Workspace {
   unsigned* m1_words;             // ceil(F/32) words: tet yields one triangle
   unsigned* m2_words;             // ceil(F/32) words: tet yields two triangles
   unsigned* tile_cnt;             // per compaction tile: T1-class count | T2-class count << 16
-  uint2* tile_excl;               // per compaction tile: exclusive (T1, T2) prefix
   d3h_tet_record* records;        // cap_valid_tets
   unsigned long long* keys;       // 4*cap_valid_tets: edge keys in valid-tet order
   unsigned* vals;
@@ -45,7 +44,8 @@ struct Workspace {
   unsigned long long* st_scan;    // one status word per bucket_scan CTA
   unsigned* group_start;          // cap_corners / kSortGroup + 2: first key of every block-local sort group
   int64_t msd_bins;               // buckets actually used for this grid: ((N-1) >> msd_shift) + 1
-  unsigned long long* st_unique;  // one status word per sort group (vertex numbering look-back)
+  unsigned long long* st_unique;  // one status word per sort group: its number of distinct keys
+  unsigned long long* st_ublock;  // one status word per 256 sort groups: their total
   unsigned* poly_cnt;             // ntiles_poly * 8: polygons per faces_aug bucket in each polygon tile
   unsigned* poly_excl;            // ntiles_poly * 8: exclusive prefix of poly_cnt over the tiles
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets

@@ -15,8 +15,9 @@
 //                       snaps the sort groups to bucket boundaries.
 //   partition_kernel    one radix pass: scatters (key, value) to its bucket.  The pass need not be stable (equal keys
 //                       are merged afterwards), so slots are claimed with warp-aggregated atomics.
-//   unique_kernel       one CTA per group of whole buckets (~512 keys): bitonic sort of (key, value) in shared memory,
-//                       head flags + block scan + decoupled look-back over the groups = vertex ids in sorted order;
+//   unique_kernel       one CTA per group of whole buckets (~256 keys): bitonic sort of (key, value) in registers /
+//                       shuffles / shared memory, head flags + block scan + chain-free prefix over the groups' counts
+//                       = vertex ids in sorted order;
 //                       scatters the ids to the corner array, writes the (a,b) tape and the per-vertex corner runs the
 //                       backward pass gathers over, and interpolates position / mSDF of every new vertex.
 //                       A group too large for shared memory (surface concentrated in a few consecutive vertex ids) is
@@ -256,7 +257,8 @@ template <typename KeyPtr, typename ValPtr>
 __device__ __forceinline__ void number_and_emit(KeyPtr k, ValPtr v, unsigned n, unsigned lo, unsigned group,
                                                 unsigned ngroups_used, unsigned t1, int64_t ncorn,
                                                 DevCounters* __restrict__ ctr, unsigned long long* __restrict__ status,
-                                                const UniqueOut& o, unsigned* s_w, unsigned long long* s_excl) {
+                                                unsigned long long* __restrict__ block_status, const UniqueOut& o,
+                                                unsigned* s_w, unsigned long long* s_part, unsigned long long* s_excl) {
   constexpr int WARPS = kUniqueThreads / 32;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned ipt = (n + kUniqueThreads - 1) / kUniqueThreads;  // items per thread, blocked
@@ -280,37 +282,39 @@ __device__ __forceinline__ void number_and_emit(KeyPtr k, ValPtr v, unsigned n, 
     if (w < (int)warp) wpre += s_w[w];
     total += s_w[w];
   }
-  if (warp == 0) {  // decoupled look-back over the groups
-    unsigned long long excl = 0ull;
-    if (group == 0) {
-      if (lane == 0) st_relaxed_u64(status, kFlagInc | total);
-    } else {
-      if (lane == 0) st_relaxed_u64(status + group, kFlagAgg | total);
-      int64_t look = (int64_t)group - 1;
-      while (true) {
-        const int64_t idx = look - lane;
-        unsigned long long w = kFlagInc;  // virtual group -1: inclusive prefix 0
-        if (idx >= 0) {
-          do { w = ld_relaxed_u64(status + idx); } while ((w >> 62) == 0ull);
-        }
-        const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
-        const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-        unsigned long long contrib = ((int)lane <= first) ? (w & kValMask) : 0ull;
+  // Exclusive vertex count of all earlier groups WITHOUT a chain: every group publishes its own count, the last group
+  // of every 256-group block also publishes the block total, and a group sums the counts of the earlier groups of its
+  // block plus the totals of the earlier blocks -- one status word per thread, all polled concurrently.  (A decoupled
+  // look-back walked ~g/32 windows per group behind the slowest sort: 40 % of this kernel's samples, profiles/.)
+  if (threadIdx.x == 0) st_relaxed_u64(status + group, kFlagAgg | total);
+  const unsigned blk = group >> 8, first = blk << 8;
+  unsigned long long part = 0ull;  // low half: earlier groups of this block, high half: earlier blocks
+  if (first + threadIdx.x < group) {
+    unsigned long long w;
+    do { w = ld_relaxed_u64(status + first + threadIdx.x); } while ((w >> 62) == 0ull);
+    part = w & 0xffffffffull;
+  }
+  for (unsigned bq = threadIdx.x; bq < blk; bq += kUniqueThreads) {
+    unsigned long long w;
+    do { w = ld_relaxed_u64(block_status + bq); } while ((w >> 62) == 0ull);
+    part += (w & 0xffffffffull) << 32;
+  }
 #pragma unroll
-        for (int of = 16; of > 0; of >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, of);
-        excl += contrib;
-        if (inc_mask) break;
-        look -= 32;
-      }
-      if (lane == 0) st_relaxed_u64(status + group, kFlagInc | (excl + total));
-    }
-    if (lane == 0) {
-      *s_excl = excl;
-      if (group + 1 == ngroups_used) {
-        const unsigned nv = (unsigned)(excl + total);
-        ctr->n_verts = nv;
-        if ((int64_t)nv <= o.cap_verts) o.tape_runs[nv] = (int32_t)ncorn;
-      }
+  for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
+  __syncthreads();  // everybody has read s_w
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long sum = 0ull;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) sum += s_part[w];
+    const unsigned long long in_block = sum & 0xffffffffull, before = sum >> 32;
+    if ((group & 255u) == 255u) st_relaxed_u64(block_status + blk, kFlagAgg | (in_block + total));
+    *s_excl = in_block + before;
+    if (group + 1 == ngroups_used) {
+      const unsigned nv = (unsigned)(in_block + before + total);
+      ctr->n_verts = nv;
+      if ((int64_t)nv <= o.cap_verts) o.tape_runs[nv] = (int32_t)ncorn;
     }
   }
   __syncthreads();
@@ -367,10 +371,11 @@ __global__ void __launch_bounds__(kUniqueThreads, 2)
 unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
               unsigned long long* __restrict__ scratch_keys, unsigned* __restrict__ scratch_vals,
               DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start,
-              unsigned long long* __restrict__ status, UniqueOut o) {
+              unsigned long long* __restrict__ status, unsigned long long* __restrict__ block_status, UniqueOut o) {
   __shared__ __align__(16) unsigned long long s_key[kLocalSortCap];
   __shared__ unsigned s_val[kLocalSortCap];
   __shared__ unsigned s_w[32];
+  __shared__ unsigned long long s_part[32];
   __shared__ unsigned long long s_excl;
   __shared__ unsigned s_group;
 
@@ -389,7 +394,7 @@ unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __res
     if (n > 4u * kUniqueThreads) sort_group_regs<8>(keys + lo, vals + lo, n, s_key, s_val);
     else if (n > 2u * kUniqueThreads) sort_group_regs<4>(keys + lo, vals + lo, n, s_key, s_val);
     else if (n > 0u) sort_group_regs<2>(keys + lo, vals + lo, n, s_key, s_val);
-    number_and_emit(s_key, s_val, n, lo, g, ngroups_used, t1, ncorn, ctr, status, o, s_w, &s_excl);
+    number_and_emit(s_key, s_val, n, lo, g, ngroups_used, t1, ncorn, ctr, status, block_status, o, s_w, s_part, &s_excl);
   } else {
     // oversized group: same network on a padded copy in global scratch (exact, slower; only degenerate inputs)
     unsigned npow2 = 2;
@@ -402,7 +407,7 @@ unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __res
     }
     __syncthreads();
     bitonic_sort_block(gk, gv, npow2);
-    number_and_emit(gk, gv, n, lo, g, ngroups_used, t1, ncorn, ctr, status, o, s_w, &s_excl);
+    number_and_emit(gk, gv, n, lo, g, ngroups_used, t1, ncorn, ctr, status, block_status, o, s_w, s_part, &s_excl);
   }
 }
 
@@ -432,7 +437,7 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
   ProfScope ps(K_UNIQUE, stream);
   unique_kernel<<<(unsigned)ws.ngroups, kUniqueThreads, 0, stream>>>(ws.keys2, ws.vals2, ws.keys_scratch,
                                                                       ws.vals_scratch, ws.ctr, ws.group_start,
-                                                                      ws.st_unique, o);
+                                                                      ws.st_unique, ws.st_ublock, o);
 }
 
 }  // namespace d3h
