@@ -1,5 +1,8 @@
 // C-ABI entry points of libd3h_tets.so (declared in include/d3h_tets.h) and the workspace carving.
 #include <chrono>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -37,6 +40,8 @@ ProfScope::~ProfScope() {
   if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
 }
 
+bool profiling_enabled() { return g_prof_on; }
+
 static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets) {
@@ -62,6 +67,7 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.nscan_ctas = (ws.msd_bins + kScanThreads - 1) / kScanThreads;
   const int64_t nwords = (n_grid + 31) / 32 + 1;
   ws.ctr = reinterpret_cast<DevCounters*>(take(sizeof(DevCounters)));
+  ws.blk = reinterpret_cast<FwdBlock*>(take(sizeof(FwdBlock)));
   ws.counts = reinterpret_cast<d3h_counts*>(take(sizeof(d3h_counts)));
   ws.occ_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
   ws.mocc_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
@@ -80,8 +86,8 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.msd_base = reinterpret_cast<unsigned*>(take((ws.msd_bins + 8) * 4));
   ws.st_scan = reinterpret_cast<unsigned long long*>(take(ws.nscan_ctas * 8));
   ws.group_start = reinterpret_cast<unsigned*>(take((ws.ngroups + 2) * 4));
-  ws.st_unique = reinterpret_cast<unsigned long long*>(take(ws.ngroups * 8));
-  ws.st_ublock = reinterpret_cast<unsigned long long*>(take((ws.ngroups / 256 + 1) * 8));
+  ws.group_heads = reinterpret_cast<unsigned*>(take((ws.ngroups + 1) * 4));
+  ws.gblock_heads = reinterpret_cast<unsigned*>(take((ws.ngroups / 256 + 2) * 4));
   ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
   ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));
@@ -154,13 +160,138 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
 }
 
 static int finish(const char* who, const d3h_forward_args* a, const Workspace& ws, cudaStream_t stream) {
-  if (a->zero_g_pos || a->zero_g_sdf || a->zero_g_msdf)
-    launch_zero_grads(a->zero_g_pos, a->zero_g_sdf, a->zero_g_msdf, a->n_grid, stream);
   if (a->counts_host && mapped_counts_pointer(a->counts_host) == nullptr)  // not device-mapped: copy at the end
     cudaMemcpyAsync(a->counts_host, ws.counts, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return D3H_E_CUDA; }
   return D3H_OK;
+}
+
+void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+  launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream);
+  launch_edge_sort(a, ws, stream);
+  launch_surface(a, ws, ws.records, stream);
+  if (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) launch_zero_grads_from_block(a, ws, stream);
+}
+
+// ---- graph cache -----------------------------------------------------------------------------------
+// One instantiated CUDA graph per launch shape.  Only the parameters of the first node (prepare_kernel, which carries
+// the argument block by value) change between launches.
+const void* prepare_kernel_address();
+
+struct GraphKey {
+  void* workspace;
+  int64_t n_tets, n_grid, tet_begin, tet_end, cap_valid_tets;
+  int watertight, has_zero, device;
+  bool operator==(const GraphKey& o) const {
+    return workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
+           tet_end == o.tet_end && cap_valid_tets == o.cap_valid_tets && watertight == o.watertight &&
+           has_zero == o.has_zero && device == o.device;
+  }
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  cudaGraphNode_t prepare_node;
+  cudaKernelNodeParams prepare_params;
+  uint64_t last_use;
+};
+static std::mutex g_graph_mu;
+static std::vector<GraphEntry> g_graphs;
+static uint64_t g_graph_clock = 0;
+static int g_graph_state = -1;  // -1 unknown, 0 disabled (D3H_DISABLE_GRAPH=1), 1 enabled
+constexpr size_t kMaxGraphs = 12;
+
+static void destroy_entry(GraphEntry& e) {
+  cudaGraphExecDestroy(e.exec);
+  cudaGraphDestroy(e.graph);
+}
+
+static int build_entry(const d3h_forward_args& a, const Workspace& ws, const GraphKey& key, GraphEntry& out) {
+  static thread_local cudaStream_t cs = nullptr;
+  if (cs == nullptr && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return -1;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return -1; }
+  launch_prepare(a, ws, cs);
+  launch_forward_sequence(a, ws, cs);
+  if (cudaStreamEndCapture(cs, &graph) != cudaSuccess || graph == nullptr) { cudaGetLastError(); return -1; }
+  size_t nn = 0;
+  cudaGraphGetNodes(graph, nullptr, &nn);
+  std::vector<cudaGraphNode_t> nodes(nn);
+  cudaGraphGetNodes(graph, nodes.data(), &nn);
+  bool found = false;
+  for (size_t i = 0; i < nn && !found; ++i) {
+    cudaGraphNodeType ty;
+    if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp;
+    if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+    if (kp.func == prepare_kernel_address()) {
+      out.prepare_node = nodes[i];
+      out.prepare_params = kp;
+      found = true;
+    }
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (!found || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    return -1;
+  }
+  out.key = key;
+  out.graph = graph;
+  out.exec = exec;
+  return 0;
+}
+
+// Returns 0 when the call was enqueued as a graph launch, -1 when the caller must launch the kernels directly.
+static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+  if (g_graph_state < 0) {
+    const char* env = getenv("D3H_DISABLE_GRAPH");
+    g_graph_state = (env && env[0] == '1') ? 0 : 1;
+  }
+  if (g_graph_state == 0 || profiling_enabled()) return -1;
+  if (a.counts_host && mapped_counts_pointer(a.counts_host) == nullptr) return -1;  // needs the trailing memcpy
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.workspace = a.workspace;
+  key.n_tets = a.n_tets; key.n_grid = a.n_grid; key.tet_begin = a.tet_begin; key.tet_end = a.tet_end;
+  key.cap_valid_tets = a.cap_valid_tets;
+  key.watertight = a.watertight_template ? 1 : 0;
+  key.has_zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) ? 1 : 0;
+  cudaGetDevice(&key.device);
+  std::lock_guard<std::mutex> lock(g_graph_mu);
+  GraphEntry* e = nullptr;
+  for (auto& g : g_graphs)
+    if (g.key == key) { e = &g; break; }
+  if (e == nullptr) {
+    GraphEntry ne;
+    memset(&ne, 0, sizeof(ne));
+    if (build_entry(a, ws, key, ne) != 0) { g_graph_state = 0; return -1; }  // capture unsupported here: stay direct
+    if (g_graphs.size() >= kMaxGraphs) {
+      size_t victim = 0;
+      for (size_t i = 1; i < g_graphs.size(); ++i)
+        if (g_graphs[i].last_use < g_graphs[victim].last_use) victim = i;
+      destroy_entry(g_graphs[victim]);
+      g_graphs[victim] = ne;
+      e = &g_graphs[victim];
+    } else {
+      g_graphs.push_back(ne);
+      e = &g_graphs.back();
+    }
+  }
+  e->last_use = ++g_graph_clock;
+  FwdBlock blk;
+  blk.a = a;
+  blk.counts_mapped = mapped_counts_pointer(a.counts_host);
+  Workspace wcopy = ws;
+  void* kargs[2] = {&blk, &wcopy};
+  cudaKernelNodeParams kp = e->prepare_params;
+  kp.kernelParams = kargs;
+  kp.extra = nullptr;
+  if (cudaGraphExecKernelNodeSetParams(e->exec, e->prepare_node, &kp) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaGraphLaunch(e->exec, stream) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return 0;
 }
 
 }  // namespace d3h
@@ -200,10 +331,10 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)s;
   Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
-  launch_prepare(*a, ws, stream);
-  launch_classify(*a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream);
-  launch_edge_sort(*a, ws, stream);
-  launch_surface(*a, ws, ws.records, stream);
+  if (launch_forward_graph(*a, ws, stream) != 0) {
+    launch_prepare(*a, ws, stream);
+    launch_forward_sequence(*a, ws, stream);
+  }
   return finish("d3h_extract_forward", a, ws, stream);
 }
 
@@ -258,6 +389,7 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet
   launch_rank_records(*a, ws, ws.records, n, stream);
   launch_edge_sort(*a, ws, stream);
   launch_surface(*a, ws, ws.records, stream);
+  if (a->zero_g_pos || a->zero_g_sdf || a->zero_g_msdf) launch_zero_grads_from_block(*a, ws, stream);
   return finish("d3h_extract_from_records", a, ws, stream);
 }
 
@@ -284,8 +416,8 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 }
 
 // ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
-static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "unique",
-                                            "poly_faces", "poly_cut", "zero", "adjoint", "rank_records"};
+static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "group_sort",
+                                            "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

@@ -34,6 +34,32 @@ __global__ void __launch_bounds__(256) zero_kernel(float4* __restrict__ p0, int6
   if (tid < tn2) t2[tid] = 0.f;
 }
 
+// Forward-side variant: the three pointers come from the argument block (they change from call to call, the launch
+// shape does not).  Buffers are 16-byte aligned (checked on the host).
+__global__ void __launch_bounds__(256) zero_block_kernel(const FwdBlock* __restrict__ blk, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* bufs[3] = {blk->a.zero_g_pos, blk->a.zero_g_sdf, blk->a.zero_g_msdf};
+  const int64_t lens[3] = {3 * n, n, n};
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    float* p = bufs[b];
+    if (p == nullptr) continue;
+    const int64_t n4 = lens[b] / 4;
+    for (int64_t i = tid; i < n4; i += stride) reinterpret_cast<float4*>(p)[i] = z;
+    if (tid < lens[b] - 4 * n4) p[4 * n4 + tid] = 0.f;
+  }
+}
+
+void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+  int64_t blocks = (5 * a.n_grid / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps(K_ZERO, stream);
+  zero_block_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ws.blk, a.n_grid);
+}
+
 void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n, cudaStream_t stream) {
   // split every buffer in a 16-byte-aligned body and a scalar tail
   auto body = [](float* p, int64_t len, float4*& b4, int64_t& n4, float*& tail, int64_t& ntail) {

@@ -50,17 +50,21 @@ __device__ __forceinline__ float4 load4_guarded(const float* __restrict__ p, int
   return s;
 }
 
-__global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ sdf, const float* __restrict__ msdf,
-                                                      int64_t n_grid, int msdf_negate, int want_mocc,
-                                                      unsigned* __restrict__ occ_bits,
-                                                      unsigned* __restrict__ mocc_bits, Workspace ws) {
+__global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (tid == 0) *ws.blk = src;  // the argument block of this call, for every later kernel
+  const float* __restrict__ sdf = src.a.sdf;
+  const float* __restrict__ msdf = src.a.msdf;
+  const int64_t n_grid = src.a.n_grid;
+  const int msdf_negate = src.a.msdf_negate;
+  const int want_mocc = src.a.watertight_template ? 0 : 1;
+  unsigned* __restrict__ occ_bits = ws.occ_bits;
+  unsigned* __restrict__ mocc_bits = ws.mocc_bits;
   if (tid < (int64_t)(sizeof(DevCounters) / 4)) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
   for (int64_t i = tid; i < ws.ntiles_compact; i += nthreads) ws.tile_cnt[i] = 0u;
   for (int64_t i = tid; i < ws.nscan_ctas; i += nthreads) ws.st_scan[i] = 0ull;
-  for (int64_t i = tid; i < ws.ngroups; i += nthreads) ws.st_unique[i] = 0ull;
-  for (int64_t i = tid; i < ws.ngroups / 256 + 1; i += nthreads) ws.st_ublock[i] = 0ull;
+  for (int64_t i = tid; i < ws.ngroups / 256 + 1; i += nthreads) ws.gblock_heads[i] = 0u;
   for (int64_t i = tid; i < (ws.msd_bins + 8 + 3) / 4; i += nthreads)  // msd_hist: 256-byte aligned region, padded by 8
     reinterpret_cast<uint4*>(ws.msd_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -87,14 +91,18 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
   }
 }
 
+const void* prepare_kernel_address() { return reinterpret_cast<const void*>(prepare_kernel); }
+
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const int64_t nquads = (a.n_grid + 3) / 4;
   int64_t blocks = (nquads + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  FwdBlock blk;
+  blk.a = a;
+  blk.counts_mapped = mapped_counts_pointer(a.counts_host);
   ProfScope ps(K_PREPARE, stream);
-  prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.sdf, a.msdf, a.n_grid, a.msdf_negate,
-                                                         a.watertight_template ? 0 : 1, ws.occ_bits, ws.mocc_bits, ws);
+  prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(blk, ws);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -109,10 +117,11 @@ __device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, in
 // no per-tet bounds test.  c = number of occupied vertices: c odd -> one triangle, c == 2 -> two, c in {0,4} -> none.
 template <bool MOCC>
 __global__ void __launch_bounds__(kClassifyThreads)
-classify_kernel(const int4* __restrict__ tets, int64_t tet_begin, int64_t tet_end,
+classify_kernel(const FwdBlock* __restrict__ blk, int64_t tet_begin, int64_t tet_end,
                 const unsigned* __restrict__ occ_bits, const unsigned* __restrict__ mocc_bits,
                 unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words, unsigned* __restrict__ tile_cnt,
                 int64_t nchunks) {
+  const int4* __restrict__ tets = reinterpret_cast<const int4*>(blk->a.tets);
   const unsigned lane = lane_id();
   const int64_t warps_total = (int64_t)gridDim.x * (kClassifyThreads / 32);
   for (int64_t chunk = ((int64_t)blockIdx.x * kClassifyThreads + threadIdx.x) >> 5; chunk < nchunks;
@@ -182,12 +191,14 @@ __device__ __forceinline__ void emit_polygon_keys(const int4 v4, int code, bool 
 
 template <bool EMIT_KEYS>
 __global__ void __launch_bounds__(kCompactThreads)
-compact_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict__ m2_words, int64_t nwords,
-               const int4* __restrict__ tets, int64_t tet_begin, const unsigned* __restrict__ occ_bits,
-               const unsigned* __restrict__ tile_cnt, int64_t ntiles, DevCounters* __restrict__ ctr,
-               d3h_tet_record* __restrict__ records, int64_t cap_records, int key_bits, int msd_shift,
-               unsigned long long* __restrict__ keys, unsigned* __restrict__ vals, unsigned* __restrict__ msd_hist) {
+compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1_words,
+               const unsigned* __restrict__ m2_words, int64_t nwords, int64_t tet_begin,
+               const unsigned* __restrict__ occ_bits, const unsigned* __restrict__ tile_cnt, int64_t ntiles,
+               DevCounters* __restrict__ ctr, d3h_tet_record* __restrict__ records, int64_t cap_records, int key_bits,
+               int msd_shift, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
+               unsigned* __restrict__ msd_hist) {
   constexpr int WARPS = kCompactThreads / 32;
+  const int4* __restrict__ tets = reinterpret_cast<const int4*>(blk->a.tets);
   __shared__ unsigned s_pre[kCompactThreads];  // exclusive per-thread prefix in the tile: T1 | T2 << 16
   __shared__ unsigned s_m1[kCompactThreads], s_m2[kCompactThreads];
   __shared__ unsigned s_w[WARPS];
@@ -318,12 +329,10 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
     ProfScope ps(K_CLASSIFY, stream);
     if (mocc)
       classify_kernel<true><<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
-          reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits, ws.mocc_bits, ws.m1_words,
-          ws.m2_words, ws.tile_cnt, nchunks);
+          ws.blk, a.tet_begin, a.tet_end, ws.occ_bits, ws.mocc_bits, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
     else
       classify_kernel<false><<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
-          reinterpret_cast<const int4*>(a.tets), a.tet_begin, a.tet_end, ws.occ_bits, nullptr, ws.m1_words,
-          ws.m2_words, ws.tile_cnt, nchunks);
+          ws.blk, a.tet_begin, a.tet_end, ws.occ_bits, nullptr, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
   }
   const int64_t nwords = nchunks * kClassifyItems;  // every word of a visited chunk is written
   const int key_bits = key_bits_for(a.n_grid);
@@ -331,12 +340,12 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   ProfScope ps(K_COMPACT, stream);
   if (emit_keys)
     compact_kernel<true><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
-        ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.tile_cnt,
-        ntiles, ws.ctr, records, cap_records, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist);
+        ws.blk, ws.m1_words, ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records,
+        cap_records, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist);
   else
     compact_kernel<false><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
-        ws.m1_words, ws.m2_words, nwords, reinterpret_cast<const int4*>(a.tets), a.tet_begin, ws.occ_bits, ws.tile_cnt,
-        ntiles, ws.ctr, records, cap_records, key_bits, msd_shift, nullptr, nullptr, nullptr);
+        ws.blk, ws.m1_words, ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records,
+        cap_records, key_bits, msd_shift, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -17,14 +17,27 @@ constexpr int kMsdBits = 17;        // MSD radix digit: top bits of the smaller 
 constexpr int kScanThreads = 1024;  // bucket_scan: one bucket per thread
 constexpr int kSortGroup = 256;     // group quantum of the block-local finish
 constexpr int kLocalSortCap = 2048; // keys a CTA sorts in shared memory (24 KB); larger groups use global scratch
-constexpr int kUniqueThreads = 256;
+constexpr int kUniqueThreads = 256;  // threads of the group sort / vertex emission CTAs
 
 constexpr int kPolyThreads = 256;   // one valid tet (= one polygon) per thread
+
+// ---- per-call argument block --------------------------------------------------------------------------
+// Everything that changes from call to call (input / output / tape pointers, output capacities, seq) lives in ONE block
+// in device memory.  The first kernel of the forward sequence receives it by value and stores it; every later kernel
+// reads it through a pointer that is fixed for the workspace.  Launch shapes depend only on (F, N, tet range,
+// cap_valid_tets), so the whole forward sequence is a CUDA graph that is captured once per shape and re-launched with
+// a single parameter update (3-4 us of host time and a 2.9 us device gap per stream launch on this box versus 1.1 us
+// per graph and 0.7 us per kernel node: profiles/bench_launch.cu).
+struct FwdBlock {
+  d3h_forward_args a;
+  d3h_counts* counts_mapped;  // device alias of a.counts_host, or nullptr
+};
 
 // ---- workspace ------------------------------------------------------------------------------------
 // Every region is 256-byte aligned.  Sizes depend on (F, N, cap_valid_tets) only.
 struct Workspace {
   DevCounters* ctr;               // 128 B
+  FwdBlock* blk;                  // the per-call argument block
   d3h_counts* counts;             // device copy of the public counts
   unsigned* occ_bits;             // ceil(N/32) words: sdf > 0
   unsigned* mocc_bits;            // ceil(N/32) words: (+-)msdf > 0 (open-mesh prefilter only)
@@ -44,8 +57,8 @@ struct Workspace {
   unsigned long long* st_scan;    // one status word per bucket_scan CTA
   unsigned* group_start;          // cap_corners / kSortGroup + 2: first key of every block-local sort group
   int64_t msd_bins;               // buckets actually used for this grid: ((N-1) >> msd_shift) + 1
-  unsigned long long* st_unique;  // one status word per sort group: its number of distinct keys
-  unsigned long long* st_ublock;  // one status word per 256 sort groups: their total
+  unsigned* group_heads;          // distinct keys of every sort group
+  unsigned* gblock_heads;         // distinct keys of every 256 sort groups
   unsigned* poly_cnt;             // ntiles_poly * 8: polygons per faces_aug bucket in each polygon tile
   unsigned* poly_excl;            // ntiles_poly * 8: exclusive prefix of poly_cnt over the tiles
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets
@@ -67,6 +80,8 @@ int persistent_grid(const void* kernel, int threads, size_t dyn_smem);
 
 // ---- stage launchers (all asynchronous on `stream`) -------------------------------------------------
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
+// the forward sequence behind launch_prepare; `a` only supplies the launch shapes, the kernels read the block
+void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
                      bool emit_keys, cudaStream_t stream);
 void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
@@ -75,15 +90,17 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
 void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
                          cudaStream_t stream);
 void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n_grid, cudaStream_t stream);
+void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 void launch_backward(const d3h_backward_args& a, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 d3h_counts* mapped_counts_pointer(d3h_counts* host);
+bool profiling_enabled();
 
 // ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
 enum KernelKind {
-  K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_UNIQUE, K_POLY_FACES, K_POLY_CUT, K_ZERO,
-  K_ADJOINT, K_RANK_RECORDS, K_COUNT
+  K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_GROUP_SORT, K_VERTEX_EMIT, K_POLY_FACES,
+  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

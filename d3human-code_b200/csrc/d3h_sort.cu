@@ -15,16 +15,18 @@
 //                       snaps the sort groups to bucket boundaries.
 //   partition_kernel    one radix pass: scatters (key, value) to its bucket.  The pass need not be stable (equal keys
 //                       are merged afterwards), so slots are claimed with warp-aggregated atomics.
-//   unique_kernel       one CTA per group of whole buckets (~256 keys): bitonic sort of (key, value) in registers /
-//                       shuffles / shared memory, head flags + block scan + chain-free prefix over the groups' counts
-//                       = vertex ids in sorted order;
+//   group_sort_kernel   one CTA per group of whole buckets (~256 keys): bitonic sort of (key, value) in registers /
+//                       shuffles / shared memory, in place; counts the group's distinct keys.  A group too large for
+//                       shared memory (surface concentrated in a few consecutive vertex ids) is sorted in global
+//                       memory instead: slower, still exact.
+//   vertex_emit_kernel  head flags + block scan + (sum of the earlier groups' counts) = vertex ids in sorted order;
 //                       scatters the ids to the corner array, writes the (a,b) tape and the per-vertex corner runs the
 //                       backward pass gathers over, and interpolates position / mSDF of every new vertex.
-//                       A group too large for shared memory (surface concentrated in a few consecutive vertex ids) is
-//                       sorted in global memory instead: slower, still exact.
 //
 // v1 used six chained 8-bit LSD passes (11 us per pass for 192k keys: the chains set the time); v2 sorted 1024-4096 key
-// groups with 512 threads (40 us) and ran the run-length pass as a separate look-back kernel (13 us).
+// groups with 512 threads (40 us) and ran the run-length pass as a separate look-back kernel (13 us); v3a fused sort
+// and numbering in one kernel whose CTAs waited on each other's counts (look-back, then direct polling): 40 % of its
+// samples sat on that wait, so the count hand-over is now a kernel boundary (0.7 us inside a CUDA graph).
 #include "d3h_internal.cuh"
 
 namespace d3h {
@@ -39,7 +41,7 @@ int msd_shift_for(int64_t n_grid) {
   return b > kMsdBits ? b - kMsdBits : 0;
 }
 
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagInc = 2ull << 62, kValMask = (1ull << 62) - 1;
+constexpr unsigned long long kFlagAgg = 1ull << 62, kValMask = (1ull << 62) - 1;
 
 // ------------------------------------------------------------------------------------------------
 // bucket scan
@@ -232,171 +234,40 @@ __device__ __forceinline__ void sort_group_regs(const unsigned long long* __rest
   __syncthreads();
 }
 
-struct UniqueOut {
-  int key_bits;
-  const float* pos;
-  const float* sdf;
-  const float* msdf;
-  int msdf_negate;
-  int32_t* tape_corners;
-  int32_t* tape_edges;
-  int32_t* tape_slots;
-  int32_t* tape_runs;
-  int64_t cap_verts, cap_verts_aug;
-  float4* w_vert;
-  float4* w_acc;
-  int32_t* owner;
-  float* verts_wt;
-  float* msdf_wt;
-  float* verts_aug;
-  float* msdf_aug;
-};
-
-// Sorted keys k[0..n) of group [lo, lo+n): numbers the runs (vertex ids), emits everything that hangs off a vertex.
-template <typename KeyPtr, typename ValPtr>
-__device__ __forceinline__ void number_and_emit(KeyPtr k, ValPtr v, unsigned n, unsigned lo, unsigned group,
-                                                unsigned ngroups_used, unsigned t1, int64_t ncorn,
-                                                DevCounters* __restrict__ ctr, unsigned long long* __restrict__ status,
-                                                unsigned long long* __restrict__ block_status, const UniqueOut& o,
-                                                unsigned* s_w, unsigned long long* s_part, unsigned long long* s_excl) {
-  constexpr int WARPS = kUniqueThreads / 32;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const unsigned ipt = (n + kUniqueThreads - 1) / kUniqueThreads;  // items per thread, blocked
-  const unsigned i0 = threadIdx.x * ipt;
-  unsigned nhead = 0;
-  for (unsigned j = 0; j < ipt; ++j) {
-    const unsigned i = i0 + j;
-    if (i < n) nhead += (i == 0 || k[i] != k[i - 1]);  // a group starts on a bucket boundary: i == 0 is always a head
-  }
-  unsigned incl = nhead;
-#pragma unroll
-  for (int of = 1; of < 32; of <<= 1) {
-    const unsigned nb = __shfl_up_sync(0xffffffffu, incl, of);
-    if (lane >= (unsigned)of) incl += nb;
-  }
-  if (lane == 31) s_w[warp] = incl;
-  __syncthreads();
-  unsigned wpre = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < WARPS; ++w) {
-    if (w < (int)warp) wpre += s_w[w];
-    total += s_w[w];
-  }
-  // Exclusive vertex count of all earlier groups WITHOUT a chain: every group publishes its own count, the last group
-  // of every 256-group block also publishes the block total, and a group sums the counts of the earlier groups of its
-  // block plus the totals of the earlier blocks -- one status word per thread, all polled concurrently.  (A decoupled
-  // look-back walked ~g/32 windows per group behind the slowest sort: 40 % of this kernel's samples, profiles/.)
-  if (threadIdx.x == 0) st_relaxed_u64(status + group, kFlagAgg | total);
-  const unsigned blk = group >> 8, first = blk << 8;
-  unsigned long long part = 0ull;  // low half: earlier groups of this block, high half: earlier blocks
-  if (first + threadIdx.x < group) {
-    unsigned long long w;
-    do { w = ld_relaxed_u64(status + first + threadIdx.x); } while ((w >> 62) == 0ull);
-    part = w & 0xffffffffull;
-  }
-  for (unsigned bq = threadIdx.x; bq < blk; bq += kUniqueThreads) {
-    unsigned long long w;
-    do { w = ld_relaxed_u64(block_status + bq); } while ((w >> 62) == 0ull);
-    part += (w & 0xffffffffull) << 32;
-  }
-#pragma unroll
-  for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
-  __syncthreads();  // everybody has read s_w
-  if (lane == 0) s_part[warp] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long sum = 0ull;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) sum += s_part[w];
-    const unsigned long long in_block = sum & 0xffffffffull, before = sum >> 32;
-    if ((group & 255u) == 255u) st_relaxed_u64(block_status + blk, kFlagAgg | (in_block + total));
-    *s_excl = in_block + before;
-    if (group + 1 == ngroups_used) {
-      const unsigned nv = (unsigned)(in_block + before + total);
-      ctr->n_verts = nv;
-      if ((int64_t)nv <= o.cap_verts) o.tape_runs[nv] = (int32_t)ncorn;
-    }
-  }
-  __syncthreads();
-
-  int64_t vid = (int64_t)(*s_excl) + wpre + (incl - nhead) - 1;  // id of the run that precedes this thread's keys
-  const unsigned long long bmask = (1ull << o.key_bits) - 1;
-  for (unsigned j = 0; j < ipt; ++j) {
-    const unsigned i = i0 + j;
-    if (i >= n) break;
-    const unsigned long long key = k[i];
-    // value = (class, 4*class_rank + corner) -> corner slot in the [3*T1 | 4*T2] layout
-    const unsigned val = v[i];
-    const unsigned r4 = val & 0x7fffffffu;
-    const int64_t slot = (val >> 31) ? (3ll * t1 + r4) : (3ll * (r4 >> 2) + (r4 & 3u));
-    if (i == 0 || key != k[i - 1]) {
-      ++vid;
-      const int a = (int)(key >> o.key_bits), b = (int)(key & bmask);
-      // zero-crossing interpolation, gshell_tets.py:291-303 (op order: SURVEY A.4)
-      float w0, w1, dd;
-      crossing_weights(__ldg(o.sdf + a), __ldg(o.sdf + b), w0, w1, dd);
-      float ma = __ldg(o.msdf + a), mb = __ldg(o.msdf + b);
-      if (o.msdf_negate) { ma = -ma; mb = -mb; }
-      const float x = lerp2(__ldg(o.pos + 3ll * a + 0), w0, __ldg(o.pos + 3ll * b + 0), w1);
-      const float y = lerp2(__ldg(o.pos + 3ll * a + 1), w0, __ldg(o.pos + 3ll * b + 1), w1);
-      const float z = lerp2(__ldg(o.pos + 3ll * a + 2), w0, __ldg(o.pos + 3ll * b + 2), w1);
-      const float m = lerp2(ma, w0, mb, w1);
-      o.w_vert[vid] = make_float4(x, y, z, m);
-      o.w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
-      o.w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      o.owner[vid] = (int32_t)slot;
-      if (vid < o.cap_verts) {
-        o.tape_edges[2 * vid] = a;
-        o.tape_edges[2 * vid + 1] = b;
-        o.tape_runs[vid] = (int32_t)(lo + i);
-        o.verts_wt[3 * vid] = x; o.verts_wt[3 * vid + 1] = y; o.verts_wt[3 * vid + 2] = z;
-        o.msdf_wt[vid] = m;
-      }
-      if (vid < o.cap_verts_aug) {
-        // rows of verts_aug not referenced by faces_aug are zero (gshell_tets.py:423-427); a watertight vertex is
-        // referenced iff its mSDF is positive (every cut case keeps exactly the positive corners)
-        const bool used = m > 0.f;
-        o.verts_aug[3 * vid] = used ? x : 0.f;
-        o.verts_aug[3 * vid + 1] = used ? y : 0.f;
-        o.verts_aug[3 * vid + 2] = used ? z : 0.f;
-        o.msdf_aug[vid] = m;
-      }
-    }
-    o.tape_corners[slot] = (int32_t)vid;
-    o.tape_slots[lo + i] = (int32_t)slot;
-  }
-}
-
-__global__ void __launch_bounds__(kUniqueThreads, 2)
-unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
-              unsigned long long* __restrict__ scratch_keys, unsigned* __restrict__ scratch_vals,
-              DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start,
-              unsigned long long* __restrict__ status, unsigned long long* __restrict__ block_status, UniqueOut o) {
+// ---- kernel A: sort every group in place, count its distinct keys ------------------------------------------
+__global__ void __launch_bounds__(kUniqueThreads)
+group_sort_kernel(unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
+                  unsigned long long* __restrict__ scratch_keys, unsigned* __restrict__ scratch_vals,
+                  const DevCounters* __restrict__ ctr, const unsigned* __restrict__ group_start,
+                  unsigned* __restrict__ group_heads, unsigned* __restrict__ gblock_heads) {
   __shared__ __align__(16) unsigned long long s_key[kLocalSortCap];
   __shared__ unsigned s_val[kLocalSortCap];
-  __shared__ unsigned s_w[32];
-  __shared__ unsigned long long s_part[32];
-  __shared__ unsigned long long s_excl;
-  __shared__ unsigned s_group;
+  __shared__ unsigned s_cnt[kUniqueThreads / 32];
 
-  const unsigned t1 = ctr->work_tri;
-  const int64_t ncorn = 3ll * t1 + 4ll * ctr->work_quad;
+  const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
   const unsigned ngroups_used = (unsigned)((ncorn + kSortGroup - 1) / kSortGroup);
-  if (threadIdx.x == 0) s_group = atomicAdd(&ctr->ticket_unique, 1u);  // groups are numbered in CTA start order
-  __syncthreads();
-  const unsigned g = s_group;
+  const unsigned g = blockIdx.x;
   if (g >= ngroups_used) return;
   const unsigned lo = __ldcg(group_start + g);
   const unsigned hi = (g + 1 == ngroups_used) ? (unsigned)ncorn : __ldcg(group_start + g + 1);
   const unsigned n = hi > lo ? hi - lo : 0u;  // 0: this group's positions belong to a bucket that started earlier
-
+  if (n == 0u) {
+    if (threadIdx.x == 0) group_heads[g] = 0u;
+    return;
+  }
+  unsigned nhead = 0;
   if (n <= (unsigned)kLocalSortCap) {
     if (n > 4u * kUniqueThreads) sort_group_regs<8>(keys + lo, vals + lo, n, s_key, s_val);
     else if (n > 2u * kUniqueThreads) sort_group_regs<4>(keys + lo, vals + lo, n, s_key, s_val);
-    else if (n > 0u) sort_group_regs<2>(keys + lo, vals + lo, n, s_key, s_val);
-    number_and_emit(s_key, s_val, n, lo, g, ngroups_used, t1, ncorn, ctr, status, block_status, o, s_w, s_part, &s_excl);
+    else sort_group_regs<2>(keys + lo, vals + lo, n, s_key, s_val);
+    for (unsigned i = threadIdx.x; i < n; i += kUniqueThreads) {
+      const unsigned long long k = s_key[i];
+      keys[lo + i] = k;
+      vals[lo + i] = s_val[i];
+      nhead += (i == 0 || k != s_key[i - 1]);  // a group starts on a bucket boundary: i == 0 is always a head
+    }
   } else {
-    // oversized group: same network on a padded copy in global scratch (exact, slower; only degenerate inputs)
+    // oversized group: classic network on a padded copy in global scratch (exact, slower; only degenerate inputs)
     unsigned npow2 = 2;
     while (npow2 < n) npow2 <<= 1;
     unsigned long long* gk = scratch_keys + 2ull * lo;  // padded copies of disjoint ranges cannot overlap at 2*lo
@@ -407,7 +278,150 @@ unique_kernel(const unsigned long long* __restrict__ keys, const unsigned* __res
     }
     __syncthreads();
     bitonic_sort_block(gk, gv, npow2);
-    number_and_emit(gk, gv, n, lo, g, ngroups_used, t1, ncorn, ctr, status, block_status, o, s_w, s_part, &s_excl);
+    for (unsigned i = threadIdx.x; i < n; i += kUniqueThreads) {
+      const unsigned long long k = gk[i];
+      keys[lo + i] = k;
+      vals[lo + i] = gv[i];
+      nhead += (i == 0 || k != gk[i - 1]);
+    }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) nhead += __shfl_xor_sync(0xffffffffu, nhead, of);
+  if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = nhead;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < kUniqueThreads / 32; ++w) tot += s_cnt[w];
+    group_heads[g] = tot;
+    if (tot) atomicAdd(gblock_heads + (g >> 8), tot);
+  }
+}
+
+// ---- kernel B: number the runs (vertex ids), emit everything that hangs off a vertex -----------------------
+__global__ void __launch_bounds__(256)
+vertex_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned long long* __restrict__ keys,
+                   const unsigned* __restrict__ vals, DevCounters* __restrict__ ctr,
+                   const unsigned* __restrict__ group_start, const unsigned* __restrict__ group_heads,
+                   const unsigned* __restrict__ gblock_heads, int key_bits, float4* __restrict__ w_vert,
+                   float4* __restrict__ w_acc, int32_t* __restrict__ owner) {
+  constexpr int WARPS = 256 / 32;
+  __shared__ unsigned s_w[WARPS];
+  __shared__ unsigned s_part[WARPS];
+
+  const unsigned t1 = ctr->work_tri;
+  const int64_t ncorn = 3ll * t1 + 4ll * ctr->work_quad;
+  const unsigned ngroups_used = (unsigned)((ncorn + kSortGroup - 1) / kSortGroup);
+  const unsigned g = blockIdx.x;
+  if (g >= ngroups_used) return;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned lo = __ldcg(group_start + g);
+  const unsigned hi = (g + 1 == ngroups_used) ? (unsigned)ncorn : __ldcg(group_start + g + 1);
+  const unsigned n = hi > lo ? hi - lo : 0u;
+  const bool is_last = g + 1 == ngroups_used;
+  if (n == 0u && !is_last) return;
+
+  // vertices of all earlier groups: the earlier groups of this 256-block + the earlier blocks (plain loads: the sort
+  // kernel has completed)
+  const unsigned blk256 = g >> 8, first = blk256 << 8;
+  unsigned part = 0;
+  if (first + threadIdx.x < g) part = __ldcg(group_heads + first + threadIdx.x);
+  for (unsigned bq = threadIdx.x; bq < blk256; bq += 256) part += __ldcg(gblock_heads + bq);
+
+  // heads of this thread's keys: blocked, ipt consecutive keys per thread
+  const unsigned ipt = (n + 255) / 256;
+  const unsigned i0 = threadIdx.x * ipt;
+  const unsigned long long* __restrict__ k = keys + lo;
+  unsigned long long prev = (i0 > 0 && i0 - 1 < n) ? k[i0 - 1] : 0ull;
+  unsigned nhead = 0;
+  for (unsigned j = 0; j < ipt; ++j) {
+    const unsigned i = i0 + j;
+    if (i < n) {
+      const unsigned long long key = k[i];
+      nhead += (i == 0 || key != prev);
+      prev = key;
+    }
+  }
+  unsigned incl = nhead;
+#pragma unroll
+  for (int of = 1; of < 32; of <<= 1) {
+    const unsigned nb = __shfl_up_sync(0xffffffffu, incl, of);
+    if (lane >= (unsigned)of) incl += nb;
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
+  if (lane == 31) s_w[warp] = incl;
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  unsigned wpre = 0, total = 0, excl = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    if (w < (int)warp) wpre += s_w[w];
+    total += s_w[w];
+    excl += s_part[w];
+  }
+  const d3h_forward_args& a = blk->a;
+  const int64_t cap_verts = a.cap_verts, cap_verts_aug = a.cap_verts_aug;
+  if (is_last && threadIdx.x == 0) {
+    const unsigned nv = excl + total;
+    ctr->n_verts = nv;
+    if ((int64_t)nv <= cap_verts) a.tape_runs[nv] = (int32_t)ncorn;
+  }
+  if (n == 0u) return;
+
+  const float* __restrict__ pos = a.pos;
+  const float* __restrict__ sdf = a.sdf;
+  const float* __restrict__ msdf = a.msdf;
+  const int msdf_negate = a.msdf_negate;
+  int32_t* __restrict__ tape_corners = a.tape_corners;
+  int32_t* __restrict__ tape_slots = a.tape_slots;
+  int64_t vid = (int64_t)excl + wpre + (incl - nhead) - 1;  // id of the run that precedes this thread's keys
+  const unsigned long long bmask = (1ull << key_bits) - 1;
+  prev = (i0 > 0 && i0 - 1 < n) ? k[i0 - 1] : 0ull;
+  for (unsigned j = 0; j < ipt; ++j) {
+    const unsigned i = i0 + j;
+    if (i >= n) break;
+    const unsigned long long key = k[i];
+    // value = (class, 4*class_rank + corner) -> corner slot in the [3*T1 | 4*T2] layout
+    const unsigned val = vals[lo + i];
+    const unsigned r4 = val & 0x7fffffffu;
+    const int64_t slot = (val >> 31) ? (3ll * t1 + r4) : (3ll * (r4 >> 2) + (r4 & 3u));
+    if (i == 0 || key != prev) {
+      ++vid;
+      const int ea = (int)(key >> key_bits), eb = (int)(key & bmask);
+      // zero-crossing interpolation, gshell_tets.py:291-303 (op order: SURVEY A.4)
+      float w0, w1, dd;
+      crossing_weights(__ldg(sdf + ea), __ldg(sdf + eb), w0, w1, dd);
+      float ma = __ldg(msdf + ea), mb = __ldg(msdf + eb);
+      if (msdf_negate) { ma = -ma; mb = -mb; }
+      const float x = lerp2(__ldg(pos + 3ll * ea + 0), w0, __ldg(pos + 3ll * eb + 0), w1);
+      const float y = lerp2(__ldg(pos + 3ll * ea + 1), w0, __ldg(pos + 3ll * eb + 1), w1);
+      const float z = lerp2(__ldg(pos + 3ll * ea + 2), w0, __ldg(pos + 3ll * eb + 2), w1);
+      const float m = lerp2(ma, w0, mb, w1);
+      w_vert[vid] = make_float4(x, y, z, m);
+      w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      owner[vid] = (int32_t)slot;
+      if (vid < cap_verts) {
+        a.tape_edges[2 * vid] = ea;
+        a.tape_edges[2 * vid + 1] = eb;
+        a.tape_runs[vid] = (int32_t)(lo + i);
+        a.verts_wt[3 * vid] = x; a.verts_wt[3 * vid + 1] = y; a.verts_wt[3 * vid + 2] = z;
+        a.msdf_wt[vid] = m;
+      }
+      if (vid < cap_verts_aug) {
+        // rows of verts_aug not referenced by faces_aug are zero (gshell_tets.py:423-427); a watertight vertex is
+        // referenced iff its mSDF is positive (every cut case keeps exactly the positive corners)
+        const bool used = m > 0.f;
+        a.verts_aug[3 * vid] = used ? x : 0.f;
+        a.verts_aug[3 * vid + 1] = used ? y : 0.f;
+        a.verts_aug[3 * vid + 2] = used ? z : 0.f;
+        a.msdf_aug[vid] = m;
+      }
+    }
+    prev = key;
+    tape_corners[slot] = (int32_t)vid;
+    tape_slots[lo + i] = (int32_t)slot;
   }
 }
 
@@ -427,17 +441,15 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
                                                                           ws.msd_fill,
                                                                           key_bits + msd_shift_for(a.n_grid));
   }
-  UniqueOut o;
-  o.key_bits = key_bits;
-  o.pos = a.pos; o.sdf = a.sdf; o.msdf = a.msdf; o.msdf_negate = a.msdf_negate;
-  o.tape_corners = a.tape_corners; o.tape_edges = a.tape_edges; o.tape_slots = a.tape_slots; o.tape_runs = a.tape_runs;
-  o.cap_verts = a.cap_verts; o.cap_verts_aug = a.cap_verts_aug;
-  o.w_vert = ws.vert; o.w_acc = reinterpret_cast<float4*>(ws.acc); o.owner = ws.owner;
-  o.verts_wt = a.verts_wt; o.msdf_wt = a.msdf_wt; o.verts_aug = a.verts_aug; o.msdf_aug = a.msdf_aug;
-  ProfScope ps(K_UNIQUE, stream);
-  unique_kernel<<<(unsigned)ws.ngroups, kUniqueThreads, 0, stream>>>(ws.keys2, ws.vals2, ws.keys_scratch,
-                                                                      ws.vals_scratch, ws.ctr, ws.group_start,
-                                                                      ws.st_unique, ws.st_ublock, o);
+  {
+    ProfScope ps(K_GROUP_SORT, stream);
+    group_sort_kernel<<<(unsigned)ws.ngroups, kUniqueThreads, 0, stream>>>(
+        ws.keys2, ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.group_start, ws.group_heads, ws.gblock_heads);
+  }
+  ProfScope ps(K_VERTEX_EMIT, stream);
+  vertex_emit_kernel<<<(unsigned)ws.ngroups, 256, 0, stream>>>(ws.blk, ws.keys2, ws.vals2, ws.ctr, ws.group_start,
+                                                               ws.group_heads, ws.gblock_heads, key_bits, ws.vert,
+                                                               reinterpret_cast<float4*>(ws.acc), ws.owner);
 }
 
 }  // namespace d3h

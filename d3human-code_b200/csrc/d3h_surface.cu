@@ -63,12 +63,14 @@ __device__ __forceinline__ int cut_case(bool quad, float m0, float m1, float m2,
 }
 
 __global__ void __launch_bounds__(kPolyThreads)
-poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __restrict__ ctr,
-                  const int32_t* __restrict__ corners, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
-                  unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_excl, int64_t* __restrict__ faces_wt,
-                  int64_t cap_faces_wt, UvParams uvp, d3h_counts* __restrict__ counts_dev,
-                  d3h_counts* __restrict__ counts_mapped, int64_t seq) {
+poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
+                  DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
+                  unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_excl, UvParams uvp,
+                  d3h_counts* __restrict__ counts_dev) {
   constexpr int WARPS = kPolyThreads / 32;
+  const int32_t* __restrict__ corners = blk->a.tape_corners;
+  int64_t* __restrict__ faces_wt = blk->a.faces_wt;
+  const int64_t cap_faces_wt = blk->a.cap_faces_wt;
   __shared__ unsigned s_cnt[6][WARPS];
   __shared__ unsigned s_last;
   __shared__ unsigned long long s_scan[3][32];
@@ -270,6 +272,8 @@ poly_faces_kernel(const d3h_tet_record* __restrict__ records, DevCounters* __res
     c.n_faces_aug = fa;
     c.bad_index = 0;
     c.overflow = (ctr->n_valid != t1 + t2) ? 1 : 0;  // record buffer overflowed: surface stages skipped
+    const int64_t seq = blk->a.seq;
+    d3h_counts* counts_mapped = blk->counts_mapped;
     c.seq = seq;
     c.reserved = 0;
     *counts_dev = c;
@@ -309,13 +313,18 @@ __device__ __forceinline__ float3 vertex_tangent(const float* __restrict__ w_acc
 }
 
 __global__ void __launch_bounds__(kPolyThreads)
-poly_cut_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* __restrict__ ctr,
-                const int32_t* __restrict__ corners, const float4* __restrict__ w_vert,
+poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
+                const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
-                const unsigned* __restrict__ poly_excl, float* __restrict__ verts_aug, float* __restrict__ v_tng_aug,
-                float* __restrict__ msdf_aug, int64_t cap_verts_aug, float* __restrict__ v_tng_wt, int64_t cap_verts,
-                int64_t* __restrict__ faces_aug, int64_t cap_faces_aug) {
+                const unsigned* __restrict__ poly_excl) {
   constexpr int WARPS = kPolyThreads / 32;
+  const int32_t* __restrict__ corners = blk->a.tape_corners;
+  float* __restrict__ verts_aug = blk->a.verts_aug;
+  float* __restrict__ v_tng_aug = blk->a.v_tng_aug;
+  float* __restrict__ msdf_aug = blk->a.msdf_aug;
+  float* __restrict__ v_tng_wt = blk->a.v_tng_wt;
+  int64_t* __restrict__ faces_aug = blk->a.faces_aug;
+  const int64_t cap_verts_aug = blk->a.cap_verts_aug, cap_verts = blk->a.cap_verts, cap_faces_aug = blk->a.cap_faces_aug;
   __shared__ unsigned s_cnt[6][WARPS];
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
   const int64_t npoly = (int64_t)t1 + t2;
@@ -413,8 +422,10 @@ poly_cut_kernel(const d3h_tet_record* __restrict__ records, const DevCounters* _
 }
 
 // Sizes of a call whose surface stages do not run at all (cap_valid_tets == 0: counting run).
-__global__ void publish_counts_kernel(const DevCounters* __restrict__ ctr, d3h_counts* __restrict__ counts_dev,
-                                      d3h_counts* __restrict__ counts_mapped, int64_t seq) {
+__global__ void publish_counts_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict__ ctr,
+                                      d3h_counts* __restrict__ counts_dev) {
+  const int64_t seq = blk->a.seq;
+  d3h_counts* counts_mapped = blk->counts_mapped;
   d3h_counts c;
   memset(&c, 0, sizeof(c));
   c.n_valid_tets = ctr->n_valid;
@@ -448,23 +459,19 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
     uvp.step = (uvp.nuv > 1) ? uvp.end / (float)(uvp.nuv - 1) : 0.f;
     uvp.pad = (float)(0.9 / (double)uvp.nuv);
   }
-  d3h_counts* mapped = mapped_counts_pointer(a.counts_host);
   if (ws.cap_tets <= 0) {
     ProfScope ps(K_POLY_FACES, stream);
-    publish_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, ws.counts, mapped, a.seq);
+    publish_counts_kernel<<<1, 1, 0, stream>>>(ws.blk, ws.ctr, ws.counts);
     return;
   }
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   {
     ProfScope ps(K_POLY_FACES, stream);
-    poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, a.tape_corners, ws.vert, ws.acc, ws.poly_cnt,
-                                                         ws.poly_excl, a.faces_wt, a.cap_faces_wt, uvp, ws.counts, mapped,
-                                                         a.seq);
+    poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(ws.blk, records, ws.ctr, ws.vert, ws.acc, ws.poly_cnt,
+                                                         ws.poly_excl, uvp, ws.counts);
   }
   ProfScope ps(K_POLY_CUT, stream);
-  poly_cut_kernel<<<nblk, kPolyThreads, 0, stream>>>(records, ws.ctr, a.tape_corners, ws.vert, ws.acc, ws.owner,
-                                                     ws.poly_excl, a.verts_aug, a.v_tng_aug, a.msdf_aug, a.cap_verts_aug,
-                                                     a.v_tng_wt, a.cap_verts, a.faces_aug, a.cap_faces_aug);
+  poly_cut_kernel<<<nblk, kPolyThreads, 0, stream>>>(ws.blk, records, ws.ctr, ws.vert, ws.acc, ws.owner, ws.poly_excl);
 }
 
 }  // namespace d3h

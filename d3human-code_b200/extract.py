@@ -257,9 +257,9 @@ LAUNCHES_BACKWARD = 1  # adjoint_kernel (the zero-fill of the dense gradients ri
 
 
 def _launches_forward(cap_tets: int, zero: bool) -> int:
-    """Kernels one d3h_extract_forward enqueues: prepare, classify, compact, [bucket_scan, partition, unique,
-    poly_faces, poly_cut | publish_counts] (+ zero_kernel when the gradient buffers are pre-zeroed)."""
-    return (4 if cap_tets <= 0 else 8) + (1 if zero else 0)
+    """Kernels one d3h_extract_forward enqueues: prepare, classify, compact, [bucket_scan, partition, group_sort,
+    vertex_emit, poly_faces, poly_cut | publish_counts] (+ zero_block_kernel when the gradient buffers are pre-zeroed)."""
+    return (4 if cap_tets <= 0 else 9) + (1 if zero else 0)
 
 
 # --------------------------------------------------------------------------------------------------
