@@ -7,10 +7,12 @@
 
 Workload (BASELINE.json configs[1]): 128^3 Kuhn tet grid (F=12,582,912, N=2,146,689), analytic capsule-union SDF +
 garment mSDF, hmSDF_Tets(type="cloth") forward + backward with upstream gradients on verts_aug and extra['msdf'].
-Each rank runs `--frames-per-rank` frames per step (default 2: 16 frames/step at 8 GPUs = configs[3]); a frame is one
-full extraction with its own per-frame tet-vertex offsets (seed = global frame index); sdf/msdf are shared, so their
-gradients accumulate over the rank's frames and are all-reduced (NCCL) with the summed offset gradient when N > 1.
-Weak scaling: per-GPU work is fixed.  value = N * frames_per_rank * F / (max-over-ranks device time per step).
+Each rank runs `--frames-per-rank` frames per step (default 16 = the configs[3] batch); a frame is one full extraction
+with its own per-frame tet-vertex offsets (seed = global frame index), all frames of a step go through ONE
+extract_frames() call (one autograd node, one library call per direction, frames spread over concurrent lanes).
+sdf/msdf are shared, so their gradients accumulate over the rank's frames (atomics) and are all-reduced (NCCL) when
+N > 1.  Weak scaling: per-GPU work is fixed.  value = N * frames_per_rank * F / (max-over-ranks device time per step).
+`single_call` reports the same frames through the drop-in class one call at a time (the reference's calling pattern).
 
 One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every key.
 """
@@ -42,7 +44,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=128, help="Kuhn grid resolution (128 = BASELINE configs[1])")
-    ap.add_argument("--frames-per-rank", type=int, default=2)
+    ap.add_argument("--frames-per-rank", type=int, default=16,
+                    help="frames per rank per step (BASELINE configs[3]: a batch of 16 video frames per step)")
+    ap.add_argument("--lanes", type=int, default=4, help="concurrent lanes the frames of a batch are spread over")
     ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -59,7 +63,8 @@ def make_inputs(res, field):
 
 def workload_name(args):
     return (f"configs[1]: {args.res}^3 Kuhn grid, {'capsule-union SDF + garment mSDF' if args.field == 'capsule' else 'sphere SDF + plane mSDF'}"
-            f", hmSDF_Tets(cloth) fwd+bwd, {args.frames_per_rank} frame(s)/rank/step with per-frame offsets")
+            f", hmSDF_Tets(cloth) semantics fwd+bwd, {args.frames_per_rank} frame(s)/rank/step with per-frame offsets "
+            f"(configs[3] batch) through extract_frames on {args.lanes} lanes")
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -189,58 +194,83 @@ def main():
     pos = [hp.to(dev).requires_grad_(True) for hp in host_pos]
 
     # dry run: shapes of the upstream gradients (constant across steps: inputs are fixed)
-    ups, counts = [], []
-    for p in pos:
-        verts, faces, _, _, v_tng, extra = hm(p, sdf, msdf, tets, "cloth")
-        g = torch.Generator(device=dev).manual_seed(1234)
-        ups.append((torch.randn(verts.shape, device=dev, generator=g), torch.randn(extra["msdf"].shape, device=dev, generator=g)))
-        counts.append(dict(E.last_counts()))
+    outs = E.extract_frames(pos, sdf, msdf, tets, types="cloth", lanes=args.lanes)
+    counts = [dict(c) for c in E.last_counts_frames()]
+    g = torch.Generator(device=dev).manual_seed(1234)
+    ups_v = [torch.randn(o[0].shape, device=dev, generator=g) for o in outs]
+    ups_m = [torch.randn(o[5]["msdf"].shape, device=dev, generator=g) for o in outs]
     c0 = counts[0]
-    balg = grids.surface_counts_bytes(F, N, c0["n_verts"], c0["n_verts_aug"], c0["n_faces_watertight"], c0["n_faces_aug"])
-    launches_per_frame = E._ExtractFn.last_launches + E.LAUNCHES_BACKWARD
+    balg = sum(grids.surface_counts_bytes(F, N, c["n_verts"], c["n_verts_aug"], c["n_faces_watertight"], c["n_faces_aug"])
+               for c in counts) / len(counts)
+    launches_per_step = E._ExtractFn.last_launches + E.LAUNCHES_BACKWARD * fpr
+    del outs
 
     def step():
+        """One training-step's worth of extraction on this rank: all frames forward (one library call, concurrent
+        lanes), then all frames backward (one library call); gradients of the shared sdf / msdf summed over the frames
+        by the kernels and over the ranks by NCCL."""
         sdf.grad = None
         msdf.grad = None
-        for p, (gv, gm) in zip(pos, ups):
+        for p in pos:
+            p.grad = None
+        outs = E.extract_frames(pos, sdf, msdf, tets, types="cloth", lanes=args.lanes)
+        torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v + ups_m)
+        if world > 1:
+            dist.all_reduce(sdf.grad)
+            dist.all_reduce(msdf.grad)
+
+    def single_call_step():
+        """The reference's own calling pattern: one drop-in call + backward per frame (hmsdf.py:548)."""
+        sdf.grad = None
+        msdf.grad = None
+        for p, gv, gm in zip(pos, ups_v, ups_m):
             p.grad = None
             verts, faces, _, _, v_tng, extra = hm(p, sdf, msdf, tets, "cloth")
             torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
-        if world > 1:
-            gp = pos[0].grad if fpr == 1 else torch.stack([p.grad for p in pos]).sum(0)
-            dist.all_reduce(gp)
-            dist.all_reduce(sdf.grad)
-            dist.all_reduce(msdf.grad)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        tmax = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        return float(tmax.item()) / steps
+
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    tmax = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / args.steps
+    ms_step = timed(step, args.steps)
     value = world * fpr * F / (ms_step * 1e-3)
 
-    # ---- per-kernel device time (CUDA events on the launching stream, recorded by the library) ----
+    # ---- the same frames through the drop-in class, one call + backward per frame (no batching, no lanes) ----
+    single = None
+    if world == 1:
+        k_single = max(3, min(args.steps, 50))
+        for _ in range(3):
+            single_call_step()
+        ms_single = timed(single_call_step, k_single) / fpr
+        single = {"ms_per_frame": ms_single, "value": F / (ms_single * 1e-3), "unit": UNIT, "steps": k_single,
+                  "note": "hmSDF_Tets()(...) + backward per frame, strictly serial on the host (the reference's calling pattern)"}
+
+    # ---- per-kernel device time (CUDA events on the launching stream, recorded by the library; one frame at a time so
+    # that every kernel is timed alone) ----
     prof = {}
     if rank == 0:
         _cabi.profile_enable(True)
-        for _ in range(args.profile_steps):
-            step() if world == 1 else [hm(p, sdf, msdf, tets, "cloth") for p in pos]
+        nprof = max(1, min(args.profile_steps, 128 // fpr))
+        for _ in range(nprof):
+            single_call_step()
         torch.cuda.synchronize()
         prof = _cabi.profile_read()
         _cabi.profile_enable(False)
@@ -254,7 +284,7 @@ def main():
         d_msdf = torch.empty_like(msdf)
         d_pos = [torch.empty_like(p) for p in pos]
         outs_host = None
-        k_e2e = max(3, min(args.steps, 30))
+        k_e2e = max(3, min(args.steps, 20))
 
         def e2e_step():
             nonlocal outs_host
@@ -265,17 +295,18 @@ def main():
                 dst.requires_grad_(True)
                 dst.grad = None
             h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
-            res = []
-            for dp, hp, (gv, gm) in zip(d_pos, host_pos, ups):
+            for dp, hp in zip(d_pos, host_pos):
                 dp.requires_grad_(False)
                 dp.copy_(hp, non_blocking=True)
                 dp.requires_grad_(True)
                 dp.grad = None
                 h2d += hp.numel() * 4
-                verts, faces, _, _, v_tng, extra = hm(dp, d_sdf, d_msdf, tets, "cloth")
-                torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
-                res.append((verts.detach(), faces, extra["msdf"].detach(), dp.grad))
-            res_flat = [t for r in res for t in r] + [d_sdf.grad, d_msdf.grad]
+            outs = E.extract_frames(d_pos, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
+            torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v + ups_m)
+            res_flat = []
+            for o, dp in zip(outs, d_pos):
+                res_flat += [o[0].detach(), o[1], o[5]["msdf"].detach(), dp.grad]
+            res_flat += [d_sdf.grad, d_msdf.grad]
             if outs_host is None:
                 outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_flat]
             for h, t in zip(outs_host, res_flat):
@@ -296,9 +327,9 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * fpr * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "steps": k_e2e, "ms_per_step": float(dt.item()) * 1e3,
-               "note": "hmSDF_Tets() called with inputs copied from pinned host memory each step (pos per frame, sdf, "
-                       "msdf); verts_aug, faces_aug, msdf and the three dense gradients copied back; static tet "
-                       "indices stay resident"}
+               "note": "extract_frames() with inputs copied from pinned host memory each step (pos per frame, sdf, "
+                       "msdf); per frame verts_aug, faces_aug, msdf and the dense pos gradient, plus the sdf / msdf "
+                       "gradients, copied back to pinned host memory; static tet indices stay resident"}
 
     if rank != 0:
         if world > 1:
@@ -331,7 +362,7 @@ def main():
             roofline = {"kernel": "classify_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": 16 * F, "us_per_launch": t * 1e6}
-    dev_ms_frame = sum(v[0] for v in prof.values()) / max(args.profile_steps * fpr, 1) if prof else None
+    dev_ms_frame = sum(v[0] for v in prof.values()) / max(nprof * fpr, 1) if prof else None
     path_roofline = {"algorithmic_bytes_per_frame": int(balg),
                      "achieved_GBps_step": balg * fpr / (ms_step * 1e-3) / 1e9,
                      "frac_step": balg * fpr / (ms_step * 1e-3) / 1e9 / peak,
@@ -362,9 +393,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "F": F, "N": N, "frames_per_step": world * fpr,
                        "counts_frame0": c0, "l2": "tet index stream is 16*F = %d MB > 126 MB L2; no explicit flush" % (16 * F // 1000000),
-                       "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
+                       "lanes": args.lanes, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches_per_frame * fpr * args.steps), "kernels": kern,
+            "single_call": single, "gpu_launches": int(launches_per_step * args.steps), "kernels": kern,
             "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:

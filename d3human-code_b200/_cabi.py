@@ -12,13 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 200
+VERSION = 300
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
-    "d3h_classify_range", "d3h_extract_from_records",
+    "d3h_extract_forward_batch", "d3h_extract_backward_batch", "d3h_classify_range", "d3h_extract_from_records",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_debug_table",
 )
 
@@ -93,6 +93,10 @@ def lib() -> C.CDLL:
     L.d3h_wait_counts.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.d3h_extract_backward.restype = C.c_int
     L.d3h_extract_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
+    L.d3h_extract_forward_batch.restype = C.c_int
+    L.d3h_extract_forward_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    L.d3h_extract_backward_batch.restype = C.c_int
+    L.d3h_extract_backward_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.d3h_classify_range.restype = C.c_int
     L.d3h_classify_range.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_from_records.restype = C.c_int

@@ -42,6 +42,46 @@ ProfScope::~ProfScope() {
 
 bool profiling_enabled() { return g_prof_on; }
 
+// ---- launch priorities ------------------------------------------------------------------------------
+int launch_priority(LaunchClass c) {
+  static int lo = 0, hi = 0;
+  static bool init = false;
+  if (!init) {
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; cudaGetLastError(); }
+    init = true;
+  }
+  return c == kLaunchStream ? lo : hi;  // numerically lower = scheduled first
+}
+
+// ---- lanes: internal streams the frames of a batch are spread over -----------------------------------------------
+constexpr int kMaxLanes = 8;
+constexpr int kMaxDevices = 16;
+struct LaneSet {
+  bool ready;
+  cudaStream_t lane[kMaxLanes];
+  cudaEvent_t fork, join[kMaxLanes];
+};
+static LaneSet g_lanes[kMaxDevices];
+static std::mutex g_lane_mu;
+
+static LaneSet* lanes_for_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lock(g_lane_mu);
+  LaneSet& ls = g_lanes[dev];
+  if (!ls.ready) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    for (int i = 0; i < kMaxLanes; ++i) {
+      if (cudaStreamCreateWithPriority(&ls.lane[i], cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&ls.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ls.ready = true;
+  }
+  return &ls;
+}
+
 static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets) {
@@ -100,18 +140,20 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
 // Device-visible alias of the caller's pinned counts buffer, or nullptr when the pointer is not mapped host memory
 // (then the counts are copied with cudaMemcpyAsync at the end of the call instead).  One driver query per new pointer.
 d3h_counts* mapped_counts_pointer(d3h_counts* host) {
-  static thread_local d3h_counts* last_host = nullptr;
-  static thread_local d3h_counts* last_dev = nullptr;
+  constexpr int kSlots = 64;  // direct-mapped on the 128-byte slot index: the frames of a batch use neighbouring slots
+  static thread_local d3h_counts* last_host[kSlots] = {nullptr};
+  static thread_local d3h_counts* last_dev[kSlots] = {nullptr};
   if (host == nullptr) return nullptr;
-  if (host == last_host) return last_dev;
+  const int slot = (int)((reinterpret_cast<uintptr_t>(host) >> 7) % kSlots);
+  if (host == last_host[slot]) return last_dev[slot];
   cudaPointerAttributes at;
   d3h_counts* dev = nullptr;
   if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
     dev = reinterpret_cast<d3h_counts*>(at.devicePointer);
   else
     cudaGetLastError();  // plain pageable memory: clear the sticky error of the query
-  last_host = host;
-  last_dev = dev;
+  last_host[slot] = host;
+  last_dev[slot] = dev;
   return dev;
 }
 
@@ -201,7 +243,7 @@ static std::mutex g_graph_mu;
 static std::vector<GraphEntry> g_graphs;
 static uint64_t g_graph_clock = 0;
 static int g_graph_state = -1;  // -1 unknown, 0 disabled (D3H_DISABLE_GRAPH=1), 1 enabled
-constexpr size_t kMaxGraphs = 12;
+constexpr size_t kMaxGraphs = 64;
 
 static void destroy_entry(GraphEntry& e) {
   cudaGraphExecDestroy(e.exec);
@@ -251,6 +293,12 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
     g_graph_state = (env && env[0] == '1') ? 0 : 1;
   }
   if (g_graph_state == 0 || profiling_enabled()) return -1;
+  {
+    // the caller is capturing this stream into its own graph: a graph launch cannot be captured, enqueue the kernels
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cap != cudaStreamCaptureStatusNone) return -1;
+  }
   if (a.counts_host && mapped_counts_pointer(a.counts_host) == nullptr) return -1;  // needs the trailing memcpy
   GraphKey key;
   memset(&key, 0, sizeof(key));
@@ -338,6 +386,99 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   return finish("d3h_extract_forward", a, ws, stream);
 }
 
+// A batch of independent extractions (video frames, or the cloth / body pair of one iteration): frame i runs on
+// internal lane i % lanes, the lanes fork from `stream` and join back into it, so for the caller the batch is ordered
+// like one call.  Frames that share a lane may share a workspace (they are serialised); frames on different lanes
+// must not.  Every frame publishes its own d3h_counts (args[i].counts_host / seq).
+extern "C" int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes,
+                                         d3h_stream_t s) {
+  if (!args || n_frames < 0 || lanes < 1) { set_error("d3h_extract_forward_batch: null args / bad sizes"); return D3H_E_BADARG; }
+  if (lanes > kMaxLanes) lanes = kMaxLanes;
+  if (lanes > n_frames) lanes = (int32_t)(n_frames > 0 ? n_frames : 1);
+  for (int64_t i = 0; i < n_frames; ++i) {
+    int rc = check_forward_args(&args[i], "d3h_extract_forward_batch");
+    if (rc) return rc;
+    for (int64_t j = 0; j < i; ++j)
+      if (args[j].workspace == args[i].workspace && (j % lanes) != (i % lanes)) {
+        set_error("d3h_extract_forward_batch: frames %lld and %lld share a workspace but run on different lanes",
+                  (long long)j, (long long)i);
+        return D3H_E_BADARG;
+      }
+  }
+  if (n_frames == 0) return D3H_OK;
+  if (n_frames == 1) return d3h_extract_forward(args, s);  // nothing to overlap: stay on the caller's stream
+  cudaStream_t stream = (cudaStream_t)s;
+  LaneSet* ls = lanes_for_current_device();
+  if (ls == nullptr) { set_error("d3h_extract_forward_batch: cannot create the lane streams"); return D3H_E_CUDA; }
+  cudaEventRecord(ls->fork, stream);
+  for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->lane[l], ls->fork, 0);
+  int rc = D3H_OK;
+  for (int64_t i = 0; i < n_frames; ++i) {
+    const d3h_forward_args* a = &args[i];
+    cudaStream_t lane = ls->lane[i % lanes];
+    Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+    if (launch_forward_graph(*a, ws, lane) != 0) {
+      launch_prepare(*a, ws, lane);
+      launch_forward_sequence(*a, ws, lane);
+    }
+    const int r = finish("d3h_extract_forward_batch", a, ws, lane);
+    if (r) rc = r;
+  }
+  for (int l = 0; l < lanes; ++l) {  // always join, also after an error: the caller's stream must not lose the lanes
+    cudaEventRecord(ls->join[l], ls->lane[l]);
+    cudaStreamWaitEvent(stream, ls->join[l], 0);
+  }
+  return rc;
+}
+
+static int check_backward_args(const d3h_backward_args* a, const char* who) {
+  if (!a) { set_error("%s: null argument struct", who); return D3H_E_BADARG; }
+  if (a->n_grid <= 0 || a->n_verts < 0 || a->n_tri_tets < 0 || a->n_quad_tets < 0 || !a->g_pos || !a->g_sdf ||
+      !a->pos || !a->sdf || !a->msdf) {
+    set_error("%s: null pointer or negative size", who);
+    return D3H_E_BADARG;
+  }
+  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->tape_slots || !a->tape_runs || !a->verts_wt || !a->msdf_wt)) {
+    set_error("%s: tape / saved outputs missing", who);
+    return D3H_E_BADARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(a->g_pos) | reinterpret_cast<uintptr_t>(a->g_sdf) |
+       reinterpret_cast<uintptr_t>(a->g_msdf)) & 15) {
+    set_error("%s: gradient buffers must be 16-byte aligned", who);
+    return D3H_E_BADARG;
+  }
+  return D3H_OK;
+}
+
+// Adjoints of a batch.  Gradient buffers may be shared between frames (sdf / msdf of a batch of video frames are the
+// same tensors): every frame accumulates with atomics, so a shared buffer ends up with the sum over the frames.  A
+// shared buffer must be zero on entry (grads_prezeroed = 1 on every frame that uses it).
+extern "C" int d3h_extract_backward_batch(const d3h_backward_args* args, int64_t n_frames, int32_t lanes,
+                                          d3h_stream_t s) {
+  if (!args || n_frames < 0 || lanes < 1) { set_error("d3h_extract_backward_batch: null args / bad sizes"); return D3H_E_BADARG; }
+  if (lanes > kMaxLanes) lanes = kMaxLanes;
+  if (lanes > n_frames) lanes = (int32_t)(n_frames > 0 ? n_frames : 1);
+  for (int64_t i = 0; i < n_frames; ++i) {
+    int rc = check_backward_args(&args[i], "d3h_extract_backward_batch");
+    if (rc) return rc;
+  }
+  if (n_frames == 0) return D3H_OK;
+  if (n_frames == 1) return d3h_extract_backward(args, s);
+  cudaStream_t stream = (cudaStream_t)s;
+  LaneSet* ls = lanes_for_current_device();
+  if (ls == nullptr) { set_error("d3h_extract_backward_batch: cannot create the lane streams"); return D3H_E_CUDA; }
+  cudaEventRecord(ls->fork, stream);
+  for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->lane[l], ls->fork, 0);
+  for (int64_t i = 0; i < n_frames; ++i) launch_backward(args[i], ls->lane[i % lanes]);
+  for (int l = 0; l < lanes; ++l) {
+    cudaEventRecord(ls->join[l], ls->lane[l]);
+    cudaStreamWaitEvent(stream, ls->join[l], 0);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d3h_extract_backward_batch: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}
+
 // stage 1 only: prepare + classify of [tet_begin, tet_end); the compact records land in `records_out`
 // (class ranks are local to the range) and the counts so far (n_valid/n_tri/n_quad) in `counts_dev_out`.
 __global__ void export_range_counts_kernel(const DevCounters* ctr, d3h_counts* out, int64_t seq) {
@@ -394,21 +535,8 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet
 }
 
 extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) {
-  if (!a) { set_error("d3h_extract_backward: null argument struct"); return D3H_E_BADARG; }
-  if (a->n_grid <= 0 || a->n_verts < 0 || a->n_tri_tets < 0 || a->n_quad_tets < 0 || !a->g_pos || !a->g_sdf ||
-      !a->pos || !a->sdf || !a->msdf) {
-    set_error("d3h_extract_backward: null pointer or negative size");
-    return D3H_E_BADARG;
-  }
-  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->tape_slots || !a->tape_runs || !a->verts_wt || !a->msdf_wt)) {
-    set_error("d3h_extract_backward: tape / saved outputs missing");
-    return D3H_E_BADARG;
-  }
-  if ((reinterpret_cast<uintptr_t>(a->g_pos) | reinterpret_cast<uintptr_t>(a->g_sdf) |
-       reinterpret_cast<uintptr_t>(a->g_msdf)) & 15) {
-    set_error("d3h_extract_backward: gradient buffers must be 16-byte aligned");
-    return D3H_E_BADARG;
-  }
+  int rc = check_backward_args(a, "d3h_extract_backward");
+  if (rc) return rc;
   launch_backward(*a, (cudaStream_t)s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_extract_backward: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }

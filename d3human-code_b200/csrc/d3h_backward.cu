@@ -57,7 +57,7 @@ void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope ps(K_ZERO, stream);
-  zero_block_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ws.blk, a.n_grid);
+  launch_k(zero_block_kernel, (unsigned)blocks, 256u, stream, kLaunchStream, ws.blk, a.n_grid);
 }
 
 void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n, cudaStream_t stream) {
@@ -79,7 +79,7 @@ void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n, cud
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope ps(K_ZERO, stream);
-  zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b0, n0, b1, n1, b2, n2, t0, tn0, t1, tn1, t2, tn2);
+  launch_k(zero_kernel, (unsigned)blocks, 256u, stream, kLaunchStream, b0, n0, b1, n1, b2, n2, t0, tn0, t1, tn1, t2, tn2);
 }
 
 // segmented (by key) inclusive suffix-sum inside a warp; lanes with equal key must be contiguous.
@@ -219,9 +219,9 @@ void launch_backward(const d3h_backward_args& a, cudaStream_t stream) {
   if (!a.grads_prezeroed) launch_zero_grads(a.g_pos, a.g_sdf, a.g_msdf, a.n_grid, stream);
   if (nv <= 0) return;
   ProfScope ps(K_ADJOINT, stream);
-  adjoint_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(
-      a.tape_edges, a.tape_corners, a.tape_slots, a.tape_runs, a.pos, a.sdf, a.msdf, a.msdf_negate, nv, a.n_tri_tets,
-      a.verts_wt, a.msdf_wt, a.g_verts_aug, a.g_msdf_aug, a.g_verts_wt, a.g_msdf_wt, a.g_pos, a.g_sdf, a.g_msdf);
+  launch_k(adjoint_kernel, (unsigned)((nv + 255) / 256), 256u, stream, kLaunchLatency, a.tape_edges, a.tape_corners,
+           a.tape_slots, a.tape_runs, a.pos, a.sdf, a.msdf, (int)a.msdf_negate, nv, a.n_tri_tets, a.verts_wt, a.msdf_wt,
+           a.g_verts_aug, a.g_msdf_aug, a.g_verts_wt, a.g_msdf_wt, a.g_pos, a.g_sdf, a.g_msdf);
 }
 
 }  // namespace d3h

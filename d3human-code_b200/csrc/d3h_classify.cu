@@ -102,7 +102,7 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
   blk.a = a;
   blk.counts_mapped = mapped_counts_pointer(a.counts_host);
   ProfScope ps(K_PREPARE, stream);
-  prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(blk, ws);
+  launch_k(prepare_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, blk, ws);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,33 +319,31 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   const int64_t nchunks = (n + kChunkTets - 1) / kChunkTets;
   const int64_t ntiles = (n + kTileTets - 1) / kTileTets;
   {
-    static int max_grid[2] = {0, 0};
+    // One-shot grid (a warp per 256-tet chunk, CTAs retire every few microseconds) at the lowest priority: measured as
+    // fast as a persistent grid (profiles/bench_stream.cu) and, unlike it, it leaves CTA slots to the latency-bound
+    // kernels of the frames running on the other lanes.
     const int mocc = a.watertight_template ? 0 : 1;
-    if (max_grid[mocc] == 0)
-      max_grid[mocc] = persistent_grid(mocc ? reinterpret_cast<const void*>(classify_kernel<true>)
-                                            : reinterpret_cast<const void*>(classify_kernel<false>), kClassifyThreads, 0);
-    int64_t nblocks = (nchunks * 32 + kClassifyThreads - 1) / kClassifyThreads;
-    if (nblocks > max_grid[mocc]) nblocks = max_grid[mocc];
+    const int64_t nblocks = (nchunks * 32 + kClassifyThreads - 1) / kClassifyThreads;
     ProfScope ps(K_CLASSIFY, stream);
     if (mocc)
-      classify_kernel<true><<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
-          ws.blk, a.tet_begin, a.tet_end, ws.occ_bits, ws.mocc_bits, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
+      launch_k(classify_kernel<true>, (unsigned)nblocks, kClassifyThreads, stream, kLaunchStream, ws.blk, a.tet_begin,
+               a.tet_end, ws.occ_bits, ws.mocc_bits, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
     else
-      classify_kernel<false><<<(unsigned)nblocks, kClassifyThreads, 0, stream>>>(
-          ws.blk, a.tet_begin, a.tet_end, ws.occ_bits, nullptr, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
+      launch_k(classify_kernel<false>, (unsigned)nblocks, kClassifyThreads, stream, kLaunchStream, ws.blk, a.tet_begin,
+               a.tet_end, ws.occ_bits, (const unsigned*)nullptr, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
   }
   const int64_t nwords = nchunks * kClassifyItems;  // every word of a visited chunk is written
   const int key_bits = key_bits_for(a.n_grid);
   const int msd_shift = msd_shift_for(a.n_grid);
   ProfScope ps(K_COMPACT, stream);
   if (emit_keys)
-    compact_kernel<true><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
-        ws.blk, ws.m1_words, ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records,
-        cap_records, key_bits, msd_shift, ws.keys, ws.vals, ws.msd_hist);
+    launch_k(compact_kernel<true>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
+             ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
+             msd_shift, ws.keys, ws.vals, ws.msd_hist);
   else
-    compact_kernel<false><<<(unsigned)ntiles, kCompactThreads, 0, stream>>>(
-        ws.blk, ws.m1_words, ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records,
-        cap_records, key_bits, msd_shift, nullptr, nullptr, nullptr);
+    launch_k(compact_kernel<false>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
+             ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
+             msd_shift, (unsigned long long*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,14 +404,14 @@ void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet
                          cudaStream_t stream) {
   {
     ProfScope ps(K_RANK_RECORDS, stream);
-    rank_records_kernel<<<1, 1024, 0, stream>>>(records, n_records, ws.ctr);
+    launch_k(rank_records_kernel, 1u, 1024u, stream, kLaunchLatency, records, n_records, ws.ctr);
   }
   int64_t blocks = (n_records + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 2) blocks = 148 * 2;
   ProfScope ps(K_COMPACT, stream);
-  keys_from_records_kernel<<<(unsigned)blocks, 256, 0, stream>>>(records, ws.ctr, key_bits_for(a.n_grid),
-                                                                 msd_shift_for(a.n_grid), ws.keys, ws.vals, ws.msd_hist);
+  launch_k(keys_from_records_kernel, (unsigned)blocks, 256u, stream, kLaunchLatency, records, ws.ctr,
+           key_bits_for(a.n_grid), msd_shift_for(a.n_grid), ws.keys, ws.vals, ws.msd_hist);
 }
 
 // ------------------------------------------------------------------------------------------------

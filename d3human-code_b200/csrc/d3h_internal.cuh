@@ -1,6 +1,8 @@
 // Internal (non-ABI) declarations shared by the translation units of libd3h_tets.so.
 #pragma once
 
+#include <cstring>
+
 #include "d3h_common.cuh"
 
 namespace d3h {
@@ -94,6 +96,32 @@ void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws
 void launch_backward(const d3h_backward_args& a, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
+
+// ---- launches with a scheduling priority ------------------------------------------------------------------------
+// Frames of a batch run on concurrent lanes (d3h_extract_forward_batch).  The O(surface) kernels are dependency-latency
+// bound and use a fraction of the SMs; the O(F) / O(N) streams are bandwidth bound and would occupy every CTA slot for
+// their whole duration.  Launching the streams at the lowest priority and everything else at the highest lets the block
+// scheduler slip the surface CTAs of one frame in between the retiring CTAs of another frame's stream, so the latency
+// chains hide under the HBM traffic.  The priority is a per-launch attribute (also recorded in captured graph nodes).
+enum LaunchClass { kLaunchStream = 0, kLaunchLatency = 1 };
+int launch_priority(LaunchClass c);
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, LaunchClass cls,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = launch_priority(cls);
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 d3h_counts* mapped_counts_pointer(d3h_counts* host);
 bool profiling_enabled();
 

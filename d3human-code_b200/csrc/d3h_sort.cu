@@ -432,24 +432,23 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
   if (capc <= 0) return;
   {
     ProfScope ps(K_BUCKET_SCAN, stream);
-    bucket_scan_kernel<<<(unsigned)ws.nscan_ctas, kScanThreads, 0, stream>>>(
-        ws.msd_hist, ws.msd_base, ws.msd_fill, ws.group_start, (int)ws.msd_bins, ws.ctr, ws.st_scan);
+    launch_k(bucket_scan_kernel, (unsigned)ws.nscan_ctas, (unsigned)kScanThreads, stream, kLaunchLatency, ws.msd_hist,
+             ws.msd_base, ws.msd_fill, ws.group_start, (int)ws.msd_bins, ws.ctr, ws.st_scan);
   }
   {
     ProfScope ps(K_PARTITION, stream);
-    partition_kernel<<<(unsigned)((capc + 255) / 256), 256, 0, stream>>>(ws.keys, ws.vals, ws.keys2, ws.vals2, ws.ctr,
-                                                                          ws.msd_fill,
-                                                                          key_bits + msd_shift_for(a.n_grid));
+    launch_k(partition_kernel, (unsigned)((capc + 255) / 256), 256u, stream, kLaunchLatency, ws.keys, ws.vals, ws.keys2,
+             ws.vals2, ws.ctr, ws.msd_fill, key_bits + msd_shift_for(a.n_grid));
   }
   {
     ProfScope ps(K_GROUP_SORT, stream);
-    group_sort_kernel<<<(unsigned)ws.ngroups, kUniqueThreads, 0, stream>>>(
-        ws.keys2, ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.group_start, ws.group_heads, ws.gblock_heads);
+    launch_k(group_sort_kernel, (unsigned)ws.ngroups, (unsigned)kUniqueThreads, stream, kLaunchLatency, ws.keys2,
+             ws.vals2, ws.keys_scratch, ws.vals_scratch, ws.ctr, ws.group_start, ws.group_heads, ws.gblock_heads);
   }
   ProfScope ps(K_VERTEX_EMIT, stream);
-  vertex_emit_kernel<<<(unsigned)ws.ngroups, 256, 0, stream>>>(ws.blk, ws.keys2, ws.vals2, ws.ctr, ws.group_start,
-                                                               ws.group_heads, ws.gblock_heads, key_bits, ws.vert,
-                                                               reinterpret_cast<float4*>(ws.acc), ws.owner);
+  launch_k(vertex_emit_kernel, (unsigned)ws.ngroups, 256u, stream, kLaunchLatency, ws.blk, ws.keys2, ws.vals2, ws.ctr,
+           ws.group_start, ws.group_heads, ws.gblock_heads, key_bits, ws.vert, reinterpret_cast<float4*>(ws.acc),
+           ws.owner);
 }
 
 }  // namespace d3h

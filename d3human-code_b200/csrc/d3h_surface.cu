@@ -461,17 +461,18 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
   }
   if (ws.cap_tets <= 0) {
     ProfScope ps(K_POLY_FACES, stream);
-    publish_counts_kernel<<<1, 1, 0, stream>>>(ws.blk, ws.ctr, ws.counts);
+    launch_k(publish_counts_kernel, 1u, 1u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.counts);
     return;
   }
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   {
     ProfScope ps(K_POLY_FACES, stream);
-    poly_faces_kernel<<<nblk, kPolyThreads, 0, stream>>>(ws.blk, records, ws.ctr, ws.vert, ws.acc, ws.poly_cnt,
-                                                         ws.poly_excl, uvp, ws.counts);
+    launch_k(poly_faces_kernel, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert,
+             ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts);
   }
   ProfScope ps(K_POLY_CUT, stream);
-  poly_cut_kernel<<<nblk, kPolyThreads, 0, stream>>>(ws.blk, records, ws.ctr, ws.vert, ws.acc, ws.owner, ws.poly_excl);
+  launch_k(poly_cut_kernel, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert, ws.acc,
+           ws.owner, ws.poly_excl);
 }
 
 }  // namespace d3h

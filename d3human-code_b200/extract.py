@@ -10,11 +10,13 @@ from __future__ import annotations
 import ctypes as C
 import weakref
 from dataclasses import dataclass, field
-from typing import Dict, Optional, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 
 from . import _cabi
+
+ctypes_array = Any
 
 _SLACK_NUM, _SLACK_DEN, _SLACK_ABS = 9, 8, 1024  # capacity = need * 9/8 + 1024 rows
 
@@ -69,8 +71,12 @@ def packed_tets(tet_fx4: torch.Tensor, n_grid: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
-# per-(device, F, N) plan: workspace + capacities predicted from the previous call
+# per-(device, F, N) plan: workspaces (one per lane) + capacities predicted from the previous call
 # --------------------------------------------------------------------------------------------------
+MAX_LANES = 8
+DEFAULT_LANES = 4
+
+
 @dataclass
 class _Plan:
     device: torch.device
@@ -82,27 +88,32 @@ class _Plan:
     cap_fw: int = 0
     cap_fa: int = 0
     seq: int = 0
-    workspace: Optional[torch.Tensor] = None
-    workspace_ptr: int = 0
+    workspaces: List[torch.Tensor] = field(default_factory=list)   # one per lane
+    workspace_bytes: int = 0
     workspace_cap_tets: int = -1
-    counts_host: Optional[torch.Tensor] = None
-    counts_ptr: int = 0
-    counts: Optional[_cabi.Counts] = None
-    args: _cabi.ForwardArgs = field(default_factory=_cabi.ForwardArgs)
-    bargs: _cabi.BackwardArgs = field(default_factory=_cabi.BackwardArgs)
+    counts_host: Optional[torch.Tensor] = None                     # pinned, one 128-byte slot per frame of a batch
+    counts: List[_cabi.Counts] = field(default_factory=list)
+    fargs: Dict[int, ctypes_array] = field(default_factory=dict)   # batch size -> (ForwardArgs * B)()
+    bargs: Dict[int, ctypes_array] = field(default_factory=dict)
 
-    def ensure_workspace(self):
+    def ensure(self, n_frames: int, lanes: int):
         if self.workspace_cap_tets != self.cap_tets:
             need = _cabi.lib().d3h_workspace_bytes(self.n_tets, self.n_grid, self.cap_tets)
-            if self.workspace is None or self.workspace.numel() < need:
-                self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-                self.workspace_ptr = self.workspace.data_ptr()
+            if need > self.workspace_bytes:
+                self.workspaces = []
+                self.workspace_bytes = need
             self.workspace_cap_tets = self.cap_tets
-        if self.counts_host is None:
+        while len(self.workspaces) < lanes:
+            self.workspaces.append(torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device))
+        if len(self.counts) < n_frames:
             # pinned host memory is device-mapped (UVA): the kernel that finalises the sizes writes them here directly
-            self.counts_host = torch.zeros(_cabi.COUNTS_WORDS, dtype=torch.int64).pin_memory()
-            self.counts_ptr = self.counts_host.data_ptr()
-            self.counts = _cabi.Counts.from_address(self.counts_ptr)
+            slots = max(n_frames, 2 * len(self.counts), 4)
+            self.counts_host = torch.zeros(slots * _cabi.COUNTS_WORDS, dtype=torch.int64).pin_memory()
+            base = self.counts_host.data_ptr()
+            self.counts = [_cabi.Counts.from_address(base + i * C.sizeof(_cabi.Counts)) for i in range(slots)]
+        if n_frames not in self.fargs:
+            self.fargs[n_frames] = (_cabi.ForwardArgs * n_frames)()
+            self.bargs[n_frames] = (_cabi.BackwardArgs * n_frames)()
 
 
 _plans: Dict[Tuple, _Plan] = {}
@@ -132,24 +143,24 @@ class ForwardResult:
     v_tng_wt: torch.Tensor
     msdf_wt: torch.Tensor
     faces_wt: torch.Tensor
-    tape: torch.Tensor          # int32 slab: edges (V,2) | corners (P) | slots (P) | runs (V+1)
+    tape: torch.Tensor          # int32 slab of the batch; this frame: edges (V,2) | corners (P) | slots (P) | runs (V+1)
+    fslab: torch.Tensor         # float slab of the batch (every float output is a view of it)
     tape_ptrs: Tuple[int, int, int, int]
     n_verts: int
     n_tri: int
     n_quad: int
     counts: Dict[str, int]
-    launches: int
-    zero_grads: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]]
 
     # views used by the tests
     @property
     def tape_edges(self):
-        return self.tape[:2 * self.n_verts].view(-1, 2)
+        o = (self.tape_ptrs[0] - self.tape.data_ptr()) // 4
+        return self.tape[o:o + 2 * self.n_verts].view(-1, 2)
 
     @property
     def tape_corners(self):
         p = 3 * self.n_tri + 4 * self.n_quad
-        o = (self.tape_ptrs[1] - self.tape_ptrs[0]) // 4
+        o = (self.tape_ptrs[1] - self.tape.data_ptr()) // 4
         return self.tape[o:o + p]
 
 
@@ -160,92 +171,132 @@ def _r4(n: int) -> int:
 
 _WAIT_TIMEOUT_US = 60_000_000
 
+#: kernels one forward extraction enqueues: prepare, classify, compact, bucket_scan, partition, group_sort, vertex_emit,
+#: poly_faces, poly_cut (+ zero_block_kernel when the gradient buffers are pre-zeroed); backward: adjoint_kernel
+LAUNCHES_FORWARD = 9
+LAUNCHES_BACKWARD = 1
 
-def forward_raw(pos: torch.Tensor, sdf: torch.Tensor, msdf: torch.Tensor, tets_i32: torch.Tensor, msdf_negate: bool,
-                watertight_template: bool, tet_range: Optional[Tuple[int, int]] = None,
-                want_grads: Tuple[bool, bool, bool] = (False, False, False)) -> ForwardResult:
-    """One forward extraction on the current stream.  Inputs: contiguous fp32 CUDA tensors, packed int32 tets.
 
-    The host blocks exactly once, on the sizes of the outputs (the reference blocks ~40 times per call): the kernel that
-    finalises them writes d3h_counts into pinned host memory ahead of the output-writing kernels and this function
-    spins on its sequence word, so the views below are built while the GPU is still finishing the call.
-    If `want_grads` names any input, the dense gradient buffers of the coming backward call are allocated here and
-    zero-filled by the forward call's tail (they are returned in `zero_grads`)."""
+def forward_frames_raw(frames, tets_i32: torch.Tensor, watertight_template: bool, lanes: int = DEFAULT_LANES,
+                       zero: Optional[List[Tuple[Optional[int], Optional[int], Optional[int]]]] = None):
+    """Forward extraction of a batch of frames in ONE library call (d3h_extract_forward_batch).
+
+    frames: [(pos, sdf, msdf, msdf_negate)] -- contiguous, 16-byte aligned fp32 CUDA tensors; tensors may be shared
+    between frames.  zero: per frame, the device pointers of dense gradient buffers (pos, sdf, msdf) that the call
+    should zero-fill for the coming backward pass (None = nothing).
+    Frames run on `lanes` concurrent lanes inside the library; the host blocks once per frame on that frame's sizes
+    (written to pinned host memory by the kernel that finalises them) -- the reference blocks ~40 times per frame.
+    Returns ([ForwardResult], launches)."""
     L = _cabi.lib()
-    dev = pos.device
-    n_grid, n_tets = pos.shape[0], tets_i32.shape[0]
+    B = len(frames)
+    pos0 = frames[0][0]
+    dev = pos0.device
+    n_grid, n_tets = pos0.shape[0], tets_i32.shape[0]
     plan = _plan_for(dev, n_tets, n_grid)
+    lanes = max(1, min(int(lanes), MAX_LANES, B))
     stream = torch.cuda.current_stream(dev).cuda_stream
     launches = 0
-    a = plan.args
+    tets_ptr = tets_i32.data_ptr()
+    wt = int(bool(watertight_template))
     with torch.cuda.device(dev):
-        zero_grads = None
-        if any(want_grads):
-            zero_grads = (torch.empty_like(pos), torch.empty_like(sdf), torch.empty_like(msdf) if want_grads[2] else None)
-            a.zero_g_pos, a.zero_g_sdf = zero_grads[0].data_ptr(), zero_grads[1].data_ptr()
-            a.zero_g_msdf = zero_grads[2].data_ptr() if zero_grads[2] is not None else None
-        else:
-            a.zero_g_pos = a.zero_g_sdf = a.zero_g_msdf = None
-        a.pos, a.sdf, a.msdf, a.tets = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), tets_i32.data_ptr()
-        a.n_grid, a.n_tets = n_grid, n_tets
-        a.tet_begin, a.tet_end = (0, n_tets) if tet_range is None else tet_range
-        a.msdf_negate, a.watertight_template = int(bool(msdf_negate)), int(bool(watertight_template))
         for attempt in range(6):
-            plan.ensure_workspace()
+            plan.ensure(B, lanes)
+            fa = plan.fargs[B]
             cv, cva, cfw, cfa, ct = plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets
-            # three slabs: float outputs, int64 faces, int32 tape
+            # three slabs for the whole batch: float outputs, int64 faces, int32 tape; frame i owns slice i of each
             o_vaug, o_tng, o_maug = 0, 3 * _r4(cva), 6 * _r4(cva)
             o_vwt = o_maug + _r4(cva)
             o_twt, o_mwt = o_vwt + 3 * _r4(cv), o_vwt + 6 * _r4(cv)
-            fslab = torch.empty(o_mwt + _r4(cv), dtype=torch.float32, device=dev)
-            islab = torch.empty(3 * (cfa + cfw), dtype=torch.int64, device=dev)
+            f_len = o_mwt + _r4(cv)
+            i_len = 3 * (cfa + cfw) + (3 * (cfa + cfw)) % 2      # keep every frame's int64 slice 16-byte aligned
             t_corn, t_slot = 2 * _r4(cv), 2 * _r4(cv) + 4 * ct
             t_runs = t_slot + 4 * ct
-            tape = torch.empty(t_runs + cv + 1, dtype=torch.int32, device=dev)
-            fp, ip, tp = fslab.data_ptr(), islab.data_ptr(), tape.data_ptr()
-            a.cap_valid_tets, a.cap_verts, a.cap_verts_aug, a.cap_faces_wt, a.cap_faces_aug = ct, cv, cva, cfw, cfa
-            a.verts_aug, a.v_tng_aug, a.msdf_aug = fp + 4 * o_vaug, fp + 4 * o_tng, fp + 4 * o_maug
-            a.verts_wt, a.v_tng_wt, a.msdf_wt = fp + 4 * o_vwt, fp + 4 * o_twt, fp + 4 * o_mwt
-            a.faces_aug, a.faces_wt = ip, ip + 24 * cfa
-            tape_ptrs = (tp, tp + 4 * t_corn, tp + 4 * t_slot, tp + 4 * t_runs)
-            a.tape_edges, a.tape_corners, a.tape_slots, a.tape_runs = tape_ptrs
-            a.workspace, a.workspace_bytes = plan.workspace_ptr, plan.workspace.numel()
-            a.counts_host = plan.counts_ptr
-            plan.seq += 1
-            a.seq = plan.seq
-            _cabi.check(L.d3h_extract_forward(C.byref(a), stream), "d3h_extract_forward")
-            launches += _launches_forward(ct, zero_grads is not None)
-            _cabi.check(L.d3h_wait_counts(plan.counts_ptr, plan.seq, _WAIT_TIMEOUT_US), "d3h_wait_counts")
-            c = plan.counts
-            fv, t1, t2, p, v, fa = c.n_valid_tets, c.n_tri_tets, c.n_quad_tets, c.n_corners, c.n_verts, c.n_faces_aug
-            if fv > ct:  # record buffer too small: surface stages were skipped, sizes below are not known yet
+            t_len = _r4(t_runs + cv + 1)
+            fslab = torch.empty(B * f_len, dtype=torch.float32, device=dev)
+            islab = torch.empty(B * i_len, dtype=torch.int64, device=dev)
+            tape = torch.empty(B * t_len, dtype=torch.int32, device=dev)
+            fp0, ip0, tp0 = fslab.data_ptr(), islab.data_ptr(), tape.data_ptr()
+            ws_bytes = plan.workspace_bytes
+            counts_base = plan.counts_host.data_ptr()
+            seq0 = plan.seq
+            plan.seq += B
+            tape_ptrs = []
+            for i, (pos, sdf, msdf, negate) in enumerate(frames):
+                a = fa[i]
+                fp, ip, tp = fp0 + 4 * i * f_len, ip0 + 8 * i * i_len, tp0 + 4 * i * t_len
+                a.pos, a.sdf, a.msdf, a.tets = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), tets_ptr
+                a.n_grid, a.n_tets, a.tet_begin, a.tet_end = n_grid, n_tets, 0, n_tets
+                a.msdf_negate, a.watertight_template = int(bool(negate)), wt
+                a.cap_valid_tets, a.cap_verts, a.cap_verts_aug, a.cap_faces_wt, a.cap_faces_aug = ct, cv, cva, cfw, cfa
+                a.verts_aug, a.v_tng_aug, a.msdf_aug = fp + 4 * o_vaug, fp + 4 * o_tng, fp + 4 * o_maug
+                a.verts_wt, a.v_tng_wt, a.msdf_wt = fp + 4 * o_vwt, fp + 4 * o_twt, fp + 4 * o_mwt
+                a.faces_aug, a.faces_wt = ip, ip + 24 * cfa
+                tps = (tp, tp + 4 * t_corn, tp + 4 * t_slot, tp + 4 * t_runs)
+                tape_ptrs.append(tps)
+                a.tape_edges, a.tape_corners, a.tape_slots, a.tape_runs = tps
+                z = zero[i] if zero is not None else (None, None, None)
+                a.zero_g_pos, a.zero_g_sdf, a.zero_g_msdf = z
+                a.workspace, a.workspace_bytes = plan.workspaces[i % lanes].data_ptr(), ws_bytes
+                a.counts_host = counts_base + i * 128
+                a.seq = seq0 + 1 + i
+                launches += (4 if ct <= 0 else LAUNCHES_FORWARD) + (1 if any(p is not None for p in z) else 0)
+            _cabi.check(L.d3h_extract_forward_batch(fa, B, lanes, stream), "d3h_extract_forward_batch")
+            sizes = []
+            grow_tets = grow_out = False
+            for i in range(B):
+                _cabi.check(L.d3h_wait_counts(counts_base + i * 128, seq0 + 1 + i, _WAIT_TIMEOUT_US), "d3h_wait_counts")
+                c = plan.counts[i]
+                fv, t1, t2, p, v, nfa = c.n_valid_tets, c.n_tri_tets, c.n_quad_tets, c.n_corners, c.n_verts, c.n_faces_aug
+                sizes.append((fv, t1, t2, p, v, nfa, tuple(c.bucket_polys)))
+                if fv > ct:
+                    grow_tets = True
+                elif v > cv or v + p > cva or t1 + 2 * t2 > cfw or nfa > cfa:
+                    grow_out = True
+            if grow_tets:  # record buffer too small: surface stages were skipped for some frame, its sizes are unknown
+                fv = max(s[0] for s in sizes)
+                t1, t2 = max(s[1] for s in sizes), max(s[2] for s in sizes)
+                p = 3 * t1 + 4 * t2
                 plan.cap_tets = _grow(fv)
                 # upper bounds that cannot overflow, so the next attempt is final
                 plan.cap_v, plan.cap_va = max(cv, p), max(cva, 2 * p)
                 plan.cap_fw, plan.cap_fa = max(cfw, t1 + 2 * t2), max(cfa, 2 * t1 + 4 * t2)
                 continue
-            va, fw = v + p, t1 + 2 * t2
-            if v > cv or va > cva or fw > cfw or fa > cfa:
+            if grow_out:
+                v, va = max(s[4] for s in sizes), max(s[4] + s[3] for s in sizes)
+                fw, nfa = max(s[1] + 2 * s[2] for s in sizes), max(s[5] for s in sizes)
                 plan.cap_v, plan.cap_va = max(cv, _grow(v)), max(cva, _grow(va))
-                plan.cap_fw, plan.cap_fa = max(cfw, _grow(fw)), max(cfa, _grow(fa))
+                plan.cap_fw, plan.cap_fa = max(cfw, _grow(fw)), max(cfa, _grow(nfa))
                 continue
             break
         else:  # pragma: no cover
-            raise RuntimeError("d3h_extract_forward: capacities did not converge")
-        bucket_polys = tuple(c.bucket_polys)
+            raise RuntimeError("d3h_extract_forward_batch: capacities did not converge")
         # next call: predict from this call's sizes (the surface moves slowly between training iterations)
+        fv = max(s[0] for s in sizes)
+        v, va = max(s[4] for s in sizes), max(s[4] + s[3] for s in sizes)
+        fw, nfa = max(s[1] + 2 * s[2] for s in sizes), max(s[5] for s in sizes)
         plan.cap_tets = max(_grow(fv), min(plan.cap_tets, 2 * _grow(fv)))
         plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va)
-        plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw), _shrink(plan.cap_fa, fa)
+        plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw), _shrink(plan.cap_fa, nfa)
         ast = torch.as_strided
-        res = ForwardResult(
-            ast(fslab, (va, 3), (3, 1), o_vaug), ast(fslab, (va, 3), (3, 1), o_tng), ast(fslab, (va,), (1,), o_maug),
-            ast(islab, (fa, 3), (3, 1), 0), ast(fslab, (v, 3), (3, 1), o_vwt), ast(fslab, (v, 3), (3, 1), o_twt),
-            ast(fslab, (v,), (1,), o_mwt), ast(islab, (fw, 3), (3, 1), 3 * cfa), tape, tape_ptrs, v, t1, t2,
-            dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
-                 n_faces_watertight=fw, n_faces_aug=fa, bucket_polys=bucket_polys),
-            launches, zero_grads)
-    return res
+        results = []
+        for i, (fv, t1, t2, p, v, nfa, buckets) in enumerate(sizes):
+            va, fw = v + p, t1 + 2 * t2
+            fo, io = i * f_len, i * i_len
+            results.append(ForwardResult(
+                ast(fslab, (va, 3), (3, 1), fo + o_vaug), ast(fslab, (va, 3), (3, 1), fo + o_tng),
+                ast(fslab, (va,), (1,), fo + o_maug), ast(islab, (nfa, 3), (3, 1), io),
+                ast(fslab, (v, 3), (3, 1), fo + o_vwt), ast(fslab, (v, 3), (3, 1), fo + o_twt),
+                ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa), tape, fslab,
+                tape_ptrs[i], v, t1, t2,
+                dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
+                     n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=buckets)))
+    return results, launches
+
+
+def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template) -> ForwardResult:
+    """One forward extraction without autograd (tests, profiling scripts)."""
+    res, _ = forward_frames_raw([(pos, sdf, msdf, msdf_negate)], tets_i32, watertight_template, lanes=1)
+    return res[0]
 
 
 def _shrink(cap: int, need: int) -> int:
@@ -253,100 +304,136 @@ def _shrink(cap: int, need: int) -> int:
     return g if (cap < g or cap > 2 * g) else cap
 
 
-LAUNCHES_BACKWARD = 1  # adjoint_kernel (the zero-fill of the dense gradients rides on the forward call)
-
-
-def _launches_forward(cap_tets: int, zero: bool) -> int:
-    """Kernels one d3h_extract_forward enqueues: prepare, classify, compact, [bucket_scan, partition, group_sort,
-    vertex_emit, poly_faces, poly_cut | publish_counts] (+ zero_block_kernel when the gradient buffers are pre-zeroed)."""
-    return (4 if cap_tets <= 0 else 9) + (1 if zero else 0)
-
-
 # --------------------------------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------------------------------
-class _ExtractFn(torch.autograd.Function):
-    """forward: (pos, sdf, msdf) -> 7 float outputs + 2 index outputs; backward: dense grads for pos / sdf / msdf.
+_OUTS_PER_FRAME = 8   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, faces_aug, faces_wt
 
-    Differentiable: verts_aug, msdf (augmented, stop-grad coefficients), vertices_watertight, msdf_watertight.
+
+class _ExtractFn(torch.autograd.Function):
+    """A batch of frames as ONE autograd node.
+
+    forward : (spec, tets_i32, *unique input tensors) -> 8 tensors per frame (6 float + 2 index outputs)
+    backward: dense gradients for every input tensor that needs one; a tensor shared by several frames (sdf / msdf of a
+              batch of video frames, everything but msdf for the cloth / body pair) receives the sum over the frames.
+
+    Differentiable outputs: verts_aug, msdf (augmented, stop-grad coefficients), vertices_watertight, msdf_watertight.
     v_tng_* are returned for API parity but are not differentiated (the reference's own training never consumes
     them, hmsdf.py:454,548); asking for their gradient raises instead of silently returning zeros.
     """
 
     @staticmethod
-    def forward(ctx, pos, sdf, msdf, tets_i32, msdf_negate, watertight_template):
-        need = ctx.needs_input_grad
-        want = (need[0] or need[1] or need[2], need[0] or need[1] or need[2], bool(need[2]) and not msdf_negate)
-        r = forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template, want_grads=want)
-        ctx.save_for_backward(pos, sdf, msdf, r.tape, r.verts_wt, r.msdf_wt)
-        ctx.meta = (r.n_verts, r.n_tri, r.n_quad, bool(msdf_negate), tets_i32.shape[0], r.tape_ptrs)
-        ctx.zero_grads = r.zero_grads
+    def forward(ctx, spec, tets_i32, *tensors):
+        frame_ids, watertight_template, lanes = spec      # frame_ids: [(pos_idx, sdf_idx, msdf_idx, negate)]
+        need = ctx.needs_input_grad[2:]
+        any_grad = any(need)
+        gbufs: List[Optional[torch.Tensor]] = [None] * len(tensors)
+        zero = None
+        if any_grad:
+            # dense gradient buffers of the coming backward call: allocated here, zero-filled by the tail of the
+            # forward call of the first frame that uses them (HBM is idle behind the latency-bound surface kernels)
+            zero, zeroed = [], set()
+            for (pi, si, mi, negate) in frame_ids:
+                z = []
+                for idx, wanted in ((pi, True), (si, True), (mi, need[mi] and not negate)):
+                    if not wanted:
+                        z.append(None)
+                        continue
+                    if gbufs[idx] is None:
+                        gbufs[idx] = torch.empty_like(tensors[idx])
+                    if idx in zeroed:
+                        z.append(None)
+                    else:
+                        zeroed.add(idx)
+                        z.append(gbufs[idx].data_ptr())
+                zero.append(tuple(z))
+        frames = [(tensors[pi], tensors[si], tensors[mi], negate) for (pi, si, mi, negate) in frame_ids]
+        results, launches = forward_frames_raw(frames, tets_i32, watertight_template, lanes, zero)
+        r0 = results[0]
+        ctx.save_for_backward(*tensors, r0.tape, r0.fslab)   # the slabs hold the tape and verts_wt / msdf_wt of all frames
+        ctx.meta = (frame_ids, tets_i32.shape[0], [(r.n_verts, r.n_tri, r.n_quad, r.tape_ptrs, r.verts_wt.data_ptr(),
+                                                      r.msdf_wt.data_ptr()) for r in results], lanes)
+        ctx.gbufs = gbufs if any_grad else None
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(r.faces_aug, r.faces_wt)
-        _ExtractFn.last_counts = r.counts
-        _ExtractFn.last_launches = r.launches
-        return r.verts_aug, r.v_tng_aug, r.msdf_aug, r.verts_wt, r.v_tng_wt, r.msdf_wt, r.faces_aug, r.faces_wt
+        flat = []
+        nondiff = []
+        for r in results:
+            flat += [r.verts_aug, r.v_tng_aug, r.msdf_aug, r.verts_wt, r.v_tng_wt, r.msdf_wt, r.faces_aug, r.faces_wt]
+            nondiff += [r.faces_aug, r.faces_wt]
+        ctx.mark_non_differentiable(*nondiff)
+        _ExtractFn.last_counts = [r.counts for r in results]
+        _ExtractFn.last_launches = launches
+        return tuple(flat)
 
     @staticmethod
-    def backward(ctx, g_verts_aug, g_tng_aug, g_msdf_aug, g_verts_wt, g_tng_wt, g_msdf_wt, _gfa, _gfw):
-        if g_tng_aug is not None or g_tng_wt is not None:
-            raise NotImplementedError(
-                "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
-                "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
-        pos, sdf, msdf, tape, verts_wt, msdf_wt = ctx.saved_tensors
-        n_verts, n_tri, n_quad, negate, n_tets, tape_ptrs = ctx.meta
-        zg, ctx.zero_grads = ctx.zero_grads, None  # the pre-zeroed buffers serve ONE backward pass
-        g_pos, g_sdf, g_msdf = backward_raw(pos, sdf, msdf, tape_ptrs, verts_wt, msdf_wt, n_verts, n_tri, n_quad,
-                                            negate, n_tets, g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt,
-                                            want_msdf=ctx.needs_input_grad[2] and not negate, prezeroed=zg)
-        return g_pos, g_sdf, g_msdf, None, None, None
+    def backward(ctx, *grads):
+        frame_ids, n_tets, metas, lanes = ctx.meta
+        saved = ctx.saved_tensors
+        tensors = saved[:-2]
+        need = ctx.needs_input_grad[2:]
+        gbufs, ctx.gbufs = ctx.gbufs, None       # the pre-zeroed buffers serve ONE backward pass
+        out = backward_frames_raw(tensors, frame_ids, n_tets, metas, grads, need, gbufs, lanes)
+        return (None, None) + tuple(out)
 
 
-def backward_raw(pos, sdf, msdf, tape_ptrs, verts_wt, msdf_wt, n_verts, n_tri, n_quad, negate, n_tets,
-                 g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt, want_msdf=True, prezeroed=None):
+def backward_frames_raw(tensors, frame_ids, n_tets, metas, grads, need, gbufs, lanes):
+    """Adjoints of a batch in ONE library call.  grads: 8 upstream gradients per frame (None = zero).
+    Returns one dense gradient (or None) per input tensor."""
     L = _cabi.lib()
-    dev = pos.device
-    n_grid = pos.shape[0]
+    dev = tensors[0].device
+    n_grid = tensors[frame_ids[0][0]].shape[0]
     plan = _plan_for(dev, n_tets, n_grid)
-
-    def ptr(t, shape):
-        if t is None:
-            return None, None
-        if t.dtype != torch.float32 or not t.is_contiguous():
-            t = t.contiguous().float()
-        assert tuple(t.shape) == shape, (tuple(t.shape), shape)
-        return t, t.data_ptr()
-
-    va = n_verts + 3 * n_tri + 4 * n_quad
+    B = len(frame_ids)
+    plan.ensure(B, 1)
+    ba = plan.bargs[B]
     with torch.cuda.device(dev):
-        g_verts_aug, p_gva = ptr(g_verts_aug, (va, 3))
-        g_msdf_aug, p_gma = ptr(g_msdf_aug, (va,))
-        g_verts_wt, p_gvw = ptr(g_verts_wt, (n_verts, 3))
-        g_msdf_wt, p_gmw = ptr(g_msdf_wt, (n_verts,))
-        if prezeroed is not None:
-            g_pos, g_sdf, g_msdf = prezeroed
-            if not want_msdf:
-                g_msdf = None
-            elif g_msdf is None:
-                g_msdf = torch.zeros_like(msdf)
-        else:
-            g_pos = torch.empty_like(pos)
-            g_sdf = torch.empty_like(sdf)
-            g_msdf = torch.empty_like(msdf) if want_msdf else None
-        b = plan.bargs
-        b.pos, b.sdf, b.msdf, b.n_grid = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), n_grid
-        b.msdf_negate = int(negate)
-        b.grads_prezeroed = int(prezeroed is not None)
-        b.tape_edges, b.tape_corners, b.tape_slots, b.tape_runs = tape_ptrs
-        b.verts_wt, b.msdf_wt = verts_wt.data_ptr(), msdf_wt.data_ptr()
-        b.n_verts, b.n_tri_tets, b.n_quad_tets = n_verts, n_tri, n_quad
-        b.g_verts_aug, b.g_msdf_aug, b.g_verts_wt, b.g_msdf_wt = p_gva, p_gma, p_gvw, p_gmw
-        b.g_pos, b.g_sdf = g_pos.data_ptr(), g_sdf.data_ptr()
-        b.g_msdf = g_msdf.data_ptr() if g_msdf is not None else None
-        b.workspace, b.workspace_bytes = None, 0
-        _cabi.check(L.d3h_extract_backward(C.byref(b), torch.cuda.current_stream(dev).cuda_stream),
-                    "d3h_extract_backward")
-    return g_pos, g_sdf, g_msdf
+        prezeroed = gbufs is not None
+        if not prezeroed:  # second backward through the same node (retain_graph): fresh zero-filled buffers
+            gbufs = [None] * len(tensors)
+            for (pi, si, mi, negate) in frame_ids:
+                for idx, wanted in ((pi, True), (si, True), (mi, need[mi] and not negate)):
+                    if wanted and gbufs[idx] is None:
+                        gbufs[idx] = torch.zeros_like(tensors[idx])
+        keep = []
+        n = 0
+        for i, (pi, si, mi, negate) in enumerate(frame_ids):
+            g = grads[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)]
+            if g[1] is not None or g[4] is not None:
+                raise NotImplementedError(
+                    "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
+                    "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
+            if g[0] is None and g[2] is None and g[3] is None and g[5] is None:
+                continue  # nothing flows into this frame
+            n_verts, n_tri, n_quad, tape_ptrs, p_vwt, p_mwt = metas[i]
+            va = n_verts + 3 * n_tri + 4 * n_quad
+            ptrs = []
+            for t, shape in ((g[0], (va, 3)), (g[2], (va,)), (g[3], (n_verts, 3)), (g[5], (n_verts,))):
+                if t is None:
+                    ptrs.append(None)
+                    continue
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.contiguous().float()
+                assert tuple(t.shape) == shape, (tuple(t.shape), shape)
+                keep.append(t)
+                ptrs.append(t.data_ptr())
+            b = ba[n]
+            n += 1
+            b.pos, b.sdf, b.msdf, b.n_grid = tensors[pi].data_ptr(), tensors[si].data_ptr(), tensors[mi].data_ptr(), n_grid
+            b.msdf_negate = int(negate)
+            b.grads_prezeroed = 1
+            b.tape_edges, b.tape_corners, b.tape_slots, b.tape_runs = tape_ptrs
+            b.verts_wt, b.msdf_wt = p_vwt, p_mwt
+            b.n_verts, b.n_tri_tets, b.n_quad_tets = n_verts, n_tri, n_quad
+            b.g_verts_aug, b.g_msdf_aug, b.g_verts_wt, b.g_msdf_wt = ptrs
+            b.g_pos, b.g_sdf = gbufs[pi].data_ptr(), gbufs[si].data_ptr()
+            gm = gbufs[mi] if (need[mi] and not negate) else None
+            b.g_msdf = gm.data_ptr() if gm is not None else None
+            b.workspace, b.workspace_bytes = None, 0
+        if n:
+            _cabi.check(L.d3h_extract_backward_batch(ba, n, max(1, min(lanes, n)),
+                                                     torch.cuda.current_stream(dev).cuda_stream),
+                        "d3h_extract_backward_batch")
+    return [gbufs[i] if need[i] else None for i in range(len(tensors))]
 
 
 _ExtractFn.last_counts = None
@@ -354,7 +441,12 @@ _ExtractFn.last_launches = 0
 
 
 def last_counts() -> Optional[Dict[str, int]]:
-    """Sizes of the most recent extraction (Fv, T1, T2, P, V, Va, Fw, Fa, bucket sizes)."""
+    """Sizes of the most recent extraction (Fv, T1, T2, P, V, Va, Fw, Fa, bucket sizes); frame 0 of a batch."""
+    c = _ExtractFn.last_counts
+    return c[0] if c else None
+
+
+def last_counts_frames() -> Optional[List[Dict[str, int]]]:
     return _ExtractFn.last_counts
 
 
@@ -364,22 +456,24 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
     return t if t.data_ptr() % 16 == 0 else t.clone()
 
 
-def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_watertight_template: bool = True):
-    """Shared body of GShell_Tets.__call__ / hmSDF_Tets.__call__: returns the reference's 6-tuple."""
+def _prep_pos(pos_nx3):
     if not pos_nx3.is_cuda:
         raise RuntimeError("d3human-code_b200 has no CPU path: inputs must live on a CUDA device "
                            "(the reference hard-codes device='cuda' as well, gshell_tets.py:108)")
-    n_grid = pos_nx3.shape[0]
     if pos_nx3.dim() != 2 or pos_nx3.shape[1] != 3:
         raise ValueError(f"pos_nx3 must have shape (N,3), got {tuple(pos_nx3.shape)}")
-    sdf = sdf_n.float().reshape(-1)       # gshell_tets.py:254 (.float()); (N,1) from the SDF MLP or (N,)
-    msdf = msdf_n.float().reshape(-1)
-    if sdf.shape[0] != n_grid or msdf.shape[0] != n_grid:
+    return _aligned(pos_nx3.float())
+
+
+def _prep_field(f, n_grid):
+    f = f.float().reshape(-1)       # gshell_tets.py:254 (.float()); (N,1) from the SDF MLP or (N,)
+    if f.shape[0] != n_grid:
         raise ValueError("sdf_n / msdf_n must have one value per grid vertex")
-    pos, sdf, msdf = _aligned(pos_nx3.float()), _aligned(sdf), _aligned(msdf)
-    tets = packed_tets(tet_fx4, n_grid)
-    verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, faces_aug, faces_wt = _ExtractFn.apply(
-        pos, sdf, msdf, tets, bool(msdf_negate), bool(output_watertight_template))
+    return _aligned(f)
+
+
+def _pack_result(r8, output_watertight_template):
+    verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, faces_aug, faces_wt = r8
     n_wt = verts_wt.shape[0]
     if output_watertight_template:  # gshell_tets.py:430-439
         extra = {
@@ -394,3 +488,66 @@ def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_w
     else:  # gshell_tets.py:440-445
         extra = {"msdf": msdf_aug, "msdf_watertight": msdf_wt, "msdf_boundary": msdf_aug[n_wt:]}
     return verts_aug, faces_aug, None, None, v_tng_aug, extra
+
+
+def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_watertight_template: bool = True):
+    """Shared body of GShell_Tets.__call__ / hmSDF_Tets.__call__: returns the reference's 6-tuple."""
+    pos = _prep_pos(pos_nx3)
+    n_grid = pos.shape[0]
+    sdf, msdf = _prep_field(sdf_n, n_grid), _prep_field(msdf_n, n_grid)
+    tets = packed_tets(tet_fx4, n_grid)
+    spec = (((0, 1, 2, bool(msdf_negate)),), bool(output_watertight_template), 1)
+    return _pack_result(_ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)
+
+
+def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watertight_template: bool = True,
+                   lanes: int = DEFAULT_LANES):
+    """A batch of extractions on the same tet grid in one autograd node and one library call per direction.
+
+    No counterpart in the reference, which would loop over the frames (BASELINE.json configs[3]: a batch of video frames
+    per step with per-frame tet-vertex offsets; also the cloth / body pair of train.py:1040-1047).
+
+    pos_frames : (B,N,3) tensor or a sequence of (N,3) tensors -- per-frame deformed grid vertices
+    sdf_n, msdf_n : one tensor shared by all frames ((N,) or (N,1)), or a sequence with one tensor per frame
+    types : None (GShell_Tets semantics), one of "cloth" / "body" for all frames, or a sequence per frame
+            (hmSDF_Tets semantics: "body" uses -msdf and, like the reference, does not back-propagate into msdf_n)
+    Returns a list with the reference's 6-tuple `(verts, faces, None, None, v_tng, extra)` for every frame.  Gradients of
+    shared tensors are summed over the frames.
+    """
+    if torch.is_tensor(pos_frames):
+        if pos_frames.dim() != 3:
+            raise ValueError(f"pos_frames must be (B,N,3), got {tuple(pos_frames.shape)}")
+        pos_list = list(pos_frames.unbind(0))
+    else:
+        pos_list = list(pos_frames)
+    B = len(pos_list)
+    if B == 0:
+        return []
+    tensors: List[torch.Tensor] = []
+    index: Dict[int, int] = {}
+
+    def intern(src, prep):
+        k = id(src)
+        if k not in index:
+            index[k] = len(tensors)
+            tensors.append(prep(src))
+        return index[k]
+
+    pos_ids = [intern(p, _prep_pos) for p in pos_list]
+    n_grid = tensors[pos_ids[0]].shape[0]
+    prep_f = lambda f: _prep_field(f, n_grid)  # noqa: E731
+    sdf_list = [sdf_n] * B if torch.is_tensor(sdf_n) else list(sdf_n)
+    msdf_list = [msdf_n] * B if torch.is_tensor(msdf_n) else list(msdf_n)
+    type_list = [types] * B if (types is None or isinstance(types, str)) else list(types)
+    if not (len(sdf_list) == len(msdf_list) == len(type_list) == B):
+        raise ValueError("sdf_n / msdf_n / types must be shared or have one entry per frame")
+    frame_ids = tuple((pos_ids[i], intern(sdf_list[i], prep_f), intern(msdf_list[i], prep_f), type_list[i] == "body")
+                      for i in range(B))
+    for t in tensors:
+        if t.shape[0] != n_grid:
+            raise ValueError("all frames must live on the same tet grid (same N)")
+    tets = packed_tets(tet_fx4, n_grid)
+    spec = (frame_ids, bool(output_watertight_template), int(lanes))
+    flat = _ExtractFn.apply(spec, tets, *tensors)
+    return [_pack_result(flat[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)], output_watertight_template)
+            for i in range(B)]

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 200 /* 0.2.0 */
+#define D3H_VERSION 300 /* 0.3.0 */
 
 enum {
   D3H_OK = 0,
@@ -172,6 +172,18 @@ int d3h_wait_counts(const d3h_counts* counts_host, int64_t seq, int64_t timeout_
 
 /* Adjoint of the float pipeline (replaces autograd through gshell_tets.py:291-303, 342-397, 427). */
 int d3h_extract_backward(const d3h_backward_args* args, d3h_stream_t stream);
+
+/* Batches of independent extractions: the video frames of one training step (BASELINE.json configs[3]) or the
+ * cloth / body pair the reference extracts every iteration (train.py:1040-1047).  No counterpart in the reference, which
+ * runs them one after the other.  Frame i runs on internal lane (i % lanes), lanes <= 8; the lanes fork from `stream`
+ * and join back into it, so the batch is ordered on `stream` like a single call.  The bandwidth-bound kernels of one
+ * frame overlap the latency-bound surface kernels of the others (per-kernel launch priorities).
+ *   forward : args[i] as for d3h_extract_forward; frames on different lanes need distinct workspaces (frames of the same
+ *             lane may share one); every frame publishes its own counts (args[i].counts_host, args[i].seq).
+ *   backward: gradient buffers may be shared between frames (sdf / msdf common to all frames): all frames accumulate
+ *             with atomics, a shared buffer must be zero on entry (grads_prezeroed = 1). */
+int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
+int d3h_extract_backward_batch(const d3h_backward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
 
 /* Tet-range sharding (multi-GPU): stage 1 classifies tets [tet_begin, tet_end) and leaves
  * compact valid-tet records in the caller's buffers; the ranks all-gather those (NCCL) and stage 2 runs the

@@ -192,6 +192,73 @@ def test_tangent_gradient_is_refused(dev):
         out[4].sum().backward()
 
 
+# ---------------------------------------------------------------------------------------------- batches of frames
+def test_extract_frames_batch_matches_oracle_per_frame(dev):
+    """BASELINE configs[3]: a batch of frames with per-frame offsets, shared sdf / msdf, mixed cloth / body types, run as
+    one autograd node on concurrent lanes: every frame bit-exact against the oracle, shared gradients = sum over frames."""
+    from d3human_code_b200.extract import extract_frames, last_counts_frames
+    res = 20
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = grids.capsule_garment_field(pos)
+    B = 5
+    types = ["cloth", "body", "cloth", "cloth", "body"]
+    pos_b = np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(B)]).astype(np.float32)
+    tp = torch.tensor(pos_b, device=dev, requires_grad=True)          # (B,N,3) tensor form
+    ts = torch.tensor(sdf[:, None], device=dev, requires_grad=True)   # shared, (N,1) like the SDF MLP output
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)           # shared
+    tt = torch.tensor(tets, device=dev)
+    outs = extract_frames(tp, ts, tm, tt, types=types, lanes=3)
+    assert len(outs) == B and len(last_counts_frames()) == B
+    rng = np.random.default_rng(11)
+    want_pos = np.zeros_like(pos_b)
+    want_sdf = np.zeros_like(sdf)
+    want_msdf = np.zeros_like(msdf)
+    loss = 0.0
+    for i, (verts, faces, uvs, uv_idx, v_tng, extra) in enumerate(outs):
+        fwd = O.extract_forward(pos_b[i], sdf, msdf, tets, -1 if types[i] == "body" else 1, True)
+        U.assert_exact(f"faces_aug[{i}]", faces.cpu().numpy(), fwd["faces_aug"])
+        U.assert_exact(f"verts_aug[{i}]", verts.detach().cpu().numpy(), fwd["verts_aug"])
+        U.assert_exact(f"msdf[{i}]", extra["msdf"].detach().cpu().numpy(), fwd["msdf"])
+        U.assert_exact(f"faces_watertight[{i}]", extra["faces_watertight"].cpu().numpy(), fwd["faces_watertight"])
+        U.assert_exact(f"vertices_watertight[{i}]", extra["vertices_watertight"].detach().cpu().numpy(),
+                       fwd["vertices_watertight"])
+        assert extra["n_verts_watertight"] == fwd["n_verts_watertight"]
+        gv = rng.standard_normal(fwd["verts_aug"].shape).astype(np.float32)
+        gm = rng.standard_normal(fwd["msdf"].shape).astype(np.float32)
+        if i == 3:   # one frame receives no upstream gradient at all
+            continue
+        loss = loss + (verts * torch.tensor(gv, device=dev)).sum() + (extra["msdf"] * torch.tensor(gm, device=dev)).sum()
+        g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, gm)
+        want_pos[i] = g_pos
+        want_sdf += g_sdf
+        if types[i] != "body":
+            want_msdf += g_msdf
+    loss.backward()
+    U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), want_pos, U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", ts.grad[:, 0].cpu().numpy(), want_sdf, U.GRAD_RTOL)
+    U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), want_msdf, U.GRAD_RTOL)
+
+
+def test_extract_frames_list_form_and_repeat(dev):
+    """Sequence-of-tensors form with per-frame sdf; two consecutive batches reuse the lanes / graphs / workspaces."""
+    from d3human_code_b200.extract import extract_frames
+    res = 16
+    pos, tets = grids.kuhn_grid(res)
+    tt = torch.tensor(tets, device=dev)
+    p = pos.astype(np.float64)
+    for rep in range(2):
+        radii = [0.3 + 0.1 * rep, 0.5, 0.7, 0.0]
+        sdfs = [(r - np.linalg.norm(p, axis=-1)).astype(np.float32) for r in radii]
+        msdf = (p[:, 1] + 0.05).astype(np.float32)
+        tp = torch.tensor(pos, device=dev)
+        outs = extract_frames([tp] * 4, [torch.tensor(s, device=dev) for s in sdfs], torch.tensor(msdf, device=dev), tt,
+                              lanes=2)
+        for i, (verts, faces, _, _, _, extra) in enumerate(outs):
+            fwd = O.extract_forward(pos, sdfs[i], msdf, tets)
+            U.assert_exact(f"faces_aug[{i}]", faces.cpu().numpy(), fwd["faces_aug"])
+            U.assert_exact(f"verts_aug[{i}]", verts.cpu().numpy(), fwd["verts_aug"])
+
+
 # ---------------------------------------------------------------------------------------------- full size
 def test_full_size_properties_128(dev):
     """BASELINE config 2 (128^3 capsules + garment): counts equal the reference's (measured by running the
