@@ -188,10 +188,11 @@ def main():
     tets = torch.from_numpy(tets_np).to(dev)                      # int64 like hmsdf.py:207-212; packed once (static)
     sdf = torch.from_numpy(sdf_np[:, None].copy()).to(dev).requires_grad_(True)   # (N,1) like the SDF MLP output
     msdf = torch.from_numpy(msdf_np).to(dev).requires_grad_(True)
-    host_pos = [torch.from_numpy(pos_np + grids.frame_offsets(N, args.res, f)).pin_memory() for f in frames]
+    # per-frame deformed grid vertices as ONE (B,N,3) tensor: one autograd leaf, one gradient buffer for the batch
+    host_pos = torch.from_numpy(np.stack([pos_np + grids.frame_offsets(N, args.res, f) for f in frames])).pin_memory()
     host_sdf = torch.from_numpy(sdf_np[:, None].copy()).pin_memory()
     host_msdf = torch.from_numpy(msdf_np).pin_memory()
-    pos = [hp.to(dev).requires_grad_(True) for hp in host_pos]
+    pos = host_pos.to(dev).requires_grad_(True)
 
     # dry run: shapes of the upstream gradients (constant across steps: inputs are fixed)
     outs = E.extract_frames(pos, sdf, msdf, tets, types="cloth", lanes=args.lanes)
@@ -209,21 +210,19 @@ def main():
         """One training-step's worth of extraction on this rank: all frames forward (one library call, concurrent
         lanes), then all frames backward (one library call); gradients of the shared sdf / msdf summed over the frames
         by the kernels and over the ranks by NCCL."""
-        sdf.grad = None
-        msdf.grad = None
-        for p in pos:
-            p.grad = None
+        sdf.grad = msdf.grad = pos.grad = None
         outs = E.extract_frames(pos, sdf, msdf, tets, types="cloth", lanes=args.lanes)
         torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v + ups_m)
         if world > 1:
             dist.all_reduce(sdf.grad)
             dist.all_reduce(msdf.grad)
 
+    pos_single = [pos.detach()[i].clone().requires_grad_(True) for i in range(min(fpr, 4))]   # separate (N,3) leaves
+
     def single_call_step():
         """The reference's own calling pattern: one drop-in call + backward per frame (hmsdf.py:548)."""
-        sdf.grad = None
-        msdf.grad = None
-        for p, gv, gm in zip(pos, ups_v, ups_m):
+        sdf.grad = msdf.grad = None
+        for p, gv, gm in zip(pos_single, ups_v, ups_m):
             p.grad = None
             verts, faces, _, _, v_tng, extra = hm(p, sdf, msdf, tets, "cloth")
             torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
@@ -259,7 +258,7 @@ def main():
         k_single = max(3, min(args.steps, 50))
         for _ in range(3):
             single_call_step()
-        ms_single = timed(single_call_step, k_single) / fpr
+        ms_single = timed(single_call_step, k_single) / len(pos_single)
         single = {"ms_per_frame": ms_single, "value": F / (ms_single * 1e-3), "unit": UNIT, "steps": k_single,
                   "note": "hmSDF_Tets()(...) + backward per frame, strictly serial on the host (the reference's calling pattern)"}
 
@@ -268,7 +267,7 @@ def main():
     prof = {}
     if rank == 0:
         _cabi.profile_enable(True)
-        nprof = max(1, min(args.profile_steps, 128 // fpr))
+        nprof = max(1, min(args.profile_steps, 128 // len(pos_single)))
         for _ in range(nprof):
             single_call_step()
         torch.cuda.synchronize()
@@ -282,7 +281,7 @@ def main():
     if not args.no_e2e:
         d_sdf = torch.empty_like(sdf)
         d_msdf = torch.empty_like(msdf)
-        d_pos = [torch.empty_like(p) for p in pos]
+        d_pos = torch.empty_like(pos)
         outs_host = None
         k_e2e = max(3, min(args.steps, 20))
 
@@ -295,18 +294,17 @@ def main():
                 dst.requires_grad_(True)
                 dst.grad = None
             h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
-            for dp, hp in zip(d_pos, host_pos):
-                dp.requires_grad_(False)
-                dp.copy_(hp, non_blocking=True)
-                dp.requires_grad_(True)
-                dp.grad = None
-                h2d += hp.numel() * 4
+            d_pos.requires_grad_(False)
+            d_pos.copy_(host_pos, non_blocking=True)
+            d_pos.requires_grad_(True)
+            d_pos.grad = None
+            h2d += host_pos.numel() * 4
             outs = E.extract_frames(d_pos, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
             torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v + ups_m)
             res_flat = []
-            for o, dp in zip(outs, d_pos):
-                res_flat += [o[0].detach(), o[1], o[5]["msdf"].detach(), dp.grad]
-            res_flat += [d_sdf.grad, d_msdf.grad]
+            for o in outs:
+                res_flat += [o[0].detach(), o[1], o[5]["msdf"].detach()]
+            res_flat += [d_pos.grad, d_sdf.grad, d_msdf.grad]
             if outs_host is None:
                 outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_flat]
             for h, t in zip(outs_host, res_flat):
@@ -362,7 +360,7 @@ def main():
             roofline = {"kernel": "classify_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": 16 * F, "us_per_launch": t * 1e6}
-    dev_ms_frame = sum(v[0] for v in prof.values()) / max(nprof * fpr, 1) if prof else None
+    dev_ms_frame = sum(v[0] for v in prof.values()) / max(nprof * len(pos_single), 1) if prof else None
     path_roofline = {"algorithmic_bytes_per_frame": int(balg),
                      "achieved_GBps_step": balg * fpr / (ms_step * 1e-3) / 1e9,
                      "frac_step": balg * fpr / (ms_step * 1e-3) / 1e9 / peak,

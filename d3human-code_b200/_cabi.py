@@ -88,19 +88,19 @@ def lib() -> C.CDLL:
     L.d3h_check_tets_i32.restype = C.c_int
     L.d3h_check_tets_i32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_forward.restype = C.c_int
-    L.d3h_extract_forward.argtypes = [C.POINTER(ForwardArgs), C.c_void_p]
+    L.d3h_extract_forward.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_wait_counts.restype = C.c_int
     L.d3h_wait_counts.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.d3h_extract_backward.restype = C.c_int
-    L.d3h_extract_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
+    L.d3h_extract_backward.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_extract_forward_batch.restype = C.c_int
     L.d3h_extract_forward_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.d3h_extract_backward_batch.restype = C.c_int
     L.d3h_extract_backward_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.d3h_classify_range.restype = C.c_int
-    L.d3h_classify_range.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.d3h_classify_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_from_records.restype = C.c_int
-    L.d3h_extract_from_records.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    L.d3h_extract_from_records.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     L.d3h_profile_enable.restype = C.c_int
     L.d3h_profile_enable.argtypes = [C.c_int]
     L.d3h_profile_kinds.restype = C.c_int

@@ -182,9 +182,13 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: tape_corners / tape_slots (4*cap_valid_tets int32) and tape_runs (cap_verts+1 int32) are required", who);
     return D3H_E_BADARG;
   }
-  if ((reinterpret_cast<uintptr_t>(a->zero_g_pos) | reinterpret_cast<uintptr_t>(a->zero_g_sdf) |
-       reinterpret_cast<uintptr_t>(a->zero_g_msdf)) & 15) {
-    set_error("%s: zero_g_* buffers must be 16-byte aligned", who);
+  if ((reinterpret_cast<uintptr_t>(a->sdf) | reinterpret_cast<uintptr_t>(a->msdf)) & 15) {
+    set_error("%s: sdf / msdf must be 16-byte aligned", who);
+    return D3H_E_BADARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(a->pos) | reinterpret_cast<uintptr_t>(a->zero_g_pos) |
+       reinterpret_cast<uintptr_t>(a->zero_g_sdf) | reinterpret_cast<uintptr_t>(a->zero_g_msdf)) & 3) {
+    set_error("%s: pos / zero_g_* must be 4-byte aligned", who);
     return D3H_E_BADARG;
   }
   if ((a->cap_verts > 0 && (!a->verts_wt || !a->v_tng_wt || !a->msdf_wt || !a->tape_edges)) ||
@@ -443,8 +447,8 @@ static int check_backward_args(const d3h_backward_args* a, const char* who) {
     return D3H_E_BADARG;
   }
   if ((reinterpret_cast<uintptr_t>(a->g_pos) | reinterpret_cast<uintptr_t>(a->g_sdf) |
-       reinterpret_cast<uintptr_t>(a->g_msdf)) & 15) {
-    set_error("%s: gradient buffers must be 16-byte aligned", who);
+       reinterpret_cast<uintptr_t>(a->g_msdf)) & 3) {
+    set_error("%s: gradient buffers must be 4-byte aligned", who);
     return D3H_E_BADARG;
   }
   return D3H_OK;

@@ -19,37 +19,37 @@
 
 namespace d3h {
 
-__global__ void __launch_bounds__(256) zero_kernel(float4* __restrict__ p0, int64_t n0, float4* __restrict__ p1,
-                                                   int64_t n1, float4* __restrict__ p2, int64_t n2, float* t0,
-                                                   int64_t tn0, float* t1, int64_t tn1, float* t2, int64_t tn2) {
+// Zero-fill of `len` floats at any 4-byte aligned address: scalar head up to the first 16-byte boundary, 16-byte
+// stores for the body, scalar tail (rows of a stacked (B,N,3) gradient start at arbitrary multiples of 4 bytes).
+__device__ __forceinline__ void zero_span(float* __restrict__ p, int64_t len, int64_t tid, int64_t stride) {
+  if (p == nullptr || len <= 0) return;
+  int64_t head = (int64_t)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 2);
+  if (head > len) head = len;
+  if (tid < head) p[tid] = 0.f;
+  float4* __restrict__ body = reinterpret_cast<float4*>(p + head);
+  const int64_t n4 = (len - head) >> 2;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = tid; i < n4; i += stride) body[i] = z;
+  const int64_t t0 = head + 4 * n4;
+  if (tid < len - t0) p[t0 + tid] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) zero_kernel(float* p0, int64_t n0, float* p1, int64_t n1, float* p2, int64_t n2) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = tid; i < n0; i += stride) p0[i] = z;
-  for (int64_t i = tid; i < n1; i += stride) p1[i] = z;
-  for (int64_t i = tid; i < n2; i += stride) p2[i] = z;
-  // scalar tails (buffers are only guaranteed 4-byte granular in length)
-  if (tid < tn0) t0[tid] = 0.f;
-  if (tid < tn1) t1[tid] = 0.f;
-  if (tid < tn2) t2[tid] = 0.f;
+  zero_span(p0, n0, tid, stride);
+  zero_span(p1, n1, tid, stride);
+  zero_span(p2, n2, tid, stride);
 }
 
 // Forward-side variant: the three pointers come from the argument block (they change from call to call, the launch
-// shape does not).  Buffers are 16-byte aligned (checked on the host).
+// shape does not).
 __global__ void __launch_bounds__(256) zero_block_kernel(const FwdBlock* __restrict__ blk, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* bufs[3] = {blk->a.zero_g_pos, blk->a.zero_g_sdf, blk->a.zero_g_msdf};
-  const int64_t lens[3] = {3 * n, n, n};
-#pragma unroll
-  for (int b = 0; b < 3; ++b) {
-    float* p = bufs[b];
-    if (p == nullptr) continue;
-    const int64_t n4 = lens[b] / 4;
-    for (int64_t i = tid; i < n4; i += stride) reinterpret_cast<float4*>(p)[i] = z;
-    if (tid < lens[b] - 4 * n4) p[4 * n4 + tid] = 0.f;
-  }
+  zero_span(blk->a.zero_g_pos, 3 * n, tid, stride);
+  zero_span(blk->a.zero_g_sdf, n, tid, stride);
+  zero_span(blk->a.zero_g_msdf, n, tid, stride);
 }
 
 void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
@@ -61,25 +61,12 @@ void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws
 }
 
 void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n, cudaStream_t stream) {
-  // split every buffer in a 16-byte-aligned body and a scalar tail
-  auto body = [](float* p, int64_t len, float4*& b4, int64_t& n4, float*& tail, int64_t& ntail) {
-    n4 = len / 4;
-    b4 = reinterpret_cast<float4*>(p);
-    tail = p + 4 * n4;
-    ntail = len - 4 * n4;
-  };
-  float4 *b0, *b1, *b2;
-  int64_t n0, n1, n2, tn0, tn1, tn2;
-  float *t0, *t1, *t2;
-  body(g_pos, g_pos ? 3 * n : 0, b0, n0, t0, tn0);
-  body(g_sdf, g_sdf ? n : 0, b1, n1, t1, tn1);
-  body(g_msdf, g_msdf ? n : 0, b2, n2, t2, tn2);
-  const int64_t work = n0 + n1 + n2;
-  int64_t blocks = (work / 4 + 255) / 256;
+  int64_t blocks = (5 * n / 16 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope ps(K_ZERO, stream);
-  launch_k(zero_kernel, (unsigned)blocks, 256u, stream, kLaunchStream, b0, n0, b1, n1, b2, n2, t0, tn0, t1, tn1, t2, tn2);
+  launch_k(zero_kernel, (unsigned)blocks, 256u, stream, kLaunchStream, g_pos, g_pos ? 3 * n : (int64_t)0, g_sdf,
+           g_sdf ? n : (int64_t)0, g_msdf, g_msdf ? n : (int64_t)0);
 }
 
 // segmented (by key) inclusive suffix-sum inside a warp; lanes with equal key must be contiguous.

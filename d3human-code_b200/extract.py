@@ -12,6 +12,7 @@ import weakref
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _cabi
@@ -71,12 +72,30 @@ def packed_tets(tet_fx4: torch.Tensor, n_grid: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
-# per-(device, F, N) plan: workspaces (one per lane) + capacities predicted from the previous call
+# argument blocks as int64 matrices: d3h_forward_args / d3h_backward_args are arrays of 8-byte words (the two int32
+# flags share one word), so the blocks of a whole batch are filled with a handful of vectorised numpy assignments
+# (pointers of frame i are affine in i) instead of ~35 ctypes attribute writes per frame
 # --------------------------------------------------------------------------------------------------
+def _columns(struct):
+    cols = {}
+    for name, _typ in struct._fields_:
+        off = getattr(struct, name).offset
+        cols[name] = off // 8
+    return cols, C.sizeof(struct) // 8
+
+
+_FC, _FW = _columns(_cabi.ForwardArgs)
+_BC, _BW = _columns(_cabi.BackwardArgs)
+assert _FC["watertight_template"] == _FC["msdf_negate"] and _BC["grads_prezeroed"] == _BC["msdf_negate"]
+_CC, _CW = _columns(_cabi.Counts)
+
 MAX_LANES = 8
 DEFAULT_LANES = 4
 
 
+# --------------------------------------------------------------------------------------------------
+# per-(device, F, N) plan: workspaces (one per lane) + capacities predicted from the previous call
+# --------------------------------------------------------------------------------------------------
 @dataclass
 class _Plan:
     device: torch.device
@@ -89,31 +108,31 @@ class _Plan:
     cap_fa: int = 0
     seq: int = 0
     workspaces: List[torch.Tensor] = field(default_factory=list)   # one per lane
+    workspace_ptrs: List[int] = field(default_factory=list)
     workspace_bytes: int = 0
     workspace_cap_tets: int = -1
     counts_host: Optional[torch.Tensor] = None                     # pinned, one 128-byte slot per frame of a batch
-    counts: List[_cabi.Counts] = field(default_factory=list)
-    fargs: Dict[int, ctypes_array] = field(default_factory=dict)   # batch size -> (ForwardArgs * B)()
-    bargs: Dict[int, ctypes_array] = field(default_factory=dict)
+    counts_np: Optional[np.ndarray] = None                         # (slots, 16) int64 view of counts_host
+    counts_ptr: int = 0
+    layouts: Dict[Tuple, Any] = field(default_factory=dict)        # (B, lanes, flags) -> _Layout
 
     def ensure(self, n_frames: int, lanes: int):
         if self.workspace_cap_tets != self.cap_tets:
             need = _cabi.lib().d3h_workspace_bytes(self.n_tets, self.n_grid, self.cap_tets)
             if need > self.workspace_bytes:
-                self.workspaces = []
+                self.workspaces, self.workspace_ptrs = [], []
                 self.workspace_bytes = need
             self.workspace_cap_tets = self.cap_tets
         while len(self.workspaces) < lanes:
-            self.workspaces.append(torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device))
-        if len(self.counts) < n_frames:
+            w = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+            self.workspaces.append(w)
+            self.workspace_ptrs.append(w.data_ptr())
+        if self.counts_np is None or self.counts_np.shape[0] < n_frames:
             # pinned host memory is device-mapped (UVA): the kernel that finalises the sizes writes them here directly
-            slots = max(n_frames, 2 * len(self.counts), 4)
-            self.counts_host = torch.zeros(slots * _cabi.COUNTS_WORDS, dtype=torch.int64).pin_memory()
-            base = self.counts_host.data_ptr()
-            self.counts = [_cabi.Counts.from_address(base + i * C.sizeof(_cabi.Counts)) for i in range(slots)]
-        if n_frames not in self.fargs:
-            self.fargs[n_frames] = (_cabi.ForwardArgs * n_frames)()
-            self.bargs[n_frames] = (_cabi.BackwardArgs * n_frames)()
+            slots = max(n_frames, 4) if self.counts_np is None else max(n_frames, 2 * self.counts_np.shape[0])
+            self.counts_host = torch.zeros(slots * _CW, dtype=torch.int64).pin_memory()
+            self.counts_np = self.counts_host.numpy().reshape(slots, _CW)
+            self.counts_ptr = self.counts_host.data_ptr()
 
 
 _plans: Dict[Tuple, _Plan] = {}
@@ -143,25 +162,31 @@ class ForwardResult:
     v_tng_wt: torch.Tensor
     msdf_wt: torch.Tensor
     faces_wt: torch.Tensor
-    tape: torch.Tensor          # int32 slab of the batch; this frame: edges (V,2) | corners (P) | slots (P) | runs (V+1)
-    fslab: torch.Tensor         # float slab of the batch (every float output is a view of it)
-    tape_ptrs: Tuple[int, int, int, int]
     n_verts: int
     n_tri: int
     n_quad: int
     counts: Dict[str, int]
 
-    # views used by the tests
-    @property
-    def tape_edges(self):
-        o = (self.tape_ptrs[0] - self.tape.data_ptr()) // 4
-        return self.tape[o:o + 2 * self.n_verts].view(-1, 2)
 
-    @property
-    def tape_corners(self):
-        p = 3 * self.n_tri + 4 * self.n_quad
-        o = (self.tape_ptrs[1] - self.tape.data_ptr()) // 4
-        return self.tape[o:o + p]
+@dataclass
+class BatchResult:
+    frames: List[ForwardResult]
+    fslab: torch.Tensor          # float slab of the batch (every float output is a view of it)
+    islab: torch.Tensor          # int64 slab (faces)
+    tape: torch.Tensor           # int32 slab; frame i: edges (V,2) | corners (P) | slots (P) | runs (V+1)
+    tape_off: Tuple[int, int, int, int, int]   # element offsets inside a frame's tape slice + slice length
+    launches: int
+    bmat: Optional[np.ndarray]   # (B, words) int64 d3h_backward_args[] prefilled for the coming backward pass
+
+    def tape_edges(self, i=0):
+        f = self.frames[i]
+        o = i * self.tape_off[4]
+        return self.tape[o:o + 2 * f.n_verts].view(-1, 2)
+
+    def tape_corners(self, i=0):
+        f = self.frames[i]
+        o = i * self.tape_off[4] + self.tape_off[1]
+        return self.tape[o:o + 3 * f.n_tri + 4 * f.n_quad]
 
 
 def _r4(n: int) -> int:
@@ -177,84 +202,174 @@ LAUNCHES_FORWARD = 9
 LAUNCHES_BACKWARD = 1
 
 
-def forward_frames_raw(frames, tets_i32: torch.Tensor, watertight_template: bool, lanes: int = DEFAULT_LANES,
-                       zero: Optional[List[Tuple[Optional[int], Optional[int], Optional[int]]]] = None):
+class _Layout:
+    """Everything about a batch that only depends on (B, lanes, capacities, flags): slab geometry, the static words of
+    the argument blocks and the per-frame byte offsets of every output / tape pointer (frame i owns slice i of the three
+    slabs, so its pointers are slab base + i * stride + constant)."""
+
+    def __init__(self, plan: _Plan, B: int, lanes: int, wt: int):
+        self.key = (B, lanes, wt, plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets, plan.workspace_bytes,
+                    plan.counts_ptr, tuple(plan.workspace_ptrs[:lanes]))
+        cv, cva, cfw, cfa, ct = plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets
+        self.caps = (cv, cva, cfw, cfa, ct)
+        o_vaug, o_tng, o_maug = 0, 3 * _r4(cva), 6 * _r4(cva)
+        o_vwt = o_maug + _r4(cva)
+        o_twt, o_mwt = o_vwt + 3 * _r4(cv), o_vwt + 6 * _r4(cv)
+        self.f_off = (o_vaug, o_tng, o_maug, o_vwt, o_twt, o_mwt)
+        self.f_len = o_mwt + _r4(cv)
+        self.i_len = 3 * (cfa + cfw) + (3 * (cfa + cfw)) % 2      # keep every frame's int64 slice 16-byte aligned
+        t_corn, t_slot = 2 * _r4(cv), 2 * _r4(cv) + 4 * ct
+        t_runs = t_slot + 4 * ct
+        self.t_len = _r4(t_runs + cv + 1)
+        self.tape_off = (0, t_corn, t_slot, t_runs, self.t_len)
+        ar = np.arange(B, dtype=np.int64)
+        c = _FC
+        A = np.zeros((B, _FW), dtype=np.int64)
+        A[:, c["n_grid"]], A[:, c["n_tets"]], A[:, c["tet_begin"]], A[:, c["tet_end"]] = plan.n_grid, plan.n_tets, 0, plan.n_tets
+        A[:, c["cap_valid_tets"]], A[:, c["cap_verts"]], A[:, c["cap_verts_aug"]] = ct, cv, cva
+        A[:, c["cap_faces_wt"]], A[:, c["cap_faces_aug"]] = cfw, cfa
+        A[:, c["workspace"]] = [plan.workspace_ptrs[i % lanes] for i in range(B)]
+        A[:, c["workspace_bytes"]] = plan.workspace_bytes
+        A[:, c["counts_host"]] = plan.counts_ptr + ar * 128
+        self.A = A
+        self.ar = ar
+        # columns verts_aug .. tape_runs are adjacent: value = base[which slab] + OFF
+        self.c0, self.c1 = c["verts_aug"], c["tape_runs"] + 1
+        assert self.c1 - self.c0 == 12
+        which = {"verts_aug": (0, 4 * o_vaug), "v_tng_aug": (0, 4 * o_tng), "msdf_aug": (0, 4 * o_maug),
+                 "faces_aug": (1, 0), "verts_wt": (0, 4 * o_vwt), "v_tng_wt": (0, 4 * o_twt), "msdf_wt": (0, 4 * o_mwt),
+                 "faces_wt": (1, 24 * cfa), "tape_edges": (2, 0), "tape_corners": (2, 4 * t_corn),
+                 "tape_slots": (2, 4 * t_slot), "tape_runs": (2, 4 * t_runs)}
+        stride = (4 * self.f_len, 8 * self.i_len, 4 * self.t_len)
+        self.OFF = np.zeros((B, 12), dtype=np.int64)
+        self.slab_of = [0] * 12
+        for name, (slab, off) in which.items():
+            k = c[name] - self.c0
+            self.OFF[:, k] = ar * stride[slab] + off
+            self.slab_of[k] = slab
+        # backward blocks: template with the static words (n_grid; grads_prezeroed = 1 is OR-ed into the flags)
+        self.Bt = np.zeros((B, _BW), dtype=np.int64)
+        self.Bt[:, _BC["n_grid"]] = plan.n_grid
+        bc = _BC
+        assert (bc["pos"], bc["sdf"], bc["msdf"]) == (0, 1, 2) and (c["pos"], c["sdf"], c["msdf"]) == (0, 1, 2)
+        assert bc["tape_runs"] - bc["tape_edges"] == 3 and bc["n_quad_tets"] - bc["n_verts"] == 2
+        assert bc["g_msdf"] - bc["g_pos"] == 2 and c["zero_g_msdf"] - c["zero_g_pos"] == 2
+        assert bc["g_msdf_wt"] - bc["g_verts_aug"] == 3
+
+
+def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
+                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None) -> BatchResult:
     """Forward extraction of a batch of frames in ONE library call (d3h_extract_forward_batch).
 
-    frames: [(pos, sdf, msdf, msdf_negate)] -- contiguous, 16-byte aligned fp32 CUDA tensors; tensors may be shared
-    between frames.  zero: per frame, the device pointers of dense gradient buffers (pos, sdf, msdf) that the call
-    should zero-fill for the coming backward pass (None = nothing).
-    Frames run on `lanes` concurrent lanes inside the library; the host blocks once per frame on that frame's sizes
-    (written to pinned host memory by the kernel that finalises them) -- the reference blocks ~40 times per frame.
-    Returns ([ForwardResult], launches)."""
+    ptrs   : (B,3) int64 array (or nested list): per frame the device pointers of pos / sdf / msdf -- contiguous fp32
+             data, sdf / msdf 16-byte aligned (the caller keeps the tensors alive); negate: per-frame msdf_negate flags
+    zero   : (B,3) pointers (0 = none) of dense gradient buffers the call zero-fills for the coming backward pass
+    grad_ptrs : (B,3) pointers of the gradient buffers (pos, sdf, msdf); when given, the d3h_backward_args of the batch
+             are prefilled here (everything but the upstream gradients is known once the sizes are)
+    Frames run on `lanes` concurrent lanes inside the library.  The host blocks once per frame on that frame's sizes
+    (written to pinned host memory by the kernel that finalises them; the reference blocks ~40 times per frame) and
+    builds the frame's output views while the GPU is still working on the later frames.
+    launcher : replaces the library call (tet-range sharding, sharding.py): launcher(A, plan, stream) enqueues the work
+             described by the argument blocks A and may return a Fv to regrow the record capacity to (retry)."""
     L = _cabi.lib()
-    B = len(frames)
-    pos0 = frames[0][0]
-    dev = pos0.device
-    n_grid, n_tets = pos0.shape[0], tets_i32.shape[0]
+    ptrs = np.asarray(ptrs, dtype=np.int64)
+    B = ptrs.shape[0]
+    n_tets = tets_i32.shape[0]
     plan = _plan_for(dev, n_tets, n_grid)
     lanes = max(1, min(int(lanes), MAX_LANES, B))
     stream = torch.cuda.current_stream(dev).cuda_stream
     launches = 0
     tets_ptr = tets_i32.data_ptr()
     wt = int(bool(watertight_template))
+    flags = np.asarray(negate, dtype=np.int64) | (wt << 32)
+    ast = torch.as_strided
+    wait = L.d3h_wait_counts
+    c = _FC
     with torch.cuda.device(dev):
         for attempt in range(6):
             plan.ensure(B, lanes)
-            fa = plan.fargs[B]
-            cv, cva, cfw, cfa, ct = plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets
+            lay = plan.layouts.get((B, lanes, wt))
+            if lay is None or lay.key[3:] != (plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets,
+                                              plan.workspace_bytes, plan.counts_ptr, tuple(plan.workspace_ptrs[:lanes])):
+                lay = plan.layouts[(B, lanes, wt)] = _Layout(plan, B, lanes, wt)
+            A = lay.A
+            cv, cva, cfw, cfa, ct = lay.caps
+            o_vaug, o_tng, o_maug, o_vwt, o_twt, o_mwt = lay.f_off
+            f_len, i_len, t_len = lay.f_len, lay.i_len, lay.t_len
             # three slabs for the whole batch: float outputs, int64 faces, int32 tape; frame i owns slice i of each
-            o_vaug, o_tng, o_maug = 0, 3 * _r4(cva), 6 * _r4(cva)
-            o_vwt = o_maug + _r4(cva)
-            o_twt, o_mwt = o_vwt + 3 * _r4(cv), o_vwt + 6 * _r4(cv)
-            f_len = o_mwt + _r4(cv)
-            i_len = 3 * (cfa + cfw) + (3 * (cfa + cfw)) % 2      # keep every frame's int64 slice 16-byte aligned
-            t_corn, t_slot = 2 * _r4(cv), 2 * _r4(cv) + 4 * ct
-            t_runs = t_slot + 4 * ct
-            t_len = _r4(t_runs + cv + 1)
             fslab = torch.empty(B * f_len, dtype=torch.float32, device=dev)
             islab = torch.empty(B * i_len, dtype=torch.int64, device=dev)
             tape = torch.empty(B * t_len, dtype=torch.int32, device=dev)
-            fp0, ip0, tp0 = fslab.data_ptr(), islab.data_ptr(), tape.data_ptr()
-            ws_bytes = plan.workspace_bytes
-            counts_base = plan.counts_host.data_ptr()
+            bases = (fslab.data_ptr(), islab.data_ptr(), tape.data_ptr())
+            counts_base = plan.counts_ptr
             seq0 = plan.seq
             plan.seq += B
-            tape_ptrs = []
-            for i, (pos, sdf, msdf, negate) in enumerate(frames):
-                a = fa[i]
-                fp, ip, tp = fp0 + 4 * i * f_len, ip0 + 8 * i * i_len, tp0 + 4 * i * t_len
-                a.pos, a.sdf, a.msdf, a.tets = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), tets_ptr
-                a.n_grid, a.n_tets, a.tet_begin, a.tet_end = n_grid, n_tets, 0, n_tets
-                a.msdf_negate, a.watertight_template = int(bool(negate)), wt
-                a.cap_valid_tets, a.cap_verts, a.cap_verts_aug, a.cap_faces_wt, a.cap_faces_aug = ct, cv, cva, cfw, cfa
-                a.verts_aug, a.v_tng_aug, a.msdf_aug = fp + 4 * o_vaug, fp + 4 * o_tng, fp + 4 * o_maug
-                a.verts_wt, a.v_tng_wt, a.msdf_wt = fp + 4 * o_vwt, fp + 4 * o_twt, fp + 4 * o_mwt
-                a.faces_aug, a.faces_wt = ip, ip + 24 * cfa
-                tps = (tp, tp + 4 * t_corn, tp + 4 * t_slot, tp + 4 * t_runs)
-                tape_ptrs.append(tps)
-                a.tape_edges, a.tape_corners, a.tape_slots, a.tape_runs = tps
-                z = zero[i] if zero is not None else (None, None, None)
-                a.zero_g_pos, a.zero_g_sdf, a.zero_g_msdf = z
-                a.workspace, a.workspace_bytes = plan.workspaces[i % lanes].data_ptr(), ws_bytes
-                a.counts_host = counts_base + i * 128
-                a.seq = seq0 + 1 + i
-                launches += (4 if ct <= 0 else LAUNCHES_FORWARD) + (1 if any(p is not None for p in z) else 0)
-            _cabi.check(L.d3h_extract_forward_batch(fa, B, lanes, stream), "d3h_extract_forward_batch")
-            sizes = []
+            A[:, 0:3] = ptrs
+            A[:, c["tets"]] = tets_ptr
+            A[:, c["msdf_negate"]] = flags
+            np.add(lay.OFF, np.array([bases[k] for k in lay.slab_of], dtype=np.int64), out=A[:, lay.c0:lay.c1])
+            if zero is not None:
+                A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = zero
+                launches += int(np.count_nonzero(np.asarray(zero).any(axis=1)))
+            else:
+                A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = 0
+            A[:, c["seq"]] = lay.ar + (seq0 + 1)
+            launches += B * (4 if ct <= 0 else LAUNCHES_FORWARD)
+            if launcher is None:
+                _cabi.check(L.d3h_extract_forward_batch(A.ctypes.data, B, lanes, stream), "d3h_extract_forward_batch")
+            else:
+                need_tets = launcher(A, plan, stream)
+                if need_tets is not None:   # the gathered records do not fit: grow like an overflowed single call
+                    plan.cap_tets = _grow(int(need_tets))
+                    p4 = 4 * plan.cap_tets
+                    plan.cap_v, plan.cap_va = max(cv, p4), max(cva, 2 * p4)
+                    plan.cap_fw, plan.cap_fa = max(cfw, 2 * plan.cap_tets), max(cfa, 4 * plan.cap_tets)
+                    continue
+            # the GPU is busy now: prefill the backward blocks of the batch
+            bmat = None
+            if grad_ptrs is not None:
+                b = _BC
+                bmat = lay.Bt.copy()
+                bmat[:, 0:3] = ptrs
+                bmat[:, b["msdf_negate"]] = np.asarray(negate, dtype=np.int64) | (1 << 32)    # grads_prezeroed = 1
+                bmat[:, b["tape_edges"]:b["tape_runs"] + 1] = A[:, c["tape_edges"]:c["tape_runs"] + 1]
+                bmat[:, b["verts_wt"]], bmat[:, b["msdf_wt"]] = A[:, c["verts_wt"]], A[:, c["msdf_wt"]]
+                bmat[:, b["g_pos"]:b["g_msdf"] + 1] = grad_ptrs
+            sizes = np.empty((B, 6), dtype=np.int64)   # fv, t1, t2, p, v, fa
+            frames: List[ForwardResult] = []
             grow_tets = grow_out = False
+            cn = plan.counts_np
             for i in range(B):
-                _cabi.check(L.d3h_wait_counts(counts_base + i * 128, seq0 + 1 + i, _WAIT_TIMEOUT_US), "d3h_wait_counts")
-                c = plan.counts[i]
-                fv, t1, t2, p, v, nfa = c.n_valid_tets, c.n_tri_tets, c.n_quad_tets, c.n_corners, c.n_verts, c.n_faces_aug
-                sizes.append((fv, t1, t2, p, v, nfa, tuple(c.bucket_polys)))
+                rc = wait(counts_base + i * 128, seq0 + 1 + i, _WAIT_TIMEOUT_US)
+                if rc:
+                    _cabi.check(rc, "d3h_wait_counts")
+                row = cn[i].tolist()
+                fv, t1, t2, p, v, nfa = row[0:6]
+                sizes[i] = row[0:6]
                 if fv > ct:
                     grow_tets = True
                 elif v > cv or v + p > cva or t1 + 2 * t2 > cfw or nfa > cfa:
                     grow_out = True
+                if grow_tets or grow_out:
+                    continue  # this attempt is void; keep reading the sizes of the other frames for the regrowth
+                # views of frame i, built while the GPU works on the later frames
+                va, fw = v + p, t1 + 2 * t2
+                fo, io = i * f_len, i * i_len
+                frames.append(ForwardResult(
+                    ast(fslab, (va, 3), (3, 1), fo + o_vaug), ast(fslab, (va, 3), (3, 1), fo + o_tng),
+                    ast(fslab, (va,), (1,), fo + o_maug), ast(islab, (nfa, 3), (3, 1), io),
+                    ast(fslab, (v, 3), (3, 1), fo + o_vwt), ast(fslab, (v, 3), (3, 1), fo + o_twt),
+                    ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa), v, t1, t2,
+                    dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
+                         n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=tuple(row[6:12]))))
+            if B == 1:
+                fw_, va_ = t1 + 2 * t2, v + p
+            else:
+                mx = sizes.max(axis=0).tolist()
+                fv, t1, t2, v, nfa = mx[0], mx[1], mx[2], mx[4], mx[5]
+                va_ = int((sizes[:, 4] + sizes[:, 3]).max())
+                fw_ = int((sizes[:, 1] + 2 * sizes[:, 2]).max())
             if grow_tets:  # record buffer too small: surface stages were skipped for some frame, its sizes are unknown
-                fv = max(s[0] for s in sizes)
-                t1, t2 = max(s[1] for s in sizes), max(s[2] for s in sizes)
                 p = 3 * t1 + 4 * t2
                 plan.cap_tets = _grow(fv)
                 # upper bounds that cannot overflow, so the next attempt is final
@@ -262,41 +377,25 @@ def forward_frames_raw(frames, tets_i32: torch.Tensor, watertight_template: bool
                 plan.cap_fw, plan.cap_fa = max(cfw, t1 + 2 * t2), max(cfa, 2 * t1 + 4 * t2)
                 continue
             if grow_out:
-                v, va = max(s[4] for s in sizes), max(s[4] + s[3] for s in sizes)
-                fw, nfa = max(s[1] + 2 * s[2] for s in sizes), max(s[5] for s in sizes)
-                plan.cap_v, plan.cap_va = max(cv, _grow(v)), max(cva, _grow(va))
-                plan.cap_fw, plan.cap_fa = max(cfw, _grow(fw)), max(cfa, _grow(nfa))
+                plan.cap_v, plan.cap_va = max(cv, _grow(v)), max(cva, _grow(va_))
+                plan.cap_fw, plan.cap_fa = max(cfw, _grow(fw_)), max(cfa, _grow(nfa))
                 continue
             break
         else:  # pragma: no cover
             raise RuntimeError("d3h_extract_forward_batch: capacities did not converge")
         # next call: predict from this call's sizes (the surface moves slowly between training iterations)
-        fv = max(s[0] for s in sizes)
-        v, va = max(s[4] for s in sizes), max(s[4] + s[3] for s in sizes)
-        fw, nfa = max(s[1] + 2 * s[2] for s in sizes), max(s[5] for s in sizes)
         plan.cap_tets = max(_grow(fv), min(plan.cap_tets, 2 * _grow(fv)))
-        plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va)
-        plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw), _shrink(plan.cap_fa, nfa)
-        ast = torch.as_strided
-        results = []
-        for i, (fv, t1, t2, p, v, nfa, buckets) in enumerate(sizes):
-            va, fw = v + p, t1 + 2 * t2
-            fo, io = i * f_len, i * i_len
-            results.append(ForwardResult(
-                ast(fslab, (va, 3), (3, 1), fo + o_vaug), ast(fslab, (va, 3), (3, 1), fo + o_tng),
-                ast(fslab, (va,), (1,), fo + o_maug), ast(islab, (nfa, 3), (3, 1), io),
-                ast(fslab, (v, 3), (3, 1), fo + o_vwt), ast(fslab, (v, 3), (3, 1), fo + o_twt),
-                ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa), tape, fslab,
-                tape_ptrs[i], v, t1, t2,
-                dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
-                     n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=buckets)))
-    return results, launches
+        plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va_)
+        plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw_), _shrink(plan.cap_fa, nfa)
+        if bmat is not None:
+            bmat[:, _BC["n_verts"]:_BC["n_quad_tets"] + 1] = sizes[:, (4, 1, 2)]
+    return BatchResult(frames, fslab, islab, tape, lay.tape_off, launches, bmat)
 
 
-def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template) -> ForwardResult:
+def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template) -> BatchResult:
     """One forward extraction without autograd (tests, profiling scripts)."""
-    res, _ = forward_frames_raw([(pos, sdf, msdf, msdf_negate)], tets_i32, watertight_template, lanes=1)
-    return res[0]
+    return forward_frames_raw([[pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr()]], [int(bool(msdf_negate))],
+                              pos.device, pos.shape[0], tets_i32, watertight_template, lanes=1)
 
 
 def _shrink(cap: int, need: int) -> int:
@@ -313,9 +412,12 @@ _OUTS_PER_FRAME = 8   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf
 class _ExtractFn(torch.autograd.Function):
     """A batch of frames as ONE autograd node.
 
-    forward : (spec, tets_i32, *unique input tensors) -> 8 tensors per frame (6 float + 2 index outputs)
+    forward : (spec, tets_i32, *input tensors) -> 8 tensors per frame (6 float + 2 index outputs)
     backward: dense gradients for every input tensor that needs one; a tensor shared by several frames (sdf / msdf of a
               batch of video frames, everything but msdf for the cloth / body pair) receives the sum over the frames.
+
+    spec = (frame refs, watertight_template, lanes); a frame ref is (pos, sdf, msdf, negate) where each of pos / sdf /
+    msdf is (input index, row): row >= 0 selects one row of a stacked (B,N,3) / (B,N) input, row < 0 the whole tensor.
 
     Differentiable outputs: verts_aug, msdf (augmented, stop-grad coefficients), vertices_watertight, msdf_watertight.
     v_tng_* are returned for API parity but are not differentiated (the reference's own training never consumes
@@ -324,116 +426,120 @@ class _ExtractFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, tets_i32, *tensors):
-        frame_ids, watertight_template, lanes = spec      # frame_ids: [(pos_idx, sdf_idx, msdf_idx, negate)]
+        refs, watertight_template, lanes = spec[:3]
+        launcher = spec[3] if len(spec) > 3 else None     # tet-range sharding (sharding.py)
         need = ctx.needs_input_grad[2:]
         any_grad = any(need)
+        B = len(refs)
+        base = [t.data_ptr() for t in tensors]
+        n_grid = tensors[refs[0][0][0]].shape[-2]
+        row_bytes = (12 * n_grid, 4 * n_grid, 4 * n_grid)
+
+        def addr(table, ref, kind):
+            idx, row = ref
+            return table[idx] + (row * row_bytes[kind] if row > 0 else 0)
+
+        ptrs = [[addr(base, r[k], k) for k in range(3)] for r in refs]
+        negate = [int(r[3]) for r in refs]
+        zero = grad_ptrs = None
         gbufs: List[Optional[torch.Tensor]] = [None] * len(tensors)
-        zero = None
         if any_grad:
             # dense gradient buffers of the coming backward call: allocated here, zero-filled by the tail of the
-            # forward call of the first frame that uses them (HBM is idle behind the latency-bound surface kernels)
-            zero, zeroed = [], set()
-            for (pi, si, mi, negate) in frame_ids:
-                z = []
-                for idx, wanted in ((pi, True), (si, True), (mi, need[mi] and not negate)):
-                    if not wanted:
-                        z.append(None)
+            # forward call of the frame that owns them (HBM is idle behind the latency-bound surface kernels)
+            gbase = [0] * len(tensors)
+            zeroed = set()
+            zero, grad_ptrs = [], []
+            for r in refs:
+                zrow, grow = [0, 0, 0], [0, 0, 0]
+                for k in range(3):
+                    idx, row = r[k]
+                    if k == 2 and not (need[idx] and not r[3]):   # "body" frames do not reach msdf (hmsdf_tets_split.py:256-264)
                         continue
                     if gbufs[idx] is None:
                         gbufs[idx] = torch.empty_like(tensors[idx])
-                    if idx in zeroed:
-                        z.append(None)
-                    else:
-                        zeroed.add(idx)
-                        z.append(gbufs[idx].data_ptr())
-                zero.append(tuple(z))
-        frames = [(tensors[pi], tensors[si], tensors[mi], negate) for (pi, si, mi, negate) in frame_ids]
-        results, launches = forward_frames_raw(frames, tets_i32, watertight_template, lanes, zero)
-        r0 = results[0]
-        ctx.save_for_backward(*tensors, r0.tape, r0.fslab)   # the slabs hold the tape and verts_wt / msdf_wt of all frames
-        ctx.meta = (frame_ids, tets_i32.shape[0], [(r.n_verts, r.n_tri, r.n_quad, r.tape_ptrs, r.verts_wt.data_ptr(),
-                                                      r.msdf_wt.data_ptr()) for r in results], lanes)
+                        gbase[idx] = gbufs[idx].data_ptr()
+                    g = grow[k] = addr(gbase, r[k], k)
+                    if (idx, row) not in zeroed:
+                        zeroed.add((idx, row))
+                        zrow[k] = g
+                zero.append(zrow)
+                grad_ptrs.append(grow)
+        res = forward_frames_raw(ptrs, negate, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero,
+                                 grad_ptrs, launcher)
+        ctx.save_for_backward(*tensors, res.tape, res.fslab)   # the slabs hold the tape and verts_wt / msdf_wt of all frames
+        ctx.bmat = res.bmat
+        ctx.meta = (refs, tets_i32.shape[0], n_grid, [(f.n_verts, f.n_tri, f.n_quad) for f in res.frames], lanes)
         ctx.gbufs = gbufs if any_grad else None
         ctx.set_materialize_grads(False)
         flat = []
         nondiff = []
-        for r in results:
+        for r in res.frames:
             flat += [r.verts_aug, r.v_tng_aug, r.msdf_aug, r.verts_wt, r.v_tng_wt, r.msdf_wt, r.faces_aug, r.faces_wt]
             nondiff += [r.faces_aug, r.faces_wt]
         ctx.mark_non_differentiable(*nondiff)
-        _ExtractFn.last_counts = [r.counts for r in results]
-        _ExtractFn.last_launches = launches
+        _ExtractFn.last_counts = [r.counts for r in res.frames]
+        _ExtractFn.last_launches = res.launches
         return tuple(flat)
 
     @staticmethod
     def backward(ctx, *grads):
-        frame_ids, n_tets, metas, lanes = ctx.meta
-        saved = ctx.saved_tensors
-        tensors = saved[:-2]
+        refs, n_tets, n_grid, sizes, lanes = ctx.meta
+        tensors = ctx.saved_tensors[:-2]
         need = ctx.needs_input_grad[2:]
         gbufs, ctx.gbufs = ctx.gbufs, None       # the pre-zeroed buffers serve ONE backward pass
-        out = backward_frames_raw(tensors, frame_ids, n_tets, metas, grads, need, gbufs, lanes)
-        return (None, None) + tuple(out)
-
-
-def backward_frames_raw(tensors, frame_ids, n_tets, metas, grads, need, gbufs, lanes):
-    """Adjoints of a batch in ONE library call.  grads: 8 upstream gradients per frame (None = zero).
-    Returns one dense gradient (or None) per input tensor."""
-    L = _cabi.lib()
-    dev = tensors[0].device
-    n_grid = tensors[frame_ids[0][0]].shape[0]
-    plan = _plan_for(dev, n_tets, n_grid)
-    B = len(frame_ids)
-    plan.ensure(B, 1)
-    ba = plan.bargs[B]
-    with torch.cuda.device(dev):
-        prezeroed = gbufs is not None
-        if not prezeroed:  # second backward through the same node (retain_graph): fresh zero-filled buffers
-            gbufs = [None] * len(tensors)
-            for (pi, si, mi, negate) in frame_ids:
-                for idx, wanted in ((pi, True), (si, True), (mi, need[mi] and not negate)):
-                    if wanted and gbufs[idx] is None:
-                        gbufs[idx] = torch.zeros_like(tensors[idx])
-        keep = []
-        n = 0
-        for i, (pi, si, mi, negate) in enumerate(frame_ids):
-            g = grads[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)]
-            if g[1] is not None or g[4] is not None:
-                raise NotImplementedError(
-                    "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
-                    "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
-            if g[0] is None and g[2] is None and g[3] is None and g[5] is None:
-                continue  # nothing flows into this frame
-            n_verts, n_tri, n_quad, tape_ptrs, p_vwt, p_mwt = metas[i]
-            va = n_verts + 3 * n_tri + 4 * n_quad
-            ptrs = []
-            for t, shape in ((g[0], (va, 3)), (g[2], (va,)), (g[3], (n_verts, 3)), (g[5], (n_verts,))):
-                if t is None:
-                    ptrs.append(None)
-                    continue
-                if t.dtype != torch.float32 or not t.is_contiguous():
-                    t = t.contiguous().float()
-                assert tuple(t.shape) == shape, (tuple(t.shape), shape)
-                keep.append(t)
-                ptrs.append(t.data_ptr())
-            b = ba[n]
-            n += 1
-            b.pos, b.sdf, b.msdf, b.n_grid = tensors[pi].data_ptr(), tensors[si].data_ptr(), tensors[mi].data_ptr(), n_grid
-            b.msdf_negate = int(negate)
-            b.grads_prezeroed = 1
-            b.tape_edges, b.tape_corners, b.tape_slots, b.tape_runs = tape_ptrs
-            b.verts_wt, b.msdf_wt = p_vwt, p_mwt
-            b.n_verts, b.n_tri_tets, b.n_quad_tets = n_verts, n_tri, n_quad
-            b.g_verts_aug, b.g_msdf_aug, b.g_verts_wt, b.g_msdf_wt = ptrs
-            b.g_pos, b.g_sdf = gbufs[pi].data_ptr(), gbufs[si].data_ptr()
-            gm = gbufs[mi] if (need[mi] and not negate) else None
-            b.g_msdf = gm.data_ptr() if gm is not None else None
-            b.workspace, b.workspace_bytes = None, 0
-        if n:
-            _cabi.check(L.d3h_extract_backward_batch(ba, n, max(1, min(lanes, n)),
-                                                     torch.cuda.current_stream(dev).cuda_stream),
-                        "d3h_extract_backward_batch")
-    return [gbufs[i] if need[i] else None for i in range(len(tensors))]
+        bmat = ctx.bmat
+        if bmat is None:
+            raise RuntimeError("backward through an extraction whose inputs did not require gradients")
+        L = _cabi.lib()
+        dev = tensors[0].device
+        with torch.cuda.device(dev):
+            if gbufs is None:  # second backward through the same node (retain_graph): fresh zero-filled buffers
+                gbufs = [None] * len(tensors)
+                bmat = bmat.copy()
+                row_bytes = (12 * n_grid, 4 * n_grid, 4 * n_grid)
+                names = ("g_pos", "g_sdf", "g_msdf")
+                for i, r in enumerate(refs):
+                    for k in range(3):
+                        idx, row = r[k]
+                        if bmat[i, _BC[names[k]]] == 0:
+                            continue
+                        if gbufs[idx] is None:
+                            gbufs[idx] = torch.zeros_like(tensors[idx])
+                        bmat[i, _BC[names[k]]] = gbufs[idx].data_ptr() + (row * row_bytes[k] if row > 0 else 0)
+            keep = []
+            live = []
+            gp = []   # per live frame: pointers of g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt (adjacent columns)
+            f32 = torch.float32
+            for i in range(len(refs)):
+                o = _OUTS_PER_FRAME * i
+                g0, g1, g2, g3, g4, g5 = grads[o:o + 6]
+                if g1 is not None or g4 is not None:
+                    raise NotImplementedError(
+                        "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
+                        "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
+                if g0 is None and g2 is None and g3 is None and g5 is None:
+                    continue  # nothing flows into this frame
+                n_verts, n_tri, n_quad = sizes[i]
+                va = n_verts + 3 * n_tri + 4 * n_quad
+                row = []
+                for t, rows in ((g0, va), (g2, va), (g3, n_verts), (g5, n_verts)):
+                    if t is None:
+                        row.append(0)
+                        continue
+                    if t.dtype is not f32 or not t.is_contiguous():
+                        t = t.contiguous().float()
+                        keep.append(t)
+                    assert t.shape[0] == rows, (tuple(t.shape), rows)
+                    row.append(t.data_ptr())
+                gp.append(row)
+                live.append(i)
+            if live:
+                m = bmat if len(live) == len(refs) else np.ascontiguousarray(bmat[live])
+                m[:, _BC["g_verts_aug"]:_BC["g_msdf_wt"] + 1] = gp
+                _cabi.check(L.d3h_extract_backward_batch(m.ctypes.data, len(live), max(1, min(lanes, len(live))),
+                                                         torch.cuda.current_stream(dev).cuda_stream),
+                            "d3h_extract_backward_batch")
+        return (None, None) + tuple(gbufs[i] if need[i] else None for i in range(len(tensors)))
 
 
 _ExtractFn.last_counts = None
@@ -456,10 +562,14 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
     return t if t.data_ptr() % 16 == 0 else t.clone()
 
 
-def _prep_pos(pos_nx3):
-    if not pos_nx3.is_cuda:
+def _check_cuda(t):
+    if not t.is_cuda:
         raise RuntimeError("d3human-code_b200 has no CPU path: inputs must live on a CUDA device "
                            "(the reference hard-codes device='cuda' as well, gshell_tets.py:108)")
+
+
+def _prep_pos(pos_nx3):
+    _check_cuda(pos_nx3)
     if pos_nx3.dim() != 2 or pos_nx3.shape[1] != 3:
         raise ValueError(f"pos_nx3 must have shape (N,3), got {tuple(pos_nx3.shape)}")
     return _aligned(pos_nx3.float())
@@ -496,7 +606,7 @@ def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_w
     n_grid = pos.shape[0]
     sdf, msdf = _prep_field(sdf_n, n_grid), _prep_field(msdf_n, n_grid)
     tets = packed_tets(tet_fx4, n_grid)
-    spec = (((0, 1, 2, bool(msdf_negate)),), bool(output_watertight_template), 1)
+    spec = ((((0, -1), (1, -1), (2, -1), bool(msdf_negate)),), bool(output_watertight_template), 1)
     return _pack_result(_ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)
 
 
@@ -507,22 +617,13 @@ def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watert
     No counterpart in the reference, which would loop over the frames (BASELINE.json configs[3]: a batch of video frames
     per step with per-frame tet-vertex offsets; also the cloth / body pair of train.py:1040-1047).
 
-    pos_frames : (B,N,3) tensor or a sequence of (N,3) tensors -- per-frame deformed grid vertices
-    sdf_n, msdf_n : one tensor shared by all frames ((N,) or (N,1)), or a sequence with one tensor per frame
+    pos_frames : (B,N,3) tensor (one autograd leaf for the whole batch) or a sequence of (N,3) tensors
+    sdf_n, msdf_n : one tensor shared by all frames ((N,) or (N,1)), a stacked (B,N) tensor, or a sequence per frame
     types : None (GShell_Tets semantics), one of "cloth" / "body" for all frames, or a sequence per frame
             (hmSDF_Tets semantics: "body" uses -msdf and, like the reference, does not back-propagate into msdf_n)
     Returns a list with the reference's 6-tuple `(verts, faces, None, None, v_tng, extra)` for every frame.  Gradients of
     shared tensors are summed over the frames.
     """
-    if torch.is_tensor(pos_frames):
-        if pos_frames.dim() != 3:
-            raise ValueError(f"pos_frames must be (B,N,3), got {tuple(pos_frames.shape)}")
-        pos_list = list(pos_frames.unbind(0))
-    else:
-        pos_list = list(pos_frames)
-    B = len(pos_list)
-    if B == 0:
-        return []
     tensors: List[torch.Tensor] = []
     index: Dict[int, int] = {}
 
@@ -533,21 +634,48 @@ def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watert
             tensors.append(prep(src))
         return index[k]
 
-    pos_ids = [intern(p, _prep_pos) for p in pos_list]
-    n_grid = tensors[pos_ids[0]].shape[0]
-    prep_f = lambda f: _prep_field(f, n_grid)  # noqa: E731
-    sdf_list = [sdf_n] * B if torch.is_tensor(sdf_n) else list(sdf_n)
-    msdf_list = [msdf_n] * B if torch.is_tensor(msdf_n) else list(msdf_n)
+    if torch.is_tensor(pos_frames):
+        if pos_frames.dim() != 3 or pos_frames.shape[2] != 3:
+            raise ValueError(f"pos_frames must be (B,N,3), got {tuple(pos_frames.shape)}")
+        _check_cuda(pos_frames)
+        B, n_grid = pos_frames.shape[0], pos_frames.shape[1]
+        if B == 0:
+            return []
+        tensors.append(_aligned(pos_frames.float()))
+        pos_refs = [(0, i) for i in range(B)]
+    else:
+        pos_list = list(pos_frames)
+        B = len(pos_list)
+        if B == 0:
+            return []
+        pos_refs = [(intern(p, _prep_pos), -1) for p in pos_list]
+        n_grid = tensors[pos_refs[0][0]].shape[0]
+
+    def field_refs(f):
+        if torch.is_tensor(f):
+            if f.dim() == 2 and f.shape[0] == B and f.shape[1] == n_grid and n_grid > 1:   # stacked (B,N)
+                if (4 * n_grid) % 16:
+                    raise ValueError("a stacked (B,N) field needs N % 4 == 0 (16-byte aligned rows); pass a list instead")
+                _check_cuda(f)
+                k = intern(f, lambda t: _aligned(t.float()))
+                return [(k, i) for i in range(B)]
+            k = intern(f, lambda t: _prep_field(t, n_grid))
+            return [(k, -1)] * B
+        fl = list(f)
+        if len(fl) != B:
+            raise ValueError("sdf_n / msdf_n / types must be shared or have one entry per frame")
+        return [(intern(t, lambda u: _prep_field(u, n_grid)), -1) for t in fl]
+
+    sdf_refs, msdf_refs = field_refs(sdf_n), field_refs(msdf_n)
     type_list = [types] * B if (types is None or isinstance(types, str)) else list(types)
-    if not (len(sdf_list) == len(msdf_list) == len(type_list) == B):
+    if len(type_list) != B:
         raise ValueError("sdf_n / msdf_n / types must be shared or have one entry per frame")
-    frame_ids = tuple((pos_ids[i], intern(sdf_list[i], prep_f), intern(msdf_list[i], prep_f), type_list[i] == "body")
-                      for i in range(B))
-    for t in tensors:
-        if t.shape[0] != n_grid:
+    for r in pos_refs:
+        if tensors[r[0]].shape[-2] != n_grid:
             raise ValueError("all frames must live on the same tet grid (same N)")
+    refs = tuple((pos_refs[i], sdf_refs[i], msdf_refs[i], type_list[i] == "body") for i in range(B))
     tets = packed_tets(tet_fx4, n_grid)
-    spec = (frame_ids, bool(output_watertight_template), int(lanes))
+    spec = (refs, bool(output_watertight_template), int(lanes))
     flat = _ExtractFn.apply(spec, tets, *tensors)
     return [_pack_result(flat[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)], output_watertight_template)
             for i in range(B)]

@@ -21,29 +21,28 @@ sdf_np, msdf_np = (grids.capsule_garment_field if args.field == "capsule" else g
 pos, sdf, msdf = (torch.from_numpy(x).to(dev) for x in (pos_np, sdf_np, msdf_np))
 tets = E.packed_tets(torch.from_numpy(tets_np).to(dev), pos.shape[0])
 F, N = tets.shape[0], pos.shape[0]
-r = E.forward_raw(pos, sdf, msdf, tets, False, True, want_grads=(True, True, True))   # learn the sizes
-r = E.forward_raw(pos, sdf, msdf, tets, False, True, want_grads=(True, True, True))   # capacities settled
+gp, gs, gm = torch.empty_like(pos), torch.empty_like(sdf), torch.empty_like(msdf)
+ptrs = [[pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr()]]
+gptrs = [[gp.data_ptr(), gs.data_ptr(), gm.data_ptr()]]
+zero = None if args.no_zero else gptrs
+for _ in range(2):   # learn the sizes, then settle the capacities
+    r = E.forward_frames_raw(ptrs, [0], dev, N, tets, True, lanes=1, zero=zero, grad_ptrs=gptrs)
 plan = E._plan_for(dev, F, N)
-a = plan.args                                   # still holds the pointers of the last call (buffers kept alive by r)
-gva = torch.randn_like(r.verts_aug); gma = torch.randn_like(r.msdf_aug)
-b = _cabi.BackwardArgs()
-b.pos, b.sdf, b.msdf, b.n_grid = pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr(), N
-b.grads_prezeroed = 0 if args.no_zero else 1
-b.tape_edges, b.tape_corners, b.tape_slots, b.tape_runs = r.tape_ptrs
-b.verts_wt, b.msdf_wt = r.verts_wt.data_ptr(), r.msdf_wt.data_ptr()
-b.n_verts, b.n_tri_tets, b.n_quad_tets = r.n_verts, r.n_tri, r.n_quad
-b.g_verts_aug, b.g_msdf_aug = gva.data_ptr(), gma.data_ptr()
-b.g_pos, b.g_sdf, b.g_msdf = (t.data_ptr() for t in r.zero_grads)
-L = _cabi.lib()
+A = plan.layouts[(1, 1, 1)].A                                # still holds the pointers of the last call (buffers kept alive by r)
+f0 = r.frames[0]
+gva = torch.randn_like(f0.verts_aug); gma = torch.randn_like(f0.msdf_aug)
+bm = r.bmat
+bm[0, E._BC["g_verts_aug"]], bm[0, E._BC["g_msdf_aug"]] = gva.data_ptr(), gma.data_ptr()
 if args.no_zero:
-    a.zero_g_pos = a.zero_g_sdf = a.zero_g_msdf = None
+    bm[0, E._BC["msdf_negate"]] = 0             # grads_prezeroed = 0: the backward call zero-fills
+L = _cabi.lib()
 s = torch.cuda.Stream()
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
 with torch.cuda.stream(s):
     with torch.cuda.graph(g, stream=s):
-        _cabi.check(L.d3h_extract_forward(C.byref(a), s.cuda_stream), "fwd")
-        _cabi.check(L.d3h_extract_backward(C.byref(b), s.cuda_stream), "bwd")
+        _cabi.check(L.d3h_extract_forward_batch(A.ctypes.data, 1, 1, s.cuda_stream), "fwd")
+        _cabi.check(L.d3h_extract_backward_batch(bm.ctypes.data, 1, 1, s.cuda_stream), "bwd")
     for _ in range(10):
         g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,7 +52,7 @@ with torch.cuda.stream(s):
     e1.record(s)
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / args.reps * 1e3
-c = r.counts
+c = f0.counts
 balg = grids.surface_counts_bytes(F, N, c["n_verts"], c["n_verts_aug"], c["n_faces_watertight"], c["n_faces_aug"])
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 print(json.dumps({"what": "graph replay of forward+backward kernels, no host in the loop", "res": args.res, "F": F, "N": N,

@@ -35,7 +35,7 @@ class Wrap:
         return r
 
 
-for name in ("d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward"):
+for name in ("d3h_extract_forward_batch", "d3h_wait_counts", "d3h_extract_backward_batch"):
     setattr(L, name, Wrap(name, getattr(L, name)))
 verts, faces, _, _, _, extra = hm(pos, sdf, msdf, tets, "cloth")
 gv, gm = torch.randn_like(verts), torch.randn_like(extra["msdf"])
@@ -48,7 +48,7 @@ for it in range(args.iters + 20):
     t1 = now()
     torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
     t2 = now()
-    f, w, b = stamps["d3h_extract_forward"][-1], stamps["d3h_wait_counts"][-1], stamps["d3h_extract_backward"][-1]
+    f, w, b = stamps["d3h_extract_forward_batch"][-1], stamps["d3h_wait_counts"][-1], stamps["d3h_extract_backward_batch"][-1]
     if it >= 20:
         rows.append((f[0] - t0, f[1] - f[0], w[0] - f[1], w[1] - w[0], t1 - w[1], b[0] - t1, b[1] - b[0], t2 - b[1], t2 - t0))
 torch.cuda.synchronize()

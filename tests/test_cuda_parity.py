@@ -137,14 +137,14 @@ def test_integer_intermediates_match_oracle(dev):
     tt = E.packed_tets(torch.tensor(tets, device=dev), pos.shape[0])
     r = E.forward_raw(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev), torch.tensor(msdf, device=dev), tt,
                       False, True)
-    c = r.counts
+    c = r.frames[0].counts
     assert c["n_valid_tets"] == fwd["fv"] and c["n_tri_tets"] == fwd["t1"] and c["n_quad_tets"] == fwd["t2"]
     assert c["n_verts"] == fwd["n_verts_watertight"] and c["n_faces_aug"] == fwd["faces_aug"].shape[0]
     assert c["bucket_polys"] == tuple(int(x // k) for x, k in zip(fwd["bucket_counts"], (1, 2, 1, 2, 3, 4)))
-    edges = r.tape_edges.cpu().numpy()
+    edges = r.tape_edges(0).cpu().numpy()
     U.assert_exact("edge_a", edges[:, 0].astype(np.int64), fwd["edge_a"])
     U.assert_exact("edge_b", edges[:, 1].astype(np.int64), fwd["edge_b"])
-    U.assert_exact("corners", r.tape_corners.cpu().numpy().astype(np.int64), fwd["corners"])
+    U.assert_exact("corners", r.tape_corners(0).cpu().numpy().astype(np.int64), fwd["corners"])
 
 
 def test_smplx_layout_split_extraction(dev):
@@ -257,6 +257,37 @@ def test_extract_frames_list_form_and_repeat(dev):
             fwd = O.extract_forward(pos, sdfs[i], msdf, tets)
             U.assert_exact(f"faces_aug[{i}]", faces.cpu().numpy(), fwd["faces_aug"])
             U.assert_exact(f"verts_aug[{i}]", verts.cpu().numpy(), fwd["verts_aug"])
+
+
+# ---------------------------------------------------------------------------------------------- tet-range sharding
+@pytest.mark.parametrize("res,field,typ,vr", [(24, "capsule", "cloth", 3), (20, "adv", "body", 2), (33, "sphere", "cloth", 8)])
+def test_tet_range_sharding_virtual_ranks_bit_identical(dev, res, field, typ, vr):
+    """BASELINE configs[4] path on one GPU: classify `vr` tet ranges separately (d3h_classify_range), concatenate the
+    records in range order, run the surface stages on the merged list (d3h_extract_from_records): identical to the
+    single call, forward and backward."""
+    from d3human_code_b200.extract import extract
+    from d3human_code_b200.sharding import extract_tet_sharded
+    pos, sdf, msdf, tets = _inputs(res, field, seed=res)
+    tt = torch.tensor(tets, device=dev)
+    outs = []
+    for fn in (lambda *a: extract(*a, msdf_negate=(typ == "body")),
+               lambda *a: extract_tet_sharded(*a, msdf_negate=(typ == "body"), virtual_ranks=vr)):
+        tp = torch.tensor(pos, device=dev, requires_grad=True)
+        ts = torch.tensor(sdf, device=dev, requires_grad=True)
+        tm = torch.tensor(msdf, device=dev, requires_grad=True)
+        verts, faces, _, _, v_tng, extra = fn(tp, ts, tm, tt)
+        (verts.square().sum() + extra["msdf"].sum() + extra["vertices_watertight"].sum()).backward()
+        outs.append((verts.detach(), faces, extra["msdf"].detach(), extra["faces_watertight"],
+                     extra["vertices_watertight"].detach(), tp.grad, ts.grad))
+    for a, b in zip(*outs):
+        assert a.shape == b.shape
+    for k in range(5):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    for k in (5, 6):   # atomics order differs between runs: compare to gradient tolerance
+        U.assert_close_normwise(f"grad{k}", outs[1][k].cpu().numpy(), outs[0][k].cpu().numpy(), U.GRAD_RTOL)
+    fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, True)
+    U.assert_exact("faces_aug", outs[1][1].cpu().numpy(), fwd["faces_aug"])
+    U.assert_exact("verts_aug", outs[1][0].cpu().numpy(), fwd["verts_aug"])
 
 
 # ---------------------------------------------------------------------------------------------- full size
