@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=20)
+    ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per pipelined chunk of the end-to-end leg")
     return ap.parse_args()
 
 
@@ -279,37 +280,65 @@ def main():
     # ---- end to end through the public API with HOST buffers ----
     e2e = None
     if not args.no_e2e:
+        # The batch is cut into chunks of `--e2e-chunk` frames that flow through three streams: H2D copies of chunk
+        # k+1 and D2H copies of chunk k-1 run under the extraction of chunk k (PCIe is full duplex, ~55 GB/s each way).
+        chunk = max(1, min(args.e2e_chunk, fpr))
+        bounds = [(i, min(i + chunk, fpr)) for i in range(0, fpr, chunk)]
         d_sdf = torch.empty_like(sdf)
         d_msdf = torch.empty_like(msdf)
-        d_pos = torch.empty_like(pos)
+        d_pos = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds]
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         outs_host = None
         k_e2e = max(3, min(args.steps, 20))
 
         def e2e_step():
             nonlocal outs_host
             h2d = d2h = 0
-            for dst, src in ((d_sdf, host_sdf), (d_msdf, host_msdf)):
-                dst.requires_grad_(False)
-                dst.copy_(src, non_blocking=True)
-                dst.requires_grad_(True)
-                dst.grad = None
-            h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
-            d_pos.requires_grad_(False)
-            d_pos.copy_(host_pos, non_blocking=True)
-            d_pos.requires_grad_(True)
-            d_pos.grad = None
-            h2d += host_pos.numel() * 4
-            outs = E.extract_frames(d_pos, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
-            torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v + ups_m)
-            res_flat = []
-            for o in outs:
-                res_flat += [o[0].detach(), o[1], o[5]["msdf"].detach()]
-            res_flat += [d_pos.grad, d_sdf.grad, d_msdf.grad]
-            if outs_host is None:
-                outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res_flat]
-            for h, t in zip(outs_host, res_flat):
-                h.copy_(t, non_blocking=True)
-                d2h += t.numel() * t.element_size()
+            cur = torch.cuda.current_stream()
+            s_in.wait_stream(cur)
+            ev_in = []
+            with torch.cuda.stream(s_in):
+                for dst, src in ((d_sdf, host_sdf), (d_msdf, host_msdf)):
+                    dst.requires_grad_(False)
+                    dst.copy_(src, non_blocking=True)
+                    dst.requires_grad_(True)
+                    dst.grad = None
+                h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
+                for dp, (lo, hi) in zip(d_pos, bounds):
+                    dp.requires_grad_(False)
+                    dp.copy_(host_pos[lo:hi], non_blocking=True)
+                    dp.requires_grad_(True)
+                    dp.grad = None
+                    h2d += dp.numel() * 4
+                    ev = torch.cuda.Event()
+                    ev.record(s_in)
+                    ev_in.append(ev)
+            keep, res_all = [], []
+            for k, (dp, (lo, hi)) in enumerate(zip(d_pos, bounds)):
+                cur.wait_event(ev_in[k])
+                outs = E.extract_frames(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
+                torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs],
+                                        ups_v[lo:hi] + ups_m[lo:hi])
+                res = []
+                for o in outs:
+                    res += [o[0].detach(), o[1], o[5]["msdf"].detach()]
+                res.append(dp.grad)
+                if k == len(bounds) - 1:
+                    res += [d_sdf.grad, d_msdf.grad]
+                s_out.wait_stream(cur)
+                res_all.append(res)
+                if outs_host is not None:
+                    with torch.cuda.stream(s_out):
+                        for h, t in zip(outs_host[k], res):
+                            h.copy_(t, non_blocking=True)
+                            d2h += t.numel() * t.element_size()
+                keep.append(outs)
+            if outs_host is None:   # first call: allocate the pinned result buffers, copy without overlap
+                outs_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res] for res in res_all]
+                for hs, res in zip(outs_host, res_all):
+                    for h, t in zip(hs, res):
+                        h.copy_(t, non_blocking=True)
+                        d2h += t.numel() * t.element_size()
             torch.cuda.synchronize()
             return h2d, d2h
 
@@ -325,9 +354,11 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * fpr * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "steps": k_e2e, "ms_per_step": float(dt.item()) * 1e3,
+               "chunk_frames": chunk,
                "note": "extract_frames() with inputs copied from pinned host memory each step (pos per frame, sdf, "
                        "msdf); per frame verts_aug, faces_aug, msdf and the dense pos gradient, plus the sdf / msdf "
-                       "gradients, copied back to pinned host memory; static tet indices stay resident"}
+                       "gradients, copied back to pinned host memory; static tet indices stay resident; chunks of "
+                       "frames pipelined over H2D / compute / D2H streams"}
 
     if rank != 0:
         if world > 1:

@@ -12,14 +12,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 300
+VERSION = 310
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
     "d3h_extract_forward_batch", "d3h_extract_backward_batch", "d3h_classify_range", "d3h_extract_from_records",
-    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_debug_table",
+    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_debug_table",
 )
 
 
@@ -59,7 +59,7 @@ class BackwardArgs(C.Structure):  # d3h_backward_args
                 ("g_verts_aug", C.c_void_p), ("g_msdf_aug", C.c_void_p), ("g_verts_wt", C.c_void_p),
                 ("g_msdf_wt", C.c_void_p),
                 ("g_pos", C.c_void_p), ("g_sdf", C.c_void_p), ("g_msdf", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("g_msdf_boundary", C.c_void_p)]
 
 
 TET_RECORD_BYTES = 32  # sizeof(d3h_tet_record)
@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
     L.d3h_profile_kernel_name.argtypes = [C.c_int]
     L.d3h_profile_read.restype = C.c_int
     L.d3h_profile_read.argtypes = [C.c_void_p, C.c_void_p]
+    L.d3h_profile_timeline.restype = C.c_int
+    L.d3h_profile_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.d3h_debug_table.restype = C.c_int
     L.d3h_debug_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
     if L.d3h_version() != VERSION:
@@ -128,6 +130,17 @@ def profile_read():
     cnt = (C.c_int * n)()
     check(L.d3h_profile_read(ms, cnt), "d3h_profile_read")
     return {L.d3h_profile_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}
+
+
+def profile_timeline(cap: int = 4096):
+    """-> [(start_ms, end_ms, kernel name, stream ordinal)] of every launch since the last read."""
+    L = lib()
+    a, b = (C.c_float * cap)(), (C.c_float * cap)()
+    k, sid = (C.c_int * cap)(), (C.c_int * cap)()
+    n = L.d3h_profile_timeline(a, b, k, sid, cap)
+    if n < 0:
+        check(n, "d3h_profile_timeline")
+    return [(a[i], b[i], L.d3h_profile_kernel_name(k[i]).decode(), sid[i]) for i in range(n)]
 
 
 def check(rc: int, what: str) -> None:

@@ -23,7 +23,7 @@ void set_error(const char* fmt, ...) {
 
 // ---- profiler -------------------------------------------------------------------------------------
 static bool g_prof_on = false;
-struct ProfRec { int kind; cudaEvent_t a, b; };
+struct ProfRec { int kind; cudaEvent_t a, b; cudaStream_t stream; };
 static ProfRec g_prof[4096];
 static int g_prof_n = 0;
 
@@ -32,6 +32,7 @@ ProfScope::ProfScope(int kind, cudaStream_t st) : slot(-1), stream(st) {
   slot = g_prof_n++;
   ProfRec& r = g_prof[slot];
   r.kind = kind;
+  r.stream = st;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, stream);
@@ -460,24 +461,13 @@ static int check_backward_args(const d3h_backward_args* a, const char* who) {
 extern "C" int d3h_extract_backward_batch(const d3h_backward_args* args, int64_t n_frames, int32_t lanes,
                                           d3h_stream_t s) {
   if (!args || n_frames < 0 || lanes < 1) { set_error("d3h_extract_backward_batch: null args / bad sizes"); return D3H_E_BADARG; }
-  if (lanes > kMaxLanes) lanes = kMaxLanes;
-  if (lanes > n_frames) lanes = (int32_t)(n_frames > 0 ? n_frames : 1);
   for (int64_t i = 0; i < n_frames; ++i) {
     int rc = check_backward_args(&args[i], "d3h_extract_backward_batch");
     if (rc) return rc;
   }
+  (void)lanes;
   if (n_frames == 0) return D3H_OK;
-  if (n_frames == 1) return d3h_extract_backward(args, s);
-  cudaStream_t stream = (cudaStream_t)s;
-  LaneSet* ls = lanes_for_current_device();
-  if (ls == nullptr) { set_error("d3h_extract_backward_batch: cannot create the lane streams"); return D3H_E_CUDA; }
-  cudaEventRecord(ls->fork, stream);
-  for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->lane[l], ls->fork, 0);
-  for (int64_t i = 0; i < n_frames; ++i) launch_backward(args[i], ls->lane[i % lanes]);
-  for (int l = 0; l < lanes; ++l) {
-    cudaEventRecord(ls->join[l], ls->lane[l]);
-    cudaStreamWaitEvent(stream, ls->join[l], 0);
-  }
+  launch_backward_batch(args, n_frames, (cudaStream_t)s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_extract_backward_batch: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
   return D3H_OK;
@@ -574,6 +564,33 @@ extern "C" int d3h_profile_read(float* ms_by_kind, int* launches_by_kind) {
   }
   g_prof_n = 0;
   return rc;
+}
+
+// Timeline variant of d3h_profile_read: start / end of every recorded launch in milliseconds since the first one, its
+// kernel kind and a small integer naming the stream it ran on (lanes of a batch run concurrently).  Clears the log.
+extern "C" int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, int* stream_id, int cap) {
+  if (!start_ms || !end_ms || !kind || !stream_id) { set_error("d3h_profile_timeline: null output"); return D3H_E_BADARG; }
+  int n = g_prof_n < cap ? g_prof_n : cap;
+  cudaStream_t seen[64];
+  int nseen = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    ProfRec& r = g_prof[i];
+    cudaEventSynchronize(r.b);
+    if (i < n) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, g_prof[0].a, r.a);
+      cudaEventElapsedTime(&b, g_prof[0].a, r.b);
+      start_ms[i] = a; end_ms[i] = b; kind[i] = r.kind;
+      int sid = -1;
+      for (int k = 0; k < nseen; ++k) if (seen[k] == r.stream) sid = k;
+      if (sid < 0 && nseen < 64) { seen[nseen] = r.stream; sid = nseen++; }
+      stream_id[i] = sid;
+    }
+  }
+  for (int i = 0; i < g_prof_n; ++i) { cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b); }
+  g_prof_n = 0;
+  cudaGetLastError();
+  return n;
 }
 
 // ---- test hook: the case tables, from the same initializer macros the __constant__ copies are built from --------

@@ -87,24 +87,46 @@ struct EdgePull {  // what one polygon edge i -> j contributes to its two end ve
   float gx_j, gy_j, gz_j, gsg_j, gmv_j;
 };
 
+// One frame's view of d3h_backward_args as the kernel needs it (passed by value, kAdjBatch frames per launch).
+struct AdjFrame {
+  const int32_t *edges, *corners, *slots, *runs;
+  const float *pos, *sdf, *msdf, *verts_wt, *msdf_wt;
+  const float *g_verts_aug, *g_msdf_aug, *g_msdf_bnd, *g_verts_wt, *g_msdf_wt;
+  float *g_pos, *g_sdf, *g_msdf;
+  int64_t nv, t1;
+  int msdf_negate, pad;
+};
+constexpr int kAdjBatch = 16;
+struct AdjBatch {
+  AdjFrame f[kAdjBatch];
+};
+
+// upstream gradient of extra['msdf'] at augmented row `row`: the caller may hand it over whole (g_msdf_aug, Va rows)
+// and / or as the boundary slice extra['msdf_boundary'] = msdf[V:] (g_msdf_bnd, Va - V rows)
+__device__ __forceinline__ float upstream_msdf(const AdjFrame& f, int64_t row) {
+  float g = 0.f;
+  if (f.g_msdf_aug != nullptr) g = __ldg(f.g_msdf_aug + row);
+  if (f.g_msdf_bnd != nullptr && row >= f.nv) g += __ldg(f.g_msdf_bnd + (row - f.nv));
+  return g;
+}
+
 // Adjoint of the boundary vertex on polygon edge i -> j whose row in the augmented arrays is `row`
 // (gshell_tets.py:353-385 forward).
-__device__ __forceinline__ EdgePull pull_edge(int64_t row, float mi, float mj, const float* __restrict__ vi,
-                                              const float* __restrict__ vj, const float* __restrict__ g_verts_aug,
-                                              const float* __restrict__ g_msdf_aug) {
+__device__ __forceinline__ EdgePull pull_edge(const AdjFrame& f, int64_t row, float mi, float mj,
+                                              const float* __restrict__ vi, const float* __restrict__ vj) {
   EdgePull r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float u0, u1, D;
   const bool nz = boundary_weights(mi, mj, u0, u1, D);
   // the row is zeroed in forward unless its polygon's cut references it (gshell_tets.py:423-427):
   // that is exactly when the mSDF sign changes across the edge
   const bool used = (mi > 0.f) != (mj > 0.f);
-  float gx = 0.f, gy = 0.f, gz = 0.f, gm = 0.f;
-  if (g_verts_aug != nullptr && used) {
-    gx = __ldg(g_verts_aug + 3 * row);
-    gy = __ldg(g_verts_aug + 3 * row + 1);
-    gz = __ldg(g_verts_aug + 3 * row + 2);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (f.g_verts_aug != nullptr && used) {
+    gx = __ldg(f.g_verts_aug + 3 * row);
+    gy = __ldg(f.g_verts_aug + 3 * row + 1);
+    gz = __ldg(f.g_verts_aug + 3 * row + 2);
   }
-  if (g_msdf_aug != nullptr) gm = __ldg(g_msdf_aug + row);
+  const float gm = upstream_msdf(f, row);
   r.gx_i = gx * u0; r.gy_i = gy * u0; r.gz_i = gz * u0; r.gsg_i = gm * u0;
   r.gx_j = gx * u1; r.gy_j = gy * u1; r.gz_j = gz * u1; r.gsg_j = gm * u1;
   if (nz) {
@@ -118,14 +140,28 @@ __device__ __forceinline__ EdgePull pull_edge(int64_t row, float mi, float mj, c
   return r;
 }
 
-__global__ void __launch_bounds__(256)
-adjoint_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ corners,
-               const int32_t* __restrict__ slots, const int32_t* __restrict__ runs, const float* __restrict__ pos,
-               const float* __restrict__ sdf, const float* __restrict__ msdf, int msdf_negate, int64_t nv, int64_t t1,
-               const float* __restrict__ verts_wt, const float* __restrict__ msdf_wt,
-               const float* __restrict__ g_verts_aug, const float* __restrict__ g_msdf_aug,
-               const float* __restrict__ g_verts_wt, const float* __restrict__ g_msdf_wt, float* __restrict__ g_pos,
-               float* __restrict__ g_sdf, float* __restrict__ g_msdf) {
+// grid.y = frame of the batch: the adjoints of all frames are one launch (their blocks run side by side)
+__global__ void __launch_bounds__(256) adjoint_kernel(const __grid_constant__ AdjBatch batch) {
+  const AdjFrame& f = batch.f[blockIdx.y];
+  const int64_t nv = f.nv, t1 = f.t1;
+  if ((int64_t)blockIdx.x * blockDim.x >= nv) return;
+  const int32_t* __restrict__ edges = f.edges;
+  const int32_t* __restrict__ corners = f.corners;
+  const int32_t* __restrict__ slots = f.slots;
+  const int32_t* __restrict__ runs = f.runs;
+  const float* __restrict__ pos = f.pos;
+  const float* __restrict__ sdf = f.sdf;
+  const float* __restrict__ msdf = f.msdf;
+  const float* __restrict__ verts_wt = f.verts_wt;
+  const float* __restrict__ msdf_wt = f.msdf_wt;
+  const float* __restrict__ g_verts_aug = f.g_verts_aug;
+  const float* __restrict__ g_verts_wt = f.g_verts_wt;
+  const float* __restrict__ g_msdf_wt = f.g_msdf_wt;
+  float* __restrict__ g_pos = f.g_pos;
+  float* __restrict__ g_sdf = f.g_sdf;
+  float* __restrict__ g_msdf = f.g_msdf;
+  const int msdf_negate = f.msdf_negate;
+  const bool any_msdf_up = f.g_msdf_aug != nullptr || f.g_msdf_bnd != nullptr;
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = v < nv;
   const unsigned active = __ballot_sync(0xffffffffu, live);
@@ -135,7 +171,7 @@ adjoint_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ co
   // g_vert, g_sg (stop-grad mSDF attribute), g_mv (mSDF through the boundary coefficients)
   float gx = 0.f, gy = 0.f, gz = 0.f, gsg = 0.f, gmv = 0.f;
 
-  if (g_verts_aug != nullptr || g_msdf_aug != nullptr) {
+  if (g_verts_aug != nullptr || any_msdf_up) {
     const int s0 = __ldg(runs + v), s1 = __ldg(runs + v + 1);
     for (int s = s0; s < s1; ++s) {
       const int64_t p = __ldg(slots + s);  // a corner of some polygon that sits on vertex v
@@ -148,8 +184,8 @@ adjoint_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ co
       const float vn[3] = {__ldg(verts_wt + 3 * jn), __ldg(verts_wt + 3 * jn + 1), __ldg(verts_wt + 3 * jn + 2)};
       const float vp[3] = {__ldg(verts_wt + 3 * jp), __ldg(verts_wt + 3 * jp + 1), __ldg(verts_wt + 3 * jp + 2)};
       // edge p -> pn: v is the i end (row nv + p); edge pp -> p: v is the j end (row nv + pp)
-      const EdgePull e0 = pull_edge(nv + p, mv, __ldg(msdf_wt + jn), pv, vn, g_verts_aug, g_msdf_aug);
-      const EdgePull e1 = pull_edge(nv + pp, __ldg(msdf_wt + jp), mv, vp, pv, g_verts_aug, g_msdf_aug);
+      const EdgePull e0 = pull_edge(f, nv + p, mv, __ldg(msdf_wt + jn), pv, vn);
+      const EdgePull e1 = pull_edge(f, nv + pp, __ldg(msdf_wt + jp), mv, vp, pv);
       gx += e0.gx_i + e1.gx_j;
       gy += e0.gy_i + e1.gy_j;
       gz += e0.gz_i + e1.gz_j;
@@ -166,9 +202,8 @@ adjoint_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ co
   if (g_verts_wt != nullptr) {
     gx += __ldg(g_verts_wt + 3 * v); gy += __ldg(g_verts_wt + 3 * v + 1); gz += __ldg(g_verts_wt + 3 * v + 2);
   }
-  if (g_msdf_aug != nullptr) gsg += __ldg(g_msdf_aug + v);
+  if (f.g_msdf_aug != nullptr) gsg += __ldg(f.g_msdf_aug + v);
   if (g_msdf_wt != nullptr) gsg += __ldg(g_msdf_wt + v);
-
   float w0, w1, dd;
   crossing_weights(__ldg(sdf + a), __ldg(sdf + b), w0, w1, dd);
   float ma = __ldg(msdf + a), mb = __ldg(msdf + b);
@@ -201,14 +236,49 @@ adjoint_kernel(const int32_t* __restrict__ edges, const int32_t* __restrict__ co
   if (g_msdf != nullptr) atomicAdd(g_msdf + b, gm_in * w1);
 }
 
-void launch_backward(const d3h_backward_args& a, cudaStream_t stream) {
-  const int64_t nv = a.n_verts;
-  if (!a.grads_prezeroed) launch_zero_grads(a.g_pos, a.g_sdf, a.g_msdf, a.n_grid, stream);
-  if (nv <= 0) return;
-  ProfScope ps(K_ADJOINT, stream);
-  launch_k(adjoint_kernel, (unsigned)((nv + 255) / 256), 256u, stream, kLaunchLatency, a.tape_edges, a.tape_corners,
-           a.tape_slots, a.tape_runs, a.pos, a.sdf, a.msdf, (int)a.msdf_negate, nv, a.n_tri_tets, a.verts_wt, a.msdf_wt,
-           a.g_verts_aug, a.g_msdf_aug, a.g_verts_wt, a.g_msdf_wt, a.g_pos, a.g_sdf, a.g_msdf);
+static AdjFrame adj_frame(const d3h_backward_args& a) {
+  AdjFrame f;
+  f.edges = a.tape_edges; f.corners = a.tape_corners; f.slots = a.tape_slots; f.runs = a.tape_runs;
+  f.pos = a.pos; f.sdf = a.sdf; f.msdf = a.msdf; f.verts_wt = a.verts_wt; f.msdf_wt = a.msdf_wt;
+  f.g_verts_aug = a.g_verts_aug; f.g_msdf_aug = a.g_msdf_aug; f.g_msdf_bnd = a.g_msdf_boundary;
+  f.g_verts_wt = a.g_verts_wt; f.g_msdf_wt = a.g_msdf_wt;
+  f.g_pos = a.g_pos; f.g_sdf = a.g_sdf; f.g_msdf = a.g_msdf;
+  f.nv = a.n_verts; f.t1 = a.n_tri_tets;
+  f.msdf_negate = a.msdf_negate; f.pad = 0;
+  return f;
 }
+
+// Adjoints of n frames: zero-fills first where the caller did not pre-zero, then ONE adjoint launch per kAdjBatch frames
+// (grid.y = frame).
+void launch_backward_batch(const d3h_backward_args* a, int64_t n, cudaStream_t stream) {
+  for (int64_t i = 0; i < n; ++i)
+    if (!a[i].grads_prezeroed) launch_zero_grads(a[i].g_pos, a[i].g_sdf, a[i].g_msdf, a[i].n_grid, stream);
+  for (int64_t i0 = 0; i0 < n; i0 += kAdjBatch) {
+    AdjBatch batch;
+    memset(&batch, 0, sizeof(batch));
+    int m = 0;
+    int64_t max_nv = 0;
+    for (int64_t i = i0; i < n && i < i0 + kAdjBatch; ++i) {
+      if (a[i].n_verts <= 0) continue;
+      batch.f[m++] = adj_frame(a[i]);
+      if (a[i].n_verts > max_nv) max_nv = a[i].n_verts;
+    }
+    if (m == 0) continue;
+    ProfScope ps(K_ADJOINT, stream);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)((max_nv + 255) / 256), (unsigned)m, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = launch_priority(kLaunchLatency);
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, adjoint_kernel, batch);
+  }
+}
+
+void launch_backward(const d3h_backward_args& a, cudaStream_t stream) { launch_backward_batch(&a, 1, stream); }
 
 }  // namespace d3h

@@ -162,6 +162,7 @@ class ForwardResult:
     v_tng_wt: torch.Tensor
     msdf_wt: torch.Tensor
     faces_wt: torch.Tensor
+    msdf_bnd: torch.Tensor      # extra['msdf_boundary'] = msdf[V:] (gshell_tets.py:397): a second view of the same rows
     n_verts: int
     n_tri: int
     n_quad: int
@@ -359,7 +360,8 @@ def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, w
                     ast(fslab, (va, 3), (3, 1), fo + o_vaug), ast(fslab, (va, 3), (3, 1), fo + o_tng),
                     ast(fslab, (va,), (1,), fo + o_maug), ast(islab, (nfa, 3), (3, 1), io),
                     ast(fslab, (v, 3), (3, 1), fo + o_vwt), ast(fslab, (v, 3), (3, 1), fo + o_twt),
-                    ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa), v, t1, t2,
+                    ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa),
+                    ast(fslab, (p,), (1,), fo + o_maug + v), v, t1, t2,
                     dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
                          n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=tuple(row[6:12]))))
             if B == 1:
@@ -406,7 +408,7 @@ def _shrink(cap: int, need: int) -> int:
 # --------------------------------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------------------------------
-_OUTS_PER_FRAME = 8   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, faces_aug, faces_wt
+_OUTS_PER_FRAME = 9   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, msdf_boundary, faces_aug, faces_wt
 
 
 class _ExtractFn(torch.autograd.Function):
@@ -474,7 +476,8 @@ class _ExtractFn(torch.autograd.Function):
         flat = []
         nondiff = []
         for r in res.frames:
-            flat += [r.verts_aug, r.v_tng_aug, r.msdf_aug, r.verts_wt, r.v_tng_wt, r.msdf_wt, r.faces_aug, r.faces_wt]
+            flat += [r.verts_aug, r.v_tng_aug, r.msdf_aug, r.verts_wt, r.v_tng_wt, r.msdf_wt, r.msdf_bnd, r.faces_aug,
+                     r.faces_wt]
             nondiff += [r.faces_aug, r.faces_wt]
         ctx.mark_non_differentiable(*nondiff)
         _ExtractFn.last_counts = [r.counts for r in res.frames]
@@ -509,20 +512,21 @@ class _ExtractFn(torch.autograd.Function):
             keep = []
             live = []
             gp = []   # per live frame: pointers of g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt (adjacent columns)
+            gb = []   # ... and of the gradient of the msdf_boundary view
             f32 = torch.float32
             for i in range(len(refs)):
                 o = _OUTS_PER_FRAME * i
-                g0, g1, g2, g3, g4, g5 = grads[o:o + 6]
+                g0, g1, g2, g3, g4, g5, g6 = grads[o:o + 7]
                 if g1 is not None or g4 is not None:
                     raise NotImplementedError(
                         "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
                         "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
-                if g0 is None and g2 is None and g3 is None and g5 is None:
+                if g0 is None and g2 is None and g3 is None and g5 is None and g6 is None:
                     continue  # nothing flows into this frame
                 n_verts, n_tri, n_quad = sizes[i]
                 va = n_verts + 3 * n_tri + 4 * n_quad
                 row = []
-                for t, rows in ((g0, va), (g2, va), (g3, n_verts), (g5, n_verts)):
+                for t, rows in ((g0, va), (g2, va), (g3, n_verts), (g5, n_verts), (g6, va - n_verts)):
                     if t is None:
                         row.append(0)
                         continue
@@ -531,11 +535,13 @@ class _ExtractFn(torch.autograd.Function):
                         keep.append(t)
                     assert t.shape[0] == rows, (tuple(t.shape), rows)
                     row.append(t.data_ptr())
+                gb.append(row.pop())
                 gp.append(row)
                 live.append(i)
             if live:
                 m = bmat if len(live) == len(refs) else np.ascontiguousarray(bmat[live])
                 m[:, _BC["g_verts_aug"]:_BC["g_msdf_wt"] + 1] = gp
+                m[:, _BC["g_msdf_boundary"]] = gb
                 _cabi.check(L.d3h_extract_backward_batch(m.ctypes.data, len(live), max(1, min(lanes, len(live))),
                                                          torch.cuda.current_stream(dev).cuda_stream),
                             "d3h_extract_backward_batch")
@@ -583,7 +589,7 @@ def _prep_field(f, n_grid):
 
 
 def _pack_result(r8, output_watertight_template):
-    verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, faces_aug, faces_wt = r8
+    verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, msdf_bnd, faces_aug, faces_wt = r8
     n_wt = verts_wt.shape[0]
     if output_watertight_template:  # gshell_tets.py:430-439
         extra = {
@@ -593,10 +599,10 @@ def _pack_result(r8, output_watertight_template):
             "v_tng_watertight": v_tng_wt,
             "msdf": msdf_aug,
             "msdf_watertight": msdf_wt,
-            "msdf_boundary": msdf_aug[n_wt:],
+            "msdf_boundary": msdf_bnd,
         }
     else:  # gshell_tets.py:440-445
-        extra = {"msdf": msdf_aug, "msdf_watertight": msdf_wt, "msdf_boundary": msdf_aug[n_wt:]}
+        extra = {"msdf": msdf_aug, "msdf_watertight": msdf_wt, "msdf_boundary": msdf_bnd}
     return verts_aug, faces_aug, None, None, v_tng_aug, extra
 
 

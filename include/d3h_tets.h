@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 300 /* 0.3.0 */
+#define D3H_VERSION 310 /* 0.3.1 */
 
 enum {
   D3H_OK = 0,
@@ -144,6 +144,9 @@ typedef struct d3h_backward_args {
   /* scratch (unused since the adjoint became a gather over tape_slots; kept for ABI stability, may be NULL) */
   void* workspace;
   int64_t workspace_bytes;
+  /* optional second upstream gradient of the augmented mSDF, for its boundary slice only: extra['msdf_boundary'] is
+   * msdf[V:] (gshell_tets.py:397), (Va - V) rows; added to g_msdf_aug[V:] by the kernel.  NULL = none */
+  const float* g_msdf_boundary;
 } d3h_backward_args;
 
 int d3h_version(void);
@@ -181,7 +184,8 @@ int d3h_extract_backward(const d3h_backward_args* args, d3h_stream_t stream);
  *   forward : args[i] as for d3h_extract_forward; frames on different lanes need distinct workspaces (frames of the same
  *             lane may share one); every frame publishes its own counts (args[i].counts_host, args[i].seq).
  *   backward: gradient buffers may be shared between frames (sdf / msdf common to all frames): all frames accumulate
- *             with atomics, a shared buffer must be zero on entry (grads_prezeroed = 1). */
+ *             with atomics, a shared buffer must be zero on entry (grads_prezeroed = 1).  The adjoints of up to 16
+ *             frames are one kernel launch (grid.y = frame); `lanes` is ignored. */
 int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
 int d3h_extract_backward_batch(const d3h_backward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
 
@@ -209,6 +213,9 @@ int d3h_profile_enable(int on);
 int d3h_profile_kinds(void);
 const char* d3h_profile_kernel_name(int kind);
 int d3h_profile_read(float* ms_by_kind, int* launches_by_kind);
+/* Timeline form: start / end (ms since the first recorded launch), kernel kind and a stream ordinal per launch, in launch
+ * order; returns the number of entries written (<= cap) and clears the log. */
+int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, int* stream_id, int cap);
 /* Host copies of the case tables the kernels index (same initialisers as the __constant__ copies; no GPU needed).
  * which: 0 num_triangles[16], 1 polygon loop edges[16][4], 2 triangle_table[16][6], 3 triangle_table_tri[8][6],
  * 4 num_triangles_tri[8], 5 triangle_table_quad[16][12], 6 num_triangles_quad[16], 7/8 tet-edge endpoints[6].

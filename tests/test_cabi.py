@@ -28,11 +28,28 @@ def test_library_exports_every_declared_symbol():
     assert lib.d3h_version() == _cabi.VERSION
 
 
-def test_struct_layouts_match_header():
-    # sizes computed by hand from include/d3h_tets.h (all members are 8-byte aligned except two int32 pairs)
-    assert C.sizeof(_cabi.Counts) == 16 * 8
-    assert C.sizeof(_cabi.ForwardArgs) == 33 * 8
-    assert C.sizeof(_cabi.BackwardArgs) == 23 * 8
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct member as gcc sees include/d3h_tets.h == the ctypes mirrors in _cabi.py."""
+    import subprocess
+    structs = {"d3h_counts": _cabi.Counts, "d3h_forward_args": _cabi.ForwardArgs, "d3h_backward_args": _cabi.BackwardArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "d3h_tets.h")}"',
+             'int main(void) {']
+    for cname, st in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("d3h_tet_record %zu\\n", sizeof(d3h_tet_record));', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, st in structs.items():
+        assert int(got[cname]) == C.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
+    assert int(got["d3h_tet_record"]) == _cabi.TET_RECORD_BYTES
+    assert C.sizeof(_cabi.Counts) == 16 * 8      # one 128-byte slot per frame in the pinned counts buffer
 
 
 def test_workspace_bytes_contract():

@@ -183,6 +183,31 @@ def test_input_validation(dev):
         g(pos, torch.zeros(7, device=dev), torch.zeros(8, device=dev), torch.tensor([[0, 1, 2, 3]], device=dev))
 
 
+def test_msdf_boundary_view_carries_gradient(dev):
+    """extra['msdf_boundary'] is msdf[V:] (gshell_tets.py:397): a loss on it must reach the inputs like a loss on the
+    slice of extra['msdf'] does in the reference."""
+    pos, sdf, msdf, tets = _inputs(16, "capsule")
+    fwd = O.extract_forward(pos, sdf, msdf, tets)
+    v = fwd["n_verts_watertight"]
+    rng = np.random.default_rng(3)
+    g_bnd = rng.standard_normal(fwd["msdf"].shape[0] - v).astype(np.float32)
+    g_full = rng.standard_normal(fwd["msdf"].shape).astype(np.float32)
+    g, _ = _classes()
+    tp = torch.tensor(pos, device=dev, requires_grad=True)
+    ts = torch.tensor(sdf, device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    verts, faces, _, _, _, extra = g(tp, ts, tm, torch.tensor(tets, device=dev))
+    assert extra["msdf_boundary"].data_ptr() == extra["msdf"][v:].data_ptr()
+    assert torch.equal(extra["msdf_boundary"], extra["msdf"][v:])
+    ((extra["msdf_boundary"] * torch.tensor(g_bnd, device=dev)).sum() + (extra["msdf"] * torch.tensor(g_full, device=dev)).sum()).backward()
+    want_up = g_full.copy()
+    want_up[v:] += g_bnd
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, np.zeros_like(fwd["verts_aug"]), want_up)
+    U.assert_close_normwise("grad_sdf", ts.grad.cpu().numpy(), g_sdf, U.GRAD_RTOL)
+    U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), g_msdf, U.GRAD_RTOL)
+    U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), g_pos, U.GRAD_RTOL)
+
+
 def test_tangent_gradient_is_refused(dev):
     pos, sdf, msdf, tets = _inputs(8, "sphere")
     g, _ = _classes()
