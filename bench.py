@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--frames-per-rank", type=int, default=16,
                     help="frames per rank per step (BASELINE configs[3]: a batch of 16 video frames per step)")
     ap.add_argument("--lanes", type=int, default=4, help="concurrent lanes the frames of a batch are spread over")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="the frames of a step are issued as this many extract_frames_async batches (host / GPU pipelining)")
     ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -194,6 +196,11 @@ def main():
     host_sdf = torch.from_numpy(sdf_np[:, None].copy()).pin_memory()
     host_msdf = torch.from_numpy(msdf_np).pin_memory()
     pos = host_pos.to(dev).requires_grad_(True)
+    # the frames of a step go through `--groups` extract_frames_async calls that are all launched up front: while the GPU
+    # extracts group k+1 the host reads the sizes of group k, wraps its outputs and runs its backward pass
+    ngroups = max(1, min(args.groups, fpr))
+    gb = [(fpr * k // ngroups, fpr * (k + 1) // ngroups) for k in range(ngroups)]
+    pos_groups = [pos.detach()[lo:hi].clone().requires_grad_(True) for lo, hi in gb]   # one (b,N,3) leaf per group
 
     # dry run: shapes of the upstream gradients (constant across steps: inputs are fixed)
     outs = E.extract_frames(pos, sdf, msdf, tets, types="cloth", lanes=args.lanes)
@@ -208,12 +215,16 @@ def main():
     del outs
 
     def step():
-        """One training-step's worth of extraction on this rank: all frames forward (one library call, concurrent
-        lanes), then all frames backward (one library call); gradients of the shared sdf / msdf summed over the frames
-        by the kernels and over the ranks by NCCL."""
-        sdf.grad = msdf.grad = pos.grad = None
-        outs = E.extract_frames(pos, sdf, msdf, tets, types="cloth", lanes=args.lanes)
-        torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v + ups_m)
+        """One training-step's worth of extraction on this rank: every group of frames is one extract_frames_async call
+        (one library call, concurrent lanes) and one backward call; gradients of the shared sdf / msdf are summed over
+        the frames by the kernels, over the groups by autograd and over the ranks by NCCL."""
+        sdf.grad = msdf.grad = None
+        for pg in pos_groups:
+            pg.grad = None
+        futs = [E.extract_frames_async(pg, sdf, msdf, tets, types="cloth", lanes=args.lanes) for pg in pos_groups]
+        for fut, (lo, hi) in zip(futs, gb):
+            outs = fut.result()
+            torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v[lo:hi] + ups_m[lo:hi])
         if world > 1:
             dist.all_reduce(sdf.grad)
             dist.all_reduce(msdf.grad)
@@ -422,7 +433,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "F": F, "N": N, "frames_per_step": world * fpr,
                        "counts_frame0": c0, "l2": "tet index stream is 16*F = %d MB > 126 MB L2; no explicit flush" % (16 * F // 1000000),
-                       "lanes": args.lanes, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
+                       "lanes": args.lanes, "groups": ngroups, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "single_call": single, "gpu_launches": int(launches_per_step * args.steps), "kernels": kern,
             "clocks": sampler.result()}

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
     "d3h_extract_forward_batch", "d3h_extract_backward_batch", "d3h_classify_range", "d3h_extract_from_records",
-    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_debug_table",
+    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
 )
 
 
@@ -110,6 +110,10 @@ def lib() -> C.CDLL:
     L.d3h_profile_read.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_profile_timeline.restype = C.c_int
     L.d3h_profile_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.d3h_trace_enable.restype = C.c_int
+    L.d3h_trace_enable.argtypes = [C.c_int]
+    L.d3h_trace_read.restype = C.c_int
+    L.d3h_trace_read.argtypes = [C.c_void_p]
     L.d3h_debug_table.restype = C.c_int
     L.d3h_debug_table.argtypes = [C.c_int, C.c_void_p, C.c_int]
     if L.d3h_version() != VERSION:
@@ -141,6 +145,25 @@ def profile_timeline(cap: int = 4096):
     if n < 0:
         check(n, "d3h_profile_timeline")
     return [(a[i], b[i], L.d3h_profile_kernel_name(k[i]).decode(), sid[i]) for i in range(n)]
+
+
+def trace_enable(on: bool) -> None:
+    check(lib().d3h_trace_enable(int(bool(on))), "d3h_trace_enable")
+
+
+def trace_read():
+    """-> {seq % 64: {kernel name: (start_ns, end_ns)}} of the forward kernels run since the last read."""
+    import numpy as np
+    L = lib()
+    t = np.zeros((64, 16, 2), dtype=np.uint64)
+    check(L.d3h_trace_read(t.ctypes.data), "d3h_trace_read")
+    out = {}
+    for f in range(64):
+        row = {L.d3h_profile_kernel_name(k).decode(): (int(t[f, k, 0]), int(t[f, k, 1]))
+               for k in range(min(16, L.d3h_profile_kinds())) if t[f, k, 0]}
+        if row:
+            out[f] = row
+    return out
 
 
 def check(rc: int, what: str) -> None:

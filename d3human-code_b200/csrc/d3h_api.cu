@@ -43,6 +43,10 @@ ProfScope::~ProfScope() {
 
 bool profiling_enabled() { return g_prof_on; }
 
+// ---- device trace table (diagnostics) ---------------------------------------------------------------
+static unsigned long long* g_trace_dev = nullptr;
+unsigned long long* trace_table() { return g_trace_dev; }
+
 // ---- launch priorities ------------------------------------------------------------------------------
 int launch_priority(LaunchClass c) {
   static int lo = 0, hi = 0;
@@ -141,21 +145,25 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
 // Device-visible alias of the caller's pinned counts buffer, or nullptr when the pointer is not mapped host memory
 // (then the counts are copied with cudaMemcpyAsync at the end of the call instead).  One driver query per new pointer.
 d3h_counts* mapped_counts_pointer(d3h_counts* host) {
-  constexpr int kSlots = 64;  // direct-mapped on the 128-byte slot index: the frames of a batch use neighbouring slots
-  static thread_local d3h_counts* last_host[kSlots] = {nullptr};
-  static thread_local d3h_counts* last_dev[kSlots] = {nullptr};
+  // cached per 4 KB page of host memory: a page belongs to one pinned allocation, whose device alias is at a constant
+  // offset (the count slots of a plan are a 32 KB ring, 8 pages)
+  constexpr int kSlots = 64;
+  static thread_local uintptr_t page[kSlots] = {0};
+  static thread_local intptr_t delta[kSlots] = {0};
+  static thread_local bool mapped[kSlots] = {false};
   if (host == nullptr) return nullptr;
-  const int slot = (int)((reinterpret_cast<uintptr_t>(host) >> 7) % kSlots);
-  if (host == last_host[slot]) return last_dev[slot];
-  cudaPointerAttributes at;
-  d3h_counts* dev = nullptr;
-  if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
-    dev = reinterpret_cast<d3h_counts*>(at.devicePointer);
-  else
-    cudaGetLastError();  // plain pageable memory: clear the sticky error of the query
-  last_host[slot] = host;
-  last_dev[slot] = dev;
-  return dev;
+  const uintptr_t h = reinterpret_cast<uintptr_t>(host);
+  const uintptr_t pg = h >> 12;
+  const int slot = (int)(pg % kSlots);
+  if (page[slot] != pg) {
+    cudaPointerAttributes at;
+    bool ok = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+    if (!ok) cudaGetLastError();  // plain pageable memory: clear the sticky error of the query
+    page[slot] = pg;
+    mapped[slot] = ok;
+    delta[slot] = ok ? (intptr_t)(reinterpret_cast<uintptr_t>(at.devicePointer) - h) : 0;
+  }
+  return mapped[slot] ? reinterpret_cast<d3h_counts*>(h + delta[slot]) : nullptr;
 }
 
 static int check_forward_args(const d3h_forward_args* a, const char* who) {
@@ -280,6 +288,11 @@ static int build_entry(const d3h_forward_args& a, const Workspace& ws, const Gra
     }
   }
   cudaGraphExec_t exec = nullptr;
+  // Instantiated WITHOUT cudaGraphInstantiateFlagUseNodePriority: every node runs at the priority of the lane stream.
+  // Measured (profiles/graph_trace.py): with per-node priorities the latency-bound kernels of the other lanes take CTA
+  // slots from the O(F) stream, which needs the whole register file to reach the HBM rate (64 regs x 4 CTAs / SM) and
+  // slows down 2x -- the batch gets 8 % slower.  What the lanes buy is the overlap of one frame's dependency bubbles
+  // with another frame's kernels, not free SM time.
   if (!found || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
     cudaGetLastError();
     cudaGraphDestroy(graph);
@@ -337,6 +350,7 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   FwdBlock blk;
   blk.a = a;
   blk.counts_mapped = mapped_counts_pointer(a.counts_host);
+  blk.trace = trace_table();
   Workspace wcopy = ws;
   void* kargs[2] = {&blk, &wcopy};
   cudaKernelNodeParams kp = e->prepare_params;
@@ -591,6 +605,41 @@ extern "C" int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, i
   g_prof_n = 0;
   cudaGetLastError();
   return n;
+}
+
+// Device-side trace (works inside the cached graphs, unlike the event profiler): every forward kernel stamps
+// %globaltimer when its block 0 starts and when its last block exits, into row (seq % 64) of a device table.  Enabling
+// allocates that 16 KB table with cudaMalloc -- the one allocation this library ever makes, diagnostics only.
+extern "C" int d3h_trace_enable(int on) {
+  const size_t bytes = (size_t)kTraceFrames * kTraceKinds * 2 * sizeof(unsigned long long);
+  if (on) {
+    if (g_trace_dev == nullptr && cudaMalloc(&g_trace_dev, bytes) != cudaSuccess) {
+      g_trace_dev = nullptr;
+      set_error("d3h_trace_enable: cudaMalloc failed");
+      cudaGetLastError();
+      return D3H_E_CUDA;
+    }
+    cudaMemset(g_trace_dev, 0, bytes);
+  } else if (g_trace_dev != nullptr) {
+    cudaDeviceSynchronize();
+    cudaFree(g_trace_dev);
+    g_trace_dev = nullptr;
+  }
+  return D3H_OK;
+}
+// Copies the table out ((64, 16, 2) uint64 nanoseconds: [seq % 64][kernel kind][start, end]; 0 = not run) and clears
+// it.  Synchronises the device.
+extern "C" int d3h_trace_read(uint64_t* out) {
+  if (!out) { set_error("d3h_trace_read: null output"); return D3H_E_BADARG; }
+  const size_t bytes = (size_t)kTraceFrames * kTraceKinds * 2 * sizeof(unsigned long long);
+  if (g_trace_dev == nullptr) { memset(out, 0, bytes); return D3H_OK; }
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out, g_trace_dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("d3h_trace_read: %s", cudaGetErrorString(cudaGetLastError()));
+    return D3H_E_CUDA;
+  }
+  cudaMemset(g_trace_dev, 0, bytes);
+  return D3H_OK;
 }
 
 // ---- test hook: the case tables, from the same initializer macros the __constant__ copies are built from --------

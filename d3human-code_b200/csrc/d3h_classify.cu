@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
   const int want_mocc = src.a.watertight_template ? 0 : 1;
   unsigned* __restrict__ occ_bits = ws.occ_bits;
   unsigned* __restrict__ mocc_bits = ws.mocc_bits;
-  if (tid < (int64_t)(sizeof(DevCounters) / 4)) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
+  if (tid < (int64_t)kCounterWordsReset) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
+  if (tid == 0) { ws.ctr->trace = src.trace; ws.ctr->trace_frame = (unsigned)src.a.seq; }
+  unsigned long long* tr = trace_begin(src.trace, (unsigned)src.a.seq, K_PREPARE);
   for (int64_t i = tid; i < ws.ntiles_compact; i += nthreads) ws.tile_cnt[i] = 0u;
   for (int64_t i = tid; i < ws.nscan_ctas; i += nthreads) ws.st_scan[i] = 0ull;
   for (int64_t i = tid; i < ws.ngroups / 256 + 1; i += nthreads) ws.gblock_heads[i] = 0u;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
       if ((lane & 7) == 0 && 4 * q < n_grid) mocc_bits[q >> 3] = mw;
     }
   }
+  trace_end(tr);
 }
 
 const void* prepare_kernel_address() { return reinterpret_cast<const void*>(prepare_kernel); }
@@ -101,6 +104,7 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
   FwdBlock blk;
   blk.a = a;
   blk.counts_mapped = mapped_counts_pointer(a.counts_host);
+  blk.trace = trace_table();
   ProfScope ps(K_PREPARE, stream);
   launch_k(prepare_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, blk, ws);
 }
@@ -122,6 +126,7 @@ classify_kernel(const FwdBlock* __restrict__ blk, int64_t tet_begin, int64_t tet
                 unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words, unsigned* __restrict__ tile_cnt,
                 int64_t nchunks) {
   const int4* __restrict__ tets = reinterpret_cast<const int4*>(blk->a.tets);
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)blk->a.seq, K_CLASSIFY);
   const unsigned lane = lane_id();
   const int64_t warps_total = (int64_t)gridDim.x * (kClassifyThreads / 32);
   for (int64_t chunk = ((int64_t)blockIdx.x * kClassifyThreads + threadIdx.x) >> 5; chunk < nchunks;
@@ -164,6 +169,7 @@ classify_kernel(const FwdBlock* __restrict__ blk, int64_t tet_begin, int64_t tet
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
     if (lane == 0 && cnt != 0u) atomicAdd(tile_cnt + (chunk * kChunkTets) / kTileTets, cnt);
   }
+  trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,6 +213,7 @@ compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1
   const unsigned tile = blockIdx.x;
   const unsigned tc = __ldcg(tile_cnt + tile);
   const bool is_last = (int64_t)tile == ntiles - 1;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_COMPACT);
   if (tc == 0u && !is_last) return;  // most tiles hold no surface
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 
@@ -310,6 +317,7 @@ compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1
       if (EMIT_KEYS) emit_polygon_keys(v4[r], code, quad[r], cr, ob, key_bits, msd_shift, keys, vals, msd_hist);
     }
   }
+  trace_end(tr);
 }
 
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,

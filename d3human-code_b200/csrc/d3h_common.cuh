@@ -99,6 +99,23 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Diagnostics (d3h_trace_enable): per call and kernel kind, [0] = time block 0 started, [1] = latest block exit.
+constexpr int kTraceFrames = 64;
+constexpr int kTraceKinds = 16;
+__device__ __forceinline__ unsigned long long* trace_begin(unsigned long long* table, unsigned frame, int kind) {
+  if (table == nullptr) return nullptr;
+  unsigned long long* slot = table + ((frame % kTraceFrames) * kTraceKinds + kind) * 2;
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) slot[0] = global_timer_ns();
+  return slot;
+}
+__device__ __forceinline__ void trace_end(unsigned long long* slot) {
+  if (slot != nullptr && threadIdx.x == 0) atomicMax(slot + 1, global_timer_ns());
+}
 __device__ __forceinline__ float fsign(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
 // fl(xa*wa) + fl(xb*wb): the reference multiplies and adds in separate kernels (no FMA), SURVEY A.4
@@ -142,8 +159,12 @@ struct DevCounters {
   unsigned work_quad;        //   Fv exceeded the record capacity (the caller re-runs with a larger workspace)
   unsigned n_verts;          // V
   unsigned bucket[6];        // polygons per faces_aug bucket
-  unsigned pad[16];
+  unsigned pad[12];
+  unsigned trace_frame;      // diagnostics (d3h_trace_*): row of the trace table this call writes to
+  unsigned pad2;
+  unsigned long long* trace; // diagnostics: device trace table or nullptr; set by prepare_kernel, not reset
 };
+constexpr int kCounterWordsReset = 28;  // words of DevCounters that prepare_kernel zeroes
 static_assert(sizeof(DevCounters) == 128, "DevCounters is one 128-byte line");
 
 }  // namespace d3h

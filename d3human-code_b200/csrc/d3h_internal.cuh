@@ -33,7 +33,9 @@ constexpr int kPolyThreads = 256;   // one valid tet (= one polygon) per thread
 struct FwdBlock {
   d3h_forward_args a;
   d3h_counts* counts_mapped;  // device alias of a.counts_host, or nullptr
+  unsigned long long* trace;  // diagnostics: device trace table (d3h_trace_enable) or nullptr
 };
+unsigned long long* trace_table();  // current device trace table or nullptr
 
 // ---- workspace ------------------------------------------------------------------------------------
 // Every region is 256-byte aligned.  Sizes depend on (F, N, cap_valid_tets) only.

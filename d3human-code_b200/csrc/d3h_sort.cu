@@ -53,6 +53,7 @@ bucket_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ bas
   __shared__ unsigned s_w[32];
   __shared__ unsigned s_cta;
   __shared__ unsigned s_excl;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_BUCKET_SCAN);
   if (threadIdx.x == 0) s_cta = atomicAdd(&ctr->ticket_scan, 1u);  // CTAs are numbered in start order: no deadlock
   __syncthreads();
   const unsigned cta = s_cta;
@@ -105,6 +106,7 @@ bucket_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ bas
       group_start[(run + c + kSortGroup - 1) / kSortGroup] = run + c;
     }
   }
+  trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -115,6 +117,7 @@ partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned*
                  unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out,
                  const DevCounters* __restrict__ ctr, unsigned* __restrict__ fill, int digit_shift) {
   const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_PARTITION);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool ok = i < ncorn;
   unsigned long long key = 0;
@@ -133,6 +136,7 @@ partition_kernel(const unsigned long long* __restrict__ keys_in, const unsigned*
   pos = __shfl_sync(peers, pos, leader) + __popc(peers & lanemask_lt());
   keys_out[pos] = key;
   vals_out[pos] = val;
+  trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -247,6 +251,7 @@ group_sort_kernel(unsigned long long* __restrict__ keys, unsigned* __restrict__ 
   const int64_t ncorn = 3ll * ctr->work_tri + 4ll * ctr->work_quad;
   const unsigned ngroups_used = (unsigned)((ncorn + kSortGroup - 1) / kSortGroup);
   const unsigned g = blockIdx.x;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_GROUP_SORT);
   if (g >= ngroups_used) return;
   const unsigned lo = __ldcg(group_start + g);
   const unsigned hi = (g + 1 == ngroups_used) ? (unsigned)ncorn : __ldcg(group_start + g + 1);
@@ -296,6 +301,7 @@ group_sort_kernel(unsigned long long* __restrict__ keys, unsigned* __restrict__ 
     group_heads[g] = tot;
     if (tot) atomicAdd(gblock_heads + (g >> 8), tot);
   }
+  trace_end(tr);
 }
 
 // ---- kernel B: number the runs (vertex ids), emit everything that hangs off a vertex -----------------------
@@ -313,6 +319,7 @@ vertex_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned long long* _
   const int64_t ncorn = 3ll * t1 + 4ll * ctr->work_quad;
   const unsigned ngroups_used = (unsigned)((ncorn + kSortGroup - 1) / kSortGroup);
   const unsigned g = blockIdx.x;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_VERTEX_EMIT);
   if (g >= ngroups_used) return;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned lo = __ldcg(group_start + g);
@@ -423,6 +430,7 @@ vertex_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned long long* _
     tape_corners[slot] = (int32_t)vid;
     tape_slots[lo + i] = (int32_t)slot;
   }
+  trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------------

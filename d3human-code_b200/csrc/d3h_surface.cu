@@ -76,6 +76,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   __shared__ unsigned long long s_scan[3][32];
 
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_POLY_FACES);
   const int64_t npoly = (int64_t)t1 + t2;
   const int64_t ntiles = (npoly + kPolyThreads - 1) / kPolyThreads;
   const unsigned tile = blockIdx.x;
@@ -196,6 +197,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   // ---- last CTA out: scan the tile counts, finalise and publish the sizes of this call ----
   __threadfence();
   __syncthreads();
+  trace_end(tr);
   if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->poly_done, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
@@ -327,6 +329,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
   const int64_t cap_verts_aug = blk->a.cap_verts_aug, cap_verts = blk->a.cap_verts, cap_faces_aug = blk->a.cap_faces_aug;
   __shared__ unsigned s_cnt[6][WARPS];
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_POLY_CUT);
   const int64_t npoly = (int64_t)t1 + t2;
   const unsigned tile = blockIdx.x;
   if ((int64_t)tile * kPolyThreads >= npoly) return;
@@ -419,6 +422,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
       if (frow < cap_faces_aug) faces_aug[3 * frow + (e % 3)] = g;
     }
   }
+  trace_end(tr);
 }
 
 // Sizes of a call whose surface stages do not run at all (cap_valid_tets == 0: counting run).

@@ -107,6 +107,7 @@ class _Plan:
     cap_fw: int = 0
     cap_fa: int = 0
     seq: int = 0
+    slot: int = 0                                                   # next free slot of the count ring
     workspaces: List[torch.Tensor] = field(default_factory=list)   # one per lane
     workspace_ptrs: List[int] = field(default_factory=list)
     workspace_bytes: int = 0
@@ -116,7 +117,7 @@ class _Plan:
     counts_ptr: int = 0
     layouts: Dict[Tuple, Any] = field(default_factory=dict)        # (B, lanes, flags) -> _Layout
 
-    def ensure(self, n_frames: int, lanes: int):
+    def ensure(self, lanes: int):
         if self.workspace_cap_tets != self.cap_tets:
             need = _cabi.lib().d3h_workspace_bytes(self.n_tets, self.n_grid, self.cap_tets)
             if need > self.workspace_bytes:
@@ -127,11 +128,10 @@ class _Plan:
             w = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
             self.workspaces.append(w)
             self.workspace_ptrs.append(w.data_ptr())
-        if self.counts_np is None or self.counts_np.shape[0] < n_frames:
+        if self.counts_np is None:
             # pinned host memory is device-mapped (UVA): the kernel that finalises the sizes writes them here directly
-            slots = max(n_frames, 4) if self.counts_np is None else max(n_frames, 2 * self.counts_np.shape[0])
-            self.counts_host = torch.zeros(slots * _CW, dtype=torch.int64).pin_memory()
-            self.counts_np = self.counts_host.numpy().reshape(slots, _CW)
+            self.counts_host = torch.zeros(_COUNT_RING * _CW, dtype=torch.int64).pin_memory()
+            self.counts_np = self.counts_host.numpy().reshape(_COUNT_RING, _CW)
             self.counts_ptr = self.counts_host.data_ptr()
 
 
@@ -231,7 +231,6 @@ class _Layout:
         A[:, c["cap_faces_wt"]], A[:, c["cap_faces_aug"]] = cfw, cfa
         A[:, c["workspace"]] = [plan.workspace_ptrs[i % lanes] for i in range(B)]
         A[:, c["workspace_bytes"]] = plan.workspace_bytes
-        A[:, c["counts_host"]] = plan.counts_ptr + ar * 128
         self.A = A
         self.ar = ar
         # columns verts_aug .. tape_runs are adjacent: value = base[which slab] + OFF
@@ -258,64 +257,70 @@ class _Layout:
         assert bc["g_msdf_wt"] - bc["g_verts_aug"] == 3
 
 
-def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
-                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None) -> BatchResult:
-    """Forward extraction of a batch of frames in ONE library call (d3h_extract_forward_batch).
+class _Pending:
+    """A batch whose forward kernels have been enqueued but whose sizes have not been read yet."""
+    __slots__ = ("inputs", "plan", "lay", "fslab", "islab", "tape", "seq0", "slot0", "bmat", "launches", "dev", "B")
+
+
+_COUNT_RING = 256   # pinned 128-byte count slots per plan: batches in flight take consecutive slots of the ring
+
+
+def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
+                   lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None) -> _Pending:
+    """Enqueue the forward extraction of a batch of frames: ONE library call (d3h_extract_forward_batch), no host wait.
 
     ptrs   : (B,3) int64 array (or nested list): per frame the device pointers of pos / sdf / msdf -- contiguous fp32
              data, sdf / msdf 16-byte aligned (the caller keeps the tensors alive); negate: per-frame msdf_negate flags
     zero   : (B,3) pointers (0 = none) of dense gradient buffers the call zero-fills for the coming backward pass
     grad_ptrs : (B,3) pointers of the gradient buffers (pos, sdf, msdf); when given, the d3h_backward_args of the batch
-             are prefilled here (everything but the upstream gradients is known once the sizes are)
-    Frames run on `lanes` concurrent lanes inside the library.  The host blocks once per frame on that frame's sizes
-    (written to pinned host memory by the kernel that finalises them; the reference blocks ~40 times per frame) and
-    builds the frame's output views while the GPU is still working on the later frames.
+             are prefilled here (everything but the upstream gradients and the sizes is known already)
     launcher : replaces the library call (tet-range sharding, sharding.py): launcher(A, plan, stream) enqueues the work
-             described by the argument blocks A and may return a Fv to regrow the record capacity to (retry)."""
+             described by the argument blocks A and may return a Fv to regrow the record capacity to (retry).
+    Frames run on `lanes` concurrent lanes inside the library."""
     L = _cabi.lib()
     ptrs = np.asarray(ptrs, dtype=np.int64)
     B = ptrs.shape[0]
+    if B > _COUNT_RING // 2:
+        raise ValueError(f"at most {_COUNT_RING // 2} frames per batch")
     n_tets = tets_i32.shape[0]
     plan = _plan_for(dev, n_tets, n_grid)
     lanes = max(1, min(int(lanes), MAX_LANES, B))
     stream = torch.cuda.current_stream(dev).cuda_stream
-    launches = 0
-    tets_ptr = tets_i32.data_ptr()
     wt = int(bool(watertight_template))
     flags = np.asarray(negate, dtype=np.int64) | (wt << 32)
-    ast = torch.as_strided
-    wait = L.d3h_wait_counts
     c = _FC
+    pend = _Pending()
+    pend.inputs = (ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs, launcher)
+    pend.plan, pend.dev, pend.B = plan, dev, B
     with torch.cuda.device(dev):
         for attempt in range(6):
-            plan.ensure(B, lanes)
+            plan.ensure(lanes)
             lay = plan.layouts.get((B, lanes, wt))
             if lay is None or lay.key[3:] != (plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets,
                                               plan.workspace_bytes, plan.counts_ptr, tuple(plan.workspace_ptrs[:lanes])):
                 lay = plan.layouts[(B, lanes, wt)] = _Layout(plan, B, lanes, wt)
             A = lay.A
             cv, cva, cfw, cfa, ct = lay.caps
-            o_vaug, o_tng, o_maug, o_vwt, o_twt, o_mwt = lay.f_off
-            f_len, i_len, t_len = lay.f_len, lay.i_len, lay.t_len
             # three slabs for the whole batch: float outputs, int64 faces, int32 tape; frame i owns slice i of each
-            fslab = torch.empty(B * f_len, dtype=torch.float32, device=dev)
-            islab = torch.empty(B * i_len, dtype=torch.int64, device=dev)
-            tape = torch.empty(B * t_len, dtype=torch.int32, device=dev)
+            fslab = torch.empty(B * lay.f_len, dtype=torch.float32, device=dev)
+            islab = torch.empty(B * lay.i_len, dtype=torch.int64, device=dev)
+            tape = torch.empty(B * lay.t_len, dtype=torch.int32, device=dev)
             bases = (fslab.data_ptr(), islab.data_ptr(), tape.data_ptr())
-            counts_base = plan.counts_ptr
-            seq0 = plan.seq
+            seq0, slot0 = plan.seq, plan.slot
             plan.seq += B
+            plan.slot = (plan.slot + B) % _COUNT_RING
             A[:, 0:3] = ptrs
-            A[:, c["tets"]] = tets_ptr
+            A[:, c["tets"]] = tets_ptr = tets_i32.data_ptr()
             A[:, c["msdf_negate"]] = flags
             np.add(lay.OFF, np.array([bases[k] for k in lay.slab_of], dtype=np.int64), out=A[:, lay.c0:lay.c1])
+            launches = B * (4 if ct <= 0 else LAUNCHES_FORWARD)
             if zero is not None:
                 A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = zero
                 launches += int(np.count_nonzero(np.asarray(zero).any(axis=1)))
             else:
                 A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = 0
+            A[:, c["counts_host"]] = plan.counts_ptr + ((slot0 + lay.ar) % _COUNT_RING) * 128
             A[:, c["seq"]] = lay.ar + (seq0 + 1)
-            launches += B * (4 if ct <= 0 else LAUNCHES_FORWARD)
             if launcher is None:
                 _cabi.check(L.d3h_extract_forward_batch(A.ctypes.data, B, lanes, stream), "d3h_extract_forward_batch")
             else:
@@ -326,72 +331,106 @@ def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, w
                     plan.cap_v, plan.cap_va = max(cv, p4), max(cva, 2 * p4)
                     plan.cap_fw, plan.cap_fa = max(cfw, 2 * plan.cap_tets), max(cfa, 4 * plan.cap_tets)
                     continue
-            # the GPU is busy now: prefill the backward blocks of the batch
-            bmat = None
-            if grad_ptrs is not None:
-                b = _BC
-                bmat = lay.Bt.copy()
-                bmat[:, 0:3] = ptrs
-                bmat[:, b["msdf_negate"]] = np.asarray(negate, dtype=np.int64) | (1 << 32)    # grads_prezeroed = 1
-                bmat[:, b["tape_edges"]:b["tape_runs"] + 1] = A[:, c["tape_edges"]:c["tape_runs"] + 1]
-                bmat[:, b["verts_wt"]], bmat[:, b["msdf_wt"]] = A[:, c["verts_wt"]], A[:, c["msdf_wt"]]
-                bmat[:, b["g_pos"]:b["g_msdf"] + 1] = grad_ptrs
-            sizes = np.empty((B, 6), dtype=np.int64)   # fv, t1, t2, p, v, fa
-            frames: List[ForwardResult] = []
-            grow_tets = grow_out = False
-            cn = plan.counts_np
-            for i in range(B):
-                rc = wait(counts_base + i * 128, seq0 + 1 + i, _WAIT_TIMEOUT_US)
-                if rc:
-                    _cabi.check(rc, "d3h_wait_counts")
-                row = cn[i].tolist()
-                fv, t1, t2, p, v, nfa = row[0:6]
-                sizes[i] = row[0:6]
-                if fv > ct:
-                    grow_tets = True
-                elif v > cv or v + p > cva or t1 + 2 * t2 > cfw or nfa > cfa:
-                    grow_out = True
-                if grow_tets or grow_out:
-                    continue  # this attempt is void; keep reading the sizes of the other frames for the regrowth
-                # views of frame i, built while the GPU works on the later frames
-                va, fw = v + p, t1 + 2 * t2
-                fo, io = i * f_len, i * i_len
-                frames.append(ForwardResult(
-                    ast(fslab, (va, 3), (3, 1), fo + o_vaug), ast(fslab, (va, 3), (3, 1), fo + o_tng),
-                    ast(fslab, (va,), (1,), fo + o_maug), ast(islab, (nfa, 3), (3, 1), io),
-                    ast(fslab, (v, 3), (3, 1), fo + o_vwt), ast(fslab, (v, 3), (3, 1), fo + o_twt),
-                    ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa),
-                    ast(fslab, (p,), (1,), fo + o_maug + v), v, t1, t2,
-                    dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
-                         n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=tuple(row[6:12]))))
-            if B == 1:
-                fw_, va_ = t1 + 2 * t2, v + p
-            else:
-                mx = sizes.max(axis=0).tolist()
-                fv, t1, t2, v, nfa = mx[0], mx[1], mx[2], mx[4], mx[5]
-                va_ = int((sizes[:, 4] + sizes[:, 3]).max())
-                fw_ = int((sizes[:, 1] + 2 * sizes[:, 2]).max())
-            if grow_tets:  # record buffer too small: surface stages were skipped for some frame, its sizes are unknown
-                p = 3 * t1 + 4 * t2
-                plan.cap_tets = _grow(fv)
-                # upper bounds that cannot overflow, so the next attempt is final
-                plan.cap_v, plan.cap_va = max(cv, p), max(cva, 2 * p)
-                plan.cap_fw, plan.cap_fa = max(cfw, t1 + 2 * t2), max(cfa, 2 * t1 + 4 * t2)
-                continue
-            if grow_out:
-                plan.cap_v, plan.cap_va = max(cv, _grow(v)), max(cva, _grow(va_))
-                plan.cap_fw, plan.cap_fa = max(cfw, _grow(fw_)), max(cfa, _grow(nfa))
-                continue
             break
         else:  # pragma: no cover
-            raise RuntimeError("d3h_extract_forward_batch: capacities did not converge")
-        # next call: predict from this call's sizes (the surface moves slowly between training iterations)
-        plan.cap_tets = max(_grow(fv), min(plan.cap_tets, 2 * _grow(fv)))
-        plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va_)
-        plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw_), _shrink(plan.cap_fa, nfa)
-        if bmat is not None:
-            bmat[:, _BC["n_verts"]:_BC["n_quad_tets"] + 1] = sizes[:, (4, 1, 2)]
-    return BatchResult(frames, fslab, islab, tape, lay.tape_off, launches, bmat)
+            raise RuntimeError("tet-range sharding: record capacity did not converge")
+        # the GPU is busy now: prefill the backward blocks of the batch
+        bmat = None
+        if grad_ptrs is not None:
+            b = _BC
+            bmat = lay.Bt.copy()
+            bmat[:, 0:3] = ptrs
+            bmat[:, b["msdf_negate"]] = np.asarray(negate, dtype=np.int64) | (1 << 32)    # grads_prezeroed = 1
+            bmat[:, b["tape_edges"]:b["tape_runs"] + 1] = A[:, c["tape_edges"]:c["tape_runs"] + 1]
+            bmat[:, b["verts_wt"]], bmat[:, b["msdf_wt"]] = A[:, c["verts_wt"]], A[:, c["msdf_wt"]]
+            bmat[:, b["g_pos"]:b["g_msdf"] + 1] = grad_ptrs
+    pend.lay, pend.fslab, pend.islab, pend.tape = lay, fslab, islab, tape
+    pend.seq0, pend.slot0, pend.bmat, pend.launches = seq0, slot0, bmat, launches
+    return pend
+
+
+def _collect_frames(pend: _Pending) -> BatchResult:
+    """Host side of a launched batch: blocks once per frame on that frame's sizes (written to pinned host memory by the
+    kernel that finalises them; the reference blocks ~40 times per frame) and builds the frame's output views while the
+    GPU is still working on the later frames.  A capacity overflow re-launches the batch with the sizes just learnt."""
+    L = _cabi.lib()
+    wait = L.d3h_wait_counts
+    ast = torch.as_strided
+    launches = 0
+    for attempt in range(6):
+        plan, lay, B = pend.plan, pend.lay, pend.B
+        fslab, islab = pend.fslab, pend.islab
+        cv, cva, cfw, cfa, ct = lay.caps
+        o_vaug, o_tng, o_maug, o_vwt, o_twt, o_mwt = lay.f_off
+        f_len, i_len = lay.f_len, lay.i_len
+        counts_base, seq0, slot0 = plan.counts_ptr, pend.seq0, pend.slot0
+        launches += pend.launches
+        sizes = np.empty((B, 6), dtype=np.int64)   # fv, t1, t2, p, v, fa
+        frames: List[ForwardResult] = []
+        grow_tets = grow_out = False
+        cn = plan.counts_np
+        for i in range(B):
+            slot = (slot0 + i) % _COUNT_RING
+            rc = wait(counts_base + slot * 128, seq0 + 1 + i, _WAIT_TIMEOUT_US)
+            if rc:
+                _cabi.check(rc, "d3h_wait_counts")
+            row = cn[slot].tolist()
+            fv, t1, t2, p, v, nfa = row[0:6]
+            sizes[i] = row[0:6]
+            if fv > ct:
+                grow_tets = True
+            elif v > cv or v + p > cva or t1 + 2 * t2 > cfw or nfa > cfa:
+                grow_out = True
+            if grow_tets or grow_out:
+                continue  # this attempt is void; keep reading the sizes of the other frames for the regrowth
+            # views of frame i, built while the GPU works on the later frames
+            va, fw = v + p, t1 + 2 * t2
+            fo, io = i * f_len, i * i_len
+            frames.append(ForwardResult(
+                ast(fslab, (va, 3), (3, 1), fo + o_vaug), ast(fslab, (va, 3), (3, 1), fo + o_tng),
+                ast(fslab, (va,), (1,), fo + o_maug), ast(islab, (nfa, 3), (3, 1), io),
+                ast(fslab, (v, 3), (3, 1), fo + o_vwt), ast(fslab, (v, 3), (3, 1), fo + o_twt),
+                ast(fslab, (v,), (1,), fo + o_mwt), ast(islab, (fw, 3), (3, 1), io + 3 * cfa),
+                ast(fslab, (p,), (1,), fo + o_maug + v), v, t1, t2,
+                dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
+                     n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=tuple(row[6:12]))))
+        if B == 1:
+            fw_, va_ = t1 + 2 * t2, v + p
+        else:
+            mx = sizes.max(axis=0).tolist()
+            fv, t1, t2, v, nfa = mx[0], mx[1], mx[2], mx[4], mx[5]
+            va_ = int((sizes[:, 4] + sizes[:, 3]).max())
+            fw_ = int((sizes[:, 1] + 2 * sizes[:, 2]).max())
+        if grow_tets or grow_out:
+            if grow_tets:  # record buffer too small: surface stages were skipped for some frame, its sizes are unknown
+                p = 3 * t1 + 4 * t2
+                plan.cap_tets = max(plan.cap_tets, _grow(fv))
+                # upper bounds that cannot overflow, so the next attempt is final
+                plan.cap_v, plan.cap_va = max(plan.cap_v, p), max(plan.cap_va, 2 * p)
+                plan.cap_fw, plan.cap_fa = max(plan.cap_fw, t1 + 2 * t2), max(plan.cap_fa, 2 * t1 + 4 * t2)
+            else:
+                plan.cap_v, plan.cap_va = max(plan.cap_v, _grow(v)), max(plan.cap_va, _grow(va_))
+                plan.cap_fw, plan.cap_fa = max(plan.cap_fw, _grow(fw_)), max(plan.cap_fa, _grow(nfa))
+            pend = _launch_frames(*pend.inputs)
+            continue
+        break
+    else:  # pragma: no cover
+        raise RuntimeError("d3h_extract_forward_batch: capacities did not converge")
+    # next call: predict from this call's sizes (the surface moves slowly between training iterations)
+    plan.cap_tets = max(_grow(fv), min(plan.cap_tets, 2 * _grow(fv)))
+    plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va_)
+    plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw_), _shrink(plan.cap_fa, nfa)
+    bmat = pend.bmat
+    if bmat is not None:
+        bmat[:, _BC["n_verts"]:_BC["n_quad_tets"] + 1] = sizes[:, (4, 1, 2)]
+    return BatchResult(frames, fslab, islab, pend.tape, lay.tape_off, launches, bmat)
+
+
+def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
+                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None) -> BatchResult:
+    """Launch + collect (see _launch_frames / _collect_frames)."""
+    return _collect_frames(_launch_frames(ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero,
+                                          grad_ptrs, launcher))
 
 
 def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template) -> BatchResult:
@@ -409,6 +448,46 @@ def _shrink(cap: int, need: int) -> int:
 # autograd
 # --------------------------------------------------------------------------------------------------
 _OUTS_PER_FRAME = 9   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, msdf_boundary, faces_aug, faces_wt
+
+
+def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launcher=None):
+    """Everything of a forward call that precedes the size read: pointer tables of the frames, dense gradient buffers
+    (allocated here, zero-filled by the tail of the forward call of the frame that owns them -- HBM is idle behind the
+    latency-bound surface kernels), and the launch.  Returns (pending batch, gradient buffers or None, N)."""
+    base = [t.data_ptr() for t in tensors]
+    n_grid = tensors[refs[0][0][0]].shape[-2]
+    row_bytes = (12 * n_grid, 4 * n_grid, 4 * n_grid)
+
+    def addr(table, ref, kind):
+        idx, row = ref
+        return table[idx] + (row * row_bytes[kind] if row > 0 else 0)
+
+    ptrs = [[addr(base, r[k], k) for k in range(3)] for r in refs]
+    negate = [int(r[3]) for r in refs]
+    zero = grad_ptrs = gbufs = None
+    if any(need):
+        gbufs = [None] * len(tensors)
+        gbase = [0] * len(tensors)
+        zeroed = set()
+        zero, grad_ptrs = [], []
+        for r in refs:
+            zrow, grow = [0, 0, 0], [0, 0, 0]
+            for k in range(3):
+                idx, row = r[k]
+                if k == 2 and not (need[idx] and not r[3]):   # "body" frames do not reach msdf (hmsdf_tets_split.py:256-264)
+                    continue
+                if gbufs[idx] is None:
+                    gbufs[idx] = torch.empty_like(tensors[idx])
+                    gbase[idx] = gbufs[idx].data_ptr()
+                g = grow[k] = addr(gbase, r[k], k)
+                if (idx, row) not in zeroed:
+                    zeroed.add((idx, row))
+                    zrow[k] = g
+            zero.append(zrow)
+            grad_ptrs.append(grow)
+    pend = _launch_frames(ptrs, negate, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs,
+                          launcher)
+    return pend, gbufs, n_grid
 
 
 class _ExtractFn(torch.autograd.Function):
@@ -430,48 +509,15 @@ class _ExtractFn(torch.autograd.Function):
     def forward(ctx, spec, tets_i32, *tensors):
         refs, watertight_template, lanes = spec[:3]
         launcher = spec[3] if len(spec) > 3 else None     # tet-range sharding (sharding.py)
-        need = ctx.needs_input_grad[2:]
-        any_grad = any(need)
-        B = len(refs)
-        base = [t.data_ptr() for t in tensors]
-        n_grid = tensors[refs[0][0][0]].shape[-2]
-        row_bytes = (12 * n_grid, 4 * n_grid, 4 * n_grid)
-
-        def addr(table, ref, kind):
-            idx, row = ref
-            return table[idx] + (row * row_bytes[kind] if row > 0 else 0)
-
-        ptrs = [[addr(base, r[k], k) for k in range(3)] for r in refs]
-        negate = [int(r[3]) for r in refs]
-        zero = grad_ptrs = None
-        gbufs: List[Optional[torch.Tensor]] = [None] * len(tensors)
-        if any_grad:
-            # dense gradient buffers of the coming backward call: allocated here, zero-filled by the tail of the
-            # forward call of the frame that owns them (HBM is idle behind the latency-bound surface kernels)
-            gbase = [0] * len(tensors)
-            zeroed = set()
-            zero, grad_ptrs = [], []
-            for r in refs:
-                zrow, grow = [0, 0, 0], [0, 0, 0]
-                for k in range(3):
-                    idx, row = r[k]
-                    if k == 2 and not (need[idx] and not r[3]):   # "body" frames do not reach msdf (hmsdf_tets_split.py:256-264)
-                        continue
-                    if gbufs[idx] is None:
-                        gbufs[idx] = torch.empty_like(tensors[idx])
-                        gbase[idx] = gbufs[idx].data_ptr()
-                    g = grow[k] = addr(gbase, r[k], k)
-                    if (idx, row) not in zeroed:
-                        zeroed.add((idx, row))
-                        zrow[k] = g
-                zero.append(zrow)
-                grad_ptrs.append(grow)
-        res = forward_frames_raw(ptrs, negate, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero,
-                                 grad_ptrs, launcher)
+        started = spec[4] if len(spec) > 4 else None      # extract_frames_async: the batch is already in flight
+        if started is None:
+            started = _prelaunch(refs, tensors, ctx.needs_input_grad[2:], tets_i32, watertight_template, lanes, launcher)
+        pend, gbufs, n_grid = started
+        res = _collect_frames(pend)
         ctx.save_for_backward(*tensors, res.tape, res.fslab)   # the slabs hold the tape and verts_wt / msdf_wt of all frames
         ctx.bmat = res.bmat
         ctx.meta = (refs, tets_i32.shape[0], n_grid, [(f.n_verts, f.n_tri, f.n_quad) for f in res.frames], lanes)
-        ctx.gbufs = gbufs if any_grad else None
+        ctx.gbufs = gbufs
         ctx.set_materialize_grads(False)
         flat = []
         nondiff = []
@@ -616,8 +662,34 @@ def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_w
     return _pack_result(_ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)
 
 
+class FramesFuture:
+    """A batch whose forward kernels are already running on the GPU (extract_frames_async).  `result()` blocks on the
+    sizes, wraps the outputs in the autograd node and returns the list of reference 6-tuples; everything the host does
+    between the launch and `result()` -- the `result()` / backward of an earlier batch, a renderer -- overlaps the GPU."""
+
+    def __init__(self, spec, tets, tensors, n_frames, watertight):
+        self._args = (spec, tets, tensors)
+        self._n, self._wt = n_frames, watertight
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            spec, tets, tensors = self._args
+            flat = _ExtractFn.apply(spec, tets, *tensors) if self._n else ()
+            self._out = [_pack_result(flat[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)], self._wt)
+                         for i in range(self._n)]
+            self._args = None
+        return self._out
+
+
 def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watertight_template: bool = True,
                    lanes: int = DEFAULT_LANES):
+    """extract_frames_async(...).result(): launch, then block on the sizes."""
+    return extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types, output_watertight_template, lanes).result()
+
+
+def extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watertight_template: bool = True,
+                         lanes: int = DEFAULT_LANES) -> FramesFuture:
     """A batch of extractions on the same tet grid in one autograd node and one library call per direction.
 
     No counterpart in the reference, which would loop over the frames (BASELINE.json configs[3]: a batch of video frames
@@ -627,8 +699,9 @@ def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watert
     sdf_n, msdf_n : one tensor shared by all frames ((N,) or (N,1)), a stacked (B,N) tensor, or a sequence per frame
     types : None (GShell_Tets semantics), one of "cloth" / "body" for all frames, or a sequence per frame
             (hmSDF_Tets semantics: "body" uses -msdf and, like the reference, does not back-propagate into msdf_n)
-    Returns a list with the reference's 6-tuple `(verts, faces, None, None, v_tng, extra)` for every frame.  Gradients of
-    shared tensors are summed over the frames.
+    Returns a FramesFuture; `.result()` is a list with the reference's 6-tuple `(verts, faces, None, None, v_tng, extra)`
+    for every frame.  Gradients of shared tensors are summed over the frames.  The forward kernels are enqueued before
+    this function returns; the host only blocks (once per frame, on the output sizes) inside `.result()`.
     """
     tensors: List[torch.Tensor] = []
     index: Dict[int, int] = {}
@@ -646,14 +719,14 @@ def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watert
         _check_cuda(pos_frames)
         B, n_grid = pos_frames.shape[0], pos_frames.shape[1]
         if B == 0:
-            return []
+            return FramesFuture(None, None, None, 0, output_watertight_template)
         tensors.append(_aligned(pos_frames.float()))
         pos_refs = [(0, i) for i in range(B)]
     else:
         pos_list = list(pos_frames)
         B = len(pos_list)
         if B == 0:
-            return []
+            return FramesFuture(None, None, None, 0, output_watertight_template)
         pos_refs = [(intern(p, _prep_pos), -1) for p in pos_list]
         n_grid = tensors[pos_refs[0][0]].shape[0]
 
@@ -681,7 +754,8 @@ def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watert
             raise ValueError("all frames must live on the same tet grid (same N)")
     refs = tuple((pos_refs[i], sdf_refs[i], msdf_refs[i], type_list[i] == "body") for i in range(B))
     tets = packed_tets(tet_fx4, n_grid)
-    spec = (refs, bool(output_watertight_template), int(lanes))
-    flat = _ExtractFn.apply(spec, tets, *tensors)
-    return [_pack_result(flat[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)], output_watertight_template)
-            for i in range(B)]
+    wt = bool(output_watertight_template)
+    grad_on = torch.is_grad_enabled()
+    need = tuple(grad_on and t.requires_grad for t in tensors)
+    started = _prelaunch(refs, tensors, need, tets, wt, int(lanes))
+    return FramesFuture((refs, wt, int(lanes), None, started), tets, tensors, B, wt)

@@ -216,6 +216,11 @@ int d3h_profile_read(float* ms_by_kind, int* launches_by_kind);
 /* Timeline form: start / end (ms since the first recorded launch), kernel kind and a stream ordinal per launch, in launch
  * order; returns the number of entries written (<= cap) and clears the log. */
 int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, int* stream_id, int cap);
+/* Device-side trace, usable inside the cached CUDA graphs: every forward kernel stamps %globaltimer when its first block
+ * starts and when its last block exits.  d3h_trace_read fills out[64][16][2] (uint64 ns; row = seq % 64, column = kernel
+ * kind as in d3h_profile_kernel_name) and clears the table.  Enabling allocates a 16 KB device table (diagnostics only). */
+int d3h_trace_enable(int on);
+int d3h_trace_read(uint64_t* out);
 /* Host copies of the case tables the kernels index (same initialisers as the __constant__ copies; no GPU needed).
  * which: 0 num_triangles[16], 1 polygon loop edges[16][4], 2 triangle_table[16][6], 3 triangle_table_tri[8][6],
  * 4 num_triangles_tri[8], 5 triangle_table_quad[16][12], 6 num_triangles_quad[16], 7/8 tet-edge endpoints[6].
