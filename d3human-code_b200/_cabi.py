@@ -12,11 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 310
+VERSION = 400
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_backward_workspace_bytes",
+    "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_workspace_bytes_static",
+    "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
     "d3h_extract_forward_batch", "d3h_extract_backward_batch", "d3h_classify_range", "d3h_extract_from_records",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
@@ -46,7 +47,8 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("tape_runs", C.c_void_p),
                 ("zero_g_pos", C.c_void_p), ("zero_g_sdf", C.c_void_p), ("zero_g_msdf", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("counts_host", C.c_void_p),
-                ("seq", C.c_int64)]
+                ("seq", C.c_int64),
+                ("edge_off", C.c_void_p), ("edge_ab", C.c_void_p), ("n_edges", C.c_int64), ("vacc", C.c_void_p)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args
@@ -59,7 +61,8 @@ class BackwardArgs(C.Structure):  # d3h_backward_args
                 ("g_verts_aug", C.c_void_p), ("g_msdf_aug", C.c_void_p), ("g_verts_wt", C.c_void_p),
                 ("g_msdf_wt", C.c_void_p),
                 ("g_pos", C.c_void_p), ("g_sdf", C.c_void_p), ("g_msdf", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("g_msdf_boundary", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("g_msdf_boundary", C.c_void_p),
+                ("vacc", C.c_void_p)]
 
 
 TET_RECORD_BYTES = 32  # sizeof(d3h_tet_record)
@@ -81,6 +84,8 @@ def lib() -> C.CDLL:
     L.d3h_last_error_string.restype = C.c_char_p
     L.d3h_workspace_bytes.restype = C.c_int64
     L.d3h_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+    L.d3h_workspace_bytes_static.restype = C.c_int64
+    L.d3h_workspace_bytes_static.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64]
     L.d3h_backward_workspace_bytes.restype = C.c_int64
     L.d3h_backward_workspace_bytes.argtypes = [C.c_int64]
     L.d3h_pack_tets_i64.restype = C.c_int

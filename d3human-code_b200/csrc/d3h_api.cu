@@ -89,7 +89,7 @@ static LaneSet* lanes_for_current_device() {
 
 static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
-Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets) {
+Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges) {
   Workspace ws;
   memset(&ws, 0, sizeof(ws));
   char* p = reinterpret_cast<char*>(base);
@@ -138,6 +138,15 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));
   ws.acc = reinterpret_cast<float*>(take(capc * 32));
   ws.owner = reinterpret_cast<int32_t*>(take(capc * 4));
+  ws.n_edges = n_edges > 0 ? n_edges : 0;
+  ws.n_eblocks = (ws.n_edges + kEdgeBlock - 1) / kEdgeBlock;
+  if (ws.n_edges > 0) {
+    const int64_t ewords = ws.n_eblocks * (kEdgeBlock / 32);
+    ws.edge_bits = reinterpret_cast<unsigned*>(take(ewords * 4));
+    ws.word_prefix = reinterpret_cast<unsigned*>(take(ewords * 4));
+    ws.eblock_cnt = reinterpret_cast<unsigned*>(take((ws.n_eblocks + 1) * 4));
+    ws.corner_rank = reinterpret_cast<unsigned*>(take(capc * 4));
+  }
   ws.total_bytes = off;
   return ws;
 }
@@ -187,7 +196,13 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: capacities must be >= 0 and cap_valid_tets <= 2^27", who);
     return D3H_E_BADARG;
   }
-  if (a->cap_valid_tets > 0 && (!a->tape_corners || !a->tape_slots || !a->tape_runs)) {
+  if (a->edge_off != nullptr &&
+      (!a->edge_ab || a->n_edges <= 0 || a->n_edges >= (1ll << 31) || (a->cap_verts > 0 && !a->vacc) ||
+       ((reinterpret_cast<uintptr_t>(a->edge_ab) | reinterpret_cast<uintptr_t>(a->vacc)) & 15))) {
+    set_error("%s: static edge table needs edge_ab (8-byte pairs, 16-byte aligned), 0 < n_edges < 2^31 and vacc", who);
+    return D3H_E_BADARG;
+  }
+  if (a->cap_valid_tets > 0 && (!a->tape_corners || (a->edge_off == nullptr && (!a->tape_slots || !a->tape_runs)))) {
     set_error("%s: tape_corners / tape_slots (4*cap_valid_tets int32) and tape_runs (cap_verts+1 int32) are required", who);
     return D3H_E_BADARG;
   }
@@ -206,7 +221,7 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: an output pointer is null while its capacity is > 0", who);
     return D3H_E_BADARG;
   }
-  const int64_t need = carve_workspace(nullptr, a->n_tets, a->n_grid, a->cap_valid_tets).total_bytes;
+  const int64_t need = carve_workspace(nullptr, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0).total_bytes;
   if (a->workspace_bytes < need) {
     set_error("%s: workspace has %lld bytes, %lld needed", who, (long long)a->workspace_bytes, (long long)need);
     return D3H_E_SMALLWS;
@@ -224,7 +239,8 @@ static int finish(const char* who, const d3h_forward_args* a, const Workspace& w
 
 void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream);
-  launch_edge_sort(a, ws, stream);
+  if (a.edge_off != nullptr) launch_edge_emit(a, ws, stream);
+  else launch_edge_sort(a, ws, stream);
   launch_surface(a, ws, ws.records, stream);
   if (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) launch_zero_grads_from_block(a, ws, stream);
 }
@@ -237,9 +253,10 @@ const void* prepare_kernel_address();
 struct GraphKey {
   void* workspace;
   int64_t n_tets, n_grid, tet_begin, tet_end, cap_valid_tets;
-  int watertight, has_zero, device;
+  int watertight, has_zero, device, is_static;
+  int64_t n_edges;
   bool operator==(const GraphKey& o) const {
-    return workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
+    return is_static == o.is_static && n_edges == o.n_edges && workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
            tet_end == o.tet_end && cap_valid_tets == o.cap_valid_tets && watertight == o.watertight &&
            has_zero == o.has_zero && device == o.device;
   }
@@ -325,6 +342,8 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.cap_valid_tets = a.cap_valid_tets;
   key.watertight = a.watertight_template ? 1 : 0;
   key.has_zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) ? 1 : 0;
+  key.is_static = a.edge_off != nullptr ? 1 : 0;
+  key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
   std::lock_guard<std::mutex> lock(g_graph_mu);
   GraphEntry* e = nullptr;
@@ -372,6 +391,10 @@ extern "C" int64_t d3h_workspace_bytes(int64_t n_tets, int64_t n_grid, int64_t c
   if (n_tets < 0 || n_grid <= 0 || cap_valid_tets < 0) return D3H_E_BADARG;
   return carve_workspace(nullptr, n_tets, n_grid, cap_valid_tets).total_bytes;
 }
+extern "C" int64_t d3h_workspace_bytes_static(int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges) {
+  if (n_tets < 0 || n_grid <= 0 || cap_valid_tets < 0 || n_edges < 0) return D3H_E_BADARG;
+  return carve_workspace(nullptr, n_tets, n_grid, cap_valid_tets, n_edges).total_bytes;
+}
 extern "C" int64_t d3h_backward_workspace_bytes(int64_t n_verts) { (void)n_verts; return 0; }
 
 extern "C" int d3h_wait_counts(const d3h_counts* counts_host, int64_t seq, int64_t timeout_us) {
@@ -397,7 +420,7 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   int rc = check_forward_args(a, "d3h_extract_forward");
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)s;
-  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
   if (launch_forward_graph(*a, ws, stream) != 0) {
     launch_prepare(*a, ws, stream);
     launch_forward_sequence(*a, ws, stream);
@@ -435,7 +458,7 @@ extern "C" int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n
   for (int64_t i = 0; i < n_frames; ++i) {
     const d3h_forward_args* a = &args[i];
     cudaStream_t lane = ls->lane[i % lanes];
-    Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+    Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
     if (launch_forward_graph(*a, ws, lane) != 0) {
       launch_prepare(*a, ws, lane);
       launch_forward_sequence(*a, ws, lane);
@@ -457,7 +480,8 @@ static int check_backward_args(const d3h_backward_args* a, const char* who) {
     set_error("%s: null pointer or negative size", who);
     return D3H_E_BADARG;
   }
-  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->tape_slots || !a->tape_runs || !a->verts_wt || !a->msdf_wt)) {
+  if (a->n_verts > 0 && (!a->tape_edges || !a->tape_corners || !a->verts_wt || !a->msdf_wt ||
+                         ((!a->tape_slots || !a->tape_runs) && !a->vacc))) {
     set_error("%s: tape / saved outputs missing", who);
     return D3H_E_BADARG;
   }
@@ -499,8 +523,12 @@ __global__ void export_range_counts_kernel(const DevCounters* ctr, d3h_counts* o
   out->seq = seq;
 }
 
-extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* records_out, int64_t cap_records,
+extern "C" int d3h_classify_range(const d3h_forward_args* a_in, d3h_tet_record* records_out, int64_t cap_records,
                                   d3h_counts* counts_dev_out, d3h_stream_t s) {
+  if (!a_in) { set_error("d3h_classify_range: null argument struct"); return D3H_E_BADARG; }
+  d3h_forward_args general = *a_in;  // the sharded stages always take the general (sort) path
+  general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
+  const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_classify_range");
   if (rc) return rc;
   if ((!records_out && cap_records > 0) || cap_records < 0 || !counts_dev_out) {
@@ -508,7 +536,7 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* rec
     return D3H_E_BADARG;
   }
   cudaStream_t stream = (cudaStream_t)s;
-  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
   launch_prepare(*a, ws, stream);
   launch_classify(*a, ws, records_out, cap_records, /*emit_keys=*/false, stream);
   export_range_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, counts_dev_out, a->seq);
@@ -520,8 +548,12 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a, d3h_tet_record* rec
 
 // stage 2 only: `records` is the rank-order concatenation of the shards' records (= global tet order);
 // n_tri_tets + n_quad_tets records.  Class ranks are recomputed over the concatenation.
-extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet_record* records, int64_t n_tri_tets,
+extern "C" int d3h_extract_from_records(const d3h_forward_args* a_in, const d3h_tet_record* records, int64_t n_tri_tets,
                                         int64_t n_quad_tets, d3h_stream_t s) {
+  if (!a_in) { set_error("d3h_extract_from_records: null argument struct"); return D3H_E_BADARG; }
+  d3h_forward_args general = *a_in;
+  general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
+  const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_extract_from_records");
   if (rc) return rc;
   const int64_t n = n_tri_tets + n_quad_tets;
@@ -530,7 +562,7 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a, const d3h_tet
     return D3H_E_BADARG;
   }
   cudaStream_t stream = (cudaStream_t)s;
-  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets);
+  Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
   d3h_forward_args b = *a;
   b.tet_begin = b.tet_end = 0;  // prepare still resets the scan state; no tets are classified here
   launch_prepare(b, ws, stream);
@@ -553,7 +585,8 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 
 // ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
 static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "group_sort",
-                                            "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records"};
+                                            "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records",
+                                            "edge_emit", "adjoint_poly"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

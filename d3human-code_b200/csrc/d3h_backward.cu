@@ -95,7 +95,8 @@ struct AdjFrame {
   const float *pos, *sdf, *msdf, *verts_wt, *msdf_wt;
   const float *g_verts_aug, *g_msdf_aug, *g_msdf_bnd, *g_verts_wt, *g_msdf_wt;
   float *g_pos, *g_sdf, *g_msdf;
-  int64_t nv, t1;
+  float* vacc;  // scatter form (static edge table calls): (nv,8) accumulator [gx gy gz gsg | gmv - - -], zero on entry
+  int64_t nv, t1, t2;
   int msdf_negate, pad;
 };
 constexpr int kAdjBatch = 16;
@@ -142,6 +143,64 @@ __device__ __forceinline__ EdgePull pull_edge(const AdjFrame& f, int64_t row, fl
   return r;
 }
 
+// Scatter form of the boundary-vertex adjoints, for calls that ran on the static edge table (no per-vertex corner lists
+// on the tape): one thread per polygon evaluates its 3-4 edges and adds what they contribute to its corners into the
+// per-vertex accumulator (one 16-byte vector atomic + one scalar atomic per corner).  adjoint_kernel then reads and
+// clears the accumulator.  grid.y = frame.
+__global__ void __launch_bounds__(256) adjoint_poly_kernel(const __grid_constant__ AdjBatch batch) {
+  const AdjFrame& f = batch.f[blockIdx.y];
+  if (f.slots != nullptr || f.vacc == nullptr) return;          // gather-form frame
+  if (f.g_verts_aug == nullptr && f.g_msdf_aug == nullptr && f.g_msdf_bnd == nullptr) return;
+  const int64_t npoly = f.t1 + f.t2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npoly) return;
+  const bool quad = i >= f.t1;
+  const int n = quad ? 4 : 3;
+  const int64_t p0 = quad ? (3 * f.t1 + 4 * (i - f.t1)) : 3 * i;
+  int L[4];
+  float pv[4][3], mv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    L[k] = (k < n) ? __ldg(f.corners + p0 + k) : 0;
+    if (k < n) {
+      pv[k][0] = __ldg(f.verts_wt + 3ll * L[k]); pv[k][1] = __ldg(f.verts_wt + 3ll * L[k] + 1);
+      pv[k][2] = __ldg(f.verts_wt + 3ll * L[k] + 2);
+      mv[k] = __ldg(f.msdf_wt + L[k]);
+    } else {
+      pv[k][0] = pv[k][1] = pv[k][2] = 0.f; mv[k] = 0.f;
+    }
+  }
+  float acc[4][5];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) acc[k][c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= n) break;
+    const int kn = (k + 1 == n) ? 0 : k + 1;
+    // select the next corner without dynamic register indexing
+    float pn[3], mn;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pn[c] = (kn == 0) ? pv[0][c] : (kn == 1) ? pv[1][c] : (kn == 2) ? pv[2][c] : pv[3][c];
+    mn = (kn == 0) ? mv[0] : (kn == 1) ? mv[1] : (kn == 2) ? mv[2] : mv[3];
+    const EdgePull e = pull_edge(f, f.nv + p0 + k, mv[k], mn, pv[k], pn);
+    acc[k][0] += e.gx_i; acc[k][1] += e.gy_i; acc[k][2] += e.gz_i; acc[k][3] += e.gsg_i; acc[k][4] += e.gmv_i;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == kn) {
+        acc[q][0] += e.gx_j; acc[q][1] += e.gy_j; acc[q][2] += e.gz_j; acc[q][3] += e.gsg_j; acc[q][4] += e.gmv_j;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= n) break;
+    float* row = f.vacc + 8ll * L[k];
+    atomicAdd(reinterpret_cast<float4*>(row), make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]));
+    if (acc[k][4] != 0.f) atomicAdd(row + 4, acc[k][4]);
+  }
+}
+
 // grid.y = frame of the batch: the adjoints of all frames are one launch (their blocks run side by side)
 __global__ void __launch_bounds__(256) adjoint_kernel(const __grid_constant__ AdjBatch batch) {
   const AdjFrame& f = batch.f[blockIdx.y];
@@ -173,7 +232,14 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const __grid_constant__ Ad
   // g_vert, g_sg (stop-grad mSDF attribute), g_mv (mSDF through the boundary coefficients)
   float gx = 0.f, gy = 0.f, gz = 0.f, gsg = 0.f, gmv = 0.f;
 
-  if (g_verts_aug != nullptr || any_msdf_up) {
+  if (slots == nullptr && f.vacc != nullptr) {
+    // scatter form: adjoint_poly_kernel has summed the boundary contributions of all corners on v; take and clear
+    float4* row = reinterpret_cast<float4*>(f.vacc + 8ll * v);
+    const float4 a0 = row[0], a1 = row[1];
+    gx = a0.x; gy = a0.y; gz = a0.z; gsg = a0.w; gmv = a1.x;
+    row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (g_verts_aug != nullptr || any_msdf_up) {
     const int s0 = __ldg(runs + v), s1 = __ldg(runs + v + 1);
     for (int s = s0; s < s1; ++s) {
       const int64_t p = __ldg(slots + s);  // a corner of some polygon that sits on vertex v
@@ -245,7 +311,8 @@ static AdjFrame adj_frame(const d3h_backward_args& a) {
   f.g_verts_aug = a.g_verts_aug; f.g_msdf_aug = a.g_msdf_aug; f.g_msdf_bnd = a.g_msdf_boundary;
   f.g_verts_wt = a.g_verts_wt; f.g_msdf_wt = a.g_msdf_wt;
   f.g_pos = a.g_pos; f.g_sdf = a.g_sdf; f.g_msdf = a.g_msdf;
-  f.nv = a.n_verts; f.t1 = a.n_tri_tets;
+  f.vacc = a.vacc;
+  f.nv = a.n_verts; f.t1 = a.n_tri_tets; f.t2 = a.n_quad_tets;
   f.msdf_negate = a.msdf_negate; f.pad = 0;
   return f;
 }
@@ -259,13 +326,29 @@ void launch_backward_batch(const d3h_backward_args* a, int64_t n, cudaStream_t s
     AdjBatch batch;
     memset(&batch, 0, sizeof(batch));
     int m = 0;
-    int64_t max_nv = 0;
+    int64_t max_nv = 0, max_poly = 0;
     for (int64_t i = i0; i < n && i < i0 + kAdjBatch; ++i) {
       if (a[i].n_verts <= 0) continue;
       batch.f[m++] = adj_frame(a[i]);
       if (a[i].n_verts > max_nv) max_nv = a[i].n_verts;
+      const bool scatter = a[i].tape_slots == nullptr && a[i].vacc != nullptr;
+      if (scatter && a[i].n_tri_tets + a[i].n_quad_tets > max_poly) max_poly = a[i].n_tri_tets + a[i].n_quad_tets;
     }
     if (m == 0) continue;
+    if (max_poly > 0) {
+      ProfScope ps(K_ADJOINT_POLY, stream);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)((max_poly + 255) / 256), (unsigned)m, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributePriority;
+      at[0].val.priority = launch_priority(kLaunchLatency);
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, adjoint_poly_kernel, batch);
+    }
     ProfScope ps(K_ADJOINT, stream);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

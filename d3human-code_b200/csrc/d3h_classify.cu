@@ -67,8 +67,15 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
   for (int64_t i = tid; i < ws.ntiles_compact; i += nthreads) ws.tile_cnt[i] = 0u;
   for (int64_t i = tid; i < ws.nscan_ctas; i += nthreads) ws.st_scan[i] = 0ull;
   for (int64_t i = tid; i < ws.ngroups / 256 + 1; i += nthreads) ws.gblock_heads[i] = 0u;
-  for (int64_t i = tid; i < (ws.msd_bins + 8 + 3) / 4; i += nthreads)  // msd_hist: 256-byte aligned region, padded by 8
-    reinterpret_cast<uint4*>(ws.msd_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (ws.n_edges > 0 && src.a.edge_off != nullptr) {
+    // static edge table path: clear the edge bitmap (n_edges / 8 bytes: 1.9 MB at 128^3) and the per-block counts
+    const int64_t nw4 = ws.n_eblocks * (kEdgeBlock / 32) / 4;
+    for (int64_t i = tid; i < nw4; i += nthreads) reinterpret_cast<uint4*>(ws.edge_bits)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = tid; i < ws.n_eblocks + 1; i += nthreads) ws.eblock_cnt[i] = 0u;
+  } else {
+    for (int64_t i = tid; i < (ws.msd_bins + 8 + 3) / 4; i += nthreads)  // msd_hist: 256-byte aligned region, padded by 8
+      reinterpret_cast<uint4*>(ws.msd_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
 
   // bitmaps: each lane takes 4 consecutive vertices (one 16-byte load), 8 lanes make one 32-bit word
   const int64_t nquads = (n_grid + 3) / 4;
@@ -195,14 +202,45 @@ __device__ __forceinline__ void emit_polygon_keys(const int4 v4, int code, bool 
   }
 }
 
-template <bool EMIT_KEYS>
+// Static edge table path: the rank of edge (a,b) in the sorted list of all tet edges of the grid is found by bisecting
+// the (at most ~14) larger neighbours of a; the edge is marked in the bitmap and the first marker counts it for its
+// 8192-edge block, so that the numbering kernel needs no scan over the blocks.
+__device__ __forceinline__ void mark_polygon_edges(const int4 v4, int code, bool quad, int64_t rec,
+                                                   const int32_t* __restrict__ edge_off,
+                                                   const int2* __restrict__ edge_ab, unsigned* __restrict__ edge_bits,
+                                                   unsigned* __restrict__ eblock_cnt,
+                                                   unsigned* __restrict__ corner_rank) {
+  const int vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  const int n = quad ? 4 : 3;
+  unsigned ranks[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  for (int k = 0; k < n; ++k) {
+    const int e = c_loop_edge[code][k];
+    const int p = vv[c_edge_p[e]], q = vv[c_edge_q[e]];
+    const int a = min(p, q), b = max(p, q);
+    int lo = __ldg(edge_off + a), hi = __ldg(edge_off + a + 1) - 1;
+    while (lo < hi) {  // first entry with .y >= b (the edge exists: it is an edge of this very tet)
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(&edge_ab[mid].y) < b) lo = mid + 1; else hi = mid;
+    }
+    const unsigned r = (unsigned)lo;
+    ranks[k] = r;
+    const unsigned bit = 1u << (r & 31u);
+    const unsigned old = atomicOr(edge_bits + (r >> 5), bit);
+    if (!(old & bit)) atomicAdd(eblock_cnt + r / kEdgeBlock, 1u);
+  }
+  reinterpret_cast<uint4*>(corner_rank)[rec] = make_uint4(ranks[0], ranks[1], ranks[2], ranks[3]);
+}
+
+// EMIT: 0 records only (tet-range shards), 1 sort keys + MSD histogram (general path), 2 static edge table marks
+template <int EMIT>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1_words,
                const unsigned* __restrict__ m2_words, int64_t nwords, int64_t tet_begin,
                const unsigned* __restrict__ occ_bits, const unsigned* __restrict__ tile_cnt, int64_t ntiles,
                DevCounters* __restrict__ ctr, d3h_tet_record* __restrict__ records, int64_t cap_records, int key_bits,
                int msd_shift, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
-               unsigned* __restrict__ msd_hist) {
+               unsigned* __restrict__ msd_hist, unsigned* __restrict__ edge_bits, unsigned* __restrict__ eblock_cnt,
+               unsigned* __restrict__ corner_rank) {
   constexpr int WARPS = kCompactThreads / 32;
   const int4* __restrict__ tets = reinterpret_cast<const int4*>(blk->a.tets);
   __shared__ unsigned s_pre[kCompactThreads];  // exclusive per-thread prefix in the tile: T1 | T2 << 16
@@ -314,7 +352,10 @@ compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1
       int4* out = reinterpret_cast<int4*>(records + ((int64_t)g1[r] + g2[r]));
       out[0] = v4[r];
       out[1] = make_int4(code, (int)cr, (int)tet[r], (int)ob);
-      if (EMIT_KEYS) emit_polygon_keys(v4[r], code, quad[r], cr, ob, key_bits, msd_shift, keys, vals, msd_hist);
+      if (EMIT == 1) emit_polygon_keys(v4[r], code, quad[r], cr, ob, key_bits, msd_shift, keys, vals, msd_hist);
+      if (EMIT == 2)
+        mark_polygon_edges(v4[r], code, quad[r], (int64_t)g1[r] + g2[r], blk->a.edge_off,
+                           reinterpret_cast<const int2*>(blk->a.edge_ab), edge_bits, eblock_cnt, corner_rank);
     }
   }
   trace_end(tr);
@@ -344,14 +385,20 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   const int key_bits = key_bits_for(a.n_grid);
   const int msd_shift = msd_shift_for(a.n_grid);
   ProfScope ps(K_COMPACT, stream);
-  if (emit_keys)
-    launch_k(compact_kernel<true>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
+  unsigned long long* const nokeys = nullptr;
+  unsigned* const nou = nullptr;
+  if (emit_keys && a.edge_off != nullptr)
+    launch_k(compact_kernel<2>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
              ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
-             msd_shift, ws.keys, ws.vals, ws.msd_hist);
+             msd_shift, nokeys, nou, nou, ws.edge_bits, ws.eblock_cnt, ws.corner_rank);
+  else if (emit_keys)
+    launch_k(compact_kernel<1>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
+             ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
+             msd_shift, ws.keys, ws.vals, ws.msd_hist, nou, nou, nou);
   else
-    launch_k(compact_kernel<false>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
+    launch_k(compact_kernel<0>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
              ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
-             msd_shift, (unsigned long long*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr);
+             msd_shift, nokeys, nou, nou, nou, nou, nou);
 }
 
 // ------------------------------------------------------------------------------------------------

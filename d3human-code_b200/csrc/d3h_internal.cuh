@@ -68,13 +68,20 @@ struct Workspace {
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets
   float* acc;                     // 8 floats per watertight vertex: normal xyz + count, tangent xyz + pad
   int32_t* owner;                 // per watertight vertex: the polygon corner slot that writes its tangent rows
+  // static edge table path (n_edges > 0)
+  unsigned* edge_bits;            // ceil(n_edges/32) words: edge is crossed by a valid tet of this call
+  unsigned* word_prefix;          // per word of edge_bits: number of marked edges before it (= first vertex id of the word)
+  unsigned* eblock_cnt;           // marked edges per 8192-edge block (one edge_emit CTA)
+  unsigned* corner_rank;          // 4 per valid-tet record: edge rank of every polygon corner
+  int64_t n_edges, n_eblocks;
   int64_t cap_tets, cap_corners;
   int64_t ntiles_compact, nscan_ctas, ngroups, ntiles_poly;
   int64_t total_bytes;
 };
 
 // Carves `base` (may be nullptr when only the size is wanted).
-Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets);
+Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges = 0);
+constexpr int kEdgeBlock = 8192;  // edges per edge_emit CTA (256 threads x one 32-bit word)
 
 int key_bits_for(int64_t n_grid);   // bits per endpoint in the packed edge key
 int msd_shift_for(int64_t n_grid);  // endpoint >> shift = MSD bucket
@@ -89,6 +96,7 @@ void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cud
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
                      bool emit_keys, cudaStream_t stream);
 void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
+void launch_edge_emit(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);  // static edge table path
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream);
 void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
@@ -131,7 +139,7 @@ bool profiling_enabled();
 // ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
 enum KernelKind {
   K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_GROUP_SORT, K_VERTEX_EMIT, K_POLY_FACES,
-  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_COUNT
+  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

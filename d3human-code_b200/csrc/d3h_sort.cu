@@ -434,6 +434,111 @@ vertex_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned long long* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// static edge table path: vertex numbering without a sort
+// ------------------------------------------------------------------------------------------------
+// The compaction kernel has marked the crossing edges of this call in a bitmap over the static, lexicographically
+// sorted list of all tet edges.  The rank of a marked edge among the marked edges IS its vertex id (the order of
+// torch.unique(dim=0), gshell_tets.py:279-287).  One CTA per 8192 edges: CTAs of blocks without a mark (most) exit on
+// the block counter, the others sum the counters of the earlier blocks themselves (as compact_kernel does), scan the
+// popcounts of their 256 words and emit one vertex per set bit.
+__global__ void __launch_bounds__(256)
+edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ edge_bits,
+                 const unsigned* __restrict__ eblock_cnt, unsigned* __restrict__ word_prefix, int64_t n_eblocks,
+                 DevCounters* __restrict__ ctr, float4* __restrict__ w_vert, float4* __restrict__ w_acc) {
+  constexpr int WARPS = 256 / 32;
+  __shared__ unsigned s_w[WARPS];
+  __shared__ unsigned s_part[WARPS];
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
+  const unsigned b = blockIdx.x;
+  const unsigned mine = __ldcg(eblock_cnt + b);
+  const bool is_last = (int64_t)b == n_eblocks - 1;
+  // an overflowed record buffer skips the surface stages (work_* = 0): leave n_verts = 0 like the general path
+  const bool skip = (ctr->work_tri + ctr->work_quad) == 0u;
+  if ((mine == 0u && !is_last) || skip) return;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned part = 0;
+  for (unsigned i = threadIdx.x; i < b; i += 256) part += __ldcg(eblock_cnt + i);
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
+  const int64_t w = (int64_t)b * 256 + threadIdx.x;
+  const unsigned bits = __ldcg(edge_bits + w);
+  const unsigned c = __popc(bits);
+  unsigned incl = c;
+#pragma unroll
+  for (int of = 1; of < 32; of <<= 1) {
+    const unsigned nb = __shfl_up_sync(0xffffffffu, incl, of);
+    if (lane >= (unsigned)of) incl += nb;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  unsigned wpre = 0, total = 0, excl = 0;
+#pragma unroll
+  for (int q = 0; q < WARPS; ++q) {
+    if (q < (int)warp) wpre += s_w[q];
+    total += s_w[q];
+    excl += s_part[q];
+  }
+  const d3h_forward_args& a = blk->a;
+  const int64_t cap_verts = a.cap_verts, cap_verts_aug = a.cap_verts_aug;
+  if (is_last && threadIdx.x == 0) ctr->n_verts = excl + total;
+  if (c == 0u) return;
+  int64_t vid = (int64_t)excl + wpre + (incl - c);
+  word_prefix[w] = (unsigned)vid;
+  const int2* __restrict__ edge_ab = reinterpret_cast<const int2*>(a.edge_ab);
+  const float* __restrict__ pos = a.pos;
+  const float* __restrict__ sdf = a.sdf;
+  const float* __restrict__ msdf = a.msdf;
+  const int msdf_negate = a.msdf_negate;
+  float4* __restrict__ vacc = reinterpret_cast<float4*>(a.vacc);
+  unsigned rest = bits;
+  while (rest) {
+    const int bit = __ffs(rest) - 1;
+    rest &= rest - 1u;
+    const int2 ab = __ldg(edge_ab + (w * 32 + bit));
+    const int ea = ab.x, eb = ab.y;
+    // zero-crossing interpolation, gshell_tets.py:291-303 (op order: SURVEY A.4)
+    float w0, w1, dd;
+    crossing_weights(__ldg(sdf + ea), __ldg(sdf + eb), w0, w1, dd);
+    float ma = __ldg(msdf + ea), mb = __ldg(msdf + eb);
+    if (msdf_negate) { ma = -ma; mb = -mb; }
+    const float x = lerp2(__ldg(pos + 3ll * ea + 0), w0, __ldg(pos + 3ll * eb + 0), w1);
+    const float y = lerp2(__ldg(pos + 3ll * ea + 1), w0, __ldg(pos + 3ll * eb + 1), w1);
+    const float z = lerp2(__ldg(pos + 3ll * ea + 2), w0, __ldg(pos + 3ll * eb + 2), w1);
+    const float m = lerp2(ma, w0, mb, w1);
+    w_vert[vid] = make_float4(x, y, z, m);
+    w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vid < cap_verts) {
+      a.tape_edges[2 * vid] = ea;
+      a.tape_edges[2 * vid + 1] = eb;
+      a.verts_wt[3 * vid] = x; a.verts_wt[3 * vid + 1] = y; a.verts_wt[3 * vid + 2] = z;
+      a.msdf_wt[vid] = m;
+      vacc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vacc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (vid < cap_verts_aug) {
+      // rows of verts_aug not referenced by faces_aug are zero (gshell_tets.py:423-427); a watertight vertex is
+      // referenced iff its mSDF is positive (every cut case keeps exactly the positive corners)
+      const bool used = m > 0.f;
+      a.verts_aug[3 * vid] = used ? x : 0.f;
+      a.verts_aug[3 * vid + 1] = used ? y : 0.f;
+      a.verts_aug[3 * vid + 2] = used ? z : 0.f;
+      a.msdf_aug[vid] = m;
+    }
+    ++vid;
+  }
+  trace_end(tr);
+}
+
+void launch_edge_emit(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+  if (ws.cap_corners <= 0 || ws.n_eblocks <= 0) return;
+  ProfScope ps(K_EDGE_EMIT, stream);
+  launch_k(edge_emit_kernel, (unsigned)ws.n_eblocks, 256u, stream, kLaunchLatency, ws.blk, ws.edge_bits, ws.eblock_cnt,
+           ws.word_prefix, ws.n_eblocks, ws.ctr, ws.vert, reinterpret_cast<float4*>(ws.acc));
+}
+
+// ------------------------------------------------------------------------------------------------
 void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const int key_bits = key_bits_for(a.n_grid);
   const int64_t capc = ws.cap_corners;

@@ -66,9 +66,11 @@ __global__ void __launch_bounds__(kPolyThreads)
 poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                   DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
                   unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_excl, UvParams uvp,
-                  d3h_counts* __restrict__ counts_dev) {
+                  d3h_counts* __restrict__ counts_dev, const unsigned* __restrict__ corner_rank,
+                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix) {
   constexpr int WARPS = kPolyThreads / 32;
-  const int32_t* __restrict__ corners = blk->a.tape_corners;
+  int32_t* __restrict__ corners = blk->a.tape_corners;
+  const bool static_edges = blk->a.edge_off != nullptr;
   int64_t* __restrict__ faces_wt = blk->a.faces_wt;
   const int64_t cap_faces_wt = blk->a.cap_faces_wt;
   __shared__ unsigned s_cnt[6][WARPS];
@@ -96,11 +98,26 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
       const int64_t p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
       int L[4];
       float4 P[4];
+      if (static_edges) {
+        // vertex id of a corner = number of marked edges before its edge in the static edge list; the corner array of
+        // the tape ([3*T1 | 4*T2], gshell_tets.py:406-407) is written here for poly_cut_kernel and the backward pass
+        const uint4 rk = __ldcg(reinterpret_cast<const uint4*>(corner_rank) + i);
+        const unsigned rr[4] = {rk.x, rk.y, rk.z, rk.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        L[k] = (k < n) ? corners[p0 + k] : 0;
-        P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 4; ++k) {
+          L[k] = 0;
+          if (k < n) {
+            const unsigned r = rr[k];
+            L[k] = (int)(__ldcg(word_prefix + (r >> 5)) + __popc(__ldcg(edge_bits + (r >> 5)) & ((1u << (r & 31u)) - 1u)));
+            corners[p0 + k] = L[k];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) L[k] = (k < n) ? corners[p0 + k] : 0;
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
       // ---- watertight faces + splats ----
       const int ntri = quad ? 2 : 1;
       for (int t = 0; t < ntri; ++t) {
@@ -176,7 +193,13 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
           const int64_t row = quad ? ((int64_t)t1 + 2ll * rank + t) : (int64_t)rank;
           float4 pv[3];
           for (int c = 0; c < 3; ++c) {
-            fv[row][c] = corners[p0 + pos_in_loop(code, c_tri_edge[code][3 * t + c])];
+            const int kk = pos_in_loop(code, c_tri_edge[code][3 * t + c]);
+            if (static_edges) {
+              const unsigned r = __ldcg(corner_rank + 4 * q + kk);
+              fv[row][c] = (int)(__ldcg(word_prefix + (r >> 5)) + __popc(__ldcg(edge_bits + (r >> 5)) & ((1u << (r & 31u)) - 1u)));
+            } else {
+              fv[row][c] = corners[p0 + kk];
+            }
             pv[c] = w_vert[fv[row][c]];
           }
           a[row][0] = __fsub_rn(pv[1].x, pv[0].x); a[row][1] = __fsub_rn(pv[1].y, pv[0].y); a[row][2] = __fsub_rn(pv[1].z, pv[0].z);
@@ -328,6 +351,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
   int64_t* __restrict__ faces_aug = blk->a.faces_aug;
   const int64_t cap_verts_aug = blk->a.cap_verts_aug, cap_verts = blk->a.cap_verts, cap_faces_aug = blk->a.cap_faces_aug;
   __shared__ unsigned s_cnt[6][WARPS];
+  const bool static_edges = blk->a.edge_off != nullptr;
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_POLY_CUT);
   const int64_t npoly = (int64_t)t1 + t2;
@@ -356,7 +380,8 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
       P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
       T[k] = (k < n) ? vertex_tangent(w_acc, L[k]) : make_float3(0.f, 0.f, 0.f);
       // the corner that opened the vertex's run in the sorted key array writes the vertex's own tangent rows
-      if (k < n && owner[L[k]] == (int32_t)(p0 + k)) {
+      // (static edge table path: no owner is known, every corner writes the same value)
+      if (k < n && (static_edges || owner[L[k]] == (int32_t)(p0 + k))) {
         const int64_t v = L[k];
         if (v < cap_verts) { v_tng_wt[3 * v] = T[k].x; v_tng_wt[3 * v + 1] = T[k].y; v_tng_wt[3 * v + 2] = T[k].z; }
         if (v < cap_verts_aug) { v_tng_aug[3 * v] = T[k].x; v_tng_aug[3 * v + 1] = T[k].y; v_tng_aug[3 * v + 2] = T[k].z; }
@@ -472,7 +497,7 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
   {
     ProfScope ps(K_POLY_FACES, stream);
     launch_k(poly_faces_kernel, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert,
-             ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts);
+             ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits, ws.word_prefix);
   }
   ProfScope ps(K_POLY_CUT, stream);
   launch_k(poly_cut_kernel, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert, ws.acc,

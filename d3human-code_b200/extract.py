@@ -8,6 +8,7 @@ for device memory, the current stream and autograd bookkeeping only.  There is n
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
@@ -72,6 +73,64 @@ def packed_tets(tet_fx4: torch.Tensor, n_grid: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+# static edge table: the sorted list of ALL distinct tet edges of a grid, built once per tet array.  With it a call
+# de-duplicates its crossing edges by marking a bitmap over the list (rank among the marked edges = vertex id, the order
+# of torch.unique(dim=0) at gshell_tets.py:279) instead of sorting their keys.
+# --------------------------------------------------------------------------------------------------
+_TET_EDGES = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))   # gshell_tets.py:187
+_static_cache: Dict[Tuple, list] = {}
+_static_mode = os.environ.get("D3H_STATIC_EDGES", "auto")       # "auto": from the 2nd call on the same tets, "1", "0"
+
+
+def set_static_edges(mode: str) -> None:
+    """'auto' (default): build the static edge table when a tet array is used a second time (a training run reuses
+    it every iteration); '1': build it on first use; '0': always take the general per-call sort path."""
+    global _static_mode
+    if mode not in ("auto", "0", "1"):
+        raise ValueError(mode)
+    _static_mode = mode
+
+
+def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
+    """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
+    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U): edges ascending in (min,max), CSR offsets per min vertex."""
+    t = tets_i32.long()
+    keys = []
+    for i, j in _TET_EDGES:
+        keys.append(torch.minimum(t[:, i], t[:, j]) * n_grid + torch.maximum(t[:, i], t[:, j]))
+    key = torch.cat(keys)
+    del keys, t
+    uk = torch.unique(key)          # ascending
+    del key
+    ea = torch.div(uk, n_grid, rounding_mode="floor")
+    edge_ab = torch.stack([ea, uk - ea * n_grid], 1).to(torch.int32).contiguous()
+    counts = torch.bincount(ea, minlength=n_grid)
+    edge_off = torch.zeros(n_grid + 1, dtype=torch.int64, device=tets_i32.device)
+    edge_off[1:] = torch.cumsum(counts, 0)
+    n_edges = int(uk.shape[0])
+    if n_edges >= 2 ** 31:
+        raise ValueError("tet grid has more than 2^31 distinct edges")
+    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges
+
+
+def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
+    """-> (edge_off, edge_ab, n_edges) or None, according to the static-edge policy."""
+    if _static_mode == "0" or tets_i32.shape[0] == 0:
+        return None
+    key = (tets_i32.data_ptr(), tets_i32.shape[0], int(n_grid), tets_i32.device.index)
+    ent = _static_cache.get(key)
+    if ent is None:
+        if len(_static_cache) > 8:
+            _static_cache.clear()
+        ent = _static_cache[key] = [0, None, tets_i32]   # the packed tensor is kept alive: its address is the key
+    ent[0] += 1
+    if ent[1] is None and (_static_mode == "1" or ent[0] >= 2):
+        with torch.cuda.device(tets_i32.device):
+            ent[1] = build_edge_table(tets_i32, n_grid)
+    return ent[1]
+
+
+# --------------------------------------------------------------------------------------------------
 # argument blocks as int64 matrices: d3h_forward_args / d3h_backward_args are arrays of 8-byte words (the two int32
 # flags share one word), so the blocks of a whole batch are filled with a handful of vectorised numpy assignments
 # (pointers of frame i are affine in i) instead of ~35 ctypes attribute writes per frame
@@ -111,19 +170,19 @@ class _Plan:
     workspaces: List[torch.Tensor] = field(default_factory=list)   # one per lane
     workspace_ptrs: List[int] = field(default_factory=list)
     workspace_bytes: int = 0
-    workspace_cap_tets: int = -1
+    workspace_cap_tets: Any = None                                  # (cap_tets, n_edges) the workspaces were sized for
     counts_host: Optional[torch.Tensor] = None                     # pinned, one 128-byte slot per frame of a batch
     counts_np: Optional[np.ndarray] = None                         # (slots, 16) int64 view of counts_host
     counts_ptr: int = 0
     layouts: Dict[Tuple, Any] = field(default_factory=dict)        # (B, lanes, flags) -> _Layout
 
-    def ensure(self, lanes: int):
-        if self.workspace_cap_tets != self.cap_tets:
-            need = _cabi.lib().d3h_workspace_bytes(self.n_tets, self.n_grid, self.cap_tets)
+    def ensure(self, lanes: int, n_edges: int = 0):
+        if self.workspace_cap_tets != (self.cap_tets, n_edges):
+            need = _cabi.lib().d3h_workspace_bytes_static(self.n_tets, self.n_grid, self.cap_tets, n_edges)
             if need > self.workspace_bytes:
                 self.workspaces, self.workspace_ptrs = [], []
                 self.workspace_bytes = need
-            self.workspace_cap_tets = self.cap_tets
+            self.workspace_cap_tets = (self.cap_tets, n_edges)
         while len(self.workspaces) < lanes:
             w = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
             self.workspaces.append(w)
@@ -150,6 +209,7 @@ def reset_plans() -> None:
     """Drop cached workspaces / capacity predictions (tests)."""
     _plans.clear()
     _packed_cache.clear()
+    _static_cache.clear()
 
 
 @dataclass
@@ -200,6 +260,8 @@ _WAIT_TIMEOUT_US = 60_000_000
 #: kernels one forward extraction enqueues: prepare, classify, compact, bucket_scan, partition, group_sort, vertex_emit,
 #: poly_faces, poly_cut (+ zero_block_kernel when the gradient buffers are pre-zeroed); backward: adjoint_kernel
 LAUNCHES_FORWARD = 9
+#: static edge table path: prepare, classify, compact, edge_emit, poly_faces, poly_cut; backward: adjoint_poly + adjoint
+LAUNCHES_FORWARD_STATIC = 6
 LAUNCHES_BACKWARD = 1
 
 
@@ -208,7 +270,7 @@ class _Layout:
     the argument blocks and the per-frame byte offsets of every output / tape pointer (frame i owns slice i of the three
     slabs, so its pointers are slab base + i * stride + constant)."""
 
-    def __init__(self, plan: _Plan, B: int, lanes: int, wt: int):
+    def __init__(self, plan: _Plan, B: int, lanes: int, wt: int, static=None):
         self.key = (B, lanes, wt, plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets, plan.workspace_bytes,
                     plan.counts_ptr, tuple(plan.workspace_ptrs[:lanes]))
         cv, cva, cfw, cfa, ct = plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets
@@ -218,6 +280,9 @@ class _Layout:
         o_twt, o_mwt = o_vwt + 3 * _r4(cv), o_vwt + 6 * _r4(cv)
         self.f_off = (o_vaug, o_tng, o_maug, o_vwt, o_twt, o_mwt)
         self.f_len = o_mwt + _r4(cv)
+        self.o_vacc = self.f_len                   # static edge table calls: (cap_v, 8) accumulator of the adjoint
+        if static is not None:
+            self.f_len += 8 * _r4(cv)
         self.i_len = 3 * (cfa + cfw) + (3 * (cfa + cfw)) % 2      # keep every frame's int64 slice 16-byte aligned
         t_corn, t_slot = 2 * _r4(cv), 2 * _r4(cv) + 4 * ct
         t_runs = t_slot + 4 * ct
@@ -231,6 +296,10 @@ class _Layout:
         A[:, c["cap_faces_wt"]], A[:, c["cap_faces_aug"]] = cfw, cfa
         A[:, c["workspace"]] = [plan.workspace_ptrs[i % lanes] for i in range(B)]
         A[:, c["workspace_bytes"]] = plan.workspace_bytes
+        if static is not None:
+            A[:, c["edge_off"]], A[:, c["edge_ab"]], A[:, c["n_edges"]] = static[0].data_ptr(), static[1].data_ptr(), static[2]
+            self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
+        self.static = static
         self.A = A
         self.ar = ar
         # columns verts_aug .. tape_runs are adjacent: value = base[which slab] + OFF
@@ -266,7 +335,7 @@ _COUNT_RING = 256   # pinned 128-byte count slots per plan: batches in flight ta
 
 
 def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
-                   lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None) -> _Pending:
+                   lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None) -> _Pending:
     """Enqueue the forward extraction of a batch of frames: ONE library call (d3h_extract_forward_batch), no host wait.
 
     ptrs   : (B,3) int64 array (or nested list): per frame the device pointers of pos / sdf / msdf -- contiguous fp32
@@ -276,6 +345,7 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
              are prefilled here (everything but the upstream gradients and the sizes is known already)
     launcher : replaces the library call (tet-range sharding, sharding.py): launcher(A, plan, stream) enqueues the work
              described by the argument blocks A and may return a Fv to regrow the record capacity to (retry).
+    static : (edge_off, edge_ab, n_edges) of build_edge_table, or None for the general per-call sort path.
     Frames run on `lanes` concurrent lanes inside the library."""
     L = _cabi.lib()
     ptrs = np.asarray(ptrs, dtype=np.int64)
@@ -290,15 +360,21 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
     flags = np.asarray(negate, dtype=np.int64) | (wt << 32)
     c = _FC
     pend = _Pending()
-    pend.inputs = (ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs, launcher)
+    if launcher is not None:
+        static = None       # the sharded stages exchange records and always sort
+    n_edges = static[2] if static is not None else 0
+    pend.inputs = (ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs, launcher, static)
     pend.plan, pend.dev, pend.B = plan, dev, B
     with torch.cuda.device(dev):
         for attempt in range(6):
-            plan.ensure(lanes)
-            lay = plan.layouts.get((B, lanes, wt))
+            plan.ensure(lanes, n_edges)
+            lkey = (B, lanes, wt, static[0].data_ptr() if static is not None else 0)
+            lay = plan.layouts.get(lkey)
             if lay is None or lay.key[3:] != (plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa, plan.cap_tets,
                                               plan.workspace_bytes, plan.counts_ptr, tuple(plan.workspace_ptrs[:lanes])):
-                lay = plan.layouts[(B, lanes, wt)] = _Layout(plan, B, lanes, wt)
+                if len(plan.layouts) > 32:
+                    plan.layouts.clear()
+                lay = plan.layouts[lkey] = _Layout(plan, B, lanes, wt, static)
             A = lay.A
             cv, cva, cfw, cfa, ct = lay.caps
             # three slabs for the whole batch: float outputs, int64 faces, int32 tape; frame i owns slice i of each
@@ -313,7 +389,9 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             A[:, c["tets"]] = tets_ptr = tets_i32.data_ptr()
             A[:, c["msdf_negate"]] = flags
             np.add(lay.OFF, np.array([bases[k] for k in lay.slab_of], dtype=np.int64), out=A[:, lay.c0:lay.c1])
-            launches = B * (4 if ct <= 0 else LAUNCHES_FORWARD)
+            if static is not None:
+                A[:, c["vacc"]] = lay.vacc_off + bases[0]
+            launches = B * (4 if ct <= 0 else (LAUNCHES_FORWARD_STATIC if static is not None else LAUNCHES_FORWARD))
             if zero is not None:
                 A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = zero
                 launches += int(np.count_nonzero(np.asarray(zero).any(axis=1)))
@@ -344,6 +422,9 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             bmat[:, b["tape_edges"]:b["tape_runs"] + 1] = A[:, c["tape_edges"]:c["tape_runs"] + 1]
             bmat[:, b["verts_wt"]], bmat[:, b["msdf_wt"]] = A[:, c["verts_wt"]], A[:, c["msdf_wt"]]
             bmat[:, b["g_pos"]:b["g_msdf"] + 1] = grad_ptrs
+            if static is not None:   # scatter-form adjoint: no per-vertex corner lists on the tape
+                bmat[:, b["tape_slots"]] = bmat[:, b["tape_runs"]] = 0
+                bmat[:, b["vacc"]] = A[:, c["vacc"]]
     pend.lay, pend.fslab, pend.islab, pend.tape = lay, fslab, islab, tape
     pend.seq0, pend.slot0, pend.bmat, pend.launches = seq0, slot0, bmat, launches
     return pend
@@ -427,16 +508,16 @@ def _collect_frames(pend: _Pending) -> BatchResult:
 
 
 def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
-                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None) -> BatchResult:
+                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None) -> BatchResult:
     """Launch + collect (see _launch_frames / _collect_frames)."""
     return _collect_frames(_launch_frames(ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero,
-                                          grad_ptrs, launcher))
+                                          grad_ptrs, launcher, static))
 
 
-def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template) -> BatchResult:
+def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template, static=None) -> BatchResult:
     """One forward extraction without autograd (tests, profiling scripts)."""
     return forward_frames_raw([[pos.data_ptr(), sdf.data_ptr(), msdf.data_ptr()]], [int(bool(msdf_negate))],
-                              pos.device, pos.shape[0], tets_i32, watertight_template, lanes=1)
+                              pos.device, pos.shape[0], tets_i32, watertight_template, lanes=1, static=static)
 
 
 def _shrink(cap: int, need: int) -> int:
@@ -450,7 +531,7 @@ def _shrink(cap: int, need: int) -> int:
 _OUTS_PER_FRAME = 9   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, msdf_boundary, faces_aug, faces_wt
 
 
-def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launcher=None):
+def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launcher=None, static=None):
     """Everything of a forward call that precedes the size read: pointer tables of the frames, dense gradient buffers
     (allocated here, zero-filled by the tail of the forward call of the frame that owns them -- HBM is idle behind the
     latency-bound surface kernels), and the launch.  Returns (pending batch, gradient buffers or None, N)."""
@@ -486,7 +567,7 @@ def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launch
             zero.append(zrow)
             grad_ptrs.append(grow)
     pend = _launch_frames(ptrs, negate, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs,
-                          launcher)
+                          launcher, static)
     return pend, gbufs, n_grid
 
 
@@ -511,7 +592,9 @@ class _ExtractFn(torch.autograd.Function):
         launcher = spec[3] if len(spec) > 3 else None     # tet-range sharding (sharding.py)
         started = spec[4] if len(spec) > 4 else None      # extract_frames_async: the batch is already in flight
         if started is None:
-            started = _prelaunch(refs, tensors, ctx.needs_input_grad[2:], tets_i32, watertight_template, lanes, launcher)
+            static = None if launcher is not None else static_edges_for(tets_i32, tensors[refs[0][0][0]].shape[-2])
+            started = _prelaunch(refs, tensors, ctx.needs_input_grad[2:], tets_i32, watertight_template, lanes, launcher,
+                                 static)
         pend, gbufs, n_grid = started
         res = _collect_frames(pend)
         ctx.save_for_backward(*tensors, res.tape, res.fslab)   # the slabs hold the tape and verts_wt / msdf_wt of all frames
@@ -757,5 +840,5 @@ def extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_
     wt = bool(output_watertight_template)
     grad_on = torch.is_grad_enabled()
     need = tuple(grad_on and t.requires_grad for t in tensors)
-    started = _prelaunch(refs, tensors, need, tets, wt, int(lanes))
+    started = _prelaunch(refs, tensors, need, tets, wt, int(lanes), None, static_edges_for(tets, n_grid))
     return FramesFuture((refs, wt, int(lanes), None, started), tets, tensors, B, wt)

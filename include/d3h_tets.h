@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 310 /* 0.3.1 */
+#define D3H_VERSION 400 /* 0.4.0 */
 
 enum {
   D3H_OK = 0,
@@ -111,6 +111,15 @@ typedef struct d3h_forward_args {
                               are final -- before the kernels that only write outputs have run -- and `seq` is the
                               last word written: poll it with d3h_wait_counts() instead of synchronising the stream */
   int64_t seq;             /* caller-chosen non-zero tag of this call, echoed in counts_host->seq */
+  /* optional: static edge table of the tet grid (d3h_edge_table_*): the tet indices of a training run never change
+   * (hmsdf.py:207-212), so the sorted list of ALL distinct tet edges is built once and every call de-duplicates its
+   * crossing edges by marking them in a bitmap over that list -- no per-call sort.  edge_off == NULL selects the general
+   * path (radix sort + run-length scan of the crossing-edge keys of this call). */
+  const int32_t* edge_off; /* (N+1) edges whose smaller endpoint is a have ranks [edge_off[a], edge_off[a+1]) */
+  const int32_t* edge_ab;  /* (n_edges,2) (a,b), a<=b, ascending lexicographically: rank -> endpoints */
+  int64_t n_edges;
+  float* vacc;             /* (cap_verts,8) per-vertex accumulator of the scatter-form adjoint, zeroed here; required
+                              with edge_off (the static path leaves no tape_slots / tape_runs) */
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */
@@ -147,6 +156,9 @@ typedef struct d3h_backward_args {
   /* optional second upstream gradient of the augmented mSDF, for its boundary slice only: extra['msdf_boundary'] is
    * msdf[V:] (gshell_tets.py:397), (Va - V) rows; added to g_msdf_aug[V:] by the kernel.  NULL = none */
   const float* g_msdf_boundary;
+  /* static-edge-table calls: tape_slots / tape_runs are NULL and the adjoint runs in scatter form through this
+   * (n_verts,8) accumulator (zero on entry -- the forward call zeroes it -- and zero again on return) */
+  float* vacc;
 } d3h_backward_args;
 
 int d3h_version(void);
@@ -154,6 +166,8 @@ const char* d3h_last_error_string(void);
 
 /* Scratch sizes.  Replaces nothing in the reference (torch allocates every temporary there). */
 int64_t d3h_workspace_bytes(int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets);
+/* ... when the calls carry a static edge table of n_edges entries (adds the edge bitmap and its prefix words) */
+int64_t d3h_workspace_bytes_static(int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges);
 int64_t d3h_backward_workspace_bytes(int64_t n_verts);
 
 /* One-time conversion of the static `tet_fx4` (int64 in the reference, hmsdf.py:207-212) to packed int32x4,

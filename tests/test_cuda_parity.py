@@ -24,6 +24,16 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True, params=["sort", "static"])
+def edges_mode(request):
+    """Every test runs twice: on the general path (per-call radix sort + run-length scan of the crossing-edge keys) and
+    on the static edge table path (bitmap over the grid's sorted edge list, built once per tet array)."""
+    from d3human_code_b200 import extract as E
+    E.set_static_edges("1" if request.param == "static" else "0")
+    yield request.param
+    E.set_static_edges("auto")
+
+
 def _classes():
     from d3human_code_b200.geometry.gshell_tets import GShell_Tets
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
@@ -129,14 +139,24 @@ def test_cuda_matches_oracle(dev, res, field, cls, typ, wt):
         U.assert_close_normwise("grad_msdf", g[2], g_msdf, U.GRAD_RTOL)
 
 
-def test_integer_intermediates_match_oracle(dev):
+def test_integer_intermediates_match_oracle(dev, edges_mode):
     """classification, case codes, sorted edge keys (interp_v), corner array, counts: bit-exact."""
     from d3human_code_b200 import extract as E
     pos, sdf, msdf, tets = _inputs(24, "adv", seed=3)
     fwd = O.extract_forward(pos, sdf, msdf, tets)
     tt = E.packed_tets(torch.tensor(tets, device=dev), pos.shape[0])
+    static = E.static_edges_for(tt, pos.shape[0])
+    assert (static is not None) == (edges_mode == "static")
+    if static is not None:   # the static table is the sorted list of all distinct tet edges
+        ea = np.minimum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
+        eb = np.maximum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
+        uk = np.unique(ea * pos.shape[0] + eb)
+        assert static[2] == uk.shape[0]
+        U.assert_exact("edge_ab", static[1].cpu().numpy().astype(np.int64), np.stack([uk // pos.shape[0], uk % pos.shape[0]], 1))
+        off = static[0].cpu().numpy()
+        assert off[0] == 0 and off[-1] == uk.shape[0] and np.all(np.diff(off) >= 0)
     r = E.forward_raw(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev), torch.tensor(msdf, device=dev), tt,
-                      False, True)
+                      False, True, static=static)
     c = r.frames[0].counts
     assert c["n_valid_tets"] == fwd["fv"] and c["n_tri_tets"] == fwd["t1"] and c["n_quad_tets"] == fwd["t2"]
     assert c["n_verts"] == fwd["n_verts_watertight"] and c["n_faces_aug"] == fwd["faces_aug"].shape[0]
