@@ -212,23 +212,45 @@ __device__ __forceinline__ void mark_polygon_edges(const int4 v4, int code, bool
                                                    unsigned* __restrict__ corner_rank) {
   const int vv[4] = {v4.x, v4.y, v4.z, v4.w};
   const int n = quad ? 4 : 3;
-  unsigned ranks[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-  for (int k = 0; k < n; ++k) {
-    const int e = c_loop_edge[code][k];
+  // the four corners advance in lockstep so that their loads are in flight together (the chains are independent)
+  int bb[4], lo[4], hi[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = c_loop_edge[code][k < n ? k : 0];
     const int p = vv[c_edge_p[e]], q = vv[c_edge_q[e]];
-    const int a = min(p, q), b = max(p, q);
-    int lo = __ldg(edge_off + a), hi = __ldg(edge_off + a + 1) - 1;
-    while (lo < hi) {  // first entry with .y >= b (the edge exists: it is an edge of this very tet)
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(&edge_ab[mid].y) < b) lo = mid + 1; else hi = mid;
-    }
-    const unsigned r = (unsigned)lo;
-    ranks[k] = r;
-    const unsigned bit = 1u << (r & 31u);
-    const unsigned old = atomicOr(edge_bits + (r >> 5), bit);
-    if (!(old & bit)) atomicAdd(eblock_cnt + r / kEdgeBlock, 1u);
+    const int a = min(p, q);
+    bb[k] = max(p, q);
+    lo[k] = __ldg(edge_off + a);
+    hi[k] = __ldg(edge_off + a + 1) - 1;
   }
-  reinterpret_cast<uint4*>(corner_rank)[rec] = make_uint4(ranks[0], ranks[1], ranks[2], ranks[3]);
+  bool more = true;
+  while (more) {  // first entry with .y >= b (the edge exists: it is an edge of this very tet)
+    int mid[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mid[k] = (lo[k] + hi[k]) >> 1;
+      y[k] = __ldg(&edge_ab[mid[k]].y);
+    }
+    more = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (lo[k] < hi[k]) {
+        if (y[k] < bb[k]) lo[k] = mid[k] + 1; else hi[k] = mid[k];
+      }
+      more = more || (lo[k] < hi[k]);
+    }
+  }
+  unsigned old[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    old[k] = 0xffffffffu;
+    if (k < n) old[k] = atomicOr(edge_bits + ((unsigned)lo[k] >> 5), 1u << ((unsigned)lo[k] & 31u));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < n && !(old[k] & (1u << ((unsigned)lo[k] & 31u)))) atomicAdd(eblock_cnt + (unsigned)lo[k] / kEdgeBlock, 1u);
+  reinterpret_cast<uint4*>(corner_rank)[rec] =
+      make_uint4((unsigned)lo[0], (unsigned)lo[1], (unsigned)lo[2], n == 4 ? (unsigned)lo[3] : 0xffffffffu);
 }
 
 // EMIT: 0 records only (tet-range shards), 1 sort keys + MSD histogram (general path), 2 static edge table marks

@@ -448,6 +448,8 @@ edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
   constexpr int WARPS = 256 / 32;
   __shared__ unsigned s_w[WARPS];
   __shared__ unsigned s_part[WARPS];
+  __shared__ unsigned s_pre[256];   // marked edges of this block before word t
+  __shared__ unsigned s_bits[256];
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
   const unsigned b = blockIdx.x;
   const unsigned mine = __ldcg(eblock_cnt + b);
@@ -457,6 +459,7 @@ edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
   if ((mine == 0u && !is_last) || skip) return;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned part = 0;
+#pragma unroll 4
   for (unsigned i = threadIdx.x; i < b; i += 256) part += __ldcg(eblock_cnt + i);
 #pragma unroll
   for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
@@ -471,6 +474,7 @@ edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
   }
   if (lane == 31) s_w[warp] = incl;
   if (lane == 0) s_part[warp] = part;
+  s_bits[threadIdx.x] = bits;
   __syncthreads();
   unsigned wpre = 0, total = 0, excl = 0;
 #pragma unroll
@@ -479,23 +483,29 @@ edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
     total += s_w[q];
     excl += s_part[q];
   }
+  s_pre[threadIdx.x] = wpre + incl - c;
+  if (c) word_prefix[w] = excl + wpre + incl - c;
   const d3h_forward_args& a = blk->a;
   const int64_t cap_verts = a.cap_verts, cap_verts_aug = a.cap_verts_aug;
   if (is_last && threadIdx.x == 0) ctr->n_verts = excl + total;
-  if (c == 0u) return;
-  int64_t vid = (int64_t)excl + wpre + (incl - c);
-  word_prefix[w] = (unsigned)vid;
+  if (total == 0u) return;
+  __syncthreads();
   const int2* __restrict__ edge_ab = reinterpret_cast<const int2*>(a.edge_ab);
   const float* __restrict__ pos = a.pos;
   const float* __restrict__ sdf = a.sdf;
   const float* __restrict__ msdf = a.msdf;
   const int msdf_negate = a.msdf_negate;
   float4* __restrict__ vacc = reinterpret_cast<float4*>(a.vacc);
-  unsigned rest = bits;
-  while (rest) {
-    const int bit = __ffs(rest) - 1;
-    rest &= rest - 1u;
-    const int2 ab = __ldg(edge_ab + (w * 32 + bit));
+  // one marked edge (= one new vertex) per thread and trip, whatever word it sits in
+  for (unsigned i = threadIdx.x; i < total; i += 256) {
+    int lo = 0, hi = 255;  // word: last t with s_pre[t] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_pre[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int bit = (int)__fns(s_bits[lo], 0, (int)(i - s_pre[lo]) + 1);
+    const int64_t vid = (int64_t)excl + i;
+    const int2 ab = __ldg(edge_ab + (((int64_t)b * 256 + lo) * 32 + bit));
     const int ea = ab.x, eb = ab.y;
     // zero-crossing interpolation, gshell_tets.py:291-303 (op order: SURVEY A.4)
     float w0, w1, dd;
@@ -510,8 +520,7 @@ edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
     w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
     w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vid < cap_verts) {
-      a.tape_edges[2 * vid] = ea;
-      a.tape_edges[2 * vid + 1] = eb;
+      reinterpret_cast<int2*>(a.tape_edges)[vid] = make_int2(ea, eb);
       a.verts_wt[3 * vid] = x; a.verts_wt[3 * vid + 1] = y; a.verts_wt[3 * vid + 2] = z;
       a.msdf_wt[vid] = m;
       vacc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -526,7 +535,6 @@ edge_emit_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       a.verts_aug[3 * vid + 2] = used ? z : 0.f;
       a.msdf_aug[vid] = m;
     }
-    ++vid;
   }
   trace_end(tr);
 }
