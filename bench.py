@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--res", type=int, default=128, help="Kuhn grid resolution (128 = BASELINE configs[1])")
     ap.add_argument("--frames-per-rank", type=int, default=16,
                     help="frames per rank per step (BASELINE configs[3]: a batch of 16 video frames per step)")
-    ap.add_argument("--lanes", type=int, default=4, help="concurrent lanes the frames of a batch are spread over")
+    ap.add_argument("--lanes", type=int, default=8, help="concurrent lanes the frames of a batch are spread over")
     ap.add_argument("--groups", type=int, default=2,
                     help="the frames of a step are issued as this many extract_frames_async batches (host / GPU pipelining)")
     ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])

@@ -61,10 +61,16 @@ int launch_priority(LaunchClass c) {
 // ---- lanes: internal streams the frames of a batch are spread over -----------------------------------------------
 constexpr int kMaxLanes = 8;
 constexpr int kMaxDevices = 16;
+constexpr int kClsEvents = 64;
 struct LaneSet {
   bool ready;
   cudaStream_t lane[kMaxLanes];
-  cudaEvent_t fork, join[kMaxLanes];
+  cudaStream_t head;                 // the heads (prepare + O(F) stream) of all frames, back to back
+  cudaEvent_t fork, join[kMaxLanes], join_head;
+  cudaEvent_t done[kMaxLanes];       // tail of the lane's last frame: its workspace may be reused
+  bool done_valid[kMaxLanes];
+  cudaEvent_t cls[kClsEvents];       // head of a frame finished (ring)
+  unsigned cls_next;
 };
 static LaneSet g_lanes[kMaxDevices];
 static std::mutex g_lane_mu;
@@ -80,8 +86,15 @@ static LaneSet* lanes_for_current_device() {
     for (int i = 0; i < kMaxLanes; ++i) {
       if (cudaStreamCreateWithPriority(&ls.lane[i], cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&ls.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&ls.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      ls.done_valid[i] = false;
     }
+    if (cudaStreamCreateWithPriority(&ls.head, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    for (int i = 0; i < kClsEvents; ++i)
+      if (cudaEventCreateWithFlags(&ls.cls[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ls.cls_next = 0;
     if (cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ls.join_head, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ls.ready = true;
   }
   return &ls;
@@ -237,8 +250,9 @@ static int finish(const char* who, const d3h_forward_args* a, const Workspace& w
   return D3H_OK;
 }
 
-void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
-  launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream);
+void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts) {
+  launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream, parts);
+  if (!(parts & kPartTail)) return;
   if (a.edge_off != nullptr) launch_edge_emit(a, ws, stream);
   else launch_edge_sort(a, ws, stream);
   launch_surface(a, ws, ws.records, stream);
@@ -253,10 +267,10 @@ const void* prepare_kernel_address();
 struct GraphKey {
   void* workspace;
   int64_t n_tets, n_grid, tet_begin, tet_end, cap_valid_tets;
-  int watertight, has_zero, device, is_static;
+  int watertight, has_zero, device, is_static, parts;
   int64_t n_edges;
   bool operator==(const GraphKey& o) const {
-    return is_static == o.is_static && n_edges == o.n_edges && workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
+    return parts == o.parts && is_static == o.is_static && n_edges == o.n_edges && workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
            tet_end == o.tet_end && cap_valid_tets == o.cap_valid_tets && watertight == o.watertight &&
            has_zero == o.has_zero && device == o.device;
   }
@@ -273,7 +287,7 @@ static std::mutex g_graph_mu;
 static std::vector<GraphEntry> g_graphs;
 static uint64_t g_graph_clock = 0;
 static int g_graph_state = -1;  // -1 unknown, 0 disabled (D3H_DISABLE_GRAPH=1), 1 enabled
-constexpr size_t kMaxGraphs = 64;
+constexpr size_t kMaxGraphs = 128;
 
 static void destroy_entry(GraphEntry& e) {
   cudaGraphExecDestroy(e.exec);
@@ -281,18 +295,19 @@ static void destroy_entry(GraphEntry& e) {
 }
 
 static int build_entry(const d3h_forward_args& a, const Workspace& ws, const GraphKey& key, GraphEntry& out) {
+  const int parts = key.parts;
   static thread_local cudaStream_t cs = nullptr;
   if (cs == nullptr && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return -1;
   cudaGraph_t graph = nullptr;
   if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return -1; }
-  launch_prepare(a, ws, cs);
-  launch_forward_sequence(a, ws, cs);
+  if (parts & kPartHead) launch_prepare(a, ws, cs);
+  launch_forward_sequence(a, ws, cs, parts);
   if (cudaStreamEndCapture(cs, &graph) != cudaSuccess || graph == nullptr) { cudaGetLastError(); return -1; }
   size_t nn = 0;
   cudaGraphGetNodes(graph, nullptr, &nn);
   std::vector<cudaGraphNode_t> nodes(nn);
   cudaGraphGetNodes(graph, nodes.data(), &nn);
-  bool found = false;
+  bool found = !(parts & kPartHead);  // the tail has no per-call parameters: its kernels read the argument block
   for (size_t i = 0; i < nn && !found; ++i) {
     cudaGraphNodeType ty;
     if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
@@ -310,7 +325,13 @@ static int build_entry(const d3h_forward_args& a, const Workspace& ws, const Gra
   // slots from the O(F) stream, which needs the whole register file to reach the HBM rate (64 regs x 4 CTAs / SM) and
   // slows down 2x -- the batch gets 8 % slower.  What the lanes buy is the overlap of one frame's dependency bubbles
   // with another frame's kernels, not free SM time.
-  if (!found || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+  static int node_prio = -1;
+  if (node_prio < 0) {
+    const char* env = getenv("D3H_NODE_PRIORITY");
+    node_prio = (env && env[0] == '1') ? 1 : 0;
+  }
+  if (!found || cudaGraphInstantiateWithFlags(&exec, graph, node_prio ? cudaGraphInstantiateFlagUseNodePriority : 0) !=
+                    cudaSuccess) {
     cudaGetLastError();
     cudaGraphDestroy(graph);
     return -1;
@@ -322,7 +343,8 @@ static int build_entry(const d3h_forward_args& a, const Workspace& ws, const Gra
 }
 
 // Returns 0 when the call was enqueued as a graph launch, -1 when the caller must launch the kernels directly.
-static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream,
+                                int parts = kPartAll) {
   if (g_graph_state < 0) {
     const char* env = getenv("D3H_DISABLE_GRAPH");
     g_graph_state = (env && env[0] == '1') ? 0 : 1;
@@ -342,6 +364,7 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.cap_valid_tets = a.cap_valid_tets;
   key.watertight = a.watertight_template ? 1 : 0;
   key.has_zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) ? 1 : 0;
+  key.parts = parts;
   key.is_static = a.edge_off != nullptr ? 1 : 0;
   key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
@@ -366,16 +389,18 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
     }
   }
   e->last_use = ++g_graph_clock;
-  FwdBlock blk;
-  blk.a = a;
-  blk.counts_mapped = mapped_counts_pointer(a.counts_host);
-  blk.trace = trace_table();
-  Workspace wcopy = ws;
-  void* kargs[2] = {&blk, &wcopy};
-  cudaKernelNodeParams kp = e->prepare_params;
-  kp.kernelParams = kargs;
-  kp.extra = nullptr;
-  if (cudaGraphExecKernelNodeSetParams(e->exec, e->prepare_node, &kp) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (parts & kPartHead) {
+    FwdBlock blk;
+    blk.a = a;
+    blk.counts_mapped = mapped_counts_pointer(a.counts_host);
+    blk.trace = trace_table();
+    Workspace wcopy = ws;
+    void* kargs[2] = {&blk, &wcopy};
+    cudaKernelNodeParams kp = e->prepare_params;
+    kp.kernelParams = kargs;
+    kp.extra = nullptr;
+    if (cudaGraphExecKernelNodeSetParams(e->exec, e->prepare_node, &kp) != cudaSuccess) { cudaGetLastError(); return -1; }
+  }
   if (cudaGraphLaunch(e->exec, stream) != cudaSuccess) { cudaGetLastError(); return -1; }
   return 0;
 }
@@ -428,12 +453,7 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   return finish("d3h_extract_forward", a, ws, stream);
 }
 
-// A batch of independent extractions (video frames, or the cloth / body pair of one iteration): frame i runs on
-// internal lane i % lanes, the lanes fork from `stream` and join back into it, so for the caller the batch is ordered
-// like one call.  Frames that share a lane may share a workspace (they are serialised); frames on different lanes
-// must not.  Every frame publishes its own d3h_counts (args[i].counts_host / seq).
-extern "C" int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes,
-                                         d3h_stream_t s) {
+static int forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t s, bool join) {
   if (!args || n_frames < 0 || lanes < 1) { set_error("d3h_extract_forward_batch: null args / bad sizes"); return D3H_E_BADARG; }
   if (lanes > kMaxLanes) lanes = kMaxLanes;
   if (lanes > n_frames) lanes = (int32_t)(n_frames > 0 ? n_frames : 1);
@@ -452,25 +472,101 @@ extern "C" int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n
   cudaStream_t stream = (cudaStream_t)s;
   LaneSet* ls = lanes_for_current_device();
   if (ls == nullptr) { set_error("d3h_extract_forward_batch: cannot create the lane streams"); return D3H_E_CUDA; }
+  {
+    // a capturing caller gets the plain sequence on its own stream (events recorded outside the capture cannot be waited)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cudaGetLastError();
+    if (cap != cudaStreamCaptureStatusNone) {
+      int rc = D3H_OK;
+      for (int64_t i = 0; i < n_frames; ++i) {
+        const int r = d3h_extract_forward(&args[i], s);
+        if (r) rc = r;
+      }
+      return rc;
+    }
+  }
+  // Default: one graph per frame, frame i on lane i % lanes.  The hardware takes equal-priority kernels in submission
+  // order, so the O(F) streams of the frames run one after the other at full rate and the latency-bound kernels of the
+  // other lanes fill in around them.
+  // D3H_SPLIT_HEAD=1 (experiment, profiles/README.md): the heads of all frames (prepare + stream) back to back on ONE
+  // stream, the tail of frame i on lane i % lanes once its head is done.  Measured slower: a stream that shares the SMs
+  // with tails needs 55-60 us instead of 35, and graph launches on one stream leave ~10 us between graphs.
+  static int split_head = -1;
+  if (split_head < 0) {
+    const char* env = getenv("D3H_SPLIT_HEAD");
+    split_head = (env && env[0] == '1') ? 1 : 0;
+  }
   cudaEventRecord(ls->fork, stream);
+  if (split_head) cudaStreamWaitEvent(ls->head, ls->fork, 0);
   for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->lane[l], ls->fork, 0);
   int rc = D3H_OK;
   for (int64_t i = 0; i < n_frames; ++i) {
     const d3h_forward_args* a = &args[i];
-    cudaStream_t lane = ls->lane[i % lanes];
+    const int l = (int)(i % lanes);
+    cudaStream_t lane = ls->lane[l];
     Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
-    if (launch_forward_graph(*a, ws, lane) != 0) {
-      launch_prepare(*a, ws, lane);
-      launch_forward_sequence(*a, ws, lane);
+    if (!split_head) {
+      if (launch_forward_graph(*a, ws, lane) != 0) {
+        launch_prepare(*a, ws, lane);
+        launch_forward_sequence(*a, ws, lane);
+      }
+    } else {
+      // the head overwrites the workspace of the frame that ran on this lane before
+      if (ls->done_valid[l]) cudaStreamWaitEvent(ls->head, ls->done[l], 0);
+      launch_prepare(*a, ws, ls->head);
+      launch_forward_sequence(*a, ws, ls->head, kPartHead);
+      cudaEvent_t cls = ls->cls[ls->cls_next++ % kClsEvents];
+      cudaEventRecord(cls, ls->head);
+      cudaStreamWaitEvent(lane, cls, 0);
+      if (launch_forward_graph(*a, ws, lane, kPartTail) != 0) launch_forward_sequence(*a, ws, lane, kPartTail);
+      cudaEventRecord(ls->done[l], lane);
+      ls->done_valid[l] = true;
     }
     const int r = finish("d3h_extract_forward_batch", a, ws, lane);
     if (r) rc = r;
   }
-  for (int l = 0; l < lanes; ++l) {  // always join, also after an error: the caller's stream must not lose the lanes
-    cudaEventRecord(ls->join[l], ls->lane[l]);
-    cudaStreamWaitEvent(stream, ls->join[l], 0);
+  if (join || rc != D3H_OK) {  // after an error always join: the caller's stream must not lose the lanes
+    for (int l = 0; l < kMaxLanes; ++l) {
+      cudaEventRecord(ls->join[l], ls->lane[l]);
+      cudaStreamWaitEvent(stream, ls->join[l], 0);
+    }
+    cudaEventRecord(ls->join_head, ls->head);
+    cudaStreamWaitEvent(stream, ls->join_head, 0);
   }
   return rc;
+}
+
+// A batch of independent extractions (video frames, or the cloth / body pair of one iteration): frame i runs on
+// internal lane i % lanes, the lanes fork from `stream` and join back into it, so for the caller the batch is ordered
+// like one call.  Frames that share a lane may share a workspace (they are serialised); frames on different lanes
+// must not.  Every frame publishes its own d3h_counts (args[i].counts_host / seq).
+extern "C" int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes,
+                                         d3h_stream_t s) {
+  return forward_batch(args, n_frames, lanes, s, /*join=*/true);
+}
+
+// Same without the join: the lanes keep running, `stream` is NOT ordered behind them until d3h_lanes_join(stream) is
+// called.  Several batches launched back to back this way queue up per lane, so the O(F) stream of the next batch
+// starts on a lane the moment that lane's frame of the previous batch is done -- no drain / refill of the pipeline at
+// the batch boundary.  The caller must join before `stream` touches any output (or frees any buffer) of the batches.
+extern "C" int d3h_extract_forward_batch_nojoin(const d3h_forward_args* args, int64_t n_frames, int32_t lanes,
+                                                d3h_stream_t s) {
+  return forward_batch(args, n_frames, lanes, s, /*join=*/false);
+}
+
+// Orders `stream` behind everything enqueued on the lanes so far.
+extern "C" int d3h_lanes_join(d3h_stream_t s) {
+  LaneSet* ls = lanes_for_current_device();
+  if (ls == nullptr) { set_error("d3h_lanes_join: cannot create the lane streams"); return D3H_E_CUDA; }
+  for (int l = 0; l < kMaxLanes; ++l) {
+    cudaEventRecord(ls->join[l], ls->lane[l]);
+    cudaStreamWaitEvent((cudaStream_t)s, ls->join[l], 0);
+  }
+  cudaEventRecord(ls->join_head, ls->head);
+  cudaStreamWaitEvent((cudaStream_t)s, ls->join_head, 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d3h_lanes_join: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
 }
 
 static int check_backward_args(const d3h_backward_args* a, const char* who) {

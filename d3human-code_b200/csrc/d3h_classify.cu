@@ -384,12 +384,12 @@ compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1
 }
 
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
-                     bool emit_keys, cudaStream_t stream) {
+                     bool emit_keys, cudaStream_t stream, int parts) {
   const int64_t n = a.tet_end - a.tet_begin;
   if (n <= 0) return;
   const int64_t nchunks = (n + kChunkTets - 1) / kChunkTets;
   const int64_t ntiles = (n + kTileTets - 1) / kTileTets;
-  {
+  if (parts & kPartHead) {
     // One-shot grid (a warp per 256-tet chunk, CTAs retire every few microseconds) at the lowest priority: measured as
     // fast as a persistent grid (profiles/bench_stream.cu) and, unlike it, it leaves CTA slots to the latency-bound
     // kernels of the frames running on the other lanes.
@@ -403,6 +403,7 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
       launch_k(classify_kernel<false>, (unsigned)nblocks, kClassifyThreads, stream, kLaunchStream, ws.blk, a.tet_begin,
                a.tet_end, ws.occ_bits, (const unsigned*)nullptr, ws.m1_words, ws.m2_words, ws.tile_cnt, nchunks);
   }
+  if (!(parts & kPartTail)) return;
   const int64_t nwords = nchunks * kClassifyItems;  // every word of a visited chunk is written
   const int key_bits = key_bits_for(a.n_grid);
   const int msd_shift = msd_shift_for(a.n_grid);

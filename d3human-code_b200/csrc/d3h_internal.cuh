@@ -92,9 +92,13 @@ int persistent_grid(const void* kernel, int threads, size_t dyn_smem);
 // ---- stage launchers (all asynchronous on `stream`) -------------------------------------------------
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 // the forward sequence behind launch_prepare; `a` only supplies the launch shapes, the kernels read the block
-void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
+// parts of a forward call: the head is the bandwidth-bound part (the O(F) classification stream behind prepare_kernel),
+// the tail everything that works on the O(surface) records.  A batch runs the heads of all frames back to back on one
+// stream and the tails on the lanes.
+enum ForwardParts { kPartHead = 1, kPartTail = 2, kPartAll = 3 };
+void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts = kPartAll);
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
-                     bool emit_keys, cudaStream_t stream);
+                     bool emit_keys, cudaStream_t stream, int parts = kPartAll);
 void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 void launch_edge_emit(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);  // static edge table path
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,

@@ -331,6 +331,8 @@ class _Pending:
     __slots__ = ("inputs", "plan", "lay", "fslab", "islab", "tape", "seq0", "slot0", "bmat", "launches", "dev", "B")
 
 
+_unjoined: Dict[Any, bool] = {}   # device index -> a batch was launched without joining the lanes yet
+
 _COUNT_RING = 256   # pinned 128-byte count slots per plan: batches in flight take consecutive slots of the ring
 
 
@@ -399,8 +401,17 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
                 A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = 0
             A[:, c["counts_host"]] = plan.counts_ptr + ((slot0 + lay.ar) % _COUNT_RING) * 128
             A[:, c["seq"]] = lay.ar + (seq0 + 1)
+            if B == 1 and _unjoined.get(dev.index):
+                # this call runs on the caller's stream and shares workspace 0 with the lanes of an un-joined batch
+                _cabi.check(L.d3h_lanes_join(stream), "d3h_lanes_join")
+                _unjoined[dev.index] = False
             if launcher is None:
-                _cabi.check(L.d3h_extract_forward_batch(A.ctypes.data, B, lanes, stream), "d3h_extract_forward_batch")
+                # no join here: the lanes keep running and the next batch may queue up behind this one lane by lane;
+                # _collect_frames orders the caller's stream behind the lanes before any output is handed out
+                _cabi.check(L.d3h_extract_forward_batch_nojoin(A.ctypes.data, B, lanes, stream),
+                            "d3h_extract_forward_batch")
+                if B > 1:
+                    _unjoined[dev.index] = True
             else:
                 need_tets = launcher(A, plan, stream)
                 if need_tets is not None:   # the gathered records do not fit: grow like an overflowed single call
@@ -482,6 +493,9 @@ def _collect_frames(pend: _Pending) -> BatchResult:
             fv, t1, t2, v, nfa = mx[0], mx[1], mx[2], mx[4], mx[5]
             va_ = int((sizes[:, 4] + sizes[:, 3]).max())
             fw_ = int((sizes[:, 1] + 2 * sizes[:, 2]).max())
+        if B > 1:
+            _cabi.check(L.d3h_lanes_join(torch.cuda.current_stream(pend.dev).cuda_stream), "d3h_lanes_join")
+            _unjoined[pend.dev.index] = False
         if grow_tets or grow_out:
             if grow_tets:  # record buffer too small: surface stages were skipped for some frame, its sizes are unknown
                 p = 3 * t1 + 4 * t2
@@ -754,6 +768,16 @@ class FramesFuture:
         self._args = (spec, tets, tensors)
         self._n, self._wt = n_frames, watertight
         self._out = None
+
+    def __del__(self):
+        # dropped without result(): the lanes may still be writing this batch's buffers, which are about to be freed
+        if self._out is None and self._n > 1 and self._args is not None:
+            try:
+                dev = self._args[2][0].device
+                with torch.cuda.device(dev):
+                    _cabi.lib().d3h_lanes_join(torch.cuda.current_stream(dev).cuda_stream)
+            except Exception:  # pragma: no cover  (interpreter shutdown)
+                pass
 
     def result(self):
         if self._out is None:

@@ -201,6 +201,11 @@ int d3h_extract_backward(const d3h_backward_args* args, d3h_stream_t stream);
  *             with atomics, a shared buffer must be zero on entry (grads_prezeroed = 1).  The adjoints of up to 16
  *             frames are one kernel launch (grid.y = frame); `lanes` is ignored. */
 int d3h_extract_forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
+/* The same without the final join: `stream` is not ordered behind the lanes until d3h_lanes_join(stream).  Batches
+ * launched back to back this way queue up per lane (no drain / refill of the lanes at the batch boundary); the caller
+ * joins before `stream` touches an output, or frees a buffer, of those batches. */
+int d3h_extract_forward_batch_nojoin(const d3h_forward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
+int d3h_lanes_join(d3h_stream_t stream);
 int d3h_extract_backward_batch(const d3h_backward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
 
 /* Tet-range sharding (multi-GPU): stage 1 classifies tets [tet_begin, tet_end) and leaves
