@@ -178,7 +178,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", device_id=dev)
+        import datetime
+        # a mismatched collective should fail within minutes, not hold the box for the default 10
+        dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     from d3human_code_b200 import _cabi, grids
     from d3human_code_b200 import extract as E
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
@@ -214,10 +216,10 @@ def main():
     launches_per_step = E._ExtractFn.last_launches + E.LAUNCHES_BACKWARD * fpr
     del outs
 
-    def step():
-        """One training-step's worth of extraction on this rank: every group of frames is one extract_frames_async call
-        (one library call, concurrent lanes) and one backward call; gradients of the shared sdf / msdf are summed over
-        the frames by the kernels, over the groups by autograd and over the ranks by NCCL."""
+    def local_step():
+        """This rank's share of a step, no collective: every group of frames is one extract_frames_async call (one
+        library call, concurrent lanes) and one backward call; gradients of the shared sdf / msdf are summed over the
+        frames by the kernels and over the groups by autograd."""
         sdf.grad = msdf.grad = None
         for pg in pos_groups:
             pg.grad = None
@@ -225,6 +227,11 @@ def main():
         for fut, (lo, hi) in zip(futs, gb):
             outs = fut.result()
             torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v[lo:hi] + ups_m[lo:hi])
+
+    def step():
+        """One training-step's worth of extraction: local_step() + the sum of the shared gradients over the ranks (NCCL).
+        Every rank must call it the same number of times."""
+        local_step()
         if world > 1:
             dist.all_reduce(sdf.grad)
             dist.all_reduce(msdf.grad)
@@ -293,7 +300,7 @@ def main():
             _cabi.trace_enable(True)
             plan = E._plan_for(dev, F, N)
             seq0 = plan.seq
-            step()
+            local_step()          # rank 0 only: must not contain a collective
             torch.cuda.synchronize()
             tr = _cabi.trace_read()
             _cabi.trace_enable(False)
