@@ -268,7 +268,9 @@ def main():
         step()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    launches0 = E.launch_counter()
     ms_step = timed(step, args.steps)
+    launches_timed = E.launch_counter() - launches0      # library kernels enqueued by this rank in the timed region
     value = world * fpr * F / (ms_step * 1e-3)
 
     # ---- the same frames through the drop-in class, one call + backward per frame (no batching, no lanes) ----
@@ -474,7 +476,7 @@ def main():
                        "counts_frame0": c0, "l2": "tet index stream is 16*F = %d MB > 126 MB L2; no explicit flush" % (16 * F // 1000000),
                        "lanes": args.lanes, "groups": ngroups, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "device_trace": dev_trace, "single_call": single, "gpu_launches": int(launches_per_step * args.steps), "kernels": kern,
+            "device_trace": dev_trace, "single_call": single, "gpu_launches": int(launches_timed), "kernels": kern,
             "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -625,6 +625,7 @@ class _ExtractFn(torch.autograd.Function):
         ctx.mark_non_differentiable(*nondiff)
         _ExtractFn.last_counts = [r.counts for r in res.frames]
         _ExtractFn.last_launches = res.launches
+        _ExtractFn.total_launches += res.launches
         return tuple(flat)
 
     @staticmethod
@@ -685,6 +686,9 @@ class _ExtractFn(torch.autograd.Function):
                 m = bmat if len(live) == len(refs) else np.ascontiguousarray(bmat[live])
                 m[:, _BC["g_verts_aug"]:_BC["g_msdf_wt"] + 1] = gp
                 m[:, _BC["g_msdf_boundary"]] = gb
+                # adjoint_kernel (+ adjoint_poly_kernel on the static edge table path) per 16 frames
+                per16 = 2 if int(m[0, _BC["tape_slots"]]) == 0 else 1
+                _ExtractFn.total_launches += per16 * ((len(live) + 15) // 16)
                 _cabi.check(L.d3h_extract_backward_batch(m.ctypes.data, len(live), max(1, min(lanes, len(live))),
                                                          torch.cuda.current_stream(dev).cuda_stream),
                             "d3h_extract_backward_batch")
@@ -693,6 +697,12 @@ class _ExtractFn(torch.autograd.Function):
 
 _ExtractFn.last_counts = None
 _ExtractFn.last_launches = 0
+_ExtractFn.total_launches = 0      # kernels enqueued by this module since import (forward + backward)
+
+
+def launch_counter() -> int:
+    """Number of library kernels enqueued so far by this process (bench.py reports the difference over its timed region)."""
+    return _ExtractFn.total_launches
 
 
 def last_counts() -> Optional[Dict[str, int]]:

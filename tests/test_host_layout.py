@@ -1,0 +1,119 @@
+"""Host logic of the batch path without a GPU: the argument blocks of a batch are an int64 matrix filled with vectorised
+numpy assignments (extract._Layout); here every row is re-read through the ctypes mirror of d3h_forward_args and the
+slab geometry is checked for overlaps, alignment and lane / workspace assignment."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from d3human_code_b200 import _cabi
+from d3human_code_b200 import extract as E
+
+
+def _plan(cap_tets=1000, cap_v=700, cap_va=4100, cap_fw=1500, cap_fa=900, lanes=3):
+    p = E._Plan(device=torch.device("cpu"), n_tets=6 * 16 ** 3, n_grid=17 ** 3)
+    p.cap_tets, p.cap_v, p.cap_va, p.cap_fw, p.cap_fa = cap_tets, cap_v, cap_va, cap_fw, cap_fa
+    p.workspace_bytes = 1 << 20
+    p.workspace_ptrs = [0x10000000 + 0x100000 * i for i in range(lanes)]
+    p.counts_ptr = 0x7f0000000000
+    return p
+
+
+def _rows(lay, bases):
+    A = lay.A.copy()
+    np.add(lay.OFF, np.array([bases[k] for k in lay.slab_of], dtype=np.int64), out=A[:, lay.c0:lay.c1])
+    if lay.static is not None:
+        A[:, E._FC["vacc"]] = lay.vacc_off + bases[0]
+    return [_cabi.ForwardArgs.from_buffer_copy(A[i].tobytes()) for i in range(A.shape[0])]
+
+
+@pytest.mark.parametrize("static", [False, True])
+def test_layout_rows_are_valid_forward_args(static):
+    B, lanes = 5, 3
+    plan = _plan(lanes=lanes)
+    st = None
+    if static:
+        st = (torch.zeros(plan.n_grid + 1, dtype=torch.int32), torch.zeros((40000, 2), dtype=torch.int32), 40000)
+    lay = E._Layout(plan, B, lanes, 1, st)
+    bases = (0x20000000, 0x30000000, 0x40000000)   # float / int64 / int32 slab
+    rows = _rows(lay, bases)
+    cv, cva, cfw, cfa, ct = lay.caps
+    assert (cv, cva, cfw, cfa, ct) == (700, 4100, 1500, 900, 1000)
+    for i, a in enumerate(rows):
+        assert (a.n_grid, a.n_tets, a.tet_begin, a.tet_end) == (plan.n_grid, plan.n_tets, 0, plan.n_tets)
+        assert (a.cap_valid_tets, a.cap_verts, a.cap_verts_aug, a.cap_faces_wt, a.cap_faces_aug) == (ct, cv, cva, cfw, cfa)
+        assert a.workspace == plan.workspace_ptrs[i % lanes] and a.workspace_bytes == plan.workspace_bytes
+        f0, f1 = bases[0] + 4 * i * lay.f_len, bases[0] + 4 * (i + 1) * lay.f_len
+        i0, i1 = bases[1] + 8 * i * lay.i_len, bases[1] + 8 * (i + 1) * lay.i_len
+        t0, t1 = bases[2] + 4 * i * lay.t_len, bases[2] + 4 * (i + 1) * lay.t_len
+        # every region lies inside the frame's slice of its slab, 16-byte aligned, and the regions do not overlap
+        fregs = [(a.verts_aug, 12 * cva), (a.v_tng_aug, 12 * cva), (a.msdf_aug, 4 * cva), (a.verts_wt, 12 * cv),
+                 (a.v_tng_wt, 12 * cv), (a.msdf_wt, 4 * cv)]
+        if static:
+            fregs.append((a.vacc, 32 * cv))
+            assert a.edge_off == st[0].data_ptr() and a.edge_ab == st[1].data_ptr() and a.n_edges == 40000
+        else:
+            assert not a.edge_off and not a.vacc and a.n_edges == 0
+        iregs = [(a.faces_aug, 24 * cfa), (a.faces_wt, 24 * cfw)]
+        tregs = [(a.tape_edges, 8 * cv), (a.tape_corners, 16 * ct), (a.tape_slots, 16 * ct), (a.tape_runs, 4 * (cv + 1))]
+        for regs, (lo, hi) in ((fregs, (f0, f1)), (iregs, (i0, i1)), (tregs, (t0, t1))):
+            spans = sorted((p, p + n) for p, n in regs)
+            assert spans[0][0] >= lo and spans[-1][1] <= hi, (i, spans, lo, hi)
+            for (p0, e0), (p1, _) in zip(spans, spans[1:]):
+                assert e0 <= p1, "regions overlap"
+            for p, _ in regs:
+                assert p % 16 == 0
+    # frames on different lanes never share a workspace, frames of one lane do
+    ws = [a.workspace for a in rows]
+    assert ws[0] == ws[3] and ws[1] == ws[4] and len({ws[0], ws[1], ws[2]}) == 3
+
+
+def test_column_maps_match_ctypes_structs():
+    for cols, words, st in ((E._FC, E._FW, _cabi.ForwardArgs), (E._BC, E._BW, _cabi.BackwardArgs), (E._CC, E._CW, _cabi.Counts)):
+        assert words * 8 == C.sizeof(st)
+        for name, _ in st._fields_:
+            assert cols[name] == getattr(st, name).offset // 8
+    # the two int32 flags of each block share one word: low half first (little endian)
+    a = _cabi.ForwardArgs()
+    a.msdf_negate, a.watertight_template = 1, 1
+    word = np.frombuffer(bytes(a), dtype=np.int64)[E._FC["msdf_negate"]]
+    assert word == 1 | (1 << 32)
+    b = _cabi.BackwardArgs()
+    b.msdf_negate, b.grads_prezeroed = 0, 1
+    assert np.frombuffer(bytes(b), dtype=np.int64)[E._BC["msdf_negate"]] == (1 << 32)
+
+
+def test_capacity_prediction_is_stable():
+    for need in (0, 1, 1000, 57740, 10 ** 6):
+        g = E._grow(need)
+        assert g >= need + 1024 and E._shrink(g, need) == g
+        assert E._shrink(g, int(need * 1.05)) >= int(need * 1.05)       # a little growth: capacity follows
+        assert E._shrink(10 * g + 5000, need) == g                       # a collapsed surface: capacity shrinks
+
+
+def test_static_edge_policy_without_gpu():
+    E.set_static_edges("0")
+    try:
+        assert E.static_edges_for(torch.zeros((4, 4), dtype=torch.int32), 8) is None
+        with pytest.raises(ValueError):
+            E.set_static_edges("maybe")
+    finally:
+        E.set_static_edges("auto")
+
+
+def test_build_edge_table_on_cpu_matches_numpy():
+    """The one-time edge table build is plain torch: it runs on CPU tensors too."""
+    from d3human_code_b200 import grids
+    pos, tets = grids.kuhn_grid(6)
+    n = pos.shape[0]
+    off, ab, u = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    ea = np.minimum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
+    eb = np.maximum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
+    uk = np.unique(ea * n + eb)
+    assert u == uk.shape[0]
+    assert np.array_equal(ab.numpy().astype(np.int64), np.stack([uk // n, uk % n], 1))
+    o = off.numpy()
+    assert o[0] == 0 and o[-1] == u
+    for a in (0, 7, n - 2):
+        assert np.array_equal(ab.numpy()[o[a]:o[a + 1], 0], np.full(o[a + 1] - o[a], a))
