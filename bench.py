@@ -7,9 +7,10 @@
 
 Workload (BASELINE.json configs[1]): 128^3 Kuhn tet grid (F=12,582,912, N=2,146,689), analytic capsule-union SDF +
 garment mSDF, hmSDF_Tets(type="cloth") forward + backward with upstream gradients on verts_aug and extra['msdf'].
-Each rank runs `--frames-per-rank` frames per step (default 16 = the configs[3] batch); a frame is one full extraction
-with its own per-frame tet-vertex offsets (seed = global frame index), all frames of a step go through ONE
-extract_frames() call (one autograd node, one library call per direction, frames spread over concurrent lanes).
+Each rank runs `--frames-per-rank` frames per step (default 32 = two configs[3] batches); a frame is one full extraction
+with its own per-frame tet-vertex offsets (seed = global frame index); the frames of a step go through `--groups`
+extract_frames_async() calls of 8 frames (one autograd node and one library call per direction each, frames spread over
+concurrent lanes), all launched up front so that the host work of one group overlaps the GPU work of the next.
 sdf/msdf are shared, so their gradients accumulate over the rank's frames (atomics) and are all-reduced (NCCL) when
 N > 1.  Weak scaling: per-GPU work is fixed.  value = N * frames_per_rank * F / (max-over-ranks device time per step).
 `single_call` reports the same frames through the drop-in class one call at a time (the reference's calling pattern).
@@ -44,10 +45,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=128, help="Kuhn grid resolution (128 = BASELINE configs[1])")
-    ap.add_argument("--frames-per-rank", type=int, default=16,
-                    help="frames per rank per step (BASELINE configs[3]: a batch of 16 video frames per step)")
+    ap.add_argument("--frames-per-rank", type=int, default=32,
+                    help="frames per rank per step (BASELINE configs[3]: batches of 16 video frames; default = 2 batches)")
     ap.add_argument("--lanes", type=int, default=8, help="concurrent lanes the frames of a batch are spread over")
-    ap.add_argument("--groups", type=int, default=2,
+    ap.add_argument("--groups", type=int, default=4,
                     help="the frames of a step are issued as this many extract_frames_async batches (host / GPU pipelining)")
     ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
