@@ -1,0 +1,111 @@
+"""BASELINE.json configurations at their named sizes (size-independent properties + the surface counts the reference
+itself produces), and the pipelined use of the batch API that bench.py relies on.
+Runs last (file name) so that a failure here cannot hide the small-size parity tests."""
+import numpy as np
+import pytest
+import torch
+
+from d3human_code_b200 import grids
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True, params=["sort", "static"])
+def edges_mode(request):
+    from d3human_code_b200 import extract as E
+    E.set_static_edges("1" if request.param == "static" else "0")
+    yield request.param
+    E.set_static_edges("auto")
+
+
+# counts measured by running the reference on CPU: Fv, V, Fw, Va, Fa
+REFERENCE_COUNTS = {
+    (64, "sphere"): (31608, 20702, 41400, 125318, 24708),
+    (128, "sphere"): (127080, 83222, 166440, 503822, 97830),
+    (64, "capsule"): (14162, 9392, 18780, 56496, 10412),
+}
+
+
+@pytest.mark.parametrize("res,field", sorted(REFERENCE_COUNTS))
+def test_named_configs_reproduce_reference_counts(dev, res, field):
+    """configs[0] (64^3 sphere + plane, the reference's own CPU-runnable case), its 128^3 version and the 64^3 capsule
+    field: every count the reference reports, a closed manifold watertight mesh, and referenced rows == non-zero rows."""
+    from d3human_code_b200.geometry.gshell_tets import GShell_Tets
+    from d3human_code_b200.extract import last_counts
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = (grids.sphere_plane_field if field == "sphere" else grids.capsule_garment_field)(pos)
+    verts, faces, _, _, v_tng, extra = GShell_Tets()(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev),
+                                                     torch.tensor(msdf, device=dev), torch.tensor(tets, device=dev))
+    c = last_counts()
+    fv, v, fw, va, fa = REFERENCE_COUNTS[(res, field)]
+    assert (c["n_valid_tets"], c["n_verts"], c["n_faces_watertight"], c["n_verts_aug"], c["n_faces_aug"]) == (fv, v, fw, va, fa)
+    assert verts.shape == (va, 3) and faces.shape == (fa, 3) and extra["n_verts_watertight"] == v
+    wt = extra["faces_watertight"]
+    e = torch.sort(torch.cat([wt[:, [0, 1]], wt[:, [1, 2]], wt[:, [2, 0]]], 0), dim=1).values
+    _, cnt = torch.unique(e[:, 0] * (v + 1) + e[:, 1], return_counts=True)
+    assert bool((cnt == 2).all())                                   # closed 2-manifold
+    used = torch.zeros(va, dtype=torch.bool, device=dev)
+    used[faces.reshape(-1)] = True
+    assert bool((verts[~used] == 0).all()) and bool((verts[used].abs().sum(1) > 0).all())
+    assert int(faces.min()) >= 0 and int(faces.max()) < va
+    # the open mesh keeps the part of the surface with positive mSDF: every kept watertight vertex has msdf > 0
+    assert bool((extra["msdf_watertight"][used[:v]] > 0).all())
+
+
+def test_pipelined_async_groups_equal_single_calls(dev):
+    """bench.py's calling pattern: several extract_frames_async batches in flight at once (they queue up per lane, share
+    the lane workspaces and the count ring), results read group by group, backward per group.  Every frame must equal
+    the drop-in single call bit for bit; shared gradients must equal the sum over all frames."""
+    from d3human_code_b200.extract import extract_frames_async
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    res, B, G = 24, 12, 3
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = grids.capsule_garment_field(pos)
+    pos_b = np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(B)]).astype(np.float32)
+    tt = torch.tensor(tets, device=dev)
+    rng = np.random.default_rng(7)
+    # ---- reference values: one drop-in call per frame ----
+    ts = torch.tensor(sdf[:, None], device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    hm = hmSDF_Tets()
+    singles, ups, gpos = [], [], []
+    for f in range(B):
+        tp = torch.tensor(pos_b[f], device=dev, requires_grad=True)
+        verts, faces, _, _, _, extra = hm(tp, ts, tm, tt, "cloth")
+        gv = torch.tensor(rng.standard_normal(tuple(verts.shape)).astype(np.float32), device=dev)
+        gm = torch.tensor(rng.standard_normal(tuple(extra["msdf"].shape)).astype(np.float32), device=dev)
+        torch.autograd.backward([verts, extra["msdf"]], [gv, gm])
+        singles.append((verts.detach().clone(), faces.clone(), extra["msdf"].detach().clone(),
+                        extra["faces_watertight"].clone()))
+        ups.append((gv, gm))
+        gpos.append(tp.grad.clone())
+    want_sdf, want_msdf = ts.grad.clone(), tm.grad.clone()
+    # ---- the same frames as G async groups, all launched before the first result is read; twice (steady state) ----
+    for rep in range(2):
+        ts2 = torch.tensor(sdf[:, None], device=dev, requires_grad=True)
+        tm2 = torch.tensor(msdf, device=dev, requires_grad=True)
+        groups = [torch.tensor(pos_b[g * B // G:(g + 1) * B // G], device=dev, requires_grad=True) for g in range(G)]
+        futs = [extract_frames_async(pg, ts2, tm2, tt, types="cloth", lanes=3) for pg in groups]
+        for g, fut in enumerate(futs):
+            outs = fut.result()
+            lo = g * B // G
+            for k, (verts, faces, _, _, _, extra) in enumerate(outs):
+                sv, sf, sm, sw = singles[lo + k]
+                assert torch.equal(verts.detach(), sv) and torch.equal(faces, sf), (rep, g, k)
+                assert torch.equal(extra["msdf"].detach(), sm) and torch.equal(extra["faces_watertight"], sw)
+            torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs],
+                                    [ups[lo + k][0] for k in range(len(outs))] + [ups[lo + k][1] for k in range(len(outs))])
+        for g, pg in enumerate(groups):
+            lo = g * B // G
+            for k in range(pg.shape[0]):
+                U.assert_close_normwise(f"grad_pos[{lo + k}]", pg.grad[k].cpu().numpy(), gpos[lo + k].cpu().numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_sdf", ts2.grad.cpu().numpy(), want_sdf.cpu().numpy(), 2 * U.GRAD_RTOL)
+        U.assert_close_normwise("grad_msdf", tm2.grad.cpu().numpy(), want_msdf.cpu().numpy(), 2 * U.GRAD_RTOL)
