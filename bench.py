@@ -15,7 +15,7 @@ sdf/msdf are shared, so their gradients accumulate over the rank's frames (atomi
 N > 1.  Weak scaling: per-GPU work is fixed.  value = N * frames_per_rank * F / (max-over-ranks device time per step).
 `single_call` reports the same frames through the drop-in class one call at a time (the reference's calling pattern).
 
-One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every key.
+One JSON line on stdout (rank 0).  See DESIGN.md, "Measurement: keys of the bench.py JSON line".
 """
 from __future__ import annotations
 
