@@ -214,7 +214,6 @@ def main():
     c0 = counts[0]
     balg = sum(grids.surface_counts_bytes(F, N, c["n_verts"], c["n_verts_aug"], c["n_faces_watertight"], c["n_faces_aug"])
                for c in counts) / len(counts)
-    launches_per_step = E._ExtractFn.last_launches + E.LAUNCHES_BACKWARD * fpr
     del outs
 
     def local_step():

@@ -11,8 +11,13 @@
 //                    adjacent: their a-side contributions are combined with a segmented warp reduction before one
 //                    atomic per run; b-side contributions use plain float atomics (fan-in ~4, max 11).
 //
+//   adjoint_poly_kernel : calls that ran on the static edge table have no per-vertex corner lists on their tape; for them
+//                    the boundary adjoints are SCATTERED (one thread per polygon, one vector atomic per corner) into a
+//                    (V,8) accumulator that adjoint_kernel reads and clears.
+//   The adjoints of up to 16 frames are one launch each (grid.y = frame).
+//
 // v2 scattered the boundary adjoints with float atomics into an (V,8) accumulator that a third kernel consumed
-// (zero 8.7 + boundary 5.2 + crossing 5.4 us at 128^3).
+// (zero 8.7 + boundary 5.2 + crossing 5.4 us at 128^3); the gather form replaced it on the sort path.
 //
 // Gradient formulas: SURVEY.md appendix A.5 (verified against the reference's autograd in tests/).
 #include "d3h_internal.cuh"

@@ -5,14 +5,15 @@
 // and the boolean-mask compactions `tet_fx4[valid_tets]`, `idx_map[num_triangles == k]` (:277, :323-324).
 //
 //   prepare_kernel   N-sized: sign bitmap of sdf (N/8 bytes: 268 KB at 128^3, L1/L2 resident) + reset of scan state.
-//   classify_kernel  F-sized, pure stream, persistent grid: every warp loads 8 x 32 tets with 16-byte no-allocate
+//   classify_kernel  F-sized, pure stream, one warp per 256-tet chunk: every warp loads 8 x 32 tets with 16-byte no-allocate
 //                    loads, looks the four signs up in the bitmap, writes two ballot words per 32 tets (tet yields
 //                    1 / 2 triangles) and adds its (T1,T2) count to the counter of its 8192-tet tile (one RED per
 //                    non-empty warp chunk).  No barrier, no fence, no tail.
 //   compact_kernel   one CTA per tile, no inter-CTA dependency: empty tiles (most of the grid) exit on the tile
 //                    counter; the others sum the counters of the earlier tiles (1536 words at 128^3, from L2), rank
 //                    their valid tets inside the tile and write the compact records and, in the fused single-GPU
-//                    path, the sort keys of their crossing edges + the MSD histogram.
+//                    path, either the sort keys of their crossing edges + the MSD histogram (general path) or the marks
+//                    of those edges in the bitmap over the grid's static edge table (mark_polygon_edges).
 //
 // History (profiles/): v1 classified and compacted in one kernel (ticket + block scan + look-back per 2048-tet tile):
 // 45 % of the warp samples parked on the barrier behind the ticket atomic, 16 % DRAM utilisation.  v2 split the stream

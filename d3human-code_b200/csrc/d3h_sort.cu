@@ -1,5 +1,11 @@
 // Stage 2: edge de-duplication and vertex numbering.
 //
+// Two paths produce the same vertex ids (rank of a crossing edge in (min,max) lexicographic order):
+//   general  this file's radix sort + run-length scan of the crossing-edge keys of the call (first call on a grid,
+//            tet-range shards, D3H_STATIC_EDGES=0);
+//   static   edge_emit_kernel below: the grid's tet array does not change during a run (hmsdf.py:207-212), so the sorted
+//            list of ALL tet edges is built once and a call only marks its crossing edges in a bitmap over that list.
+//
 // Replaces gshell_tets.py:277-287: `sort_edges` (:209-217), `torch.unique(all_edges, dim=0, return_inverse=True)`
 // (:279), the crossing mask (:282) and `mapping`/`idx_map`/`interp_v` (:283-287) -- and, fused into the same kernel,
 // the zero-crossing interpolation of :291-303.

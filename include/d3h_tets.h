@@ -97,8 +97,9 @@ typedef struct d3h_forward_args {
   /* tape for the backward pass (device) */
   int32_t* tape_edges;     /* (cap_verts,2)   (a,b), a<b: grid vertices of each crossing edge, sorted (interp_v, gshell_tets.py:287) */
   int32_t* tape_corners;   /* (4*cap_valid_tets) polygon corner -> watertight vertex id, layout [3*T1 | 4*T2] */
-  int32_t* tape_slots;     /* (4*cap_valid_tets) corner slots grouped by watertight vertex (the sorted inverse map) */
-  int32_t* tape_runs;      /* (cap_verts + 1) start of every vertex's run in tape_slots; [V] = P */
+  int32_t* tape_slots;     /* (4*cap_valid_tets) corner slots grouped by watertight vertex (the sorted inverse map);
+                              general path only: not written when edge_off is given */
+  int32_t* tape_runs;      /* (cap_verts + 1) start of every vertex's run in tape_slots; [V] = P; general path only */
   /* optional: dense gradient buffers of the coming backward call, zero-filled here while the latency-bound surface
    * stages leave HBM idle (pass them to d3h_extract_backward with grads_prezeroed = 1); NULL = not wanted */
   float* zero_g_pos;       /* (N,3) */
