@@ -171,10 +171,6 @@ def _tet_sharded_launcher(ranges: Sequence[Tuple[int, int]], exchange: Optional[
     return launcher
 
 
-class _TetShardedFn(E._ExtractFn):
-    """Same autograd node as extract(), with the forward library call replaced by classify-range + gather + surface."""
-
-
 def extract_tet_sharded(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False,
                         output_watertight_template: bool = True, group=None, virtual_ranks: Optional[int] = None):
     """One extraction whose O(F) classification is split over the ranks of `group` (or over `virtual_ranks` sequential
