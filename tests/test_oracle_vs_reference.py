@@ -95,3 +95,41 @@ def test_oracle_matches_live_reference(res, field, cls, typ, wt):
         assert tm.grad is None and g_msdf is None
     else:
         U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), U.GRAD_RTOL)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_matches_live_reference_on_random_tet_soups(seed):
+    """Unstructured input far from a lattice: random vertex quadruples (a non-manifold tet soup, shared edges with
+    arbitrary multiplicity), random positions, fields with exact zeros, random class / type / template flag.  The oracle
+    must track the reference bit for bit on integers, positions and mSDF, and to tolerance on gradients."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(8, 60))
+    f = int(rng.integers(1, 400))
+    tets = np.stack([rng.permutation(n)[:4] for _ in range(f)]).astype(np.int64)
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    sdf = rng.standard_normal(n).astype(np.float32)
+    msdf = rng.standard_normal(n).astype(np.float32)
+    sdf[::7] = 0.0
+    msdf[::5] = 0.0
+    cls = "GShell_Tets" if seed % 2 == 0 else "hmSDF_Tets"
+    typ = None if cls == "GShell_Tets" else ("cloth", "body")[(seed // 2) % 2]
+    wt = seed % 3 != 0
+    (verts, faces, _, _, v_tng, extra), (tp, ts, tm) = _run_reference(cls, typ, wt, pos, sdf, msdf, tets)
+    fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, wt)
+    U.assert_exact("faces_aug", fwd["faces_aug"], faces.numpy())
+    U.assert_exact("verts_aug", fwd["verts_aug"], verts.detach().numpy())
+    U.assert_exact("msdf", fwd["msdf"], extra["msdf"].detach().numpy())
+    assert tuple(extra.keys()) == fwd["extra_keys"]
+    if wt:
+        U.assert_exact("faces_watertight", fwd["faces_watertight"], extra["faces_watertight"].numpy())
+        U.assert_exact("vertices_watertight", fwd["vertices_watertight"], extra["vertices_watertight"].detach().numpy())
+    if verts.shape[0] == 0 or not verts.requires_grad:
+        return
+    gv = rng.standard_normal(fwd["verts_aug"].shape).astype(np.float32)
+    gm = rng.standard_normal(fwd["msdf"].shape).astype(np.float32)
+    ((verts * torch.tensor(gv)).sum() + (extra["msdf"] * torch.tensor(gm)).sum()).backward()
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, gm)
+    U.assert_close_normwise("grad_pos", g_pos, tp.grad.numpy(), U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", g_sdf, ts.grad.numpy()[:, 0], 5 * U.GRAD_RTOL)
+    if typ != "body":
+        U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), U.GRAD_RTOL)
