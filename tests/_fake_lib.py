@@ -1,0 +1,170 @@
+"""A CPU stand-in for libd3h_tets.so, for testing the Python HOST logic without a GPU (tests only).
+
+It implements the C-ABI entry points the host calls (same names, same argument blocks read from the same raw
+addresses) and computes the results with the numpy oracle, honouring the capacity / overflow contract of the real
+library: outputs are truncated to the caller's capacities, true sizes come back in d3h_counts, a too-small record
+capacity skips the surface stages.  The product never sees this module; `tests/test_host_fake_lib.py` installs it with
+monkeypatch in place of `_cabi.lib()` and runs the real `extract.py` code paths on CPU tensors.
+"""
+import ctypes as C
+
+import numpy as np
+
+from d3human_code_b200 import _cabi
+from oracle import gshell_oracle as O
+
+
+def _arr(ptr, n, ctype):
+    if not ptr or n <= 0:
+        return np.zeros(0, dtype=np.dtype(ctype))
+    return np.ctypeslib.as_array((ctype * int(n)).from_address(int(ptr)))
+
+
+class FakeLib:
+    def __init__(self):
+        self.tapes = {}          # tape_edges pointer -> oracle forward dict (the "tape" of the fake)
+        self.forward_calls = 0   # frames
+        self.batch_calls = 0
+        self.backward_calls = 0
+        self.joins = 0
+        self.error = b""
+
+    # ---- trivial entry points -------------------------------------------------------------------------------------
+    def d3h_version(self):
+        return _cabi.VERSION
+
+    def d3h_last_error_string(self):
+        return self.error
+
+    def d3h_workspace_bytes(self, n_tets, n_grid, cap):
+        return self.d3h_workspace_bytes_static(n_tets, n_grid, cap, 0)
+
+    def d3h_workspace_bytes_static(self, n_tets, n_grid, cap, n_edges):
+        return 4096 + 64 * cap + n_edges // 4      # monotone in the capacities like the real one
+
+    def d3h_lanes_join(self, stream):
+        self.joins += 1
+        return 0
+
+    def d3h_wait_counts(self, ptr, seq, timeout_us):
+        c = _cabi.Counts.from_address(int(ptr))
+        if c.seq != seq:
+            self.error = b"fake: counts not published"
+            return _cabi.D3H_E_TIMEOUT
+        return 0
+
+    # ---- forward --------------------------------------------------------------------------------------------------
+    def d3h_extract_forward_batch(self, ptr, n_frames, lanes, stream):
+        return self.d3h_extract_forward_batch_nojoin(ptr, n_frames, lanes, stream)
+
+    def d3h_extract_forward_batch_nojoin(self, ptr, n_frames, lanes, stream):
+        self.batch_calls += 1
+        size = C.sizeof(_cabi.ForwardArgs)
+        seen = {}
+        for i in range(n_frames):
+            a = _cabi.ForwardArgs.from_address(int(ptr) + i * size)
+            lane = i % max(1, min(lanes, n_frames))
+            if seen.setdefault(a.workspace, lane) != lane:
+                self.error = b"fake: frames on different lanes share a workspace"
+                return _cabi.D3H_E_BADARG
+            rc = self._forward(a)
+            if rc:
+                return rc
+        return 0
+
+    def _forward(self, a):
+        self.forward_calls += 1
+        n, f = a.n_grid, a.n_tets
+        if (a.sdf | a.msdf) & 15 or a.workspace & 63 or a.tets & 15:   # (CPU allocations are 64-byte aligned)
+            self.error = b"fake: misaligned pointer"
+            return _cabi.D3H_E_BADARG
+        pos = _arr(a.pos, 3 * n, C.c_float).reshape(n, 3)
+        sdf = _arr(a.sdf, n, C.c_float)
+        msdf = _arr(a.msdf, n, C.c_float)
+        tets = _arr(a.tets, 4 * f, C.c_int32).reshape(f, 4)
+        fwd = O.extract_forward(pos.copy(), sdf.copy(), msdf.copy(), tets, -1 if a.msdf_negate else 1,
+                                bool(a.watertight_template))
+        for zp, ln in ((a.zero_g_pos, 3 * n), (a.zero_g_sdf, n), (a.zero_g_msdf, n)):
+            if zp:
+                _arr(zp, ln, C.c_float)[:] = 0.0
+        fv, t1, t2 = fwd["fv"], fwd["t1"], fwd["t2"]
+        c = _cabi.Counts.from_address(int(a.counts_host))
+        c.n_valid_tets, c.n_tri_tets, c.n_quad_tets, c.n_corners = fv, t1, t2, 3 * t1 + 4 * t2
+        c.bad_index = 0
+        if fv > a.cap_valid_tets:      # record buffer too small: the surface stages are skipped
+            c.n_verts = c.n_faces_aug = 0
+            for k in range(6):
+                c.bucket_polys[k] = 0
+            c.overflow = 1
+            c.seq = a.seq
+            return 0
+        v = fwd["n_verts_watertight"]
+        va, fa, fw = fwd["verts_aug"].shape[0], fwd["faces_aug"].shape[0], fwd["faces_watertight"].shape[0]
+
+        def put(ptr, cap_rows, src, ctype, width):
+            rows = min(cap_rows, src.shape[0])
+            if rows > 0:
+                _arr(ptr, rows * width, ctype).reshape(rows, width)[:] = src[:rows].reshape(rows, width)
+
+        put(a.verts_aug, a.cap_verts_aug, fwd["verts_aug"], C.c_float, 3)
+        put(a.v_tng_aug, a.cap_verts_aug, fwd["v_tng_aug"], C.c_float, 3)
+        put(a.msdf_aug, a.cap_verts_aug, fwd["msdf"], C.c_float, 1)
+        put(a.faces_aug, a.cap_faces_aug, fwd["faces_aug"], C.c_int64, 3)
+        put(a.verts_wt, a.cap_verts, fwd["vertices_watertight"], C.c_float, 3)
+        put(a.v_tng_wt, a.cap_verts, fwd["v_tng_watertight"], C.c_float, 3)
+        put(a.msdf_wt, a.cap_verts, fwd["msdf_watertight"], C.c_float, 1)
+        put(a.faces_wt, a.cap_faces_wt, fwd["faces_watertight"], C.c_int64, 3)
+        put(a.tape_edges, a.cap_verts, np.stack([fwd["edge_a"], fwd["edge_b"]], 1).astype(np.int32), C.c_int32, 2)
+        put(a.tape_corners, 4 * a.cap_valid_tets, fwd["corners"].astype(np.int32), C.c_int32, 1)
+        if a.edge_off:
+            if not a.vacc or not a.edge_ab or a.n_edges <= 0:
+                self.error = b"fake: static edge table without vacc / edge_ab"
+                return _cabi.D3H_E_BADARG
+            _arr(a.vacc, 8 * min(a.cap_verts, v), C.c_float)[:] = 0.0
+        self.tapes[int(a.tape_edges)] = fwd
+        c.n_verts, c.n_faces_aug = v, fa
+        per = (1, 2, 1, 2, 3, 4)
+        for k in range(6):
+            c.bucket_polys[k] = int(fwd["bucket_counts"][k]) // per[k]
+        c.overflow = 0
+        c.seq = a.seq
+        return 0
+
+    # ---- backward -------------------------------------------------------------------------------------------------
+    def d3h_extract_backward_batch(self, ptr, n_frames, lanes, stream):
+        size = C.sizeof(_cabi.BackwardArgs)
+        for i in range(n_frames):
+            b = _cabi.BackwardArgs.from_address(int(ptr) + i * size)
+            self.backward_calls += 1
+            fwd = self.tapes.get(int(b.tape_edges))
+            if fwd is None:
+                self.error = b"fake: unknown tape"
+                return _cabi.D3H_E_BADARG
+            if not b.tape_slots and not b.vacc:
+                self.error = b"fake: neither corner lists nor vacc"
+                return _cabi.D3H_E_BADARG
+            v = fwd["n_verts_watertight"]
+            va = fwd["verts_aug"].shape[0]
+            if (b.n_verts, b.n_tri_tets, b.n_quad_tets) != (v, fwd["t1"], fwd["t2"]):
+                self.error = b"fake: sizes of the backward block do not match the forward call"
+                return _cabi.D3H_E_BADARG
+            gva = _arr(b.g_verts_aug, 3 * va, C.c_float).reshape(-1, 3) if b.g_verts_aug else None
+            gma = _arr(b.g_msdf_aug, va, C.c_float).copy() if b.g_msdf_aug else None
+            if b.g_msdf_boundary:
+                if gma is None:
+                    gma = np.zeros(va, np.float32)
+                gma[v:] += _arr(b.g_msdf_boundary, va - v, C.c_float)
+            gvw = _arr(b.g_verts_wt, 3 * v, C.c_float).reshape(-1, 3) if b.g_verts_wt else None
+            gmw = _arr(b.g_msdf_wt, v, C.c_float) if b.g_msdf_wt else None
+            g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gva, gma, gvw, gmw)
+            n = b.n_grid
+            outs = ((b.g_pos, 3 * n, g_pos), (b.g_sdf, n, g_sdf), (b.g_msdf, n, g_msdf))
+            for p, ln, g in outs:
+                if not p:
+                    continue
+                dst = _arr(p, ln, C.c_float)
+                if not b.grads_prezeroed:
+                    dst[:] = 0.0
+                if g is not None:
+                    dst += np.asarray(g, np.float32).reshape(-1)     # shared buffers accumulate over the frames
+        return 0
