@@ -130,6 +130,73 @@ class FakeLib:
         c.seq = a.seq
         return 0
 
+    # ---- tet-range sharding ----------------------------------------------------------------------------------------
+    def d3h_classify_range(self, ptr, records_out, cap_records, counts_dev_out, stream):
+        a = _cabi.ForwardArgs.from_address(int(ptr))
+        n, f = a.n_grid, a.n_tets
+        sdf = _arr(a.sdf, n, C.c_float)
+        msdf = _arr(a.msdf, n, C.c_float)
+        tets = _arr(a.tets, 4 * f, C.c_int32).reshape(f, 4)
+        occ = sdf > 0
+        m = -msdf if a.msdf_negate else msdf
+        lo, hi = a.tet_begin, a.tet_end
+        sub = tets[lo:hi].astype(np.int64)
+        o = occ[sub]
+        code = (o * np.array([1, 2, 4, 8])).sum(1)
+        valid = (code != 0) & (code != 15)
+        if not a.watertight_template:
+            valid &= (m[sub] > 0).any(1)
+        ids = np.nonzero(valid)[0]
+        cls2 = np.isin(code[ids], (3, 5, 6, 9, 10, 12))
+        rank1, rank2 = np.cumsum(~cls2) - 1, np.cumsum(cls2) - 1
+        n_valid = ids.shape[0]
+        rec = np.zeros((n_valid, 8), np.int32)
+        rec[:, :4] = sub[ids]
+        rec[:, 4] = code[ids]
+        rec[:, 5] = np.where(cls2, rank2, rank1)
+        rec[:, 6] = lo + ids
+        rec[:, 7] = np.where(cls2, rank1 + 1, rank2 + 1)
+        fits = n_valid <= cap_records
+        if fits and n_valid:
+            _arr(records_out, 8 * n_valid, C.c_int32).reshape(-1, 8)[:] = rec
+        for p in (counts_dev_out, a.counts_host):
+            if not p:
+                continue
+            c = _cabi.Counts.from_address(int(p))
+            c.n_valid_tets, c.n_tri_tets, c.n_quad_tets = n_valid, int((~cls2).sum()), int(cls2.sum())
+            c.n_corners = 3 * c.n_tri_tets + 4 * c.n_quad_tets
+            c.overflow = 0 if fits else 1
+            c.seq = a.seq
+        return 0
+
+    def d3h_extract_from_records(self, ptr, records, n_tri, n_quad, stream):
+        a = _cabi.ForwardArgs.from_address(int(ptr))
+        n_rec = n_tri + n_quad
+        if n_rec > a.cap_valid_tets:
+            self.error = b"fake: records do not fit cap_valid_tets"
+            return _cabi.D3H_E_BADARG
+        rec = _arr(records, 8 * n_rec, C.c_int32).reshape(-1, 8)
+        if n_rec and not np.all(np.diff(rec[:, 6]) > 0):
+            self.error = b"fake: records are not in global tet order"
+            return _cabi.D3H_E_BADARG
+        # the surface stages only ever look at the valid tets: run the oracle on the full tet array the records came
+        # from (same result, and the UV atlas keeps the size of the full grid) after checking the records against it
+        f = a.n_tets
+        tets = _arr(a.tets, 4 * f, C.c_int32).reshape(f, 4)
+        if n_rec and not np.array_equal(tets[rec[:, 6]], rec[:, :4]):
+            self.error = b"fake: record vertices do not match their tet ids"
+            return _cabi.D3H_E_BADARG
+        self.from_records_calls = getattr(self, "from_records_calls", 0) + 1
+        saved = a.edge_off
+        a.edge_off = None             # the sharded stages always take the general path
+        rc = self._forward(a)
+        a.edge_off = saved
+        c = _cabi.Counts.from_address(int(a.counts_host))
+        if rc == 0 and c.n_valid_tets != n_rec:
+            self.error = b"fake: gathered records are not the valid tets of the grid"
+            return _cabi.D3H_E_BADARG
+        return rc
+
     # ---- backward -------------------------------------------------------------------------------------------------
     def d3h_extract_backward_batch(self, ptr, n_frames, lanes, stream):
         size = C.sizeof(_cabi.BackwardArgs)

@@ -19,6 +19,9 @@ from tests._fake_lib import FakeLib
 class _Stream:
     cuda_stream = 0
 
+    def synchronize(self):
+        pass
+
 
 @pytest.fixture(params=["sort", "static"])
 def host(request, monkeypatch):
@@ -183,3 +186,25 @@ def test_input_validation_on_host(host):
         E.extract_frames(torch.tensor(pos), torch.tensor(sdf), torch.tensor(msdf), tt)        # not (B,N,3)
     with pytest.raises(ValueError):
         E.extract_frames([torch.tensor(pos)] * 2, [torch.tensor(sdf)] * 3, torch.tensor(msdf), tt)
+
+
+@pytest.mark.parametrize("vr", [1, 3, 8])
+def test_tet_range_sharding_host_logic(host, vr):
+    """sharding.extract_tet_sharded with virtual ranks: per-range classification, concatenation of the records in range
+    order, replicated surface stages -- same result as the plain call, also when the record capacity has to grow."""
+    from d3human_code_b200 import sharding as S
+    pos, sdf, msdf, tets = _case(10)
+    tp = torch.tensor(pos, requires_grad=True)
+    ts = torch.tensor(sdf, requires_grad=True)
+    tm = torch.tensor(msdf, requires_grad=True)
+    out = S.extract_tet_sharded(tp, ts, tm, torch.tensor(tets), virtual_ranks=vr)
+    fwd = O.extract_forward(pos, sdf, msdf, tets)
+    _check_frame(out, fwd)
+    assert host.from_records_calls >= 1
+    gv = np.ones_like(fwd["verts_aug"])
+    out[0].sum().backward()
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, None)
+    U.assert_close_normwise("grad_pos", tp.grad.numpy(), g_pos, 1e-6)
+    U.assert_close_normwise("grad_sdf", ts.grad.numpy(), g_sdf, 1e-6)
+    ranges = [S.tet_range(tets.shape[0], vr, r) for r in range(vr)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == tets.shape[0]
