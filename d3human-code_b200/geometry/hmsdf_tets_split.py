@@ -7,7 +7,7 @@ torch.no_grad() there (:256-264), so msdf_n.grad stays None while pos / sdf stil
 """
 from __future__ import annotations
 
-from ..extract import extract
+from ..extract import extract, extract_frames
 from .gshell_tets import _TetsExtractor
 
 
@@ -15,3 +15,13 @@ class hmSDF_Tets(_TetsExtractor):
     def __call__(self, pos_nx3, sdf_n, msdf_n, tet_fx4, type, output_watertight_template=True):
         return extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate=(type == "body"),
                        output_watertight_template=output_watertight_template)
+
+    def split(self, pos_nx3, sdf_n, msdf_n, tet_fx4, output_watertight_template=True):
+        """Both extractions of one split-stage iteration in one call (extension; the reference calls the class twice,
+        train.py:1040-1047 via hmsdf.py:548): returns `(cloth_tuple, body_tuple)`, each the reference's 6-tuple, exactly
+        what `self(..., "cloth")` and `self(..., "body")` return.  The two run as one batch on concurrent lanes and as one
+        autograd node; gradients of `pos_nx3` / `sdf_n` are the sum over both, `msdf_n` only receives the cloth part
+        (the reference negates msdf under no_grad for the body, hmsdf_tets_split.py:256-264)."""
+        cloth, body = extract_frames([pos_nx3, pos_nx3], sdf_n, msdf_n, tet_fx4, types=["cloth", "body"],
+                                     output_watertight_template=output_watertight_template, lanes=2)
+        return cloth, body

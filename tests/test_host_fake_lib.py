@@ -208,3 +208,23 @@ def test_tet_range_sharding_host_logic(host, vr):
     U.assert_close_normwise("grad_sdf", ts.grad.numpy(), g_sdf, 1e-6)
     ranges = [S.tet_range(tets.shape[0], vr, r) for r in range(vr)]
     assert ranges[0][0] == 0 and ranges[-1][1] == tets.shape[0]
+
+
+def test_split_pair_is_cloth_plus_body(host):
+    """hmSDF_Tets.split: one call for the cloth / body pair of an iteration == the two reference-style calls."""
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    pos, sdf, msdf, tets = _case(8)
+    tp = torch.tensor(pos, requires_grad=True)
+    ts = torch.tensor(sdf[:, None], requires_grad=True)
+    tm = torch.tensor(msdf, requires_grad=True)
+    cloth, body = hmSDF_Tets().split(tp, ts, tm, torch.tensor(tets))
+    fc = O.extract_forward(pos, sdf, msdf, tets, 1, True)
+    fb = O.extract_forward(pos, sdf, msdf, tets, -1, True)
+    _check_frame(cloth, fc)
+    _check_frame(body, fb)
+    (cloth[0].sum() + body[0].sum() + cloth[5]["msdf"].sum() + body[5]["msdf"].sum()).backward()
+    gc = O.extract_backward(fc, np.ones_like(fc["verts_aug"]), np.ones_like(fc["msdf"]))
+    gb = O.extract_backward(fb, np.ones_like(fb["verts_aug"]), np.ones_like(fb["msdf"]))
+    U.assert_close_normwise("grad_pos", tp.grad.numpy(), gc[0] + gb[0], 1e-6)
+    U.assert_close_normwise("grad_sdf", ts.grad.numpy()[:, 0], gc[1] + gb[1], 1e-6)
+    U.assert_close_normwise("grad_msdf", tm.grad.numpy(), gc[2], 1e-6)      # cloth only

@@ -109,3 +109,33 @@ def test_pipelined_async_groups_equal_single_calls(dev):
                 U.assert_close_normwise(f"grad_pos[{lo + k}]", pg.grad[k].cpu().numpy(), gpos[lo + k].cpu().numpy(), U.GRAD_RTOL)
         U.assert_close_normwise("grad_sdf", ts2.grad.cpu().numpy(), want_sdf.cpu().numpy(), 2 * U.GRAD_RTOL)
         U.assert_close_normwise("grad_msdf", tm2.grad.cpu().numpy(), want_msdf.cpu().numpy(), 2 * U.GRAD_RTOL)
+
+
+def test_split_pair_matches_two_calls(dev):
+    """hmSDF_Tets.split (cloth + body of one iteration as one batch, train.py:1040-1047) == the two reference-style calls,
+    bit for bit forward; gradients of the shared pos / sdf are the sums, msdf only gets the cloth part."""
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    g = grids.smplx_layout_grid(24, dilate=0.15, seed=2)       # configs[2] layout: scrambled, unstructured
+    pos, tets = g["v"], g["f"]
+    sdf, msdf = grids.capsule_garment_field(pos)
+    hm = hmSDF_Tets()
+    tt = torch.tensor(tets, device=dev)
+
+    def leaves():
+        return (torch.tensor(pos, device=dev, requires_grad=True), torch.tensor(sdf[:, None], device=dev, requires_grad=True),
+                torch.tensor(msdf, device=dev, requires_grad=True))
+
+    tp, ts, tm = leaves()
+    cloth, body = hm.split(tp, ts, tm, tt)
+    (cloth[0].square().sum() + body[0].square().sum() + cloth[5]["msdf"].sum() - body[5]["msdf"].sum()).backward()
+    tp2, ts2, tm2 = leaves()
+    c2 = hm(tp2, ts2, tm2, tt, "cloth")
+    b2 = hm(tp2, ts2, tm2, tt, "body")
+    (c2[0].square().sum() + b2[0].square().sum() + c2[5]["msdf"].sum() - b2[5]["msdf"].sum()).backward()
+    for a, b in ((cloth, c2), (body, b2)):
+        assert torch.equal(a[0].detach(), b[0].detach()) and torch.equal(a[1], b[1])
+        assert torch.equal(a[5]["msdf"].detach(), b[5]["msdf"].detach())
+        assert torch.equal(a[5]["faces_watertight"], b[5]["faces_watertight"])
+    U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), tp2.grad.cpu().numpy(), U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", ts.grad.cpu().numpy(), ts2.grad.cpu().numpy(), U.GRAD_RTOL)
+    U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), tm2.grad.cpu().numpy(), U.GRAD_RTOL)
