@@ -635,7 +635,11 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a_in, d3h_tet_record* 
   Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
   launch_prepare(*a, ws, stream);
   launch_classify(*a, ws, records_out, cap_records, /*emit_keys=*/false, stream);
+#ifndef D3H_CPU_EMU
   export_range_counts_kernel<<<1, 1, 0, stream>>>(ws.ctr, counts_dev_out, a->seq);
+#else   // tests/emu: g++ has no <<< >>>
+  launch_k(export_range_counts_kernel, 1u, 1u, stream, kLaunchLatency, ws.ctr, counts_dev_out, a->seq);
+#endif
   if (a->counts_host) cudaMemcpyAsync(a->counts_host, counts_dev_out, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_classify_range: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }

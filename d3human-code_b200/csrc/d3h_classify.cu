@@ -536,9 +536,15 @@ extern "C" int d3h_pack_tets_i64(const int64_t* tets, int64_t n_tets, int64_t n_
   if (n_tets == 0) return D3H_OK;
   int64_t blocks = (n_tets + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+#ifndef D3H_CPU_EMU
   pack_tets_i64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const longlong2*>(tets), n_tets, n_grid, reinterpret_cast<int4*>(out_tets),
       reinterpret_cast<unsigned long long*>(bad_count_dev));
+#else   // tests/emu: g++ has no <<< >>>
+  launch_k(pack_tets_i64_kernel, (unsigned)blocks, 256u, (cudaStream_t)stream, kLaunchStream,
+           reinterpret_cast<const longlong2*>(tets), n_tets, n_grid, reinterpret_cast<int4*>(out_tets),
+           reinterpret_cast<unsigned long long*>(bad_count_dev));
+#endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_pack_tets_i64: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
   return D3H_OK;
@@ -554,8 +560,13 @@ extern "C" int d3h_check_tets_i32(const int32_t* tets, int64_t n_tets, int64_t n
   if (n_tets == 0) return D3H_OK;
   int64_t blocks = (n_tets + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+#ifndef D3H_CPU_EMU
   check_tets_i32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const int4*>(tets), n_tets, n_grid, reinterpret_cast<unsigned long long*>(bad_count_dev));
+#else   // tests/emu: g++ has no <<< >>>
+  launch_k(check_tets_i32_kernel, (unsigned)blocks, 256u, (cudaStream_t)stream, kLaunchStream,
+           reinterpret_cast<const int4*>(tets), n_tets, n_grid, reinterpret_cast<unsigned long long*>(bad_count_dev));
+#endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("d3h_check_tets_i32: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
   return D3H_OK;

@@ -68,6 +68,7 @@ static __device__ __constant__ int8_t c_num_cut_quad[16] = D3H_T_NUM_CUT_QUAD;
 // small device helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+#ifndef D3H_CPU_EMU
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -104,6 +105,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#else
+// tests/emu (functional CPU emulation of the kernels, test infrastructure only): no PTX
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return *p; }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) { return *p; }
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) { *p = v; }
+__device__ __forceinline__ int4 ld_stream_int4(const int4* p) { return *p; }
+__device__ __forceinline__ unsigned long long global_timer_ns() { return emu::now_ns(); }
+#endif
 // Diagnostics (d3h_trace_enable): per call and kernel kind, [0] = time block 0 started, [1] = latest block exit.
 constexpr int kTraceFrames = 64;
 constexpr int kTraceKinds = 16;

@@ -1,0 +1,34 @@
+"""TEST INFRASTRUCTURE ONLY: compile the product's .cu files with g++ against tests/emu/cuda_runtime.h (a functional CPU
+emulation of the CUDA constructs they use) into tests/emu/_build/libd3h_tets_emu.so.  See tests/emu/cuda_runtime.h."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "d3human-code_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libd3h_tets_emu.so")
+SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_surface.cu", "d3h_backward.cu"]
+
+
+def build(force=False):
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu_core.cpp")]
+    deps.append(os.path.join(ROOT, "include", "d3h_tets.h"))
+    if not force and os.path.isfile(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    # -ffp-contract=off: the float pipeline must round like the GPU build (-fmad=false); -x c++ for the .cu files
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+           "-DD3H_CPU_EMU=1", "-I", HERE]
+    for s in SOURCES:
+        cmd += ["-x", "c++", os.path.join(CSRC, s)]
+    cmd += ["-x", "c++", os.path.join(HERE, "emu_core.cpp"), "-o", OUT]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stderr[-6000:])
+        raise RuntimeError("g++ failed building the emulated library")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -1,0 +1,159 @@
+// TEST INFRASTRUCTURE ONLY: fibre scheduler of the CPU emulation (see tests/emu/cuda_runtime.h).
+#include <stdio.h>
+#include <time.h>
+#include <ucontext.h>
+
+#include <vector>
+
+#include "cuda_runtime.h"
+
+namespace emu {
+
+Idx g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+
+namespace {
+constexpr size_t kStack = 256 * 1024;
+enum State { kRunnable, kAtBarrier, kAtCollective, kDone };
+struct Fibre {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  State st = kDone;
+  unsigned barrier_gen = 0;
+  // pending warp collective
+  unsigned coll_mask = 0;
+  unsigned long long coll_val = 0;
+  unsigned long long coll_out[32];
+};
+struct BlockState {
+  std::vector<Fibre> f;
+  unsigned n = 0, alive = 0, at_barrier = 0, barrier_gen = 0;
+  unsigned cur = 0;
+  ucontext_t sched;
+  const std::function<void()>* body = nullptr;
+};
+BlockState B;
+std::vector<char*> g_stacks;
+
+void fibre_entry() {
+  (*B.body)();
+  B.f[B.cur].st = kDone;
+  --B.alive;
+  // a thread that exits never reaches the barrier the others wait at: release them if it was the last one missing
+  if (B.alive > 0 && B.at_barrier == B.alive) { B.at_barrier = 0; ++B.barrier_gen; }
+  swapcontext(&B.f[B.cur].ctx, &B.sched);
+}
+
+void yield_to_scheduler() { swapcontext(&B.f[B.cur].ctx, &B.sched); }
+
+// completes every collective of warp `w` whose participants have all arrived
+void try_complete_collectives(unsigned w) {
+  const unsigned base = w * 32;
+  const unsigned lanes = (B.n - base) < 32u ? (B.n - base) : 32u;
+  for (unsigned l = 0; l < lanes; ++l) {
+    Fibre& a = B.f[base + l];
+    if (a.st != kAtCollective) continue;
+    const unsigned mask = a.coll_mask;
+    bool ready = true;
+    for (unsigned j = 0; j < 32 && ready; ++j) {
+      if (!((mask >> j) & 1u)) continue;
+      if (j >= lanes) continue;                       // lanes beyond the block do not exist
+      const Fibre& p = B.f[base + j];
+      if (p.st == kDone) continue;                    // exited lanes cannot arrive (result for them is undefined)
+      if (p.st != kAtCollective || p.coll_mask != mask) ready = false;
+    }
+    if (!ready) continue;
+    unsigned long long vals[32];
+    for (unsigned j = 0; j < 32; ++j) {
+      const bool in = ((mask >> j) & 1u) && j < lanes && B.f[base + j].st == kAtCollective;
+      vals[j] = in ? B.f[base + j].coll_val : 0ull;
+    }
+    for (unsigned j = 0; j < lanes; ++j) {
+      Fibre& p = B.f[base + j];
+      if (((mask >> j) & 1u) && p.st == kAtCollective && p.coll_mask == mask) {
+        memcpy(p.coll_out, vals, sizeof(vals));
+        p.st = kRunnable;
+      }
+    }
+  }
+}
+}  // namespace
+
+void block_barrier() {
+  Fibre& me = B.f[B.cur];
+  me.st = kAtBarrier;
+  me.barrier_gen = B.barrier_gen;
+  if (++B.at_barrier == B.alive) { B.at_barrier = 0; ++B.barrier_gen; }
+  yield_to_scheduler();
+}
+
+void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32]) {
+  Fibre& me = B.f[B.cur];
+  const unsigned lane = B.cur & 31u;
+  if (!((mask >> lane) & 1u)) {
+    fprintf(stderr, "emu: lane %u calls a warp collective whose mask %08x does not name it\n", lane, mask);
+    abort();
+  }
+  me.coll_mask = mask;
+  me.coll_val = v;
+  me.st = kAtCollective;
+  try_complete_collectives(B.cur >> 5);
+  if (me.st != kRunnable) yield_to_scheduler();
+  memcpy(out, me.coll_out, sizeof(me.coll_out));
+}
+
+unsigned long long now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+
+static void run_block(const std::function<void()>& body, unsigned nthreads) {
+  if (B.f.size() < nthreads) B.f.resize(nthreads);
+  while (g_stacks.size() < nthreads) g_stacks.push_back((char*)malloc(kStack));
+  B.n = B.alive = nthreads;
+  B.at_barrier = 0;
+  B.barrier_gen = 0;
+  B.body = &body;
+  for (unsigned t = 0; t < nthreads; ++t) {
+    Fibre& f = B.f[t];
+    f.stack = g_stacks[t];
+    f.st = kRunnable;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStack;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, fibre_entry, 0);
+  }
+  while (B.alive > 0) {
+    bool progressed = false;
+    for (unsigned t = 0; t < nthreads; ++t) {
+      Fibre& f = B.f[t];
+      if (f.st == kAtBarrier && f.barrier_gen != B.barrier_gen) f.st = kRunnable;
+      if (f.st == kAtCollective) try_complete_collectives(t >> 5);
+      if (f.st != kRunnable) continue;
+      B.cur = t;
+      g_threadIdx = Idx{t, 0, 0};
+      progressed = true;
+      swapcontext(&B.sched, &f.ctx);
+    }
+    if (!progressed && B.alive > 0) {
+      fprintf(stderr, "emu: deadlock in block (%u,%u): %u threads alive, %u at the barrier\n", g_blockIdx.x, g_blockIdx.y,
+              B.alive, B.at_barrier);
+      abort();
+    }
+  }
+}
+
+void run_grid(dim3 grid, dim3 block, const std::function<void()>& body) {
+  if (block.y != 1 || block.z != 1) { fprintf(stderr, "emu: only 1-D blocks are supported\n"); abort(); }
+  g_gridDim = Idx{grid.x, grid.y, grid.z};
+  g_blockDim = Idx{block.x, block.y, block.z};
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_blockIdx = Idx{bx, by, bz};
+        run_block(body, block.x);
+      }
+}
+
+}  // namespace emu

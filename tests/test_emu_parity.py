@@ -1,0 +1,152 @@
+"""The `-m gpu` parity tests, run on the CPU against a functional emulation of the CUDA kernels.
+
+`tests/emu/build_emu.py` compiles the product's .cu files unchanged with g++ against `tests/emu/cuda_runtime.h`
+(every CUDA thread is a fibre; barriers and warp collectives are rendezvous points) and this module points the ctypes
+binding at the result, then calls the very test functions of `tests/test_cuda_parity.py` / `tests/test_z_configs.py`
+with a CPU device.  What this checks is the LOGIC of the kernels (indexing, scans, sorts, tables, float op order) and
+the whole host path through the real C ABI; it cannot see data races, memory-ordering bugs or anything about speed --
+those are what the GPU runs are for.  Test infrastructure only: the product loads `lib/libd3h_tets.so` (nvcc, sm_100a)
+and nothing else.
+"""
+import contextlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from d3human_code_b200 import _cabi
+from d3human_code_b200 import extract as E
+from tests import _util as U
+from tests import test_cuda_parity as G
+from tests import test_z_configs as Z
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+def _packed_tets_cpu(tet_fx4, n_grid):
+    """extract.packed_tets without the CUDA-only parts: same library calls, same IndexError on bad indices."""
+    L = _cabi.lib()
+    n_tets = tet_fx4.shape[0]
+    bad = torch.zeros(1, dtype=torch.int64)
+    if tet_fx4.dtype == torch.int32 and tet_fx4.is_contiguous() and tet_fx4.data_ptr() % 16 == 0:
+        out = tet_fx4
+        _cabi.check(L.d3h_check_tets_i32(out.data_ptr(), n_tets, n_grid, bad.data_ptr(), 0), "d3h_check_tets_i32")
+    else:
+        src = tet_fx4.contiguous().to(torch.int64)
+        out = torch.empty((n_tets, 4), dtype=torch.int32)
+        _cabi.check(L.d3h_pack_tets_i64(src.data_ptr(), n_tets, n_grid, out.data_ptr(), bad.data_ptr(), 0), "d3h_pack_tets_i64")
+    if int(bad.item()):
+        raise IndexError(f"tet_fx4 holds {int(bad.item())} vertex indices outside [0, {n_grid})")
+    key = (tet_fx4.data_ptr(), tuple(tet_fx4.shape), tet_fx4.dtype, int(n_grid))
+    return _packed_cache.setdefault(key, out)       # a stable address per tet array, like the real cache
+
+
+_packed_cache = {}
+
+
+@pytest.fixture(scope="module")
+def emu_lib_path():
+    return build_emu.build()
+
+
+@pytest.fixture(params=["sort", "static"])
+def edges_mode(request):
+    return request.param
+
+
+@pytest.fixture
+def dev(emu_lib_path, edges_mode, monkeypatch):
+    """A 'device' for the GPU test functions: CPU tensors + the emulated library behind the real C ABI binding."""
+    monkeypatch.setattr(_cabi, "LIB_PATH", emu_lib_path)
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(E, "_check_cuda", lambda t: None)
+    monkeypatch.setattr(E, "packed_tets", _packed_tets_cpu)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "device", lambda dev=None: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    orig_ensure = E._Plan.ensure
+
+    def ensure(self, lanes, n_edges=0):       # CPU allocations are 64-byte aligned, the ABI wants 256 for the workspace
+        orig_ensure(self, lanes, n_edges)
+        for i, w in enumerate(self.workspaces):
+            if w.data_ptr() % 256:
+                big = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8)
+                off = (-big.data_ptr()) % 256
+                self.workspaces[i] = big[off:off + self.workspace_bytes]
+                self.workspace_ptrs[i] = self.workspaces[i].data_ptr()
+
+    monkeypatch.setattr(E._Plan, "ensure", ensure)
+    E.reset_plans()
+    _packed_cache.clear()
+    E.set_static_edges("1" if edges_mode == "static" else "0")
+    yield torch.device("cpu")
+    E.set_static_edges("auto")
+    E.reset_plans()
+
+
+def test_emulated_library_is_the_real_abi(dev):
+    L = _cabi.lib()
+    assert L.d3h_version() == _cabi.VERSION
+    for name in _cabi.EXPORTED_SYMBOLS:
+        assert hasattr(L, name)
+
+
+@pytest.mark.parametrize("name", U.golden_cases())
+def test_golden(dev, name):
+    G.test_cuda_matches_golden(dev, name)
+
+
+@pytest.mark.parametrize("res,field,cls,typ,wt", [
+    (16, "sphere", "GShell_Tets", None, True),
+    (24, "capsule", "hmSDF_Tets", "cloth", True),
+    (24, "capsule", "hmSDF_Tets", "body", True),
+    (12, "adv", "GShell_Tets", None, True),
+    (12, "adv", "hmSDF_Tets", "body", True),
+    (10, "adv", "GShell_Tets", None, False),
+    (10, "adv", "hmSDF_Tets", "body", False),
+])
+def test_oracle(dev, res, field, cls, typ, wt):
+    G.test_cuda_matches_oracle(dev, res, field, cls, typ, wt)
+
+
+def test_integer_intermediates(dev, edges_mode):
+    G.test_integer_intermediates_match_oracle(dev, edges_mode)
+
+
+def test_smplx_layout(dev):
+    G.test_smplx_layout_split_extraction(dev)
+
+
+def test_regrowth(dev):
+    G.test_capacity_regrowth_and_reuse(dev)
+
+
+def test_validation_and_refusals(dev):
+    G.test_input_validation(dev)
+    G.test_tangent_gradient_is_refused(dev)
+    G.test_msdf_boundary_view_carries_gradient(dev)
+
+
+def test_batches(dev):
+    G.test_extract_frames_batch_matches_oracle_per_frame(dev)
+    G.test_extract_frames_list_form_and_repeat(dev)
+
+
+@pytest.mark.parametrize("res,field,typ,vr", [(16, "capsule", "cloth", 3), (12, "adv", "body", 2)])
+def test_tet_range_sharding(dev, res, field, typ, vr):
+    G.test_tet_range_sharding_virtual_ranks_bit_identical(dev, res, field, typ, vr)
+
+
+def test_pipelined_groups_and_split(dev):
+    Z.test_pipelined_async_groups_equal_single_calls(dev)
+    Z.test_split_pair_matches_two_calls(dev)
