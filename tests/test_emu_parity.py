@@ -150,3 +150,36 @@ def test_tet_range_sharding(dev, res, field, typ, vr):
 def test_pipelined_groups_and_split(dev):
     Z.test_pipelined_async_groups_equal_single_calls(dev)
     Z.test_split_pair_matches_two_calls(dev)
+
+
+@pytest.mark.parametrize("seed,n,f", [(0, 9, 60), (1, 40, 400), (2, 25, 3000), (3, 12, 6000), (4, 300, 5000), (5, 6, 2500)])
+def test_random_tet_soups(dev, seed, n, f):
+    """Non-manifold tet soups (random vertex quadruples): edges shared by hundreds of tets, vertices with hundreds of
+    neighbours -- the oversized-group path of the sort, long neighbour lists of the static edge table, dense buckets.
+    tests/test_oracle_vs_reference.py shows the oracle tracks the reference on such input."""
+    from oracle import gshell_oracle as O
+    rng = np.random.default_rng(500 + seed)
+    tets = np.stack([rng.permutation(n)[:4] for _ in range(f)]).astype(np.int64)
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    sdf = rng.standard_normal(n).astype(np.float32)
+    msdf = rng.standard_normal(n).astype(np.float32)
+    sdf[::7] = 0.0
+    msdf[::5] = 0.0
+    typ = (None, "cloth", "body")[seed % 3]
+    cls = "GShell_Tets" if typ is None else "hmSDF_Tets"
+    fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, True)
+    rng2 = np.random.default_rng(1)
+    grads = dict(g_verts_aug=rng2.standard_normal(fwd["verts_aug"].shape).astype(np.float32),
+                 g_msdf=rng2.standard_normal(fwd["msdf"].shape).astype(np.float32),
+                 g_msdf_watertight=None, g_vertices_watertight=None)
+    out, g = G._run(dev, pos, sdf, msdf, tets, cls, typ, True, grads)
+    U.assert_exact("faces_aug", out["faces_aug"], fwd["faces_aug"])
+    U.assert_exact("verts_aug", out["verts_aug"], fwd["verts_aug"])
+    U.assert_exact("msdf", out["msdf"], fwd["msdf"])
+    U.assert_exact("faces_watertight", out["faces_watertight"], fwd["faces_watertight"])
+    U.assert_exact("vertices_watertight", out["vertices_watertight"], fwd["vertices_watertight"])
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, grads["g_verts_aug"], grads["g_msdf"])
+    U.assert_close_normwise("grad_pos", g[0], g_pos, 5 * U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", g[1], g_sdf, 5 * U.GRAD_RTOL)
+    if typ != "body":
+        U.assert_close_normwise("grad_msdf", g[2], g_msdf, 5 * U.GRAD_RTOL)
