@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 400
+VERSION = 410
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -48,7 +48,11 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("zero_g_pos", C.c_void_p), ("zero_g_sdf", C.c_void_p), ("zero_g_msdf", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("counts_host", C.c_void_p),
                 ("seq", C.c_int64),
-                ("edge_off", C.c_void_p), ("edge_ab", C.c_void_p), ("n_edges", C.c_int64), ("vacc", C.c_void_p)]
+                ("edge_off", C.c_void_p), ("edge_ab", C.c_void_p), ("n_edges", C.c_int64), ("vacc", C.c_void_p),
+                ("pair_verts_aug", C.c_void_p), ("pair_v_tng_aug", C.c_void_p), ("pair_msdf_aug", C.c_void_p),
+                ("pair_faces_aug", C.c_void_p), ("pair_verts_wt", C.c_void_p), ("pair_v_tng_wt", C.c_void_p),
+                ("pair_msdf_wt", C.c_void_p), ("pair_faces_wt", C.c_void_p), ("pair_vacc", C.c_void_p),
+                ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args

@@ -126,7 +126,9 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   const int64_t nwords = (n_grid + 31) / 32 + 1;
   ws.ctr = reinterpret_cast<DevCounters*>(take(sizeof(DevCounters)));
   ws.blk = reinterpret_cast<FwdBlock*>(take(sizeof(FwdBlock)));
+  ws.blk2 = reinterpret_cast<FwdBlock*>(take(sizeof(FwdBlock)));
   ws.counts = reinterpret_cast<d3h_counts*>(take(sizeof(d3h_counts)));
+  ws.counts2 = reinterpret_cast<d3h_counts*>(take(sizeof(d3h_counts)));
   ws.occ_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
   ws.mocc_bits = reinterpret_cast<unsigned*>(take(nwords * 4));
   ws.m1_words = reinterpret_cast<unsigned*>(take((nwords_f + kCompactThreads) * 4));
@@ -446,9 +448,22 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)s;
   Workspace ws = carve_workspace(a->workspace, a->n_tets, a->n_grid, a->cap_valid_tets, a->edge_off ? a->n_edges : 0);
+  const bool pair = a->pair_counts_host != nullptr;
+  if (pair && ((a->cap_verts_aug > 0 && (!a->pair_verts_aug || !a->pair_v_tng_aug || !a->pair_msdf_aug)) ||
+               (a->cap_verts > 0 && (!a->pair_verts_wt || !a->pair_v_tng_wt || !a->pair_msdf_wt)) ||
+               (a->cap_faces_aug > 0 && !a->pair_faces_aug) || (a->cap_faces_wt > 0 && !a->pair_faces_wt) ||
+               (a->edge_off != nullptr && a->cap_verts > 0 && !a->pair_vacc))) {
+    set_error("d3h_extract_forward: pair_counts_host is set but a pair_* output is missing");
+    return D3H_E_BADARG;
+  }
   if (launch_forward_graph(*a, ws, stream) != 0) {
     launch_prepare(*a, ws, stream);
     launch_forward_sequence(*a, ws, stream);
+  }
+  if (pair) {
+    launch_pair_replay(*a, ws, ws.records, stream);
+    if (mapped_counts_pointer(a->pair_counts_host) == nullptr)   // not device-mapped: copy at the end
+      cudaMemcpyAsync(a->pair_counts_host, ws.counts2, sizeof(d3h_counts), cudaMemcpyDeviceToHost, stream);
   }
   return finish("d3h_extract_forward", a, ws, stream);
 }
@@ -686,7 +701,7 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 // ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
 static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "group_sort",
                                             "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records",
-                                            "edge_emit", "adjoint_poly"};
+                                            "edge_emit", "adjoint_poly", "pair_replay"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

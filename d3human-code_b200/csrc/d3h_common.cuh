@@ -170,7 +170,9 @@ struct DevCounters {
   unsigned work_quad;        //   Fv exceeded the record capacity (the caller re-runs with a larger workspace)
   unsigned n_verts;          // V
   unsigned bucket[6];        // polygons per faces_aug bucket
-  unsigned pad[12];
+  unsigned poly_done2;       // the same two for the replayed mSDF cut of a cloth / body pair
+  unsigned bucket2[6];
+  unsigned pad[5];
   unsigned trace_frame;      // diagnostics (d3h_trace_*): row of the trace table this call writes to
   unsigned pad2;
   unsigned long long* trace; // diagnostics: device trace table or nullptr; set by prepare_kernel, not reset

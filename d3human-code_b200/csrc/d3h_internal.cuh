@@ -42,7 +42,9 @@ unsigned long long* trace_table();  // current device trace table or nullptr
 struct Workspace {
   DevCounters* ctr;               // 128 B
   FwdBlock* blk;                  // the per-call argument block
+  FwdBlock* blk2;                 // argument block of the second extraction of a cloth / body pair
   d3h_counts* counts;             // device copy of the public counts
+  d3h_counts* counts2;            // ... of the second extraction of a cloth / body pair
   unsigned* occ_bits;             // ceil(N/32) words: sdf > 0
   unsigned* mocc_bits;            // ceil(N/32) words: (+-)msdf > 0 (open-mesh prefilter only)
   unsigned* m1_words;             // ceil(F/32) words: tet yields one triangle
@@ -103,6 +105,9 @@ void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream
 void launch_edge_emit(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);  // static edge table path
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream);
+// second extraction of a cloth / body pair: replays the mSDF cut on the shared surface (d3h_forward_args.pair_*)
+void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
+                        cudaStream_t stream);
 void launch_rank_records(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t n_records,
                          cudaStream_t stream);
 void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n_grid, cudaStream_t stream);
@@ -143,7 +148,7 @@ bool profiling_enabled();
 // ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
 enum KernelKind {
   K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_GROUP_SORT, K_VERTEX_EMIT, K_POLY_FACES,
-  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_COUNT
+  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_PAIR_REPLAY, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

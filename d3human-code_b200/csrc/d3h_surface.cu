@@ -62,6 +62,10 @@ __device__ __forceinline__ int cut_case(bool quad, float m0, float m1, float m2,
   return ncut ? (ncut - 1) : -1;
 }
 
+// REPLAY = second extraction of a cloth / body pair (d3h_forward_args.pair_*): `blk` is the pair's argument block (its
+// outputs, the opposite msdf_negate), the interpolated mSDF of every vertex is the exact negation of the stored one,
+// normals / tangents were accumulated by the first extraction and are not splatted again.
+template <bool REPLAY>
 __global__ void __launch_bounds__(kPolyThreads)
 poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                   DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
@@ -70,7 +74,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
                   const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix) {
   constexpr int WARPS = kPolyThreads / 32;
   int32_t* __restrict__ corners = blk->a.tape_corners;
-  const bool static_edges = blk->a.edge_off != nullptr;
+  const bool static_edges = !REPLAY && blk->a.edge_off != nullptr;  // a replay finds the corner array on the tape
   int64_t* __restrict__ faces_wt = blk->a.faces_wt;
   const int64_t cap_faces_wt = blk->a.cap_faces_wt;
   __shared__ unsigned s_cnt[6][WARPS];
@@ -138,6 +142,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
           faces_wt[3 * row + 1] = vi[1];
           faces_wt[3 * row + 2] = vi[2];
         }
+        if (REPLAY) continue;  // normals / tangents were accumulated by the first extraction of the pair
         const float ax = __fsub_rn(pv[1].x, pv[0].x), ay = __fsub_rn(pv[1].y, pv[0].y), az = __fsub_rn(pv[1].z, pv[0].z);
         const float bx = __fsub_rn(pv[2].x, pv[0].x), by = __fsub_rn(pv[2].y, pv[0].y), bz = __fsub_rn(pv[2].z, pv[0].z);
         // accumulator row of a vertex: [nx ny nz count | tx ty tz -]; one 16-byte vector atomic per half (sm_90+)
@@ -165,7 +170,8 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
       }
       unsigned mcase;
       int ncut;
-      bucket = cut_case(quad, P[0].w, P[1].w, P[2].w, P[3].w, mcase, ncut);
+      const float sg = REPLAY ? -1.f : 1.f;  // exact: the pair's interpolated mSDF is the negation
+      bucket = cut_case(quad, sg * P[0].w, sg * P[1].w, sg * P[2].w, sg * P[3].w, mcase, ncut);
     }
     // ---- polygons per bucket in this tile ----
 #pragma unroll
@@ -181,7 +187,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
       poly_cnt[(int64_t)tile * 8 + threadIdx.x] = run;
     }
     // the (3,3) torch.cross quirk: the three face normals are crossed along the *face* axis
-    if (cross_quirk && i == 0) {
+    if (!REPLAY && cross_quirk && i == 0) {
       float a[3][3], b[3][3];
       int fv[3][3];
       for (int64_t q = 0; q < npoly; ++q) {
@@ -221,7 +227,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   __threadfence();
   __syncthreads();
   trace_end(tr);
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctr->poly_done, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(REPLAY ? &ctr->poly_done2 : &ctr->poly_done, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -285,7 +291,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
     int64_t fa = 0;
     d3h_counts c;
     for (int b = 0; b < 6; ++b) {
-      ctr->bucket[b] = bk[b];
+      if (REPLAY) ctr->bucket2[b] = bk[b]; else ctr->bucket[b] = bk[b];
       c.bucket_polys[b] = bk[b];
       fa += (int64_t)bk[b] * ncut_of[b];
     }
@@ -337,6 +343,7 @@ __device__ __forceinline__ float3 vertex_tangent(const float* __restrict__ w_acc
                          __fsub_rn(t.z, __fmul_rn(dp, n.z)));
 }
 
+template <bool REPLAY>
 __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
@@ -378,6 +385,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
     for (int k = 0; k < 4; ++k) {
       L[k] = (k < n) ? corners[p0 + k] : 0;
       P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (REPLAY) P[k].w = -P[k].w;  // the pair's interpolated mSDF: exact negation
       T[k] = (k < n) ? vertex_tangent(w_acc, L[k]) : make_float3(0.f, 0.f, 0.f);
       // the corner that opened the vertex's run in the sorted key array writes the vertex's own tangent rows
       // (static edge table path: no owner is known, every corner writes the same value)
@@ -405,7 +413,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
     const int ncut_of[6] = {1, 2, 1, 2, 3, 4};
 #pragma unroll
     for (int b = 0; b < 6; ++b)
-      if (b < bucket) fbase += (int64_t)ctr->bucket[b] * ncut_of[b];
+      if (b < bucket) fbase += (int64_t)(REPLAY ? ctr->bucket2[b] : ctr->bucket[b]) * ncut_of[b];
     unsigned before = poly_excl[(int64_t)tile * 8 + bucket];
     for (int w = 0; w < (int)warp; ++w) before += s_cnt[bucket][w];
     brank = (int64_t)before + __popc(my_ballot & lanemask_lt());
@@ -476,18 +484,21 @@ __global__ void publish_counts_kernel(const FwdBlock* __restrict__ blk, const De
 }
 
 // ------------------------------------------------------------------------------------------------
+static UvParams uv_params(int64_t n_tets) {
+  UvParams uvp;
+  // map_uv(face_gidx_pre, num_tets*2): N = int(ceil(sqrt((max_idx+1)//2))), gshell_tets.py:220,319
+  const int64_t half = (2 * n_tets + 1) / 2;
+  uvp.nuv = (int)ceil(sqrt((double)half));
+  if (uvp.nuv < 1) uvp.nuv = 1;
+  uvp.end = (float)(1.0 - (1.0 / (double)uvp.nuv));
+  uvp.step = (uvp.nuv > 1) ? uvp.end / (float)(uvp.nuv - 1) : 0.f;
+  uvp.pad = (float)(0.9 / (double)uvp.nuv);
+  return uvp;
+}
+
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream) {
-  UvParams uvp;
-  {
-    // map_uv(face_gidx_pre, num_tets*2): N = int(ceil(sqrt((max_idx+1)//2))), gshell_tets.py:220,319
-    const int64_t half = (2 * a.n_tets + 1) / 2;
-    uvp.nuv = (int)ceil(sqrt((double)half));
-    if (uvp.nuv < 1) uvp.nuv = 1;
-    uvp.end = (float)(1.0 - (1.0 / (double)uvp.nuv));
-    uvp.step = (uvp.nuv > 1) ? uvp.end / (float)(uvp.nuv - 1) : 0.f;
-    uvp.pad = (float)(0.9 / (double)uvp.nuv);
-  }
+  const UvParams uvp = uv_params(a.n_tets);
   if (ws.cap_tets <= 0) {
     ProfScope ps(K_POLY_FACES, stream);
     launch_k(publish_counts_kernel, 1u, 1u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.counts);
@@ -496,12 +507,76 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   {
     ProfScope ps(K_POLY_FACES, stream);
-    launch_k(poly_faces_kernel, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert,
-             ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits, ws.word_prefix);
+    launch_k(poly_faces_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
+             ws.vert, ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits, ws.word_prefix);
   }
   ProfScope ps(K_POLY_CUT, stream);
-  launch_k(poly_cut_kernel, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert, ws.acc,
-           ws.owner, ws.poly_excl);
+  launch_k(poly_cut_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert,
+           ws.acc, ws.owner, ws.poly_excl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// second extraction of a cloth / body pair
+// ------------------------------------------------------------------------------------------------
+// Stores the pair's argument block and writes everything of the second extraction that hangs off a watertight vertex:
+// same position, mSDF negated, verts_aug row kept iff the negated mSDF is positive (gshell_tets.py:423-427).
+__global__ void __launch_bounds__(256) pair_vertex_kernel(FwdBlock src, Workspace ws) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (tid == 0) *ws.blk2 = src;
+  const d3h_forward_args& a = src.a;
+  const int64_t nv = ws.ctr->n_verts;
+  const float4* __restrict__ w_vert = ws.vert;
+  float4* __restrict__ vacc = reinterpret_cast<float4*>(a.vacc);
+  for (int64_t v = tid; v < nv; v += nthreads) {
+    const float4 p = w_vert[v];
+    const float m = -p.w;
+    if (v < a.cap_verts) {
+      a.verts_wt[3 * v] = p.x; a.verts_wt[3 * v + 1] = p.y; a.verts_wt[3 * v + 2] = p.z;
+      a.msdf_wt[v] = m;
+      if (vacc != nullptr) {
+        vacc[2 * v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vacc[2 * v + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (v < a.cap_verts_aug) {
+      const bool used = m > 0.f;
+      a.verts_aug[3 * v] = used ? p.x : 0.f;
+      a.verts_aug[3 * v + 1] = used ? p.y : 0.f;
+      a.verts_aug[3 * v + 2] = used ? p.z : 0.f;
+      a.msdf_aug[v] = m;
+    }
+  }
+}
+
+void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
+                        cudaStream_t stream) {
+  FwdBlock blk2;
+  blk2.a = a;
+  blk2.a.msdf_negate = a.msdf_negate ? 0 : 1;
+  blk2.a.verts_aug = a.pair_verts_aug; blk2.a.v_tng_aug = a.pair_v_tng_aug; blk2.a.msdf_aug = a.pair_msdf_aug;
+  blk2.a.faces_aug = a.pair_faces_aug; blk2.a.verts_wt = a.pair_verts_wt; blk2.a.v_tng_wt = a.pair_v_tng_wt;
+  blk2.a.msdf_wt = a.pair_msdf_wt; blk2.a.faces_wt = a.pair_faces_wt; blk2.a.vacc = a.pair_vacc;
+  blk2.a.counts_host = a.pair_counts_host;
+  blk2.a.seq = a.pair_seq;
+  blk2.a.zero_g_pos = blk2.a.zero_g_sdf = blk2.a.zero_g_msdf = nullptr;
+  blk2.counts_mapped = mapped_counts_pointer(a.pair_counts_host);
+  blk2.trace = nullptr;
+  ProfScope ps(K_PAIR_REPLAY, stream);
+  int64_t vblocks = (ws.cap_corners + 255) / 256;
+  if (vblocks < 1) vblocks = 1;
+  if (vblocks > 148 * 4) vblocks = 148 * 4;
+  launch_k(pair_vertex_kernel, (unsigned)vblocks, 256u, stream, kLaunchLatency, blk2, ws);
+  if (ws.cap_tets <= 0) {
+    launch_k(publish_counts_kernel, 1u, 1u, stream, kLaunchLatency, ws.blk2, ws.ctr, ws.counts2);
+    return;
+  }
+  const UvParams uvp = uv_params(a.n_tets);
+  const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
+  launch_k(poly_faces_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
+           ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix);
+  launch_k(poly_cut_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
+           ws.acc, ws.owner, ws.poly_excl);
 }
 
 }  // namespace d3h

@@ -337,7 +337,8 @@ _COUNT_RING = 256   # pinned 128-byte count slots per plan: batches in flight ta
 
 
 def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
-                   lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None) -> _Pending:
+                   lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None,
+                   fused_pair: bool = False) -> _Pending:
     """Enqueue the forward extraction of a batch of frames: ONE library call (d3h_extract_forward_batch), no host wait.
 
     ptrs   : (B,3) int64 array (or nested list): per frame the device pointers of pos / sdf / msdf -- contiguous fp32
@@ -348,6 +349,9 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
     launcher : replaces the library call (tet-range sharding, sharding.py): launcher(A, plan, stream) enqueues the work
              described by the argument blocks A and may return a Fv to regrow the record capacity to (retry).
     static : (edge_off, edge_ab, n_edges) of build_edge_table, or None for the general per-call sort path.
+    fused_pair : the two frames are the cloth / body pair of one iteration (same pos / sdf / msdf, opposite msdf_negate):
+             ONE library call classifies and de-duplicates once and replays only the mSDF cut for the second frame
+             (d3h_forward_args.pair_*).
     Frames run on `lanes` concurrent lanes inside the library."""
     L = _cabi.lib()
     ptrs = np.asarray(ptrs, dtype=np.int64)
@@ -365,7 +369,12 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
     if launcher is not None:
         static = None       # the sharded stages exchange records and always sort
     n_edges = static[2] if static is not None else 0
-    pend.inputs = (ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs, launcher, static)
+    if fused_pair:
+        if B != 2 or launcher is not None or not np.array_equal(ptrs[0], ptrs[1]) or int(negate[0]) == int(negate[1]):
+            raise ValueError("a fused pair is two frames on the same pos / sdf / msdf with opposite msdf_negate")
+        lanes = 1
+    pend.inputs = (ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs, launcher, static,
+                   fused_pair)
     pend.plan, pend.dev, pend.B = plan, dev, B
     with torch.cuda.device(dev):
         for attempt in range(6):
@@ -401,11 +410,27 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
                 A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = 0
             A[:, c["counts_host"]] = plan.counts_ptr + ((slot0 + lay.ar) % _COUNT_RING) * 128
             A[:, c["seq"]] = lay.ar + (seq0 + 1)
-            if B == 1 and _unjoined.get(dev.index):
+            A[:, c["pair_verts_aug"]:c["pair_seq"] + 1] = 0
+            if fused_pair:
+                # frame 1 is produced by the call of frame 0: its outputs, accumulator, count slot and tag ride along
+                for dst, src in (("pair_verts_aug", "verts_aug"), ("pair_v_tng_aug", "v_tng_aug"), ("pair_msdf_aug", "msdf_aug"),
+                                 ("pair_faces_aug", "faces_aug"), ("pair_verts_wt", "verts_wt"), ("pair_v_tng_wt", "v_tng_wt"),
+                                 ("pair_msdf_wt", "msdf_wt"), ("pair_faces_wt", "faces_wt"), ("pair_vacc", "vacc"),
+                                 ("pair_counts_host", "counts_host"), ("pair_seq", "seq")):
+                    A[0, c[dst]] = A[1, c[src]]
+                if zero is not None:   # one call: every zero-fill duty moves to frame 0 (a buffer has one duty holder)
+                    z = np.asarray(zero, dtype=np.int64)
+                    A[0, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = z[0] | z[1]
+                    A[1, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = 0
+            if (B == 1 or fused_pair) and _unjoined.get(dev.index):
                 # this call runs on the caller's stream and shares workspace 0 with the lanes of an un-joined batch
                 _cabi.check(L.d3h_lanes_join(stream), "d3h_lanes_join")
                 _unjoined[dev.index] = False
-            if launcher is None:
+            if fused_pair:
+                _cabi.check(L.d3h_extract_forward_batch(A.ctypes.data, 1, 1, stream), "d3h_extract_forward (pair)")
+                launches += 3         # pair_vertex + replayed poly_faces / poly_cut; frame 1 launches nothing else
+                launches -= (4 if ct <= 0 else (LAUNCHES_FORWARD_STATIC if static is not None else LAUNCHES_FORWARD))
+            elif launcher is None:
                 # no join here: the lanes keep running and the next batch may queue up behind this one lane by lane;
                 # _collect_frames orders the caller's stream behind the lanes before any output is handed out
                 _cabi.check(L.d3h_extract_forward_batch_nojoin(A.ctypes.data, B, lanes, stream),
@@ -433,6 +458,8 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             bmat[:, b["tape_edges"]:b["tape_runs"] + 1] = A[:, c["tape_edges"]:c["tape_runs"] + 1]
             bmat[:, b["verts_wt"]], bmat[:, b["msdf_wt"]] = A[:, c["verts_wt"]], A[:, c["msdf_wt"]]
             bmat[:, b["g_pos"]:b["g_msdf"] + 1] = grad_ptrs
+            if fused_pair:           # one tape for both frames: the one frame 0's call writes
+                bmat[1, b["tape_edges"]:b["tape_runs"] + 1] = bmat[0, b["tape_edges"]:b["tape_runs"] + 1]
             if static is not None:   # scatter-form adjoint: no per-vertex corner lists on the tape
                 bmat[:, b["tape_slots"]] = bmat[:, b["tape_runs"]] = 0
                 bmat[:, b["vacc"]] = A[:, c["vacc"]]
@@ -493,7 +520,7 @@ def _collect_frames(pend: _Pending) -> BatchResult:
             fv, t1, t2, v, nfa = mx[0], mx[1], mx[2], mx[4], mx[5]
             va_ = int((sizes[:, 4] + sizes[:, 3]).max())
             fw_ = int((sizes[:, 1] + 2 * sizes[:, 2]).max())
-        if B > 1:
+        if B > 1 and not pend.inputs[11]:     # (a fused pair runs on the caller's stream: nothing to join)
             _cabi.check(L.d3h_lanes_join(torch.cuda.current_stream(pend.dev).cuda_stream), "d3h_lanes_join")
             _unjoined[pend.dev.index] = False
         if grow_tets or grow_out:
@@ -522,10 +549,11 @@ def _collect_frames(pend: _Pending) -> BatchResult:
 
 
 def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
-                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None) -> BatchResult:
+                       lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None,
+                       fused_pair: bool = False) -> BatchResult:
     """Launch + collect (see _launch_frames / _collect_frames)."""
     return _collect_frames(_launch_frames(ptrs, negate, dev, n_grid, tets_i32, watertight_template, lanes, zero,
-                                          grad_ptrs, launcher, static))
+                                          grad_ptrs, launcher, static, fused_pair))
 
 
 def forward_raw(pos, sdf, msdf, tets_i32, msdf_negate, watertight_template, static=None) -> BatchResult:
@@ -545,7 +573,7 @@ def _shrink(cap: int, need: int) -> int:
 _OUTS_PER_FRAME = 9   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, msdf_boundary, faces_aug, faces_wt
 
 
-def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launcher=None, static=None):
+def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launcher=None, static=None, fused_pair=False):
     """Everything of a forward call that precedes the size read: pointer tables of the frames, dense gradient buffers
     (allocated here, zero-filled by the tail of the forward call of the frame that owns them -- HBM is idle behind the
     latency-bound surface kernels), and the launch.  Returns (pending batch, gradient buffers or None, N)."""
@@ -581,7 +609,7 @@ def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launch
             zero.append(zrow)
             grad_ptrs.append(grow)
     pend = _launch_frames(ptrs, negate, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs,
-                          launcher, static)
+                          launcher, static, fused_pair)
     return pend, gbufs, n_grid
 
 
@@ -800,13 +828,14 @@ class FramesFuture:
 
 
 def extract_frames(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watertight_template: bool = True,
-                   lanes: int = DEFAULT_LANES):
+                   lanes: int = DEFAULT_LANES, fused_pair: bool = False):
     """extract_frames_async(...).result(): launch, then block on the sizes."""
-    return extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types, output_watertight_template, lanes).result()
+    return extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types, output_watertight_template, lanes,
+                                fused_pair).result()
 
 
 def extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_watertight_template: bool = True,
-                         lanes: int = DEFAULT_LANES) -> FramesFuture:
+                         lanes: int = DEFAULT_LANES, fused_pair: bool = False) -> FramesFuture:
     """A batch of extractions on the same tet grid in one autograd node and one library call per direction.
 
     No counterpart in the reference, which would loop over the frames (BASELINE.json configs[3]: a batch of video frames
@@ -816,6 +845,9 @@ def extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_
     sdf_n, msdf_n : one tensor shared by all frames ((N,) or (N,1)), a stacked (B,N) tensor, or a sequence per frame
     types : None (GShell_Tets semantics), one of "cloth" / "body" for all frames, or a sequence per frame
             (hmSDF_Tets semantics: "body" uses -msdf and, like the reference, does not back-propagate into msdf_n)
+    fused_pair : EXPERIMENTAL (validated on the CPU emulation of the kernels only, tests/test_emu_parity.py): the two
+            frames are the cloth / body pair of one iteration (same tensors, types cloth and body); one library call
+            classifies and de-duplicates once and only replays the mSDF cut for the second frame.
     Returns a FramesFuture; `.result()` is a list with the reference's 6-tuple `(verts, faces, None, None, v_tng, extra)`
     for every frame.  Gradients of shared tensors are summed over the frames.  The forward kernels are enqueued before
     this function returns; the host only blocks (once per frame, on the output sizes) inside `.result()`.
@@ -874,5 +906,11 @@ def extract_frames_async(pos_frames, sdf_n, msdf_n, tet_fx4, types=None, output_
     wt = bool(output_watertight_template)
     grad_on = torch.is_grad_enabled()
     need = tuple(grad_on and t.requires_grad for t in tensors)
-    started = _prelaunch(refs, tensors, need, tets, wt, int(lanes), None, static_edges_for(tets, n_grid))
+    if fused_pair and not (B == 2 and refs[0][:3] == refs[1][:3] and refs[0][3] != refs[1][3]):
+        raise ValueError("fused_pair needs exactly two frames on the same pos / sdf / msdf tensors, types cloth and body")
+    if fused_pair and not wt:
+        # output_watertight_template=False keeps only tets with a positive mSDF vertex (gshell_tets.py:275): the set of
+        # valid tets depends on the mSDF sign, cloth and body do not share their classification
+        raise ValueError("fused_pair needs output_watertight_template=True")
+    started = _prelaunch(refs, tensors, need, tets, wt, int(lanes), None, static_edges_for(tets, n_grid), fused_pair)
     return FramesFuture((refs, wt, int(lanes), None, started), tets, tensors, B, wt)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 400 /* 0.4.0 */
+#define D3H_VERSION 410 /* 0.4.1 */
 
 enum {
   D3H_OK = 0,
@@ -121,6 +121,23 @@ typedef struct d3h_forward_args {
   int64_t n_edges;
   float* vacc;             /* (cap_verts,8) per-vertex accumulator of the scatter-form adjoint, zeroed here; required
                               with edge_off (the static path leaves no tape_slots / tape_runs) */
+  /* optional (d3h_extract_forward only): the PAIR of extractions of one split-stage iteration, hmSDF_Tets(type="cloth")
+   * and hmSDF_Tets(type="body") on the same pos / sdf / msdf (train.py:1040-1047).  The second extraction uses the mSDF
+   * with the opposite sign of `msdf_negate`; classification, edge de-duplication, vertex positions, normals and tangents
+   * are shared (the interpolated mSDF of the second one is the exact negation), only the mSDF cut is redone.  Same
+   * capacities as the first set; the tape (tape_edges / tape_corners / tape_slots / tape_runs) is common to both.
+   * pair_verts_aug == NULL: no second extraction. */
+  float* pair_verts_aug;
+  float* pair_v_tng_aug;
+  float* pair_msdf_aug;
+  int64_t* pair_faces_aug;
+  float* pair_verts_wt;
+  float* pair_v_tng_wt;
+  float* pair_msdf_wt;
+  int64_t* pair_faces_wt;
+  float* pair_vacc;        /* (cap_verts,8) accumulator of the second extraction's scatter-form adjoint (with edge_off) */
+  d3h_counts* pair_counts_host; /* sizes of the second extraction (n_faces_aug, bucket_polys differ), pinned like counts_host */
+  int64_t pair_seq;
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */

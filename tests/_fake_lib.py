@@ -23,6 +23,7 @@ def _arr(ptr, n, ctype):
 class FakeLib:
     def __init__(self):
         self.tapes = {}          # tape_edges pointer -> oracle forward dict (the "tape" of the fake)
+        self.tapes_pair = None   # forward dict of the second extraction of the last fused pair
         self.forward_calls = 0   # frames
         self.batch_calls = 0
         self.backward_calls = 0
@@ -72,7 +73,23 @@ class FakeLib:
                 return rc
         return 0
 
-    def _forward(self, a):
+    def _forward(self, a, pair_of=None):
+        if pair_of is None and a.pair_counts_host:
+            # fused cloth / body pair: the second extraction is the same call with the sign flipped and the pair_* outputs
+            rc = self._forward(a, pair_of=False)
+            if rc:
+                return rc
+            b = _cabi.ForwardArgs.from_buffer_copy(bytes(a))
+            b.msdf_negate = 0 if a.msdf_negate else 1
+            for name in ("verts_aug", "v_tng_aug", "msdf_aug", "faces_aug", "verts_wt", "v_tng_wt", "msdf_wt", "faces_wt", "vacc"):
+                setattr(b, name, getattr(a, "pair_" + name))
+            b.counts_host, b.seq = a.pair_counts_host, a.pair_seq
+            b.zero_g_pos = b.zero_g_sdf = b.zero_g_msdf = None
+            b.pair_counts_host = None
+            rc = self._forward(b, pair_of=True)
+            # one tape for both: the backward blocks of frame 1 point at frame 0's tape, but carry the negated sign
+            self.tapes[(int(a.tape_edges), 1)] = self.tapes_pair
+            return rc
         self.forward_calls += 1
         n, f = a.n_grid, a.n_tets
         if (a.sdf | a.msdf) & 15 or a.workspace & 63 or a.tets & 15:   # (CPU allocations are 64-byte aligned)
@@ -121,7 +138,10 @@ class FakeLib:
                 self.error = b"fake: static edge table without vacc / edge_ab"
                 return _cabi.D3H_E_BADARG
             _arr(a.vacc, 8 * min(a.cap_verts, v), C.c_float)[:] = 0.0
-        self.tapes[int(a.tape_edges)] = fwd
+        if pair_of:
+            self.tapes_pair = fwd                 # same tape address as the first extraction of the pair
+        else:
+            self.tapes[int(a.tape_edges)] = fwd
         c.n_verts, c.n_faces_aug = v, fa
         per = (1, 2, 1, 2, 3, 4)
         for k in range(6):
@@ -204,6 +224,9 @@ class FakeLib:
             b = _cabi.BackwardArgs.from_address(int(ptr) + i * size)
             self.backward_calls += 1
             fwd = self.tapes.get(int(b.tape_edges))
+            pair_fwd = self.tapes.get((int(b.tape_edges), 1))
+            if pair_fwd is not None and fwd is not None and (-1 if b.msdf_negate else 1) != fwd["_msdf_sign"]:
+                fwd = pair_fwd                    # second extraction of a fused pair
             if fwd is None:
                 self.error = b"fake: unknown tape"
                 return _cabi.D3H_E_BADARG

@@ -183,3 +183,47 @@ def test_random_tet_soups(dev, seed, n, f):
     U.assert_close_normwise("grad_sdf", g[1], g_sdf, 5 * U.GRAD_RTOL)
     if typ != "body":
         U.assert_close_normwise("grad_msdf", g[2], g_msdf, 5 * U.GRAD_RTOL)
+
+
+@pytest.mark.parametrize("res,field,wt", [(12, "capsule", True), (10, "adv", True), (8, "adv", False), (6, "sphere", True)])
+def test_fused_pair_equals_two_calls(dev, res, field, wt):
+    """hmSDF_Tets.split(fused=True): one classification / de-duplication for the cloth / body pair, only the mSDF cut is
+    replayed -- bit-identical to the two separate calls, gradients equal to their sum."""
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    pos, sdf, msdf, tets = G._inputs(res, field, seed=res)
+    hm = hmSDF_Tets()
+    tt = torch.tensor(tets)
+
+    def leaves():
+        return (torch.tensor(pos, requires_grad=True), torch.tensor(sdf, requires_grad=True),
+                torch.tensor(msdf, requires_grad=True))
+
+    def loss(c, b):
+        out = c[0].square().sum() + b[0].square().sum() + c[5]["msdf"].sum() - 2.0 * b[5]["msdf"].sum()
+        if wt:
+            out = out + c[5]["vertices_watertight"].sum() + (b[5]["msdf_watertight"] ** 2).sum()
+        return out
+
+    for rep in range(2):      # second round: capacities settled, no re-run
+        tp, ts, tm = leaves()
+        cloth, body = hm.split(tp, ts, tm, tt, output_watertight_template=wt, fused=True)
+        loss(cloth, body).backward()
+        tp2, ts2, tm2 = leaves()
+        c2 = hm(tp2, ts2, tm2, tt, "cloth", wt)
+        b2 = hm(tp2, ts2, tm2, tt, "body", wt)
+        loss(c2, b2).backward()
+        for a, b in ((cloth, c2), (body, b2)):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), rep
+            assert tuple(a[5].keys()) == tuple(b[5].keys())
+            for k in a[5]:
+                if torch.is_tensor(a[5][k]) and "tng" not in k:
+                    assert torch.equal(a[5][k], b[5][k]), (rep, k)
+            U.assert_tangents_close("v_tng_aug", a[4].detach().numpy(), b[4].detach().numpy(), 2.0 if field == "adv" else U.TNG_CUDA_ATOL)
+        U.assert_close_normwise("grad_pos", tp.grad.numpy(), tp2.grad.numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_sdf", ts.grad.numpy(), ts2.grad.numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_msdf", tm.grad.numpy(), tm2.grad.numpy(), U.GRAD_RTOL)
+
+
+@pytest.mark.parametrize("res,field", [(12, "capsule"), (8, "adv")])
+def test_gpu_fused_pair_test_body(dev, res, field):
+    Z.test_zz_fused_pair_equals_two_calls(dev, res, field)

@@ -210,14 +210,15 @@ def test_tet_range_sharding_host_logic(host, vr):
     assert ranges[0][0] == 0 and ranges[-1][1] == tets.shape[0]
 
 
-def test_split_pair_is_cloth_plus_body(host):
+@pytest.mark.parametrize("fused", [False, True])
+def test_split_pair_is_cloth_plus_body(host, fused):
     """hmSDF_Tets.split: one call for the cloth / body pair of an iteration == the two reference-style calls."""
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
     pos, sdf, msdf, tets = _case(8)
     tp = torch.tensor(pos, requires_grad=True)
     ts = torch.tensor(sdf[:, None], requires_grad=True)
     tm = torch.tensor(msdf, requires_grad=True)
-    cloth, body = hmSDF_Tets().split(tp, ts, tm, torch.tensor(tets))
+    cloth, body = hmSDF_Tets().split(tp, ts, tm, torch.tensor(tets), fused=fused)
     fc = O.extract_forward(pos, sdf, msdf, tets, 1, True)
     fb = O.extract_forward(pos, sdf, msdf, tets, -1, True)
     _check_frame(cloth, fc)

@@ -172,3 +172,41 @@ def test_random_tet_soups(dev, seed, n, f):
     U.assert_close_normwise("grad_sdf", g[1], g_sdf, 5 * U.GRAD_RTOL)
     if typ != "body":
         U.assert_close_normwise("grad_msdf", g[2], g_msdf, 5 * U.GRAD_RTOL)
+
+
+@pytest.mark.parametrize("res,field", [(24, "capsule"), (12, "adv")])
+def test_zz_fused_pair_equals_two_calls(dev, res, field):
+    """hmSDF_Tets.split(fused=True): one classification / edge de-duplication / vertex interpolation for
+    the cloth / body pair of an iteration, only the mSDF cut is replayed for the body.  Bit-identical to the two separate
+    calls; gradients equal to their sum.  Developed on the CPU emulation of the kernels (tests/test_emu_parity.py); this is
+    its check on the real GPU -- kept as the very last test of the suite."""
+    from tests import test_cuda_parity as G
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    pos, sdf, msdf, tets = G._inputs(res, field, seed=res)
+    hm = hmSDF_Tets()
+    tt = torch.tensor(tets, device=dev)
+
+    def leaves():
+        return (torch.tensor(pos, device=dev, requires_grad=True), torch.tensor(sdf, device=dev, requires_grad=True),
+                torch.tensor(msdf, device=dev, requires_grad=True))
+
+    def loss(c, b):
+        return (c[0].square().sum() + b[0].square().sum() + c[5]["msdf"].sum() - 2.0 * b[5]["msdf"].sum()
+                + c[5]["vertices_watertight"].sum() + (b[5]["msdf_watertight"] ** 2).sum())
+
+    for rep in range(2):
+        tp, ts, tm = leaves()
+        cloth, body = hm.split(tp, ts, tm, tt, fused=True)
+        loss(cloth, body).backward()
+        tp2, ts2, tm2 = leaves()
+        c2 = hm(tp2, ts2, tm2, tt, "cloth")
+        b2 = hm(tp2, ts2, tm2, tt, "body")
+        loss(c2, b2).backward()
+        for a, b in ((cloth, c2), (body, b2)):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), rep
+            for k in a[5]:
+                if torch.is_tensor(a[5][k]) and "tng" not in k:
+                    assert torch.equal(a[5][k], b[5][k]), (rep, k)
+        U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), tp2.grad.cpu().numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_sdf", ts.grad.cpu().numpy(), ts2.grad.cpu().numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), tm2.grad.cpu().numpy(), U.GRAD_RTOL)
