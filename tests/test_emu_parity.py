@@ -227,3 +227,55 @@ def test_fused_pair_equals_two_calls(dev, res, field, wt):
 @pytest.mark.parametrize("res,field", [(12, "capsule"), (8, "adv")])
 def test_gpu_fused_pair_test_body(dev, res, field):
     Z.test_zz_fused_pair_equals_two_calls(dev, res, field)
+
+
+def _fuzz_case(case):
+    from d3human_code_b200 import grids
+    rng = np.random.default_rng(case)
+    kind = int(rng.integers(0, 4))
+    if kind == 0:      # lattice, smooth field
+        res = int(rng.integers(1, 9))
+        pos, tets = grids.kuhn_grid(res)
+        c, r = rng.standard_normal(3) * 0.3, rng.uniform(0.05, 1.5)
+        sdf = (r - np.linalg.norm(pos - c, axis=1)).astype(np.float32)
+        msdf = (pos @ rng.standard_normal(3) + rng.normal() * 0.2).astype(np.float32)
+    elif kind == 1:    # lattice, adversarial field (exact zeros)
+        res = int(rng.integers(1, 7))
+        pos, tets = grids.kuhn_grid(res)
+        pos, sdf, msdf = grids.adversarial_field(pos, res, seed=case)
+    elif kind == 2:    # tet soup
+        n, f = int(rng.integers(4, 80)), int(rng.integers(1, 1500))
+        tets = np.stack([rng.permutation(n)[:4] for _ in range(f)]).astype(np.int64)
+        pos = rng.standard_normal((n, 3)).astype(np.float32)
+        sdf, msdf = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+        sdf[::3] = 0
+        msdf[::4] = 0
+    else:              # degenerate: constant fields with one flipped vertex
+        res = int(rng.integers(1, 4))
+        pos, tets = grids.kuhn_grid(res)
+        sdf = np.full(pos.shape[0], rng.choice([-1.0, 1.0, 0.0]), np.float32)
+        sdf[int(rng.integers(0, pos.shape[0]))] = rng.choice([-1.0, 1.0])
+        msdf = np.full(pos.shape[0], rng.choice([-1.0, 1.0, 0.0]), np.float32)
+    typ = [None, "cloth", "body"][int(rng.integers(0, 3))]
+    wt = bool(rng.integers(0, 4) != 0)
+    return pos, sdf, msdf, tets, typ, wt
+
+
+def test_fuzz_forward_against_oracle(dev):
+    """60 seeded random inputs (lattices, adversarial fields, tet soups, degenerate fields; 1650 such cases were run once
+    while writing this): every integer output, position and mSDF value bit-exact against the oracle."""
+    from oracle import gshell_oracle as O
+    for case in range(60):
+        pos, sdf, msdf, tets, typ, wt = _fuzz_case(case)
+        if case % 5 == 0:
+            E.reset_plans()
+            _packed_cache.clear()
+        out = E.extract(torch.tensor(pos), torch.tensor(sdf), torch.tensor(msdf), torch.tensor(tets),
+                        msdf_negate=(typ == "body"), output_watertight_template=wt)
+        fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, wt)
+        U.assert_exact(f"verts_aug[{case}]", out[0].numpy(), fwd["verts_aug"])
+        U.assert_exact(f"faces_aug[{case}]", out[1].numpy(), fwd["faces_aug"])
+        U.assert_exact(f"msdf[{case}]", out[5]["msdf"].numpy(), fwd["msdf"])
+        if wt:
+            U.assert_exact(f"faces_watertight[{case}]", out[5]["faces_watertight"].numpy(), fwd["faces_watertight"])
+            U.assert_exact(f"vertices_watertight[{case}]", out[5]["vertices_watertight"].numpy(), fwd["vertices_watertight"])
