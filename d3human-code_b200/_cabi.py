@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 410
+VERSION = 420
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -52,7 +52,7 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("pair_verts_aug", C.c_void_p), ("pair_v_tng_aug", C.c_void_p), ("pair_msdf_aug", C.c_void_p),
                 ("pair_faces_aug", C.c_void_p), ("pair_verts_wt", C.c_void_p), ("pair_v_tng_wt", C.c_void_p),
                 ("pair_msdf_wt", C.c_void_p), ("pair_faces_wt", C.c_void_p), ("pair_vacc", C.c_void_p),
-                ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64)]
+                ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64), ("tet_edge_rank", C.c_void_p)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args

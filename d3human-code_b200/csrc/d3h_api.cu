@@ -217,6 +217,10 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: static edge table needs edge_ab (8-byte pairs, 16-byte aligned), 0 < n_edges < 2^31 and vacc", who);
     return D3H_E_BADARG;
   }
+  if (a->tet_edge_rank != nullptr && (a->edge_off == nullptr || (reinterpret_cast<uintptr_t>(a->tet_edge_rank) & 15))) {
+    set_error("%s: tet_edge_rank needs the static edge table and 16-byte alignment", who);
+    return D3H_E_BADARG;
+  }
   if (a->cap_valid_tets > 0 && (!a->tape_corners || (a->edge_off == nullptr && (!a->tape_slots || !a->tape_runs)))) {
     set_error("%s: tape_corners / tape_slots (4*cap_valid_tets int32) and tape_runs (cap_verts+1 int32) are required", who);
     return D3H_E_BADARG;
@@ -367,7 +371,7 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.watertight = a.watertight_template ? 1 : 0;
   key.has_zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) ? 1 : 0;
   key.parts = parts;
-  key.is_static = a.edge_off != nullptr ? 1 : 0;
+  key.is_static = a.edge_off != nullptr ? (a.tet_edge_rank != nullptr ? 2 : 1) : 0;
   key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
   std::lock_guard<std::mutex> lock(g_graph_mu);

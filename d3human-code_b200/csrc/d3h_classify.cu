@@ -206,6 +206,34 @@ __device__ __forceinline__ void emit_polygon_keys(const int4 v4, int code, bool 
 // Static edge table path: the rank of edge (a,b) in the sorted list of all tet edges of the grid is found by bisecting
 // the (at most ~14) larger neighbours of a; the edge is marked in the bitmap and the first marker counts it for its
 // 8192-edge block, so that the numbering kernel needs no scan over the blocks.
+// Variant with the per-tet rank table (d3h_forward_args.tet_edge_rank): no bisection, two 16-byte loads per valid tet.
+__device__ __forceinline__ void mark_polygon_edges_ranked(int64_t tet, int code, bool quad, int64_t rec,
+                                                          const int32_t* __restrict__ tet_edge_rank,
+                                                          unsigned* __restrict__ edge_bits,
+                                                          unsigned* __restrict__ eblock_cnt,
+                                                          unsigned* __restrict__ corner_rank) {
+  const int4 r03 = __ldg(reinterpret_cast<const int4*>(tet_edge_rank) + 2 * tet);
+  const int4 r45 = __ldg(reinterpret_cast<const int4*>(tet_edge_rank) + 2 * tet + 1);
+  const int rr[6] = {r03.x, r03.y, r03.z, r03.w, r45.x, r45.y};
+  const int n = quad ? 4 : 3;
+  unsigned rk[4], old[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = c_loop_edge[code][k < n ? k : 0];
+    unsigned r = 0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      if (q == e) r = (unsigned)rr[q];      // select without dynamic register indexing
+    rk[k] = r;
+    old[k] = 0xffffffffu;
+    if (k < n) old[k] = atomicOr(edge_bits + (r >> 5), 1u << (r & 31u));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < n && !(old[k] & (1u << (rk[k] & 31u)))) atomicAdd(eblock_cnt + rk[k] / kEdgeBlock, 1u);
+  reinterpret_cast<uint4*>(corner_rank)[rec] = make_uint4(rk[0], rk[1], rk[2], n == 4 ? rk[3] : 0xffffffffu);
+}
+
 __device__ __forceinline__ void mark_polygon_edges(const int4 v4, int code, bool quad, int64_t rec,
                                                    const int32_t* __restrict__ edge_off,
                                                    const int2* __restrict__ edge_ab, unsigned* __restrict__ edge_bits,
@@ -254,7 +282,8 @@ __device__ __forceinline__ void mark_polygon_edges(const int4 v4, int code, bool
       make_uint4((unsigned)lo[0], (unsigned)lo[1], (unsigned)lo[2], n == 4 ? (unsigned)lo[3] : 0xffffffffu);
 }
 
-// EMIT: 0 records only (tet-range shards), 1 sort keys + MSD histogram (general path), 2 static edge table marks
+// EMIT: 0 records only (tet-range shards), 1 sort keys + MSD histogram (general path), 2 static edge table marks,
+// 3 the same with the per-tet rank table (experimental)
 template <int EMIT>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1_words,
@@ -379,6 +408,9 @@ compact_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ m1
       if (EMIT == 2)
         mark_polygon_edges(v4[r], code, quad[r], (int64_t)g1[r] + g2[r], blk->a.edge_off,
                            reinterpret_cast<const int2*>(blk->a.edge_ab), edge_bits, eblock_cnt, corner_rank);
+      if (EMIT == 3)
+        mark_polygon_edges_ranked(tet[r], code, quad[r], (int64_t)g1[r] + g2[r], blk->a.tet_edge_rank, edge_bits,
+                                  eblock_cnt, corner_rank);
     }
   }
   trace_end(tr);
@@ -411,7 +443,11 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
   ProfScope ps(K_COMPACT, stream);
   unsigned long long* const nokeys = nullptr;
   unsigned* const nou = nullptr;
-  if (emit_keys && a.edge_off != nullptr)
+  if (emit_keys && a.edge_off != nullptr && a.tet_edge_rank != nullptr)
+    launch_k(compact_kernel<3>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
+             ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
+             msd_shift, nokeys, nou, nou, ws.edge_bits, ws.eblock_cnt, ws.corner_rank);
+  else if (emit_keys && a.edge_off != nullptr)
     launch_k(compact_kernel<2>, (unsigned)ntiles, kCompactThreads, stream, kLaunchLatency, ws.blk, ws.m1_words,
              ws.m2_words, nwords, a.tet_begin, ws.occ_bits, ws.tile_cnt, ntiles, ws.ctr, records, cap_records, key_bits,
              msd_shift, nokeys, nou, nou, ws.edge_bits, ws.eblock_cnt, ws.corner_rank);

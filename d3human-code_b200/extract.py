@@ -80,6 +80,13 @@ def packed_tets(tet_fx4: torch.Tensor, n_grid: int) -> torch.Tensor:
 _TET_EDGES = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))   # gshell_tets.py:187
 _static_cache: Dict[Tuple, list] = {}
 _static_mode = os.environ.get("D3H_STATIC_EDGES", "auto")       # "auto": from the 2nd call on the same tets, "1", "0"
+_tet_edge_ranks = os.environ.get("D3H_TET_EDGE_RANKS", "0") == "1"   # EXPERIMENTAL per-tet edge-rank table (+32 B / tet)
+
+
+def set_tet_edge_ranks(on: bool) -> None:
+    """EXPERIMENTAL: also build the per-tet edge-rank table with the static edge table (tables already built keep their form)."""
+    global _tet_edge_ranks
+    _tet_edge_ranks = bool(on)
 
 
 def set_static_edges(mode: str) -> None:
@@ -93,7 +100,8 @@ def set_static_edges(mode: str) -> None:
 
 def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
-    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U): edges ascending in (min,max), CSR offsets per min vertex."""
+    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank or None): edges ascending in (min,max), CSR offsets
+    per min vertex."""
     t = tets_i32.long()
     keys = []
     for i, j in _TET_EDGES:
@@ -110,7 +118,15 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     n_edges = int(uk.shape[0])
     if n_edges >= 2 ** 31:
         raise ValueError("tet grid has more than 2^31 distinct edges")
-    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges
+    tet_rank = None
+    if _tet_edge_ranks:   # EXPERIMENTAL companion table: rank of the 6 edges of every tet, (F,8) int32 rows
+        t = tets_i32.long()
+        tet_rank = torch.zeros((tets_i32.shape[0], 8), dtype=torch.int32, device=tets_i32.device)
+        for e, (i, j) in enumerate(_TET_EDGES):
+            k = torch.minimum(t[:, i], t[:, j]) * n_grid + torch.maximum(t[:, i], t[:, j])
+            tet_rank[:, e] = torch.searchsorted(uk, k).to(torch.int32)
+        del t
+    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank
 
 
 def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
@@ -298,6 +314,8 @@ class _Layout:
         A[:, c["workspace_bytes"]] = plan.workspace_bytes
         if static is not None:
             A[:, c["edge_off"]], A[:, c["edge_ab"]], A[:, c["n_edges"]] = static[0].data_ptr(), static[1].data_ptr(), static[2]
+            if len(static) > 3 and static[3] is not None:
+                A[:, c["tet_edge_rank"]] = static[3].data_ptr()
             self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
         self.static = static
         self.A = A

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 410 /* 0.4.1 */
+#define D3H_VERSION 420 /* 0.4.2 */
 
 enum {
   D3H_OK = 0,
@@ -138,6 +138,11 @@ typedef struct d3h_forward_args {
   float* pair_vacc;        /* (cap_verts,8) accumulator of the second extraction's scatter-form adjoint (with edge_off) */
   d3h_counts* pair_counts_host; /* sizes of the second extraction (n_faces_aug, bucket_polys differ), pinned like counts_host */
   int64_t pair_seq;
+  /* optional companion of the static edge table (EXPERIMENTAL, opt-in): rank in edge_ab of the 6 edges of every tet,
+   * (F,8) int32 rows (edges in the order of gshell_tets.py:187, 2 words of padding), 16-byte aligned.  With it the
+   * compaction kernel reads the ranks of a valid tet's edges instead of bisecting the neighbour lists (32 B per valid
+   * tet instead of ~5 dependent loads per corner); costs 32 B per tet of device memory.  NULL: bisect. */
+  const int32_t* tet_edge_rank;
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */

@@ -52,5 +52,11 @@ for name, fn in variants.items():
         torch.cuda.synchronize()
         print(f"{name:12s} {'fwd+bwd' if bwd else 'fwd    '} {(time.perf_counter() - t0) / 200 * 1e6:8.1f} us")
 PY
+echo "== per-tet edge-rank table variant (compact_kernel<3>) vs bisection: single-lane trace and bench"
+for v in 0 1; do
+  echo "-- D3H_TET_EDGE_RANKS=$v"
+  D3H_TET_EDGE_RANKS=$v timeout 120 python profiles/graph_trace.py --frames 4 --lanes 1 | tail -1
+  D3H_TET_EDGE_RANKS=$v timeout 200 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value']/1e9)"
+done
 echo "== device trace, 16 frames on 8 lanes"
 timeout 120 python profiles/graph_trace.py --frames 16 --lanes 8 | grep "^#" | grep -v "per frame"

@@ -279,3 +279,20 @@ def test_fuzz_forward_against_oracle(dev):
         if wt:
             U.assert_exact(f"faces_watertight[{case}]", out[5]["faces_watertight"].numpy(), fwd["faces_watertight"])
             U.assert_exact(f"vertices_watertight[{case}]", out[5]["vertices_watertight"].numpy(), fwd["vertices_watertight"])
+
+
+def test_tet_edge_rank_table_variant(dev, edges_mode):
+    """EXPERIMENTAL D3H_TET_EDGE_RANKS: the compaction kernel reads the edge ranks of a valid tet from a per-tet table
+    instead of bisecting the neighbour lists -- same results."""
+    if edges_mode != "static":
+        pytest.skip("variant of the static edge table path")
+    E.set_tet_edge_ranks(True)
+    try:
+        G.test_cuda_matches_oracle(dev, 12, "adv", "GShell_Tets", None, True)
+        G.test_cuda_matches_oracle(dev, 16, "capsule", "hmSDF_Tets", "body", True)
+        G.test_extract_frames_batch_matches_oracle_per_frame(dev)
+        test_random_tet_soups(dev, 3, 12, 6000)
+        plan_keys = list(E._static_cache.values())
+        assert plan_keys and all(ent[1] is None or ent[1][3] is not None for ent in plan_keys)   # the table was really used
+    finally:
+        E.set_tet_edge_ranks(False)

@@ -107,7 +107,18 @@ def test_build_edge_table_on_cpu_matches_numpy():
     from d3human_code_b200 import grids
     pos, tets = grids.kuhn_grid(6)
     n = pos.shape[0]
-    off, ab, u = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    off, ab, u, tet_rank = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    assert tet_rank is None
+    E.set_tet_edge_ranks(True)
+    try:
+        _, _, _, tet_rank = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    finally:
+        E.set_tet_edge_ranks(False)
+    assert tet_rank.shape == (tets.shape[0], 8) and tet_rank.dtype == torch.int32
+    pairs = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+    for e, (i, j) in enumerate(pairs):     # the rank of every tet edge points back at its endpoints
+        got = ab.numpy()[tet_rank.numpy()[:, e]]
+        assert np.array_equal(got[:, 0], np.minimum(tets[:, i], tets[:, j])) and np.array_equal(got[:, 1], np.maximum(tets[:, i], tets[:, j]))
     ea = np.minimum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
     eb = np.maximum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
     uk = np.unique(ea * n + eb)
