@@ -173,15 +173,23 @@ def main():
 
     import torch
     import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # D3H_BENCH_DEVICE=cpu is a TEST hook (tests/test_emu_bench.py): a control-flow dry run of this script on CPU tensors,
+    # gloo and the emulated kernels of tests/emu -- it exists to catch collective mismatches between ranks without a GPU;
+    # the product has no CPU path and the numbers of such a run mean nothing.
+    dev_type = os.environ.get("D3H_BENCH_DEVICE", "cuda")
+    if dev_type == "cuda":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU path)")
+        torch.cuda.set_device(local_rank)
+    dev = torch.device(dev_type, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         # a mismatched collective should fail within minutes, not hold the box for the default 10
-        dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
+        if dev_type == "cuda":
+            dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
+        else:
+            dist.init_process_group(backend="gloo", timeout=datetime.timedelta(seconds=120))
     from d3human_code_b200 import _cabi, grids
     from d3human_code_b200 import extract as E
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
@@ -300,7 +308,7 @@ def main():
     if rank == 0:
         try:
             _cabi.trace_enable(True)
-            plan = E._plan_for(dev, F, N)
+            plan = E._plan_for(pos.device, F, N)
             seq0 = plan.seq
             local_step()          # rank 0 only: must not contain a collective
             torch.cuda.synchronize()
@@ -421,7 +429,7 @@ def main():
     if prof:
         kern = {k: {"ms_total": round(v[0], 4), "launches": v[1], "us_avg": round(1e3 * v[0] / v[1], 3)} for k, v in prof.items()}
         ms, n = prof.get("classify", (0.0, 0))
-        if n:
+        if n and ms > 0:
             t = ms / n * 1e-3
             achieved = 16.0 * F / t / 1e9
             traffic = None

@@ -1,0 +1,92 @@
+"""Control-flow dry run of bench.py on CPU: two gloo ranks, CPU tensors, the emulated kernels (tests/emu), tiny grid.
+Round 1 lost 120 GPU-minutes to a collective that only rank 0 entered; this test runs the same script, same argument
+parsing, same step / timing / diagnostics / end-to-end legs on two ranks and fails fast if a rank is left waiting.  The
+numbers it prints mean nothing."""
+import contextlib
+import io
+import json
+import os
+import socket
+import sys
+import time
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+
+def _worker(rank, world, port, out_dir, argv):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), D3H_BENCH_DEVICE="cpu")
+    sys.path.insert(0, ROOT)
+    from tests.test_emu_multirank import _patch_for_cpu
+    _patch_for_cpu()
+    torch.cuda.current_stream = lambda dev=None: _Stream()
+    torch.cuda.Event = _Event
+    torch.cuda.Stream = _Stream
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.synchronize = lambda dev=None: None
+    import bench
+    sys.argv = ["bench.py"] + argv
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.main()
+    with open(os.path.join(out_dir, f"out_{rank}.txt"), "w") as fh:
+        fh.write(buf.getvalue())
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_control_flow(tmp_path, world):
+    import torch.multiprocessing as mp
+    argv = ["--gpus", str(world), "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "4", "--groups", "2",
+            "--lanes", "2", "--profile-steps", "1", "--e2e-chunk", "2", "--no-cpu-baseline"]
+    ctx = mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), argv), nprocs=world, join=False,
+                             start_method="spawn")
+    deadline = time.time() + 240
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                p.terminate()
+            pytest.fail("bench.py did not finish: a rank is waiting in a collective the others never entered")
+    line = [l for l in open(tmp_path / "out_0.txt") if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["n_gpus"] == world and d["steps"] == 2 and d["unit"] == "tets/s" and d["higher_is_better"] is True
+    assert d["config"]["frames_per_step"] == 4 * world and d["config"]["groups"] == 2
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"] is not None and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["device_trace"] is not None and "error" not in d["device_trace"]
+    for r in range(1, world):                    # only rank 0 prints
+        assert not [l for l in open(tmp_path / f"out_{r}.txt") if l.startswith("{")]
