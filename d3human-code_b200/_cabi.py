@@ -1,4 +1,4 @@
-"""ctypes binding of libd3h_tets.so (C ABI declared in include/d3h_tets.h).
+"""ctypes binding of libd3h_tets.so (C ABI declared in include/d3h_tets.h and include/d3h_mesh.h).
 
 The library is the product: there is no Python / PyTorch fallback.  If it is missing or fails to load, every
 entry point raises.  PyTorch is only used by the callers for device memory and streams.
@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 420
+VERSION = 430
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -20,6 +20,8 @@ EXPORTED_SYMBOLS = (
     "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
     "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_classify_range", "d3h_extract_from_records",
+    "d3h_mesh_edges_workspace_bytes", "d3h_mesh_edges", "d3h_mesh_wait_counts", "d3h_mesh_normals_forward",
+    "d3h_mesh_normals_backward",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
 )
 
@@ -114,6 +116,20 @@ def lib() -> C.CDLL:
     L.d3h_classify_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_from_records.restype = C.c_int
     L.d3h_extract_from_records.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    # include/d3h_mesh.h
+    L.d3h_mesh_edges_workspace_bytes.restype = C.c_int64
+    L.d3h_mesh_edges_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    L.d3h_mesh_edges.restype = C.c_int
+    L.d3h_mesh_edges.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.d3h_mesh_wait_counts.restype = C.c_int
+    L.d3h_mesh_wait_counts.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.d3h_mesh_normals_forward.restype = C.c_int
+    L.d3h_mesh_normals_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+    L.d3h_mesh_normals_backward.restype = C.c_int
+    L.d3h_mesh_normals_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]
     L.d3h_profile_enable.restype = C.c_int
     L.d3h_profile_enable.argtypes = [C.c_int]
     L.d3h_profile_kinds.restype = C.c_int

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 420 /* 0.4.2 */
+#define D3H_VERSION 430 /* 0.4.3 */
 
 enum {
   D3H_OK = 0,

@@ -34,3 +34,24 @@ def load_reference_class(which: str = "GShell_Tets", device: str = "cpu"):
     mod = types.ModuleType("_d3h_ref_" + which)
     exec(compile(src, rel, "exec"), mod.__dict__)
     return getattr(mod, which)()
+
+
+def load_reference_mesh(device: str = "cpu"):
+    """-> the reference's `render/mesh.py` as a module living on `device` (Mesh :139, auto_normals :418).
+
+    `render/mesh.py:14-15` imports `obj` -> `material` -> `mlptexture`, which needs tinycudann (render/mlptexture.py:11);
+    none of it is used by Mesh / auto_normals, so the import is stubbed like nvdiffrast above."""
+    for name in ("nvdiffrast", "nvdiffrast.torch", "imageio", "tinycudann"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["nvdiffrast"].torch = sys.modules["nvdiffrast.torch"]
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    rel = "render/mesh.py"
+    with open(os.path.join(REF_ROOT, rel)) as fh:
+        src = fh.read()
+    if device != "cuda":
+        src = src.replace("device='cuda'", f"device='{device}'").replace('device="cuda"', f'device="{device}"')
+    mod = types.ModuleType("_d3h_ref_mesh")
+    mod.__package__ = "render"
+    exec(compile(src, rel, "exec"), mod.__dict__)
+    return mod

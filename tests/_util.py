@@ -17,7 +17,13 @@ TNG_CUDA_P99 = 1e-4
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """extraction fixtures (oracle/make_golden.py); the mesh_* files belong to oracle/make_golden_mesh.py"""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if not n.startswith("mesh_")]
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN_DIR, name + ".npz")
 
 
 def load_golden(name):

@@ -8,12 +8,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "d3human-code_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libd3h_tets_emu.so")
-SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_surface.cu", "d3h_backward.cu"]
+SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu"]
 
 
 def build(force=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu_core.cpp")]
-    deps.append(os.path.join(ROOT, "include", "d3h_tets.h"))
+    deps += [os.path.join(ROOT, "include", h) for h in ("d3h_tets.h", "d3h_mesh.h")]
     if not force and os.path.isfile(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

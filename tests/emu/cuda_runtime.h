@@ -176,6 +176,12 @@ static inline float4 atomicAdd(float4* p, float4 v) {
   return o;
 }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+static inline unsigned atomicSub(unsigned* p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+  unsigned long long o = *p;
+  if (o == cmp) *p = v;
+  return o;
+}
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
   unsigned long long o = *p;
   if (v > o) *p = v;
@@ -242,6 +248,7 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, con
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)malloc(n); return *p ? cudaSuccess : 2; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 

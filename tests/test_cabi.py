@@ -1,4 +1,4 @@
-"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/d3h_tets.h declares,
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/d3h_tets.h and include/d3h_mesh.h declare,
 validates arguments without touching a GPU, and carries the reference's case tables."""
 import ctypes as C
 import os
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "d3h_tets.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("d3h_tets.h", "d3h_mesh.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(d3h_[a-z0-9_]+)\s*\(", text)))
 

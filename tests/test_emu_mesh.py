@@ -1,0 +1,70 @@
+"""tests/test_zz_mesh.py (the `-m gpu` parity tests of the mesh stage) run on the CPU against the functional emulation
+of the CUDA kernels (tests/emu/): checks the LOGIC of csrc/d3h_mesh.cu and the host path through the real C ABI.  Races,
+memory ordering and speed are what the GPU runs are for.  Test infrastructure only."""
+import contextlib
+
+import pytest
+import torch
+
+from d3human_code_b200 import _cabi
+from d3human_code_b200 import extract as E
+from d3human_code_b200.render import mesh as M
+from tests import test_zz_mesh as Z
+from tests.test_emu_parity import _Stream, _packed_cache, _packed_tets_cpu, build_emu
+
+
+@pytest.fixture(scope="module")
+def emu_lib_path():
+    return build_emu.build()
+
+
+@pytest.fixture
+def dev(emu_lib_path, monkeypatch):
+    monkeypatch.setattr(_cabi, "LIB_PATH", emu_lib_path)
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(M, "_check_cuda", lambda t: None)
+    monkeypatch.setattr(E, "_check_cuda", lambda t: None)
+    monkeypatch.setattr(E, "packed_tets", _packed_tets_cpu)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "device", lambda dev=None: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    orig_ensure = E._Plan.ensure
+
+    def ensure(self, lanes, n_edges=0):       # CPU allocations are 64-byte aligned, the ABI wants 256 for the workspace
+        orig_ensure(self, lanes, n_edges)
+        for i, w in enumerate(self.workspaces):
+            if w.data_ptr() % 256:
+                big = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8)
+                off = (-big.data_ptr()) % 256
+                self.workspaces[i] = big[off:off + self.workspace_bytes]
+                self.workspace_ptrs[i] = self.workspaces[i].data_ptr()
+
+    monkeypatch.setattr(E._Plan, "ensure", ensure)
+    E.reset_plans()
+    M.reset()
+    _packed_cache.clear()
+    yield torch.device("cpu")
+    E.reset_plans()
+    M.reset()
+
+
+@pytest.mark.parametrize("name", Z.CASES)
+def test_golden(dev, name):
+    Z.test_mesh_matches_golden(dev, name)
+
+
+@pytest.mark.parametrize("n,seed", [(9, 0), (40, 1), (80, 2)])
+def test_oracle(dev, n, seed):
+    Z.test_mesh_matches_oracle(dev, n, seed)
+
+
+def test_hub(dev):
+    Z.test_hub_vertex_with_many_neighbours(dev)
+
+
+def test_drop_in(dev):
+    Z.test_drop_in_semantics(dev)
+
+
+def test_on_extraction_output(dev):
+    Z.test_mesh_on_extraction_output(dev)
