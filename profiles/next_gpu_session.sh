@@ -52,6 +52,8 @@ for name, fn in variants.items():
         torch.cuda.synchronize()
         print(f"{name:12s} {'fwd+bwd' if bwd else 'fwd    '} {(time.perf_counter() - t0) / 200 * 1e6:8.1f} us")
 PY
+echo "== mesh stage (8f row 2): Mesh.edges / auto_normals vs the same torch ops"
+timeout 200 python profiles/mesh_bench.py 2>&1 | tail -1
 echo "== per-tet edge-rank table variant (compact_kernel<3>) vs bisection: single-lane trace and bench"
 for v in 0 1; do
   echo "-- D3H_TET_EDGE_RANKS=$v"
