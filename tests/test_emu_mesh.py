@@ -68,3 +68,8 @@ def test_drop_in(dev):
 
 def test_on_extraction_output(dev):
     Z.test_mesh_on_extraction_output(dev)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_soups(dev, seed):
+    Z.test_random_triangle_soups(dev, seed)

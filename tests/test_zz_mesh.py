@@ -23,7 +23,8 @@ pytestmark = pytest.mark.gpu
 
 NRM_ATOL = 2e-6
 NRM_COND = 4e-7
-COND_MAX = 1e4
+COND_MAX = 1e4        # above: the face normals of the vertex cancel, no stable normal
+GRAD_COND_MAX = 1e3   # gradients are compared on meshes whose worst vertex is below this (the adjoint carries 1 / |sum|)
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +68,7 @@ def _check(out, edges, v_nrm, cond, g_pos=None, what=""):
     _check_normals(out["v_nrm"], v_nrm, cond, what)
     if g_pos is not None:
         assert np.isfinite(out["g_pos"]).all(), what
-        if cond.max() < COND_MAX:
+        if cond.max() < GRAD_COND_MAX:
             U.assert_close_normwise(what + " g_pos", out["g_pos"], g_pos, U.GRAD_RTOL)
 
 
@@ -235,3 +236,24 @@ def test_full_size_properties(dev):
     assert bool((ko[1:] > ko[:-1]).all())
     fe = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]).sort(dim=1).values
     assert torch.equal(torch.unique(fe[:, 0] * verts.shape[0] + fe[:, 1]), ko)   # same set as a plain sort + unique
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_triangle_soups(dev, seed):
+    """Seeded soups: repeated faces and edges, degenerate faces, isolated vertices, dense graphs (every pair of a small
+    vertex set is an edge: long hash probes, long neighbour segments)."""
+    rng = np.random.default_rng(100 + seed)
+    nv = int(rng.integers(3, 400))
+    nf = int(rng.integers(1, 6000 if seed % 3 == 0 else 300))
+    pos = rng.standard_normal((nv + int(rng.integers(0, 50)), 3)).astype(np.float32)
+    faces = rng.integers(0, nv, size=(nf, 3)).astype(np.int64)
+    if nf > 4:
+        faces[1] = faces[0]
+        faces[2] = faces[0][::-1]
+        faces[3, 2] = faces[3, 0]
+    g = rng.standard_normal(pos.shape).astype(np.float32)
+    out = _run(dev, pos, faces, g)
+    cond = MO.normal_condition(pos, faces)
+    stable_mesh = cond.max() < GRAD_COND_MAX
+    _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), cond,
+           MO.auto_normals_backward(pos, faces, g) if stable_mesh else None, f"soup{seed}")
