@@ -1,0 +1,71 @@
+"""BASELINE.json configs[4] at its full size on one GPU: 256^3 Kuhn lattice (F = 100,663,296 tets, N = 16,974,593
+vertices), sphere + plane field, the tet array classified in 8 contiguous ranges (d3h_classify_range), the records
+concatenated in range order and the surface stages run on the merged list (d3h_extract_from_records) -- against the
+single call and against the numpy oracle (which finishes this size in about a second after 4 s of grid construction).
+Integer outputs, positions and mSDF values bit-exact, gradients 1e-5 normwise.  The real multi-rank version of the same
+code path is tests/test_multi_gpu.py; the collective there (all-gather of the records) does not change the data.
+
+Sorts last: written when no GPU was available; the code path is validated at small sizes on the GPU
+(test_cuda_parity.py) and on the kernel emulation, this size had never been run anywhere.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gshell_oracle as O
+from d3human_code_b200 import grids
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+# sizes of the oracle's result for this configuration (oracle/gshell_oracle.py, run in the build container)
+EXPECTED = dict(n_valid_tets=507744, n_verts=332462, n_faces_watertight=664920, n_verts_aug=2012870, n_faces_aug=387972)
+
+
+def test_config5_256_cubed_eight_tet_shards():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    dev = torch.device("cuda:0")
+    import psutil
+    if psutil.virtual_memory().available < 24 << 30:
+        pytest.skip("needs 24 GB of host memory for the 256^3 lattice and the oracle")
+    if torch.cuda.mem_get_info(dev)[0] < 24 << 30:
+        pytest.skip("needs 24 GB of free device memory")
+    from d3human_code_b200 import extract as E
+    from d3human_code_b200.sharding import extract_tet_sharded
+    pos, tets = grids.kuhn_grid(256, dtype=np.int32)
+    sdf, msdf = grids.sphere_plane_field(pos)
+    fwd = O.extract_forward(pos, sdf, msdf, tets, n_threads=8)
+    assert fwd["valid_ids"].shape[0] == EXPECTED["n_valid_tets"] and fwd["n_verts_watertight"] == EXPECTED["n_verts"]
+    assert fwd["faces_watertight"].shape[0] == EXPECTED["n_faces_watertight"] == 2 * EXPECTED["n_verts"] - 4  # closed, genus 0
+    assert fwd["verts_aug"].shape[0] == EXPECTED["n_verts_aug"] and fwd["faces_aug"].shape[0] == EXPECTED["n_faces_aug"]
+
+    E.set_static_edges("0")        # the per-call sort path: no 600 M-row edge table for a one-off grid
+    try:
+        tt = torch.tensor(tets, device=dev)
+        outs = []
+        for fn in (lambda *a: E.extract(*a), lambda *a: extract_tet_sharded(*a, virtual_ranks=8)):
+            tp = torch.tensor(pos, device=dev, requires_grad=True)
+            ts = torch.tensor(sdf, device=dev, requires_grad=True)
+            tm = torch.tensor(msdf, device=dev, requires_grad=True)
+            verts, faces, _, _, v_tng, extra = fn(tp, ts, tm, tt)
+            (verts.square().sum() + extra["msdf"].sum()).backward()
+            outs.append(dict(verts_aug=verts.detach(), faces_aug=faces, msdf=extra["msdf"].detach(),
+                             faces_watertight=extra["faces_watertight"],
+                             vertices_watertight=extra["vertices_watertight"].detach(),
+                             msdf_watertight=extra["msdf_watertight"].detach(),
+                             g_pos=tp.grad, g_sdf=ts.grad, g_msdf=tm.grad))
+        single, sharded = outs
+        for k in ("verts_aug", "faces_aug", "msdf", "faces_watertight", "vertices_watertight", "msdf_watertight"):
+            assert torch.equal(single[k], sharded[k]), k                      # 8 shards == one call, bit for bit
+            U.assert_exact(k, sharded[k].cpu().numpy(), fwd[k])               # == the oracle, bit for bit
+        g_verts = (2.0 * fwd["verts_aug"].astype(np.float64)).astype(np.float32)
+        g_pos, g_sdf, g_m = O.extract_backward(fwd, g_verts_aug=g_verts, g_msdf=np.ones_like(fwd["msdf"]))
+        for name, out in (("single", single), ("sharded", sharded)):
+            U.assert_close_normwise(name + " g_pos", out["g_pos"].cpu().numpy(), g_pos, U.GRAD_RTOL)
+            U.assert_close_normwise(name + " g_sdf", out["g_sdf"].cpu().numpy().reshape(-1), g_sdf, U.GRAD_RTOL)
+            U.assert_close_normwise(name + " g_msdf", out["g_msdf"].cpu().numpy(), g_m, U.GRAD_RTOL)
+    finally:
+        E.set_static_edges("auto")
+        E.reset_plans()
+        torch.cuda.empty_cache()
