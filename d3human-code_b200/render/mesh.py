@@ -13,10 +13,14 @@ Differences by design, results being the reference's:
     constructor is never run.  Meshes that share one faces tensor share one edge list (cache on data_ptr / version).
   * a face index outside [0, V) raises IndexError when the edges are read (the reference would return the edge).
   * normals are computed in fp32 whatever the dtype of v_pos and cast back.
+  * two `auto_normals` calls on the same (v_pos, t_pos_idx) tensor objects return the SAME normals tensor while the
+    first result is alive (hmsdf.py:558-561 and :589-593 do exactly that every iteration); D3H_MESH_SHARE_NORMALS=0
+    turns it off for callers that modify normals in place.
 The rest of the reference module (OBJ loading, AABB helpers, tangent space, Laplacian) is outside this row.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Dict, Tuple
 
@@ -84,6 +88,7 @@ def reset() -> None:
     """Drop cached workspaces and edge lists (tests)."""
     _states.clear()
     _edge_cache.clear()
+    del _normals_memo[:]
 
 
 # ---- edges --------------------------------------------------------------------------------------------------------
@@ -238,6 +243,24 @@ class _AutoNormalsFn(torch.autograd.Function):
         return g_pos.to(ctx.in_dtype), None
 
 
+# `getMesh_split` runs auto_normals twice on the very same (verts, faces) pair (hmsdf.py:558-561 and :589-593).  The
+# result of the last few calls is remembered through weak references: a second call with the same two tensor objects
+# (unchanged versions, same grad mode) returns the same normals tensor while somebody still holds it.
+_normals_memo: list = []
+_NORMALS_MEMO = 4
+share_normals = os.environ.get("D3H_MESH_SHARE_NORMALS", "1") != "0"
+
+
+def _memo_lookup(v_pos, faces, needs_grad):
+    for ent in _normals_memo:
+        rp, vp, rf, vf, ro, vo = ent
+        out = ro()
+        if (out is not None and rp() is v_pos and rf() is faces and vp == v_pos._version and vf == faces._version
+                and vo == out._version and out.requires_grad == needs_grad):
+            return out
+    return None
+
+
 def vertex_normals(v_pos: torch.Tensor, t_pos_idx: torch.Tensor) -> torch.Tensor:
     """(V,3) positions, (F,3) faces -> (V,3) unit normals (render/mesh.py:420-441); differentiable w.r.t. v_pos."""
     _check_cuda(v_pos)
@@ -246,7 +269,16 @@ def vertex_normals(v_pos: torch.Tensor, t_pos_idx: torch.Tensor) -> torch.Tensor
         raise ValueError(f"v_pos must have shape (V,3), got {tuple(v_pos.shape)}")
     if t_pos_idx.dim() != 2 or t_pos_idx.shape[1] != 3:
         raise ValueError(f"t_pos_idx must have shape (F,3), got {tuple(t_pos_idx.shape)}")
-    return _AutoNormalsFn.apply(v_pos, t_pos_idx)
+    if not share_normals:
+        return _AutoNormalsFn.apply(v_pos, t_pos_idx)
+    needs_grad = torch.is_grad_enabled() and v_pos.requires_grad
+    out = _memo_lookup(v_pos, t_pos_idx, needs_grad)
+    if out is None:
+        out = _AutoNormalsFn.apply(v_pos, t_pos_idx)
+        _normals_memo.insert(0, (weakref.ref(v_pos), v_pos._version, weakref.ref(t_pos_idx), t_pos_idx._version,
+                                 weakref.ref(out), out._version))
+        del _normals_memo[_NORMALS_MEMO:]
+    return out
 
 
 def auto_normals(imesh: Mesh) -> Mesh:

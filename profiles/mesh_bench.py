@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--reps", type=int, default=200)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    mesh.share_normals = False      # time the kernels, not the memo of repeated calls
     pos, tets = grids.kuhn_grid(args.res)
     sdf, msdf = grids.capsule_garment_field(pos)
     verts, faces, _, _, _, extra = hmSDF_Tets()(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev),

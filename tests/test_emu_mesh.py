@@ -66,6 +66,10 @@ def test_drop_in(dev):
     Z.test_drop_in_semantics(dev)
 
 
+def test_shared_normals(dev):
+    Z.test_repeated_auto_normals_share_one_result(dev)
+
+
 def test_on_extraction_output(dev):
     Z.test_mesh_on_extraction_output(dev)
 

@@ -166,6 +166,31 @@ def test_drop_in_semantics(dev):
     assert p64.grad.dtype == torch.float64 and bool(torch.isfinite(p64.grad).all())
 
 
+def test_repeated_auto_normals_share_one_result(dev):
+    """hmsdf.py:558-561 / :589-593: the same (verts, faces) goes through auto_normals twice per iteration."""
+    mesh = _mesh()
+    pos, faces = _height_field(10, 4)
+    p = torch.tensor(pos, device=dev, requires_grad=True)
+    f = torch.tensor(faces, device=dev)
+    before = mesh.launch_counter()
+    a = mesh.auto_normals(mesh.Mesh(p, f))
+    mid = mesh.launch_counter()
+    b = mesh.auto_normals(mesh.Mesh(p, f, material="m"))
+    assert b.v_nrm is a.v_nrm and mesh.launch_counter() == mid > before
+    with torch.no_grad():
+        c = mesh.auto_normals(mesh.Mesh(p, f))
+    assert c.v_nrm is not a.v_nrm and not c.v_nrm.requires_grad and torch.equal(c.v_nrm, a.v_nrm)
+    (a.v_nrm.sum() + 2.0 * b.v_nrm.sum()).backward()                   # both users' gradients arrive
+    want = MO.auto_normals_backward(pos, faces, np.full(pos.shape, 3.0, np.float32))
+    U.assert_close_normwise("g_pos", p.grad.cpu().numpy(), want, U.GRAD_RTOL)
+    d = mesh.auto_normals(mesh.Mesh(p.detach().clone().requires_grad_(True), f))
+    assert d.v_nrm is not a.v_nrm                                       # another positions tensor: computed again
+    with torch.no_grad():
+        p.mul_(1.5)                                                     # in-place change of the positions: stale entry
+    e = mesh.auto_normals(mesh.Mesh(p, f))
+    assert e.v_nrm is not a.v_nrm
+
+
 def test_mesh_on_extraction_output(dev):
     """The call sequence of hmsdf.py:548-593: extraction -> Mesh -> auto_normals, gradient back to the grid."""
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
