@@ -36,6 +36,10 @@ class Counts(C.Structure):  # d3h_counts
 COUNTS_WORDS = C.sizeof(Counts) // 8  # int64 words
 
 
+class MeshCounts(C.Structure):  # d3h_mesh_counts (include/d3h_mesh.h)
+    _fields_ = [("n_edges", C.c_int64), ("bad_index", C.c_int64), ("overflow", C.c_int64), ("seq", C.c_int64)]
+
+
 class ForwardArgs(C.Structure):  # d3h_forward_args
     _fields_ = [("pos", C.c_void_p), ("sdf", C.c_void_p), ("msdf", C.c_void_p), ("tets", C.c_void_p),
                 ("n_grid", C.c_int64), ("n_tets", C.c_int64), ("tet_begin", C.c_int64), ("tet_end", C.c_int64),

@@ -31,8 +31,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header(tmp_path):
     """sizeof / offsetof of every struct member as gcc sees include/d3h_tets.h == the ctypes mirrors in _cabi.py."""
     import subprocess
-    structs = {"d3h_counts": _cabi.Counts, "d3h_forward_args": _cabi.ForwardArgs, "d3h_backward_args": _cabi.BackwardArgs}
-    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "d3h_tets.h")}"',
+    structs = {"d3h_counts": _cabi.Counts, "d3h_forward_args": _cabi.ForwardArgs, "d3h_backward_args": _cabi.BackwardArgs,
+               "d3h_mesh_counts": _cabi.MeshCounts}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "d3h_mesh.h")}"',
              'int main(void) {']
     for cname, st in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
@@ -50,6 +51,23 @@ def test_struct_layouts_match_header(tmp_path):
             assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
     assert int(got["d3h_tet_record"]) == _cabi.TET_RECORD_BYTES
     assert C.sizeof(_cabi.Counts) == 16 * 8      # one 128-byte slot per frame in the pinned counts buffer
+
+
+def test_mesh_entry_points_validate_arguments():
+    lib = _cabi.lib()
+    a = lib.d3h_mesh_edges_workspace_bytes(100_000, 300_000)
+    b = lib.d3h_mesh_edges_workspace_bytes(200_000, 300_000)
+    assert 0 < a < b and a % 256 == 0
+    assert lib.d3h_mesh_edges_workspace_bytes(-1, 10) == _cabi.D3H_E_BADARG
+    assert lib.d3h_mesh_edges_workspace_bytes(1 << 30, 10) == _cabi.D3H_E_BADARG          # 3F must stay below 2^31
+    assert lib.d3h_mesh_edges(None, 10, 10, None, 30, None, 0, None, None, 1, None) == _cabi.D3H_E_BADARG
+    assert b"null" in lib.d3h_last_error_string()
+    assert lib.d3h_mesh_wait_counts(None, 1, 10) == _cabi.D3H_E_BADARG
+    assert lib.d3h_mesh_normals_forward(None, None, 10, 10, None, None, None, None) == _cabi.D3H_E_BADARG
+    assert lib.d3h_mesh_normals_backward(None, None, -1, 0, None, None, None, None) == _cabi.D3H_E_BADARG
+    slot = _cabi.MeshCounts(5, 0, 0, 7)                                                   # host-only: the spin wait
+    assert lib.d3h_mesh_wait_counts(C.byref(slot), 7, 1000) == 0
+    assert lib.d3h_mesh_wait_counts(C.byref(slot), 8, 2000) == _cabi.D3H_E_TIMEOUT
 
 
 def test_workspace_bytes_contract():
