@@ -225,9 +225,11 @@ def test_mesh_on_extraction_output(dev):
     U.assert_close_normwise("g_msdf", tm.grad.cpu().numpy(), g_m, U.GRAD_RTOL)
 
 
-def test_full_size_properties(dev):
-    """128^3 sphere (BASELINE.json configs[1] size): the watertight surface is a closed 2-manifold of genus 0, so
-    E = 3F/2 and V - E + F = 2; normals are unit length and point along -grad(sdf) = the radial direction."""
+def test_full_size_128(dev):
+    """128^3 sphere (BASELINE.json configs[1] size).  The watertight surface is a closed 2-manifold of genus 0, so
+    E = 3F/2 and V - E + F = 2; edge lists and normals of the watertight and of the open surface equal the oracle's.
+    (The Kuhn lattice mixes left- and right-handed tets, so the reference's triangle table orients neighbouring faces
+    inconsistently and thousands of vertex normals nearly cancel: the comparison is condition-aware, see the header.)"""
     if dev.type != "cuda":
         pytest.skip("full size: GPU only")
     from d3human_code_b200.geometry.gshell_tets import GShell_Tets
@@ -236,49 +238,27 @@ def test_full_size_properties(dev):
     sdf, msdf = grids.sphere_plane_field(pos)
     verts, faces, _, _, _, extra = GShell_Tets()(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev),
                                                  torch.tensor(msdf, device=dev), torch.tensor(tets, device=dev))
+    fwd = O.extract_forward(pos, sdf, msdf, tets, n_threads=8)
     wt = mesh.Mesh(extra["vertices_watertight"], extra["faces_watertight"])
     V, F, E = wt.v_pos.shape[0], wt.t_pos_idx.shape[0], wt.edges.shape[0]
+    assert (V, F) == (83222, 166440)                                    # SURVEY 8(a) [probe]
     assert 2 * E == 3 * F and V - E + F == 2
     e = wt.edges
     assert bool((e[:, 0] < e[:, 1]).all())
     key = e[:, 0] * V + e[:, 1]
     assert bool((key[1:] > key[:-1]).all())                             # strictly ascending lexicographic order
-    nrm = mesh.auto_normals(wt).v_nrm
-    assert float((nrm.norm(dim=1) - 1).abs().max()) < 1e-5
-    radial = torch.nn.functional.normalize(wt.v_pos, dim=1)
-    assert float((nrm * radial).sum(1).abs().min()) > 0.9
-    s = torch.sign((nrm * radial).sum(1))
-    assert bool((s == s[0]).all())                                      # consistent orientation
+    assert np.array_equal(e.cpu().numpy(), MO.mesh_edges(fwd["faces_watertight"]))
+    _check_normals(mesh.auto_normals(wt).v_nrm.cpu().numpy(),
+                   MO.auto_normals(fwd["vertices_watertight"], fwd["faces_watertight"]),
+                   MO.normal_condition(fwd["vertices_watertight"], fwd["faces_watertight"]), "watertight 128")
     open_mesh = mesh.Mesh(verts, faces)                                 # open surface cut by the mSDF: most rows unused
     n_open = mesh.auto_normals(open_mesh).v_nrm
     used = torch.zeros(verts.shape[0], dtype=torch.bool, device=dev)
     used[faces.reshape(-1)] = True
     assert bool((n_open[~used] == torch.tensor([0.0, 0.0, 1.0], device=dev)).all())
-    Eo, Fo = open_mesh.edges.shape[0], faces.shape[0]
-    assert 3 * Fo // 2 <= Eo <= 3 * Fo                                  # boundary vertices are per polygon: not a manifold
-    eo = open_mesh.edges
-    ko = eo[:, 0] * verts.shape[0] + eo[:, 1]
-    assert bool((ko[1:] > ko[:-1]).all())
+    assert np.array_equal(open_mesh.edges.cpu().numpy(), MO.mesh_edges(fwd["faces_aug"]))
+    _check_normals(n_open.cpu().numpy(), MO.auto_normals(fwd["verts_aug"], fwd["faces_aug"]),
+                   MO.normal_condition(fwd["verts_aug"], fwd["faces_aug"]), "open 128")
     fe = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]).sort(dim=1).values
+    ko = open_mesh.edges[:, 0] * verts.shape[0] + open_mesh.edges[:, 1]
     assert torch.equal(torch.unique(fe[:, 0] * verts.shape[0] + fe[:, 1]), ko)   # same set as a plain sort + unique
-
-
-@pytest.mark.parametrize("seed", range(12))
-def test_random_triangle_soups(dev, seed):
-    """Seeded soups: repeated faces and edges, degenerate faces, isolated vertices, dense graphs (every pair of a small
-    vertex set is an edge: long hash probes, long neighbour segments)."""
-    rng = np.random.default_rng(100 + seed)
-    nv = int(rng.integers(3, 400))
-    nf = int(rng.integers(1, 6000 if seed % 3 == 0 else 300))
-    pos = rng.standard_normal((nv + int(rng.integers(0, 50)), 3)).astype(np.float32)
-    faces = rng.integers(0, nv, size=(nf, 3)).astype(np.int64)
-    if nf > 4:
-        faces[1] = faces[0]
-        faces[2] = faces[0][::-1]
-        faces[3, 2] = faces[3, 0]
-    g = rng.standard_normal(pos.shape).astype(np.float32)
-    out = _run(dev, pos, faces, g)
-    cond = MO.normal_condition(pos, faces)
-    stable_mesh = cond.max() < GRAD_COND_MAX
-    _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), cond,
-           MO.auto_normals_backward(pos, faces, g) if stable_mesh else None, f"soup{seed}")
