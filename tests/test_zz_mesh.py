@@ -262,3 +262,24 @@ def test_full_size_128(dev):
     fe = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]).sort(dim=1).values
     ko = open_mesh.edges[:, 0] * verts.shape[0] + open_mesh.edges[:, 1]
     assert torch.equal(torch.unique(fe[:, 0] * verts.shape[0] + fe[:, 1]), ko)   # same set as a plain sort + unique
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_triangle_soups(dev, seed):
+    """Seeded soups: repeated faces and edges, degenerate faces, isolated vertices, dense graphs (every pair of a small
+    vertex set is an edge: long hash probes, long neighbour segments)."""
+    rng = np.random.default_rng(100 + seed)
+    nv = int(rng.integers(3, 400))
+    nf = int(rng.integers(1, 6000 if seed % 3 == 0 else 300))
+    pos = rng.standard_normal((nv + int(rng.integers(0, 50)), 3)).astype(np.float32)
+    faces = rng.integers(0, nv, size=(nf, 3)).astype(np.int64)
+    if nf > 4:
+        faces[1] = faces[0]
+        faces[2] = faces[0][::-1]
+        faces[3, 2] = faces[3, 0]
+    g = rng.standard_normal(pos.shape).astype(np.float32)
+    out = _run(dev, pos, faces, g)
+    cond = MO.normal_condition(pos, faces)
+    stable_mesh = cond.max() < GRAD_COND_MAX
+    _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), cond,
+           MO.auto_normals_backward(pos, faces, g) if stable_mesh else None, f"soup{seed}")
