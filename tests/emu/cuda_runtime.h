@@ -58,6 +58,7 @@ void block_barrier();
 // outside the mask) through `out`
 void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32]);
 unsigned long long now_ns();
+void set_shuffle(unsigned long long seed);
 }  // namespace emu
 // the built-in variables are plain globals (references): struct members named gridDim / blockDim keep working
 static emu::Idx& threadIdx = emu::g_threadIdx;

@@ -34,6 +34,23 @@ struct BlockState {
 BlockState B;
 std::vector<char*> g_stacks;
 
+// D3H_EMU_SHUFFLE=<seed>: blocks run in a random order and every scheduler sweep starts at a random thread, in a random
+// direction.  Results must not depend on either (on the GPU both are arbitrary): a shared variable read without the
+// barrier that orders it after its writer, or an assumption that lower block indices ran first, shows up as a parity
+// failure under some seed.  0 / unset = blocks and threads in index order.
+unsigned long long g_rng = 0;
+bool g_shuffle = false, g_shuffle_init = false;
+unsigned rnd(unsigned n) {  // xorshift64*, uniform enough for shuffling
+  g_rng ^= g_rng >> 12; g_rng ^= g_rng << 25; g_rng ^= g_rng >> 27;
+  return (unsigned)(((g_rng * 2685821657736338717ull) >> 33) % (n ? n : 1));
+}
+void init_shuffle() {
+  if (g_shuffle_init) return;
+  g_shuffle_init = true;
+  const char* e = getenv("D3H_EMU_SHUFFLE");
+  if (e && atoll(e) != 0) { g_shuffle = true; g_rng = 0x9E3779B97F4A7C15ull ^ (unsigned long long)atoll(e); }
+}
+
 void fibre_entry() {
   (*B.body)();
   B.f[B.cur].st = kDone;
@@ -77,6 +94,12 @@ void try_complete_collectives(unsigned w) {
   }
 }
 }  // namespace
+
+void set_shuffle(unsigned long long seed) {
+  g_shuffle_init = true;
+  g_shuffle = seed != 0;
+  g_rng = 0x9E3779B97F4A7C15ull ^ seed;
+}
 
 void block_barrier() {
   Fibre& me = B.f[B.cur];
@@ -126,7 +149,10 @@ static void run_block(const std::function<void()>& body, unsigned nthreads) {
   }
   while (B.alive > 0) {
     bool progressed = false;
-    for (unsigned t = 0; t < nthreads; ++t) {
+    const unsigned off = g_shuffle ? rnd(nthreads) : 0u;
+    const bool back = g_shuffle && (rnd(2) == 1u);
+    for (unsigned k = 0; k < nthreads; ++k) {
+      const unsigned t = back ? (off + nthreads - k) % nthreads : (off + k) % nthreads;
       Fibre& f = B.f[t];
       if (f.st == kAtBarrier && f.barrier_gen != B.barrier_gen) f.st = kRunnable;
       if (f.st == kAtCollective) try_complete_collectives(t >> 5);
@@ -148,6 +174,19 @@ void run_grid(dim3 grid, dim3 block, const std::function<void()>& body) {
   if (block.y != 1 || block.z != 1) { fprintf(stderr, "emu: only 1-D blocks are supported\n"); abort(); }
   g_gridDim = Idx{grid.x, grid.y, grid.z};
   g_blockDim = Idx{block.x, block.y, block.z};
+  init_shuffle();
+  if (g_shuffle) {
+    const unsigned long long total = (unsigned long long)grid.x * grid.y * grid.z;
+    std::vector<unsigned> order(total);
+    for (unsigned long long i = 0; i < total; ++i) order[i] = (unsigned)i;
+    for (unsigned long long i = total; i > 1; --i) std::swap(order[i - 1], order[rnd((unsigned)i)]);
+    for (unsigned long long i = 0; i < total; ++i) {
+      const unsigned b = order[i];
+      g_blockIdx = Idx{b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
+      run_block(body, block.x);
+    }
+    return;
+  }
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -157,3 +196,6 @@ void run_grid(dim3 grid, dim3 block, const std::function<void()>& body) {
 }
 
 }  // namespace emu
+
+// tests/test_emu_shuffle.py: switch the shuffled schedule on (seed != 0) or off from Python
+extern "C" void d3h_emu_set_shuffle(unsigned long long seed) { emu::set_shuffle(seed); }

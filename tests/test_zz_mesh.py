@@ -179,7 +179,8 @@ def test_repeated_auto_normals_share_one_result(dev):
     assert b.v_nrm is a.v_nrm and mesh.launch_counter() == mid > before
     with torch.no_grad():
         c = mesh.auto_normals(mesh.Mesh(p, f))
-    assert c.v_nrm is not a.v_nrm and not c.v_nrm.requires_grad and torch.equal(c.v_nrm, a.v_nrm)
+    assert c.v_nrm is not a.v_nrm and not c.v_nrm.requires_grad
+    assert float((c.v_nrm - a.v_nrm.detach()).abs().max()) <= NRM_ATOL          # float atomics: not bit-reproducible run to run
     (a.v_nrm.sum() + 2.0 * b.v_nrm.sum()).backward()                   # both users' gradients arrive
     want = MO.auto_normals_backward(pos, faces, np.full(pos.shape, 3.0, np.float32))
     U.assert_close_normwise("g_pos", p.grad.cpu().numpy(), want, U.GRAD_RTOL)
