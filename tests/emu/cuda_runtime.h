@@ -9,6 +9,9 @@
 // runs until it reaches a block barrier or a warp collective, where it yields to the scheduler; the collective completes
 // when every lane named in its mask has arrived.  There is no real concurrency, so atomics are plain read-modify-writes
 // and memory ordering is sequential: data races and missing fences are NOT detected, performance means nothing.
+// Two things a GPU does are imitated to make order / initialisation bugs visible: __shared__ variables live in one ELF
+// section that is filled with 0xCB before every block (a fresh CTA's shared memory is arbitrary), and the schedule can be
+// shuffled (D3H_EMU_SHUFFLE / d3h_emu_set_shuffle: random block order, random start and direction of every thread sweep).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -25,7 +28,8 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+// every __shared__ variable lands in one ELF section so that the scheduler can poison it before each block runs
+#define __shared__ static __attribute__((section("emu_shared")))
 #define __constant__
 #define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))

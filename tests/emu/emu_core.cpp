@@ -130,7 +130,13 @@ unsigned long long now_ns() {
   return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
 
+extern "C" char __start_emu_shared[] __attribute__((weak));
+extern "C" char __stop_emu_shared[] __attribute__((weak));
+
 static void run_block(const std::function<void()>& body, unsigned nthreads) {
+  // shared memory of a fresh CTA holds arbitrary data on the GPU: never zeros by contract
+  if (__start_emu_shared != nullptr && __stop_emu_shared > __start_emu_shared)
+    memset(__start_emu_shared, 0xCB, (size_t)(__stop_emu_shared - __start_emu_shared));
   if (B.f.size() < nthreads) B.f.resize(nthreads);
   while (g_stacks.size() < nthreads) g_stacks.push_back((char*)malloc(kStack));
   B.n = B.alive = nthreads;

@@ -2,10 +2,13 @@
 starts at a random thread in a random direction (tests/emu/emu_core.cpp, `d3h_emu_set_shuffle`).  On the GPU both orders
 are arbitrary, so results must not depend on them: a shared variable read without the barrier that orders it after its
 writer, a counter consumed before every block has added to it, or a test that expects float atomics to be reproducible
-fails under some seed.  A selection of the emulated parity tests, two seeds each.  Test infrastructure only."""
+fails under some seed.  The second seed also POISONS every `torch.empty` / `torch.empty_like` result (0xCB bytes): on the
+GPU fresh allocations and reused workspaces hold arbitrary data, so nothing may rely on zero-filled scratch or outputs.
+A selection of the emulated parity tests, two seeds each.  Test infrastructure only."""
 import ctypes
 
 import pytest
+import torch
 
 from tests import test_emu_mesh as EM
 from tests import test_emu_parity as EP
@@ -14,11 +17,23 @@ from tests import test_zz_mesh as ZM
 emu_lib_path = EP.emu_lib_path          # module-scoped fixture: builds tests/emu/_build/libd3h_tets_emu.so
 
 
+def _poisoned(fn):
+    def wrapper(*args, **kwargs):
+        t = fn(*args, **kwargs)
+        if t.numel() and t.is_contiguous():
+            t.view(torch.uint8).fill_(0xCB)
+        return t
+    return wrapper
+
+
 @pytest.fixture(params=[11, 12])
-def shuffled(request, emu_lib_path):
+def shuffled(request, emu_lib_path, monkeypatch):
     lib = ctypes.CDLL(emu_lib_path)
     lib.d3h_emu_set_shuffle.argtypes = [ctypes.c_ulonglong]
     lib.d3h_emu_set_shuffle(request.param)
+    if request.param == 12:
+        monkeypatch.setattr(torch, "empty", _poisoned(torch.empty))
+        monkeypatch.setattr(torch, "empty_like", _poisoned(torch.empty_like))
     yield request.param
     lib.d3h_emu_set_shuffle(0)
 
