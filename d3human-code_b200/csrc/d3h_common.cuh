@@ -108,13 +108,22 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 #else
 // tests/emu (functional CPU emulation of the kernels, test infrastructure only): no PTX
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return *p; }
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { *p = v; }
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) { return *p; }
-__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) { *p = v; }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return emu_load_relaxed(p); }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { emu_store_relaxed(p, v); }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) { return emu_load_relaxed(p); }
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) { emu_store_relaxed(p, v); }
 __device__ __forceinline__ int4 ld_stream_int4(const int4* p) { return *p; }
 __device__ __forceinline__ unsigned long long global_timer_ns() { return emu::now_ns(); }
 #endif
+// Several threads may store the SAME value to one address (every corner of a vertex writes the vertex's tangent rows on
+// the static edge path).  A plain store; the race detector of the CPU emulation is told that it is deliberate.
+__device__ __forceinline__ void store_same_value(float* p, float v) {
+#ifdef D3H_CPU_EMU
+  emu_store_relaxed(p, v);
+#else
+  *p = v;
+#endif
+}
 // Diagnostics (d3h_trace_enable): per call and kernel kind, [0] = time block 0 started, [1] = latest block exit.
 constexpr int kTraceFrames = 64;
 constexpr int kTraceKinds = 16;

@@ -391,8 +391,16 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
       // (static edge table path: no owner is known, every corner writes the same value)
       if (k < n && (static_edges || owner[L[k]] == (int32_t)(p0 + k))) {
         const int64_t v = L[k];
-        if (v < cap_verts) { v_tng_wt[3 * v] = T[k].x; v_tng_wt[3 * v + 1] = T[k].y; v_tng_wt[3 * v + 2] = T[k].z; }
-        if (v < cap_verts_aug) { v_tng_aug[3 * v] = T[k].x; v_tng_aug[3 * v + 1] = T[k].y; v_tng_aug[3 * v + 2] = T[k].z; }
+        if (v < cap_verts) {
+          store_same_value(v_tng_wt + 3 * v, T[k].x);
+          store_same_value(v_tng_wt + 3 * v + 1, T[k].y);
+          store_same_value(v_tng_wt + 3 * v + 2, T[k].z);
+        }
+        if (v < cap_verts_aug) {
+          store_same_value(v_tng_aug + 3 * v, T[k].x);
+          store_same_value(v_tng_aug + 3 * v + 1, T[k].y);
+          store_same_value(v_tng_aug + 3 * v + 2, T[k].z);
+        }
       }
     }
     bucket = cut_case(quad, P[0].w, P[1].w, P[2].w, P[3].w, mcase, ncut);

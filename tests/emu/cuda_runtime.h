@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <type_traits>
 
 #define D3H_CPU_EMU 1
 #define __global__
@@ -63,6 +64,8 @@ void block_barrier();
 void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32]);
 unsigned long long now_ns();
 void set_shuffle(unsigned long long seed);
+void warp_sync_release();
+void warp_sync_acquire();
 }  // namespace emu
 // the built-in variables are plain globals (references): struct members named gridDim / blockDim keep working
 static emu::Idx& threadIdx = emu::g_threadIdx;
@@ -76,9 +79,11 @@ static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 static inline void __threadfence_block() {}
 static inline unsigned emu_lane() { return emu::g_threadIdx.x & 31u; }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) {
+static inline void __syncwarp(unsigned mask = 0xffffffffu) {  // rendezvous + memory ordering among the named lanes
   unsigned long long o[32];
+  emu::warp_sync_release();
   emu::warp_exchange(mask, 0, o);
+  emu::warp_sync_acquire();
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
   unsigned long long o[32];
@@ -160,8 +165,9 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
-template <typename T> static inline T __ldcg(const T* p) { return *p; }
-template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline T emu_load_relaxed(const T* p);
+template <typename T> static inline T __ldcg(const T* p) { return emu_load_relaxed(p); }  // L2 loads: may watch atomics
+template <typename T> static inline T __ldcs(const T* p) { return emu_load_relaxed(p); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
@@ -169,17 +175,55 @@ static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 
-// ---- atomics (no concurrency in the emulation: plain read-modify-write) ----------------------------------------------
-template <typename T> static inline T emu_rmw_add(T* p, T v) { T o = *p; *p = o + v; return o; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { return emu_rmw_add(p, v); }
-static inline int atomicAdd(int* p, int v) { return emu_rmw_add(p, v); }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return emu_rmw_add(p, v); }
-static inline float atomicAdd(float* p, float v) { return emu_rmw_add(p, v); }
-static inline float4 atomicAdd(float4* p, float4 v) {
-  float4 o = *p;
-  p->x = o.x + v.x; p->y = o.y + v.y; p->z = o.z + v.z; p->w = o.w + v.w;
-  return o;
+// ---- atomics ---------------------------------------------------------------------------------------------------------
+// Default build: no concurrency, plain read-modify-writes.  EMU_TSAN build: real seq_cst atomics, so that ThreadSanitizer
+// treats them as synchronisation (ticket / last-block patterns) and does not report the atomic accesses themselves.
+#ifdef EMU_TSAN
+template <typename T> static inline T emu_rmw_add(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float emu_rmw_add(float* p, float v) {
+  unsigned* u = reinterpret_cast<unsigned*>(p);
+  unsigned old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+  float f;
+  do {
+    memcpy(&f, &old, 4);
+    f += v;
+    memcpy(&want, &f, 4);
+  } while (!__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED));
+  memcpy(&f, &old, 4);
+  return f;
 }
+template <typename T> static inline T emu_load_relaxed(const T* p) {
+  if constexpr (sizeof(T) == 4 || sizeof(T) == 8) {
+    typedef typename std::conditional<sizeof(T) == 4, unsigned, unsigned long long>::type U;
+    U u = __atomic_load_n(reinterpret_cast<const U*>(p), __ATOMIC_RELAXED);
+    T r;
+    memcpy(&r, &u, sizeof(T));
+    return r;
+  } else {
+    return *p;
+  }
+}
+template <typename T> static inline void emu_store_relaxed(T* p, T v) {
+  typedef typename std::conditional<sizeof(T) == 4, unsigned, unsigned long long>::type U;
+  U u;
+  memcpy(&u, &v, sizeof(T));
+  __atomic_store_n(reinterpret_cast<U*>(p), u, __ATOMIC_RELAXED);
+}
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicSub(unsigned* p, unsigned v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+  __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {}
+  return old;
+}
+#else
+template <typename T> static inline T emu_rmw_add(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> static inline T emu_load_relaxed(const T* p) { return *p; }
+template <typename T> static inline void emu_store_relaxed(T* p, T v) { *p = v; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline unsigned atomicSub(unsigned* p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
@@ -190,6 +234,16 @@ static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long 
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
   unsigned long long o = *p;
   if (v > o) *p = v;
+  return o;
+}
+#endif
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return emu_rmw_add(p, v); }
+static inline int atomicAdd(int* p, int v) { return emu_rmw_add(p, v); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return emu_rmw_add(p, v); }
+static inline float atomicAdd(float* p, float v) { return emu_rmw_add(p, v); }
+static inline float4 atomicAdd(float4* p, float4 v) {  // the hardware's vector atomic is four independent scalar adds
+  float4 o;
+  o.x = emu_rmw_add(&p->x, v.x); o.y = emu_rmw_add(&p->y, v.y); o.z = emu_rmw_add(&p->z, v.z); o.w = emu_rmw_add(&p->w, v.w);
   return o;
 }
 

@@ -7,6 +7,18 @@
 
 #include "cuda_runtime.h"
 
+// EMU_TSAN (tests/emu/build_emu.py, tsan=True): every emulated CUDA thread is a ThreadSanitizer fibre.  Fibre switches
+// carry NO synchronisation; happens-before edges are added exactly where CUDA gives them: __syncthreads (block-wide),
+// __syncwarp (the named lanes), kernel boundaries, and device atomics (cuda_runtime.h maps them to seq_cst atomics).
+// TSan then reports two emulated threads touching the same shared or global address without such an edge -- the offline
+// stand-in for `compute-sanitizer --tool racecheck` (which only sees shared memory).
+#ifdef EMU_TSAN
+#include <sanitizer/tsan_interface.h>
+#define TSAN_ONLY(x) x
+#else
+#define TSAN_ONLY(x)
+#endif
+
 namespace emu {
 
 Idx g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
@@ -15,6 +27,7 @@ namespace {
 constexpr size_t kStack = 256 * 1024;
 enum State { kRunnable, kAtBarrier, kAtCollective, kDone };
 struct Fibre {
+  TSAN_ONLY(void* tsan = nullptr;)
   ucontext_t ctx;
   char* stack = nullptr;
   State st = kDone;
@@ -28,11 +41,17 @@ struct BlockState {
   std::vector<Fibre> f;
   unsigned n = 0, alive = 0, at_barrier = 0, barrier_gen = 0;
   unsigned cur = 0;
+  TSAN_ONLY(void* sched_tsan = nullptr;)
+  char barrier_obj = 0;      // TSan sync object of __syncthreads
+  char warp_obj[32] = {0};   // ... of __syncwarp, one per warp
   ucontext_t sched;
   const std::function<void()>* body = nullptr;
 };
 BlockState B;
 std::vector<char*> g_stacks;
+char g_launch_obj = 0;  // TSan sync objects: scheduler -> threads of the next block ...
+char g_done_obj = 0;    // ... and exiting threads -> scheduler (two objects: an exiting thread must not order itself
+                        // before a thread of the same block that merely starts later)
 
 // D3H_EMU_SHUFFLE=<seed>: blocks run in a random order and every scheduler sweep starts at a random thread, in a random
 // direction.  Results must not depend on either (on the GPU both are arbitrary): a shared variable read without the
@@ -52,15 +71,21 @@ void init_shuffle() {
 }
 
 void fibre_entry() {
+  TSAN_ONLY(__tsan_acquire(&g_launch_obj);)   // everything before the launch happened before this thread
   (*B.body)();
+  TSAN_ONLY(__tsan_release(&g_done_obj);)     // ... and this thread happens before whatever follows the block
   B.f[B.cur].st = kDone;
   --B.alive;
   // a thread that exits never reaches the barrier the others wait at: release them if it was the last one missing
   if (B.alive > 0 && B.at_barrier == B.alive) { B.at_barrier = 0; ++B.barrier_gen; }
+  TSAN_ONLY(__tsan_switch_to_fiber(B.sched_tsan, __tsan_switch_to_fiber_no_sync);)
   swapcontext(&B.f[B.cur].ctx, &B.sched);
 }
 
-void yield_to_scheduler() { swapcontext(&B.f[B.cur].ctx, &B.sched); }
+void yield_to_scheduler() {
+  TSAN_ONLY(__tsan_switch_to_fiber(B.sched_tsan, __tsan_switch_to_fiber_no_sync);)
+  swapcontext(&B.f[B.cur].ctx, &B.sched);
+}
 
 // completes every collective of warp `w` whose participants have all arrived
 void try_complete_collectives(unsigned w) {
@@ -105,9 +130,15 @@ void block_barrier() {
   Fibre& me = B.f[B.cur];
   me.st = kAtBarrier;
   me.barrier_gen = B.barrier_gen;
+  TSAN_ONLY(__tsan_release(&B.barrier_obj);)
   if (++B.at_barrier == B.alive) { B.at_barrier = 0; ++B.barrier_gen; }
   yield_to_scheduler();
+  TSAN_ONLY(__tsan_acquire(&B.barrier_obj);)  // every thread of the block released before anybody got here
 }
+
+// __syncwarp: memory ordering among the lanes of `mask` (the rendezvous itself is a warp_exchange)
+void warp_sync_release() { TSAN_ONLY(__tsan_release(&B.warp_obj[(B.cur >> 5) & 31u]);) }
+void warp_sync_acquire() { TSAN_ONLY(__tsan_acquire(&B.warp_obj[(B.cur >> 5) & 31u]);) }
 
 void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32]) {
   Fibre& me = B.f[B.cur];
@@ -135,16 +166,24 @@ extern "C" char __stop_emu_shared[] __attribute__((weak));
 
 static void run_block(const std::function<void()>& body, unsigned nthreads) {
   // shared memory of a fresh CTA holds arbitrary data on the GPU: never zeros by contract
-  if (__start_emu_shared != nullptr && __stop_emu_shared > __start_emu_shared)
+  if (__start_emu_shared != nullptr && __stop_emu_shared > __start_emu_shared) {
     memset(__start_emu_shared, 0xCB, (size_t)(__stop_emu_shared - __start_emu_shared));
+  }
+  // Every block has its OWN shared memory, but the emulation re-uses one set of static variables: blocks are therefore
+  // ordered one after the other for ThreadSanitizer (block k -> scheduler -> block k+1).  This hides races between
+  // DIFFERENT blocks on global memory; races inside a block -- what a missing __syncthreads / __syncwarp causes -- are
+  // what this build is for.
+  TSAN_ONLY(__tsan_release(&g_launch_obj);)
   if (B.f.size() < nthreads) B.f.resize(nthreads);
   while (g_stacks.size() < nthreads) g_stacks.push_back((char*)malloc(kStack));
   B.n = B.alive = nthreads;
   B.at_barrier = 0;
   B.barrier_gen = 0;
   B.body = &body;
+  TSAN_ONLY(B.sched_tsan = __tsan_get_current_fiber();)
   for (unsigned t = 0; t < nthreads; ++t) {
     Fibre& f = B.f[t];
+    TSAN_ONLY(if (f.tsan == nullptr) f.tsan = __tsan_create_fiber(0);)
     f.stack = g_stacks[t];
     f.st = kRunnable;
     getcontext(&f.ctx);
@@ -166,6 +205,7 @@ static void run_block(const std::function<void()>& body, unsigned nthreads) {
       B.cur = t;
       g_threadIdx = Idx{t, 0, 0};
       progressed = true;
+      TSAN_ONLY(__tsan_switch_to_fiber(f.tsan, __tsan_switch_to_fiber_no_sync);)
       swapcontext(&B.sched, &f.ctx);
     }
     if (!progressed && B.alive > 0) {
@@ -174,6 +214,7 @@ static void run_block(const std::function<void()>& body, unsigned nthreads) {
       abort();
     }
   }
+  TSAN_ONLY(__tsan_acquire(&g_done_obj);)
 }
 
 void run_grid(dim3 grid, dim3 block, const std::function<void()>& body) {
@@ -181,6 +222,8 @@ void run_grid(dim3 grid, dim3 block, const std::function<void()>& body) {
   g_gridDim = Idx{grid.x, grid.y, grid.z};
   g_blockDim = Idx{block.x, block.y, block.z};
   init_shuffle();
+  TSAN_ONLY(__tsan_release(&g_launch_obj);)
+  struct AcquireAtExit { ~AcquireAtExit() { TSAN_ONLY(__tsan_acquire(&g_done_obj);) } } acquire_at_exit;
   if (g_shuffle) {
     const unsigned long long total = (unsigned long long)grid.x * grid.y * grid.z;
     std::vector<unsigned> order(total);

@@ -2,6 +2,7 @@
 the kernels (tests/emu/build_emu.py, sanitize=True).  Started by tests/test_emu_sanitize.py with libasan preloaded:
 
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python tests/emu/san_runner.py <pytest args>
+    D3H_EMU_VARIANT=tsan LD_PRELOAD=$(gcc -print-file-name=libtsan.so) python tests/emu/san_runner.py <pytest args>
 """
 import os
 import sys
@@ -12,6 +13,7 @@ sys.path.insert(0, HERE)
 import build_emu  # noqa: E402
 import pytest  # noqa: E402
 
-_san = build_emu.build(sanitize=True)
-build_emu.build = lambda force=False, sanitize=False: _san
+_variant = os.environ.get("D3H_EMU_VARIANT", "san")      # "san": ASan + UBSan; "tsan": ThreadSanitizer fibres
+_san = build_emu.build(sanitize=_variant == "san", tsan=_variant == "tsan")
+build_emu.build = lambda force=False, sanitize=False, tsan=False: _san
 sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider"] + sys.argv[1:]))
