@@ -13,18 +13,20 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
-SELECTION = [                              # about a minute; D3H_RACECHECK_FULL=1: every golden case, regrowth (10 minutes)
+SELECTION = [                              # about 45 s
     "tests/test_emu_mesh.py",
-    "tests/test_emu_parity.py::test_golden[sort-capsule12_cloth]",
-    "tests/test_emu_parity.py::test_golden[static-capsule12_body]",
-    "tests/test_emu_parity.py::test_golden[static-adv5_open]",
-    "tests/test_emu_parity.py::test_golden[sort-three_faces]",
+    "tests/test_emu_parity.py::test_golden",
+    "tests/test_emu_parity.py::test_regrowth",
+    "tests/test_emu_parity.py::test_batches",
     "tests/test_emu_parity.py::test_fused_pair_equals_two_calls",
     "tests/test_emu_parity.py::test_tet_edge_rank_table_variant",
 ]
-FULL = ["tests/test_emu_mesh.py", "tests/test_emu_parity.py::test_golden", "tests/test_emu_parity.py::test_regrowth",
-        "tests/test_emu_parity.py::test_fused_pair_equals_two_calls", "tests/test_emu_parity.py::test_tet_edge_rank_table_variant",
-        "tests/test_emu_parity.py::test_batches"]
+FULL = SELECTION + [                       # D3H_RACECHECK_FULL=1: another minute (clean at the end of round 1)
+    "tests/test_emu_parity.py::test_integer_intermediates",
+    "tests/test_emu_parity.py::test_tet_range_sharding",
+    "tests/test_emu_parity.py::test_random_tet_soups",
+    "tests/test_emu_parity.py::test_pipelined_groups_and_split",
+]
 
 PROBE = r"""
 #include <cuda_runtime.h>
