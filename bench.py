@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mesh-stage", action="store_true", help="skip the Mesh / auto_normals leg (SURVEY 8f row 2)")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per pipelined chunk of the end-to-end leg")
     return ap.parse_args()
@@ -477,6 +478,26 @@ def main():
                                   f"with the O(F) stage on {cores} threads",
                         "ms_per_frame": best * 1e3}
 
+    # ---- the stage right behind the extraction: Mesh.edges + auto_normals fwd / bwd of this package on
+    # frame 0's surfaces against the same PyTorch ops on the device.  Last leg, never fatal: the headline is complete.
+    mesh_stage = None
+    if world == 1 and not args.no_mesh_stage:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_mesh_bench", os.path.join(ROOT, "profiles", "mesh_bench.py"))
+            mb = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mb)
+            with torch.no_grad():
+                verts, faces, _, _, _, extra = hm(pos_single[0].detach(), sdf.detach(), msdf.detach(), tets, "cloth")
+            l0 = mb.mesh.launch_counter()
+            mesh_stage = mb.measure([("open", verts.detach(), faces),
+                                     ("watertight", extra["vertices_watertight"].detach(), extra["faces_watertight"])],
+                                    max(3, min(args.steps, 100)), sync=None if dev_type == "cuda" else "cpu")
+            mesh_stage["gpu_launches"] = mb.mesh.launch_counter() - l0
+            mesh_stage["unit"] = "us per call (median, CUDA events; edges include the host's size read)"
+        except Exception as exc:  # noqa: BLE001
+            mesh_stage = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -485,7 +506,7 @@ def main():
                        "lanes": args.lanes, "groups": ngroups, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "device_trace": dev_trace, "single_call": single, "gpu_launches": int(launches_timed), "kernels": kern,
-            "clocks": sampler.result()}
+            "mesh_stage": mesh_stage, "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -37,19 +37,63 @@ def torch_normals(p, f):  # the op sequence of render/mesh.py:420-441
     return n / torch.sqrt(torch.clamp((n * n).sum(-1, keepdim=True), min=1e-20))
 
 
-def timed(fn, reps):
-    for _ in range(10):
+def timed(fn, reps, sync=None):
+    """median CUDA-event time of one call in microseconds (wall clock when there is no CUDA device: bench dry runs)"""
+    cuda = torch.cuda.is_available() and sync is None
+    for _ in range(min(10, reps)):
         fn()
-    torch.cuda.synchronize()
+    if cuda:
+        torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        b.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
+        if cuda:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        else:
+            import time
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e6)
     return float(np.median(ts))
+
+
+def measure(surfaces, reps, sync=None):
+    """surfaces: [(name, v (V,3) detached, f (F,3))] on the device -> {name: sizes and per-call times in microseconds}.
+    Also checks the results against the torch ops (edges equal, normals to 1e-3: ill-conditioned vertices differ)."""
+    keep = mesh.share_normals
+    mesh.share_normals = False      # time the kernels, not the memo of repeated calls
+    out = {}
+    try:
+        for name, v, f in surfaces:
+            g = torch.randn_like(v)
+            row = {"V": int(v.shape[0]), "F": int(f.shape[0])}
+
+            def ours_edges():
+                mesh._edge_cache.clear()     # time the kernels, not the per-faces-tensor cache
+                return mesh.Mesh(v, f).edges
+
+            row["E"] = int(ours_edges().shape[0])
+            row["edges_equal_torch"] = bool(torch.equal(ours_edges(), torch_edges(f)))
+            row["edges_us"] = timed(ours_edges, reps, sync)
+            row["edges_torch_us"] = timed(lambda: torch_edges(f), reps, sync)
+            row["normals_fwd_us"] = timed(lambda: mesh.vertex_normals(v, f), reps, sync)
+            row["normals_fwd_torch_us"] = timed(lambda: torch_normals(v, f), reps, sync)
+            row["normals_median_abs_diff_vs_torch"] = float((mesh.vertex_normals(v, f) - torch_normals(v, f)).abs().median())
+
+            def fb(fn):
+                p = v.clone().requires_grad_(True)
+                (fn(p, f) * g).sum().backward()
+
+            row["normals_fwd_bwd_us"] = timed(lambda: fb(mesh.vertex_normals), reps, sync)
+            row["normals_fwd_bwd_torch_us"] = timed(lambda: fb(torch_normals), reps, sync)
+            out[name] = row
+    finally:
+        mesh.share_normals = keep
+    return out
 
 
 def main():
@@ -58,37 +102,15 @@ def main():
     ap.add_argument("--reps", type=int, default=200)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
-    mesh.share_normals = False      # time the kernels, not the memo of repeated calls
     pos, tets = grids.kuhn_grid(args.res)
     sdf, msdf = grids.capsule_garment_field(pos)
     verts, faces, _, _, _, extra = hmSDF_Tets()(torch.tensor(pos, device=dev), torch.tensor(sdf, device=dev),
                                                 torch.tensor(msdf, device=dev), torch.tensor(tets, device=dev), "cloth")
+    l0 = mesh.launch_counter()
     out = {"workload": f"kuhn{args.res}_capsule_garment surfaces", "reps": args.reps}
-    for name, v, f in (("open", verts.detach(), faces), ("watertight", extra["vertices_watertight"].detach(),
-                                                         extra["faces_watertight"])):
-        g = torch.randn_like(v)
-        row = {"V": v.shape[0], "F": f.shape[0]}
-
-        def ours_edges():
-            mesh.reset()
-            return mesh.Mesh(v, f).edges
-
-        row["E"] = int(ours_edges().shape[0])
-        assert torch.equal(ours_edges(), torch_edges(f))
-        row["edges_us"] = timed(ours_edges, args.reps)
-        row["edges_torch_us"] = timed(lambda: torch_edges(f), args.reps)
-        row["normals_fwd_us"] = timed(lambda: mesh.vertex_normals(v, f), args.reps)
-        row["normals_fwd_torch_us"] = timed(lambda: torch_normals(v, f), args.reps)
-        assert float((mesh.vertex_normals(v, f) - torch_normals(v, f)).abs().max()) < 1e-3
-
-        def fb(fn):
-            p = v.clone().requires_grad_(True)
-            (fn(p, f) * g).sum().backward()
-
-        row["normals_fwd_bwd_us"] = timed(lambda: fb(mesh.vertex_normals), args.reps)
-        row["normals_fwd_bwd_torch_us"] = timed(lambda: fb(torch_normals), args.reps)
-        out[name] = row
-    out["gpu_launches"] = mesh.launch_counter()
+    out.update(measure([("open", verts.detach(), faces),
+                        ("watertight", extra["vertices_watertight"].detach(), extra["faces_watertight"])], args.reps))
+    out["gpu_launches"] = mesh.launch_counter() - l0
     print(json.dumps(out))
 
 

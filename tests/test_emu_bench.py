@@ -54,6 +54,8 @@ def _worker(rank, world, port, out_dir, argv):
     sys.path.insert(0, ROOT)
     from tests.test_emu_multirank import _patch_for_cpu
     _patch_for_cpu()
+    from d3human_code_b200.render import mesh as M
+    M._check_cuda = lambda t: None
     torch.cuda.current_stream = lambda dev=None: _Stream()
     torch.cuda.Event = _Event
     torch.cuda.Stream = _Stream
@@ -88,5 +90,13 @@ def test_bench_control_flow(tmp_path, world):
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"] is not None and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["device_trace"] is not None and "error" not in d["device_trace"]
+    if world == 1:                               # the mesh-stage leg ran (on the emulated kernels) and agrees with torch
+        ms = d["mesh_stage"]
+        assert "error" not in ms, ms
+        for name in ("open", "watertight"):
+            assert ms[name]["edges_equal_torch"] is True and ms[name]["E"] > 0 and ms[name]["normals_fwd_us"] > 0
+        assert ms["gpu_launches"] > 0
+    else:
+        assert d["mesh_stage"] is None
     for r in range(1, world):                    # only rank 0 prints
         assert not [l for l in open(tmp_path / f"out_{r}.txt") if l.startswith("{")]
