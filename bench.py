@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mesh-stage", action="store_true", help="skip the Mesh / auto_normals leg (SURVEY 8f row 2)")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the plain-PyTorch-on-this-GPU leg (SURVEY 8d)")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per pipelined chunk of the end-to-end leg")
     return ap.parse_args()
@@ -477,6 +478,24 @@ def main():
                         "sample": f"best of {reps} full fwd+bwd extractions of one frame of the same workload, numpy oracle "
                                   f"with the O(F) stage on {cores} threads",
                         "ms_per_frame": best * 1e3}
+        try:  # the same path as plain PyTorch ops on the host cores: how the reference itself behaves on a CPU
+            from oracle import gshell_torch as GT
+            cp = torch.from_numpy(p0.copy()).requires_grad_(True)
+            cs, cm = torch.from_numpy(sdf_np[:, None].copy()).requires_grad_(True), torch.from_numpy(msdf_np.copy()).requires_grad_(True)
+            ct = torch.from_numpy(tets_np)
+            tbest = 1e9
+            for _ in range(2):
+                cp.grad = cs.grad = cm.grad = None
+                t0 = time.perf_counter()
+                v, _f, _, _, _, ex = GT.extract(cp, cs, cm, ct, 1, True)
+                torch.autograd.backward([v, ex["msdf"]], [torch.ones_like(v), torch.ones_like(ex["msdf"])])
+                tbest = min(tbest, time.perf_counter() - t0)
+            cpu_baseline["torch_port"] = {"value": F / tbest, "unit": UNIT, "ms_per_frame": tbest * 1e3,
+                                          "threads": torch.get_num_threads(),
+                                          "note": "oracle/gshell_torch.py on CPU tensors, best of 2: the reference's op "
+                                                  "sequence on the host (the numpy figure above is the faster, conservative one)"}
+        except Exception as exc:  # noqa: BLE001
+            cpu_baseline["torch_port"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     # ---- the stage right behind the extraction: Mesh.edges + auto_normals fwd / bwd of this package on
     # frame 0's surfaces against the same PyTorch ops on the device.  Last leg, never fatal: the headline is complete.
@@ -498,6 +517,39 @@ def main():
         except Exception as exc:  # noqa: BLE001
             mesh_stage = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- the reference's way on the same GPU: the path as plain PyTorch ops + autograd (oracle/gshell_torch.py, a port
+    # pinned against the reference's golden vectors; the reference tree itself is not on this box).  SURVEY 8(d).  Never fatal.
+    torch_baseline = None
+    if world == 1 and not args.no_torch_baseline:
+        try:
+            from oracle import gshell_torch as GT
+            tp = pos_single[0].detach().clone().requires_grad_(True)
+            ts_, tm_ = sdf.detach().clone().requires_grad_(True), msdf.detach().clone().requires_grad_(True)
+
+            def torch_step():
+                tp.grad = ts_.grad = tm_.grad = None
+                v, f_, _, _, _, ex = GT.extract(tp, ts_, tm_, tets, 1, True)
+                torch.autograd.backward([v, ex["msdf"]], [ups_v[0], ups_m[0]])
+
+            for _ in range(2):
+                torch_step()
+            reps, t_all = 0, time.perf_counter()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            while reps < 20 and time.perf_counter() - t_all < 10.0:
+                torch_step()
+                reps += 1
+            ev1.record()
+            barrier()
+            ms = ev0.elapsed_time(ev1) / max(reps, 1)
+            torch_baseline = {"value": F / (ms * 1e-3), "unit": UNIT, "ms_per_frame": ms, "kind": "port", "reps": reps,
+                              "note": "the same extraction fwd+bwd of one frame as plain PyTorch ops + autograd on this GPU "
+                                      "(boolean-mask compactions, torch.unique(dim=0), scatter_add, the full UV table), "
+                                      "the way the reference runs it; oracle/gshell_torch.py"}
+        except Exception as exc:  # noqa: BLE001
+            torch_baseline = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -506,7 +558,7 @@ def main():
                        "lanes": args.lanes, "groups": ngroups, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "device_trace": dev_trace, "single_call": single, "gpu_launches": int(launches_timed), "kernels": kern,
-            "mesh_stage": mesh_stage, "clocks": sampler.result()}
+            "mesh_stage": mesh_stage, "torch_gpu_baseline": torch_baseline, "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -74,7 +74,9 @@ def _worker(rank, world, port, out_dir, argv):
 def test_bench_control_flow(tmp_path, world):
     import torch.multiprocessing as mp
     argv = ["--gpus", str(world), "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "4", "--groups", "2",
-            "--lanes", "2", "--profile-steps", "1", "--e2e-chunk", "2", "--no-cpu-baseline"]
+            "--lanes", "2", "--profile-steps", "1", "--e2e-chunk", "2"]
+    if world > 1:
+        argv.append("--no-cpu-baseline")     # N = 1 runs the CPU baseline leg as well (tiny grid: a fraction of a second)
     ctx = mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), argv), nprocs=world, join=False,
                              start_method="spawn")
     deadline = time.time() + 240
@@ -96,7 +98,11 @@ def test_bench_control_flow(tmp_path, world):
         for name in ("open", "watertight"):
             assert ms[name]["edges_equal_torch"] is True and ms[name]["E"] > 0 and ms[name]["normals_fwd_us"] > 0
         assert ms["gpu_launches"] > 0
+        cb = d["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["value"] > 0 and "error" not in cb["torch_port"] and cb["torch_port"]["value"] > 0
+        tb = d["torch_gpu_baseline"]             # the plain-PyTorch port ran (on CPU here) and produced a number
+        assert "error" not in tb and tb["value"] > 0 and tb["kind"] == "port", tb
     else:
-        assert d["mesh_stage"] is None
+        assert d["mesh_stage"] is None and d["torch_gpu_baseline"] is None
     for r in range(1, world):                    # only rank 0 prints
         assert not [l for l in open(tmp_path / f"out_{r}.txt") if l.startswith("{")]
