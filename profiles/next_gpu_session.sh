@@ -21,7 +21,9 @@ timeout 300 python bench.py 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
 print({k: d[k] for k in ('value', 'ms_per_step', 'gpu_launches')}, d['roofline']['frac'], d['roofline'].get('device_timer', {}).get('frac'),
-      d['path_roofline']['frac_step'], d['e2e']['value'] if d['e2e'] else None, d['single_call'])"
+      d['path_roofline']['frac_step'], d['e2e']['value'] if d['e2e'] else None, d['single_call'])
+print('torch on this GPU:', d.get('torch_gpu_baseline'))
+print('mesh stage:', d.get('mesh_stage'))"
 echo "== fused cloth/body pair vs plain split vs two calls (us per pair, fwd only and fwd+bwd)"
 timeout 200 python - <<'PY'
 import time, numpy as np, torch
