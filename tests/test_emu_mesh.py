@@ -77,3 +77,8 @@ def test_on_extraction_output(dev):
 @pytest.mark.parametrize("seed", range(12))
 def test_soups(dev, seed):
     Z.test_random_triangle_soups(dev, seed)
+
+
+@pytest.mark.parametrize("nv", [4095, 4096, 4097, 8192, 12289])
+def test_scan_tile_boundaries(dev, nv):
+    Z.test_vertex_counts_around_the_scan_tile(dev, nv)

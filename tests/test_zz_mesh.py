@@ -284,3 +284,15 @@ def test_random_triangle_soups(dev, seed):
     stable_mesh = cond.max() < GRAD_COND_MAX
     _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), cond,
            MO.auto_normals_backward(pos, faces, g) if stable_mesh else None, f"soup{seed}")
+
+
+@pytest.mark.parametrize("nv", [4095, 4096, 4097, 8192, 12289])
+def test_vertex_counts_around_the_scan_tile(dev, nv):
+    """Vertex counts at and around multiples of the 4096-vertex scan tile; the last vertices carry edges."""
+    rng = np.random.default_rng(nv)
+    pos = rng.standard_normal((nv, 3)).astype(np.float32)
+    faces = rng.integers(0, nv, size=(3000, 3)).astype(np.int64)
+    faces[:8] = np.array([[nv - 1, nv - 2, nv - 3], [nv - 1, 0, nv - 2], [4095 % nv, 4096 % nv, 4094 % nv], [0, 1, nv - 1],
+                          [nv - 3, nv - 1, 1], [4096 % nv, 0, nv - 1], [2, 4095 % nv, 4096 % nv], [nv - 2, 4096 % nv, 3]])
+    out = _run(dev, pos, faces)
+    _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), MO.normal_condition(pos, faces), None, f"nv{nv}")
