@@ -292,6 +292,24 @@ def main():
         ms_single = timed(single_call_step, k_single) / len(pos_single)
         single = {"ms_per_frame": ms_single, "value": F / (ms_single * 1e-3), "unit": UNIT, "steps": k_single,
                   "note": "hmSDF_Tets()(...) + backward per frame, strictly serial on the host (the reference's calling pattern)"}
+        # forward and backward separately: CUDA events around each half of one drop-in call, median
+        try:
+            f_ms, b_ms = [], []
+            p1, gv1, gm1 = pos_single[0], ups_v[0], ups_m[0]
+            for _ in range(min(max(k_single, 10), 100)):
+                sdf.grad = msdf.grad = p1.grad = None
+                ea, eb_, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                ea.record()
+                verts, faces, _, _, v_tng, extra = hm(p1, sdf, msdf, tets, "cloth")
+                eb_.record()
+                torch.autograd.backward([verts, extra["msdf"]], [gv1, gm1])
+                ec.record()
+                barrier()
+                f_ms.append(ea.elapsed_time(eb_))
+                b_ms.append(eb_.elapsed_time(ec))
+            single["fwd_ms_median"], single["bwd_ms_median"] = float(np.median(f_ms)), float(np.median(b_ms))
+        except Exception as exc:  # noqa: BLE001
+            single["fwd_bwd_split_error"] = f"{type(exc).__name__}: {exc}"[:200]
 
     # ---- per-kernel device time (CUDA events on the launching stream, recorded by the library; one frame at a time so
     # that every kernel is timed alone) ----

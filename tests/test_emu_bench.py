@@ -98,6 +98,7 @@ def test_bench_control_flow(tmp_path, world):
         for name in ("open", "watertight"):
             assert ms[name]["edges_equal_torch"] is True and ms[name]["E"] > 0 and ms[name]["normals_fwd_us"] > 0
         assert ms["gpu_launches"] > 0
+        assert d["single_call"]["fwd_ms_median"] > 0 and d["single_call"]["bwd_ms_median"] > 0
         cb = d["cpu_baseline"]
         assert cb["kind"] == "port" and cb["value"] > 0 and "error" not in cb["torch_port"] and cb["torch_port"]["value"] > 0
         tb = d["torch_gpu_baseline"]             # the plain-PyTorch port ran (on CPU here) and produced a number
