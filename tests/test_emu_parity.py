@@ -226,7 +226,7 @@ def test_fused_pair_equals_two_calls(dev, res, field, wt):
 
 @pytest.mark.parametrize("res,field", [(12, "capsule"), (8, "adv")])
 def test_gpu_fused_pair_test_body(dev, res, field):
-    Z.test_zz_fused_pair_equals_two_calls(dev, res, field)
+    Z.fused_pair_equals_two_calls(dev, res, field)
 
 
 def _fuzz_case(case):

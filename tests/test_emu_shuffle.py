@@ -60,7 +60,7 @@ def test_extraction_oracle(shuffled, dev):
 def test_fused_pair(shuffled, dev, edges_mode, res, field):
     if edges_mode != "static":
         pytest.skip("the fused pair runs on the static edge path")
-    EP.Z.test_zz_fused_pair_equals_two_calls(dev, res, field)
+    EP.Z.fused_pair_equals_two_calls(dev, res, field)
 
 
 @pytest.mark.parametrize("name", ["mesh_extracted", "mesh_soup", "mesh_three", "mesh_fan"])

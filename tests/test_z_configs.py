@@ -174,12 +174,11 @@ def test_random_tet_soups(dev, seed, n, f):
         U.assert_close_normwise("grad_msdf", g[2], g_msdf, 5 * U.GRAD_RTOL)
 
 
-@pytest.mark.parametrize("res,field", [(24, "capsule"), (12, "adv")])
-def test_zz_fused_pair_equals_two_calls(dev, res, field):
+def fused_pair_equals_two_calls(dev, res, field):      # collected by tests/test_zzzz_fused_pair.py (sorts last: opt-in path)
     """hmSDF_Tets.split(fused=True): one classification / edge de-duplication / vertex interpolation for
     the cloth / body pair of an iteration, only the mSDF cut is replayed for the body.  Bit-identical to the two separate
     calls; gradients equal to their sum.  Developed on the CPU emulation of the kernels (tests/test_emu_parity.py); this is
-    its check on the real GPU -- kept as the very last test of the suite."""
+    its check on the real GPU -- run as the very last test of the suite (tests/test_zzzz_fused_pair.py)."""
     from tests import test_cuda_parity as G
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
     pos, sdf, msdf, tets = G._inputs(res, field, seed=res)

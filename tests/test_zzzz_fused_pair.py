@@ -1,0 +1,29 @@
+"""GPU check of the OPT-IN fused cloth / body pair (hmSDF_Tets.split(fused=True)).  The very last file of
+the suite: the path is not the default, was developed on the kernel emulation and has never run on a GPU, so a failure
+here must not keep the tests of the default path (run with -x) from running.  Body: tests/test_z_configs.py."""
+import pytest
+import torch
+
+from tests import test_z_configs as Z
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True, params=["sort", "static"])
+def edges_mode(request):
+    from d3human_code_b200 import extract as E
+    E.set_static_edges("1" if request.param == "static" else "0")
+    yield request.param
+    E.set_static_edges("auto")
+
+
+@pytest.mark.parametrize("res,field", [(24, "capsule"), (12, "adv")])
+def test_fused_pair_equals_two_calls(dev, res, field):
+    Z.fused_pair_equals_two_calls(dev, res, field)
