@@ -705,7 +705,8 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 // ---- diagnostics: per-kernel device time, measured with CUDA events on the launching stream -----------------------
 static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "group_sort",
                                             "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records",
-                                            "edge_emit", "adjoint_poly", "pair_replay"};
+                                            "edge_emit", "adjoint_poly", "pair_replay", "mesh_edges", "mesh_normals",
+                                            "mesh_adjoint"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

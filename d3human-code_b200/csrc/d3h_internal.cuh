@@ -148,7 +148,8 @@ bool profiling_enabled();
 // ---- optional per-kernel timing (d3h_profile_*): CUDA events recorded on the launching stream around each launch ----
 enum KernelKind {
   K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_GROUP_SORT, K_VERTEX_EMIT, K_POLY_FACES,
-  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_PAIR_REPLAY, K_COUNT
+  K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_PAIR_REPLAY, K_MESH_EDGES, K_MESH_NORMALS,
+  K_MESH_ADJOINT, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

@@ -468,6 +468,7 @@ extern "C" int d3h_mesh_edges(const int64_t* faces, int64_t n_faces, int64_t n_v
   cudaStream_t stream = (cudaStream_t)s;
   d3h_mesh_counts* mapped =
       reinterpret_cast<d3h_mesh_counts*>(mapped_counts_pointer(reinterpret_cast<d3h_counts*>(counts_host)));
+  ProfScope ps(K_MESH_EDGES, stream);  // d3h_profile_*: the whole edge pipeline as one entry
   cudaMemsetAsync(w.table, 0xff, (size_t)w.cap_table * 8, stream);
   cudaMemsetAsync(w.ucount, 0, (size_t)w.zero_bytes, stream);
   if (n_faces > 0)
@@ -546,6 +547,7 @@ extern "C" int d3h_mesh_normals_forward(const float* pos, const int64_t* faces, 
   if (rc) return rc;
   if (n_verts == 0) return D3H_OK;
   cudaStream_t stream = (cudaStream_t)s;
+  ProfScope ps(K_MESH_NORMALS, stream);
   cudaMemsetAsync(acc, 0, (size_t)n_verts * 16, stream);
   if (n_faces == 3)
     launch_k(mesh_normal_splat3_kernel, 1u, 32u, stream, kLaunchLatency, pos, faces, n_verts, acc, bad);
@@ -568,6 +570,7 @@ extern "C" int d3h_mesh_normals_backward(const float* pos, const int64_t* faces,
     return D3H_E_BADARG;
   }
   cudaStream_t stream = (cudaStream_t)s;
+  ProfScope ps(K_MESH_ADJOINT, stream);
   cudaMemsetAsync(g_pos, 0, (size_t)n_verts * 12, stream);
   if (n_faces == 3)
     launch_k(mesh_normal_adjoint3_kernel, 1u, 32u, stream, kLaunchLatency, pos, faces, n_verts, acc, g_nrm, g_pos);

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from d3human_code_b200 import grids  # noqa: E402
+from d3human_code_b200 import _cabi, grids  # noqa: E402
 from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets  # noqa: E402
 from d3human_code_b200.render import mesh  # noqa: E402
 
@@ -90,6 +90,14 @@ def measure(surfaces, reps, sync=None):
 
             row["normals_fwd_bwd_us"] = timed(lambda: fb(mesh.vertex_normals), reps, sync)
             row["normals_fwd_bwd_torch_us"] = timed(lambda: fb(torch_normals), reps, sync)
+            # device time of each entry point alone (events recorded by the library around its launches)
+            _cabi.profile_read()
+            _cabi.profile_enable(True)
+            for _ in range(5):
+                ours_edges()
+                fb(mesh.vertex_normals)
+            _cabi.profile_enable(False)
+            row["device_us"] = {k: 1e3 * ms / max(n, 1) for k, (ms, n) in _cabi.profile_read().items() if k.startswith("mesh_")}
             out[name] = row
     finally:
         mesh.share_normals = keep
