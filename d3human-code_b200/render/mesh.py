@@ -206,6 +206,58 @@ class Mesh:
         return self._edges
 
 
+def accelerate(reference_mesh_cls):
+    """For a maintainer who keeps the reference's own `render/mesh.py` (OBJ loading, AABB helpers, Laplacian, ...): returns
+    `(FastMesh, auto_normals)` where FastMesh is a SUBCLASS of the reference's Mesh (render/mesh.py:139) -- every method and
+    attribute of the original stays -- whose constructor no longer runs torch.unique (the edge list is produced by the
+    kernels on first access of `.edges`), and an `auto_normals` that builds FastMesh objects.  At the bottom of the
+    reference module:
+
+        from d3human_code_b200.render.mesh import accelerate
+        Mesh, auto_normals = accelerate(Mesh)
+    """
+
+    class FastMesh(reference_mesh_cls):
+        def __init__(self, *args, **kwargs):
+            self._d3h_constructing = True
+            self._edges = None
+            super().__init__(*args, **kwargs)     # ends with self.get_edge(), which only takes note while constructing
+            self._d3h_constructing = False
+
+        @property
+        def edges(self):
+            if self._edges is None and not self._d3h_constructing and getattr(self, "_edge_faces", None) is not None:
+                self.get_edge()
+            return self._edges
+
+        @edges.setter
+        def edges(self, value):
+            self._edges = value
+
+        def get_edge(self):
+            if self._d3h_constructing:            # called by the reference constructor (:162): remember what to use
+                self._edge_faces = self.t_pos_idx
+                self._edge_verts = None if self.v_pos is None else int(self.v_pos.shape[0])
+                self._edges = None
+                return None
+            faces, n_verts = self._edge_faces, self._edge_verts
+            if n_verts is None:
+                n_verts = int(faces.max().item()) + 1 if faces.numel() else 0
+            self._edges = _edges_cached(faces, n_verts)
+            return self._edges
+
+    FastMesh.__name__ = getattr(reference_mesh_cls, "__name__", "Mesh")
+    FastMesh.__qualname__ = FastMesh.__name__
+
+    def fast_auto_normals(imesh):
+        v_nrm = vertex_normals(imesh.v_pos, imesh.t_pos_idx)
+        if torch.is_anomaly_enabled():
+            assert torch.all(torch.isfinite(v_nrm))
+        return FastMesh(v_nrm=v_nrm, t_nrm_idx=imesh.t_pos_idx, base=imesh)
+
+    return FastMesh, fast_auto_normals
+
+
 # ---- normals -------------------------------------------------------------------------------------------------------
 class _AutoNormalsFn(torch.autograd.Function):
     @staticmethod

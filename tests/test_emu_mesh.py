@@ -82,3 +82,38 @@ def test_soups(dev, seed):
 @pytest.mark.parametrize("nv", [4095, 4096, 4097, 8192, 12289])
 def test_scan_tile_boundaries(dev, nv):
     Z.test_vertex_counts_around_the_scan_tile(dev, nv)
+
+
+def test_accelerate_the_reference_module(dev):
+    """INTEGRATION.md section 4, second variant: the reference's own render/mesh.py with `Mesh, auto_normals =
+    accelerate(Mesh)` at its bottom -- every other function of the module keeps working on the subclass.  Needs the live
+    reference (build container only); runs on the emulated kernels."""
+    import numpy as np
+    from oracle.ref_loader import load_reference_mesh, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    ref = load_reference_mesh("cpu")
+    ref_mesh_cls, ref_auto_normals = ref.Mesh, ref.auto_normals
+    pos, faces = Z._height_field(14, 7)
+    p = torch.tensor(pos, requires_grad=True)
+    f = torch.tensor(faces)
+    want_mesh = ref_auto_normals(ref_mesh_cls(p, f))                    # the reference, untouched
+    (want_mesh.v_nrm * 2.0).sum().backward()
+    want_grad, p.grad = p.grad.clone(), None
+
+    ref.Mesh, ref.auto_normals = M.accelerate(ref.Mesh)                 # what the maintainer adds
+    before = M.launch_counter()
+    m = ref.Mesh(p, f, material="mat")
+    assert isinstance(m, ref_mesh_cls) and M.launch_counter() == before  # no edge computation in the constructor
+    assert np.array_equal(m.edges.numpy(), want_mesh.edges.numpy()) and M.launch_counter() > before
+    nm = ref.auto_normals(m)
+    assert isinstance(nm, ref.Mesh) and nm.material == "mat" and nm.t_nrm_idx is f
+    assert float((nm.v_nrm - want_mesh.v_nrm).detach().abs().max()) <= Z.NRM_ATOL
+    (nm.v_nrm * 2.0).sum().backward()
+    assert float((p.grad - want_grad).abs().max()) <= 1e-5 * float(want_grad.abs().max())
+    c = nm.clone()                                                      # the reference's own clone(), :203-238
+    assert isinstance(c, ref.Mesh) and torch.equal(c.v_nrm, nm.v_nrm.detach()) and torch.equal(c.edges, m.edges)
+    lo, hi = ref.aabb(nm)                                               # an untouched helper of the reference module
+    assert torch.equal(lo, p.detach().min(0).values) and torch.equal(hi, p.detach().max(0).values)
+    n2 = ref.unit_size(nm)                                              # builds a Mesh through the module's global name
+    assert isinstance(n2, ref.Mesh) and np.array_equal(n2.edges.numpy(), want_mesh.edges.numpy())
