@@ -3,6 +3,7 @@
 # each step under its own timeout so that a hang cannot hold the box.  Usage (1 GPU):
 #   gpurun --timeout 900 -- 'bash profiles/next_gpu_session.sh 2>&1 | tee gpurun_out/next_session.log'
 # then (2 GPUs, charged twice):  gpurun --gpus 2 --timeout 400 -- 'bash profiles/next_gpu_session.sh multi'
+# and the ncu evidence:          gpurun --timeout 1500 -- 'bash profiles/next_gpu_session.sh profile'
 set -u
 cd "$(dirname "$0")/.."
 if [ "${1:-}" = "multi" ]; then
@@ -12,7 +13,22 @@ if [ "${1:-}" = "multi" ]; then
       bench.py --gpus "$N" --steps 50 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-400
   exit 0
 fi
-echo "== parity (incl. the tests never run on a GPU: test_z_configs.py)"
+if [ "${1:-}" = "profile" ]; then
+  # ncu evidence for the CURRENT defaults (32 frames / 4 groups / 8 lanes): launch list + one --set full capture of the
+  # dominant kernel and of the mesh kernels.  Never a bench value: ncu serialises and replays.  Copy the results from
+  # gpurun_out/ to profiles/r02_* and summarise with launch_summary.py / ncu -i ... --page raw --csv.
+  mkdir -p gpurun_out
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-torch-baseline > gpurun_out/r02_launches.log 2>&1
+  tail -1 gpurun_out/r02_launches.log | cut -c1-200
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:classify_kernel -c 3 -o gpurun_out/r02_classify \
+      python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-torch-baseline --no-mesh-stage > gpurun_out/r02_classify.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mesh_ -c 24 -o gpurun_out/r02_mesh \
+      python profiles/mesh_bench.py --reps 3 > gpurun_out/r02_mesh.log 2>&1
+  ls -la gpurun_out | tail -8
+  exit 0
+fi
+echo "== parity (incl. the tests never run on a GPU: test_z_configs.py, test_zy_config5.py, test_zz_mesh.py, test_zzzz_fused_pair.py)"
 timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -8
 echo "== smoke"
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
