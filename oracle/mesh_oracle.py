@@ -53,7 +53,8 @@ def normal_sums(pos: np.ndarray, faces: np.ndarray) -> np.ndarray:
 
 
 def normal_condition(pos: np.ndarray, faces: np.ndarray) -> np.ndarray:
-    """Per vertex: sum of |face normal| over |sum of face normals| (1 for vertices without faces).  The fp32 sum is
+    """Per vertex: sum of |face normal| over |sum of face normals| (1 for vertices without faces; corners of faces with a
+    repeated index count the face's squared side instead of its vanishing normal, see below).  The fp32 sum is
     accumulated in a different order by float atomics (the reference's CUDA scatter_add included), which moves the unit
     normal by about 1e-7 x this number; vertices whose normals cancel (1e4 and above) have no stable normal at all."""
     pos = np.asarray(pos, F32)
@@ -68,6 +69,18 @@ def normal_condition(pos: np.ndarray, faces: np.ndarray) -> np.ndarray:
         np.add.at(mag, faces[:, c], np.linalg.norm(fn, axis=1))
     s = np.linalg.norm(normal_sums(pos, faces).astype(np.float64), axis=1)
     used = mag > 0
+    if not used.any():  # no face has a non-zero normal: every vertex keeps the default (0,0,1)
+        return cond
+    # A face with a repeated index has a zero normal in exact arithmetic, but the fused cross product leaves a rounding
+    # residue (~1e-9).  A vertex that only belongs to such faces gets that residue as its "sum", a 1 / |sum| ~ 1e9 gradient,
+    # and -- because the gradient of the repeated corner is added and subtracted at the same vertex -- swamps the fp32
+    # gradients of its neighbours (in the reference as well).  For the corners of such faces the sum is therefore counted
+    # against the face's side length, not against its (vanishing) normal.
+    rep = (faces[:, 0] == faces[:, 1]) | (faces[:, 1] == faces[:, 2]) | (faces[:, 2] == faces[:, 0])
+    if rep.any():
+        side2 = np.maximum((a.astype(np.float64) ** 2).sum(-1), (b.astype(np.float64) ** 2).sum(-1))
+        for c in range(3):
+            np.maximum.at(mag, faces[rep, c], 1e-2 * side2[rep])
     cond[used] = mag[used] / np.maximum(s[used], 1e-300)
     return cond
 

@@ -117,3 +117,8 @@ def test_accelerate_the_reference_module(dev):
     assert torch.equal(lo, p.detach().min(0).values) and torch.equal(hi, p.detach().max(0).values)
     n2 = ref.unit_size(nm)                                              # builds a Mesh through the module's global name
     assert isinstance(n2, ref.Mesh) and np.array_equal(n2.edges.numpy(), want_mesh.edges.numpy())
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_degenerate_soups(dev, seed):
+    Z.test_degenerate_soups(dev, seed)

@@ -72,3 +72,10 @@ def test_mesh_oracle_hub_and_memo(shuffled, mesh_dev):
     ZM.test_mesh_matches_oracle(mesh_dev, 80, 2)
     ZM.test_hub_vertex_with_many_neighbours(mesh_dev)
     ZM.test_repeated_auto_normals_share_one_result(mesh_dev)
+
+
+def test_mesh_soups(shuffled, mesh_dev):
+    for seed in (0, 6):
+        ZM.test_random_triangle_soups(mesh_dev, seed)
+    for seed in (0, 5, 15):
+        ZM.test_degenerate_soups(mesh_dev, seed)

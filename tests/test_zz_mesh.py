@@ -296,3 +296,24 @@ def test_vertex_counts_around_the_scan_tile(dev, nv):
                           [nv - 3, nv - 1, 1], [4096 % nv, 0, nv - 1], [2, 4095 % nv, 4096 % nv], [nv - 2, 4096 % nv, 3]])
     out = _run(dev, pos, faces)
     _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), MO.normal_condition(pos, faces), None, f"nv{nv}")
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_degenerate_soups(dev, seed):
+    """Soups over a handful of vertices: most faces repeat an index (zero normal up to the rounding residue of the fused
+    cross product), many vertices are isolated, positions on a coarse lattice make sums cancel exactly.  Edges must be
+    exact; normals are compared where they are stable, gradients where no vertex amplifies a residue (see
+    oracle/mesh_oracle.normal_condition) -- found by a 400-seed campaign on the kernel emulation."""
+    rng = np.random.default_rng(10_000 + seed)
+    nv = int(rng.integers(1, 9000)) if seed % 7 == 0 else int(rng.integers(1, 300))
+    nf = int(rng.integers(0, 4000)) if seed % 5 == 0 else int(rng.integers(0, 120))
+    used = int(rng.integers(1, nv + 1)) if seed % 2 else int(rng.integers(1, 6))
+    pos = rng.standard_normal((nv, 3)).astype(np.float32)
+    if seed % 3 == 0:
+        pos = (np.round(pos * 2) / 2).astype(np.float32)
+    faces = rng.integers(0, used, size=(nf, 3)).astype(np.int64)
+    g = rng.standard_normal(pos.shape).astype(np.float32)
+    out = _run(dev, pos, faces, g if nf else None)
+    cond = MO.normal_condition(pos, faces)
+    _check(out, MO.mesh_edges(faces), MO.auto_normals(pos, faces), cond,
+           MO.auto_normals_backward(pos, faces, g) if nf and cond.max() < GRAD_COND_MAX else None, f"degenerate{seed}")
