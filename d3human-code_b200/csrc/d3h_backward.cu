@@ -138,12 +138,14 @@ __device__ __forceinline__ EdgePull pull_edge(const AdjFrame& f, int64_t row, fl
   r.gx_i = gx * u0; r.gy_i = gy * u0; r.gz_i = gz * u0; r.gsg_i = gm * u0;
   r.gx_j = gx * u1; r.gy_j = gy * u1; r.gz_j = gz * u1; r.gsg_j = gm * u1;
   if (nz) {
-    const float gu0 = gx * vi[0] + gy * vi[1] + gz * vi[2];
-    const float gu1 = gx * vj[0] + gy * vj[1] + gz * vj[2];
-    const float inv = 1.f / D;
-    const float gD = -(gu0 * u0 + gu1 * u1) * inv;
-    r.gmv_i = gu1 * inv + gD;
-    r.gmv_j = -(gu0 * inv + gD);
+    // gu1/D - (gu0*u0 + gu1*u1)/D is u0 * g.(vj - vi) / D with gu0 ~ gu1: in fp32 the cancellation costs ~|v| / |vj - vi|
+    // (the grid resolution) of relative accuracy, so the per-edge terms are formed in fp64 (inputs and result fp32)
+    const double gu0 = (double)gx * vi[0] + (double)gy * vi[1] + (double)gz * vi[2];
+    const double gu1 = (double)gx * vj[0] + (double)gy * vj[1] + (double)gz * vj[2];
+    const double inv = 1.0 / (double)D;
+    const double gD = -(gu0 * (double)u0 + gu1 * (double)u1) * inv;
+    r.gmv_i = (float)(gu1 * inv + gD);
+    r.gmv_j = (float)(-(gu0 * inv + gD));
   }
   return r;
 }
@@ -283,17 +285,21 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const __grid_constant__ Ad
   if (msdf_negate) { ma = -ma; mb = -mb; }
   const float pax = __ldg(pos + 3ll * a), pay = __ldg(pos + 3ll * a + 1), paz = __ldg(pos + 3ll * a + 2);
   const float pbx = __ldg(pos + 3ll * b), pby = __ldg(pos + 3ll * b + 1), pbz = __ldg(pos + 3ll * b + 2);
-  const float gw0 = gx * pax + gy * pay + gz * paz + gmv * ma;
-  const float gw1 = gx * pbx + gy * pby + gz * pbz + gmv * mb;
-  const float inv = 1.f / dd;
-  const float gdd = -(gw0 * w0 + gw1 * w1) * inv;
+  // g_sdf = gw1/dd - (gw0*w0 + gw1*w1)/dd = w0 * (gw1 - gw0) / dd with gw0 ~ gw1 (both ~ g.pos, their difference
+  // ~ g.edge): fp32 loses |pos| / |edge| = the grid resolution in relative accuracy (4.6e-5 at 256^3, measured), so
+  // the per-edge terms are formed in fp64 from the fp32 inputs; the accumulation into g_sdf stays fp32 atomics
+  const double gw0 = (double)gx * pax + (double)gy * pay + (double)gz * paz + (double)gmv * ma;
+  const double gw1 = (double)gx * pbx + (double)gy * pby + (double)gz * pbz + (double)gmv * mb;
+  const double inv = 1.0 / (double)dd;
+  const double gdd = -(gw0 * (double)w0 + gw1 * (double)w1) * inv;
+  const float gs_a = (float)(gw1 * inv + gdd), gs_b = (float)(-(gw0 * inv + gdd));
   const float gm_in = gmv + gsg;
 
   // a side: runs of equal `a` are contiguous (edges sorted lexicographically) -> one atomic per run and warp
   float sax = seg_reduce_to_head(gx * w0, a, active);
   float say = seg_reduce_to_head(gy * w0, a, active);
   float saz = seg_reduce_to_head(gz * w0, a, active);
-  float sas = seg_reduce_to_head(gw1 * inv + gdd, a, active);
+  float sas = seg_reduce_to_head(gs_a, a, active);
   float sam = seg_reduce_to_head(gm_in * w0, a, active);
   const unsigned lane = lane_id();
   const int a_prev = __shfl_up_sync(active, a, 1);
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const __grid_constant__ Ad
   }
   // b side
   atomicAdd(g_pos + 3ll * b, gx * w1); atomicAdd(g_pos + 3ll * b + 1, gy * w1); atomicAdd(g_pos + 3ll * b + 2, gz * w1);
-  atomicAdd(g_sdf + b, -(gw0 * inv + gdd));
+  atomicAdd(g_sdf + b, gs_b);
   if (g_msdf != nullptr) atomicAdd(g_msdf + b, gm_in * w1);
 }
 

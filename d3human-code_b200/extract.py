@@ -133,7 +133,9 @@ def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
     """-> (edge_off, edge_ab, n_edges) or None, according to the static-edge policy."""
     if _static_mode == "0" or tets_i32.shape[0] == 0:
         return None
-    key = (tets_i32.data_ptr(), tets_i32.shape[0], int(n_grid), tets_i32.device.index)
+    # the version counter is part of the key: an int32 tet_fx4 is used in place (packed_tets returns the caller's tensor),
+    # an in-place edit must not find the edge table of the old contents
+    key = (tets_i32.data_ptr(), tets_i32._version, tets_i32.shape[0], int(n_grid), tets_i32.device.index)
     ent = _static_cache.get(key)
     if ent is None:
         if len(_static_cache) > 8:

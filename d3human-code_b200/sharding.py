@@ -82,11 +82,12 @@ def allreduce_shared_grads(grads: Sequence[Optional[torch.Tensor]], group=None, 
         all_v = [torch.empty_like(send_v) for _ in range(world)]
         dist.all_gather(all_i, send_i, group=group)
         dist.all_gather(all_v, send_v, group=group)
-        rank = dist.get_rank(group)
-        for r in range(world):   # rank order: every rank adds in the same order -> identical results everywhere
-            if r == rank or counts[r] == 0:
-                continue
-            flat.index_add_(0, all_i[r][:counts[r]], all_v[r][:counts[r]])
+        # every rank clears its own entries and adds ALL lists (its own included) in rank order: the same additions
+        # in the same order everywhere, so replicated parameters stay bit-identical across the ranks
+        flat[idx] = 0
+        for r in range(world):
+            if counts[r]:
+                flat.index_add_(0, all_i[r][:counts[r]], all_v[r][:counts[r]])
 
 
 # ------------------------------------------------------------------------------------------------------------ tet ranges
@@ -113,11 +114,12 @@ def gather_records(local: torch.Tensor, n_local: int, group=None) -> Tuple[torch
     return torch.cat([parts[r][:counts[r]] for r in range(world)], 0), counts
 
 
-def _tet_sharded_launcher(ranges: Sequence[Tuple[int, int]], exchange: Optional[Callable], dev) -> Callable:
+def _tet_sharded_launcher(ranges: Sequence[Tuple[int, int]], exchange: Optional[Callable], dev, group=None) -> Callable:
     """Builds the launcher that replaces d3h_extract_forward_batch in extract.forward_frames_raw.
 
     ranges  : tet ranges this process classifies itself (one for a real rank; several = virtual ranks on one GPU)
-    exchange: (records (n,8) int32, n) -> (all records in global tet order, per-rank counts) or None (single process)"""
+    exchange: (records (n,8) int32, n) -> (all records in global tet order, per-rank counts) or None (single process)
+    group   : the process group of `exchange`: the overflow / total reduction must run over the same ranks"""
     L = _cabi.lib()
     c = E._FC
 
@@ -149,7 +151,7 @@ def _tet_sharded_launcher(ranges: Sequence[Tuple[int, int]], exchange: Optional[
             # ranks that overflowed still take part in the collective (with an empty list) so that nobody hangs
             flag = torch.tensor([total_valid, int(overflow)], dtype=torch.int64, device=dev)
             import torch.distributed as dist
-            dist.all_reduce(flag)
+            dist.all_reduce(flag, group=group)
             total_valid, overflow = int(flag[0]), bool(int(flag[1]))
             merged, _ = exchange(local, local.shape[0])
         else:
@@ -189,6 +191,6 @@ def extract_tet_sharded(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = Fal
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         ranges = [tet_range(n_tets, world, rank)]
         exchange = (lambda rec, n: gather_records(rec, n, group)) if world > 1 else None
-    launcher = _tet_sharded_launcher(ranges, exchange, pos.device)
+    launcher = _tet_sharded_launcher(ranges, exchange, pos.device, group)
     spec = ((((0, -1), (1, -1), (2, -1), bool(msdf_negate)),), bool(output_watertight_template), 1, launcher)
     return E._pack_result(E._ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)

@@ -133,3 +133,43 @@ def test_oracle_matches_live_reference_on_random_tet_soups(seed):
     U.assert_close_normwise("grad_sdf", g_sdf, ts.grad.numpy()[:, 0], 5 * U.GRAD_RTOL)
     if typ != "body":
         U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), U.GRAD_RTOL)
+
+
+# The oracle's adjoint is float64 (the exact gradient of the fp32 forward); the reference back-propagates in fp32 and
+# forms gw1/dd - (gw0*w0 + gw1*w1)/dd with gw0 ~ gw1, so ITS gradients carry a cancellation error that grows with the
+# grid resolution (|pos| / |edge|).  Measured in this container (live reference, CPU, vs the oracle, normwise):
+#   64^3 sphere 1.2e-5 / capsule 2.7e-6, 128^3 sphere 1.6e-5 / capsule 3.6e-5 (g_sdf; g_msdf 1.9e-5), 256^3 5.2e-5.
+# So "oracle == reference to 1e-5" only holds at small sizes; at the BASELINE sizes the honest pin is: integers,
+# positions and mSDF bit-exact, gradients within the reference's own fp32 noise.  The CUDA kernels are held to 1e-5
+# against the ORACLE (tests/test_y_fullsize_parity.py), i.e. they are closer to the exact gradient than the reference.
+def reference_gradient_noise_bound(res):
+    return 4e-7 * res
+
+
+@pytest.mark.parametrize("res,field,cls,typ", [
+    (64, "sphere", "GShell_Tets", None),          # BASELINE configs[0]
+    (64, "capsule", "hmSDF_Tets", "cloth"),
+    (64, "capsule", "hmSDF_Tets", "body"),
+    (128, "capsule", "hmSDF_Tets", "cloth"),      # BASELINE configs[1]
+])
+def test_oracle_matches_live_reference_at_named_sizes(res, field, cls, typ):
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = (grids.sphere_plane_field if field == "sphere" else grids.capsule_garment_field)(pos)
+    (verts, faces, _, _, v_tng, extra), (tp, ts, tm) = _run_reference(cls, typ, True, pos, sdf, msdf, tets)
+    fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, True)
+    U.assert_exact("faces_aug", fwd["faces_aug"], faces.numpy())
+    U.assert_exact("verts_aug", fwd["verts_aug"], verts.detach().numpy())
+    U.assert_exact("msdf", fwd["msdf"], extra["msdf"].detach().numpy())
+    U.assert_exact("faces_watertight", fwd["faces_watertight"], extra["faces_watertight"].numpy())
+    U.assert_exact("vertices_watertight", fwd["vertices_watertight"], extra["vertices_watertight"].detach().numpy())
+    gv = (2.0 * fwd["verts_aug"].astype(np.float64)).astype(np.float32)     # d/dverts of sum(verts^2)
+    gm = np.ones_like(fwd["msdf"])
+    ((verts * torch.tensor(gv)).sum() + (extra["msdf"] * torch.tensor(gm)).sum()).backward()
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, gm)
+    bound = reference_gradient_noise_bound(res)
+    U.assert_close_normwise("grad_pos", g_pos, tp.grad.numpy(), U.GRAD_RTOL)       # no cancellation on this branch
+    U.assert_close_normwise("grad_sdf", g_sdf, ts.grad.numpy()[:, 0], bound)
+    if typ == "body":
+        assert tm.grad is None and g_msdf is None
+    else:
+        U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), bound)

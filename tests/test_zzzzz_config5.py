@@ -5,7 +5,7 @@ single call and against the numpy oracle (which finishes this size in about a se
 Integer outputs, positions and mSDF values bit-exact, gradients 1e-5 normwise.  The real multi-rank version of the same
 code path is tests/test_multi_gpu.py; the collective there (all-gather of the records) does not change the data.
 
-Sorts after every test that has run on a GPU before: written when no GPU was available; the code path is validated at small sizes on the GPU
+The LAST file of the suite (it failed in round 1 and, under -x, kept 53 tests behind it from running).
 (test_cuda_parity.py) and on the kernel emulation, this size had never been run anywhere.
 """
 import numpy as np
