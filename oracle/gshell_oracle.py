@@ -348,6 +348,56 @@ def _compute_tangents(verts, v_nrm, faces, num_tets):
     return _safe_normalize((tng - (proj * v_nrm).astype(F32)).astype(F32))
 
 
+def tangent_condition(fwd):
+    """Per-row condition number of v_tng_aug (Va,) for the parity tests: how strongly a unit round-off in the ORDER of
+    the scatter additions (sequential on the CPU reference, float atomics in arbitrary order on a GPU -- the
+    reference's own CUDA scatter_add_ included) moves the unit tangent of a row.
+
+    A watertight vertex's tangent is normalize(t - (t.n) n) with n = normalize(sum of face normals) and
+    t = normalize(sum of per-face tangents / count) (gshell_tets.py:9-34, 40-78).  Re-ordering a sum S = sum x_f moves
+    its direction by ~eps * sum|x_f| / |S|; the Gram-Schmidt step divides by s = |t - (t.n) n|.  So
+        kappa = (sum|t_f| / |sum t_f| + 2 sum|n_f| / |sum n_f| + 3) / s,
+    and a boundary row (lerp of its two corners' tangents with weights u0, u1, :380-385) inherits |u0| k_i + |u1| k_j.
+    inf where a sum cancels exactly (the Kuhn lattice mixes left- and right-handed tets, so the reference's triangle
+    table orients neighbouring faces inconsistently: such vertices are common on the synthetic grids)."""
+    f8 = np.float64
+    verts = fwd["vertices_watertight"].astype(f8)
+    faces = fwd["faces_watertight"]
+    nv = verts.shape[0]
+    kap = np.full(nv, np.inf)
+    if faces.shape[0] and faces.shape[0] != 3:      # (the 3-face torch.cross quirk is covered by a golden vector)
+        p = [verts[faces[:, i]] for i in range(3)]
+        t = [vertex_uv(faces[:, i], fwd["_num_tets"]).astype(f8) for i in range(3)]
+        pe1, pe2 = p[1] - p[0], p[2] - p[0]
+        uve1, uve2 = t[1] - t[0], t[2] - t[0]
+        fn = np.cross(pe1, pe2)
+        den = uve1[:, 0] * uve2[:, 1] - uve1[:, 1] * uve2[:, 0]
+        den = np.where(den > 0, np.maximum(den, 1e-6), np.minimum(den, -1e-6))
+        tang = (pe1 * uve2[:, 1:2] - pe2 * uve1[:, 1:2]) / den[:, None]
+        sn, st = np.zeros((nv, 3)), np.zeros((nv, 3))
+        an, at = np.zeros(nv), np.zeros(nv)
+        for i in range(3):
+            np.add.at(sn, faces[:, i], fn)
+            np.add.at(st, faces[:, i], tang)
+            np.add.at(an, faces[:, i], np.linalg.norm(fn, axis=1))
+            np.add.at(at, faces[:, i], np.linalg.norm(tang, axis=1))
+        ln, lt = np.linalg.norm(sn, axis=1), np.linalg.norm(st, axis=1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            n = sn / ln[:, None]
+            tt = st / lt[:, None]
+            g = tt - (tt * n).sum(-1, keepdims=True) * n
+            s = np.linalg.norm(g, axis=1)
+            kap = (at / lt + 2.0 * an / ln + 3.0) / s
+        kap[~np.isfinite(kap)] = np.inf
+        # the reference's thresholds (1e-20 on squared lengths) switch branches: treat anything near them as unstable
+        kap[(ln * ln < 1e-18) | (lt * lt < 1e-18) | (s * s < 1e-18)] = np.inf
+    corners, nxt = fwd["corners"], fwd["_nxt"]
+    u0, u1 = np.abs(fwd["_u0"].astype(f8)), np.abs(fwd["_u1"].astype(f8))
+    with np.errstate(invalid="ignore"):
+        kb = np.where(u0 > 0, u0 * kap[corners], 0.0) + np.where(u1 > 0, u1 * kap[nxt], 0.0)
+    return np.concatenate([kap, kb])
+
+
 # --------------------------------------------------------------------------------------
 # backward (hand-derived adjoint of the float pipeline; SURVEY A.5)
 # --------------------------------------------------------------------------------------

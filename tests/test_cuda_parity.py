@@ -4,7 +4,8 @@
 plus size-independent properties at the BASELINE.json full size (128^3).
 
 Tolerances (BASELINE.json north_star): topology / indices / counts / ordering bit-exact, positions 1e-6 relative
-(asserted bit-exact), gradients 1e-5 normwise, tangents: worst row 5e-3, 99% of rows 1e-4 absolute on unit vectors (float-atomic scatter order, see tests/_util.py).
+(asserted bit-exact), gradients 1e-5 normwise, tangents: per-row bound 2e-6 + 4e-7 * kappa from the condition of the
+row's scatter sums (float-atomic order; oracle.tangent_condition, tests/_util.py).
 """
 import numpy as np
 import pytest
@@ -77,7 +78,11 @@ def test_cuda_matches_golden(dev, name):
     rec = U.load_golden(name)
     grads = {k: rec.get(k) for k in ("g_verts_aug", "g_msdf", "g_msdf_watertight", "g_vertices_watertight")}
     out, g = _run(dev, rec["pos"], rec["sdf"], rec["msdf"], rec["tets"], rec["cls"], rec["type"], rec["wt"], grads)
-    U.check_forward_against_golden(out, rec, tng_atol=U.TNG_CUDA_ATOL, tng_p99=U.TNG_CUDA_P99)
+    # tangents: condition-aware bound from the oracle's forward on the golden inputs (the exactly-three-faces fixture
+    # exercises the torch.cross quirk, where the bound does not apply: flat tolerance there)
+    fwd = O.extract_forward(rec["pos"], rec["sdf"], rec["msdf"], rec["tets"], rec["sign"], rec["wt"])
+    kappa = O.tangent_condition(fwd) if fwd["faces_watertight"].shape[0] != 3 else None
+    U.check_forward_against_golden(out, rec, tng_atol=U.TNG_CUDA_ATOL, tng_p99=U.TNG_CUDA_P99, kappa=kappa)
     if "grad_pos" in rec:
         U.check_grads_against_golden(g[0], g[1], g[2], rec)
     else:
@@ -126,9 +131,10 @@ def test_cuda_matches_oracle(dev, res, field, cls, typ, wt):
         assert out["n_verts_watertight"] == fwd["n_verts_watertight"]
         U.assert_exact("faces_watertight", out["faces_watertight"], fwd["faces_watertight"])
         U.assert_exact("vertices_watertight", out["vertices_watertight"], fwd["vertices_watertight"])
-    # random fields hold near-degenerate faces (exact zeros in sdf): their normals are rounding residue
-    tol, p99 = (U.TNG_CUDA_ATOL, U.TNG_CUDA_P99) if field != "adv" else (2.0, 1e-2)
-    U.assert_tangents_close("v_tng_aug", out["v_tng_aug"], fwd["v_tng_aug"], tol, p99)
+    # tangents: per-row bound from the condition of the row's scatter sums (random fields hold near-degenerate faces --
+    # exact zeros in sdf -- whose normals are rounding residue: those rows, and only those, are unchecked)
+    U.assert_tangents_conditioned("v_tng_aug", out["v_tng_aug"], fwd["v_tng_aug"], O.tangent_condition(fwd),
+                                  max_unchecked_frac=0.01 if field != "adv" else 0.2)
     g_pos, g_sdf, g_msdf = O.extract_backward(fwd, grads["g_verts_aug"], grads["g_msdf"], grads["g_vertices_watertight"],
                                               grads["g_msdf_watertight"])
     U.assert_close_normwise("grad_pos", g[0], g_pos, U.GRAD_RTOL)

@@ -88,7 +88,8 @@ def test_elementwise_parity_with_gradients(dev, res, field, cls, typ, upstream):
     for k in ("faces_aug", "verts_aug", "msdf", "msdf_watertight", "msdf_boundary", "faces_watertight", "vertices_watertight"):
         U.assert_exact(k, out[k], fwd[k])
     assert out["n_verts_watertight"] == fwd["n_verts_watertight"]
-    U.assert_tangents_close("v_tng_aug", out["v_tng_aug"], fwd["v_tng_aug"], U.TNG_CUDA_ATOL, U.TNG_CUDA_P99)
+    unchecked = U.assert_tangents_conditioned("v_tng_aug", out["v_tng_aug"], fwd["v_tng_aug"], O.tangent_condition(fwd),
+                                              max_unchecked_frac=0.005)
     want = O.extract_backward(fwd, grads["g_verts_aug"], grads["g_msdf"])
     port = _torch_port_grads(dev, pos, sdf, msdf, tets, sign, grads)
     names = ("grad_pos", "grad_sdf", "grad_msdf")
@@ -100,7 +101,7 @@ def test_elementwise_parity_with_gradients(dev, res, field, cls, typ, upstream):
         err_k = _normwise(np.asarray(got).reshape(ref.shape), ref)
         err_p = _normwise(np.asarray(prt).reshape(ref.shape), ref)
         report[name] = (err_k, err_p)
-    print(f"\n[{res}^3 {field} {typ} {upstream}] normwise distance from the f64 oracle (kernel, fp32 torch port): "
+    print(f"\n[{res}^3 {field} {typ} {upstream}] tangent rows too ill-conditioned to check: {unchecked:.4f}; normwise distance from the f64 oracle (kernel, fp32 torch port): "
           + ", ".join(f"{k} {a:.2e} / {b:.2e}" for k, (a, b) in report.items()))
     for name, (err_k, err_p) in report.items():
         assert err_k <= U.GRAD_RTOL, f"{name}: kernel {err_k:.3e} > {U.GRAD_RTOL:g}"
