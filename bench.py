@@ -448,27 +448,32 @@ def main():
     kern = {}
     if prof:
         kern = {k: {"ms_total": round(v[0], 4), "launches": v[1], "us_avg": round(1e3 * v[0] / v[1], 3)} for k, v in prof.items()}
-        ms, n = prof.get("classify", (0.0, 0))
+        dom = "edge_scan" if "edge_scan" in prof else "classify"
+        ms, n = prof.get(dom, (0.0, 0))
+        dom_bytes = 16.0 * F
+        if dom == "edge_scan":   # 4 B per edge (larger endpoint) + 4 B per vertex (CSR offsets) + the sign bitmap
+            st = E.static_edges_for(E.packed_tets(tets, N), N)
+            dom_bytes = 4.0 * st[2] + 4.0 * (N + 1) + N / 8.0
         if n and ms > 0:
             t = ms / n * 1e-3
-            achieved = 16.0 * F / t / 1e9
+            achieved = dom_bytes / t / 1e9
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "classify_traffic.json")) as fh:
                     tj = json.load(fh)
-                    if int(tj.get("F", 0)) == F:
+                    if int(tj.get("F", 0)) == F and tj.get("kernel", "classify") == dom:
                         traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
-            roofline = {"kernel": "classify_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            roofline = {"kernel": dom + "_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": 16 * F, "us_per_launch": t * 1e6,
+                        "algorithmic_bytes_per_launch": int(dom_bytes), "us_per_launch": t * 1e6,
                         "timing": "CUDA events recorded around each launch on its stream, one frame at a time (includes "
                                   "the ~3-5 us event / launch gap)"}
-            if dev_trace and "us_mean" in dev_trace and "classify" in dev_trace["us_mean"]:
-                td = dev_trace["us_mean"]["classify"] * 1e-6
-                roofline["device_timer"] = {"us_per_launch": td * 1e6, "achieved": 16.0 * F / td / 1e9,
-                                            "frac": 16.0 * F / td / 1e9 / peak,
+            if dev_trace and "us_mean" in dev_trace and dom in dev_trace["us_mean"]:
+                td = dev_trace["us_mean"][dom] * 1e-6
+                roofline["device_timer"] = {"us_per_launch": td * 1e6, "achieved": dom_bytes / td / 1e9,
+                                            "frac": dom_bytes / td / 1e9 / peak,
                                             "note": "first block start to last block exit (%globaltimer), inside the "
                                                     "batched step with the other lanes running"}
     dev_ms_frame = sum(v[0] for v in prof.values()) / max(nprof * len(pos_single), 1) if prof else None

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libd3h_tets.so")
 
 D3H_OK, D3H_E_BADARG, D3H_E_CUDA, D3H_E_SMALLWS, D3H_E_TIMEOUT = 0, -1, -2, -3, -4
-VERSION = 430
+VERSION = 440
 
 #: every symbol include/d3h_tets.h declares (tests/test_cabi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -58,7 +58,8 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("pair_verts_aug", C.c_void_p), ("pair_v_tng_aug", C.c_void_p), ("pair_msdf_aug", C.c_void_p),
                 ("pair_faces_aug", C.c_void_p), ("pair_verts_wt", C.c_void_p), ("pair_v_tng_wt", C.c_void_p),
                 ("pair_msdf_wt", C.c_void_p), ("pair_faces_wt", C.c_void_p), ("pair_vacc", C.c_void_p),
-                ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64), ("tet_edge_rank", C.c_void_p)]
+                ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64), ("tet_edge_rank", C.c_void_p),
+                ("edge_b", C.c_void_p), ("etet_off", C.c_void_p), ("etets", C.c_void_p)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args
@@ -188,12 +189,12 @@ def trace_read():
     """-> {seq % 64: {kernel name: (start_ns, end_ns)}} of the forward kernels run since the last read."""
     import numpy as np
     L = lib()
-    t = np.zeros((64, 16, 2), dtype=np.uint64)
+    t = np.zeros((64, 24, 2), dtype=np.uint64)
     check(L.d3h_trace_read(t.ctypes.data), "d3h_trace_read")
     out = {}
     for f in range(64):
         row = {L.d3h_profile_kernel_name(k).decode(): (int(t[f, k, 0]), int(t[f, k, 1]))
-               for k in range(min(16, L.d3h_profile_kinds())) if t[f, k, 0]}
+               for k in range(min(24, L.d3h_profile_kinds())) if t[f, k, 0]}
         if row:
             out[f] = row
     return out

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libd3h_tets.so")
-SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu"]
+SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_scan.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "0"]
 

@@ -119,6 +119,7 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   const int64_t nchunks = (n_tets + kChunkTets - 1) / kChunkTets;
   const int64_t nwords_f = nchunks * kClassifyItems;
   ws.ntiles_compact = (n_tets + kTileTets - 1) / kTileTets;
+  ws.nwords_tet = nwords_f + kCompactThreads;
   ws.ngroups = capc / kSortGroup + 1;
   ws.ntiles_poly = (cap + kPolyThreads - 1) / kPolyThreads;
   ws.msd_bins = ((n_grid - 1) >> msd_shift_for(n_grid)) + 1;
@@ -161,6 +162,11 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
     ws.word_prefix = reinterpret_cast<unsigned*>(take(ewords * 4));
     ws.eblock_cnt = reinterpret_cast<unsigned*>(take((ws.n_eblocks + 1) * 4));
     ws.corner_rank = reinterpret_cast<unsigned*>(take(capc * 4));
+    ws.tile_list = reinterpret_cast<unsigned*>(take((ws.ntiles_compact + 1) * 4));
+    ws.eblock_list = reinterpret_cast<unsigned*>(take((ws.n_eblocks + 1) * 4));
+    ws.vlist = reinterpret_cast<int2*>(take(cap * 8));
+    ws.elist = reinterpret_cast<int32_t*>(take(capc * 4));
+    ws.tet_word_prefix = reinterpret_cast<uint2*>(take((nwords_f + kCompactThreads) * 8));
   }
   ws.total_bytes = off;
   return ws;
@@ -221,6 +227,11 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: tet_edge_rank needs the static edge table and 16-byte alignment", who);
     return D3H_E_BADARG;
   }
+  if (a->etets != nullptr &&
+      (!a->edge_off || !a->edge_b || !a->etet_off || !a->tet_edge_rank || a->tet_begin != 0 || a->tet_end != a->n_tets)) {
+    set_error("%s: the edge-scan path needs edge_off / edge_b / etet_off / etets / tet_edge_rank and the whole tet range", who);
+    return D3H_E_BADARG;
+  }
   if (a->cap_valid_tets > 0 && (!a->tape_corners || (a->edge_off == nullptr && (!a->tape_slots || !a->tape_runs)))) {
     set_error("%s: tape_corners / tape_slots (4*cap_valid_tets int32) and tape_runs (cap_verts+1 int32) are required", who);
     return D3H_E_BADARG;
@@ -257,10 +268,16 @@ static int finish(const char* who, const d3h_forward_args* a, const Workspace& w
 }
 
 void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts) {
-  launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream, parts);
-  if (!(parts & kPartTail)) return;
-  if (a.edge_off != nullptr) launch_edge_emit(a, ws, stream);
-  else launch_edge_sort(a, ws, stream);
+  if (edge_scan_path(a)) {
+    // no classification stream: the walk over the static edge list marks crossing edges and valid tets
+    if (parts & kPartHead) launch_edge_scan(a, ws, stream);
+    if (!(parts & kPartTail)) return;
+  } else {
+    launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream, parts);
+    if (!(parts & kPartTail)) return;
+    if (a.edge_off != nullptr) launch_edge_emit(a, ws, stream);
+    else launch_edge_sort(a, ws, stream);
+  }
   launch_surface(a, ws, ws.records, stream);
   if (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) launch_zero_grads_from_block(a, ws, stream);
 }
@@ -371,7 +388,7 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.watertight = a.watertight_template ? 1 : 0;
   key.has_zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) ? 1 : 0;
   key.parts = parts;
-  key.is_static = a.edge_off != nullptr ? (a.tet_edge_rank != nullptr ? 2 : 1) : 0;
+  key.is_static = a.edge_off != nullptr ? (a.etets != nullptr ? 3 : (a.tet_edge_rank != nullptr ? 2 : 1)) : 0;
   key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
   std::lock_guard<std::mutex> lock(g_graph_mu);
@@ -643,6 +660,7 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a_in, d3h_tet_record* 
   if (!a_in) { set_error("d3h_classify_range: null argument struct"); return D3H_E_BADARG; }
   d3h_forward_args general = *a_in;  // the sharded stages always take the general (sort) path
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
+  general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_classify_range");
   if (rc) return rc;
@@ -672,6 +690,7 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a_in, const d3h_
   if (!a_in) { set_error("d3h_extract_from_records: null argument struct"); return D3H_E_BADARG; }
   d3h_forward_args general = *a_in;
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
+  general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_extract_from_records");
   if (rc) return rc;
@@ -706,7 +725,7 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "group_sort",
                                             "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records",
                                             "edge_emit", "adjoint_poly", "pair_replay", "mesh_edges", "mesh_normals",
-                                            "mesh_adjoint"};
+                                            "mesh_adjoint", "edge_scan"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;
@@ -780,7 +799,7 @@ extern "C" int d3h_trace_enable(int on) {
   }
   return D3H_OK;
 }
-// Copies the table out ((64, 16, 2) uint64 nanoseconds: [seq % 64][kernel kind][start, end]; 0 = not run) and clears
+// Copies the table out ((64, 24, 2) uint64 nanoseconds: [seq % 64][kernel kind][start, end]; 0 = not run) and clears
 // it.  Synchronises the device.
 extern "C" int d3h_trace_read(uint64_t* out) {
   if (!out) { set_error("d3h_trace_read: null output"); return D3H_E_BADARG; }

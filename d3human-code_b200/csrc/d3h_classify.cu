@@ -73,6 +73,14 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
     const int64_t nw4 = ws.n_eblocks * (kEdgeBlock / 32) / 4;
     for (int64_t i = tid; i < nw4; i += nthreads) reinterpret_cast<uint4*>(ws.edge_bits)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int64_t i = tid; i < ws.n_eblocks + 1; i += nthreads) ws.eblock_cnt[i] = 0u;
+    if (src.a.etets != nullptr) {
+      // edge-scan path: the tet bitmaps are MARKED (atomicOr) instead of written by the classification stream
+      const int64_t nt4 = ws.nwords_tet / 4;   // nwords_tet is a multiple of 8
+      for (int64_t i = tid; i < nt4; i += nthreads) {
+        reinterpret_cast<uint4*>(ws.m1_words)[i] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(ws.m2_words)[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
   } else {
     for (int64_t i = tid; i < (ws.msd_bins + 8 + 3) / 4; i += nthreads)  // msd_hist: 256-byte aligned region, padded by 8
       reinterpret_cast<uint4*>(ws.msd_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -120,9 +128,6 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
 // ------------------------------------------------------------------------------------------------
 // K1: streaming classification (persistent grid)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, int v) {
-  return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u;
-}
 
 // One warp classifies kChunkTets consecutive tets per loop trip.  MOCC adds the open-mesh prefilter (gshell_tets.py:275).
 // A tet past the end of the range is loaded as (0,0,0,0): four equal vertices are never a sign change, so the tail needs

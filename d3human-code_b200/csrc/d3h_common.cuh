@@ -126,7 +126,7 @@ __device__ __forceinline__ void store_same_value(float* p, float v) {
 }
 // Diagnostics (d3h_trace_enable): per call and kernel kind, [0] = time block 0 started, [1] = latest block exit.
 constexpr int kTraceFrames = 64;
-constexpr int kTraceKinds = 16;
+constexpr int kTraceKinds = 24;
 __device__ __forceinline__ unsigned long long* trace_begin(unsigned long long* table, unsigned frame, int kind) {
   if (table == nullptr) return nullptr;
   unsigned long long* slot = table + ((frame % kTraceFrames) * kTraceKinds + kind) * 2;
@@ -135,6 +135,10 @@ __device__ __forceinline__ unsigned long long* trace_begin(unsigned long long* t
 }
 __device__ __forceinline__ void trace_end(unsigned long long* slot) {
   if (slot != nullptr && threadIdx.x == 0) atomicMax(slot + 1, global_timer_ns());
+}
+// bit v of a vertex bitmap (sdf > 0, or msdf > 0)
+__device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, int v) {
+  return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u;
 }
 __device__ __forceinline__ float fsign(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
@@ -181,7 +185,11 @@ struct DevCounters {
   unsigned bucket[6];        // polygons per faces_aug bucket
   unsigned poly_done2;       // the same two for the replayed mSDF cut of a cloth / body pair
   unsigned bucket2[6];
-  unsigned pad[5];
+  unsigned n_tile_list;      // edge-scan path: entries of Workspace::tile_list / eblock_list (non-empty compaction tiles /
+  unsigned n_eblock_list;    //   edge blocks, in the order their first mark arrived)
+  unsigned n_vlist;          // edge-scan path: entries appended to Workspace::vlist (valid tets) / elist (crossing edges);
+  unsigned n_elist;          //   true counts, may exceed the list capacities
+  unsigned pad[1];
   unsigned trace_frame;      // diagnostics (d3h_trace_*): row of the trace table this call writes to
   unsigned pad2;
   unsigned long long* trace; // diagnostics: device trace table or nullptr; set by prepare_kernel, not reset

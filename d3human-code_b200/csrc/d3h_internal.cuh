@@ -75,7 +75,13 @@ struct Workspace {
   unsigned* word_prefix;          // per word of edge_bits: number of marked edges before it (= first vertex id of the word)
   unsigned* eblock_cnt;           // marked edges per 8192-edge block (one edge_emit CTA)
   unsigned* corner_rank;          // 4 per valid-tet record: edge rank of every polygon corner
+  unsigned* tile_list;            // edge-scan path: ids of the non-empty compaction tiles (ntiles_compact entries)
+  unsigned* eblock_list;          //                 ids of the non-empty edge blocks (n_eblocks entries)
+  int2* vlist;                    //                 (tet id, occupancy code) of every valid tet, unordered (cap_tets)
+  int32_t* elist;                 //                 rank of every crossing edge, unordered (cap_corners)
+  uint2* tet_word_prefix;         //                 per word of m1 / m2: (T1-class, T2-class) valid tets before it
   int64_t n_edges, n_eblocks;
+  int64_t nwords_tet;             // words of m1_words / m2_words (32 tets each), padded to whole compaction tiles
   int64_t cap_tets, cap_corners;
   int64_t ntiles_compact, nscan_ctas, ngroups, ntiles_poly;
   int64_t total_bytes;
@@ -103,6 +109,10 @@ void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_rec
                      bool emit_keys, cudaStream_t stream, int parts = kPartAll);
 void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 void launch_edge_emit(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);  // static edge table path
+// edge-scan path (d3h_forward_args.etets): replaces the classification stream + compaction by a walk over the static edge
+// list, then compacts / numbers only the tiles and edge blocks that were marked
+void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
+inline bool edge_scan_path(const d3h_forward_args& a) { return a.edge_off != nullptr && a.etets != nullptr; }
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream);
 // second extraction of a cloth / body pair: replays the mSDF cut on the shared surface (d3h_forward_args.pair_*)
@@ -149,7 +159,7 @@ bool profiling_enabled();
 enum KernelKind {
   K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_GROUP_SORT, K_VERTEX_EMIT, K_POLY_FACES,
   K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_PAIR_REPLAY, K_MESH_EDGES, K_MESH_NORMALS,
-  K_MESH_ADJOINT, K_COUNT
+  K_MESH_ADJOINT, K_EDGE_SCAN, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

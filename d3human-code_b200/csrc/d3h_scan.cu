@@ -1,0 +1,350 @@
+// The edge-scan path: stage 1 and 2 of the extraction WITHOUT streaming the tet array.
+//
+// A training run extracts from the same tet grid every iteration (hmsdf.py:207-212), so the host builds, once per
+// grid, the sorted list of all distinct tet edges (edge_off / edge_b: CSR by smaller endpoint), the tets around every
+// edge (etet_off / etets) and the rank of every tet's six edges in that list (tet_edge_rank).  With them:
+//
+//   edge_scan_kernel   one thread per grid vertex a walks the larger neighbours b of a (4 bytes per EDGE instead of the
+//                      16 bytes per TET of classify_kernel: 68 MB instead of 201 MB at 128^3).  sign(sdf[a]) !=
+//                      sign(sdf[b]) is exactly the crossing mask of gshell_tets.py:281; the tets around a crossing
+//                      edge are exactly the valid tets of :261-275 (a tet has mixed signs iff one of its edges
+//                      crosses).  The thread marks the edge in the bitmap over the edge list, marks the tets around it
+//                      in the T1 / T2 bitmaps (the first marker of a tet counts it for its 8192-tet tile) and appends
+//                      both to unordered work lists (staged in shared memory: one global atomic per CTA and list).
+//   scan_prefix_kernel one CTA per non-empty tile / edge block: exclusive prefix of the popcounts of its 256 bitmap
+//                      words, on top of the sum of the counters of the earlier tiles / blocks (no look-back chain).
+//                      rank among the marked tets = record id (tet order, the order of the boolean-mask compaction
+//                      :277, :323-324); rank among the marked edges = vertex id (the order of torch.unique(dim=0), :279).
+//   scan_emit_kernel   one thread per list entry, whatever tile or block it sits in (balanced): a valid tet becomes its
+//                      record + the vertex ids of its polygon corners (tape_corners), a crossing edge becomes its
+//                      interpolated vertex (:291-303).
+//
+// poly_faces_kernel / poly_cut_kernel / the adjoint are shared with the other paths.
+#include "d3h_internal.cuh"
+
+namespace d3h {
+
+constexpr int kScanVertsPerCta = 256;
+constexpr int kStageEdges = 512;   // crossing edges / valid tets a CTA stages in shared memory before its one
+constexpr int kStageTets = 768;    //   reservation in the global lists; beyond that they are appended one by one
+
+struct ScanLists {
+  unsigned* tile_cnt; unsigned* tile_list;
+  unsigned* eblock_cnt; unsigned* eblock_list;
+  int2* vlist; int32_t* elist;
+  int64_t cap_vlist, cap_elist;
+};
+
+template <bool MOCC>
+__global__ void __launch_bounds__(kScanVertsPerCta)
+edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
+                 const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
+                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, DevCounters* __restrict__ ctr,
+                 ScanLists L) {
+  __shared__ unsigned s_ne, s_nt, s_ebase, s_tbase;
+  __shared__ int s_e[kStageEdges];
+  __shared__ int2 s_t[kStageTets];
+  const d3h_forward_args& a = blk->a;
+  const int32_t* __restrict__ edge_off = a.edge_off;
+  const int32_t* __restrict__ edge_b = a.edge_b;
+  const int32_t* __restrict__ etet_off = a.etet_off;
+  const int32_t* __restrict__ etets = a.etets;
+  const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
+  const int64_t n_grid = a.n_grid;
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
+  if (threadIdx.x == 0) { s_ne = 0u; s_nt = 0u; }
+  __syncthreads();
+  const int64_t v = (int64_t)blockIdx.x * kScanVertsPerCta + threadIdx.x;
+  if (v < n_grid) {
+    const unsigned oa = occ_of(occ_bits, (int)v);       // one word per warp: a broadcast load
+    const int e0 = __ldg(edge_off + v), e1 = __ldg(edge_off + v + 1);
+    for (int base = e0; base < e1; base += 8) {
+      int b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = (base + j < e1) ? __ldg(edge_b + base + j) : -1;
+      unsigned x = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b[j] >= 0) x |= (occ_of(occ_bits, b[j]) ^ oa) << j;
+      while (x) {   // crossing edges of this vertex (rare: the surface touches < 2 % of the vertices)
+        const int e = base + (__ffs((int)x) - 1);
+        x &= x - 1u;
+        const int t0 = __ldg(etet_off + e), t1 = __ldg(etet_off + e + 1);
+        bool any = false;
+        for (int i = t0; i < t1; ++i) {
+          const int t = __ldg(etets + i);
+          const int4 q = __ldg(tets + t);
+          const unsigned code = occ_of(occ_bits, q.x) | (occ_of(occ_bits, q.y) << 1) | (occ_of(occ_bits, q.z) << 2) |
+                                (occ_of(occ_bits, q.w) << 3);
+          if (MOCC) {   // open-mesh prefilter, gshell_tets.py:275: keep tets with a vertex of positive mSDF
+            const unsigned keep = occ_of(mocc_bits, q.x) | occ_of(mocc_bits, q.y) | occ_of(mocc_bits, q.z) |
+                                  occ_of(mocc_bits, q.w);
+            if (!keep) continue;
+          }
+          any = true;
+          const bool quad = __popc(code) == 2;
+          const unsigned bit = 1u << (t & 31);
+          const unsigned old = atomicOr((quad ? m2_words : m1_words) + (t >> 5), bit);
+          if (old & bit) continue;   // another crossing edge of this tet came first
+          const unsigned tile = (unsigned)t / (unsigned)kTileTets;
+          if (atomicAdd(L.tile_cnt + tile, quad ? 0x10000u : 1u) == 0u)
+            L.tile_list[atomicAdd(&ctr->n_tile_list, 1u)] = tile;
+          const unsigned slot = atomicAdd(&s_nt, 1u);
+          if (slot < (unsigned)kStageTets) {
+            s_t[slot] = make_int2(t, (int)code);
+          } else {
+            const unsigned g = atomicAdd(&ctr->n_vlist, 1u);
+            if ((int64_t)g < L.cap_vlist) L.vlist[g] = make_int2(t, (int)code);
+          }
+        }
+        if (!any) continue;          // (only with the prefilter) no valid tet keeps this edge: torch.unique never sees it
+        atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
+        const unsigned eb = (unsigned)e / (unsigned)kEdgeBlock;
+        if (atomicAdd(L.eblock_cnt + eb, 1u) == 0u) L.eblock_list[atomicAdd(&ctr->n_eblock_list, 1u)] = eb;
+        const unsigned slot = atomicAdd(&s_ne, 1u);
+        if (slot < (unsigned)kStageEdges) {
+          s_e[slot] = e;
+        } else {
+          const unsigned g = atomicAdd(&ctr->n_elist, 1u);
+          if ((int64_t)g < L.cap_elist) L.elist[g] = e;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned ne = min(s_ne, (unsigned)kStageEdges), nt = min(s_nt, (unsigned)kStageTets);
+  if (ne == 0u && nt == 0u) { trace_end(tr); return; }
+  if (threadIdx.x == 0) {
+    s_ebase = ne ? atomicAdd(&ctr->n_elist, ne) : 0u;
+    s_tbase = nt ? atomicAdd(&ctr->n_vlist, nt) : 0u;
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < ne; i += kScanVertsPerCta)
+    if ((int64_t)(s_ebase + i) < L.cap_elist) L.elist[s_ebase + i] = s_e[i];
+  for (unsigned i = threadIdx.x; i < nt; i += kScanVertsPerCta)
+    if ((int64_t)(s_tbase + i) < L.cap_vlist) L.vlist[s_tbase + i] = s_t[i];
+  trace_end(tr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive prefixes of the marked tets (per word of the T1 / T2 bitmaps) and of the marked edges (per word of the edge
+// bitmap).  grid = grid_tiles + grid_blocks CTAs; a CTA of the first group takes the listed tiles li = blockIdx.x,
+// + grid_tiles, ..., a CTA of the second group the listed edge blocks likewise.  The first CTA of each group also
+// publishes the grid totals.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict__ m2_words,
+                   const unsigned* __restrict__ tile_cnt, const unsigned* __restrict__ tile_list, int64_t ntiles,
+                   uint2* __restrict__ tet_word_prefix, const unsigned* __restrict__ edge_bits,
+                   const unsigned* __restrict__ eblock_cnt, const unsigned* __restrict__ eblock_list, int64_t n_eblocks,
+                   unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
+                   unsigned grid_tiles) {
+  constexpr int WARPS = 256 / 32;
+  __shared__ unsigned long long s_sum[WARPS];
+  __shared__ unsigned long long s_w[WARPS];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const bool tiles = blockIdx.x < grid_tiles;
+  const unsigned first = tiles ? blockIdx.x : blockIdx.x - grid_tiles;
+  const unsigned stride = tiles ? grid_tiles : gridDim.x - grid_tiles;
+  const unsigned* __restrict__ cnt = tiles ? tile_cnt : eblock_cnt;
+  const unsigned* __restrict__ list = tiles ? tile_list : eblock_list;
+  const unsigned n_list = tiles ? ctr->n_tile_list : ctr->n_eblock_list;
+  const int64_t n_all = tiles ? ntiles : n_eblocks;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_COMPACT);
+
+  if (first == 0u) {   // totals of the whole grid
+    unsigned long long sum = 0ull;
+    for (int64_t i = threadIdx.x; i < n_all; i += 256) {
+      const unsigned c = __ldcg(cnt + i);
+      sum += tiles ? ((unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32)) : (unsigned long long)c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_sum[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0ull;
+      for (int w = 0; w < WARPS; ++w) tot += s_sum[w];
+      if (tiles) {
+        const unsigned t1 = (unsigned)(tot & 0xffffffffull), t2 = (unsigned)(tot >> 32);
+        ctr->n_tri = t1;
+        ctr->n_quad = t2;
+        ctr->n_valid = t1 + t2;
+        const bool fits = (int64_t)t1 + t2 <= cap_records;
+        ctr->work_tri = fits ? t1 : 0u;
+        ctr->work_quad = fits ? t2 : 0u;
+      } else {
+        ctr->n_verts = (unsigned)tot;
+      }
+    }
+    __syncthreads();
+  }
+
+  for (unsigned li = first; li < n_list; li += stride) {
+    const unsigned id = list[li];
+    unsigned long long sum = 0ull;   // tiles: T1 in the low half, T2 in the high half
+    for (unsigned i = threadIdx.x; i < id; i += 256) {
+      const unsigned c = __ldcg(cnt + i);
+      sum += tiles ? ((unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32)) : (unsigned long long)c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int64_t w = (int64_t)id * 256 + threadIdx.x;
+    unsigned long long c;
+    if (tiles) c = (unsigned long long)__popc(__ldcg(m1_words + w)) | ((unsigned long long)__popc(__ldcg(m2_words + w)) << 32);
+    else c = (unsigned long long)__popc(__ldcg(edge_bits + w));
+    unsigned long long incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long nb = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += nb;
+    }
+    if (lane == 0) s_sum[warp] = sum;
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long excl = 0ull, wpre = 0ull;
+#pragma unroll
+    for (int q = 0; q < WARPS; ++q) {
+      excl += s_sum[q];
+      if (q < (int)warp) wpre += s_w[q];
+    }
+    const unsigned long long pre = excl + wpre + incl - c;
+    if (tiles) tet_word_prefix[w] = make_uint2((unsigned)(pre & 0xffffffffull), (unsigned)(pre >> 32));
+    else if (c) word_prefix[w] = (unsigned)pre;
+    __syncthreads();   // s_sum / s_w are rewritten by the next trip
+  }
+  trace_end(tr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one thread per work-list entry.  CTAs [0, grid_tets) take the valid tets, the others the crossing edges.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict__ ctr, const int2* __restrict__ vlist,
+                 const int32_t* __restrict__ elist, const unsigned* __restrict__ m1_words,
+                 const unsigned* __restrict__ m2_words, const uint2* __restrict__ tet_word_prefix,
+                 const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix,
+                 d3h_tet_record* __restrict__ records, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
+                 int64_t cap_corners, unsigned grid_tets) {
+  const d3h_forward_args& a = blk->a;
+  unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
+  if (blockIdx.x < grid_tets) {
+    // ---- valid tets -> records (tet order) + polygon corner -> vertex id ----
+    const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;   // 0 / 0 when the record buffer is too small
+    const int64_t n = (int64_t)t1 + t2;
+    const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
+    const int4* __restrict__ ranks = reinterpret_cast<const int4*>(a.tet_edge_rank);
+    int32_t* __restrict__ corners = a.tape_corners;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)grid_tets * 256) {
+      const int2 it = vlist[j];
+      const int t = it.x, code = it.y;
+      const int4 v4 = __ldg(tets + t);
+      const int4 r03 = __ldg(ranks + 2 * (int64_t)t), r45 = __ldg(ranks + 2 * (int64_t)t + 1);
+      const unsigned w = (unsigned)t >> 5, below = (1u << (t & 31)) - 1u;
+      const uint2 pre = tet_word_prefix[w];
+      const unsigned g1 = pre.x + __popc(__ldcg(m1_words + w) & below), g2 = pre.y + __popc(__ldcg(m2_words + w) & below);
+      const bool quad = __popc((unsigned)code) == 2;
+      const unsigned cr = quad ? g2 : g1, ob = quad ? g1 : g2;
+      int4* out = reinterpret_cast<int4*>(records + ((int64_t)g1 + g2));
+      out[0] = v4;
+      out[1] = make_int4(code, (int)cr, t, (int)ob);
+      const int nc = quad ? 4 : 3;
+      const int64_t p0 = quad ? (3ll * t1 + 4ll * cr) : 3ll * cr;
+      const int rr[6] = {r03.x, r03.y, r03.z, r03.w, r45.x, r45.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < nc) {
+          const int e = c_loop_edge[code][k];
+          unsigned r = 0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q)
+            if (q == e) r = (unsigned)rr[q];   // select without dynamic register indexing
+          corners[p0 + k] = (int)(__ldcg(word_prefix + (r >> 5)) + __popc(__ldcg(edge_bits + (r >> 5)) & ((1u << (r & 31u)) - 1u)));
+        }
+      }
+    }
+  } else {
+    // ---- crossing edges -> watertight vertices (zero-crossing interpolation, gshell_tets.py:291-303) ----
+    const int64_t nv_all = (int64_t)ctr->n_verts;
+    const int64_t n = nv_all < cap_corners ? nv_all : cap_corners;
+    const unsigned grid_edges = gridDim.x - grid_tets;
+    const int2* __restrict__ edge_ab = reinterpret_cast<const int2*>(a.edge_ab);
+    const float* __restrict__ pos = a.pos;
+    const float* __restrict__ sdf = a.sdf;
+    const float* __restrict__ msdf = a.msdf;
+    const int msdf_negate = a.msdf_negate;
+    const int64_t cap_verts = a.cap_verts, cap_verts_aug = a.cap_verts_aug;
+    float4* __restrict__ vacc = reinterpret_cast<float4*>(a.vacc);
+    for (int64_t j = (int64_t)(blockIdx.x - grid_tets) * 256 + threadIdx.x; j < n; j += (int64_t)grid_edges * 256) {
+      const unsigned e = (unsigned)elist[j];
+      const int2 ab = __ldg(edge_ab + e);
+      const int64_t vid = (int64_t)__ldcg(word_prefix + (e >> 5)) + __popc(__ldcg(edge_bits + (e >> 5)) & ((1u << (e & 31u)) - 1u));
+      if (vid >= cap_corners) continue;   // (cannot happen while the records fit: V <= 4 Fv)
+      const int ea = ab.x, eb = ab.y;
+      float w0, w1, dd;
+      crossing_weights(__ldg(sdf + ea), __ldg(sdf + eb), w0, w1, dd);
+      float ma = __ldg(msdf + ea), mb = __ldg(msdf + eb);
+      if (msdf_negate) { ma = -ma; mb = -mb; }
+      const float x = lerp2(__ldg(pos + 3ll * ea + 0), w0, __ldg(pos + 3ll * eb + 0), w1);
+      const float y = lerp2(__ldg(pos + 3ll * ea + 1), w0, __ldg(pos + 3ll * eb + 1), w1);
+      const float z = lerp2(__ldg(pos + 3ll * ea + 2), w0, __ldg(pos + 3ll * eb + 2), w1);
+      const float m = lerp2(ma, w0, mb, w1);
+      w_vert[vid] = make_float4(x, y, z, m);
+      w_acc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w_acc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vid < cap_verts) {
+        reinterpret_cast<int2*>(a.tape_edges)[vid] = make_int2(ea, eb);
+        a.verts_wt[3 * vid] = x; a.verts_wt[3 * vid + 1] = y; a.verts_wt[3 * vid + 2] = z;
+        a.msdf_wt[vid] = m;
+        vacc[2 * vid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vacc[2 * vid + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (vid < cap_verts_aug) {
+        // rows of verts_aug not referenced by faces_aug are zero (gshell_tets.py:423-427); a watertight vertex is
+        // referenced iff its mSDF is positive (every cut case keeps exactly the positive corners)
+        const bool used = m > 0.f;
+        a.verts_aug[3 * vid] = used ? x : 0.f;
+        a.verts_aug[3 * vid + 1] = used ? y : 0.f;
+        a.verts_aug[3 * vid + 2] = used ? z : 0.f;
+        a.msdf_aug[vid] = m;
+      }
+    }
+  }
+  trace_end(tr);
+}
+
+void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+  ScanLists L;
+  L.tile_cnt = ws.tile_cnt; L.tile_list = ws.tile_list;
+  L.eblock_cnt = ws.eblock_cnt; L.eblock_list = ws.eblock_list;
+  L.vlist = ws.vlist; L.elist = ws.elist;
+  L.cap_vlist = ws.cap_tets; L.cap_elist = ws.cap_corners;
+  {
+    ProfScope ps(K_EDGE_SCAN, stream);
+    const unsigned nblk = (unsigned)((a.n_grid + kScanVertsPerCta - 1) / kScanVertsPerCta);
+    if (a.watertight_template)
+      launch_k(edge_scan_kernel<false>, nblk, (unsigned)kScanVertsPerCta, stream, kLaunchStream, ws.blk, ws.occ_bits,
+               (const unsigned*)nullptr, ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
+    else
+      launch_k(edge_scan_kernel<true>, nblk, (unsigned)kScanVertsPerCta, stream, kLaunchStream, ws.blk, ws.occ_bits,
+               ws.mocc_bits, ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
+  }
+  const int64_t maxg = 148 * 4;
+  {
+    ProfScope ps(K_COMPACT, stream);
+    const unsigned gt = (unsigned)(ws.ntiles_compact < maxg ? ws.ntiles_compact : maxg);
+    const unsigned ge = (unsigned)(ws.n_eblocks < maxg ? ws.n_eblocks : maxg);
+    launch_k(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt, ws.tile_list,
+             ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.eblock_list, ws.n_eblocks,
+             ws.word_prefix, ws.ctr, ws.cap_tets, gt);
+  }
+  if (ws.cap_corners <= 0) return;   // counting run: sizes only
+  ProfScope ps(K_EDGE_EMIT, stream);
+  const int64_t bt = (ws.cap_tets + 255) / 256, be = (ws.cap_corners + 255) / 256;
+  const unsigned gt = (unsigned)(bt < maxg ? bt : maxg), ge = (unsigned)(be < maxg ? be : maxg);
+  launch_k(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, ws.elist, ws.m1_words,
+           ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
+           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, gt);
+}
+
+}  // namespace d3h

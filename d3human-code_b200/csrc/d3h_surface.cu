@@ -74,7 +74,8 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
                   const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix) {
   constexpr int WARPS = kPolyThreads / 32;
   int32_t* __restrict__ corners = blk->a.tape_corners;
-  const bool static_edges = !REPLAY && blk->a.edge_off != nullptr;  // a replay finds the corner array on the tape
+  // a replay finds the corner array on the tape, and so does the edge-scan path (scan_emit_kernel wrote it)
+  const bool static_edges = !REPLAY && blk->a.edge_off != nullptr && blk->a.etets == nullptr;
   int64_t* __restrict__ faces_wt = blk->a.faces_wt;
   const int64_t cap_faces_wt = blk->a.cap_faces_wt;
   __shared__ unsigned s_cnt[6][WARPS];

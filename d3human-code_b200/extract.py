@@ -80,7 +80,17 @@ def packed_tets(tet_fx4: torch.Tensor, n_grid: int) -> torch.Tensor:
 _TET_EDGES = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))   # gshell_tets.py:187
 _static_cache: Dict[Tuple, list] = {}
 _static_mode = os.environ.get("D3H_STATIC_EDGES", "auto")       # "auto": from the 2nd call on the same tets, "1", "0"
-_tet_edge_ranks = os.environ.get("D3H_TET_EDGE_RANKS", "0") == "1"   # EXPERIMENTAL per-tet edge-rank table (+32 B / tet)
+_tet_edge_ranks = os.environ.get("D3H_TET_EDGE_RANKS", "0") == "1"   # per-tet edge-rank table for compact_kernel<3> (+32 B / tet)
+#: edge-scan path (csrc/d3h_scan.cu): with the static tables a call walks the edge list (4 B / edge) instead of streaming
+#: the tet array (16 B / tet); needs the edge -> tet incidence and the per-tet edge ranks (+56 B / tet of static tables)
+_edge_scan = os.environ.get("D3H_EDGE_SCAN", "1") == "1"
+
+
+def set_edge_scan(on: bool) -> None:
+    """Tables already built keep their form (reset_plans() drops them)."""
+    global _edge_scan
+    _edge_scan = bool(on)
+
 
 
 def set_tet_edge_ranks(on: bool) -> None:
@@ -100,33 +110,42 @@ def set_static_edges(mode: str) -> None:
 
 def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
-    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank or None): edges ascending in (min,max), CSR offsets
-    per min vertex."""
+    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets): edges ascending in
+    (min,max), CSR offsets per min vertex.  The last four are None unless asked for:
+      tet_rank (F,8) int32 : rank in the edge list of the six edges of every tet (order of gshell_tets.py:187, 2 pad words)
+      edge_b   (U,)  int32 : the larger endpoints, contiguous (the 4-byte-per-edge stream of the edge-scan path)
+      etet_off (U+1,), etets (6F,) int32 : the tets around every edge, ascending tet ids."""
     t = tets_i32.long()
-    keys = []
-    for i, j in _TET_EDGES:
-        keys.append(torch.minimum(t[:, i], t[:, j]) * n_grid + torch.maximum(t[:, i], t[:, j]))
-    key = torch.cat(keys)
-    del keys, t
-    uk = torch.unique(key)          # ascending
-    del key
+    n_tets = t.shape[0]
+    key6 = torch.stack([torch.minimum(t[:, i], t[:, j]) * n_grid + torch.maximum(t[:, i], t[:, j]) for i, j in _TET_EDGES], 1)
+    del t
+    uk = torch.unique(key6.reshape(-1))          # ascending
     ea = torch.div(uk, n_grid, rounding_mode="floor")
     edge_ab = torch.stack([ea, uk - ea * n_grid], 1).to(torch.int32).contiguous()
     counts = torch.bincount(ea, minlength=n_grid)
     edge_off = torch.zeros(n_grid + 1, dtype=torch.int64, device=tets_i32.device)
     edge_off[1:] = torch.cumsum(counts, 0)
+    del ea, counts
     n_edges = int(uk.shape[0])
     if n_edges >= 2 ** 31:
         raise ValueError("tet grid has more than 2^31 distinct edges")
-    tet_rank = None
-    if _tet_edge_ranks:   # EXPERIMENTAL companion table: rank of the 6 edges of every tet, (F,8) int32 rows
-        t = tets_i32.long()
-        tet_rank = torch.zeros((tets_i32.shape[0], 8), dtype=torch.int32, device=tets_i32.device)
-        for e, (i, j) in enumerate(_TET_EDGES):
-            k = torch.minimum(t[:, i], t[:, j]) * n_grid + torch.maximum(t[:, i], t[:, j])
-            tet_rank[:, e] = torch.searchsorted(uk, k).to(torch.int32)
-        del t
-    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank
+    tet_rank = edge_b = etet_off = etets = None
+    if _tet_edge_ranks or _edge_scan:
+        rank6 = torch.searchsorted(uk, key6.reshape(-1)).reshape(n_tets, 6)
+        del key6
+        tet_rank = torch.zeros((n_tets, 8), dtype=torch.int32, device=tets_i32.device)
+        tet_rank[:, :6] = rank6.to(torch.int32)
+        if _edge_scan:
+            flat = rank6.reshape(-1)             # entry t*6 + e
+            order = torch.argsort(flat, stable=True)
+            etets = torch.div(order, 6, rounding_mode="floor").to(torch.int32).contiguous()
+            del order
+            etet_off = torch.zeros(n_edges + 1, dtype=torch.int64, device=tets_i32.device)
+            etet_off[1:] = torch.cumsum(torch.bincount(flat, minlength=n_edges), 0)
+            etet_off = etet_off.to(torch.int32).contiguous()
+            edge_b = edge_ab[:, 1].contiguous()
+        del rank6
+    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets
 
 
 def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
@@ -135,7 +154,8 @@ def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
         return None
     # the version counter is part of the key: an int32 tet_fx4 is used in place (packed_tets returns the caller's tensor),
     # an in-place edit must not find the edge table of the old contents
-    key = (tets_i32.data_ptr(), tets_i32._version, tets_i32.shape[0], int(n_grid), tets_i32.device.index)
+    key = (tets_i32.data_ptr(), tets_i32._version, tets_i32.shape[0], int(n_grid), tets_i32.device.index, _edge_scan,
+           _tet_edge_ranks)
     ent = _static_cache.get(key)
     if ent is None:
         if len(_static_cache) > 8:
@@ -318,6 +338,9 @@ class _Layout:
             A[:, c["edge_off"]], A[:, c["edge_ab"]], A[:, c["n_edges"]] = static[0].data_ptr(), static[1].data_ptr(), static[2]
             if len(static) > 3 and static[3] is not None:
                 A[:, c["tet_edge_rank"]] = static[3].data_ptr()
+            if len(static) > 6 and static[6] is not None:
+                A[:, c["edge_b"]], A[:, c["etet_off"]], A[:, c["etets"]] = (static[4].data_ptr(), static[5].data_ptr(),
+                                                                            static[6].data_ptr())
             self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
         self.static = static
         self.A = A

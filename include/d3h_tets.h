@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 430 /* 0.4.3 */
+#define D3H_VERSION 440 /* 0.4.4 */
 
 enum {
   D3H_OK = 0,
@@ -143,6 +143,14 @@ typedef struct d3h_forward_args {
    * compaction kernel reads the ranks of a valid tet's edges instead of bisecting the neighbour lists (32 B per valid
    * tet instead of ~5 dependent loads per corner); costs 32 B per tet of device memory.  NULL: bisect. */
   const int32_t* tet_edge_rank;
+  /* optional: the EDGE-SCAN path (needs edge_off / edge_ab / tet_edge_rank as well).  With the incidence lists of the
+   * static edge table the call never streams the tet array: one kernel walks the edge list (4 bytes per edge instead of
+   * 16 per tet), marks the edges whose endpoints differ in sign -- exactly the crossing edges torch.unique would keep,
+   * gshell_tets.py:279-287 -- and, through the edge -> tet incidence, the tets around them (exactly the valid tets,
+   * :261-275).  Everything downstream is unchanged.  NULL: classify the tets (classify_kernel). */
+  const int32_t* edge_b;   /* (n_edges)   larger endpoint of every edge: edge_ab[:,1], contiguous */
+  const int32_t* etet_off; /* (n_edges+1) tets around edge r: etets[etet_off[r] .. etet_off[r+1]) */
+  const int32_t* etets;    /* (6F)        tet ids */
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */
@@ -259,8 +267,8 @@ int d3h_profile_read(float* ms_by_kind, int* launches_by_kind);
  * order; returns the number of entries written (<= cap) and clears the log. */
 int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, int* stream_id, int cap);
 /* Device-side trace, usable inside the cached CUDA graphs: every forward kernel stamps %globaltimer when its first block
- * starts and when its last block exits.  d3h_trace_read fills out[64][16][2] (uint64 ns; row = seq % 64, column = kernel
- * kind as in d3h_profile_kernel_name) and clears the table.  Enabling allocates a 16 KB device table (diagnostics only). */
+ * starts and when its last block exits.  d3h_trace_read fills out[64][24][2] (uint64 ns; row = seq % 64, column = kernel
+ * kind as in d3h_profile_kernel_name) and clears the table.  enabling allocates a 24 KB device table (diagnostics only). */
 int d3h_trace_enable(int on);
 int d3h_trace_read(uint64_t* out);
 /* Host copies of the case tables the kernels index (same initialisers as the __constant__ copies; no GPU needed).

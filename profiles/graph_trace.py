@@ -12,10 +12,11 @@ ap.add_argument("--res", type=int, default=128)
 ap.add_argument("--frames", type=int, default=16)
 ap.add_argument("--lanes", type=int, default=4)
 ap.add_argument("--full", action="store_true")
+ap.add_argument("--field", default="capsule")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 pos_np, tets_np = grids.kuhn_grid(args.res)
-sdf_np, msdf_np = grids.capsule_garment_field(pos_np)
+sdf_np, msdf_np = (grids.capsule_garment_field if args.field == "capsule" else grids.sphere_plane_field)(pos_np)
 N = pos_np.shape[0]
 pos = torch.from_numpy(np.stack([pos_np + grids.frame_offsets(N, args.res, f) for f in range(args.frames)])).to(dev).requires_grad_(True)
 sdf = torch.from_numpy(sdf_np[:, None].copy()).to(dev).requires_grad_(True)
@@ -39,7 +40,7 @@ for i in range(args.frames):
 t0 = min(r[0] for r in rows)
 t1 = max(r[1] for r in rows)
 print(f"# {args.frames} frames on {args.lanes} lanes, graph launches: forward span {(t1 - t0) / 1e3:.1f} us = {(t1 - t0) / 1e3 / args.frames:.1f} us/frame")
-order = ["prepare", "classify", "compact", "bucket_scan", "partition", "group_sort", "vertex_emit", "edge_emit", "poly_faces", "poly_cut", "zero"]
+order = ["prepare", "classify", "edge_scan", "compact", "bucket_scan", "partition", "group_sort", "vertex_emit", "edge_emit", "poly_faces", "poly_cut", "zero"]
 print("# per frame: start of prepare -> end of poly_cut (us), lane = frame % lanes; then per-kernel durations")
 for i in range(args.frames):
     mine = {r[2]: r for r in rows if r[3] == i}

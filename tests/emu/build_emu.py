@@ -10,7 +10,7 @@ CSRC = os.path.join(ROOT, "d3human-code_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libd3h_tets_emu.so")
 OUT_SAN = os.path.join(HERE, "_build", "libd3h_tets_emu_san.so")
 OUT_TSAN = os.path.join(HERE, "_build", "libd3h_tets_emu_tsan.so")
-SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu"]
+SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_scan.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu"]
 
 
 def build(force=False, sanitize=False, tsan=False):

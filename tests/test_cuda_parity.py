@@ -25,14 +25,17 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(autouse=True, params=["sort", "static"])
+@pytest.fixture(autouse=True, params=["sort", "static", "scan"])
 def edges_mode(request):
-    """Every test runs twice: on the general path (per-call radix sort + run-length scan of the crossing-edge keys) and
-    on the static edge table path (bitmap over the grid's sorted edge list, built once per tet array)."""
+    """Every test runs three times: on the general path (per-call radix sort + run-length scan of the crossing-edge keys),
+    on the static edge table path (tet stream + bitmap over the grid's sorted edge list, built once per tet array) and on
+    the edge-scan path (walk over the static edge list instead of the tet stream; the default of a training run)."""
     from d3human_code_b200 import extract as E
-    E.set_static_edges("1" if request.param == "static" else "0")
+    E.set_static_edges("0" if request.param == "sort" else "1")
+    E.set_edge_scan(request.param == "scan")
     yield request.param
     E.set_static_edges("auto")
+    E.set_edge_scan(True)
 
 
 def _classes():
@@ -152,7 +155,8 @@ def test_integer_intermediates_match_oracle(dev, edges_mode):
     fwd = O.extract_forward(pos, sdf, msdf, tets)
     tt = E.packed_tets(torch.tensor(tets, device=dev), pos.shape[0])
     static = E.static_edges_for(tt, pos.shape[0])
-    assert (static is not None) == (edges_mode == "static")
+    assert (static is not None) == (edges_mode != "sort")
+    assert (static is not None and static[6] is not None) == (edges_mode == "scan")
     if static is not None:   # the static table is the sorted list of all distinct tet edges
         ea = np.minimum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)
         eb = np.maximum(tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]).reshape(-1).astype(np.int64)

@@ -59,7 +59,7 @@ def emu_lib_path():
     return build_emu.build()
 
 
-@pytest.fixture(params=["sort", "static"])
+@pytest.fixture(params=["sort", "static", "scan"])
 def edges_mode(request):
     return request.param
 
@@ -88,9 +88,11 @@ def dev(emu_lib_path, edges_mode, monkeypatch):
     monkeypatch.setattr(E._Plan, "ensure", ensure)
     E.reset_plans()
     _packed_cache.clear()
-    E.set_static_edges("1" if edges_mode == "static" else "0")
+    E.set_static_edges("0" if edges_mode == "sort" else "1")
+    E.set_edge_scan(edges_mode == "scan")
     yield torch.device("cpu")
     E.set_static_edges("auto")
+    E.set_edge_scan(True)
     E.reset_plans()
 
 

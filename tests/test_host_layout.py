@@ -107,13 +107,30 @@ def test_build_edge_table_on_cpu_matches_numpy():
     from d3human_code_b200 import grids
     pos, tets = grids.kuhn_grid(6)
     n = pos.shape[0]
-    off, ab, u, tet_rank = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
-    assert tet_rank is None
-    E.set_tet_edge_ranks(True)
+    E.set_edge_scan(False)
     try:
-        _, _, _, tet_rank = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        off, ab, u, tet_rank, edge_b, etet_off, etets = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        assert tet_rank is None and edge_b is None and etets is None
+        E.set_tet_edge_ranks(True)
+        _, _, _, tet_rank, edge_b, _, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        assert edge_b is None
     finally:
         E.set_tet_edge_ranks(False)
+        E.set_edge_scan(True)
+    # the tables of the edge-scan path: larger endpoints + the tets around every edge
+    _, ab2, u2, tet_rank2, edge_b, etet_off, etets = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    assert u2 == u and torch.equal(ab2, ab) and torch.equal(tet_rank2, tet_rank)
+    assert torch.equal(edge_b, ab[:, 1]) and edge_b.is_contiguous() and edge_b.dtype == torch.int32
+    eo, et = etet_off.numpy(), etets.numpy()
+    assert eo[0] == 0 and eo[-1] == 6 * tets.shape[0] and etets.dtype == torch.int32
+    want = [set() for _ in range(u)]
+    for t, row in enumerate(tet_rank.numpy()[:, :6]):
+        for r in row:
+            want[r].add(t)
+    for r in (0, 1, u // 2, u - 1):
+        seg = et[eo[r]:eo[r + 1]]
+        assert set(seg.tolist()) == want[r] and np.all(np.diff(seg) >= 0)
+    assert all(eo[r + 1] - eo[r] == len(want[r]) for r in range(u))    # (no tet of a lattice repeats an edge)
     assert tet_rank.shape == (tets.shape[0], 8) and tet_rank.dtype == torch.int32
     pairs = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
     for e, (i, j) in enumerate(pairs):     # the rank of every tet edge points back at its endpoints

@@ -18,12 +18,17 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(autouse=True, params=["sort", "static"])
+@pytest.fixture(autouse=True, params=["sort", "static", "scan"])
 def edges_mode(request):
+    """Every test runs three times: on the general path (per-call radix sort + run-length scan of the crossing-edge keys),
+    on the static edge table path (tet stream + bitmap over the grid's sorted edge list, built once per tet array) and on
+    the edge-scan path (walk over the static edge list instead of the tet stream; the default of a training run)."""
     from d3human_code_b200 import extract as E
-    E.set_static_edges("1" if request.param == "static" else "0")
+    E.set_static_edges("0" if request.param == "sort" else "1")
+    E.set_edge_scan(request.param == "scan")
     yield request.param
     E.set_static_edges("auto")
+    E.set_edge_scan(True)
 
 
 # counts measured by running the reference on CPU (SURVEY.md B.4): Fv, V, Fw, Va, Fa
