@@ -10,7 +10,9 @@
 //                      edge are exactly the valid tets of :261-275 (a tet has mixed signs iff one of its edges
 //                      crosses).  The thread marks the edge in the bitmap over the edge list, marks the tets around it
 //                      in the T1 / T2 bitmaps (the first marker of a tet counts it for its 8192-tet tile) and appends
-//                      both to unordered work lists (staged in shared memory: one global atomic per CTA and list).
+//                      both to unordered work lists (one global atomic per warp and list).  Two phases per CTA: the
+//                      stream (4 vertices per thread, 32 neighbour loads in flight) collects the crossing edges in
+//                      shared memory; then one thread per crossing edge walks the tets around it, 8 at a time.
 //   scan_prefix_kernel one CTA per non-empty tile / edge block: exclusive prefix of the popcounts of its 256 bitmap
 //                      words, on top of the sum of the counters of the earlier tiles / blocks (no look-back chain).
 //                      rank among the marked tets = record id (tet order, the order of the boolean-mask compaction
@@ -24,9 +26,10 @@
 
 namespace d3h {
 
-constexpr int kScanVertsPerCta = 256;
-constexpr int kStageEdges = 512;   // crossing edges / valid tets a CTA stages in shared memory before its one
-constexpr int kStageTets = 768;    //   reservation in the global lists; beyond that they are appended one by one
+constexpr int kEScanThreads = 256;
+constexpr int kScanVPT = 4;                                  // vertices per thread: 4 x 8 neighbour loads in flight
+constexpr int kScanVertsPerCta = kEScanThreads * kScanVPT;    // 1024
+constexpr int kStageEdges = 3072;   // crossing edges a CTA collects in shared memory (12 KB) before it processes them
 
 struct ScanLists {
   unsigned* tile_cnt; unsigned* tile_list;
@@ -35,94 +38,183 @@ struct ScanLists {
   int64_t cap_vlist, cap_elist;
 };
 
+// The tets around crossing edge `e`: mark them in the T1 / T2 bitmaps; the first marker of a tet counts it for its tile
+// and queues it.  All loads of a batch of 8 tets are issued together (the chain per batch is etets -> tets -> signs ->
+// atomics, whatever the number of tets).  Called by all 32 lanes (lanes without an edge pass e < 0): the queue slots of
+// a warp are reserved with one global atomic.
 template <bool MOCC>
-__global__ void __launch_bounds__(kScanVertsPerCta)
+__device__ __forceinline__ void mark_tets_around(int e, const d3h_forward_args& a, const unsigned* __restrict__ occ_bits,
+                                                 const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
+                                                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits,
+                                                 DevCounters* __restrict__ ctr, const ScanLists& L) {
+  const int32_t* __restrict__ etets = a.etets;
+  const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
+  const unsigned lane = lane_id();
+  int t0 = 0, t1 = 0;
+  if (e >= 0) { t0 = __ldg(a.etet_off + e); t1 = __ldg(a.etet_off + e + 1); }
+  bool any = false;
+  while (__any_sync(0xffffffffu, t0 < t1)) {
+    int t[8];
+    int4 q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = (t0 + j < t1) ? __ldg(etets + t0 + j) : -1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = (t[j] >= 0) ? __ldg(tets + t[j]) : make_int4(0, 0, 0, 0);
+    unsigned code[8], fresh = 0u;   // fresh: bit j = this lane marked tet j first
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      code[j] = occ_of(occ_bits, q[j].x) | (occ_of(occ_bits, q[j].y) << 1) | (occ_of(occ_bits, q[j].z) << 2) |
+                (occ_of(occ_bits, q[j].w) << 3);
+      if (MOCC && t[j] >= 0) {   // open-mesh prefilter, gshell_tets.py:275: keep tets with a vertex of positive mSDF
+        const unsigned keep = occ_of(mocc_bits, q[j].x) | occ_of(mocc_bits, q[j].y) | occ_of(mocc_bits, q[j].z) |
+                              occ_of(mocc_bits, q[j].w);
+        if (!keep) t[j] = -1;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t[j] < 0) continue;
+      any = true;
+      const bool quad = __popc(code[j]) == 2;
+      const unsigned bit = 1u << (t[j] & 31);
+      const unsigned old = atomicOr((quad ? m2_words : m1_words) + (t[j] >> 5), bit);
+      if (!(old & bit)) fresh |= 1u << j;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((fresh >> j) & 1u)) continue;
+      const unsigned tile = (unsigned)t[j] / (unsigned)kTileTets;
+      if (atomicAdd(L.tile_cnt + tile, __popc(code[j]) == 2 ? 0x10000u : 1u) == 0u)
+        L.tile_list[atomicAdd(&ctr->n_tile_list, 1u)] = tile;
+    }
+    // queue the freshly marked tets: one reservation per warp
+    const unsigned nf = __popc(fresh);
+    unsigned incl = nf;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += nb;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      unsigned base = 0u;
+      if (lane == 31) base = atomicAdd(&ctr->n_vlist, total);
+      base = __shfl_sync(0xffffffffu, base, 31) + incl - nf;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!((fresh >> j) & 1u)) continue;
+        if ((int64_t)base < L.cap_vlist) L.vlist[base] = make_int2(t[j], (int)code[j]);
+        ++base;
+      }
+    }
+    t0 += 8;
+  }
+  // the edge itself: a bit in the bitmap over the edge list, a count for its block, a slot in the edge queue
+  // (`any` is false only with the prefilter, when no valid tet keeps the edge: torch.unique never sees it then)
+  const unsigned keep = __ballot_sync(0xffffffffu, any);
+  if (keep) {
+    unsigned base = 0u;
+    if (lane == 0) base = atomicAdd(&ctr->n_elist, (unsigned)__popc(keep));
+    base = __shfl_sync(0xffffffffu, base, 0) + __popc(keep & lanemask_lt());
+    if (any) {
+      atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
+      const unsigned eb = (unsigned)e / (unsigned)kEdgeBlock;
+      if (atomicAdd(L.eblock_cnt + eb, 1u) == 0u) L.eblock_list[atomicAdd(&ctr->n_eblock_list, 1u)] = eb;
+      if ((int64_t)base < L.cap_elist) L.elist[base] = e;
+    }
+  }
+}
+
+template <bool MOCC>
+__global__ void __launch_bounds__(kEScanThreads)
 edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
                  const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
                  unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, DevCounters* __restrict__ ctr,
                  ScanLists L) {
-  __shared__ unsigned s_ne, s_nt, s_ebase, s_tbase;
+  __shared__ unsigned s_ne;
   __shared__ int s_e[kStageEdges];
-  __shared__ int2 s_t[kStageTets];
   const d3h_forward_args& a = blk->a;
   const int32_t* __restrict__ edge_off = a.edge_off;
   const int32_t* __restrict__ edge_b = a.edge_b;
-  const int32_t* __restrict__ etet_off = a.etet_off;
-  const int32_t* __restrict__ etets = a.etets;
-  const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
   const int64_t n_grid = a.n_grid;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
-  if (threadIdx.x == 0) { s_ne = 0u; s_nt = 0u; }
+  if (threadIdx.x == 0) s_ne = 0u;
   __syncthreads();
-  const int64_t v = (int64_t)blockIdx.x * kScanVertsPerCta + threadIdx.x;
-  if (v < n_grid) {
-    const unsigned oa = occ_of(occ_bits, (int)v);       // one word per warp: a broadcast load
-    const int e0 = __ldg(edge_off + v), e1 = __ldg(edge_off + v + 1);
-    for (int base = e0; base < e1; base += 8) {
-      int b[8];
+  // ---- phase 1: the stream.  Thread t takes vertices base + t, base + t + 256, ... (coalesced offset loads); the
+  // neighbour loads of all its vertices are in flight together ----
+  const int64_t vbase = (int64_t)blockIdx.x * kScanVertsPerCta + threadIdx.x;
+  int e0[kScanVPT], e1[kScanVPT];
+  unsigned oa[kScanVPT];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = (base + j < e1) ? __ldg(edge_b + base + j) : -1;
-      unsigned x = 0u;
+  for (int k = 0; k < kScanVPT; ++k) {
+    const int64_t v = vbase + (int64_t)k * kEScanThreads;
+    e0[k] = e1[k] = 0;
+    oa[k] = 0u;
+    if (v < n_grid) {
+      e0[k] = __ldg(edge_off + v);
+      e1[k] = __ldg(edge_off + v + 1);
+      oa[k] = occ_of(occ_bits, (int)v);
+    }
+  }
+  int b[kScanVPT][8];
+#pragma unroll
+  for (int k = 0; k < kScanVPT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[k][j] = (e0[k] + j < e1[k]) ? __ldg(edge_b + e0[k] + j) : -1;
+#pragma unroll
+  for (int k = 0; k < kScanVPT; ++k) {
+    unsigned x = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b[k][j] >= 0) x |= (occ_of(occ_bits, b[k][j]) ^ oa[k]) << j;
+    while (x) {   // crossing edges of this vertex (rare: the surface touches < 2 % of the vertices)
+      const int e = e0[k] + (__ffs((int)x) - 1);
+      x &= x - 1u;
+      const unsigned slot = atomicAdd(&s_ne, 1u);
+      if (slot < (unsigned)kStageEdges) s_e[slot] = e;
+    }
+    // vertices with more than 8 larger neighbours (unstructured grids): the rest of the list, 8 at a time
+    for (int base = e0[k] + 8; base < e1[k]; base += 8) {
+      int bb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bb[j] = (base + j < e1[k]) ? __ldg(edge_b + base + j) : -1;
+      unsigned y = 0u;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (b[j] >= 0) x |= (occ_of(occ_bits, b[j]) ^ oa) << j;
-      while (x) {   // crossing edges of this vertex (rare: the surface touches < 2 % of the vertices)
-        const int e = base + (__ffs((int)x) - 1);
-        x &= x - 1u;
-        const int t0 = __ldg(etet_off + e), t1 = __ldg(etet_off + e + 1);
-        bool any = false;
-        for (int i = t0; i < t1; ++i) {
-          const int t = __ldg(etets + i);
-          const int4 q = __ldg(tets + t);
-          const unsigned code = occ_of(occ_bits, q.x) | (occ_of(occ_bits, q.y) << 1) | (occ_of(occ_bits, q.z) << 2) |
-                                (occ_of(occ_bits, q.w) << 3);
-          if (MOCC) {   // open-mesh prefilter, gshell_tets.py:275: keep tets with a vertex of positive mSDF
-            const unsigned keep = occ_of(mocc_bits, q.x) | occ_of(mocc_bits, q.y) | occ_of(mocc_bits, q.z) |
-                                  occ_of(mocc_bits, q.w);
-            if (!keep) continue;
-          }
-          any = true;
-          const bool quad = __popc(code) == 2;
-          const unsigned bit = 1u << (t & 31);
-          const unsigned old = atomicOr((quad ? m2_words : m1_words) + (t >> 5), bit);
-          if (old & bit) continue;   // another crossing edge of this tet came first
-          const unsigned tile = (unsigned)t / (unsigned)kTileTets;
-          if (atomicAdd(L.tile_cnt + tile, quad ? 0x10000u : 1u) == 0u)
-            L.tile_list[atomicAdd(&ctr->n_tile_list, 1u)] = tile;
-          const unsigned slot = atomicAdd(&s_nt, 1u);
-          if (slot < (unsigned)kStageTets) {
-            s_t[slot] = make_int2(t, (int)code);
-          } else {
-            const unsigned g = atomicAdd(&ctr->n_vlist, 1u);
-            if ((int64_t)g < L.cap_vlist) L.vlist[g] = make_int2(t, (int)code);
-          }
-        }
-        if (!any) continue;          // (only with the prefilter) no valid tet keeps this edge: torch.unique never sees it
-        atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
-        const unsigned eb = (unsigned)e / (unsigned)kEdgeBlock;
-        if (atomicAdd(L.eblock_cnt + eb, 1u) == 0u) L.eblock_list[atomicAdd(&ctr->n_eblock_list, 1u)] = eb;
+        if (bb[j] >= 0) y |= (occ_of(occ_bits, bb[j]) ^ oa[k]) << j;
+      while (y) {
+        const int e = base + (__ffs((int)y) - 1);
+        y &= y - 1u;
         const unsigned slot = atomicAdd(&s_ne, 1u);
-        if (slot < (unsigned)kStageEdges) {
-          s_e[slot] = e;
-        } else {
-          const unsigned g = atomicAdd(&ctr->n_elist, 1u);
-          if ((int64_t)g < L.cap_elist) L.elist[g] = e;
-        }
+        if (slot < (unsigned)kStageEdges) s_e[slot] = e;
       }
     }
   }
   __syncthreads();
-  const unsigned ne = min(s_ne, (unsigned)kStageEdges), nt = min(s_nt, (unsigned)kStageTets);
-  if (ne == 0u && nt == 0u) { trace_end(tr); return; }
-  if (threadIdx.x == 0) {
-    s_ebase = ne ? atomicAdd(&ctr->n_elist, ne) : 0u;
-    s_tbase = nt ? atomicAdd(&ctr->n_vlist, nt) : 0u;
+  const unsigned found = s_ne;
+  if (found == 0u) { trace_end(tr); return; }
+  // ---- phase 2: the crossing edges of the CTA, one per thread and trip ----
+  if (found <= (unsigned)kStageEdges) {
+    for (unsigned i0 = 0; i0 < found; i0 += kEScanThreads) {   // warp-uniform trip count (warp collectives inside)
+      const unsigned i = i0 + threadIdx.x;
+      mark_tets_around<MOCC>(i < found ? s_e[i] : -1, a, occ_bits, mocc_bits, m1_words, m2_words, edge_bits, ctr, L);
+    }
+  } else {
+    // more crossing edges than the stage holds (a CTA lying inside a sheet of the surface of a very irregular grid):
+    // walk the vertices again, every lane handing over one edge at a time
+#pragma unroll
+    for (int k = 0; k < kScanVPT; ++k) {
+      int e = e0[k];
+      while (__any_sync(0xffffffffu, e < e1[k])) {
+        int mine = -1;
+        while (e < e1[k] && mine < 0) {
+          if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) != 0u) mine = e;
+          ++e;
+        }
+        mark_tets_around<MOCC>(mine, a, occ_bits, mocc_bits, m1_words, m2_words, edge_bits, ctr, L);
+      }
+    }
   }
-  __syncthreads();
-  for (unsigned i = threadIdx.x; i < ne; i += kScanVertsPerCta)
-    if ((int64_t)(s_ebase + i) < L.cap_elist) L.elist[s_ebase + i] = s_e[i];
-  for (unsigned i = threadIdx.x; i < nt; i += kScanVertsPerCta)
-    if ((int64_t)(s_tbase + i) < L.cap_vlist) L.vlist[s_tbase + i] = s_t[i];
   trace_end(tr);
 }
 
@@ -323,10 +415,10 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     ProfScope ps(K_EDGE_SCAN, stream);
     const unsigned nblk = (unsigned)((a.n_grid + kScanVertsPerCta - 1) / kScanVertsPerCta);
     if (a.watertight_template)
-      launch_k(edge_scan_kernel<false>, nblk, (unsigned)kScanVertsPerCta, stream, kLaunchStream, ws.blk, ws.occ_bits,
+      launch_k(edge_scan_kernel<false>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits,
                (const unsigned*)nullptr, ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
     else
-      launch_k(edge_scan_kernel<true>, nblk, (unsigned)kScanVertsPerCta, stream, kLaunchStream, ws.blk, ws.occ_bits,
+      launch_k(edge_scan_kernel<true>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits,
                ws.mocc_bits, ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
   }
   const int64_t maxg = 148 * 4;

@@ -248,6 +248,8 @@ def reset_plans() -> None:
     _plans.clear()
     _packed_cache.clear()
     _static_cache.clear()
+    from . import single
+    single.reset()
 
 
 @dataclass
@@ -776,14 +778,23 @@ def launch_counter() -> int:
     return _ExtractFn.total_launches
 
 
+def _counts_list():
+    c = _ExtractFn.last_counts
+    if isinstance(c, tuple):     # the single-call path leaves the raw sizes: (Fv, T1, T2, P, V, Va, Fw, Fa, buckets)
+        fv, t1, t2, p, v, va, fw, nfa, buckets = c
+        c = _ExtractFn.last_counts = [dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v,
+                                           n_verts_aug=va, n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=buckets)]
+    return c
+
+
 def last_counts() -> Optional[Dict[str, int]]:
     """Sizes of the most recent extraction (Fv, T1, T2, P, V, Va, Fw, Fa, bucket sizes); frame 0 of a batch."""
-    c = _ExtractFn.last_counts
+    c = _counts_list()
     return c[0] if c else None
 
 
 def last_counts_frames() -> Optional[List[Dict[str, int]]]:
-    return _ExtractFn.last_counts
+    return _counts_list()
 
 
 def _aligned(t: torch.Tensor) -> torch.Tensor:
@@ -831,7 +842,14 @@ def _pack_result(r8, output_watertight_template):
 
 
 def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_watertight_template: bool = True):
-    """Shared body of GShell_Tets.__call__ / hmSDF_Tets.__call__: returns the reference's 6-tuple."""
+    """Shared body of GShell_Tets.__call__ / hmSDF_Tets.__call__: returns the reference's 6-tuple.  One frame: the lean
+    host path of single.py (same kernels, same plan)."""
+    from . import single
+    return single.extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate, output_watertight_template)
+
+
+def extract_generic(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_watertight_template: bool = True):
+    """The same through the batch machinery with B = 1 (kept for A/B timing and as a cross-check in the tests)."""
     pos = _prep_pos(pos_nx3)
     n_grid = pos.shape[0]
     sdf, msdf = _prep_field(sdf_n, n_grid), _prep_field(msdf_n, n_grid)

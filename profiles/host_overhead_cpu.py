@@ -25,6 +25,8 @@ class NullLib:
     def d3h_lanes_join(self, s): return 0
     def d3h_wait_counts(self, p, seq, t): return 0
     def d3h_extract_backward_batch(self, p, n, l, s): return 0
+    def d3h_extract_forward(self, ptr, stream): return self.d3h_extract_forward_batch_nojoin(ptr, 1, 1, stream)
+    def d3h_extract_backward(self, ptr, stream): return 0
     def d3h_extract_forward_batch_nojoin(self, ptr, n, lanes, stream):
         size = C.sizeof(_cabi.ForwardArgs)
         for i in range(n):
@@ -72,7 +74,13 @@ o = E.extract(pos1, sdf, msdf, tets)
 gv1, gm1 = torch.zeros_like(o[0]), torch.zeros_like(o[5]["msdf"])
 ob = E.extract_frames(posb, sdf, msdf, tets, types="cloth")
 gvb, gmb = [torch.zeros_like(x[0]) for x in ob], [torch.zeros_like(x[5]["msdf"]) for x in ob]
-for fn, name, per in ((single, "drop-in single call fwd+bwd", 1), (batch, f"batch of {B} frames fwd+bwd", B)):
+def single_generic():
+    pos1.grad = sdf.grad = msdf.grad = None
+    verts, faces, _, _, _, extra = E.extract_generic(pos1, sdf, msdf, tets)
+    torch.autograd.backward([verts, extra["msdf"]], [gv1, gm1])
+
+
+for fn, name, per in ((single, "drop-in single call fwd+bwd", 1), (single_generic, "  (through the batch machinery)", 1), (batch, f"batch of {B} frames fwd+bwd", B)):
     for _ in range(20):
         fn()
     t0 = time.perf_counter()

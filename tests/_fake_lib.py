@@ -58,6 +58,13 @@ class FakeLib:
     def d3h_extract_forward_batch(self, ptr, n_frames, lanes, stream):
         return self.d3h_extract_forward_batch_nojoin(ptr, n_frames, lanes, stream)
 
+    def d3h_extract_forward(self, ptr, stream):          # the single-call path (single.py)
+        self.single_calls = getattr(self, "single_calls", 0) + 1
+        return self._forward(_cabi.ForwardArgs.from_address(int(ptr)))
+
+    def d3h_extract_backward(self, ptr, stream):
+        return self.d3h_extract_backward_batch(ptr, 1, 1, stream)
+
     def d3h_extract_forward_batch_nojoin(self, ptr, n_frames, lanes, stream):
         self.batch_calls += 1
         size = C.sizeof(_cabi.ForwardArgs)

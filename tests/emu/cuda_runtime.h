@@ -93,6 +93,8 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     if (((mask >> l) & 1u) && o[l]) r |= 1u << l;
   return r;
 }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 template <typename T>
 static inline unsigned long long emu_bits(T v) {
   static_assert(sizeof(T) <= 8, "shuffle of a wide type");
