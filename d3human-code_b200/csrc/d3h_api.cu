@@ -149,8 +149,9 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.group_start = reinterpret_cast<unsigned*>(take((ws.ngroups + 2) * 4));
   ws.group_heads = reinterpret_cast<unsigned*>(take((ws.ngroups + 1) * 4));
   ws.gblock_heads = reinterpret_cast<unsigned*>(take((ws.ngroups / 256 + 2) * 4));
-  ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
-  ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
+  // bucket counts / prefixes per 32-polygon group (one warp of poly_faces_kernel): 8 words per group
+  ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * (kPolyThreads / 32) * 32));
+  ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * (kPolyThreads / 32) * 32));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));
   ws.acc = reinterpret_cast<float*>(take(capc * 32));
   ws.owner = reinterpret_cast<int32_t*>(take(capc * 4));
@@ -267,19 +268,34 @@ static int finish(const char* who, const d3h_forward_args* a, const Workspace& w
   return D3H_OK;
 }
 
-void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts) {
+// `side` (graph capture only): a second stream of the same capture.  The zero-fill of the gradient buffers depends on
+// nothing but the argument block, so in a captured graph it runs as a parallel branch right behind prepare_kernel: its
+// 43 MB of stores hide under the latency-bound kernels of the surface stages instead of extending the chain by ~5 us.
+void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts,
+                             cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
+  const bool zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) && (parts & kPartTail);
+  const bool branch = zero && side != nullptr && (parts & kPartHead);
+  if (branch) {
+    cudaEventRecord(fork, stream);
+    cudaStreamWaitEvent(side, fork, 0);
+    launch_zero_grads_from_block(a, ws, side);
+    cudaEventRecord(join, side);
+  }
   if (edge_scan_path(a)) {
     // no classification stream: the walk over the static edge list marks crossing edges and valid tets
     if (parts & kPartHead) launch_edge_scan(a, ws, stream);
-    if (!(parts & kPartTail)) return;
   } else {
     launch_classify(a, ws, ws.records, ws.cap_tets, /*emit_keys=*/true, stream, parts);
-    if (!(parts & kPartTail)) return;
-    if (a.edge_off != nullptr) launch_edge_emit(a, ws, stream);
-    else launch_edge_sort(a, ws, stream);
+    if (parts & kPartTail) {
+      if (a.edge_off != nullptr) launch_edge_emit(a, ws, stream);
+      else launch_edge_sort(a, ws, stream);
+    }
   }
-  launch_surface(a, ws, ws.records, stream);
-  if (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) launch_zero_grads_from_block(a, ws, stream);
+  if (parts & kPartTail) {
+    launch_surface(a, ws, ws.records, stream);
+    if (zero && !branch) launch_zero_grads_from_block(a, ws, stream);
+  }
+  if (branch) cudaStreamWaitEvent(stream, join, 0);
 }
 
 // ---- graph cache -----------------------------------------------------------------------------------
@@ -319,12 +335,21 @@ static void destroy_entry(GraphEntry& e) {
 
 static int build_entry(const d3h_forward_args& a, const Workspace& ws, const GraphKey& key, GraphEntry& out) {
   const int parts = key.parts;
-  static thread_local cudaStream_t cs = nullptr;
+  static thread_local cudaStream_t cs = nullptr, cs2 = nullptr;
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   if (cs == nullptr && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return -1;
+  if (cs2 == nullptr && cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking) != cudaSuccess) return -1;
+  if (ev_fork == nullptr && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return -1;
+  if (ev_join == nullptr && cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return -1;
+  static int zero_branch = -1;
+  if (zero_branch < 0) {
+    const char* env = getenv("D3H_ZERO_BRANCH");
+    zero_branch = (env && env[0] == '0') ? 0 : 1;
+  }
   cudaGraph_t graph = nullptr;
   if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return -1; }
   if (parts & kPartHead) launch_prepare(a, ws, cs);
-  launch_forward_sequence(a, ws, cs, parts);
+  launch_forward_sequence(a, ws, cs, parts, zero_branch ? cs2 : nullptr, ev_fork, ev_join);
   if (cudaStreamEndCapture(cs, &graph) != cudaSuccess || graph == nullptr) { cudaGetLastError(); return -1; }
   size_t nn = 0;
   cudaGraphGetNodes(graph, nullptr, &nn);
@@ -725,7 +750,7 @@ extern "C" int d3h_extract_backward(const d3h_backward_args* a, d3h_stream_t s) 
 static const char* kKernelNames[K_COUNT] = {"prepare", "classify", "compact", "bucket_scan", "partition", "group_sort",
                                             "vertex_emit", "poly_faces", "poly_cut", "zero", "adjoint", "rank_records",
                                             "edge_emit", "adjoint_poly", "pair_replay", "mesh_edges", "mesh_normals",
-                                            "mesh_adjoint", "edge_scan"};
+                                            "mesh_adjoint", "edge_scan", "edge_mark"};
 extern "C" int d3h_profile_enable(int on) {
   g_prof_on = on != 0;
   return D3H_OK;

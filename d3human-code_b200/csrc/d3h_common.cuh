@@ -189,7 +189,7 @@ struct DevCounters {
   unsigned n_eblock_list;    //   edge blocks, in the order their first mark arrived)
   unsigned n_vlist;          // edge-scan path: entries appended to Workspace::vlist (valid tets) / elist (crossing edges);
   unsigned n_elist;          //   true counts, may exceed the list capacities
-  unsigned pad[1];
+  unsigned n_elist_raw;      // edge-scan path: crossing edges found by the stream (before the open-mesh prefilter)
   unsigned trace_frame;      // diagnostics (d3h_trace_*): row of the trace table this call writes to
   unsigned pad2;
   unsigned long long* trace; // diagnostics: device trace table or nullptr; set by prepare_kernel, not reset

@@ -104,7 +104,8 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
 // the tail everything that works on the O(surface) records.  A batch runs the heads of all frames back to back on one
 // stream and the tails on the lanes.
 enum ForwardParts { kPartHead = 1, kPartTail = 2, kPartAll = 3 };
-void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts = kPartAll);
+void launch_forward_sequence(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream, int parts = kPartAll,
+                             cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 void launch_classify(const d3h_forward_args& a, const Workspace& ws, d3h_tet_record* records, int64_t cap_records,
                      bool emit_keys, cudaStream_t stream, int parts = kPartAll);
 void launch_edge_sort(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
@@ -159,7 +160,7 @@ bool profiling_enabled();
 enum KernelKind {
   K_PREPARE = 0, K_CLASSIFY, K_COMPACT, K_BUCKET_SCAN, K_PARTITION, K_GROUP_SORT, K_VERTEX_EMIT, K_POLY_FACES,
   K_POLY_CUT, K_ZERO, K_ADJOINT, K_RANK_RECORDS, K_EDGE_EMIT, K_ADJOINT_POLY, K_PAIR_REPLAY, K_MESH_EDGES, K_MESH_NORMALS,
-  K_MESH_ADJOINT, K_EDGE_SCAN, K_COUNT
+  K_MESH_ADJOINT, K_EDGE_SCAN, K_EDGE_MARK, K_COUNT
 };
 struct ProfScope {
   ProfScope(int kind, cudaStream_t stream);

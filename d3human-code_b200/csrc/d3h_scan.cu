@@ -34,7 +34,9 @@ constexpr int kStageEdges = 3072;   // crossing edges a CTA collects in shared m
 struct ScanLists {
   unsigned* tile_cnt; unsigned* tile_list;
   unsigned* eblock_cnt; unsigned* eblock_list;
-  int2* vlist; int32_t* elist;
+  int2* vlist;
+  int32_t* elist_raw;   // crossing edges as the stream found them
+  int32_t* elist;       // ... that survive the open-mesh prefilter (the same array without the prefilter)
   int64_t cap_vlist, cap_elist;
 };
 
@@ -109,29 +111,28 @@ __device__ __forceinline__ void mark_tets_around(int e, const d3h_forward_args& 
     }
     t0 += 8;
   }
-  // the edge itself: a bit in the bitmap over the edge list, a count for its block, a slot in the edge queue
-  // (`any` is false only with the prefilter, when no valid tet keeps the edge: torch.unique never sees it then)
-  const unsigned keep = __ballot_sync(0xffffffffu, any);
-  if (keep) {
-    unsigned base = 0u;
-    if (lane == 0) base = atomicAdd(&ctr->n_elist, (unsigned)__popc(keep));
-    base = __shfl_sync(0xffffffffu, base, 0) + __popc(keep & lanemask_lt());
-    if (any) {
-      atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
-      const unsigned eb = (unsigned)e / (unsigned)kEdgeBlock;
-      if (atomicAdd(L.eblock_cnt + eb, 1u) == 0u) L.eblock_list[atomicAdd(&ctr->n_eblock_list, 1u)] = eb;
-      if ((int64_t)base < L.cap_elist) L.elist[base] = e;
+  // the edge itself: a bit in the bitmap over the edge list and a count for its block.  With the prefilter `any` may be
+  // false (no valid tet keeps the edge: torch.unique never sees it) and the surviving edges are queued again.
+  if (any) {
+    atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
+    const unsigned eb = (unsigned)e / (unsigned)kEdgeBlock;
+    if (atomicAdd(L.eblock_cnt + eb, 1u) == 0u) L.eblock_list[atomicAdd(&ctr->n_eblock_list, 1u)] = eb;
+  }
+  if (MOCC) {
+    const unsigned keep = __ballot_sync(0xffffffffu, any);
+    if (keep) {
+      unsigned base = 0u;
+      if (lane == 0) base = atomicAdd(&ctr->n_elist, (unsigned)__popc(keep));
+      base = __shfl_sync(0xffffffffu, base, 0) + __popc(keep & lanemask_lt());
+      if (any && (int64_t)base < L.cap_elist) L.elist[base] = e;
     }
   }
 }
 
-template <bool MOCC>
 __global__ void __launch_bounds__(kEScanThreads)
-edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
-                 const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
-                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, DevCounters* __restrict__ ctr,
+edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, DevCounters* __restrict__ ctr,
                  ScanLists L) {
-  __shared__ unsigned s_ne;
+  __shared__ unsigned s_ne, s_base;
   __shared__ int s_e[kStageEdges];
   const d3h_forward_args& a = blk->a;
   const int32_t* __restrict__ edge_off = a.edge_off;
@@ -191,29 +192,48 @@ edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
     }
   }
   __syncthreads();
+  // ---- hand the crossing edges of the CTA to the marking kernel: one reservation in the global queue ----
   const unsigned found = s_ne;
   if (found == 0u) { trace_end(tr); return; }
-  // ---- phase 2: the crossing edges of the CTA, one per thread and trip ----
-  if (found <= (unsigned)kStageEdges) {
-    for (unsigned i0 = 0; i0 < found; i0 += kEScanThreads) {   // warp-uniform trip count (warp collectives inside)
-      const unsigned i = i0 + threadIdx.x;
-      mark_tets_around<MOCC>(i < found ? s_e[i] : -1, a, occ_bits, mocc_bits, m1_words, m2_words, edge_bits, ctr, L);
-    }
-  } else {
-    // more crossing edges than the stage holds (a CTA lying inside a sheet of the surface of a very irregular grid):
-    // walk the vertices again, every lane handing over one edge at a time
+  const unsigned staged = min(found, (unsigned)kStageEdges);
+  if (threadIdx.x == 0) s_base = atomicAdd(&ctr->n_elist_raw, found);
+  __syncthreads();
+  const unsigned base = s_base;
+  for (unsigned i = threadIdx.x; i < staged; i += kEScanThreads)
+    if ((int64_t)(base + i) < L.cap_elist) L.elist_raw[base + i] = s_e[i];
+  if (found > (unsigned)kStageEdges) {
+    // more crossing edges than the stage holds (a CTA inside a sheet of the surface of a very irregular grid): walk the
+    // vertices again; the first kStageEdges hits went through the stage, the others take the slots behind them
+    if (threadIdx.x == 0) s_ne = 0u;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < kScanVPT; ++k) {
-      int e = e0[k];
-      while (__any_sync(0xffffffffu, e < e1[k])) {
-        int mine = -1;
-        while (e < e1[k] && mine < 0) {
-          if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) != 0u) mine = e;
-          ++e;
-        }
-        mark_tets_around<MOCC>(mine, a, occ_bits, mocc_bits, m1_words, m2_words, edge_bits, ctr, L);
+      for (int e = e0[k]; e < e1[k]; ++e) {
+        if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) == 0u) continue;
+        const unsigned slot = atomicAdd(&s_ne, 1u);
+        if ((int64_t)(base + slot) < L.cap_elist) L.elist_raw[base + slot] = e;   // (rewrites the staged ones, same set)
       }
     }
+  }
+  trace_end(tr);
+}
+
+// One thread per crossing edge of the whole grid (all resident at once: the chain etet_off -> etets -> tets -> signs ->
+// atomics is paid once, not once per trip of a busy CTA).
+template <bool MOCC>
+__global__ void __launch_bounds__(256)
+edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
+                 const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
+                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, DevCounters* __restrict__ ctr,
+                 ScanLists L) {
+  const d3h_forward_args& a = blk->a;
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
+  const int64_t raw = (int64_t)ctr->n_elist_raw;
+  const int64_t n = raw < L.cap_elist ? raw : L.cap_elist;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t j0 = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31u); j0 < n; j0 += stride) {   // warp-uniform trips
+    const int64_t j = j0 + lane_id();
+    mark_tets_around<MOCC>(j < n ? L.elist_raw[j] : -1, a, occ_bits, mocc_bits, m1_words, m2_words, edge_bits, ctr, L);
   }
   trace_end(tr);
 }
@@ -261,8 +281,13 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
         const unsigned t1 = (unsigned)(tot & 0xffffffffull), t2 = (unsigned)(tot >> 32);
         ctr->n_tri = t1;
         ctr->n_quad = t2;
-        ctr->n_valid = t1 + t2;
-        const bool fits = (int64_t)t1 + t2 <= cap_records;
+        // the queue of crossing edges holds 4 * cap_records entries; edges beyond that were dropped and the tets around
+        // them never marked: report enough valid tets for the caller to grow (the counts of an overflowed call only
+        // serve that purpose) -- a crossing edge needs at most a quarter of a record
+        const int64_t raw = (int64_t)ctr->n_elist_raw;
+        const bool queue_ok = raw <= 4 * cap_records;
+        ctr->n_valid = queue_ok ? t1 + t2 : max(t1 + t2, (unsigned)((raw + 3) / 4));
+        const bool fits = queue_ok && (int64_t)t1 + t2 <= cap_records;
         ctr->work_tri = fits ? t1 : 0u;
         ctr->work_quad = fits ? t2 : 0u;
       } else {
@@ -409,17 +434,26 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   ScanLists L;
   L.tile_cnt = ws.tile_cnt; L.tile_list = ws.tile_list;
   L.eblock_cnt = ws.eblock_cnt; L.eblock_list = ws.eblock_list;
-  L.vlist = ws.vlist; L.elist = ws.elist;
+  L.vlist = ws.vlist;
+  L.elist_raw = ws.elist;
+  // with the open-mesh prefilter the marking kernel re-queues the edges that survive (corner_rank is idle on this path)
+  L.elist = a.watertight_template ? ws.elist : reinterpret_cast<int32_t*>(ws.corner_rank);
   L.cap_vlist = ws.cap_tets; L.cap_elist = ws.cap_corners;
   {
     ProfScope ps(K_EDGE_SCAN, stream);
     const unsigned nblk = (unsigned)((a.n_grid + kScanVertsPerCta - 1) / kScanVertsPerCta);
+    launch_k(edge_scan_kernel, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, ws.ctr, L);
+  }
+  {
+    ProfScope ps(K_EDGE_MARK, stream);
+    const int64_t be = (ws.cap_corners + 255) / 256;
+    const unsigned nblk = (unsigned)(be < 148 * 8 ? (be > 0 ? be : 1) : 148 * 8);
     if (a.watertight_template)
-      launch_k(edge_scan_kernel<false>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits,
-               (const unsigned*)nullptr, ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
+      launch_k(edge_mark_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.occ_bits, (const unsigned*)nullptr,
+               ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
     else
-      launch_k(edge_scan_kernel<true>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits,
-               ws.mocc_bits, ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
+      launch_k(edge_mark_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.occ_bits, ws.mocc_bits, ws.m1_words,
+               ws.m2_words, ws.edge_bits, ws.ctr, L);
   }
   const int64_t maxg = 148 * 4;
   {
@@ -434,7 +468,7 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   ProfScope ps(K_EDGE_EMIT, stream);
   const int64_t bt = (ws.cap_tets + 255) / 256, be = (ws.cap_corners + 255) / 256;
   const unsigned gt = (unsigned)(bt < maxg ? bt : maxg), ge = (unsigned)(be < maxg ? be : maxg);
-  launch_k(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, ws.elist, ws.m1_words,
+  launch_k(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, ws.m1_words,
            ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
            reinterpret_cast<float4*>(ws.acc), ws.cap_corners, gt);
 }

@@ -78,7 +78,6 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   const bool static_edges = !REPLAY && blk->a.edge_off != nullptr && blk->a.etets == nullptr;
   int64_t* __restrict__ faces_wt = blk->a.faces_wt;
   const int64_t cap_faces_wt = blk->a.cap_faces_wt;
-  __shared__ unsigned s_cnt[6][WARPS];
   __shared__ unsigned s_last;
   __shared__ unsigned long long s_scan[3][32];
 
@@ -174,19 +173,14 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
       const float sg = REPLAY ? -1.f : 1.f;  // exact: the pair's interpolated mSDF is the negation
       bucket = cut_case(quad, sg * P[0].w, sg * P[1].w, sg * P[2].w, sg * P[3].w, mcase, ncut);
     }
-    // ---- polygons per bucket in this tile ----
+    // ---- polygons per bucket in this group of 32 polygons (one warp): lane b keeps the count of bucket b ----
+    unsigned mine = 0u;
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
       const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
-      if (lane == 0) s_cnt[b][warp] = __popc(m);
+      if (lane == (unsigned)b) mine = __popc(m);
     }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      unsigned run = 0;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) run += s_cnt[threadIdx.x][w];
-      poly_cnt[(int64_t)tile * 8 + threadIdx.x] = run;
-    }
+    if (lane < 8u) poly_cnt[((int64_t)tile * WARPS + warp) * 8 + lane] = mine;   // (entries 6, 7: zero)
     // the (3,3) torch.cross quirk: the three face normals are crossed along the *face* axis
     if (!REPLAY && cross_quirk && i == 0) {
       float a[3][3], b[3][3];
@@ -232,12 +226,13 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // thread t owns tiles [t*per, (t+1)*per); buckets are scanned as three pairs packed in 64-bit words
-  const int64_t per = (ntiles + kPolyThreads - 1) / kPolyThreads;
+  // thread t owns groups [t*per, (t+1)*per); buckets are scanned as three pairs packed in 64-bit words
+  const int64_t ngroups = (npoly + 31) / 32;
+  const int64_t per = (ngroups + kPolyThreads - 1) / kPolyThreads;
   const int64_t tl0 = (int64_t)threadIdx.x * per;
   unsigned long long sum[3] = {0ull, 0ull, 0ull};
   for (int64_t q = 0; q < per; ++q) {
-    if (tl0 + q < ntiles) {
+    if (tl0 + q < ngroups) {
       const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(poly_cnt + (tl0 + q) * 8));
       const uint2 c45 = __ldcg(reinterpret_cast<const uint2*>(poly_cnt + (tl0 + q) * 8 + 4));
       sum[0] += (unsigned long long)c03.x | ((unsigned long long)c03.y << 32);
@@ -269,7 +264,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
     total[wd] = tot;
   }
   for (int64_t q = 0; q < per; ++q) {
-    if (tl0 + q < ntiles) {
+    if (tl0 + q < ngroups) {
       const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(poly_cnt + (tl0 + q) * 8));
       const uint2 c45 = __ldcg(reinterpret_cast<const uint2*>(poly_cnt + (tl0 + q) * 8 + 4));
       unsigned* e = poly_excl + (tl0 + q) * 8;
@@ -344,6 +339,45 @@ __device__ __forceinline__ float3 vertex_tangent(const float* __restrict__ w_acc
                          __fsub_rn(t.z, __fmul_rn(dp, n.z)));
 }
 
+// Four lanes per polygon (lane k = corner k; the fourth lane of a triangle polygon idles): a 256-thread CTA takes 64
+// polygons = two of poly_faces_kernel's 32-polygon groups.  Every lane evaluates ONE vertex frame and ONE boundary
+// vertex and writes at most one cut triangle; the values of the neighbouring corner travel by warp shuffles.  (v1 gave
+// a whole polygon to one thread: four vertex frames in sequence on 226 CTAs, 14 us for 58 k polygons.)
+constexpr int kCutPolysPerCta = kPolyThreads / 4;
+
+// cut tables as shared-memory words (the case code differs from lane to lane: __constant__ would serialise)
+struct CutTables {
+  unsigned long long quad[16];   // 12 locals x 4 bits
+  unsigned tri[8];               //  6 locals x 4 bits
+  unsigned char nq[16], nt[8];   // number of cut triangles
+  unsigned char uq[16], ut[8];   // locals referenced by the cut triangles (bit mask)
+};
+
+__device__ __forceinline__ void load_cut_tables(CutTables& T) {
+  const unsigned t = threadIdx.x;
+  if (t < 16u) {
+    unsigned long long w = 0ull;
+    unsigned used = 0u;
+    const int n = c_num_cut_quad[t];
+    for (int e = 0; e < 12; ++e) {
+      const int loc = c_cut_quad[t][e];
+      w |= (unsigned long long)(loc & 0xf) << (4 * e);
+      if (e < 3 * n) used |= 1u << loc;
+    }
+    T.quad[t] = w; T.nq[t] = (unsigned char)n; T.uq[t] = (unsigned char)used;
+  } else if (t < 24u) {
+    const unsigned c = t - 16u;
+    unsigned w = 0u, used = 0u;
+    const int n = c_num_cut_tri[c];
+    for (int e = 0; e < 6; ++e) {
+      const int loc = c_cut_tri[c][e];
+      w |= (unsigned)(loc & 0xf) << (4 * e);
+      if (e < 3 * n) used |= 1u << loc;
+    }
+    T.tri[c] = w; T.nt[c] = (unsigned char)n; T.ut[c] = (unsigned char)used;
+  }
+}
+
 template <bool REPLAY>
 __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
@@ -351,6 +385,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
                 const unsigned* __restrict__ poly_excl) {
   constexpr int WARPS = kPolyThreads / 32;
+  constexpr unsigned FULL = 0xffffffffu;
   const int32_t* __restrict__ corners = blk->a.tape_corners;
   float* __restrict__ verts_aug = blk->a.verts_aug;
   float* __restrict__ v_tng_aug = blk->a.v_tng_aug;
@@ -359,109 +394,124 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
   int64_t* __restrict__ faces_aug = blk->a.faces_aug;
   const int64_t cap_verts_aug = blk->a.cap_verts_aug, cap_verts = blk->a.cap_verts, cap_faces_aug = blk->a.cap_faces_aug;
   __shared__ unsigned s_cnt[6][WARPS];
+  __shared__ CutTables s_tab;
   const bool static_edges = blk->a.edge_off != nullptr;
   const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_POLY_CUT);
   const int64_t npoly = (int64_t)t1 + t2;
   const unsigned tile = blockIdx.x;
-  if ((int64_t)tile * kPolyThreads >= npoly) return;
+  if ((int64_t)tile * kCutPolysPerCta >= npoly) return;
+  load_cut_tables(s_tab);
   const int64_t nv = ctr->n_verts;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const int64_t i = (int64_t)tile * kPolyThreads + threadIdx.x;
+  const unsigned k = lane & 3u, lane0 = lane & ~3u;                 // corner of this lane, first lane of its polygon
+  const int64_t i = (int64_t)tile * kCutPolysPerCta + warp * 8 + (lane >> 2);
+  const bool live = i < npoly;
 
-  int bucket = -1, ncut = 0, n = 3;
-  unsigned mcase = 0;
-  bool quad = false;
+  bool quad = false, corner = false;
+  int n = 3, L = 0;
   int64_t p0 = 0;
-  int L[4] = {0, 0, 0, 0};
-  float4 P[4];
-  float3 T[4];
-  if (i < npoly) {
+  float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+  float3 T = make_float3(0.f, 0.f, 0.f);
+  if (live) {
     const int4 meta = reinterpret_cast<const int4*>(records + i)[1];
     const int code = meta.x, rank = meta.y;
     quad = __popc((unsigned)code) == 2;
     n = quad ? 4 : 3;
     p0 = quad ? (3ll * t1 + 4ll * rank) : 3ll * rank;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      L[k] = (k < n) ? corners[p0 + k] : 0;
-      P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (REPLAY) P[k].w = -P[k].w;  // the pair's interpolated mSDF: exact negation
-      T[k] = (k < n) ? vertex_tangent(w_acc, L[k]) : make_float3(0.f, 0.f, 0.f);
+    corner = (int)k < n;
+    if (corner) {
+      L = corners[p0 + k];
+      P = w_vert[L];
+      if (REPLAY) P.w = -P.w;  // the pair's interpolated mSDF: exact negation
+      T = vertex_tangent(w_acc, L);
       // the corner that opened the vertex's run in the sorted key array writes the vertex's own tangent rows
-      // (static edge table path: no owner is known, every corner writes the same value)
-      if (k < n && (static_edges || owner[L[k]] == (int32_t)(p0 + k))) {
-        const int64_t v = L[k];
+      // (static edge table paths: no owner is known, every corner writes the same value)
+      if (static_edges || owner[L] == (int32_t)(p0 + k)) {
+        const int64_t v = L;
         if (v < cap_verts) {
-          store_same_value(v_tng_wt + 3 * v, T[k].x);
-          store_same_value(v_tng_wt + 3 * v + 1, T[k].y);
-          store_same_value(v_tng_wt + 3 * v + 2, T[k].z);
+          store_same_value(v_tng_wt + 3 * v, T.x);
+          store_same_value(v_tng_wt + 3 * v + 1, T.y);
+          store_same_value(v_tng_wt + 3 * v + 2, T.z);
         }
         if (v < cap_verts_aug) {
-          store_same_value(v_tng_aug + 3 * v, T[k].x);
-          store_same_value(v_tng_aug + 3 * v + 1, T[k].y);
-          store_same_value(v_tng_aug + 3 * v + 2, T[k].z);
+          store_same_value(v_tng_aug + 3 * v, T.x);
+          store_same_value(v_tng_aug + 3 * v + 1, T.y);
+          store_same_value(v_tng_aug + 3 * v + 2, T.z);
         }
       }
     }
-    bucket = cut_case(quad, P[0].w, P[1].w, P[2].w, P[3].w, mcase, ncut);
   }
-  // ---- ordered rank of the polygon inside its bucket: tile prefix + warps before + lanes before ----
+  __syncthreads();   // the tables
+  // ---- mSDF cut case from the four corner signs (gshell_tets.py:338-339, 401-404) ----
+  const unsigned mo = (__ballot_sync(FULL, corner && P.w > 0.f) >> lane0) & 0xfu;   // bit c = corner c
+  unsigned mcase;
+  int ncut = 0, bucket = -1;
+  unsigned used_mask = 0u;
+  unsigned long long cut = 0ull;
+  if (quad) {
+    mcase = ((mo & 1u) << 3) | ((mo & 2u) << 1) | ((mo & 4u) >> 1) | ((mo & 8u) >> 3);
+    if (live) { ncut = s_tab.nq[mcase]; used_mask = s_tab.uq[mcase]; cut = s_tab.quad[mcase]; }
+    bucket = ncut ? (1 + ncut) : -1;
+  } else {
+    mcase = ((mo & 1u) << 2) | (mo & 2u) | ((mo & 4u) >> 2);
+    if (live) { ncut = s_tab.nt[mcase]; used_mask = s_tab.ut[mcase]; cut = s_tab.tri[mcase]; }
+    bucket = ncut ? (ncut - 1) : -1;
+  }
+  // ---- ordered rank of the polygon inside its bucket: group prefix + warps of the group before + polygons before ----
   unsigned my_ballot = 0;
 #pragma unroll
   for (int b = 0; b < 6; ++b) {
-    const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
+    const unsigned m = __ballot_sync(FULL, bucket == b && k == 0u);
     if (bucket == b) my_ballot = m;
     if (lane == 0) s_cnt[b][warp] = __popc(m);
   }
   __syncthreads();
-  if (i >= npoly) return;
-  // face-row base of each bucket: buckets hold polygons cut into (1,2 | 1,2,3,4) triangles
-  int64_t fbase = 0, brank = 0;
+  int64_t row0 = 0;
   if (bucket >= 0) {
     const int ncut_of[6] = {1, 2, 1, 2, 3, 4};
+    int64_t fbase = 0;
 #pragma unroll
     for (int b = 0; b < 6; ++b)
       if (b < bucket) fbase += (int64_t)(REPLAY ? ctr->bucket2[b] : ctr->bucket[b]) * ncut_of[b];
-    unsigned before = poly_excl[(int64_t)tile * 8 + bucket];
-    for (int w = 0; w < (int)warp; ++w) before += s_cnt[bucket][w];
-    brank = (int64_t)before + __popc(my_ballot & lanemask_lt());
+    unsigned before = poly_excl[(i >> 5) * 8 + bucket];
+    for (unsigned w = warp & ~3u; w < warp; ++w) before += s_cnt[bucket][w];   // 4 warps = one 32-polygon group
+    row0 = fbase + ((int64_t)before + __popc(my_ballot & ((1u << lane0) - 1u))) * ncut;   // polygons before this one
   }
-  // locals referenced by this polygon's cut triangles
-  unsigned used_mask = 0;
-  for (int e = 0; e < 3 * ncut; ++e) used_mask |= 1u << (quad ? c_cut_quad[mcase][e] : c_cut_tri[mcase][e]);
-
-  // ---- boundary vertex on every polygon edge k -> k+1 ----
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k >= n) break;
-    const int kn = (k + 1 == n) ? 0 : k + 1;
-    const float4 pi = P[k], pj = (kn == 0) ? P[0] : (kn == 1) ? P[1] : (kn == 2) ? P[2] : P[3];
-    const float3 ti = T[k], tj = (kn == 0) ? T[0] : (kn == 1) ? T[1] : (kn == 2) ? T[2] : T[3];
+  // ---- boundary vertex on polygon edge k -> k+1: this lane's corner and the next one's ----
+  const unsigned kn = ((int)k + 1 == n) ? 0u : k + 1u;
+  const unsigned src = lane0 + (corner ? kn : k);
+  float4 Pj;
+  float3 Tj;
+  Pj.x = __shfl_sync(FULL, P.x, src); Pj.y = __shfl_sync(FULL, P.y, src);
+  Pj.z = __shfl_sync(FULL, P.z, src); Pj.w = __shfl_sync(FULL, P.w, src);
+  Tj.x = __shfl_sync(FULL, T.x, src); Tj.y = __shfl_sync(FULL, T.y, src); Tj.z = __shfl_sync(FULL, T.z, src);
+  if (corner) {
     float u0, u1, D;
-    boundary_weights(pi.w, pj.w, u0, u1, D);
+    boundary_weights(P.w, Pj.w, u0, u1, D);
     const int64_t row = nv + p0 + k;
     if (row < cap_verts_aug) {
       const bool used = (used_mask >> (n + k)) & 1u;
-      verts_aug[3 * row + 0] = used ? lerp2(pi.x, u0, pj.x, u1) : 0.f;
-      verts_aug[3 * row + 1] = used ? lerp2(pi.y, u0, pj.y, u1) : 0.f;
-      verts_aug[3 * row + 2] = used ? lerp2(pi.z, u0, pj.z, u1) : 0.f;
-      v_tng_aug[3 * row + 0] = lerp2(ti.x, u0, tj.x, u1);
-      v_tng_aug[3 * row + 1] = lerp2(ti.y, u0, tj.y, u1);
-      v_tng_aug[3 * row + 2] = lerp2(ti.z, u0, tj.z, u1);
-      msdf_aug[row] = lerp2(pi.w, u0, pj.w, u1);
+      verts_aug[3 * row + 0] = used ? lerp2(P.x, u0, Pj.x, u1) : 0.f;
+      verts_aug[3 * row + 1] = used ? lerp2(P.y, u0, Pj.y, u1) : 0.f;
+      verts_aug[3 * row + 2] = used ? lerp2(P.z, u0, Pj.z, u1) : 0.f;
+      v_tng_aug[3 * row + 0] = lerp2(T.x, u0, Tj.x, u1);
+      v_tng_aug[3 * row + 1] = lerp2(T.y, u0, Tj.y, u1);
+      v_tng_aug[3 * row + 2] = lerp2(T.z, u0, Tj.z, u1);
+      msdf_aug[row] = lerp2(P.w, u0, Pj.w, u1);
     }
   }
-  // ---- cut triangles ----
-  if (ncut > 0) {
-    const int64_t row0 = fbase + brank * ncut;
-    for (int e = 0; e < 3 * ncut; ++e) {
-      const int loc = quad ? c_cut_quad[mcase][e] : c_cut_tri[mcase][e];
-      int64_t g;
-      if (loc < n) g = (loc == 0) ? L[0] : (loc == 1) ? L[1] : (loc == 2) ? L[2] : L[3];
-      else g = nv + p0 + (loc - n);
-      const int64_t frow = row0 + e / 3;
-      if (frow < cap_faces_aug) faces_aug[3 * frow + (e % 3)] = g;
+  // ---- cut triangles: lane k writes triangle k of its polygon ----
+  const bool tri_here = (int)k < ncut;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int loc = (int)((cut >> (4 * (3 * k + c))) & 0xfull);
+    const bool is_corner = tri_here && loc < n;
+    const int Lv = __shfl_sync(FULL, L, lane0 + (is_corner ? (unsigned)loc : k));
+    if (tri_here) {
+      const int64_t g = is_corner ? (int64_t)Lv : nv + p0 + (loc - n);
+      const int64_t frow = row0 + k;
+      if (frow < cap_faces_aug) faces_aug[3 * frow + c] = g;
     }
   }
   trace_end(tr);
@@ -505,6 +555,11 @@ static UvParams uv_params(int64_t n_tets) {
   return uvp;
 }
 
+static unsigned cut_blocks(const Workspace& ws) {
+  const int64_t n = (ws.cap_tets + kCutPolysPerCta - 1) / kCutPolysPerCta;
+  return (unsigned)(n > 0 ? n : 1);
+}
+
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream) {
   const UvParams uvp = uv_params(a.n_tets);
@@ -520,8 +575,8 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
              ws.vert, ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits, ws.word_prefix);
   }
   ProfScope ps(K_POLY_CUT, stream);
-  launch_k(poly_cut_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr, ws.vert,
-           ws.acc, ws.owner, ws.poly_excl);
+  launch_k(poly_cut_kernel<false>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
+           ws.vert, ws.acc, ws.owner, ws.poly_excl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -584,8 +639,8 @@ void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   launch_k(poly_faces_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
            ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix);
-  launch_k(poly_cut_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
-           ws.acc, ws.owner, ws.poly_excl);
+  launch_k(poly_cut_kernel<true>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr,
+           ws.vert, ws.acc, ws.owner, ws.poly_excl);
 }
 
 }  // namespace d3h

@@ -302,6 +302,16 @@ _WAIT_TIMEOUT_US = 60_000_000
 LAUNCHES_FORWARD = 9
 #: static edge table path: prepare, classify, compact, edge_emit, poly_faces, poly_cut; backward: adjoint_poly + adjoint
 LAUNCHES_FORWARD_STATIC = 6
+#: edge-scan path: prepare, edge_scan, edge_mark, scan_prefix, scan_emit, poly_faces, poly_cut
+LAUNCHES_FORWARD_SCAN = 7
+
+
+def forward_launches(static, cap_tets: int) -> int:
+    """Kernels one forward extraction enqueues on the given path (without the zero-fill of the gradient buffers)."""
+    scan = static is not None and len(static) > 6 and static[6] is not None
+    if cap_tets <= 0:          # counting run: the surface stages are replaced by publish_counts_kernel
+        return 5 if scan else 4
+    return LAUNCHES_FORWARD_SCAN if scan else (LAUNCHES_FORWARD_STATIC if static is not None else LAUNCHES_FORWARD)
 LAUNCHES_BACKWARD = 1
 
 
@@ -447,7 +457,7 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             np.add(lay.OFF, np.array([bases[k] for k in lay.slab_of], dtype=np.int64), out=A[:, lay.c0:lay.c1])
             if static is not None:
                 A[:, c["vacc"]] = lay.vacc_off + bases[0]
-            launches = B * (4 if ct <= 0 else (LAUNCHES_FORWARD_STATIC if static is not None else LAUNCHES_FORWARD))
+            launches = B * forward_launches(static, ct)
             if zero is not None:
                 A[:, c["zero_g_pos"]:c["zero_g_msdf"] + 1] = zero
                 launches += int(np.count_nonzero(np.asarray(zero).any(axis=1)))
@@ -474,7 +484,7 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             if fused_pair:
                 _cabi.check(L.d3h_extract_forward_batch(A.ctypes.data, 1, 1, stream), "d3h_extract_forward (pair)")
                 launches += 3         # pair_vertex + replayed poly_faces / poly_cut; frame 1 launches nothing else
-                launches -= (4 if ct <= 0 else (LAUNCHES_FORWARD_STATIC if static is not None else LAUNCHES_FORWARD))
+                launches -= forward_launches(static, ct)
             elif launcher is None:
                 # no join here: the lanes keep running and the next batch may queue up behind this one lane by lane;
                 # _collect_frames orders the caller's stream behind the lanes before any output is handed out

@@ -179,8 +179,7 @@ def _forward(st: _State, pos, sdf, msdf, need):
     for _attempt in range(6):
         fslab, islab, g, cptr, seq, slot, gbufs = _launch(st, pos, sdf, msdf, need)
         cv, cva, cfw, cfa, ct = g.caps
-        launches += (4 if ct <= 0 else (E.LAUNCHES_FORWARD_STATIC if st.static is not None else E.LAUNCHES_FORWARD)) + \
-            (1 if gbufs[0] is not None else 0)
+        launches += E.forward_launches(st.static, ct) + (1 if gbufs[0] is not None else 0)
         rc = L.d3h_wait_counts(cptr, seq, E._WAIT_TIMEOUT_US)
         if rc:
             _cabi.check(rc, "d3h_wait_counts")
