@@ -149,9 +149,10 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
   ws.group_start = reinterpret_cast<unsigned*>(take((ws.ngroups + 2) * 4));
   ws.group_heads = reinterpret_cast<unsigned*>(take((ws.ngroups + 1) * 4));
   ws.gblock_heads = reinterpret_cast<unsigned*>(take((ws.ngroups / 256 + 2) * 4));
-  // bucket counts / prefixes per 32-polygon group (one warp of poly_faces_kernel): 8 words per group
-  ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * (kPolyThreads / 32) * 32));
-  ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * (kPolyThreads / 32) * 32));
+  ws.poly_cnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
+  ws.poly_excl = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * 32));
+  // ... and per 32-polygon group (one warp of poly_faces_kernel): 8 words per group
+  ws.poly_gcnt = reinterpret_cast<unsigned*>(take((ws.ntiles_poly + 1) * (kPolyThreads / 32) * 32));
   ws.vert = reinterpret_cast<float4*>(take(capc * 16));
   ws.acc = reinterpret_cast<float*>(take(capc * 32));
   ws.owner = reinterpret_cast<int32_t*>(take(capc * 4));
@@ -163,8 +164,6 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
     ws.word_prefix = reinterpret_cast<unsigned*>(take(ewords * 4));
     ws.eblock_cnt = reinterpret_cast<unsigned*>(take((ws.n_eblocks + 1) * 4));
     ws.corner_rank = reinterpret_cast<unsigned*>(take(capc * 4));
-    ws.tile_list = reinterpret_cast<unsigned*>(take((ws.ntiles_compact + 1) * 4));
-    ws.eblock_list = reinterpret_cast<unsigned*>(take((ws.n_eblocks + 1) * 4));
     ws.vlist = reinterpret_cast<int2*>(take(cap * 8));
     ws.elist = reinterpret_cast<int32_t*>(take(capc * 4));
     ws.tet_word_prefix = reinterpret_cast<uint2*>(take((nwords_f + kCompactThreads) * 8));

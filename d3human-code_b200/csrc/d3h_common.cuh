@@ -185,8 +185,7 @@ struct DevCounters {
   unsigned bucket[6];        // polygons per faces_aug bucket
   unsigned poly_done2;       // the same two for the replayed mSDF cut of a cloth / body pair
   unsigned bucket2[6];
-  unsigned n_tile_list;      // edge-scan path: entries of Workspace::tile_list / eblock_list (non-empty compaction tiles /
-  unsigned n_eblock_list;    //   edge blocks, in the order their first mark arrived)
+  unsigned pad0[2];
   unsigned n_vlist;          // edge-scan path: entries appended to Workspace::vlist (valid tets) / elist (crossing edges);
   unsigned n_elist;          //   true counts, may exceed the list capacities
   unsigned n_elist_raw;      // edge-scan path: crossing edges found by the stream (before the open-mesh prefilter)

@@ -67,6 +67,7 @@ struct Workspace {
   unsigned* gblock_heads;         // distinct keys of every 256 sort groups
   unsigned* poly_cnt;             // ntiles_poly * 8: polygons per faces_aug bucket in each polygon tile
   unsigned* poly_excl;            // ntiles_poly * 8: exclusive prefix of poly_cnt over the tiles
+  unsigned* poly_gcnt;            // ntiles_poly * 8 * 8: the same counts per group of 32 polygons
   float4* vert;                   // (x,y,z,msdf) per watertight vertex, 4*cap_valid_tets
   float* acc;                     // 8 floats per watertight vertex: normal xyz + count, tangent xyz + pad
   int32_t* owner;                 // per watertight vertex: the polygon corner slot that writes its tangent rows
@@ -75,9 +76,7 @@ struct Workspace {
   unsigned* word_prefix;          // per word of edge_bits: number of marked edges before it (= first vertex id of the word)
   unsigned* eblock_cnt;           // marked edges per 8192-edge block (one edge_emit CTA)
   unsigned* corner_rank;          // 4 per valid-tet record: edge rank of every polygon corner
-  unsigned* tile_list;            // edge-scan path: ids of the non-empty compaction tiles (ntiles_compact entries)
-  unsigned* eblock_list;          //                 ids of the non-empty edge blocks (n_eblocks entries)
-  int2* vlist;                    //                 (tet id, occupancy code) of every valid tet, unordered (cap_tets)
+  int2* vlist;                    // edge-scan path: (tet id, occupancy code) of every valid tet, unordered (cap_tets)
   int32_t* elist;                 //                 rank of every crossing edge, unordered (cap_corners)
   uint2* tet_word_prefix;         //                 per word of m1 / m2: (T1-class, T2-class) valid tets before it
   int64_t n_edges, n_eblocks;

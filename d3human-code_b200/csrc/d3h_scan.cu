@@ -13,6 +13,7 @@
 //                      both to unordered work lists (one global atomic per warp and list).  Two phases per CTA: the
 //                      stream (4 vertices per thread, 32 neighbour loads in flight) collects the crossing edges in
 //                      shared memory; then one thread per crossing edge walks the tets around it, 8 at a time.
+//   edge_mark_kernel   one thread per crossing edge walks the tets around it (8 at a time, all loads of a batch in flight).
 //   scan_prefix_kernel one CTA per non-empty tile / edge block: exclusive prefix of the popcounts of its 256 bitmap
 //                      words, on top of the sum of the counters of the earlier tiles / blocks (no look-back chain).
 //                      rank among the marked tets = record id (tet order, the order of the boolean-mask compaction
@@ -32,8 +33,8 @@ constexpr int kScanVertsPerCta = kEScanThreads * kScanVPT;    // 1024
 constexpr int kStageEdges = 3072;   // crossing edges a CTA collects in shared memory (12 KB) before it processes them
 
 struct ScanLists {
-  unsigned* tile_cnt; unsigned* tile_list;
-  unsigned* eblock_cnt; unsigned* eblock_list;
+  unsigned* tile_cnt;     // valid tets per 8192-tet compaction tile: T1 class | T2 class << 16
+  unsigned* eblock_cnt;   // crossing edges per 8192-edge block
   int2* vlist;
   int32_t* elist_raw;   // crossing edges as the stream found them
   int32_t* elist;       // ... that survive the open-mesh prefilter (the same array without the prefilter)
@@ -82,13 +83,12 @@ __device__ __forceinline__ void mark_tets_around(int e, const d3h_forward_args& 
       const unsigned old = atomicOr((quad ? m2_words : m1_words) + (t[j] >> 5), bit);
       if (!(old & bit)) fresh |= 1u << j;
     }
+    // count the tet for its tile: the result is not used, so this is a fire-and-forget reduction (a tile on the surface
+    // collects ~2000 of them; waiting for the returned values was 40 % of this kernel's stall samples)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (!((fresh >> j) & 1u)) continue;
-      const unsigned tile = (unsigned)t[j] / (unsigned)kTileTets;
-      if (atomicAdd(L.tile_cnt + tile, __popc(code[j]) == 2 ? 0x10000u : 1u) == 0u)
-        L.tile_list[atomicAdd(&ctr->n_tile_list, 1u)] = tile;
-    }
+    for (int j = 0; j < 8; ++j)
+      if ((fresh >> j) & 1u)
+        atomicAdd(L.tile_cnt + (unsigned)t[j] / (unsigned)kTileTets, __popc(code[j]) == 2 ? 0x10000u : 1u);
     // queue the freshly marked tets: one reservation per warp
     const unsigned nf = __popc(fresh);
     unsigned incl = nf;
@@ -115,8 +115,7 @@ __device__ __forceinline__ void mark_tets_around(int e, const d3h_forward_args& 
   // false (no valid tet keeps the edge: torch.unique never sees it) and the surviving edges are queued again.
   if (any) {
     atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
-    const unsigned eb = (unsigned)e / (unsigned)kEdgeBlock;
-    if (atomicAdd(L.eblock_cnt + eb, 1u) == 0u) L.eblock_list[atomicAdd(&ctr->n_eblock_list, 1u)] = eb;
+    atomicAdd(L.eblock_cnt + (unsigned)e / (unsigned)kEdgeBlock, 1u);
   }
   if (MOCC) {
     const unsigned keep = __ballot_sync(0xffffffffu, any);
@@ -246,9 +245,9 @@ edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __restrict__ m2_words,
-                   const unsigned* __restrict__ tile_cnt, const unsigned* __restrict__ tile_list, int64_t ntiles,
+                   const unsigned* __restrict__ tile_cnt, int64_t ntiles,
                    uint2* __restrict__ tet_word_prefix, const unsigned* __restrict__ edge_bits,
-                   const unsigned* __restrict__ eblock_cnt, const unsigned* __restrict__ eblock_list, int64_t n_eblocks,
+                   const unsigned* __restrict__ eblock_cnt, int64_t n_eblocks,
                    unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
                    unsigned grid_tiles) {
   constexpr int WARPS = 256 / 32;
@@ -259,8 +258,6 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
   const unsigned first = tiles ? blockIdx.x : blockIdx.x - grid_tiles;
   const unsigned stride = tiles ? grid_tiles : gridDim.x - grid_tiles;
   const unsigned* __restrict__ cnt = tiles ? tile_cnt : eblock_cnt;
-  const unsigned* __restrict__ list = tiles ? tile_list : eblock_list;
-  const unsigned n_list = tiles ? ctr->n_tile_list : ctr->n_eblock_list;
   const int64_t n_all = tiles ? ntiles : n_eblocks;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_COMPACT);
 
@@ -297,16 +294,16 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
     __syncthreads();
   }
 
-  for (unsigned li = first; li < n_list; li += stride) {
-    const unsigned id = list[li];
+  for (int64_t id = first; id < n_all; id += stride) {
+    if (__ldcg(cnt + id) == 0u) continue;   // most tiles / blocks hold no surface (block-uniform)
     unsigned long long sum = 0ull;   // tiles: T1 in the low half, T2 in the high half
-    for (unsigned i = threadIdx.x; i < id; i += 256) {
+    for (int64_t i = threadIdx.x; i < id; i += 256) {
       const unsigned c = __ldcg(cnt + i);
       sum += tiles ? ((unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32)) : (unsigned long long)c;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const int64_t w = (int64_t)id * 256 + threadIdx.x;
+    const int64_t w = id * 256 + threadIdx.x;
     unsigned long long c;
     if (tiles) c = (unsigned long long)__popc(__ldcg(m1_words + w)) | ((unsigned long long)__popc(__ldcg(m2_words + w)) << 32);
     else c = (unsigned long long)__popc(__ldcg(edge_bits + w));
@@ -432,8 +429,8 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
 
 void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   ScanLists L;
-  L.tile_cnt = ws.tile_cnt; L.tile_list = ws.tile_list;
-  L.eblock_cnt = ws.eblock_cnt; L.eblock_list = ws.eblock_list;
+  L.tile_cnt = ws.tile_cnt;
+  L.eblock_cnt = ws.eblock_cnt;
   L.vlist = ws.vlist;
   L.elist_raw = ws.elist;
   // with the open-mesh prefilter the marking kernel re-queues the edges that survive (corner_rank is idle on this path)
@@ -460,9 +457,9 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     ProfScope ps(K_COMPACT, stream);
     const unsigned gt = (unsigned)(ws.ntiles_compact < maxg ? ws.ntiles_compact : maxg);
     const unsigned ge = (unsigned)(ws.n_eblocks < maxg ? ws.n_eblocks : maxg);
-    launch_k(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt, ws.tile_list,
-             ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.eblock_list, ws.n_eblocks,
-             ws.word_prefix, ws.ctr, ws.cap_tets, gt);
+    launch_k(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt,
+             ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.n_eblocks, ws.word_prefix, ws.ctr,
+             ws.cap_tets, gt);
   }
   if (ws.cap_corners <= 0) return;   // counting run: sizes only
   ProfScope ps(K_EDGE_EMIT, stream);

@@ -69,7 +69,8 @@ template <bool REPLAY>
 __global__ void __launch_bounds__(kPolyThreads)
 poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                   DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
-                  unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_excl, UvParams uvp,
+                  unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_gcnt, unsigned* __restrict__ poly_excl,
+                  UvParams uvp,
                   d3h_counts* __restrict__ counts_dev, const unsigned* __restrict__ corner_rank,
                   const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix) {
   constexpr int WARPS = kPolyThreads / 32;
@@ -78,6 +79,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   const bool static_edges = !REPLAY && blk->a.edge_off != nullptr && blk->a.etets == nullptr;
   int64_t* __restrict__ faces_wt = blk->a.faces_wt;
   const int64_t cap_faces_wt = blk->a.cap_faces_wt;
+  __shared__ unsigned s_cnt[8][WARPS];
   __shared__ unsigned s_last;
   __shared__ unsigned long long s_scan[3][32];
 
@@ -173,14 +175,25 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
       const float sg = REPLAY ? -1.f : 1.f;  // exact: the pair's interpolated mSDF is the negation
       bucket = cut_case(quad, sg * P[0].w, sg * P[1].w, sg * P[2].w, sg * P[3].w, mcase, ncut);
     }
-    // ---- polygons per bucket in this group of 32 polygons (one warp): lane b keeps the count of bucket b ----
+    // ---- polygons per bucket: per group of 32 polygons (one warp; poly_cut_kernel ranks inside a tile with them) and
+    // per tile of 256 (scanned below by the last CTA).  Lane b keeps the count of bucket b ----
     unsigned mine = 0u;
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
       const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
       if (lane == (unsigned)b) mine = __popc(m);
     }
-    if (lane < 8u) poly_cnt[((int64_t)tile * WARPS + warp) * 8 + lane] = mine;   // (entries 6, 7: zero)
+    if (lane < 8u) {   // (entries 6, 7: zero)
+      poly_gcnt[((int64_t)tile * WARPS + warp) * 8 + lane] = mine;
+      s_cnt[lane][warp] = mine;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      unsigned run = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) run += s_cnt[threadIdx.x][w];
+      poly_cnt[(int64_t)tile * 8 + threadIdx.x] = run;
+    }
     // the (3,3) torch.cross quirk: the three face normals are crossed along the *face* axis
     if (!REPLAY && cross_quirk && i == 0) {
       float a[3][3], b[3][3];
@@ -226,13 +239,12 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // thread t owns groups [t*per, (t+1)*per); buckets are scanned as three pairs packed in 64-bit words
-  const int64_t ngroups = (npoly + 31) / 32;
-  const int64_t per = (ngroups + kPolyThreads - 1) / kPolyThreads;
+  // thread t owns tiles [t*per, (t+1)*per); buckets are scanned as three pairs packed in 64-bit words
+  const int64_t per = (ntiles + kPolyThreads - 1) / kPolyThreads;
   const int64_t tl0 = (int64_t)threadIdx.x * per;
   unsigned long long sum[3] = {0ull, 0ull, 0ull};
   for (int64_t q = 0; q < per; ++q) {
-    if (tl0 + q < ngroups) {
+    if (tl0 + q < ntiles) {
       const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(poly_cnt + (tl0 + q) * 8));
       const uint2 c45 = __ldcg(reinterpret_cast<const uint2*>(poly_cnt + (tl0 + q) * 8 + 4));
       sum[0] += (unsigned long long)c03.x | ((unsigned long long)c03.y << 32);
@@ -264,7 +276,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
     total[wd] = tot;
   }
   for (int64_t q = 0; q < per; ++q) {
-    if (tl0 + q < ngroups) {
+    if (tl0 + q < ntiles) {
       const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(poly_cnt + (tl0 + q) * 8));
       const uint2 c45 = __ldcg(reinterpret_cast<const uint2*>(poly_cnt + (tl0 + q) * 8 + 4));
       unsigned* e = poly_excl + (tl0 + q) * 8;
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
-                const unsigned* __restrict__ poly_excl) {
+                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl) {
   constexpr int WARPS = kPolyThreads / 32;
   constexpr unsigned FULL = 0xffffffffu;
   const int32_t* __restrict__ corners = blk->a.tape_corners;
@@ -474,8 +486,12 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
 #pragma unroll
     for (int b = 0; b < 6; ++b)
       if (b < bucket) fbase += (int64_t)(REPLAY ? ctr->bucket2[b] : ctr->bucket[b]) * ncut_of[b];
-    unsigned before = poly_excl[(i >> 5) * 8 + bucket];
-    for (unsigned w = warp & ~3u; w < warp; ++w) before += s_cnt[bucket][w];   // 4 warps = one 32-polygon group
+    // polygons of this bucket before this one: tiles of 256 before (scanned by poly_faces_kernel), groups of 32 before
+    // inside the tile, warps of this kernel before inside the group (4 warps = one group)
+    const int64_t grp = i >> 5;
+    unsigned before = poly_excl[(grp >> 3) * 8 + bucket];
+    for (int64_t q = grp & ~int64_t(7); q < grp; ++q) before += __ldg(poly_gcnt + q * 8 + bucket);
+    for (unsigned w = warp & ~3u; w < warp; ++w) before += s_cnt[bucket][w];
     row0 = fbase + ((int64_t)before + __popc(my_ballot & ((1u << lane0) - 1u))) * ncut;   // polygons before this one
   }
   // ---- boundary vertex on polygon edge k -> k+1: this lane's corner and the next one's ----
@@ -572,11 +588,12 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
   {
     ProfScope ps(K_POLY_FACES, stream);
     launch_k(poly_faces_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
-             ws.vert, ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits, ws.word_prefix);
+             ws.vert, ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits,
+             ws.word_prefix);
   }
   ProfScope ps(K_POLY_CUT, stream);
   launch_k(poly_cut_kernel<false>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
-           ws.vert, ws.acc, ws.owner, ws.poly_excl);
+           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,9 +655,9 @@ void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3
   const UvParams uvp = uv_params(a.n_tets);
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   launch_k(poly_faces_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
-           ws.acc, ws.poly_cnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix);
+           ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix);
   launch_k(poly_cut_kernel<true>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr,
-           ws.vert, ws.acc, ws.owner, ws.poly_excl);
+           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl);
 }
 
 }  // namespace d3h

@@ -40,7 +40,7 @@ for i in range(args.frames):
 t0 = min(r[0] for r in rows)
 t1 = max(r[1] for r in rows)
 print(f"# {args.frames} frames on {args.lanes} lanes, graph launches: forward span {(t1 - t0) / 1e3:.1f} us = {(t1 - t0) / 1e3 / args.frames:.1f} us/frame")
-order = ["prepare", "classify", "edge_scan", "compact", "bucket_scan", "partition", "group_sort", "vertex_emit", "edge_emit", "poly_faces", "poly_cut", "zero"]
+order = ["prepare", "classify", "edge_scan", "edge_mark", "compact", "bucket_scan", "partition", "group_sort", "vertex_emit", "edge_emit", "poly_faces", "poly_cut", "zero"]
 print("# per frame: start of prepare -> end of poly_cut (us), lane = frame % lanes; then per-kernel durations")
 for i in range(args.frames):
     mine = {r[2]: r for r in rows if r[3] == i}
