@@ -164,8 +164,13 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
     ws.word_prefix = reinterpret_cast<unsigned*>(take(ewords * 4));
     ws.eblock_cnt = reinterpret_cast<unsigned*>(take((ws.n_eblocks + 1) * 4));
     ws.corner_rank = reinterpret_cast<unsigned*>(take(capc * 4));
-    ws.vlist = reinterpret_cast<int2*>(take(cap * 8));
-    ws.elist = reinterpret_cast<int32_t*>(take(capc * 4));
+    // work queues of the edge-scan path: kQueues sub-queues, each 8 / kQueues of the total capacity (8x the expected fill)
+    ws.cap_qv = cap > 0 ? (cap * 8 + kQueues - 1) / kQueues : 0;
+    ws.cap_qe = capc > 0 ? (capc * 8 + kQueues - 1) / kQueues : 0;
+    ws.q_cnt = reinterpret_cast<unsigned*>(take(3 * kQueues * 4));
+    ws.vlist = reinterpret_cast<int2*>(take(ws.cap_qv * kQueues * 8));
+    ws.elist = reinterpret_cast<int32_t*>(take(ws.cap_qe * kQueues * 4));
+    ws.elist2 = reinterpret_cast<int32_t*>(take(ws.cap_qe * kQueues * 4));
     ws.tet_word_prefix = reinterpret_cast<uint2*>(take((nwords_f + kCompactThreads) * 8));
   }
   ws.total_bytes = off;

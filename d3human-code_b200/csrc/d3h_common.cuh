@@ -185,10 +185,7 @@ struct DevCounters {
   unsigned bucket[6];        // polygons per faces_aug bucket
   unsigned poly_done2;       // the same two for the replayed mSDF cut of a cloth / body pair
   unsigned bucket2[6];
-  unsigned pad0[2];
-  unsigned n_vlist;          // edge-scan path: entries appended to Workspace::vlist (valid tets) / elist (crossing edges);
-  unsigned n_elist;          //   true counts, may exceed the list capacities
-  unsigned n_elist_raw;      // edge-scan path: crossing edges found by the stream (before the open-mesh prefilter)
+  unsigned pad[5];
   unsigned trace_frame;      // diagnostics (d3h_trace_*): row of the trace table this call writes to
   unsigned pad2;
   unsigned long long* trace; // diagnostics: device trace table or nullptr; set by prepare_kernel, not reset

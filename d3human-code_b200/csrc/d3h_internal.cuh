@@ -76,8 +76,12 @@ struct Workspace {
   unsigned* word_prefix;          // per word of edge_bits: number of marked edges before it (= first vertex id of the word)
   unsigned* eblock_cnt;           // marked edges per 8192-edge block (one edge_emit CTA)
   unsigned* corner_rank;          // 4 per valid-tet record: edge rank of every polygon corner
-  int2* vlist;                    // edge-scan path: (tet id, occupancy code) of every valid tet, unordered (cap_tets)
-  int32_t* elist;                 //                 rank of every crossing edge, unordered (cap_corners)
+  // edge-scan path: unordered work queues, kQueues sub-queues each (see d3h_scan.cu)
+  unsigned* q_cnt;                // [3][kQueues] entries appended per sub-queue: raw edges, valid tets, filtered edges
+  int2* vlist;                    // kQueues x cap_qv: (tet id, occupancy code) of every valid tet
+  int32_t* elist;                 // kQueues x cap_qe: rank of every crossing edge
+  int32_t* elist2;                // kQueues x cap_qe: ... that survives the open-mesh prefilter
+  int64_t cap_qe, cap_qv;         // entries per sub-queue
   uint2* tet_word_prefix;         //                 per word of m1 / m2: (T1-class, T2-class) valid tets before it
   int64_t n_edges, n_eblocks;
   int64_t nwords_tet;             // words of m1_words / m2_words (32 tets each), padded to whole compaction tiles
@@ -88,6 +92,7 @@ struct Workspace {
 
 // Carves `base` (may be nullptr when only the size is wanted).
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges = 0);
+constexpr int kQueues = 64;        // sub-queues of the edge-scan path's work queues
 constexpr int kEdgeBlock = 8192;  // edges per edge_emit CTA (256 threads x one 32-bit word)
 
 int key_bits_for(int64_t n_grid);   // bits per endpoint in the packed edge key

@@ -6,148 +6,90 @@
 //
 //   edge_scan_kernel   one thread per grid vertex a walks the larger neighbours b of a (4 bytes per EDGE instead of the
 //                      16 bytes per TET of classify_kernel: 68 MB instead of 201 MB at 128^3).  sign(sdf[a]) !=
-//                      sign(sdf[b]) is exactly the crossing mask of gshell_tets.py:281; the tets around a crossing
-//                      edge are exactly the valid tets of :261-275 (a tet has mixed signs iff one of its edges
-//                      crosses).  The thread marks the edge in the bitmap over the edge list, marks the tets around it
-//                      in the T1 / T2 bitmaps (the first marker of a tet counts it for its 8192-tet tile) and appends
-//                      both to unordered work lists (one global atomic per warp and list).  Two phases per CTA: the
-//                      stream (4 vertices per thread, 32 neighbour loads in flight) collects the crossing edges in
-//                      shared memory; then one thread per crossing edge walks the tets around it, 8 at a time.
-//   edge_mark_kernel   one thread per crossing edge walks the tets around it (8 at a time, all loads of a batch in flight).
+//                      sign(sdf[b]) is exactly the crossing mask of gshell_tets.py:281.  Crossing edges go to work queues.
+//   edge_mark_kernel   one thread per crossing edge walks the tets around it, 8 at a time with all loads of a batch in
+//                      flight: the tets around a crossing edge are exactly the valid tets of :261-275 (a tet has mixed
+//                      signs iff one of its edges crosses).  Marks the edge in the bitmap over the edge list and the
+//                      tets in the T1 / T2 bitmaps; the first marker of a tet counts it for its 8192-tet tile and
+//                      queues it.
 //   scan_prefix_kernel one CTA per non-empty tile / edge block: exclusive prefix of the popcounts of its 256 bitmap
 //                      words, on top of the sum of the counters of the earlier tiles / blocks (no look-back chain).
 //                      rank among the marked tets = record id (tet order, the order of the boolean-mask compaction
 //                      :277, :323-324); rank among the marked edges = vertex id (the order of torch.unique(dim=0), :279).
-//   scan_emit_kernel   one thread per list entry, whatever tile or block it sits in (balanced): a valid tet becomes its
+//   scan_emit_kernel   one thread per queue entry, whatever tile or block it sits in (balanced): a valid tet becomes its
 //                      record + the vertex ids of its polygon corners (tape_corners), a crossing edge becomes its
 //                      interpolated vertex (:291-303).
 //
+// Work queues: the order of the entries does not matter, so every warp appends with ONE atomic -- but ~1500 warps
+// reserving on the same counter serialise at ~18 ns per atomic (measured: 27 us for the marking kernel, all of it
+// waiting for that one address).  The queues are therefore split in kQueues sub-queues, a warp uses sub-queue
+// (global warp id) % kQueues, and the consumers give every sub-queue its own CTAs.
+//
 // poly_faces_kernel / poly_cut_kernel / the adjoint are shared with the other paths.
+#include <cstdlib>
+
 #include "d3h_internal.cuh"
 
 namespace d3h {
 
 constexpr int kEScanThreads = 256;
-constexpr int kScanVPT = 4;                                  // vertices per thread: 4 x 8 neighbour loads in flight
-constexpr int kScanVertsPerCta = kEScanThreads * kScanVPT;    // 1024
-constexpr int kStageEdges = 3072;   // crossing edges a CTA collects in shared memory (12 KB) before it processes them
+// vertices per thread of the stream (x 8 neighbour loads in flight each): D3H_SCAN_VPT = 1, 2 or 4 (default)
+static int scan_vpt() {
+  static int v = 0;
+  if (v == 0) {
+    const char* env = getenv("D3H_SCAN_VPT");
+    v = (env && (env[0] == '1' || env[0] == '2')) ? (env[0] - '0') : 4;
+  }
+  return v;
+}
 
 struct ScanLists {
   unsigned* tile_cnt;     // valid tets per 8192-tet compaction tile: T1 class | T2 class << 16
   unsigned* eblock_cnt;   // crossing edges per 8192-edge block
-  int2* vlist;
-  int32_t* elist_raw;   // crossing edges as the stream found them
-  int32_t* elist;       // ... that survive the open-mesh prefilter (the same array without the prefilter)
-  int64_t cap_vlist, cap_elist;
+  unsigned* q_cnt;        // [3][kQueues] entries appended to every sub-queue (true counts, may exceed the capacity):
+                          //   0 crossing edges as the stream found them, 1 valid tets, 2 edges that survive the prefilter
+  int32_t* elist_raw;     // kQueues x cap_qe
+  int2* vlist;            // kQueues x cap_qv: (tet id, occupancy code)
+  int32_t* elist;         // kQueues x cap_qe; == elist_raw without the open-mesh prefilter
+  int64_t cap_qe, cap_qv; // entries per sub-queue
 };
 
-// The tets around crossing edge `e`: mark them in the T1 / T2 bitmaps; the first marker of a tet counts it for its tile
-// and queues it.  All loads of a batch of 8 tets are issued together (the chain per batch is etets -> tets -> signs ->
-// atomics, whatever the number of tets).  Called by all 32 lanes (lanes without an edge pass e < 0): the queue slots of
-// a warp are reserved with one global atomic.
-template <bool MOCC>
-__device__ __forceinline__ void mark_tets_around(int e, const d3h_forward_args& a, const unsigned* __restrict__ occ_bits,
-                                                 const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
-                                                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits,
-                                                 DevCounters* __restrict__ ctr, const ScanLists& L) {
-  const int32_t* __restrict__ etets = a.etets;
-  const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
+// One reservation per warp: `n` entries of this lane -> first slot of the lane in sub-queue q (all 32 lanes call).
+__device__ __forceinline__ int64_t warp_reserve(unsigned* __restrict__ counter, unsigned n) {
   const unsigned lane = lane_id();
-  int t0 = 0, t1 = 0;
-  if (e >= 0) { t0 = __ldg(a.etet_off + e); t1 = __ldg(a.etet_off + e + 1); }
-  bool any = false;
-  while (__any_sync(0xffffffffu, t0 < t1)) {
-    int t[8];
-    int4 q[8];
+  unsigned incl = n;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = (t0 + j < t1) ? __ldg(etets + t0 + j) : -1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q[j] = (t[j] >= 0) ? __ldg(tets + t[j]) : make_int4(0, 0, 0, 0);
-    unsigned code[8], fresh = 0u;   // fresh: bit j = this lane marked tet j first
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      code[j] = occ_of(occ_bits, q[j].x) | (occ_of(occ_bits, q[j].y) << 1) | (occ_of(occ_bits, q[j].z) << 2) |
-                (occ_of(occ_bits, q[j].w) << 3);
-      if (MOCC && t[j] >= 0) {   // open-mesh prefilter, gshell_tets.py:275: keep tets with a vertex of positive mSDF
-        const unsigned keep = occ_of(mocc_bits, q[j].x) | occ_of(mocc_bits, q[j].y) | occ_of(mocc_bits, q[j].z) |
-                              occ_of(mocc_bits, q[j].w);
-        if (!keep) t[j] = -1;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (t[j] < 0) continue;
-      any = true;
-      const bool quad = __popc(code[j]) == 2;
-      const unsigned bit = 1u << (t[j] & 31);
-      const unsigned old = atomicOr((quad ? m2_words : m1_words) + (t[j] >> 5), bit);
-      if (!(old & bit)) fresh |= 1u << j;
-    }
-    // count the tet for its tile: the result is not used, so this is a fire-and-forget reduction (a tile on the surface
-    // collects ~2000 of them; waiting for the returned values was 40 % of this kernel's stall samples)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if ((fresh >> j) & 1u)
-        atomicAdd(L.tile_cnt + (unsigned)t[j] / (unsigned)kTileTets, __popc(code[j]) == 2 ? 0x10000u : 1u);
-    // queue the freshly marked tets: one reservation per warp
-    const unsigned nf = __popc(fresh);
-    unsigned incl = nf;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += nb;
-    }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total) {
-      unsigned base = 0u;
-      if (lane == 31) base = atomicAdd(&ctr->n_vlist, total);
-      base = __shfl_sync(0xffffffffu, base, 31) + incl - nf;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!((fresh >> j) & 1u)) continue;
-        if ((int64_t)base < L.cap_vlist) L.vlist[base] = make_int2(t[j], (int)code[j]);
-        ++base;
-      }
-    }
-    t0 += 8;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += nb;
   }
-  // the edge itself: a bit in the bitmap over the edge list and a count for its block.  With the prefilter `any` may be
-  // false (no valid tet keeps the edge: torch.unique never sees it) and the surviving edges are queued again.
-  if (any) {
-    atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
-    atomicAdd(L.eblock_cnt + (unsigned)e / (unsigned)kEdgeBlock, 1u);
-  }
-  if (MOCC) {
-    const unsigned keep = __ballot_sync(0xffffffffu, any);
-    if (keep) {
-      unsigned base = 0u;
-      if (lane == 0) base = atomicAdd(&ctr->n_elist, (unsigned)__popc(keep));
-      base = __shfl_sync(0xffffffffu, base, 0) + __popc(keep & lanemask_lt());
-      if (any && (int64_t)base < L.cap_elist) L.elist[base] = e;
-    }
-  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0u) return -1;
+  unsigned base = 0u;
+  if (lane == 31) base = atomicAdd(counter, total);
+  return (int64_t)__shfl_sync(0xffffffffu, base, 31) + incl - n;
 }
 
+// The stream.  A warp takes 32 * VPT consecutive vertices (lane l: vertices base + l, base + l + 32, ...: coalesced offset
+// loads) and all neighbour loads of a thread's vertices are in flight together.  No shared memory, no barrier: a warp
+// that found crossing edges (rare: the surface touches < 2 % of the vertices) reserves their slots in its sub-queue
+// with one atomic and retires on its own.
+template <int VPT>
 __global__ void __launch_bounds__(kEScanThreads)
-edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, DevCounters* __restrict__ ctr,
-                 ScanLists L) {
-  __shared__ unsigned s_ne, s_base;
-  __shared__ int s_e[kStageEdges];
+edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
   const d3h_forward_args& a = blk->a;
   const int32_t* __restrict__ edge_off = a.edge_off;
   const int32_t* __restrict__ edge_b = a.edge_b;
   const int64_t n_grid = a.n_grid;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
-  if (threadIdx.x == 0) s_ne = 0u;
-  __syncthreads();
-  // ---- phase 1: the stream.  Thread t takes vertices base + t, base + t + 256, ... (coalesced offset loads); the
-  // neighbour loads of all its vertices are in flight together ----
-  const int64_t vbase = (int64_t)blockIdx.x * kScanVertsPerCta + threadIdx.x;
-  int e0[kScanVPT], e1[kScanVPT];
-  unsigned oa[kScanVPT];
+  const unsigned lane = lane_id();
+  const int64_t gwarp = (int64_t)blockIdx.x * (kEScanThreads / 32) + (threadIdx.x >> 5);
+  const int64_t wbase = gwarp * (32 * VPT);
+  int e0[VPT], e1[VPT];
+  unsigned oa[VPT];
 #pragma unroll
-  for (int k = 0; k < kScanVPT; ++k) {
-    const int64_t v = vbase + (int64_t)k * kEScanThreads;
+  for (int k = 0; k < VPT; ++k) {
+    const int64_t v = wbase + k * 32 + lane;
     e0[k] = e1[k] = 0;
     oa[k] = 0u;
     if (v < n_grid) {
@@ -156,83 +98,130 @@ edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       oa[k] = occ_of(occ_bits, (int)v);
     }
   }
-  int b[kScanVPT][8];
+  int b[VPT][8];
 #pragma unroll
-  for (int k = 0; k < kScanVPT; ++k)
+  for (int k = 0; k < VPT; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) b[k][j] = (e0[k] + j < e1[k]) ? __ldg(edge_b + e0[k] + j) : -1;
+  unsigned x[VPT];      // bit j: neighbour j of vertex k has the other sign
+  unsigned cnt = 0u;
+  bool more = false;    // a vertex with more than 8 larger neighbours (unstructured grids)
 #pragma unroll
-  for (int k = 0; k < kScanVPT; ++k) {
-    unsigned x = 0u;
+  for (int k = 0; k < VPT; ++k) {
+    x[k] = 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (b[k][j] >= 0) x |= (occ_of(occ_bits, b[k][j]) ^ oa[k]) << j;
-    while (x) {   // crossing edges of this vertex (rare: the surface touches < 2 % of the vertices)
-      const int e = e0[k] + (__ffs((int)x) - 1);
-      x &= x - 1u;
-      const unsigned slot = atomicAdd(&s_ne, 1u);
-      if (slot < (unsigned)kStageEdges) s_e[slot] = e;
-    }
-    // vertices with more than 8 larger neighbours (unstructured grids): the rest of the list, 8 at a time
-    for (int base = e0[k] + 8; base < e1[k]; base += 8) {
-      int bb[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bb[j] = (base + j < e1[k]) ? __ldg(edge_b + base + j) : -1;
-      unsigned y = 0u;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (bb[j] >= 0) y |= (occ_of(occ_bits, bb[j]) ^ oa[k]) << j;
-      while (y) {
-        const int e = base + (__ffs((int)y) - 1);
-        y &= y - 1u;
-        const unsigned slot = atomicAdd(&s_ne, 1u);
-        if (slot < (unsigned)kStageEdges) s_e[slot] = e;
-      }
-    }
+      if (b[k][j] >= 0) x[k] |= (occ_of(occ_bits, b[k][j]) ^ oa[k]) << j;
+    cnt += __popc(x[k]);
+    more = more || (e0[k] + 8 < e1[k]);
   }
-  __syncthreads();
-  // ---- hand the crossing edges of the CTA to the marking kernel: one reservation in the global queue ----
-  const unsigned found = s_ne;
-  if (found == 0u) { trace_end(tr); return; }
-  const unsigned staged = min(found, (unsigned)kStageEdges);
-  if (threadIdx.x == 0) s_base = atomicAdd(&ctr->n_elist_raw, found);
-  __syncthreads();
-  const unsigned base = s_base;
-  for (unsigned i = threadIdx.x; i < staged; i += kEScanThreads)
-    if ((int64_t)(base + i) < L.cap_elist) L.elist_raw[base + i] = s_e[i];
-  if (found > (unsigned)kStageEdges) {
-    // more crossing edges than the stage holds (a CTA inside a sheet of the surface of a very irregular grid): walk the
-    // vertices again; the first kStageEdges hits went through the stage, the others take the slots behind them
-    if (threadIdx.x == 0) s_ne = 0u;
-    __syncthreads();
+  if (__any_sync(0xffffffffu, more)) {
+    // the rest of the long neighbour lists: counted here, written below
 #pragma unroll
-    for (int k = 0; k < kScanVPT; ++k) {
-      for (int e = e0[k]; e < e1[k]; ++e) {
-        if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) == 0u) continue;
-        const unsigned slot = atomicAdd(&s_ne, 1u);
-        if ((int64_t)(base + slot) < L.cap_elist) L.elist_raw[base + slot] = e;   // (rewrites the staged ones, same set)
-      }
+    for (int k = 0; k < VPT; ++k)
+      for (int e = e0[k] + 8; e < e1[k]; ++e) cnt += occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k];
+  }
+  const unsigned q = (unsigned)(gwarp % kQueues);
+  int64_t slot = warp_reserve(L.q_cnt + q, cnt);
+  if (slot < 0) { trace_end(tr); return; }
+  int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    unsigned y = x[k];
+    while (y) {
+      const int e = e0[k] + (__ffs((int)y) - 1);
+      y &= y - 1u;
+      if (slot < L.cap_qe) out[slot] = e;
+      ++slot;
+    }
+    for (int e = e0[k] + 8; e < e1[k]; ++e) {
+      if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) == 0u) continue;
+      if (slot < L.cap_qe) out[slot] = e;
+      ++slot;
     }
   }
   trace_end(tr);
 }
 
 // One thread per crossing edge of the whole grid (all resident at once: the chain etet_off -> etets -> tets -> signs ->
-// atomics is paid once, not once per trip of a busy CTA).
+// atomics is paid once).  CTA c serves sub-queue c % kQueues.  All loads of a batch of 8 tets are issued together.
 template <bool MOCC>
 __global__ void __launch_bounds__(256)
 edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
                  const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
-                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, DevCounters* __restrict__ ctr,
-                 ScanLists L) {
+                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, ScanLists L) {
   const d3h_forward_args& a = blk->a;
+  const int32_t* __restrict__ etets = a.etets;
+  const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
-  const int64_t raw = (int64_t)ctr->n_elist_raw;
-  const int64_t n = raw < L.cap_elist ? raw : L.cap_elist;
-  const int64_t stride = (int64_t)gridDim.x * 256;
-  for (int64_t j0 = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31u); j0 < n; j0 += stride) {   // warp-uniform trips
-    const int64_t j = j0 + lane_id();
-    mark_tets_around<MOCC>(j < n ? L.elist_raw[j] : -1, a, occ_bits, mocc_bits, m1_words, m2_words, edge_bits, ctr, L);
+  const unsigned lane = lane_id();
+  const unsigned q = blockIdx.x % kQueues, part = blockIdx.x / kQueues, parts = gridDim.x / kQueues;
+  const int64_t raw = (int64_t)L.q_cnt[q];
+  const int64_t n = raw < L.cap_qe ? raw : L.cap_qe;
+  const int32_t* __restrict__ in = L.elist_raw + (int64_t)q * L.cap_qe;
+  // the valid tets found by this warp go to sub-queue (its global warp id) % kQueues
+  const unsigned qv = (unsigned)((blockIdx.x * 8u + (threadIdx.x >> 5)) % kQueues);
+  int2* __restrict__ vout = L.vlist + (int64_t)qv * L.cap_qv;
+  for (int64_t j0 = (int64_t)part * 256 + (threadIdx.x & ~31u); j0 < n; j0 += (int64_t)parts * 256) {   // warp-uniform
+    const int64_t j = j0 + lane;
+    const int e = j < n ? in[j] : -1;
+    int t0 = 0, t1 = 0;
+    if (e >= 0) { t0 = __ldg(a.etet_off + e); t1 = __ldg(a.etet_off + e + 1); }
+    bool any = false;
+    while (__any_sync(0xffffffffu, t0 < t1)) {
+      int t[8];
+      int4 v4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = (t0 + i < t1) ? __ldg(etets + t0 + i) : -1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v4[i] = (t[i] >= 0) ? __ldg(tets + t[i]) : make_int4(0, 0, 0, 0);
+      unsigned code[8], fresh = 0u;   // fresh: bit i = this lane marked tet i first
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        code[i] = occ_of(occ_bits, v4[i].x) | (occ_of(occ_bits, v4[i].y) << 1) | (occ_of(occ_bits, v4[i].z) << 2) |
+                  (occ_of(occ_bits, v4[i].w) << 3);
+        if (MOCC && t[i] >= 0) {   // open-mesh prefilter, gshell_tets.py:275: keep tets with a vertex of positive mSDF
+          const unsigned keep = occ_of(mocc_bits, v4[i].x) | occ_of(mocc_bits, v4[i].y) | occ_of(mocc_bits, v4[i].z) |
+                                occ_of(mocc_bits, v4[i].w);
+          if (!keep) t[i] = -1;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (t[i] < 0) continue;
+        any = true;
+        const bool quad = __popc(code[i]) == 2;
+        const unsigned bit = 1u << (t[i] & 31);
+        const unsigned old = atomicOr((quad ? m2_words : m1_words) + (t[i] >> 5), bit);
+        if (!(old & bit)) fresh |= 1u << i;
+      }
+      // count the tet for its tile: the result is not used, so this is a fire-and-forget reduction (a tile on the
+      // surface collects ~2000 of them; waiting for returned values was 40 % of this kernel's stall samples)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((fresh >> i) & 1u)
+          atomicAdd(L.tile_cnt + (unsigned)t[i] / (unsigned)kTileTets, __popc(code[i]) == 2 ? 0x10000u : 1u);
+      int64_t slot = warp_reserve(L.q_cnt + kQueues + qv, (unsigned)__popc(fresh));
+      if (slot >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!((fresh >> i) & 1u)) continue;
+          if (slot < L.cap_qv) vout[slot] = make_int2(t[i], (int)code[i]);
+          ++slot;
+        }
+      }
+      t0 += 8;
+    }
+    // the edge itself: a bit in the bitmap over the edge list and a count for its block.  With the prefilter `any` may
+    // be false (no valid tet keeps the edge: torch.unique never sees it) and the surviving edges are queued again.
+    if (any) {
+      atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
+      atomicAdd(L.eblock_cnt + (unsigned)e / (unsigned)kEdgeBlock, 1u);
+    }
+    if (MOCC) {
+      const int64_t slot = warp_reserve(L.q_cnt + 2 * kQueues + q, any ? 1u : 0u);
+      if (any && slot >= 0 && slot < L.cap_qe) L.elist[(int64_t)q * L.cap_qe + slot] = e;
+    }
   }
   trace_end(tr);
 }
@@ -249,7 +238,7 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
                    uint2* __restrict__ tet_word_prefix, const unsigned* __restrict__ edge_bits,
                    const unsigned* __restrict__ eblock_cnt, int64_t n_eblocks,
                    unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
-                   unsigned grid_tiles) {
+                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles) {
   constexpr int WARPS = 256 / 32;
   __shared__ unsigned long long s_sum[WARPS];
   __shared__ unsigned long long s_w[WARPS];
@@ -278,12 +267,24 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
         const unsigned t1 = (unsigned)(tot & 0xffffffffull), t2 = (unsigned)(tot >> 32);
         ctr->n_tri = t1;
         ctr->n_quad = t2;
-        // the queue of crossing edges holds 4 * cap_records entries; edges beyond that were dropped and the tets around
-        // them never marked: report enough valid tets for the caller to grow (the counts of an overflowed call only
-        // serve that purpose) -- a crossing edge needs at most a quarter of a record
-        const int64_t raw = (int64_t)ctr->n_elist_raw;
-        const bool queue_ok = raw <= 4 * cap_records;
-        ctr->n_valid = queue_ok ? t1 + t2 : max(t1 + t2, (unsigned)((raw + 3) / 4));
+        // a sub-queue that overflowed dropped entries: crossing edges whose tets were never marked, or valid tets that
+        // never become records.  Report enough valid tets for the caller to grow (the counts of an overflowed call only
+        // serve that purpose)
+        int64_t raw = 0, max_e = 0, max_v = 0;
+        for (int q = 0; q < kQueues; ++q) {
+          const int64_t ne = (int64_t)q_cnt[q], nt = (int64_t)q_cnt[kQueues + q];
+          raw += ne;
+          max_e = ne > max_e ? ne : max_e;
+          max_v = nt > max_v ? nt : max_v;
+        }
+        const bool queue_ok = max_e <= cap_qe && max_v <= cap_qv;
+        // records needed for every sub-queue to hold what it was offered (a sub-queue has 1/8 of the record capacity
+        // for tets and 1/2 of it for edges), and the expected number of valid tets when none could be marked yet
+        int64_t need = 2 * raw;
+        need = 8 * max_v > need ? 8 * max_v : need;
+        need = 2 * max_e > need ? 2 * max_e : need;
+        need = cap_records + 1 > need ? cap_records + 1 : need;
+        ctr->n_valid = queue_ok ? t1 + t2 : max(t1 + t2, (unsigned)need);
         const bool fits = queue_ok && (int64_t)t1 + t2 <= cap_records;
         ctr->work_tri = fits ? t1 : 0u;
         ctr->work_quad = fits ? t2 : 0u;
@@ -331,25 +332,28 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// one thread per work-list entry.  CTAs [0, grid_tets) take the valid tets, the others the crossing edges.
+// one thread per queue entry.  CTAs [0, grid_tets) take the valid tets, the others the crossing edges; CTA c of either
+// group serves sub-queue c % kQueues.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict__ ctr, const int2* __restrict__ vlist,
-                 const int32_t* __restrict__ elist, const unsigned* __restrict__ m1_words,
+                 const int32_t* __restrict__ elist, int filtered, const unsigned* __restrict__ m1_words,
                  const unsigned* __restrict__ m2_words, const uint2* __restrict__ tet_word_prefix,
                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix,
                  d3h_tet_record* __restrict__ records, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
-                 int64_t cap_corners, unsigned grid_tets) {
+                 int64_t cap_corners, const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tets) {
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
   if (blockIdx.x < grid_tets) {
     // ---- valid tets -> records (tet order) + polygon corner -> vertex id ----
     const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;   // 0 / 0 when the record buffer is too small
-    const int64_t n = (int64_t)t1 + t2;
+    const unsigned q = blockIdx.x % kQueues, part = blockIdx.x / kQueues, parts = grid_tets / kQueues;
+    const int64_t n = (t1 + t2 == 0u) ? 0 : (int64_t)q_cnt[kQueues + q];   // (fits: checked by scan_prefix_kernel)
+    vlist += (int64_t)q * cap_qv;
     const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
     const int4* __restrict__ ranks = reinterpret_cast<const int4*>(a.tet_edge_rank);
     int32_t* __restrict__ corners = a.tape_corners;
-    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)grid_tets * 256) {
+    for (int64_t j = (int64_t)part * 256 + threadIdx.x; j < n; j += (int64_t)parts * 256) {
       const int2 it = vlist[j];
       const int t = it.x, code = it.y;
       const int4 v4 = __ldg(tets + t);
@@ -379,9 +383,11 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
     }
   } else {
     // ---- crossing edges -> watertight vertices (zero-crossing interpolation, gshell_tets.py:291-303) ----
-    const int64_t nv_all = (int64_t)ctr->n_verts;
-    const int64_t n = nv_all < cap_corners ? nv_all : cap_corners;
-    const unsigned grid_edges = gridDim.x - grid_tets;
+    const unsigned c = blockIdx.x - grid_tets, grid_edges = gridDim.x - grid_tets;
+    const unsigned q = c % kQueues, part = c / kQueues, parts = grid_edges / kQueues;
+    const int64_t nq = (int64_t)q_cnt[(filtered ? 2 : 0) * kQueues + q];
+    const int64_t n = nq < cap_qe ? nq : cap_qe;
+    elist += (int64_t)q * cap_qe;
     const int2* __restrict__ edge_ab = reinterpret_cast<const int2*>(a.edge_ab);
     const float* __restrict__ pos = a.pos;
     const float* __restrict__ sdf = a.sdf;
@@ -389,7 +395,7 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
     const int msdf_negate = a.msdf_negate;
     const int64_t cap_verts = a.cap_verts, cap_verts_aug = a.cap_verts_aug;
     float4* __restrict__ vacc = reinterpret_cast<float4*>(a.vacc);
-    for (int64_t j = (int64_t)(blockIdx.x - grid_tets) * 256 + threadIdx.x; j < n; j += (int64_t)grid_edges * 256) {
+    for (int64_t j = (int64_t)part * 256 + threadIdx.x; j < n; j += (int64_t)parts * 256) {
       const unsigned e = (unsigned)elist[j];
       const int2 ab = __ldg(edge_ab + e);
       const int64_t vid = (int64_t)__ldcg(word_prefix + (e >> 5)) + __popc(__ldcg(edge_bits + (e >> 5)) & ((1u << (e & 31u)) - 1u));
@@ -431,26 +437,40 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   ScanLists L;
   L.tile_cnt = ws.tile_cnt;
   L.eblock_cnt = ws.eblock_cnt;
+  L.q_cnt = ws.q_cnt;
   L.vlist = ws.vlist;
   L.elist_raw = ws.elist;
-  // with the open-mesh prefilter the marking kernel re-queues the edges that survive (corner_rank is idle on this path)
-  L.elist = a.watertight_template ? ws.elist : reinterpret_cast<int32_t*>(ws.corner_rank);
-  L.cap_vlist = ws.cap_tets; L.cap_elist = ws.cap_corners;
+  // with the open-mesh prefilter the marking kernel re-queues the edges that survive
+  const int filtered = a.watertight_template ? 0 : 1;
+  L.elist = filtered ? ws.elist2 : ws.elist;
+  L.cap_qe = ws.cap_qe; L.cap_qv = ws.cap_qv;
   {
     ProfScope ps(K_EDGE_SCAN, stream);
-    const unsigned nblk = (unsigned)((a.n_grid + kScanVertsPerCta - 1) / kScanVertsPerCta);
-    launch_k(edge_scan_kernel, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, ws.ctr, L);
+    const int vpt = scan_vpt();
+    const int64_t per_cta = (int64_t)kEScanThreads * vpt;
+    const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
+    if (vpt == 1)
+      launch_k(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+    else if (vpt == 2)
+      launch_k(edge_scan_kernel<2>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+    else
+      launch_k(edge_scan_kernel<4>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
   }
+  // CTAs per sub-queue of the consumers: enough for one entry per thread at the expected fill (a sub-queue holds
+  // 8 / kQueues of the capacity; the expected fill is 1 / kQueues of it)
+  auto parts_for = [](int64_t cap_q) {
+    int64_t p = (cap_q / 8 + 255) / 256;
+    return (unsigned)(p < 1 ? 1 : (p > 16 ? 16 : p));
+  };
   {
     ProfScope ps(K_EDGE_MARK, stream);
-    const int64_t be = (ws.cap_corners + 255) / 256;
-    const unsigned nblk = (unsigned)(be < 148 * 8 ? (be > 0 ? be : 1) : 148 * 8);
-    if (a.watertight_template)
+    const unsigned nblk = kQueues * parts_for(ws.cap_qe);
+    if (!filtered)
       launch_k(edge_mark_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.occ_bits, (const unsigned*)nullptr,
-               ws.m1_words, ws.m2_words, ws.edge_bits, ws.ctr, L);
+               ws.m1_words, ws.m2_words, ws.edge_bits, L);
     else
       launch_k(edge_mark_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.occ_bits, ws.mocc_bits, ws.m1_words,
-               ws.m2_words, ws.edge_bits, ws.ctr, L);
+               ws.m2_words, ws.edge_bits, L);
   }
   const int64_t maxg = 148 * 4;
   {
@@ -459,15 +479,14 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const unsigned ge = (unsigned)(ws.n_eblocks < maxg ? ws.n_eblocks : maxg);
     launch_k(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt,
              ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.n_eblocks, ws.word_prefix, ws.ctr,
-             ws.cap_tets, gt);
+             ws.cap_tets, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt);
   }
   if (ws.cap_corners <= 0) return;   // counting run: sizes only
   ProfScope ps(K_EDGE_EMIT, stream);
-  const int64_t bt = (ws.cap_tets + 255) / 256, be = (ws.cap_corners + 255) / 256;
-  const unsigned gt = (unsigned)(bt < maxg ? bt : maxg), ge = (unsigned)(be < maxg ? be : maxg);
-  launch_k(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, ws.m1_words,
+  const unsigned gt = kQueues * parts_for(ws.cap_qv), ge = kQueues * parts_for(ws.cap_qe);
+  launch_k(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, filtered, ws.m1_words,
            ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
-           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, gt);
+           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt);
 }
 
 }  // namespace d3h
