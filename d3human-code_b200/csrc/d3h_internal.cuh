@@ -93,6 +93,7 @@ struct Workspace {
 // Carves `base` (may be nullptr when only the size is wanted).
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges = 0);
 constexpr int kQueues = 64;        // sub-queues of the edge-scan path's work queues
+constexpr int kQStride = 32;       // words between two sub-queue counters (one 128-byte line each)
 constexpr int kEdgeBlock = 8192;  // edges per edge_emit CTA (256 threads x one 32-bit word)
 
 int key_bits_for(int64_t n_grid);   // bits per endpoint in the packed edge key

@@ -46,7 +46,8 @@ static int scan_vpt() {
 struct ScanLists {
   unsigned* tile_cnt;     // valid tets per 8192-tet compaction tile: T1 class | T2 class << 16
   unsigned* eblock_cnt;   // crossing edges per 8192-edge block
-  unsigned* q_cnt;        // [3][kQueues] entries appended to every sub-queue (true counts, may exceed the capacity):
+  unsigned* q_cnt;        // [3][kQueues] x kQStride words: entries appended to every sub-queue (true counts, may exceed the
+                          //   capacity), one counter per 128-byte line (atomics on one line serialise):
                           //   0 crossing edges as the stream found them, 1 valid tets, 2 edges that survive the prefilter
   int32_t* elist_raw;     // kQueues x cap_qe
   int2* vlist;            // kQueues x cap_qv: (tet id, occupancy code)
@@ -122,7 +123,7 @@ edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       for (int e = e0[k] + 8; e < e1[k]; ++e) cnt += occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k];
   }
   const unsigned q = (unsigned)(gwarp % kQueues);
-  int64_t slot = warp_reserve(L.q_cnt + q, cnt);
+  int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
   if (slot < 0) { trace_end(tr); return; }
   int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
 #pragma unroll
@@ -156,7 +157,7 @@ edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
   const unsigned lane = lane_id();
   const unsigned q = blockIdx.x % kQueues, part = blockIdx.x / kQueues, parts = gridDim.x / kQueues;
-  const int64_t raw = (int64_t)L.q_cnt[q];
+  const int64_t raw = (int64_t)L.q_cnt[kQStride * q];
   const int64_t n = raw < L.cap_qe ? raw : L.cap_qe;
   const int32_t* __restrict__ in = L.elist_raw + (int64_t)q * L.cap_qe;
   // the valid tets found by this warp go to sub-queue (its global warp id) % kQueues
@@ -201,7 +202,7 @@ edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       for (int i = 0; i < 8; ++i)
         if ((fresh >> i) & 1u)
           atomicAdd(L.tile_cnt + (unsigned)t[i] / (unsigned)kTileTets, __popc(code[i]) == 2 ? 0x10000u : 1u);
-      int64_t slot = warp_reserve(L.q_cnt + kQueues + qv, (unsigned)__popc(fresh));
+      int64_t slot = warp_reserve(L.q_cnt + kQStride * (kQueues + qv), (unsigned)__popc(fresh));
       if (slot >= 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -219,7 +220,7 @@ edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       atomicAdd(L.eblock_cnt + (unsigned)e / (unsigned)kEdgeBlock, 1u);
     }
     if (MOCC) {
-      const int64_t slot = warp_reserve(L.q_cnt + 2 * kQueues + q, any ? 1u : 0u);
+      const int64_t slot = warp_reserve(L.q_cnt + kQStride * (2 * kQueues + q), any ? 1u : 0u);
       if (any && slot >= 0 && slot < L.cap_qe) L.elist[(int64_t)q * L.cap_qe + slot] = e;
     }
   }
@@ -272,7 +273,7 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
         // serve that purpose)
         int64_t raw = 0, max_e = 0, max_v = 0;
         for (int q = 0; q < kQueues; ++q) {
-          const int64_t ne = (int64_t)q_cnt[q], nt = (int64_t)q_cnt[kQueues + q];
+          const int64_t ne = (int64_t)q_cnt[kQStride * q], nt = (int64_t)q_cnt[kQStride * (kQueues + q)];
           raw += ne;
           max_e = ne > max_e ? ne : max_e;
           max_v = nt > max_v ? nt : max_v;
@@ -348,7 +349,7 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
     // ---- valid tets -> records (tet order) + polygon corner -> vertex id ----
     const unsigned t1 = ctr->work_tri, t2 = ctr->work_quad;   // 0 / 0 when the record buffer is too small
     const unsigned q = blockIdx.x % kQueues, part = blockIdx.x / kQueues, parts = grid_tets / kQueues;
-    const int64_t n = (t1 + t2 == 0u) ? 0 : (int64_t)q_cnt[kQueues + q];   // (fits: checked by scan_prefix_kernel)
+    const int64_t n = (t1 + t2 == 0u) ? 0 : (int64_t)q_cnt[kQStride * (kQueues + q)];   // (fits: checked by scan_prefix_kernel)
     vlist += (int64_t)q * cap_qv;
     const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
     const int4* __restrict__ ranks = reinterpret_cast<const int4*>(a.tet_edge_rank);
@@ -385,7 +386,7 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
     // ---- crossing edges -> watertight vertices (zero-crossing interpolation, gshell_tets.py:291-303) ----
     const unsigned c = blockIdx.x - grid_tets, grid_edges = gridDim.x - grid_tets;
     const unsigned q = c % kQueues, part = c / kQueues, parts = grid_edges / kQueues;
-    const int64_t nq = (int64_t)q_cnt[(filtered ? 2 : 0) * kQueues + q];
+    const int64_t nq = (int64_t)q_cnt[kQStride * ((filtered ? 2 : 0) * kQueues + q)];
     const int64_t n = nq < cap_qe ? nq : cap_qe;
     elist += (int64_t)q * cap_qe;
     const int2* __restrict__ edge_ab = reinterpret_cast<const int2*>(a.edge_ab);

@@ -603,6 +603,50 @@ def _collect_frames(pend: _Pending) -> BatchResult:
     return BatchResult(frames, fslab, islab, pend.tape, lay.tape_off, launches, bmat)
 
 
+def _collect_packed(pend: _Pending):
+    """_collect_frames without the per-frame views: waits for the sizes of every frame (one library call each), checks
+    the capacities of the whole batch with a few numpy operations, regrows and re-launches on overflow.
+    -> (pend, sizes (B,6) int64 [fv, t1, t2, p, v, fa], launches)"""
+    L = _cabi.lib()
+    wait = L.d3h_wait_counts
+    launches = 0
+    for attempt in range(6):
+        plan, lay, B = pend.plan, pend.lay, pend.B
+        cv, cva, cfw, cfa, ct = lay.caps
+        launches += pend.launches
+        base, seq0, slot0 = plan.counts_ptr, pend.seq0, pend.slot0
+        for i in range(B):
+            rc = wait(base + ((slot0 + i) % _COUNT_RING) * 128, seq0 + 1 + i, _WAIT_TIMEOUT_US)
+            if rc:
+                _cabi.check(rc, "d3h_wait_counts")
+        sizes = plan.counts_np[(slot0 + lay.ar) % _COUNT_RING, 0:6].copy()
+        if B > 1 and not pend.inputs[11]:
+            _cabi.check(L.d3h_lanes_join(torch.cuda.current_stream(pend.dev).cuda_stream), "d3h_lanes_join")
+            _unjoined[pend.dev.index] = False
+        fv, t1, t2, p, v, nfa = (int(x) for x in sizes.max(axis=0))
+        va_ = int((sizes[:, 4] + sizes[:, 3]).max())
+        fw_ = int((sizes[:, 1] + 2 * sizes[:, 2]).max())
+        if fv > ct:   # record buffer too small: surface stages were skipped for some frame, its sizes are unknown
+            pc = 3 * t1 + 4 * t2
+            plan.cap_tets = max(plan.cap_tets, _grow(fv))
+            plan.cap_v, plan.cap_va = max(plan.cap_v, pc), max(plan.cap_va, 2 * pc)
+            plan.cap_fw, plan.cap_fa = max(plan.cap_fw, t1 + 2 * t2), max(plan.cap_fa, 2 * t1 + 4 * t2)
+        elif v > cv or va_ > cva or fw_ > cfw or nfa > cfa:
+            plan.cap_v, plan.cap_va = max(plan.cap_v, _grow(v)), max(plan.cap_va, _grow(va_))
+            plan.cap_fw, plan.cap_fa = max(plan.cap_fw, _grow(fw_)), max(plan.cap_fa, _grow(nfa))
+        else:
+            break
+        pend = _launch_frames(*pend.inputs)
+    else:  # pragma: no cover
+        raise RuntimeError("d3h_extract_forward_batch: capacities did not converge")
+    plan.cap_tets = max(_grow(fv), min(plan.cap_tets, 2 * _grow(fv)))
+    plan.cap_v, plan.cap_va = _shrink(plan.cap_v, v), _shrink(plan.cap_va, va_)
+    plan.cap_fw, plan.cap_fa = _shrink(plan.cap_fw, fw_), _shrink(plan.cap_fa, nfa)
+    if pend.bmat is not None:
+        pend.bmat[:, _BC["n_verts"]:_BC["n_quad_tets"] + 1] = sizes[:, (4, 1, 2)]
+    return pend, sizes, launches
+
+
 def forward_frames_raw(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, watertight_template: bool,
                        lanes: int = DEFAULT_LANES, zero=None, grad_ptrs=None, launcher=None, static=None,
                        fused_pair: bool = False) -> BatchResult:
@@ -628,42 +672,61 @@ def _shrink(cap: int, need: int) -> int:
 _OUTS_PER_FRAME = 9   # verts_aug, v_tng_aug, msdf_aug, verts_wt, v_tng_wt, msdf_wt, msdf_boundary, faces_aug, faces_wt
 
 
+_ref_cache: Dict[Tuple, Tuple] = {}
+
+
+def _ref_arrays(refs, need):
+    """Index pattern of a batch as numpy arrays, cached on (refs, need): the same calling pattern repeats every step.
+    -> IDX (B,3) tensor index of pos / sdf / msdf per frame, ROW (B,3) row inside a stacked tensor (0: whole tensor),
+       NEG (B,) msdf_negate flags, GMASK (B,3) the frame accumulates into the gradient of that tensor, ZMASK (B,3) ... and
+       is the one that zero-fills it, USED (n_tensors,) tensors that need a gradient buffer."""
+    key = (refs, need)
+    hit = _ref_cache.get(key)
+    if hit is not None:
+        return hit
+    B = len(refs)
+    idx = np.array([[r[k][0] for k in range(3)] for r in refs], dtype=np.int64).reshape(B, 3)
+    row = np.array([[max(r[k][1], 0) for k in range(3)] for r in refs], dtype=np.int64).reshape(B, 3)
+    neg = np.array([int(r[3]) for r in refs], dtype=np.int64)
+    gmask = np.zeros((B, 3), dtype=bool)
+    zmask = np.zeros((B, 3), dtype=bool)
+    used = np.zeros(len(need), dtype=bool)
+    if any(need):
+        zeroed = set()
+        for i, r in enumerate(refs):
+            for k in range(3):
+                t, rw = r[k]
+                if k == 2 and not (need[t] and not r[3]):   # "body" frames do not reach msdf (hmsdf_tets_split.py:256-264)
+                    continue
+                gmask[i, k] = True
+                used[t] = True
+                if (t, rw) not in zeroed:
+                    zeroed.add((t, rw))
+                    zmask[i, k] = True
+    if len(_ref_cache) > 64:
+        _ref_cache.clear()
+    out = _ref_cache[key] = (idx, row, neg, gmask, zmask, used)
+    return out
+
+
 def _prelaunch(refs, tensors, need, tets_i32, watertight_template, lanes, launcher=None, static=None, fused_pair=False):
     """Everything of a forward call that precedes the size read: pointer tables of the frames, dense gradient buffers
     (allocated here, zero-filled by the tail of the forward call of the frame that owns them -- HBM is idle behind the
     latency-bound surface kernels), and the launch.  Returns (pending batch, gradient buffers or None, N)."""
-    base = [t.data_ptr() for t in tensors]
+    need = tuple(bool(x) for x in need)
+    idx, row, neg, gmask, zmask, used = _ref_arrays(refs, need)
     n_grid = tensors[refs[0][0][0]].shape[-2]
-    row_bytes = (12 * n_grid, 4 * n_grid, 4 * n_grid)
-
-    def addr(table, ref, kind):
-        idx, row = ref
-        return table[idx] + (row * row_bytes[kind] if row > 0 else 0)
-
-    ptrs = [[addr(base, r[k], k) for k in range(3)] for r in refs]
-    negate = [int(r[3]) for r in refs]
+    row_bytes = np.array([12 * n_grid, 4 * n_grid, 4 * n_grid], dtype=np.int64)
+    off = row * row_bytes
+    base = np.array([t.data_ptr() for t in tensors], dtype=np.int64)
+    ptrs = base[idx] + off
     zero = grad_ptrs = gbufs = None
-    if any(need):
-        gbufs = [None] * len(tensors)
-        gbase = [0] * len(tensors)
-        zeroed = set()
-        zero, grad_ptrs = [], []
-        for r in refs:
-            zrow, grow = [0, 0, 0], [0, 0, 0]
-            for k in range(3):
-                idx, row = r[k]
-                if k == 2 and not (need[idx] and not r[3]):   # "body" frames do not reach msdf (hmsdf_tets_split.py:256-264)
-                    continue
-                if gbufs[idx] is None:
-                    gbufs[idx] = torch.empty_like(tensors[idx])
-                    gbase[idx] = gbufs[idx].data_ptr()
-                g = grow[k] = addr(gbase, r[k], k)
-                if (idx, row) not in zeroed:
-                    zeroed.add((idx, row))
-                    zrow[k] = g
-            zero.append(zrow)
-            grad_ptrs.append(grow)
-    pend = _launch_frames(ptrs, negate, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs,
+    if used.any():
+        gbufs = [torch.empty_like(t) if u else None for t, u in zip(tensors, used)]
+        gbase = np.array([g.data_ptr() if g is not None else 0 for g in gbufs], dtype=np.int64)
+        grad_ptrs = np.where(gmask, gbase[idx] + off, 0)
+        zero = np.where(zmask, grad_ptrs, 0)
+    pend = _launch_frames(ptrs, neg, tensors[0].device, n_grid, tets_i32, watertight_template, lanes, zero, grad_ptrs,
                           launcher, static, fused_pair)
     return pend, gbufs, n_grid
 
@@ -868,6 +931,114 @@ def extract_generic(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, 
     return _pack_result(_ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)
 
 
+class PackedFrames:
+    """The B frames of a batch as PADDED tensors: frame i owns slice i, rows [0, n_i) of it are valid, the rest is
+    uninitialised.  What a batched consumer wants anyway (nvdiffrast's range mode takes exactly this: one vertex /
+    triangle buffer per batch plus per-frame ranges), and it keeps the host work per batch O(1): six strided views and
+    one autograd node instead of nine views per frame.
+
+    verts_aug, v_tng_aug (B, cap_va, 3); msdf (B, cap_va); faces_aug (B, cap_fa, 3) int64;
+    vertices_watertight, v_tng_watertight (B, cap_v, 3); msdf_watertight (B, cap_v); faces_watertight (B, cap_fw, 3)
+    n_verts_aug, n_faces_aug, n_verts_watertight, n_faces_watertight: int64 numpy arrays (B,)
+    Differentiable: verts_aug, msdf, vertices_watertight, msdf_watertight (upstream gradients in the same padded
+    shapes; rows beyond n_i are never read).  `frame(i)` narrows to the reference's 6-tuple of frame i."""
+
+    def __init__(self, outs, sizes, wt):
+        (self.verts_aug, self.v_tng_aug, self.msdf, self.vertices_watertight, self.v_tng_watertight,
+         self.msdf_watertight, self.faces_aug, self.faces_watertight) = outs
+        self.sizes = sizes
+        self.n_verts_watertight = sizes[:, 4]
+        self.n_verts_aug = sizes[:, 4] + sizes[:, 3]
+        self.n_faces_aug = sizes[:, 5]
+        self.n_faces_watertight = sizes[:, 1] + 2 * sizes[:, 2]
+        self._wt = wt
+
+    def __len__(self):
+        return self.sizes.shape[0]
+
+    def frame(self, i: int):
+        v, va = int(self.n_verts_watertight[i]), int(self.n_verts_aug[i])
+        fa, fw = int(self.n_faces_aug[i]), int(self.n_faces_watertight[i])
+        msdf = self.msdf[i, :va]
+        r8 = (self.verts_aug[i, :va], self.v_tng_aug[i, :va], msdf, self.vertices_watertight[i, :v],
+              self.v_tng_watertight[i, :v], self.msdf_watertight[i, :v], msdf[v:], self.faces_aug[i, :fa],
+              self.faces_watertight[i, :fw])
+        return _pack_result(r8, self._wt)
+
+
+class _PackedFn(torch.autograd.Function):
+    """A batch of frames as one autograd node with PADDED batched outputs (see PackedFrames)."""
+
+    @staticmethod
+    def forward(ctx, spec, tets_i32, *tensors):
+        refs, watertight_template, lanes, _launcher, started = spec
+        pend, gbufs, n_grid = started
+        pend, sizes, launches = _collect_packed(pend)
+        lay, B = pend.lay, pend.B
+        fslab, islab = pend.fslab, pend.islab
+        cv, cva, cfw, cfa, ct = lay.caps
+        o_vaug, o_tng, o_maug, o_vwt, o_twt, o_mwt = lay.f_off
+        fl, il = lay.f_len, lay.i_len
+        ast = torch.as_strided
+        outs = (ast(fslab, (B, cva, 3), (fl, 3, 1), o_vaug), ast(fslab, (B, cva, 3), (fl, 3, 1), o_tng),
+                ast(fslab, (B, cva), (fl, 1), o_maug), ast(fslab, (B, cv, 3), (fl, 3, 1), o_vwt),
+                ast(fslab, (B, cv, 3), (fl, 3, 1), o_twt), ast(fslab, (B, cv), (fl, 1), o_mwt),
+                ast(islab, (B, cfa, 3), (il, 3, 1), 0), ast(islab, (B, cfw, 3), (il, 3, 1), 3 * cfa))
+        ctx.save_for_backward(*tensors, pend.tape, fslab)
+        ctx.bmat, ctx.gbufs, ctx.sizes, ctx.lanes, ctx.nref = pend.bmat, gbufs, sizes, lanes, len(refs)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(outs[6], outs[7])
+        _ExtractFn.last_counts = None
+        _PackedFn.last_sizes = sizes
+        _ExtractFn.last_launches = launches
+        _ExtractFn.total_launches += launches
+        return outs
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3, g4, g5, _g6, _g7):
+        if g1 is not None or g4 is not None:
+            raise NotImplementedError("gradients through v_tng (vertex tangents) are not implemented (see _ExtractFn)")
+        tensors = ctx.saved_tensors[:-2]
+        need = ctx.needs_input_grad[2:]
+        gbufs, ctx.gbufs = ctx.gbufs, None
+        bmat = ctx.bmat
+        if bmat is None or gbufs is None:
+            raise RuntimeError("backward through a packed batch needs inputs that require gradients, and runs once "
+                               "(use extract_frames for retain_graph)")
+        B = ctx.nref
+        if g0 is None and g2 is None and g3 is None and g5 is None:
+            return (None, None) + tuple(gbufs[i] if need[i] else None for i in range(len(tensors)))
+        keep = []
+        ar = np.arange(B, dtype=np.int64)
+
+        def ptrs(t, inner):
+            """per-frame pointers of a padded (B, cap, ...) gradient: rows must be dense, frames may be strided"""
+            if t is None:
+                return 0
+            if t.dtype is not torch.float32 or t.stride()[1:] != inner:
+                t = t.float().contiguous()
+                keep.append(t)
+            return t.data_ptr() + ar * (4 * t.stride(0))
+
+        b = _BC
+        bmat[:, b["g_verts_aug"]] = ptrs(g0, (3, 1))
+        bmat[:, b["g_msdf_aug"]] = ptrs(g2, (1,))
+        bmat[:, b["g_verts_wt"]] = ptrs(g3, (3, 1))
+        bmat[:, b["g_msdf_wt"]] = ptrs(g5, (1,))
+        bmat[:, b["g_msdf_boundary"]] = 0
+        dev = tensors[0].device
+        per16 = 2 if int(bmat[0, b["tape_slots"]]) == 0 else 1
+        _ExtractFn.total_launches += per16 * ((B + 15) // 16)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().d3h_extract_backward_batch(bmat.ctypes.data, B, max(1, min(ctx.lanes, B)),
+                                                               torch.cuda.current_stream(dev).cuda_stream),
+                        "d3h_extract_backward_batch")
+        return (None, None) + tuple(gbufs[i] if need[i] else None for i in range(len(tensors)))
+
+
+_PackedFn.last_sizes = None
+
+
 class FramesFuture:
     """A batch whose forward kernels are already running on the GPU (extract_frames_async).  `result()` blocks on the
     sizes, wraps the outputs in the autograd node and returns the list of reference 6-tuples; everything the host does
@@ -887,6 +1058,17 @@ class FramesFuture:
                     _cabi.lib().d3h_lanes_join(torch.cuda.current_stream(dev).cuda_stream)
             except Exception:  # pragma: no cover  (interpreter shutdown)
                 pass
+
+    def packed(self) -> "PackedFrames":
+        """The batch as padded tensors (PackedFrames) instead of a list of per-frame tuples: O(1) host work per batch."""
+        if self._out is None:
+            spec, tets, tensors = self._args
+            if not self._n:
+                raise ValueError("an empty batch has no packed form")
+            outs = _PackedFn.apply(spec, tets, *tensors)
+            self._out = PackedFrames(outs, _PackedFn.last_sizes, self._wt)
+            self._args = None
+        return self._out
 
     def result(self):
         if self._out is None:

@@ -74,13 +74,21 @@ o = E.extract(pos1, sdf, msdf, tets)
 gv1, gm1 = torch.zeros_like(o[0]), torch.zeros_like(o[5]["msdf"])
 ob = E.extract_frames(posb, sdf, msdf, tets, types="cloth")
 gvb, gmb = [torch.zeros_like(x[0]) for x in ob], [torch.zeros_like(x[5]["msdf"]) for x in ob]
+def batch_packed():
+    posb.grad = sdf.grad = msdf.grad = None
+    pk = E.extract_frames_async(posb, sdf, msdf, tets, types="cloth", lanes=8).packed()
+    torch.autograd.backward([pk.verts_aug, pk.msdf], [gvp, gmp])
+
+
 def single_generic():
     pos1.grad = sdf.grad = msdf.grad = None
     verts, faces, _, _, _, extra = E.extract_generic(pos1, sdf, msdf, tets)
     torch.autograd.backward([verts, extra["msdf"]], [gv1, gm1])
 
 
-for fn, name, per in ((single, "drop-in single call fwd+bwd", 1), (single_generic, "  (through the batch machinery)", 1), (batch, f"batch of {B} frames fwd+bwd", B)):
+pk0 = E.extract_frames_async(posb, sdf, msdf, tets, types="cloth", lanes=8).packed()
+gvp, gmp = torch.zeros_like(pk0.verts_aug), torch.zeros_like(pk0.msdf)
+for fn, name, per in ((batch_packed, f"packed batch of {B} frames fwd+bwd", B), (single, "drop-in single call fwd+bwd", 1), (single_generic, "  (through the batch machinery)", 1), (batch, f"batch of {B} frames fwd+bwd", B)):
     for _ in range(20):
         fn()
     t0 = time.perf_counter()

@@ -314,6 +314,59 @@ def test_extract_frames_list_form_and_repeat(dev):
             U.assert_exact(f"verts_aug[{i}]", verts.cpu().numpy(), fwd["verts_aug"])
 
 
+def test_packed_batch_equals_per_frame_results(dev):
+    """extract_frames_async(...).packed(): the same batch as padded (B, cap, ...) tensors and ONE autograd node with O(1)
+    outputs.  Valid rows equal the per-frame API bit for bit, `frame(i)` narrows to the reference tuple, gradients through
+    the padded tensors (upstream rows beyond the valid ones are poison) equal the per-frame gradients."""
+    from d3human_code_b200.extract import extract_frames, extract_frames_async
+    res, B = 20, 5
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = grids.capsule_garment_field(pos)
+    types = ["cloth", "body", "cloth", "cloth", "body"]
+    pos_b = np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(B)]).astype(np.float32)
+    tt = torch.tensor(tets, device=dev)
+
+    def leaves():
+        return (torch.tensor(pos_b, device=dev, requires_grad=True), torch.tensor(sdf[:, None], device=dev, requires_grad=True),
+                torch.tensor(msdf, device=dev, requires_grad=True))
+
+    tp, ts, tm = leaves()
+    outs = extract_frames(tp, ts, tm, tt, types=types, lanes=3)
+    rng = np.random.default_rng(2)
+    ups = []
+    for verts, faces, _, _, _, extra in outs:
+        ups.append((torch.tensor(rng.standard_normal(tuple(verts.shape)).astype(np.float32), device=dev),
+                    torch.tensor(rng.standard_normal(tuple(extra["msdf"].shape)).astype(np.float32), device=dev),
+                    torch.tensor(rng.standard_normal(tuple(extra["vertices_watertight"].shape)).astype(np.float32), device=dev)))
+    torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs] + [o[5]["vertices_watertight"] for o in outs],
+                            [u[0] for u in ups] + [u[1] for u in ups] + [u[2] for u in ups])
+    for rep in range(2):      # twice: the second batch reuses graphs, workspaces and predicted capacities
+        tp2, ts2, tm2 = leaves()
+        pk = extract_frames_async(tp2, ts2, tm2, tt, types=types, lanes=3).packed()
+        assert len(pk) == B and pk.verts_aug.dim() == 3 and pk.faces_aug.dtype == torch.int64
+        gv = torch.full_like(pk.verts_aug, float("nan"))
+        gm = torch.full_like(pk.msdf, float("nan"))
+        gw = torch.full_like(pk.vertices_watertight, float("nan"))
+        for i, (verts, faces, _, _, v_tng, extra) in enumerate(outs):
+            va, v, fa, fw = (int(pk.n_verts_aug[i]), int(pk.n_verts_watertight[i]), int(pk.n_faces_aug[i]),
+                             int(pk.n_faces_watertight[i]))
+            assert (va, fa, v, fw) == (verts.shape[0], faces.shape[0], extra["n_verts_watertight"], extra["faces_watertight"].shape[0])
+            assert torch.equal(pk.verts_aug[i, :va].detach(), verts.detach()) and torch.equal(pk.faces_aug[i, :fa], faces)
+            assert torch.equal(pk.msdf[i, :va].detach(), extra["msdf"].detach())
+            assert torch.equal(pk.vertices_watertight[i, :v].detach(), extra["vertices_watertight"].detach())
+            assert torch.equal(pk.faces_watertight[i, :fw], extra["faces_watertight"])
+            assert torch.equal(pk.msdf_watertight[i, :v].detach(), extra["msdf_watertight"].detach())
+            f = pk.frame(i)
+            assert torch.equal(f[0].detach(), verts.detach()) and torch.equal(f[1], faces) and f[2] is None and f[3] is None
+            assert tuple(f[5].keys()) == tuple(extra.keys()) and f[5]["n_verts_watertight"] == v
+            assert torch.equal(f[5]["msdf_boundary"].detach(), extra["msdf_boundary"].detach())
+            gv[i, :va], gm[i, :va], gw[i, :v] = ups[i]
+        torch.autograd.backward([pk.verts_aug, pk.msdf, pk.vertices_watertight], [gv, gm, gw])
+        U.assert_close_normwise("grad_pos", tp2.grad.cpu().numpy(), tp.grad.cpu().numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_sdf", ts2.grad.cpu().numpy(), ts.grad.cpu().numpy(), U.GRAD_RTOL)
+        U.assert_close_normwise("grad_msdf", tm2.grad.cpu().numpy(), tm.grad.cpu().numpy(), U.GRAD_RTOL)
+
+
 # ---------------------------------------------------------------------------------------------- tet-range sharding
 @pytest.mark.parametrize("res,field,typ,vr", [(24, "capsule", "cloth", 3), (20, "adv", "body", 2), (33, "sphere", "cloth", 8)])
 def test_tet_range_sharding_virtual_ranks_bit_identical(dev, res, field, typ, vr):

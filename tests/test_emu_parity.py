@@ -144,6 +144,10 @@ def test_batches(dev):
     G.test_extract_frames_list_form_and_repeat(dev)
 
 
+def test_packed_batch(dev):
+    G.test_packed_batch_equals_per_frame_results(dev)
+
+
 @pytest.mark.parametrize("res,field,typ,vr", [(16, "capsule", "cloth", 3), (12, "adv", "body", 2)])
 def test_tet_range_sharding(dev, res, field, typ, vr):
     G.test_tet_range_sharding_virtual_ranks_bit_identical(dev, res, field, typ, vr)
