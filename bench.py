@@ -56,7 +56,18 @@ def parse():
     ap.add_argument("--no-mesh-stage", action="store_true", help="skip the Mesh / auto_normals leg (SURVEY 8f row 2)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the plain-PyTorch-on-this-GPU leg (SURVEY 8d)")
     ap.add_argument("--profile-steps", type=int, default=20)
-    ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per pipelined chunk of the end-to-end leg")
+    ap.add_argument("--e2e-chunk", type=int, default=4, help="frames per pipelined chunk of the end-to-end leg")
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong", "tets"],
+                    help="weak: --frames-per-rank frames on every rank (default); strong: BASELINE configs[3] as written, "
+                         "--frames-total frames sharded over the ranks; tets: configs[4], one 256^3 extraction whose tet "
+                         "ranges are sharded over the ranks + NCCL all-gather of the valid-tet records")
+    ap.add_argument("--frames-total", type=int, default=16, help="--mode strong: frames per step over ALL ranks")
+    ap.add_argument("--blocks", type=int, default=5,
+                    help="the timed block of --steps steps is repeated this many times; value = median block")
+    ap.add_argument("--api", default="packed", choices=["packed", "frames"],
+                    help="batch results as padded (B,cap,..) tensors (O(1) host work per batch) or as per-frame tuples")
+    ap.add_argument("--no-cold", action="store_true", help="skip the L2-flushed single-call leg")
+    ap.add_argument("--no-split-pair", action="store_true", help="skip the configs[2] cloth/body pair leg")
     return ap.parse_args()
 
 
@@ -68,9 +79,38 @@ def make_inputs(res, field):
 
 
 def workload_name(args):
-    return (f"configs[1]: {args.res}^3 Kuhn grid, {'capsule-union SDF + garment mSDF' if args.field == 'capsule' else 'sphere SDF + plane mSDF'}"
+    field = 'capsule-union SDF + garment mSDF' if args.field == 'capsule' else 'sphere SDF + plane mSDF'
+    if args.mode == "strong":
+        return (f"configs[3]: {args.res}^3 Kuhn grid, {field}, hmSDF_Tets(cloth) semantics fwd+bwd, a batch of "
+                f"{args.frames_total} frames/step with per-frame offsets sharded over the ranks (strong scaling)")
+    return (f"configs[1]: {args.res}^3 Kuhn grid, {field}"
             f", hmSDF_Tets(cloth) semantics fwd+bwd, {args.frames_per_rank} frame(s)/rank/step with per-frame offsets "
             f"(configs[3] batch) through extract_frames on {args.lanes} lanes")
+
+
+def frames_of_rank(args, world, rank):
+    """Global frame indices this rank extracts every step."""
+    if args.mode == "strong":
+        from d3human_code_b200 import sharding
+        return list(sharding.frame_slice(args.frames_total, world, rank))
+    return [rank * args.frames_per_rank + i for i in range(args.frames_per_rank)]
+
+
+def make_config(args, world, F, N, counts0, ngroups, frames_per_step):
+    """The `config` object of the JSON line: identical for the GPU arm and the --impl reference arm."""
+    return {"workload": workload_name(args), "F": int(F), "N": int(N), "frames_per_step": int(frames_per_step),
+            "counts_frame0": counts0,
+            "l2": "per step every frame reads its own 26 MB of positions and writes 26 MB of gradients (%d MB per rank and "
+                  "step > 126 MB L2); the static edge list (68 MB at 128^3) is re-read by every frame as in training, "
+                  "where the tet grid is static; no explicit flush in the headline, `cold` = L2-flushed single call"
+                  % (52 * max(1, frames_per_step // max(world, 1))),
+            "lanes": args.lanes, "groups": ngroups, "mode": args.mode,
+            "parallelism": (("frames x%d" % world) if args.mode != "tets" else ("tet ranges x%d" % world)) if world > 1 else "single GPU"}
+
+
+def group_bounds(n, groups):
+    g = max(1, min(groups, n))
+    return [(n * k // g, n * (k + 1) // g) for k in range(g)]
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -122,29 +162,45 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def run_reference(args, rank):
+def run_reference(args, rank, world):
     """The reference's CPU implementation of the path, timed on this box's host cores: the numpy port in oracle/
-    (the reference itself is PyTorch code that does not travel to the GPU box)."""
+    (the reference itself is PyTorch code that does not travel to the GPU box).  Same config / metric / unit / steps /
+    warm-up as the GPU arm; a step is a BOUNDED SAMPLE of the workload: one frame (fwd+bwd) of the step's frames."""
     if rank != 0:
         return
     from oracle import gshell_oracle as O
     cores = os.cpu_count() or 1
+    if args.mode == "tets":
+        res = args.res if args.res != 128 else 256
+        args.res, args.field = res, "sphere"
     pos, sdf, msdf, tets = make_inputs(args.res, args.field)
-    F = tets.shape[0]
+    F, N = tets.shape[0], pos.shape[0]
     from d3human_code_b200 import grids
-    pos = pos + grids.frame_offsets(pos.shape[0], args.res, 0)
+    if args.mode != "tets":
+        pos = pos + grids.frame_offsets(pos.shape[0], args.res, 0)
+    state = {}
 
     def step():
         fwd = O.extract_forward(pos, sdf, msdf, tets, 1, True, n_threads=cores)
         gv = np.ones_like(fwd["verts_aug"])
         gm = np.ones_like(fwd["msdf"])
         O.extract_backward(fwd, gv, gm)
+        state["fwd"] = fwd
 
-    # bounded sample: every step is ONE frame of the workload (fwd+bwd); cap the whole run at ~2 minutes
     step()
     t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
-    steps = max(1, min(args.steps, int(100.0 / max(one, 1e-3))))
-    warm = max(0, min(args.warmup, 3))
+    fwd = state["fwd"]
+    t1, t2 = int(fwd["t1"]), int(fwd["t2"])
+    v, va = int(fwd["vertices_watertight"].shape[0]), int(fwd["verts_aug"].shape[0])
+    counts0 = dict(n_valid_tets=int(fwd["fv"]), n_tri_tets=t1, n_quad_tets=t2, n_corners=3 * t1 + 4 * t2, n_verts=v,
+                   n_verts_aug=va, n_faces_watertight=t1 + 2 * t2, n_faces_aug=int(fwd["faces_aug"].shape[0]),
+                   bucket_polys=[int(c) // k for c, k in zip(fwd["bucket_counts"], (1, 2, 1, 2, 3, 4))])
+    warm = max(args.warmup, 3)
+    steps = args.steps
+    note = ""
+    if (steps + warm) * one > 240.0:      # keep the whole run within a few minutes on a slow host
+        steps = max(1, int(240.0 / one) - warm)
+        note = f" (--steps {args.steps} cut to {steps} to bound the run)"
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -152,15 +208,128 @@ def run_reference(args, rank):
         step()
     dt = (time.perf_counter() - t0) / steps
     value = F / dt
-    sample = f"{steps} step(s), each one full fwd+bwd extraction of one frame of the workload on the host CPU"
+    if args.mode == "tets":
+        fps, ngroups = 1, 1
+    else:
+        nf = len(frames_of_rank(args, world, 0))
+        fps = args.frames_total if args.mode == "strong" else world * args.frames_per_rank
+        ngroups = len(group_bounds(nf, args.groups))
+    sample = (f"{steps} step(s), each ONE frame (a full fwd+bwd extraction) of the step's {fps} frames on the host CPU, "
+              f"numpy port with the O(F) stage on {cores} threads{note}")
+    config = make_config(args, world, F, N, counts0, ngroups, fps) if args.mode != "tets" else tets_config(args, world, F, N, counts0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args), "F": int(F), "N": int(pos.shape[0])},
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak" if args.mode == "weak" else "strong",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": config,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def tets_config(args, world, F, N, counts0):
+    return {"workload": f"configs[4]: {args.res}^3 Kuhn grid, sphere SDF + plane mSDF, ONE extraction fwd+bwd per step, "
+                        f"tet ranges sharded over the ranks, NCCL all-gather of the compact valid-tet records, surface "
+                        f"stages replicated (bit-identical to one GPU)",
+            "F": int(F), "N": int(N), "frames_per_step": 1, "counts_frame0": counts0,
+            "l2": "the tet stream of a rank is 16*F/ranks bytes (1.6 GB on one GPU) > 126 MB L2", "lanes": 1, "groups": 1,
+            "mode": "tets", "parallelism": ("tet ranges x%d" % world) if world > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------------- configs[4]
+def run_tets(args, rank, local_rank, world, dev, dev_type):
+    """--mode tets: BASELINE configs[4].  One 256^3 extraction (sphere + plane) per step whose only O(F) stage, the
+    classification stream over the tet array, is split in `world` contiguous tet ranges (sharding.extract_tet_sharded):
+    every rank classifies its range, the compact 32-byte valid-tet records are all-gathered (NCCL; rank order = global tet
+    order) and the O(surface) stages run replicated, so every rank ends with the whole mesh, bit-identical to one GPU.
+    value = F / (max-over-ranks device time of fwd+bwd).  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from d3human_code_b200 import extract as E, grids, sharding
+    res = args.res if args.res != 128 else 256
+    args.res = res
+    pos_np, tets_np = grids.kuhn_grid(res)
+    sdf_np, msdf_np = grids.sphere_plane_field(pos_np)
+    F, N = int(tets_np.shape[0]), int(pos_np.shape[0])
+    tets = torch.from_numpy(tets_np).to(dev)
+    del tets_np
+    pos = torch.from_numpy(pos_np).to(dev).requires_grad_(True)
+    sdf = torch.from_numpy(sdf_np[:, None].copy()).to(dev).requires_grad_(True)
+    msdf = torch.from_numpy(msdf_np).to(dev).requires_grad_(True)
+    E.set_static_edges("0")      # the sharded path exchanges records and sorts their edges; no static table at 256^3
+
+    def fwd():
+        return sharding.extract_tet_sharded(pos, sdf, msdf, tets, msdf_negate=False, group=None,
+                                            virtual_ranks=1 if world == 1 else None)
+
+    verts, faces, _, _, _, extra = fwd()
+    c0 = dict(E.last_counts())
+    c0["bucket_polys"] = list(c0["bucket_polys"])
+    g = torch.Generator(device=dev).manual_seed(1234)
+    gv = torch.randn(verts.shape, device=dev, generator=g)
+    gm = torch.randn(extra["msdf"].shape, device=dev, generator=g)
+    checksum = int(faces.sum().item()) ^ int(verts.shape[0])
+
+    def step():
+        pos.grad = sdf.grad = msdf.grad = None
+        v, f, _, _, _, ex = fwd()
+        torch.autograd.backward([v, ex["msdf"]], [gv, gm])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    steps = min(args.steps, 50)
+    l0 = E.launch_counter()
+    blocks = [timed(steps) for _ in range(max(1, args.blocks))]
+    launches = (E.launch_counter() - l0) // max(1, args.blocks)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms = float(np.median(blocks))
+    # every rank must hold the same mesh
+    cs = torch.tensor([checksum], dtype=torch.int64, device=dev)
+    same = True
+    if world > 1:
+        allc = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allc, cs)
+        same = all(int(c.item()) == checksum for c in allc)
+    if rank == 0:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        balg = grids.surface_counts_bytes(F, N, c0["n_verts"], c0["n_verts_aug"], c0["n_faces_watertight"], c0["n_faces_aug"])
+        line = {"metric": METRIC, "value": F / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": tets_config(args, world, F, N, c0),
+                "ms_per_step_blocks": [round(b, 5) for b in blocks],
+                "path_roofline": {"algorithmic_bytes_per_frame": int(balg), "achieved_GBps_step": balg / (ms * 1e-3) / 1e9,
+                                  "frac_step": balg / (ms * 1e-3) / 1e9 / peak, "peak": peak, "peak_source": peak_src},
+                "ranks_hold_same_mesh": bool(same), "comm_nranks_ok": bool(world == 1 or dist.get_world_size() == world),
+                "gpu_launches": int(launches), "clocks": sampler.result()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -170,7 +339,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import torch
@@ -196,14 +365,23 @@ def main():
     from d3human_code_b200 import extract as E
     from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
 
+    if args.mode == "tets":
+        run_tets(args, rank, local_rank, world, dev, dev_type)
+        return
     pos_np, sdf_np, msdf_np, tets_np = make_inputs(args.res, args.field)
     F, N = int(tets_np.shape[0]), int(pos_np.shape[0])
-    fpr = args.frames_per_rank
-    frames = [rank * fpr + i for i in range(fpr)]
+    frames = frames_of_rank(args, world, rank)
+    fpr = len(frames)
+    fps = args.frames_total if args.mode == "strong" else world * fpr      # frames per step over all ranks
+    if fpr == 0:
+        raise SystemExit("--mode strong needs --frames-total >= number of ranks")
     hm = hmSDF_Tets()
     tets = torch.from_numpy(tets_np).to(dev)                      # int64 like hmsdf.py:207-212; packed once (static)
-    sdf = torch.from_numpy(sdf_np[:, None].copy()).to(dev).requires_grad_(True)   # (N,1) like the SDF MLP output
+    # sdf (N,1) like the SDF MLP output, msdf (N,).  Their gradients accumulate over the rank's frames and are summed over
+    # the ranks: both .grad tensors are views of ONE flat buffer, so the exchange is one all-reduce of 8N bytes
+    sdf = torch.from_numpy(sdf_np[:, None].copy()).to(dev).requires_grad_(True)
     msdf = torch.from_numpy(msdf_np).to(dev).requires_grad_(True)
+    flat_grad = torch.zeros(2 * N, dtype=torch.float32, device=dev)
     # per-frame deformed grid vertices as ONE (B,N,3) tensor: one autograd leaf, one gradient buffer for the batch
     host_pos = torch.from_numpy(np.stack([pos_np + grids.frame_offsets(N, args.res, f) for f in frames])).pin_memory()
     host_sdf = torch.from_numpy(sdf_np[:, None].copy()).pin_memory()
@@ -211,8 +389,8 @@ def main():
     pos = host_pos.to(dev).requires_grad_(True)
     # the frames of a step go through `--groups` extract_frames_async calls that are all launched up front: while the GPU
     # extracts group k+1 the host reads the sizes of group k, wraps its outputs and runs its backward pass
-    ngroups = max(1, min(args.groups, fpr))
-    gb = [(fpr * k // ngroups, fpr * (k + 1) // ngroups) for k in range(ngroups)]
+    gb = group_bounds(fpr, args.groups)
+    ngroups = len(gb)
     pos_groups = [pos.detach()[lo:hi].clone().requires_grad_(True) for lo, hi in gb]   # one (b,N,3) leaf per group
 
     # dry run: shapes of the upstream gradients (constant across steps: inputs are fixed)
@@ -222,29 +400,47 @@ def main():
     ups_v = [torch.randn(o[0].shape, device=dev, generator=g) for o in outs]
     ups_m = [torch.randn(o[5]["msdf"].shape, device=dev, generator=g) for o in outs]
     c0 = counts[0]
+    c0["bucket_polys"] = list(c0["bucket_polys"])
     balg = sum(grids.surface_counts_bytes(F, N, c["n_verts"], c["n_verts_aug"], c["n_faces_watertight"], c["n_faces_aug"])
                for c in counts) / len(counts)
     del outs
+    # padded upstream gradients for the packed API: rows beyond a frame's Va are never read, so one generous buffer per
+    # group serves whatever capacity the plan settles on
+    va_max = max(c["n_verts_aug"] for c in counts)
+    pad_rows = 2 * va_max + 4096
+    pups_v = [torch.zeros((hi - lo, pad_rows, 3), device=dev) for lo, hi in gb]
+    pups_m = [torch.zeros((hi - lo, pad_rows), device=dev) for lo, hi in gb]
+    for k, (lo, hi) in enumerate(gb):
+        for i in range(lo, hi):
+            pups_v[k][i - lo, :ups_v[i].shape[0]] = ups_v[i]
+            pups_m[k][i - lo, :ups_m[i].shape[0]] = ups_m[i]
 
     def local_step():
         """This rank's share of a step, no collective: every group of frames is one extract_frames_async call (one
         library call, concurrent lanes) and one backward call; gradients of the shared sdf / msdf are summed over the
-        frames by the kernels and over the groups by autograd."""
-        sdf.grad = msdf.grad = None
+        frames by the kernels and over the groups by autograd (in place, into the flat buffer)."""
+        flat_grad.zero_()
+        sdf.grad, msdf.grad = flat_grad[:N].view(N, 1), flat_grad[N:]
         for pg in pos_groups:
             pg.grad = None
         futs = [E.extract_frames_async(pg, sdf, msdf, tets, types="cloth", lanes=args.lanes) for pg in pos_groups]
-        for fut, (lo, hi) in zip(futs, gb):
-            outs = fut.result()
-            torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v[lo:hi] + ups_m[lo:hi])
+        for k, (fut, (lo, hi)) in enumerate(zip(futs, gb)):
+            if args.api == "packed":
+                pk = fut.packed()
+                cva = pk.verts_aug.shape[1]
+                if cva > pad_rows:
+                    raise RuntimeError("bench: padded upstream gradients too small for the plan's capacity")
+                torch.autograd.backward([pk.verts_aug, pk.msdf], [pups_v[k][:, :cva], pups_m[k][:, :cva]])
+            else:
+                outs = fut.result()
+                torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs], ups_v[lo:hi] + ups_m[lo:hi])
 
     def step():
-        """One training-step's worth of extraction: local_step() + the sum of the shared gradients over the ranks (NCCL).
-        Every rank must call it the same number of times."""
+        """One training-step's worth of extraction: local_step() + the sum of the shared gradients over the ranks (ONE
+        NCCL all-reduce of the flat sdf|msdf gradient buffer).  Every rank must call it the same number of times."""
         local_step()
         if world > 1:
-            dist.all_reduce(sdf.grad)
-            dist.all_reduce(msdf.grad)
+            dist.all_reduce(flat_grad)
 
     pos_single = [pos.detach()[i].clone().requires_grad_(True) for i in range(min(fpr, 4))]   # separate (N,3) leaves
 
@@ -278,10 +474,51 @@ def main():
         step()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = E.launch_counter()
-    ms_step = timed(step, args.steps)
-    launches_timed = E.launch_counter() - launches0      # library kernels enqueued by this rank in the timed region
-    value = world * fpr * F / (ms_step * 1e-3)
+    # the timed block (exactly --steps steps between two barriers, CUDA events, max over ranks) is repeated --blocks
+    # times back to back; the reported time is the MEDIAN block (one block is tens of ms: a single one is at the mercy
+    # of a clock ramp or a host hiccup)
+    block_ms, launches_timed = [], 0
+    for _ in range(max(1, args.blocks)):
+        launches0 = E.launch_counter()
+        block_ms.append(timed(step, args.steps))
+        launches_timed = E.launch_counter() - launches0  # library kernels enqueued by this rank in one timed block
+    ms_step = float(np.median(block_ms))
+    value = fps * F / (ms_step * 1e-3)
+
+    # ---- where a step's time goes on every rank: the local part (no collective) and the exchange alone ----
+    ranks_info = None
+    k_br = max(3, min(args.steps, 30))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for _ in range(k_br):
+        local_step()
+    e1.record()
+    t_host = (time.perf_counter() - t_host0) / k_br * 1e3      # host time to ISSUE a step (the GPU may lag behind)
+    torch.cuda.synchronize()
+    loc_ms = e0.elapsed_time(e1) / k_br
+    ar_ms = 0.0
+    if world > 1:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k_br):
+            dist.all_reduce(flat_grad)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1) / k_br
+    mine = torch.tensor([loc_ms, ar_ms, t_host, float(fpr)], device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    ranks_info = {"local_step_ms": [round(float(t[0]), 4) for t in allr], "allreduce_ms": [round(float(t[1]), 4) for t in allr],
+                  "host_issue_ms": [round(float(t[2]), 4) for t in allr], "frames": [int(t[3]) for t in allr],
+                  "allreduce_bytes": int(flat_grad.numel() * 4), "steps": k_br,
+                  "note": "per rank: device time of a step without the collective, of the collective alone (one all-reduce "
+                          "of the flat sdf|msdf gradient), and the host time to issue a step"}
 
     # ---- the same frames through the drop-in class, one call + backward per frame (no batching, no lanes) ----
     single = None
@@ -310,6 +547,33 @@ def main():
             single["fwd_ms_median"], single["bwd_ms_median"] = float(np.median(f_ms)), float(np.median(b_ms))
         except Exception as exc:  # noqa: BLE001
             single["fwd_bwd_split_error"] = f"{type(exc).__name__}: {exc}"[:200]
+
+    # ---- cold figure: the same single call with L2 flushed before every call (a 256 MB fill) ----
+    cold = None
+    if world == 1 and not args.no_cold:
+        try:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            f_ms, b_ms = [], []
+            p1, gv1, gm1 = pos_single[0], ups_v[0], ups_m[0]
+            for rep in range(min(max(args.steps, 10), 50)):
+                sdf.grad = msdf.grad = p1.grad = None
+                flush.fill_(rep & 255)
+                ea, eb_, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                ea.record()
+                verts, faces, _, _, v_tng, extra = hm(p1, sdf, msdf, tets, "cloth")
+                eb_.record()
+                torch.autograd.backward([verts, extra["msdf"]], [gv1, gm1])
+                ec.record()
+                barrier()
+                f_ms.append(ea.elapsed_time(eb_))
+                b_ms.append(eb_.elapsed_time(ec))
+            tot = float(np.median(f_ms)) + float(np.median(b_ms))
+            cold = {"fwd_ms_median": float(np.median(f_ms)), "bwd_ms_median": float(np.median(b_ms)), "ms_per_frame": tot,
+                    "value": F / (tot * 1e-3), "unit": UNIT,
+                    "note": "single drop-in call + backward with L2 flushed (256 MB device fill) before every call"}
+            del flush
+        except Exception as exc:  # noqa: BLE001
+            cold = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     # ---- per-kernel device time (CUDA events on the launching stream, recorded by the library; one frame at a time so
     # that every kernel is timed alone) ----
@@ -354,10 +618,15 @@ def main():
     if not args.no_e2e:
         # The batch is cut into chunks of `--e2e-chunk` frames that flow through three streams: H2D copies of chunk
         # k+1 and D2H copies of chunk k-1 run under the extraction of chunk k (PCIe is full duplex, ~55 GB/s each way).
+        # Results copied back per frame: verts_aug, faces_aug, msdf, and the pos gradient in COMPACT form -- the ids of
+        # the grid vertices the frame touched (its crossing edges, FramesFuture.tape_edges) and their gradient rows
+        # (extract.gather_touched): the dense (N,3) gradient is > 99 % zeros.  The sdf | msdf gradients of the step (one
+        # flat buffer) follow the last chunk.
         chunk = max(1, min(args.e2e_chunk, fpr))
         bounds = [(i, min(i + chunk, fpr)) for i in range(0, fpr, chunk)]
         d_sdf = torch.empty_like(sdf)
         d_msdf = torch.empty_like(msdf)
+        d_flat = torch.zeros_like(flat_grad)
         d_pos = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds]
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         outs_host = None
@@ -374,7 +643,6 @@ def main():
                     dst.requires_grad_(False)
                     dst.copy_(src, non_blocking=True)
                     dst.requires_grad_(True)
-                    dst.grad = None
                 h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
                 for dp, (lo, hi) in zip(d_pos, bounds):
                     dp.requires_grad_(False)
@@ -385,18 +653,21 @@ def main():
                     ev = torch.cuda.Event()
                     ev.record(s_in)
                     ev_in.append(ev)
+            d_flat.zero_()
+            d_sdf.grad, d_msdf.grad = d_flat[:N].view(N, 1), d_flat[N:]
             keep, res_all = [], []
             for k, (dp, (lo, hi)) in enumerate(zip(d_pos, bounds)):
                 cur.wait_event(ev_in[k])
-                outs = E.extract_frames(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
+                fut = E.extract_frames_async(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
+                outs = fut.result()
                 torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs],
                                         ups_v[lo:hi] + ups_m[lo:hi])
                 res = []
-                for o in outs:
-                    res += [o[0].detach(), o[1], o[5]["msdf"].detach()]
-                res.append(dp.grad)
+                for i, o in enumerate(outs):
+                    edges = fut.tape_edges(i)
+                    res += [o[0].detach(), o[1], o[5]["msdf"].detach(), edges, E.gather_touched(dp.grad[i], edges)]
                 if k == len(bounds) - 1:
-                    res += [d_sdf.grad, d_msdf.grad]
+                    res.append(d_flat)
                 s_out.wait_stream(cur)
                 res_all.append(res)
                 if outs_host is not None:
@@ -404,7 +675,7 @@ def main():
                         for h, t in zip(outs_host[k], res):
                             h.copy_(t, non_blocking=True)
                             d2h += t.numel() * t.element_size()
-                keep.append(outs)
+                keep.append((outs, fut))
             if outs_host is None:   # first call: allocate the pinned result buffers, copy without overlap
                 outs_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res] for res in res_all]
                 for hs, res in zip(outs_host, res_all):
@@ -424,13 +695,23 @@ def main():
         dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * fpr * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
+        # the PCIe floor of this step: its H2D bytes alone, copied from the same pinned buffers with nothing else running
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            for dp, (lo, hi) in zip(d_pos, bounds):
+                dp.detach().copy_(host_pos[lo:hi], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_only = (time.perf_counter() - t0) / 3
+        e2e = {"value": fps * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "steps": k_e2e, "ms_per_step": float(dt.item()) * 1e3,
-               "chunk_frames": chunk,
-               "note": "extract_frames() with inputs copied from pinned host memory each step (pos per frame, sdf, "
-                       "msdf); per frame verts_aug, faces_aug, msdf and the dense pos gradient, plus the sdf / msdf "
-                       "gradients, copied back to pinned host memory; static tet indices stay resident; chunks of "
-                       "frames pipelined over H2D / compute / D2H streams"}
+               "chunk_frames": chunk, "h2d_only_ms_per_step": h2d_only * 1e3,
+               "h2d_GBps": (int(h2d_b) - 8 * N) / h2d_only / 1e9,
+               "note": "extract_frames_async() with inputs copied from pinned host memory each step (pos per frame, sdf, "
+                       "msdf); per frame verts_aug, faces_aug, msdf and the COMPACT pos gradient (touched vertex ids + "
+                       "their rows), plus the flat sdf|msdf gradient, copied back to pinned host memory; static tet "
+                       "indices stay resident; chunks of frames pipelined over H2D / compute / D2H streams.  "
+                       "h2d_only_ms_per_step: the same per-frame positions copied alone = the PCIe floor of the step"}
 
     if rank != 0:
         if world > 1:
@@ -459,9 +740,9 @@ def main():
             achieved = dom_bytes / t / 1e9
             traffic = None
             try:
-                with open(os.path.join(ROOT, "profiles", "classify_traffic.json")) as fh:
-                    tj = json.load(fh)
-                    if int(tj.get("F", 0)) == F and tj.get("kernel", "classify") == dom:
+                with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as fh:
+                    tj = json.load(fh).get(dom, {})
+                    if int(tj.get("F", 0)) == F:
                         traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
@@ -481,7 +762,13 @@ def main():
                      "achieved_GBps_step": balg * fpr / (ms_step * 1e-3) / 1e9,
                      "frac_step": balg * fpr / (ms_step * 1e-3) / 1e9 / peak,
                      "kernel_ms_per_frame": dev_ms_frame,
-                     "frac_kernels_only": (balg / (dev_ms_frame * 1e-3) / 1e9 / peak) if dev_ms_frame else None}
+                     "frac_kernels_only": (balg / (dev_ms_frame * 1e-3) / 1e9 / peak) if dev_ms_frame else None,
+                     "frac_single_call": (balg / (single["ms_per_frame"] * 1e-3) / 1e9 / peak) if single else None,
+                     "note": "B_alg = 16F + 40N + 44Va + 28V + 24Fa + 24Fw (SURVEY 8d; 16F = the packed tet array read once). "
+                             "The edge-scan path does not read the tet array at all (it walks the 4-byte-per-edge static "
+                             "list, 68 MB instead of 201 MB), so these fractions count bytes the kernels no longer move: "
+                             "they measure speed against the SURVEY's roofline, `roofline` measures the dominant kernel "
+                             "against the bytes it really moves"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -540,6 +827,50 @@ def main():
         except Exception as exc:  # noqa: BLE001
             mesh_stage = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- BASELINE configs[2]: body + garment split extraction on a grid in the script/get_tet_smpl.py layout (unstructured,
+    # scrambled vertex labels and tet order) at the f3c.json resolution: the cloth / body pair of one training iteration
+    # (train.py:1040-1047) as two drop-in calls, as one split() batch, and as the fused pair.  Never fatal.
+    split_pair = None
+    if world == 1 and not args.no_split_pair:
+        try:
+            sg = grids.smplx_layout_grid(args.res)
+            sv, sf = sg["v"], sg["f"]
+            ssdf, smsdf = grids.capsule_garment_field(sv)
+            qp = torch.from_numpy(sv).to(dev).requires_grad_(True)
+            qs = torch.from_numpy(ssdf[:, None].copy()).to(dev).requires_grad_(True)
+            qm = torch.from_numpy(smsdf).to(dev).requires_grad_(True)
+            qt = torch.from_numpy(sf).to(dev)
+
+            def pair_two():
+                return hm(qp, qs, qm, qt, "cloth"), hm(qp, qs, qm, qt, "body")
+
+            variants = {"two_calls": pair_two, "split": lambda: hm.split(qp, qs, qm, qt),
+                        "split_fused": lambda: hm.split(qp, qs, qm, qt, fused=True)}
+            split_pair = {"workload": f"configs[2]: SMPL-X-layout grid from the {args.res}^3 lattice, cloth + body pair fwd+bwd",
+                          "F": int(sf.shape[0]), "N": int(sv.shape[0]), "unit": "ms per pair (median, CUDA events)"}
+            cb_ = pair_two()
+            gq = torch.Generator(device=dev).manual_seed(7)
+            gvs = [torch.randn(o[0].shape, device=dev, generator=gq) for o in cb_]
+            gms = [torch.randn(o[5]["msdf"].shape, device=dev, generator=gq) for o in cb_]
+            split_pair["counts"] = {"cloth_faces": int(cb_[0][1].shape[0]), "body_faces": int(cb_[1][1].shape[0]),
+                                    "verts_aug": int(cb_[0][0].shape[0])}
+            for name, fn in variants.items():
+                ts_ = []
+                for rep in range(8 + min(max(args.steps, 10), 60)):
+                    qp.grad = qs.grad = qm.grad = None
+                    ea, eb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record()
+                    c_, b_ = fn()
+                    torch.autograd.backward([c_[0], c_[5]["msdf"], b_[0], b_[5]["msdf"]], [gvs[0], gms[0], gvs[1], gms[1]])
+                    eb_.record()
+                    barrier()
+                    if rep >= 8:
+                        ts_.append(ea.elapsed_time(eb_))
+                split_pair[name + "_ms"] = float(np.median(ts_))
+            split_pair["value"] = 2 * int(sf.shape[0]) / (min(split_pair[k + "_ms"] for k in variants) * 1e-3)
+        except Exception as exc:  # noqa: BLE001
+            split_pair = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- the reference's way on the same GPU: the path as plain PyTorch ops + autograd (oracle/gshell_torch.py, a port
     # pinned against the reference's golden vectors; the reference tree itself is not on this box).  SURVEY 8(d).  Never fatal.
     torch_baseline = None
@@ -574,13 +905,14 @@ def main():
             torch_baseline = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak" if args.mode == "weak" else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "F": F, "N": N, "frames_per_step": world * fpr,
-                       "counts_frame0": c0, "l2": "tet index stream is 16*F = %d MB > 126 MB L2; no explicit flush" % (16 * F // 1000000),
-                       "lanes": args.lanes, "groups": ngroups, "parallelism": f"frames x{world}" if world > 1 else "single GPU"},
+            "config": make_config(args, world, F, N, c0, ngroups, fps),
+            "ms_per_step_blocks": [round(b, 5) for b in block_ms],
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "device_trace": dev_trace, "single_call": single, "gpu_launches": int(launches_timed), "kernels": kern,
+            "ranks": ranks_info, "device_trace": dev_trace, "single_call": single, "cold": cold,
+            "gpu_launches": int(launches_timed), "kernels": kern, "split_pair": split_pair,
             "mesh_stage": mesh_stage, "torch_gpu_baseline": torch_baseline, "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_workspace_bytes_static",
     "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
-    "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_classify_range", "d3h_extract_from_records",
+    "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_gather_rows", "d3h_classify_range", "d3h_extract_from_records",
     "d3h_mesh_edges_workspace_bytes", "d3h_mesh_edges", "d3h_mesh_wait_counts", "d3h_mesh_normals_forward",
     "d3h_mesh_normals_backward",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
@@ -117,6 +117,8 @@ def lib() -> C.CDLL:
     L.d3h_lanes_join.argtypes = [C.c_void_p]
     L.d3h_extract_backward_batch.restype = C.c_int
     L.d3h_extract_backward_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    L.d3h_gather_rows.restype = C.c_int
+    L.d3h_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     L.d3h_classify_range.restype = C.c_int
     L.d3h_classify_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_extract_from_records.restype = C.c_int

@@ -377,4 +377,36 @@ void launch_backward_batch(const d3h_backward_args* a, int64_t n, cudaStream_t s
 
 void launch_backward(const d3h_backward_args& a, cudaStream_t stream) { launch_backward_batch(&a, 1, stream); }
 
+// out[i][:] = src[ids[i]][:], rows of `width` floats (compact gradient return, see d3h_gather_rows)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int32_t* __restrict__ ids, int64_t n_ids,
+                                                          const float* __restrict__ src, int64_t n_rows, int width,
+                                                          float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t total = n_ids * width;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+    const int64_t i = k / width;
+    const int c = (int)(k - i * width);
+    const int64_t r = (int64_t)__ldg(ids + i);
+    out[k] = (r >= 0 && r < n_rows) ? __ldg(src + r * width + c) : 0.f;
+  }
+}
+
 }  // namespace d3h
+
+using namespace d3h;
+
+extern "C" int d3h_gather_rows(const int32_t* ids, int64_t n_ids, const float* src, int64_t n_rows, int32_t width,
+                               float* out, d3h_stream_t stream) {
+  if (n_ids < 0 || n_rows < 0 || width <= 0 || width > 16 || (n_ids > 0 && (!ids || !src || !out))) {
+    set_error("d3h_gather_rows: bad argument (null pointer, negative size, or width outside [1, 16])");
+    return D3H_E_BADARG;
+  }
+  if (n_ids == 0) return D3H_OK;
+  int64_t blocks = (n_ids * width + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(gather_rows_kernel, (unsigned)blocks, 256u, (cudaStream_t)stream, kLaunchLatency, ids, n_ids, src, n_rows,
+           (int)width, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d3h_gather_rows: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}

@@ -205,6 +205,8 @@ class _Plan:
     cap_fa: int = 0
     seq: int = 0
     slot: int = 0                                                   # next free slot of the count ring
+    inflight: int = 0                                               # frames launched whose sizes have not been read yet
+    last_stream: Any = None                                         # torch stream of the most recent launch on this plan
     workspaces: List[torch.Tensor] = field(default_factory=list)   # one per lane
     workspace_ptrs: List[int] = field(default_factory=list)
     workspace_bytes: int = 0
@@ -416,7 +418,17 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
     n_tets = tets_i32.shape[0]
     plan = _plan_for(dev, n_tets, n_grid)
     lanes = max(1, min(int(lanes), MAX_LANES, B))
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    cur_stream = torch.cuda.current_stream(dev)
+    stream = cur_stream.cuda_stream
+    if plan.inflight + B > _COUNT_RING:
+        # the pinned count ring has one slot per frame in flight: wrapping it would overwrite sizes nobody has read yet
+        raise RuntimeError(f"{plan.inflight} frames are in flight on this grid and {B} more do not fit the count ring of "
+                           f"{_COUNT_RING}: call result() / packed() on the earlier futures first")
+    if plan.last_stream is not None and plan.last_stream.cuda_stream != stream:
+        # workspaces, lanes and the count ring are per grid, not per stream: a launch from another stream is ordered
+        # behind the previous user of the plan
+        cur_stream.wait_stream(plan.last_stream)
+    plan.last_stream = cur_stream
     wt = int(bool(watertight_template))
     flags = np.asarray(negate, dtype=np.int64) | (wt << 32)
     c = _FC
@@ -451,6 +463,7 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             seq0, slot0 = plan.seq, plan.slot
             plan.seq += B
             plan.slot = (plan.slot + B) % _COUNT_RING
+            plan.inflight += B
             A[:, 0:3] = ptrs
             A[:, c["tets"]] = tets_ptr = tets_i32.data_ptr()
             A[:, c["msdf_negate"]] = flags
@@ -495,6 +508,7 @@ def _launch_frames(ptrs, negate, dev, n_grid: int, tets_i32: torch.Tensor, water
             else:
                 need_tets = launcher(A, plan, stream)
                 if need_tets is not None:   # the gathered records do not fit: grow like an overflowed single call
+                    plan.inflight -= B
                     plan.cap_tets = _grow(int(need_tets))
                     p4 = 4 * plan.cap_tets
                     plan.cap_v, plan.cap_va = max(cv, p4), max(cva, 2 * p4)
@@ -568,6 +582,7 @@ def _collect_frames(pend: _Pending) -> BatchResult:
                 ast(fslab, (p,), (1,), fo + o_maug + v), v, t1, t2,
                 dict(n_valid_tets=fv, n_tri_tets=t1, n_quad_tets=t2, n_corners=p, n_verts=v, n_verts_aug=va,
                      n_faces_watertight=fw, n_faces_aug=nfa, bucket_polys=tuple(row[6:12]))))
+        plan.inflight -= B        # every size of this attempt has been read
         if B == 1:
             fw_, va_ = t1 + 2 * t2, v + p
         else:
@@ -620,6 +635,7 @@ def _collect_packed(pend: _Pending):
             if rc:
                 _cabi.check(rc, "d3h_wait_counts")
         sizes = plan.counts_np[(slot0 + lay.ar) % _COUNT_RING, 0:6].copy()
+        plan.inflight -= B
         if B > 1 and not pend.inputs[11]:
             _cabi.check(L.d3h_lanes_join(torch.cuda.current_stream(pend.dev).cuda_stream), "d3h_lanes_join")
             _unjoined[pend.dev.index] = False
@@ -771,6 +787,7 @@ class _ExtractFn(torch.autograd.Function):
         ctx.mark_non_differentiable(*nondiff)
         _ExtractFn.last_counts = [r.counts for r in res.frames]
         _ExtractFn.last_launches = res.launches
+        _ExtractFn.last_tape = (res.tape, res.tape_off[4], [f.n_verts for f in res.frames])
         _ExtractFn.total_launches += res.launches
         return tuple(flat)
 
@@ -843,6 +860,7 @@ class _ExtractFn(torch.autograd.Function):
 
 _ExtractFn.last_counts = None
 _ExtractFn.last_launches = 0
+_ExtractFn.last_tape = None       # (tape slab, slice length, V per frame) of the most recent batch
 _ExtractFn.total_launches = 0      # kernels enqueued by this module since import (forward + backward)
 
 
@@ -931,6 +949,31 @@ def extract_generic(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, 
     return _pack_result(_ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)
 
 
+def _tape_edges(tape3, i: int) -> torch.Tensor:
+    tape, t_len, nv = tape3
+    o = i * t_len
+    return tape[o:o + 2 * int(nv[i])].view(-1, 2)
+
+
+def gather_touched(grad: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    """Compact form of a dense per-grid-vertex gradient of ONE frame: the rows an extraction can have touched are the end
+    points of its crossing edges (`edges` = FramesFuture.tape_edges(i), (V,2) int32).  Returns grad[edges.reshape(-1)] as a
+    (2V, width) tensor (library kernel d3h_gather_rows); dense[edges.reshape(-1)] = rows restores the dense gradient
+    (every other row is zero; repeated ids carry identical rows).  ~2V rows instead of N: what a host-side consumer copies
+    back instead of a (N,3) buffer that is > 99 % zeros."""
+    g = grad.reshape(grad.shape[0], -1) if grad.dim() > 1 else grad.reshape(-1, 1)
+    if g.dtype is not torch.float32 or not g.is_contiguous():
+        g = g.float().contiguous()
+    ids = edges.reshape(-1)
+    out = torch.empty((ids.shape[0], g.shape[1]), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _cabi.check(_cabi.lib().d3h_gather_rows(ids.data_ptr(), ids.shape[0], g.data_ptr(), g.shape[0], g.shape[1],
+                                                out.data_ptr(), torch.cuda.current_stream(g.device).cuda_stream),
+                    "d3h_gather_rows")
+    _ExtractFn.total_launches += 1 if ids.shape[0] else 0
+    return out
+
+
 class PackedFrames:
     """The B frames of a batch as PADDED tensors: frame i owns slice i, rows [0, n_i) of it are valid, the rest is
     uninitialised.  What a batched consumer wants anyway (nvdiffrast's range mode takes exactly this: one vertex /
@@ -952,9 +995,14 @@ class PackedFrames:
         self.n_faces_aug = sizes[:, 5]
         self.n_faces_watertight = sizes[:, 1] + 2 * sizes[:, 2]
         self._wt = wt
+        self._tape = None
 
     def __len__(self):
         return self.sizes.shape[0]
+
+    def tape_edges(self, i: int) -> torch.Tensor:
+        """(V_i, 2) int32: the crossing edges of frame i, row k = the grid vertices vertex k was interpolated between."""
+        return _tape_edges(self._tape, i)
 
     def frame(self, i: int):
         v, va = int(self.n_verts_watertight[i]), int(self.n_verts_aug[i])
@@ -990,6 +1038,7 @@ class _PackedFn(torch.autograd.Function):
         ctx.mark_non_differentiable(outs[6], outs[7])
         _ExtractFn.last_counts = None
         _PackedFn.last_sizes = sizes
+        _ExtractFn.last_tape = (pend.tape, lay.tape_off[4], sizes[:, 4].tolist())
         _ExtractFn.last_launches = launches
         _ExtractFn.total_launches += launches
         return outs
@@ -1048,9 +1097,16 @@ class FramesFuture:
         self._args = (spec, tets, tensors)
         self._n, self._wt = n_frames, watertight
         self._out = None
+        self._tape = None
 
     def __del__(self):
         # dropped without result(): the lanes may still be writing this batch's buffers, which are about to be freed
+        if self._out is None and self._n and self._args is not None:
+            try:
+                pend = self._args[0][4][0]
+                pend.plan.inflight = max(0, pend.plan.inflight - pend.B)   # its count slots are free again
+            except Exception:  # pragma: no cover
+                pass
         if self._out is None and self._n > 1 and self._args is not None:
             try:
                 dev = self._args[2][0].device
@@ -1058,6 +1114,13 @@ class FramesFuture:
                     _cabi.lib().d3h_lanes_join(torch.cuda.current_stream(dev).cuda_stream)
             except Exception:  # pragma: no cover  (interpreter shutdown)
                 pass
+
+    def tape_edges(self, i: int) -> torch.Tensor:
+        """(V_i, 2) int32 crossing edges of frame i (after result() / packed()): the grid vertices the frame's gradients
+        can touch -- see gather_touched."""
+        if self._tape is None:
+            raise RuntimeError("tape_edges: call result() or packed() first")
+        return _tape_edges(self._tape, i)
 
     def packed(self) -> "PackedFrames":
         """The batch as padded tensors (PackedFrames) instead of a list of per-frame tuples: O(1) host work per batch."""
@@ -1067,6 +1130,7 @@ class FramesFuture:
                 raise ValueError("an empty batch has no packed form")
             outs = _PackedFn.apply(spec, tets, *tensors)
             self._out = PackedFrames(outs, _PackedFn.last_sizes, self._wt)
+            self._out._tape = self._tape = _ExtractFn.last_tape
             self._args = None
         return self._out
 
@@ -1076,6 +1140,7 @@ class FramesFuture:
             flat = _ExtractFn.apply(spec, tets, *tensors) if self._n else ()
             self._out = [_pack_result(flat[_OUTS_PER_FRAME * i:_OUTS_PER_FRAME * (i + 1)], self._wt)
                          for i in range(self._n)]
+            self._tape = _ExtractFn.last_tape if self._n else None
             self._args = None
         return self._out
 

@@ -154,6 +154,8 @@ def _launch(st: _State, pos, sdf, msdf, need):
             fa.zero_g_msdf = 0
     else:
         fa.zero_g_pos = fa.zero_g_sdf = fa.zero_g_msdf = 0
+    if plan.inflight >= E._COUNT_RING:
+        raise RuntimeError("the count ring of this grid is full of un-read batches: call result() on the earlier futures")
     slot = plan.slot
     plan.slot = (slot + 1) % E._COUNT_RING
     plan.seq += 1
@@ -165,7 +167,15 @@ def _launch(st: _State, pos, sdf, msdf, need):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _cabi.check(L.d3h_lanes_join(stream), "d3h_lanes_join")
         E._unjoined[st.dev_index] = False
-    rc = L.d3h_extract_forward(st.fa_ref, _raw_stream(st.dev_index))
+    rs = _raw_stream(st.dev_index)
+    ls = plan.last_stream
+    if ls is None or ls.cuda_stream != rs:
+        # workspace and count ring are per grid, not per stream: a call from another stream queues behind the last user
+        cur = torch.cuda.current_stream(dev)
+        if ls is not None:
+            cur.wait_stream(ls)
+        plan.last_stream = cur
+    rc = L.d3h_extract_forward(st.fa_ref, rs)
     if rc:
         _cabi.check(rc, "d3h_extract_forward")
     return fslab, islab, g, cptr, seq, slot, (gp, gs, gm)

@@ -239,6 +239,14 @@ int d3h_extract_forward_batch_nojoin(const d3h_forward_args* args, int64_t n_fra
 int d3h_lanes_join(d3h_stream_t stream);
 int d3h_extract_backward_batch(const d3h_backward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t stream);
 
+/* Compact gradient return.  The rows of a dense (N, width) gradient that one extraction can have touched are the end
+ * points of its crossing edges: `ids` = the frame's tape_edges read as a flat list of 2V vertex ids (the crossing edges
+ * of gshell_tets.py:281-287).  out[i][:] = src[ids[i]][:] (ids outside [0, n_rows) give zero rows); an id that occurs
+ * several times yields the same row every time, so a consumer ASSIGNS dense[ids] = out.  Lets a host-side caller fetch
+ * ~2V rows instead of N (the dense gradient is > 99 % zeros). */
+int d3h_gather_rows(const int32_t* ids, int64_t n_ids, const float* src, int64_t n_rows, int32_t width, float* out,
+                    d3h_stream_t stream);
+
 /* Tet-range sharding (multi-GPU): stage 1 classifies tets [tet_begin, tet_end) and leaves
  * compact valid-tet records in the caller's buffers; the ranks all-gather those (NCCL) and stage 2 runs the
  * surface stages on the concatenated records.  d3h_extract_forward == stage 1 on [0,F) + stage 2. */

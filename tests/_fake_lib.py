@@ -43,6 +43,12 @@ class FakeLib:
     def d3h_workspace_bytes_static(self, n_tets, n_grid, cap, n_edges):
         return 4096 + 64 * cap + n_edges // 4      # monotone in the capacities like the real one
 
+    def d3h_gather_rows(self, ids, n_ids, src, n_rows, width, out, stream):
+        i = _arr(ids, n_ids, C.c_int32)
+        g = _arr(src, n_rows * width, C.c_float).reshape(n_rows, width)
+        _arr(out, n_ids * width, C.c_float).reshape(n_ids, width)[:] = g[i]
+        return 0
+
     def d3h_lanes_join(self, stream):
         self.joins += 1
         return 0

@@ -367,6 +367,36 @@ def test_packed_batch_equals_per_frame_results(dev):
         U.assert_close_normwise("grad_msdf", tm2.grad.cpu().numpy(), tm.grad.cpu().numpy(), U.GRAD_RTOL)
 
 
+def test_compact_gradient_return(dev):
+    """FramesFuture.tape_edges(i) + gather_touched: the dense pos gradient of a frame is zero outside the end points of its
+    crossing edges, and the gathered rows restore it exactly (what a host-side consumer copies back instead of (N,3))."""
+    from d3human_code_b200.extract import extract_frames_async, gather_touched
+    res, B = 20, 3
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = grids.capsule_garment_field(pos)
+    pos_b = np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(B)]).astype(np.float32)
+    tp = torch.tensor(pos_b, device=dev, requires_grad=True)
+    ts = torch.tensor(sdf[:, None], device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    fut = extract_frames_async(tp, ts, tm, torch.tensor(tets, device=dev), types="cloth", lanes=2)
+    with pytest.raises(RuntimeError):
+        fut.tape_edges(0)
+    outs = fut.result()
+    torch.autograd.backward([o[0].square().sum() + o[5]["msdf"].sum() for o in outs])
+    for i, o in enumerate(outs):
+        edges = fut.tape_edges(i)
+        fwd = O.extract_forward(pos_b[i], sdf, msdf, tets)
+        assert edges.dtype == torch.int32 and np.array_equal(edges.cpu().numpy(), np.stack([fwd["edge_a"], fwd["edge_b"]], 1))
+        rows = gather_touched(tp.grad[i], edges)
+        assert rows.shape == (2 * edges.shape[0], 3)
+        dense = torch.zeros_like(tp.grad[i])
+        dense[edges.reshape(-1).long()] = rows
+        assert torch.equal(dense, tp.grad[i])
+    assert gather_touched(tp.grad[0], fut.tape_edges(0)[:0]).shape == (0, 3)
+    col = gather_touched(ts.grad, fut.tape_edges(0))      # (N,1) field gradients work the same way
+    assert torch.equal(col[:, 0], ts.grad[fut.tape_edges(0).reshape(-1).long(), 0])
+
+
 # ---------------------------------------------------------------------------------------------- tet-range sharding
 @pytest.mark.parametrize("res,field,typ,vr", [(24, "capsule", "cloth", 3), (20, "adv", "body", 2), (33, "sphere", "cloth", 8)])
 def test_tet_range_sharding_virtual_ranks_bit_identical(dev, res, field, typ, vr):

@@ -107,3 +107,61 @@ def test_bench_control_flow(tmp_path, world):
         assert d["mesh_stage"] is None and d["torch_gpu_baseline"] is None
     for r in range(1, world):                    # only rank 0 prints
         assert not [l for l in open(tmp_path / f"out_{r}.txt") if l.startswith("{")]
+    assert len(d["ms_per_step_blocks"]) == 5 and d["config"]["mode"] == "weak"
+    rk = d["ranks"]
+    assert len(rk["local_step_ms"]) == world and rk["frames"] == [4] * world and all(t > 0 for t in rk["local_step_ms"])
+    assert (world == 1) == (sum(rk["allreduce_ms"]) == 0)
+    if world == 1:
+        assert "error" not in d["cold"] and d["cold"]["ms_per_frame"] > 0, d["cold"]
+        sp = d["split_pair"]
+        assert "error" not in sp and sp["two_calls_ms"] > 0 and sp["split_ms"] > 0 and sp["split_fused_ms"] > 0, sp
+        # the compact gradient return: far fewer bytes back than the dense (N,3) gradients it replaces
+        assert d["e2e"]["d2h_bytes_per_step"] < d["e2e"]["h2d_bytes_per_step"] * 4
+
+
+def _run(tmp_path, world, argv, timeout=240):
+    import torch.multiprocessing as mp
+    ctx = mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), argv), nprocs=world, join=False,
+                             start_method="spawn")
+    deadline = time.time() + timeout
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                p.terminate()
+            pytest.fail("bench.py did not finish: a rank is waiting in a collective the others never entered")
+    lines = [l for l in open(tmp_path / "out_0.txt") if l.startswith("{")]
+    for r in range(1, world):
+        assert not [l for l in open(tmp_path / f"out_{r}.txt") if l.startswith("{")]
+    return json.loads(lines[-1])
+
+
+def test_bench_strong_mode_two_ranks(tmp_path):
+    """--mode strong (BASELINE configs[3] as written): a fixed batch of frames sharded over the ranks."""
+    d = _run(tmp_path, 2, ["--gpus", "2", "--steps", "2", "--warmup", "1", "--res", "6", "--mode", "strong", "--frames-total",
+                           "5", "--groups", "2", "--lanes", "2", "--profile-steps", "1", "--no-cpu-baseline", "--blocks", "2"])
+    assert d["scaling"] == "strong" and d["config"]["frames_per_step"] == 5 and d["ranks"]["frames"] == [3, 2]
+    assert d["value"] > 0 and d["config"]["mode"] == "strong"
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_tets_mode(tmp_path, world):
+    """--mode tets (BASELINE configs[4]): tet-range shards + all-gather of the records; every rank ends with the same mesh."""
+    d = _run(tmp_path, world, ["--gpus", str(world), "--steps", "2", "--warmup", "1", "--res", "8", "--mode", "tets", "--blocks", "2"])
+    assert d["scaling"] == "strong" and d["ranks_hold_same_mesh"] is True and d["comm_nranks_ok"] is True
+    assert d["config"]["mode"] == "tets" and d["config"]["F"] == 6 * 8 ** 3 and d["value"] > 0 and d["gpu_launches"] > 0
+
+
+def test_reference_arm_prints_the_same_config(tmp_path):
+    """--impl reference: same metric / unit / config / steps / warm-up as the GPU arm (the driver compares them)."""
+    argv = ["--gpus", "1", "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "4", "--groups", "2", "--lanes", "2",
+            "--profile-steps", "1", "--no-cpu-baseline", "--no-e2e", "--no-mesh-stage", "--no-torch-baseline", "--no-cold",
+            "--no-split-pair"]
+    ours = _run(tmp_path, 1, argv)
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"] + argv, capture_output=True,
+                         text=True, timeout=200)
+    ref = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert ref["impl"] == "reference" and ref["config"] == ours["config"], (ref["config"], ours["config"])
+    for k in ("metric", "unit", "steps", "warmup", "higher_is_better", "scaling", "n_gpus"):
+        assert ref[k] == ours[k], k
+    assert ref["cpu_baseline"]["kind"] == "port" and ref["e2e"]["h2d_bytes_per_step"] == 0

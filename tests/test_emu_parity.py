@@ -148,6 +148,10 @@ def test_packed_batch(dev):
     G.test_packed_batch_equals_per_frame_results(dev)
 
 
+def test_compact_gradient_return(dev):
+    G.test_compact_gradient_return(dev)
+
+
 @pytest.mark.parametrize("res,field,typ,vr", [(16, "capsule", "cloth", 3), (12, "adv", "body", 2)])
 def test_tet_range_sharding(dev, res, field, typ, vr):
     G.test_tet_range_sharding_virtual_ranks_bit_identical(dev, res, field, typ, vr)

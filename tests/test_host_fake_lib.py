@@ -229,3 +229,28 @@ def test_split_pair_is_cloth_plus_body(host, fused):
     U.assert_close_normwise("grad_pos", tp.grad.numpy(), gc[0] + gb[0], 1e-6)
     U.assert_close_normwise("grad_sdf", ts.grad.numpy()[:, 0], gc[1] + gb[1], 1e-6)
     U.assert_close_normwise("grad_msdf", tm.grad.numpy(), gc[2], 1e-6)      # cloth only
+
+
+def test_count_ring_refuses_to_wrap_over_unread_batches(host):
+    """batches in flight take consecutive slots of the pinned count ring (256 per grid).  A launch that would
+    wrap over slots nobody has read yet must raise instead of overwriting them; reading (or dropping) the earlier futures
+    frees the slots."""
+    from d3human_code_b200 import extract as E
+    pos, tets = grids.kuhn_grid(4)
+    sdf, msdf = grids.sphere_plane_field(pos)
+    B = 100
+    tp = torch.tensor(np.stack([pos] * B))
+    ts, tm, tt = torch.tensor(sdf), torch.tensor(msdf), torch.tensor(tets)
+    f1 = E.extract_frames_async(tp, ts, tm, tt, lanes=2)
+    f2 = E.extract_frames_async(tp, ts, tm, tt, lanes=2)
+    with pytest.raises(RuntimeError, match="in flight"):
+        E.extract_frames_async(tp, ts, tm, tt, lanes=2)
+    assert len(f1.result()) == B
+    f3 = E.extract_frames_async(tp, ts, tm, tt, lanes=2)      # fits again
+    del f2                                                     # dropped without result(): its slots are released
+    import gc
+    gc.collect()
+    f4 = E.extract_frames_async(tp, ts, tm, tt, lanes=2)
+    assert len(f3.result()) == B and len(f4.result()) == B
+    plan = E._plan_for(tp.device, tets.shape[0], pos.shape[0])
+    assert plan.inflight == 0
