@@ -58,6 +58,15 @@ int launch_priority(LaunchClass c) {
   return c == kLaunchStream ? lo : hi;  // numerically lower = scheduled first
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* env = getenv("D3H_PDL");
+    v = (env && env[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // ---- lanes: internal streams the frames of a batch are spread over -----------------------------------------------
 constexpr int kMaxLanes = 8;
 constexpr int kMaxDevices = 16;
@@ -235,6 +244,11 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
   if (a->etets != nullptr &&
       (!a->edge_off || !a->edge_b || !a->etet_off || !a->tet_edge_rank || a->tet_begin != 0 || a->tet_end != a->n_tets)) {
     set_error("%s: the edge-scan path needs edge_off / edge_b / etet_off / etets / tet_edge_rank and the whole tet range", who);
+    return D3H_E_BADARG;
+  }
+  if ((a->etets8 != nullptr && a->etets == nullptr) || (reinterpret_cast<uintptr_t>(a->etets8) & 15) ||
+      (a->etets != nullptr && (reinterpret_cast<uintptr_t>(a->edge_b) & 15))) {
+    set_error("%s: etets8 needs the edge-scan tables; etets8 and edge_b must be 16-byte aligned", who);
     return D3H_E_BADARG;
   }
   if (a->cap_valid_tets > 0 && (!a->tape_corners || (a->edge_off == nullptr && (!a->tape_slots || !a->tape_runs)))) {
@@ -417,7 +431,7 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.watertight = a.watertight_template ? 1 : 0;
   key.has_zero = (a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf) ? 1 : 0;
   key.parts = parts;
-  key.is_static = a.edge_off != nullptr ? (a.etets != nullptr ? 3 : (a.tet_edge_rank != nullptr ? 2 : 1)) : 0;
+  key.is_static = a.edge_off != nullptr ? (a.etets != nullptr ? (a.etets8 != nullptr ? 4 : 3) : (a.tet_edge_rank != nullptr ? 2 : 1)) : 0;
   key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
   std::lock_guard<std::mutex> lock(g_graph_mu);
@@ -690,6 +704,7 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a_in, d3h_tet_record* 
   d3h_forward_args general = *a_in;  // the sharded stages always take the general (sort) path
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
   general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
+  general.etets8 = nullptr;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_classify_range");
   if (rc) return rc;
@@ -720,6 +735,7 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a_in, const d3h_
   d3h_forward_args general = *a_in;
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
   general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
+  general.etets8 = nullptr;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_extract_from_records");
   if (rc) return rc;

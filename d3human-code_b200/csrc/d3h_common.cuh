@@ -136,6 +136,16 @@ __device__ __forceinline__ unsigned long long* trace_begin(unsigned long long* t
 __device__ __forceinline__ void trace_end(unsigned long long* slot) {
   if (slot != nullptr && threadIdx.x == 0) atomicMax(slot + 1, global_timer_ns());
 }
+// Programmatic dependent launch (kernels launched with launch_k_dep): the kernel may be scheduled while its predecessor
+// in the stream is still running -- its blocks arrive, load their parameters and stop HERE until the predecessor has
+// completed and flushed its writes; it lets its own successor do the same.  Must be the first statement of the kernel
+// (nothing before it may touch global memory).  A no-op for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_enter() {
+#ifndef D3H_CPU_EMU
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 // bit v of a vertex bitmap (sdf > 0, or msdf > 0)
 __device__ __forceinline__ unsigned occ_of(const unsigned* __restrict__ bits, int v) {
   return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u;

@@ -158,6 +158,33 @@ inline void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cu
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+// The same for a kernel that starts with pdl_enter(): launched with programmatic stream serialization (D3H_PDL=0 turns
+// it off), the launch latency of the kernel overlaps the tail of its predecessor -- the forward chain of one frame is
+// seven dependent kernels of a few microseconds each.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k_dep(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, LaunchClass cls,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = launch_priority(cls);
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+#ifndef D3H_CPU_EMU
+  if (pdl_enabled()) {
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+#endif
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 d3h_counts* mapped_counts_pointer(d3h_counts* host);
 bool profiling_enabled();
 

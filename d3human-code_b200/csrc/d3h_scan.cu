@@ -78,6 +78,7 @@ __device__ __forceinline__ int64_t warp_reserve(unsigned* __restrict__ counter, 
 template <int VPT>
 __global__ void __launch_bounds__(kEScanThreads)
 edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
+  pdl_enter();
   const d3h_forward_args& a = blk->a;
   const int32_t* __restrict__ edge_off = a.edge_off;
   const int32_t* __restrict__ edge_b = a.edge_b;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256)
 edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
                  const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
                  unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, ScanLists L) {
+  pdl_enter();
   const d3h_forward_args& a = blk->a;
   const int32_t* __restrict__ etets = a.etets;
   const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
@@ -227,6 +229,112 @@ edge_mark_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
   trace_end(tr);
 }
 
+// The same with the fixed-width incidence rows (d3h_forward_args.etets8) and WITHOUT waiting for an atomic: which of the
+// threads that meet a valid tet (one per crossing edge of the tet, 3 or 4) counts and queues it is decided by a rule
+// instead of by the value an atomicOr returns -- the thread of the tet's FIRST crossing edge in the order of
+// gshell_tets.py:187.  The first crossing edge always starts at the tet's vertex 0 (if the signs of vertices 1, 2, 3 all
+// equalled the sign of vertex 0 the tet would not be valid), so the owner is the edge (vertex 0, first vertex j whose
+// sign differs).  Also exact for tets that repeat a vertex: equal ids have equal signs, and the incidence lists name
+// every (edge, tet) pair once.  Chain of dependent loads per thread: queue entry -> incidence row (+ end points, in
+// parallel; both prefetched into L2 by the stream) -> tets -> sign bits; the marks and counts are fire-and-forget.
+template <bool MOCC>
+__global__ void __launch_bounds__(256)
+edge_mark_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits,
+                      const unsigned* __restrict__ mocc_bits, unsigned* __restrict__ m1_words,
+                      unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, ScanLists L) {
+  pdl_enter();
+  const d3h_forward_args& a = blk->a;
+  const int32_t* __restrict__ etets = a.etets;
+  const int4* __restrict__ rows = reinterpret_cast<const int4*>(a.etets8);
+  const int2* __restrict__ edge_ab = reinterpret_cast<const int2*>(a.edge_ab);
+  const int4* __restrict__ tets = reinterpret_cast<const int4*>(a.tets);
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
+  const unsigned lane = lane_id();
+  const unsigned q = blockIdx.x % kQueues, part = blockIdx.x / kQueues, parts = gridDim.x / kQueues;
+  const int64_t raw = (int64_t)L.q_cnt[kQStride * q];
+  const int64_t n = raw < L.cap_qe ? raw : L.cap_qe;
+  const int32_t* __restrict__ in = L.elist_raw + (int64_t)q * L.cap_qe;
+  const unsigned qv = (unsigned)((blockIdx.x * 8u + (threadIdx.x >> 5)) % kQueues);
+  int2* __restrict__ vout = L.vlist + (int64_t)qv * L.cap_qv;
+  for (int64_t j0 = (int64_t)part * 256 + (threadIdx.x & ~31u); j0 < n; j0 += (int64_t)parts * 256) {   // warp-uniform
+    const int64_t j = j0 + lane;
+    const int e = j < n ? in[j] : -1;
+    int4 r0 = make_int4(-1, -1, -1, -1), r1 = r0;
+    int2 ab = make_int2(-1, -1);
+    if (e >= 0) {
+      r0 = __ldg(rows + 2ll * e);
+      r1 = __ldg(rows + 2ll * e + 1);
+      ab = __ldg(edge_ab + e);
+    }
+    const bool crowded = r1.w == -2;    // more than 8 tets around the edge: walk the CSR list instead
+    int t0 = 0, t1 = 0;
+    if (crowded) { t0 = __ldg(a.etet_off + e); t1 = __ldg(a.etet_off + e + 1); }
+    bool any = false, first = true;
+    do {
+      int t[8];
+      if (!crowded) {
+        t[0] = first ? r0.x : -1; t[1] = first ? r0.y : -1; t[2] = first ? r0.z : -1; t[3] = first ? r0.w : -1;
+        t[4] = first ? r1.x : -1; t[5] = first ? r1.y : -1; t[6] = first ? r1.z : -1; t[7] = first ? r1.w : -1;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = (t0 + i < t1) ? __ldg(etets + t0 + i) : -1;
+      }
+      int4 v4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v4[i] = (t[i] >= 0) ? __ldg(tets + t[i]) : make_int4(0, 0, 0, 0);
+      unsigned code[8], own = 0u;   // own: bit i = this edge is the first crossing edge of tet i
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        code[i] = occ_of(occ_bits, v4[i].x) | (occ_of(occ_bits, v4[i].y) << 1) | (occ_of(occ_bits, v4[i].z) << 2) |
+                  (occ_of(occ_bits, v4[i].w) << 3);
+        if (MOCC && t[i] >= 0) {   // open-mesh prefilter, gshell_tets.py:275: keep tets with a vertex of positive mSDF
+          const unsigned keep = occ_of(mocc_bits, v4[i].x) | occ_of(mocc_bits, v4[i].y) | occ_of(mocc_bits, v4[i].z) |
+                                occ_of(mocc_bits, v4[i].w);
+          if (!keep) t[i] = -1;
+        }
+        if (t[i] < 0) continue;
+        // signs relative to vertex 0; the first vertex j in 1..3 that differs closes the tet's first crossing edge
+        const unsigned rel = (code[i] & 1u) ? (~code[i] & 0xeu) : (code[i] & 0xeu);
+        const int jf = __ffs((int)rel) - 1;                                        // 1..3
+        const int other = (ab.x == v4[i].x) ? ab.y : ((ab.y == v4[i].x) ? ab.x : -1);   // -1: vertex 0 is not on this edge
+        const int vj = jf == 1 ? v4[i].y : (jf == 2 ? v4[i].z : v4[i].w);
+        // (first-match semantics: a vertex id that repeats inside the tet has the same sign everywhere, so if `other`
+        // equals v_jf it is the first differing vertex whichever copy is meant)
+        if (other >= 0 && other == vj) own |= 1u << i;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (t[i] < 0) continue;
+        any = true;
+        if (!((own >> i) & 1u)) continue;
+        const bool quad = __popc(code[i]) == 2;
+        atomicOr((quad ? m2_words : m1_words) + (t[i] >> 5), 1u << (t[i] & 31));          // (results unused: reductions)
+        atomicAdd(L.tile_cnt + (unsigned)t[i] / (unsigned)kTileTets, quad ? 0x10000u : 1u);
+      }
+      int64_t slot = warp_reserve(L.q_cnt + kQStride * (kQueues + qv), (unsigned)__popc(own));
+      if (slot >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!((own >> i) & 1u)) continue;
+          if (slot < L.cap_qv) vout[slot] = make_int2(t[i], (int)code[i]);
+          ++slot;
+        }
+      }
+      t0 += 8;
+      first = false;
+    } while (__any_sync(0xffffffffu, crowded && t0 < t1));
+    if (any) {
+      atomicOr(edge_bits + ((unsigned)e >> 5), 1u << ((unsigned)e & 31u));
+      atomicAdd(L.eblock_cnt + (unsigned)e / (unsigned)kEdgeBlock, 1u);
+    }
+    if (MOCC) {
+      const int64_t slot = warp_reserve(L.q_cnt + kQStride * (2 * kQueues + q), any ? 1u : 0u);
+      if (any && slot >= 0 && slot < L.cap_qe) L.elist[(int64_t)q * L.cap_qe + slot] = e;
+    }
+  }
+  trace_end(tr);
+}
+
 // ------------------------------------------------------------------------------------------------
 // exclusive prefixes of the marked tets (per word of the T1 / T2 bitmaps) and of the marked edges (per word of the edge
 // bitmap).  grid = grid_tiles + grid_blocks CTAs; a CTA of the first group takes the listed tiles li = blockIdx.x,
@@ -240,6 +348,7 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
                    const unsigned* __restrict__ eblock_cnt, int64_t n_eblocks,
                    unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
                    const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles) {
+  pdl_enter();
   constexpr int WARPS = 256 / 32;
   __shared__ unsigned long long s_sum[WARPS];
   __shared__ unsigned long long s_w[WARPS];
@@ -343,6 +452,7 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix,
                  d3h_tet_record* __restrict__ records, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
                  int64_t cap_corners, const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tets) {
+  pdl_enter();
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
   if (blockIdx.x < grid_tets) {
@@ -451,11 +561,11 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const int64_t per_cta = (int64_t)kEScanThreads * vpt;
     const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
     if (vpt == 1)
-      launch_k(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+      launch_k_dep(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     else if (vpt == 2)
-      launch_k(edge_scan_kernel<2>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+      launch_k_dep(edge_scan_kernel<2>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     else
-      launch_k(edge_scan_kernel<4>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+      launch_k_dep(edge_scan_kernel<4>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
   }
   // CTAs per sub-queue of the consumers: enough for one entry per thread at the expected fill (a sub-queue holds
   // 8 / kQueues of the capacity; the expected fill is 1 / kQueues of it)
@@ -466,26 +576,29 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   {
     ProfScope ps(K_EDGE_MARK, stream);
     const unsigned nblk = kQueues * parts_for(ws.cap_qe);
+    // opt-in (the host passes etets8 only with D3H_MARK_ROWS=1): measured 22.1 us against 23.6 us for the default on the
+    // 128^3 capsule frame (r02h) -- not worth the 32 bytes per edge of the table by default
+    const bool rows = a.etets8 != nullptr;
     if (!filtered)
-      launch_k(edge_mark_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.occ_bits, (const unsigned*)nullptr,
-               ws.m1_words, ws.m2_words, ws.edge_bits, L);
+      launch_k_dep(rows ? edge_mark_rows_kernel<false> : edge_mark_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk,
+               ws.occ_bits, (const unsigned*)nullptr, ws.m1_words, ws.m2_words, ws.edge_bits, L);
     else
-      launch_k(edge_mark_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.occ_bits, ws.mocc_bits, ws.m1_words,
-               ws.m2_words, ws.edge_bits, L);
+      launch_k_dep(rows ? edge_mark_rows_kernel<true> : edge_mark_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk,
+               ws.occ_bits, ws.mocc_bits, ws.m1_words, ws.m2_words, ws.edge_bits, L);
   }
   const int64_t maxg = 148 * 4;
   {
     ProfScope ps(K_COMPACT, stream);
     const unsigned gt = (unsigned)(ws.ntiles_compact < maxg ? ws.ntiles_compact : maxg);
     const unsigned ge = (unsigned)(ws.n_eblocks < maxg ? ws.n_eblocks : maxg);
-    launch_k(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt,
+    launch_k_dep(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt,
              ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.n_eblocks, ws.word_prefix, ws.ctr,
              ws.cap_tets, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt);
   }
   if (ws.cap_corners <= 0) return;   // counting run: sizes only
   ProfScope ps(K_EDGE_EMIT, stream);
   const unsigned gt = kQueues * parts_for(ws.cap_qv), ge = kQueues * parts_for(ws.cap_qe);
-  launch_k(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, filtered, ws.m1_words,
+  launch_k_dep(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, filtered, ws.m1_words,
            ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
            reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt);
 }

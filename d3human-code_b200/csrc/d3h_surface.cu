@@ -73,6 +73,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
                   UvParams uvp,
                   d3h_counts* __restrict__ counts_dev, const unsigned* __restrict__ corner_rank,
                   const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix) {
+  pdl_enter();
   constexpr int WARPS = kPolyThreads / 32;
   int32_t* __restrict__ corners = blk->a.tape_corners;
   // a replay finds the corner array on the tape, and so does the edge-scan path (scan_emit_kernel wrote it)
@@ -396,6 +397,7 @@ poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restri
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
                 const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl) {
+  pdl_enter();
   constexpr int WARPS = kPolyThreads / 32;
   constexpr unsigned FULL = 0xffffffffu;
   const int32_t* __restrict__ corners = blk->a.tape_corners;
@@ -587,12 +589,12 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   {
     ProfScope ps(K_POLY_FACES, stream);
-    launch_k(poly_faces_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
-             ws.vert, ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits,
-             ws.word_prefix);
+    launch_k_dep(poly_faces_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
+                 ws.vert, ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits,
+                 ws.word_prefix);
   }
   ProfScope ps(K_POLY_CUT, stream);
-  launch_k(poly_cut_kernel<false>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
+  launch_k_dep(poly_cut_kernel<false>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
            ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl);
 }
 

@@ -84,12 +84,20 @@ _tet_edge_ranks = os.environ.get("D3H_TET_EDGE_RANKS", "0") == "1"   # per-tet e
 #: edge-scan path (csrc/d3h_scan.cu): with the static tables a call walks the edge list (4 B / edge) instead of streaming
 #: the tet array (16 B / tet); needs the edge -> tet incidence and the per-tet edge ranks (+56 B / tet of static tables)
 _edge_scan = os.environ.get("D3H_EDGE_SCAN", "1") == "1"
+#: opt-in: fixed-width incidence rows (etets8, +32 B / edge) for the rule-based marking kernel (edge_mark_rows_kernel)
+_mark_rows = os.environ.get("D3H_MARK_ROWS", "0") == "1"
 
 
 def set_edge_scan(on: bool) -> None:
     """Tables already built keep their form (reset_plans() drops them)."""
     global _edge_scan
     _edge_scan = bool(on)
+
+
+def set_mark_rows(on: bool) -> None:
+    """Build the fixed-width incidence rows with the next edge table (the library uses them when D3H_MARK_ROWS=1)."""
+    global _mark_rows
+    _mark_rows = bool(on)
 
 
 
@@ -110,11 +118,12 @@ def set_static_edges(mode: str) -> None:
 
 def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
-    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets): edges ascending in
-    (min,max), CSR offsets per min vertex.  The last four are None unless asked for:
+    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets, etets8): edges ascending
+    in (min,max), CSR offsets per min vertex.  The last five are None unless asked for:
       tet_rank (F,8) int32 : rank in the edge list of the six edges of every tet (order of gshell_tets.py:187, 2 pad words)
       edge_b   (U,)  int32 : the larger endpoints, contiguous (the 4-byte-per-edge stream of the edge-scan path)
-      etet_off (U+1,), etets (6F,) int32 : the tets around every edge, ascending tet ids."""
+      etet_off (U+1,), etets (<=6F,) int32 : the tets around every edge, ascending and distinct tet ids
+      etets8 (U,8) int32 : the first 8 of them per edge in fixed-width rows (-1 padding, [7] = -2: more than 8)."""
     t = tets_i32.long()
     n_tets = t.shape[0]
     key6 = torch.stack([torch.minimum(t[:, i], t[:, j]) * n_grid + torch.maximum(t[:, i], t[:, j]) for i, j in _TET_EDGES], 1)
@@ -129,7 +138,7 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     n_edges = int(uk.shape[0])
     if n_edges >= 2 ** 31:
         raise ValueError("tet grid has more than 2^31 distinct edges")
-    tet_rank = edge_b = etet_off = etets = None
+    tet_rank = edge_b = etet_off = etets = etets8 = None
     if _tet_edge_ranks or _edge_scan:
         rank6 = torch.searchsorted(uk, key6.reshape(-1)).reshape(n_tets, 6)
         del key6
@@ -138,14 +147,32 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
         if _edge_scan:
             flat = rank6.reshape(-1)             # entry t*6 + e
             order = torch.argsort(flat, stable=True)
-            etets = torch.div(order, 6, rounding_mode="floor").to(torch.int32).contiguous()
+            eid = flat[order]                    # edge of every (edge, tet) incidence, ascending; tets ascending per edge
+            tid = torch.div(order, 6, rounding_mode="floor")
             del order
-            etet_off = torch.zeros(n_edges + 1, dtype=torch.int64, device=tets_i32.device)
-            etet_off[1:] = torch.cumsum(torch.bincount(flat, minlength=n_edges), 0)
-            etet_off = etet_off.to(torch.int32).contiguous()
+            # a tet that lists a vertex twice meets one of its edges twice: keep every (edge, tet) pair once
+            keep = torch.ones_like(eid, dtype=torch.bool)
+            keep[1:] = (eid[1:] != eid[:-1]) | (tid[1:] != tid[:-1])
+            if not bool(keep.all()):
+                eid, tid = eid[keep], tid[keep]
+            del keep
+            etets = tid.to(torch.int32).contiguous()
+            off64 = torch.zeros(n_edges + 1, dtype=torch.int64, device=tets_i32.device)
+            off64[1:] = torch.cumsum(torch.bincount(eid, minlength=n_edges), 0)
+            etet_off = off64.to(torch.int32).contiguous()
             edge_b = edge_ab[:, 1].contiguous()
+            if _mark_rows:
+                # fixed-width rows: the first 8 tets of every edge (one 32-byte load per crossing edge), -2 in the last
+                # slot of an edge with more than 8
+                within = torch.arange(eid.shape[0], device=eid.device) - off64[eid]
+                sel = within < 8
+                etets8 = torch.full((n_edges, 8), -1, dtype=torch.int32, device=tets_i32.device)
+                etets8[eid[sel], within[sel]] = etets[sel]
+                etets8[(off64[1:] - off64[:-1]) > 8, 7] = -2
+                del within, sel
+            del eid, tid, off64
         del rank6
-    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets
+    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets, etets8
 
 
 def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
@@ -155,7 +182,7 @@ def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
     # the version counter is part of the key: an int32 tet_fx4 is used in place (packed_tets returns the caller's tensor),
     # an in-place edit must not find the edge table of the old contents
     key = (tets_i32.data_ptr(), tets_i32._version, tets_i32.shape[0], int(n_grid), tets_i32.device.index, _edge_scan,
-           _tet_edge_ranks)
+           _tet_edge_ranks, _mark_rows)
     ent = _static_cache.get(key)
     if ent is None:
         if len(_static_cache) > 8:
@@ -355,6 +382,8 @@ class _Layout:
             if len(static) > 6 and static[6] is not None:
                 A[:, c["edge_b"]], A[:, c["etet_off"]], A[:, c["etets"]] = (static[4].data_ptr(), static[5].data_ptr(),
                                                                             static[6].data_ptr())
+                if len(static) > 7 and static[7] is not None:
+                    A[:, c["etets8"]] = static[7].data_ptr()
             self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
         self.static = static
         self.A = A

@@ -53,6 +53,8 @@ class _State:
                 fa.tet_edge_rank = static[3].data_ptr()
             if static[6] is not None:
                 fa.edge_b, fa.etet_off, fa.etets = static[4].data_ptr(), static[5].data_ptr(), static[6].data_ptr()
+                if len(static) > 7 and static[7] is not None:
+                    fa.etets8 = static[7].data_ptr()
         ba.n_grid, ba.msdf_negate, ba.grads_prezeroed = n_grid, int(negate), 1
         self.fa, self.ba = fa, ba
         self.fa_ref, self.ba_ref = C.addressof(fa), C.addressof(ba)

@@ -150,7 +150,11 @@ typedef struct d3h_forward_args {
    * :261-275).  Everything downstream is unchanged.  NULL: classify the tets (classify_kernel). */
   const int32_t* edge_b;   /* (n_edges)   larger endpoint of every edge: edge_ab[:,1], contiguous */
   const int32_t* etet_off; /* (n_edges+1) tets around edge r: etets[etet_off[r] .. etet_off[r+1]) */
-  const int32_t* etets;    /* (6F)        tet ids */
+  const int32_t* etets;    /* (<= 6F)     tet ids, ascending and distinct per edge */
+  /* optional companion of the edge-scan path: the same incidence in fixed-width rows, one 32-byte row per edge --
+   * the first 8 tets around edge r, padded with -1; [7] == -2 marks an edge with more than 8 tets (the kernel then walks
+   * etet_off / etets for it).  One dependent load per crossing edge instead of two.  16-byte aligned.  NULL: CSR only. */
+  const int32_t* etets8;   /* (n_edges,8) */
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */

@@ -271,6 +271,33 @@ def _fuzz_case(case):
     return pos, sdf, msdf, tets, typ, wt
 
 
+@pytest.mark.parametrize("seed,n,f,wt", [(0, 10, 400, True), (1, 30, 2500, True), (2, 16, 1500, False)])
+def test_tet_soups_with_repeated_vertices(dev, edges_mode, seed, n, f, wt):
+    Z.test_tet_soups_with_repeated_vertices(dev, seed, n, f, wt)
+
+
+def test_mark_rows_variant(dev, edges_mode):
+    """Opt-in marking kernel over fixed-width incidence rows (edge_mark_rows_kernel, D3H_MARK_ROWS=1): the owner of a valid
+    tet is elected by rule (its first crossing edge), no atomic result is awaited.  Lattices, crowded edges (> 8 tets: the
+    CSR fallback) and tets that repeat a vertex."""
+    if edges_mode != "scan":
+        pytest.skip("variant of the edge-scan path")
+    E.set_mark_rows(True)
+    E.reset_plans()
+    try:
+        G.test_cuda_matches_oracle(dev, 12, "adv", "GShell_Tets", None, True)
+        G.test_cuda_matches_oracle(dev, 16, "capsule", "hmSDF_Tets", "body", False)
+        G.test_extract_frames_batch_matches_oracle_per_frame(dev)
+        test_random_tet_soups(dev, 3, 12, 6000)
+        Z.test_tet_soups_with_repeated_vertices(dev, 1, 30, 2500, True)
+        Z.test_tet_soups_with_repeated_vertices(dev, 2, 16, 1500, False)
+        ents = [ent for ent in E._static_cache.values() if ent[1] is not None]
+        assert ents and all(ent[1][7] is not None for ent in ents)     # the rows were really built and passed
+    finally:
+        E.set_mark_rows(False)
+        E.reset_plans()
+
+
 def test_fuzz_forward_against_oracle(dev):
     """60 seeded random inputs (lattices, adversarial fields, tet soups, degenerate fields; 1650 such cases were run once
     while writing this): every integer output, position and mSDF value bit-exact against the oracle."""

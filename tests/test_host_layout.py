@@ -109,16 +109,17 @@ def test_build_edge_table_on_cpu_matches_numpy():
     n = pos.shape[0]
     E.set_edge_scan(False)
     try:
-        off, ab, u, tet_rank, edge_b, etet_off, etets = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        off, ab, u, tet_rank, edge_b, etet_off, etets, etets8 = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
         assert tet_rank is None and edge_b is None and etets is None
         E.set_tet_edge_ranks(True)
-        _, _, _, tet_rank, edge_b, _, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        _, _, _, tet_rank, edge_b, _, _, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
         assert edge_b is None
     finally:
         E.set_tet_edge_ranks(False)
         E.set_edge_scan(True)
     # the tables of the edge-scan path: larger endpoints + the tets around every edge
-    _, ab2, u2, tet_rank2, edge_b, etet_off, etets = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    E.set_mark_rows(True)
+    _, ab2, u2, tet_rank2, edge_b, etet_off, etets, etets8 = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
     assert u2 == u and torch.equal(ab2, ab) and torch.equal(tet_rank2, tet_rank)
     assert torch.equal(edge_b, ab[:, 1]) and edge_b.is_contiguous() and edge_b.dtype == torch.int32
     eo, et = etet_off.numpy(), etets.numpy()
@@ -131,6 +132,13 @@ def test_build_edge_table_on_cpu_matches_numpy():
         seg = et[eo[r]:eo[r + 1]]
         assert set(seg.tolist()) == want[r] and np.all(np.diff(seg) >= 0)
     assert all(eo[r + 1] - eo[r] == len(want[r]) for r in range(u))    # (no tet of a lattice repeats an edge)
+    # fixed-width incidence rows: the first 8 tets of every edge, -1 padding (a Kuhn lattice has at most 8 tets per edge)
+    e8 = etets8.numpy()
+    assert e8.shape == (u, 8) and etets8.dtype == torch.int32 and not (e8 == -2).any()
+    for r in (0, 1, u // 2, u - 1):
+        k = eo[r + 1] - eo[r]
+        assert np.array_equal(e8[r, :k], et[eo[r]:eo[r + 1]]) and (e8[r, k:] == -1).all()
+    E.set_mark_rows(False)
     assert tet_rank.shape == (tets.shape[0], 8) and tet_rank.dtype == torch.int32
     pairs = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
     for e, (i, j) in enumerate(pairs):     # the rank of every tet edge points back at its endpoints
@@ -145,3 +153,22 @@ def test_build_edge_table_on_cpu_matches_numpy():
     assert o[0] == 0 and o[-1] == u
     for a in (0, 7, n - 2):
         assert np.array_equal(ab.numpy()[o[a]:o[a + 1], 0], np.full(o[a + 1] - o[a], a))
+
+
+def test_edge_table_incidence_of_degenerate_and_crowded_edges():
+    """A tet that repeats a vertex meets one of its edges twice (listed once); an edge with more than 8 tets is flagged
+    in the fixed-width rows (-2 in the last slot) and keeps its full list in the CSR form."""
+    n = 24
+    fan = [[0, 1, 2 + k, 3 + k] for k in range(10)]            # edge (0,1) is shared by 10 tets
+    tets = np.array(fan + [[14, 14, 15, 16], [17, 18, 17, 19]], dtype=np.int32)
+    E.set_mark_rows(True)
+    _, ab, u, tet_rank, edge_b, etet_off, etets, etets8 = E.build_edge_table(torch.tensor(tets), n)
+    ab, eo, et, e8 = ab.numpy(), etet_off.numpy(), etets.numpy(), etets8.numpy()
+    r01 = int(np.flatnonzero((ab[:, 0] == 0) & (ab[:, 1] == 1))[0])
+    assert np.array_equal(et[eo[r01]:eo[r01 + 1]], np.arange(10)) and e8[r01, 7] == -2 and np.array_equal(e8[r01, :7], np.arange(7))
+    r45 = int(np.flatnonzero((ab[:, 0] == 14) & (ab[:, 1] == 15))[0])           # edges (0,2) and (1,2) of tet 10
+    assert np.array_equal(et[eo[r45]:eo[r45 + 1]], [10]) and np.array_equal(e8[r45], [10, -1, -1, -1, -1, -1, -1, -1])
+    r78 = int(np.flatnonzero((ab[:, 0] == 17) & (ab[:, 1] == 18))[0])           # edges (0,1) and (1,2) of tet 11
+    assert np.array_equal(et[eo[r78]:eo[r78 + 1]], [11])
+    assert eo[-1] == et.shape[0] < 6 * tets.shape[0]
+    E.set_mark_rows(False)

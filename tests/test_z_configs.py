@@ -179,6 +179,37 @@ def test_random_tet_soups(dev, seed, n, f):
         U.assert_close_normwise("grad_msdf", g[2], g_msdf, 5 * U.GRAD_RTOL)
 
 
+@pytest.mark.parametrize("seed,n,f,wt", [(0, 10, 400, True), (1, 30, 2500, True), (2, 16, 1500, False)])
+def test_tet_soups_with_repeated_vertices(dev, seed, n, f, wt):
+    """Tets drawn WITH replacement: some list a vertex twice (or more), so a tet meets one of its edges twice and has
+    self-edges (v,v).  The marking kernel elects the thread of a tet's first crossing edge by rule instead of by atomic;
+    this is the input where that rule has to agree with the reference's plain enumeration.  Both edge paths (fixture)."""
+    from oracle import gshell_oracle as O
+    from tests import test_cuda_parity as G
+    rng = np.random.default_rng(900 + seed)
+    tets = rng.integers(0, n, size=(f, 4)).astype(np.int64)
+    assert (np.sort(tets, 1)[:, 1:] == np.sort(tets, 1)[:, :-1]).any()
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    sdf = rng.standard_normal(n).astype(np.float32)
+    msdf = rng.standard_normal(n).astype(np.float32)
+    sdf[::6] = 0.0
+    fwd = O.extract_forward(pos, sdf, msdf, tets, 1, wt)
+    rng2 = np.random.default_rng(1)
+    grads = dict(g_verts_aug=rng2.standard_normal(fwd["verts_aug"].shape).astype(np.float32),
+                 g_msdf=rng2.standard_normal(fwd["msdf"].shape).astype(np.float32),
+                 g_msdf_watertight=None, g_vertices_watertight=None)
+    out, g = G._run(dev, pos, sdf, msdf, tets, "GShell_Tets", None, wt, grads)
+    U.assert_exact("faces_aug", out["faces_aug"], fwd["faces_aug"])
+    U.assert_exact("verts_aug", out["verts_aug"], fwd["verts_aug"])
+    U.assert_exact("msdf", out["msdf"], fwd["msdf"])
+    if wt:
+        U.assert_exact("faces_watertight", out["faces_watertight"], fwd["faces_watertight"])
+    g_pos, g_sdf, g_msdf = O.extract_backward(fwd, grads["g_verts_aug"], grads["g_msdf"])
+    U.assert_close_normwise("grad_pos", g[0], g_pos, 5 * U.GRAD_RTOL)
+    U.assert_close_normwise("grad_sdf", g[1], g_sdf, 5 * U.GRAD_RTOL)
+    U.assert_close_normwise("grad_msdf", g[2], g_msdf, 5 * U.GRAD_RTOL)
+
+
 def fused_pair_equals_two_calls(dev, res, field):      # collected by tests/test_zzzz_fused_pair.py (sorts last: opt-in path)
     """hmSDF_Tets.split(fused=True): one classification / edge de-duplication / vertex interpolation for
     the cloth / body pair of an iteration, only the mSDF cut is replayed for the body.  Bit-identical to the two separate
