@@ -109,7 +109,9 @@ def make_config(args, world, F, N, counts0, ngroups, frames_per_step):
 
 
 def group_bounds(n, groups):
-    g = max(1, min(groups, n))
+    # at least 8 frames per group: a group is one library call on up to 8 lanes, smaller ones cannot fill them and the
+    # host cost per group (launch, size read, backward) stops being hidden
+    g = max(1, min(groups, n // 8))
     return [(n * k // g, n * (k + 1) // g) for k in range(g)]
 
 

@@ -1,0 +1,640 @@
+// SDF field query: positional encoding + the MLP of geometry/mlp.py:9-45 on the tensor cores.
+//
+// Every GEMM of the forward and backward pass is one of two kernels built on the same core:
+//
+//   * operands are fp32 in global memory; producer warps load 32-column (128-byte) slices with coalesced 16-byte loads,
+//     split every value into hi (low 13 mantissa bits cleared = exactly representable in TF32) and lo = x - hi, and store
+//     both into shared memory in the canonical K-major SWIZZLE_128B layout of the tcgen05 shared-memory descriptors
+//     (8-row x 128-byte atoms, 16-byte chunk c of row r at chunk position c ^ (r % 8));
+//   * one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N <= 256, K = 8 per instruction) three times per
+//     k-step: hi.hi + lo.hi + hi.lo -- the 3xTF32 scheme, fp32-level accuracy at tensor-core speed -- accumulating in
+//     tensor memory; tcgen05.commit on an mbarrier hands the shared-memory stage back to the producers;
+//   * after the last k-step the same warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per instruction),
+//     apply bias / Softplus(beta=100) / the activation's derivative, and store fp32 rows.
+//
+// mlp_linear_kernel : c = f(a w^T + bias), tile = 128 rows of a x all N <= 256 output columns, K walked in 32-column slices.
+// mlp_wgrad_kernel  : dw += dz^T a, the contraction runs over the POINTS: the producers transpose 32-point slices of dz
+//                     and a on their way into shared memory (lanes <-> points, conflict-free), every CTA owns a point
+//                     range and 128 of dz's columns and adds its partial result to dw with red.global.add.f32.
+//
+// No CPU emulation of this file (tests/emu does not list it): tensor-core instructions have no stand-in there; the
+// parity tests of this stage are GPU-only and compare against oracle/mlp_oracle.py (float64).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/d3h_mlp.h"
+#include "d3h_internal.cuh"
+
+namespace d3h {
+namespace mlp {
+
+constexpr int kTileM = 128;          // rows of the accumulator (tensor-memory lanes)
+constexpr int kSliceK = 32;          // fp32 values per shared-memory row: 128 bytes = one swizzle row
+constexpr int kProducerWarps = 8;
+constexpr int kThreads = (kProducerWarps + 1) * 32;   // + the MMA / tensor-memory warp
+constexpr int kStages = 2;
+constexpr float kBeta = 100.f, kThreshold = 20.f;     // nn.Softplus(beta=100), default threshold (mlp.py:16)
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy stores to shared memory -> visible to the async proxy (the tensor core reads through it)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive columns of the accumulator -> 32 registers per thread (lane = row of this warp's quarter)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor of a K-major SWIZZLE_128B tile (rows of 128 bytes, 8-row atoms 1024 bytes apart):
+// start address and offsets in 16-byte units; leading byte offset 1 (unused with swizzle), stride byte offset 64,
+// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  The tile base must be 1024-byte aligned (base_offset = 0).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor of kind::tf32: fp32 accumulator (bits 4-5 = 1), A and B TF32 (format 2 at bits 7-9 / 10-12),
+// both K-major (bits 15, 16 = 0), N / 8 at bits 17-22, M / 16 at bits 24-28.
+__device__ __forceinline__ uint32_t instr_desc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a swizzled tile
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__device__ __forceinline__ float softplus100(float z) {
+  const float t = z * kBeta;
+  return t > kThreshold ? z : log1pf(expf(t)) / kBeta;     // torch: (x*beta > threshold) ? x : log1p(exp(x*beta)) / beta
+}
+// d softplus / dz from the OUTPUT y = softplus(z): sigmoid(beta z) = 1 - exp(-beta y)  (exactly 1 - e^-20.. in the linear
+// branch, where torch's backward returns 1: the difference is < 2.1e-9)
+__device__ __forceinline__ float softplus100_grad_from_output(float y) { return 1.f - expf(-kBeta * y); }
+
+struct StageBuffers {       // byte offsets inside the dynamic shared memory of one stage
+  uint32_t a_hi, a_lo, b_hi, b_lo, bytes;
+};
+__host__ __device__ inline StageBuffers stage_layout(int rows_b) {
+  StageBuffers s;
+  s.a_hi = 0;
+  s.a_lo = kTileM * 128;
+  s.b_hi = 2 * kTileM * 128;
+  s.b_lo = s.b_hi + rows_b * 128;
+  s.bytes = s.b_lo + rows_b * 128;
+  return s;
+}
+
+// The MMA warp: waits for a filled stage, issues the 3 x 4 instructions of the slice, commits the stage back.
+__device__ __forceinline__ void mma_warp_loop(uint8_t* smem, const StageBuffers& sl, uint64_t* full, uint64_t* empty,
+                                              uint64_t* done, uint32_t tmem_d, int n, int64_t n_slices) {
+  const uint32_t idesc = instr_desc(kTileM, n);
+  const unsigned lane = threadIdx.x & 31u;
+  for (int64_t it = 0; it < n_slices; ++it) {
+    const int s = (int)(it % kStages);
+    const uint32_t parity = (uint32_t)((it / kStages) & 1);
+    mbar_wait(full + s, parity);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t base = smem_u32(smem + (size_t)s * sl.bytes);
+      const uint64_t dah = smem_desc(base + sl.a_hi), dal = smem_desc(base + sl.a_lo);
+      const uint64_t dbh = smem_desc(base + sl.b_hi), dbl = smem_desc(base + sl.b_lo);
+#pragma unroll
+      for (int ks = 0; ks < kSliceK / 8; ++ks) {
+        const uint64_t adv = (uint64_t)(ks * 2);     // 8 TF32 values = 32 bytes = 2 units of the start-address field
+        umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+        umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+      }
+      umma_commit(empty + s);                         // the stage may be refilled once these have read it
+      if (it == n_slices - 1) umma_commit(done);      // ... and the accumulator is complete
+    }
+    __syncwarp();
+  }
+}
+
+struct LinearArgs {
+  const float* a; int64_t lda;
+  const float* w; int64_t ldw;
+  const float* bias;
+  const float* y; int64_t ldy;
+  float* c; int64_t ldc;
+  int64_t m;
+  int k, n, mode;
+};
+
+// ---------------------------------------------------------------------------------------------- c = f(a w^T + bias)
+__global__ void __launch_bounds__(kThreads, 1) mlp_linear_kernel(LinearArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t s_full[kStages], s_empty[kStages], s_done;
+  __shared__ uint32_t s_tmem;
+  const StageBuffers sl = stage_layout(g.n);
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  const int64_t n_slices = g.k / kSliceK;
+  const uint32_t tmem_cols = g.n <= 32 ? 32u : (g.n <= 64 ? 64u : (g.n <= 128 ? 128u : 256u));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, kProducerWarps * 32); mbar_init(s_empty + s, 1); }
+    mbar_init(&s_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(&s_tmem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = s_tmem;
+
+  if (warp < kProducerWarps) {
+    // ---- producers: thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 i ----
+    const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+    for (int64_t it = 0; it < n_slices; ++it) {
+      const int s = (int)(it % kStages);
+      mbar_wait(s_empty + s, (uint32_t)(((it / kStages) & 1) ^ 1));     // (a fresh barrier passes the first round)
+      uint8_t* st = smem + (size_t)s * sl.bytes;
+      const int64_t kcol = it * kSliceK + 4 * c;
+      float4 va[kTileM / 32];
+#pragma unroll
+      for (int i = 0; i < kTileM / 32; ++i) {
+        const int64_t r = row0 + r0 + 32 * i;
+        va[i] = r < g.m ? __ldg(reinterpret_cast<const float4*>(g.a + r * g.lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // the weight rows, eight at a time (N <= 256 rows: up to 8 rounds)
+      for (int j0 = 0; j0 < g.n; j0 += 128) {
+        float4 vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = j0 + r0 + 32 * i;
+          vb[i] = r < g.n ? __ldg(reinterpret_cast<const float4*>(g.w + (int64_t)r * g.ldw + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = j0 + r0 + 32 * i;
+          if (r >= g.n) continue;
+          const float4 h = make_float4(tf32_hi(vb[i].x), tf32_hi(vb[i].y), tf32_hi(vb[i].z), tf32_hi(vb[i].w));
+          const float4 l = make_float4(vb[i].x - h.x, vb[i].y - h.y, vb[i].z - h.z, vb[i].w - h.w);
+          *reinterpret_cast<float4*>(st + sl.b_hi + swz(r, c)) = h;
+          *reinterpret_cast<float4*>(st + sl.b_lo + swz(r, c)) = l;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kTileM / 32; ++i) {
+        const int r = r0 + 32 * i;
+        const float4 h = make_float4(tf32_hi(va[i].x), tf32_hi(va[i].y), tf32_hi(va[i].z), tf32_hi(va[i].w));
+        const float4 l = make_float4(va[i].x - h.x, va[i].y - h.y, va[i].z - h.z, va[i].w - h.w);
+        *reinterpret_cast<float4*>(st + sl.a_hi + swz(r, c)) = h;
+        *reinterpret_cast<float4*>(st + sl.a_lo + swz(r, c)) = l;
+      }
+      fence_proxy_async();
+      mbar_arrive(s_full + s);
+    }
+    // ---- epilogue: warp w reads lanes [32 (w & 3), +32) = rows of the tile, column half (w >> 2) ----
+    mbar_wait(&s_done, 0u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t r = row0 + 32 * q + lane;
+    const int ncol_half = g.n / 2;                      // N % 64 == 0: each half is a whole number of 32-column loads
+    for (int c0 = half * ncol_half; c0 < (half + 1) * ncol_half; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);     // (reads past N stay inside the allocation)
+      const int ncols = min(32, (half + 1) * ncol_half - c0);
+      if (r < g.m) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j >= ncols) break;
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float z = v[j + u];
+            if (g.bias != nullptr) z += __ldg(g.bias + c0 + j + u);
+            o[u] = g.mode == 1 ? softplus100(z) : z;
+          }
+          if (g.mode == 2) {
+            const float4 yy = __ldg(reinterpret_cast<const float4*>(g.y + r * g.ldy + c0 + j));
+            o[0] *= softplus100_grad_from_output(yy.x); o[1] *= softplus100_grad_from_output(yy.y);
+            o[2] *= softplus100_grad_from_output(yy.z); o[3] *= softplus100_grad_from_output(yy.w);
+          }
+          *reinterpret_cast<float4*>(g.c + r * g.ldc + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    mma_warp_loop(smem, sl, s_full, s_empty, &s_done, tmem_d, g.n, n_slices);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+struct WgradArgs {
+  const float* dz; int64_t ldz;
+  const float* a; int64_t lda;
+  float* dw; int64_t lddw;
+  float* db;
+  int64_t m, points_per_cta;
+  int n, k;
+};
+
+// ---------------------------------------------------------------------------------------------- dw += dz^T a
+// grid = (point ranges, N / 128).  Accumulator: 128 columns of dz (lanes) x K columns of a.
+__global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_kernel(WgradArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t s_full[kStages], s_empty[kStages], s_done;
+  __shared__ uint32_t s_tmem;
+  const StageBuffers sl = stage_layout(g.k);
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const int64_t p_begin = (int64_t)blockIdx.x * g.points_per_cta;
+  const int64_t p_end = min(g.m, p_begin + g.points_per_cta);
+  const int ch0 = blockIdx.y * kTileM;
+  const int64_t n_slices = p_end > p_begin ? (p_end - p_begin + kSliceK - 1) / kSliceK : 0;
+  const uint32_t tmem_cols = g.k <= 32 ? 32u : (g.k <= 64 ? 64u : (g.k <= 128 ? 128u : 256u));
+  if (n_slices == 0) return;     // (whole CTA)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, kProducerWarps * 32); mbar_init(s_empty + s, 1); }
+    mbar_init(&s_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(&s_tmem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = s_tmem;
+
+  if (warp < kProducerWarps) {
+    // ---- producers, transposing: lane = point of the slice (k index), warp w takes 16-byte column groups w, w + 8, ...
+    // of that point's row; the four values of a group go to four tile rows (rows = columns of dz / a) at k = lane ----
+    float bsum[4][4];              // bias gradient: this thread's share of sum_m dz[m, ch] for its 16 columns of dz
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bsum[i][0] = bsum[i][1] = bsum[i][2] = bsum[i][3] = 0.f;
+    const int kc = (int)lane >> 2, kw = ((int)lane & 3) * 4;       // 16-byte chunk and byte offset of k = lane in a row
+    for (int64_t it = 0; it < n_slices; ++it) {
+      const int s = (int)(it % kStages);
+      mbar_wait(s_empty + s, (uint32_t)(((it / kStages) & 1) ^ 1));
+      uint8_t* st = smem + (size_t)s * sl.bytes;
+      const int64_t p = p_begin + it * kSliceK + lane;
+      const bool live = p < p_end;
+      float4 vz[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)      // 128 columns of dz = 32 groups of 4: groups warp + 8 i
+        vz[i] = live ? __ldg(reinterpret_cast<const float4*>(g.dz + p * g.ldz + ch0 + 4 * ((int)warp + 8 * i)))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int f0 = 0; f0 < g.k / 4; f0 += 32) {       // K columns of a = K / 4 groups: groups f0 + warp + 8 i
+        float4 va[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = f0 + (int)warp + 8 * i;
+          va[i] = (live && 4 * f < g.k) ? __ldg(reinterpret_cast<const float4*>(g.a + p * g.lda + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = f0 + (int)warp + 8 * i;
+          if (4 * f >= g.k) continue;
+          const float x[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = 4 * f + u;
+            const float h = tf32_hi(x[u]);
+            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
+            *reinterpret_cast<float*>(st + sl.b_hi + off) = h;
+            *reinterpret_cast<float*>(st + sl.b_lo + off) = x[u] - h;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = (int)warp + 8 * i;
+        const float x[4] = {vz[i].x, vz[i].y, vz[i].z, vz[i].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = 4 * f + u;
+          const float h = tf32_hi(x[u]);
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
+          *reinterpret_cast<float*>(st + sl.a_hi + off) = h;
+          *reinterpret_cast<float*>(st + sl.a_lo + off) = x[u] - h;
+          bsum[i][u] += x[u];
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(s_full + s);
+    }
+    if (g.db != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float v = bsum[i][u];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) atomicAdd(g.db + ch0 + 4 * ((int)warp + 8 * i) + u, v);
+        }
+    }
+    // ---- epilogue: lanes of the accumulator = columns of dz, columns = columns of a ----
+    mbar_wait(&s_done, 0u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int row = ch0 + 32 * q + (int)lane;             // row of dw
+    const int ncol_half = g.k / 2;
+    for (int c0 = half * ncol_half; c0 < (half + 1) * ncol_half; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      const int ncols = min(32, (half + 1) * ncol_half - c0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(g.dw + (int64_t)row * g.lddw + c0 + j, v[j]);
+    }
+    tc_fence_before();
+  } else {
+    mma_warp_loop(smem, sl, s_full, s_empty, &s_done, tmem_d, g.k, n_slices);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- small kernels
+__global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x, int64_t m, int n_freq, float* __restrict__ out,
+                                                    int64_t ld, int n_cols) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float p[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+  float* o = out + i * ld;
+  o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  float f = 1.f;                                   // freq_bands = 2 ** linspace(0, n_freq - 1, n_freq): exact powers of two
+  for (int k = 0; k < n_freq; ++k, f *= 2.f) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float a = f * p[d];
+      o[3 + 6 * k + d] = sinf(a);
+      o[6 + 6 * k + d] = cosf(a);
+    }
+  }
+  for (int c = 3 * (2 * n_freq + 1); c < n_cols; ++c) o[c] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) embed_backward_kernel(const float* __restrict__ x, int64_t m, int n_freq,
+                                                             const float* __restrict__ g_emb, int64_t ld,
+                                                             float* __restrict__ g_x, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float* ge = g_emb + i * ld;
+  float f = 1.f;
+  float acc[3] = {ge[0], ge[1], ge[2]};
+  for (int k = 0; k < n_freq; ++k, f *= 2.f) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float a = f * x[3 * i + d];
+      acc[d] += f * (cosf(a) * ge[3 + 6 * k + d] - sinf(a) * ge[6 + 6 * k + d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) g_x[3 * i + d] = accumulate ? g_x[3 * i + d] + acc[d] : acc[d];
+}
+
+// out[m, j] = a[m, :] . w[j, :] + bias[j]; one warp per row, d_out <= 8
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ a, int64_t lda, int64_t m, int k,
+                                                   const float* __restrict__ w, const float* __restrict__ bias, int d_out,
+                                                   float* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  if (row >= m) return;
+  for (int j = 0; j < d_out; ++j) {
+    float s = 0.f;
+    for (int c = (int)lane; c < k; c += 32) s = fmaf(a[row * lda + c], __ldg(w + (int64_t)j * k + c), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row * d_out + j] = s + (bias ? bias[j] : 0.f);
+  }
+}
+
+// dz = (g w) * softplus'(a), dw += g^T a, db += sum g.  One warp per row for dz; the weight gradient is reduced per CTA
+// in shared memory first (k <= 256, d_out <= 8).
+__global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ a, int64_t lda, int64_t m, int k,
+                                                            const float* __restrict__ w, int d_out, const float* __restrict__ g,
+                                                            float* __restrict__ dz, int64_t ldz, float* __restrict__ dw,
+                                                            float* __restrict__ db, int rows_per_cta) {
+  __shared__ float s_dw[8 * 256];
+  __shared__ float s_db[8];
+  for (int i = threadIdx.x; i < d_out * k; i += blockDim.x) s_dw[i] = 0.f;
+  if (threadIdx.x < 8) s_db[threadIdx.x] = 0.f;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = min(m, r_begin + rows_per_cta);
+  float acc[8][8];       // [j][column slot]: columns lane, lane + 32, ... (k <= 256 -> 8 slots)
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  float gsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t row = r_begin + warp; row < r_end; row += 8) {
+    float gj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gj[j] = j < d_out ? g[row * d_out + j] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = (int)lane + 32 * c;
+      if (col >= k) break;
+      const float av = a[row * lda + col];
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < d_out) { t = fmaf(gj[j], __ldg(w + (int64_t)j * k + col), t); acc[j][c] = fmaf(gj[j], av, acc[j][c]); }
+      dz[row * ldz + col] = t * softplus100_grad_from_output(av);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gsum[j] += gj[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j >= d_out) break;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = (int)lane + 32 * c;
+      if (col < k) atomicAdd(&s_dw[j * k + col], acc[j][c]);
+    }
+    if (lane == 0) atomicAdd(&s_db[j], gsum[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d_out * k; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+  if (db != nullptr && threadIdx.x < d_out) atomicAdd(db + threadIdx.x, s_db[threadIdx.x]);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace mlp
+}  // namespace d3h
+
+using namespace d3h;
+using namespace d3h::mlp;
+
+static int finish_launch(const char* who) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}
+
+extern "C" int d3h_mlp_embed(const float* x, int64_t m, int32_t n_freq, float* out, int64_t ld, int32_t n_cols,
+                             d3h_stream_t stream) {
+  if (m < 0 || n_freq < 0 || n_freq > 16 || n_cols < 3 * (2 * n_freq + 1) || ld < n_cols || (m > 0 && (!x || !out))) {
+    set_error("d3h_mlp_embed: bad argument (n_cols must hold the 3 (2 n_freq + 1) channels, ld >= n_cols)");
+    return D3H_E_BADARG;
+  }
+  if (m == 0) return D3H_OK;
+  embed_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, m, n_freq, out, ld, n_cols);
+  return finish_launch("d3h_mlp_embed");
+}
+
+extern "C" int d3h_mlp_embed_backward(const float* x, int64_t m, int32_t n_freq, const float* g_emb, int64_t ld,
+                                      float* g_x, int32_t accumulate, d3h_stream_t stream) {
+  if (m < 0 || n_freq < 0 || n_freq > 16 || ld < 3 * (2 * n_freq + 1) || (m > 0 && (!x || !g_emb || !g_x))) {
+    set_error("d3h_mlp_embed_backward: bad argument");
+    return D3H_E_BADARG;
+  }
+  if (m == 0) return D3H_OK;
+  embed_backward_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, m, n_freq, g_emb, ld, g_x, accumulate);
+  return finish_launch("d3h_mlp_embed_backward");
+}
+
+extern "C" int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, int64_t ldw, int32_t n,
+                              const float* bias, int32_t mode, const float* y, int64_t ldy, float* c, int64_t ldc,
+                              d3h_stream_t stream) {
+  if (m < 0 || k <= 0 || (k % kSliceK) || n < 64 || n > 256 || (n % 64) || mode < 0 || mode > 2 || lda < k || ldw < k ||
+      ldc < n || (lda % 4) || (ldw % 4) || (ldc % 4) || !w || (m > 0 && (!a || !c)) || !aligned16(a) || !aligned16(w) ||
+      !aligned16(c) || (mode == 2 && (!y || ldy < n || (ldy % 4) || !aligned16(y)))) {
+    set_error("d3h_mlp_linear: bad argument (K %% 32 == 0, N in {64, 128, 192, 256}, leading dimensions multiples of 4 "
+              "and >= the row length, 16-byte aligned pointers, mode 2 needs y)");
+    return D3H_E_BADARG;
+  }
+  if (m == 0) return D3H_OK;
+  const size_t smem = (size_t)kStages * stage_layout(n).bytes;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * stage_layout(256).bytes));
+    attr = true;
+  }
+  LinearArgs g{a, lda, w, ldw, bias, y, ldy, c, ldc, m, k, n, mode};
+  mlp_linear_kernel<<<(unsigned)((m + kTileM - 1) / kTileM), kThreads, smem, (cudaStream_t)stream>>>(g);
+  return finish_launch("d3h_mlp_linear");
+}
+
+extern "C" int d3h_mlp_wgrad(const float* dz, int64_t ldz, const float* a, int64_t lda, int64_t m, int32_t n, int32_t k,
+                             float* dw, int64_t lddw, float* db, d3h_stream_t stream) {
+  if (m < 0 || n <= 0 || (n % kTileM) || n > 256 || k < 64 || k > 256 || (k % 64) || ldz < n || lda < k || lddw < k ||
+      (ldz % 4) || (lda % 4) || !dw || (m > 0 && (!dz || !a)) || !aligned16(dz) || !aligned16(a)) {
+    set_error("d3h_mlp_wgrad: bad argument (N in {128, 256}, K in {64, 128, 192, 256}, leading dimensions multiples "
+              "of 4, 16-byte aligned pointers)");
+    return D3H_E_BADARG;
+  }
+  if (m == 0) return D3H_OK;
+  const size_t smem = (size_t)kStages * stage_layout(k).bytes;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * stage_layout(256).bytes));
+    attr = true;
+  }
+  // one CTA per SM and column tile: every CTA walks a contiguous range of points (a multiple of the 32-point slice)
+  int64_t ranges = 148 / (n / kTileM);
+  int64_t per = ((m + ranges - 1) / ranges + kSliceK - 1) / kSliceK * kSliceK;
+  ranges = (m + per - 1) / per;
+  WgradArgs g{dz, ldz, a, lda, dw, lddw, db, m, per, n, k};
+  mlp_wgrad_kernel<<<dim3((unsigned)ranges, (unsigned)(n / kTileM)), kThreads, smem, (cudaStream_t)stream>>>(g);
+  return finish_launch("d3h_mlp_wgrad");
+}
+
+extern "C" int d3h_mlp_head(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, const float* bias,
+                            int32_t d_out, float* out, d3h_stream_t stream) {
+  if (m < 0 || k <= 0 || d_out <= 0 || d_out > 8 || lda < k || !w || (m > 0 && (!a || !out))) {
+    set_error("d3h_mlp_head: bad argument (1 <= d_out <= 8)");
+    return D3H_E_BADARG;
+  }
+  if (m == 0) return D3H_OK;
+  head_kernel<<<(unsigned)((m + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a, lda, m, k, w, bias, d_out, out);
+  return finish_launch("d3h_mlp_head");
+}
+
+extern "C" int d3h_mlp_head_backward(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, int32_t d_out,
+                                     const float* g, float* dz, int64_t ldz, float* dw, float* db, d3h_stream_t stream) {
+  if (m < 0 || k <= 0 || k > 256 || d_out <= 0 || d_out > 8 || lda < k || ldz < k || !w || !dw || (m > 0 && (!a || !g || !dz))) {
+    set_error("d3h_mlp_head_backward: bad argument (K <= 256, 1 <= d_out <= 8)");
+    return D3H_E_BADARG;
+  }
+  if (m == 0) return D3H_OK;
+  const int rows = 2048;
+  head_backward_kernel<<<(unsigned)((m + rows - 1) / rows), 256, 0, (cudaStream_t)stream>>>(a, lda, m, k, w, d_out, g, dz, ldz, dw,
+                                                                                           db, rows);
+  return finish_launch("d3h_mlp_head_backward");
+}

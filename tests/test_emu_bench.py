@@ -73,8 +73,8 @@ def _worker(rank, world, port, out_dir, argv):
 @pytest.mark.parametrize("world", [1, 2])
 def test_bench_control_flow(tmp_path, world):
     import torch.multiprocessing as mp
-    argv = ["--gpus", str(world), "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "4", "--groups", "2",
-            "--lanes", "2", "--profile-steps", "1", "--e2e-chunk", "2"]
+    argv = ["--gpus", str(world), "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "16", "--groups", "2",
+            "--lanes", "2", "--profile-steps", "1", "--e2e-chunk", "8"]
     if world > 1:
         argv.append("--no-cpu-baseline")     # N = 1 runs the CPU baseline leg as well (tiny grid: a fraction of a second)
     ctx = mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), argv), nprocs=world, join=False,
@@ -88,7 +88,7 @@ def test_bench_control_flow(tmp_path, world):
     line = [l for l in open(tmp_path / "out_0.txt") if l.startswith("{")][-1]
     d = json.loads(line)
     assert d["n_gpus"] == world and d["steps"] == 2 and d["unit"] == "tets/s" and d["higher_is_better"] is True
-    assert d["config"]["frames_per_step"] == 4 * world and d["config"]["groups"] == 2
+    assert d["config"]["frames_per_step"] == 16 * world and d["config"]["groups"] == 2
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"] is not None and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["device_trace"] is not None and "error" not in d["device_trace"]
@@ -109,7 +109,7 @@ def test_bench_control_flow(tmp_path, world):
         assert not [l for l in open(tmp_path / f"out_{r}.txt") if l.startswith("{")]
     assert len(d["ms_per_step_blocks"]) == 5 and d["config"]["mode"] == "weak"
     rk = d["ranks"]
-    assert len(rk["local_step_ms"]) == world and rk["frames"] == [4] * world and all(t > 0 for t in rk["local_step_ms"])
+    assert len(rk["local_step_ms"]) == world and rk["frames"] == [16] * world and all(t > 0 for t in rk["local_step_ms"])
     assert (world == 1) == (sum(rk["allreduce_ms"]) == 0)
     if world == 1:
         assert "error" not in d["cold"] and d["cold"]["ms_per_frame"] > 0, d["cold"]
@@ -153,7 +153,7 @@ def test_bench_tets_mode(tmp_path, world):
 
 def test_reference_arm_prints_the_same_config(tmp_path):
     """--impl reference: same metric / unit / config / steps / warm-up as the GPU arm (the driver compares them)."""
-    argv = ["--gpus", "1", "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "4", "--groups", "2", "--lanes", "2",
+    argv = ["--gpus", "1", "--steps", "2", "--warmup", "1", "--res", "6", "--frames-per-rank", "16", "--groups", "2", "--lanes", "2",
             "--profile-steps", "1", "--no-cpu-baseline", "--no-e2e", "--no-mesh-stage", "--no-torch-baseline", "--no-cold",
             "--no-split-pair"]
     ours = _run(tmp_path, 1, argv)

@@ -43,7 +43,7 @@ def _worker(rank, world, port, out_dir):
         assert torch.equal(extra["faces_watertight"], e1["faces_watertight"])
         torch.save((verts.detach().cpu(), faces.cpu(), tp.grad.cpu()), os.path.join(out_dir, f"tet_{rank}.pt"))
         # ---- frames: 4 frames over the ranks, shared sdf / msdf gradients reduced (dense == sparse) ----
-        B = 4
+        B = max(4, world)
         mine = S.frame_slice(B, world, rank)
         pos_b = torch.tensor(np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in mine]), device=dev)
         grads = []
@@ -61,25 +61,28 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_ranks_tet_ranges_and_frames(tmp_path):
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ranks_tet_ranges_and_frames(tmp_path, world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     import torch.multiprocessing as mp
     from d3human_code_b200 import grids
     from d3human_code_b200.extract import extract_frames
-    world = 2
     mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True, start_method="spawn")
-    t0, t1 = (torch.load(tmp_path / f"tet_{r}.pt") for r in range(world))
-    assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1])
-    assert torch.allclose(t0[2], t1[2], rtol=1e-5, atol=1e-6 * float(t0[2].abs().max()))
-    f0, f1 = (torch.load(tmp_path / f"frames_{r}.pt") for r in range(world))
-    assert torch.equal(f0[0], f1[0]) and torch.equal(f0[1], f1[1])
-    # the reduced gradient equals the gradient of all 4 frames on one GPU
+    t0 = torch.load(tmp_path / "tet_0.pt")
+    f0 = torch.load(tmp_path / "frames_0.pt")
+    for r in range(1, world):
+        t1 = torch.load(tmp_path / f"tet_{r}.pt")
+        assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1])
+        assert torch.allclose(t0[2], t1[2], rtol=1e-5, atol=1e-6 * float(t0[2].abs().max()))
+        f1 = torch.load(tmp_path / f"frames_{r}.pt")
+        assert torch.equal(f0[0], f1[0]) and torch.equal(f0[1], f1[1])
+    # the reduced gradient equals the gradient of all the frames on one GPU
     dev = torch.device("cuda:0")
     res = 32
     pos, tets = grids.kuhn_grid(res)
     sdf, msdf = grids.sphere_plane_field(pos)
-    pos_b = torch.tensor(np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(4)]), device=dev)
+    pos_b = torch.tensor(np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(max(4, world))]), device=dev)
     ts = torch.tensor(sdf, device=dev, requires_grad=True)
     tm = torch.tensor(msdf, device=dev, requires_grad=True)
     outs = extract_frames(pos_b, ts, tm, torch.tensor(tets, device=dev), types="cloth")
