@@ -1,0 +1,204 @@
+"""`MLP`: drop-in for the reference's SDF network (geometry/mlp.py:9-45) -- same constructor, same sub-modules and
+parameter names (`emb`, `net.0.weight`, ...), so state_dicts and optimizers are interchangeable -- whose forward and
+backward pass run as hand-written sm_100a kernels behind the C ABI of include/d3h_mlp.h: positional encoding, every
+nn.Linear as a tcgen05 (tensor memory) GEMM with the 3xTF32 split and the bias + Softplus(beta=100) fused into its
+epilogue, the weight gradients as tensor-core contractions over the points.  SURVEY.md section 8(f) row 3: this is the
+network D3-Human evaluates on every grid vertex before each extraction (geometry/hmsdf.py:434-444).
+
+Supported: d_hidden in {128, 256}, d_out <= 8, any n_freq / n_hidden / skip_in, fp32 (use_float16=True raises: D3-Human
+trains with use_float16=False, train.py:1626).  Gradients flow to every parameter and to the query points (first order;
+the eikonal term of hmsdf.py:856-880 differentiates the network output twice and is outside this path).  CUDA tensors
+only -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+from .. import _cabi
+from .embedding import Embedding
+
+
+def _ceil(x: int, q: int) -> int:
+    return (x + q - 1) // q * q
+
+
+class _Plan:
+    """Static description of the layer chain (from the module's hyper-parameters)."""
+
+    def __init__(self, n_freq, d_hidden, d_out, n_hidden, skip_in):
+        self.n_freq, self.dh, self.d_out, self.n_hidden = n_freq, d_hidden, d_out, n_hidden
+        self.skip = tuple(sorted(set(int(s) for s in skip_in if 0 <= int(s) < n_hidden)))
+        self.e = 3 * (2 * n_freq + 1)
+        self.e_pad = _ceil(self.e, 64)          # GEMM K granularity 32, N granularity 64 (the encoding is also an output
+        #                                         width in the backward pass)
+        # hidden layer li (1-based in MLP.net order: 0 = first Linear) reads [act | emb] when (li - 1) in skip_in
+        self.wide = [False] + [(i in self.skip) for i in range(n_hidden)]
+        # leading dimension of the buffer holding the OUTPUT of layer li (= the input of layer li + 1)
+        self.ld_out = [self.dh + self.e_pad if (li + 1 <= n_hidden and self.wide[li + 1]) else self.dh
+                       for li in range(n_hidden + 1)]
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _MLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: _Plan, x, *wb):
+        L = _cabi.lib()
+        dev = x.device
+        m = x.shape[0]
+        nl = plan.n_hidden + 2
+        ws, bs = wb[:nl], wb[nl:]
+        dh, e, ep = plan.dh, plan.e, plan.e_pad
+        f32 = torch.float32
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            emb = torch.empty((m, ep), dtype=f32, device=dev)
+            _cabi.check(L.d3h_mlp_embed(x.data_ptr(), m, plan.n_freq, emb.data_ptr(), ep, ep, st), "d3h_mlp_embed")
+            acts: List[torch.Tensor] = []
+            a_ptr, lda, k = emb.data_ptr(), ep, ep
+            for li in range(plan.n_hidden + 1):
+                w = ws[li]
+                if li == 0:
+                    wp = torch.zeros((dh, ep), dtype=f32, device=dev)
+                    wp[:, :e] = w
+                elif plan.wide[li]:
+                    wp = torch.zeros((dh, dh + ep), dtype=f32, device=dev)
+                    wp[:, :dh + e] = w
+                else:
+                    wp = w.contiguous()
+                out = torch.empty((m, plan.ld_out[li]), dtype=f32, device=dev)
+                if plan.ld_out[li] != dh:      # the next layer reads cat([x, emb]) (mlp.py:41): the encoding sits behind
+                    _cabi.check(L.d3h_mlp_embed(x.data_ptr(), m, plan.n_freq, out.data_ptr() + 4 * dh, plan.ld_out[li], ep, st),
+                                "d3h_mlp_embed")
+                _cabi.check(L.d3h_mlp_linear(a_ptr, lda, m, k, wp.data_ptr(), wp.shape[1], dh, bs[li].data_ptr(), 1, None, 0,
+                                             out.data_ptr(), plan.ld_out[li], st), "d3h_mlp_linear")
+                acts.append(out)
+                a_ptr, lda, k = out.data_ptr(), plan.ld_out[li], plan.ld_out[li]
+            y = torch.empty((m, plan.d_out), dtype=f32, device=dev)
+            w_out = ws[-1].contiguous()
+            _cabi.check(L.d3h_mlp_head(a_ptr, lda, m, dh, w_out.data_ptr(), bs[-1].data_ptr(), plan.d_out, y.data_ptr(), st),
+                        "d3h_mlp_head")
+        ctx.plan = plan
+        ctx.save_for_backward(x, emb, *acts, *ws)
+        _MLPFn.launches += 3 + 2 * (plan.n_hidden + 1) - 1 + len(plan.skip)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        plan = ctx.plan
+        L = _cabi.lib()
+        saved = ctx.saved_tensors
+        x, emb = saved[0], saved[1]
+        nh = plan.n_hidden
+        acts = saved[2:2 + nh + 1]
+        ws = saved[2 + nh + 1:]
+        dev = x.device
+        m = x.shape[0]
+        dh, e, ep = plan.dh, plan.e, plan.e_pad
+        f32 = torch.float32
+        need_x = ctx.needs_input_grad[1]
+        gy = gy.contiguous().float()
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            gws = [torch.zeros((dh, ep), dtype=f32, device=dev)]
+            gws += [torch.zeros((dh, dh + ep) if plan.wide[li] else (dh, dh), dtype=f32, device=dev) for li in range(1, nh + 1)]
+            gws.append(torch.zeros((plan.d_out, dh), dtype=f32, device=dev))
+            gbs = [torch.zeros(dh, dtype=f32, device=dev) for _ in range(nh + 1)] + [torch.zeros(plan.d_out, dtype=f32, device=dev)]
+            g_emb = torch.zeros((m, ep), dtype=f32, device=dev) if need_x else None
+            tmp_e = torch.empty((m, ep), dtype=f32, device=dev) if need_x else None
+            dz = torch.empty((m, dh), dtype=f32, device=dev)
+            dz2 = torch.empty((m, dh), dtype=f32, device=dev) if nh > 0 else None
+            last = acts[nh]
+            _cabi.check(L.d3h_mlp_head_backward(last.data_ptr(), plan.ld_out[nh], m, dh, ws[-1].contiguous().data_ptr(), plan.d_out,
+                                                gy.data_ptr(), dz.data_ptr(), dh, gws[-1].data_ptr(), gbs[-1].data_ptr(), st),
+                        "d3h_mlp_head_backward")
+            for li in range(nh, -1, -1):
+                # ---- weight / bias gradient of layer li: dz^T [input] ----
+                if li == 0:
+                    _cabi.check(L.d3h_mlp_wgrad(dz.data_ptr(), dh, emb.data_ptr(), ep, m, dh, ep, gws[0].data_ptr(), ep,
+                                                gbs[0].data_ptr(), st), "d3h_mlp_wgrad")
+                else:
+                    src = acts[li - 1]
+                    ld = plan.ld_out[li - 1]
+                    _cabi.check(L.d3h_mlp_wgrad(dz.data_ptr(), dh, src.data_ptr(), ld, m, dh, dh, gws[li].data_ptr(),
+                                                gws[li].shape[1], gbs[li].data_ptr(), st), "d3h_mlp_wgrad")
+                    if plan.wide[li]:
+                        _cabi.check(L.d3h_mlp_wgrad(dz.data_ptr(), dh, src.data_ptr() + 4 * dh, ld, m, dh, ep,
+                                                    gws[li].data_ptr() + 4 * dh, gws[li].shape[1], None, st), "d3h_mlp_wgrad")
+                # ---- gradient of the layer's input ----
+                w = ws[li]
+                if need_x and (li == 0 or plan.wide[li]):
+                    # the encoding's share: dz . W[:, -e:]  ->  (M, e_pad), added to g_emb
+                    wt = torch.zeros((ep, dh), dtype=f32, device=dev)
+                    wt[:e] = (w if li == 0 else w[:, dh:dh + e]).t()
+                    _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), dh, ep, None, 0, None, 0,
+                                                 tmp_e.data_ptr(), ep, st), "d3h_mlp_linear")
+                    g_emb += tmp_e
+                if li > 0:
+                    wt = w[:, :dh].t().contiguous()
+                    prev = acts[li - 1]
+                    _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), dh, dh, None, 2, prev.data_ptr(),
+                                                 plan.ld_out[li - 1], dz2.data_ptr(), dh, st), "d3h_mlp_linear")
+                    dz, dz2 = dz2, dz
+            gx = None
+            if need_x:
+                gx = torch.empty_like(x)
+                _cabi.check(L.d3h_mlp_embed_backward(x.data_ptr(), m, plan.n_freq, g_emb.data_ptr(), ep, gx.data_ptr(), 0, st),
+                            "d3h_mlp_embed_backward")
+        gw_out = [gws[0][:, :e]]
+        for li in range(1, nh + 1):
+            gw_out.append(gws[li][:, :dh + e] if plan.wide[li] else gws[li])
+        gw_out.append(gws[-1])
+        _MLPFn.launches += 2 + 3 * (nh + 1) + 2 * len(plan.skip)
+        return (None, gx) + tuple(gw_out) + tuple(gbs)
+
+
+_MLPFn.launches = 0     # library kernels enqueued so far (bench.py reports the difference over its timed region)
+
+
+def launch_counter() -> int:
+    return _MLPFn.launches
+
+
+class MLP(nn.Module):
+    def __init__(self, n_freq=6, d_hidden=128, d_out=1, n_hidden=3, skip_in=[], use_float16=False):
+        super().__init__()
+        self.emb = Embedding(3, n_freq)
+        layers = [nn.Linear(self.emb.out_channels, d_hidden), nn.Softplus(beta=100)]
+        count = 2
+        self.skip_count = []
+        self.skip_in = skip_in
+        for i in range(n_hidden):
+            if i in skip_in:
+                layers.append(nn.Linear(d_hidden + self.emb.out_channels, d_hidden))
+                self.skip_count.append(count)
+            else:
+                layers.append(nn.Linear(d_hidden, d_hidden))
+            count += 1
+            layers.append(nn.Softplus(beta=100))
+            count += 1
+        layers.append(nn.Linear(d_hidden, d_out))
+        self.net = nn.ModuleList(layers)
+        self.use_float16 = use_float16
+        if d_hidden not in (128, 256) or not (1 <= d_out <= 8):
+            raise NotImplementedError("d3human-code_b200 MLP: d_hidden in {128, 256} and d_out <= 8 (D3-Human: 256 / 1)")
+        self._plan = _Plan(n_freq, d_hidden, d_out, n_hidden, skip_in)
+
+    def forward(self, x):
+        if self.use_float16:
+            raise NotImplementedError("d3human-code_b200 MLP computes in fp32 (3xTF32 on the tensor cores); D3-Human trains "
+                                      "with use_float16=False (train.py:1626)")
+        if not x.is_cuda:
+            raise RuntimeError("d3human-code_b200 has no CPU path: MLP needs CUDA tensors")
+        lin = [m for m in self.net if isinstance(m, nn.Linear)]
+        shape = x.shape
+        pts = x.reshape(-1, 3).float().contiguous()
+        if pts.data_ptr() % 16:
+            pts = pts.clone()
+        y = _MLPFn.apply(self._plan, pts, *[l.weight for l in lin], *[l.bias for l in lin])
+        return y.reshape(*shape[:-1], self._plan.d_out)

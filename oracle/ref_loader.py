@@ -55,3 +55,21 @@ def load_reference_mesh(device: str = "cpu"):
     mod.__package__ = "render"
     exec(compile(src, rel, "exec"), mod.__dict__)
     return mod
+
+
+def load_reference_mlp():
+    """-> the reference's `geometry/mlp.py` as a module (MLP :9-45) next to its `geometry/embedding.py`, without executing
+    anything else of the `geometry` package (hmsdf.py needs pysdf / trimesh / nvdiffrast)."""
+    import importlib.util
+    pkg_name = "_d3h_ref_geometry"
+    if pkg_name + ".mlp" in sys.modules:
+        return sys.modules[pkg_name + ".mlp"]
+    pkg = types.ModuleType(pkg_name)
+    pkg.__path__ = [os.path.join(REF_ROOT, "geometry")]
+    sys.modules[pkg_name] = pkg
+    for sub in ("embedding", "mlp"):
+        spec = importlib.util.spec_from_file_location(f"{pkg_name}.{sub}", os.path.join(REF_ROOT, "geometry", sub + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkg_name}.{sub}"] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules[pkg_name + ".mlp"]

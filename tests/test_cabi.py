@@ -1,4 +1,4 @@
-"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/d3h_tets.h and include/d3h_mesh.h declare,
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/d3h_tets.h, d3h_mesh.h and d3h_mlp.h declare,
 validates arguments without touching a GPU, and carries the reference's case tables."""
 import ctypes as C
 import os
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_functions():
-    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("d3h_tets.h", "d3h_mesh.h"))
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("d3h_tets.h", "d3h_mesh.h", "d3h_mlp.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(d3h_[a-z0-9_]+)\s*\(", text)))
 
@@ -141,3 +141,20 @@ def test_no_cpu_path():
     pos = torch.zeros(8, 3)
     with pytest.raises(RuntimeError, match="no CPU path"):
         GShell_Tets()(pos, torch.zeros(8), torch.zeros(8), torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_mlp_entry_points_validate_their_arguments():
+    """include/d3h_mlp.h: shape / alignment rules are checked before anything is launched (no GPU needed)."""
+    lib = _cabi.lib()
+    buf = np.zeros(4096, dtype=np.float32)
+    p = buf.ctypes.data + (-buf.ctypes.data % 16)
+    assert lib.d3h_mlp_linear(p, 64, 0, 64, p, 64, 256, None, 1, None, 0, p, 256, None) == 0            # M = 0: nothing to do
+    assert lib.d3h_mlp_linear(p, 64, 8, 48, p, 64, 256, None, 1, None, 0, p, 256, None) == _cabi.D3H_E_BADARG   # K % 32
+    assert lib.d3h_mlp_linear(p, 64, 8, 64, p, 64, 48, None, 1, None, 0, p, 256, None) == _cabi.D3H_E_BADARG    # N
+    assert lib.d3h_mlp_linear(p + 4, 64, 8, 64, p, 64, 256, None, 1, None, 0, p, 256, None) == _cabi.D3H_E_BADARG  # alignment
+    assert lib.d3h_mlp_linear(p, 64, 8, 64, p, 64, 256, None, 2, None, 0, p, 256, None) == _cabi.D3H_E_BADARG   # mode 2 needs y
+    assert b"d3h_mlp_linear" in lib.d3h_last_error_string()
+    assert lib.d3h_mlp_wgrad(p, 256, p, 64, 8, 192, 64, p, 64, None, None) == _cabi.D3H_E_BADARG               # N not 128 / 256
+    assert lib.d3h_mlp_embed(p, 8, 6, p, 32, 32, None) == _cabi.D3H_E_BADARG                                   # 39 channels do not fit
+    assert lib.d3h_mlp_head(p, 256, 8, 256, p, None, 9, p, None) == _cabi.D3H_E_BADARG                         # d_out > 8
+    assert lib.d3h_mlp_embed(p, 0, 6, p, 64, 64, None) == 0

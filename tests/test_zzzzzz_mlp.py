@@ -1,0 +1,196 @@
+"""SDF field query on the tensor cores (include/d3h_mlp.h, d3human-code_b200/geometry/mlp.py) against
+the float64 oracle (oracle/mlp_oracle.py) and the golden vectors written from the live reference module
+(tests/golden/mlp_*.npz).  GPU only: tcgen05 has no CPU emulation.  Last file of the suite: a new stage must not stop
+(-x) the tests of the extraction.
+
+Tolerances.  The reference computes in fp32 (TF32 off, torch default); the kernels use the 3xTF32 split with fp32
+accumulation in tensor memory, whose error is that of a re-ordered fp32 sum.  Forward: |y - y_oracle| <= 1e-5 max|y|;
+gradients: normwise 5e-5 (the reference's own fp32 backward is 2e-5 away from the float64 oracle, tests/test_mlp_oracle.py).
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from d3human_code_b200 import _cabi
+from oracle import mlp_oracle as MO
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, GRAD_TOL, GEMM_TOL = 1e-5, 5e-5, 3e-6
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mlp_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _st(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("m,k,n,mode", [(128, 64, 256, 0), (1000, 256, 256, 1), (77, 320, 256, 1), (4133, 256, 64, 0),
+                                        (300, 256, 256, 2), (129, 32, 128, 0), (20000, 256, 256, 1)])
+def test_linear_tensor_core_gemm_matches_float64(dev, m, k, n, mode):
+    """d3h_mlp_linear: c = f(a w^T + bias) for the three epilogues, M not a multiple of the 128-row tile, leading
+    dimensions larger than the row lengths.  Reference: float64 matmul of the same fp32 inputs."""
+    rng = np.random.default_rng(m + k + n + mode)
+    lda, ldw, ldc, ldy = k + 8, k + 4, n + 12, n + 4
+    a = rng.standard_normal((m, lda)).astype(np.float32)
+    w = (rng.standard_normal((n, ldw)) / np.sqrt(k)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    y = np.abs(rng.standard_normal((m, ldy)) * 0.02).astype(np.float32)
+    ta, tw, tb, ty = (torch.tensor(t, device=dev) for t in (a, w, bias, y))
+    tc = torch.full((m, ldc), 7.0, device=dev)
+    L = _cabi.lib()
+    _cabi.check(L.d3h_mlp_linear(ta.data_ptr(), lda, m, k, tw.data_ptr(), ldw, n, tb.data_ptr() if mode != 2 else None, mode,
+                                 ty.data_ptr() if mode == 2 else None, ldy if mode == 2 else 0, tc.data_ptr(), ldc, _st(dev)),
+                "d3h_mlp_linear")
+    z = a[:, :k].astype(np.float64) @ w[:, :k].astype(np.float64).T
+    if mode != 2:
+        z = z + bias
+    want = {0: z, 1: MO.softplus(z), 2: z * (1.0 - np.exp(-100.0 * y[:, :n].astype(np.float64)))}[mode]
+    got = tc.cpu().numpy()
+    assert _rel(got[:, :n], want) < GEMM_TOL, _rel(got[:, :n], want)
+    assert (got[:, n:] == 7.0).all()          # nothing written outside the N columns
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 128, 64), (1000, 256, 256), (4133, 256, 64), (33, 128, 256), (50000, 256, 256)])
+def test_wgrad_contraction_over_points_matches_float64(dev, m, n, k):
+    """d3h_mlp_wgrad: dw += dz^T a, db += sum dz (accumulating), M not a multiple of the 32-point slice."""
+    rng = np.random.default_rng(m + n + k)
+    ldz, lda, lddw = n + 4, k + 8, k + 4
+    dz = rng.standard_normal((m, ldz)).astype(np.float32)
+    a = rng.standard_normal((m, lda)).astype(np.float32)
+    tdz, ta = torch.tensor(dz, device=dev), torch.tensor(a, device=dev)
+    dw = torch.full((n, lddw), 1.0, device=dev)
+    db = torch.full((n,), 2.0, device=dev)
+    _cabi.check(_cabi.lib().d3h_mlp_wgrad(tdz.data_ptr(), ldz, ta.data_ptr(), lda, m, n, k, dw.data_ptr(), lddw, db.data_ptr(),
+                                          _st(dev)), "d3h_mlp_wgrad")
+    want = dz[:, :n].astype(np.float64).T @ a[:, :k].astype(np.float64)
+    scale = np.sqrt(m)
+    got = dw.cpu().numpy()
+    assert np.abs(got[:, :k] - 1.0 - want).max() < 1e-5 * scale * 4, np.abs(got[:, :k] - 1.0 - want).max()
+    assert (got[:, k:] == 1.0).all()
+    assert np.abs(db.cpu().numpy() - 2.0 - dz[:, :n].astype(np.float64).sum(0)).max() < 1e-5 * scale * 4
+
+
+def test_embedding_and_head_match_oracle(dev):
+    from d3human_code_b200.geometry.embedding import Embedding
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1.2, 1.2, size=(1001, 3)).astype(np.float32)
+    for n_freq in (1, 6, 8):
+        tx = torch.tensor(x, device=dev, requires_grad=True)
+        emb = Embedding(3, n_freq)
+        y = emb(tx)
+        assert y.shape == (1001, emb.out_channels)
+        assert np.abs(y.detach().cpu().numpy() - MO.embed(x, n_freq)).max() < 4e-6 * 2 ** n_freq    # argument 2^k x: ulp(2^k)
+        g = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        (y * torch.tensor(g, device=dev)).sum().backward()
+        assert _rel(tx.grad.cpu().numpy(), MO.embed_backward(x, n_freq, g.astype(np.float64))) < 1e-5
+    a = rng.standard_normal((515, 256)).astype(np.float32)
+    w, b = rng.standard_normal((3, 256)).astype(np.float32), rng.standard_normal(3).astype(np.float32)
+    ta, tw, tb = (torch.tensor(t, device=dev) for t in (a, w, b))
+    out = torch.empty((515, 3), device=dev)
+    _cabi.check(_cabi.lib().d3h_mlp_head(ta.data_ptr(), 256, 515, 256, tw.data_ptr(), tb.data_ptr(), 3, out.data_ptr(), _st(dev)),
+                "d3h_mlp_head")
+    assert _rel(out.cpu().numpy(), a.astype(np.float64) @ w.astype(np.float64).T + b) < 3e-6
+
+
+# ------------------------------------------------------------------------------------------------ the module
+def _load_into(net, w, b):
+    lin = [m for m in net.net if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for l, wi, bi in zip(lin, w, b):
+            l.weight.copy_(torch.tensor(wi))
+            l.bias.copy_(torch.tensor(bi))
+    return lin
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "two_skips" not in p], ids=lambda p: os.path.basename(p)[:-4])
+def test_mlp_matches_golden_vectors_of_the_reference(dev, path):
+    """Same parameters / inputs as the live reference module produced the goldens with: outputs and every gradient."""
+    from d3human_code_b200.geometry.mlp import MLP
+    d = np.load(path)
+    n_freq, d_hidden, n_hidden, _m = (int(v) for v in d["cfg"])
+    skip_in = [int(s) for s in d["skip_in"]]
+    n = n_hidden + 2
+    net = MLP(n_freq=n_freq, d_hidden=d_hidden, d_out=1, n_hidden=n_hidden, skip_in=skip_in).to(dev)
+    lin = _load_into(net, [d[f"w{i}"] for i in range(n)], [d[f"b{i}"] for i in range(n)])
+    x = torch.tensor(d["x"], device=dev, requires_grad=True)
+    y = net(x)
+    assert _rel(y.detach().cpu().numpy(), d["y"]) < FWD_TOL, _rel(y.detach().cpu().numpy(), d["y"])
+    (y * torch.tensor(d["gy"], device=dev)).sum().backward()
+    errs = {"gx": _rel(x.grad.cpu().numpy(), d["gx"])}
+    for i, l in enumerate(lin):
+        errs[f"gw{i}"] = _rel(l.weight.grad.cpu().numpy(), d[f"gw{i}"])
+        errs[f"gb{i}"] = _rel(l.bias.grad.cpu().numpy(), d[f"gb{i}"])
+    assert max(errs.values()) < GRAD_TOL, errs
+
+
+@pytest.mark.parametrize("seed,m", [(0, 1), (1, 127), (2, 4097), (3, 100000)])
+def test_mlp_matches_oracle_on_random_networks(dev, seed, m):
+    """The D3-Human configuration (n_freq 6, 256 wide, 6 hidden layers, skip_in [3]; train.py:1622-1625) and variations, at
+    batch sizes around the tile size and at the reference's batch_point_num = 100000 (hmsdf.py:187)."""
+    from d3human_code_b200.geometry.mlp import MLP
+    rng = np.random.default_rng(seed)
+    cfg = [dict(n_freq=6, d_hidden=256, n_hidden=6, skip_in=[3]), dict(n_freq=4, d_hidden=128, n_hidden=2, skip_in=[0, 1]),
+           dict(n_freq=8, d_hidden=256, n_hidden=1, skip_in=[]), dict(n_freq=6, d_hidden=256, n_hidden=6, skip_in=[3])][seed]
+    torch.manual_seed(seed)
+    net = MLP(d_out=1, **cfg).to(dev)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.5)
+    lin = [mod for mod in net.net if isinstance(mod, torch.nn.Linear)]
+    x = rng.uniform(-1, 1, size=(m, 3)).astype(np.float32)
+    tx = torch.tensor(x, device=dev, requires_grad=True)
+    y = net(tx)
+    yo, cache = MO.forward(x, [l.weight.detach().cpu().numpy() for l in lin], [l.bias.detach().cpu().numpy() for l in lin],
+                           cfg["n_freq"], tuple(cfg["skip_in"]))
+    assert y.shape == (m, 1)
+    assert _rel(y.detach().cpu().numpy(), yo) < FWD_TOL, _rel(y.detach().cpu().numpy(), yo)
+    gy = rng.standard_normal((m, 1)).astype(np.float32)
+    (y * torch.tensor(gy, device=dev)).sum().backward()
+    gx, gw, gb = MO.backward(cache, gy)
+    errs = {"gx": _rel(tx.grad.cpu().numpy(), gx)}
+    for i, l in enumerate(lin):
+        errs[f"gw{i}"] = _rel(l.weight.grad.cpu().numpy(), gw[i])
+        errs[f"gb{i}"] = _rel(l.bias.grad.cpu().numpy(), gb[i])
+    assert max(errs.values()) < GRAD_TOL, errs
+
+
+def test_mlp_state_dict_is_the_reference_layout_and_feeds_the_extraction(dev):
+    """Drop-in: parameter names of the reference module; its output goes straight into hmSDF_Tets and the loss
+    back-propagates through the extraction into the network's weights (hmsdf.py:434-455)."""
+    from d3human_code_b200 import grids
+    from d3human_code_b200.geometry.hmsdf_tets_split import hmSDF_Tets
+    from d3human_code_b200.geometry.mlp import MLP
+    net = MLP(n_freq=6, d_hidden=256, n_hidden=6, skip_in=[3]).to(dev)
+    keys = list(net.state_dict().keys())
+    assert keys[:2] == ["net.0.weight", "net.0.bias"] and keys[-2:] == ["net.14.weight", "net.14.bias"] and len(keys) == 16
+    assert net.net[8].weight.shape == (256, 256 + 39)
+    pos, tets = grids.kuhn_grid(16)
+    tp = torch.tensor(pos, device=dev)
+    with torch.no_grad():      # bias the output so that the zero level set crosses the grid
+        sdf0 = net(tp)
+        net.net[14].bias -= sdf0.median()
+    sdf = net(tp)
+    msdf = torch.tensor(grids.capsule_garment_field(pos)[1], device=dev)
+    verts, faces, _, _, _, extra = hmSDF_Tets()(tp, sdf, msdf, torch.tensor(tets, device=dev), "cloth")
+    assert faces.shape[0] > 0
+    verts.square().sum().backward()
+    g = net.net[0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    with pytest.raises(NotImplementedError):
+        MLP(use_float16=True).to(dev)(tp)
