@@ -2,10 +2,16 @@
 //
 // Every GEMM of the forward and backward pass is one of two kernels built on the same core:
 //
-//   * operands are fp32 in global memory; producer warps load 32-column (128-byte) slices with coalesced 16-byte loads,
-//     split every value into hi (low 13 mantissa bits cleared = exactly representable in TF32) and lo = x - hi, and store
-//     both into shared memory in the canonical K-major SWIZZLE_128B layout of the tcgen05 shared-memory descriptors
-//     (8-row x 128-byte atoms, 16-byte chunk c of row r at chunk position c ^ (r % 8));
+//   * activations are fp32 in global memory; producer warps load 32-column (128-byte) slices with coalesced 16-byte loads
+//     (the loads of slice i+1 are in flight while the tensor core works on slice i), split every value into hi (low 13
+//     mantissa bits cleared = exactly representable in TF32) and lo = x - hi, and store both into shared memory in the
+//     canonical K-major SWIZZLE_128B layout of the tcgen05 shared-memory descriptors (8-row x 128-byte atoms, 16-byte
+//     chunk c of row r at chunk position c ^ (r % 8));
+//   * weights are split and laid out in exactly that shared-memory image ONCE per call (mlp_pack_weight_kernel): a slice
+//     of the weight operand is then one 64 KB bulk copy global -> shared (cp.async.bulk + mbarrier complete_tx, issued
+//     by the MMA thread), no thread touches it;
+//   * one 96 KB stage per CTA and two CTAs per SM (2 x 256 tensor-memory columns): while one CTA waits for its
+//     operands or runs its epilogue the other one keeps the tensor core busy;
 //   * one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N <= 256, K = 8 per instruction) three times per
 //     k-step: hi.hi + lo.hi + hi.lo -- the 3xTF32 scheme, fp32-level accuracy at tensor-core speed -- accumulating in
 //     tensor memory; tcgen05.commit on an mbarrier hands the shared-memory stage back to the producers;
@@ -32,7 +38,7 @@ constexpr int kTileM = 128;          // rows of the accumulator (tensor-memory l
 constexpr int kSliceK = 32;          // fp32 values per shared-memory row: 128 bytes = one swizzle row
 constexpr int kProducerWarps = 8;
 constexpr int kThreads = (kProducerWarps + 1) * 32;   // + the MMA / tensor-memory warp
-constexpr int kStages = 2;
+constexpr int kCtasPerSm = 2;
 constexpr float kBeta = 100.f, kThreshold = 20.f;     // nn.Softplus(beta=100), default threshold (mlp.py:16)
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -59,6 +65,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // generic-proxy stores to shared memory -> visible to the async proxy (the tensor core reads through it)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bulk copy global -> shared through the async proxy (TMA, no tensor map: one contiguous piece); completion is counted
+// in bytes on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -130,13 +146,19 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
+// Softplus(beta = 100): torch computes (x*beta > threshold) ? x : log1p(exp(x*beta)) / beta.  Most pre-activations are far
+// from zero on the 1/beta scale, so the common cases cost no or one transcendental; the fast intrinsics are accurate to
+// ~1e-6 relative for |t| <= 20 and the result is divided by beta (absolute error < 1e-8).
 __device__ __forceinline__ float softplus100(float z) {
   const float t = z * kBeta;
-  return t > kThreshold ? z : log1pf(expf(t)) / kBeta;     // torch: (x*beta > threshold) ? x : log1p(exp(x*beta)) / beta
+  if (t > kThreshold) return z;
+  const float e = __expf(t);
+  const float l = e < 2.44140625e-4f ? e * (1.f - 0.5f * e) : __logf(1.f + e);     // log1p(e); 2^-12: e^3/3 < 5e-12
+  return l * (1.f / kBeta);
 }
 // d softplus / dz from the OUTPUT y = softplus(z): sigmoid(beta z) = 1 - exp(-beta y)  (exactly 1 - e^-20.. in the linear
 // branch, where torch's backward returns 1: the difference is < 2.1e-9)
-__device__ __forceinline__ float softplus100_grad_from_output(float y) { return 1.f - expf(-kBeta * y); }
+__device__ __forceinline__ float softplus100_grad_from_output(float y) { return 1.f - __expf(-kBeta * y); }
 
 struct StageBuffers {       // byte offsets inside the dynamic shared memory of one stage
   uint32_t a_hi, a_lo, b_hi, b_lo, bytes;
@@ -151,37 +173,52 @@ __host__ __device__ inline StageBuffers stage_layout(int rows_b) {
   return s;
 }
 
-// The MMA warp: waits for a filled stage, issues the 3 x 4 instructions of the slice, commits the stage back.
-__device__ __forceinline__ void mma_warp_loop(uint8_t* smem, const StageBuffers& sl, uint64_t* full, uint64_t* empty,
-                                              uint64_t* done, uint32_t tmem_d, int n, int64_t n_slices) {
-  const uint32_t idesc = instr_desc(kTileM, n);
-  const unsigned lane = threadIdx.x & 31u;
-  for (int64_t it = 0; it < n_slices; ++it) {
-    const int s = (int)(it % kStages);
-    const uint32_t parity = (uint32_t)((it / kStages) & 1);
-    mbar_wait(full + s, parity);
-    tc_fence_after();
-    if (lane == 0) {
-      const uint32_t base = smem_u32(smem + (size_t)s * sl.bytes);
-      const uint64_t dah = smem_desc(base + sl.a_hi), dal = smem_desc(base + sl.a_lo);
-      const uint64_t dbh = smem_desc(base + sl.b_hi), dbl = smem_desc(base + sl.b_lo);
+// The 3 x 4 instructions of one 32-wide slice: lo.hi + hi.lo + hi.hi (small terms first), K = 8 per instruction.
+__device__ __forceinline__ void issue_slice(uint32_t base, const StageBuffers& sl, uint32_t tmem_d, uint32_t idesc, bool first) {
+  const uint64_t dah = smem_desc(base + sl.a_hi), dal = smem_desc(base + sl.a_lo);
+  const uint64_t dbh = smem_desc(base + sl.b_hi), dbl = smem_desc(base + sl.b_lo);
 #pragma unroll
-      for (int ks = 0; ks < kSliceK / 8; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * 2);     // 8 TF32 values = 32 bytes = 2 units of the start-address field
-        umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-        umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-        umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
-      }
-      umma_commit(empty + s);                         // the stage may be refilled once these have read it
-      if (it == n_slices - 1) umma_commit(done);      // ... and the accumulator is complete
+  for (int ks = 0; ks < kSliceK / 8; ++ks) {
+    const uint64_t adv = (uint64_t)(ks * 2);     // 8 TF32 values = 32 bytes = 2 units of the start-address field
+    umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (!first || ks > 0) ? 1u : 0u);
+    umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+    umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+  }
+}
+
+// Weight operand in its shared-memory image: for every 32-column slice s of B (n_pad rows x k_pad columns, zero outside
+// the valid part) a block of n_pad x 128 bytes of hi values followed by the same of lo values, both swizzled.
+//   B[n][k] = transpose ? w[(row0 + k) ldw + col0 + n] : w[(row0 + n) ldw + col0 + k],  n < n_valid, k < k_valid
+struct PackArgs {
+  const float* w; int64_t ldw;
+  float* out;
+  int n_valid, k_valid, transpose, row0, col0, n_pad, k_pad;
+};
+__global__ void __launch_bounds__(256) mlp_pack_weight_kernel(PackArgs g) {
+  const int chunks = g.k_pad / 4;                      // 16-byte chunks per row of B
+  const int64_t total = (int64_t)g.n_pad * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / chunks), ch = (int)(i % chunks);
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = 4 * ch + u;
+      x[u] = 0.f;
+      if (n < g.n_valid && k < g.k_valid)
+        x[u] = g.transpose ? g.w[(int64_t)(g.row0 + k) * g.ldw + g.col0 + n] : g.w[(int64_t)(g.row0 + n) * g.ldw + g.col0 + k];
     }
-    __syncwarp();
+    const float4 h = make_float4(tf32_hi(x[0]), tf32_hi(x[1]), tf32_hi(x[2]), tf32_hi(x[3]));
+    const float4 l = make_float4(x[0] - h.x, x[1] - h.y, x[2] - h.z, x[3] - h.w);
+    const int s = ch / 8, c = ch % 8;
+    uint8_t* blk = reinterpret_cast<uint8_t*>(g.out) + (size_t)s * 2 * g.n_pad * 128;
+    *reinterpret_cast<float4*>(blk + swz(n, c)) = h;
+    *reinterpret_cast<float4*>(blk + (size_t)g.n_pad * 128 + swz(n, c)) = l;
   }
 }
 
 struct LinearArgs {
   const float* a; int64_t lda;
-  const float* w; int64_t ldw;
+  const float* wp;           // packed weight image (mlp_pack_weight_kernel)
   const float* bias;
   const float* y; int64_t ldy;
   float* c; int64_t ldc;
@@ -190,18 +227,19 @@ struct LinearArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- c = f(a w^T + bias)
-__global__ void __launch_bounds__(kThreads, 1) mlp_linear_kernel(LinearArgs g) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_linear_kernel(LinearArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t s_full[kStages], s_empty[kStages], s_done;
+  __shared__ uint64_t s_full, s_empty, s_done;
   __shared__ uint32_t s_tmem;
   const StageBuffers sl = stage_layout(g.n);
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const int64_t row0 = (int64_t)blockIdx.x * kTileM;
-  const int64_t n_slices = g.k / kSliceK;
-  const uint32_t tmem_cols = g.n <= 32 ? 32u : (g.n <= 64 ? 64u : (g.n <= 128 ? 128u : 256u));
+  const int n_slices = g.k / kSliceK;
+  const uint32_t tmem_cols = g.n <= 64 ? 64u : (g.n <= 128 ? 128u : 256u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, kProducerWarps * 32); mbar_init(s_empty + s, 1); }
+    mbar_init(&s_full, kProducerWarps * 32 + 1);     // the producers + the thread that announces the bulk copy
+    mbar_init(&s_empty, 1);
     mbar_init(&s_done, 1);
     fence_barrier_init();
   }
@@ -212,47 +250,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_linear_kernel(LinearArgs g) {
   const uint32_t tmem_d = s_tmem;
 
   if (warp < kProducerWarps) {
-    // ---- producers: thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 i ----
+    // ---- producers: thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 i of the activation slice ----
     const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-    for (int64_t it = 0; it < n_slices; ++it) {
-      const int s = (int)(it % kStages);
-      mbar_wait(s_empty + s, (uint32_t)(((it / kStages) & 1) ^ 1));     // (a fresh barrier passes the first round)
-      uint8_t* st = smem + (size_t)s * sl.bytes;
-      const int64_t kcol = it * kSliceK + 4 * c;
-      float4 va[kTileM / 32];
+    const float* src[kTileM / 32];
 #pragma unroll
-      for (int i = 0; i < kTileM / 32; ++i) {
-        const int64_t r = row0 + r0 + 32 * i;
-        va[i] = r < g.m ? __ldg(reinterpret_cast<const float4*>(g.a + r * g.lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      // the weight rows, eight at a time (N <= 256 rows: up to 8 rounds)
-      for (int j0 = 0; j0 < g.n; j0 += 128) {
-        float4 vb[4];
+    for (int i = 0; i < kTileM / 32; ++i) {
+      const int64_t r = row0 + r0 + 32 * i;
+      src[i] = r < g.m ? g.a + r * g.lda + 4 * c : nullptr;
+    }
+    float4 va[kTileM / 32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = j0 + r0 + 32 * i;
-          vb[i] = r < g.n ? __ldg(reinterpret_cast<const float4*>(g.w + (int64_t)r * g.ldw + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = j0 + r0 + 32 * i;
-          if (r >= g.n) continue;
-          const float4 h = make_float4(tf32_hi(vb[i].x), tf32_hi(vb[i].y), tf32_hi(vb[i].z), tf32_hi(vb[i].w));
-          const float4 l = make_float4(vb[i].x - h.x, vb[i].y - h.y, vb[i].z - h.z, vb[i].w - h.w);
-          *reinterpret_cast<float4*>(st + sl.b_hi + swz(r, c)) = h;
-          *reinterpret_cast<float4*>(st + sl.b_lo + swz(r, c)) = l;
-        }
-      }
+    for (int i = 0; i < kTileM / 32; ++i) va[i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < n_slices; ++it) {
+      mbar_wait(&s_empty, (uint32_t)((it & 1) ^ 1));      // the MMAs of slice it - 1 have read the stage (fresh: passes)
 #pragma unroll
       for (int i = 0; i < kTileM / 32; ++i) {
         const int r = r0 + 32 * i;
         const float4 h = make_float4(tf32_hi(va[i].x), tf32_hi(va[i].y), tf32_hi(va[i].z), tf32_hi(va[i].w));
         const float4 l = make_float4(va[i].x - h.x, va[i].y - h.y, va[i].z - h.z, va[i].w - h.w);
-        *reinterpret_cast<float4*>(st + sl.a_hi + swz(r, c)) = h;
-        *reinterpret_cast<float4*>(st + sl.a_lo + swz(r, c)) = l;
+        *reinterpret_cast<float4*>(smem + sl.a_hi + swz(r, c)) = h;
+        *reinterpret_cast<float4*>(smem + sl.a_lo + swz(r, c)) = l;
       }
       fence_proxy_async();
-      mbar_arrive(s_full + s);
+      mbar_arrive(&s_full);
+      if (it + 1 < n_slices) {                            // in flight while the tensor core works on slice `it`
+#pragma unroll
+        for (int i = 0; i < kTileM / 32; ++i)
+          if (src[i]) va[i] = __ldg(reinterpret_cast<const float4*>(src[i] + (it + 1) * kSliceK));
+      }
     }
     // ---- epilogue: warp w reads lanes [32 (w & 3), +32) = rows of the tile, column half (w >> 2) ----
     mbar_wait(&s_done, 0u);
@@ -262,12 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_linear_kernel(LinearArgs g) {
     const int ncol_half = g.n / 2;                      // N % 64 == 0: each half is a whole number of 32-column loads
     for (int c0 = half * ncol_half; c0 < (half + 1) * ncol_half; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);     // (reads past N stay inside the allocation)
-      const int ncols = min(32, (half + 1) * ncol_half - c0);
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
       if (r < g.m) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          if (j >= ncols) break;
           float o[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -286,7 +309,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_linear_kernel(LinearArgs g) {
     }
     tc_fence_before();
   } else {
-    mma_warp_loop(smem, sl, s_full, s_empty, &s_done, tmem_d, g.n, n_slices);
+    // ---- one thread: announces and issues the bulk copy of the weight slice, then the MMAs of the slice ----
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(kTileM, g.n);
+      const uint32_t wbytes = (uint32_t)(2 * g.n * 128);
+      const uint32_t base = smem_u32(smem);
+      for (int it = 0; it < n_slices; ++it) {
+        mbar_wait(&s_empty, (uint32_t)((it & 1) ^ 1));
+        mbar_expect_tx(&s_full, wbytes);
+        bulk_copy_g2s(smem + sl.b_hi, reinterpret_cast<const uint8_t*>(g.wp) + (size_t)it * wbytes, wbytes, &s_full);
+        mbar_wait(&s_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        issue_slice(base, sl, tmem_d, idesc, it == 0);
+        umma_commit(&s_empty);                        // the stage may be refilled once these have read it
+        if (it == n_slices - 1) umma_commit(&s_done); // ... and the accumulator is complete
+      }
+    }
+    __syncwarp();
     tc_fence_before();
   }
   __syncthreads();
@@ -306,10 +345,13 @@ struct WgradArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- dw += dz^T a
-// grid = (point ranges, N / 128).  Accumulator: 128 columns of dz (lanes) x K columns of a.
-__global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_kernel(WgradArgs g) {
+// grid = (point ranges, N / 128).  Accumulator: 128 columns of dz (lanes) x K columns of a.  Both operands are
+// activations: the producers transpose 32-point slices on their way into shared memory -- lane = point of the slice
+// (the k index of the MMA), warp w takes the 16-byte column groups w, w + 8, ... of that point's row, and the four values
+// of a group go to four tile rows at k = lane (32 lanes -> 32 distinct words of one 128-byte row: no bank conflict).
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t s_full[kStages], s_empty[kStages], s_done;
+  __shared__ uint64_t s_full, s_empty, s_done;
   __shared__ uint32_t s_tmem;
   const StageBuffers sl = stage_layout(g.k);
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -317,11 +359,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_kernel(WgradArgs g) {
   const int64_t p_end = min(g.m, p_begin + g.points_per_cta);
   const int ch0 = blockIdx.y * kTileM;
   const int64_t n_slices = p_end > p_begin ? (p_end - p_begin + kSliceK - 1) / kSliceK : 0;
-  const uint32_t tmem_cols = g.k <= 32 ? 32u : (g.k <= 64 ? 64u : (g.k <= 128 ? 128u : 256u));
+  const uint32_t tmem_cols = g.k <= 64 ? 64u : (g.k <= 128 ? 128u : 256u);
   if (n_slices == 0) return;     // (whole CTA)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, kProducerWarps * 32); mbar_init(s_empty + s, 1); }
+    mbar_init(&s_full, kProducerWarps * 32);
+    mbar_init(&s_empty, 1);
     mbar_init(&s_done, 1);
     fence_barrier_init();
   }
@@ -332,43 +375,40 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_kernel(WgradArgs g) {
   const uint32_t tmem_d = s_tmem;
 
   if (warp < kProducerWarps) {
-    // ---- producers, transposing: lane = point of the slice (k index), warp w takes 16-byte column groups w, w + 8, ...
-    // of that point's row; the four values of a group go to four tile rows (rows = columns of dz / a) at k = lane ----
     float bsum[4][4];              // bias gradient: this thread's share of sum_m dz[m, ch] for its 16 columns of dz
 #pragma unroll
     for (int i = 0; i < 4; ++i) bsum[i][0] = bsum[i][1] = bsum[i][2] = bsum[i][3] = 0.f;
     const int kc = (int)lane >> 2, kw = ((int)lane & 3) * 4;       // 16-byte chunk and byte offset of k = lane in a row
-    for (int64_t it = 0; it < n_slices; ++it) {
-      const int s = (int)(it % kStages);
-      mbar_wait(s_empty + s, (uint32_t)(((it / kStages) & 1) ^ 1));
-      uint8_t* st = smem + (size_t)s * sl.bytes;
+    const int a_groups = g.k / 4;                                   // 16-byte column groups of a row of a: 16 .. 64
+    float4 vz[4], va[8];
+    auto load_slice = [&](int64_t it) {
       const int64_t p = p_begin + it * kSliceK + lane;
       const bool live = p < p_end;
-      float4 vz[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)      // 128 columns of dz = 32 groups of 4: groups warp + 8 i
         vz[i] = live ? __ldg(reinterpret_cast<const float4*>(g.dz + p * g.ldz + ch0 + 4 * ((int)warp + 8 * i)))
                      : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int f0 = 0; f0 < g.k / 4; f0 += 32) {       // K columns of a = K / 4 groups: groups f0 + warp + 8 i
-        float4 va[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int f = f0 + (int)warp + 8 * i;
-          va[i] = (live && 4 * f < g.k) ? __ldg(reinterpret_cast<const float4*>(g.a + p * g.lda + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int i = 0; i < 8; ++i) {    // K columns of a: groups warp + 8 i
+        const int f = (int)warp + 8 * i;
+        va[i] = (live && f < a_groups) ? __ldg(reinterpret_cast<const float4*>(g.a + p * g.lda + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_slice(0);
+    for (int64_t it = 0; it < n_slices; ++it) {
+      mbar_wait(&s_empty, (uint32_t)((it & 1) ^ 1));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int f = f0 + (int)warp + 8 * i;
-          if (4 * f >= g.k) continue;
-          const float x[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+      for (int i = 0; i < 8; ++i) {
+        const int f = (int)warp + 8 * i;
+        if (f >= a_groups) continue;
+        const float x[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = 4 * f + u;
-            const float h = tf32_hi(x[u]);
-            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
-            *reinterpret_cast<float*>(st + sl.b_hi + off) = h;
-            *reinterpret_cast<float*>(st + sl.b_lo + off) = x[u] - h;
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int r = 4 * f + u;
+          const float h = tf32_hi(x[u]);
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
+          *reinterpret_cast<float*>(smem + sl.b_hi + off) = h;
+          *reinterpret_cast<float*>(smem + sl.b_lo + off) = x[u] - h;
         }
       }
 #pragma unroll
@@ -380,13 +420,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_kernel(WgradArgs g) {
           const int r = 4 * f + u;
           const float h = tf32_hi(x[u]);
           const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
-          *reinterpret_cast<float*>(st + sl.a_hi + off) = h;
-          *reinterpret_cast<float*>(st + sl.a_lo + off) = x[u] - h;
+          *reinterpret_cast<float*>(smem + sl.a_hi + off) = h;
+          *reinterpret_cast<float*>(smem + sl.a_lo + off) = x[u] - h;
           bsum[i][u] += x[u];
         }
       }
       fence_proxy_async();
-      mbar_arrive(s_full + s);
+      mbar_arrive(&s_full);
+      if (it + 1 < n_slices) load_slice(it + 1);       // in flight while the tensor core works on slice `it`
     }
     if (g.db != nullptr) {
 #pragma unroll
@@ -408,14 +449,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_kernel(WgradArgs g) {
     for (int c0 = half * ncol_half; c0 < (half + 1) * ncol_half; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
-      const int ncols = min(32, (half + 1) * ncol_half - c0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) atomicAdd(g.dw + (int64_t)row * g.lddw + c0 + j, v[j]);
+      for (int j = 0; j < 32; ++j) atomicAdd(g.dw + (int64_t)row * g.lddw + c0 + j, v[j]);
     }
     tc_fence_before();
   } else {
-    mma_warp_loop(smem, sl, s_full, s_empty, &s_done, tmem_d, g.k, n_slices);
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(kTileM, g.k);
+      const uint32_t base = smem_u32(smem);
+      for (int64_t it = 0; it < n_slices; ++it) {
+        mbar_wait(&s_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        issue_slice(base, sl, tmem_d, idesc, it == 0);
+        umma_commit(&s_empty);
+        if (it == n_slices - 1) umma_commit(&s_done);
+      }
+    }
+    __syncwarp();
     tc_fence_before();
   }
   __syncthreads();
@@ -569,24 +619,41 @@ extern "C" int d3h_mlp_embed_backward(const float* x, int64_t m, int32_t n_freq,
   return finish_launch("d3h_mlp_embed_backward");
 }
 
-extern "C" int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, int64_t ldw, int32_t n,
+extern "C" int64_t d3h_mlp_packed_weight_bytes(int32_t n_pad, int32_t k_pad) { return (int64_t)8 * n_pad * k_pad; }
+
+extern "C" int d3h_mlp_pack_weight(const float* w, int64_t ldw, int32_t n_valid, int32_t k_valid, int32_t transpose,
+                                   int32_t row0, int32_t col0, int32_t n_pad, int32_t k_pad, float* packed,
+                                   d3h_stream_t stream) {
+  if (!w || !packed || n_valid < 0 || k_valid < 0 || n_valid > n_pad || k_valid > k_pad || n_pad < 64 || n_pad > 256 ||
+      (n_pad % 64) || k_pad <= 0 || (k_pad % kSliceK) || row0 < 0 || col0 < 0 || ldw <= 0 || !aligned16(packed)) {
+    set_error("d3h_mlp_pack_weight: bad argument (n_pad in {64, 128, 192, 256}, k_pad %% 32 == 0, valid sizes within the padded "
+              "ones, packed 16-byte aligned)");
+    return D3H_E_BADARG;
+  }
+  PackArgs g{w, ldw, packed, n_valid, k_valid, transpose ? 1 : 0, row0, col0, n_pad, k_pad};
+  const int64_t total = (int64_t)n_pad * (k_pad / 4);
+  mlp_pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g);
+  return finish_launch("d3h_mlp_pack_weight");
+}
+
+extern "C" int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k, const float* w_packed, int32_t n,
                               const float* bias, int32_t mode, const float* y, int64_t ldy, float* c, int64_t ldc,
                               d3h_stream_t stream) {
-  if (m < 0 || k <= 0 || (k % kSliceK) || n < 64 || n > 256 || (n % 64) || mode < 0 || mode > 2 || lda < k || ldw < k ||
-      ldc < n || (lda % 4) || (ldw % 4) || (ldc % 4) || !w || (m > 0 && (!a || !c)) || !aligned16(a) || !aligned16(w) ||
+  if (m < 0 || k <= 0 || (k % kSliceK) || n < 64 || n > 256 || (n % 64) || mode < 0 || mode > 2 || lda < k ||
+      ldc < n || (lda % 4) || (ldc % 4) || !w_packed || (m > 0 && (!a || !c)) || !aligned16(a) || !aligned16(w_packed) ||
       !aligned16(c) || (mode == 2 && (!y || ldy < n || (ldy % 4) || !aligned16(y)))) {
     set_error("d3h_mlp_linear: bad argument (K %% 32 == 0, N in {64, 128, 192, 256}, leading dimensions multiples of 4 "
               "and >= the row length, 16-byte aligned pointers, mode 2 needs y)");
     return D3H_E_BADARG;
   }
   if (m == 0) return D3H_OK;
-  const size_t smem = (size_t)kStages * stage_layout(n).bytes;
+  const size_t smem = stage_layout(n).bytes;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(mlp_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * stage_layout(256).bytes));
+    cudaFuncSetAttribute(mlp_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_layout(256).bytes);
     attr = true;
   }
-  LinearArgs g{a, lda, w, ldw, bias, y, ldy, c, ldc, m, k, n, mode};
+  LinearArgs g{a, lda, w_packed, bias, y, ldy, c, ldc, m, k, n, mode};
   mlp_linear_kernel<<<(unsigned)((m + kTileM - 1) / kTileM), kThreads, smem, (cudaStream_t)stream>>>(g);
   return finish_launch("d3h_mlp_linear");
 }
@@ -600,14 +667,14 @@ extern "C" int d3h_mlp_wgrad(const float* dz, int64_t ldz, const float* a, int64
     return D3H_E_BADARG;
   }
   if (m == 0) return D3H_OK;
-  const size_t smem = (size_t)kStages * stage_layout(k).bytes;
+  const size_t smem = stage_layout(k).bytes;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * stage_layout(256).bytes));
+    cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_layout(256).bytes);
     attr = true;
   }
-  // one CTA per SM and column tile: every CTA walks a contiguous range of points (a multiple of the 32-point slice)
-  int64_t ranges = 148 / (n / kTileM);
+  // two CTAs per SM and column tile: every CTA walks a contiguous range of points (a multiple of the 32-point slice)
+  int64_t ranges = (int64_t)kCtasPerSm * 148 / (n / kTileM);
   int64_t per = ((m + ranges - 1) / ranges + kSliceK - 1) / kSliceK * kSliceK;
   ranges = (m + per - 1) / per;
   WgradArgs g{dz, ldz, a, lda, dw, lddw, db, m, per, n, k};

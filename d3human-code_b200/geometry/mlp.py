@@ -45,6 +45,16 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _pack(L, w, n_valid, k_valid, transpose, col0, n_pad, k_pad, st):
+    """nn.Linear.weight (or a transposed column slice of it) -> the kernel's operand image (d3h_mlp_pack_weight)."""
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    out = torch.empty(2 * n_pad * k_pad, dtype=torch.float32, device=w.device)
+    _cabi.check(L.d3h_mlp_pack_weight(w.data_ptr(), w.stride(0), n_valid, k_valid, int(transpose), 0, col0, n_pad, k_pad,
+                                      out.data_ptr(), st), "d3h_mlp_pack_weight")
+    return out
+
+
 class _MLPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan: _Plan, x, *wb):
@@ -62,20 +72,13 @@ class _MLPFn(torch.autograd.Function):
             acts: List[torch.Tensor] = []
             a_ptr, lda, k = emb.data_ptr(), ep, ep
             for li in range(plan.n_hidden + 1):
-                w = ws[li]
-                if li == 0:
-                    wp = torch.zeros((dh, ep), dtype=f32, device=dev)
-                    wp[:, :e] = w
-                elif plan.wide[li]:
-                    wp = torch.zeros((dh, dh + ep), dtype=f32, device=dev)
-                    wp[:, :dh + e] = w
-                else:
-                    wp = w.contiguous()
+                kv = e if li == 0 else (dh + e if plan.wide[li] else dh)
+                wp = _pack(L, ws[li], dh, kv, False, 0, dh, k, st)
                 out = torch.empty((m, plan.ld_out[li]), dtype=f32, device=dev)
                 if plan.ld_out[li] != dh:      # the next layer reads cat([x, emb]) (mlp.py:41): the encoding sits behind
                     _cabi.check(L.d3h_mlp_embed(x.data_ptr(), m, plan.n_freq, out.data_ptr() + 4 * dh, plan.ld_out[li], ep, st),
                                 "d3h_mlp_embed")
-                _cabi.check(L.d3h_mlp_linear(a_ptr, lda, m, k, wp.data_ptr(), wp.shape[1], dh, bs[li].data_ptr(), 1, None, 0,
+                _cabi.check(L.d3h_mlp_linear(a_ptr, lda, m, k, wp.data_ptr(), dh, bs[li].data_ptr(), 1, None, 0,
                                              out.data_ptr(), plan.ld_out[li], st), "d3h_mlp_linear")
                 acts.append(out)
                 a_ptr, lda, k = out.data_ptr(), plan.ld_out[li], plan.ld_out[li]
@@ -85,7 +88,7 @@ class _MLPFn(torch.autograd.Function):
                         "d3h_mlp_head")
         ctx.plan = plan
         ctx.save_for_backward(x, emb, *acts, *ws)
-        _MLPFn.launches += 3 + 2 * (plan.n_hidden + 1) - 1 + len(plan.skip)
+        _MLPFn.launches += 2 + 2 * (plan.n_hidden + 1) + len(plan.skip)
         return y
 
     @staticmethod
@@ -134,15 +137,14 @@ class _MLPFn(torch.autograd.Function):
                 w = ws[li]
                 if need_x and (li == 0 or plan.wide[li]):
                     # the encoding's share: dz . W[:, -e:]  ->  (M, e_pad), added to g_emb
-                    wt = torch.zeros((ep, dh), dtype=f32, device=dev)
-                    wt[:e] = (w if li == 0 else w[:, dh:dh + e]).t()
-                    _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), dh, ep, None, 0, None, 0,
+                    wt = _pack(L, w, e, dh, True, 0 if li == 0 else dh, ep, dh, st)
+                    _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), ep, None, 0, None, 0,
                                                  tmp_e.data_ptr(), ep, st), "d3h_mlp_linear")
                     g_emb += tmp_e
                 if li > 0:
-                    wt = w[:, :dh].t().contiguous()
+                    wt = _pack(L, w, dh, dh, True, 0, dh, dh, st)
                     prev = acts[li - 1]
-                    _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), dh, dh, None, 2, prev.data_ptr(),
+                    _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), dh, None, 2, prev.data_ptr(),
                                                  plan.ld_out[li - 1], dz2.data_ptr(), dh, st), "d3h_mlp_linear")
                     dz, dz2 = dz2, dz
             gx = None
@@ -154,7 +156,7 @@ class _MLPFn(torch.autograd.Function):
         for li in range(1, nh + 1):
             gw_out.append(gws[li][:, :dh + e] if plan.wide[li] else gws[li])
         gw_out.append(gws[-1])
-        _MLPFn.launches += 2 + 3 * (nh + 1) + 2 * len(plan.skip)
+        _MLPFn.launches += 2 + 3 * (nh + 1) + nh + 3 * len(plan.skip) + (2 if need_x else 0)
         return (None, gx) + tuple(gw_out) + tuple(gbs)
 
 

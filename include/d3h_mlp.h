@@ -40,16 +40,26 @@ int d3h_mlp_embed(const float* x, int64_t m, int32_t n_freq, float* out, int64_t
 int d3h_mlp_embed_backward(const float* x, int64_t m, int32_t n_freq, const float* g_emb, int64_t ld, float* g_x,
                            int32_t accumulate, d3h_stream_t stream);
 
+/* The weight operand of d3h_mlp_linear in the layout the kernel consumes: B (n_pad x k_pad, zero outside the valid
+ * part) split into hi / lo and stored as the shared-memory image of every 32-column slice, so that the kernel fetches a
+ * slice with one bulk copy.  Run once per call and weight (the weights change every optimiser step; 8 n_pad k_pad bytes):
+ *     B[n][k] = transpose ? w[(row0 + k) ldw + col0 + n] : w[(row0 + n) ldw + col0 + k]     for n < n_valid, k < k_valid
+ * transpose = 0 packs nn.Linear.weight (rows = outputs) for the forward pass, transpose = 1 its transpose (or a column
+ * slice of it) for the input gradient.  n_pad in {64, 128, 192, 256}, k_pad % 32 == 0, `packed` 16-byte aligned. */
+int64_t d3h_mlp_packed_weight_bytes(int32_t n_pad, int32_t k_pad);
+int d3h_mlp_pack_weight(const float* w, int64_t ldw, int32_t n_valid, int32_t k_valid, int32_t transpose, int32_t row0,
+                        int32_t col0, int32_t n_pad, int32_t k_pad, float* packed, d3h_stream_t stream);
+
 /* One nn.Linear (+ activation) of MLP.net on the tensor cores:
- *     c[m, n] = f( sum_k a[m, k] w[n, k] + bias[n] )
- *   a (M, lda), w (N, ldw) = nn.Linear.weight (or a transposed / sliced copy for the backward pass), c (M, ldc)
- *   K % 32 == 0 (zero-pad the input columns), N in {64, 128, 192, 256}, all pointers 16-byte aligned, lda / ldw / ldc /
- *   ldy multiples of 4.  bias may be NULL.
+ *     c[m, n] = f( sum_k a[m, k] B[n, k] + bias[n] )
+ *   a (M, lda), B = `w_packed` (d3h_mlp_pack_weight with n_pad = N, k_pad = K), c (M, ldc)
+ *   K % 32 == 0 (zero-pad the input columns), N in {64, 128, 192, 256}, all pointers 16-byte aligned, lda / ldc / ldy
+ *   multiples of 4.  bias may be NULL.
  *   mode 0: f = identity
  *   mode 1: f = Softplus(beta = 100, threshold = 20)                      (geometry/mlp.py:16,27)
- *   mode 2: c = (a w^T) * softplus'(z) with softplus'(z) = 1 - exp(-100 y) recovered from the layer's saved OUTPUT
+ *   mode 2: c = (a B^T) * softplus'(z) with softplus'(z) = 1 - exp(-100 y) recovered from the layer's saved OUTPUT
  *           y = softplus(z) given in `y` (M, ldy) -- the backward pass through the activation of the previous layer. */
-int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, int64_t ldw, int32_t n,
+int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k, const float* w_packed, int32_t n,
                    const float* bias, int32_t mode, const float* y, int64_t ldy, float* c, int64_t ldc,
                    d3h_stream_t stream);
 

@@ -54,7 +54,10 @@ def test_linear_tensor_core_gemm_matches_float64(dev, m, k, n, mode):
     ta, tw, tb, ty = (torch.tensor(t, device=dev) for t in (a, w, bias, y))
     tc = torch.full((m, ldc), 7.0, device=dev)
     L = _cabi.lib()
-    _cabi.check(L.d3h_mlp_linear(ta.data_ptr(), lda, m, k, tw.data_ptr(), ldw, n, tb.data_ptr() if mode != 2 else None, mode,
+    assert L.d3h_mlp_packed_weight_bytes(n, k) == 8 * n * k
+    wp = torch.empty(2 * n * k, device=dev)
+    _cabi.check(L.d3h_mlp_pack_weight(tw.data_ptr(), ldw, n, k, 0, 0, 0, n, k, wp.data_ptr(), _st(dev)), "d3h_mlp_pack_weight")
+    _cabi.check(L.d3h_mlp_linear(ta.data_ptr(), lda, m, k, wp.data_ptr(), n, tb.data_ptr() if mode != 2 else None, mode,
                                  ty.data_ptr() if mode == 2 else None, ldy if mode == 2 else 0, tc.data_ptr(), ldc, _st(dev)),
                 "d3h_mlp_linear")
     z = a[:, :k].astype(np.float64) @ w[:, :k].astype(np.float64).T
@@ -194,3 +197,22 @@ def test_mlp_state_dict_is_the_reference_layout_and_feeds_the_extraction(dev):
     assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
     with pytest.raises(NotImplementedError):
         MLP(use_float16=True).to(dev)(tp)
+
+
+def test_packed_weight_transposed_slice_with_padding(dev):
+    """d3h_mlp_pack_weight with transpose / column offset / zero padding (the operands of the input-gradient GEMMs):
+    c = a B^T with B[n][k] = w[k][col0 + n] for n < 39, zero up to 64."""
+    rng = np.random.default_rng(5)
+    m, dh, e, ep = 333, 256, 39, 64
+    w = rng.standard_normal((dh, dh + e)).astype(np.float32)
+    a = rng.standard_normal((m, dh)).astype(np.float32)
+    tw, ta = torch.tensor(w, device=dev), torch.tensor(a, device=dev)
+    L = _cabi.lib()
+    wp = torch.empty(2 * ep * dh, device=dev)
+    _cabi.check(L.d3h_mlp_pack_weight(tw.data_ptr(), dh + e, e, dh, 1, 0, dh, ep, dh, wp.data_ptr(), _st(dev)), "d3h_mlp_pack_weight")
+    out = torch.empty((m, ep), device=dev)
+    _cabi.check(L.d3h_mlp_linear(ta.data_ptr(), dh, m, dh, wp.data_ptr(), ep, None, 0, None, 0, out.data_ptr(), ep, _st(dev)),
+                "d3h_mlp_linear")
+    want = a.astype(np.float64) @ w[:, dh:].astype(np.float64)
+    got = out.cpu().numpy()
+    assert _rel(got[:, :e], want) < GEMM_TOL and (got[:, e:] == 0).all()
