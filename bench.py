@@ -68,6 +68,7 @@ def parse():
                     help="batch results as padded (B,cap,..) tensors (O(1) host work per batch) or as per-frame tuples")
     ap.add_argument("--no-cold", action="store_true", help="skip the L2-flushed single-call leg")
     ap.add_argument("--no-split-pair", action="store_true", help="skip the configs[2] cloth/body pair leg")
+    ap.add_argument("--no-sdf-query", action="store_true", help="skip the SDF-network leg (SURVEY 8f row 3)")
     return ap.parse_args()
 
 
@@ -873,6 +874,20 @@ def main():
         except Exception as exc:  # noqa: BLE001
             split_pair = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- the stage in FRONT of the extraction: the SDF network on all N grid vertices in batches of 100000
+    # (hmsdf.py:187, 434-444), tcgen05 / 3xTF32 kernels of this package against the same module in plain PyTorch fp32.
+    # Never fatal.
+    sdf_query = None
+    if world == 1 and not args.no_sdf_query and dev_type == "cuda":
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_mlp_bench", os.path.join(ROOT, "profiles", "mlp_bench.py"))
+            mq = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mq)
+            sdf_query = mq.measure(points=N, reps=3, dev=dev, tf32_leg=False)
+        except Exception as exc:  # noqa: BLE001
+            sdf_query = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- the reference's way on the same GPU: the path as plain PyTorch ops + autograd (oracle/gshell_torch.py, a port
     # pinned against the reference's golden vectors; the reference tree itself is not on this box).  SURVEY 8(d).  Never fatal.
     torch_baseline = None
@@ -915,7 +930,7 @@ def main():
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "ranks": ranks_info, "device_trace": dev_trace, "single_call": single, "cold": cold,
             "gpu_launches": int(launches_timed), "kernels": kern, "split_pair": split_pair,
-            "mesh_stage": mesh_stage, "torch_gpu_baseline": torch_baseline, "clocks": sampler.result()}
+            "mesh_stage": mesh_stage, "sdf_query": sdf_query, "torch_gpu_baseline": torch_baseline, "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_gather_rows", "d3h_classify_range", "d3h_extract_from_records",
     "d3h_mesh_edges_workspace_bytes", "d3h_mesh_edges", "d3h_mesh_wait_counts", "d3h_mesh_normals_forward",
     "d3h_mesh_normals_backward",
-    "d3h_mlp_embed", "d3h_mlp_embed_backward", "d3h_mlp_packed_weight_bytes", "d3h_mlp_pack_weight", "d3h_mlp_linear", "d3h_mlp_wgrad", "d3h_mlp_head", "d3h_mlp_head_backward",
+    "d3h_mlp_embed", "d3h_mlp_embed_backward", "d3h_mlp_packed_weight_bytes", "d3h_mlp_pack_weight", "d3h_mlp_linear", "d3h_mlp_wgrad_workspace_bytes", "d3h_mlp_wgrad", "d3h_mlp_head", "d3h_mlp_head_backward",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
 )
 
@@ -138,24 +138,28 @@ def lib() -> C.CDLL:
     L.d3h_mesh_normals_backward.restype = C.c_int
     L.d3h_mesh_normals_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]
-    # include/d3h_mlp.h
-    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
-    L.d3h_mlp_embed.restype = C.c_int
-    L.d3h_mlp_embed.argtypes = [vp, i64, i32, vp, i64, i32, vp]
-    L.d3h_mlp_embed_backward.restype = C.c_int
-    L.d3h_mlp_embed_backward.argtypes = [vp, i64, i32, vp, i64, vp, i32, vp]
-    L.d3h_mlp_linear.restype = C.c_int
-    L.d3h_mlp_linear.argtypes = [vp, i64, i64, i32, vp, i32, vp, i32, vp, i64, vp, i64, vp]
-    L.d3h_mlp_packed_weight_bytes.restype = C.c_int64
-    L.d3h_mlp_packed_weight_bytes.argtypes = [i32, i32]
-    L.d3h_mlp_pack_weight.restype = C.c_int
-    L.d3h_mlp_pack_weight.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp]
-    L.d3h_mlp_wgrad.restype = C.c_int
-    L.d3h_mlp_wgrad.argtypes = [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp]
-    L.d3h_mlp_head.restype = C.c_int
-    L.d3h_mlp_head.argtypes = [vp, i64, i64, i32, vp, vp, i32, vp, vp]
-    L.d3h_mlp_head_backward.restype = C.c_int
-    L.d3h_mlp_head_backward.argtypes = [vp, i64, i64, i32, vp, i32, vp, vp, i64, vp, vp, vp]
+    # include/d3h_mlp.h (the CPU emulation of tests/emu has no tensor-core stage: its library lacks these symbols; the
+    # real library always exports them, tests/test_cabi.py)
+    if hasattr(L, "d3h_mlp_linear"):
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+        L.d3h_mlp_embed.restype = C.c_int
+        L.d3h_mlp_embed.argtypes = [vp, i64, i32, vp, i64, i32, vp]
+        L.d3h_mlp_embed_backward.restype = C.c_int
+        L.d3h_mlp_embed_backward.argtypes = [vp, i64, i32, vp, i64, vp, i32, vp]
+        L.d3h_mlp_linear.restype = C.c_int
+        L.d3h_mlp_linear.argtypes = [vp, i64, i64, i32, vp, i32, vp, i32, vp, i64, vp, i64, vp]
+        L.d3h_mlp_packed_weight_bytes.restype = C.c_int64
+        L.d3h_mlp_packed_weight_bytes.argtypes = [i32, i32]
+        L.d3h_mlp_pack_weight.restype = C.c_int
+        L.d3h_mlp_pack_weight.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+        L.d3h_mlp_wgrad.restype = C.c_int
+        L.d3h_mlp_wgrad.argtypes = [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp, i64, vp]
+        L.d3h_mlp_wgrad_workspace_bytes.restype = C.c_int64
+        L.d3h_mlp_wgrad_workspace_bytes.argtypes = [i64, i32, i32]
+        L.d3h_mlp_head.restype = C.c_int
+        L.d3h_mlp_head.argtypes = [vp, i64, i64, i32, vp, vp, i32, vp, vp]
+        L.d3h_mlp_head_backward.restype = C.c_int
+        L.d3h_mlp_head_backward.argtypes = [vp, i64, i64, i32, vp, i32, vp, vp, i64, vp, vp, vp]
     L.d3h_profile_enable.restype = C.c_int
     L.d3h_profile_enable.argtypes = [C.c_int]
     L.d3h_profile_kinds.restype = C.c_int

@@ -258,25 +258,34 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_linear_kernel(Linear
       const int64_t r = row0 + r0 + 32 * i;
       src[i] = r < g.m ? g.a + r * g.lda + 4 * c : nullptr;
     }
-    float4 va[kTileM / 32];
+    // two slices of loads in flight: registers va (slice it) and vb (slice it + 1)
+    float4 va[kTileM / 32], vb[kTileM / 32];
+    auto load = [&](float4 (&v)[kTileM / 32], int slice) {
 #pragma unroll
-    for (int i = 0; i < kTileM / 32; ++i) va[i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = 0; it < n_slices; ++it) {
+      for (int i = 0; i < kTileM / 32; ++i)
+        v[i] = (src[i] && slice < n_slices) ? __ldg(reinterpret_cast<const float4*>(src[i] + slice * kSliceK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto publish = [&](const float4 (&v)[kTileM / 32], int it) {
       mbar_wait(&s_empty, (uint32_t)((it & 1) ^ 1));      // the MMAs of slice it - 1 have read the stage (fresh: passes)
 #pragma unroll
       for (int i = 0; i < kTileM / 32; ++i) {
         const int r = r0 + 32 * i;
-        const float4 h = make_float4(tf32_hi(va[i].x), tf32_hi(va[i].y), tf32_hi(va[i].z), tf32_hi(va[i].w));
-        const float4 l = make_float4(va[i].x - h.x, va[i].y - h.y, va[i].z - h.z, va[i].w - h.w);
+        const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+        const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
         *reinterpret_cast<float4*>(smem + sl.a_hi + swz(r, c)) = h;
         *reinterpret_cast<float4*>(smem + sl.a_lo + swz(r, c)) = l;
       }
       fence_proxy_async();
       mbar_arrive(&s_full);
-      if (it + 1 < n_slices) {                            // in flight while the tensor core works on slice `it`
-#pragma unroll
-        for (int i = 0; i < kTileM / 32; ++i)
-          if (src[i]) va[i] = __ldg(reinterpret_cast<const float4*>(src[i] + (it + 1) * kSliceK));
+    };
+    load(va, 0);
+    load(vb, 1);
+    for (int it = 0; it < n_slices; it += 2) {
+      publish(va, it);
+      load(va, it + 2);                                   // in flight while the tensor core works on slices it, it + 1
+      if (it + 1 < n_slices) {
+        publish(vb, it + 1);
+        load(vb, it + 3);
       }
     }
     // ---- epilogue: warp w reads lanes [32 (w & 3), +32) = rows of the tile, column half (w >> 2) ----
@@ -338,14 +347,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_linear_kernel(Linear
 struct WgradArgs {
   const float* dz; int64_t ldz;
   const float* a; int64_t lda;
-  float* dw; int64_t lddw;
-  float* db;
+  float* part;               // (ranges, n, k) partial products, one slab per point range (plain stores, summed afterwards)
+  float* part_b;             // (ranges, n) partial column sums of dz, or nullptr
   int64_t m, points_per_cta;
   int n, k;
 };
 
 // ---------------------------------------------------------------------------------------------- dw += dz^T a
-// grid = (point ranges, N / 128).  Accumulator: 128 columns of dz (lanes) x K columns of a.  Both operands are
+// grid = (point ranges, N / 128).  Accumulator: 128 columns of dz (lanes) x K columns of a; every CTA stores its partial
+// product to its own slab of the workspace (65536 atomics per CTA on one 256 KB matrix were the bottleneck of the first
+// version: 60 of 83 ms of the backward pass) and wgrad_reduce_kernel adds the slabs to dw.  Both operands are
 // activations: the producers transpose 32-point slices on their way into shared memory -- lane = point of the slice
 // (the k index of the MMA), warp w takes the 16-byte column groups w, w + 8, ... of that point's row, and the four values
 // of a group go to four tile rows at k = lane (32 lanes -> 32 distinct words of one 128-byte row: no bank conflict).
@@ -429,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradAr
       mbar_arrive(&s_full);
       if (it + 1 < n_slices) load_slice(it + 1);       // in flight while the tensor core works on slice `it`
     }
-    if (g.db != nullptr) {
+    if (g.part_b != nullptr) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -437,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradAr
           float v = bsum[i][u];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) atomicAdd(g.db + ch0 + 4 * ((int)warp + 8 * i) + u, v);
+          if (lane == 0) g.part_b[(int64_t)blockIdx.x * g.n + ch0 + 4 * ((int)warp + 8 * i) + u] = v;
         }
     }
     // ---- epilogue: lanes of the accumulator = columns of dz, columns = columns of a ----
@@ -446,11 +457,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradAr
     const int q = warp & 3, half = warp >> 2;
     const int row = ch0 + 32 * q + (int)lane;             // row of dw
     const int ncol_half = g.k / 2;
+    float* __restrict__ dst = g.part + ((int64_t)blockIdx.x * g.n + row) * g.k;
     for (int c0 = half * ncol_half; c0 < (half + 1) * ncol_half; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(g.dw + (int64_t)row * g.lddw + c0 + j, v[j]);
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     tc_fence_before();
   } else {
@@ -472,6 +484,26 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradAr
   if (warp == kProducerWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+// dw[r][c] += sum over the point ranges of part[range][r][c]; db likewise.  One thread per output element, the slabs are
+// read coalesced.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_b,
+                                                           int ranges, int n, int k, float* __restrict__ dw, int64_t lddw,
+                                                           float* __restrict__ db) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nk = (int64_t)n * k;
+  if (i < nk) {
+    float s = 0.f;
+    for (int r = 0; r < ranges; ++r) s += part[(int64_t)r * nk + i];
+    const int row = (int)(i / k), col = (int)(i % k);
+    dw[(int64_t)row * lddw + col] += s;
+  } else if (db != nullptr && i < nk + n) {
+    const int c = (int)(i - nk);
+    float s = 0.f;
+    for (int r = 0; r < ranges; ++r) s += part_b[(int64_t)r * n + c];
+    db[c] += s;
   }
 }
 
@@ -658,27 +690,51 @@ extern "C" int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k,
   return finish_launch("d3h_mlp_linear");
 }
 
+// point ranges of a wgrad call: two CTAs per SM and column tile, at least 16 slices (512 points) each
+static void wgrad_ranges(int64_t m, int n, int64_t* ranges, int64_t* per) {
+  int64_t r = (int64_t)kCtasPerSm * 148 / (n / kTileM);
+  int64_t p = ((m + r - 1) / r + kSliceK - 1) / kSliceK * kSliceK;
+  if (p < 16 * kSliceK) p = 16 * kSliceK;
+  *per = p;
+  *ranges = (m + p - 1) / p;
+}
+
+extern "C" int64_t d3h_mlp_wgrad_workspace_bytes(int64_t m, int32_t n, int32_t k) {
+  if (m <= 0 || n <= 0 || (n % kTileM) || k <= 0) return 0;
+  int64_t ranges, per;
+  wgrad_ranges(m, n, &ranges, &per);
+  return ranges * ((int64_t)n * k + n) * 4;
+}
+
 extern "C" int d3h_mlp_wgrad(const float* dz, int64_t ldz, const float* a, int64_t lda, int64_t m, int32_t n, int32_t k,
-                             float* dw, int64_t lddw, float* db, d3h_stream_t stream) {
+                             float* dw, int64_t lddw, float* db, void* workspace, int64_t workspace_bytes,
+                             d3h_stream_t stream) {
   if (m < 0 || n <= 0 || (n % kTileM) || n > 256 || k < 64 || k > 256 || (k % 64) || ldz < n || lda < k || lddw < k ||
-      (ldz % 4) || (lda % 4) || !dw || (m > 0 && (!dz || !a)) || !aligned16(dz) || !aligned16(a)) {
+      (ldz % 4) || (lda % 4) || !dw || (m > 0 && (!dz || !a)) || !aligned16(dz) || !aligned16(a) || !aligned16(workspace)) {
     set_error("d3h_mlp_wgrad: bad argument (N in {128, 256}, K in {64, 128, 192, 256}, leading dimensions multiples "
               "of 4, 16-byte aligned pointers)");
     return D3H_E_BADARG;
   }
   if (m == 0) return D3H_OK;
+  if (!workspace || workspace_bytes < d3h_mlp_wgrad_workspace_bytes(m, n, k)) {
+    set_error("d3h_mlp_wgrad: workspace has %lld bytes, %lld needed", (long long)workspace_bytes,
+              (long long)d3h_mlp_wgrad_workspace_bytes(m, n, k));
+    return D3H_E_SMALLWS;
+  }
   const size_t smem = stage_layout(k).bytes;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_layout(256).bytes);
     attr = true;
   }
-  // two CTAs per SM and column tile: every CTA walks a contiguous range of points (a multiple of the 32-point slice)
-  int64_t ranges = (int64_t)kCtasPerSm * 148 / (n / kTileM);
-  int64_t per = ((m + ranges - 1) / ranges + kSliceK - 1) / kSliceK * kSliceK;
-  ranges = (m + per - 1) / per;
-  WgradArgs g{dz, ldz, a, lda, dw, lddw, db, m, per, n, k};
+  int64_t ranges, per;
+  wgrad_ranges(m, n, &ranges, &per);
+  float* part = reinterpret_cast<float*>(workspace);
+  float* part_b = db ? part + ranges * (int64_t)n * k : nullptr;
+  WgradArgs g{dz, ldz, a, lda, part, part_b, m, per, n, k};
   mlp_wgrad_kernel<<<dim3((unsigned)ranges, (unsigned)(n / kTileM)), kThreads, smem, (cudaStream_t)stream>>>(g);
+  const int64_t total = (int64_t)n * k + (db ? n : 0);
+  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part, part_b, (int)ranges, n, k, dw, lddw, db);
   return finish_launch("d3h_mlp_wgrad");
 }
 

@@ -116,6 +116,8 @@ class _MLPFn(torch.autograd.Function):
             tmp_e = torch.empty((m, ep), dtype=f32, device=dev) if need_x else None
             dz = torch.empty((m, dh), dtype=f32, device=dev)
             dz2 = torch.empty((m, dh), dtype=f32, device=dev) if nh > 0 else None
+            ws_bytes = int(L.d3h_mlp_wgrad_workspace_bytes(m, dh, max(dh, ep)))
+            wsp = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
             last = acts[nh]
             _cabi.check(L.d3h_mlp_head_backward(last.data_ptr(), plan.ld_out[nh], m, dh, ws[-1].contiguous().data_ptr(), plan.d_out,
                                                 gy.data_ptr(), dz.data_ptr(), dh, gws[-1].data_ptr(), gbs[-1].data_ptr(), st),
@@ -124,15 +126,16 @@ class _MLPFn(torch.autograd.Function):
                 # ---- weight / bias gradient of layer li: dz^T [input] ----
                 if li == 0:
                     _cabi.check(L.d3h_mlp_wgrad(dz.data_ptr(), dh, emb.data_ptr(), ep, m, dh, ep, gws[0].data_ptr(), ep,
-                                                gbs[0].data_ptr(), st), "d3h_mlp_wgrad")
+                                                gbs[0].data_ptr(), wsp.data_ptr(), ws_bytes, st), "d3h_mlp_wgrad")
                 else:
                     src = acts[li - 1]
                     ld = plan.ld_out[li - 1]
                     _cabi.check(L.d3h_mlp_wgrad(dz.data_ptr(), dh, src.data_ptr(), ld, m, dh, dh, gws[li].data_ptr(),
-                                                gws[li].shape[1], gbs[li].data_ptr(), st), "d3h_mlp_wgrad")
+                                                gws[li].shape[1], gbs[li].data_ptr(), wsp.data_ptr(), ws_bytes, st), "d3h_mlp_wgrad")
                     if plan.wide[li]:
                         _cabi.check(L.d3h_mlp_wgrad(dz.data_ptr(), dh, src.data_ptr() + 4 * dh, ld, m, dh, ep,
-                                                    gws[li].data_ptr() + 4 * dh, gws[li].shape[1], None, st), "d3h_mlp_wgrad")
+                                                    gws[li].data_ptr() + 4 * dh, gws[li].shape[1], None, wsp.data_ptr(), ws_bytes, st),
+                                    "d3h_mlp_wgrad")
                 # ---- gradient of the layer's input ----
                 w = ws[li]
                 if need_x and (li == 0 or plan.wide[li]):

@@ -65,9 +65,12 @@ int d3h_mlp_linear(const float* a, int64_t lda, int64_t m, int32_t k, const floa
 
 /* Weight / bias gradient of one nn.Linear: dw[n, k] += sum_m dz[m, n] a[m, k], db[n] += sum_m dz[m, n]
  * (dw, db ACCUMULATE: zero them first).  dz (M, ldz) with N in {128, 256}; a (M, lda) with K in {64, 128, 192, 256};
- * dw (N, lddw).  db may be NULL.  Tensor cores as above, contraction over the M points. */
+ * dw (N, lddw).  db may be NULL.  Tensor cores as above, contraction over the M points: every CTA owns a range of
+ * points and writes its partial product to `workspace` (d3h_mlp_wgrad_workspace_bytes, 16-byte aligned), a second kernel
+ * adds the partial products to dw / db. */
+int64_t d3h_mlp_wgrad_workspace_bytes(int64_t m, int32_t n, int32_t k);
 int d3h_mlp_wgrad(const float* dz, int64_t ldz, const float* a, int64_t lda, int64_t m, int32_t n, int32_t k, float* dw,
-                  int64_t lddw, float* db, d3h_stream_t stream);
+                  int64_t lddw, float* db, void* workspace, int64_t workspace_bytes, d3h_stream_t stream);
 
 /* The output layer Linear(K, d_out) for small d_out (1 for the SDF): out[m, j] = sum_k a[m, k] w[j, k] + bias[j]. */
 int d3h_mlp_head(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, const float* bias, int32_t d_out,

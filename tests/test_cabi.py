@@ -154,7 +154,7 @@ def test_mlp_entry_points_validate_their_arguments():
     assert lib.d3h_mlp_linear(p + 4, 64, 8, 64, p, 256, None, 1, None, 0, p, 256, None) == _cabi.D3H_E_BADARG  # alignment
     assert lib.d3h_mlp_linear(p, 64, 8, 64, p, 256, None, 2, None, 0, p, 256, None) == _cabi.D3H_E_BADARG   # mode 2 needs y
     assert b"d3h_mlp_linear" in lib.d3h_last_error_string()
-    assert lib.d3h_mlp_wgrad(p, 256, p, 64, 8, 192, 64, p, 64, None, None) == _cabi.D3H_E_BADARG               # N not 128 / 256
+    assert lib.d3h_mlp_wgrad(p, 256, p, 64, 8, 192, 64, p, 64, None, p, 1 << 20, None) == _cabi.D3H_E_BADARG               # N not 128 / 256
     assert lib.d3h_mlp_embed(p, 8, 6, p, 32, 32, None) == _cabi.D3H_E_BADARG                                   # 39 channels do not fit
     assert lib.d3h_mlp_head(p, 256, 8, 256, p, None, 9, p, None) == _cabi.D3H_E_BADARG                         # d_out > 8
     assert lib.d3h_mlp_embed(p, 0, 6, p, 64, 64, None) == 0

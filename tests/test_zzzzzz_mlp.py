@@ -79,8 +79,13 @@ def test_wgrad_contraction_over_points_matches_float64(dev, m, n, k):
     tdz, ta = torch.tensor(dz, device=dev), torch.tensor(a, device=dev)
     dw = torch.full((n, lddw), 1.0, device=dev)
     db = torch.full((n,), 2.0, device=dev)
-    _cabi.check(_cabi.lib().d3h_mlp_wgrad(tdz.data_ptr(), ldz, ta.data_ptr(), lda, m, n, k, dw.data_ptr(), lddw, db.data_ptr(),
-                                          _st(dev)), "d3h_mlp_wgrad")
+    L = _cabi.lib()
+    nbytes = int(L.d3h_mlp_wgrad_workspace_bytes(m, n, k))
+    ws = torch.empty(nbytes // 4, device=dev)
+    assert L.d3h_mlp_wgrad(tdz.data_ptr(), ldz, ta.data_ptr(), lda, m, n, k, dw.data_ptr(), lddw, db.data_ptr(), ws.data_ptr(),
+                           nbytes - 16, _st(dev)) == _cabi.D3H_E_SMALLWS
+    _cabi.check(L.d3h_mlp_wgrad(tdz.data_ptr(), ldz, ta.data_ptr(), lda, m, n, k, dw.data_ptr(), lddw, db.data_ptr(),
+                                ws.data_ptr(), nbytes, _st(dev)), "d3h_mlp_wgrad")
     want = dz[:, :n].astype(np.float64).T @ a[:, :k].astype(np.float64)
     scale = np.sqrt(m)
     got = dw.cpu().numpy()
