@@ -390,6 +390,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradAr
 #pragma unroll
     for (int i = 0; i < 4; ++i) bsum[i][0] = bsum[i][1] = bsum[i][2] = bsum[i][3] = 0.f;
     const int kc = (int)lane >> 2, kw = ((int)lane & 3) * 4;       // 16-byte chunk and byte offset of k = lane in a row
+    const uint32_t row_base = (uint32_t)((warp >> 1) * 1024);      // 8-row atom of this warp's first column group
+    uint32_t off_u[4];                                             // row inside the atom + swizzled chunk + word, per value u
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r7 = 4 * ((int)warp & 1) + u;
+      off_u[u] = (uint32_t)(r7 * 128 + ((kc ^ r7) << 4) + kw);
+    }
     const int a_groups = g.k / 4;                                   // 16-byte column groups of a row of a: 16 .. 64
     float4 vz[4], va[8];
     auto load_slice = [&](int64_t it) {
@@ -408,29 +415,26 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) mlp_wgrad_kernel(WgradAr
     load_slice(0);
     for (int64_t it = 0; it < n_slices; ++it) {
       mbar_wait(&s_empty, (uint32_t)((it & 1) ^ 1));
+      // tile row of value u of column group f = warp + 8 i: r = 4 f + u, so r >> 3 = (warp >> 1) + 4 i and r & 7 = 4 (warp & 1) + u
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int f = (int)warp + 8 * i;
-        if (f >= a_groups) continue;
+        if ((int)warp + 8 * i >= a_groups) continue;
         const float x[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = 4 * f + u;
           const float h = tf32_hi(x[u]);
-          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
+          const uint32_t off = row_base + 4096u * i + off_u[u];
           *reinterpret_cast<float*>(smem + sl.b_hi + off) = h;
           *reinterpret_cast<float*>(smem + sl.b_lo + off) = x[u] - h;
         }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int f = (int)warp + 8 * i;
         const float x[4] = {vz[i].x, vz[i].y, vz[i].z, vz[i].w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = 4 * f + u;
           const float h = tf32_hi(x[u]);
-          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) + kw);
+          const uint32_t off = row_base + 4096u * i + off_u[u];
           *reinterpret_cast<float*>(smem + sl.a_hi + off) = h;
           *reinterpret_cast<float*>(smem + sl.a_lo + off) = x[u] - h;
           bsum[i][u] += x[u];
@@ -525,6 +529,33 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
     }
   }
   for (int c = 3 * (2 * n_freq + 1); c < n_cols; ++c) o[c] = 0.f;
+}
+
+// The same with one thread per (point, group of four output columns): 16-byte stores, 16 lanes cover a 256-byte row.
+// Needs n_cols % 4 == 0, ld % 4 == 0 and a 16-byte aligned `out` (the padded operand buffers of the GEMMs).
+__global__ void __launch_bounds__(256) embed4_kernel(const float* __restrict__ x, int64_t m, int n_freq, float* __restrict__ out,
+                                                     int64_t ld, int n_cols) {
+  const int groups = n_cols / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * groups) return;
+  const int64_t pt = i / groups;
+  const int g = (int)(i % groups);
+  const int e = 3 * (2 * n_freq + 1);
+  float o[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = 4 * g + u;
+    float v = 0.f;
+    if (c < 3) {
+      v = x[3 * pt + c];
+    } else if (c < e) {
+      const int k = (c - 3) / 6, r = (c - 3) % 6;
+      const float a = (float)(1 << k) * x[3 * pt + (r % 3)];
+      v = r < 3 ? sinf(a) : cosf(a);
+    }
+    o[u] = v;
+  }
+  *reinterpret_cast<float4*>(out + pt * ld + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(256) embed_backward_kernel(const float* __restrict__ x, int64_t m, int n_freq,
@@ -636,7 +667,10 @@ extern "C" int d3h_mlp_embed(const float* x, int64_t m, int32_t n_freq, float* o
     return D3H_E_BADARG;
   }
   if (m == 0) return D3H_OK;
-  embed_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, m, n_freq, out, ld, n_cols);
+  if ((n_cols % 4) == 0 && (ld % 4) == 0 && aligned16(out))
+    embed4_kernel<<<(unsigned)((m * (n_cols / 4) + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, m, n_freq, out, ld, n_cols);
+  else
+    embed_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, m, n_freq, out, ld, n_cols);
   return finish_launch("d3h_mlp_embed");
 }
 
@@ -756,7 +790,7 @@ extern "C" int d3h_mlp_head_backward(const float* a, int64_t lda, int64_t m, int
     return D3H_E_BADARG;
   }
   if (m == 0) return D3H_OK;
-  const int rows = 2048;
+  const int rows = 256;       // 8 warps x 32 rows: enough CTAs to fill the machine at the reference's 100000-point batches
   head_backward_kernel<<<(unsigned)((m + rows - 1) / rows), 256, 0, (cudaStream_t)stream>>>(a, lda, m, k, w, d_out, g, dz, ldz, dw,
                                                                                            db, rows);
   return finish_launch("d3h_mlp_head_backward");

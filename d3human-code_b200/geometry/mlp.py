@@ -45,13 +45,25 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+_pack_cache = {}
+
+
 def _pack(L, w, n_valid, k_valid, transpose, col0, n_pad, k_pad, st):
-    """nn.Linear.weight (or a transposed column slice of it) -> the kernel's operand image (d3h_mlp_pack_weight)."""
+    """nn.Linear.weight (or a transposed column slice of it) -> the kernel's operand image (d3h_mlp_pack_weight).
+    Cached on the parameter's storage and version: D3-Human evaluates the network on ~22 batches of points between two
+    optimiser steps (hmsdf.py:436-444), the weights only change in between (in place: the version counter moves)."""
     if w.stride(1) != 1:
         w = w.contiguous()
+    key = (w.data_ptr(), w._version, w.stride(0), n_valid, k_valid, bool(transpose), col0, n_pad, k_pad, w.device.index, st)
+    hit = _pack_cache.get(key)
+    if hit is not None:
+        return hit
+    if len(_pack_cache) > 256:
+        _pack_cache.clear()
     out = torch.empty(2 * n_pad * k_pad, dtype=torch.float32, device=w.device)
     _cabi.check(L.d3h_mlp_pack_weight(w.data_ptr(), w.stride(0), n_valid, k_valid, int(transpose), 0, col0, n_pad, k_pad,
                                       out.data_ptr(), st), "d3h_mlp_pack_weight")
+    _pack_cache[key] = out
     return out
 
 
@@ -108,10 +120,15 @@ class _MLPFn(torch.autograd.Function):
         gy = gy.contiguous().float()
         with torch.cuda.device(dev):
             st = _stream(dev)
-            gws = [torch.zeros((dh, ep), dtype=f32, device=dev)]
-            gws += [torch.zeros((dh, dh + ep) if plan.wide[li] else (dh, dh), dtype=f32, device=dev) for li in range(1, nh + 1)]
-            gws.append(torch.zeros((plan.d_out, dh), dtype=f32, device=dev))
-            gbs = [torch.zeros(dh, dtype=f32, device=dev) for _ in range(nh + 1)] + [torch.zeros(plan.d_out, dtype=f32, device=dev)]
+            # every weight / bias gradient is a view of ONE zero-filled buffer (the kernels accumulate)
+            shapes = [(dh, ep)] + [((dh, dh + ep) if plan.wide[li] else (dh, dh)) for li in range(1, nh + 1)] + [(plan.d_out, dh)]
+            sizes = [a * b for a, b in shapes] + [dh] * (nh + 1) + [plan.d_out]
+            offs = [0]
+            for n_ in sizes:
+                offs.append(offs[-1] + (n_ + 3) // 4 * 4)
+            flat = torch.zeros(offs[-1], dtype=f32, device=dev)
+            gws = [flat[offs[i]:offs[i] + sizes[i]].view(shapes[i]) for i in range(nh + 2)]
+            gbs = [flat[offs[nh + 2 + i]:offs[nh + 2 + i] + sizes[nh + 2 + i]] for i in range(nh + 2)]
             g_emb = torch.zeros((m, ep), dtype=f32, device=dev) if need_x else None
             tmp_e = torch.empty((m, ep), dtype=f32, device=dev) if need_x else None
             dz = torch.empty((m, dh), dtype=f32, device=dev)
