@@ -45,31 +45,27 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-_pack_cache = {}
-
-
-def _pack(L, w, n_valid, k_valid, transpose, col0, n_pad, k_pad, st):
+def _pack(cache, tag, L, w, n_valid, k_valid, transpose, col0, n_pad, k_pad, st):
     """nn.Linear.weight (or a transposed column slice of it) -> the kernel's operand image (d3h_mlp_pack_weight).
-    Cached on the parameter's storage and version: D3-Human evaluates the network on ~22 batches of points between two
-    optimiser steps (hmsdf.py:436-444), the weights only change in between (in place: the version counter moves)."""
+    Cached PER MODULE (`cache` is the module's dict, `tag` names the layer and variant) on the parameter's storage and
+    version counter: D3-Human evaluates the network on ~22 batches of points between two optimiser steps
+    (hmsdf.py:436-444), the weights only change in between (in place: the version counter moves)."""
     if w.stride(1) != 1:
         w = w.contiguous()
-    key = (w.data_ptr(), w._version, w.stride(0), n_valid, k_valid, bool(transpose), col0, n_pad, k_pad, w.device.index, st)
-    hit = _pack_cache.get(key)
-    if hit is not None:
-        return hit
-    if len(_pack_cache) > 256:
-        _pack_cache.clear()
+    stamp = (w.data_ptr(), w._version, w.stride(0), st)
+    hit = cache.get(tag)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
     out = torch.empty(2 * n_pad * k_pad, dtype=torch.float32, device=w.device)
     _cabi.check(L.d3h_mlp_pack_weight(w.data_ptr(), w.stride(0), n_valid, k_valid, int(transpose), 0, col0, n_pad, k_pad,
                                       out.data_ptr(), st), "d3h_mlp_pack_weight")
-    _pack_cache[key] = out
+    cache[tag] = (stamp, out)
     return out
 
 
 class _MLPFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan: _Plan, x, *wb):
+    def forward(ctx, plan: _Plan, cache, x, *wb):
         L = _cabi.lib()
         dev = x.device
         m = x.shape[0]
@@ -85,7 +81,7 @@ class _MLPFn(torch.autograd.Function):
             a_ptr, lda, k = emb.data_ptr(), ep, ep
             for li in range(plan.n_hidden + 1):
                 kv = e if li == 0 else (dh + e if plan.wide[li] else dh)
-                wp = _pack(L, ws[li], dh, kv, False, 0, dh, k, st)
+                wp = _pack(cache, (li, "fwd"), L, ws[li], dh, kv, False, 0, dh, k, st)
                 out = torch.empty((m, plan.ld_out[li]), dtype=f32, device=dev)
                 if plan.ld_out[li] != dh:      # the next layer reads cat([x, emb]) (mlp.py:41): the encoding sits behind
                     _cabi.check(L.d3h_mlp_embed(x.data_ptr(), m, plan.n_freq, out.data_ptr() + 4 * dh, plan.ld_out[li], ep, st),
@@ -98,14 +94,14 @@ class _MLPFn(torch.autograd.Function):
             w_out = ws[-1].contiguous()
             _cabi.check(L.d3h_mlp_head(a_ptr, lda, m, dh, w_out.data_ptr(), bs[-1].data_ptr(), plan.d_out, y.data_ptr(), st),
                         "d3h_mlp_head")
-        ctx.plan = plan
+        ctx.plan, ctx.cache = plan, cache
         ctx.save_for_backward(x, emb, *acts, *ws)
         _MLPFn.launches += 2 + 2 * (plan.n_hidden + 1) + len(plan.skip)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        plan = ctx.plan
+        plan, cache = ctx.plan, ctx.cache
         L = _cabi.lib()
         saved = ctx.saved_tensors
         x, emb = saved[0], saved[1]
@@ -116,7 +112,7 @@ class _MLPFn(torch.autograd.Function):
         m = x.shape[0]
         dh, e, ep = plan.dh, plan.e, plan.e_pad
         f32 = torch.float32
-        need_x = ctx.needs_input_grad[1]
+        need_x = ctx.needs_input_grad[2]
         gy = gy.contiguous().float()
         with torch.cuda.device(dev):
             st = _stream(dev)
@@ -157,12 +153,12 @@ class _MLPFn(torch.autograd.Function):
                 w = ws[li]
                 if need_x and (li == 0 or plan.wide[li]):
                     # the encoding's share: dz . W[:, -e:]  ->  (M, e_pad), added to g_emb
-                    wt = _pack(L, w, e, dh, True, 0 if li == 0 else dh, ep, dh, st)
+                    wt = _pack(cache, (li, "emb_t"), L, w, e, dh, True, 0 if li == 0 else dh, ep, dh, st)
                     _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), ep, None, 0, None, 0,
                                                  tmp_e.data_ptr(), ep, st), "d3h_mlp_linear")
                     g_emb += tmp_e
                 if li > 0:
-                    wt = _pack(L, w, dh, dh, True, 0, dh, dh, st)
+                    wt = _pack(cache, (li, "act_t"), L, w, dh, dh, True, 0, dh, dh, st)
                     prev = acts[li - 1]
                     _cabi.check(L.d3h_mlp_linear(dz.data_ptr(), dh, m, dh, wt.data_ptr(), dh, None, 2, prev.data_ptr(),
                                                  plan.ld_out[li - 1], dz2.data_ptr(), dh, st), "d3h_mlp_linear")
@@ -177,7 +173,7 @@ class _MLPFn(torch.autograd.Function):
             gw_out.append(gws[li][:, :dh + e] if plan.wide[li] else gws[li])
         gw_out.append(gws[-1])
         _MLPFn.launches += 2 + 3 * (nh + 1) + nh + 3 * len(plan.skip) + (2 if need_x else 0)
-        return (None, gx) + tuple(gw_out) + tuple(gbs)
+        return (None, None, gx) + tuple(gw_out) + tuple(gbs)
 
 
 _MLPFn.launches = 0     # library kernels enqueued so far (bench.py reports the difference over its timed region)
@@ -210,6 +206,7 @@ class MLP(nn.Module):
         if d_hidden not in (128, 256) or not (1 <= d_out <= 8):
             raise NotImplementedError("d3human-code_b200 MLP: d_hidden in {128, 256} and d_out <= 8 (D3-Human: 256 / 1)")
         self._plan = _Plan(n_freq, d_hidden, d_out, n_hidden, skip_in)
+        self._packs = {}      # operand images of the weights, per layer and variant (see _pack)
 
     def forward(self, x):
         if self.use_float16:
@@ -222,5 +219,5 @@ class MLP(nn.Module):
         pts = x.reshape(-1, 3).float().contiguous()
         if pts.data_ptr() % 16:
             pts = pts.clone()
-        y = _MLPFn.apply(self._plan, pts, *[l.weight for l in lin], *[l.bias for l in lin])
+        y = _MLPFn.apply(self._plan, self._packs, pts, *[l.weight for l in lin], *[l.bias for l in lin])
         return y.reshape(*shape[:-1], self._plan.d_out)

@@ -221,3 +221,30 @@ def test_packed_weight_transposed_slice_with_padding(dev):
     want = a.astype(np.float64) @ w[:, dh:].astype(np.float64)
     got = out.cpu().numpy()
     assert _rel(got[:, :e], want) < GEMM_TOL and (got[:, e:] == 0).all()
+
+
+def test_packed_weight_cache_follows_in_place_updates_and_new_modules(dev):
+    """The operand images of the weights are cached per module on (storage, version): an optimiser step (in-place update)
+    must be seen by the next call, and a NEW module whose parameters land on the addresses of a freed one must not find the
+    old images (the allocator recycles them at once)."""
+    from d3human_code_b200.geometry.mlp import MLP
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, size=(500, 3)).astype(np.float32)
+    tx = torch.tensor(x, device=dev)
+
+    def check(net):
+        lin = [mod for mod in net.net if isinstance(mod, torch.nn.Linear)]
+        y = net(tx)
+        yo, _ = MO.forward(x, [l.weight.detach().cpu().numpy() for l in lin], [l.bias.detach().cpu().numpy() for l in lin], 6, (3,))
+        assert _rel(y.detach().cpu().numpy(), yo) < FWD_TOL
+
+    for seed in range(3):
+        torch.manual_seed(100 + seed)
+        net = MLP(n_freq=6, d_hidden=256, n_hidden=6, skip_in=[3]).to(dev)
+        check(net)
+        check(net)                                   # second call: cache hit
+        opt = torch.optim.SGD(net.parameters(), lr=0.5)
+        net(tx).sum().backward()
+        opt.step()                                   # in-place update of every weight
+        check(net)
+        del net, opt
