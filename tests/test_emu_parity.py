@@ -298,6 +298,23 @@ def test_mark_rows_variant(dev, edges_mode):
         E.reset_plans()
 
 
+def test_scan_pipe_variant(dev, edges_mode, monkeypatch):
+    """Opt-in persistent, software-pipelined edge scan (edge_scan_pipe_kernel, D3H_SCAN_PIPE=1): three chunks in flight per
+    warp.  Lattices (ragged last chunk), crowded vertices (> 8 larger neighbours) and a batch."""
+    if edges_mode != "scan":
+        pytest.skip("variant of the edge-scan path")
+    for vpt in ("1", "2"):
+        monkeypatch.setenv("D3H_SCAN_PIPE", "1")
+        monkeypatch.setenv("D3H_SCAN_VPT_PIPE", vpt)
+        E.reset_plans()
+        G.test_cuda_matches_oracle(dev, 12, "adv", "GShell_Tets", None, True)
+        G.test_cuda_matches_oracle(dev, 17, "capsule", "hmSDF_Tets", "body", False)
+        G.test_extract_frames_batch_matches_oracle_per_frame(dev)
+        test_random_tet_soups(dev, 3, 12, 6000)
+        test_random_tet_soups(dev, 4, 300, 5000)
+    E.reset_plans()
+
+
 def test_fuzz_forward_against_oracle(dev):
     """60 seeded random inputs (lattices, adversarial fields, tet soups, degenerate fields; 1650 such cases were run once
     while writing this): every integer output, position and mSDF value bit-exact against the oracle."""

@@ -243,8 +243,10 @@ def test_packed_weight_cache_follows_in_place_updates_and_new_modules(dev):
         net = MLP(n_freq=6, d_hidden=256, n_hidden=6, skip_in=[3]).to(dev)
         check(net)
         check(net)                                   # second call: cache hit
-        opt = torch.optim.SGD(net.parameters(), lr=0.5)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-4)
+        w_before = net.net[4].weight.detach().clone()
         net(tx).sum().backward()
         opt.step()                                   # in-place update of every weight
+        assert not torch.equal(w_before, net.net[4].weight.detach())
         check(net)
         del net, opt
