@@ -43,13 +43,6 @@ static int scan_vpt() {
   return v;
 }
 
-// D3H_SCAN_PIPE=1: the persistent software-pipelined stream instead of one chunk per warp (read at every launch /
-// graph capture: set it before the first call of a process)
-static bool scan_pipe() {
-  const char* env = getenv("D3H_SCAN_PIPE");
-  return env && env[0] == '1';
-}
-
 struct ScanLists {
   unsigned* tile_cnt;     // valid tets per 8192-tet compaction tile: T1 class | T2 class << 16
   unsigned* eblock_cnt;   // crossing edges per 8192-edge block
@@ -147,102 +140,6 @@ edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) == 0u) continue;
       if (slot < L.cap_qe) out[slot] = e;
       ++slot;
-    }
-  }
-  trace_end(tr);
-}
-
-// The stream as a PERSISTENT, software-pipelined kernel.  edge_scan_kernel pays three dependent rounds per warp (offsets ->
-// larger end points -> sign words) and runs at half the HBM rate because of it (r02f: 3.3 TB/s, long-scoreboard stalls,
-// neither bandwidth- nor issue-bound).  Here a warp walks chunks gw, gw + W, gw + 2W, ... of 32 * VPT vertices and keeps
-// three chunks in flight: while it tests the neighbours of chunk c it has already issued the end-point loads of chunk
-// c + W and the offset loads of chunk c + 2W, so every trip of the loop costs one round instead of three.
-template <int VPT>
-__global__ void __launch_bounds__(kEScanThreads)
-edge_scan_pipe_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L, int64_t n_chunks) {
-  pdl_enter();
-  const d3h_forward_args& a = blk->a;
-  const int32_t* __restrict__ edge_off = a.edge_off;
-  const int32_t* __restrict__ edge_b = a.edge_b;
-  const int64_t n_grid = a.n_grid;
-  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
-  const unsigned lane = lane_id();
-  const int64_t n_warps = (int64_t)gridDim.x * (kEScanThreads / 32);
-  const int64_t gw = (int64_t)blockIdx.x * (kEScanThreads / 32) + (threadIdx.x >> 5);
-  const unsigned q = (unsigned)(gw % kQueues);
-  int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
-
-  int e0a[VPT], e1a[VPT], e0b[VPT], e1b[VPT], e0c[VPT], e1c[VPT];
-  unsigned oaa[VPT], oab[VPT], oac[VPT];
-  int ba[VPT][8], bb[VPT][8];
-  auto load_off = [&](int64_t chunk, int (&e0)[VPT], int (&e1)[VPT], unsigned (&oa)[VPT]) {
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      const int64_t v = chunk * (32 * VPT) + k * 32 + lane;
-      e0[k] = e1[k] = 0;
-      oa[k] = 0u;
-      if (chunk < n_chunks && v < n_grid) {
-        e0[k] = __ldg(edge_off + v);
-        e1[k] = __ldg(edge_off + v + 1);
-        oa[k] = occ_of(occ_bits, (int)v);
-      }
-    }
-  };
-  auto load_b = [&](const int (&e0)[VPT], const int (&e1)[VPT], int (&b)[VPT][8]) {
-#pragma unroll
-    for (int k = 0; k < VPT; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) b[k][j] = (e0[k] + j < e1[k]) ? __ldg(edge_b + e0[k] + j) : -1;
-  };
-  load_off(gw, e0a, e1a, oaa);
-  load_off(gw + n_warps, e0b, e1b, oab);
-  load_b(e0a, e1a, ba);
-  for (int64_t c = gw; c < n_chunks; c += n_warps) {
-    load_b(e0b, e1b, bb);                              // chunk c + W: its offsets arrived during the previous trip
-    load_off(c + 2 * n_warps, e0c, e1c, oac);          // chunk c + 2W
-    // ---- chunk c: neighbours with the other sign ----
-    unsigned x[VPT];
-    unsigned cnt = 0u;
-    bool more = false;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      x[k] = 0u;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (ba[k][j] >= 0) x[k] |= (occ_of(occ_bits, ba[k][j]) ^ oaa[k]) << j;
-      cnt += __popc(x[k]);
-      more = more || (e0a[k] + 8 < e1a[k]);
-    }
-    if (__any_sync(0xffffffffu, more)) {
-#pragma unroll
-      for (int k = 0; k < VPT; ++k)
-        for (int e = e0a[k] + 8; e < e1a[k]; ++e) cnt += occ_of(occ_bits, __ldg(edge_b + e)) ^ oaa[k];
-    }
-    int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
-    if (slot >= 0) {
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        unsigned y = x[k];
-        while (y) {
-          const int e = e0a[k] + (__ffs((int)y) - 1);
-          y &= y - 1u;
-          if (slot < L.cap_qe) out[slot] = e;
-          ++slot;
-        }
-        for (int e = e0a[k] + 8; e < e1a[k]; ++e) {
-          if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oaa[k]) == 0u) continue;
-          if (slot < L.cap_qe) out[slot] = e;
-          ++slot;
-        }
-      }
-    }
-    // ---- rotate the pipeline ----
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      e0a[k] = e0b[k]; e1a[k] = e1b[k]; oaa[k] = oab[k];
-      e0b[k] = e0c[k]; e1b[k] = e1c[k]; oab[k] = oac[k];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ba[k][j] = bb[k][j];
     }
   }
   trace_end(tr);
@@ -663,25 +560,7 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const int vpt = scan_vpt();
     const int64_t per_cta = (int64_t)kEScanThreads * vpt;
     const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
-    if (scan_pipe()) {
-      // persistent: one CTA slot per resident CTA, chunks of 32 * VPT vertices dealt round-robin to the warps
-      const char* pe = getenv("D3H_SCAN_VPT_PIPE");
-      const int pv = (pe && pe[0] == '1') ? 1 : 2;
-      const int64_t n_chunks = (a.n_grid + 32 * pv - 1) / (32 * pv);
-      static int ctas1 = 0, ctas2 = 0;
-      if (ctas1 == 0) {
-        ctas1 = persistent_grid(reinterpret_cast<const void*>(edge_scan_pipe_kernel<1>), kEScanThreads, 0);
-        ctas2 = persistent_grid(reinterpret_cast<const void*>(edge_scan_pipe_kernel<2>), kEScanThreads, 0);
-      }
-      int64_t grid = pv == 1 ? ctas1 : ctas2;
-      const int64_t need = (n_chunks + kEScanThreads / 32 - 1) / (kEScanThreads / 32);
-      if (grid > need) grid = need;
-      if (grid < 1) grid = 1;
-      if (pv == 1)
-        launch_k_dep(edge_scan_pipe_kernel<1>, (unsigned)grid, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L, n_chunks);
-      else
-        launch_k_dep(edge_scan_pipe_kernel<2>, (unsigned)grid, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L, n_chunks);
-    } else if (vpt == 1)
+    if (vpt == 1)
       launch_k_dep(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     else if (vpt == 2)
       launch_k_dep(edge_scan_kernel<2>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);

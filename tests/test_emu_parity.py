@@ -100,6 +100,8 @@ def test_emulated_library_is_the_real_abi(dev):
     L = _cabi.lib()
     assert L.d3h_version() == _cabi.VERSION
     for name in _cabi.EXPORTED_SYMBOLS:
+        if name.startswith("d3h_mlp_"):      # the tensor-core stage (csrc/d3h_mlp.cu) has no emulation: GPU-tested only
+            continue
         assert hasattr(L, name)
 
 
@@ -296,23 +298,6 @@ def test_mark_rows_variant(dev, edges_mode):
     finally:
         E.set_mark_rows(False)
         E.reset_plans()
-
-
-def test_scan_pipe_variant(dev, edges_mode, monkeypatch):
-    """Opt-in persistent, software-pipelined edge scan (edge_scan_pipe_kernel, D3H_SCAN_PIPE=1): three chunks in flight per
-    warp.  Lattices (ragged last chunk), crowded vertices (> 8 larger neighbours) and a batch."""
-    if edges_mode != "scan":
-        pytest.skip("variant of the edge-scan path")
-    for vpt in ("1", "2"):
-        monkeypatch.setenv("D3H_SCAN_PIPE", "1")
-        monkeypatch.setenv("D3H_SCAN_VPT_PIPE", vpt)
-        E.reset_plans()
-        G.test_cuda_matches_oracle(dev, 12, "adv", "GShell_Tets", None, True)
-        G.test_cuda_matches_oracle(dev, 17, "capsule", "hmSDF_Tets", "body", False)
-        G.test_extract_frames_batch_matches_oracle_per_frame(dev)
-        test_random_tet_soups(dev, 3, 12, 6000)
-        test_random_tet_soups(dev, 4, 300, 5000)
-    E.reset_plans()
 
 
 def test_fuzz_forward_against_oracle(dev):
