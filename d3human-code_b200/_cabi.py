@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "d3h_version", "d3h_last_error_string", "d3h_workspace_bytes", "d3h_workspace_bytes_static",
     "d3h_backward_workspace_bytes",
     "d3h_pack_tets_i64", "d3h_check_tets_i32", "d3h_extract_forward", "d3h_wait_counts", "d3h_extract_backward",
-    "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_gather_rows", "d3h_classify_range", "d3h_extract_from_records",
+    "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_tangent_backward", "d3h_gather_rows", "d3h_classify_range", "d3h_extract_from_records",
     "d3h_mesh_edges_workspace_bytes", "d3h_mesh_edges", "d3h_mesh_wait_counts", "d3h_mesh_normals_forward",
     "d3h_mesh_normals_backward",
     "d3h_mlp_embed", "d3h_mlp_embed_backward", "d3h_mlp_packed_weight_bytes", "d3h_mlp_pack_weight", "d3h_mlp_linear", "d3h_mlp_wgrad_workspace_bytes", "d3h_mlp_wgrad", "d3h_mlp_head", "d3h_mlp_head_backward",
@@ -74,7 +74,14 @@ class BackwardArgs(C.Structure):  # d3h_backward_args
                 ("g_msdf_wt", C.c_void_p),
                 ("g_pos", C.c_void_p), ("g_sdf", C.c_void_p), ("g_msdf", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("g_msdf_boundary", C.c_void_p),
-                ("vacc", C.c_void_p)]
+                ("vacc", C.c_void_p), ("g_verts_tng", C.c_void_p), ("g_mvert_tng", C.c_void_p)]
+
+
+class TangentBackwardArgs(C.Structure):  # d3h_tangent_backward_args
+    _fields_ = [("verts_wt", C.c_void_p), ("msdf_wt", C.c_void_p), ("v_tng_wt", C.c_void_p), ("faces_wt", C.c_void_p),
+                ("tape_corners", C.c_void_p), ("n_verts", C.c_int64), ("n_tri_tets", C.c_int64), ("n_quad_tets", C.c_int64),
+                ("n_tets", C.c_int64), ("g_tng_aug", C.c_void_p), ("g_tng_wt", C.c_void_p), ("g_verts", C.c_void_p),
+                ("g_mvert", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 TET_RECORD_BYTES = 32  # sizeof(d3h_tet_record)
@@ -118,6 +125,8 @@ def lib() -> C.CDLL:
     L.d3h_lanes_join.argtypes = [C.c_void_p]
     L.d3h_extract_backward_batch.restype = C.c_int
     L.d3h_extract_backward_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    L.d3h_tangent_backward.restype = C.c_int
+    L.d3h_tangent_backward.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_gather_rows.restype = C.c_int
     L.d3h_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     L.d3h_classify_range.restype = C.c_int

@@ -99,6 +99,7 @@ struct AdjFrame {
   const int32_t *edges, *corners, *slots, *runs;
   const float *pos, *sdf, *msdf, *verts_wt, *msdf_wt;
   const float *g_verts_aug, *g_msdf_aug, *g_msdf_bnd, *g_verts_wt, *g_msdf_wt;
+  const float *g_verts_tng, *g_mvert_tng;   // through the tangent branch (d3h_tangent_backward), or nullptr
   float *g_pos, *g_sdf, *g_msdf;
   float* vacc;  // scatter form (static edge table calls): (nv,8) accumulator [gx gy gz gsg | gmv - - -], zero on entry
   int64_t nv, t1, t2;
@@ -279,6 +280,10 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const __grid_constant__ Ad
   }
   if (f.g_msdf_aug != nullptr) gsg += __ldg(f.g_msdf_aug + v);
   if (g_msdf_wt != nullptr) gsg += __ldg(g_msdf_wt + v);
+  if (f.g_verts_tng != nullptr) {
+    gx += __ldg(f.g_verts_tng + 3 * v); gy += __ldg(f.g_verts_tng + 3 * v + 1); gz += __ldg(f.g_verts_tng + 3 * v + 2);
+  }
+  if (f.g_mvert_tng != nullptr) gmv += __ldg(f.g_mvert_tng + v);
   float w0, w1, dd;
   crossing_weights(__ldg(sdf + a), __ldg(sdf + b), w0, w1, dd);
   float ma = __ldg(msdf + a), mb = __ldg(msdf + b);
@@ -321,6 +326,7 @@ static AdjFrame adj_frame(const d3h_backward_args& a) {
   f.pos = a.pos; f.sdf = a.sdf; f.msdf = a.msdf; f.verts_wt = a.verts_wt; f.msdf_wt = a.msdf_wt;
   f.g_verts_aug = a.g_verts_aug; f.g_msdf_aug = a.g_msdf_aug; f.g_msdf_bnd = a.g_msdf_boundary;
   f.g_verts_wt = a.g_verts_wt; f.g_msdf_wt = a.g_msdf_wt;
+  f.g_verts_tng = a.g_verts_tng; f.g_mvert_tng = a.g_mvert_tng;
   f.g_pos = a.g_pos; f.g_sdf = a.g_sdf; f.g_msdf = a.g_msdf;
   f.vacc = a.vacc;
   f.nv = a.n_verts; f.t1 = a.n_tri_tets; f.t2 = a.n_quad_tets;

@@ -599,6 +599,183 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
 }
 
 // ------------------------------------------------------------------------------------------------
+// tangent branch of the backward pass (d3h_tangent_backward; optional)
+//
+// workspace rows, 16 floats per watertight vertex:  [0..2] sum of face normals N   [3] face count c
+//   [4..6] sum of face tangents S   [8..10] upstream gradient of the final tangent g_T   [12..14] g_N   -- then reused:
+//   [4..6] g_S after the vertex pass.  g_mvert / g_verts are the outputs.
+// Per-vertex chain in double: the gradients of the normalisations divide by |N| and |W| (small where faces cancel).
+// ------------------------------------------------------------------------------------------------
+struct TngArgs {
+  d3h_tangent_backward_args a;
+  float* ws;
+  UvParams uvp;
+};
+
+// boundary vertices (gshell_tets.py:380-385): thread per polygon, rows V + p0 + k of v_tng_aug
+__global__ void __launch_bounds__(256) tng_boundary_kernel(TngArgs g) {
+  const d3h_tangent_backward_args& a = g.a;
+  const int64_t t1 = a.n_tri_tets, npoly = a.n_tri_tets + a.n_quad_tets;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npoly) return;
+  const bool quad = i >= t1;
+  const int n = quad ? 4 : 3;
+  const int64_t p0 = quad ? (3 * t1 + 4 * (i - t1)) : 3 * i;
+  for (int k = 0; k < n; ++k) {
+    const int kn = (k + 1 == n) ? 0 : k + 1;
+    const int vi = __ldg(a.tape_corners + p0 + k), vj = __ldg(a.tape_corners + p0 + kn);
+    const int64_t row = a.n_verts + p0 + k;
+    const float gx = __ldg(a.g_tng_aug + 3 * row), gy = __ldg(a.g_tng_aug + 3 * row + 1), gz = __ldg(a.g_tng_aug + 3 * row + 2);
+    if (gx == 0.f && gy == 0.f && gz == 0.f) continue;
+    float u0, u1, D;
+    const bool nz = boundary_weights(__ldg(a.msdf_wt + vi), __ldg(a.msdf_wt + vj), u0, u1, D);
+    float* ri = g.ws + 16ll * vi + 8;
+    float* rj = g.ws + 16ll * vj + 8;
+    atomicAdd(ri, gx * u0); atomicAdd(ri + 1, gy * u0); atomicAdd(ri + 2, gz * u0);
+    atomicAdd(rj, gx * u1); atomicAdd(rj + 1, gy * u1); atomicAdd(rj + 2, gz * u1);
+    if (nz) {
+      const double gu0 = (double)gx * a.v_tng_wt[3ll * vi] + (double)gy * a.v_tng_wt[3ll * vi + 1] + (double)gz * a.v_tng_wt[3ll * vi + 2];
+      const double gu1 = (double)gx * a.v_tng_wt[3ll * vj] + (double)gy * a.v_tng_wt[3ll * vj + 1] + (double)gz * a.v_tng_wt[3ll * vj + 2];
+      const double inv = 1.0 / (double)D;
+      const double gD = -(gu0 * (double)u0 + gu1 * (double)u1) * inv;
+      atomicAdd(a.g_mvert + vi, (float)(gu1 * inv + gD));
+      atomicAdd(a.g_mvert + vj, (float)(-(gu0 * inv + gD)));
+    }
+  }
+}
+
+struct FaceGeom {
+  int v[3];
+  float e1[3], e2[3];
+  float u1y, u2y, den;
+};
+__device__ __forceinline__ FaceGeom face_geom(const TngArgs& g, int64_t f) {
+  FaceGeom r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r.v[c] = (int)g.a.faces_wt[3 * f + c];
+  const float* p = g.a.verts_wt;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    r.e1[c] = __fsub_rn(p[3ll * r.v[1] + c], p[3ll * r.v[0] + c]);
+    r.e2[c] = __fsub_rn(p[3ll * r.v[2] + c], p[3ll * r.v[0] + c]);
+  }
+  const float2 uv0 = vertex_uv(g.uvp, r.v[0]), uv1 = vertex_uv(g.uvp, r.v[1]), uv2 = vertex_uv(g.uvp, r.v[2]);
+  const float u1x = __fsub_rn(uv1.x, uv0.x), u2x = __fsub_rn(uv2.x, uv0.x);
+  r.u1y = __fsub_rn(uv1.y, uv0.y);
+  r.u2y = __fsub_rn(uv2.y, uv0.y);
+  float den = __fsub_rn(__fmul_rn(u1x, r.u2y), __fmul_rn(r.u1y, u2x));
+  r.den = (den > 0.f) ? fmaxf(den, 1e-6f) : fminf(den, -1e-6f);
+  return r;
+}
+
+// forward sums again: N, c, S per vertex (thread per watertight face)
+__global__ void __launch_bounds__(256) tng_accumulate_kernel(TngArgs g, int64_t n_faces) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_faces) return;
+  const FaceGeom q = face_geom(g, f);
+  const float nx = cross_comp(q.e1[1], q.e2[2], q.e1[2], q.e2[1]);
+  const float ny = cross_comp(q.e1[2], q.e2[0], q.e1[0], q.e2[2]);
+  const float nz = cross_comp(q.e1[0], q.e2[1], q.e1[1], q.e2[0]);
+  const float tx = __fdiv_rn(__fsub_rn(__fmul_rn(q.e1[0], q.u2y), __fmul_rn(q.e2[0], q.u1y)), q.den);
+  const float ty = __fdiv_rn(__fsub_rn(__fmul_rn(q.e1[1], q.u2y), __fmul_rn(q.e2[1], q.u1y)), q.den);
+  const float tz = __fdiv_rn(__fsub_rn(__fmul_rn(q.e1[2], q.u2y), __fmul_rn(q.e2[2], q.u1y)), q.den);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float* row = g.ws + 16ll * q.v[c];
+    atomicAdd(reinterpret_cast<float4*>(row), make_float4(nx, ny, nz, 1.f));
+    atomicAdd(reinterpret_cast<float4*>(row) + 1, make_float4(tx, ty, tz, 0.f));
+  }
+}
+
+// y = x / sqrt(max(x.x, 1e-20)) (render/util.py:25-29) and its adjoint
+__device__ __forceinline__ void normalize_fwd(const double (&x)[3], double (&y)[3], double& len, bool& free) {
+  const double d = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  free = d > 1e-20;
+  len = sqrt(free ? d : 1e-20);
+  y[0] = x[0] / len; y[1] = x[1] / len; y[2] = x[2] / len;
+}
+__device__ __forceinline__ void normalize_bwd(const double (&y)[3], double len, bool free, const double (&gy)[3], double (&gx)[3]) {
+  const double dot = free ? (y[0] * gy[0] + y[1] * gy[1] + y[2] * gy[2]) : 0.0;   // (clamped: the length is a constant)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gx[c] = (gy[c] - y[c] * dot) / len;
+}
+
+// thread per vertex: through normalise -> Gram-Schmidt -> normalise -> mean (tangent) and normalise (normal)
+__global__ void __launch_bounds__(256) tng_vertex_kernel(TngArgs g) {
+  const d3h_tangent_backward_args& a = g.a;
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= a.n_verts) return;
+  float* row = g.ws + 16ll * v;
+  double gt[3] = {row[8], row[9], row[10]};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (a.g_tng_wt != nullptr) gt[c] += a.g_tng_wt[3 * v + c];
+    if (a.g_tng_aug != nullptr) gt[c] += a.g_tng_aug[3 * v + c];
+  }
+  const double cnt = row[3];
+  double gs[3] = {0.0, 0.0, 0.0}, gn_sum[3] = {0.0, 0.0, 0.0};
+  if (cnt > 0.0 && (gt[0] != 0.0 || gt[1] != 0.0 || gt[2] != 0.0)) {
+    const double ns[3] = {row[0], row[1], row[2]};
+    const bool nondeg = ns[0] * ns[0] + ns[1] * ns[1] + ns[2] * ns[2] > 1e-20;       // else (0,0,1): a constant
+    const double nin[3] = {nondeg ? ns[0] : 0.0, nondeg ? ns[1] : 0.0, nondeg ? ns[2] : 1.0};
+    const double am[3] = {row[4] / cnt, row[5] / cnt, row[6] / cnt};
+    double n[3], t1[3], w[3], t2[3], ln, lt, lw;
+    bool fn, ft, fw;
+    normalize_fwd(nin, n, ln, fn);
+    normalize_fwd(am, t1, lt, ft);
+    const double proj = t1[0] * n[0] + t1[1] * n[1] + t1[2] * n[2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[c] = t1[c] - proj * n[c];
+    normalize_fwd(w, t2, lw, fw);
+    double gw[3], gt1[3], gn[3], ga[3], gnin[3];
+    normalize_bwd(t2, lw, fw, gt, gw);
+    const double ngw = n[0] * gw[0] + n[1] * gw[1] + n[2] * gw[2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gt1[c] = gw[c] - n[c] * ngw;
+      gn[c] = -(proj * gw[c] + ngw * t1[c]);
+    }
+    normalize_bwd(t1, lt, ft, gt1, ga);
+    normalize_bwd(n, ln, fn, gn, gnin);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gs[c] = ga[c] / cnt;
+      gn_sum[c] = nondeg ? gnin[c] : 0.0;
+    }
+  }
+  row[4] = (float)gs[0]; row[5] = (float)gs[1]; row[6] = (float)gs[2];
+  row[12] = (float)gn_sum[0]; row[13] = (float)gn_sum[1]; row[14] = (float)gn_sum[2];
+}
+
+// thread per face: g_S and g_N of its three vertices -> the edge vectors -> the vertex positions
+__global__ void __launch_bounds__(256) tng_scatter_kernel(TngArgs g, int64_t n_faces) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_faces) return;
+  const FaceGeom q = face_geom(g, f);
+  double gt[3] = {0.0, 0.0, 0.0}, gf[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* row = g.ws + 16ll * q.v[c];
+    gt[0] += row[4]; gt[1] += row[5]; gt[2] += row[6];
+    gf[0] += row[12]; gf[1] += row[13]; gf[2] += row[14];
+  }
+  if (gt[0] == 0.0 && gt[1] == 0.0 && gt[2] == 0.0 && gf[0] == 0.0 && gf[1] == 0.0 && gf[2] == 0.0) return;
+  const double e1[3] = {q.e1[0], q.e1[1], q.e1[2]}, e2[3] = {q.e2[0], q.e2[1], q.e2[2]};
+  // fn = e1 x e2: g_e1 = e2 x g_fn, g_e2 = g_fn x e1;  tang = (e1 u2y - e2 u1y) / den
+  const double c1[3] = {e2[1] * gf[2] - e2[2] * gf[1], e2[2] * gf[0] - e2[0] * gf[2], e2[0] * gf[1] - e2[1] * gf[0]};
+  const double c2[3] = {gf[1] * e1[2] - gf[2] * e1[1], gf[2] * e1[0] - gf[0] * e1[2], gf[0] * e1[1] - gf[1] * e1[0]};
+  float* out = g.a.g_verts;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double gnom = gt[c] / (double)q.den;
+    const double g1 = gnom * (double)q.u2y + c1[c], g2 = -gnom * (double)q.u1y + c2[c];
+    atomicAdd(out + 3ll * q.v[1] + c, (float)g1);
+    atomicAdd(out + 3ll * q.v[2] + c, (float)g2);
+    atomicAdd(out + 3ll * q.v[0] + c, (float)(-(g1 + g2)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // second extraction of a cloth / body pair
 // ------------------------------------------------------------------------------------------------
 // Stores the pair's argument block and writes everything of the second extraction that hangs off a watertight vertex:
@@ -663,3 +840,37 @@ void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3
 }
 
 }  // namespace d3h
+
+
+extern "C" int d3h_tangent_backward(const d3h_tangent_backward_args* a, d3h_stream_t s) {
+  using namespace d3h;
+  if (!a) { set_error("d3h_tangent_backward: null argument struct"); return D3H_E_BADARG; }
+  const int64_t nv = a->n_verts, npoly = a->n_tri_tets + a->n_quad_tets, nf = a->n_tri_tets + 2 * a->n_quad_tets;
+  if (nv < 0 || a->n_tri_tets < 0 || a->n_quad_tets < 0 || a->n_tets <= 0 || (nv > 0 && (!a->verts_wt || !a->msdf_wt ||
+      !a->v_tng_wt || !a->g_verts || !a->g_mvert || !a->workspace)) || (nf > 0 && !a->faces_wt) || (npoly > 0 && !a->tape_corners) ||
+      (reinterpret_cast<uintptr_t>(a->workspace) & 15) || a->workspace_bytes < 64 * nv) {
+    set_error("d3h_tangent_backward: bad argument (null pointer, negative size, or workspace smaller than 64 bytes per vertex)");
+    return D3H_E_BADARG;
+  }
+  if (nf == 3) {
+    set_error("d3h_tangent_backward: a watertight mesh of exactly three faces (torch.cross without dim, gshell_tets.py:19) is not supported");
+    return D3H_E_BADARG;
+  }
+  cudaStream_t stream = (cudaStream_t)s;
+  if (nv == 0) return D3H_OK;
+  cudaMemsetAsync(a->workspace, 0, (size_t)64 * nv, stream);
+  cudaMemsetAsync(a->g_verts, 0, (size_t)12 * nv, stream);
+  cudaMemsetAsync(a->g_mvert, 0, (size_t)4 * nv, stream);
+  TngArgs g;
+  g.a = *a;
+  g.ws = reinterpret_cast<float*>(a->workspace);
+  g.uvp = uv_params(a->n_tets);
+  if (a->g_tng_aug != nullptr && npoly > 0)
+    launch_k(tng_boundary_kernel, (unsigned)((npoly + 255) / 256), 256u, stream, kLaunchLatency, g);
+  if (nf > 0) launch_k(tng_accumulate_kernel, (unsigned)((nf + 255) / 256), 256u, stream, kLaunchLatency, g, nf);
+  launch_k(tng_vertex_kernel, (unsigned)((nv + 255) / 256), 256u, stream, kLaunchLatency, g);
+  if (nf > 0) launch_k(tng_scatter_kernel, (unsigned)((nf + 255) / 256), 256u, stream, kLaunchLatency, g, nf);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d3h_tangent_backward: %s", cudaGetErrorString(e)); return D3H_E_CUDA; }
+  return D3H_OK;
+}

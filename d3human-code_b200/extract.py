@@ -644,7 +644,9 @@ def _collect_frames(pend: _Pending) -> BatchResult:
     bmat = pend.bmat
     if bmat is not None:
         bmat[:, _BC["n_verts"]:_BC["n_quad_tets"] + 1] = sizes[:, (4, 1, 2)]
-    return BatchResult(frames, fslab, islab, pend.tape, lay.tape_off, launches, bmat)
+    res = BatchResult(frames, fslab, islab, pend.tape, lay.tape_off, launches, bmat)
+    res.geom = (cv, cfa, i_len)      # cap_v, cap_fa, int64 words per frame of the index slab (tangent branch of the backward)
+    return res
 
 
 def _collect_packed(pend: _Pending):
@@ -786,9 +788,9 @@ class _ExtractFn(torch.autograd.Function):
     spec = (frame refs, watertight_template, lanes); a frame ref is (pos, sdf, msdf, negate) where each of pos / sdf /
     msdf is (input index, row): row >= 0 selects one row of a stacked (B,N,3) / (B,N) input, row < 0 the whole tensor.
 
-    Differentiable outputs: verts_aug, msdf (augmented, stop-grad coefficients), vertices_watertight, msdf_watertight.
-    v_tng_* are returned for API parity but are not differentiated (the reference's own training never consumes
-    them, hmsdf.py:454,548); asking for their gradient raises instead of silently returning zeros.
+    Differentiable outputs: verts_aug, msdf (augmented, stop-grad coefficients), vertices_watertight, msdf_watertight, and
+    -- through the optional tangent branch (tangent_branch / d3h_tangent_backward; the reference's own training never
+    consumes them, hmsdf.py:454,548) -- v_tng_aug and v_tng_watertight.
     """
 
     @staticmethod
@@ -803,8 +805,10 @@ class _ExtractFn(torch.autograd.Function):
         pend, gbufs, n_grid = started
         res = _collect_frames(pend)
         ctx.save_for_backward(*tensors, res.tape, res.fslab)   # the slabs hold the tape and verts_wt / msdf_wt of all frames
+        ctx.islab = res.islab                                  # faces_watertight: only read by the tangent branch of the backward pass
         ctx.bmat = res.bmat
         ctx.meta = (refs, tets_i32.shape[0], n_grid, [(f.n_verts, f.n_tri, f.n_quad) for f in res.frames], lanes)
+        ctx.caps = res.geom
         ctx.gbufs = gbufs
         ctx.set_materialize_grads(False)
         flat = []
@@ -847,19 +851,23 @@ class _ExtractFn(torch.autograd.Function):
                         bmat[i, _BC[names[k]]] = gbufs[idx].data_ptr() + (row * row_bytes[k] if row > 0 else 0)
             keep = []
             live = []
+            tng = []  # frames with upstream tangent gradients: (frame, g_verts, g_mvert, kept tensors)
+            cap_v, cap_fa, i_len = ctx.caps
             gp = []   # per live frame: pointers of g_verts_aug, g_msdf_aug, g_verts_wt, g_msdf_wt (adjacent columns)
             gb = []   # ... and of the gradient of the msdf_boundary view
             f32 = torch.float32
             for i in range(len(refs)):
                 o = _OUTS_PER_FRAME * i
                 g0, g1, g2, g3, g4, g5, g6 = grads[o:o + 7]
-                if g1 is not None or g4 is not None:
-                    raise NotImplementedError(
-                        "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
-                        "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
-                if g0 is None and g2 is None and g3 is None and g5 is None and g6 is None:
+                if g0 is None and g1 is None and g2 is None and g3 is None and g4 is None and g5 is None and g6 is None:
                     continue  # nothing flows into this frame
                 n_verts, n_tri, n_quad = sizes[i]
+                if g1 is not None or g4 is not None:
+                    # optional branch: through the tangents -> extra per-vertex gradients for the adjoint
+                    tng.append((i,) + tangent_branch(
+                        dev, n_tets, int(bmat[i, _BC["verts_wt"]]), int(bmat[i, _BC["msdf_wt"]]),
+                        int(bmat[i, _BC["verts_wt"]]) + 12 * _r4(cap_v), ctx.islab.data_ptr() + 8 * (i * i_len + 3 * cap_fa),
+                        int(bmat[i, _BC["tape_corners"]]), n_verts, n_tri, n_quad, g1, g4))
                 va = n_verts + 3 * n_tri + 4 * n_quad
                 row = []
                 for t, rows in ((g0, va), (g2, va), (g3, n_verts), (g5, n_verts), (g6, va - n_verts)):
@@ -875,6 +883,10 @@ class _ExtractFn(torch.autograd.Function):
                 gp.append(row)
                 live.append(i)
             if live:
+                bmat[:, _BC["g_verts_tng"]] = 0
+                bmat[:, _BC["g_mvert_tng"]] = 0
+                for i, gvt, gmt, _k in tng:
+                    bmat[i, _BC["g_verts_tng"]], bmat[i, _BC["g_mvert_tng"]] = gvt.data_ptr(), gmt.data_ptr()
                 m = bmat if len(live) == len(refs) else np.ascontiguousarray(bmat[live])
                 m[:, _BC["g_verts_aug"]:_BC["g_msdf_wt"] + 1] = gp
                 m[:, _BC["g_msdf_boundary"]] = gb
@@ -976,6 +988,41 @@ def extract_generic(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, 
     tets = packed_tets(tet_fx4, n_grid)
     spec = ((((0, -1), (1, -1), (2, -1), bool(msdf_negate)),), bool(output_watertight_template), 1)
     return _pack_result(_ExtractFn.apply(spec, tets, pos, sdf, msdf), output_watertight_template)
+
+
+def tangent_branch(dev, n_tets, verts_wt_ptr, msdf_wt_ptr, v_tng_wt_ptr, faces_wt_ptr, corners_ptr, v, t1, t2, g_aug, g_wt):
+    """Backward pass through the tangents (d3h_tangent_backward; SURVEY A.5 optional branch): upstream gradients of
+    v_tng_aug (Va,3) / extra['v_tng_watertight'] (V,3) -> (g_verts (V,3), g_mvert (V)) for d3h_backward_args.g_*_tng."""
+    f32 = torch.float32
+    keep = []
+
+    def ptr(t, rows):
+        if t is None:
+            return 0
+        if t.dtype is not f32 or not t.is_contiguous():
+            t = t.contiguous().float()
+        keep.append(t)
+        assert t.shape[0] == rows, (tuple(t.shape), rows)
+        return t.data_ptr()
+
+    g_verts = torch.empty((v, 3), dtype=f32, device=dev)
+    g_mvert = torch.empty((v,), dtype=f32, device=dev)
+    ws = torch.empty(16 * max(v, 1), dtype=f32, device=dev)
+    a = _cabi.TangentBackwardArgs()
+    a.verts_wt, a.msdf_wt, a.v_tng_wt, a.faces_wt, a.tape_corners = verts_wt_ptr, msdf_wt_ptr, v_tng_wt_ptr, faces_wt_ptr, corners_ptr
+    a.n_verts, a.n_tri_tets, a.n_quad_tets, a.n_tets = v, t1, t2, n_tets
+    a.g_tng_aug, a.g_tng_wt = ptr(g_aug, v + 3 * t1 + 4 * t2), ptr(g_wt, v)
+    a.g_verts, a.g_mvert = g_verts.data_ptr(), g_mvert.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), 64 * v
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().d3h_tangent_backward(C.addressof(a), torch.cuda.current_stream(dev).cuda_stream)
+    if rc:
+        msg = _cabi.lib().d3h_last_error_string().decode("utf-8", "replace")
+        if "three faces" in msg:
+            raise NotImplementedError(msg)
+        _cabi.check(rc, "d3h_tangent_backward")
+    _ExtractFn.total_launches += 4
+    return g_verts, g_mvert, (keep, ws)
 
 
 def _tape_edges(tape3, i: int) -> torch.Tensor:

@@ -225,8 +225,8 @@ class _SingleFn(torch.autograd.Function):
     """One frame as one autograd node: forward = one library call, backward = one library call.
 
     Differentiable outputs: verts_aug, extra['msdf'], vertices_watertight, msdf_watertight, msdf_boundary (= msdf[V:]).
-    v_tng_* are outputs of the node so that asking for their gradient raises (the reference's training never consumes
-    them, hmsdf.py:454,548) instead of silently yielding zeros.  The int64 face arrays are handed over through `st`."""
+    v_tng_* are differentiable through the optional tangent branch (extract.tangent_branch; the reference's training
+    never consumes them, hmsdf.py:454,548).  The int64 face arrays are handed over through `st`."""
 
     @staticmethod
     def forward(ctx, st, pos, sdf, msdf):
@@ -243,6 +243,7 @@ class _SingleFn(torch.autograd.Function):
         msdf_bnd = _ast(fslab, (p,), (1,), o[2] + v)
         st.side = (_ast(islab, (nfa, 3), (3, 1), 0), _ast(islab, (fw, 3), (3, 1), 3 * g.caps[3]), counts)
         ctx.st, ctx.geom, ctx.fslab, ctx.gbufs, ctx.sizes = st, g, fslab, gbufs, (v, t1, t2, va)
+        ctx.islab = islab                 # faces_watertight: only read by the tangent branch of the backward pass
         ctx.save_for_backward(pos, sdf, msdf)
         ctx.set_materialize_grads(False)
         E._ExtractFn.total_launches += launches
@@ -251,10 +252,6 @@ class _SingleFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g0, g1, g2, g3, g4, g5, g6):
-        if g1 is not None or g4 is not None:
-            raise NotImplementedError(
-                "gradients through v_tng (vertex tangents) are not implemented; D3-Human never uses them "
-                "(hmsdf.py:454,548 drop v_tng). Detach v_tng before using it in a loss.")
         st, g = ctx.st, ctx.geom
         pos, sdf, msdf = ctx.saved_tensors
         need = ctx.needs_input_grad[1:]
@@ -266,11 +263,20 @@ class _SingleFn(torch.autograd.Function):
             gbufs = (torch.zeros_like(pos), torch.zeros_like(sdf),
                      torch.zeros_like(msdf) if (need[2] and not st.negate) else None)
         gp, gs, gm = gbufs
-        if g0 is None and g2 is None and g3 is None and g5 is None and g6 is None:
+        if g0 is None and g1 is None and g2 is None and g3 is None and g4 is None and g5 is None and g6 is None:
             return None, gp if need[0] else None, gs if need[1] else None, gm if need[2] else None
         v, t1, t2, va = ctx.sizes
         ba = st.ba
         keep = []
+        ba.g_verts_tng = ba.g_mvert_tng = 0
+        if g1 is not None or g4 is not None:
+            # optional branch: through the tangents -> extra per-vertex gradients for the adjoint kernel
+            fb_ = ctx.fslab.data_ptr()
+            gvt, gmt, kept = E.tangent_branch(
+                st.dev, st.n_tets, fb_ + 4 * g.o[3], fb_ + 4 * g.o[5], fb_ + 4 * g.o[4], ctx.islab.data_ptr() + 24 * g.caps[3],
+                fb_ + 4 * (g.o_tape + g.t_corn), v, t1, t2, g1, g4)
+            keep.append((gvt, gmt, kept))
+            ba.g_verts_tng, ba.g_mvert_tng = gvt.data_ptr(), gmt.data_ptr()
 
         def ptr(t, rows):
             if t is None:

@@ -194,7 +194,37 @@ typedef struct d3h_backward_args {
   /* static-edge-table calls: tape_slots / tape_runs are NULL and the adjoint runs in scatter form through this
    * (n_verts,8) accumulator (zero on entry -- the forward call zeroes it -- and zero again on return) */
   float* vacc;
+  /* optional: what arrives through the TANGENT branch (d3h_tangent_backward, SURVEY A.5 "optional branch"): gradient
+   * w.r.t. the watertight vertex positions (V,3) and w.r.t. the interpolated mSDF through the boundary coefficients (V);
+   * added to the per-vertex gradients before the crossing-edge step.  NULL = none. */
+  const float* g_verts_tng;
+  const float* g_mvert_tng;
 } d3h_backward_args;
+
+/* ---- tangent branch of the backward pass (optional) ---------------------------------------------------------------
+ * Adjoint of auto_normals (gshell_tets.py:9-34), compute_tangents (:40-78: per-face tangents from the vertex-id UVs,
+ * scatter-mean, normalise, Gram-Schmidt against the normal, normalise) and of the boundary interpolation of the tangents
+ * (:380-385), for upstream gradients on v_tng_aug (Va,3) and / or extra['v_tng_watertight'] (V,3).  D3-Human never
+ * back-propagates through the tangents (hmsdf.py:454,548 drop them); provided for API completeness.  Writes g_verts
+ * (V,3) and g_mvert (V) -- pass them to d3h_extract_backward as g_verts_tng / g_mvert_tng.  `workspace`: 16 floats per
+ * watertight vertex, 16-byte aligned.  A watertight mesh of exactly three faces (the torch.cross quirk, :19) is refused
+ * with D3H_E_BADARG. */
+typedef struct d3h_tangent_backward_args {
+  const float* verts_wt;        /* (V,3)  extra['vertices_watertight'] of the forward call */
+  const float* msdf_wt;         /* (V)    */
+  const float* v_tng_wt;        /* (V,3)  extra['v_tng_watertight'] */
+  const int64_t* faces_wt;      /* (Fw,3) */
+  const int32_t* tape_corners;  /* polygon corner -> watertight vertex id, [3*T1 | 4*T2] */
+  int64_t n_verts, n_tri_tets, n_quad_tets;
+  int64_t n_tets;               /* F of the grid (defines the UV atlas, gshell_tets.py:319) */
+  const float* g_tng_aug;       /* (Va,3) or NULL */
+  const float* g_tng_wt;        /* (V,3)  or NULL */
+  float* g_verts;               /* (V,3) out */
+  float* g_mvert;               /* (V)   out */
+  void* workspace;
+  int64_t workspace_bytes;      /* >= 64 * V */
+} d3h_tangent_backward_args;
+int d3h_tangent_backward(const d3h_tangent_backward_args* args, d3h_stream_t stream);
 
 int d3h_version(void);
 const char* d3h_last_error_string(void);

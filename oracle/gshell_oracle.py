@@ -401,14 +401,106 @@ def tangent_condition(fwd):
 # --------------------------------------------------------------------------------------
 # backward (hand-derived adjoint of the float pipeline)
 # --------------------------------------------------------------------------------------
-def extract_backward(fwd, g_verts_aug=None, g_msdf=None, g_vertices_watertight=None, g_msdf_watertight=None):
+def tangent_backward(fwd, g_v_tng_aug=None, g_v_tng_watertight=None):
+    """Adjoint of the tangent branch (gshell_tets.py:9-34 auto_normals, :40-78 compute_tangents, :380-385 the boundary
+    interpolation of the tangents; SURVEY A.5 "optional branch"), float64.
+    -> (g_vert (V,3): gradient w.r.t. the watertight vertex positions, g_mv (V,): w.r.t. msdf_vert through the boundary
+    coefficients); both are ADDED to what extract_backward accumulates before the crossing-edge step.
+    Not covered: a watertight mesh of exactly three faces (the torch.cross quirk, :19)."""
+    f8 = np.float64
+    nv = fwd["n_verts_watertight"]
+    faces = fwd["faces_watertight"]
+    if faces.shape[0] == 3:
+        raise NotImplementedError("tangent gradients on a three-face mesh (torch.cross without dim)")
+    verts = fwd["vertices_watertight"].astype(f8)
+    corners, nxt = fwd["corners"], fwd["_nxt"]
+    tng = fwd["v_tng_watertight"].astype(f8)
+    g_t2 = np.zeros((nv, 3), f8)
+    g_mv = np.zeros(nv, f8)
+    if g_v_tng_watertight is not None:
+        g_t2 += np.asarray(g_v_tng_watertight, f8)
+    if g_v_tng_aug is not None:
+        g_aug = np.asarray(g_v_tng_aug, f8)
+        g_t2 += g_aug[:nv]
+        g_bt = g_aug[nv:]                                  # (v_tng_aug rows are NOT zeroed for unused vertices, A.2.11)
+        u0, u1, nz, big_d = fwd["_u0"].astype(f8), fwd["_u1"].astype(f8), fwd["_nz"], fwd["_D"].astype(f8)
+        np.add.at(g_t2, corners, g_bt * u0[:, None])
+        np.add.at(g_t2, nxt, g_bt * u1[:, None])
+        g_u0 = np.sum(g_bt * tng[corners], -1)
+        g_u1 = np.sum(g_bt * tng[nxt], -1)
+        safe_d = np.where(nz, big_d, 1.0)
+        g_d = np.where(nz, -(g_u0 * u0 + g_u1 * u1) / safe_d, 0.0)
+        np.add.at(g_mv, corners, np.where(nz, g_u1 / safe_d + g_d, 0.0))
+        np.add.at(g_mv, nxt, np.where(nz, -(g_u0 / safe_d + g_d), 0.0))
+    g_vert = np.zeros((nv, 3), f8)
+    if faces.shape[0] == 0:
+        return g_vert, g_mv
+    # ---- forward intermediates again, in float64 ----
+    i0, i1, i2 = faces[:, 0], faces[:, 1], faces[:, 2]
+    e1, e2 = verts[i1] - verts[i0], verts[i2] - verts[i0]
+    fn = np.cross(e1, e2)
+    n_sum = np.zeros((nv, 3), f8)
+    for c in range(3):
+        np.add.at(n_sum, faces[:, c], fn)
+    uv = [vertex_uv(faces[:, i], fwd["_num_tets"]).astype(f8) for i in range(3)]
+    uve1, uve2 = uv[1] - uv[0], uv[2] - uv[0]
+    den = uve1[:, 0] * uve2[:, 1] - uve1[:, 1] * uve2[:, 0]
+    den = np.where(den > 0, np.maximum(den, 1e-6), np.minimum(den, -1e-6))
+    tang = (e1 * uve2[:, 1:2] - e2 * uve1[:, 1:2]) / den[:, None]
+    t_sum = np.zeros((nv, 3), f8)
+    cnt = np.zeros(nv, f8)
+    for c in range(3):
+        np.add.at(t_sum, faces[:, c], tang)
+        np.add.at(cnt, faces[:, c], 1.0)
+
+    def normalize_bwd(x, gy, eps=1e-20):
+        """y = x / sqrt(max(x.x, eps)) -> (y, g_x)"""
+        d = np.sum(x * x, -1, keepdims=True)
+        length = np.sqrt(np.maximum(d, eps))
+        y = x / length
+        free = d > eps                                      # (clamped branch: the length is a constant)
+        gx = np.where(free, (gy - y * np.sum(y * gy, -1, keepdims=True)) / length, gy / length)
+        return y, gx
+
+    nondeg = np.sum(n_sum * n_sum, -1, keepdims=True) > 1e-20
+    n_in = np.where(nondeg, n_sum, np.array([0.0, 0.0, 1.0]))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = t_sum / cnt[:, None]
+    live = cnt > 0                                          # (a vertex of no face has a NaN tangent in the reference too)
+    a = np.where(live[:, None], a, 0.0)
+    n_unit, _ = normalize_bwd(n_in, np.zeros_like(n_in))
+    t1, _ = normalize_bwd(a, np.zeros_like(a))
+    proj = np.sum(t1 * n_unit, -1, keepdims=True)
+    w = t1 - proj * n_unit
+    _, g_w = normalize_bwd(w, g_t2)
+    g_t1 = g_w - n_unit * np.sum(n_unit * g_w, -1, keepdims=True)
+    g_n = -(proj * g_w + np.sum(n_unit * g_w, -1, keepdims=True) * t1)
+    _, g_a = normalize_bwd(a, g_t1)
+    g_s = np.where(live[:, None], g_a / np.where(live, cnt, 1.0)[:, None], 0.0)
+    _, g_nin = normalize_bwd(n_in, g_n)
+    g_nsum = np.where(nondeg, g_nin, 0.0)
+    # ---- faces ----
+    g_tang = g_s[i0] + g_s[i1] + g_s[i2]
+    g_nom = g_tang / den[:, None]
+    g_fn = g_nsum[i0] + g_nsum[i1] + g_nsum[i2]
+    g_e1 = g_nom * uve2[:, 1:2] + np.cross(e2, g_fn)
+    g_e2 = -g_nom * uve1[:, 1:2] + np.cross(g_fn, e1)
+    np.add.at(g_vert, i1, g_e1)
+    np.add.at(g_vert, i2, g_e2)
+    np.add.at(g_vert, i0, -(g_e1 + g_e2))
+    return g_vert, g_mv
+
+
+def extract_backward(fwd, g_verts_aug=None, g_msdf=None, g_vertices_watertight=None, g_msdf_watertight=None,
+                     g_v_tng_aug=None, g_v_tng_watertight=None, g_mvert_extra=None):
     """Gradients w.r.t. (pos, sdf, msdf) for upstream gradients on verts_aug, extra['msdf'],
     extra['vertices_watertight'], extra['msdf_watertight'].  float64 accumulation.
 
     Mirrors what autograd does through gshell_tets.py:291-303 (crossing interpolation, the stop-grad
     copy at :303), :342-397 (boundary interpolation; coefficients detached for the msdf attribute, :388-389)
     and the in-place zeroing at :427 (zeroed rows receive no gradient).
-    The tangent branch (:326-327, :380-385) is not differentiated here.
+    g_v_tng_aug / g_v_tng_watertight: upstream gradients of the tangents (tangent_backward above).
+    g_mvert_extra (V,): a gradient w.r.t. msdf_vert handed in directly (what d3h_backward_args.g_mvert_tng carries).
     """
     f8 = np.float64
     nv, n_grid = fwd["n_verts_watertight"], fwd["_n_grid"]
@@ -427,6 +519,12 @@ def extract_backward(fwd, g_verts_aug=None, g_msdf=None, g_vertices_watertight=N
     if g_msdf_watertight is not None:
         g_sg += np.asarray(g_msdf_watertight, f8)
     g_mv = np.zeros(nv, f8)  # grad wrt msdf_vert (through boundary coefficients)
+    if g_mvert_extra is not None:
+        g_mv += np.asarray(g_mvert_extra, f8)
+    if g_v_tng_aug is not None or g_v_tng_watertight is not None:
+        gt_vert, gt_mv = tangent_backward(fwd, g_v_tng_aug, g_v_tng_watertight)
+        g_vert += gt_vert
+        g_mv += gt_mv
 
     # boundary vertices
     u0, u1, nz, big_d = fwd["_u0"].astype(f8), fwd["_u1"].astype(f8), fwd["_nz"], fwd["_D"].astype(f8)

@@ -155,6 +155,7 @@ class FakeLib:
             self.tapes_pair = fwd                 # same tape address as the first extraction of the pair
         else:
             self.tapes[int(a.tape_edges)] = fwd
+            self.tapes[("corners", int(a.tape_corners))] = fwd      # the tangent branch finds the call by its corner array
         c.n_verts, c.n_faces_aug = v, fa
         per = (1, 2, 1, 2, 3, 4)
         for k in range(6):
@@ -230,6 +231,24 @@ class FakeLib:
             return _cabi.D3H_E_BADARG
         return rc
 
+    # ---- tangent branch (include/d3h_tets.h: d3h_tangent_backward) -----------------------------------------------------
+    def d3h_tangent_backward(self, ptr, stream):
+        a = _cabi.TangentBackwardArgs.from_address(int(ptr))
+        fwd = self.tapes.get(("corners", int(a.tape_corners)))
+        if fwd is None:
+            self.error = b"fake: unknown tape (tangent branch)"
+            return _cabi.D3H_E_BADARG
+        if fwd["faces_watertight"].shape[0] == 3:
+            self.error = b"fake: a watertight mesh of exactly three faces is not supported"
+            return _cabi.D3H_E_BADARG
+        v, va = fwd["n_verts_watertight"], fwd["verts_aug"].shape[0]
+        g_aug = _arr(a.g_tng_aug, 3 * va, C.c_float).reshape(-1, 3) if a.g_tng_aug else None
+        g_wt = _arr(a.g_tng_wt, 3 * v, C.c_float).reshape(-1, 3) if a.g_tng_wt else None
+        g_vert, g_mv = O.tangent_backward(fwd, g_aug, g_wt)
+        _arr(a.g_verts, 3 * v, C.c_float)[:] = g_vert.astype(np.float32).reshape(-1)
+        _arr(a.g_mvert, v, C.c_float)[:] = g_mv.astype(np.float32)
+        return 0
+
     # ---- backward -------------------------------------------------------------------------------------------------
     def d3h_extract_backward_batch(self, ptr, n_frames, lanes, stream):
         size = C.sizeof(_cabi.BackwardArgs)
@@ -259,7 +278,11 @@ class FakeLib:
                 gma[v:] += _arr(b.g_msdf_boundary, va - v, C.c_float)
             gvw = _arr(b.g_verts_wt, 3 * v, C.c_float).reshape(-1, 3) if b.g_verts_wt else None
             gmw = _arr(b.g_msdf_wt, v, C.c_float) if b.g_msdf_wt else None
-            g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gva, gma, gvw, gmw)
+            if b.g_verts_tng:     # through the tangent branch: added to the per-vertex gradients
+                extra_v = _arr(b.g_verts_tng, 3 * v, C.c_float).reshape(-1, 3)
+                gvw = extra_v.copy() if gvw is None else gvw + extra_v
+            gmx = _arr(b.g_mvert_tng, v, C.c_float) if b.g_mvert_tng else None
+            g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gva, gma, gvw, gmw, None, None, gmx)
             n = b.n_grid
             outs = ((b.g_pos, 3 * n, g_pos), (b.g_sdf, n, g_sdf), (b.g_msdf, n, g_msdf))
             for p, ln, g in outs:

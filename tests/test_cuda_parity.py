@@ -238,13 +238,85 @@ def test_msdf_boundary_view_carries_gradient(dev):
     U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), g_pos, U.GRAD_RTOL)
 
 
-def test_tangent_gradient_is_refused(dev):
-    pos, sdf, msdf, tets = _inputs(8, "sphere")
-    g, _ = _classes()
-    tp = torch.tensor(pos, device=dev, requires_grad=True)
-    out = g(tp, torch.tensor(sdf, device=dev), torch.tensor(msdf, device=dev), torch.tensor(tets, device=dev))
-    with pytest.raises(NotImplementedError):
-        out[4].sum().backward()
+def _tangent_upstream(fwd, rng, kappa_max=15.0):
+    """Upstream gradients of v_tng_aug / v_tng_watertight that vanish on ill-conditioned rows (where face normals or
+    tangents cancel the gradient of the unit vector grows like 1 / |sum| -- in the reference's autograd as well)."""
+    kap = O.tangent_condition(fwd)
+    nv = fwd["n_verts_watertight"]
+    ok = (kap < kappa_max).astype(np.float32)[:, None]
+    return (rng.standard_normal(fwd["v_tng_aug"].shape).astype(np.float32) * ok,
+            rng.standard_normal((nv, 3)).astype(np.float32) * ok[:nv])
+
+
+@pytest.mark.parametrize("res,field,cls,typ", [(12, "sphere", "GShell_Tets", None), (16, "capsule", "hmSDF_Tets", "cloth"),
+                                               (14, "capsule", "hmSDF_Tets", "body"), (24, "sphere", "hmSDF_Tets", "cloth")])
+def test_tangent_gradients_match_oracle(dev, res, field, cls, typ):
+    """SURVEY A.5 optional branch: gradients through v_tng (normals, per-face tangents from the vertex-id UVs, Gram-Schmidt,
+    boundary interpolation of the tangents) -- d3h_tangent_backward against the oracle's float64 adjoint (pinned against
+    the reference's autograd in tests/test_oracle_vs_reference.py), alone and together with the other upstream gradients."""
+    pos, sdf, msdf, tets = _inputs(res, field)
+    rng = np.random.default_rng(res)
+    pos = (pos + 0.2 / res * rng.standard_normal(pos.shape)).astype(np.float32)      # break the lattice symmetry
+    fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, True)
+    g_aug, g_wt = _tangent_upstream(fwd, rng)
+    g, h = _classes()
+    tt = torch.tensor(tets, device=dev)
+    for with_rest in (False, True):
+        tp = torch.tensor(pos, device=dev, requires_grad=True)
+        ts = torch.tensor(sdf, device=dev, requires_grad=True)
+        tm = torch.tensor(msdf, device=dev, requires_grad=True)
+        verts, faces, _, _, v_tng, extra = g(tp, ts, tm, tt) if cls == "GShell_Tets" else h(tp, ts, tm, tt, typ)
+        loss = (v_tng * torch.tensor(g_aug, device=dev)).sum() + (extra["v_tng_watertight"] * torch.tensor(g_wt, device=dev)).sum()
+        gv = gm = None
+        if with_rest:
+            gv = rng.standard_normal(fwd["verts_aug"].shape).astype(np.float32)
+            gm = rng.standard_normal(fwd["msdf"].shape).astype(np.float32)
+            loss = loss + (verts * torch.tensor(gv, device=dev)).sum() + (extra["msdf"] * torch.tensor(gm, device=dev)).sum()
+        loss.backward()
+        g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, gm, None, None, g_aug, g_wt)
+        U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), g_pos, 1e-4)
+        U.assert_close_normwise("grad_sdf", ts.grad.cpu().numpy(), g_sdf, 1e-4)
+        if typ == "body":
+            assert tm.grad is None
+        else:
+            U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), g_msdf, 1e-4)
+
+
+def test_tangent_gradients_in_a_batch_and_three_face_refusal(dev):
+    """The same through extract_frames (one autograd node for several frames; only some frames carry tangent gradients);
+    the exactly-three-faces mesh (torch.cross without dim) is refused."""
+    from d3human_code_b200.extract import extract_frames
+    res = 14
+    pos, sdf, msdf, tets = _inputs(res, "capsule")
+    rng = np.random.default_rng(3)
+    pos_b = np.stack([(pos + 0.2 / res * rng.standard_normal(pos.shape)).astype(np.float32) for _ in range(3)])
+    fwds = [O.extract_forward(pos_b[i], sdf, msdf, tets, 1, True) for i in range(3)]
+    tp = torch.tensor(pos_b, device=dev, requires_grad=True)
+    ts = torch.tensor(sdf, device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    outs = extract_frames(tp, ts, tm, torch.tensor(tets, device=dev), types="cloth", lanes=2)
+    ups = [_tangent_upstream(f, rng) for f in fwds]
+    gv1 = rng.standard_normal(fwds[1]["verts_aug"].shape).astype(np.float32)
+    loss = (outs[0][4] * torch.tensor(ups[0][0], device=dev)).sum() + (outs[1][0] * torch.tensor(gv1, device=dev)).sum() \
+        + (outs[2][5]["v_tng_watertight"] * torch.tensor(ups[2][1], device=dev)).sum()
+    loss.backward()
+    want_sdf = np.zeros_like(sdf, dtype=np.float64)
+    wants = [O.extract_backward(fwds[0], None, None, None, None, ups[0][0], None),
+             O.extract_backward(fwds[1], gv1, None),
+             O.extract_backward(fwds[2], None, None, None, None, None, ups[2][1])]
+    for i, w in enumerate(wants):
+        U.assert_close_normwise(f"grad_pos[{i}]", tp.grad[i].cpu().numpy(), w[0], 1e-4)
+        want_sdf += w[1]
+    U.assert_close_normwise("grad_sdf", ts.grad.cpu().numpy(), want_sdf, 1e-4)
+    rec = U.load_golden([n for n in U.golden_cases() if "three" in n or "3face" in n or "cross" in n][0]) \
+        if [n for n in U.golden_cases() if "three" in n or "3face" in n or "cross" in n] else None
+    if rec is not None:
+        g, h = _classes()
+        t3 = torch.tensor(rec["pos"], device=dev, requires_grad=True)
+        out = g(t3, torch.tensor(rec["sdf"], device=dev), torch.tensor(rec["msdf"], device=dev), torch.tensor(rec["tets"], device=dev))
+        if out[5]["faces_watertight"].shape[0] == 3:
+            with pytest.raises(NotImplementedError):
+                out[4].sum().backward()
 
 
 # ---------------------------------------------------------------------------------------------- batches of frames

@@ -137,7 +137,6 @@ def test_regrowth(dev):
 
 def test_validation_and_refusals(dev):
     G.test_input_validation(dev)
-    G.test_tangent_gradient_is_refused(dev)
     G.test_msdf_boundary_view_carries_gradient(dev)
 
 
@@ -298,6 +297,16 @@ def test_mark_rows_variant(dev, edges_mode):
     finally:
         E.set_mark_rows(False)
         E.reset_plans()
+
+
+@pytest.mark.parametrize("res,field,cls,typ", [(12, "sphere", "GShell_Tets", None), (12, "capsule", "hmSDF_Tets", "cloth"),
+                                               (12, "capsule", "hmSDF_Tets", "body")])
+def test_tangent_gradients(dev, edges_mode, res, field, cls, typ):
+    G.test_tangent_gradients_match_oracle(dev, res, field, cls, typ)
+
+
+def test_tangent_gradients_batch(dev, edges_mode):
+    G.test_tangent_gradients_in_a_batch_and_three_face_refusal(dev)
 
 
 def test_fuzz_forward_against_oracle(dev):

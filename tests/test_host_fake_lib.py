@@ -93,8 +93,15 @@ def test_single_call_views_and_gradients(host, typ, wt):
         assert tm.grad is None
     else:
         U.assert_close_normwise("grad_msdf", tm.grad.numpy(), g_msdf, 1e-6)
-    with pytest.raises(NotImplementedError):
-        E.extract(tp, ts, tm, torch.tensor(tets))[4].sum().backward()
+    # gradients through the tangents (SURVEY A.5 optional branch): the host routes them through d3h_tangent_backward and
+    # hands its two per-vertex arrays to the adjoint call
+    tp.grad = ts.grad = tm.grad = None
+    out = E.extract(tp, ts, tm, torch.tensor(tets), msdf_negate=(typ == "body"), output_watertight_template=wt)
+    gt = np.random.default_rng(9).standard_normal(fwd["v_tng_aug"].shape).astype(np.float32)
+    (out[4] * torch.tensor(gt)).sum().backward()
+    g_pos, g_sdf, _ = O.extract_backward(fwd, None, None, None, None, gt, None)
+    U.assert_close_normwise("grad_pos (tangents)", tp.grad.numpy(), g_pos, 1e-5)
+    U.assert_close_normwise("grad_sdf (tangents)", ts.grad.numpy()[:, 0], g_sdf, 1e-5)
 
 
 def test_capacity_regrowth_and_shrink(host):

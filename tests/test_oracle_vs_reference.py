@@ -175,3 +175,45 @@ def test_oracle_matches_live_reference_at_named_sizes(res, field, cls, typ):
         assert tm.grad is None and g_msdf is None
     else:
         U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), bound)
+
+
+# ---------------------------------------------------------------------------------------------- tangent gradients
+def _well_conditioned_tangent_upstream(fwd, rng, kappa_max=15.0):
+    """Upstream gradients of v_tng_aug / v_tng_watertight that vanish on ill-conditioned rows (cancelling face normals /
+    tangents: the gradient of a unit vector grows like 1 / |sum|, in the reference's autograd as well)."""
+    kap = O.tangent_condition(fwd)
+    nv = fwd["n_verts_watertight"]
+    ok = (kap < kappa_max).astype(np.float32)[:, None]
+    g_aug = rng.standard_normal(fwd["v_tng_aug"].shape).astype(np.float32) * ok
+    g_wt = rng.standard_normal((nv, 3)).astype(np.float32) * ok[:nv]
+    return g_aug, g_wt
+
+
+@pytest.mark.parametrize("res,field,cls,typ", [(12, "sphere", "GShell_Tets", None), (16, "capsule", "hmSDF_Tets", "cloth"),
+                                               (14, "capsule", "hmSDF_Tets", "body"), (15, "sphere", "GShell_Tets", None)])
+def test_oracle_tangent_gradients_match_live_reference(res, field, cls, typ):
+    """SURVEY A.5 optional branch: gradients through v_tng (auto_normals, compute_tangents, Gram-Schmidt, the boundary
+    interpolation of the tangents) -- the oracle's hand-derived float64 adjoint against the reference's fp32 autograd."""
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = (grids.sphere_plane_field if field == "sphere" else grids.capsule_garment_field)(pos)
+    rng = np.random.default_rng(res)
+    pos = (pos + 0.2 / res * rng.standard_normal(pos.shape)).astype(np.float32)      # break the lattice symmetry
+    (verts, faces, _, _, v_tng, extra), (tp, ts, tm) = _run_reference(cls, typ, True, pos, sdf, msdf, tets)
+    fwd = O.extract_forward(pos, sdf, msdf, tets, -1 if typ == "body" else 1, True)
+    g_aug, g_wt = _well_conditioned_tangent_upstream(fwd, rng)
+    assert (np.abs(g_aug).sum(-1) > 0).mean() > 0.3          # a good share of the rows takes part
+    # 1. the tangent branch alone, 2. together with the position / mSDF outputs
+    for with_rest in (False, True):
+        tp.grad = ts.grad = tm.grad = None
+        loss = (v_tng * torch.tensor(g_aug)).sum() + (extra["v_tng_watertight"] * torch.tensor(g_wt)).sum()
+        gv = gm = None
+        if with_rest:
+            gv = rng.standard_normal(fwd["verts_aug"].shape).astype(np.float32)
+            gm = rng.standard_normal(fwd["msdf"].shape).astype(np.float32)
+            loss = loss + (verts * torch.tensor(gv)).sum() + (extra["msdf"] * torch.tensor(gm)).sum()
+        loss.backward(retain_graph=True)
+        g_pos, g_sdf, g_msdf = O.extract_backward(fwd, gv, gm, None, None, g_aug, g_wt)
+        U.assert_close_normwise("grad_pos", g_pos, tp.grad.numpy(), 2e-4)
+        U.assert_close_normwise("grad_sdf", g_sdf, ts.grad.numpy()[:, 0], 2e-4)
+        if typ != "body":
+            U.assert_close_normwise("grad_msdf", g_msdf, tm.grad.numpy(), 2e-4)
