@@ -593,57 +593,57 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ a, 
   }
 }
 
-// dz = (g w) * softplus'(a), dw += g^T a, db += sum g.  One warp per row for dz; the weight gradient is reduced per CTA
-// in shared memory first (k <= 256, d_out <= 8).
+// dz = (g w) * softplus'(a), dw += g^T a, db += sum g in one sweep over a.  Block = 64 x 4 threads: thread (x, y) owns the
+// 16-byte column groups x, x + 64, ... of rows y, y + 4, ... of the CTA's row range (coalesced 16-byte loads / stores),
+// keeps its share of dw in registers, the four row-threads are summed through shared memory, one atomic per column and CTA.
+constexpr int kHeadRows = 128;     // rows per CTA
+template <int DOUT>
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ a, int64_t lda, int64_t m, int k,
-                                                            const float* __restrict__ w, int d_out, const float* __restrict__ g,
+                                                            const float* __restrict__ w, const float* __restrict__ g,
                                                             float* __restrict__ dz, int64_t ldz, float* __restrict__ dw,
-                                                            float* __restrict__ db, int rows_per_cta) {
-  __shared__ float s_dw[8 * 256];
-  __shared__ float s_db[8];
-  for (int i = threadIdx.x; i < d_out * k; i += blockDim.x) s_dw[i] = 0.f;
-  if (threadIdx.x < 8) s_db[threadIdx.x] = 0.f;
-  __syncthreads();
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t r_end = min(m, r_begin + rows_per_cta);
-  float acc[8][8];       // [j][column slot]: columns lane, lane + 32, ... (k <= 256 -> 8 slots)
+                                                            float* __restrict__ db) {
+  __shared__ float s_dw[4][DOUT][256];
+  __shared__ float s_db[4][DOUT];
+  const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
+  const int64_t r_begin = (int64_t)blockIdx.x * kHeadRows, r_end = min(m, r_begin + kHeadRows);
+  const int groups = k / 4;                       // (k % 4 == 0, k <= 256: one group per thread x)
+  float4 wv[DOUT], acc[DOUT];
+  float gsum[DOUT];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < DOUT; ++j) {
+    wv[j] = x < groups ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)j * k) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gsum[j] = 0.f;
+  }
+  for (int64_t r = r_begin + y; r < r_end; r += 4) {
+    float gj[DOUT];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
-  float gsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t row = r_begin + warp; row < r_end; row += 8) {
-    float gj[8];
+    for (int j = 0; j < DOUT; ++j) { gj[j] = __ldg(g + r * DOUT + j); gsum[j] += gj[j]; }
+    if (x < groups) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a + r * lda) + x);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gj[j] = j < d_out ? g[row * d_out + j] : 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int col = (int)lane + 32 * c;
-      if (col >= k) break;
-      const float av = a[row * lda + col];
-      float t = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < d_out) { t = fmaf(gj[j], __ldg(w + (int64_t)j * k + col), t); acc[j][c] = fmaf(gj[j], av, acc[j][c]); }
-      dz[row * ldz + col] = t * softplus100_grad_from_output(av);
+      for (int j = 0; j < DOUT; ++j) {
+        t.x = fmaf(gj[j], wv[j].x, t.x); t.y = fmaf(gj[j], wv[j].y, t.y); t.z = fmaf(gj[j], wv[j].z, t.z); t.w = fmaf(gj[j], wv[j].w, t.w);
+        acc[j].x = fmaf(gj[j], av.x, acc[j].x); acc[j].y = fmaf(gj[j], av.y, acc[j].y);
+        acc[j].z = fmaf(gj[j], av.z, acc[j].z); acc[j].w = fmaf(gj[j], av.w, acc[j].w);
+      }
+      t.x *= softplus100_grad_from_output(av.x); t.y *= softplus100_grad_from_output(av.y);
+      t.z *= softplus100_grad_from_output(av.z); t.w *= softplus100_grad_from_output(av.w);
+      *(reinterpret_cast<float4*>(dz + r * ldz) + x) = t;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gsum[j] += gj[j];
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (j >= d_out) break;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int col = (int)lane + 32 * c;
-      if (col < k) atomicAdd(&s_dw[j * k + col], acc[j][c]);
-    }
-    if (lane == 0) atomicAdd(&s_db[j], gsum[j]);
+  for (int j = 0; j < DOUT; ++j) {
+    s_dw[y][j][4 * x] = acc[j].x; s_dw[y][j][4 * x + 1] = acc[j].y; s_dw[y][j][4 * x + 2] = acc[j].z; s_dw[y][j][4 * x + 3] = acc[j].w;
+    if (x == 0) s_db[y][j] = gsum[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < d_out * k; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
-  if (db != nullptr && threadIdx.x < d_out) atomicAdd(db + threadIdx.x, s_db[threadIdx.x]);
+  for (int i = threadIdx.x; i < DOUT * k; i += 256) {
+    const int j = i / k, c = i % k;
+    atomicAdd(dw + i, s_dw[0][j][c] + s_dw[1][j][c] + s_dw[2][j][c] + s_dw[3][j][c]);
+  }
+  if (db != nullptr && threadIdx.x < DOUT) atomicAdd(db + threadIdx.x, s_db[0][threadIdx.x] + s_db[1][threadIdx.x] + s_db[2][threadIdx.x] + s_db[3][threadIdx.x]);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -785,13 +785,24 @@ extern "C" int d3h_mlp_head(const float* a, int64_t lda, int64_t m, int32_t k, c
 
 extern "C" int d3h_mlp_head_backward(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, int32_t d_out,
                                      const float* g, float* dz, int64_t ldz, float* dw, float* db, d3h_stream_t stream) {
-  if (m < 0 || k <= 0 || k > 256 || d_out <= 0 || d_out > 8 || lda < k || ldz < k || !w || !dw || (m > 0 && (!a || !g || !dz))) {
-    set_error("d3h_mlp_head_backward: bad argument (K <= 256, 1 <= d_out <= 8)");
+  if (m < 0 || k <= 0 || k > 256 || (k % 4) || d_out <= 0 || d_out > 8 || lda < k || ldz < k || (lda % 4) || (ldz % 4) || !w || !dw ||
+      (m > 0 && (!a || !g || !dz)) || !aligned16(a) || !aligned16(dz) || !aligned16(w)) {
+    set_error("d3h_mlp_head_backward: bad argument (K <= 256 and a multiple of 4, 1 <= d_out <= 8, leading dimensions multiples of 4, "
+              "16-byte aligned a / dz / w)");
     return D3H_E_BADARG;
   }
   if (m == 0) return D3H_OK;
-  const int rows = 256;       // 8 warps x 32 rows: enough CTAs to fill the machine at the reference's 100000-point batches
-  head_backward_kernel<<<(unsigned)((m + rows - 1) / rows), 256, 0, (cudaStream_t)stream>>>(a, lda, m, k, w, d_out, g, dz, ldz, dw,
-                                                                                           db, rows);
+  const unsigned blocks = (unsigned)((m + kHeadRows - 1) / kHeadRows);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d_out) {
+    case 1: head_backward_kernel<1><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    case 2: head_backward_kernel<2><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    case 3: head_backward_kernel<3><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    case 4: head_backward_kernel<4><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    case 5: head_backward_kernel<5><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    case 6: head_backward_kernel<6><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    case 7: head_backward_kernel<7><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+    default: head_backward_kernel<8><<<blocks, 256, 0, st>>>(a, lda, m, k, w, g, dz, ldz, dw, db); break;
+  }
   return finish_launch("d3h_mlp_head_backward");
 }

@@ -78,7 +78,8 @@ int d3h_mlp_head(const float* a, int64_t lda, int64_t m, int32_t k, const float*
 
 /* Its backward pass in one sweep over a (the saved output of the last hidden layer, softplus applied):
  *   dz[m, k] = (sum_j g[m, j] w[j, k]) * (1 - exp(-100 a[m, k]))      gradient at the last hidden pre-activation
- *   dw[j, k] += sum_m g[m, j] a[m, k],  db[j] += sum_m g[m, j]        (ACCUMULATE) */
+ *   dw[j, k] += sum_m g[m, j] a[m, k],  db[j] += sum_m g[m, j]        (ACCUMULATE)
+ * K <= 256 and a multiple of 4, lda / ldz multiples of 4, a / dz / w 16-byte aligned. */
 int d3h_mlp_head_backward(const float* a, int64_t lda, int64_t m, int32_t k, const float* w, int32_t d_out,
                           const float* g, float* dz, int64_t ldz, float* dw, float* db, d3h_stream_t stream);
 

@@ -250,3 +250,25 @@ def test_packed_weight_cache_follows_in_place_updates_and_new_modules(dev):
         assert not torch.equal(w_before, net.net[4].weight.detach())
         check(net)
         del net, opt
+
+
+@pytest.mark.parametrize("m,d_out", [(1, 1), (515, 1), (4133, 3), (100000, 1)])
+def test_head_backward_matches_float64(dev, m, d_out):
+    """d3h_mlp_head_backward: dz = (g w) * softplus'(a), dw += g^T a, db += sum g (accumulating)."""
+    rng = np.random.default_rng(m + d_out)
+    k, lda, ldz = 256, 260, 264
+    a = np.abs(rng.standard_normal((m, lda)) * 0.02).astype(np.float32)
+    w = rng.standard_normal((d_out, k)).astype(np.float32)
+    g = rng.standard_normal((m, d_out)).astype(np.float32)
+    ta, tw, tg = (torch.tensor(t, device=dev) for t in (a, w, g))
+    dz = torch.full((m, ldz), 5.0, device=dev)
+    dw = torch.full((d_out, k), 1.0, device=dev)
+    db = torch.full((d_out,), 2.0, device=dev)
+    _cabi.check(_cabi.lib().d3h_mlp_head_backward(ta.data_ptr(), lda, m, k, tw.data_ptr(), d_out, tg.data_ptr(), dz.data_ptr(), ldz,
+                                                  dw.data_ptr(), db.data_ptr(), _st(dev)), "d3h_mlp_head_backward")
+    a64, g64 = a[:, :k].astype(np.float64), g.astype(np.float64)
+    want_dz = (g64 @ w.astype(np.float64)) * (1.0 - np.exp(-100.0 * a64))
+    got = dz.cpu().numpy()
+    assert _rel(got[:, :k], want_dz) < 1e-5 and (got[:, k:] == 5.0).all()
+    assert np.abs(dw.cpu().numpy() - 1.0 - g64.T @ a64).max() < 1e-5 * np.sqrt(m) * 4
+    assert np.abs(db.cpu().numpy() - 2.0 - g64.sum(0)).max() < 1e-5 * np.sqrt(m) * 4
