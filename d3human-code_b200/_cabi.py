@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = (
     "d3h_extract_forward_batch", "d3h_extract_forward_batch_nojoin", "d3h_lanes_join", "d3h_extract_backward_batch", "d3h_tangent_backward", "d3h_gather_rows", "d3h_classify_range", "d3h_extract_from_records",
     "d3h_mesh_edges_workspace_bytes", "d3h_mesh_edges", "d3h_mesh_wait_counts", "d3h_mesh_normals_forward",
     "d3h_mesh_normals_backward",
+    "d3h_lbs_blend", "d3h_lbs_blend_backward", "d3h_lbs_nearest_workspace_bytes", "d3h_lbs_nearest", "d3h_lbs_apply",
+    "d3h_lbs_apply_backward",
     "d3h_mlp_embed", "d3h_mlp_embed_backward", "d3h_mlp_packed_weight_bytes", "d3h_mlp_pack_weight", "d3h_mlp_linear", "d3h_mlp_wgrad_workspace_bytes", "d3h_mlp_wgrad", "d3h_mlp_head", "d3h_mlp_head_backward",
     "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
 )
@@ -169,6 +171,21 @@ def lib() -> C.CDLL:
         L.d3h_mlp_head.argtypes = [vp, i64, i64, i32, vp, vp, i32, vp, vp]
         L.d3h_mlp_head_backward.restype = C.c_int
         L.d3h_mlp_head_backward.argtypes = [vp, i64, i64, i32, vp, i32, vp, vp, i64, vp, vp, vp]
+    # include/d3h_lbs.h (not part of the CPU emulation either)
+    if hasattr(L, "d3h_lbs_apply"):
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+        L.d3h_lbs_blend.restype = C.c_int
+        L.d3h_lbs_blend.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+        L.d3h_lbs_blend_backward.restype = C.c_int
+        L.d3h_lbs_blend_backward.argtypes = [vp, vp, i64, i32, vp, vp]
+        L.d3h_lbs_nearest_workspace_bytes.restype = C.c_int64
+        L.d3h_lbs_nearest_workspace_bytes.argtypes = [i64]
+        L.d3h_lbs_nearest.restype = C.c_int
+        L.d3h_lbs_nearest.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp]
+        L.d3h_lbs_apply.restype = C.c_int
+        L.d3h_lbs_apply.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
+        L.d3h_lbs_apply_backward.restype = C.c_int
+        L.d3h_lbs_apply_backward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.d3h_profile_enable.restype = C.c_int
     L.d3h_profile_enable.argtypes = [C.c_int]
     L.d3h_profile_kinds.restype = C.c_int

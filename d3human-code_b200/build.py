@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libd3h_tets.so")
-SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_scan.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu", "d3h_mlp.cu"]
+SOURCES = ["d3h_api.cu", "d3h_classify.cu", "d3h_sort.cu", "d3h_scan.cu", "d3h_surface.cu", "d3h_backward.cu", "d3h_mesh.cu", "d3h_mlp.cu", "d3h_lbs.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "0"]
 
@@ -23,7 +23,7 @@ def _stale() -> bool:
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("d3h_tets.h", "d3h_mesh.h", "d3h_mlp.h")] + [__file__]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("d3h_tets.h", "d3h_mesh.h", "d3h_mlp.h", "d3h_lbs.h")] + [__file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -73,3 +73,27 @@ def load_reference_mlp():
         sys.modules[f"{pkg_name}.{sub}"] = mod
         spec.loader.exec_module(mod)
     return sys.modules[pkg_name + ".mlp"]
+
+
+def load_reference_lbs_methods():
+    """-> (interpolate_weights, apply_lbs_inverse): the two methods of `deform/smplx_exavatar_deformer.py:363-421` as plain
+    functions of a duck-typed `self` (attributes vs_template, lbs_weights, k), compiled from the reference source text with
+    a brute-force stand-in for `pytorch3d.ops.knn_points` (K nearest by squared distance, ascending; pytorch3d is not
+    installed here).  The class itself cannot be built: it loads the SMPL-X model files."""
+    import ast
+    import torch
+
+    def knn_points(p1, p2, K=1):
+        d = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)          # (N, P1, P2)
+        dist, idx = torch.topk(d, K, dim=2, largest=False, sorted=True)
+        return dist, idx, None
+
+    path = os.path.join(REF_ROOT, "deform", "smplx_exavatar_deformer.py")
+    with open(path) as fh:
+        tree = ast.parse(fh.read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "SMPLX_Deformer"][0]
+    wanted = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("interpolate_weights", "apply_lbs_inverse")]
+    mod = ast.Module(body=wanted, type_ignores=[])
+    ns = {"torch": torch, "knn_points": knn_points}
+    exec(compile(mod, path, "exec"), ns)
+    return ns["interpolate_weights"], ns["apply_lbs_inverse"]

@@ -20,7 +20,7 @@ def golden_cases():
     """extraction fixtures (oracle/make_golden.py); the mesh_* files belong to oracle/make_golden_mesh.py, the mlp_* files
     to oracle/make_golden_mlp.py"""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("mesh_", "mlp_"))]
+    return [n for n in names if not n.startswith(("mesh_", "mlp_", "lbs_"))]
 
 
 def golden_path(name):

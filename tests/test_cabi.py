@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_functions():
-    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("d3h_tets.h", "d3h_mesh.h", "d3h_mlp.h"))
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("d3h_tets.h", "d3h_mesh.h", "d3h_mlp.h", "d3h_lbs.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(d3h_[a-z0-9_]+)\s*\(", text)))
 
