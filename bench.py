@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--no-cold", action="store_true", help="skip the L2-flushed single-call leg")
     ap.add_argument("--no-split-pair", action="store_true", help="skip the configs[2] cloth/body pair leg")
     ap.add_argument("--no-sdf-query", action="store_true", help="skip the SDF-network leg (SURVEY 8f row 3)")
+    ap.add_argument("--no-lbs-stage", action="store_true", help="skip the skinning leg (SURVEY 8f row 4)")
     return ap.parse_args()
 
 
@@ -888,6 +889,19 @@ def main():
         except Exception as exc:  # noqa: BLE001
             sdf_query = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- the stage BEHIND the extraction and the mesh wrapper: skinning of the extracted vertices, this
+    # package against the reference's op sequence in PyTorch on the same device.  Never fatal.
+    lbs_stage = None
+    if world == 1 and not args.no_lbs_stage and dev_type == "cuda" and args.res == 128:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_lbs_bench", os.path.join(ROOT, "profiles", "lbs_bench.py"))
+            lb = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(lb)
+            lbs_stage = lb.measure(reps=5, dev=dev)
+        except Exception as exc:  # noqa: BLE001
+            lbs_stage = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- the reference's way on the same GPU: the path as plain PyTorch ops + autograd (oracle/gshell_torch.py, a port
     # pinned against the reference's golden vectors; the reference tree itself is not on this box).  SURVEY 8(d).  Never fatal.
     torch_baseline = None
@@ -930,7 +944,7 @@ def main():
             "roofline": roofline, "path_roofline": path_roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "ranks": ranks_info, "device_trace": dev_trace, "single_call": single, "cold": cold,
             "gpu_launches": int(launches_timed), "kernels": kern, "split_pair": split_pair,
-            "mesh_stage": mesh_stage, "sdf_query": sdf_query, "torch_gpu_baseline": torch_baseline, "clocks": sampler.result()}
+            "mesh_stage": mesh_stage, "sdf_query": sdf_query, "lbs_stage": lbs_stage, "torch_gpu_baseline": torch_baseline, "clocks": sampler.result()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
