@@ -552,6 +552,23 @@ def main():
         except Exception as exc:  # noqa: BLE001
             single["fwd_bwd_split_error"] = f"{type(exc).__name__}: {exc}"[:200]
 
+    # ---- the dominant kernel timed alone: back-to-back launches of edge_scan_kernel on the state the last single call left
+    # in its workspace, CUDA events around the whole run on the launching stream (d3h_profile_scan_kernel) ----
+    scan_alone_us = scan_warm_us = None
+    if rank == 0 and dev_type == "cuda":
+        try:
+            from d3human_code_b200 import single as S1
+            with torch.no_grad():
+                hm(pos_single[0].detach(), sdf.detach(), msdf.detach(), tets, "cloth")
+            flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            scan_alone_us = S1.profile_scan_kernel(tets, N, reps=50, flush=flush_buf)
+            scan_warm_us = S1.profile_scan_kernel(tets, N, reps=50, flush=None)
+            del flush_buf
+            E._ExtractFn.total_launches += 102 if scan_alone_us else 0
+        except Exception as exc:  # noqa: BLE001
+            scan_alone_us = None
+            sys.stderr.write(f"profile_scan_kernel: {type(exc).__name__}: {exc}\n")
+
     # ---- cold figure: the same single call with L2 flushed before every call (a 256 MB fill) ----
     cold = None
     if world == 1 and not args.no_cold:
@@ -740,7 +757,8 @@ def main():
             st = E.static_edges_for(E.packed_tets(tets, N), N)
             dom_bytes = 4.0 * st[2] + 4.0 * (N + 1) + N / 8.0
         if n and ms > 0:
-            t = ms / n * 1e-3
+            t_events = ms / n * 1e-3      # one launch at a time between two events: includes the ~3-7 us launch / event gap
+            t = scan_alone_us * 1e-6 if (dom == "edge_scan" and scan_alone_us) else t_events
             achieved = dom_bytes / t / 1e9
             traffic = None
             try:
@@ -753,8 +771,13 @@ def main():
             roofline = {"kernel": dom + "_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(dom_bytes), "us_per_launch": t * 1e6,
-                        "timing": "CUDA events recorded around each launch on its stream, one frame at a time (includes "
-                                  "the ~3-5 us event / launch gap)"}
+                        "timing": ("the kernel alone (d3h_profile_scan_kernel): 50 launches, each between its own pair of CUDA "
+                                   "events on the launching stream, L2 flushed by a 256 MB fill before every launch"
+                                   if (dom == "edge_scan" and scan_alone_us) else
+                                   "CUDA events recorded around each launch on its stream, one frame at a time"),
+                        "warm_l2_us_per_launch": scan_warm_us,
+                        "events_one_launch_at_a_time": {"us_per_launch": t_events * 1e6, "frac": dom_bytes / t_events / 1e9 / peak,
+                                                        "note": "includes the ~3-7 us launch / event gap of a lone launch"}}
             if dev_trace and "us_mean" in dev_trace and dom in dev_trace["us_mean"]:
                 td = dev_trace["us_mean"][dom] * 1e-6
                 roofline["device_timer"] = {"us_per_launch": td * 1e6, "achieved": dom_bytes / td / 1e9,

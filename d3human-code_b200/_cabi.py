@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "d3h_lbs_blend", "d3h_lbs_blend_backward", "d3h_lbs_nearest_workspace_bytes", "d3h_lbs_nearest", "d3h_lbs_apply",
     "d3h_lbs_apply_backward",
     "d3h_mlp_embed", "d3h_mlp_embed_backward", "d3h_mlp_packed_weight_bytes", "d3h_mlp_pack_weight", "d3h_mlp_linear", "d3h_mlp_wgrad_workspace_bytes", "d3h_mlp_wgrad", "d3h_mlp_head", "d3h_mlp_head_backward",
-    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
+    "d3h_profile_enable", "d3h_profile_kinds", "d3h_profile_kernel_name", "d3h_profile_read", "d3h_profile_timeline", "d3h_profile_scan_kernel", "d3h_trace_enable", "d3h_trace_read", "d3h_debug_table",
 )
 
 
@@ -195,6 +195,8 @@ def lib() -> C.CDLL:
     L.d3h_profile_read.argtypes = [C.c_void_p, C.c_void_p]
     L.d3h_profile_timeline.restype = C.c_int
     L.d3h_profile_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.d3h_profile_scan_kernel.restype = C.c_int
+    L.d3h_profile_scan_kernel.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.d3h_trace_enable.restype = C.c_int
     L.d3h_trace_enable.argtypes = [C.c_int]
     L.d3h_trace_read.restype = C.c_int

@@ -119,6 +119,7 @@ void launch_edge_emit(const d3h_forward_args& a, const Workspace& ws, cudaStream
 // list, then compacts / numbers only the tiles and edge blocks that were marked
 void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
 inline bool edge_scan_path(const d3h_forward_args& a) { return a.edge_off != nullptr && a.etets != nullptr; }
+void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);   // diagnostics: the stream kernel alone
 void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_tet_record* records,
                     cudaStream_t stream);
 // second extraction of a cloth / body pair: replays the mSDF cut on the shared surface (d3h_forward_args.pair_*)

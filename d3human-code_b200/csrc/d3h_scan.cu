@@ -544,6 +544,28 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
   trace_end(tr);
 }
 
+static ScanLists scan_lists(const d3h_forward_args& a, const Workspace& ws) {
+  ScanLists L;
+  L.tile_cnt = ws.tile_cnt;
+  L.eblock_cnt = ws.eblock_cnt;
+  L.q_cnt = ws.q_cnt;
+  L.vlist = ws.vlist;
+  L.elist_raw = ws.elist;
+  L.elist = a.watertight_template ? ws.elist : ws.elist2;
+  L.cap_qe = ws.cap_qe; L.cap_qv = ws.cap_qv;
+  return L;
+}
+
+void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
+  const ScanLists L = scan_lists(a, ws);
+  const int vpt = scan_vpt();
+  const int64_t per_cta = (int64_t)kEScanThreads * vpt;
+  const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
+  if (vpt == 1) launch_k(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+  else if (vpt == 2) launch_k(edge_scan_kernel<2>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+  else launch_k(edge_scan_kernel<4>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+}
+
 void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   ScanLists L;
   L.tile_cnt = ws.tile_cnt;

@@ -339,3 +339,20 @@ def extract(pos_nx3, sdf_n, msdf_n, tet_fx4, msdf_negate: bool = False, output_w
     else:   # gshell_tets.py:440-445
         extra = {"msdf": msdf_aug, "msdf_watertight": msdf_wt, "msdf_boundary": msdf_bnd}
     return verts_aug, faces_aug, None, None, v_tng_aug, extra
+
+
+def profile_scan_kernel(tet_fx4, n_grid: int, reps: int = 50, flush=None, msdf_negate: bool = False,
+                        output_watertight_template: bool = True):
+    """Diagnostics (bench.py `roofline`): microseconds per launch of edge_scan_kernel timed alone -- `reps` launches on
+    the workspace state the LAST single call on this grid left behind, each between its own pair of CUDA events, with the
+    uint8 tensor `flush` (larger than L2) filled before every launch (d3h_profile_scan_kernel).  None when the grid is not
+    on the edge-scan path (yet)."""
+    st = _state_for(tet_fx4, n_grid, bool(output_watertight_template), bool(msdf_negate))
+    if st.static is None or st.static[6] is None or not st.fa.workspace:
+        return None
+    ms = C.c_float(0.0)
+    rc = st.L.d3h_profile_scan_kernel(st.fa_ref, int(reps), flush.data_ptr() if flush is not None else None,
+                                      flush.numel() if flush is not None else 0, C.byref(ms), _raw_stream(st.dev_index))
+    if rc:
+        _cabi.check(rc, "d3h_profile_scan_kernel")
+    return float(ms.value) * 1e3 / reps

@@ -308,6 +308,15 @@ int d3h_profile_read(float* ms_by_kind, int* launches_by_kind);
 /* Timeline form: start / end (ms since the first recorded launch), kernel kind and a stream ordinal per launch, in launch
  * order; returns the number of entries written (<= cap) and clears the log. */
 int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, int* stream_id, int cap);
+
+/* Diagnostics: the dominant kernel of the edge-scan path timed ALONE -- `reps` launches of edge_scan_kernel on the state
+ * the last forward call with these arguments left in its workspace (argument block, sign bitmap), each between its own
+ * pair of CUDA events on `stream`; before every launch `flush` (caller-owned, > L2 size; NULL = no flush) is filled so
+ * that the static edge list is read from HBM, not from L2.  *ms_total = sum of the per-launch times (synchronises the
+ * stream).  The work queues of the workspace overflow harmlessly (writes are capacity-checked); the next forward call
+ * resets them.  bench.py divides the kernel's algorithmic bytes by ms_total / reps for `roofline`. */
+int d3h_profile_scan_kernel(const d3h_forward_args* args, int32_t reps, void* flush, int64_t flush_bytes, float* ms_total,
+                            d3h_stream_t stream);
 /* Device-side trace, usable inside the cached CUDA graphs: every forward kernel stamps %globaltimer when its first block
  * starts and when its last block exits.  d3h_trace_read fills out[64][24][2] (uint64 ns; row = seq % 64, column = kernel
  * kind as in d3h_profile_kernel_name) and clears the table.  enabling allocates a 24 KB device table (diagnostics only). */
