@@ -560,7 +560,7 @@ def main():
             from d3human_code_b200 import single as S1
             with torch.no_grad():
                 hm(pos_single[0].detach(), sdf.detach(), msdf.detach(), tets, "cloth")
-            flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
             scan_alone_us = S1.profile_scan_kernel(tets, N, reps=50, flush=flush_buf)
             scan_warm_us = S1.profile_scan_kernel(tets, N, reps=50, flush=None)
             del flush_buf
@@ -772,7 +772,7 @@ def main():
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(dom_bytes), "us_per_launch": t * 1e6,
                         "timing": ("the kernel alone (d3h_profile_scan_kernel): 50 launches, each between its own pair of CUDA "
-                                   "events on the launching stream, L2 flushed by a 256 MB fill before every launch"
+                                   "events on the launching stream, L2 evicted by reading a 256 MB buffer before every launch"
                                    if (dom == "edge_scan" and scan_alone_us) else
                                    "CUDA events recorded around each launch on its stream, one frame at a time"),
                         "warm_l2_us_per_launch": scan_warm_us,

@@ -311,8 +311,8 @@ int d3h_profile_timeline(float* start_ms, float* end_ms, int* kind, int* stream_
 
 /* Diagnostics: the dominant kernel of the edge-scan path timed ALONE -- `reps` launches of edge_scan_kernel on the state
  * the last forward call with these arguments left in its workspace (argument block, sign bitmap), each between its own
- * pair of CUDA events on `stream`; before every launch `flush` (caller-owned, > L2 size; NULL = no flush) is filled so
- * that the static edge list is read from HBM, not from L2.  *ms_total = sum of the per-launch times (synchronises the
+ * pair of CUDA events on `stream`; before every launch `flush` (caller-owned, > L2 size, 16-byte aligned; NULL = no flush)
+ * is READ through so that the static edge list comes from HBM, not from L2 (a fill would leave dirty lines behind).  *ms_total = sum of the per-launch times (synchronises the
  * stream).  The work queues of the workspace overflow harmlessly (writes are capacity-checked); the next forward call
  * resets them.  bench.py divides the kernel's algorithmic bytes by ms_total / reps for `roofline`. */
 int d3h_profile_scan_kernel(const d3h_forward_args* args, int32_t reps, void* flush, int64_t flush_bytes, float* ms_total,

@@ -13,18 +13,21 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
-SELECTION = [                              # about 45 s
-    "tests/test_emu_mesh.py",
+SELECTION = [                              # ~40 s: every golden case on the three edge paths + the newest kernels
     "tests/test_emu_parity.py::test_golden",
     "tests/test_emu_parity.py::test_regrowth",
+    "tests/test_emu_parity.py::test_tangent_gradients",
+]
+FULL = SELECTION + [                       # D3H_RACECHECK_FULL=1: another four minutes (clean at the end of round 2)
+    "tests/test_emu_mesh.py",
     "tests/test_emu_parity.py::test_batches",
     "tests/test_emu_parity.py::test_fused_pair_equals_two_calls",
     "tests/test_emu_parity.py::test_tet_edge_rank_table_variant",
-]
-FULL = SELECTION + [                       # D3H_RACECHECK_FULL=1: another minute (clean at the end of round 1)
+    "tests/test_emu_parity.py::test_mark_rows_variant",
     "tests/test_emu_parity.py::test_integer_intermediates",
     "tests/test_emu_parity.py::test_tet_range_sharding",
     "tests/test_emu_parity.py::test_random_tet_soups",
+    "tests/test_emu_parity.py::test_tet_soups_with_repeated_vertices",
     "tests/test_emu_parity.py::test_pipelined_groups_and_split",
 ]
 
