@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the plain-PyTorch-on-this-GPU leg (SURVEY 8d)")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--e2e-chunk", type=int, default=4, help="frames per pipelined chunk of the end-to-end leg")
+    ap.add_argument("--e2e-pos", choices=["copy", "mapped"], default="copy",
+                    help="end-to-end leg: per-frame positions copied to the device every step (copy), or read by the "
+                         "kernels straight from the pinned, device-mapped host buffer (mapped: only the rows of crossing-"
+                         "edge end points cross PCIe)")
     ap.add_argument("--mode", default="weak", choices=["weak", "strong", "tets"],
                     help="weak: --frames-per-rank frames on every rank (default); strong: BASELINE configs[3] as written, "
                          "--frames-total frames sharded over the ranks; tets: configs[4], one 256^3 extraction whose tet "
@@ -648,7 +652,17 @@ def main():
         d_sdf = torch.empty_like(sdf)
         d_msdf = torch.empty_like(msdf)
         d_flat = torch.zeros_like(flat_grad)
-        d_pos = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds]
+        mapped = args.e2e_pos == "mapped"
+        if mapped:
+            # CUDA tensors that ALIAS the pinned host buffer (unified addressing: pinned allocations are device-mapped at
+            # the same address): the kernels fetch the rows they need over PCIe, nothing is copied up front
+            class _Alias:
+                def __init__(self, t):
+                    self.__cuda_array_interface__ = {"shape": tuple(t.shape), "typestr": "<f4", "version": 2,
+                                                     "data": (t.data_ptr(), False), "strides": None}
+            d_pos = [torch.as_tensor(_Alias(host_pos[lo:hi]), device=dev) for lo, hi in bounds]
+        else:
+            d_pos = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds]
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         outs_host = None
         k_e2e = max(3, min(args.steps, 20))
@@ -667,10 +681,11 @@ def main():
                 h2d += host_sdf.numel() * 4 + host_msdf.numel() * 4
                 for dp, (lo, hi) in zip(d_pos, bounds):
                     dp.requires_grad_(False)
-                    dp.copy_(host_pos[lo:hi], non_blocking=True)
+                    if not mapped:
+                        dp.copy_(host_pos[lo:hi], non_blocking=True)
+                        h2d += dp.numel() * 4
                     dp.requires_grad_(True)
                     dp.grad = None
-                    h2d += dp.numel() * 4
                     ev = torch.cuda.Event()
                     ev.record(s_in)
                     ev_in.append(ev)
@@ -719,14 +734,15 @@ def main():
         # the PCIe floor of this step: its H2D bytes alone, copied from the same pinned buffers with nothing else running
         barrier()
         t0 = time.perf_counter()
+        floor_dst = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds] if mapped else d_pos
         for _ in range(3):
-            for dp, (lo, hi) in zip(d_pos, bounds):
+            for dp, (lo, hi) in zip(floor_dst, bounds):
                 dp.detach().copy_(host_pos[lo:hi], non_blocking=True)
         torch.cuda.synchronize()
         h2d_only = (time.perf_counter() - t0) / 3
         e2e = {"value": fps * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "steps": k_e2e, "ms_per_step": float(dt.item()) * 1e3,
-               "chunk_frames": chunk, "h2d_only_ms_per_step": h2d_only * 1e3,
+               "chunk_frames": chunk, "h2d_only_ms_per_step": h2d_only * 1e3, "pos": args.e2e_pos,
                "h2d_GBps": (int(h2d_b) - 8 * N) / h2d_only / 1e9,
                "note": "extract_frames_async() with inputs copied from pinned host memory each step (pos per frame, sdf, "
                        "msdf); per frame verts_aug, faces_aug, msdf and the COMPACT pos gradient (touched vertex ids + "
@@ -756,6 +772,11 @@ def main():
         if dom == "edge_scan":   # 4 B per edge (larger endpoint) + 4 B per vertex (CSR offsets) + the sign bitmap
             st = E.static_edges_for(E.packed_tets(tets, N), N)
             dom_bytes = 4.0 * st[2] + 4.0 * (N + 1) + N / 8.0
+            if len(st) > 9 and st[8] is not None:
+                # transposed rows (edge_scan_rows_kernel): 4 B per edge + 4 B per chunk of 32 vertices (row offsets) + the
+                # sign bitmap; the CSR offsets are only read by the few lanes that found a crossing edge, the padding
+                # slots of the rows (+2.5 % at 128^3) are not counted
+                dom_bytes = 4.0 * st[2] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
         if n and ms > 0:
             t_events = ms / n * 1e-3      # one launch at a time between two events: includes the ~3-7 us launch / event gap
             t = scan_alone_us * 1e-6 if (dom == "edge_scan" and scan_alone_us) else t_events

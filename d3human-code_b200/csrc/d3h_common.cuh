@@ -100,6 +100,12 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
                : "l"(p));
   return r;
 }
+// the same for one 4-byte word (coalesced rows of the transposed edge list: read once, must not evict the sign bitmap)
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p) {
+  int r;
+  asm("ld.global.nc.L1::no_allocate.L2::256B.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -113,6 +119,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) { return emu_load_relaxed(p); }
 __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) { emu_store_relaxed(p, v); }
 __device__ __forceinline__ int4 ld_stream_int4(const int4* p) { return *p; }
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p) { return *p; }
 __device__ __forceinline__ unsigned long long global_timer_ns() { return emu::now_ns(); }
 #endif
 // Several threads may store the SAME value to one address (every corner of a vertex writes the vertex's tangent rows on

@@ -33,6 +33,7 @@
 namespace d3h {
 
 constexpr int kEScanThreads = 256;
+constexpr int kScanChunksPerWarp = 4;   // edge_scan_rows_kernel: 128 vertices per warp, 32 row loads in flight per lane
 // vertices per thread of the stream (x 8 neighbour loads in flight each): D3H_SCAN_VPT = 1, 2 or 4 (default)
 static int scan_vpt() {
   static int v = 0;
@@ -139,6 +140,103 @@ edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
     for (int e = e0[k] + 8; e < e1[k]; ++e) {
       if ((occ_of(occ_bits, __ldg(edge_b + e)) ^ oa[k]) == 0u) continue;
       if (slot < L.cap_qe) out[slot] = e;
+      ++slot;
+    }
+  }
+  trace_end(tr);
+}
+
+// The stream over the TRANSPOSED edge list (d3h_forward_args.edge_rows, the default when the host built it).  The kernel
+// above is bound by its instructions, not by DRAM (ncu r02q: 26 instructions per edge, issue slots 61 % busy at 3.1 TB/s):
+// lane l's neighbours start at edge_off[v], 7 words apart from lane l+1's, so every load needs its own address, bound
+// check and predicate, and one load instruction touches 7 cache lines.  Here a chunk of 32 consecutive vertices owns
+// whole 128-byte rows (row j, lane l = the j-th larger neighbour of vertex 32c + l): one base address per chunk, row j at
+// an immediate offset, one line per load.  Nothing is predicated: a lane always reads 8 rows -- past the chunk's last row
+// lie the rows of the next chunk (8 spare rows close the table), valid vertex ids whose sign bits are fetched and then
+// masked off by the chunk's row count; a missing neighbour inside the chunk is the vertex itself (same sign: never a
+// crossing).  Six instructions per slot: row load, word index, address, sign word load, shift, funnel shift into the
+// result mask.  edge_off is only read by the few lanes that found a crossing edge.
+template <int CPW>   // chunks per warp: 8 * CPW row loads in flight per lane
+__global__ void __launch_bounds__(kEScanThreads)
+edge_scan_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
+  pdl_enter();
+  const d3h_forward_args& a = blk->a;
+  const int32_t* __restrict__ rows = a.edge_rows;
+  const int64_t n_grid = a.n_grid;
+  const int64_t n_chunks = (n_grid + 31) >> 5;
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
+  const unsigned lane = lane_id();
+  const int64_t gwarp = (int64_t)blockIdx.x * (kEScanThreads / 32) + (threadIdx.x >> 5);
+  const int64_t c0 = gwarp * CPW;
+  // row ranges of the warp's chunks: lanes 0 .. CPW fetch CPW + 1 consecutive offsets (clamped to the end of the
+  // table: a chunk beyond the grid has no rows), everybody gets them by shuffle; the chunk's own signs are one word
+  int roff, own = 0;
+  {
+    const int64_t c = c0 + lane < n_chunks ? c0 + lane : n_chunks;
+    roff = __ldg(a.edge_row_off + c);
+    if (lane < (unsigned)CPW && c < n_chunks) own = (int)__ldg(occ_bits + c);
+  }
+  int r0[CPW], w[CPW];
+  unsigned oa[CPW];
+#pragma unroll
+  for (int k = 0; k < CPW; ++k) {
+    r0[k] = __shfl_sync(0xffffffffu, roff, k);
+    w[k] = __shfl_sync(0xffffffffu, roff, k + 1) - r0[k];
+    oa[k] = ((unsigned)__shfl_sync(0xffffffffu, own, k) >> lane) & 1u;
+  }
+  int b[CPW][8];
+#pragma unroll
+  for (int k = 0; k < CPW; ++k) {
+    const int32_t* __restrict__ p = rows + ((int64_t)r0[k] << 5) + lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[k][j] = ld_stream_s32(p + 32 * j);
+  }
+  __syncwarp();   // scheduling fence: all row loads are issued before the first sign look-up waits for one of them
+  unsigned x[CPW];      // bit j: neighbour j of the lane's vertex in chunk k has the other sign
+  unsigned cnt = 0u;
+  bool more = false;    // a chunk with more than 8 rows (unstructured grids)
+#pragma unroll
+  for (int k = 0; k < CPW; ++k) {
+    unsigned acc = 0u;   // the sign bit of slot j is pushed in at the top: slot 0 ends up in bit 24, slot 7 in bit 31
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      acc = __funnelshift_r(acc, __ldg(occ_bits + (b[k][j] >> 5)) >> (b[k][j] & 31), 1);
+    acc = (acc >> 24) ^ (oa[k] ? 0xffu : 0u);
+    const int wk = w[k] < 8 ? w[k] : 8;
+    acc &= (1u << wk) - 1u;                                   // rows of the chunk only
+    if (((c0 + k) << 5) + lane >= n_grid) acc = 0u;           // lanes beyond the grid in the last chunk
+    x[k] = acc;
+    cnt += __popc(acc);
+    more = more || w[k] > 8;
+  }
+  if (more) {   // (warp-uniform) the rest of the long neighbour lists: counted here, written below
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) {
+      if (((c0 + k) << 5) + lane >= n_grid) continue;
+      const int32_t* __restrict__ p = rows + ((int64_t)r0[k] << 5) + lane;
+      for (int j = 8; j < w[k]; ++j) cnt += occ_of(occ_bits, ld_stream_s32(p + 32 * j)) ^ oa[k];
+    }
+  }
+  const unsigned q = (unsigned)(gwarp % kQueues);
+  int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
+  if (slot < 0) { trace_end(tr); return; }
+  int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
+#pragma unroll
+  for (int k = 0; k < CPW; ++k) {
+    const int64_t v = ((c0 + k) << 5) + lane;
+    unsigned y = x[k];
+    if ((y == 0u && w[k] <= 8) || v >= n_grid) continue;
+    const int e0 = __ldg(a.edge_off + v);
+    while (y) {
+      const int e = e0 + (__ffs((int)y) - 1);
+      y &= y - 1u;
+      if (slot < L.cap_qe) out[slot] = e;
+      ++slot;
+    }
+    const int32_t* __restrict__ p = rows + ((int64_t)r0[k] << 5) + lane;
+    for (int j = 8; j < w[k]; ++j) {
+      if ((occ_of(occ_bits, ld_stream_s32(p + 32 * j)) ^ oa[k]) == 0u) continue;
+      if (slot < L.cap_qe) out[slot] = e0 + j;
       ++slot;
     }
   }
@@ -558,6 +656,12 @@ static ScanLists scan_lists(const d3h_forward_args& a, const Workspace& ws) {
 
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const ScanLists L = scan_lists(a, ws);
+  if (a.edge_rows != nullptr) {
+    const int64_t n_chunks = (a.n_grid + 31) / 32, per_cta = (kEScanThreads / 32) * kScanChunksPerWarp;
+    launch_k(edge_scan_rows_kernel<kScanChunksPerWarp>, (unsigned)((n_chunks + per_cta - 1) / per_cta), (unsigned)kEScanThreads,
+             stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+    return;
+  }
   const int vpt = scan_vpt();
   const int64_t per_cta = (int64_t)kEScanThreads * vpt;
   const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
@@ -582,7 +686,11 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const int vpt = scan_vpt();
     const int64_t per_cta = (int64_t)kEScanThreads * vpt;
     const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
-    if (vpt == 1)
+    if (a.edge_rows != nullptr) {
+      const int64_t n_chunks = (a.n_grid + 31) / 32, chunks_per_cta = (kEScanThreads / 32) * kScanChunksPerWarp;
+      launch_k_dep(edge_scan_rows_kernel<kScanChunksPerWarp>, (unsigned)((n_chunks + chunks_per_cta - 1) / chunks_per_cta),
+                   (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+    } else if (vpt == 1)
       launch_k_dep(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     else if (vpt == 2)
       launch_k_dep(edge_scan_kernel<2>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);

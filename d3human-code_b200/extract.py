@@ -84,6 +84,9 @@ _tet_edge_ranks = os.environ.get("D3H_TET_EDGE_RANKS", "0") == "1"   # per-tet e
 #: edge-scan path (csrc/d3h_scan.cu): with the static tables a call walks the edge list (4 B / edge) instead of streaming
 #: the tet array (16 B / tet); needs the edge -> tet incidence and the per-tet edge ranks (+56 B / tet of static tables)
 _edge_scan = os.environ.get("D3H_EDGE_SCAN", "1") == "1"
+#: transposed copy of the edge list for the stream kernel (edge_scan_rows_kernel: coalesced 128-byte rows per chunk of 32
+#: vertices); replaces edge_b.  D3H_SCAN_ROWS=0 keeps the CSR walk (edge_scan_kernel)
+_scan_rows = os.environ.get("D3H_SCAN_ROWS", "1") == "1"
 #: opt-in: fixed-width incidence rows (etets8, +32 B / edge) for the rule-based marking kernel (edge_mark_rows_kernel)
 _mark_rows = os.environ.get("D3H_MARK_ROWS", "0") == "1"
 
@@ -92,6 +95,12 @@ def set_edge_scan(on: bool) -> None:
     """Tables already built keep their form (reset_plans() drops them)."""
     global _edge_scan
     _edge_scan = bool(on)
+
+
+def set_scan_rows(on: bool) -> None:
+    """Build the transposed edge rows with the next edge table (tables already built keep their form)."""
+    global _scan_rows
+    _scan_rows = bool(on)
 
 
 def set_mark_rows(on: bool) -> None:
@@ -118,8 +127,10 @@ def set_static_edges(mode: str) -> None:
 
 def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
-    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets, etets8): edges ascending
-    in (min,max), CSR offsets per min vertex.  The last five are None unless asked for:
+    Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets, etets8, edge_rows,
+    edge_row_off): edges ascending in (min,max), CSR offsets per min vertex.  The last seven are None unless asked for:
+      edge_rows, edge_row_off : the larger end points transposed per chunk of 32 vertices (layout: include/d3h_tets.h);
+                                edge_b is None then
       tet_rank (F,8) int32 : rank in the edge list of the six edges of every tet (order of gshell_tets.py:187, 2 pad words)
       edge_b   (U,)  int32 : the larger endpoints, contiguous (the 4-byte-per-edge stream of the edge-scan path)
       etet_off (U+1,), etets (<=6F,) int32 : the tets around every edge, ascending and distinct tet ids
@@ -138,7 +149,7 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     n_edges = int(uk.shape[0])
     if n_edges >= 2 ** 31:
         raise ValueError("tet grid has more than 2^31 distinct edges")
-    tet_rank = edge_b = etet_off = etets = etets8 = None
+    tet_rank = edge_b = etet_off = etets = etets8 = edge_rows = edge_row_off = None
     if _tet_edge_ranks or _edge_scan:
         rank6 = torch.searchsorted(uk, key6.reshape(-1)).reshape(n_tets, 6)
         del key6
@@ -160,7 +171,10 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
             off64 = torch.zeros(n_edges + 1, dtype=torch.int64, device=tets_i32.device)
             off64[1:] = torch.cumsum(torch.bincount(eid, minlength=n_edges), 0)
             etet_off = off64.to(torch.int32).contiguous()
-            edge_b = edge_ab[:, 1].contiguous()
+            if _scan_rows:
+                edge_rows, edge_row_off = build_edge_rows(edge_off, edge_ab, n_grid)
+            else:
+                edge_b = edge_ab[:, 1].contiguous()
             if _mark_rows:
                 # fixed-width rows: the first 8 tets of every edge (one 32-byte load per crossing edge), -2 in the last
                 # slot of an edge with more than 8
@@ -172,7 +186,43 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
                 del within, sel
             del eid, tid, off64
         del rank6
-    return edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets, etets8
+    return (edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets, etets8, edge_rows,
+            edge_row_off)
+
+
+def build_edge_rows(edge_off: torch.Tensor, edge_ab: torch.Tensor, n_grid: int):
+    """The larger end points of the sorted edge list, transposed per chunk of 32 consecutive vertices (one-time setup).
+    -> (edge_rows (32 (R + 8),) int32, edge_row_off (ceil(N/32)+1,) int32); chunk c owns rows [off[c], off[c+1]), as many as
+    its vertex of highest degree has larger neighbours; entry 32 r + l = neighbour r - off[c] of vertex 32 c + l, or the
+    vertex itself where it has fewer, or 0 beyond the grid (d3h_forward_args.edge_rows)."""
+    dev = edge_ab.device
+    off = edge_off.long()
+    n_chunks = (n_grid + 31) // 32
+    deg = torch.zeros(n_chunks * 32, dtype=torch.int64, device=dev)
+    deg[:n_grid] = off[1:] - off[:-1]
+    width = deg.view(n_chunks, 32).max(1).values
+    row_off = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
+    row_off[1:] = torch.cumsum(width, 0)
+    n_rows = int(row_off[-1])
+    if n_rows >= 2 ** 31 // 32:
+        raise ValueError("tet grid too large for the transposed edge rows")
+    # every slot starts as its own vertex ...
+    chunk_of_row = torch.repeat_interleave(torch.arange(n_chunks, device=dev), width)
+    rows = chunk_of_row[:, None] * 32 + torch.arange(32, device=dev)[None, :]
+    rows[rows >= n_grid] = 0
+    # 8 spare rows close the table: the stream kernel always reads 8 rows from a chunk's first one
+    flat = rows.to(torch.int32).reshape(-1)
+    store = torch.zeros(flat.shape[0] + 8 * 32 + 32, dtype=torch.int32, device=dev)
+    lead = (-store.data_ptr() % 128) // 4          # (CUDA allocations are 512-byte aligned; CPU tensors of the tests are not)
+    rows = store[lead:lead + flat.shape[0] + 8 * 32]
+    rows[:flat.shape[0]] = flat
+    del flat
+    # ... and edge e = edge_off[a] + j goes to row off[a >> 5] + j, lane a & 31
+    a = edge_ab[:, 0].long()
+    j = torch.arange(edge_ab.shape[0], device=dev) - off[a]
+    rows[(row_off[a >> 5] + j) * 32 + (a & 31)] = edge_ab[:, 1]
+    assert rows.data_ptr() % 128 == 0 and rows.is_contiguous()
+    return rows, row_off.to(torch.int32).contiguous()
 
 
 def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
@@ -182,7 +232,7 @@ def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
     # the version counter is part of the key: an int32 tet_fx4 is used in place (packed_tets returns the caller's tensor),
     # an in-place edit must not find the edge table of the old contents
     key = (tets_i32.data_ptr(), tets_i32._version, tets_i32.shape[0], int(n_grid), tets_i32.device.index, _edge_scan,
-           _tet_edge_ranks, _mark_rows)
+           _tet_edge_ranks, _mark_rows, _scan_rows)
     ent = _static_cache.get(key)
     if ent is None:
         if len(_static_cache) > 8:
@@ -380,10 +430,13 @@ class _Layout:
             if len(static) > 3 and static[3] is not None:
                 A[:, c["tet_edge_rank"]] = static[3].data_ptr()
             if len(static) > 6 and static[6] is not None:
-                A[:, c["edge_b"]], A[:, c["etet_off"]], A[:, c["etets"]] = (static[4].data_ptr(), static[5].data_ptr(),
-                                                                            static[6].data_ptr())
+                A[:, c["etet_off"]], A[:, c["etets"]] = static[5].data_ptr(), static[6].data_ptr()
+                if static[4] is not None:
+                    A[:, c["edge_b"]] = static[4].data_ptr()
                 if len(static) > 7 and static[7] is not None:
                     A[:, c["etets8"]] = static[7].data_ptr()
+                if len(static) > 9 and static[8] is not None:
+                    A[:, c["edge_rows"]], A[:, c["edge_row_off"]] = static[8].data_ptr(), static[9].data_ptr()
             self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
         self.static = static
         self.A = A

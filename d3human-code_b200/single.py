@@ -52,9 +52,13 @@ class _State:
             if static[3] is not None:
                 fa.tet_edge_rank = static[3].data_ptr()
             if static[6] is not None:
-                fa.edge_b, fa.etet_off, fa.etets = static[4].data_ptr(), static[5].data_ptr(), static[6].data_ptr()
+                fa.etet_off, fa.etets = static[5].data_ptr(), static[6].data_ptr()
+                if static[4] is not None:
+                    fa.edge_b = static[4].data_ptr()
                 if len(static) > 7 and static[7] is not None:
                     fa.etets8 = static[7].data_ptr()
+                if len(static) > 9 and static[8] is not None:
+                    fa.edge_rows, fa.edge_row_off = static[8].data_ptr(), static[9].data_ptr()
         ba.n_grid, ba.msdf_negate, ba.grads_prezeroed = n_grid, int(negate), 1
         self.fa, self.ba = fa, ba
         self.fa_ref, self.ba_ref = C.addressof(fa), C.addressof(ba)

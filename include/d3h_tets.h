@@ -155,6 +155,17 @@ typedef struct d3h_forward_args {
    * the first 8 tets around edge r, padded with -1; [7] == -2 marks an edge with more than 8 tets (the kernel then walks
    * etet_off / etets for it).  One dependent load per crossing edge instead of two.  16-byte aligned.  NULL: CSR only. */
   const int32_t* etets8;   /* (n_edges,8) */
+  /* optional companion of the edge-scan path: the larger end points once more, TRANSPOSED per chunk of 32 consecutive
+   * grid vertices, so that the walk over the edge list is made of fully coalesced 128-byte rows (lane l of a warp owns
+   * vertex 32c + l).  Chunk c owns rows [edge_row_off[c], edge_row_off[c+1]) -- as many as its vertex of highest
+   * degree has larger neighbours; entry (row r, lane l) = edge_rows[32 r + l] = the (r - edge_row_off[c])-th larger
+   * neighbour of vertex 32c + l in ascending order, i.e. end point b of edge edge_off[32c + l] + r - edge_row_off[c],
+   * or the vertex ITSELF where it has fewer (an edge to itself never crosses), 0 for the lanes beyond n_grid in the
+   * last chunk.  EIGHT SPARE ROWS of zeros follow the last row (the kernel reads 8 rows from a chunk's first row
+   * whatever the chunk's row count and masks the surplus).  128-byte aligned.  With it edge_b may be NULL.
+   * NULL: walk edge_b through edge_off. */
+  const int32_t* edge_rows;    /* (32 * (edge_row_off[ceil(N/32)] + 8)) */
+  const int32_t* edge_row_off; /* (ceil(N/32) + 1) */
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */

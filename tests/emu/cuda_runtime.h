@@ -152,6 +152,9 @@ static inline unsigned __match_any_sync(unsigned mask, T v) {
 // ---- integer / float intrinsics ----------------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned n) {
+  return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (n & 31u));
+}
 static inline unsigned __fns(unsigned mask, unsigned base, int offset) {  // offset-th set bit at or above `base`
   if (offset <= 0) return 0xffffffffu;  // (negative offsets search downwards; not used by these kernels)
   int seen = 0;

@@ -59,9 +59,14 @@ def emu_lib_path():
     return build_emu.build()
 
 
-@pytest.fixture(params=["sort", "static", "scan"])
+@pytest.fixture(params=["sort", "static", "scan", "scan_csr"])
 def edges_mode(request):
-    return request.param
+    if request.param == "scan_csr" and request.node.originalname not in ("test_golden", "test_oracle", "test_random_tet_soups",
+                                                                         "test_tet_soups_with_repeated_vertices"):
+        pytest.skip("the CSR walk of the edge-scan path is covered by the golden / oracle / soup tests")
+    E.set_scan_rows(request.param != "scan_csr")
+    yield "scan" if request.param == "scan_csr" else request.param
+    E.set_scan_rows(True)
 
 
 @pytest.fixture

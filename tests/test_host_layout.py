@@ -109,17 +109,22 @@ def test_build_edge_table_on_cpu_matches_numpy():
     n = pos.shape[0]
     E.set_edge_scan(False)
     try:
-        off, ab, u, tet_rank, edge_b, etet_off, etets, etets8 = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
-        assert tet_rank is None and edge_b is None and etets is None
+        off, ab, u, tet_rank, edge_b, etet_off, etets, etets8, rows, row_off = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        assert tet_rank is None and edge_b is None and etets is None and rows is None and row_off is None
         E.set_tet_edge_ranks(True)
-        _, _, _, tet_rank, edge_b, _, _, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        _, _, _, tet_rank, edge_b, _, _, _, _, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
         assert edge_b is None
     finally:
         E.set_tet_edge_ranks(False)
         E.set_edge_scan(True)
     # the tables of the edge-scan path: larger endpoints + the tets around every edge
     E.set_mark_rows(True)
-    _, ab2, u2, tet_rank2, edge_b, etet_off, etets, etets8 = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    E.set_scan_rows(False)
+    try:
+        _, ab2, u2, tet_rank2, edge_b, etet_off, etets, etets8, rows, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    finally:
+        E.set_scan_rows(True)
+    assert rows is None
     assert u2 == u and torch.equal(ab2, ab) and torch.equal(tet_rank2, tet_rank)
     assert torch.equal(edge_b, ab[:, 1]) and edge_b.is_contiguous() and edge_b.dtype == torch.int32
     eo, et = etet_off.numpy(), etets.numpy()
@@ -162,7 +167,7 @@ def test_edge_table_incidence_of_degenerate_and_crowded_edges():
     fan = [[0, 1, 2 + k, 3 + k] for k in range(10)]            # edge (0,1) is shared by 10 tets
     tets = np.array(fan + [[14, 14, 15, 16], [17, 18, 17, 19]], dtype=np.int32)
     E.set_mark_rows(True)
-    _, ab, u, tet_rank, edge_b, etet_off, etets, etets8 = E.build_edge_table(torch.tensor(tets), n)
+    _, ab, u, tet_rank, edge_b, etet_off, etets, etets8, _, _ = E.build_edge_table(torch.tensor(tets), n)
     ab, eo, et, e8 = ab.numpy(), etet_off.numpy(), etets.numpy(), etets8.numpy()
     r01 = int(np.flatnonzero((ab[:, 0] == 0) & (ab[:, 1] == 1))[0])
     assert np.array_equal(et[eo[r01]:eo[r01 + 1]], np.arange(10)) and e8[r01, 7] == -2 and np.array_equal(e8[r01, :7], np.arange(7))
@@ -172,3 +177,45 @@ def test_edge_table_incidence_of_degenerate_and_crowded_edges():
     assert np.array_equal(et[eo[r78]:eo[r78 + 1]], [11])
     assert eo[-1] == et.shape[0] < 6 * tets.shape[0]
     E.set_mark_rows(False)
+
+
+def _check_edge_rows(off, ab, rows, row_off, n):
+    """Every slot of the transposed rows against the CSR list it restates (include/d3h_tets.h: edge_rows)."""
+    off, ab, rows, row_off = off.numpy().astype(np.int64), ab.numpy(), rows.numpy(), row_off.numpy().astype(np.int64)
+    n_chunks = (n + 31) // 32
+    assert row_off.shape == (n_chunks + 1,) and row_off[0] == 0 and rows.shape == (32 * (row_off[-1] + 8),)
+    assert (rows[32 * row_off[-1]:] == 0).all()                   # the spare rows
+    deg = off[1:] - off[:-1]
+    for c in range(n_chunks):
+        lo, hi = 32 * c, min(32 * c + 32, n)
+        w = row_off[c + 1] - row_off[c]
+        assert w == deg[lo:hi].max()
+        if w == 0:
+            continue
+        blk = rows[32 * row_off[c]:32 * row_off[c + 1]].reshape(w, 32)
+        for l in range(32):
+            v = lo + l
+            if v >= n:
+                assert (blk[:, l] == 0).all()
+                continue
+            d = deg[v]
+            assert np.array_equal(blk[:d, l], ab[off[v]:off[v] + d, 1]) and (blk[d:, l] == v).all()
+
+
+def test_edge_rows_restates_the_csr_list():
+    """The transposed edge rows of the stream kernel: lattice (7 larger neighbours inside, fewer at the faces, a grid size
+    that is no multiple of 32) and a small irregular soup with a vertex of degree > 8 and isolated vertices."""
+    from d3human_code_b200 import grids
+    pos, tets = grids.kuhn_grid(6)
+    n = pos.shape[0]
+    assert n % 32 != 0
+    off, ab, u, _, edge_b, _, _, _, rows, row_off = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    assert edge_b is None and rows.dtype == torch.int32 and row_off.dtype == torch.int32 and rows.is_contiguous()
+    _check_edge_rows(off, ab, rows, row_off, n)
+    assert int(row_off[-1]) * 32 >= u
+    n = 70
+    fan = [[0, 1 + k, 2 + k, 3 + k] for k in range(0, 30, 2)]      # vertex 0: 32 larger neighbours... a long chunk
+    tets = np.array(fan + [[40, 41, 42, 43], [64, 65, 66, 69]], dtype=np.int32)
+    off, ab, u, _, _, _, _, _, rows, row_off = E.build_edge_table(torch.tensor(tets), n)
+    _check_edge_rows(off, ab, rows, row_off, n)
+    assert int(row_off[1] - row_off[0]) > 8
