@@ -33,7 +33,6 @@
 namespace d3h {
 
 constexpr int kEScanThreads = 256;
-constexpr int kScanChunksPerWarp = 4;   // edge_scan_rows_kernel: 128 vertices per warp, 32 row loads in flight per lane
 // vertices per thread of the stream (x 8 neighbour loads in flight each): D3H_SCAN_VPT = 1, 2 or 4 (default)
 static int scan_vpt() {
   static int v = 0;
@@ -156,8 +155,8 @@ edge_scan_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
 // masked off by the chunk's row count; a missing neighbour inside the chunk is the vertex itself (same sign: never a
 // crossing).  Six instructions per slot: row load, word index, address, sign word load, shift, funnel shift into the
 // result mask.  edge_off is only read by the few lanes that found a crossing edge.
-template <int CPW>   // chunks per warp: 8 * CPW row loads in flight per lane
-__global__ void __launch_bounds__(kEScanThreads)
+template <int CPW, bool PHASED>   // chunks per warp: 8 * CPW row loads in flight per lane
+__global__ void __launch_bounds__(kEScanThreads, CPW == 4 ? 3 : (CPW == 2 ? 5 : 8))
 edge_scan_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
   pdl_enter();
   const d3h_forward_args& a = blk->a;
@@ -185,22 +184,40 @@ edge_scan_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
     oa[k] = ((unsigned)__shfl_sync(0xffffffffu, own, k) >> lane) & 1u;
   }
   int b[CPW][8];
+  int all_b = 0;
 #pragma unroll
   for (int k = 0; k < CPW; ++k) {
     const int32_t* __restrict__ p = rows + ((int64_t)r0[k] << 5) + lane;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[k][j] = ld_stream_s32(p + 32 * j);
+    for (int j = 0; j < 8; ++j) {
+      b[k][j] = ld_stream_s32(p + 32 * j);
+      all_b |= b[k][j];
+    }
   }
-  __syncwarp();   // scheduling fence: all row loads are issued before the first sign look-up waits for one of them
+  // Three phases, each waiting for memory ONCE: all row loads, all sign-word loads, the bit arithmetic.  Left alone,
+  // ptxas interleaves them in groups of four and a warp waits for DRAM eight times in a row (r02v: 21 us, every stall on
+  // the first use of a load).  The phases are tied by data: vertex ids are non-negative, so `all_b >> 31` is a zero the
+  // compiler cannot know -- added to the bitmap's address it makes every sign look-up depend on every row load, and-ed
+  // with the OR of the sign words it seeds the result mask.
+  const unsigned* __restrict__ occ = PHASED ? occ_bits + (all_b >> 31) : occ_bits;
+  unsigned word[CPW][8];
+  unsigned all_w = 0u;
+#pragma unroll
+  for (int k = 0; k < CPW; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      word[k][j] = __ldg(occ + (b[k][j] >> 5));
+      all_w |= word[k][j];
+    }
+  const unsigned seed = PHASED ? (all_w & (unsigned)(all_b >> 31)) : 0u;
   unsigned x[CPW];      // bit j: neighbour j of the lane's vertex in chunk k has the other sign
   unsigned cnt = 0u;
   bool more = false;    // a chunk with more than 8 rows (unstructured grids)
 #pragma unroll
   for (int k = 0; k < CPW; ++k) {
-    unsigned acc = 0u;   // the sign bit of slot j is pushed in at the top: slot 0 ends up in bit 24, slot 7 in bit 31
+    unsigned acc = seed;   // the sign bit of slot j is pushed in at the top: slot 0 ends up in bit 24, slot 7 in bit 31
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      acc = __funnelshift_r(acc, __ldg(occ_bits + (b[k][j] >> 5)) >> (b[k][j] & 31), 1);
+    for (int j = 0; j < 8; ++j) acc = __funnelshift_r(acc, word[k][j] >> (b[k][j] & 31), 1);
     acc = (acc >> 24) ^ (oa[k] ? 0xffu : 0u);
     const int wk = w[k] < 8 ? w[k] : 8;
     acc &= (1u << wk) - 1u;                                   // rows of the chunk only
@@ -241,6 +258,25 @@ edge_scan_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
     }
   }
   trace_end(tr);
+}
+
+// launch of the stream over the transposed rows: D3H_SCAN_CPW = 1, 2 (default) or 4 chunks per warp, D3H_SCAN_PHASED=0
+// leaves the instruction order to the compiler (A/B switches)
+template <typename Launch>
+static void launch_scan_rows(const d3h_forward_args& a, Launch&& launch) {
+  static int cpw = 0, phased = 1;
+  if (cpw == 0) {
+    const char* env = getenv("D3H_SCAN_CPW");
+    cpw = (env && (env[0] == '1' || env[0] == '4')) ? (env[0] - '0') : 2;
+    const char* ph = getenv("D3H_SCAN_PHASED");
+    phased = !(ph && ph[0] == '0');
+  }
+  const int64_t n_chunks = (a.n_grid + 31) / 32, per_cta = (int64_t)(kEScanThreads / 32) * cpw;
+  const unsigned nblk = (unsigned)((n_chunks + per_cta - 1) / per_cta);
+  if (!phased) launch(edge_scan_rows_kernel<4, false>, (unsigned)((n_chunks + 31) / 32));
+  else if (cpw == 1) launch(edge_scan_rows_kernel<1, true>, nblk);
+  else if (cpw == 4) launch(edge_scan_rows_kernel<4, true>, nblk);
+  else launch(edge_scan_rows_kernel<2, true>, nblk);
 }
 
 // One thread per crossing edge of the whole grid (all resident at once: the chain etet_off -> etets -> tets -> signs ->
@@ -657,9 +693,9 @@ static ScanLists scan_lists(const d3h_forward_args& a, const Workspace& ws) {
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const ScanLists L = scan_lists(a, ws);
   if (a.edge_rows != nullptr) {
-    const int64_t n_chunks = (a.n_grid + 31) / 32, per_cta = (kEScanThreads / 32) * kScanChunksPerWarp;
-    launch_k(edge_scan_rows_kernel<kScanChunksPerWarp>, (unsigned)((n_chunks + per_cta - 1) / per_cta), (unsigned)kEScanThreads,
-             stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+    launch_scan_rows(a, [&](auto kernel, unsigned nblk) {
+      launch_k(kernel, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+    });
     return;
   }
   const int vpt = scan_vpt();
@@ -687,9 +723,9 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const int64_t per_cta = (int64_t)kEScanThreads * vpt;
     const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
     if (a.edge_rows != nullptr) {
-      const int64_t n_chunks = (a.n_grid + 31) / 32, chunks_per_cta = (kEScanThreads / 32) * kScanChunksPerWarp;
-      launch_k_dep(edge_scan_rows_kernel<kScanChunksPerWarp>, (unsigned)((n_chunks + chunks_per_cta - 1) / chunks_per_cta),
-                   (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+      launch_scan_rows(a, [&](auto kernel, unsigned nb) {
+        launch_k_dep(kernel, nb, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
+      });
     } else if (vpt == 1)
       launch_k_dep(edge_scan_kernel<1>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     else if (vpt == 2)
