@@ -260,18 +260,170 @@ edge_scan_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
   trace_end(tr);
 }
 
-// launch of the stream over the transposed rows: D3H_SCAN_CPW = 1, 2 (default) or 4 chunks per warp, D3H_SCAN_PHASED=0
-// leaves the instruction order to the compiler (A/B switches)
+// The same as a PERSISTENT, software-pipelined kernel (default).  Timed alone, every one-shot variant above -- one, two or
+// four chunks per warp, phased or not, and the CSR walk -- takes the same ~21 us (r02w): a warp lives ~5000 cycles (offset
+// load, row loads, sign words, each a full memory latency) and has row loads in flight for a third of them, so the bytes in
+// flight per SM are the same whatever the shape, and they are too few for DRAM.  Here a warp keeps streaming: while it
+// looks up the signs of group g its row loads of group g + W (W = warps of the grid) and the row offsets of group g + 2W
+// are already under way, so every resident warp has 8 * CPW rows in flight all the time.
+template <int CPW>
+__global__ void __launch_bounds__(kEScanThreads, CPW == 2 ? 3 : 5)
+edge_scan_pipe_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
+  pdl_enter();
+  const d3h_forward_args& a = blk->a;
+  const int32_t* __restrict__ rows = a.edge_rows;
+  const int32_t* __restrict__ row_off = a.edge_row_off;
+  const int64_t n_grid = a.n_grid;
+  const int64_t n_chunks = (n_grid + 31) >> 5;
+  const int64_t n_groups = (n_chunks + CPW - 1) / CPW;
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
+  const unsigned lane = lane_id();
+  const int64_t gwarp = (int64_t)blockIdx.x * (kEScanThreads / 32) + (threadIdx.x >> 5);
+  const int64_t W = (int64_t)gridDim.x * (kEScanThreads / 32);
+  const unsigned q = (unsigned)(gwarp % kQueues);
+  int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
+  // row offsets of a group: lanes 0 .. CPW hold CPW + 1 consecutive entries; a chunk beyond the grid has no rows (its
+  // offsets are the end of the table: the 8 spare rows)
+  auto load_off = [&](int64_t g) {
+    int64_t c = g * CPW + lane;
+    c = c < n_chunks ? c : n_chunks;
+    return lane <= (unsigned)CPW ? __ldg(row_off + c) : 0;
+  };
+  int64_t g = gwarp;
+  if (g >= n_groups) { trace_end(tr); return; }
+  int roff = load_off(g), roff_next = load_off(g + W);
+  int b[CPW][8];
+#pragma unroll
+  for (int k = 0; k < CPW; ++k) {
+    const int32_t* __restrict__ p = rows + ((int64_t)__shfl_sync(0xffffffffu, roff, k) << 5) + lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[k][j] = ld_stream_s32(p + 32 * j);
+  }
+  for (;;) {
+    // ---- group g + W: rows; group g + 2W: offsets ----
+    int bn[CPW][8];
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) {
+      const int32_t* __restrict__ p = rows + ((int64_t)__shfl_sync(0xffffffffu, roff_next, k) << 5) + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bn[k][j] = ld_stream_s32(p + 32 * j);
+    }
+    const int roff_next2 = load_off(g + 2 * W);
+    // ---- group g ----
+    const int64_t c0 = g * CPW;
+    int own = 0;
+    if (lane < (unsigned)CPW && c0 + lane < n_chunks) own = (int)__ldg(occ_bits + c0 + lane);   // the chunk's own signs
+    int r0[CPW], w[CPW];
+    unsigned oa[CPW];
+    int all_b = 0;
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) {
+      r0[k] = __shfl_sync(0xffffffffu, roff, k);
+      w[k] = __shfl_sync(0xffffffffu, roff, k + 1) - r0[k];
+      oa[k] = ((unsigned)__shfl_sync(0xffffffffu, own, k) >> lane) & 1u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) all_b |= b[k][j];
+    }
+    // (vertex ids are non-negative: `all_b >> 31` is a zero the compiler cannot know; it ties every sign look-up to
+    // every row load of the group and seeds the result mask with the OR of the sign words, see edge_scan_rows_kernel)
+    const unsigned* __restrict__ occ = occ_bits + (all_b >> 31);
+    unsigned word[CPW][8];
+    unsigned all_w = 0u;
+#pragma unroll
+    for (int k = 0; k < CPW; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        word[k][j] = __ldg(occ + (b[k][j] >> 5));
+        all_w |= word[k][j];
+      }
+    const unsigned seed = all_w & (unsigned)(all_b >> 31);
+    unsigned x[CPW];
+    unsigned cnt = 0u;
+    bool more = false;
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) {
+      unsigned acc = seed;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = __funnelshift_r(acc, word[k][j] >> (b[k][j] & 31), 1);
+      acc = (acc >> 24) ^ (oa[k] ? 0xffu : 0u);
+      const int wk = w[k] < 8 ? w[k] : 8;
+      acc &= (1u << wk) - 1u;
+      if (((c0 + k) << 5) + lane >= n_grid) acc = 0u;
+      x[k] = acc;
+      cnt += __popc(acc);
+      more = more || w[k] > 8;
+    }
+    if (more) {   // (warp-uniform) the rest of the long neighbour lists: counted here, written below
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        if (((c0 + k) << 5) + lane >= n_grid) continue;
+        const int32_t* __restrict__ p = rows + ((int64_t)r0[k] << 5) + lane;
+        for (int j = 8; j < w[k]; ++j) cnt += occ_of(occ_bits, ld_stream_s32(p + 32 * j)) ^ oa[k];
+      }
+    }
+    int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
+    if (slot >= 0) {
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        const int64_t v = ((c0 + k) << 5) + lane;
+        unsigned y = x[k];
+        if ((y == 0u && w[k] <= 8) || v >= n_grid) continue;
+        const int e0 = __ldg(a.edge_off + v);
+        while (y) {
+          const int e = e0 + (__ffs((int)y) - 1);
+          y &= y - 1u;
+          if (slot < L.cap_qe) out[slot] = e;
+          ++slot;
+        }
+        const int32_t* __restrict__ p = rows + ((int64_t)r0[k] << 5) + lane;
+        for (int j = 8; j < w[k]; ++j) {
+          if ((occ_of(occ_bits, ld_stream_s32(p + 32 * j)) ^ oa[k]) == 0u) continue;
+          if (slot < L.cap_qe) out[slot] = e0 + j;
+          ++slot;
+        }
+      }
+    }
+    g += W;
+    if (g >= n_groups) break;
+    roff = roff_next;
+    roff_next = roff_next2;
+#pragma unroll
+    for (int k = 0; k < CPW; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[k][j] = bn[k][j];
+  }
+  trace_end(tr);
+}
+
+// launch of the stream over the transposed rows.  A/B switches: D3H_SCAN_PIPE=0 the one-shot kernel instead of the
+// persistent one; D3H_SCAN_CPW = chunks per warp (pipe: 1 or 2 (default); one-shot: 1, 2 (default) or 4);
+// D3H_SCAN_PHASED=0 leaves the instruction order of the one-shot kernel to the compiler
 template <typename Launch>
 static void launch_scan_rows(const d3h_forward_args& a, Launch&& launch) {
-  static int cpw = 0, phased = 1;
+  static int cpw = 0, phased = 1, pipe = 1, grid1 = 0, grid2 = 0;
   if (cpw == 0) {
     const char* env = getenv("D3H_SCAN_CPW");
     cpw = (env && (env[0] == '1' || env[0] == '4')) ? (env[0] - '0') : 2;
     const char* ph = getenv("D3H_SCAN_PHASED");
     phased = !(ph && ph[0] == '0');
+    const char* pp = getenv("D3H_SCAN_PIPE");
+    pipe = !(pp && pp[0] == '0');
+    grid1 = persistent_grid(reinterpret_cast<const void*>(edge_scan_pipe_kernel<1>), kEScanThreads, 0);
+    grid2 = persistent_grid(reinterpret_cast<const void*>(edge_scan_pipe_kernel<2>), kEScanThreads, 0);
+    const char* gg = getenv("D3H_SCAN_GRID");   // tests: a small grid makes every warp take many groups
+    if (gg && atoi(gg) > 0) grid1 = grid2 = atoi(gg);
   }
-  const int64_t n_chunks = (a.n_grid + 31) / 32, per_cta = (int64_t)(kEScanThreads / 32) * cpw;
+  const int64_t n_chunks = (a.n_grid + 31) / 32;
+  if (pipe) {
+    const int c = cpw == 1 ? 1 : 2;
+    const int64_t need = (n_chunks + 8 * c - 1) / (8 * c);   // CTAs of a one-shot launch
+    const int64_t cap = c == 1 ? grid1 : grid2;
+    const unsigned nblk = (unsigned)(need < cap ? need : cap);
+    if (c == 1) launch(edge_scan_pipe_kernel<1>, nblk);
+    else launch(edge_scan_pipe_kernel<2>, nblk);
+    return;
+  }
+  const int64_t per_cta = (int64_t)(kEScanThreads / 32) * cpw;
   const unsigned nblk = (unsigned)((n_chunks + per_cta - 1) / per_cta);
   if (!phased) launch(edge_scan_rows_kernel<4, false>, (unsigned)((n_chunks + 31) / 32));
   else if (cpw == 1) launch(edge_scan_rows_kernel<1, true>, nblk);
