@@ -777,6 +777,11 @@ def main():
                 # sign bitmap; the CSR offsets are only read by the few lanes that found a crossing edge, the padding
                 # slots of the rows (+2.5 % at 128^3) are not counted
                 dom_bytes = 4.0 * st[2] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
+            if len(st) > 11 and st[10] is not None:
+                # run-length compressed edge list (edge_scan_runs_kernel): 8 B per (difference, mask) entry + 4 B per
+                # chunk (entry offsets) + the sign bitmap read twice (own word + the windows of the entries come from L1 / L2:
+                # counted once)
+                dom_bytes = 8.0 * st[10].shape[0] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
         if n and ms > 0:
             t_events = ms / n * 1e-3      # one launch at a time between two events: includes the ~3-7 us launch / event gap
             t = scan_alone_us * 1e-6 if (dom == "edge_scan" and scan_alone_us) else t_events

@@ -63,7 +63,8 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("pair_msdf_wt", C.c_void_p), ("pair_faces_wt", C.c_void_p), ("pair_vacc", C.c_void_p),
                 ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64), ("tet_edge_rank", C.c_void_p),
                 ("edge_b", C.c_void_p), ("etet_off", C.c_void_p), ("etets", C.c_void_p), ("etets8", C.c_void_p),
-                ("edge_rows", C.c_void_p), ("edge_row_off", C.c_void_p)]
+                ("edge_rows", C.c_void_p), ("edge_row_off", C.c_void_p),
+                ("edge_runs", C.c_void_p), ("edge_run_off", C.c_void_p)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args

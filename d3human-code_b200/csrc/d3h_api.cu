@@ -242,14 +242,19 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     return D3H_E_BADARG;
   }
   if (a->etets != nullptr &&
-      (!a->edge_off || (!a->edge_b && !a->edge_rows) || !a->etet_off || !a->tet_edge_rank || a->tet_begin != 0 ||
+      (!a->edge_off || (!a->edge_b && !a->edge_rows && !a->edge_runs) || !a->etet_off || !a->tet_edge_rank || a->tet_begin != 0 ||
        a->tet_end != a->n_tets)) {
-    set_error("%s: the edge-scan path needs edge_off / edge_b or edge_rows / etet_off / etets / tet_edge_rank and the whole tet range", who);
+    set_error("%s: the edge-scan path needs edge_off / edge_b or edge_rows or edge_runs / etet_off / etets / tet_edge_rank and the whole tet range", who);
     return D3H_E_BADARG;
   }
   if ((a->edge_rows != nullptr) != (a->edge_row_off != nullptr) || (a->edge_rows != nullptr && a->etets == nullptr) ||
       (reinterpret_cast<uintptr_t>(a->edge_rows) & 127)) {
     set_error("%s: edge_rows (128-byte aligned) and edge_row_off come together and with the edge-scan tables", who);
+    return D3H_E_BADARG;
+  }
+  if ((a->edge_runs != nullptr) != (a->edge_run_off != nullptr) || (a->edge_runs != nullptr && a->etets == nullptr) ||
+      (reinterpret_cast<uintptr_t>(a->edge_runs) & 7)) {
+    set_error("%s: edge_runs (8-byte aligned) and edge_run_off come together and with the edge-scan tables", who);
     return D3H_E_BADARG;
   }
   if ((a->etets8 != nullptr && a->etets == nullptr) || (reinterpret_cast<uintptr_t>(a->etets8) & 15) ||
@@ -439,6 +444,7 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.parts = parts;
   key.is_static = a.edge_off != nullptr ? (a.etets != nullptr ? (a.etets8 != nullptr ? 4 : 3) : (a.tet_edge_rank != nullptr ? 2 : 1)) : 0;
   if (a.edge_rows != nullptr) key.is_static += 8;   // another stream kernel
+  if (a.edge_runs != nullptr) key.is_static += 16;
   key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
   std::lock_guard<std::mutex> lock(g_graph_mu);
@@ -758,6 +764,7 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a_in, d3h_tet_record* 
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
   general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
   general.etets8 = nullptr; general.edge_rows = nullptr; general.edge_row_off = nullptr;
+  general.edge_runs = nullptr; general.edge_run_off = nullptr;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_classify_range");
   if (rc) return rc;
@@ -789,6 +796,7 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a_in, const d3h_
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
   general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
   general.etets8 = nullptr; general.edge_rows = nullptr; general.edge_row_off = nullptr;
+  general.edge_runs = nullptr; general.edge_run_off = nullptr;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_extract_from_records");
   if (rc) return rc;

@@ -260,7 +260,7 @@ edge_scan_rows_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
   trace_end(tr);
 }
 
-// The same as a PERSISTENT, software-pipelined kernel (default).  Timed alone, every one-shot variant above -- one, two or
+// The same as a PERSISTENT, software-pipelined kernel (opt-in, D3H_SCAN_PIPE=1: measured 23.5 us against 22.7 us, r02x).  Timed alone, every one-shot variant above -- one, two or
 // four chunks per warp, phased or not, and the CSR walk -- takes the same ~21 us (r02w): a warp lives ~5000 cycles (offset
 // load, row loads, sign words, each a full memory latency) and has row loads in flight for a third of them, so the bytes in
 // flight per SM are the same whatever the shape, and they are too few for DRAM.  Here a warp keeps streaming: while it
@@ -395,25 +395,88 @@ edge_scan_pipe_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
   trace_end(tr);
 }
 
-// launch of the stream over the transposed rows.  A/B switches: D3H_SCAN_PIPE=0 the one-shot kernel instead of the
-// persistent one; D3H_SCAN_CPW = chunks per warp (pipe: 1 or 2 (default); one-shot: 1, 2 (default) or 4);
+// The stream over the RUN-LENGTH compressed edge list (d3h_forward_args.edge_runs; the default whenever the host built it).
+// Every kernel above spends its time on per-edge work: 6 to 26 instructions to fetch one sign bit, ~9 M warp instructions
+// per call at an IPC bounded by the dependent look-ups -- ~20 us whatever the shape (r02w / r02x).  On a grid numbered along
+// its axes the 32 vertices of a chunk have the same few end-point differences d, and the signs of the 32 far end points
+// 32c + l + d are 32 CONSECUTIVE bits of the sign bitmap: one funnel shift of two adjacent words.  So a THREAD takes a
+// whole chunk: per entry (d, mask) one 8-byte load, two word loads, a funnel shift, an xor with the chunk's own word and
+// an and with the mask give the crossing flags of 32 edges.  The lanes of a warp are consecutive chunks, so their word
+// loads coalesce.  7 entries per chunk on the Kuhn lattice: 3.7 MB instead of 59 MB and ~0.2 M warp instructions.
+__global__ void __launch_bounds__(kEScanThreads)
+edge_scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
+  pdl_enter();
+  const d3h_forward_args& a = blk->a;
+  const int2* __restrict__ runs = reinterpret_cast<const int2*>(a.edge_runs);
+  const int32_t* __restrict__ run_off = a.edge_run_off;
+  const int64_t n_chunks = (a.n_grid + 31) >> 5;
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
+  const int64_t c = (int64_t)blockIdx.x * kEScanThreads + threadIdx.x;
+  const int64_t gwarp = c >> 5;
+  int k0 = 0, k1 = 0;
+  unsigned own = 0u;
+  if (c < n_chunks) {
+    k0 = __ldg(run_off + c);
+    k1 = __ldg(run_off + c + 1);
+    own = __ldg(occ_bits + c);     // signs of vertices 32c .. 32c + 31
+  }
+  // crossing flags of entry k: bit l = the edge (32c + l, 32c + l + d) exists and its end points differ in sign.  The
+  // window may take its upper bits from the word behind the last vertex (allocated, never in a mask).
+  auto crossing = [&](int k) {
+    const int2 e = __ldg(runs + k);
+    const int64_t b0 = (c << 5) + e.x;
+    const unsigned lo = __ldg(occ_bits + (b0 >> 5)), hi = __ldg(occ_bits + (b0 >> 5) + 1);
+    return (__funnelshift_r(lo, hi, (unsigned)b0 & 31u) ^ own) & (unsigned)e.y;
+  };
+  unsigned cnt = 0u;
+  for (int k = k0; k < k1; k += 4) {   // four entries at a time: their loads are in flight together
+    unsigned x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (k + i < k1) ? crossing(k + i) : 0u;
+    cnt += __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]);
+  }
+  const unsigned q = (unsigned)(gwarp % kQueues);
+  int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
+  if (slot < 0 || cnt == 0u) { trace_end(tr); return; }
+  // the few chunks on the surface: entries once more, every crossing edge with its rank in the sorted list
+  int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
+  for (int k = k0; k < k1; ++k) {
+    unsigned x = crossing(k);
+    while (x) {
+      const int l = __ffs((int)x) - 1;
+      x &= x - 1u;
+      int rank = 0;   // entries of the chunk with a smaller difference that hold this lane
+      for (int kk = k0; kk < k; ++kk) rank += (int)(((unsigned)__ldg(runs + kk).y >> l) & 1u);
+      if (slot < L.cap_qe) out[slot] = __ldg(a.edge_off + (c << 5) + l) + rank;
+      ++slot;
+    }
+  }
+  trace_end(tr);
+}
+
+// launch of the stream over the compressed or transposed edge list.  A/B switches: D3H_SCAN_PIPE=1 the persistent kernel
+// instead of the one-shot one; D3H_SCAN_CPW = chunks per warp (pipe: 1 or 2 (default); one-shot: 1, 2 (default) or 4);
 // D3H_SCAN_PHASED=0 leaves the instruction order of the one-shot kernel to the compiler
 template <typename Launch>
 static void launch_scan_rows(const d3h_forward_args& a, Launch&& launch) {
-  static int cpw = 0, phased = 1, pipe = 1, grid1 = 0, grid2 = 0;
+  static int cpw = 0, phased = 1, pipe = 0, grid1 = 0, grid2 = 0;
   if (cpw == 0) {
     const char* env = getenv("D3H_SCAN_CPW");
     cpw = (env && (env[0] == '1' || env[0] == '4')) ? (env[0] - '0') : 2;
     const char* ph = getenv("D3H_SCAN_PHASED");
     phased = !(ph && ph[0] == '0');
     const char* pp = getenv("D3H_SCAN_PIPE");
-    pipe = !(pp && pp[0] == '0');
+    pipe = pp && pp[0] == '1';
     grid1 = persistent_grid(reinterpret_cast<const void*>(edge_scan_pipe_kernel<1>), kEScanThreads, 0);
     grid2 = persistent_grid(reinterpret_cast<const void*>(edge_scan_pipe_kernel<2>), kEScanThreads, 0);
     const char* gg = getenv("D3H_SCAN_GRID");   // tests: a small grid makes every warp take many groups
     if (gg && atoi(gg) > 0) grid1 = grid2 = atoi(gg);
   }
   const int64_t n_chunks = (a.n_grid + 31) / 32;
+  if (a.edge_runs != nullptr) {
+    launch(edge_scan_runs_kernel, (unsigned)((n_chunks + kEScanThreads - 1) / kEScanThreads));
+    return;
+  }
   if (pipe) {
     const int c = cpw == 1 ? 1 : 2;
     const int64_t need = (n_chunks + 8 * c - 1) / (8 * c);   // CTAs of a one-shot launch
@@ -844,7 +907,7 @@ static ScanLists scan_lists(const d3h_forward_args& a, const Workspace& ws) {
 
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const ScanLists L = scan_lists(a, ws);
-  if (a.edge_rows != nullptr) {
+  if (a.edge_rows != nullptr || a.edge_runs != nullptr) {
     launch_scan_rows(a, [&](auto kernel, unsigned nblk) {
       launch_k(kernel, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     });
@@ -874,7 +937,7 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const int vpt = scan_vpt();
     const int64_t per_cta = (int64_t)kEScanThreads * vpt;
     const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
-    if (a.edge_rows != nullptr) {
+    if (a.edge_rows != nullptr || a.edge_runs != nullptr) {
       launch_scan_rows(a, [&](auto kernel, unsigned nb) {
         launch_k_dep(kernel, nb, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
       });

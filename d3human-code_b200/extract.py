@@ -87,6 +87,11 @@ _edge_scan = os.environ.get("D3H_EDGE_SCAN", "1") == "1"
 #: transposed copy of the edge list for the stream kernel (edge_scan_rows_kernel: coalesced 128-byte rows per chunk of 32
 #: vertices); replaces edge_b.  D3H_SCAN_ROWS=0 keeps the CSR walk (edge_scan_kernel)
 _scan_rows = os.environ.get("D3H_SCAN_ROWS", "1") == "1"
+#: run-length compressed edge list for the stream kernel (edge_scan_runs_kernel: one (difference, lane mask) entry stands
+#: for up to 32 edges); built instead of the rows when the grid averages >= _RUNS_MIN_EDGES edges per entry (lattices
+#: numbered along their axes: 32).  D3H_SCAN_RUNS=0 never builds it
+_scan_runs = os.environ.get("D3H_SCAN_RUNS", "1") == "1"
+_RUNS_MIN_EDGES = 4
 #: opt-in: fixed-width incidence rows (etets8, +32 B / edge) for the rule-based marking kernel (edge_mark_rows_kernel)
 _mark_rows = os.environ.get("D3H_MARK_ROWS", "0") == "1"
 
@@ -101,6 +106,12 @@ def set_scan_rows(on: bool) -> None:
     """Build the transposed edge rows with the next edge table (tables already built keep their form)."""
     global _scan_rows
     _scan_rows = bool(on)
+
+
+def set_scan_runs(on: bool) -> None:
+    """Allow the run-length compressed edge list with the next edge table (tables already built keep their form)."""
+    global _scan_runs
+    _scan_runs = bool(on)
 
 
 def set_mark_rows(on: bool) -> None:
@@ -128,9 +139,12 @@ def set_static_edges(mode: str) -> None:
 def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
     Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets, etets8, edge_rows,
-    edge_row_off): edges ascending in (min,max), CSR offsets per min vertex.  The last seven are None unless asked for:
+    edge_row_off, edge_runs, edge_run_off): edges ascending in (min,max), CSR offsets per min vertex.  The last nine are
+    None unless asked for:
       edge_rows, edge_row_off : the larger end points transposed per chunk of 32 vertices (layout: include/d3h_tets.h);
                                 edge_b is None then
+      edge_runs, edge_run_off : the edge list run-length compressed by end-point difference per chunk (include/d3h_tets.h);
+                                edge_rows and edge_b are None then
       tet_rank (F,8) int32 : rank in the edge list of the six edges of every tet (order of gshell_tets.py:187, 2 pad words)
       edge_b   (U,)  int32 : the larger endpoints, contiguous (the 4-byte-per-edge stream of the edge-scan path)
       etet_off (U+1,), etets (<=6F,) int32 : the tets around every edge, ascending and distinct tet ids
@@ -149,7 +163,7 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     n_edges = int(uk.shape[0])
     if n_edges >= 2 ** 31:
         raise ValueError("tet grid has more than 2^31 distinct edges")
-    tet_rank = edge_b = etet_off = etets = etets8 = edge_rows = edge_row_off = None
+    tet_rank = edge_b = etet_off = etets = etets8 = edge_rows = edge_row_off = edge_runs = edge_run_off = None
     if _tet_edge_ranks or _edge_scan:
         rank6 = torch.searchsorted(uk, key6.reshape(-1)).reshape(n_tets, 6)
         del key6
@@ -171,7 +185,11 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
             off64 = torch.zeros(n_edges + 1, dtype=torch.int64, device=tets_i32.device)
             off64[1:] = torch.cumsum(torch.bincount(eid, minlength=n_edges), 0)
             etet_off = off64.to(torch.int32).contiguous()
-            if _scan_rows:
+            if _scan_runs:
+                edge_runs, edge_run_off = build_edge_runs(edge_ab, n_grid)
+            if edge_runs is not None:
+                pass
+            elif _scan_rows:
                 edge_rows, edge_row_off = build_edge_rows(edge_off, edge_ab, n_grid)
             else:
                 edge_b = edge_ab[:, 1].contiguous()
@@ -187,7 +205,34 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
             del eid, tid, off64
         del rank6
     return (edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets, etets8, edge_rows,
-            edge_row_off)
+            edge_row_off, edge_runs, edge_run_off)
+
+
+def build_edge_runs(edge_ab: torch.Tensor, n_grid: int, min_edges_per_entry: Optional[float] = None):
+    """The sorted edge list run-length compressed by end-point difference per chunk of 32 consecutive vertices (one-time
+    setup): -> (edge_runs (K,2) int32 rows (d, mask), edge_run_off (ceil(N/32)+1,) int32), entries of a chunk ascending in
+    d, bit l of mask set iff (32c + l, 32c + l + d) is an edge (d3h_forward_args.edge_runs) -- or (None, None) when the
+    grid averages fewer than `min_edges_per_entry` edges per entry (vertex numbering without structure: the transposed
+    rows are the better table).  Self edges (d = 0, tets that repeat a vertex) stay: they never cross (the window is the
+    chunk's own word) but they count for the ranks of the vertex's other edges."""
+    if min_edges_per_entry is None:
+        min_edges_per_entry = _RUNS_MIN_EDGES
+    dev = edge_ab.device
+    n_chunks = (n_grid + 31) // 32
+    a, b = edge_ab[:, 0].long(), edge_ab[:, 1].long()
+    key = (a >> 5) * n_grid + (b - a)                     # (chunk, difference): ascending = the order of the entries
+    uk, inv = torch.unique(key, return_inverse=True)
+    n_runs = int(uk.shape[0])
+    if n_runs == 0 or a.shape[0] < min_edges_per_entry * n_runs:
+        return None, None
+    mask = torch.zeros(n_runs, dtype=torch.int64, device=dev)
+    mask.scatter_add_(0, inv, torch.ones_like(a) << (a & 31))     # distinct edges: every (entry, lane) is added once
+    mask = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask)       # as int32 bit patterns
+    chunk = torch.div(uk, n_grid, rounding_mode="floor")
+    runs = torch.stack([uk - chunk * n_grid, mask], 1).to(torch.int32).contiguous()
+    run_off = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
+    run_off[1:] = torch.cumsum(torch.bincount(chunk, minlength=n_chunks), 0)
+    return runs, run_off.to(torch.int32).contiguous()
 
 
 def build_edge_rows(edge_off: torch.Tensor, edge_ab: torch.Tensor, n_grid: int):
@@ -232,7 +277,7 @@ def static_edges_for(tets_i32: torch.Tensor, n_grid: int):
     # the version counter is part of the key: an int32 tet_fx4 is used in place (packed_tets returns the caller's tensor),
     # an in-place edit must not find the edge table of the old contents
     key = (tets_i32.data_ptr(), tets_i32._version, tets_i32.shape[0], int(n_grid), tets_i32.device.index, _edge_scan,
-           _tet_edge_ranks, _mark_rows, _scan_rows)
+           _tet_edge_ranks, _mark_rows, _scan_rows, _scan_runs)
     ent = _static_cache.get(key)
     if ent is None:
         if len(_static_cache) > 8:
@@ -437,6 +482,8 @@ class _Layout:
                     A[:, c["etets8"]] = static[7].data_ptr()
                 if len(static) > 9 and static[8] is not None:
                     A[:, c["edge_rows"]], A[:, c["edge_row_off"]] = static[8].data_ptr(), static[9].data_ptr()
+                if len(static) > 11 and static[10] is not None:
+                    A[:, c["edge_runs"]], A[:, c["edge_run_off"]] = static[10].data_ptr(), static[11].data_ptr()
             self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
         self.static = static
         self.A = A

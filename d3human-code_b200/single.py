@@ -59,6 +59,8 @@ class _State:
                     fa.etets8 = static[7].data_ptr()
                 if len(static) > 9 and static[8] is not None:
                     fa.edge_rows, fa.edge_row_off = static[8].data_ptr(), static[9].data_ptr()
+                if len(static) > 11 and static[10] is not None:
+                    fa.edge_runs, fa.edge_run_off = static[10].data_ptr(), static[11].data_ptr()
         ba.n_grid, ba.msdf_negate, ba.grads_prezeroed = n_grid, int(negate), 1
         self.fa, self.ba = fa, ba
         self.fa_ref, self.ba_ref = C.addressof(fa), C.addressof(ba)

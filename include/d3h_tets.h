@@ -166,6 +166,17 @@ typedef struct d3h_forward_args {
    * NULL: walk edge_b through edge_off. */
   const int32_t* edge_rows;    /* (32 * (edge_row_off[ceil(N/32)] + 8)) */
   const int32_t* edge_row_off; /* (ceil(N/32) + 1) */
+  /* optional companion of the edge-scan path, preferred over edge_rows / edge_b when given: the edge list of a chunk of 32
+   * consecutive vertices RUN-LENGTH compressed by end-point difference.  Chunk c owns entries
+   * [edge_run_off[c], edge_run_off[c+1]) of edge_runs, 8 bytes each: (d, mask), ascending in d, d >= 0 -- bit l of mask is
+   * set iff (32c + l, 32c + l + d) is an edge of the grid.  On a lattice numbered along its axes every vertex has the same
+   * few differences, so a chunk needs ~7 entries instead of ~224 end points, and the signs of all 32 far end points of an
+   * entry are ONE 32-bit window of the sign bitmap: 32 edges are tested with a funnel shift and an xor.  The rank of an
+   * edge in the sorted list is edge_off[a] + (number of entries of the chunk with a smaller d whose mask holds a's lane).
+   * Worth it when entries are shared by several lanes (the host builds it when the grid averages >= 4 edges per entry);
+   * exact for any grid. */
+  const int32_t* edge_runs;    /* (2 * edge_run_off[ceil(N/32)]) int32 pairs, 8-byte aligned */
+  const int32_t* edge_run_off; /* (ceil(N/32) + 1) */
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */

@@ -59,14 +59,16 @@ def emu_lib_path():
     return build_emu.build()
 
 
-@pytest.fixture(params=["sort", "static", "scan", "scan_csr"])
+@pytest.fixture(params=["sort", "static", "scan", "scan_rows", "scan_csr"])
 def edges_mode(request):
-    if request.param == "scan_csr" and request.node.originalname not in ("test_golden", "test_oracle", "test_random_tet_soups",
-                                                                         "test_tet_soups_with_repeated_vertices"):
-        pytest.skip("the CSR walk of the edge-scan path is covered by the golden / oracle / soup tests")
+    if request.param in ("scan_rows", "scan_csr") and request.node.originalname not in (
+            "test_golden", "test_oracle", "test_random_tet_soups", "test_tet_soups_with_repeated_vertices"):
+        pytest.skip("the other forms of the static edge list are covered by the golden / oracle / soup tests")
     E.set_scan_rows(request.param != "scan_csr")
-    yield "scan" if request.param == "scan_csr" else request.param
+    E.set_scan_runs(request.param == "scan")
+    yield "scan" if request.param.startswith("scan") else request.param
     E.set_scan_rows(True)
+    E.set_scan_runs(True)
 
 
 @pytest.fixture

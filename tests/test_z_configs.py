@@ -18,27 +18,31 @@ def dev():
     return torch.device("cuda:0")
 
 
-#: tests that also run on the edge-scan path WITHOUT the transposed edge rows (edge_scan_kernel walking edge_b by CSR offsets)
+#: tests that also run on the edge-scan path with the other forms of the static edge list: "scan" lets the host choose
+#: (run-length compressed on lattices, transposed rows on unstructured numberings), "scan_rows" forbids the compression,
+#: "scan_csr" also the rows (edge_scan_kernel walking edge_b by CSR offsets)
 _CSR_WALK_TESTS = ("test_cuda_matches_golden", "test_cuda_matches_oracle", "test_smplx_layout_split_extraction",
                    "test_random_tet_soups", "test_tet_soups_with_repeated_vertices")
 
 
-@pytest.fixture(autouse=True, params=["sort", "static", "scan", "scan_csr"])
+@pytest.fixture(autouse=True, params=["sort", "static", "scan", "scan_rows", "scan_csr"])
 def edges_mode(request):
     """Every test runs three times: on the general path (per-call radix sort + run-length scan of the crossing-edge keys),
     on the static edge table path (tet stream + bitmap over the grid's sorted edge list, built once per tet array) and on
     the edge-scan path (walk over the static edge list instead of the tet stream; the default of a training run).  A few
     run a fourth time on the edge-scan path with the CSR walk instead of the transposed edge rows."""
     from d3human_code_b200 import extract as E
-    if request.param == "scan_csr" and request.node.originalname not in _CSR_WALK_TESTS:
-        pytest.skip("the CSR walk of the edge-scan path is covered by the golden / oracle / soup tests")
+    if request.param in ("scan_rows", "scan_csr") and request.node.originalname not in _CSR_WALK_TESTS:
+        pytest.skip("the other forms of the static edge list are covered by the golden / oracle / soup tests")
     E.set_static_edges("0" if request.param == "sort" else "1")
     E.set_edge_scan(request.param.startswith("scan"))
     E.set_scan_rows(request.param != "scan_csr")
-    yield "scan" if request.param == "scan_csr" else request.param
+    E.set_scan_runs(request.param == "scan")
+    yield "scan" if request.param.startswith("scan") else request.param
     E.set_static_edges("auto")
     E.set_edge_scan(True)
     E.set_scan_rows(True)
+    E.set_scan_runs(True)
 
 
 # counts measured by running the reference on CPU (SURVEY.md B.4): Fv, V, Fw, Va, Fa
