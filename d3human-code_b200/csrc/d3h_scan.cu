@@ -436,19 +436,36 @@ edge_scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
     cnt += __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]);
   }
   const unsigned q = (unsigned)(gwarp % kQueues);
-  int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
-  if (slot < 0 || cnt == 0u) { trace_end(tr); return; }
-  // the few chunks on the surface: entries once more, every crossing edge with its rank in the sorted list
+  const int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
+  if (slot < 0) { trace_end(tr); return; }
+  // The few chunks on the surface, one after the other with the WHOLE warp: lane l plays vertex 32c + l of the chunk, every
+  // load of an entry is a broadcast, the lane's rank in its vertex's edge list is counted on the way (a thread walking its
+  // chunk alone needs up to 224 dependent look-ups: 47 us for the kernel, r02y).
   int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
-  for (int k = k0; k < k1; ++k) {
-    unsigned x = crossing(k);
-    while (x) {
-      const int l = __ffs((int)x) - 1;
-      x &= x - 1u;
-      int rank = 0;   // entries of the chunk with a smaller difference that hold this lane
-      for (int kk = k0; kk < k; ++kk) rank += (int)(((unsigned)__ldg(runs + kk).y >> l) & 1u);
-      if (slot < L.cap_qe) out[slot] = __ldg(a.edge_off + (c << 5) + l) + rank;
-      ++slot;
+  const unsigned lane = lane_id();
+  unsigned todo = __ballot_sync(0xffffffffu, cnt != 0u);
+  while (todo) {
+    const int src = __ffs((int)todo) - 1;
+    todo &= todo - 1u;
+    const int64_t cs = c - lane + src;
+    const int ks0 = __shfl_sync(0xffffffffu, k0, src), ks1 = __shfl_sync(0xffffffffu, k1, src);
+    const unsigned owns = __shfl_sync(0xffffffffu, own, src);
+    int64_t at = (int64_t)__shfl_sync(0xffffffffu, (unsigned)(slot & 0xffffffffll), src) |
+                 ((int64_t)__shfl_sync(0xffffffffu, (unsigned)(slot >> 32), src) << 32);
+    const int64_t v = (cs << 5) + lane;
+    const int e0 = v < a.n_grid ? __ldg(a.edge_off + v) : 0;
+    int rank = 0;   // entries so far that hold this lane = rank of the next edge of vertex v in the sorted list
+    for (int k = ks0; k < ks1; ++k) {
+      const int2 e = __ldg(runs + k);
+      const int64_t b0 = (cs << 5) + e.x;
+      const unsigned lo = __ldg(occ_bits + (b0 >> 5)), hi = __ldg(occ_bits + (b0 >> 5) + 1);
+      const unsigned x = (__funnelshift_r(lo, hi, (unsigned)b0 & 31u) ^ owns) & (unsigned)e.y;
+      if ((x >> lane) & 1u) {
+        const int64_t s = at + __popc(x & ((1u << lane) - 1u));
+        if (s < L.cap_qe) out[s] = e0 + rank;
+      }
+      at += __popc(x);
+      rank += (int)(((unsigned)e.y >> lane) & 1u);
     }
   }
   trace_end(tr);
