@@ -767,6 +767,7 @@ def main():
     if prof:
         kern = {k: {"ms_total": round(v[0], 4), "launches": v[1], "us_avg": round(1e3 * v[0] / v[1], 3)} for k, v in prof.items()}
         dom = "edge_scan" if "edge_scan" in prof else "classify"
+        dom_name = dom + "_kernel"
         ms, n = prof.get(dom, (0.0, 0))
         dom_bytes = 16.0 * F
         if dom == "edge_scan":   # 4 B per edge (larger endpoint) + 4 B per vertex (CSR offsets) + the sign bitmap
@@ -777,11 +778,14 @@ def main():
                 # sign bitmap; the CSR offsets are only read by the few lanes that found a crossing edge, the padding
                 # slots of the rows (+2.5 % at 128^3) are not counted
                 dom_bytes = 4.0 * st[2] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
-            if len(st) > 11 and st[10] is not None:
-                # run-length compressed edge list (edge_scan_runs_kernel): 8 B per (difference, mask) entry + 4 B per
-                # chunk (entry offsets) + the sign bitmap read twice (own word + the windows of the entries come from L1 / L2:
-                # counted once)
-                dom_bytes = 8.0 * st[10].shape[0] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
+            if len(st) > 11 and st[10][0] is not None:
+                # run-length compressed tables (scan_runs_kernel): 12 B per edge entry (difference, mask, chunk), 20 B per
+                # tet entry (three differences, mask, chunk), the sign bitmap once (the windows come from L1 / L2), and
+                # one 128-byte id row per entry that found something (~ one per 6 crossing edges / 2 valid tets: not
+                # known here, left out)
+                dom_bytes = 12.0 * st[10][0].shape[0] + N / 8.0
+                if st[11][0] is not None:
+                    dom_bytes += 20.0 * st[11][0].shape[0]
         if n and ms > 0:
             t_events = ms / n * 1e-3      # one launch at a time between two events: includes the ~3-7 us launch / event gap
             t = scan_alone_us * 1e-6 if (dom == "edge_scan" and scan_alone_us) else t_events

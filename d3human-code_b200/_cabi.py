@@ -64,7 +64,8 @@ class ForwardArgs(C.Structure):  # d3h_forward_args
                 ("pair_counts_host", C.c_void_p), ("pair_seq", C.c_int64), ("tet_edge_rank", C.c_void_p),
                 ("edge_b", C.c_void_p), ("etet_off", C.c_void_p), ("etets", C.c_void_p), ("etets8", C.c_void_p),
                 ("edge_rows", C.c_void_p), ("edge_row_off", C.c_void_p),
-                ("edge_runs", C.c_void_p), ("edge_run_off", C.c_void_p)]
+                ("edge_runs", C.c_void_p), ("edge_run_chunk", C.c_void_p), ("edge_run_ids", C.c_void_p), ("n_edge_runs", C.c_int64),
+                ("tet_runs", C.c_void_p), ("tet_run_chunk", C.c_void_p), ("tet_run_ids", C.c_void_p), ("n_tet_runs", C.c_int64)]
 
 
 class BackwardArgs(C.Structure):  # d3h_backward_args

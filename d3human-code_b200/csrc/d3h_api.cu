@@ -252,9 +252,16 @@ static int check_forward_args(const d3h_forward_args* a, const char* who) {
     set_error("%s: edge_rows (128-byte aligned) and edge_row_off come together and with the edge-scan tables", who);
     return D3H_E_BADARG;
   }
-  if ((a->edge_runs != nullptr) != (a->edge_run_off != nullptr) || (a->edge_runs != nullptr && a->etets == nullptr) ||
-      (reinterpret_cast<uintptr_t>(a->edge_runs) & 7)) {
-    set_error("%s: edge_runs (8-byte aligned) and edge_run_off come together and with the edge-scan tables", who);
+  if (a->edge_runs != nullptr &&
+      (!a->edge_run_chunk || !a->edge_run_ids || a->n_edge_runs <= 0 || a->n_edge_runs >= (1ll << 26) || a->etets == nullptr ||
+       (reinterpret_cast<uintptr_t>(a->edge_runs) & 7))) {
+    set_error("%s: edge_runs (8-byte aligned) needs edge_run_chunk, edge_run_ids, 0 < n_edge_runs < 2^26 and the edge-scan tables", who);
+    return D3H_E_BADARG;
+  }
+  if (a->tet_runs != nullptr &&
+      (!a->tet_run_chunk || !a->tet_run_ids || a->n_tet_runs <= 0 || a->n_tet_runs >= (1ll << 26) || a->edge_runs == nullptr ||
+       (reinterpret_cast<uintptr_t>(a->tet_runs) & 15))) {
+    set_error("%s: tet_runs (16-byte aligned) needs tet_run_chunk, tet_run_ids, 0 < n_tet_runs < 2^26 and edge_runs", who);
     return D3H_E_BADARG;
   }
   if ((a->etets8 != nullptr && a->etets == nullptr) || (reinterpret_cast<uintptr_t>(a->etets8) & 15) ||
@@ -336,9 +343,9 @@ struct GraphKey {
   void* workspace;
   int64_t n_tets, n_grid, tet_begin, tet_end, cap_valid_tets;
   int watertight, has_zero, device, is_static, parts;
-  int64_t n_edges;
+  int64_t n_edges, n_edge_runs, n_tet_runs;   // (launch grids are captured: everything they are computed from is part of the key)
   bool operator==(const GraphKey& o) const {
-    return parts == o.parts && is_static == o.is_static && n_edges == o.n_edges && workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
+    return parts == o.parts && is_static == o.is_static && n_edges == o.n_edges && n_edge_runs == o.n_edge_runs && n_tet_runs == o.n_tet_runs && workspace == o.workspace && n_tets == o.n_tets && n_grid == o.n_grid && tet_begin == o.tet_begin &&
            tet_end == o.tet_end && cap_valid_tets == o.cap_valid_tets && watertight == o.watertight &&
            has_zero == o.has_zero && device == o.device;
   }
@@ -445,6 +452,9 @@ static int launch_forward_graph(const d3h_forward_args& a, const Workspace& ws, 
   key.is_static = a.edge_off != nullptr ? (a.etets != nullptr ? (a.etets8 != nullptr ? 4 : 3) : (a.tet_edge_rank != nullptr ? 2 : 1)) : 0;
   if (a.edge_rows != nullptr) key.is_static += 8;   // another stream kernel
   if (a.edge_runs != nullptr) key.is_static += 16;
+  if (a.tet_runs != nullptr) key.is_static += 32;
+  key.n_edge_runs = a.edge_runs != nullptr ? a.n_edge_runs : 0;
+  key.n_tet_runs = a.tet_runs != nullptr ? a.n_tet_runs : 0;
   key.n_edges = a.edge_off != nullptr ? a.n_edges : 0;
   cudaGetDevice(&key.device);
   std::lock_guard<std::mutex> lock(g_graph_mu);
@@ -764,7 +774,8 @@ extern "C" int d3h_classify_range(const d3h_forward_args* a_in, d3h_tet_record* 
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
   general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
   general.etets8 = nullptr; general.edge_rows = nullptr; general.edge_row_off = nullptr;
-  general.edge_runs = nullptr; general.edge_run_off = nullptr;
+  general.edge_runs = nullptr; general.edge_run_chunk = nullptr; general.edge_run_ids = nullptr; general.n_edge_runs = 0;
+  general.tet_runs = nullptr; general.tet_run_chunk = nullptr; general.tet_run_ids = nullptr; general.n_tet_runs = 0;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_classify_range");
   if (rc) return rc;
@@ -796,7 +807,8 @@ extern "C" int d3h_extract_from_records(const d3h_forward_args* a_in, const d3h_
   general.edge_off = nullptr; general.edge_ab = nullptr; general.n_edges = 0;
   general.tet_edge_rank = nullptr; general.edge_b = nullptr; general.etet_off = nullptr; general.etets = nullptr;
   general.etets8 = nullptr; general.edge_rows = nullptr; general.edge_row_off = nullptr;
-  general.edge_runs = nullptr; general.edge_run_off = nullptr;
+  general.edge_runs = nullptr; general.edge_run_chunk = nullptr; general.edge_run_ids = nullptr; general.n_edge_runs = 0;
+  general.tet_runs = nullptr; general.tet_run_chunk = nullptr; general.tet_run_ids = nullptr; general.n_tet_runs = 0;
   const d3h_forward_args* a = &general;
   int rc = check_forward_args(a, "d3h_extract_from_records");
   if (rc) return rc;

@@ -395,77 +395,134 @@ edge_scan_pipe_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restri
   trace_end(tr);
 }
 
-// The stream over the RUN-LENGTH compressed edge list (d3h_forward_args.edge_runs; the default whenever the host built it).
-// Every kernel above spends its time on per-edge work: 6 to 26 instructions to fetch one sign bit, ~9 M warp instructions
-// per call at an IPC bounded by the dependent look-ups -- ~20 us whatever the shape (r02w / r02x).  On a grid numbered along
-// its axes the 32 vertices of a chunk have the same few end-point differences d, and the signs of the 32 far end points
-// 32c + l + d are 32 CONSECUTIVE bits of the sign bitmap: one funnel shift of two adjacent words.  So a THREAD takes a
-// whole chunk: per entry (d, mask) one 8-byte load, two word loads, a funnel shift, an xor with the chunk's own word and
-// an and with the mask give the crossing flags of 32 edges.  The lanes of a warp are consecutive chunks, so their word
-// loads coalesce.  7 entries per chunk on the Kuhn lattice: 3.7 MB instead of 59 MB and ~0.2 M warp instructions.
+// The scan over the RUN-LENGTH compressed tables (d3h_forward_args.edge_runs / tet_runs; the default whenever the host
+// built them).  Every kernel above spends its time on per-edge work: 6 to 26 instructions to fetch one sign bit, ~9 M warp
+// instructions per call at an IPC bounded by the dependent look-ups -- ~20 us whatever the shape (r02w / r02x).  On a grid
+// numbered along its axes the 32 vertices of a chunk have the same few end-point differences d, and the signs of the 32
+// far end points 32c + l + d are 32 CONSECUTIVE bits of the sign bitmap: one funnel shift of two adjacent words.  A THREAD
+// takes an entry (chunk, d, mask): one xor with the chunk's own word and an and with the mask give the crossing flags of
+// 32 edges.  ~7 entries per chunk on the Kuhn lattice: 5.6 MB instead of 59 MB, ~0.5 M warp instructions.
+//
+// With the tet array compressed the same way (tet_runs; watertight template) the CTAs behind the edge entries find the
+// VALID TETS (mixed signs, gshell_tets.py:261-275): a thread takes an entry (chunk of the first vertex, d1, d2, d3, mask),
+// three windows beside the chunk's own word are the occupancy codes of 32 tets.  That replaces edge_mark_kernel (~22 us of
+// dependent look-ups: edge -> incidence list -> tet -> signs -> returned atomics): every crossing edge and every valid tet
+// is met exactly once, so marks and counts are fire-and-forget and only the queue slots cost one returned atomic per warp.
+//
+// The entries that found something (the surface: a few per cent) are expanded by the whole warp, lane l = lane l of the
+// entry, eight entries at a time so that the loads of their id rows are in flight together (a lane expanding its own
+// entries one after the other makes the kernel 47 us: r02y).
+__device__ __forceinline__ unsigned sign_window(const unsigned* __restrict__ occ_bits, int64_t b0) {
+  // bits b0 .. b0 + 31 of the sign bitmap; b0 may start up to 31 bits before the first vertex (lanes outside the mask)
+  // and the upper bits may come from the word behind the last vertex (allocated, never in a mask)
+  const int64_t i = b0 >> 5;
+  const unsigned lo = i >= 0 ? __ldg(occ_bits + i) : 0u, hi = __ldg(occ_bits + i + 1);
+  return __funnelshift_r(lo, hi, (unsigned)b0 & 31u);
+}
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+  return (int64_t)__shfl_sync(0xffffffffu, (unsigned)(v & 0xffffffffll), src) |
+         ((int64_t)__shfl_sync(0xffffffffu, (unsigned)(v >> 32), src) << 32);
+}
+
+constexpr int kRunBatch = 8;   // entries expanded together
+
+template <bool MARK>   // MARK: crossing edges are marked here (no edge_mark_kernel behind)
 __global__ void __launch_bounds__(kEScanThreads)
-edge_scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L) {
+scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, unsigned* __restrict__ m1_words,
+                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, ScanLists L, unsigned nb_edges) {
   pdl_enter();
   const d3h_forward_args& a = blk->a;
-  const int2* __restrict__ runs = reinterpret_cast<const int2*>(a.edge_runs);
-  const int32_t* __restrict__ run_off = a.edge_run_off;
-  const int64_t n_chunks = (a.n_grid + 31) >> 5;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
-  const int64_t c = (int64_t)blockIdx.x * kEScanThreads + threadIdx.x;
-  const int64_t gwarp = c >> 5;
-  int k0 = 0, k1 = 0;
-  unsigned own = 0u;
-  if (c < n_chunks) {
-    k0 = __ldg(run_off + c);
-    k1 = __ldg(run_off + c + 1);
-    own = __ldg(occ_bits + c);     // signs of vertices 32c .. 32c + 31
-  }
-  // crossing flags of entry k: bit l = the edge (32c + l, 32c + l + d) exists and its end points differ in sign.  The
-  // window may take its upper bits from the word behind the last vertex (allocated, never in a mask).
-  auto crossing = [&](int k) {
-    const int2 e = __ldg(runs + k);
-    const int64_t b0 = (c << 5) + e.x;
-    const unsigned lo = __ldg(occ_bits + (b0 >> 5)), hi = __ldg(occ_bits + (b0 >> 5) + 1);
-    return (__funnelshift_r(lo, hi, (unsigned)b0 & 31u) ^ own) & (unsigned)e.y;
-  };
-  unsigned cnt = 0u;
-  for (int k = k0; k < k1; k += 4) {   // four entries at a time: their loads are in flight together
-    unsigned x[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = (k + i < k1) ? crossing(k + i) : 0u;
-    cnt += __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]);
-  }
-  const unsigned q = (unsigned)(gwarp % kQueues);
-  const int64_t slot = warp_reserve(L.q_cnt + kQStride * q, cnt);
-  if (slot < 0) { trace_end(tr); return; }
-  // The few chunks on the surface, one after the other with the WHOLE warp: lane l plays vertex 32c + l of the chunk, every
-  // load of an entry is a broadcast, the lane's rank in its vertex's edge list is counted on the way (a thread walking its
-  // chunk alone needs up to 224 dependent look-ups: 47 us for the kernel, r02y).
-  int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
   const unsigned lane = lane_id();
-  unsigned todo = __ballot_sync(0xffffffffu, cnt != 0u);
-  while (todo) {
-    const int src = __ffs((int)todo) - 1;
-    todo &= todo - 1u;
-    const int64_t cs = c - lane + src;
-    const int ks0 = __shfl_sync(0xffffffffu, k0, src), ks1 = __shfl_sync(0xffffffffu, k1, src);
-    const unsigned owns = __shfl_sync(0xffffffffu, own, src);
-    int64_t at = (int64_t)__shfl_sync(0xffffffffu, (unsigned)(slot & 0xffffffffll), src) |
-                 ((int64_t)__shfl_sync(0xffffffffu, (unsigned)(slot >> 32), src) << 32);
-    const int64_t v = (cs << 5) + lane;
-    const int e0 = v < a.n_grid ? __ldg(a.edge_off + v) : 0;
-    int rank = 0;   // entries so far that hold this lane = rank of the next edge of vertex v in the sorted list
-    for (int k = ks0; k < ks1; ++k) {
-      const int2 e = __ldg(runs + k);
-      const int64_t b0 = (cs << 5) + e.x;
-      const unsigned lo = __ldg(occ_bits + (b0 >> 5)), hi = __ldg(occ_bits + (b0 >> 5) + 1);
-      const unsigned x = (__funnelshift_r(lo, hi, (unsigned)b0 & 31u) ^ owns) & (unsigned)e.y;
-      if ((x >> lane) & 1u) {
-        const int64_t s = at + __popc(x & ((1u << lane) - 1u));
-        if (s < L.cap_qe) out[s] = e0 + rank;
+  const unsigned below = (1u << lane) - 1u;
+  const bool edges = blockIdx.x < nb_edges;
+  const int64_t i = (int64_t)(edges ? blockIdx.x : blockIdx.x - nb_edges) * kEScanThreads + threadIdx.x;   // entry
+  const unsigned gwarp = (blockIdx.x * kEScanThreads + threadIdx.x) >> 5;
+  const unsigned q = gwarp % kQueues;
+  if (edges) {
+    unsigned x = 0u;     // crossing flags: bit l = the edge (32c + l, 32c + l + d) exists and its end points differ in sign
+    if (i < a.n_edge_runs) {
+      const int64_t c = __ldg(a.edge_run_chunk + i);
+      const int2 e = __ldg(reinterpret_cast<const int2*>(a.edge_runs) + i);
+      x = (sign_window(occ_bits, (c << 5) + e.x) ^ __ldg(occ_bits + c)) & (unsigned)e.y;
+    }
+    const int64_t slot = warp_reserve(L.q_cnt + kQStride * q, (unsigned)__popc(x));
+    if (slot < 0) { trace_end(tr); return; }
+    int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
+    unsigned todo = __ballot_sync(0xffffffffu, x != 0u);
+    while (todo) {
+      unsigned xs[kRunBatch];
+      int64_t at[kRunBatch];
+      int r[kRunBatch];
+#pragma unroll
+      for (int b = 0; b < kRunBatch; ++b) {
+        xs[b] = 0u;
+        r[b] = 0;
+        if (todo) {   // (warp-uniform)
+          const int src = __ffs((int)todo) - 1;
+          todo &= todo - 1u;
+          xs[b] = __shfl_sync(0xffffffffu, x, src);
+          at[b] = shfl_i64(slot, src);
+          // rank of the lane's edge in the sorted edge list
+          if ((xs[b] >> lane) & 1u) r[b] = __ldg(a.edge_run_ids + ((i - lane + src) << 5) + lane);
+        }
       }
-      at += __popc(x);
-      rank += (int)(((unsigned)e.y >> lane) & 1u);
+#pragma unroll
+      for (int b = 0; b < kRunBatch; ++b) {
+        if (!((xs[b] >> lane) & 1u)) continue;
+        const unsigned e = (unsigned)r[b];
+        if (MARK) {   // (results unused: reductions)
+          atomicOr(edge_bits + (e >> 5), 1u << (e & 31u));
+          atomicAdd(L.eblock_cnt + e / (unsigned)kEdgeBlock, 1u);
+        }
+        const int64_t s = at[b] + __popc(xs[b] & below);
+        if (s < L.cap_qe) out[s] = (int)e;
+      }
+    }
+  } else {
+    unsigned x = 0u, own = 0u, w1 = 0u, w2 = 0u, w3 = 0u;   // x: tets of the entry whose signs are mixed
+    if (i < a.n_tet_runs) {
+      const int64_t c = __ldg(a.tet_run_chunk + i);
+      const int4 e = __ldg(reinterpret_cast<const int4*>(a.tet_runs) + i);
+      own = __ldg(occ_bits + c);
+      w1 = sign_window(occ_bits, (c << 5) + e.x);
+      w2 = sign_window(occ_bits, (c << 5) + e.y);
+      w3 = sign_window(occ_bits, (c << 5) + e.z);
+      x = ((own ^ w1) | (own ^ w2) | (own ^ w3)) & (unsigned)e.w;
+    }
+    const int64_t slot = warp_reserve(L.q_cnt + kQStride * (kQueues + q), (unsigned)__popc(x));
+    if (slot < 0) { trace_end(tr); return; }
+    int2* __restrict__ vout = L.vlist + (int64_t)q * L.cap_qv;
+    // occupancy code of the lane's tet in every entry of the warp: bit v = sign of the tet's vertex v
+    unsigned todo = __ballot_sync(0xffffffffu, x != 0u);
+    while (todo) {
+      unsigned xs[kRunBatch], code[kRunBatch];
+      int64_t at[kRunBatch];
+      int t[kRunBatch];
+#pragma unroll
+      for (int b = 0; b < kRunBatch; ++b) {
+        xs[b] = 0u;
+        t[b] = 0;
+        code[b] = 0u;
+        if (todo) {   // (warp-uniform)
+          const int src = __ffs((int)todo) - 1;
+          todo &= todo - 1u;
+          xs[b] = __shfl_sync(0xffffffffu, x, src);
+          at[b] = shfl_i64(slot, src);
+          code[b] = ((__shfl_sync(0xffffffffu, own, src) >> lane) & 1u) | (((__shfl_sync(0xffffffffu, w1, src) >> lane) & 1u) << 1) |
+                    (((__shfl_sync(0xffffffffu, w2, src) >> lane) & 1u) << 2) | (((__shfl_sync(0xffffffffu, w3, src) >> lane) & 1u) << 3);
+          if ((xs[b] >> lane) & 1u) t[b] = __ldg(a.tet_run_ids + ((i - lane + src) << 5) + lane);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kRunBatch; ++b) {
+        if (!((xs[b] >> lane) & 1u)) continue;
+        const bool quad = __popc(code[b]) == 2;
+        atomicOr((quad ? m2_words : m1_words) + (t[b] >> 5), 1u << (t[b] & 31));           // (results unused: reductions)
+        atomicAdd(L.tile_cnt + (unsigned)t[b] / (unsigned)kTileTets, quad ? 0x10000u : 1u);
+        const int64_t s = at[b] + __popc(xs[b] & below);
+        if (s < L.cap_qv) vout[s] = make_int2(t[b], (int)code[b]);
+      }
     }
   }
   trace_end(tr);
@@ -490,10 +547,6 @@ static void launch_scan_rows(const d3h_forward_args& a, Launch&& launch) {
     if (gg && atoi(gg) > 0) grid1 = grid2 = atoi(gg);
   }
   const int64_t n_chunks = (a.n_grid + 31) / 32;
-  if (a.edge_runs != nullptr) {
-    launch(edge_scan_runs_kernel, (unsigned)((n_chunks + kEScanThreads - 1) / kEScanThreads));
-    return;
-  }
   if (pipe) {
     const int c = cpw == 1 ? 1 : 2;
     const int64_t need = (n_chunks + 8 * c - 1) / (8 * c);   // CTAs of a one-shot launch
@@ -924,7 +977,19 @@ static ScanLists scan_lists(const d3h_forward_args& a, const Workspace& ws) {
 
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const ScanLists L = scan_lists(a, ws);
-  if (a.edge_rows != nullptr || a.edge_runs != nullptr) {
+  if (a.edge_runs != nullptr) {   // the launch of launch_edge_scan (its marks and counts land in scratch state)
+    const bool both = a.tet_runs != nullptr && a.watertight_template;
+    const unsigned nbe = (unsigned)((a.n_edge_runs + kEScanThreads - 1) / kEScanThreads);
+    const unsigned nbt = both ? (unsigned)((a.n_tet_runs + kEScanThreads - 1) / kEScanThreads) : 0u;
+    if (both)
+      launch_k(scan_runs_kernel<true>, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
+               ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
+    else
+      launch_k(scan_runs_kernel<false>, nbe, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
+               ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
+    return;
+  }
+  if (a.edge_rows != nullptr) {
     launch_scan_rows(a, [&](auto kernel, unsigned nblk) {
       launch_k(kernel, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
     });
@@ -949,12 +1014,25 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   const int filtered = a.watertight_template ? 0 : 1;
   L.elist = filtered ? ws.elist2 : ws.elist;
   L.cap_qe = ws.cap_qe; L.cap_qv = ws.cap_qv;
-  {
+  const bool runs_both = a.tet_runs != nullptr && a.edge_runs != nullptr && !filtered;
+  if (a.edge_runs != nullptr) {
+    // crossing edges from the compressed edge list and, with the compressed tet array (watertight template), the valid
+    // tets as well: one launch, edges marked on the spot, no marking kernel
+    ProfScope ps(K_EDGE_SCAN, stream);
+    const unsigned nbe = (unsigned)((a.n_edge_runs + kEScanThreads - 1) / kEScanThreads);
+    const unsigned nbt = runs_both ? (unsigned)((a.n_tet_runs + kEScanThreads - 1) / kEScanThreads) : 0u;
+    if (runs_both)
+      launch_k_dep(scan_runs_kernel<true>, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
+                   ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
+    else
+      launch_k_dep(scan_runs_kernel<false>, nbe, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
+                   ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
+  } else {
     ProfScope ps(K_EDGE_SCAN, stream);
     const int vpt = scan_vpt();
     const int64_t per_cta = (int64_t)kEScanThreads * vpt;
     const unsigned nblk = (unsigned)((a.n_grid + per_cta - 1) / per_cta);
-    if (a.edge_rows != nullptr || a.edge_runs != nullptr) {
+    if (a.edge_rows != nullptr) {
       launch_scan_rows(a, [&](auto kernel, unsigned nb) {
         launch_k_dep(kernel, nb, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
       });
@@ -971,7 +1049,7 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     int64_t p = (cap_q / 8 + 255) / 256;
     return (unsigned)(p < 1 ? 1 : (p > 16 ? 16 : p));
   };
-  {
+  if (!runs_both) {
     ProfScope ps(K_EDGE_MARK, stream);
     const unsigned nblk = kQueues * parts_for(ws.cap_qe);
     // opt-in (the host passes etets8 only with D3H_MARK_ROWS=1): measured 22.1 us against 23.6 us for the default on the

@@ -139,12 +139,13 @@ def set_static_edges(mode: str) -> None:
 def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     """One-time setup on the device (torch sort of the 6F edge keys; not on the per-call path).
     Returns (edge_off (N+1,) int32, edge_ab (U,2) int32, U, tet_rank, edge_b, etet_off, etets, etets8, edge_rows,
-    edge_row_off, edge_runs, edge_run_off): edges ascending in (min,max), CSR offsets per min vertex.  The last nine are
-    None unless asked for:
+    edge_row_off, (edge_runs, edge_run_chunk, edge_run_ids), (tet_runs, tet_run_chunk, tet_run_ids)): edges ascending in
+    (min,max), CSR offsets per min vertex.  Entries 3 .. 9 and the members of the two triples are None unless asked for:
       edge_rows, edge_row_off : the larger end points transposed per chunk of 32 vertices (layout: include/d3h_tets.h);
                                 edge_b is None then
-      edge_runs, edge_run_off : the edge list run-length compressed by end-point difference per chunk (include/d3h_tets.h);
-                                edge_rows and edge_b are None then
+      edge_runs, edge_run_chunk, edge_run_ids : the edge list run-length compressed by end-point difference per chunk
+                                (include/d3h_tets.h); edge_rows and edge_b are None then
+      tet_runs, tet_run_chunk, tet_run_ids : the tet array compressed by shape per chunk (build_tet_runs), with edge_runs
       tet_rank (F,8) int32 : rank in the edge list of the six edges of every tet (order of gshell_tets.py:187, 2 pad words)
       edge_b   (U,)  int32 : the larger endpoints, contiguous (the 4-byte-per-edge stream of the edge-scan path)
       etet_off (U+1,), etets (<=6F,) int32 : the tets around every edge, ascending and distinct tet ids
@@ -163,7 +164,8 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
     n_edges = int(uk.shape[0])
     if n_edges >= 2 ** 31:
         raise ValueError("tet grid has more than 2^31 distinct edges")
-    tet_rank = edge_b = etet_off = etets = etets8 = edge_rows = edge_row_off = edge_runs = edge_run_off = None
+    tet_rank = edge_b = etet_off = etets = etets8 = edge_rows = edge_row_off = None
+    edge_runs = edge_run_chunk = edge_run_ids = tet_runs = tet_run_chunk = tet_run_ids = None
     if _tet_edge_ranks or _edge_scan:
         rank6 = torch.searchsorted(uk, key6.reshape(-1)).reshape(n_tets, 6)
         del key6
@@ -186,9 +188,9 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
             off64[1:] = torch.cumsum(torch.bincount(eid, minlength=n_edges), 0)
             etet_off = off64.to(torch.int32).contiguous()
             if _scan_runs:
-                edge_runs, edge_run_off = build_edge_runs(edge_ab, n_grid)
+                edge_runs, edge_run_chunk, edge_run_ids = build_edge_runs(edge_off, edge_ab, n_grid)
             if edge_runs is not None:
-                pass
+                tet_runs, tet_run_chunk, tet_run_ids = build_tet_runs(tets_i32, n_grid)
             elif _scan_rows:
                 edge_rows, edge_row_off = build_edge_rows(edge_off, edge_ab, n_grid)
             else:
@@ -205,34 +207,79 @@ def build_edge_table(tets_i32: torch.Tensor, n_grid: int):
             del eid, tid, off64
         del rank6
     return (edge_off.to(torch.int32).contiguous(), edge_ab, n_edges, tet_rank, edge_b, etet_off, etets, etets8, edge_rows,
-            edge_row_off, edge_runs, edge_run_off)
+            edge_row_off, (edge_runs, edge_run_chunk, edge_run_ids), (tet_runs, tet_run_chunk, tet_run_ids))
 
 
-def build_edge_runs(edge_ab: torch.Tensor, n_grid: int, min_edges_per_entry: Optional[float] = None):
+def build_tet_runs(tets_i32: torch.Tensor, n_grid: int, min_tets_per_entry: Optional[float] = None):
+    """The tet array compressed by shape per chunk of 32 consecutive FIRST vertices (one-time setup; companion of
+    build_edge_runs): -> (tet_runs (K,4) int32 rows (d1, d2, d3, mask), tet_run_chunk (K,) int32, tet_run_ids (K,32)
+    int32) as d3h_forward_args.tet_runs describes, or (None, None, None) when the grid averages fewer than
+    `min_tets_per_entry` tets per entry or two tets list the same vertices in the same order."""
+    if min_tets_per_entry is None:
+        min_tets_per_entry = _RUNS_MIN_EDGES
+    dev = tets_i32.device
+    n_tets = tets_i32.shape[0]
+    t = tets_i32.long()
+    v0 = t[:, 0]
+    span = 2 * n_grid                                     # differences lie in (-N, N)
+    k12 = (t[:, 1] - v0 + n_grid) * span + (t[:, 2] - v0 + n_grid)
+    u12, i12 = torch.unique(k12, return_inverse=True)
+    k123 = i12 * span + (t[:, 3] - v0 + n_grid)
+    del k12, i12
+    upat, pid = torch.unique(k123, return_inverse=True)   # the distinct shapes (6 on a Kuhn lattice)
+    del k123, t
+    n_pat = int(upat.shape[0])
+    uk, inv = torch.unique((v0 >> 5) * n_pat + pid, return_inverse=True)   # entries ascending in (chunk, shape)
+    del pid
+    n_runs = int(uk.shape[0])
+    if n_runs == 0 or n_tets < min_tets_per_entry * n_runs or n_runs >= 2 ** 26:
+        return None, None, None
+    slot = inv * 32 + (v0 & 31)
+    ids = torch.full((n_runs * 32,), -1, dtype=torch.int32, device=dev)
+    ids[slot] = torch.arange(n_tets, dtype=torch.int32, device=dev)
+    if int((ids >= 0).sum()) != n_tets:                   # two tets in one slot: identical vertex lists
+        return None, None, None
+    mask = torch.zeros(n_runs, dtype=torch.int64, device=dev)
+    mask.scatter_add_(0, inv, torch.ones_like(v0) << (v0 & 31))
+    mask = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask)
+    chunk = torch.div(uk, n_pat, rounding_mode="floor")
+    k123 = upat[uk - chunk * n_pat]
+    q12 = torch.div(k123, span, rounding_mode="floor")
+    d3 = k123 - q12 * span - n_grid
+    k12 = u12[q12]
+    d1 = torch.div(k12, span, rounding_mode="floor")
+    d2 = k12 - d1 * span - n_grid
+    runs = torch.stack([d1 - n_grid, d2, d3, mask], 1).to(torch.int32).contiguous()
+    return runs, chunk.to(torch.int32).contiguous(), ids.view(n_runs, 32)
+
+
+def build_edge_runs(edge_off: torch.Tensor, edge_ab: torch.Tensor, n_grid: int, min_edges_per_entry: Optional[float] = None):
     """The sorted edge list run-length compressed by end-point difference per chunk of 32 consecutive vertices (one-time
-    setup): -> (edge_runs (K,2) int32 rows (d, mask), edge_run_off (ceil(N/32)+1,) int32), entries of a chunk ascending in
-    d, bit l of mask set iff (32c + l, 32c + l + d) is an edge (d3h_forward_args.edge_runs) -- or (None, None) when the
-    grid averages fewer than `min_edges_per_entry` edges per entry (vertex numbering without structure: the transposed
-    rows are the better table).  Self edges (d = 0, tets that repeat a vertex) stay: they never cross (the window is the
-    chunk's own word) but they count for the ranks of the vertex's other edges."""
+    setup): -> (edge_runs (K,2) int32 rows (d, mask), edge_run_chunk (K,) int32, edge_run_ids (K,32) int32), entries
+    ascending in (chunk, d), bit l of mask set iff (32c + l, 32c + l + d) is an edge, whose rank in the sorted list is
+    ids[k, l] (d3h_forward_args.edge_runs) -- or (None, None, None) when the grid averages fewer than
+    `min_edges_per_entry` edges per entry (vertex numbering without structure: the transposed rows are the better
+    table).  Self edges (d = 0, tets that repeat a vertex) never cross (the window is the chunk's own word); they are kept
+    for simplicity."""
     if min_edges_per_entry is None:
         min_edges_per_entry = _RUNS_MIN_EDGES
     dev = edge_ab.device
-    n_chunks = (n_grid + 31) // 32
+    n_edges = edge_ab.shape[0]
     a, b = edge_ab[:, 0].long(), edge_ab[:, 1].long()
     key = (a >> 5) * n_grid + (b - a)                     # (chunk, difference): ascending = the order of the entries
     uk, inv = torch.unique(key, return_inverse=True)
     n_runs = int(uk.shape[0])
-    if n_runs == 0 or a.shape[0] < min_edges_per_entry * n_runs:
-        return None, None
+    if n_runs == 0 or n_edges < min_edges_per_entry * n_runs or n_runs >= 2 ** 26:
+        return None, None, None
+    lane = a & 31
     mask = torch.zeros(n_runs, dtype=torch.int64, device=dev)
-    mask.scatter_add_(0, inv, torch.ones_like(a) << (a & 31))     # distinct edges: every (entry, lane) is added once
+    mask.scatter_add_(0, inv, torch.ones_like(a) << lane)           # distinct edges: every (entry, lane) is added once
     mask = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask)       # as int32 bit patterns
+    ids = torch.full((n_runs * 32,), -1, dtype=torch.int32, device=dev)
+    ids[inv * 32 + lane] = torch.arange(n_edges, dtype=torch.int32, device=dev)
     chunk = torch.div(uk, n_grid, rounding_mode="floor")
     runs = torch.stack([uk - chunk * n_grid, mask], 1).to(torch.int32).contiguous()
-    run_off = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
-    run_off[1:] = torch.cumsum(torch.bincount(chunk, minlength=n_chunks), 0)
-    return runs, run_off.to(torch.int32).contiguous()
+    return runs, chunk.to(torch.int32).contiguous(), ids.view(n_runs, 32)
 
 
 def build_edge_rows(edge_off: torch.Tensor, edge_ab: torch.Tensor, n_grid: int):
@@ -482,8 +529,16 @@ class _Layout:
                     A[:, c["etets8"]] = static[7].data_ptr()
                 if len(static) > 9 and static[8] is not None:
                     A[:, c["edge_rows"]], A[:, c["edge_row_off"]] = static[8].data_ptr(), static[9].data_ptr()
-                if len(static) > 11 and static[10] is not None:
-                    A[:, c["edge_runs"]], A[:, c["edge_run_off"]] = static[10].data_ptr(), static[11].data_ptr()
+                if len(static) > 11 and static[10][0] is not None:
+                    er = static[10]
+                    A[:, c["edge_runs"]], A[:, c["edge_run_chunk"]], A[:, c["edge_run_ids"]] = (
+                        er[0].data_ptr(), er[1].data_ptr(), er[2].data_ptr())
+                    A[:, c["n_edge_runs"]] = er[0].shape[0]
+                    tr = static[11]
+                    if tr[0] is not None:
+                        A[:, c["tet_runs"]], A[:, c["tet_run_chunk"]], A[:, c["tet_run_ids"]] = (
+                            tr[0].data_ptr(), tr[1].data_ptr(), tr[2].data_ptr())
+                        A[:, c["n_tet_runs"]] = tr[0].shape[0]
             self.vacc_off = ar * (4 * self.f_len) + 4 * self.o_vacc
         self.static = static
         self.A = A

@@ -59,8 +59,13 @@ class _State:
                     fa.etets8 = static[7].data_ptr()
                 if len(static) > 9 and static[8] is not None:
                     fa.edge_rows, fa.edge_row_off = static[8].data_ptr(), static[9].data_ptr()
-                if len(static) > 11 and static[10] is not None:
-                    fa.edge_runs, fa.edge_run_off = static[10].data_ptr(), static[11].data_ptr()
+                if len(static) > 11 and static[10][0] is not None:
+                    er, tr = static[10], static[11]
+                    fa.edge_runs, fa.edge_run_chunk, fa.edge_run_ids = er[0].data_ptr(), er[1].data_ptr(), er[2].data_ptr()
+                    fa.n_edge_runs = er[0].shape[0]
+                    if tr[0] is not None:
+                        fa.tet_runs, fa.tet_run_chunk, fa.tet_run_ids = tr[0].data_ptr(), tr[1].data_ptr(), tr[2].data_ptr()
+                        fa.n_tet_runs = tr[0].shape[0]
         ba.n_grid, ba.msdf_negate, ba.grads_prezeroed = n_grid, int(negate), 1
         self.fa, self.ba = fa, ba
         self.fa_ref, self.ba_ref = C.addressof(fa), C.addressof(ba)

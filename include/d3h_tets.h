@@ -166,17 +166,30 @@ typedef struct d3h_forward_args {
    * NULL: walk edge_b through edge_off. */
   const int32_t* edge_rows;    /* (32 * (edge_row_off[ceil(N/32)] + 8)) */
   const int32_t* edge_row_off; /* (ceil(N/32) + 1) */
-  /* optional companion of the edge-scan path, preferred over edge_rows / edge_b when given: the edge list of a chunk of 32
-   * consecutive vertices RUN-LENGTH compressed by end-point difference.  Chunk c owns entries
-   * [edge_run_off[c], edge_run_off[c+1]) of edge_runs, 8 bytes each: (d, mask), ascending in d, d >= 0 -- bit l of mask is
-   * set iff (32c + l, 32c + l + d) is an edge of the grid.  On a lattice numbered along its axes every vertex has the same
-   * few differences, so a chunk needs ~7 entries instead of ~224 end points, and the signs of all 32 far end points of an
-   * entry are ONE 32-bit window of the sign bitmap: 32 edges are tested with a funnel shift and an xor.  The rank of an
-   * edge in the sorted list is edge_off[a] + (number of entries of the chunk with a smaller d whose mask holds a's lane).
-   * Worth it when entries are shared by several lanes (the host builds it when the grid averages >= 4 edges per entry);
-   * exact for any grid. */
-  const int32_t* edge_runs;    /* (2 * edge_run_off[ceil(N/32)]) int32 pairs, 8-byte aligned */
-  const int32_t* edge_run_off; /* (ceil(N/32) + 1) */
+  /* optional companion of the edge-scan path, preferred over edge_rows / edge_b when given: the edge list RUN-LENGTH
+   * compressed by end-point difference per chunk of 32 consecutive vertices.  Entry k = (d, mask) = edge_runs[2k], [2k+1]
+   * of chunk c = edge_run_chunk[k], entries ascending in (c, d), d >= 0: bit l of mask is set iff (32c + l, 32c + l + d) is
+   * an edge of the grid, and edge_run_ids[32k + l] is its rank in the sorted edge list (edge_ab; -1 where the bit is
+   * clear).  On a lattice numbered along its axes every vertex has the same few differences, so a chunk needs ~7 entries
+   * instead of ~224 end points, and the signs of all 32 far end points of an entry are ONE 32-bit window of the sign
+   * bitmap: 32 edges are tested with a funnel shift and an xor.  Worth it when entries are shared by several lanes (the
+   * host builds it when the grid averages >= 4 edges per entry); exact for any grid. */
+  const int32_t* edge_runs;      /* (n_edge_runs, 2) int32, 8-byte aligned */
+  const int32_t* edge_run_chunk; /* (n_edge_runs) */
+  const int32_t* edge_run_ids;   /* (n_edge_runs, 32) */
+  int64_t n_edge_runs;
+  /* optional companion of edge_runs: the TET array compressed the same way, so that the valid tets (mixed signs,
+   * gshell_tets.py:261-275) are found from the sign bitmap without walking the tets around every crossing edge.  A tet
+   * (v0, v1, v2, v3) is filed under the chunk of its FIRST vertex, lane v0 & 31, and its shape (v1 - v0, v2 - v0, v3 - v0):
+   * entry k = (d1, d2, d3, mask) = tet_runs[4k .. 4k+3] of chunk tet_run_chunk[k] -- bit l of mask is set iff the grid
+   * holds the tet (32c + l, 32c + l + d1, 32c + l + d2, 32c + l + d3), whose index is tet_run_ids[32k + l] (-1 elsewhere).
+   * The occupancy codes of the 32 tets of an entry are four 32-bit windows of the sign bitmap.  Needs edge_runs; used on
+   * the watertight template only (output_watertight_template = 1).  The host builds it when the grid averages >= 4 tets
+   * per entry and no two tets list the same vertices in the same order. */
+  const int32_t* tet_runs;       /* (n_tet_runs, 4) int32, 16-byte aligned */
+  const int32_t* tet_run_chunk;  /* (n_tet_runs) */
+  const int32_t* tet_run_ids;    /* (n_tet_runs, 32) */
+  int64_t n_tet_runs;
 } d3h_forward_args;
 
 /* ---- backward ------------------------------------------------------------------------------------ */

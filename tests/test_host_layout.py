@@ -109,10 +109,10 @@ def test_build_edge_table_on_cpu_matches_numpy():
     n = pos.shape[0]
     E.set_edge_scan(False)
     try:
-        off, ab, u, tet_rank, edge_b, etet_off, etets, etets8, rows, row_off, runs, run_off = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
-        assert tet_rank is None and edge_b is None and etets is None and rows is None and row_off is None and runs is None
+        off, ab, u, tet_rank, edge_b, etet_off, etets, etets8, rows, row_off, eruns, truns = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        assert tet_rank is None and edge_b is None and etets is None and rows is None and row_off is None and eruns[0] is None and truns[0] is None
         E.set_tet_edge_ranks(True)
-        _, _, _, tet_rank, edge_b, _, _, _, _, _, _, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        _, _, _, tet_rank, edge_b, *_ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
         assert edge_b is None
     finally:
         E.set_tet_edge_ranks(False)
@@ -122,7 +122,7 @@ def test_build_edge_table_on_cpu_matches_numpy():
     E.set_scan_rows(False)
     E.set_scan_runs(False)
     try:
-        _, ab2, u2, tet_rank2, edge_b, etet_off, etets, etets8, rows, _, runs, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        _, ab2, u2, tet_rank2, edge_b, etet_off, etets, etets8, rows, _, (runs, _, _), _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
     finally:
         E.set_scan_rows(True)
         E.set_scan_runs(True)
@@ -169,7 +169,7 @@ def test_edge_table_incidence_of_degenerate_and_crowded_edges():
     fan = [[0, 1, 2 + k, 3 + k] for k in range(10)]            # edge (0,1) is shared by 10 tets
     tets = np.array(fan + [[14, 14, 15, 16], [17, 18, 17, 19]], dtype=np.int32)
     E.set_mark_rows(True)
-    _, ab, u, tet_rank, edge_b, etet_off, etets, etets8, _, _, _, _ = E.build_edge_table(torch.tensor(tets), n)
+    _, ab, u, tet_rank, edge_b, etet_off, etets, etets8, *_ = E.build_edge_table(torch.tensor(tets), n)
     ab, eo, et, e8 = ab.numpy(), etet_off.numpy(), etets.numpy(), etets8.numpy()
     r01 = int(np.flatnonzero((ab[:, 0] == 0) & (ab[:, 1] == 1))[0])
     assert np.array_equal(et[eo[r01]:eo[r01 + 1]], np.arange(10)) and e8[r01, 7] == -2 and np.array_equal(e8[r01, :7], np.arange(7))
@@ -213,7 +213,7 @@ def test_edge_rows_restates_the_csr_list():
     assert n % 32 != 0
     E.set_scan_runs(False)
     try:
-        off, ab, u, _, edge_b, _, _, _, rows, row_off, runs, _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+        off, ab, u, _, edge_b, _, _, _, rows, row_off, (runs, _, _), _ = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
     finally:
         E.set_scan_runs(True)
     assert runs is None
@@ -223,38 +223,32 @@ def test_edge_rows_restates_the_csr_list():
     n = 70
     fan = [[0, 1 + k, 2 + k, 3 + k] for k in range(0, 30, 2)]      # vertex 0: 32 larger neighbours... a long chunk
     tets = np.array(fan + [[40, 41, 42, 43], [64, 65, 66, 69]], dtype=np.int32)
-    off, ab, u, _, _, _, _, _, rows, row_off, runs, _ = E.build_edge_table(torch.tensor(tets), n)
+    off, ab, u, _, _, _, _, _, rows, row_off, (runs, _, _), _ = E.build_edge_table(torch.tensor(tets), n)
     assert runs is None                      # an irregular soup: too few edges per entry, the rows are built instead
     _check_edge_rows(off, ab, rows, row_off, n)
     assert int(row_off[1] - row_off[0]) > 8
 
 
-def _check_edge_runs(off, ab, runs, run_off, n):
-    """The run-length compressed edge list against the CSR list it restates (include/d3h_tets.h: edge_runs): the entries
-    of a chunk ascend in d, their masks name exactly the grid's edges, and the rank rule gives back the edge ids."""
-    off, ab, runs, run_off = off.numpy().astype(np.int64), ab.numpy().astype(np.int64), runs.numpy().astype(np.int64), run_off.numpy().astype(np.int64)
-    n_chunks = (n + 31) // 32
-    assert run_off.shape == (n_chunks + 1,) and run_off[0] == 0 and run_off[-1] == runs.shape[0]
-    seen = 0
-    for c in range(n_chunks):
-        ent = runs[run_off[c]:run_off[c + 1]]
-        assert np.all(np.diff(ent[:, 0]) > 0) and np.all(ent[:, 0] >= 0)
-        rank = np.zeros(32, dtype=np.int64)
-        for d, m in ent:
-            m &= 0xFFFFFFFF
-            assert m != 0
-            for l in range(32):
-                if (m >> l) & 1:
-                    v = 32 * c + l
-                    e = off[v] + rank[l]
-                    assert v < n and e < off[v + 1] and ab[e, 0] == v and ab[e, 1] == v + d
-                    rank[l] += 1
-                    seen += 1
+def _check_edge_runs(ab, runs, chunk, ids, n):
+    """The run-length compressed edge list against the sorted list it restates (include/d3h_tets.h: edge_runs): entries
+    ascend in (chunk, d), masks and id rows name exactly the grid's edges."""
+    ab, runs, chunk, ids = ab.numpy().astype(np.int64), runs.numpy().astype(np.int64), chunk.numpy().astype(np.int64), ids.numpy()
+    assert chunk.shape == (runs.shape[0],) and ids.shape == (runs.shape[0], 32)
+    key = chunk * n + runs[:, 0]
+    assert np.all(np.diff(key) > 0) and np.all(runs[:, 0] >= 0)
+    seen = np.zeros(ab.shape[0], dtype=bool)
+    for k in range(runs.shape[0]):
+        d, m = runs[k]
+        m &= 0xFFFFFFFF
+        assert m != 0
         for l in range(32):
-            v = 32 * c + l
-            if v < n:
-                assert rank[l] == off[v + 1] - off[v]
-    assert seen == ab.shape[0]
+            e = ids[k, l]
+            assert (e >= 0) == bool((m >> l) & 1)
+            if e >= 0:
+                v = 32 * chunk[k] + l
+                assert v < n and ab[e, 0] == v and ab[e, 1] == v + d and not seen[e]
+                seen[e] = True
+    assert seen.all()
 
 
 def test_edge_runs_restate_the_csr_list():
@@ -263,11 +257,13 @@ def test_edge_runs_restate_the_csr_list():
     from d3human_code_b200 import grids
     pos, tets = grids.kuhn_grid(6)
     n = pos.shape[0]
-    off, ab, u, _, edge_b, _, _, _, rows, _, runs, run_off = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
+    off, ab, u, _, edge_b, _, _, _, rows, _, (runs, run_chunk, run_ids), (truns, trun_chunk, trun_ids) = E.build_edge_table(torch.tensor(tets, dtype=torch.int32), n)
     assert edge_b is None and rows is None and runs.dtype == torch.int32 and runs.shape[1] == 2 and runs.is_contiguous()
     assert runs.shape[0] * 4 <= u
     assert (runs[:, 1] < 0).any()
-    _check_edge_runs(off, ab, runs, run_off, n)
+    _check_edge_runs(ab, runs, run_chunk, run_ids, n)
+    _check_tet_runs(tets, truns, trun_chunk, trun_ids, n)
+    assert truns.shape[0] * 4 <= tets.shape[0]
     rng = np.random.default_rng(5)
     n = 100
     tets = rng.integers(0, n, size=(300, 4)).astype(np.int32)
@@ -278,9 +274,44 @@ def test_edge_runs_restate_the_csr_list():
     finally:
         E.set_scan_runs(True)
     assert (ab[:, 0] == ab[:, 1]).any()
-    runs, run_off = E.build_edge_runs(ab, n, min_edges_per_entry=0)
-    _check_edge_runs(off, ab, runs, run_off, n)
+    runs, run_chunk, run_ids = E.build_edge_runs(off, ab, n, min_edges_per_entry=0)
+    _check_edge_runs(ab, runs, run_chunk, run_ids, n)
     # a grid without structure in its numbering: hardly any entry is shared by two lanes -> not worth it
     tets = rng.integers(0, 5000, size=(300, 4)).astype(np.int32)
-    _, ab, *_ = E.build_edge_table(torch.tensor(tets), 5000)
-    assert E.build_edge_runs(ab, 5000) == (None, None)
+    off, ab, *_ = E.build_edge_table(torch.tensor(tets), 5000)
+    assert E.build_edge_runs(off, ab, 5000) == (None, None, None)
+
+
+def _check_tet_runs(tets, runs, chunk, ids, n):
+    """The compressed tet array against the tets it restates (include/d3h_tets.h: tet_runs)."""
+    runs, chunk, ids = runs.numpy().astype(np.int64), chunk.numpy().astype(np.int64), ids.numpy()
+    assert chunk.shape == (runs.shape[0],) and ids.shape == (runs.shape[0], 32) and np.all(np.diff(chunk) >= 0)
+    seen = np.zeros(tets.shape[0], dtype=bool)
+    for k in range(runs.shape[0]):
+        d1, d2, d3, m = runs[k]
+        m &= 0xFFFFFFFF
+        assert m != 0
+        for l in range(32):
+            t = ids[k, l]
+            assert (t >= 0) == bool((m >> l) & 1)
+            if t >= 0:
+                v0 = 32 * chunk[k] + l
+                assert tuple(tets[t]) == (v0, v0 + d1, v0 + d2, v0 + d3) and not seen[t]
+                seen[t] = True
+    assert seen.all()
+
+
+def test_tet_runs_of_soups_and_refusals():
+    """Shapes with negative differences and repeated vertices; duplicates of a tet and numberings without structure
+    are refused (the marking kernel walks the incidence lists then)."""
+    rng = np.random.default_rng(11)
+    n = 64
+    tets = rng.integers(0, n, size=(4000, 4)).astype(np.int32)
+    tets = np.unique(tets, axis=0)
+    tets[::9, 2] = tets[::9, 0]
+    tets = np.unique(tets, axis=0)
+    runs, chunk, ids = E.build_tet_runs(torch.tensor(tets), n, min_tets_per_entry=0)
+    assert (runs[:, :3] < 0).any()
+    _check_tet_runs(tets, runs, chunk, ids, n)
+    assert E.build_tet_runs(torch.tensor(np.concatenate([tets, tets[:1]])), n, min_tets_per_entry=0) == (None, None, None)
+    assert E.build_tet_runs(torch.tensor(tets), n) == (None, None, None)
