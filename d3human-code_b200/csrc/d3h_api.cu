@@ -176,7 +176,7 @@ Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t ca
     // work queues of the edge-scan path: kQueues sub-queues, each 8 / kQueues of the total capacity (8x the expected fill)
     ws.cap_qv = cap > 0 ? (cap * 8 + kQueues - 1) / kQueues : 0;
     ws.cap_qe = capc > 0 ? (capc * 8 + kQueues - 1) / kQueues : 0;
-    ws.q_cnt = reinterpret_cast<unsigned*>(take(3 * kQueues * kQStride * 4));
+    ws.q_cnt = reinterpret_cast<unsigned*>(take(4 * kQueues * kQStride * 4));
     ws.vlist = reinterpret_cast<int2*>(take(ws.cap_qv * kQueues * 8));
     ws.elist = reinterpret_cast<int32_t*>(take(ws.cap_qe * kQueues * 4));
     ws.elist2 = reinterpret_cast<int32_t*>(take(ws.cap_qe * kQueues * 4));

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
     for (int64_t i = tid; i < nw4; i += nthreads) reinterpret_cast<uint4*>(ws.edge_bits)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int64_t i = tid; i < ws.n_eblocks + 1; i += nthreads) ws.eblock_cnt[i] = 0u;
     if (src.a.etets != nullptr) {
-      if (tid < 3 * kQueues) ws.q_cnt[kQStride * tid] = 0u;
+      if (tid < 4 * kQueues) ws.q_cnt[kQStride * tid] = 0u;
       // edge-scan path: the tet bitmaps are MARKED (atomicOr) instead of written by the classification stream
       const int64_t nt4 = ws.nwords_tet / 4;   // nwords_tet is a multiple of 8
       for (int64_t i = tid; i < nt4; i += nthreads) {

@@ -77,7 +77,7 @@ struct Workspace {
   unsigned* eblock_cnt;           // marked edges per 8192-edge block (one edge_emit CTA)
   unsigned* corner_rank;          // 4 per valid-tet record: edge rank of every polygon corner
   // edge-scan path: unordered work queues, kQueues sub-queues each (see d3h_scan.cu)
-  unsigned* q_cnt;                // [3][kQueues] entries appended per sub-queue: raw edges, valid tets, filtered edges
+  unsigned* q_cnt;                // [4][kQueues] entries appended per sub-queue: raw edges, valid tets, filtered edges; [3]: items of the run-length scan
   int2* vlist;                    // kQueues x cap_qv: (tet id, occupancy code) of every valid tet
   int32_t* elist;                 // kQueues x cap_qe: rank of every crossing edge
   int32_t* elist2;                // kQueues x cap_qe: ... that survives the open-mesh prefilter

@@ -424,21 +424,35 @@ __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
          ((int64_t)__shfl_sync(0xffffffffu, (unsigned)(v >> 32), src) << 32);
 }
 
-constexpr int kRunBatch = 8;   // entries expanded together
+// Work items of the expansion: an entry that found something.  Edge items live in the (otherwise unused) second edge
+// queue, tet items in the record buffer (written later, by scan_emit_kernel); their counters are the first two words of
+// the fourth counter group, the third word flags a dropped item (scan_prefix_kernel reports an overflow then).
+struct EdgeItem { int entry_q; unsigned x; int64_t at; };                           // 16 bytes; entry | sub-queue << 26
+struct TetItem { int entry_q; unsigned x; int64_t at; unsigned own, w1, w2, w3; };  // 32 bytes
+constexpr int kItemEdges = 3 * kQueues, kItemTets = 3 * kQueues + 1, kItemDropped = 3 * kQueues + 2;
 
-template <bool MARK>   // MARK: crossing edges are marked here (no edge_mark_kernel behind)
+// One slot per lane with `has` in the item list behind `counter` (one atomic per warp); -1: no room
+__device__ __forceinline__ int64_t item_slot(unsigned* __restrict__ counter, bool has, int64_t cap, unsigned* __restrict__ dropped) {
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  unsigned base = 0u;
+  if (lane_id() == 0) base = atomicAdd(counter, (unsigned)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const int64_t s = (int64_t)base + __popc(m & ((1u << lane_id()) - 1u));
+  if (has && s >= cap) { atomicOr(dropped, 1u); return -1; }
+  return has ? s : -1;
+}
+
+// Pass A: a thread per entry.  The warps that find nothing (all but a few per cent) leave after the test.
+template <bool MARK>   // MARK: with the compressed tet array (crossing edges are marked by the expansion, no edge_mark_kernel)
 __global__ void __launch_bounds__(kEScanThreads)
-scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, unsigned* __restrict__ m1_words,
-                 unsigned* __restrict__ m2_words, unsigned* __restrict__ edge_bits, ScanLists L, unsigned nb_edges) {
+scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L, EdgeItem* __restrict__ eitems,
+                 int64_t cap_eitems, TetItem* __restrict__ titems, int64_t cap_titems, unsigned nb_edges) {
   pdl_enter();
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
-  const unsigned lane = lane_id();
-  const unsigned below = (1u << lane) - 1u;
   const bool edges = blockIdx.x < nb_edges;
   const int64_t i = (int64_t)(edges ? blockIdx.x : blockIdx.x - nb_edges) * kEScanThreads + threadIdx.x;   // entry
-  const unsigned gwarp = (blockIdx.x * kEScanThreads + threadIdx.x) >> 5;
-  const unsigned q = gwarp % kQueues;
+  const unsigned q = ((blockIdx.x * kEScanThreads + threadIdx.x) >> 5) % kQueues;
   if (edges) {
     unsigned x = 0u;     // crossing flags: bit l = the edge (32c + l, 32c + l + d) exists and its end points differ in sign
     if (i < a.n_edge_runs) {
@@ -446,39 +460,10 @@ scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       const int2 e = __ldg(reinterpret_cast<const int2*>(a.edge_runs) + i);
       x = (sign_window(occ_bits, (c << 5) + e.x) ^ __ldg(occ_bits + c)) & (unsigned)e.y;
     }
-    const int64_t slot = warp_reserve(L.q_cnt + kQStride * q, (unsigned)__popc(x));
-    if (slot < 0) { trace_end(tr); return; }
-    int32_t* __restrict__ out = L.elist_raw + (int64_t)q * L.cap_qe;
-    unsigned todo = __ballot_sync(0xffffffffu, x != 0u);
-    while (todo) {
-      unsigned xs[kRunBatch];
-      int64_t at[kRunBatch];
-      int r[kRunBatch];
-#pragma unroll
-      for (int b = 0; b < kRunBatch; ++b) {
-        xs[b] = 0u;
-        r[b] = 0;
-        if (todo) {   // (warp-uniform)
-          const int src = __ffs((int)todo) - 1;
-          todo &= todo - 1u;
-          xs[b] = __shfl_sync(0xffffffffu, x, src);
-          at[b] = shfl_i64(slot, src);
-          // rank of the lane's edge in the sorted edge list
-          if ((xs[b] >> lane) & 1u) r[b] = __ldg(a.edge_run_ids + ((i - lane + src) << 5) + lane);
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < kRunBatch; ++b) {
-        if (!((xs[b] >> lane) & 1u)) continue;
-        const unsigned e = (unsigned)r[b];
-        if (MARK) {   // (results unused: reductions)
-          atomicOr(edge_bits + (e >> 5), 1u << (e & 31u));
-          atomicAdd(L.eblock_cnt + e / (unsigned)kEdgeBlock, 1u);
-        }
-        const int64_t s = at[b] + __popc(xs[b] & below);
-        if (s < L.cap_qe) out[s] = (int)e;
-      }
-    }
+    if (!__any_sync(0xffffffffu, x != 0u)) { trace_end(tr); return; }
+    const int64_t at = warp_reserve(L.q_cnt + kQStride * q, (unsigned)__popc(x));
+    const int64_t s = item_slot(L.q_cnt + kQStride * kItemEdges, x != 0u, cap_eitems, L.q_cnt + kQStride * kItemDropped);
+    if (s >= 0) eitems[s] = EdgeItem{(int)i | (int)(q << 26), x, at};
   } else {
     unsigned x = 0u, own = 0u, w1 = 0u, w2 = 0u, w3 = 0u;   // x: tets of the entry whose signs are mixed
     if (i < a.n_tet_runs) {
@@ -490,39 +475,58 @@ scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       w3 = sign_window(occ_bits, (c << 5) + e.z);
       x = ((own ^ w1) | (own ^ w2) | (own ^ w3)) & (unsigned)e.w;
     }
-    const int64_t slot = warp_reserve(L.q_cnt + kQStride * (kQueues + q), (unsigned)__popc(x));
-    if (slot < 0) { trace_end(tr); return; }
-    int2* __restrict__ vout = L.vlist + (int64_t)q * L.cap_qv;
-    // occupancy code of the lane's tet in every entry of the warp: bit v = sign of the tet's vertex v
-    unsigned todo = __ballot_sync(0xffffffffu, x != 0u);
-    while (todo) {
-      unsigned xs[kRunBatch], code[kRunBatch];
-      int64_t at[kRunBatch];
-      int t[kRunBatch];
-#pragma unroll
-      for (int b = 0; b < kRunBatch; ++b) {
-        xs[b] = 0u;
-        t[b] = 0;
-        code[b] = 0u;
-        if (todo) {   // (warp-uniform)
-          const int src = __ffs((int)todo) - 1;
-          todo &= todo - 1u;
-          xs[b] = __shfl_sync(0xffffffffu, x, src);
-          at[b] = shfl_i64(slot, src);
-          code[b] = ((__shfl_sync(0xffffffffu, own, src) >> lane) & 1u) | (((__shfl_sync(0xffffffffu, w1, src) >> lane) & 1u) << 1) |
-                    (((__shfl_sync(0xffffffffu, w2, src) >> lane) & 1u) << 2) | (((__shfl_sync(0xffffffffu, w3, src) >> lane) & 1u) << 3);
-          if ((xs[b] >> lane) & 1u) t[b] = __ldg(a.tet_run_ids + ((i - lane + src) << 5) + lane);
-        }
+    if (!__any_sync(0xffffffffu, x != 0u)) { trace_end(tr); return; }
+    const int64_t at = warp_reserve(L.q_cnt + kQStride * (kQueues + q), (unsigned)__popc(x));
+    const int64_t s = item_slot(L.q_cnt + kQStride * kItemTets, x != 0u, cap_titems, L.q_cnt + kQStride * kItemDropped);
+    if (s >= 0) titems[s] = TetItem{(int)i | (int)(q << 26), x, at, own, w1, w2, w3};
+  }
+  trace_end(tr);
+}
+
+// Pass B: a warp per item, lane l = lane l of the entry: one coalesced row of ids, the marks and counts (reductions: every
+// crossing edge and every valid tet is met exactly once) and the queue entries.  Warps [0, warps_edges) of the grid take
+// the edge items, the others the tet items.
+template <bool MARK>
+__global__ void __launch_bounds__(256)
+runs_expand_kernel(const FwdBlock* __restrict__ blk, unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words,
+                   unsigned* __restrict__ edge_bits, ScanLists L, const EdgeItem* __restrict__ eitems, int64_t cap_eitems,
+                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned warps_edges) {
+  pdl_enter();
+  const d3h_forward_args& a = blk->a;
+  unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
+  const unsigned lane = lane_id();
+  const unsigned below = (1u << lane) - 1u;
+  const unsigned gwarp = (blockIdx.x * 256u + threadIdx.x) >> 5, nwarps = gridDim.x * 8u;
+  if (gwarp < warps_edges) {
+    int64_t n = (int64_t)L.q_cnt[kQStride * kItemEdges];
+    n = n < cap_eitems ? n : cap_eitems;
+    for (int64_t j = gwarp; j < n; j += warps_edges) {
+      const EdgeItem it = eitems[j];
+      if (!((it.x >> lane) & 1u)) continue;
+      const unsigned e = (unsigned)__ldg(a.edge_run_ids + ((int64_t)(it.entry_q & 0x3ffffff) << 5) + lane);   // rank in the edge list
+      if (MARK) {
+        atomicOr(edge_bits + (e >> 5), 1u << (e & 31u));
+        atomicAdd(L.eblock_cnt + e / (unsigned)kEdgeBlock, 1u);
       }
-#pragma unroll
-      for (int b = 0; b < kRunBatch; ++b) {
-        if (!((xs[b] >> lane) & 1u)) continue;
-        const bool quad = __popc(code[b]) == 2;
-        atomicOr((quad ? m2_words : m1_words) + (t[b] >> 5), 1u << (t[b] & 31));           // (results unused: reductions)
-        atomicAdd(L.tile_cnt + (unsigned)t[b] / (unsigned)kTileTets, quad ? 0x10000u : 1u);
-        const int64_t s = at[b] + __popc(xs[b] & below);
-        if (s < L.cap_qv) vout[s] = make_int2(t[b], (int)code[b]);
-      }
+      const int64_t s = it.at + __popc(it.x & below);
+      if (s < L.cap_qe) L.elist_raw[(int64_t)((unsigned)it.entry_q >> 26) * L.cap_qe + s] = (int)e;
+    }
+  } else if (MARK) {
+    int64_t n = (int64_t)L.q_cnt[kQStride * kItemTets];
+    n = n < cap_titems ? n : cap_titems;
+    const unsigned warps_tets = nwarps - warps_edges;
+    for (int64_t j = gwarp - warps_edges; j < n; j += warps_tets) {
+      const TetItem it = titems[j];
+      if (!((it.x >> lane) & 1u)) continue;
+      const int t = __ldg(a.tet_run_ids + ((int64_t)(it.entry_q & 0x3ffffff) << 5) + lane);
+      // occupancy code: bit v = sign of the tet's vertex v
+      const unsigned code = ((it.own >> lane) & 1u) | (((it.w1 >> lane) & 1u) << 1) | (((it.w2 >> lane) & 1u) << 2) |
+                            (((it.w3 >> lane) & 1u) << 3);
+      const bool quad = __popc(code) == 2;
+      atomicOr((quad ? m2_words : m1_words) + (t >> 5), 1u << (t & 31));
+      atomicAdd(L.tile_cnt + (unsigned)t / (unsigned)kTileTets, quad ? 0x10000u : 1u);
+      const int64_t s = it.at + __popc(it.x & below);
+      if (s < L.cap_qv) L.vlist[(int64_t)((unsigned)it.entry_q >> 26) * L.cap_qv + s] = make_int2(t, (int)code);
     }
   }
   trace_end(tr);
@@ -806,13 +810,15 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
           max_e = ne > max_e ? ne : max_e;
           max_v = nt > max_v ? nt : max_v;
         }
-        const bool queue_ok = max_e <= cap_qe && max_v <= cap_qv;
+        const bool dropped = q_cnt[kQStride * (3 * kQueues + 2)] != 0u;   // run-length tables: an item list was too small
+        const bool queue_ok = max_e <= cap_qe && max_v <= cap_qv && !dropped;
         // records needed for every sub-queue to hold what it was offered (a sub-queue has 1/8 of the record capacity
         // for tets and 1/2 of it for edges), and the expected number of valid tets when none could be marked yet
         int64_t need = 2 * raw;
         need = 8 * max_v > need ? 8 * max_v : need;
         need = 2 * max_e > need ? 2 * max_e : need;
         need = cap_records + 1 > need ? cap_records + 1 : need;
+        if (dropped) need = 2 * cap_records > need ? 2 * cap_records : need;
         ctr->n_valid = queue_ok ? t1 + t2 : max(t1 + t2, (unsigned)need);
         const bool fits = queue_ok && (int64_t)t1 + t2 <= cap_records;
         ctr->work_tri = fits ? t1 : 0u;
@@ -975,18 +981,40 @@ static ScanLists scan_lists(const d3h_forward_args& a, const Workspace& ws) {
   return L;
 }
 
+static void launch_scan_runs(const d3h_forward_args& a, const Workspace& ws, const ScanLists& L, cudaStream_t stream, bool dep,
+                             bool expand) {
+  const bool both = a.tet_runs != nullptr && a.watertight_template;
+  const unsigned nbe = (unsigned)((a.n_edge_runs + kEScanThreads - 1) / kEScanThreads);
+  const unsigned nbt = both ? (unsigned)((a.n_tet_runs + kEScanThreads - 1) / kEScanThreads) : 0u;
+  EdgeItem* eitems = reinterpret_cast<EdgeItem*>(ws.elist2);
+  TetItem* titems = reinterpret_cast<TetItem*>(ws.records);
+  const int64_t cap_e = ws.cap_qe * kQueues * 4 / (int64_t)sizeof(EdgeItem), cap_t = ws.cap_tets;
+  {
+    ProfScope ps(K_EDGE_SCAN, stream);
+    auto go = [&](auto kernel) {
+      if (dep) launch_k_dep(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe);
+      else launch_k(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe);
+    };
+    if (both) go(scan_runs_kernel<true>);
+    else go(scan_runs_kernel<false>);
+  }
+  if (!expand) return;
+  // a warp per item; the lists hold a few thousand to a few ten thousand items: one wave of CTAs, a few items per warp
+  ProfScope ps(K_EDGE_MARK, stream);
+  const unsigned nblk = 148u * 8u, nwarps = nblk * 8u;
+  const unsigned warps_edges = both ? (nwarps * 2u) / 5u : nwarps;
+  if (both)
+    launch_k_dep(runs_expand_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, warps_edges);
+  else
+    launch_k_dep(runs_expand_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, warps_edges);
+}
+
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
   const ScanLists L = scan_lists(a, ws);
-  if (a.edge_runs != nullptr) {   // the launch of launch_edge_scan (its marks and counts land in scratch state)
-    const bool both = a.tet_runs != nullptr && a.watertight_template;
-    const unsigned nbe = (unsigned)((a.n_edge_runs + kEScanThreads - 1) / kEScanThreads);
-    const unsigned nbt = both ? (unsigned)((a.n_tet_runs + kEScanThreads - 1) / kEScanThreads) : 0u;
-    if (both)
-      launch_k(scan_runs_kernel<true>, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
-               ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
-    else
-      launch_k(scan_runs_kernel<false>, nbe, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
-               ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
+  if (a.edge_runs != nullptr) {   // pass A of launch_scan_runs (its counts land in scratch state)
+    launch_scan_runs(a, ws, L, stream, /*dep=*/false, /*expand=*/false);
     return;
   }
   if (a.edge_rows != nullptr) {
@@ -1017,16 +1045,8 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   const bool runs_both = a.tet_runs != nullptr && a.edge_runs != nullptr && !filtered;
   if (a.edge_runs != nullptr) {
     // crossing edges from the compressed edge list and, with the compressed tet array (watertight template), the valid
-    // tets as well: one launch, edges marked on the spot, no marking kernel
-    ProfScope ps(K_EDGE_SCAN, stream);
-    const unsigned nbe = (unsigned)((a.n_edge_runs + kEScanThreads - 1) / kEScanThreads);
-    const unsigned nbt = runs_both ? (unsigned)((a.n_tet_runs + kEScanThreads - 1) / kEScanThreads) : 0u;
-    if (runs_both)
-      launch_k_dep(scan_runs_kernel<true>, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
-                   ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
-    else
-      launch_k_dep(scan_runs_kernel<false>, nbe, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits,
-                   ws.m1_words, ws.m2_words, ws.edge_bits, L, nbe);
+    // tets as well: pass A tests every entry, pass B expands the few that found something -- no marking kernel
+    launch_scan_runs(a, ws, L, stream, /*dep=*/true, /*expand=*/true);
   } else {
     ProfScope ps(K_EDGE_SCAN, stream);
     const int vpt = scan_vpt();

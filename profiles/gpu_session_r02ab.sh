@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
-# round 2, GPU call aa: thread-per-entry scan over the run-length tables (edges + tets), no marking kernel
+# round 2, GPU call ab: two-pass scan over the run-length tables (test every entry, expand the few items with a warp each)
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r02aa
+T=r02ab
 run() { env "$@" timeout 200 python profiles/scan_ab.py 2>&1 | tail -1; }
 run D3H_SCAN_RUNS=1
 echo "== parity (extraction files, all edge paths)"
@@ -17,5 +17,5 @@ echo "== device trace, one lane / 8 lanes"
 timeout 120 python profiles/graph_trace.py --frames 4 --lanes 1 | tail -1
 timeout 120 python profiles/graph_trace.py --frames 32 --lanes 8 | tail -3
 echo "== ncu: scan_runs"
-D3H_DISABLE_GRAPH=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'scan_runs_kernel|scan_emit|scan_prefix' -s 9 -c 6 -o gpurun_out/${T}_scanruns python profiles/graph_trace.py --frames 2 --lanes 1 > gpurun_out/${T}_ncu1.log 2>&1
+D3H_DISABLE_GRAPH=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'scan_runs_kernel|runs_expand_kernel|poly_cut|poly_faces' -s 12 -c 8 -o gpurun_out/${T}_scanruns python profiles/graph_trace.py --frames 2 --lanes 1 > gpurun_out/${T}_ncu1.log 2>&1
 ls -la gpurun_out/${T}_*.ncu-rep
