@@ -485,28 +485,49 @@ scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
 
 // Pass B: a warp per item, lane l = lane l of the entry: one coalesced row of ids, the marks and counts (reductions: every
 // crossing edge and every valid tet is met exactly once) and the queue entries.  Warps [0, warps_edges) of the grid take
-// the edge items, the others the tet items.
+// the edge items, the others the tet items, every CTA a contiguous piece of its list.
+//
+// The per-tile / per-block counts are the hot spot: a compaction tile on the surface collects ~2000 valid tets, and
+// reductions on one address pass the L2 at ~18 ns each -- 21 us for this kernel, as for edge_mark_kernel before it (r02ab).
+// Items come in entry order, so the few hundred tets of a CTA fall into one or two tiles: the counts are collected in a
+// small shared table (key = counter index) and flushed with one reduction per key and CTA.
+constexpr int kAggSlots = 64;
+struct CountAgg {
+  unsigned key[kAggSlots], val[kAggSlots];
+};
+__device__ __forceinline__ void agg_add(CountAgg& g, unsigned* __restrict__ counters, unsigned key, unsigned v) {
+  const unsigned slot = key % kAggSlots;
+  const unsigned old = atomicCAS(&g.key[slot], 0xffffffffu, key);
+  if (old == 0xffffffffu || old == key) atomicAdd(&g.val[slot], v);
+  else atomicAdd(counters + key, v);   // the slot belongs to another counter
+}
+
 template <bool MARK>
 __global__ void __launch_bounds__(256)
 runs_expand_kernel(const FwdBlock* __restrict__ blk, unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words,
                    unsigned* __restrict__ edge_bits, ScanLists L, const EdgeItem* __restrict__ eitems, int64_t cap_eitems,
-                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned warps_edges) {
+                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned ctas_edges) {
   pdl_enter();
+  __shared__ CountAgg agg;
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
-  const unsigned lane = lane_id();
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned below = (1u << lane) - 1u;
-  const unsigned gwarp = (blockIdx.x * 256u + threadIdx.x) >> 5, nwarps = gridDim.x * 8u;
-  if (gwarp < warps_edges) {
+  if (threadIdx.x < kAggSlots) { agg.key[threadIdx.x] = 0xffffffffu; agg.val[threadIdx.x] = 0u; }
+  __syncthreads();
+  const bool edges = blockIdx.x < ctas_edges;
+  unsigned* __restrict__ counters = edges ? L.eblock_cnt : L.tile_cnt;
+  if (edges) {
     int64_t n = (int64_t)L.q_cnt[kQStride * kItemEdges];
     n = n < cap_eitems ? n : cap_eitems;
-    for (int64_t j = gwarp; j < n; j += warps_edges) {
+    const int64_t per = (n + ctas_edges - 1) / ctas_edges, j0 = per * blockIdx.x, j1 = j0 + per < n ? j0 + per : n;
+    for (int64_t j = j0 + warp; j < j1; j += 8) {
       const EdgeItem it = eitems[j];
       if (!((it.x >> lane) & 1u)) continue;
       const unsigned e = (unsigned)__ldg(a.edge_run_ids + ((int64_t)(it.entry_q & 0x3ffffff) << 5) + lane);   // rank in the edge list
       if (MARK) {
         atomicOr(edge_bits + (e >> 5), 1u << (e & 31u));
-        atomicAdd(L.eblock_cnt + e / (unsigned)kEdgeBlock, 1u);
+        agg_add(agg, counters, e / (unsigned)kEdgeBlock, 1u);
       }
       const int64_t s = it.at + __popc(it.x & below);
       if (s < L.cap_qe) L.elist_raw[(int64_t)((unsigned)it.entry_q >> 26) * L.cap_qe + s] = (int)e;
@@ -514,8 +535,9 @@ runs_expand_kernel(const FwdBlock* __restrict__ blk, unsigned* __restrict__ m1_w
   } else if (MARK) {
     int64_t n = (int64_t)L.q_cnt[kQStride * kItemTets];
     n = n < cap_titems ? n : cap_titems;
-    const unsigned warps_tets = nwarps - warps_edges;
-    for (int64_t j = gwarp - warps_edges; j < n; j += warps_tets) {
+    const unsigned ctas_tets = gridDim.x - ctas_edges;
+    const int64_t per = (n + ctas_tets - 1) / ctas_tets, j0 = per * (blockIdx.x - ctas_edges), j1 = j0 + per < n ? j0 + per : n;
+    for (int64_t j = j0 + warp; j < j1; j += 8) {
       const TetItem it = titems[j];
       if (!((it.x >> lane) & 1u)) continue;
       const int t = __ldg(a.tet_run_ids + ((int64_t)(it.entry_q & 0x3ffffff) << 5) + lane);
@@ -524,11 +546,14 @@ runs_expand_kernel(const FwdBlock* __restrict__ blk, unsigned* __restrict__ m1_w
                             (((it.w3 >> lane) & 1u) << 3);
       const bool quad = __popc(code) == 2;
       atomicOr((quad ? m2_words : m1_words) + (t >> 5), 1u << (t & 31));
-      atomicAdd(L.tile_cnt + (unsigned)t / (unsigned)kTileTets, quad ? 0x10000u : 1u);
+      agg_add(agg, counters, (unsigned)t / (unsigned)kTileTets, quad ? 0x10000u : 1u);
       const int64_t s = it.at + __popc(it.x & below);
       if (s < L.cap_qv) L.vlist[(int64_t)((unsigned)it.entry_q >> 26) * L.cap_qv + s] = make_int2(t, (int)code);
     }
   }
+  __syncthreads();
+  if (threadIdx.x < kAggSlots && agg.key[threadIdx.x] != 0xffffffffu && agg.val[threadIdx.x] != 0u)
+    atomicAdd(counters + agg.key[threadIdx.x], agg.val[threadIdx.x]);
   trace_end(tr);
 }
 
@@ -1001,14 +1026,14 @@ static void launch_scan_runs(const d3h_forward_args& a, const Workspace& ws, con
   if (!expand) return;
   // a warp per item; the lists hold a few thousand to a few ten thousand items: one wave of CTAs, a few items per warp
   ProfScope ps(K_EDGE_MARK, stream);
-  const unsigned nblk = 148u * 8u, nwarps = nblk * 8u;
-  const unsigned warps_edges = both ? (nwarps * 2u) / 5u : nwarps;
+  const unsigned nblk = 148u * 8u;
+  const unsigned ctas_edges = both ? (nblk * 2u) / 5u : nblk;
   if (both)
     launch_k_dep(runs_expand_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
-                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, warps_edges);
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges);
   else
     launch_k_dep(runs_expand_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
-                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, warps_edges);
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges);
 }
 
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
