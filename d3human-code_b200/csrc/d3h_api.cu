@@ -48,6 +48,11 @@ static unsigned long long* g_trace_dev = nullptr;
 unsigned long long* trace_table() { return g_trace_dev; }
 
 // ---- launch priorities ------------------------------------------------------------------------------
+BatchCtx& batch_ctx() {
+  static thread_local BatchCtx ctx = {1, {}};
+  return ctx;
+}
+
 int launch_priority(LaunchClass c) {
   static int lo = 0, hi = 0;
   static bool init = false;
@@ -80,6 +85,7 @@ struct LaneSet {
   bool done_valid[kMaxLanes];
   cudaEvent_t cls[kClsEvents];       // head of a frame finished (ring)
   unsigned cls_next;
+  bool busy;                         // frames were put on the lanes since the last join (a fused batch joins them first)
 };
 static LaneSet g_lanes[kMaxDevices];
 static std::mutex g_lane_mu;
@@ -601,6 +607,84 @@ extern "C" int d3h_extract_forward(const d3h_forward_args* a, d3h_stream_t s) {
   return finish("d3h_extract_forward", a, ws, stream);
 }
 
+// The frames of a batch in ONE launch per kernel (grid.y = frame; see FrameSet in d3h_internal.cuh): possible when every
+// frame takes the run-length path on the watertight template with the same grid, tables and capacities (so the workspaces
+// have one layout), publishes its counts through mapped memory and wants no second extraction.  Frames that share a
+// workspace go into consecutive launches.
+static bool fusable(const d3h_forward_args* args, int64_t n_frames) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* env = getenv("D3H_FUSE_FRAMES");
+    enabled = (env && env[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || n_frames < 2) return false;
+  const d3h_forward_args& r = args[0];
+  for (int64_t i = 0; i < n_frames; ++i) {
+    const d3h_forward_args& a = args[i];
+    if (!a.edge_runs || !a.tet_runs || !a.watertight_template || a.pair_verts_aug || a.cap_valid_tets <= 0 ||
+        !a.counts_host || mapped_counts_pointer(a.counts_host) == nullptr)
+      return false;
+    if (a.n_tets != r.n_tets || a.n_grid != r.n_grid || a.tets != r.tets || a.cap_valid_tets != r.cap_valid_tets ||
+        a.n_edges != r.n_edges || a.edge_off != r.edge_off || a.edge_ab != r.edge_ab || a.tet_edge_rank != r.tet_edge_rank ||
+        a.etet_off != r.etet_off || a.etets != r.etets || a.edge_runs != r.edge_runs || a.edge_run_chunk != r.edge_run_chunk ||
+        a.edge_run_ids != r.edge_run_ids || a.n_edge_runs != r.n_edge_runs || a.tet_runs != r.tet_runs ||
+        a.tet_run_chunk != r.tet_run_chunk || a.tet_run_ids != r.tet_run_ids || a.n_tet_runs != r.n_tet_runs ||
+        a.tet_begin != r.tet_begin || a.tet_end != r.tet_end || a.workspace_bytes != r.workspace_bytes ||
+        (a.zero_g_pos != nullptr) != (r.zero_g_pos != nullptr) || (a.zero_g_sdf != nullptr) != (r.zero_g_sdf != nullptr) ||
+        (a.zero_g_msdf != nullptr) != (r.zero_g_msdf != nullptr))
+      return false;
+  }
+  return true;
+}
+
+static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, cudaStream_t stream, LaneSet* ls) {
+  BatchCtx& ctx = batch_ctx();
+  int rc = D3H_OK;
+  if (ls->busy) {   // frames of an earlier per-lane batch may still be at work in these workspaces
+    for (int l = 0; l < kMaxLanes; ++l) {
+      cudaEventRecord(ls->join[l], ls->lane[l]);
+      cudaStreamWaitEvent(stream, ls->join[l], 0);
+    }
+    cudaEventRecord(ls->join_head, ls->head);
+    cudaStreamWaitEvent(stream, ls->join_head, 0);
+    ls->busy = false;
+  }
+  int64_t i0 = 0;
+  while (i0 < n_frames) {
+    // the longest run of frames with distinct workspaces, at most kMaxFused
+    int64_t i1 = i0 + 1;
+    while (i1 < n_frames && i1 - i0 < kMaxFused) {
+      bool clash = false;
+      for (int64_t j = i0; j < i1; ++j) clash = clash || args[j].workspace == args[i1].workspace;
+      if (clash) break;
+      ++i1;
+    }
+    const d3h_forward_args& a = args[i0];
+    const Workspace ws = carve_workspace(a.workspace, a.n_tets, a.n_grid, a.cap_valid_tets, a.n_edges);
+    ctx.frames = (int)(i1 - i0);
+    for (int64_t j = i0; j < i1; ++j)
+      ctx.fs.off[j - i0] = (int64_t)(reinterpret_cast<intptr_t>(args[j].workspace) - reinterpret_cast<intptr_t>(a.workspace));
+    launch_prepare_frames(args + i0, ws, stream);
+    // the zero-fill of the gradient buffers depends on nothing but the argument blocks: a side stream takes it
+    const bool zero = a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf;
+    if (zero) {
+      cudaEventRecord(ls->fork, stream);
+      cudaStreamWaitEvent(ls->lane[0], ls->fork, 0);
+      launch_zero_grads_from_block(a, ws, ls->lane[0]);
+      cudaEventRecord(ls->join[0], ls->lane[0]);
+    }
+    launch_edge_scan(a, ws, stream);
+    launch_surface(a, ws, ws.records, stream);
+    if (zero) cudaStreamWaitEvent(stream, ls->join[0], 0);
+    ctx.frames = 1;
+    memset(&ctx.fs, 0, sizeof(ctx.fs));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("d3h_extract_forward_batch: %s", cudaGetErrorString(e)); rc = D3H_E_CUDA; }
+    i0 = i1;
+  }
+  return rc;
+}
+
 static int forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t lanes, d3h_stream_t s, bool join) {
   if (!args || n_frames < 0 || lanes < 1) { set_error("d3h_extract_forward_batch: null args / bad sizes"); return D3H_E_BADARG; }
   if (lanes > kMaxLanes) lanes = kMaxLanes;
@@ -633,7 +717,8 @@ static int forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t
       return rc;
     }
   }
-  // Default: one graph per frame, frame i on lane i % lanes.  The hardware takes equal-priority kernels in submission
+  if (fusable(args, n_frames)) return forward_batch_fused(args, n_frames, stream, ls);
+  // Otherwise: one graph per frame, frame i on lane i % lanes.  The hardware takes equal-priority kernels in submission
   // order, so the O(F) streams of the frames run one after the other at full rate and the latency-bound kernels of the
   // other lanes fill in around them.
   // D3H_SPLIT_HEAD=1 (experiment, profiles/README.md): the heads of all frames (prepare + stream) back to back on ONE
@@ -644,6 +729,7 @@ static int forward_batch(const d3h_forward_args* args, int64_t n_frames, int32_t
     const char* env = getenv("D3H_SPLIT_HEAD");
     split_head = (env && env[0] == '1') ? 1 : 0;
   }
+  ls->busy = true;
   cudaEventRecord(ls->fork, stream);
   if (split_head) cudaStreamWaitEvent(ls->head, ls->fork, 0);
   for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->lane[l], ls->fork, 0);

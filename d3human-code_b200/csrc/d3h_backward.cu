@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256) zero_kernel(float* p0, int64_t n0, float*
 
 // Forward-side variant: the three pointers come from the argument block (they change from call to call, the launch
 // shape does not).
-__global__ void __launch_bounds__(256) zero_block_kernel(const FwdBlock* __restrict__ blk, int64_t n) {
+__global__ void __launch_bounds__(256) zero_block_kernel(const FwdBlock* __restrict__ blk, int64_t n, FrameSet fs) {
+  blk = frame_ptr(blk, fs.off[blockIdx.y]);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)blk->a.seq, K_ZERO);
@@ -64,7 +65,7 @@ void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope ps(K_ZERO, stream);
-  launch_k(zero_block_kernel, (unsigned)blocks, 256u, stream, kLaunchLatency, ws.blk, a.n_grid);
+  launch_k(zero_block_kernel, (unsigned)blocks, 256u, stream, kLaunchLatency, ws.blk, a.n_grid, batch_ctx().fs);
 }
 
 void launch_zero_grads(float* g_pos, float* g_sdf, float* g_msdf, int64_t n, cudaStream_t stream) {

@@ -51,7 +51,7 @@ __device__ __forceinline__ float4 load4_guarded(const float* __restrict__ p, int
   return s;
 }
 
-__global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws) {
+__device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspace& ws) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   if (tid == 0) *ws.blk = src;  // the argument block of this call, for every later kernel
@@ -111,6 +111,14 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
   trace_end(tr);
 }
 
+__global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws) { prepare_body(src, ws); }
+
+// several frames in one launch: frame blockIdx.y, its argument block from the set, its workspace by offset
+__global__ void __launch_bounds__(256) prepare_frames_kernel(FwdBlockSet set, Workspace ws, FrameSet fs) {
+  shift_workspace(ws, fs.off[blockIdx.y]);
+  prepare_body(set.f[blockIdx.y], ws);
+}
+
 const void* prepare_kernel_address() { return reinterpret_cast<const void*>(prepare_kernel); }
 
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
@@ -124,6 +132,23 @@ void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t
   blk.trace = trace_table();
   ProfScope ps(K_PREPARE, stream);
   launch_k(prepare_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, blk, ws);
+}
+
+// the frames of batch_ctx() in one launch; `a` are their argument structs, `ws` is the workspace of the first
+void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaStream_t stream) {
+  const int frames = batch_ctx().frames;
+  const int64_t nquads = (a[0].n_grid + 3) / 4;
+  int64_t blocks = (nquads + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8 / frames) blocks = 148 * 8 / frames;
+  static thread_local FwdBlockSet set;
+  for (int f = 0; f < frames; ++f) {
+    set.f[f].a = a[f];
+    set.f[f].counts_mapped = mapped_counts_pointer(a[f].counts_host);
+    set.f[f].trace = trace_table();
+  }
+  ProfScope ps(K_PREPARE, stream);
+  launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -90,6 +90,19 @@ struct Workspace {
   int64_t total_bytes;
 };
 
+// the same workspace of another frame of the launch (see FrameSet below): every region moved by `shift` bytes
+__device__ __forceinline__ void shift_workspace(Workspace& w, int64_t shift) {
+#define D3H_SHIFT(m) w.m = w.m ? reinterpret_cast<decltype(w.m)>(reinterpret_cast<uintptr_t>(w.m) + shift) : w.m
+  D3H_SHIFT(ctr); D3H_SHIFT(blk); D3H_SHIFT(blk2); D3H_SHIFT(counts); D3H_SHIFT(counts2); D3H_SHIFT(occ_bits);
+  D3H_SHIFT(mocc_bits); D3H_SHIFT(m1_words); D3H_SHIFT(m2_words); D3H_SHIFT(tile_cnt); D3H_SHIFT(records); D3H_SHIFT(keys);
+  D3H_SHIFT(vals); D3H_SHIFT(keys2); D3H_SHIFT(vals2); D3H_SHIFT(keys_scratch); D3H_SHIFT(vals_scratch); D3H_SHIFT(msd_hist);
+  D3H_SHIFT(msd_fill); D3H_SHIFT(msd_base); D3H_SHIFT(st_scan); D3H_SHIFT(group_start); D3H_SHIFT(group_heads);
+  D3H_SHIFT(gblock_heads); D3H_SHIFT(poly_cnt); D3H_SHIFT(poly_excl); D3H_SHIFT(poly_gcnt); D3H_SHIFT(vert); D3H_SHIFT(acc);
+  D3H_SHIFT(owner); D3H_SHIFT(edge_bits); D3H_SHIFT(word_prefix); D3H_SHIFT(eblock_cnt); D3H_SHIFT(corner_rank);
+  D3H_SHIFT(q_cnt); D3H_SHIFT(vlist); D3H_SHIFT(elist); D3H_SHIFT(elist2); D3H_SHIFT(tet_word_prefix);
+#undef D3H_SHIFT
+}
+
 // Carves `base` (may be nullptr when only the size is wanted).
 Workspace carve_workspace(void* base, int64_t n_tets, int64_t n_grid, int64_t cap_valid_tets, int64_t n_edges = 0);
 constexpr int kQueues = 64;        // sub-queues of the edge-scan path's work queues
@@ -104,6 +117,7 @@ int persistent_grid(const void* kernel, int threads, size_t dyn_smem);
 
 // ---- stage launchers (all asynchronous on `stream`) -------------------------------------------------
 void launch_prepare(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream);
+void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaStream_t stream);
 // the forward sequence behind launch_prepare; `a` only supplies the launch shapes, the kernels read the block
 // parts of a forward call: the head is the bandwidth-bound part (the O(F) classification stream behind prepare_kernel),
 // the tail everything that works on the O(surface) records.  A batch runs the heads of all frames back to back on one
@@ -143,12 +157,35 @@ void set_error(const char* fmt, ...);
 enum LaunchClass { kLaunchStream = 0, kLaunchLatency = 1 };
 int launch_priority(LaunchClass c);
 
+// ---- several frames in ONE launch (d3h_extract_forward_batch on the run-length tables) ---------------------------------
+// With one graph per frame on concurrent lanes a 32-frame step is 256 kernel nodes of a few microseconds each, and the
+// front end starts one node per ~5 us whatever the lanes (r02ac: the kernels of a frame sum to 60 us, its span on a lane is
+// 244 us).  The kernels of the run-length path therefore take the frame from blockIdx.y: every workspace pointer they
+// are given belongs to frame 0, FrameSet.off[f] is the byte offset of frame f's workspace (all frames of a launch have
+// the same capacities, hence the same layout).  A single call is a launch with one frame and offset 0.
+constexpr int kMaxFused = 8;
+struct FrameSet {
+  int64_t off[kMaxFused];
+};
+struct FwdBlockSet {   // the argument blocks of the frames of a launch, by value (kernel parameters may take 32 KB)
+  FwdBlock f[kMaxFused];
+};
+struct BatchCtx {
+  int frames;     // gridDim.y of every launch made through launch_k / launch_k_dep
+  FrameSet fs;
+};
+BatchCtx& batch_ctx();   // of the calling thread; {1, {0}} outside d3h_extract_forward_batch
+template <typename T>
+__device__ __forceinline__ T* frame_ptr(T* p, int64_t shift) {
+  return p ? reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + shift) : p;
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, LaunchClass cls,
                      Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.gridDim = dim3(grid, (unsigned)batch_ctx().frames, 1);
   cfg.blockDim = dim3(block, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
@@ -168,7 +205,7 @@ inline void launch_k_dep(void (*kernel)(KArgs...), unsigned grid, unsigned block
                          Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.gridDim = dim3(grid, (unsigned)batch_ctx().frames, 1);
   cfg.blockDim = dim3(block, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;

@@ -55,6 +55,15 @@ struct ScanLists {
   int64_t cap_qe, cap_qv; // entries per sub-queue
 };
 
+__device__ __forceinline__ void shift_lists(ScanLists& L, int64_t shift) {
+  L.tile_cnt = frame_ptr(L.tile_cnt, shift);
+  L.eblock_cnt = frame_ptr(L.eblock_cnt, shift);
+  L.q_cnt = frame_ptr(L.q_cnt, shift);
+  L.elist_raw = frame_ptr(L.elist_raw, shift);
+  L.vlist = frame_ptr(L.vlist, shift);
+  L.elist = frame_ptr(L.elist, shift);
+}
+
 // One reservation per warp: `n` entries of this lane -> first slot of the lane in sub-queue q (all 32 lanes call).
 __device__ __forceinline__ int64_t warp_reserve(unsigned* __restrict__ counter, unsigned n) {
   const unsigned lane = lane_id();
@@ -446,8 +455,14 @@ __device__ __forceinline__ int64_t item_slot(unsigned* __restrict__ counter, boo
 template <bool MARK>   // MARK: with the compressed tet array (crossing edges are marked by the expansion, no edge_mark_kernel)
 __global__ void __launch_bounds__(kEScanThreads)
 scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L, EdgeItem* __restrict__ eitems,
-                 int64_t cap_eitems, TetItem* __restrict__ titems, int64_t cap_titems, unsigned nb_edges) {
+                 int64_t cap_eitems, TetItem* __restrict__ titems, int64_t cap_titems, unsigned nb_edges, FrameSet fs) {
   pdl_enter();
+  {
+    const int64_t shift = fs.off[blockIdx.y];
+    blk = frame_ptr(blk, shift); occ_bits = frame_ptr(occ_bits, shift); eitems = frame_ptr(eitems, shift);
+    titems = frame_ptr(titems, shift);
+    shift_lists(L, shift);
+  }
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
   const bool edges = blockIdx.x < nb_edges;
@@ -506,8 +521,14 @@ template <bool MARK>
 __global__ void __launch_bounds__(256)
 runs_expand_kernel(const FwdBlock* __restrict__ blk, unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words,
                    unsigned* __restrict__ edge_bits, ScanLists L, const EdgeItem* __restrict__ eitems, int64_t cap_eitems,
-                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned ctas_edges) {
+                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned ctas_edges, FrameSet fs) {
   pdl_enter();
+  {
+    const int64_t shift = fs.off[blockIdx.y];
+    blk = frame_ptr(blk, shift); m1_words = frame_ptr(m1_words, shift); m2_words = frame_ptr(m2_words, shift);
+    edge_bits = frame_ptr(edge_bits, shift); eitems = frame_ptr(eitems, shift); titems = frame_ptr(titems, shift);
+    shift_lists(L, shift);
+  }
   __shared__ CountAgg agg;
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_MARK);
@@ -795,8 +816,15 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
                    uint2* __restrict__ tet_word_prefix, const unsigned* __restrict__ edge_bits,
                    const unsigned* __restrict__ eblock_cnt, int64_t n_eblocks,
                    unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
-                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles) {
+                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles, FrameSet fs) {
   pdl_enter();
+  {
+    const int64_t shift = fs.off[blockIdx.y];
+    m1_words = frame_ptr(m1_words, shift); m2_words = frame_ptr(m2_words, shift); tile_cnt = frame_ptr(tile_cnt, shift);
+    tet_word_prefix = frame_ptr(tet_word_prefix, shift); edge_bits = frame_ptr(edge_bits, shift);
+    eblock_cnt = frame_ptr(eblock_cnt, shift); word_prefix = frame_ptr(word_prefix, shift); ctr = frame_ptr(ctr, shift);
+    q_cnt = frame_ptr(q_cnt, shift);
+  }
   constexpr int WARPS = 256 / 32;
   __shared__ unsigned long long s_sum[WARPS];
   __shared__ unsigned long long s_w[WARPS];
@@ -901,8 +929,17 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
                  const unsigned* __restrict__ m2_words, const uint2* __restrict__ tet_word_prefix,
                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix,
                  d3h_tet_record* __restrict__ records, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
-                 int64_t cap_corners, const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tets) {
+                 int64_t cap_corners, const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tets,
+                 FrameSet fs) {
   pdl_enter();
+  {
+    const int64_t shift = fs.off[blockIdx.y];
+    blk = frame_ptr(blk, shift); ctr = frame_ptr(ctr, shift); vlist = frame_ptr(vlist, shift); elist = frame_ptr(elist, shift);
+    m1_words = frame_ptr(m1_words, shift); m2_words = frame_ptr(m2_words, shift);
+    tet_word_prefix = frame_ptr(tet_word_prefix, shift); edge_bits = frame_ptr(edge_bits, shift);
+    word_prefix = frame_ptr(word_prefix, shift); records = frame_ptr(records, shift); w_vert = frame_ptr(w_vert, shift);
+    w_acc = frame_ptr(w_acc, shift); q_cnt = frame_ptr(q_cnt, shift);
+  }
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
   if (blockIdx.x < grid_tets) {
@@ -1017,8 +1054,8 @@ static void launch_scan_runs(const d3h_forward_args& a, const Workspace& ws, con
   {
     ProfScope ps(K_EDGE_SCAN, stream);
     auto go = [&](auto kernel) {
-      if (dep) launch_k_dep(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe);
-      else launch_k(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe);
+      if (dep) launch_k_dep(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe, batch_ctx().fs);
+      else launch_k(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe, batch_ctx().fs);
     };
     if (both) go(scan_runs_kernel<true>);
     else go(scan_runs_kernel<false>);
@@ -1030,10 +1067,10 @@ static void launch_scan_runs(const d3h_forward_args& a, const Workspace& ws, con
   const unsigned ctas_edges = both ? (nblk * 2u) / 5u : nblk;
   if (both)
     launch_k_dep(runs_expand_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
-                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges);
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges, batch_ctx().fs);
   else
     launch_k_dep(runs_expand_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
-                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges);
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges, batch_ctx().fs);
 }
 
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
@@ -1114,14 +1151,14 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const unsigned ge = (unsigned)(ws.n_eblocks < maxg ? ws.n_eblocks : maxg);
     launch_k_dep(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt,
              ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.n_eblocks, ws.word_prefix, ws.ctr,
-             ws.cap_tets, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt);
+             ws.cap_tets, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().fs);
   }
   if (ws.cap_corners <= 0) return;   // counting run: sizes only
   ProfScope ps(K_EDGE_EMIT, stream);
   const unsigned gt = kQueues * parts_for(ws.cap_qv), ge = kQueues * parts_for(ws.cap_qe);
   launch_k_dep(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, filtered, ws.m1_words,
            ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
-           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt);
+           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().fs);
 }
 
 }  // namespace d3h

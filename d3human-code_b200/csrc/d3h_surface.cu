@@ -72,8 +72,16 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
                   unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_gcnt, unsigned* __restrict__ poly_excl,
                   UvParams uvp,
                   d3h_counts* __restrict__ counts_dev, const unsigned* __restrict__ corner_rank,
-                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix) {
+                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix, FrameSet fs) {
   pdl_enter();
+  {
+    const int64_t shift = fs.off[blockIdx.y];
+    blk = frame_ptr(blk, shift); records = frame_ptr(records, shift); ctr = frame_ptr(ctr, shift);
+    w_vert = frame_ptr(w_vert, shift); w_acc = frame_ptr(w_acc, shift); poly_cnt = frame_ptr(poly_cnt, shift);
+    poly_gcnt = frame_ptr(poly_gcnt, shift); poly_excl = frame_ptr(poly_excl, shift); counts_dev = frame_ptr(counts_dev, shift);
+    corner_rank = frame_ptr(corner_rank, shift); edge_bits = frame_ptr(edge_bits, shift);
+    word_prefix = frame_ptr(word_prefix, shift);
+  }
   constexpr int WARPS = kPolyThreads / 32;
   int32_t* __restrict__ corners = blk->a.tape_corners;
   // a replay finds the corner array on the tape, and so does the edge-scan path (scan_emit_kernel wrote it)
@@ -396,8 +404,14 @@ __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
-                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl) {
+                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl, FrameSet fs) {
   pdl_enter();
+  {
+    const int64_t shift = fs.off[blockIdx.y];
+    blk = frame_ptr(blk, shift); records = frame_ptr(records, shift); ctr = frame_ptr(ctr, shift);
+    w_vert = frame_ptr(w_vert, shift); w_acc = frame_ptr(w_acc, shift); owner = frame_ptr(owner, shift);
+    poly_gcnt = frame_ptr(poly_gcnt, shift); poly_excl = frame_ptr(poly_excl, shift);
+  }
   constexpr int WARPS = kPolyThreads / 32;
   constexpr unsigned FULL = 0xffffffffu;
   const int32_t* __restrict__ corners = blk->a.tape_corners;
@@ -591,11 +605,11 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
     ProfScope ps(K_POLY_FACES, stream);
     launch_k_dep(poly_faces_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
                  ws.vert, ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits,
-                 ws.word_prefix);
+                 ws.word_prefix, batch_ctx().fs);
   }
   ProfScope ps(K_POLY_CUT, stream);
   launch_k_dep(poly_cut_kernel<false>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
-           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl);
+           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl, batch_ctx().fs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -834,9 +848,10 @@ void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3
   const UvParams uvp = uv_params(a.n_tets);
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   launch_k(poly_faces_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
-           ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix);
+           ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix,
+           FrameSet{});
   launch_k(poly_cut_kernel<true>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr,
-           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl);
+           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl, FrameSet{});
 }
 
 }  // namespace d3h

@@ -220,6 +220,10 @@ static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long 
   __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
   return cmp;
 }
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) {
+  __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
   unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {}
@@ -233,6 +237,11 @@ static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p =
 static inline unsigned atomicSub(unsigned* p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
   unsigned long long o = *p;
+  if (o == cmp) *p = v;
+  return o;
+}
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) {
+  unsigned o = *p;
   if (o == cmp) *p = v;
   return o;
 }
