@@ -629,9 +629,7 @@ static bool fusable(const d3h_forward_args* args, int64_t n_frames) {
         a.etet_off != r.etet_off || a.etets != r.etets || a.edge_runs != r.edge_runs || a.edge_run_chunk != r.edge_run_chunk ||
         a.edge_run_ids != r.edge_run_ids || a.n_edge_runs != r.n_edge_runs || a.tet_runs != r.tet_runs ||
         a.tet_run_chunk != r.tet_run_chunk || a.tet_run_ids != r.tet_run_ids || a.n_tet_runs != r.n_tet_runs ||
-        a.tet_begin != r.tet_begin || a.tet_end != r.tet_end || a.workspace_bytes != r.workspace_bytes ||
-        (a.zero_g_pos != nullptr) != (r.zero_g_pos != nullptr) || (a.zero_g_sdf != nullptr) != (r.zero_g_sdf != nullptr) ||
-        (a.zero_g_msdf != nullptr) != (r.zero_g_msdf != nullptr))
+        a.tet_begin != r.tet_begin || a.tet_end != r.tet_end || a.workspace_bytes != r.workspace_bytes)
       return false;
   }
   return true;
@@ -666,7 +664,8 @@ static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, c
       ctx.fs.off[j - i0] = (int64_t)(reinterpret_cast<intptr_t>(args[j].workspace) - reinterpret_cast<intptr_t>(a.workspace));
     launch_prepare_frames(args + i0, ws, stream);
     // the zero-fill of the gradient buffers depends on nothing but the argument blocks: a side stream takes it
-    const bool zero = a.zero_g_pos || a.zero_g_sdf || a.zero_g_msdf;
+    bool zero = false;
+    for (int64_t j = i0; j < i1; ++j) zero = zero || args[j].zero_g_pos || args[j].zero_g_sdf || args[j].zero_g_msdf;
     if (zero) {
       cudaEventRecord(ls->fork, stream);
       cudaStreamWaitEvent(ls->lane[0], ls->fork, 0);

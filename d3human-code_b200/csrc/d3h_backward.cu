@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) zero_kernel(float* p0, int64_t n0, float*
 
 // Forward-side variant: the three pointers come from the argument block (they change from call to call, the launch
 // shape does not).
-__global__ void __launch_bounds__(256) zero_block_kernel(const FwdBlock* __restrict__ blk, int64_t n, FrameSet fs) {
+__global__ void __launch_bounds__(256) zero_block_kernel(const FwdBlock* __restrict__ blk, int64_t n, const __grid_constant__ FrameSet fs) {
   blk = frame_ptr(blk, fs.off[blockIdx.y]);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

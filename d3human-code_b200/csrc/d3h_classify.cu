@@ -114,7 +114,7 @@ __device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspac
 __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws) { prepare_body(src, ws); }
 
 // several frames in one launch: frame blockIdx.y, its argument block from the set, its workspace by offset
-__global__ void __launch_bounds__(256) prepare_frames_kernel(FwdBlockSet set, Workspace ws, FrameSet fs) {
+__global__ void __launch_bounds__(256) prepare_frames_kernel(FwdBlockSet set, Workspace ws, const __grid_constant__ FrameSet fs) {
   shift_workspace(ws, fs.off[blockIdx.y]);
   prepare_body(set.f[blockIdx.y], ws);
 }

@@ -176,8 +176,8 @@ struct BatchCtx {
 };
 BatchCtx& batch_ctx();   // of the calling thread; {1, {0}} outside d3h_extract_forward_batch
 template <typename T>
-__device__ __forceinline__ T* frame_ptr(T* p, int64_t shift) {
-  return p ? reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + shift) : p;
+__device__ __forceinline__ T* frame_ptr(T* p, int64_t shift) {   // (a null pointer of a multi-frame launch must not be tested afterwards)
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + shift);
 }
 
 template <typename... KArgs, typename... Args>

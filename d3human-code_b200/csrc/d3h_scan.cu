@@ -455,14 +455,11 @@ __device__ __forceinline__ int64_t item_slot(unsigned* __restrict__ counter, boo
 template <bool MARK>   // MARK: with the compressed tet array (crossing edges are marked by the expansion, no edge_mark_kernel)
 __global__ void __launch_bounds__(kEScanThreads)
 scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ occ_bits, ScanLists L, EdgeItem* __restrict__ eitems,
-                 int64_t cap_eitems, TetItem* __restrict__ titems, int64_t cap_titems, unsigned nb_edges, FrameSet fs) {
+                 int64_t cap_eitems, TetItem* __restrict__ titems, int64_t cap_titems, unsigned nb_edges, const __grid_constant__ FrameSet fs) {
   pdl_enter();
-  {
-    const int64_t shift = fs.off[blockIdx.y];
-    blk = frame_ptr(blk, shift); occ_bits = frame_ptr(occ_bits, shift); eitems = frame_ptr(eitems, shift);
-    titems = frame_ptr(titems, shift);
-    shift_lists(L, shift);
-  }
+  const int64_t shift = fs.off[blockIdx.y];   // (the lists and item buffers are shifted by the few warps that need them)
+  blk = frame_ptr(blk, shift);
+  occ_bits = frame_ptr(occ_bits, shift);
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(blk->trace, (unsigned)a.seq, K_EDGE_SCAN);
   const bool edges = blockIdx.x < nb_edges;
@@ -476,9 +473,10 @@ scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       x = (sign_window(occ_bits, (c << 5) + e.x) ^ __ldg(occ_bits + c)) & (unsigned)e.y;
     }
     if (!__any_sync(0xffffffffu, x != 0u)) { trace_end(tr); return; }
-    const int64_t at = warp_reserve(L.q_cnt + kQStride * q, (unsigned)__popc(x));
-    const int64_t s = item_slot(L.q_cnt + kQStride * kItemEdges, x != 0u, cap_eitems, L.q_cnt + kQStride * kItemDropped);
-    if (s >= 0) eitems[s] = EdgeItem{(int)i | (int)(q << 26), x, at};
+    unsigned* __restrict__ q_cnt = frame_ptr(L.q_cnt, shift);
+    const int64_t at = warp_reserve(q_cnt + kQStride * q, (unsigned)__popc(x));
+    const int64_t s = item_slot(q_cnt + kQStride * kItemEdges, x != 0u, cap_eitems, q_cnt + kQStride * kItemDropped);
+    if (s >= 0) frame_ptr(eitems, shift)[s] = EdgeItem{(int)i | (int)(q << 26), x, at};
   } else {
     unsigned x = 0u, own = 0u, w1 = 0u, w2 = 0u, w3 = 0u;   // x: tets of the entry whose signs are mixed
     if (i < a.n_tet_runs) {
@@ -491,9 +489,10 @@ scan_runs_kernel(const FwdBlock* __restrict__ blk, const unsigned* __restrict__ 
       x = ((own ^ w1) | (own ^ w2) | (own ^ w3)) & (unsigned)e.w;
     }
     if (!__any_sync(0xffffffffu, x != 0u)) { trace_end(tr); return; }
-    const int64_t at = warp_reserve(L.q_cnt + kQStride * (kQueues + q), (unsigned)__popc(x));
-    const int64_t s = item_slot(L.q_cnt + kQStride * kItemTets, x != 0u, cap_titems, L.q_cnt + kQStride * kItemDropped);
-    if (s >= 0) titems[s] = TetItem{(int)i | (int)(q << 26), x, at, own, w1, w2, w3};
+    unsigned* __restrict__ q_cnt = frame_ptr(L.q_cnt, shift);
+    const int64_t at = warp_reserve(q_cnt + kQStride * (kQueues + q), (unsigned)__popc(x));
+    const int64_t s = item_slot(q_cnt + kQStride * kItemTets, x != 0u, cap_titems, q_cnt + kQStride * kItemDropped);
+    if (s >= 0) frame_ptr(titems, shift)[s] = TetItem{(int)i | (int)(q << 26), x, at, own, w1, w2, w3};
   }
   trace_end(tr);
 }
@@ -521,7 +520,7 @@ template <bool MARK>
 __global__ void __launch_bounds__(256)
 runs_expand_kernel(const FwdBlock* __restrict__ blk, unsigned* __restrict__ m1_words, unsigned* __restrict__ m2_words,
                    unsigned* __restrict__ edge_bits, ScanLists L, const EdgeItem* __restrict__ eitems, int64_t cap_eitems,
-                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned ctas_edges, FrameSet fs) {
+                   const TetItem* __restrict__ titems, int64_t cap_titems, unsigned ctas_edges, const __grid_constant__ FrameSet fs) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];
@@ -816,7 +815,7 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
                    uint2* __restrict__ tet_word_prefix, const unsigned* __restrict__ edge_bits,
                    const unsigned* __restrict__ eblock_cnt, int64_t n_eblocks,
                    unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
-                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles, FrameSet fs) {
+                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles, const __grid_constant__ FrameSet fs) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];
@@ -930,7 +929,7 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix,
                  d3h_tet_record* __restrict__ records, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
                  int64_t cap_corners, const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tets,
-                 FrameSet fs) {
+                 const __grid_constant__ FrameSet fs) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];

@@ -72,7 +72,7 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
                   unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_gcnt, unsigned* __restrict__ poly_excl,
                   UvParams uvp,
                   d3h_counts* __restrict__ counts_dev, const unsigned* __restrict__ corner_rank,
-                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix, FrameSet fs) {
+                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix, const __grid_constant__ FrameSet fs) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
-                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl, FrameSet fs) {
+                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl, const __grid_constant__ FrameSet fs) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];
