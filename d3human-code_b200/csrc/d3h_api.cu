@@ -49,7 +49,7 @@ unsigned long long* trace_table() { return g_trace_dev; }
 
 // ---- launch priorities ------------------------------------------------------------------------------
 BatchCtx& batch_ctx() {
-  static thread_local BatchCtx ctx = {1, {}};
+  static thread_local BatchCtx ctx = {1, {}, 1, {}};
   return ctx;
 }
 
@@ -635,6 +635,15 @@ static bool fusable(const d3h_forward_args* args, int64_t n_frames) {
   return true;
 }
 
+static bool shared_topology_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* env = getenv("D3H_SHARE_TOPOLOGY");
+    on = (env && env[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, cudaStream_t stream, LaneSet* ls) {
   BatchCtx& ctx = batch_ctx();
   int rc = D3H_OK;
@@ -660,8 +669,13 @@ static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, c
     const d3h_forward_args& a = args[i0];
     const Workspace ws = carve_workspace(a.workspace, a.n_tets, a.n_grid, a.cap_valid_tets, a.n_edges);
     ctx.frames = (int)(i1 - i0);
-    for (int64_t j = i0; j < i1; ++j)
+    bool shared = shared_topology_enabled();
+    for (int64_t j = i0; j < i1; ++j) {
       ctx.fs.off[j - i0] = (int64_t)(reinterpret_cast<intptr_t>(args[j].workspace) - reinterpret_cast<intptr_t>(a.workspace));
+      shared = shared && args[j].sdf == a.sdf && args[j].msdf == a.msdf && args[j].msdf_negate == a.msdf_negate;
+    }
+    ctx.topo_frames = shared ? 1 : ctx.frames;
+    for (int f = 0; f < ctx.frames; ++f) ctx.topo.off[f] = shared ? 0 : ctx.fs.off[f];
     launch_prepare_frames(args + i0, ws, stream);
     // the zero-fill of the gradient buffers depends on nothing but the argument blocks: a side stream takes it
     bool zero = false;
@@ -675,8 +689,9 @@ static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, c
     launch_edge_scan(a, ws, stream);
     launch_surface(a, ws, ws.records, stream);
     if (zero) cudaStreamWaitEvent(stream, ls->join[0], 0);
-    ctx.frames = 1;
+    ctx.frames = ctx.topo_frames = 1;
     memset(&ctx.fs, 0, sizeof(ctx.fs));
+    memset(&ctx.topo, 0, sizeof(ctx.topo));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("d3h_extract_forward_batch: %s", cudaGetErrorString(e)); rc = D3H_E_CUDA; }
     i0 = i1;

@@ -51,10 +51,17 @@ __device__ __forceinline__ float4 load4_guarded(const float* __restrict__ p, int
   return s;
 }
 
-__device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspace& ws) {
+// block_only: a frame that takes its topology from the first frame of the launch needs its argument block and fresh
+// counters, no bitmaps and no scan state
+__device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspace& ws, bool block_only = false) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   if (tid == 0) *ws.blk = src;  // the argument block of this call, for every later kernel
+  if (block_only) {
+    if (tid < (int64_t)kCounterWordsReset) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
+    if (tid == 0) { ws.ctr->trace = src.trace; ws.ctr->trace_frame = (unsigned)src.a.seq; }
+    return;
+  }
   const float* __restrict__ sdf = src.a.sdf;
   const float* __restrict__ msdf = src.a.msdf;
   const int64_t n_grid = src.a.n_grid;
@@ -114,9 +121,10 @@ __device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspac
 __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws) { prepare_body(src, ws); }
 
 // several frames in one launch: frame blockIdx.y, its argument block from the set, its workspace by offset
-__global__ void __launch_bounds__(256) prepare_frames_kernel(FwdBlockSet set, Workspace ws, const __grid_constant__ FrameSet fs) {
+__global__ void __launch_bounds__(256) prepare_frames_kernel(const __grid_constant__ FwdBlockSet set, Workspace ws,
+                                                             const __grid_constant__ FrameSet fs, int shared_topology) {
   shift_workspace(ws, fs.off[blockIdx.y]);
-  prepare_body(set.f[blockIdx.y], ws);
+  prepare_body(set.f[blockIdx.y], ws, shared_topology && blockIdx.y > 0);
 }
 
 const void* prepare_kernel_address() { return reinterpret_cast<const void*>(prepare_kernel); }
@@ -148,7 +156,8 @@ void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaS
     set.f[f].trace = trace_table();
   }
   ProfScope ps(K_PREPARE, stream);
-  launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs);
+  launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs,
+           (batch_ctx().topo_frames == 1 && frames > 1) ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -173,8 +173,14 @@ struct FwdBlockSet {   // the argument blocks of the frames of a launch, by valu
 struct BatchCtx {
   int frames;     // gridDim.y of every launch made through launch_k / launch_k_dep
   FrameSet fs;
+  // Frames that share sdf, msdf and the template have ONE topology (crossing edges, valid tets, their numbering): it is
+  // found once, in the workspace of the launch's first frame, and only the kernels that touch positions (vertex
+  // interpolation, normals / tangents, the mSDF cut with its boundary vertices) run per frame.  topo.off[f] is where
+  // frame f finds the topology: 0 when shared, fs.off[f] otherwise; topo_frames = 1 when shared, frames otherwise.
+  int topo_frames;
+  FrameSet topo;
 };
-BatchCtx& batch_ctx();   // of the calling thread; {1, {0}} outside d3h_extract_forward_batch
+BatchCtx& batch_ctx();   // of the calling thread; one frame, zero offsets outside d3h_extract_forward_batch
 template <typename T>
 __device__ __forceinline__ T* frame_ptr(T* p, int64_t shift) {   // (a null pointer of a multi-frame launch must not be tested afterwards)
   return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + shift);

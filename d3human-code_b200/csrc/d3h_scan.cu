@@ -815,7 +815,8 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
                    uint2* __restrict__ tet_word_prefix, const unsigned* __restrict__ edge_bits,
                    const unsigned* __restrict__ eblock_cnt, int64_t n_eblocks,
                    unsigned* __restrict__ word_prefix, DevCounters* __restrict__ ctr, int64_t cap_records,
-                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles, const __grid_constant__ FrameSet fs) {
+                   const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tiles,
+                   const __grid_constant__ FrameSet fs, const __grid_constant__ FrameSet also, int n_also) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];
@@ -875,8 +876,13 @@ scan_prefix_kernel(const unsigned* __restrict__ m1_words, const unsigned* __rest
         const bool fits = queue_ok && (int64_t)t1 + t2 <= cap_records;
         ctr->work_tri = fits ? t1 : 0u;
         ctr->work_quad = fits ? t2 : 0u;
+        for (int f = 1; f < n_also; ++f) {   // frames that share this topology (BatchCtx): the totals into their counters too
+          DevCounters* c2 = frame_ptr(ctr, also.off[f] - also.off[0]);
+          c2->n_tri = t1; c2->n_quad = t2; c2->n_valid = ctr->n_valid; c2->work_tri = ctr->work_tri; c2->work_quad = ctr->work_quad;
+        }
       } else {
         ctr->n_verts = (unsigned)tot;
+        for (int f = 1; f < n_also; ++f) frame_ptr(ctr, also.off[f] - also.off[0])->n_verts = (unsigned)tot;
       }
     }
     __syncthreads();
@@ -929,15 +935,16 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix,
                  d3h_tet_record* __restrict__ records, float4* __restrict__ w_vert, float4* __restrict__ w_acc,
                  int64_t cap_corners, const unsigned* __restrict__ q_cnt, int64_t cap_qe, int64_t cap_qv, unsigned grid_tets,
-                 const __grid_constant__ FrameSet fs) {
+                 const __grid_constant__ FrameSet fs, const __grid_constant__ FrameSet topo) {
   pdl_enter();
   {
-    const int64_t shift = fs.off[blockIdx.y];
-    blk = frame_ptr(blk, shift); ctr = frame_ptr(ctr, shift); vlist = frame_ptr(vlist, shift); elist = frame_ptr(elist, shift);
-    m1_words = frame_ptr(m1_words, shift); m2_words = frame_ptr(m2_words, shift);
-    tet_word_prefix = frame_ptr(tet_word_prefix, shift); edge_bits = frame_ptr(edge_bits, shift);
-    word_prefix = frame_ptr(word_prefix, shift); records = frame_ptr(records, shift); w_vert = frame_ptr(w_vert, shift);
-    w_acc = frame_ptr(w_acc, shift); q_cnt = frame_ptr(q_cnt, shift);
+    // what the frame writes sits in its own workspace, the topology it reads possibly in the first frame's (BatchCtx)
+    const int64_t shift = fs.off[blockIdx.y], tshift = topo.off[blockIdx.y];
+    blk = frame_ptr(blk, shift); ctr = frame_ptr(ctr, shift); records = frame_ptr(records, shift);
+    w_vert = frame_ptr(w_vert, shift); w_acc = frame_ptr(w_acc, shift);
+    vlist = frame_ptr(vlist, tshift); elist = frame_ptr(elist, tshift); m1_words = frame_ptr(m1_words, tshift);
+    m2_words = frame_ptr(m2_words, tshift); tet_word_prefix = frame_ptr(tet_word_prefix, tshift);
+    edge_bits = frame_ptr(edge_bits, tshift); word_prefix = frame_ptr(word_prefix, tshift); q_cnt = frame_ptr(q_cnt, tshift);
   }
   const d3h_forward_args& a = blk->a;
   unsigned long long* tr = trace_begin(ctr->trace, ctr->trace_frame, K_EDGE_EMIT);
@@ -1053,8 +1060,8 @@ static void launch_scan_runs(const d3h_forward_args& a, const Workspace& ws, con
   {
     ProfScope ps(K_EDGE_SCAN, stream);
     auto go = [&](auto kernel) {
-      if (dep) launch_k_dep(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe, batch_ctx().fs);
-      else launch_k(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe, batch_ctx().fs);
+      if (dep) launch_k_dep(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe, batch_ctx().topo);
+      else launch_k(kernel, nbe + nbt, (unsigned)kEScanThreads, stream, kLaunchLatency, ws.blk, ws.occ_bits, L, eitems, cap_e, titems, cap_t, nbe, batch_ctx().topo);
     };
     if (both) go(scan_runs_kernel<true>);
     else go(scan_runs_kernel<false>);
@@ -1066,10 +1073,10 @@ static void launch_scan_runs(const d3h_forward_args& a, const Workspace& ws, con
   const unsigned ctas_edges = both ? (nblk * 2u) / 5u : nblk;
   if (both)
     launch_k_dep(runs_expand_kernel<true>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
-                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges, batch_ctx().fs);
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges, batch_ctx().topo);
   else
     launch_k_dep(runs_expand_kernel<false>, nblk, 256u, stream, kLaunchLatency, ws.blk, ws.m1_words, ws.m2_words, ws.edge_bits, L,
-                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges, batch_ctx().fs);
+                 (const EdgeItem*)eitems, cap_e, (const TetItem*)titems, cap_t, ctas_edges, batch_ctx().topo);
 }
 
 void launch_edge_scan_only(const d3h_forward_args& a, const Workspace& ws, cudaStream_t stream) {
@@ -1104,6 +1111,10 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   L.elist = filtered ? ws.elist2 : ws.elist;
   L.cap_qe = ws.cap_qe; L.cap_qv = ws.cap_qv;
   const bool runs_both = a.tet_runs != nullptr && a.edge_runs != nullptr && !filtered;
+  // the kernels that find the topology run once for frames that share it (BatchCtx); restored before the emit kernel
+  BatchCtx& ctx = batch_ctx();
+  const int all_frames = ctx.frames;
+  ctx.frames = ctx.topo_frames;
   if (a.edge_runs != nullptr) {
     // crossing edges from the compressed edge list and, with the compressed tet array (watertight template), the valid
     // tets as well: pass A tests every entry, pass B expands the few that found something -- no marking kernel
@@ -1150,14 +1161,16 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     const unsigned ge = (unsigned)(ws.n_eblocks < maxg ? ws.n_eblocks : maxg);
     launch_k_dep(scan_prefix_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.m1_words, ws.m2_words, ws.tile_cnt,
              ws.ntiles_compact, ws.tet_word_prefix, ws.edge_bits, ws.eblock_cnt, ws.n_eblocks, ws.word_prefix, ws.ctr,
-             ws.cap_tets, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().fs);
+             ws.cap_tets, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().topo, batch_ctx().fs,
+             batch_ctx().topo_frames == 1 ? all_frames : 1);
   }
+  ctx.frames = all_frames;
   if (ws.cap_corners <= 0) return;   // counting run: sizes only
   ProfScope ps(K_EDGE_EMIT, stream);
   const unsigned gt = kQueues * parts_for(ws.cap_qv), ge = kQueues * parts_for(ws.cap_qe);
   launch_k_dep(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, filtered, ws.m1_words,
            ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
-           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().fs);
+           reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().fs, batch_ctx().topo);
 }
 
 }  // namespace d3h
