@@ -57,10 +57,11 @@ def parse():
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the plain-PyTorch-on-this-GPU leg (SURVEY 8d)")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--e2e-chunk", type=int, default=4, help="frames per pipelined chunk of the end-to-end leg")
-    ap.add_argument("--e2e-pos", choices=["copy", "mapped"], default="copy",
+    ap.add_argument("--e2e-pos", choices=["copy", "mapped", "both"], default="both",
                     help="end-to-end leg: per-frame positions copied to the device every step (copy), or read by the "
-                         "kernels straight from the pinned, device-mapped host buffer (mapped: only the rows of crossing-"
-                         "edge end points cross PCIe)")
+                         "kernels straight from the pinned, device-mapped host buffer (mapped: extract.mapped_view, only "
+                         "the rows of crossing-edge end points cross PCIe); both = mapped as `e2e`, copy next to it")
+    ap.add_argument("--e2e-chunk-mapped", type=int, default=8, help="frames per chunk of the mapped end-to-end leg")
     ap.add_argument("--mode", default="weak", choices=["weak", "strong", "tets"],
                     help="weak: --frames-per-rank frames on every rank (default); strong: BASELINE configs[3] as written, "
                          "--frames-total frames sharded over the ranks; tets: configs[4], one 256^3 extraction whose tet "
@@ -640,27 +641,22 @@ def main():
 
     # ---- end to end through the public API with HOST buffers ----
     e2e = None
-    if not args.no_e2e:
+    def e2e_leg(mapped):
         # The batch is cut into chunks of `--e2e-chunk` frames that flow through three streams: H2D copies of chunk
         # k+1 and D2H copies of chunk k-1 run under the extraction of chunk k (PCIe is full duplex, ~55 GB/s each way).
         # Results copied back per frame: verts_aug, faces_aug, msdf, and the pos gradient in COMPACT form -- the ids of
         # the grid vertices the frame touched (its crossing edges, FramesFuture.tape_edges) and their gradient rows
         # (extract.gather_touched): the dense (N,3) gradient is > 99 % zeros.  The sdf | msdf gradients of the step (one
         # flat buffer) follow the last chunk.
-        chunk = max(1, min(args.e2e_chunk, fpr))
+        chunk = max(1, min(args.e2e_chunk_mapped if mapped else args.e2e_chunk, fpr))
         bounds = [(i, min(i + chunk, fpr)) for i in range(0, fpr, chunk)]
         d_sdf = torch.empty_like(sdf)
         d_msdf = torch.empty_like(msdf)
         d_flat = torch.zeros_like(flat_grad)
-        mapped = args.e2e_pos == "mapped"
         if mapped:
             # CUDA tensors that ALIAS the pinned host buffer (unified addressing: pinned allocations are device-mapped at
             # the same address): the kernels fetch the rows they need over PCIe, nothing is copied up front
-            class _Alias:
-                def __init__(self, t):
-                    self.__cuda_array_interface__ = {"shape": tuple(t.shape), "typestr": "<f4", "version": 2,
-                                                     "data": (t.data_ptr(), False), "strides": None}
-            d_pos = [torch.as_tensor(_Alias(host_pos[lo:hi]), device=dev) for lo, hi in bounds]
+            d_pos = [E.mapped_view(host_pos[lo:hi], dev) for lo, hi in bounds]
         else:
             d_pos = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds]
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -702,6 +698,8 @@ def main():
                 for i, o in enumerate(outs):
                     edges = fut.tape_edges(i)
                     res += [o[0].detach(), o[1], o[5]["msdf"].detach(), edges, E.gather_touched(dp.grad[i], edges)]
+                    if mapped:      # rows of `pos` the kernels read in place: both end points of every crossing edge,
+                        h2d += 2 * edges.numel() * 12   # once by the vertex interpolation and once by its adjoint
                 if k == len(bounds) - 1:
                     res.append(d_flat)
                 s_out.wait_stream(cur)
@@ -740,22 +738,39 @@ def main():
                 dp.detach().copy_(host_pos[lo:hi], non_blocking=True)
         torch.cuda.synchronize()
         h2d_only = (time.perf_counter() - t0) / 3
-        e2e = {"value": fps * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
+        return {"value": fps * F / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "steps": k_e2e, "ms_per_step": float(dt.item()) * 1e3,
-               "chunk_frames": chunk, "h2d_only_ms_per_step": h2d_only * 1e3, "pos": args.e2e_pos,
-               "h2d_GBps": (int(h2d_b) - 8 * N) / h2d_only / 1e9,
+               "chunk_frames": chunk, "h2d_only_ms_per_step": h2d_only * 1e3, "pos": "mapped" if mapped else "copy",
+               "h2d_GBps": (4 * host_pos.numel()) / h2d_only / 1e9,
+               "positions": ("read in place from pinned host memory (extract.mapped_view): h2d_bytes_per_step counts the rows "
+                             "the kernels fetch (end points of the crossing edges, forward and backward, 12 B each; PCIe "
+                             "sector granularity not included) + sdf + msdf") if mapped else "copied to the device every step",
                "note": "extract_frames_async() with inputs copied from pinned host memory each step (pos per frame, sdf, "
                        "msdf); per frame verts_aug, faces_aug, msdf and the COMPACT pos gradient (touched vertex ids + "
                        "their rows), plus the flat sdf|msdf gradient, copied back to pinned host memory; static tet "
                        "indices stay resident; chunks of frames pipelined over H2D / compute / D2H streams.  "
                        "h2d_only_ms_per_step: the same per-frame positions copied alone = the PCIe floor of the step"}
+    if not args.no_e2e:
+        if args.e2e_pos == "copy" or dev_type != "cuda":      # (the CPU dry run of the tests has no mapped memory)
+            e2e = e2e_leg(False)
+        else:
+            # headline: the positions stay in pinned host memory and the kernels read the rows they need (mapped_view);
+            # the same leg with the positions copied to the device first is reported next to it
+            e2e = e2e_leg(True)
+            if args.e2e_pos == "both":
+                e2e["positions_copied_first"] = e2e_leg(False)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (classify: the only O(F) kernel) ----
+    # ---- roofline of the dominant kernel ----
+    # Since the run-length tables (round 2) no kernel of the path streams an O(F) or O(U) array any more: the kernels that
+    # are left work on the surface (a few MB per frame) and are bound by dependent look-ups and instruction issue, not by
+    # HBM.  The kernel reported is the one with the largest share of a frame's device time (single-frame pass, CUDA events
+    # around each launch), against the bytes it has to move (formulas below and in DESIGN.md); `path_roofline` keeps the
+    # SURVEY's B_alg for the whole call.
     peak, peak_src = FALLBACK_HBM_GBS, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -766,28 +781,35 @@ def main():
     kern = {}
     if prof:
         kern = {k: {"ms_total": round(v[0], 4), "launches": v[1], "us_avg": round(1e3 * v[0] / v[1], 3)} for k, v in prof.items()}
-        dom = "edge_scan" if "edge_scan" in prof else "classify"
-        dom_name = dom + "_kernel"
-        ms, n = prof.get(dom, (0.0, 0))
-        dom_bytes = 16.0 * F
-        if dom == "edge_scan":   # 4 B per edge (larger endpoint) + 4 B per vertex (CSR offsets) + the sign bitmap
-            st = E.static_edges_for(E.packed_tets(tets, N), N)
-            dom_bytes = 4.0 * st[2] + 4.0 * (N + 1) + N / 8.0
-            if len(st) > 9 and st[8] is not None:
-                # transposed rows (edge_scan_rows_kernel): 4 B per edge + 4 B per chunk of 32 vertices (row offsets) + the
-                # sign bitmap; the CSR offsets are only read by the few lanes that found a crossing edge, the padding
-                # slots of the rows (+2.5 % at 128^3) are not counted
-                dom_bytes = 4.0 * st[2] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
+        st = E.static_edges_for(E.packed_tets(tets, N), N) if "edge_scan" in prof else None
+        V_, Va_, Fw_, Fa_ = c0["n_verts"], c0["n_verts_aug"], c0["n_faces_watertight"], c0["n_faces_aug"]
+        Fv_ = c0["n_valid_tets"]
+        alg = {"classify": 16.0 * F,
+               # sdf read, sign bitmap written, scan state cleared (two tet bitmaps, edge bitmap)
+               "prepare": 4.0 * N + N / 8.0 + F / 4.0 + (st[2] / 8.0 if st else 0.0),
+               # vertex: edge id + end points (8) + sdf / msdf / pos of both ends (40) in, 44 + 32 + 20 out (SURVEY: 44 B per
+               # vertex out); valid tet: queue entry (8) + tet (16) + edge ranks (32) in, record (32) + corners (16) out
+               "edge_emit": V_ * (4 + 8 + 40 + 96.0) + Fv_ * (8 + 16 + 32 + 32 + 16.0),
+               # record (32) + corner ids (16) + 3.5 vertex rows (16 B) in per valid tet, 24 B per watertight face out, normals
+               "poly_faces": Fv_ * (32 + 16 + 56.0) + 24.0 * Fw_ + 32.0 * V_,
+               # record + corners per valid tet in, 28 B per augmented vertex (verts_aug, v_tng_aug, msdf) + 24 B per face out
+               "poly_cut": Fv_ * (32 + 16.0) + 48.0 * V_ + 28.0 * Va_ + 24.0 * Fa_,
+               "zero": 20.0 * N}
+        if st is not None:
+            scan_bytes = 4.0 * st[2] + 4.0 * (N + 1) + N / 8.0            # CSR walk: 4 B per edge + offsets + sign bitmap
+            if len(st) > 9 and st[8] is not None:                          # transposed rows
+                scan_bytes = 4.0 * st[2] + 4.0 * ((N + 31) // 32 + 1) + N / 8.0
             if len(st) > 11 and st[10][0] is not None:
-                # run-length compressed tables (scan_runs_kernel): 12 B per edge entry (difference, mask, chunk), 20 B per
-                # tet entry (three differences, mask, chunk), the sign bitmap once (the windows come from L1 / L2), and
-                # one 128-byte id row per entry that found something (~ one per 6 crossing edges / 2 valid tets: not
-                # known here, left out)
-                dom_bytes = 12.0 * st[10][0].shape[0] + N / 8.0
-                if st[11][0] is not None:
-                    dom_bytes += 20.0 * st[11][0].shape[0]
-        if n and ms > 0:
-            t_events = ms / n * 1e-3      # one launch at a time between two events: includes the ~3-7 us launch / event gap
+                # run-length tables (scan_runs_kernel): 12 B per edge entry (difference, mask, chunk), 20 B per tet entry
+                # (three differences, mask, chunk), the sign bitmap once (the windows come from L1 / L2)
+                scan_bytes = 12.0 * st[10][0].shape[0] + N / 8.0 + (20.0 * st[11][0].shape[0] if st[11][0] is not None else 0.0)
+            alg["edge_scan"] = scan_bytes
+        cand = {k: prof[k][0] / prof[k][1] for k in alg if k in prof and prof[k][1] and prof[k][0] > 0 and k != "zero"}
+        if cand:
+            dom = max(cand, key=cand.get)
+            ms, n = prof[dom]
+            dom_bytes = alg[dom]
+            t_events = ms / n * 1e-3      # one launch at a time between two events: includes the ~3 us launch / event gap
             t = scan_alone_us * 1e-6 if (dom == "edge_scan" and scan_alone_us) else t_events
             achieved = dom_bytes / t / 1e9
             traffic = None
@@ -798,22 +820,24 @@ def main():
                         traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
-            roofline = {"kernel": dom + "_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            names = {"edge_scan": "scan_runs_kernel" if (st and len(st) > 11 and st[10][0] is not None) else "edge_scan_kernel",
+                     "edge_emit": "scan_emit_kernel"}
+            roofline = {"kernel": names.get(dom, dom + "_kernel"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(dom_bytes), "us_per_launch": t * 1e6,
-                        "timing": ("the kernel alone (d3h_profile_scan_kernel): 50 launches, each between its own pair of CUDA "
-                                   "events on the launching stream, L2 evicted by reading a 256 MB buffer before every launch"
-                                   if (dom == "edge_scan" and scan_alone_us) else
-                                   "CUDA events recorded around each launch on its stream, one frame at a time"),
-                        "warm_l2_us_per_launch": scan_warm_us,
-                        "events_one_launch_at_a_time": {"us_per_launch": t_events * 1e6, "frac": dom_bytes / t_events / 1e9 / peak,
-                                                        "note": "includes the ~3-7 us launch / event gap of a lone launch"}}
-            if dev_trace and "us_mean" in dev_trace and dom in dev_trace["us_mean"]:
-                td = dev_trace["us_mean"][dom] * 1e-6
-                roofline["device_timer"] = {"us_per_launch": td * 1e6, "achieved": dom_bytes / td / 1e9,
-                                            "frac": dom_bytes / td / 1e9 / peak,
-                                            "note": "first block start to last block exit (%globaltimer), inside the "
-                                                    "batched step with the other lanes running"}
+                        "timing": "CUDA events recorded around each launch on its stream, one frame at a time "
+                                  "(includes the ~3 us launch / event gap of a lone launch)",
+                        "note": "largest share of a frame's device time; latency- and issue-bound on O(surface) data, no "
+                                "O(F) / O(U) stream is left on the path (DESIGN.md section 4)",
+                        "share_of_frame_kernel_time": cand[dom] / sum(cand.values()),
+                        "all_kernels": {k: {"us_per_launch": round(cand[k] * 1e3, 2), "algorithmic_bytes": int(alg[k]),
+                                            "frac": alg[k] / (cand[k] * 1e-3) / 1e9 / peak} for k in cand}}
+            if scan_alone_us and "edge_scan" in alg:
+                roofline["scan_kernel_alone"] = {"us_per_launch_l2_flushed": scan_alone_us, "us_per_launch_warm": scan_warm_us,
+                                                 "algorithmic_bytes": int(alg["edge_scan"]),
+                                                 "frac": alg["edge_scan"] / (scan_alone_us * 1e-6) / 1e9 / peak,
+                                                 "timing": "d3h_profile_scan_kernel: 50 launches, each between its own pair of "
+                                                           "CUDA events, L2 evicted by reading 256 MB before every launch"}
     dev_ms_frame = sum(v[0] for v in prof.values()) / max(nprof * len(pos_single), 1) if prof else None
     path_roofline = {"algorithmic_bytes_per_frame": int(balg),
                      "achieved_GBps_step": balg * fpr / (ms_step * 1e-3) / 1e9,

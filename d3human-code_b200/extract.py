@@ -1186,6 +1186,38 @@ def _tape_edges(tape3, i: int) -> torch.Tensor:
     return tape[o:o + 2 * int(nv[i])].view(-1, 2)
 
 
+class _MappedAlias:
+    """__cuda_array_interface__ of a pinned host tensor (its device alias under unified addressing)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.__cuda_array_interface__ = {"shape": tuple(t.shape), "typestr": "<f4", "version": 2, "strides": None,
+                                         "data": (t.data_ptr(), False)}
+        self.keep = t
+
+
+def mapped_view(host: torch.Tensor, device=None) -> torch.Tensor:
+    """A CUDA tensor that ALIASES a pinned host tensor (float32, contiguous): pinned allocations are device-mapped at the
+    same address, so kernels can read them in place over PCIe.  Meant for the per-frame grid positions `pos` of a caller
+    that keeps them in host memory: an extraction reads only the rows of crossing-edge end points (~2 V of N rows, forward
+    and backward), so handing the mapped view to GShell_Tets / extract_frames moves ~1 MB per frame instead of copying the
+    26 MB of (N,3) positions first.  The view shares the host tensor's memory: keep it alive and do not write to it
+    while a call is in flight.  Gradients w.r.t. such a `pos` are ordinary device tensors."""
+    if host.is_cuda:
+        return host
+    if host.dtype is not torch.float32 or not host.is_contiguous() or not host.is_pinned():
+        raise ValueError("mapped_view: needs a pinned, contiguous float32 host tensor")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.as_tensor(_MappedAlias(host), device=dev)
+    _mapped_keepalive[out.data_ptr()] = host          # (the alias does not own the memory)
+    if len(_mapped_keepalive) > 64:
+        for k in list(_mapped_keepalive)[:-32]:
+            del _mapped_keepalive[k]
+    return out
+
+
+_mapped_keepalive: Dict[int, torch.Tensor] = {}
+
+
 def gather_touched(grad: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
     """Compact form of a dense per-grid-vertex gradient of ONE frame: the rows an extraction can have touched are the end
     points of its crossing edges (`edges` = FramesFuture.tape_edges(i), (V,2) int32).  Returns grad[edges.reshape(-1)] as a

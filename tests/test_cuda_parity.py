@@ -191,6 +191,38 @@ def test_integer_intermediates_match_oracle(dev, edges_mode):
     U.assert_exact("corners", r.tape_corners(0).cpu().numpy().astype(np.int64), fwd["corners"])
 
 
+def test_mapped_host_positions_equal_device_positions(dev):
+    """extract.mapped_view: the grid positions stay in pinned host memory and the kernels read the rows they need in place
+    (a single call, then a batch of frames that share sdf / msdf): outputs are bit-identical to the same calls on device
+    tensors, gradients equal up to the order of the float atomics."""
+    from d3human_code_b200 import extract as E
+    if dev.type != "cuda":
+        pytest.skip("needs pinned, device-mapped host memory")
+    pos, sdf, msdf, tets = _inputs(24, "capsule", seed=2)
+    _, h = _classes()
+    ts, tm = torch.tensor(sdf, device=dev), torch.tensor(msdf, device=dev)
+    tt = torch.tensor(tets, device=dev)
+    frames = np.stack([pos + np.float32(0.003 * f) for f in range(3)]).astype(np.float32)
+    host = torch.from_numpy(frames).pin_memory()
+    for _ in range(2):      # (the second round runs on the static tables)
+        got = {}
+        for kind in ("device", "mapped"):
+            tp = (torch.from_numpy(frames).to(dev) if kind == "device" else E.mapped_view(host, dev)).requires_grad_(True)
+            assert tp.is_cuda
+            v, f, _, _, tng, ex = h(tp[0], ts, tm, tt, "cloth")
+            outs = E.extract_frames(tp, ts, tm, tt, types="cloth")
+            loss = v.sum() * 0.5 + ex["msdf"].sum() + sum((o[0] * (i + 1)).sum() + o[5]["msdf"].sum() for i, o in enumerate(outs))
+            loss.backward()
+            got[kind] = [tp.grad, v, f, ex["msdf"]] + [t for o in outs for t in (o[0], o[1], o[5]["msdf"])]
+            torch.cuda.synchronize()
+        for a, b in zip(got["device"][1:], got["mapped"][1:]):
+            assert torch.equal(a.detach().cpu(), b.detach().cpu())
+        ga, gb = got["device"][0].cpu().numpy(), got["mapped"][0].cpu().numpy()      # (float atomics: order of additions)
+        U.assert_close_normwise("grad_pos", gb, ga, U.GRAD_RTOL)
+    with pytest.raises(ValueError):
+        E.mapped_view(torch.from_numpy(frames))          # not pinned
+
+
 def test_smplx_layout_split_extraction(dev):
     """config 3: unstructured (scrambled) grid in the script/get_tet_smpl.py layout, cloth then body on the same sdf."""
     g = grids.smplx_layout_grid(32, dilate=0.15, seed=1)
