@@ -48,8 +48,10 @@ def parse():
     ap.add_argument("--frames-per-rank", type=int, default=32,
                     help="frames per rank per step (BASELINE configs[3]: batches of 16 video frames; default = 2 batches)")
     ap.add_argument("--lanes", type=int, default=8, help="concurrent lanes the frames of a batch are spread over")
-    ap.add_argument("--groups", type=int, default=4,
-                    help="the frames of a step are issued as this many extract_frames_async batches (host / GPU pipelining)")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="the frames of a step are issued as this many extract_frames_async batches (host / GPU pipelining; "
+                         "a batch runs its frames fused, 8 per launch: with 2 groups a 32-frame step is 4 rounds of launches "
+                         "and 2 host round trips -- 1.32 ms against 1.57 ms with 4 groups, r02ag)")
     ap.add_argument("--field", default="capsule", choices=["capsule", "sphere"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -107,10 +109,11 @@ def make_config(args, world, F, N, counts0, ngroups, frames_per_step):
     """The `config` object of the JSON line: identical for the GPU arm and the --impl reference arm."""
     return {"workload": workload_name(args), "F": int(F), "N": int(N), "frames_per_step": int(frames_per_step),
             "counts_frame0": counts0,
-            "l2": "per step every frame reads its own 26 MB of positions and writes 26 MB of gradients (%d MB per rank and "
-                  "step > 126 MB L2); the static edge list (68 MB at 128^3) is re-read by every frame as in training, "
-                  "where the tet grid is static; no explicit flush in the headline, `cold` = L2-flushed single call"
-                  % (52 * max(1, frames_per_step // max(world, 1))),
+            "l2": "per step every frame writes 26 MB of position gradients (zero-filled, then scattered into) next to its "
+                  "surface buffers (%d MB per rank and step > 126 MB L2); the static run-length tables (14 MB at 128^3) are "
+                  "re-read by every batch as in training, where the tet grid is static; no explicit flush in the headline, "
+                  "`cold` = L2-flushed single call"
+                  % (34 * max(1, frames_per_step // max(world, 1))),
             "lanes": args.lanes, "groups": ngroups, "mode": args.mode,
             "parallelism": (("frames x%d" % world) if args.mode != "tets" else ("tet ranges x%d" % world)) if world > 1 else "single GPU"}
 
