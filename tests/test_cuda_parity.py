@@ -412,6 +412,48 @@ def test_extract_frames_batch_matches_oracle_per_frame(dev):
     U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), want_msdf, U.GRAD_RTOL)
 
 
+def test_fused_frames_shared_topology_and_regrowth(dev, edges_mode):
+    """Frames of one type on the run-length path run fused (grid.y = frame) and, sharing sdf / msdf, find their topology
+    once: 11 frames on 4 workspaces (three rounds of launches) against the oracle frame by frame, gradients of the shared
+    tensors summed over the frames -- then once more after the plan's capacities were cut down (every list overflows: the
+    call reports it and the host re-runs with room)."""
+    from d3human_code_b200 import extract as E
+    res, B = 20, 11
+    pos, tets = grids.kuhn_grid(res)
+    sdf, msdf = grids.capsule_garment_field(pos)
+    pos_b = np.stack([pos + grids.frame_offsets(pos.shape[0], res, f) for f in range(B)]).astype(np.float32)
+    ts = torch.tensor(sdf[:, None], device=dev, requires_grad=True)
+    tm = torch.tensor(msdf, device=dev, requires_grad=True)
+    tt = torch.tensor(tets, device=dev)
+    rng = np.random.default_rng(5)
+    fwd = [O.extract_forward(pos_b[i], sdf, msdf, tets, 1, True) for i in range(B)]
+    ups = [(rng.standard_normal(f["verts_aug"].shape).astype(np.float32), rng.standard_normal(f["msdf"].shape).astype(np.float32))
+           for f in fwd]
+    want_sdf, want_msdf = np.zeros_like(sdf), np.zeros_like(msdf)
+    want_pos = np.zeros_like(pos_b)
+    for i, f in enumerate(fwd):
+        w = O.extract_backward(f, ups[i][0], ups[i][1])
+        want_pos[i], want_sdf, want_msdf = w[0], want_sdf + w[1], want_msdf + w[2]
+    for shrink in (False, False, True):
+        if shrink:
+            for plan in E._plans.values():
+                plan.cap_tets, plan.cap_v, plan.cap_va, plan.cap_fw, plan.cap_fa = 96, 48, 96, 48, 48
+        tp = torch.tensor(pos_b, device=dev, requires_grad=True)
+        ts.grad = tm.grad = None
+        outs = E.extract_frames(tp, ts, tm, tt, types="cloth", lanes=4)
+        loss = 0.0
+        for i, o in enumerate(outs):
+            U.assert_exact(f"faces_aug[{i}]", o[1].cpu().numpy(), fwd[i]["faces_aug"])
+            U.assert_exact(f"verts_aug[{i}]", o[0].detach().cpu().numpy(), fwd[i]["verts_aug"])
+            U.assert_exact(f"msdf[{i}]", o[5]["msdf"].detach().cpu().numpy(), fwd[i]["msdf"])
+            U.assert_exact(f"faces_watertight[{i}]", o[5]["faces_watertight"].cpu().numpy(), fwd[i]["faces_watertight"])
+            loss = loss + (o[0] * torch.tensor(ups[i][0], device=dev)).sum() + (o[5]["msdf"] * torch.tensor(ups[i][1], device=dev)).sum()
+        loss.backward()
+        U.assert_close_normwise("grad_pos", tp.grad.cpu().numpy(), want_pos, U.GRAD_RTOL)
+        U.assert_close_normwise("grad_sdf", ts.grad.cpu().numpy().reshape(-1), want_sdf, 1e-4)
+        U.assert_close_normwise("grad_msdf", tm.grad.cpu().numpy(), want_msdf, 1e-4)
+
+
 def test_extract_frames_list_form_and_repeat(dev):
     """Sequence-of-tensors form with per-frame sdf; two consecutive batches reuse the lanes / graphs / workspaces."""
     from d3human_code_b200.extract import extract_frames

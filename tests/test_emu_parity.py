@@ -130,6 +130,10 @@ def test_oracle(dev, res, field, cls, typ, wt):
     G.test_cuda_matches_oracle(dev, res, field, cls, typ, wt)
 
 
+def test_fused_frames_shared_topology_and_regrowth(dev, edges_mode):
+    G.test_fused_frames_shared_topology_and_regrowth(dev, edges_mode)
+
+
 def test_integer_intermediates(dev, edges_mode):
     G.test_integer_intermediates_match_oracle(dev, edges_mode)
 
