@@ -664,7 +664,6 @@ def main():
             d_pos = [torch.empty_like(pos[lo:hi]) for lo, hi in bounds]
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         outs_host = None
-        e2e_ups = {}
         k_e2e = max(3, min(args.steps, 20))
 
         def e2e_step():
@@ -695,23 +694,13 @@ def main():
             for k, (dp, (lo, hi)) in enumerate(zip(d_pos, bounds)):
                 cur.wait_event(ev_in[k])
                 fut = E.extract_frames_async(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
-                # the padded batch form: one autograd node with O(1) outputs; every frame's rows are narrowed for the copy
-                pk = fut.packed()
-                cva = pk.verts_aug.shape[1]
-                if k not in e2e_ups or e2e_ups[k][0].shape[1] < cva:
-                    rows = max(cva, pad_rows)     # (upstream gradients: constant across steps, as in the device-resident leg)
-                    uv_, um_ = torch.zeros((hi - lo, rows, 3), device=dev), torch.zeros((hi - lo, rows), device=dev)
-                    for i in range(lo, hi):
-                        uv_[i - lo, :ups_v[i].shape[0]] = ups_v[i]
-                        um_[i - lo, :ups_m[i].shape[0]] = ups_m[i]
-                    e2e_ups[k] = (uv_, um_)
-                torch.autograd.backward([pk.verts_aug, pk.msdf], [e2e_ups[k][0][:, :cva], e2e_ups[k][1][:, :cva]])
+                outs = fut.result()
+                torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs],
+                                        ups_v[lo:hi] + ups_m[lo:hi])
                 res = []
-                va_n, fa_n = pk.n_verts_aug.tolist(), pk.n_faces_aug.tolist()
-                for i in range(hi - lo):
-                    edges = pk.tape_edges(i)
-                    res += [pk.verts_aug[i, :va_n[i]].detach(), pk.faces_aug[i, :fa_n[i]], pk.msdf[i, :va_n[i]].detach(), edges,
-                            E.gather_touched(dp.grad[i], edges)]
+                for i, o in enumerate(outs):
+                    edges = fut.tape_edges(i)
+                    res += [o[0].detach(), o[1], o[5]["msdf"].detach(), edges, E.gather_touched(dp.grad[i], edges)]
                     if mapped:      # rows of `pos` the kernels read in place: both end points of every crossing edge,
                         h2d += 2 * edges.numel() * 12   # once by the vertex interpolation and once by its adjoint
                 if k == len(bounds) - 1:
@@ -723,7 +712,7 @@ def main():
                         for h, t in zip(outs_host[k], res):
                             h.copy_(t, non_blocking=True)
                             d2h += t.numel() * t.element_size()
-                keep.append((pk, fut))
+                keep.append((outs, fut))
             if outs_host is None:   # first call: allocate the pinned result buffers, copy without overlap
                 outs_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res] for res in res_all]
                 for hs, res in zip(outs_host, res_all):
