@@ -58,6 +58,7 @@ __device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspac
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   if (tid == 0) *ws.blk = src;  // the argument block of this call, for every later kernel
   if (block_only) {
+    if (blockIdx.x != 0) return;
     if (tid < (int64_t)kCounterWordsReset) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
     if (tid == 0) { ws.ctr->trace = src.trace; ws.ctr->trace_frame = (unsigned)src.a.seq; }
     return;
@@ -148,7 +149,10 @@ void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaS
   const int64_t nquads = (a[0].n_grid + 3) / 4;
   int64_t blocks = (nquads + 255) / 256;
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 8 / frames) blocks = 148 * 8 / frames;
+  // with a shared topology only the first frame has bitmaps to build and state to clear: it keeps the whole grid (the
+  // CTAs of the other frames store their argument block and leave)
+  const bool shared = batch_ctx().topo_frames == 1 && frames > 1;
+  if (!shared && blocks > 148 * 8 / frames) blocks = 148 * 8 / frames;
   static thread_local FwdBlockSet set;
   for (int f = 0; f < frames; ++f) {
     set.f[f].a = a[f];
@@ -156,8 +160,7 @@ void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaS
     set.f[f].trace = trace_table();
   }
   ProfScope ps(K_PREPARE, stream);
-  launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs,
-           (batch_ctx().topo_frames == 1 && frames > 1) ? 1 : 0);
+  launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs, shared ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

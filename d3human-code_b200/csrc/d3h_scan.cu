@@ -940,6 +940,8 @@ scan_emit_kernel(const FwdBlock* __restrict__ blk, const DevCounters* __restrict
   {
     // what the frame writes sits in its own workspace, the topology it reads possibly in the first frame's (BatchCtx)
     const int64_t shift = fs.off[blockIdx.y], tshift = topo.off[blockIdx.y];
+    // ... and then the records and corner ids are the first frame's business alone (poly_faces_kernel reads them there)
+    if (shift != tshift && blockIdx.x < grid_tets) return;
     blk = frame_ptr(blk, shift); ctr = frame_ptr(ctr, shift); records = frame_ptr(records, shift);
     w_vert = frame_ptr(w_vert, shift); w_acc = frame_ptr(w_acc, shift);
     vlist = frame_ptr(vlist, tshift); elist = frame_ptr(elist, tshift); m1_words = frame_ptr(m1_words, tshift);

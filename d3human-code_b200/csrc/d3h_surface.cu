@@ -72,11 +72,16 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
                   unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_gcnt, unsigned* __restrict__ poly_excl,
                   UvParams uvp,
                   d3h_counts* __restrict__ counts_dev, const unsigned* __restrict__ corner_rank,
-                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix, const __grid_constant__ FrameSet fs) {
+                  const unsigned* __restrict__ edge_bits, const unsigned* __restrict__ word_prefix, const __grid_constant__ FrameSet fs,
+                  const __grid_constant__ FrameSet topo) {
   pdl_enter();
+  // frames that share their topology (BatchCtx): the records and the corner ids were made once, by the first frame of the
+  // launch; this frame reads them there and leaves a copy of the corner ids on its own tape (poly_cut_kernel, backward)
+  const int32_t* __restrict__ corners_src = frame_ptr(blk, topo.off[blockIdx.y])->a.tape_corners;
   {
     const int64_t shift = fs.off[blockIdx.y];
-    blk = frame_ptr(blk, shift); records = frame_ptr(records, shift); ctr = frame_ptr(ctr, shift);
+    records = frame_ptr(records, topo.off[blockIdx.y]);
+    blk = frame_ptr(blk, shift); ctr = frame_ptr(ctr, shift);
     w_vert = frame_ptr(w_vert, shift); w_acc = frame_ptr(w_acc, shift); poly_cnt = frame_ptr(poly_cnt, shift);
     poly_gcnt = frame_ptr(poly_gcnt, shift); poly_excl = frame_ptr(poly_excl, shift); counts_dev = frame_ptr(counts_dev, shift);
     corner_rank = frame_ptr(corner_rank, shift); edge_bits = frame_ptr(edge_bits, shift);
@@ -129,7 +134,12 @@ poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __rest
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) L[k] = (k < n) ? corners[p0 + k] : 0;
+        for (int k = 0; k < 4; ++k) L[k] = (k < n) ? corners_src[p0 + k] : 0;
+        if (corners_src != corners) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < n) corners[p0 + k] = L[k];
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) P[k] = (k < n) ? w_vert[L[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -404,11 +414,13 @@ __global__ void __launch_bounds__(kPolyThreads)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
-                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl, const __grid_constant__ FrameSet fs) {
+                const unsigned* __restrict__ poly_gcnt, const unsigned* __restrict__ poly_excl, const __grid_constant__ FrameSet fs,
+                const __grid_constant__ FrameSet topo) {
   pdl_enter();
   {
     const int64_t shift = fs.off[blockIdx.y];
-    blk = frame_ptr(blk, shift); records = frame_ptr(records, shift); ctr = frame_ptr(ctr, shift);
+    records = frame_ptr(records, topo.off[blockIdx.y]);   // (shared topology: the first frame's records)
+    blk = frame_ptr(blk, shift); ctr = frame_ptr(ctr, shift);
     w_vert = frame_ptr(w_vert, shift); w_acc = frame_ptr(w_acc, shift); owner = frame_ptr(owner, shift);
     poly_gcnt = frame_ptr(poly_gcnt, shift); poly_excl = frame_ptr(poly_excl, shift);
   }
@@ -605,11 +617,11 @@ void launch_surface(const d3h_forward_args& a, const Workspace& ws, const d3h_te
     ProfScope ps(K_POLY_FACES, stream);
     launch_k_dep(poly_faces_kernel<false>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
                  ws.vert, ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts, ws.corner_rank, ws.edge_bits,
-                 ws.word_prefix, batch_ctx().fs);
+                 ws.word_prefix, batch_ctx().fs, batch_ctx().topo);
   }
   ProfScope ps(K_POLY_CUT, stream);
   launch_k_dep(poly_cut_kernel<false>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk, records, ws.ctr,
-           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl, batch_ctx().fs);
+           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl, batch_ctx().fs, batch_ctx().topo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -849,9 +861,9 @@ void launch_pair_replay(const d3h_forward_args& a, const Workspace& ws, const d3
   const unsigned nblk = (unsigned)(ws.ntiles_poly > 0 ? ws.ntiles_poly : 1);
   launch_k(poly_faces_kernel<true>, nblk, (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr, ws.vert,
            ws.acc, ws.poly_cnt, ws.poly_gcnt, ws.poly_excl, uvp, ws.counts2, ws.corner_rank, ws.edge_bits, ws.word_prefix,
-           FrameSet{});
+           FrameSet{}, FrameSet{});
   launch_k(poly_cut_kernel<true>, cut_blocks(ws), (unsigned)kPolyThreads, stream, kLaunchLatency, ws.blk2, records, ws.ctr,
-           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl, FrameSet{});
+           ws.vert, ws.acc, ws.owner, ws.poly_gcnt, ws.poly_excl, FrameSet{}, FrameSet{});
 }
 
 }  // namespace d3h
