@@ -656,7 +656,12 @@ def main():
         d_sdf = torch.empty_like(sdf)
         d_msdf = torch.empty_like(msdf)
         d_flat = torch.zeros_like(flat_grad)
-        if mapped:
+        diag = os.environ.get("D3H_E2E_DIAG", "")   # diagnostics only: "resident" = positions already on the device,
+        no_d2h = "nod2h" in diag                     # "nod2h" = results stay on the device
+        if "resident" in diag:
+            mapped = True
+            d_pos = [host_pos[lo:hi].to(dev) for lo, hi in bounds]
+        elif mapped:
             # CUDA tensors that ALIAS the pinned host buffer (unified addressing: pinned allocations are device-mapped at
             # the same address): the kernels fetch the rows they need over PCIe, nothing is copied up front
             d_pos = [E.mapped_view(host_pos[lo:hi], dev) for lo, hi in bounds]
@@ -707,7 +712,7 @@ def main():
                     res.append(d_flat)
                 s_out.wait_stream(cur)
                 res_all.append(res)
-                if outs_host is not None:
+                if outs_host is not None and not no_d2h:
                     with torch.cuda.stream(s_out):
                         for h, t in zip(outs_host[k], res):
                             h.copy_(t, non_blocking=True)

@@ -56,13 +56,14 @@ __device__ __forceinline__ float4 load4_guarded(const float* __restrict__ p, int
 __device__ __forceinline__ void prepare_body(const FwdBlock& src, const Workspace& ws, bool block_only = false) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  if (tid == 0) *ws.blk = src;  // the argument block of this call, for every later kernel
-  if (block_only) {
-    if (blockIdx.x != 0) return;
-    if (tid < (int64_t)kCounterWordsReset) reinterpret_cast<unsigned*>(ws.ctr)[tid] = 0u;
-    if (tid == 0) { ws.ctr->trace = src.trace; ws.ctr->trace_frame = (unsigned)src.a.seq; }
+  if (block_only) {   // (one CTA)
+    if (threadIdx.x == 0) *ws.blk = src;
+    if (threadIdx.x < kCounterWordsReset) reinterpret_cast<unsigned*>(ws.ctr)[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) { ws.ctr->trace = src.trace; ws.ctr->trace_frame = (unsigned)src.a.seq; }
     return;
   }
+  if (tid == 0) *ws.blk = src;  // the argument block of this call, for every later kernel
   const float* __restrict__ sdf = src.a.sdf;
   const float* __restrict__ msdf = src.a.msdf;
   const int64_t n_grid = src.a.n_grid;
@@ -124,8 +125,19 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
 // several frames in one launch: frame blockIdx.y, its argument block from the set, its workspace by offset
 __global__ void __launch_bounds__(256) prepare_frames_kernel(const __grid_constant__ FwdBlockSet set, Workspace ws,
                                                              const __grid_constant__ FrameSet fs, int shared_topology) {
+  if (shared_topology) {
+    // grid.y == 1: the first frame has the bitmaps to build and the scan state to clear; CTA f also stores the argument
+    // block of frame f and resets its counters (all that a frame needs which takes its topology from the first)
+    if (blockIdx.x >= 1 && (int)blockIdx.x < shared_topology) {
+      Workspace w2 = ws;
+      shift_workspace(w2, fs.off[blockIdx.x]);
+      prepare_body(set.f[blockIdx.x], w2, true);
+    }
+    prepare_body(set.f[0], ws);
+    return;
+  }
   shift_workspace(ws, fs.off[blockIdx.y]);
-  prepare_body(set.f[blockIdx.y], ws, shared_topology && blockIdx.y > 0);
+  prepare_body(set.f[blockIdx.y], ws);
 }
 
 const void* prepare_kernel_address() { return reinterpret_cast<const void*>(prepare_kernel); }
@@ -160,7 +172,14 @@ void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaS
     set.f[f].trace = trace_table();
   }
   ProfScope ps(K_PREPARE, stream);
-  launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs, shared ? 1 : 0);
+  if (shared) {   // one frame's worth of CTAs (at least one per frame), shared_topology = number of frames
+    if (blocks < frames) blocks = frames;
+    batch_ctx().frames = 1;
+    launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs, frames);
+    batch_ctx().frames = frames;
+  } else {
+    launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs, 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
