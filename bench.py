@@ -696,9 +696,18 @@ def main():
             d_flat.zero_()
             d_sdf.grad, d_msdf.grad = d_flat[:N].view(N, 1), d_flat[N:]
             keep, res_all = [], []
+            futs = None
+            if mapped:
+                # nothing to wait for but sdf / msdf: every chunk is launched up front (as in the device-resident step), the
+                # host reads the sizes of chunk k while the GPU extracts chunk k + 1
+                cur.wait_stream(s_in)
+                futs = [E.extract_frames_async(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes) for dp in d_pos]
             for k, (dp, (lo, hi)) in enumerate(zip(d_pos, bounds)):
-                cur.wait_event(ev_in[k])
-                fut = E.extract_frames_async(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
+                if futs is None:
+                    cur.wait_event(ev_in[k])
+                    fut = E.extract_frames_async(dp, d_sdf, d_msdf, tets, types="cloth", lanes=args.lanes)
+                else:
+                    fut = futs[k]
                 outs = fut.result()
                 torch.autograd.backward([o[0] for o in outs] + [o[5]["msdf"] for o in outs],
                                         ups_v[lo:hi] + ups_m[lo:hi])
@@ -710,7 +719,9 @@ def main():
                         h2d += 2 * edges.numel() * 12   # once by the vertex interpolation and once by its adjoint
                 if k == len(bounds) - 1:
                     res.append(d_flat)
-                s_out.wait_stream(cur)
+                ev_out = torch.cuda.Event()      # (an event, not the stream: later chunks are already queued behind this one)
+                ev_out.record(cur)
+                s_out.wait_event(ev_out)
                 res_all.append(res)
                 if outs_host is not None and not no_d2h:
                     with torch.cuda.stream(s_out):
