@@ -94,7 +94,8 @@ def workload_name(args):
                 f"{args.frames_total} frames/step with per-frame offsets sharded over the ranks (strong scaling)")
     return (f"configs[1]: {args.res}^3 Kuhn grid, {field}"
             f", hmSDF_Tets(cloth) semantics fwd+bwd, {args.frames_per_rank} frame(s)/rank/step with per-frame offsets "
-            f"(configs[3] batch) through extract_frames on {args.lanes} lanes")
+            f"(configs[3] batch) through extract_frames ({args.lanes} workspaces: the frames of a batch run fused, up to 8 per "
+            f"launch, and share one topology since they share sdf / msdf)")
 
 
 def frames_of_rank(args, world, rank):
