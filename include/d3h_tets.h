@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D3H_VERSION 440 /* 0.4.4 */
+#define D3H_VERSION 500 /* 0.5.0: d3h_forward_args grew (edge_rows, edge_runs, tet_runs) */
 
 enum {
   D3H_OK = 0,
