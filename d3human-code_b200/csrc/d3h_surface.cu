@@ -65,8 +65,15 @@ __device__ __forceinline__ int cut_case(bool quad, float m0, float m1, float m2,
 // REPLAY = second extraction of a cloth / body pair (d3h_forward_args.pair_*): `blk` is the pair's argument block (its
 // outputs, the opposite msdf_negate), the interpolated mSDF of every vertex is the exact negation of the stored one,
 // normals / tangents were accumulated by the first extraction and are not splatted again.
+// resident CTAs per SM the compiler has to leave room for (register cap): A/B by -D at build time
+#ifndef D3H_FACES_MINB
+#define D3H_FACES_MINB 4   // 64 registers instead of 80
+#endif
+#ifndef D3H_CUT_MINB
+#define D3H_CUT_MINB 4     // 62 registers (5 would be 48 + a 28-byte spill)
+#endif
 template <bool REPLAY>
-__global__ void __launch_bounds__(kPolyThreads)
+__global__ void __launch_bounds__(kPolyThreads, D3H_FACES_MINB)
 poly_faces_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                   DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert, float* __restrict__ w_acc,
                   unsigned* __restrict__ poly_cnt, unsigned* __restrict__ poly_gcnt, unsigned* __restrict__ poly_excl,
@@ -410,7 +417,7 @@ __device__ __forceinline__ void load_cut_tables(CutTables& T) {
 }
 
 template <bool REPLAY>
-__global__ void __launch_bounds__(kPolyThreads)
+__global__ void __launch_bounds__(kPolyThreads, D3H_CUT_MINB)
 poly_cut_kernel(const FwdBlock* __restrict__ blk, const d3h_tet_record* __restrict__ records,
                 const DevCounters* __restrict__ ctr, const float4* __restrict__ w_vert,
                 const float* __restrict__ w_acc, const int32_t* __restrict__ owner,
