@@ -26,6 +26,13 @@
 // (global warp id) % kQueues, and the consumers give every sub-queue its own CTAs.
 //
 // poly_faces_kernel / poly_cut_kernel / the adjoint are shared with the other paths.
+//
+// Forms of the static edge list, chosen once per grid by the host (extract.build_edge_table):
+//   run-length tables  scan_runs_kernel + runs_expand_kernel (DEFAULT on grids numbered along the axes of a lattice; with the
+//                      compressed tet array they also find the valid tets, and edge_mark_kernel is not launched)
+//   transposed rows    edge_scan_rows_kernel (grids without that structure; edge_scan_pipe_kernel: opt-in persistent variant)
+//   CSR walk           edge_scan_kernel (D3H_SCAN_ROWS=0)
+// Kernels that a batch runs with gridDim.y = frame take the frame's workspace by offset (FrameSet, d3h_internal.cuh).
 #include <cstdlib>
 
 #include "d3h_internal.cuh"
