@@ -20,6 +20,8 @@
 // (zero 8.7 + boundary 5.2 + crossing 5.4 us at 128^3); the gather form replaced it on the sort path.
 //
 // Gradient formulas: SURVEY.md appendix A.5 (verified against the reference's autograd in tests/).
+#include <cstdlib>
+
 #include "d3h_internal.cuh"
 
 namespace d3h {
@@ -64,6 +66,22 @@ void launch_zero_grads_from_block(const d3h_forward_args& a, const Workspace& ws
   int64_t blocks = (5 * a.n_grid / 16 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  // A fused batch runs the fill on a side stream next to the latency-bound kernels of the main chain.  A small launch (a
+  // few CTAs per SM that keep HBM busy without taking the CTA slots of those kernels) was measured and is SLOWER: 1.51 /
+  // 1.34-1.40 / 1.27 ms per step with 148 / 296 / 592 CTAs against 1.22 ms with 1184 or the full grid (r02at).
+  // D3H_ZERO_CTAS = CTAs of the whole launch (A/B); default: no cap.
+  const int frames = batch_ctx().frames;
+  if (frames > 1) {
+    static int total = -1;
+    if (total < 0) {
+      const char* env = getenv("D3H_ZERO_CTAS");
+      total = (env && atoi(env) > 0) ? atoi(env) : 0;
+    }
+    if (total > 0) {
+      const int64_t per = total / frames > 0 ? total / frames : 1;
+      if (blocks > per) blocks = per;
+    }
+  }
   ProfScope ps(K_ZERO, stream);
   launch_k(zero_block_kernel, (unsigned)blocks, 256u, stream, kLaunchLatency, ws.blk, a.n_grid, batch_ctx().fs);
 }
