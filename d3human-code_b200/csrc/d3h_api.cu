@@ -49,7 +49,7 @@ unsigned long long* trace_table() { return g_trace_dev; }
 
 // ---- launch priorities ------------------------------------------------------------------------------
 BatchCtx& batch_ctx() {
-  static thread_local BatchCtx ctx = {1, {}, 1, {}};
+  static thread_local BatchCtx ctx = {1, {}, 1, {}, false};
   return ctx;
 }
 
@@ -657,6 +657,7 @@ static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, c
     ls->busy = false;
   }
   int64_t i0 = 0;
+  const d3h_forward_args* topo_of = nullptr;   // first frame of the launch whose topology is still standing in its workspace
   while (i0 < n_frames) {
     // the longest run of frames with distinct workspaces, at most kMaxFused
     int64_t i1 = i0 + 1;
@@ -676,6 +677,11 @@ static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, c
     }
     ctx.topo_frames = shared ? 1 : ctx.frames;
     for (int f = 0; f < ctx.frames; ++f) ctx.topo.off[f] = shared ? 0 : ctx.fs.off[f];
+    // rounds of one call (frames beyond the number of workspaces): the same field again, found by the round before in the
+    // very workspace this round's first frame uses -- keep it
+    ctx.reuse_topology = shared && ctx.frames > 1 && topo_of != nullptr && topo_of->workspace == a.workspace &&
+                         topo_of->sdf == a.sdf && topo_of->msdf == a.msdf && topo_of->msdf_negate == a.msdf_negate;
+    topo_of = (shared && ctx.frames > 1) ? &a : nullptr;
     launch_prepare_frames(args + i0, ws, stream);
     // the zero-fill of the gradient buffers depends on nothing but the argument blocks: a side stream takes it
     bool zero = false;
@@ -690,6 +696,7 @@ static int forward_batch_fused(const d3h_forward_args* args, int64_t n_frames, c
     launch_surface(a, ws, ws.records, stream);
     if (zero) cudaStreamWaitEvent(stream, ls->join[0], 0);
     ctx.frames = ctx.topo_frames = 1;
+    ctx.reuse_topology = false;
     memset(&ctx.fs, 0, sizeof(ctx.fs));
     memset(&ctx.topo, 0, sizeof(ctx.topo));
     cudaError_t e = cudaGetLastError();

@@ -125,6 +125,27 @@ __global__ void __launch_bounds__(256) prepare_kernel(FwdBlock src, Workspace ws
 // several frames in one launch: frame blockIdx.y, its argument block from the set, its workspace by offset
 __global__ void __launch_bounds__(256) prepare_frames_kernel(const __grid_constant__ FwdBlockSet set, Workspace ws,
                                                              const __grid_constant__ FrameSet fs, int shared_topology) {
+  if (shared_topology < 0) {
+    // grid.y == 1, -shared_topology frames: the topology of the launch before still stands in the first frame's workspace
+    // (BatchCtx.reuse_topology).  CTA f stores the argument block of frame f, resets its counters and takes the totals from
+    // the counts that launch published in that workspace (its own frame there had the same totals).
+    if ((int)blockIdx.x < -shared_topology) {
+      const d3h_counts* __restrict__ tc = ws.counts;
+      Workspace w2 = ws;
+      shift_workspace(w2, fs.off[blockIdx.x]);
+      prepare_body(set.f[blockIdx.x], w2, true);
+      if (threadIdx.x == 0) {
+        const bool ok = tc->overflow == 0;
+        w2.ctr->n_valid = (unsigned)tc->n_valid_tets;
+        w2.ctr->n_tri = (unsigned)tc->n_tri_tets;
+        w2.ctr->n_quad = (unsigned)tc->n_quad_tets;
+        w2.ctr->work_tri = ok ? (unsigned)tc->n_tri_tets : 0u;
+        w2.ctr->work_quad = ok ? (unsigned)tc->n_quad_tets : 0u;
+        w2.ctr->n_verts = (unsigned)tc->n_verts;
+      }
+    }
+    return;
+  }
   if (shared_topology) {
     // grid.y == 1: the first frame has the bitmaps to build and the scan state to clear; CTA f also stores the argument
     // block of frame f and resets its counters (all that a frame needs which takes its topology from the first)
@@ -172,7 +193,11 @@ void launch_prepare_frames(const d3h_forward_args* a, const Workspace& ws, cudaS
     set.f[f].trace = trace_table();
   }
   ProfScope ps(K_PREPARE, stream);
-  if (shared) {   // one frame's worth of CTAs (at least one per frame), shared_topology = number of frames
+  if (shared && batch_ctx().reuse_topology) {   // a CTA per frame
+    batch_ctx().frames = 1;
+    launch_k(prepare_frames_kernel, (unsigned)frames, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs, -frames);
+    batch_ctx().frames = frames;
+  } else if (shared) {   // one frame's worth of CTAs (at least one per frame), shared_topology = number of frames
     if (blocks < frames) blocks = frames;
     batch_ctx().frames = 1;
     launch_k(prepare_frames_kernel, (unsigned)blocks, 256, stream, kLaunchLatency, set, ws, batch_ctx().fs, frames);

@@ -179,6 +179,9 @@ struct BatchCtx {
   // frame f finds the topology: 0 when shared, fs.off[f] otherwise; topo_frames = 1 when shared, frames otherwise.
   int topo_frames;
   FrameSet topo;
+  // a later launch of the same call whose frames share the topology of an earlier launch AND whose first frame lives in
+  // the workspace that holds it: nothing is searched again, the frames only get their argument blocks and the totals
+  bool reuse_topology;
 };
 BatchCtx& batch_ctx();   // of the calling thread; one frame, zero offsets outside d3h_extract_forward_batch
 template <typename T>

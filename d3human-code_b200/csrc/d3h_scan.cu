@@ -1124,6 +1124,23 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
   BatchCtx& ctx = batch_ctx();
   const int all_frames = ctx.frames;
   ctx.frames = ctx.topo_frames;
+  // CTAs per sub-queue of the consumers: enough for one entry per thread at the expected fill (a sub-queue holds
+  // 8 / kQueues of the capacity; the expected fill is 1 / kQueues of it)
+  auto parts_for = [](int64_t cap_q) {
+    int64_t p = (cap_q / 8 + 255) / 256;
+    return (unsigned)(p < 1 ? 1 : (p > 16 ? 16 : p));
+  };
+  if (ctx.reuse_topology && runs_both) {
+    // the launch before found this topology in this very workspace: straight to the per-frame kernels
+    ctx.frames = all_frames;
+    if (ws.cap_corners <= 0) return;
+    ProfScope ps(K_EDGE_EMIT, stream);
+    const unsigned gt = kQueues * parts_for(ws.cap_qv), ge = kQueues * parts_for(ws.cap_qe);
+    launch_k_dep(scan_emit_kernel, gt + ge, 256u, stream, kLaunchLatency, ws.blk, ws.ctr, ws.vlist, L.elist, filtered, ws.m1_words,
+                 ws.m2_words, ws.tet_word_prefix, ws.edge_bits, ws.word_prefix, ws.records, ws.vert,
+                 reinterpret_cast<float4*>(ws.acc), ws.cap_corners, ws.q_cnt, ws.cap_qe, ws.cap_qv, gt, batch_ctx().fs, batch_ctx().topo);
+    return;
+  }
   if (a.edge_runs != nullptr) {
     // crossing edges from the compressed edge list and, with the compressed tet array (watertight template), the valid
     // tets as well: pass A tests every entry, pass B expands the few that found something -- no marking kernel
@@ -1144,12 +1161,6 @@ void launch_edge_scan(const d3h_forward_args& a, const Workspace& ws, cudaStream
     else
       launch_k_dep(edge_scan_kernel<4>, nblk, (unsigned)kEScanThreads, stream, kLaunchStream, ws.blk, ws.occ_bits, L);
   }
-  // CTAs per sub-queue of the consumers: enough for one entry per thread at the expected fill (a sub-queue holds
-  // 8 / kQueues of the capacity; the expected fill is 1 / kQueues of it)
-  auto parts_for = [](int64_t cap_q) {
-    int64_t p = (cap_q / 8 + 255) / 256;
-    return (unsigned)(p < 1 ? 1 : (p > 16 ? 16 : p));
-  };
   if (!runs_both) {
     ProfScope ps(K_EDGE_MARK, stream);
     const unsigned nblk = kQueues * parts_for(ws.cap_qe);
