@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import bench  # noqa: E402
 from d3human_code_b200 import extract as E, grids  # noqa: E402
 
-frames, groups, lanes = int(os.environ.get("FRAMES", 32)), int(os.environ.get("GROUPS", 4)), 8
+# (NGROUPS, not GROUPS: bash keeps a read-only array of that name)
+frames, groups, lanes = int(os.environ.get("FRAMES", 32)), int(os.environ.get("NGROUPS", 2)), 8
 dev = torch.device("cuda:0")
 pos_np, sdf_np, msdf_np, tets_np = bench.make_inputs(128, "capsule")
 N = pos_np.shape[0]
