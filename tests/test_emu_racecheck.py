@@ -17,6 +17,7 @@ SELECTION = [                              # ~40 s: every golden case on the thr
     "tests/test_emu_parity.py::test_golden",
     "tests/test_emu_parity.py::test_regrowth",
     "tests/test_emu_parity.py::test_tangent_gradients",
+    "tests/test_emu_parity.py::test_fused_frames_shared_topology_and_regrowth",   # fused frames, shared / kept topology
 ]
 FULL = SELECTION + [                       # D3H_RACECHECK_FULL=1: another four minutes (clean at the end of round 2)
     "tests/test_emu_mesh.py",

@@ -18,6 +18,7 @@ SELECTION = [                             # ~40 s: every golden case on the thre
     "tests/test_emu_parity.py::test_golden",
     "tests/test_emu_parity.py::test_regrowth",
     "tests/test_emu_parity.py::test_tangent_gradients",
+    "tests/test_emu_parity.py::test_fused_frames_shared_topology_and_regrowth",   # fused frames, shared / kept topology
     "tests/test_emu_parity.py::test_compact_gradient_return",
 ]
 FULL = SELECTION + [                      # D3H_SAN_FULL=1: another four minutes (clean at the end of round 2)
